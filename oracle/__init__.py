@@ -1,0 +1,124 @@
+"""oracle -- CPU checkers for the hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this package.  Nothing under art_b200/ does.
+
+Two checkers:
+  port : oracle/libartoracle.so, our plain-C restatement (oracle/*_port.c)
+  ref  : oracle/_ref/libartref{,_det}.so, the reference's own function bodies
+         compiled where they lie (oracle/build_ref.py); `det` adds the
+         zero-scratch-per-tile patch that makes the reference schedule-independent.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_c_float_p = ctypes.POINTER(ctypes.c_float)
+
+
+def _fp(a):
+    return a.ctypes.data_as(_c_float_p)
+
+
+def build(force=False):
+    """Compile the port (always possible) and, when /root/reference is present, _ref."""
+    lib = os.path.join(HERE, "libartoracle.so")
+    srcs = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith("_port.c")]
+    if force or not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs):
+        subprocess.check_call(["make", "-C", HERE, "-s", "-B", "libartoracle.so"])
+    ref_lib = os.path.join(HERE, "_ref", "libartref_det.so")
+    if os.path.isdir("/root/reference/rtengine") and (force or not os.path.exists(ref_lib)):
+        subprocess.check_call(["python3", os.path.join(HERE, "build_ref.py")])
+
+
+class _Port:
+    def __init__(self):
+        build()
+        self.lib = ctypes.CDLL(os.path.join(HERE, "libartoracle.so"))
+
+    def _planes(self, raw):
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        H, W = raw.shape
+        return raw, H, W, [np.zeros((H, W), np.float32) for _ in range(3)]
+
+    def rcd(self, raw, filters):
+        raw, H, W, (r, g, b) = self._planes(raw)
+        rc = self.lib.artoracle_rcd(W, H, ctypes.c_uint(filters), _fp(raw), ctypes.c_long(W),
+                                    _fp(r), _fp(g), _fp(b), ctypes.c_long(W))
+        assert rc == 0
+        return r, g, b
+
+    def border_interpolate2(self, raw, filters, bord):
+        raw, H, W, (r, g, b) = self._planes(raw)
+        self.lib.artoracle_border_interpolate2(W, H, ctypes.c_uint(filters), bord, _fp(raw), ctypes.c_long(W),
+                                               _fp(r), _fp(g), _fp(b), ctypes.c_long(W))
+        return r, g, b
+
+    def amaze(self, raw, filters, initial_gain=1.0, border=4):
+        raw, H, W, (r, g, b) = self._planes(raw)
+        rc = self.lib.artoracle_amaze(W, H, ctypes.c_uint(filters), _fp(raw), ctypes.c_long(W),
+                                      _fp(r), _fp(g), _fp(b), ctypes.c_long(W),
+                                      ctypes.c_float(initial_gain), border)
+        assert rc == 0
+        return r, g, b
+
+
+class _Ref:
+    def __init__(self, det=True):
+        path = os.path.join(HERE, "_ref", "libartref_det.so" if det else "libartref.so")
+        if not os.path.exists(path):
+            build()
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = ctypes.CDLL(path)
+        self.det = det
+
+    def _planes(self, raw):
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        H, W = raw.shape
+        return raw, H, W, [np.zeros((H, W), np.float32) for _ in range(3)]
+
+    def max_threads(self):
+        return int(self.lib.artref_max_threads())
+
+    def rcd(self, raw, filters, nthreads=0):
+        raw, H, W, (r, g, b) = self._planes(raw)
+        self.lib.artref_rcd(W, H, ctypes.c_uint(filters), _fp(raw), ctypes.c_long(W),
+                            _fp(r), _fp(g), _fp(b), ctypes.c_long(W), nthreads)
+        return r, g, b
+
+    def amaze(self, raw, filters, initial_gain=1.0, border=4, nthreads=0):
+        raw, H, W, (r, g, b) = self._planes(raw)
+        self.lib.artref_amaze(W, H, ctypes.c_uint(filters), _fp(raw), ctypes.c_long(W),
+                              _fp(r), _fp(g), _fp(b), ctypes.c_long(W),
+                              ctypes.c_double(initial_gain), border, nthreads)
+        return r, g, b
+
+    def border_interpolate2(self, raw, filters, bord):
+        raw, H, W, (r, g, b) = self._planes(raw)
+        self.lib.artref_border_interpolate2(W, H, ctypes.c_uint(filters), bord, _fp(raw), ctypes.c_long(W),
+                                            _fp(r), _fp(g), _fp(b), ctypes.c_long(W))
+        return r, g, b
+
+
+_cache = {}
+
+
+def port():
+    if "port" not in _cache:
+        _cache["port"] = _Port()
+    return _cache["port"]
+
+
+def ref(det=True):
+    key = "ref_det" if det else "ref"
+    if key not in _cache:
+        _cache[key] = _Ref(det)
+    return _cache[key]
+
+
+def have_ref():
+    return os.path.exists(os.path.join(HERE, "_ref", "libartref_det.so")) or os.path.isdir("/root/reference/rtengine")

@@ -1,0 +1,300 @@
+#!/usr/bin/env python3
+"""Build oracle/_ref/libartref*.so from the reference sources WHERE THEY LIE.
+
+TEST INFRASTRUCTURE ONLY -- nothing in art_b200/ may import, link or execute this.
+
+The reference (artpixls/ART, /root/reference) cannot be built whole here (glibmm,
+gtkmm, lcms2, fftw3f, exiv2 ... are absent), and its hot-path
+translation units cannot be compiled unmodified for the same reason.  What does
+work is compiling the reference's own *function bodies*: this script locates each
+hot-path function by its signature inside /root/reference/rtengine/*.cc, cuts the
+body out by brace matching, writes it to oracle/_ref/src/ (git-ignored scratch,
+never committed) and compiles it inside a ~60-line shim class that supplies only
+the members the body touches (W, H, FC(), rawData, red/green/blue, initialGain,
+border, plistener).  The reference's own headers (array2D.h, rt_math.h, sleef.h,
+opthelper.h, helpersse2.h, median.h ...) are included directly from
+/root/reference/rtengine.
+
+Two libraries are produced:
+  libartref.so      the bodies exactly as they stand in the reference
+  libartref_det.so  the same plus the "zero the per-thread scratch at the start
+                    of every tile" patch (a memset inserted at extraction time).
+                    The stock code reuses calloc'ed per-thread scratch across
+                    tiles, which makes a few pixels depend on the OpenMP
+                    schedule; the _det build is the
+                    canonical, schedule-independent oracle and the tests report
+                    the difference between the two as the reference's own
+                    self-noise floor.
+
+Flags: g++ -std=c++11 -O3 -fopenmp -ffp-contract=off, default x86-64 => the
+__SSE2__ code paths, which is what every x86-64 build of ART executes.
+
+If /root/reference is absent (the GPU box) this script is a no-op: the prebuilt
+.so files travel with the repo snapshot.
+"""
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("ART_REFERENCE", "/root/reference")
+RT = os.path.join(REF, "rtengine")
+OUT = os.path.join(HERE, "_ref")
+SRC = os.path.join(OUT, "src")
+
+
+def cut_function(path, signature_regex):
+    """Return the text of the function whose header matches signature_regex
+    (from the header through the matching closing brace)."""
+    text = open(path, encoding="utf-8", errors="replace").read()
+    m = re.search(signature_regex, text)
+    if not m:
+        raise RuntimeError("signature %r not found in %s" % (signature_regex, path))
+    i = text.index("{", m.end() - 1)
+    depth = 0
+    j = i
+    in_line_comment = in_block_comment = False
+    in_str = None
+    while j < len(text):
+        c = text[j]
+        nxt = text[j + 1] if j + 1 < len(text) else ""
+        if in_line_comment:
+            if c == "\n":
+                in_line_comment = False
+        elif in_block_comment:
+            if c == "*" and nxt == "/":
+                in_block_comment = False
+                j += 1
+        elif in_str:
+            if c == "\\":
+                j += 1
+            elif c == in_str:
+                in_str = None
+        elif c == "/" and nxt == "/":
+            in_line_comment = True
+        elif c == "/" and nxt == "*":
+            in_block_comment = True
+        elif c in "\"'":
+            in_str = c
+        elif c == "{":
+            depth += 1
+        elif c == "}":
+            depth -= 1
+            if depth == 0:
+                return text[m.start(): j + 1]
+        j += 1
+    raise RuntimeError("unbalanced braces after %r in %s" % (signature_regex, path))
+
+
+def insert_before(body, anchor_regex, patch):
+    m = re.search(anchor_regex, body)
+    if not m:
+        raise RuntimeError("patch anchor %r not found" % anchor_regex)
+    return body[: m.start()] + patch + body[m.start():]
+
+
+def insert_after(body, anchor_regex, patch):
+    m = re.search(anchor_regex, body)
+    if not m:
+        raise RuntimeError("patch anchor %r not found" % anchor_regex)
+    return body[: m.end()] + patch + body[m.end():]
+
+
+SHIM_GLIBMM = r"""
+// stand-in for <glibmm.h>: only Glib::ustring::compose is touched by the bodies
+#pragma once
+#include <string>
+namespace Glib {
+struct ustring : public std::string {
+    ustring() {}
+    ustring(const char* s) : std::string(s) {}
+    ustring(const std::string& s) : std::string(s) {}
+    template <class... A> static ustring compose(const ustring& f, A&&...) { return f; }
+};
+}
+"""
+
+SHIM_TU = r"""
+// Shim translation unit: hosts reference function bodies cut out of
+// /root/reference/rtengine at build time (see oracle/build_ref.py).
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <cstdio>
+#include <iostream>
+#include <memory>
+#include <algorithm>
+#include <omp.h>
+#include "glibmm.h"
+#include "array2D.h"
+#include "rt_math.h"
+#include "sleef.h"
+#include "opthelper.h"
+#include "median.h"
+
+#define M(x) Glib::ustring(x)
+#define BENCHFUN
+
+namespace {
+unsigned fc(const unsigned int cfa[2][2], int r, int c) { return cfa[r & 1][c & 1]; }
+}
+
+namespace rtengine {
+
+struct ProgressListener {
+    void setProgressStr(const Glib::ustring&) {}
+    void setProgress(double) {}
+};
+struct StopWatch { StopWatch(const char*) {} };
+
+struct RawImageSource {
+    int W, H;
+    unsigned filters;
+    int border;
+    double initialGain;
+    ProgressListener* plistener;
+    array2D<float> rawData, red, green, blue;
+
+    RawImageSource(int w, int h, unsigned f, float** raw, float** r, float** g, float** b)
+        : W(w), H(h), filters(f), border(4), initialGain(1.0), plistener(nullptr),
+          rawData(w, h, raw, ARRAY2D_BYREFERENCE), red(w, h, r, ARRAY2D_BYREFERENCE),
+          green(w, h, g, ARRAY2D_BYREFERENCE), blue(w, h, b, ARRAY2D_BYREFERENCE) {}
+
+    unsigned FC(int row, int col) const
+    {
+        return (filters >> ((((row) << 1 & 14) + ((col) & 1)) << 1) & 3);
+    }
+    void igv_interpolate(int, int) {}
+    void rcd_demosaic();
+    void amaze_demosaic_RT(int winx, int winy, int winw, int winh, const array2D<float> &rawData,
+                           array2D<float> &red, array2D<float> &green, array2D<float> &blue);
+    void border_interpolate2(int winw, int winh, int lborders, const array2D<float> &rawData,
+                             array2D<float> &red, array2D<float> &green, array2D<float> &blue);
+};
+
+#include "rcd_body.inc"
+#include "amaze_body.inc"
+#include "border_body.inc"
+
+} // namespace rtengine
+
+namespace {
+struct Rows {
+    float **raw, **r, **g, **b;
+    Rows(int H, const float* raw_, long rs, float* r_, float* g_, float* b_, long os)
+    {
+        raw = new float*[H]; r = new float*[H]; g = new float*[H]; b = new float*[H];
+        for (int i = 0; i < H; ++i) {
+            raw[i] = const_cast<float*>(raw_) + (long)i * rs;
+            r[i] = r_ + (long)i * os; g[i] = g_ + (long)i * os; b[i] = b_ + (long)i * os;
+        }
+    }
+    ~Rows() { delete[] raw; delete[] r; delete[] g; delete[] b; }
+};
+}
+
+extern "C" {
+
+// strides in floats.  nthreads<=0 => leave OpenMP default.
+int artref_rcd(int W, int H, unsigned filters, const float* raw, long raw_stride,
+               float* r, float* g, float* b, long out_stride, int nthreads)
+{
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+    Rows rows(H, raw, raw_stride, r, g, b, out_stride);
+    rtengine::RawImageSource src(W, H, filters, rows.raw, rows.r, rows.g, rows.b);
+    src.rcd_demosaic();
+    return 0;
+}
+
+int artref_amaze(int W, int H, unsigned filters, const float* raw, long raw_stride,
+                 float* r, float* g, float* b, long out_stride,
+                 double initialGain, int border, int nthreads)
+{
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+    Rows rows(H, raw, raw_stride, r, g, b, out_stride);
+    rtengine::RawImageSource src(W, H, filters, rows.raw, rows.r, rows.g, rows.b);
+    src.initialGain = initialGain;
+    src.border = border;
+    src.amaze_demosaic_RT(0, 0, W, H, src.rawData, src.red, src.green, src.blue);
+    return 0;
+}
+
+int artref_border_interpolate2(int W, int H, unsigned filters, int lborders, const float* raw, long raw_stride,
+                               float* r, float* g, float* b, long out_stride)
+{
+    Rows rows(H, raw, raw_stride, r, g, b, out_stride);
+    rtengine::RawImageSource src(W, H, filters, rows.raw, rows.r, rows.g, rows.b);
+    src.border_interpolate2(W, H, lborders, src.rawData, src.red, src.green, src.blue);
+    return 0;
+}
+
+int artref_is_deterministic_build(void)
+{
+#ifdef ARTREF_DET
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+int artref_max_threads(void) { return omp_get_max_threads(); }
+
+} // extern "C"
+"""
+
+
+def extract(det):
+    sub = os.path.join(SRC, "det" if det else "stock")
+    os.makedirs(sub, exist_ok=True)
+    rcd = cut_function(os.path.join(RT, "rcd_demosaic.cc"), r"void\s+RawImageSource::rcd_demosaic\s*\(\s*\)")
+    amaze = cut_function(os.path.join(RT, "amaze_demosaic_RT.cc"),
+                         r"void\s+RawImageSource::amaze_demosaic_RT\s*\([^)]*\)")
+    border = cut_function(os.path.join(RT, "demosaic_algos.cc"),
+                          r"void\s+RawImageSource::border_interpolate2\s*\([^)]*\)")
+    if det:
+        # AMaZE: clear the whole per-thread scratch at the top of every tile
+        amaze = insert_before(
+            amaze, r"memset\(&nyquist\[3 \* tsh\]",
+            "memset(data, 0, 14 * sizeof(float) * ts * ts + sizeof(char) * ts * tsh + 18 * cldf * 64);\n                ")
+        # RCD: same idea -- VH_Dir outside [4,rows-4)x[4,cols-4) and friends read as 0
+        rcd = insert_after(
+            rcd, r"const int tilecols = [^;]*;",
+            "\n            memset(cfa, 0, sizeof(float) * tileSize * tileSize);"
+            "\n            memset(rgb, 0, 3 * sizeof *rgb);"
+            "\n            memset(VH_Dir, 0, sizeof(float) * tileSize * tileSize);"
+            "\n            memset(PQ_Dir, 0, sizeof(float) * (tileSize * tileSize / 2));"
+            "\n            memset(P_CDiff_Hpf, 0, sizeof(float) * (tileSize * tileSize / 2));"
+            "\n            memset(Q_CDiff_Hpf, 0, sizeof(float) * (tileSize * tileSize / 2));")
+    open(os.path.join(sub, "rcd_body.inc"), "w").write(rcd)
+    open(os.path.join(sub, "amaze_body.inc"), "w").write(amaze)
+    open(os.path.join(sub, "border_body.inc"), "w").write(border)
+    open(os.path.join(sub, "glibmm.h"), "w").write(SHIM_GLIBMM)
+    open(os.path.join(sub, "shim.cc"), "w").write(SHIM_TU)
+    return sub
+
+
+def build(det):
+    sub = extract(det)
+    lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
+    cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), "-o", lib]
+    if det:
+        cmd.insert(1, "-DARTREF_DET")
+    subprocess.check_call(cmd)
+    return lib
+
+
+def main():
+    if not os.path.isdir(RT):
+        print("build_ref: %s absent -- keeping prebuilt oracle/_ref (if any)" % RT)
+        return 0
+    os.makedirs(OUT, exist_ok=True)
+    for det in (False, True):
+        print("built", build(det))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
