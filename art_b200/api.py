@@ -1,0 +1,176 @@
+"""ctypes binding of include/art_hotpath.h -- one Python method per C entry point."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(HERE, "..", "include", "art_hotpath.h")
+
+BAYER_AMAZE = 0
+BAYER_RCD = 1
+
+_c_float_p = ctypes.POINTER(ctypes.c_float)
+_c_float_pp = ctypes.POINTER(_c_float_p)
+
+
+class HotPathError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("art_hotpath error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib_path():
+    return os.path.join(HERE, "libart_hotpath.so")
+
+
+def _declared_symbols():
+    """Every function name include/art_hotpath.h declares."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(art_hp_[a-z0-9_]+)\s*\(", text)))
+
+
+ABI_SYMBOLS = _declared_symbols()
+_lib = None
+
+
+def load_library(build_if_missing=True):
+    """Load libart_hotpath.so; raises if it is absent and cannot be built.  Never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise FileNotFoundError(path)
+        from . import build as _build
+        _build.build()
+    lib = ctypes.CDLL(path)
+    vp, i, u, sz, d = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_size_t, ctypes.c_double
+    sig = {
+        "art_hp_abi_version": (i, []),
+        "art_hp_device_count": (i, []),
+        "art_hp_create": (i, [ctypes.POINTER(vp), i]),
+        "art_hp_destroy": (None, [vp]),
+        "art_hp_last_error": (ctypes.c_char_p, [vp]),
+        "art_hp_set_stream": (i, [vp, vp]),
+        "art_hp_get_stream": (vp, [vp]),
+        "art_hp_sync": (i, [vp]),
+        "art_hp_launch_count": (ctypes.c_ulonglong, [vp]),
+        "art_hp_host_alloc": (vp, [sz]),
+        "art_hp_host_free": (None, [vp]),
+        "art_hp_demosaic_bayer": (i, [vp, i, i, i, u, vp, vp, vp, vp, d, i]),
+        "art_hp_demosaic_bayer_dev": (i, [vp, i, i, i, u, vp, sz, vp, vp, vp, sz, d, i]),
+        "art_hp_border_interpolate2_dev": (i, [vp, i, i, u, i, vp, sz, vp, vp, vp, sz]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def row_table(a):
+    """H row pointers into a 2-D float32 array (what rtengine::array2D<float> holds)."""
+    assert a.dtype == np.float32 and a.ndim == 2 and a.strides[1] == 4
+    H = a.shape[0]
+    base = a.ctypes.data
+    tbl = (ctypes.c_void_p * H)(*[base + r * a.strides[0] for r in range(H)])
+    return tbl
+
+
+class PinnedArray:
+    """A float32 (H, W) numpy view over art_hp_host_alloc'ed (pinned) memory."""
+
+    def __init__(self, lib, H, W):
+        self._lib = lib
+        n = H * W * 4
+        self.ptr = lib.art_hp_host_alloc(n)
+        if not self.ptr:
+            raise MemoryError("art_hp_host_alloc(%d)" % n)
+        buf = (ctypes.c_float * (H * W)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.float32).reshape(H, W)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.art_hp_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class HotPath:
+    """One context = one GPU.  Thread-compatible, not thread-safe."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.art_hp_create(ctypes.byref(h), device)
+        if rc != 0:
+            raise HotPathError(rc, "art_hp_create(device=%d) failed (2 = no CUDA device; there is no CPU fallback)" % device)
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.art_hp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HotPathError(rc, (self.lib.art_hp_last_error(self.h) or b"").decode())
+
+    # -- context ---------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.art_hp_set_stream(self.h, ctypes.c_void_p(cuda_stream or 0)))
+
+    def get_stream(self):
+        return self.lib.art_hp_get_stream(self.h) or 0
+
+    def sync(self):
+        self._check(self.lib.art_hp_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.art_hp_launch_count(self.h))
+
+    def pinned(self, H, W):
+        return PinnedArray(self.lib, H, W)
+
+    # -- demosaic ----------------------------------------------------------
+    def demosaic_bayer(self, method, raw, filters, red=None, green=None, blue=None, initial_gain=1.0, border=4):
+        """Host entry: numpy (H, W) float32 in, three (H, W) float32 planes out."""
+        raw = np.asarray(raw)
+        if raw.dtype != np.float32 or raw.ndim != 2 or raw.strides[1] != 4:
+            raw = np.ascontiguousarray(raw, dtype=np.float32)
+        H, W = raw.shape
+        outs = []
+        for o in (red, green, blue):
+            outs.append(np.empty((H, W), np.float32) if o is None else o)
+        tabs = [row_table(a) for a in [raw] + outs]
+        self._check(self.lib.art_hp_demosaic_bayer(self.h, method, W, H, filters, tabs[0], tabs[1], tabs[2], tabs[3],
+                                                   float(initial_gain), int(border)))
+        return tuple(outs)
+
+    def demosaic_bayer_dev(self, method, W, H, filters, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch,
+                           initial_gain=1.0, border=4):
+        """Device entry: raw device addresses (ints), pitches in floats; asynchronous."""
+        self._check(self.lib.art_hp_demosaic_bayer_dev(self.h, method, W, H, filters, d_raw, raw_pitch,
+                                                       d_r, d_g, d_b, out_pitch, float(initial_gain), int(border)))
+
+    def border_interpolate2_dev(self, W, H, filters, lborders, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch):
+        self._check(self.lib.art_hp_border_interpolate2_dev(self.h, W, H, filters, lborders, d_raw, raw_pitch,
+                                                            d_r, d_g, d_b, out_pitch))

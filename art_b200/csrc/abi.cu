@@ -1,0 +1,304 @@
+// libart_hotpath.so -- C-ABI entry points, context, host<->device staging.
+// The compute lives in rcd.cu / amaze.cu / ...; this file holds no pixel arithmetic.
+#include "ctx.h"
+
+#include <algorithm>
+#include <thread>
+
+namespace {
+
+constexpr size_t kStageBytes = 32u << 20;   // per half; two halves double-buffer pageable copies
+
+int host_threads()
+{
+    unsigned n = std::thread::hardware_concurrency();
+    if (n == 0) n = 4;
+    return (int)std::min(n, 16u);
+}
+
+// copy `nrows` rows of `wbytes` bytes between a row-pointer table and a packed buffer, in parallel
+void rows_memcpy(const float* const* rows, int row0, int nrows, size_t wbytes, char* packed, bool to_packed)
+{
+    const int nt = std::max(1, std::min(host_threads(), nrows / 64));
+    auto work = [&](int t) {
+        const int a = (int)((long long)nrows * t / nt), b = (int)((long long)nrows * (t + 1) / nt);
+        for (int i = a; i < b; ++i) {
+            if (to_packed) memcpy(packed + (size_t)i * wbytes, rows[row0 + i], wbytes);
+            else memcpy(const_cast<float*>(rows[row0 + i]), packed + (size_t)i * wbytes, wbytes);
+        }
+    };
+    if (nt == 1) { work(0); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
+
+// true when rows[i] = rows[0] + i*stride for one stride (what array2D / PlanarPtr allocate)
+bool constant_stride(const float* const* rows, int H, ptrdiff_t* stride)
+{
+    if (H < 2) { *stride = 0; return true; }
+    const ptrdiff_t s = rows[1] - rows[0];
+    for (int i = 2; i < H; ++i)
+        if (rows[i] - rows[i - 1] != s) return false;
+    *stride = s;
+    return s > 0;
+}
+
+bool is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int ensure_stage(art_hp_ctx* ctx)
+{
+    if (ctx->h_stage[0]) return ART_HP_OK;
+    for (int i = 0; i < 2; ++i) ART_CUDA(ctx, cudaMallocHost(&ctx->h_stage[i], kStageBytes));
+    ctx->h_stage_bytes = kStageBytes;
+    return ART_HP_OK;
+}
+
+struct Plane {
+    const float* const* rows;   // host row table
+    float* dev;                 // device plane
+};
+
+// Move planes between host row tables and device planes (pitch in floats) on `st`.
+// Pinned, constant-stride host memory goes straight through cudaMemcpy2DAsync; anything else is
+// staged through the context's two pinned halves, host memcpy overlapping the DMA of the other half.
+int transfer(art_hp_ctx* ctx, cudaStream_t st, const Plane* planes, int nplanes, int W, int H, size_t pitch, bool to_device)
+{
+    const size_t wbytes = (size_t)W * sizeof(float);
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    bool staged_any = false;
+    int half = 0;
+    bool busy[2] = {false, false};
+    // for D2H we must copy out of a half only after its DMA finished; remember what to drain
+    struct Pending { int plane, row0, nrows; } pend[2] = {{0, 0, 0}, {0, 0, 0}};
+    auto drain = [&](int h) -> int {
+        if (!busy[h]) return ART_HP_OK;
+        ART_CUDA(ctx, cudaEventSynchronize(ctx->ev[h]));
+        if (!to_device)
+            rows_memcpy(planes[pend[h].plane].rows, pend[h].row0, pend[h].nrows, wbytes, (char*)ctx->h_stage[h], false);
+        busy[h] = false;
+        return ART_HP_OK;
+    };
+    for (int p = 0; p < nplanes; ++p) {
+        ptrdiff_t stride = 0;
+        const bool cs = constant_stride(planes[p].rows, H, &stride);
+        if (cs && is_pinned(planes[p].rows[0])) {
+            const size_t spitch = (H > 1 ? (size_t)stride : (size_t)W) * sizeof(float);
+            if (to_device)
+                ART_CUDA(ctx, cudaMemcpy2DAsync(planes[p].dev, pitch * sizeof(float), planes[p].rows[0], spitch, wbytes, H, kind, st));
+            else
+                ART_CUDA(ctx, cudaMemcpy2DAsync(const_cast<float*>(planes[p].rows[0]), spitch, planes[p].dev, pitch * sizeof(float), wbytes, H, kind, st));
+            continue;
+        }
+        staged_any = true;
+        int rc = ensure_stage(ctx);
+        if (rc) return rc;
+        const int chunk = (int)std::max<size_t>(1, ctx->h_stage_bytes / wbytes);
+        for (int r0 = 0; r0 < H; r0 += chunk) {
+            const int n = std::min(chunk, H - r0);
+            rc = drain(half);
+            if (rc) return rc;
+            char* hs = (char*)ctx->h_stage[half];
+            float* d = planes[p].dev + (size_t)r0 * pitch;
+            if (to_device) {
+                rows_memcpy(planes[p].rows, r0, n, wbytes, hs, true);
+                ART_CUDA(ctx, cudaMemcpy2DAsync(d, pitch * sizeof(float), hs, wbytes, wbytes, n, kind, st));
+            } else {
+                ART_CUDA(ctx, cudaMemcpy2DAsync(hs, wbytes, d, pitch * sizeof(float), wbytes, n, kind, st));
+                pend[half] = {p, r0, n};
+            }
+            ART_CUDA(ctx, cudaEventRecord(ctx->ev[half], st));
+            busy[half] = true;
+            half ^= 1;
+        }
+    }
+    if (staged_any) {
+        int rc = drain(half);
+        if (rc) return rc;
+        rc = drain(half ^ 1);
+        if (rc) return rc;
+    }
+    return ART_HP_OK;
+}
+
+bool rgb_bayer(unsigned filters)
+{
+    // RawImage::FC (rtengine/rawimage.h L186-189) over the 8x2 period of the descriptor: rows must
+    // repeat with period 2, no site may be colour 3 (rcd_demosaic.cc L56-66), and the 2x2 cell must be
+    // G on one diagonal with R and B on the other.
+    auto FC = [filters](int r, int c) { return (filters >> ((((r) << 1 & 14) + ((c) & 1)) << 1)) & 3u; };
+    for (int r = 0; r < 8; ++r)
+        for (int c = 0; c < 2; ++c)
+            if (FC(r, c) == 3u || FC(r, c) != FC(r & 1, c)) return false;
+    const unsigned f00 = FC(0, 0), f01 = FC(0, 1), f10 = FC(1, 0), f11 = FC(1, 1);
+    return (f00 == 1 && f11 == 1 && f01 != 1 && f10 != 1 && f01 != f10) ||
+           (f01 == 1 && f10 == 1 && f00 != 1 && f11 != 1 && f00 != f11);
+}
+
+}  // namespace
+
+int art_reserve(art_hp_ctx* ctx, DevBuf& b, size_t bytes)
+{
+    if (b.bytes >= bytes) return ART_HP_OK;
+    if (b.p) {
+        ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ART_CUDA(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(ART_HP_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    b.bytes = bytes;
+    return ART_HP_OK;
+}
+
+extern "C" {
+
+int art_hp_abi_version(void) { return ART_HP_ABI_VERSION; }
+
+int art_hp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int art_hp_create(art_hp_ctx** out, int device_id)
+{
+    if (!out) return ART_HP_ERR_INVALID;
+    *out = nullptr;
+    int n = art_hp_device_count();
+    if (n <= 0) return ART_HP_ERR_NO_DEVICE;
+    if (device_id < 0 || device_id >= n) return ART_HP_ERR_INVALID;
+    if (cudaSetDevice(device_id) != cudaSuccess) { cudaGetLastError(); return ART_HP_ERR_CUDA; }
+    art_hp_ctx* ctx = new art_hp_ctx();
+    ctx->device = device_id;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); art_hp_destroy(ctx); return ART_HP_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return ART_HP_OK;
+}
+
+void art_hp_destroy(art_hp_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    for (int i = 0; i < 2; ++i) if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+const char* art_hp_last_error(const art_hp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int art_hp_set_stream(art_hp_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return ART_HP_OK;
+}
+
+void* art_hp_get_stream(art_hp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int art_hp_sync(art_hp_ctx* ctx)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+unsigned long long art_hp_launch_count(const art_hp_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+
+void* art_hp_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void art_hp_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int art_hp_demosaic_bayer_dev(art_hp_ctx* ctx, int method, int W, int H, unsigned filters,
+                              const float* d_raw, size_t raw_pitch,
+                              float* d_red, float* d_green, float* d_blue, size_t out_pitch,
+                              double initialGain, int border)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_raw || !d_red || !d_green || !d_blue) return ctx->fail(ART_HP_ERR_INVALID, "null plane pointer");
+    if (W < 32 || H < 32 || W > 65536 || H > 65536) return ctx->fail(ART_HP_ERR_INVALID, "frame %dx%d out of range [32,65536]", W, H);
+    if (raw_pitch < (size_t)W || out_pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "pitch smaller than width");
+    if (!rgb_bayer(filters)) return ctx->fail(ART_HP_ERR_INVALID, "filters=0x%08x is not an RGB Bayer pattern", filters);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    switch (method) {
+    case ART_HP_BAYER_RCD:
+        return art_rcd_dev(ctx, W, H, filters, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch);
+    case ART_HP_BAYER_AMAZE:
+        if (!(initialGain > 0.0)) return ctx->fail(ART_HP_ERR_INVALID, "initialGain must be > 0");
+        return art_amaze_dev(ctx, W, H, filters, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch, initialGain, border);
+    default:
+        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "unknown bayer method %d", method);
+    }
+}
+
+int art_hp_border_interpolate2_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, int lborders,
+                                   const float* d_raw, size_t raw_pitch,
+                                   float* d_red, float* d_green, float* d_blue, size_t out_pitch)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_raw || !d_red || !d_green || !d_blue) return ctx->fail(ART_HP_ERR_INVALID, "null plane pointer");
+    if (lborders < 1 || 2 * lborders >= W || 2 * lborders >= H) return ctx->fail(ART_HP_ERR_INVALID, "border %d does not fit %dx%d", lborders, W, H);
+    if (!rgb_bayer(filters)) return ctx->fail(ART_HP_ERR_INVALID, "filters=0x%08x is not an RGB Bayer pattern", filters);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_border_dev(ctx, W, H, filters, lborders, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch);
+}
+
+int art_hp_demosaic_bayer(art_hp_ctx* ctx, int method, int W, int H, unsigned filters,
+                          const float* const* rawData,
+                          float* const* red, float* const* green, float* const* blue,
+                          double initialGain, int border)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!rawData || !red || !green || !blue) return ctx->fail(ART_HP_ERR_INVALID, "null row table");
+    if (W < 32 || H < 32 || W > 65536 || H > 65536) return ctx->fail(ART_HP_ERR_INVALID, "frame %dx%d out of range [32,65536]", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    int rc;
+    if ((rc = art_reserve(ctx, ctx->d_raw, plane))) return rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+    Plane in = {rawData, (float*)ctx->d_raw.p};
+    if ((rc = transfer(ctx, ctx->stream, &in, 1, W, H, pitch, true))) return rc;
+    rc = art_hp_demosaic_bayer_dev(ctx, method, W, H, filters, (const float*)ctx->d_raw.p, pitch,
+                                   (float*)ctx->d_out[0].p, (float*)ctx->d_out[1].p, (float*)ctx->d_out[2].p, pitch,
+                                   initialGain, border);
+    if (rc) return rc;
+    Plane out[3] = {{red, (float*)ctx->d_out[0].p}, {green, (float*)ctx->d_out[1].p}, {blue, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, out, 3, W, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+/*
+ * art_hotpath.h -- C-ABI of the B200-native raw-development hot path.
+ *
+ * This is the drop-in boundary for the reference's rtengine hot path
+ * (artpixls/ART).  The reference has no plugin/FFI layer for this path: the
+ * call sites are C++ member functions reached from rtengine/simpleprocess.cc
+ * (ImageProcessor, L112-490).  Each entry point below names the reference
+ * member it replaces (file:line under /root/reference) and keeps that member's
+ * argument meaning: caller-owned buffers, `float* const*` row-pointer tables
+ * exactly as rtengine::array2D<float> (rtengine/array2D.h L74-296) and
+ * PlanarPtr hold them, in-place mutation where the reference mutates in place.
+ * INTEGRATION.md shows the <=10-line patch per call site.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every call returns an
+ *     art_hp_status (0 = OK) and art_hp_last_error() gives the text;
+ *   - a context owns one GPU (one process per GPU, one context per process
+ *     is the intended deployment), its stream, device scratch and pinned
+ *     staging; a context is thread-compatible, not thread-safe (the
+ *     reference serialises the same way: one ImProcFunctions per image);
+ *   - `*_dev` variants take device pointers + a pitch in floats and do no
+ *     host<->device copies: they are what a resident pipeline chains;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     returns ART_HP_ERR_NO_DEVICE.
+ */
+#ifndef ART_HOTPATH_H
+#define ART_HOTPATH_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ART_HP_ABI_VERSION 1
+
+typedef enum art_hp_status {
+    ART_HP_OK = 0,
+    ART_HP_ERR_INVALID = 1,      /* bad argument (null pointer, non-RGB CFA, size out of range) */
+    ART_HP_ERR_NO_DEVICE = 2,    /* no usable CUDA device */
+    ART_HP_ERR_CUDA = 3,         /* a CUDA runtime call failed; see art_hp_last_error */
+    ART_HP_ERR_NOMEM = 4,
+    ART_HP_ERR_UNSUPPORTED = 5
+} art_hp_status;
+
+/* RAWParams::BayerSensor::Method subset (reference rtengine/procparams.h; dispatch in
+ * rtengine/rawimagesource.cc L1872-1924) */
+typedef enum art_hp_bayer_method {
+    ART_HP_BAYER_AMAZE = 0,      /* RawImageSource::amaze_demosaic_RT, rtengine/amaze_demosaic_RT.cc L41-1595 */
+    ART_HP_BAYER_RCD = 1         /* RawImageSource::rcd_demosaic,      rtengine/rcd_demosaic.cc L51-347   */
+} art_hp_bayer_method;
+
+typedef struct art_hp_ctx art_hp_ctx;
+
+/* ---- context ---------------------------------------------------------- */
+int  art_hp_abi_version(void);
+/* number of visible CUDA devices (0 when there is none; never fails) */
+int  art_hp_device_count(void);
+/* create a context on CUDA device `device_id` */
+int  art_hp_create(art_hp_ctx** out, int device_id);
+void art_hp_destroy(art_hp_ctx* ctx);
+const char* art_hp_last_error(const art_hp_ctx* ctx);
+/* run on a caller-owned cudaStream_t (NULL restores the context's own stream) */
+int  art_hp_set_stream(art_hp_ctx* ctx, void* cuda_stream);
+void* art_hp_get_stream(art_hp_ctx* ctx);
+/* block until everything queued on the context's stream is done */
+int  art_hp_sync(art_hp_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+unsigned long long art_hp_launch_count(const art_hp_ctx* ctx);
+
+/* pinned host memory for callers that want zero-staging transfers
+ * (what an AlignedBuffer, rtengine/alignedbuffer.h, would be backed by) */
+void* art_hp_host_alloc(size_t bytes);
+void  art_hp_host_free(void* p);
+
+/* ---- demosaic --------------------------------------------------------- */
+/*
+ * Replaces RawImageSource::amaze_demosaic_RT(0,0,W,H,rawData,red,green,blue)
+ * (rtengine/amaze_demosaic_RT.cc L41) and RawImageSource::rcd_demosaic()
+ * (rtengine/rcd_demosaic.cc L51), as dispatched by RawImageSource::demosaic
+ * (rtengine/rawimagesource.cc L1872-1924).
+ *   filters      dcraw CFA descriptor, e.g. 0x94949494 for RGGB
+ *                (RawImage::FC, rtengine/rawimage.h L186-189); must describe an RGB 2x2 pattern
+ *   rawData      H row pointers, W floats each, values in the scaleColors
+ *                domain 0..65535 (rtengine/rawimagesource.cc L2677-2859)
+ *   red/green/blue  H row pointers each, W floats per row, fully overwritten
+ *   initialGain  RawImageSource::initialGain (AMaZE clip points, amaze_demosaic_RT.cc L53-54)
+ *   border       RawImageSource::border (AMaZE: border<4 => 3-px border_interpolate2, L1587-1589)
+ * Host pointers; the call returns when the outputs are complete.
+ */
+int art_hp_demosaic_bayer(art_hp_ctx* ctx, int method, int W, int H, unsigned filters,
+                          const float* const* rawData,
+                          float* const* red, float* const* green, float* const* blue,
+                          double initialGain, int border);
+
+/* Device-resident form: planes already in HBM, pitch in floats, asynchronous on the
+ * context's stream. */
+int art_hp_demosaic_bayer_dev(art_hp_ctx* ctx, int method, int W, int H, unsigned filters,
+                              const float* d_raw, size_t raw_pitch,
+                              float* d_red, float* d_green, float* d_blue, size_t out_pitch,
+                              double initialGain, int border);
+
+/* Replaces RawImageSource::border_interpolate2(W,H,lborders,rawData,red,green,blue)
+ * (rtengine/demosaic_algos.cc L200-353). Device-resident. */
+int art_hp_border_interpolate2_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, int lborders,
+                                   const float* d_raw, size_t raw_pitch,
+                                   float* d_red, float* d_green, float* d_blue, size_t out_pitch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ART_HOTPATH_H */

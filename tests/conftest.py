@@ -1,0 +1,21 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def hot_path():
+    """One context for the whole GPU session.  Fails loudly (no fallback) if the library or GPU is missing."""
+    import art_b200
+    hp = art_b200.HotPath(0)
+    yield hp
+    hp.close()

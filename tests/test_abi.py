@@ -1,0 +1,59 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every
+symbol include/art_hotpath.h declares; without a GPU it refuses to compute (no CPU fallback)."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+import art_b200
+from art_b200 import api
+
+
+def test_header_declares_symbols():
+    assert "art_hp_create" in api.ABI_SYMBOLS and "art_hp_demosaic_bayer" in api.ABI_SYMBOLS
+    assert len(api.ABI_SYMBOLS) >= 14
+
+
+def test_library_exports_every_declared_symbol():
+    lib = art_b200.load_library()
+    out = subprocess.check_output(["nm", "-D", "--defined-only", art_b200.lib_path()], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [s for s in api.ABI_SYMBOLS if s not in exported]
+    assert not missing, "declared in include/art_hotpath.h but not exported: %s" % missing
+    for s in api.ABI_SYMBOLS:
+        assert getattr(lib, s) is not None
+    assert lib.art_hp_abi_version() == 1
+
+
+def test_header_is_plain_c():
+    """The boundary header must compile as C (no C++ or torch types in the signatures)."""
+    src = '#include "art_hotpath.h"\nint main(void){return art_hp_abi_version()==0;}\n'
+    inc = os.path.join(os.path.dirname(art_b200.lib_path()), "..", "include")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c", "-"],
+                   input=src, text=True, check=True)
+
+
+def test_no_cpu_fallback_without_gpu():
+    lib = art_b200.load_library()
+    if lib.art_hp_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(art_b200.HotPathError) as e:
+        art_b200.HotPath(0)
+    assert e.value.code == 2   # ART_HP_ERR_NO_DEVICE
+
+
+def test_product_does_not_reference_oracle():
+    """Nothing under art_b200/ may import, link or execute oracle/ (tier rule 3)."""
+    root = os.path.dirname(art_b200.lib_path())
+    bad = []
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dp, f), errors="replace").read()
+                for needle in ("import oracle", "from oracle", "libartoracle", "libartref", "oracle/"):
+                    if needle in text and f != "__init__.py":
+                        bad.append((f, needle))
+    assert not bad, bad
+    out = subprocess.check_output(["ldd", art_b200.lib_path()], text=True)
+    assert "artoracle" not in out and "artref" not in out
