@@ -184,7 +184,9 @@ def main():
     method = art_b200.BAYER_RCD if args.method == "rcd" else art_b200.BAYER_AMAZE
     raw = synth.bayer_frame(W, H, filters, seed=1002 + rank)
 
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library launches on it and the timing events are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     hp.set_stream(stream.cuda_stream)
     pitch = (W + 31) // 32 * 32
     d_raw = torch.zeros((H, pitch), dtype=torch.float32, device="cuda")
