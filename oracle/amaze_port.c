@@ -121,7 +121,9 @@ typedef struct {
     int ex, ey;
 } amz_job;
 
-static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
+/* stop_after: 0 = run everything; otherwise return after the stage with that number (numbering of the
+ * CUDA passes in art_b200/csrc/amaze.cu, used by tests to localise a divergence pass by pass). */
+static void amaze_tile(const amz_job* J, amz_t* S, int top, int left, int stop_after)
 {
     const int W = J->W, H = J->H;
     const unsigned F = J->filters;
@@ -183,6 +185,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
 #undef PUT
 #undef RAW
 
+    if (stop_after == 1) return;
     /* ---- horizontal and vertical gradients (L342-350) */
     for (int rr = 2; rr < rr1 - 2; rr++)
         for (int indx = rr * TS; indx < rr * TS + cc1; indx += 4)
@@ -195,6 +198,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
                 delhvsqsum[i] = sq(delh) + sq(delv);
             }
 
+    if (stop_after == 2) return;
     /* ---- interpolate vertical and horizontal colour differences (L380-431) */
     for (int rr = 4; rr < rr1 - 4; rr++)
         for (int indx = rr * TS + 4; indx < rr * TS + cc1 - 7; indx += 4)
@@ -230,6 +234,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
                 dginth[i] = vminf_(sq(glha - grha), sq(glar - grar));
             }
 
+    if (stop_after == 3) return;
     /* ---- variance select + saturation bounds, in place (L536-581) */
     for (int rr = 4; rr < rr1 - 4; rr++)
         for (int indx = rr * TS + 4; indx < rr * TS + cc1 - 4; indx += 4) {
@@ -275,6 +280,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
             for (int l = 0; l < 4; ++l) { hcd[indx + l] = nh[l]; vcd[indx + l] = nv[l]; cddiffsq[indx + l] = nd[l]; }
         }
 
+    if (stop_after == 5) return;
     /* ---- hvwt (L681-723): 4 R/B sites (stride 2) per vector */
     for (int rr = 6; rr < rr1 - 6; rr++)
         for (int indx = rr * TS + 6 + (fc_(F, rr, 2) & 1); indx < rr * TS + cc1 - 6; indx += 8)
@@ -306,6 +312,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
                 hvwt[i >> 1] = dec ? varwt : diffwt;
             }
 
+    if (stop_after == 6) return;
     /* ---- nyquist test value (L789-844): vector part then scalar remainder (different association!) */
     for (int rr = 6; rr < rr1 - 6; rr++) {
         int cc = 6 + (fc_(F, rr, 2) & 1);
@@ -354,6 +361,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
                 nystartcol = nystartcol > cc ? cc : nystartcol;
                 nyendcol = nyendcol < cc ? cc : nyendcol;
             }
+    if (stop_after == 7) return;
     const int doNyquist = nystartrow != nyendrow && nystartcol != nyendcol;
     if (doNyquist) {
         nyendrow++;
@@ -412,6 +420,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
                 }
     }
 
+    if (stop_after == 8) return;
     /* ---- populate G at R/B sites; in-place hvwt recurrence down the rows (L958-974) */
     float* Dgrb0 = S->Dgrb0; float* Dgrb1 = S->Dgrb1; float* Dgrb2 = S->Dgrb2;
     for (int rr = 8; rr < rr1 - 8; rr++)
@@ -424,6 +433,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
             Dgrb2[2 * (indx >> 1) + 1] = nyquist2[indx >> 1] ? sq(rgbgreen[indx] - 0.5f * (rgbgreen[indx - v1] + rgbgreen[indx + v1])) : 0.f;
         }
 
+    if (stop_after == 10) return;
     /* ---- refine Nyquist areas using G curvatures (L980-999) */
     if (doNyquist)
         for (int rr = nystartrow; rr < nyendrow; rr++)
@@ -443,6 +453,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
                     rgbgreen[indx] = cfa[indx] + Dgrb0[indx >> 1];
                 }
 
+    if (stop_after == 11) return;
     /* ---- diagonal gradients and colour-difference squares (L1004-1026) */
     float *delp = S->delp, *delm = S->delm, *Dgrbsq1m = S->Dgrbsq1m, *Dgrbsq1p = S->Dgrbsq1p;
     for (int rr = 6; rr < rr1 - 6; rr++) {
@@ -462,6 +473,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
             }
     }
 
+    if (stop_after == 12) return;
     /* ---- diagonal interpolation correction: rbm, rbp, pmwt (L1057-1121) */
     float *rbm = S->rbm, *rbp = S->rbp, *pmwt = S->pmwt, *rbint = S->rbint;
     for (int rr = 8; rr < rr1 - 8; rr++)
@@ -511,6 +523,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
                                                               Dgrbsq1p[(i - 2 + v1) >> 1] + Dgrbsq1p[(i + 2 + v1) >> 1] + Dgrbsq1p[(i + v2 - 1) >> 1] + Dgrbsq1p[(i + v2 + 1) >> 1]))) + rbvarm);
             }
 
+    if (stop_after == 13) return;
     /* ---- in-place pmwt recurrence down the rows + rbint (L1213-1223) */
     for (int rr = 10; rr < rr1 - 10; rr++)
         for (int indx = rr * TS + 10 + (fc_(F, rr, 2) & 1), indx1 = indx >> 1; indx < rr * TS + cc1 - 10; indx += 8, indx1 += 4)
@@ -523,6 +536,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
                 rbint[k] = 0.5f * (cfa[i] + vintpf_(t, rbp[k], rbm[k]));
             }
 
+    if (stop_after == 15) return;
     /* ---- G via R+B where the diagonal weights discriminate better (L1241-1294) */
     for (int rr = 12; rr < rr1 - 12; rr++)
         for (int indx = rr * TS + 12 + (fc_(F, rr, 2) & 1), indx1 = indx >> 1; indx < rr * TS + cc1 - 12; indx += 8, indx1 += 4)
@@ -567,6 +581,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
                 Dgrb0[k] = greenv - cfa[i];
             }
 
+    if (stop_after == 16) return;
     /* ---- split G-B from G-R at B sites (L1382-1386) */
     for (int rr = 13 - J->ey; rr < rr1 - 12; rr += 2)
         for (int indx1 = (rr * TS + 13 - J->ex) >> 1; indx1 < (rr * TS + cc1 - 12) >> 1; indx1++) {
@@ -574,6 +589,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
             Dgrb0[indx1] = 0;
         }
 
+    if (stop_after == 17) return;
     /* ---- chrominance interpolation to the opposite R/B sites (L1394-1408) */
     for (int rr = 14; rr < rr1 - 14; rr++)
         for (int cc = 14 + (fc_(F, rr, 2) & 1), indx = rr * TS + cc, c = 1 - (int)fc_(F, rr, cc) / 2; cc < cc1 - 14; cc += 8, indx += 8) {
@@ -597,6 +613,7 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
             for (int l = 0; l < 4; ++l) D[(indx + 2 * l) >> 1] = res[l];
         }
 
+    if (stop_after == 18) return;
     /* ---- write R,B (L1441-1548) and G (L1551-1565).  The vector body and the scalar tails compute the
      *      same expressions, so one scalar loop restates both. */
     for (int rr = 16; rr < rr1 - 16; rr++) {
@@ -625,20 +642,44 @@ static void amaze_tile(const amz_job* J, amz_t* S, int top, int left)
 void artoracle_border_interpolate2(int W, int H, unsigned filters, int bord, const float* raw, long rs,
                                    float* R, float* G, float* B, long os);
 
+static void amz_job_init(amz_job* J, int W, int H, unsigned filters, const float* raw, long rs,
+                         float* R, float* G, float* B, long os, float initialGain)
+{
+    J->W = W; J->H = H; J->filters = filters; J->raw = raw; J->rs = rs; J->R = R; J->G = G; J->B = B; J->os = os;
+    J->clip_pt = (float)(1.0 / (double)initialGain);       /* L53-54: const float = 1.0 / initialGain (double) */
+    J->clip_pt8 = (float)(0.8 / (double)initialGain);
+    /* (ey,ex): offset of the R site in the 2x2 cell (L70-86) */
+    if (fc_(filters, 0, 0) == 1) {
+        if (fc_(filters, 0, 1) == 0) { J->ey = 0; J->ex = 1; } else { J->ey = 1; J->ex = 0; }
+    } else {
+        if (fc_(filters, 0, 0) == 0) { J->ey = 0; J->ex = 0; } else { J->ey = 1; J->ex = 1; }
+    }
+}
+
+/* debug: the scratch block of tile `tile` (row-major over the tile grid) after stage `stop_after` */
+size_t artoracle_amaze_slab_bytes(void) { return SCRATCH_BYTES; }
+int artoracle_amaze_slab(int W, int H, unsigned filters, const float* raw, long rs, float initialGain,
+                         int stop_after, int tile, void* out)
+{
+    amz_job J;
+    amz_job_init(&J, W, H, filters, raw, rs, NULL, NULL, NULL, 0, initialGain);
+    const int ntx = (W + 16 + (TS - 32) - 1) / (TS - 32);
+    char* buf = (char*)malloc(SCRATCH_BYTES + 63);
+    if (!buf) return 1;
+    amz_t S;
+    amz_bind(&S, (char*)(((uintptr_t)buf + 63) / 64 * 64));
+    amaze_tile(&J, &S, -16 + (tile / ntx) * (TS - 32), -16 + (tile % ntx) * (TS - 32), stop_after);
+    memcpy(out, S.base, SCRATCH_BYTES);
+    free(buf);
+    return 0;
+}
+
 /* strides in floats */
 int artoracle_amaze(int W, int H, unsigned filters, const float* raw, long rs,
                     float* R, float* G, float* B, long os, float initialGain, int border)
 {
     amz_job J;
-    J.W = W; J.H = H; J.filters = filters; J.raw = raw; J.rs = rs; J.R = R; J.G = G; J.B = B; J.os = os;
-    J.clip_pt = (float)(1.0 / (double)initialGain);       /* L53-54: const float = 1.0 / initialGain (double) */
-    J.clip_pt8 = (float)(0.8 / (double)initialGain);
-    /* (ey,ex): offset of the R site in the 2x2 cell (L70-86) */
-    if (fc_(filters, 0, 0) == 1) {
-        if (fc_(filters, 0, 1) == 0) { J.ey = 0; J.ex = 1; } else { J.ey = 1; J.ex = 0; }
-    } else {
-        if (fc_(filters, 0, 0) == 0) { J.ey = 0; J.ex = 0; } else { J.ey = 1; J.ex = 1; }
-    }
+    amz_job_init(&J, W, H, filters, raw, rs, R, G, B, os, initialGain);
     const int nty = (H + 16 + (TS - 32) - 1) / (TS - 32), ntx = (W + 16 + (TS - 32) - 1) / (TS - 32);   /* top=-16+128i < H */
     int fail = 0;
 #pragma omp parallel
@@ -654,7 +695,7 @@ int artoracle_amaze(int W, int H, unsigned filters, const float* raw, long rs,
             for (int ty = 0; ty < nty; ++ty)
                 for (int tx = 0; tx < ntx; ++tx) {
                     const int top = -16 + ty * (TS - 32), left = -16 + tx * (TS - 32);
-                    if (top < H && left < W) amaze_tile(&J, &S, top, left);
+                    if (top < H && left < W) amaze_tile(&J, &S, top, left, 0);
                 }
             free(buf);
         }

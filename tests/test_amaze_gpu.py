@@ -1,0 +1,120 @@
+"""GPU parity for AMaZE: the CUDA path (through the C-ABI) against the oracle.  Bit-exact, including the
+frame sizes that trigger the reference's border-overflow quirk; plus a pass-by-pass comparison of the
+per-tile scratch block that localises any divergence."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import art_b200
+import oracle
+from art_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+TS = 160
+FULL, HALF, GAP = TS * TS * 4, TS * (TS // 2) * 4, 128
+PLANES = [("rgbgreen", FULL), ("delhvsqsum/pmwt", FULL), ("dirwts0", FULL), ("dirwts1", FULL), ("vcd/rbm,rbp", FULL),
+          ("hcd", FULL), ("vcdalt/Dgrb", FULL), ("hcdalt", FULL), ("cddiffsq/nyquist2/delp,delm", FULL + GAP),
+          ("hvwt", HALF), ("dgintv/Dgrb2", FULL), ("dginth", FULL), ("Dgrbsq1m", HALF), ("Dgrbsq1p", HALF),
+          ("cfa", FULL), ("nyquist", TS * (TS // 2)), ("nyqutest", HALF)]
+
+
+def plane_offsets():
+    off, out = 0, []
+    for name, size in PLANES:
+        out.append((name, off, size))
+        off += size + GAP
+    return out
+
+
+def _cmp(got, want, what):
+    for g, w, ch in zip(got, want, "RGB"):
+        n = int((g != w).sum())
+        assert n == 0, "%s plane %s: %d of %d samples differ (max abs %.6g)" % (
+            what, ch, n, g.size, float(np.abs(g - w).max()))
+
+
+@pytest.mark.parametrize("name", ["amaze_rggb_scene", "amaze_grbg_noise"])
+def test_cuda_matches_golden(hot_path, name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    got = hot_path.demosaic_bayer(art_b200.BAYER_AMAZE, z["raw"].astype(np.float32), int(z["filters"]))
+    _cmp(got, (z["red"], z["green"], z["blue"]), name)
+
+
+def test_scratch_block_pass_by_pass(hot_path):
+    """Every stage of every checked tile leaves the same bytes in the scratch block as the oracle."""
+    import torch
+    lib = hot_path.lib
+    plib = oracle.port().lib
+    plib.artoracle_amaze_slab_bytes.restype = ctypes.c_size_t
+    nbytes = int(plib.artoracle_amaze_slab_bytes())
+    lib.art_hpdbg_amaze_slab.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint, ctypes.c_void_p,
+                                         ctypes.c_size_t, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
+    f = synth.GRBG
+    W, H = 409, 300          # ragged right tile (cc1 = 41) and the column-overflow quirk
+    raw = synth.bayer_frame(W, H, f, seed=31, noise_a=40.0)
+    raw[40:90, 200:260] = synth.random_frame(60, 50, seed=2)      # Nyquist-heavy patch
+    d_raw = torch.from_numpy(raw).cuda()
+    ntx = (W + 16 + 127) // 128
+    nty = (H + 16 + 127) // 128
+    offs = plane_offsets()
+    stages = [1, 2, 3, 5, 6, 7, 8, 10, 11, 12, 13, 15, 16, 17, 18]
+    for tile in sorted({0, 1, ntx - 1, ntx + 1, ntx * nty - 1}):
+        for st in stages:
+            a = np.zeros(nbytes, np.uint8)
+            b = np.zeros(nbytes, np.uint8)
+            rc = lib.art_hpdbg_amaze_slab(hot_path.h, W, H, f, ctypes.c_void_p(d_raw.data_ptr()), W, 1.0, st, tile,
+                                          a.ctypes.data_as(ctypes.c_void_p), nbytes)
+            assert rc == 0
+            rc = plib.artoracle_amaze_slab(W, H, ctypes.c_uint(f), raw.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                           ctypes.c_long(W), ctypes.c_float(1.0), st, tile, b.ctypes.data_as(ctypes.c_void_p))
+            assert rc == 0
+            bad = []
+            for name, off, size in offs:
+                if name == "nyqutest":
+                    continue          # the CUDA path keeps the test value in a register (only its sign is used)
+                d = a[off:off + size] != b[off:off + size]
+                if d.any():
+                    idx = np.nonzero(d)[0]
+                    bad.append("%s: %d bytes, first at float %d (row %d col %d)" % (
+                        name, idx.size, idx[0] // 4, (idx[0] // 4) // TS, (idx[0] // 4) % TS))
+            assert not bad, "tile %d stage %d: %s" % (tile, st, "; ".join(bad))
+
+
+CASES = [(640, 500, "scene", 1.0, 4), (401, 367, "noise", 1.0, 4), (300, 260, "scene", 1.0, 4),
+         (409, 389, "noise", 1.0, 4), (170, 154, "scene", 1.0, 4), (518, 275, "scene", 1.7, 4),
+         (333, 301, "noise", 2.5, 3), (1000, 700, "scene", 1.0, 4)]
+
+
+@pytest.mark.parametrize("pattern", ["RGGB", "BGGR", "GRBG", "GBRG"])
+@pytest.mark.parametrize("W,H,kind,gain,border", CASES)
+def test_cuda_matches_oracle(hot_path, pattern, W, H, kind, gain, border):
+    f = synth.BAYER_FILTERS[pattern]
+    raw = synth.bayer_frame(W, H, f, seed=W + H) if kind == "scene" else synth.random_frame(W, H, seed=W * H)
+    got = hot_path.demosaic_bayer(art_b200.BAYER_AMAZE, raw, f, initial_gain=gain, border=border)
+    _cmp(got, oracle.port().amaze(raw, f, gain, border), "%s %dx%d %s" % (pattern, W, H, kind))
+
+
+def test_banded_equals_single_band(hot_path):
+    """Scratch-limited banding (several tile rows at a time) must not change a single bit."""
+    f = synth.RGGB
+    raw = synth.bayer_frame(900, 1300, f, seed=8)
+    one = hot_path.demosaic_bayer(art_b200.BAYER_AMAZE, raw, f)
+    os.environ["ART_HP_AMAZE_SCRATCH_MB"] = "24"       # ~2 tile rows of 8 tiles
+    try:
+        many = hot_path.demosaic_bayer(art_b200.BAYER_AMAZE, raw, f)
+    finally:
+        del os.environ["ART_HP_AMAZE_SCRATCH_MB"]
+    _cmp(many, one, "banded")
+
+
+def test_cuda_matches_reference_body_config2(hot_path):
+    """BASELINE configs[1]: 8192x5464 RGGB against the reference's own code (oracle/_ref) when it travelled."""
+    f = synth.RGGB
+    raw = synth.bayer_frame(8192, 5464, f, seed=1002)
+    got = hot_path.demosaic_bayer(art_b200.BAYER_AMAZE, raw, f)
+    want = oracle.ref(det=True).amaze(raw, f) if oracle.have_ref() else oracle.port().amaze(raw, f)
+    _cmp(got, want, "config2")
