@@ -59,11 +59,17 @@ def load_library(build_if_missing=True):
         "art_hp_get_stream": (vp, [vp]),
         "art_hp_sync": (i, [vp]),
         "art_hp_launch_count": (ctypes.c_ulonglong, [vp]),
+        "art_hp_profile_enable": (i, [vp, i]),
+        "art_hp_profile_collect": (i, [vp]),
+        "art_hp_profile_entry": (i, [vp, i, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(d), ctypes.POINTER(i)]),
         "art_hp_host_alloc": (vp, [sz]),
         "art_hp_host_free": (None, [vp]),
         "art_hp_demosaic_bayer": (i, [vp, i, i, i, u, vp, vp, vp, vp, d, i]),
         "art_hp_demosaic_bayer_dev": (i, [vp, i, i, i, u, vp, sz, vp, vp, vp, sz, d, i]),
         "art_hp_border_interpolate2_dev": (i, [vp, i, i, u, i, vp, sz, vp, vp, vp, sz]),
+        "art_hp_band_align": (i, [i, ctypes.POINTER(i), ctypes.POINTER(i)]),
+        "art_hp_band_halo": (i, [i]),
+        "art_hp_demosaic_bayer_rows_dev": (i, [vp, i, i, i, u, vp, sz, vp, vp, vp, sz, d, i, i, i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -147,6 +153,19 @@ class HotPath:
     def launch_count(self):
         return int(self.lib.art_hp_launch_count(self.h))
 
+    def profile_enable(self, on=True):
+        self._check(self.lib.art_hp_profile_enable(self.h, 1 if on else 0))
+
+    def profile_collect(self):
+        """{kernel name: (total ms, calls)} since profile_enable(True)."""
+        n = self.lib.art_hp_profile_collect(self.h)
+        out = {}
+        for k in range(max(n, 0)):
+            name, ms, calls = ctypes.c_char_p(), ctypes.c_double(), ctypes.c_int()
+            self._check(self.lib.art_hp_profile_entry(self.h, k, ctypes.byref(name), ctypes.byref(ms), ctypes.byref(calls)))
+            out[name.value.decode()] = (ms.value, calls.value)
+        return out
+
     def pinned(self, H, W):
         return PinnedArray(self.lib, H, W)
 
@@ -170,6 +189,12 @@ class HotPath:
         """Device entry: raw device addresses (ints), pitches in floats; asynchronous."""
         self._check(self.lib.art_hp_demosaic_bayer_dev(self.h, method, W, H, filters, d_raw, raw_pitch,
                                                        d_r, d_g, d_b, out_pitch, float(initial_gain), int(border)))
+
+    def demosaic_bayer_rows_dev(self, method, W, H, filters, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch,
+                                row_begin, row_end, initial_gain=1.0, border=4):
+        """Row-band form: only output rows [row_begin,row_end); pointers address row 0 of the frame."""
+        self._check(self.lib.art_hp_demosaic_bayer_rows_dev(self.h, method, W, H, filters, d_raw, raw_pitch, d_r, d_g, d_b,
+                                                            out_pitch, float(initial_gain), int(border), row_begin, row_end))
 
     def border_interpolate2_dev(self, W, H, filters, lborders, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch):
         self._check(self.lib.art_hp_border_interpolate2_dev(self.h, W, H, filters, lborders, d_raw, raw_pitch,

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <thread>
+#include <utility>
 
 namespace {
 
@@ -69,8 +70,10 @@ struct Plane {
 // Move planes between host row tables and device planes (pitch in floats) on `st`.
 // Pinned, constant-stride host memory goes straight through cudaMemcpy2DAsync; anything else is
 // staged through the context's two pinned halves, host memcpy overlapping the DMA of the other half.
-int transfer(art_hp_ctx* ctx, cudaStream_t st, const Plane* planes, int nplanes, int W, int H, size_t pitch, bool to_device)
+int transfer(art_hp_ctx* ctx, cudaStream_t st, const Plane* planes, int nplanes, int W, int row_begin, int row_end, size_t pitch, bool to_device)
 {
+    const int H = row_end - row_begin;
+    if (H <= 0) return ART_HP_OK;
     const size_t wbytes = (size_t)W * sizeof(float);
     const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
     bool staged_any = false;
@@ -82,19 +85,21 @@ int transfer(art_hp_ctx* ctx, cudaStream_t st, const Plane* planes, int nplanes,
         if (!busy[h]) return ART_HP_OK;
         ART_CUDA(ctx, cudaEventSynchronize(ctx->ev[h]));
         if (!to_device)
-            rows_memcpy(planes[pend[h].plane].rows, pend[h].row0, pend[h].nrows, wbytes, (char*)ctx->h_stage[h], false);
+            rows_memcpy(planes[pend[h].plane].rows + row_begin, pend[h].row0, pend[h].nrows, wbytes, (char*)ctx->h_stage[h], false);
         busy[h] = false;
         return ART_HP_OK;
     };
     for (int p = 0; p < nplanes; ++p) {
         ptrdiff_t stride = 0;
-        const bool cs = constant_stride(planes[p].rows, H, &stride);
-        if (cs && is_pinned(planes[p].rows[0])) {
+        const float* const* hrows = planes[p].rows + row_begin;
+        float* dbase = planes[p].dev + (size_t)row_begin * pitch;
+        const bool cs = constant_stride(hrows, H, &stride);
+        if (cs && is_pinned(hrows[0])) {
             const size_t spitch = (H > 1 ? (size_t)stride : (size_t)W) * sizeof(float);
             if (to_device)
-                ART_CUDA(ctx, cudaMemcpy2DAsync(planes[p].dev, pitch * sizeof(float), planes[p].rows[0], spitch, wbytes, H, kind, st));
+                ART_CUDA(ctx, cudaMemcpy2DAsync(dbase, pitch * sizeof(float), hrows[0], spitch, wbytes, H, kind, st));
             else
-                ART_CUDA(ctx, cudaMemcpy2DAsync(const_cast<float*>(planes[p].rows[0]), spitch, planes[p].dev, pitch * sizeof(float), wbytes, H, kind, st));
+                ART_CUDA(ctx, cudaMemcpy2DAsync(const_cast<float*>(hrows[0]), spitch, dbase, pitch * sizeof(float), wbytes, H, kind, st));
             continue;
         }
         staged_any = true;
@@ -106,9 +111,9 @@ int transfer(art_hp_ctx* ctx, cudaStream_t st, const Plane* planes, int nplanes,
             rc = drain(half);
             if (rc) return rc;
             char* hs = (char*)ctx->h_stage[half];
-            float* d = planes[p].dev + (size_t)r0 * pitch;
+            float* d = dbase + (size_t)r0 * pitch;
             if (to_device) {
-                rows_memcpy(planes[p].rows, r0, n, wbytes, hs, true);
+                rows_memcpy(hrows, r0, n, wbytes, hs, true);
                 ART_CUDA(ctx, cudaMemcpy2DAsync(d, pitch * sizeof(float), hs, wbytes, wbytes, n, kind, st));
             } else {
                 ART_CUDA(ctx, cudaMemcpy2DAsync(hs, wbytes, d, pitch * sizeof(float), wbytes, n, kind, st));
@@ -186,7 +191,8 @@ int art_hp_create(art_hp_ctx** out, int device_id)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { cudaGetLastError(); art_hp_destroy(ctx); return ART_HP_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
@@ -205,6 +211,7 @@ void art_hp_destroy(art_hp_ctx* ctx)
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     delete ctx;
 }
 
@@ -228,6 +235,45 @@ int art_hp_sync(art_hp_ctx* ctx)
 
 unsigned long long art_hp_launch_count(const art_hp_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
 
+int art_hp_profile_enable(art_hp_ctx* ctx, int on)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& sp : ctx->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
+    ctx->spans.clear();
+    ctx->stats.clear();
+    ctx->profiling = on != 0;
+    return ART_HP_OK;
+}
+
+int art_hp_profile_collect(art_hp_ctx* ctx)
+{
+    if (!ctx) return -1;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    for (auto& sp : ctx->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+        ProfStat* st = nullptr;
+        for (auto& x : ctx->stats) if (x.name == sp.name) { st = &x; break; }
+        if (!st) { ctx->stats.push_back(ProfStat{sp.name, 0.0, 0}); st = &ctx->stats.back(); }
+        st->ms += ms;
+        st->calls += 1;
+        cudaEventDestroy(sp.e0);
+        cudaEventDestroy(sp.e1);
+    }
+    ctx->spans.clear();
+    return (int)ctx->stats.size();
+}
+
+int art_hp_profile_entry(art_hp_ctx* ctx, int index, const char** name, double* total_ms, int* calls)
+{
+    if (!ctx || index < 0 || index >= (int)ctx->stats.size()) return ART_HP_ERR_INVALID;
+    if (name) *name = ctx->stats[index].name.c_str();
+    if (total_ms) *total_ms = ctx->stats[index].ms;
+    if (calls) *calls = ctx->stats[index].calls;
+    return ART_HP_OK;
+}
+
 void* art_hp_host_alloc(size_t bytes)
 {
     void* p = nullptr;
@@ -240,26 +286,60 @@ void art_hp_host_free(void* p)
     if (p) cudaFreeHost(p);
 }
 
-int art_hp_demosaic_bayer_dev(art_hp_ctx* ctx, int method, int W, int H, unsigned filters,
-                              const float* d_raw, size_t raw_pitch,
-                              float* d_red, float* d_green, float* d_blue, size_t out_pitch,
-                              double initialGain, int border)
+int art_hp_band_align(int method, int* period, int* offset)
+{
+    int p, o;
+    switch (method) {
+    case ART_HP_BAYER_AMAZE: p = 128; o = 0; break;     // tiles at stride ts-32 from -16, writing [16, ts-16)
+    case ART_HP_BAYER_RCD: p = 176; o = 9; break;       // tiles at stride 176, writing [9, 185)
+    default: return ART_HP_ERR_UNSUPPORTED;
+    }
+    if (period) *period = p;
+    if (offset) *offset = o;
+    return ART_HP_OK;
+}
+
+int art_hp_band_halo(int method)
+{
+    switch (method) {
+    case ART_HP_BAYER_AMAZE: return 16;
+    case ART_HP_BAYER_RCD: return 9;
+    default: return -1;
+    }
+}
+
+int art_hp_demosaic_bayer_rows_dev(art_hp_ctx* ctx, int method, int W, int H, unsigned filters,
+                                   const float* d_raw, size_t raw_pitch,
+                                   float* d_red, float* d_green, float* d_blue, size_t out_pitch,
+                                   double initialGain, int border, int row_begin, int row_end)
 {
     if (!ctx) return ART_HP_ERR_INVALID;
     if (!d_raw || !d_red || !d_green || !d_blue) return ctx->fail(ART_HP_ERR_INVALID, "null plane pointer");
     if (W < 32 || H < 32 || W > 65536 || H > 65536) return ctx->fail(ART_HP_ERR_INVALID, "frame %dx%d out of range [32,65536]", W, H);
     if (raw_pitch < (size_t)W || out_pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "pitch smaller than width");
     if (!rgb_bayer(filters)) return ctx->fail(ART_HP_ERR_INVALID, "filters=0x%08x is not an RGB Bayer pattern", filters);
+    int P = 0, O = 0;
+    if (art_hp_band_align(method, &P, &O)) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "unknown bayer method %d", method);
+    auto aligned = [&](int r, int edge) { return r == edge || (r > O && r < H && (r - O) % P == 0); };
+    if (row_begin < 0 || row_end > H || row_begin >= row_end || !aligned(row_begin, 0) || !aligned(row_end, H))
+        return ctx->fail(ART_HP_ERR_INVALID, "rows [%d,%d) are not cut on the tile grid (period %d, offset %d) of a %d-row frame", row_begin, row_end, P, O, H);
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
     switch (method) {
     case ART_HP_BAYER_RCD:
-        return art_rcd_dev(ctx, W, H, filters, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch);
-    case ART_HP_BAYER_AMAZE:
-        if (!(initialGain > 0.0)) return ctx->fail(ART_HP_ERR_INVALID, "initialGain must be > 0");
-        return art_amaze_dev(ctx, W, H, filters, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch, initialGain, border);
+        return art_rcd_dev(ctx, W, H, filters, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch, row_begin, row_end);
     default:
-        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "unknown bayer method %d", method);
+        if (!(initialGain > 0.0)) return ctx->fail(ART_HP_ERR_INVALID, "initialGain must be > 0");
+        return art_amaze_dev(ctx, W, H, filters, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch, initialGain, border, row_begin, row_end);
     }
+}
+
+int art_hp_demosaic_bayer_dev(art_hp_ctx* ctx, int method, int W, int H, unsigned filters,
+                              const float* d_raw, size_t raw_pitch,
+                              float* d_red, float* d_green, float* d_blue, size_t out_pitch,
+                              double initialGain, int border)
+{
+    return art_hp_demosaic_bayer_rows_dev(ctx, method, W, H, filters, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch,
+                                          initialGain, border, 0, H);
 }
 
 int art_hp_border_interpolate2_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, int lborders,
@@ -271,7 +351,7 @@ int art_hp_border_interpolate2_dev(art_hp_ctx* ctx, int W, int H, unsigned filte
     if (lborders < 1 || 2 * lborders >= W || 2 * lborders >= H) return ctx->fail(ART_HP_ERR_INVALID, "border %d does not fit %dx%d", lborders, W, H);
     if (!rgb_bayer(filters)) return ctx->fail(ART_HP_ERR_INVALID, "filters=0x%08x is not an RGB Bayer pattern", filters);
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
-    return art_border_dev(ctx, W, H, filters, lborders, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch);
+    return art_border_dev(ctx, W, H, filters, lborders, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch, 0, H);
 }
 
 int art_hp_demosaic_bayer(art_hp_ctx* ctx, int method, int W, int H, unsigned filters,
@@ -290,13 +370,60 @@ int art_hp_demosaic_bayer(art_hp_ctx* ctx, int method, int W, int H, unsigned fi
     for (int i = 0; i < 3; ++i)
         if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
     Plane in = {rawData, (float*)ctx->d_raw.p};
-    if ((rc = transfer(ctx, ctx->stream, &in, 1, W, H, pitch, true))) return rc;
+    Plane out[3] = {{red, (float*)ctx->d_out[0].p}, {green, (float*)ctx->d_out[1].p}, {blue, (float*)ctx->d_out[2].p}};
+    if (method == ART_HP_BAYER_AMAZE && border >= 4 && initialGain > 0.0 && rgb_bayer(filters)) {
+        // Banded pipeline: the raw rows of band k+1 travel host->device and the finished rows of band k-1
+        // travel device->host (two DMA engines) while band k is being demosaiced.  Bands are whole
+        // reference tile rows, so results do not change.
+        struct Cb {
+            art_hp_ctx* ctx; const Plane* in; const Plane* out; int W; size_t pitch; int uploaded;
+            std::vector<cudaEvent_t> evs; std::vector<std::pair<int, int>> rows; std::vector<cudaEvent_t> upl;
+        } cb{ctx, &in, out, W, pitch, 0, {}, {}, {}};
+        auto hook = [](void* u, int phase, int r0, int r1) -> int {
+            Cb* c = (Cb*)u;
+            cudaEvent_t e;
+            if (phase == 0) {
+                if (r1 <= c->uploaded) return ART_HP_OK;
+                int rc2 = transfer(c->ctx, c->ctx->copy_stream, c->in, 1, c->W, c->uploaded, r1, c->pitch, true);
+                if (rc2) return rc2;
+                c->uploaded = r1;
+                if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return c->ctx->fail(ART_HP_ERR_CUDA, "cudaEventCreate failed");
+                c->upl.push_back(e);
+                cudaEventRecord(e, c->ctx->copy_stream);
+                if (cudaStreamWaitEvent(c->ctx->stream, e, 0) != cudaSuccess) return c->ctx->fail(ART_HP_ERR_CUDA, "cudaStreamWaitEvent failed");
+                return ART_HP_OK;
+            }
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return c->ctx->fail(ART_HP_ERR_CUDA, "cudaEventCreate failed");
+            cudaEventRecord(e, c->ctx->stream);
+            c->evs.push_back(e);
+            c->rows.push_back({r0, r1});
+            return ART_HP_OK;
+        };
+        const int nty = (H + 16 + 127) / 128;
+        const int band = std::max(2, (nty + 5) / 6);          // ~6 bands per frame
+        rc = art_amaze_dev_banded(ctx, W, H, filters, (const float*)ctx->d_raw.p, pitch,
+                                  (float*)ctx->d_out[0].p, (float*)ctx->d_out[1].p, (float*)ctx->d_out[2].p, pitch,
+                                  initialGain, border, band, hook, &cb, 0, H);
+        // all kernels are queued; now drain band by band on the device->host stream
+        for (size_t k = 0; k < cb.evs.size() && rc == ART_HP_OK; ++k) {
+            if (cudaStreamWaitEvent(ctx->d2h_stream, cb.evs[k], 0) != cudaSuccess) { rc = ctx->fail(ART_HP_ERR_CUDA, "cudaStreamWaitEvent failed"); break; }
+            rc = transfer(ctx, ctx->d2h_stream, out, 3, W, cb.rows[k].first, cb.rows[k].second, pitch, false);
+        }
+        cudaError_t e1 = cudaStreamSynchronize(ctx->d2h_stream), e2 = cudaStreamSynchronize(ctx->stream);
+        cudaError_t e0 = cudaStreamSynchronize(ctx->copy_stream);
+        for (cudaEvent_t e : cb.evs) cudaEventDestroy(e);
+        for (cudaEvent_t e : cb.upl) cudaEventDestroy(e);
+        if (rc) return rc;
+        if (e0 != cudaSuccess) return ctx->fail(ART_HP_ERR_CUDA, "copy stream sync failed: %s", cudaGetErrorString(e0));
+        if (e1 != cudaSuccess || e2 != cudaSuccess) return ctx->fail(ART_HP_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        return ART_HP_OK;
+    }
+    if ((rc = transfer(ctx, ctx->stream, &in, 1, W, 0, H, pitch, true))) return rc;
     rc = art_hp_demosaic_bayer_dev(ctx, method, W, H, filters, (const float*)ctx->d_raw.p, pitch,
                                    (float*)ctx->d_out[0].p, (float*)ctx->d_out[1].p, (float*)ctx->d_out[2].p, pitch,
                                    initialGain, border);
     if (rc) return rc;
-    Plane out[3] = {{red, (float*)ctx->d_out[0].p}, {green, (float*)ctx->d_out[1].p}, {blue, (float*)ctx->d_out[2].p}};
-    if ((rc = transfer(ctx, ctx->stream, out, 3, W, H, pitch, false))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, out, 3, W, 0, H, pitch, false))) return rc;
     ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;
 }

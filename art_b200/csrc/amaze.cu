@@ -834,11 +834,15 @@ static int amaze_band(art_hp_ctx* ctx, AmzArgs a, int stop_after)
     int pass = 0;
 #define LAUNCH(kern, grid, block)                                      \
     do {                                                               \
+        art_prof_begin(ctx, #kern);                                    \
         kern<<<grid, block, 0, st>>>(a);                               \
+        art_prof_end(ctx);                                             \
         ctx->launches++;                                               \
         if (++pass == stop_after) { ART_CUDA(ctx, cudaGetLastError()); return ART_HP_OK; } \
     } while (0)
+    art_prof_begin(ctx, "memset_slabs");
     ART_CUDA(ctx, cudaMemsetAsync(a.slabs, 0, (size_t)nt * SLAB_BYTES, st));
+    art_prof_end(ctx);
     const dim3 fr_block(TS, FR_ROWS), hr_block(TSH, HR_ROWS);
     const dim3 fr_grid((TS + FR_ROWS - 1) / FR_ROWS, nt), hr_grid((TS + HR_ROWS - 1) / HR_ROWS, nt);
     LAUNCH(k_fill, nt, 256);                                           // 1
@@ -860,7 +864,9 @@ static int amaze_band(art_hp_ctx* ctx, AmzArgs a, int stop_after)
     LAUNCH(k_split, dim3((TS / 2 + HR_ROWS - 1) / HR_ROWS, nt), hr_block);   // 17
     LAUNCH(k_chroma, hr_grid, hr_block);                               // 18
     if (stop_after == 0) {
+        art_prof_begin(ctx, "k_write");
         k_write<<<fr_grid, fr_block, 0, st>>>(a);
+        art_prof_end(ctx);
         ctx->launches++;
     }
 #undef LAUNCH
@@ -893,24 +899,40 @@ static int band_rows(int ntx, int nty)
     return (int)rows;
 }
 
-int art_amaze_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, const float* raw, size_t rp,
-                  float* R, float* G, float* B, size_t op, double initialGain, int border)
+int art_amaze_dev_banded(art_hp_ctx* ctx, int W, int H, unsigned filters, const float* raw, size_t rp,
+                         float* R, float* G, float* B, size_t op, double initialGain, int border,
+                         int band_tile_rows, art_band_cb cb, void* user, int row_begin, int row_end)
 {
     AmzArgs a;
     int nty = 0;
     amaze_setup(ctx, a, W, H, filters, raw, rp, R, G, B, op, initialGain, &nty);
-    const int rows = band_rows(a.ntx, nty);
+    int rows = band_rows(a.ntx, nty);
+    if (band_tile_rows > 0 && band_tile_rows < rows) rows = band_tile_rows;
     int rc = art_reserve(ctx, ctx->d_scratch, (size_t)rows * a.ntx * SLAB_BYTES + (size_t)rows * a.ntx * 4 * sizeof(int) + 256);
     if (rc) return rc;
     a.slabs = (char*)ctx->d_scratch.p;
     a.bbox = (int*)(a.slabs + (size_t)rows * a.ntx * SLAB_BYTES);
-    for (int ty0 = 0; ty0 < nty; ty0 += rows) {
+    // tile rows covering the requested output rows (tile row ty writes rows [128 ty, 128 ty + 128))
+    const int ty_begin = row_begin / (TS - 32), ty_end = std::min(nty, (row_end + (TS - 32) - 1) / (TS - 32));
+    for (int ty0 = ty_begin; ty0 < ty_end; ty0 += rows) {
+        const int nr = std::min(rows, ty_end - ty0);
         a.ty0 = ty0;
-        a.ntiles = std::min(rows, nty - ty0) * a.ntx;
+        a.ntiles = nr * a.ntx;
+        // tile row ty reads raw rows [128*ty - 16, 128*ty + 144) plus, at the frame edges, mirror rows that
+        // lie inside [0, 33) (top) and [H-17, H) (bottom); it writes image rows [128*ty, 128*ty + 128)
+        // (L1441: rr in [16, rr1-16), row = rr + top)
+        if (cb && (rc = cb(user, 0, 0, std::min(H, std::max(33, (TS - 32) * (ty0 + nr) + 16))))) return rc;
         if ((rc = amaze_band(ctx, a, 0))) return rc;
+        if (cb && (rc = cb(user, 1, std::min(H, (TS - 32) * ty0), std::min(H, (TS - 32) * (ty0 + nr))))) return rc;
     }
-    if (border < 4) return art_border_dev(ctx, W, H, filters, 3, raw, rp, R, G, B, op);      // L1587-1589
+    if (border < 4) return art_border_dev(ctx, W, H, filters, 3, raw, rp, R, G, B, op, row_begin, row_end);      // L1587-1589
     return ART_HP_OK;
+}
+
+int art_amaze_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, const float* raw, size_t rp,
+                  float* R, float* G, float* B, size_t op, double initialGain, int border, int row_begin, int row_end)
+{
+    return art_amaze_dev_banded(ctx, W, H, filters, raw, rp, R, G, B, op, initialGain, border, 0, nullptr, nullptr, row_begin, row_end);
 }
 
 // Debug hook (not part of the ABI header; used by tests to localise a divergence): run passes

@@ -15,14 +15,22 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+struct ProfSpan { const char* name; cudaEvent_t e0, e1; };
+struct ProfStat { std::string name; double ms = 0.0; int calls = 0; };
+
 struct art_hp_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;       // the stream work is queued on (own or caller's)
-    cudaStream_t copy_stream = nullptr;  // second stream for copy/compute overlap
+    cudaStream_t copy_stream = nullptr;  // host->device copies that overlap compute
+    cudaStream_t d2h_stream = nullptr;   // device->host copies that overlap compute (other DMA engine)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long launches = 0;
+    // optional per-kernel timing (art_hp_profile_*): CUDA events around every launch
+    bool profiling = false;
+    std::vector<ProfSpan> spans;
+    std::vector<ProfStat> stats;
     std::string err;
     // device scratch, grown on demand and kept across calls
     DevBuf d_raw, d_out[3], d_scratch;
@@ -50,15 +58,40 @@ struct art_hp_ctx {
                                cudaGetErrorString(e_), __FILE__, __LINE__);                   \
     } while (0)
 
+// RAII-free span helpers used by the launch sites
+static inline void art_prof_begin(art_hp_ctx* ctx, const char* name)
+{
+    if (!ctx->profiling) return;
+    ProfSpan sp{name, nullptr, nullptr};
+    cudaEventCreate(&sp.e0);
+    cudaEventCreate(&sp.e1);
+    cudaEventRecord(sp.e0, ctx->stream);
+    ctx->spans.push_back(sp);
+}
+static inline void art_prof_end(art_hp_ctx* ctx)
+{
+    if (!ctx->profiling || ctx->spans.empty()) return;
+    cudaEventRecord(ctx->spans.back().e1, ctx->stream);
+}
+
 static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
 // grow-only device buffer
 int art_reserve(art_hp_ctx* ctx, DevBuf& b, size_t bytes);
 
 // kernels (device-resident planes, pitch in floats); each returns an art_hp_status
+// row_begin/row_end: output rows to produce (tile-grid aligned, see art_hp_demosaic_bayer_rows_dev)
 int art_rcd_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, const float* raw, size_t rp,
-                float* R, float* G, float* B, size_t op);
+                float* R, float* G, float* B, size_t op, int row_begin, int row_end);
 int art_border_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, int bord, const float* raw, size_t rp,
-                   float* R, float* G, float* B, size_t op);
+                   float* R, float* G, float* B, size_t op, int row_begin, int row_end);
 int art_amaze_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, const float* raw, size_t rp,
-                  float* R, float* G, float* B, size_t op, double initialGain, int border);
+                  float* R, float* G, float* B, size_t op, double initialGain, int border, int row_begin, int row_end);
+// Same, but in bands of `band_tile_rows` reference tile rows (0 = as many as the scratch budget allows);
+// `cb(user, 0, 0, need_end)` is called before a band is queued: the band reads raw rows [0, need_end);
+// `cb(user, 1, row0, row1)` after its kernels are queued: the band completes image rows [row0, row1).
+// The host entry uses both to overlap host->device and device->host copies with the other bands.
+typedef int (*art_band_cb)(void* user, int phase, int row0, int row1);
+int art_amaze_dev_banded(art_hp_ctx* ctx, int W, int H, unsigned filters, const float* raw, size_t rp,
+                         float* R, float* G, float* B, size_t op, double initialGain, int border,
+                         int band_tile_rows, art_band_cb cb, void* user, int row_begin, int row_end);

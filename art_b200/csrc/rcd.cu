@@ -16,6 +16,8 @@
 // reference build.
 #include "ctx.h"
 
+#include <algorithm>
+
 namespace {
 
 constexpr int TS = 194;   // reference tileSize        (rcd_demosaic.cc L84)
@@ -47,6 +49,7 @@ struct RcdArgs {
     float *R, *G, *B; size_t op;
     int W, H; unsigned filters;
     int ntw;
+    int tr0;          // first reference tile row of this launch
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) rcd_kernel(RcdArgs a)
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rcd_kernel(RcdArgs a)
     const int tid = threadIdx.x;
     // which reference tile and which quarter of it
     const int tc = blockIdx.x >> 1, sc = blockIdx.x & 1;
-    const int tr = blockIdx.y >> 1, sr = blockIdx.y & 1;
+    const int tr = a.tr0 + (blockIdx.y >> 1), sr = blockIdx.y & 1;
     const int R0 = tr * TN, C0 = tc * TN;
     const int T = min(TS, a.H - R0), C = min(TS, a.W - C0);        // tile rows / cols (L113-124)
     if (T <= 2 * TB || C <= 2 * TB) return;                         // nothing to write (L114-121 + empty write loop)
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) rcd_kernel(RcdArgs a)
 
 // border_interpolate2 (demosaic_algos.cc L200-353): one thread per ring pixel.
 __global__ void border_kernel(const float* __restrict__ raw, size_t rp, float* __restrict__ R, float* __restrict__ G,
-                              float* __restrict__ B, size_t op, int W, int H, unsigned filters, int bord)
+                              float* __restrict__ B, size_t op, int W, int H, unsigned filters, int bord, int row_begin, int row_end)
 {
     // ring pixels enumerated as: full rows [0,bord) and [H-bord,H) (W each), then for the middle rows
     // the 2*bord edge columns
@@ -291,6 +294,7 @@ __global__ void border_kernel(const float* __restrict__ raw, size_t rp, float* _
         i = bord + rr;
         j = cc < bord ? cc : W - 2 * bord + cc;
     }
+    if (i < row_begin || i >= row_end) return;
     float sum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int i1 = i - 1; i1 < i + 2; ++i1)
         for (int j1 = j - 1; j1 < j + 2; ++j1)
@@ -316,18 +320,20 @@ __global__ void border_kernel(const float* __restrict__ raw, size_t rp, float* _
 }  // namespace
 
 int art_border_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, int bord, const float* raw, size_t rp,
-                   float* R, float* G, float* B, size_t op)
+                   float* R, float* G, float* B, size_t op, int row_begin, int row_end)
 {
     const long long n = 2ll * bord * W + (long long)(H - 2 * bord) * 2 * bord;
     const int bs = 256;
-    border_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, ctx->stream>>>(raw, rp, R, G, B, op, W, H, filters, bord);
+    art_prof_begin(ctx, "border_kernel");
+    border_kernel<<<(unsigned)((n + bs - 1) / bs), bs, 0, ctx->stream>>>(raw, rp, R, G, B, op, W, H, filters, bord, row_begin, row_end);
+    art_prof_end(ctx);
     ctx->launches++;
     ART_CUDA(ctx, cudaGetLastError());
     return ART_HP_OK;
 }
 
 int art_rcd_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, const float* raw, size_t rp,
-                float* R, float* G, float* B, size_t op)
+                float* R, float* G, float* B, size_t op, int row_begin, int row_end)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -335,10 +341,16 @@ int art_rcd_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, const float* ra
         attr_set = true;
     }
     const int nth = H / TN + ((H % TN) ? 1 : 0), ntw = W / TN + ((W % TN) ? 1 : 0);   // L86-87
-    RcdArgs a{raw, rp, R, G, B, op, W, H, filters, ntw};
-    dim3 grid(2 * ntw, 2 * nth);
+    // reference tile row tr writes image rows [176 tr + 9, 176 tr + 185) (L305-316); bands are cut at 176 k + 9
+    const int tr_begin = row_begin <= TB ? 0 : (row_begin - TB) / TN;
+    const int tr_end = row_end >= H ? nth : std::min(nth, (row_end - TB) / TN);
+    if (tr_end <= tr_begin) return art_border_dev(ctx, W, H, filters, TB, raw, rp, R, G, B, op, row_begin, row_end);
+    RcdArgs a{raw, rp, R, G, B, op, W, H, filters, ntw, tr_begin};
+    dim3 grid(2 * ntw, 2 * (tr_end - tr_begin));
+    art_prof_begin(ctx, "rcd_kernel");
     rcd_kernel<<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(a);
+    art_prof_end(ctx);
     ctx->launches++;
     ART_CUDA(ctx, cudaGetLastError());
-    return art_border_dev(ctx, W, H, filters, TB, raw, rp, R, G, B, op);   // L342
+    return art_border_dev(ctx, W, H, filters, TB, raw, rp, R, G, B, op, row_begin, row_end);   // L342
 }

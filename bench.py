@@ -32,6 +32,20 @@ sys.path.insert(0, ROOT)
 W45, H45 = 8192, 5464            # BASELINE configs[1..2]: 44.76 MP
 BYTES_PER_PX = 16                # demosaic = 4 B read + 12 B written per pixel
 
+# Algorithmic bytes per TILE pixel of each AMaZE kernel (DESIGN.md "AMaZE", table "planes per pass"):
+# 4 B per full-resolution plane read or written, 2 B per half-resolution plane, once each.  A frame has
+# ntiles * 160 * 160 tile pixels (the reference's 160x160 tiles at stride 128 cover every pixel 1.56x).
+AMAZE_KERNEL_BYTES = {
+    "k_fill": 4 * 0.64 + 8, "k_grad": 4 + 12, "k_dirinterp": 12 + 24, "k_hcd": 12 + 4, "k_vcd": 16 + 8,
+    "k_hvwt": 24 + 2, "k_nyqtest": 8 + 0.5, "k_green": 18.5 + 10, "k_diag": 4 + 8, "k_rbdiag": 12 + 6,
+    "k_rbint": 10 + 2, "k_greenrb": 20 + 6, "k_chroma": 2 + 2, "k_write": 10 + 12 * 0.64,
+}
+# DRAM bytes per launch from the committed ncu --set full capture (profiles/ncu_full_amaze_r1.csv,
+# dram__bytes_read.sum + dram__bytes_write.sum at 8192x5464); None = not captured
+NCU_TRAFFIC = {"k_dirinterp": 0.974235e9 + 1.551996e9, "k_rbdiag": 0.854833e9 + 0.355250e9, "k_grad": 0.282756e9 + 0.768683e9,
+               "k_write": 0.565864e9 + 0.500666e9, "k_vcd": 1.110983e9 + 0.500444e9, "k_split": 0.081761e9 + 0.071985e9,
+               "rcd_kernel": 181.060608e6 + 475.030528e6}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -104,32 +118,49 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_runner(method):
-    """(callable(raw, filters) -> planes, kind, cores).  Prefers the reference's own bodies."""
+def cpu_reference_runner(method, raw, filters):
+    """(callable() -> None, kind, threads).  Prefers the reference's own function bodies (oracle/_ref, the
+    stock build exactly as the reference ships it).  Output planes are allocated once, outside the timed
+    region (the reference allocates red/green/blue at load time, rawimagesource.cc L1458-1460), and the
+    OpenMP thread count is the faster of {all hardware threads, half of them} on this box."""
+    import numpy as np
     import oracle
+    H, W = raw.shape
+    out = [np.zeros((H, W), np.float32) for _ in range(3)]
     try:
-        ref = oracle.ref(det=False)      # the stock reference, exactly as it ships
+        ref = oracle.ref(det=False)
         fn = ref.rcd if method == "rcd" else ref.amaze
-        return (lambda raw, f: fn(raw, f)), "reference", ref.max_threads()
-    except Exception:
+        hw = os.cpu_count() or ref.max_threads()
+        best = None
+        for nt in sorted({hw, max(1, hw // 2)}, reverse=True):
+            kw = {"nthreads": nt, "out": out}
+            fn(raw, filters, **kw)                       # warm-up at this thread count
+            t0 = time.perf_counter()
+            fn(raw, filters, **kw)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, nt)
+        nt = best[1]
+        return (lambda: fn(raw, filters, nthreads=nt, out=out)), "reference", nt
+    except (OSError, FileNotFoundError):
         port = oracle.port()
         fn = port.rcd if method == "rcd" else port.amaze
-        return (lambda raw, f: fn(raw, f)), "port", os.cpu_count() or 1
+        return (lambda: fn(raw, filters)), "port", os.cpu_count() or 1
 
 
 def time_cpu(method, raw, filters, budget_s=12.0, max_runs=5):
-    run, kind, cores = cpu_reference_runner(method)
-    run(raw, filters)                                  # warm-up (page faults, OpenMP pool)
+    run, kind, cores = cpu_reference_runner(method, raw, filters)
+    run()                                              # warm-up
     ts = []
     t_end = time.perf_counter() + budget_s
     while len(ts) < max_runs and (not ts or time.perf_counter() < t_end):
         t0 = time.perf_counter()
-        run(raw, filters)
+        run()
         ts.append(time.perf_counter() - t0)
     med = statistics.median(ts)
     H, W = raw.shape
     return {"value": W * H / med / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": kind,
-            "sample": "%d full %dx%d frames after 1 warm-up, median" % (len(ts), W, H)}
+            "sample": "%d full %dx%d frames after warm-up, median; OpenMP threads = %d (faster of all/half)" % (len(ts), W, H, cores)}
 
 
 def main():
@@ -152,16 +183,16 @@ def main():
         if rank != 0:
             return 0
         raw = synth.bayer_frame(W, H, filters, seed=1002)
-        run, kind, cores = cpu_reference_runner(args.method)
+        run, kind, cores = cpu_reference_runner(args.method, raw, filters)
         for _ in range(max(1, min(args.warmup, 2))):
-            run(raw, filters)
+            run()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            run(raw, filters)
+            run()
         dt = time.perf_counter() - t0
         val = args.steps * W * H / dt / 1e6
         cb = {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": kind,
-              "sample": "%d full %dx%d frames (this run's steps)" % (args.steps, W, H)}
+              "sample": "%d full %dx%d frames (this run's steps); OpenMP threads = %d (faster of all/half)" % (args.steps, W, H, cores)}
         print(json.dumps({"impl": "reference", "metric": "Mpixel/s", "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -253,9 +284,33 @@ def main():
     clocks = sampler.stop() if sampler else None
     checksum = float(pins[2].array[H // 2, W // 2])
 
+    # ---- per-kernel device time (CUDA events around every launch, on the launching stream), outside
+    #      the timed regions above so the extra events do not perturb `value`
+    kern = {}
+    if rank == 0:
+        hp.profile_enable(True)
+        for _ in range(args.steps):
+            step_dev()
+        prof = hp.profile_collect()
+        hp.profile_enable(False)
+        kern = {k: v[0] / max(1, v[1]) for k, v in prof.items()}            # mean ms per launch
+        calls = {k: v[1] // args.steps for k, v in prof.items()}            # launches per step
+
     if rank == 0:
         peak, how = peaks()
-        achieved = BYTES_PER_PX * W * H / (ms_per_step * 1e-3) / 1e9
+        step_achieved = BYTES_PER_PX * W * H / (ms_per_step * 1e-3) / 1e9
+        per_step = {k: kern[k] * calls[k] for k in kern}                     # ms per step per kernel
+        top = max((k for k in per_step if k != "memset_slabs"), key=lambda k: per_step[k])
+        share = per_step[top] / sum(per_step.values())
+        if args.method == "rcd":
+            units, unit_bytes, unit_name = W * H, BYTES_PER_PX, "pixel"
+        else:
+            ntiles = ((W + 16 + 127) // 128) * ((H + 16 + 127) // 128)
+            units, unit_bytes, unit_name = ntiles * 160 * 160, AMAZE_KERNEL_BYTES.get(top), "tile pixel"
+        if unit_bytes is None:
+            achieved = None
+        else:
+            achieved = unit_bytes * units / calls[top] / (kern[top] * 1e-3) / 1e9
         out = {
             "metric": "Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -263,9 +318,16 @@ def main():
             "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": W * H * 4, "d2h_bytes_per_step": W * H * 12,
                     "steps": e2e_steps, "host_memory": "pinned (art_hp_host_alloc)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": how,
-                         "note": "algorithmic bytes (16 B/px) / mean device time of one step (all kernels of the step)"},
+            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": NCU_TRAFFIC.get(top), "peak_source": how,
+                         "kernel_ms": kern[top], "launches_per_step": calls[top], "share_of_step": share,
+                         "algorithmic_bytes_per_unit": unit_bytes, "unit_name": unit_name, "units_per_step": units,
+                         "note": "dominant kernel by device time; achieved = algorithmic bytes per launch / mean CUDA-event "
+                                 "duration of that kernel (events on the launching stream, separate pass of --steps steps)"},
+            "step_roofline": {"achieved": step_achieved, "frac": step_achieved / peak, "unit": "GB/s",
+                              "note": "whole step: 16 B per output pixel / ms_per_step (shows the traffic the multi-pass design adds)"},
+            "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
             "clocks": clocks, "checksum_green_center": checksum,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -68,6 +68,14 @@ int  art_hp_sync(art_hp_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 unsigned long long art_hp_launch_count(const art_hp_ctx* ctx);
 
+/* Optional per-kernel timing (the reference's BENCHFUN/StopWatch, rtengine/StopWatch.h L33-75, is the
+ * analogue): when enabled every kernel launch is bracketed by CUDA events on the context's stream.
+ * art_hp_profile_collect() synchronises, folds the spans into per-kernel totals and returns how many
+ * distinct kernels were seen; art_hp_profile_entry() reads one (name is owned by the context). */
+int  art_hp_profile_enable(art_hp_ctx* ctx, int on);
+int  art_hp_profile_collect(art_hp_ctx* ctx);
+int  art_hp_profile_entry(art_hp_ctx* ctx, int index, const char** name, double* total_ms, int* calls);
+
 /* pinned host memory for callers that want zero-staging transfers
  * (what an AlignedBuffer, rtengine/alignedbuffer.h, would be backed by) */
 void* art_hp_host_alloc(size_t bytes);
@@ -99,6 +107,22 @@ int art_hp_demosaic_bayer_dev(art_hp_ctx* ctx, int method, int W, int H, unsigne
                               const float* d_raw, size_t raw_pitch,
                               float* d_red, float* d_green, float* d_blue, size_t out_pitch,
                               double initialGain, int border);
+
+/* Row-band form for sharding one frame across GPUs: computes only the output
+ * rows [row_begin, row_end) of the full W x H frame.  Bands must be cut on the method's reference tile
+ * grid so that results are identical to the full-frame call: art_hp_band_align(method) gives the period P
+ * and offset O; row_begin must be 0 or O + k*P, row_end must be H or O + k*P (AMaZE: P=128, O=0 --
+ * amaze_demosaic_RT.cc L182; RCD: P=176, O=9 -- rcd_demosaic.cc L82-87, L305-316).
+ * d_raw/d_red/... are the addresses of ROW 0 of the frame; only rows
+ * [row_begin - art_hp_band_halo(method), row_end + halo) of d_raw (clipped to the frame, plus the
+ * mirror rows [0,33) / [H-17,H) when the band touches the top / bottom edge) are read and only rows
+ * [row_begin,row_end) of the outputs are written, so a rank may back the rest with nothing. */
+int art_hp_band_align(int method, int* period, int* offset);
+int art_hp_band_halo(int method);
+int art_hp_demosaic_bayer_rows_dev(art_hp_ctx* ctx, int method, int W, int H, unsigned filters,
+                                   const float* d_raw, size_t raw_pitch,
+                                   float* d_red, float* d_green, float* d_blue, size_t out_pitch,
+                                   double initialGain, int border, int row_begin, int row_end);
 
 /* Replaces RawImageSource::border_interpolate2(W,H,lborders,rawData,red,green,blue)
  * (rtengine/demosaic_algos.cc L200-353). Device-resident. */

@@ -76,22 +76,24 @@ class _Ref:
         self.lib = ctypes.CDLL(path)
         self.det = det
 
-    def _planes(self, raw):
+    def _planes(self, raw, out=None):
         raw = np.ascontiguousarray(raw, dtype=np.float32)
         H, W = raw.shape
-        return raw, H, W, [np.zeros((H, W), np.float32) for _ in range(3)]
+        if out is None:
+            out = [np.zeros((H, W), np.float32) for _ in range(3)]
+        return raw, H, W, out
 
     def max_threads(self):
         return int(self.lib.artref_max_threads())
 
-    def rcd(self, raw, filters, nthreads=0):
-        raw, H, W, (r, g, b) = self._planes(raw)
+    def rcd(self, raw, filters, nthreads=0, out=None):
+        raw, H, W, (r, g, b) = self._planes(raw, out)
         self.lib.artref_rcd(W, H, ctypes.c_uint(filters), _fp(raw), ctypes.c_long(W),
                             _fp(r), _fp(g), _fp(b), ctypes.c_long(W), nthreads)
         return r, g, b
 
-    def amaze(self, raw, filters, initial_gain=1.0, border=4, nthreads=0):
-        raw, H, W, (r, g, b) = self._planes(raw)
+    def amaze(self, raw, filters, initial_gain=1.0, border=4, nthreads=0, out=None):
+        raw, H, W, (r, g, b) = self._planes(raw, out)
         self.lib.artref_amaze(W, H, ctypes.c_uint(filters), _fp(raw), ctypes.c_long(W),
                               _fp(r), _fp(g), _fp(b), ctypes.c_long(W),
                               ctypes.c_double(initial_gain), border, nthreads)

@@ -118,3 +118,37 @@ def test_cuda_matches_reference_body_config2(hot_path):
     got = hot_path.demosaic_bayer(art_b200.BAYER_AMAZE, raw, f)
     want = oracle.ref(det=True).amaze(raw, f) if oracle.have_ref() else oracle.port().amaze(raw, f)
     _cmp(got, want, "config2")
+
+
+@pytest.mark.parametrize("method,name", [(art_b200.BAYER_AMAZE, "amaze"), (art_b200.BAYER_RCD, "rcd")])
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_bands_equal_full_frame(hot_path, method, name, world):
+    """Sharding one frame by row bands (what N GPUs do, art_b200/dist.py) reproduces the full-frame result
+    bit for bit: each band is computed by a separate call that only sees the raw rows its rank would hold."""
+    import torch
+    from art_b200 import dist as adist
+    f = synth.GBRG
+    W, H = 700, 1000
+    raw = synth.bayer_frame(W, H, f, seed=77)
+    full = hot_path.demosaic_bayer(method, raw, f)
+    outs = [torch.zeros((H, W), dtype=torch.float32, device="cuda") for _ in range(3)]
+    for band in adist.row_bands(H, world, method):
+        (r0, r1), (lo, hi) = band["out"], band["need"]
+        if r1 <= r0:
+            continue
+        # the rank holds only rows [lo,hi); everything else is poisoned
+        d_raw = torch.full((H, W), float("nan"), dtype=torch.float32, device="cuda")
+        d_raw[lo:hi] = torch.from_numpy(raw[lo:hi]).cuda()
+        hot_path.demosaic_bayer_rows_dev(method, W, H, f, d_raw.data_ptr(), W, outs[0].data_ptr(), outs[1].data_ptr(),
+                                         outs[2].data_ptr(), W, r0, r1)
+        hot_path.sync()
+    got = [o.cpu().numpy() for o in outs]
+    _cmp(got, full, "%s bands x%d" % (name, world))
+
+
+def test_rows_api_rejects_off_grid_bands(hot_path):
+    import torch
+    d = torch.zeros((256, 256), dtype=torch.float32, device="cuda")
+    with pytest.raises(art_b200.HotPathError):
+        hot_path.demosaic_bayer_rows_dev(art_b200.BAYER_AMAZE, 256, 256, synth.RGGB, d.data_ptr(), 256, d.data_ptr(),
+                                         d.data_ptr(), d.data_ptr(), 256, 100, 256)
