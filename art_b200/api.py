@@ -67,6 +67,8 @@ def load_library(build_if_missing=True):
         "art_hp_demosaic_bayer": (i, [vp, i, i, i, u, vp, vp, vp, vp, d, i]),
         "art_hp_demosaic_bayer_dev": (i, [vp, i, i, i, u, vp, sz, vp, vp, vp, sz, d, i]),
         "art_hp_border_interpolate2_dev": (i, [vp, i, i, u, i, vp, sz, vp, vp, vp, sz]),
+        "art_hp_scale_convert": (i, [vp, i, i, vp, vp, vp, ctypes.POINTER(ctypes.c_float), i, ctypes.POINTER(d)]),
+        "art_hp_scale_convert_dev": (i, [vp, i, i, vp, vp, vp, sz, ctypes.POINTER(ctypes.c_float), i, ctypes.POINTER(d)]),
         "art_hp_band_align": (i, [i, ctypes.POINTER(i), ctypes.POINTER(i)]),
         "art_hp_band_halo": (i, [i]),
         "art_hp_demosaic_bayer_rows_dev": (i, [vp, i, i, i, u, vp, sz, vp, vp, vp, sz, d, i, i, i]),
@@ -195,6 +197,25 @@ class HotPath:
         """Row-band form: only output rows [row_begin,row_end); pointers address row 0 of the frame."""
         self._check(self.lib.art_hp_demosaic_bayer_rows_dev(self.h, method, W, H, filters, d_raw, raw_pitch, d_r, d_g, d_b,
                                                             out_pitch, float(initial_gain), int(border), row_begin, row_end))
+
+    @staticmethod
+    def _mul_mat(mul, mat):
+        m = (ctypes.c_float * 3)(*[float(x) for x in mul])
+        mm = None
+        if mat is not None:
+            mm = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(mat, dtype=np.float64).reshape(9)])
+        return m, mm
+
+    def scale_convert(self, red, green, blue, mul, do_clip, mat=None):
+        """Host entry, in place on three (H, W) float32 arrays: getImage gain/clip + 3x3 camera->working."""
+        H, W = red.shape
+        tabs = [row_table(a) for a in (red, green, blue)]
+        m, mm = self._mul_mat(mul, mat)
+        self._check(self.lib.art_hp_scale_convert(self.h, W, H, tabs[0], tabs[1], tabs[2], m, int(bool(do_clip)), mm))
+
+    def scale_convert_dev(self, W, H, d_r, d_g, d_b, pitch, mul, do_clip, mat=None):
+        m, mm = self._mul_mat(mul, mat)
+        self._check(self.lib.art_hp_scale_convert_dev(self.h, W, H, d_r, d_g, d_b, pitch, m, int(bool(do_clip)), mm))
 
     def border_interpolate2_dev(self, W, H, filters, lborders, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch):
         self._check(self.lib.art_hp_border_interpolate2_dev(self.h, W, H, filters, lborders, d_raw, raw_pitch,

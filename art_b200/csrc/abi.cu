@@ -428,4 +428,34 @@ int art_hp_demosaic_bayer(art_hp_ctx* ctx, int method, int W, int H, unsigned fi
     return ART_HP_OK;
 }
 
+int art_hp_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* d_red, float* d_green, float* d_blue, size_t pitch,
+                             const float mul[3], int doClip, const double mat[9])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_red || !d_green || !d_blue || !mul) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d pitch %zu", W, H, pitch);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_scale_convert_dev(ctx, W, H, d_red, d_green, d_blue, pitch, mul, doClip, mat);
+}
+
+int art_hp_scale_convert(art_hp_ctx* ctx, int W, int H, float* const* red, float* const* green, float* const* blue,
+                         const float mul[3], int doClip, const double mat[9])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!red || !green || !blue || !mul) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    int rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+    Plane io[3] = {{red, (float*)ctx->d_out[0].p}, {green, (float*)ctx->d_out[1].p}, {blue, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_scale_convert_dev(ctx, W, H, io[0].dev, io[1].dev, io[2].dev, pitch, mul, doClip, mat))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
 }  // extern "C"

@@ -1,7 +1,9 @@
 // Internal context of libart_hotpath.so -- not part of the ABI.
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdarg>
+#include <cstdint>
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
@@ -95,3 +97,7 @@ typedef int (*art_band_cb)(void* user, int phase, int row0, int row1);
 int art_amaze_dev_banded(art_hp_ctx* ctx, int W, int H, unsigned filters, const float* raw, size_t rp,
                          float* R, float* G, float* B, size_t op, double initialGain, int border,
                          int band_tile_rows, art_band_cb cb, void* user, int row_begin, int row_end);
+
+// getImage gain/clip + colorSpaceConversion_ matrix branch, in place on device planes
+int art_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch,
+                          const float mul[3], int doClip, const double* mat);

@@ -1,0 +1,101 @@
+// Per-pixel stages of the hot path (HBM-bound streaming kernels).
+//
+// scale_convert: RawImageSource::getImage's gain/clip step (reference rtengine/rawimagesource.cc
+// L943-1025 at skip == 1: `rtot *= rm; if (doClip) rtot = CLIP(rtot)`) fused with the matrix branch of
+// RawImageSource::colorSpaceConversion_ (L3184-3213: double coefficients times float samples, summed
+// in double, rounded to float once).  One pass over the three planes: 12 B read + 12 B written per pixel
+// where the reference makes two passes (48 B/px).
+#include "ctx.h"
+
+namespace {
+
+struct ScArgs {
+    float *r, *g, *b; size_t pitch;
+    int W, H;
+    float mul[3];
+    int do_clip, do_mat;
+    double mat[9];
+};
+
+__device__ __forceinline__ float clip65535(float a)
+{   // rt_math.h L97-101: CLIP(a) = LIM(a, 0, MAXVALF) = max(0, min(a, 65535))
+    const float m = a < 65535.f ? a : 65535.f;     // std::min(a, hi)
+    return 0.f < m ? m : 0.f;                       // std::max(lo, m)
+}
+
+__device__ __forceinline__ void sc_pixel(const ScArgs& a, float& r, float& g, float& b)
+{
+    r *= a.mul[0]; g *= a.mul[1]; b *= a.mul[2];
+    if (a.do_clip) { r = clip65535(r); g = clip65535(g); b = clip65535(b); }
+    if (a.do_mat) {
+        const double dr = r, dg = g, db = b;
+        const float nr = (float)(a.mat[0] * dr + a.mat[1] * dg + a.mat[2] * db);
+        const float ng = (float)(a.mat[3] * dr + a.mat[4] * dg + a.mat[5] * db);
+        const float nb = (float)(a.mat[6] * dr + a.mat[7] * dg + a.mat[8] * db);
+        r = nr; g = ng; b = nb;
+    }
+}
+
+// one thread per 4 consecutive pixels of a row (float4), grid-stride over rows
+__global__ void __launch_bounds__(256) k_scale_convert(ScArgs a)
+{
+    const int w4 = a.W >> 2;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int y = blockIdx.y; y < a.H; y += gridDim.y) {
+        const size_t row = (size_t)y * a.pitch;
+        if (x < w4) {
+            float4* pr = reinterpret_cast<float4*>(a.r + row) + x;
+            float4* pg = reinterpret_cast<float4*>(a.g + row) + x;
+            float4* pb = reinterpret_cast<float4*>(a.b + row) + x;
+            float4 r = *pr, g = *pg, b = *pb;
+            sc_pixel(a, r.x, g.x, b.x); sc_pixel(a, r.y, g.y, b.y); sc_pixel(a, r.z, g.z, b.z); sc_pixel(a, r.w, g.w, b.w);
+            *pr = r; *pg = g; *pb = b;
+        } else if (x == w4) {
+            for (int c = w4 * 4; c < a.W; ++c) {      // ragged tail of the row
+                float r = a.r[row + c], g = a.g[row + c], b = a.b[row + c];
+                sc_pixel(a, r, g, b);
+                a.r[row + c] = r; a.g[row + c] = g; a.b[row + c] = b;
+            }
+        }
+    }
+}
+
+// scalar fallback for planes whose base/pitch are not 16-byte aligned
+__global__ void __launch_bounds__(256) k_scale_convert_scalar(ScArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.W) return;
+    for (int y = blockIdx.y; y < a.H; y += gridDim.y) {
+        const size_t i = (size_t)y * a.pitch + x;
+        float r = a.r[i], g = a.g[i], b = a.b[i];
+        sc_pixel(a, r, g, b);
+        a.r[i] = r; a.g[i] = g; a.b[i] = b;
+    }
+}
+
+}  // namespace
+
+int art_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch,
+                          const float mul[3], int doClip, const double* mat)
+{
+    ScArgs a;
+    a.r = r; a.g = g; a.b = b; a.pitch = pitch; a.W = W; a.H = H;
+    for (int i = 0; i < 3; ++i) a.mul[i] = mul[i];
+    a.do_clip = doClip; a.do_mat = mat != nullptr;
+    for (int i = 0; i < 9; ++i) a.mat[i] = mat ? mat[i] : 0.0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) == 0 && (pitch & 3) == 0;
+    const int rows = std::min(H, 148 * 8);
+    if (aligned) {
+        dim3 grid(((W >> 2) + 1 + 255) / 256, rows);
+        art_prof_begin(ctx, "k_scale_convert");
+        k_scale_convert<<<grid, 256, 0, ctx->stream>>>(a);
+    } else {
+        dim3 grid((W + 255) / 256, rows);
+        art_prof_begin(ctx, "k_scale_convert_scalar");
+        k_scale_convert_scalar<<<grid, 256, 0, ctx->stream>>>(a);
+    }
+    art_prof_end(ctx);
+    ctx->launches++;
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}

@@ -130,6 +130,22 @@ int art_hp_border_interpolate2_dev(art_hp_ctx* ctx, int W, int H, unsigned filte
                                    const float* d_raw, size_t raw_pitch,
                                    float* d_red, float* d_green, float* d_blue, size_t out_pitch);
 
+/* ---- gain / clip / camera->working colour space ------------------------- */
+/*
+ * Replaces the per-pixel part of RawImageSource::getImage (rtengine/rawimagesource.cc L943-1025, full
+ * resolution i.e. skip == 1, no flips: `x *= mul[c]; if (doClip) x = CLIP(x)`) followed by the matrix
+ * branch of RawImageSource::colorSpaceConversion_ (L3184-3213): mat = workingSpaceInverse * camMatrix, row
+ * major double[9], applied as (float)(m0*r + m1*g + m2*b) in double.  mat == NULL skips the matrix.
+ * In place on three planes.  The caller computes mul[] (rm,gm,bm, L790-928) and mat exactly as the
+ * reference does on the host; they are 3 + 9 numbers.
+ */
+int art_hp_scale_convert(art_hp_ctx* ctx, int W, int H,
+                         float* const* red, float* const* green, float* const* blue,
+                         const float mul[3], int doClip, const double mat[9]);
+int art_hp_scale_convert_dev(art_hp_ctx* ctx, int W, int H,
+                             float* d_red, float* d_green, float* d_blue, size_t pitch,
+                             const float mul[3], int doClip, const double mat[9]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,9 @@ class _Port:
                                                _fp(r), _fp(g), _fp(b), ctypes.c_long(W))
         return r, g, b
 
+    def scale_convert(self, planes, mul, do_clip, mat=None):
+        return _scale_convert(self.lib, "artoracle_scale_convert", planes, mul, do_clip, mat)
+
     def amaze(self, raw, filters, initial_gain=1.0, border=4):
         raw, H, W, (r, g, b) = self._planes(raw)
         rc = self.lib.artoracle_amaze(W, H, ctypes.c_uint(filters), _fp(raw), ctypes.c_long(W),
@@ -66,7 +69,19 @@ class _Port:
         return r, g, b
 
 
+def _scale_convert(lib, fname, planes, mul, do_clip, mat):
+    outs = [np.array(p, dtype=np.float32, order="C", copy=True) for p in planes]
+    H, W = outs[0].shape
+    m = (ctypes.c_float * 3)(*[float(x) for x in mul])
+    mm = None if mat is None else (ctypes.c_double * 9)(*[float(x) for x in np.asarray(mat, np.float64).reshape(9)])
+    getattr(lib, fname)(W, H, _fp(outs[0]), _fp(outs[1]), _fp(outs[2]), ctypes.c_long(W), m, int(bool(do_clip)), mm)
+    return tuple(outs)
+
+
 class _Ref:
+    def scale_convert(self, planes, mul, do_clip, mat=None):
+        return _scale_convert(self.lib, "artref_scale_convert", planes, mul, do_clip, mat)
+
     def __init__(self, det=True):
         path = os.path.join(HERE, "_ref", "libartref_det.so" if det else "libartref.so")
         if not os.path.exists(path):

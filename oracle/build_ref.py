@@ -87,6 +87,24 @@ def cut_function(path, signature_regex):
     raise RuntimeError("unbalanced braces after %r in %s" % (signature_regex, path))
 
 
+def cut_block(path, start_regex):
+    """Return the statement that starts at start_regex and runs through the matching close of its first '{'."""
+    text = open(path, encoding="utf-8", errors="replace").read()
+    m = re.search(start_regex, text)
+    if not m:
+        raise RuntimeError("anchor %r not found in %s" % (start_regex, path))
+    i = text.index("{", m.end() - 1)
+    depth = 0
+    for j in range(i, len(text)):
+        if text[j] == "{":
+            depth += 1
+        elif text[j] == "}":
+            depth -= 1
+            if depth == 0:
+                return text[m.start(): j + 1]
+    raise RuntimeError("unbalanced braces")
+
+
 def insert_before(body, anchor_regex, patch):
     m = re.search(anchor_regex, body)
     if not m:
@@ -178,6 +196,21 @@ struct RawImageSource {
 #include "amaze_body.inc"
 #include "border_body.inc"
 
+// ---- colorSpaceConversion_ matrix branch (rawimagesource.cc L3197-3211): the reference's own loop
+struct ImShim {
+    int W, H; float *R, *G, *B; long s;
+    int getHeight() const { return H; }
+    int getWidth() const { return W; }
+    float& r(int i, int j) { return R[(long)i * s + j]; }
+    float& g(int i, int j) { return G[(long)i * s + j]; }
+    float& b(int i, int j) { return B[(long)i * s + j]; }
+};
+void ref_matrix_convert(ImShim* im, double mat[3][3], bool multithread)
+{
+    (void)multithread;
+#include "csconv_loop.inc"
+}
+
 } // namespace rtengine
 
 namespace {
@@ -230,6 +263,28 @@ int artref_border_interpolate2(int W, int H, unsigned filters, int lborders, con
     return 0;
 }
 
+// getImage gain/clip (rawimagesource.cc L957-971 at skip == 1) with the reference's own CLIP (rt_math.h),
+// then the colorSpaceConversion_ matrix loop cut from the reference.  mat == NULL skips the matrix.
+int artref_scale_convert(int W, int H, float* r, float* g, float* b, long stride,
+                         const float* mul, int doClip, const double* mat)
+{
+    const float rm = mul[0], gm = mul[1], bm = mul[2];
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            float rtot = r[(long)i * stride + j], gtot = g[(long)i * stride + j], btot = b[(long)i * stride + j];
+            rtot *= rm; gtot *= gm; btot *= bm;
+            if (doClip) { rtot = rtengine::CLIP(rtot); gtot = rtengine::CLIP(gtot); btot = rtengine::CLIP(btot); }
+            r[(long)i * stride + j] = rtot; g[(long)i * stride + j] = gtot; b[(long)i * stride + j] = btot;
+        }
+    if (mat) {
+        double m[3][3];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m[i][j] = mat[3 * i + j];
+        rtengine::ImShim im{W, H, r, g, b, stride};
+        rtengine::ref_matrix_convert(&im, m, true);
+    }
+    return 0;
+}
+
 int artref_is_deterministic_build(void)
 {
 #ifdef ARTREF_DET
@@ -270,6 +325,9 @@ def extract(det):
     open(os.path.join(sub, "rcd_body.inc"), "w").write(rcd)
     open(os.path.join(sub, "amaze_body.inc"), "w").write(amaze)
     open(os.path.join(sub, "border_body.inc"), "w").write(border)
+    csconv = cut_block(os.path.join(RT, "rawimagesource.cc"),
+                       r"for \(int i = 0; i < im->getHeight\(\); i\+\+\)\s*for \(int j = 0; j < im->getWidth\(\); j\+\+\) \{(?=\s*float newr = mat\[0\]\[0\])")
+    open(os.path.join(sub, "csconv_loop.inc"), "w").write(csconv)
     open(os.path.join(sub, "glibmm.h"), "w").write(SHIM_GLIBMM)
     open(os.path.join(sub, "shim.cc"), "w").write(SHIM_TU)
     return sub

@@ -1,0 +1,40 @@
+"""Pin the per-pixel oracle (oracle/pointwise_port.c) against the reference's own CLIP + matrix loop
+(oracle/_ref, cut from rawimagesource.cc L3197-3211).  Bit-exact."""
+import numpy as np
+import pytest
+
+import oracle
+
+needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built and /root/reference absent")
+
+# ProPhoto working space inverse x a plausible camera matrix (values only need to be generic doubles)
+MAT = np.array([[1.3459433, -0.2556075, -0.0511118], [-0.5445989, 1.5081673, 0.0205351], [0.0000000, 0.0000000, 1.2118128]]) @ \
+      np.array([[0.6594, 0.2521, 0.0528], [0.2661, 0.9712, -0.2373], [0.0292, -0.2046, 1.0003]])
+
+
+def planes(H, W, seed, lo=-500.0, hi=80000.0):
+    rng = np.random.default_rng(seed)
+    return [rng.uniform(lo, hi, size=(H, W)).astype(np.float32) for _ in range(3)]
+
+
+@needs_ref
+@pytest.mark.parametrize("do_clip", [0, 1])
+@pytest.mark.parametrize("use_mat", [False, True])
+def test_port_matches_reference(do_clip, use_mat):
+    p = planes(97, 131, seed=3)
+    mul = (1.9371, 1.0, 1.4182)
+    got = oracle.port().scale_convert(p, mul, do_clip, MAT if use_mat else None)
+    want = oracle.ref().scale_convert(p, mul, do_clip, MAT if use_mat else None)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
+def test_port_numpy_restatement():
+    """Independent numpy restatement: double accumulation left to right, one rounding."""
+    p = planes(40, 50, seed=4)
+    mul = np.float32([2.1, 1.0, 1.6])
+    got = oracle.port().scale_convert(p, mul, 1, MAT)
+    x = [np.clip(q * m, np.float32(0), np.float32(65535)) for q, m in zip(p, mul)]
+    for k in range(3):
+        want = (MAT[k, 0] * x[0].astype(np.float64) + MAT[k, 1] * x[1].astype(np.float64) + MAT[k, 2] * x[2].astype(np.float64)).astype(np.float32)
+        assert np.array_equal(got[k], want)
