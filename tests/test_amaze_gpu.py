@@ -61,7 +61,7 @@ def test_scratch_block_pass_by_pass(hot_path):
     ntx = (W + 16 + 127) // 128
     nty = (H + 16 + 127) // 128
     offs = plane_offsets()
-    stages = [1, 2, 3, 5, 6, 7, 8, 10, 11, 12, 13, 15, 16, 17, 18]
+    stages = [1, 2, 3, 5, 6, 7, 8, 10, 11, 12, 13, 15, 17, 18]   # 16: the CUDA pass 16 also does the split (oracle stage 17)
     for tile in sorted({0, 1, ntx - 1, ntx + 1, ntx * nty - 1}):
         for st in stages:
             a = np.zeros(nbytes, np.uint8)
@@ -77,6 +77,13 @@ def test_scratch_block_pass_by_pass(hot_path):
                 if name == "nyqutest":
                     continue          # the CUDA path keeps the test value in a register (only its sign is used)
                 d = a[off:off + size] != b[off:off + size]
+                if name == "vcdalt/Dgrb" and st >= 17:
+                    # the CUDA path drops the dead store Dgrb[0] = 0 of the split pass (amaze.cu, k_greenrb):
+                    # ignore first-half cells where the oracle holds exactly 0.0f
+                    zero = np.zeros(size, bool)
+                    half = TS * (TS // 2) * 4
+                    zero[:half] = np.repeat(b[off:off + half].view(np.float32) == 0.0, 4)
+                    d &= ~zero
                 if d.any():
                     idx = np.nonzero(d)[0]
                     bad.append("%s: %d bytes, first at float %d (row %d col %d)" % (
