@@ -67,6 +67,8 @@ def load_library(build_if_missing=True):
         "art_hp_demosaic_bayer": (i, [vp, i, i, i, u, vp, vp, vp, vp, d, i]),
         "art_hp_demosaic_bayer_dev": (i, [vp, i, i, i, u, vp, sz, vp, vp, vp, sz, d, i]),
         "art_hp_border_interpolate2_dev": (i, [vp, i, i, u, i, vp, sz, vp, vp, vp, sz]),
+        "art_hp_scale_colors_bayer": (i, [vp, i, i, u, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+        "art_hp_scale_colors_bayer_dev": (i, [vp, i, i, u, vp, sz, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
         "art_hp_scale_convert": (i, [vp, i, i, vp, vp, vp, ctypes.POINTER(ctypes.c_float), i, ctypes.POINTER(d)]),
         "art_hp_scale_convert_dev": (i, [vp, i, i, vp, vp, vp, sz, ctypes.POINTER(ctypes.c_float), i, ctypes.POINTER(d)]),
         "art_hp_band_align": (i, [i, ctypes.POINTER(i), ctypes.POINTER(i)]),
@@ -197,6 +199,23 @@ class HotPath:
         """Row-band form: only output rows [row_begin,row_end); pointers address row 0 of the frame."""
         self._check(self.lib.art_hp_demosaic_bayer_rows_dev(self.h, method, W, H, filters, d_raw, raw_pitch, d_r, d_g, d_b,
                                                             out_pitch, float(initial_gain), int(border), row_begin, row_end))
+
+    def scale_colors_bayer(self, raw, filters, cblacksom, scale_mul):
+        """Host entry, in place on a (H, W) float32 array; returns chmax[3]."""
+        H, W = raw.shape
+        tab = row_table(raw)
+        bl = (ctypes.c_float * 4)(*[float(x) for x in cblacksom])
+        mu = (ctypes.c_float * 4)(*[float(x) for x in scale_mul])
+        ch = (ctypes.c_float * 3)()
+        self._check(self.lib.art_hp_scale_colors_bayer(self.h, W, H, filters, tab, bl, mu, ch))
+        return [float(ch[0]), float(ch[1]), float(ch[2])]
+
+    def scale_colors_bayer_dev(self, W, H, filters, d_raw, pitch, cblacksom, scale_mul):
+        bl = (ctypes.c_float * 4)(*[float(x) for x in cblacksom])
+        mu = (ctypes.c_float * 4)(*[float(x) for x in scale_mul])
+        ch = (ctypes.c_float * 3)()
+        self._check(self.lib.art_hp_scale_colors_bayer_dev(self.h, W, H, filters, d_raw, pitch, bl, mu, ch))
+        return [float(ch[0]), float(ch[1]), float(ch[2])]
 
     @staticmethod
     def _mul_mat(mul, mat):

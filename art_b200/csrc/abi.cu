@@ -205,7 +205,7 @@ void art_hp_destroy(art_hp_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch};
+    DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch, &ctx->d_small};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; ++i) if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -424,6 +424,42 @@ int art_hp_demosaic_bayer(art_hp_ctx* ctx, int method, int W, int H, unsigned fi
                                    initialGain, border);
     if (rc) return rc;
     if ((rc = transfer(ctx, ctx->stream, out, 3, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+int art_hp_scale_colors_bayer_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* d_raw, size_t pitch,
+                                  const float cblacksom[4], const float scale_mul[4], float chmax[3])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_raw || !cblacksom || !scale_mul || !chmax) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 2 || H < 2 || pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d pitch %zu", W, H, pitch);
+    if (!rgb_bayer(filters)) return ctx->fail(ART_HP_ERR_INVALID, "filters=0x%08x is not an RGB Bayer pattern", filters);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = art_reserve(ctx, ctx->d_small, 256);
+    if (rc) return rc;
+    if ((rc = art_scale_colors_dev(ctx, W, H, filters, d_raw, pitch, cblacksom, scale_mul, (int*)ctx->d_small.p))) return rc;
+    int bits[3];
+    ART_CUDA(ctx, cudaMemcpyAsync(bits, ctx->d_small.p, sizeof bits, cudaMemcpyDeviceToHost, ctx->stream));
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 3; ++i) memcpy(&chmax[i], &bits[i], sizeof(float));
+    return ART_HP_OK;
+}
+
+int art_hp_scale_colors_bayer(art_hp_ctx* ctx, int W, int H, unsigned filters, float* const* rawData,
+                              const float cblacksom[4], const float scale_mul[4], float chmax[3])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!rawData || !cblacksom || !scale_mul || !chmax) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 2 || H < 2) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    int rc;
+    if ((rc = art_reserve(ctx, ctx->d_raw, pitch * (size_t)H * sizeof(float)))) return rc;
+    Plane io = {rawData, (float*)ctx->d_raw.p};
+    if ((rc = transfer(ctx, ctx->stream, &io, 1, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_hp_scale_colors_bayer_dev(ctx, W, H, filters, io.dev, pitch, cblacksom, scale_mul, chmax))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, &io, 1, W, 0, H, pitch, false))) return rc;
     ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;
 }

@@ -35,7 +35,7 @@ struct art_hp_ctx {
     std::vector<ProfStat> stats;
     std::string err;
     // device scratch, grown on demand and kept across calls
-    DevBuf d_raw, d_out[3], d_scratch;
+    DevBuf d_raw, d_out[3], d_scratch, d_small;
     // pinned staging (two halves for double buffering)
     void* h_stage[2] = {nullptr, nullptr};
     size_t h_stage_bytes = 0;
@@ -101,3 +101,6 @@ int art_amaze_dev_banded(art_hp_ctx* ctx, int W, int H, unsigned filters, const 
 // getImage gain/clip + colorSpaceConversion_ matrix branch, in place on device planes
 int art_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch,
                           const float mul[3], int doClip, const double* mat);
+// scaleColors (Bayer): in place; d_chmax_bits = 3 device ints receiving the float bit patterns of chmax[0..2]
+int art_scale_colors_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* raw, size_t pitch,
+                         const float black[4], const float mul[4], int* d_chmax_bits);

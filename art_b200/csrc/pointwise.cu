@@ -73,7 +73,64 @@ __global__ void __launch_bounds__(256) k_scale_convert_scalar(ScArgs a)
     }
 }
 
+// scaleColors, Bayer branch (rawimagesource.cc L2731-2772): black subtraction + per-CFA-channel scaling in
+// place, and the per-colour maxima chmax[] (max is exact under any association, so a tree reduce is fine;
+// values are >= 0, hence atomicMax on the int bit pattern orders them correctly).
+struct ScaleColorsArgs {
+    float* raw; size_t pitch; int W, H; unsigned filters;
+    float black[4], mul[4];
+    int* chmax_bits;          // 3 ints, zeroed by the caller
+};
+
+__device__ __forceinline__ unsigned fc_pw(unsigned filters, int row, int col)
+{   // RawImage::FC, rtengine/rawimage.h L186-189
+    return (filters >> ((((row) << 1 & 14) + ((col) & 1)) << 1) & 3);
+}
+
+__global__ void __launch_bounds__(256) k_scale_colors(ScaleColorsArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    float mx[3] = {0.f, 0.f, 0.f};
+    if (x < a.W) {
+        for (int y = blockIdx.y; y < a.H; y += gridDim.y) {
+            const int c = fc_pw(a.filters, y, x);
+            const int c4 = (c == 1 && !(y & 1)) ? 3 : c;              // 0=R, 1=G1, 2=B, 3=G2
+            float* p = a.raw + (size_t)y * a.pitch + x;
+            const float d = *p - a.black[c4];
+            const float val = (0.f < d ? d : 0.f) * a.mul[c4];       // max(0.f, raw - black) * mul
+            *p = val;
+            // a column holds at most two colours; keep the three running maxima branch-free
+            mx[0] = (c == 0 && mx[0] < val) ? val : mx[0];
+            mx[1] = (c == 1 && mx[1] < val) ? val : mx[1];
+            mx[2] = (c == 2 && mx[2] < val) ? val : mx[2];
+        }
+    }
+    #pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = mx[k];
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const float w = __shfl_xor_sync(0xffffffffu, v, o); v = v < w ? w : v; }
+        if ((threadIdx.x & 31) == 0 && v > 0.f) atomicMax(a.chmax_bits + k, __float_as_int(v));
+    }
+}
+
 }  // namespace
+
+int art_scale_colors_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* raw, size_t pitch,
+                         const float black[4], const float mul[4], int* d_chmax_bits)
+{
+    ScaleColorsArgs a;
+    a.raw = raw; a.pitch = pitch; a.W = W; a.H = H; a.filters = filters; a.chmax_bits = d_chmax_bits;
+    for (int i = 0; i < 4; ++i) { a.black[i] = black[i]; a.mul[i] = mul[i]; }
+    ART_CUDA(ctx, cudaMemsetAsync(d_chmax_bits, 0, 3 * sizeof(int), ctx->stream));
+    dim3 grid((W + 255) / 256, std::min(H, 148 * 4));
+    art_prof_begin(ctx, "k_scale_colors");
+    k_scale_colors<<<grid, 256, 0, ctx->stream>>>(a);
+    art_prof_end(ctx);
+    ctx->launches++;
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}
 
 int art_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch,
                           const float mul[3], int doClip, const double* mat)

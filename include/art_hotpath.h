@@ -130,6 +130,18 @@ int art_hp_border_interpolate2_dev(art_hp_ctx* ctx, int W, int H, unsigned filte
                                    const float* d_raw, size_t raw_pitch,
                                    float* d_red, float* d_green, float* d_blue, size_t out_pitch);
 
+/* ---- raw scaling ---------------------------------------------------------- */
+/*
+ * Replaces the Bayer branch of RawImageSource::scaleColors (rtengine/rawimagesource.cc L2731-2772):
+ * rawData = max(0, rawData - cblacksom[c4]) * scale_mul[c4] in place (c4: 0=R, 1=G on odd rows, 2=B,
+ * 3=G on even rows) and chmax[c] = per-colour maximum of the result.  cblacksom / scale_mul are the four
+ * numbers the reference computes on the host (L2711-2719); dynamicRowNoiseFilter is not supported.
+ */
+int art_hp_scale_colors_bayer(art_hp_ctx* ctx, int W, int H, unsigned filters, float* const* rawData,
+                              const float cblacksom[4], const float scale_mul[4], float chmax[3]);
+int art_hp_scale_colors_bayer_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* d_raw, size_t pitch,
+                                  const float cblacksom[4], const float scale_mul[4], float chmax[3]);
+
 /* ---- gain / clip / camera->working colour space ------------------------- */
 /*
  * Replaces the per-pixel part of RawImageSource::getImage (rtengine/rawimagesource.cc L943-1025, full

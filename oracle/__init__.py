@@ -60,6 +60,9 @@ class _Port:
     def scale_convert(self, planes, mul, do_clip, mat=None):
         return _scale_convert(self.lib, "artoracle_scale_convert", planes, mul, do_clip, mat)
 
+    def scale_colors_bayer(self, raw, filters, black, mul):
+        return _scale_colors(self.lib, "artoracle_scale_colors_bayer", raw, filters, black, mul)
+
     def amaze(self, raw, filters, initial_gain=1.0, border=4):
         raw, H, W, (r, g, b) = self._planes(raw)
         rc = self.lib.artoracle_amaze(W, H, ctypes.c_uint(filters), _fp(raw), ctypes.c_long(W),
@@ -78,7 +81,20 @@ def _scale_convert(lib, fname, planes, mul, do_clip, mat):
     return tuple(outs)
 
 
+def _scale_colors(lib, fname, raw, filters, black, mul):
+    out = np.array(raw, dtype=np.float32, order="C", copy=True)
+    H, W = out.shape
+    bl = (ctypes.c_float * 4)(*[float(x) for x in black])
+    mu = (ctypes.c_float * 4)(*[float(x) for x in mul])
+    ch = (ctypes.c_float * 3)()
+    getattr(lib, fname)(W, H, ctypes.c_uint(filters), _fp(out), ctypes.c_long(W), bl, mu, ch)
+    return out, [float(ch[0]), float(ch[1]), float(ch[2])]
+
+
 class _Ref:
+    def scale_colors_bayer(self, raw, filters, black, mul):
+        return _scale_colors(self.lib, "artref_scale_colors_bayer", raw, filters, black, mul)
+
     def scale_convert(self, planes, mul, do_clip, mat=None):
         return _scale_convert(self.lib, "artref_scale_convert", planes, mul, do_clip, mat)
 

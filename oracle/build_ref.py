@@ -205,6 +205,18 @@ struct ImShim {
     float& g(int i, int j) { return G[(long)i * s + j]; }
     float& b(int i, int j) { return B[(long)i * s + j]; }
 };
+// ---- scaleColors, Bayer branch (rawimagesource.cc L2742-2761): the reference's own row/col loop
+struct RiShim { float get_optical_black(int, int) const { return 0.f; } };
+void ref_scalecolors_bayer(int winx, int winy, int winw, int winh, unsigned filters, float** rawData,
+                           const float* cblacksom, const float* scale_mul, float* tmpchmax)
+{
+    RiShim ri_; RiShim* ri = &ri_;
+    const bool dyn_row_noise = false;
+    auto FC = [filters](int row, int col) { return (int)((filters >> ((((row) << 1 & 14) + ((col) & 1)) << 1)) & 3); };
+    using std::max;
+#include "scalecolors_loop.inc"
+}
+
 void ref_matrix_convert(ImShim* im, double mat[3][3], bool multithread)
 {
     (void)multithread;
@@ -285,6 +297,18 @@ int artref_scale_convert(int W, int H, float* r, float* g, float* b, long stride
     return 0;
 }
 
+int artref_scale_colors_bayer(int W, int H, unsigned filters, float* raw, long stride,
+                              const float* cblacksom, const float* scale_mul, float* chmax)
+{
+    float** rows = new float*[H];
+    for (int i = 0; i < H; ++i) rows[i] = raw + (long)i * stride;
+    float t[3] = {0.f, 0.f, 0.f};
+    rtengine::ref_scalecolors_bayer(0, 0, W, H, filters, rows, cblacksom, scale_mul, t);
+    chmax[0] = t[0]; chmax[1] = t[1]; chmax[2] = t[2];
+    delete[] rows;
+    return 0;
+}
+
 int artref_is_deterministic_build(void)
 {
 #ifdef ARTREF_DET
@@ -328,6 +352,9 @@ def extract(det):
     csconv = cut_block(os.path.join(RT, "rawimagesource.cc"),
                        r"for \(int i = 0; i < im->getHeight\(\); i\+\+\)\s*for \(int j = 0; j < im->getWidth\(\); j\+\+\) \{(?=\s*float newr = mat\[0\]\[0\])")
     open(os.path.join(sub, "csconv_loop.inc"), "w").write(csconv)
+    scl = cut_block(os.path.join(RT, "rawimagesource.cc"),
+                    r"for \(int row = winy; row < winy \+ winh; row \+\+\)\s*\{(?=\s*for \(int col = winx; col < winx \+ winw; col\+\+\) \{\s*const int c  = FC\(row, col\);)")
+    open(os.path.join(sub, "scalecolors_loop.inc"), "w").write(scl)
     open(os.path.join(sub, "glibmm.h"), "w").write(SHIM_GLIBMM)
     open(os.path.join(sub, "shim.cc"), "w").write(SHIM_TU)
     return sub

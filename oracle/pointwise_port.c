@@ -35,3 +35,26 @@ int artoracle_scale_convert(int W, int H, float* r, float* g, float* b, long str
         }
     return 0;
 }
+
+/* RawImageSource::scaleColors, Bayer branch (rawimagesource.cc L2731-2772, dynamicRowNoiseFilter off):
+ * val = max(0.f, raw - cblacksom[c4]) * scale_mul[c4]; chmax[c] = max(chmax[c], val). */
+static inline unsigned fc_pw_(unsigned filters, int row, int col)
+{
+    return (filters >> ((((row) << 1 & 14) + ((col) & 1)) << 1) & 3);
+}
+int artoracle_scale_colors_bayer(int W, int H, unsigned filters, float* raw, long stride,
+                                 const float* cblacksom, const float* scale_mul, float* chmax)
+{
+    float mx[3] = {0.f, 0.f, 0.f};
+    for (int row = 0; row < H; ++row)
+        for (int col = 0; col < W; ++col) {
+            const int c = fc_pw_(filters, row, col);
+            const int c4 = (c == 1 && !(row & 1)) ? 3 : c;
+            const float d = raw[(size_t)row * stride + col] - cblacksom[c4];
+            const float val = (0.f < d ? d : 0.f) * scale_mul[c4];
+            raw[(size_t)row * stride + col] = val;
+            mx[c] = mx[c] < val ? val : mx[c];
+        }
+    chmax[0] = mx[0]; chmax[1] = mx[1]; chmax[2] = mx[2];
+    return 0;
+}

@@ -38,3 +38,17 @@ def test_port_numpy_restatement():
     for k in range(3):
         want = (MAT[k, 0] * x[0].astype(np.float64) + MAT[k, 1] * x[1].astype(np.float64) + MAT[k, 2] * x[2].astype(np.float64)).astype(np.float32)
         assert np.array_equal(got[k], want)
+
+
+@needs_ref
+@pytest.mark.parametrize("pattern", ["RGGB", "BGGR", "GRBG", "GBRG"])
+def test_scale_colors_port_matches_reference(pattern):
+    from art_b200 import synth
+    f = synth.BAYER_FILTERS[pattern]
+    rng = np.random.default_rng(11)
+    raw = rng.integers(0, 16384, size=(75, 102)).astype(np.float32)
+    black = (511.0, 512.5, 510.0, 513.25)
+    mul = (8.1234, 4.0625, 6.3321, 4.0631)
+    got, gmax = oracle.port().scale_colors_bayer(raw, f, black, mul)
+    want, wmax = oracle.ref().scale_colors_bayer(raw, f, black, mul)
+    assert np.array_equal(got, want) and gmax == wmax

@@ -65,3 +65,18 @@ def test_demosaic_then_convert_resident(hot_path):
     want = oracle.port().scale_convert(oracle.port().amaze(raw, f), mul, 1, MAT)
     for o, w in zip(outs, want):
         assert np.array_equal(o.cpu().numpy(), w)
+
+
+@pytest.mark.parametrize("pattern", ["RGGB", "GBRG"])
+@pytest.mark.parametrize("W,H", [(640, 480), (333, 77)])
+def test_scale_colors_bayer(hot_path, pattern, W, H):
+    from art_b200 import synth
+    f = synth.BAYER_FILTERS[pattern]
+    rng = np.random.default_rng(W)
+    raw = rng.integers(0, 16384, size=(H, W)).astype(np.float32)
+    black = (511.0, 512.5, 510.0, 513.25)
+    mul = (8.1234, 4.0625, 6.3321, 4.0631)
+    want, wmax = oracle.port().scale_colors_bayer(raw, f, black, mul)
+    got = raw.copy()
+    gmax = hot_path.scale_colors_bayer(got, f, black, mul)
+    assert np.array_equal(got, want) and gmax == wmax
