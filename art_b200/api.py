@@ -67,6 +67,8 @@ def load_library(build_if_missing=True):
         "art_hp_demosaic_bayer": (i, [vp, i, i, i, u, vp, vp, vp, vp, d, i]),
         "art_hp_demosaic_bayer_dev": (i, [vp, i, i, i, u, vp, sz, vp, vp, vp, sz, d, i]),
         "art_hp_border_interpolate2_dev": (i, [vp, i, i, u, i, vp, sz, vp, vp, vp, sz]),
+        "art_hp_gauss": (i, [vp, vp, vp, i, i, d, i]),
+        "art_hp_gauss_dev": (i, [vp, vp, sz, vp, sz, i, i, d, i]),
         "art_hp_scale_colors_bayer": (i, [vp, i, i, u, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
         "art_hp_scale_colors_bayer_dev": (i, [vp, i, i, u, vp, sz, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
         "art_hp_scale_convert": (i, [vp, i, i, vp, vp, vp, ctypes.POINTER(ctypes.c_float), i, ctypes.POINTER(d)]),
@@ -199,6 +201,21 @@ class HotPath:
         """Row-band form: only output rows [row_begin,row_end); pointers address row 0 of the frame."""
         self._check(self.lib.art_hp_demosaic_bayer_rows_dev(self.h, method, W, H, filters, d_raw, raw_pitch, d_r, d_g, d_b,
                                                             out_pitch, float(initial_gain), int(border), row_begin, row_end))
+
+    def gauss(self, src, sigma, dst=None, gausstype=0):
+        """Host entry.  dst=None -> out of place into a new array; dst is src -> the in-place variants."""
+        H, W = src.shape
+        if dst is src:
+            tab = row_table(src)
+            self._check(self.lib.art_hp_gauss(self.h, tab, tab, W, H, float(sigma), gausstype))
+            return src
+        if dst is None:
+            dst = np.empty_like(src)
+        self._check(self.lib.art_hp_gauss(self.h, row_table(src), row_table(dst), W, H, float(sigma), gausstype))
+        return dst
+
+    def gauss_dev(self, d_src, src_pitch, d_dst, dst_pitch, W, H, sigma, gausstype=0):
+        self._check(self.lib.art_hp_gauss_dev(self.h, d_src, src_pitch, d_dst, dst_pitch, W, H, float(sigma), gausstype))
 
     def scale_colors_bayer(self, raw, filters, cblacksom, scale_mul):
         """Host entry, in place on a (H, W) float32 array; returns chmax[3]."""

@@ -428,6 +428,43 @@ int art_hp_demosaic_bayer(art_hp_ctx* ctx, int method, int W, int H, unsigned fi
     return ART_HP_OK;
 }
 
+int art_hp_gauss_dev(art_hp_ctx* ctx, const float* d_src, size_t src_pitch, float* d_dst, size_t dst_pitch,
+                     int W, int H, double sigma, int gausstype)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_src || !d_dst) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (gausstype != 0) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "only GAUSS_STANDARD is on the hot path");
+    if (W < 4 || H < 4 || src_pitch < (size_t)W || dst_pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    if (!(sigma >= 0.0)) return ctx->fail(ART_HP_ERR_INVALID, "sigma must be >= 0");
+    if (d_src == d_dst && src_pitch != dst_pitch) return ctx->fail(ART_HP_ERR_INVALID, "in-place call with two pitches");
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_gauss_dev(ctx, d_src, src_pitch, d_dst, dst_pitch, W, H, sigma);
+}
+
+int art_hp_gauss(art_hp_ctx* ctx, float* const* src, float* const* dst, int W, int H, double sigma, int gausstype)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!src || !dst) return ctx->fail(ART_HP_ERR_INVALID, "null row table");
+    if (gausstype != 0) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "only GAUSS_STANDARD is on the hot path");
+    if (W < 4 || H < 4) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    const bool inplace = (src == dst);                       // the reference compares the row tables (gauss.cc L1441, L1447)
+    int rc;
+    if ((rc = art_reserve(ctx, ctx->d_out[0], plane))) return rc;
+    if (!inplace && (rc = art_reserve(ctx, ctx->d_out[1], plane))) return rc;
+    float* ds = (float*)ctx->d_out[0].p;
+    float* dd = inplace ? ds : (float*)ctx->d_out[1].p;
+    Plane in = {src, ds};
+    if ((rc = transfer(ctx, ctx->stream, &in, 1, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_gauss_dev(ctx, ds, pitch, dd, pitch, W, H, sigma))) return rc;
+    Plane out = {dst, dd};
+    if ((rc = transfer(ctx, ctx->stream, &out, 1, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
 int art_hp_scale_colors_bayer_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* d_raw, size_t pitch,
                                   const float cblacksom[4], const float scale_mul[4], float chmax[3])
 {

@@ -104,3 +104,5 @@ int art_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, flo
 // scaleColors (Bayer): in place; d_chmax_bits = 3 device ints receiving the float bit patterns of chmax[0..2]
 int art_scale_colors_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* raw, size_t pitch,
                          const float black[4], const float mul[4], int* d_chmax_bits);
+// gaussianBlur, GAUSS_STANDARD (src == dst allowed)
+int art_gauss_dev(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, size_t dp, int W, int H, double sigma);

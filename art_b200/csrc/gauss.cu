@@ -1,0 +1,409 @@
+// gaussianBlur (GAUSS_STANDARD, no box buffer) for sm_100a.
+//
+// Replaces gaussianBlur / gaussianBlurImpl (reference rtengine/gauss.cc L1387-1574) for the branches an
+// x86-64 build takes with gausstype == GAUSS_STANDARD: copy (sigma < 0.25), gauss3x3 (L129-174) or the
+// separable 3-tap pair (L446-526) for sigma < 0.6, the Young-van Vliet recursive filter with Triggs-Sdika
+// boundaries in float (gaussHorizontalSse L554-665, gaussVerticalSse L716-856; the H%4 leftover rows and
+// W%8 leftover columns go through the scalar loops that compute in double) for sigma < 25 and in double
+// (gaussHorizontal L669-713, gaussVertical L1148-1225) above.
+//
+// The recursive filter is a serial recurrence along each line and must be evaluated in the reference's
+// order to be bit-exact; the parallelism is across lines.  Vertical pass: one thread per column (coalesced
+// by construction), software-prefetched loads.  Horizontal pass: one warp per 32 rows walking the row in
+// 32-column tiles that are transposed through shared memory, so global traffic stays coalesced while each
+// lane runs its own row's recurrence.  The causal pass stores its output in the destination plane (float)
+// or in a double scratch plane (sigma >= 25), the anticausal pass sweeps back over it.
+// Compiled with -fmad=false: bit-identical to the reference build.
+#include "ctx.h"
+
+#include <cmath>
+
+namespace {
+
+struct Coef {
+    float Bf, b1f, b2f, b3f, Mf[9];      // float-lane form (coefficients rounded to float, L569-573)
+    double B, b1, b2, b3, M[9];          // scalar-remainder / double form
+};
+
+void yvv_factors(double sigma, double& b1, double& b2, double& b3, double& B, double M[9])
+{   // calculateYvVFactors<double>, gauss.cc L94-126
+    double q;
+    if (sigma < 2.5) q = 3.97156 - 4.14554 * std::sqrt(1.0 - 0.26891 * sigma);
+    else q = 0.98711 * sigma - 0.96330;
+    double b0 = 1.57825 + 2.44413 * q + 1.4281 * q * q + 0.422205 * q * q * q;
+    b1 = 2.44413 * q + 2.85619 * q * q + 1.26661 * q * q * q;
+    b2 = -1.4281 * q * q - 1.26661 * q * q * q;
+    b3 = 0.422205 * q * q * q;
+    B = 1.0 - (b1 + b2 + b3) / b0;
+    b1 /= b0; b2 /= b0; b3 /= b0;
+    M[0] = -b3 * b1 + 1.0 - b3 * b3 - b2;
+    M[1] = (b3 + b1) * (b2 + b3 * b1);
+    M[2] = b3 * (b1 + b3 * b2);
+    M[3] = b1 + b3 * b2;
+    M[4] = -(b2 - 1.0) * (b2 + b3 * b1);
+    M[5] = -(b3 * b1 + b3 * b3 + b2 - 1.0) * b3;
+    M[6] = b3 * b1 + b2 + b1 * b1 - b2 * b2;
+    M[7] = b1 * b2 + b3 * b2 * b2 - b1 * b3 * b3 - b3 * b3 * b3 - b3 * b2 + b3;
+    M[8] = b3 * (b1 + b3 * b2);
+}
+
+// ---- line state machines.  MODE 0: float lanes; 1: scalar remainder (double math, float storage); 2: double
+template <int MODE> struct Acc;
+template <> struct Acc<0> { using T = float; };
+template <> struct Acc<1> { using T = float; };    // state variables are the float scratch values
+template <> struct Acc<2> { using T = double; };
+
+template <int MODE>
+struct Line {
+    using T = typename Acc<MODE>::T;
+    T r, m2, m3;        // tmp[j-1], tmp[j-2], tmp[j-3] going forward; tmp[j+1], [j+2], [j+3] going back
+    float x0;           // first sample
+    __device__ __forceinline__ T first(const Coef& c, float x)
+    {
+        x0 = x;
+        if (MODE == 0) m3 = x * (c.Bf + c.b1f + c.b2f + c.b3f);
+        else if (MODE == 1) m3 = (float)(x * (c.B + c.b1 + c.b2 + c.b3));
+        else m3 = c.B * x + c.b1 * x + c.b2 * x + c.b3 * x;
+        return m3;
+    }
+    __device__ __forceinline__ T second(const Coef& c, float x)
+    {
+        if (MODE == 0) m2 = x * c.Bf + m3 * c.b1f + x0 * (c.b2f + c.b3f);
+        else if (MODE == 1) m2 = (float)(c.B * x + c.b1 * m3 + x0 * (c.b2 + c.b3));
+        else m2 = c.B * x + c.b1 * m3 + c.b2 * x0 + c.b3 * x0;
+        return m2;
+    }
+    __device__ __forceinline__ T third(const Coef& c, float x)
+    {
+        if (MODE == 0) r = x * c.Bf + m2 * c.b1f + m3 * c.b2f + x0 * c.b3f;
+        else if (MODE == 1) r = (float)(c.B * x + c.b1 * m2 + c.b2 * m3 + c.b3 * x0);
+        else r = c.B * x + c.b1 * m2 + c.b2 * m3 + c.b3 * x0;
+        return r;
+    }
+    // j >= 3: new = B x + b1 tmp[j-1] + b2 tmp[j-2] + b3 tmp[j-3]
+    __device__ __forceinline__ T fwd(const Coef& c, float x)
+    {
+        T n;
+        if (MODE == 0) n = x * c.Bf + r * c.b1f + m2 * c.b2f + m3 * c.b3f;
+        else if (MODE == 1) n = (float)(c.B * x + c.b1 * r + c.b2 * m2 + c.b3 * m3);
+        else n = c.B * x + c.b1 * r + c.b2 * m2 + c.b3 * m3;
+        m3 = m2; m2 = r; r = n;
+        return n;
+    }
+    // Triggs-Sdika boundary at the line end; xl = last input sample.  On entry r, m2, m3 = tmp[n-1], tmp[n-2], tmp[n-3];
+    // returns the three final outputs o1 = out[n-1], o2 = out[n-2], o3 = out[n-3] and primes the backward state.
+    __device__ __forceinline__ void boundary(const Coef& c, float xl, T& o1, T& o2, T& o3)
+    {
+        if (MODE == 0) {
+            const float p1 = xl + c.Mf[6] * (r - xl) + c.Mf[7] * (m2 - xl) + c.Mf[8] * (m3 - xl);
+            const float p0 = xl + c.Mf[3] * (r - xl) + c.Mf[4] * (m2 - xl) + c.Mf[5] * (m3 - xl);
+            o1 = xl + c.Mf[0] * (r - xl) + c.Mf[1] * (m2 - xl) + c.Mf[2] * (m3 - xl);
+            o2 = c.Bf * m2 + c.b1f * o1 + c.b2f * p0 + c.b3f * p1;
+            o3 = c.Bf * m3 + c.b1f * o2 + c.b2f * o1 + c.b3f * p0;
+        } else if (MODE == 1) {
+            const float m1 = (float)(xl + c.M[0] * (r - xl) + c.M[1] * (m2 - xl) + c.M[2] * (m3 - xl));
+            const float p0 = (float)(xl + c.M[3] * (r - xl) + c.M[4] * (m2 - xl) + c.M[5] * (m3 - xl));
+            const float p1 = (float)(xl + c.M[6] * (r - xl) + c.M[7] * (m2 - xl) + c.M[8] * (m3 - xl));
+            o1 = m1;
+            o2 = (float)(c.B * m2 + c.b1 * o1 + c.b2 * p0 + c.b3 * p1);
+            o3 = (float)(c.B * m3 + c.b1 * o2 + c.b2 * o1 + c.b3 * p0);
+        } else {
+            const double m1 = xl + c.M[0] * (r - xl) + c.M[1] * (m2 - xl) + c.M[2] * (m3 - xl);
+            const double p0 = xl + c.M[3] * (r - xl) + c.M[4] * (m2 - xl) + c.M[5] * (m3 - xl);
+            const double p1 = xl + c.M[6] * (r - xl) + c.M[7] * (m2 - xl) + c.M[8] * (m3 - xl);
+            o1 = m1;
+            o2 = c.B * m2 + c.b1 * o1 + c.b2 * p0 + c.b3 * p1;
+            o3 = c.B * m3 + c.b1 * o2 + c.b2 * o1 + c.b3 * p0;
+        }
+        r = o3; m2 = o2; m3 = o1;      // out[j+1], out[j+2], out[j+3] for j = n-4
+    }
+    // j <= n-4: out[j] = B tmp[j] + b1 out[j+1] + b2 out[j+2] + b3 out[j+3]
+    __device__ __forceinline__ T bwd(const Coef& c, T t)
+    {
+        T n;
+        if (MODE == 0) n = t * c.Bf + r * c.b1f + m2 * c.b2f + m3 * c.b3f;
+        else if (MODE == 1) n = (float)(c.B * t + c.b1 * r + c.b2 * m2 + c.b3 * m3);
+        else n = c.B * t + c.b1 * r + c.b2 * m2 + c.b3 * m3;
+        m3 = m2; m2 = r; r = n;
+        return n;
+    }
+};
+
+struct GArgs {
+    const float* src; size_t sp;
+    float* dst; size_t dp;
+    double* dscr; size_t dsp;       // double scratch plane (sigma >= 25), pitch in doubles
+    int W, H;
+    int big;                        // 1: all-double form
+    Coef c;
+};
+
+// ------------------------------------------------------------------ vertical pass: thread per column
+template <int MODE>
+__device__ __forceinline__ void vline(const GArgs& a, int col)
+{
+    using T = typename Acc<MODE>::T;
+    Line<MODE> L;
+    const int H = a.H;
+    const float* x = a.src + col;
+    float* y = a.dst + col;
+    double* d = MODE == 2 ? a.dscr + col : nullptr;
+    // causal sweep; the input of row j+PF is loaded before the output of row j is stored (in-place safe)
+    constexpr int PF = 8;
+    float q[PF];
+    #pragma unroll
+    for (int k = 0; k < PF; ++k) q[k] = (k < H) ? x[(size_t)k * a.sp] : 0.f;
+    float xl = 0.f;
+    for (int j0 = 0; j0 < H; j0 += PF) {
+        #pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int j = j0 + k;
+            if (j < H) {
+                const float xv = q[k];
+                const int jn = j + PF;
+                q[k] = (jn < H) ? x[(size_t)jn * a.sp] : 0.f;
+                T t;
+                if (j == 0) t = L.first(a.c, xv);
+                else if (j == 1) t = L.second(a.c, xv);
+                else if (j == 2) t = L.third(a.c, xv);
+                else t = L.fwd(a.c, xv);
+                if (MODE == 2) d[(size_t)j * a.dsp] = t; else y[(size_t)j * a.dp] = (float)t;
+                xl = xv;
+            }
+        }
+    }
+    T o1, o2, o3;
+    L.boundary(a.c, xl, o1, o2, o3);
+    y[(size_t)(H - 1) * a.dp] = (float)o1;
+    y[(size_t)(H - 2) * a.dp] = (float)o2;
+    y[(size_t)(H - 3) * a.dp] = (float)o3;
+    // anticausal sweep over the stored causal output
+    T p[PF];
+    #pragma unroll
+    for (int k = 0; k < PF; ++k) { const int j = H - 4 - k; p[k] = (j >= 0) ? (MODE == 2 ? (T)d[(size_t)j * a.dsp] : (T)y[(size_t)j * a.dp]) : (T)0; }
+    for (int j0 = H - 4; j0 >= 0; j0 -= PF) {
+        #pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int j = j0 - k;
+            if (j >= 0) {
+                const T t = p[k];
+                const int jn = j - PF;
+                p[k] = (jn >= 0) ? (MODE == 2 ? (T)d[(size_t)jn * a.dsp] : (T)y[(size_t)jn * a.dp]) : (T)0;
+                y[(size_t)j * a.dp] = (float)L.bwd(a.c, t);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_gauss_v(GArgs a)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= a.W) return;
+    if (a.big) vline<2>(a, col);
+    else if (col < a.W - (a.W % 8)) vline<0>(a, col);       // 8-column vector groups (L750)
+    else vline<1>(a, col);                                  // scalar remainder (L843)
+}
+
+// ------------------------------------------------------------------ horizontal pass: warp per 32 rows
+template <int MODE>
+__device__ __forceinline__ void hline(const GArgs& a, int row0, int lane, float (*tile)[33], double (*dtile)[33])
+{
+    using T = typename Acc<MODE>::T;
+    Line<MODE> L;
+    const int W = a.W;
+    const int nrows = min(32, a.H - row0);
+    const bool mine = lane < nrows;
+    float xl = 0.f;
+    // causal sweep, tile by tile
+    for (int c0 = 0; c0 < W; c0 += 32) {
+        const int nc = min(32, W - c0);
+        for (int r = 0; r < nrows; ++r) if (lane < nc) tile[r][lane] = a.src[(size_t)(row0 + r) * a.sp + c0 + lane];
+        __syncwarp();
+        if (mine)
+            for (int k = 0; k < nc; ++k) {
+                const int j = c0 + k;
+                const float xv = tile[lane][k];
+                T t;
+                if (j == 0) t = L.first(a.c, xv);
+                else if (j == 1) t = L.second(a.c, xv);
+                else if (j == 2) t = L.third(a.c, xv);
+                else t = L.fwd(a.c, xv);
+                if (MODE == 2) dtile[lane][k] = t; else tile[lane][k] = (float)t;
+                xl = xv;
+            }
+        __syncwarp();
+        for (int r = 0; r < nrows; ++r)
+            if (lane < nc) {
+                if (MODE == 2) a.dscr[(size_t)(row0 + r) * a.dsp + c0 + lane] = dtile[r][lane];
+                else a.dst[(size_t)(row0 + r) * a.dp + c0 + lane] = tile[r][lane];
+            }
+        __syncwarp();
+    }
+    T o1 = 0, o2 = 0, o3 = 0;
+    if (mine) L.boundary(a.c, xl, o1, o2, o3);
+    // anticausal sweep: tiles from the right; the last three columns come from the boundary step
+    const int ntile = (W + 31) / 32;
+    for (int tix = ntile - 1; tix >= 0; --tix) {
+        const int c0 = tix * 32, nc = min(32, W - c0);
+        for (int r = 0; r < nrows; ++r)
+            if (lane < nc) {
+                if (MODE == 2) dtile[r][lane] = a.dscr[(size_t)(row0 + r) * a.dsp + c0 + lane];
+                else tile[r][lane] = a.dst[(size_t)(row0 + r) * a.dp + c0 + lane];
+            }
+        __syncwarp();
+        if (mine)
+            for (int k = nc - 1; k >= 0; --k) {
+                const int j = c0 + k;
+                T v;
+                if (j == W - 1) v = o1;
+                else if (j == W - 2) v = o2;
+                else if (j == W - 3) v = o3;
+                else v = L.bwd(a.c, MODE == 2 ? (T)dtile[lane][k] : (T)tile[lane][k]);
+                tile[lane][k] = (float)v;
+            }
+        __syncwarp();
+        for (int r = 0; r < nrows; ++r) if (lane < nc) a.dst[(size_t)(row0 + r) * a.dp + c0 + lane] = tile[r][lane];
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(64) k_gauss_h(GArgs a)
+{
+    __shared__ float tile[2][32][33];
+    __shared__ double dtile[2][32][33];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = (blockIdx.x * 2 + w) * 32;
+    if (row0 >= a.H) return;
+    // rows of a warp can mix forms (the last H%4 rows use the scalar remainder): run each form over the
+    // whole warp with the rows of the other form masked out
+    if (a.big) { hline<2>(a, row0, lane, tile[w], dtile[w]); return; }
+    const int nfl = a.H - (a.H % 4);                          // rows < nfl are in 4-row vector groups (L586)
+    if (row0 + 32 <= nfl) { hline<0>(a, row0, lane, tile[w], dtile[w]); return; }
+    // mixed warp: split by masking -- the float rows first, then the remainder rows
+    GArgs b = a;
+    if (row0 < nfl) { b.H = nfl; hline<0>(b, row0, lane, tile[w], dtile[w]); }
+    b = a;
+    const int r1 = max(row0, nfl);
+    hline<1>(b, r1, lane, tile[w], dtile[w]);
+}
+
+// ------------------------------------------------------------------ sigma < 0.6
+struct G3Args {
+    const float* src; size_t sp; float* dst; size_t dp; int W, H;
+    float c0, c1, c2, b0, b1;
+};
+
+__global__ void __launch_bounds__(256) k_gauss3x3(G3Args a)
+{   // gauss3x3, L129-174
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.W) return;
+    for (int i = blockIdx.y; i < a.H; i += gridDim.y) {
+        const float* s = a.src + (size_t)i * a.sp;
+        float v;
+        const bool er = (i == 0 || i == a.H - 1), ec = (j == 0 || j == a.W - 1);
+        if (er && ec) v = s[j];
+        else if (er) v = a.b1 * (s[j - 1] + s[j + 1]) + a.b0 * s[j];
+        else if (ec) { const float* u = s - a.sp; const float* d = s + a.sp; v = a.b1 * (u[j] + d[j]) + a.b0 * s[j]; }
+        else {
+            const float* u = s - a.sp;
+            const float* d = s + a.sp;
+            v = a.c2 * (u[j - 1] + u[j + 1] + d[j - 1] + d[j + 1]) + a.c1 * (u[j] + s[j - 1] + s[j + 1] + d[j]) + a.c0 * s[j];
+        }
+        a.dst[(size_t)i * a.dp + j] = v;
+    }
+}
+
+// separable 3-tap pair (gaussHorizontal3 L446-464, gaussVertical3 L467-526): pass 0 src -> dst (rows), pass 1 src -> dst (columns)
+__global__ void __launch_bounds__(256) k_gauss3sep(G3Args a, int vertical)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.W) return;
+    for (int i = blockIdx.y; i < a.H; i += gridDim.y) {
+        const float* s = a.src + (size_t)i * a.sp;
+        float v;
+        if (!vertical) v = (j == 0 || j == a.W - 1) ? s[j] : (a.c1 * (s[j - 1] + s[j + 1]) + a.c0 * s[j]);
+        else if (i == 0 || i == a.H - 1) v = s[j];
+        else { const float* u = s - a.sp; const float* d = s + a.sp; v = a.c1 * (d[j] + u[j]) + s[j] * a.c0; }
+        a.dst[(size_t)i * a.dp + j] = v;
+    }
+}
+
+}  // namespace
+
+int art_gauss_dev(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, size_t dp, int W, int H, double sigma)
+{
+    cudaStream_t st = ctx->stream;
+    const bool inplace = (src == dst);
+    if (sigma < 0.25) {       // L1438-1444
+        if (!inplace) ART_CUDA(ctx, cudaMemcpy2DAsync(dst, dp * sizeof(float), src, sp * sizeof(float), (size_t)W * sizeof(float), H, cudaMemcpyDeviceToDevice, st));
+        return ART_HP_OK;
+    }
+    const dim3 pgrid((W + 255) / 256, std::min(H, 148 * 4));
+    if (sigma < 0.6) {
+        G3Args g{src, sp, dst, dp, W, H, 0, 0, 0, 0, 0};
+        if (!inplace) {       // L1446-1478
+            double c0 = 1.0, c1 = std::exp(-0.5 * ((1.0 / sigma) * (1.0 / sigma))), c2 = std::exp(-((1.0 / sigma) * (1.0 / sigma)));
+            const double sum = c0 + 4.0 * (c1 + c2);
+            c0 /= sum; c1 /= sum; c2 /= sum;
+            double b1 = std::exp(-1.0 / (2.0 * sigma * sigma));
+            const double bsum = 2.0 * b1 + 1.0;
+            b1 /= bsum;
+            g.c0 = (float)c0; g.c1 = (float)c1; g.c2 = (float)c2; g.b0 = (float)(1.0 / bsum); g.b1 = (float)b1;
+            art_prof_begin(ctx, "k_gauss3x3");
+            k_gauss3x3<<<pgrid, 256, 0, st>>>(g);
+            art_prof_end(ctx);
+            ctx->launches++;
+        } else {              // L1479-1487: horizontal into a scratch plane, vertical back
+            double c1d = std::exp(-1.0 / (2.0 * sigma * sigma));
+            const double csum = 2.0 * c1d + 1.0;
+            c1d /= csum;
+            g.c1 = (float)c1d; g.c0 = (float)(1.0 / csum);
+            const size_t tp = round_up((size_t)W, 32);
+            int rc = art_reserve(ctx, ctx->d_scratch, tp * (size_t)H * sizeof(float));
+            if (rc) return rc;
+            float* tmp = (float*)ctx->d_scratch.p;
+            G3Args h = g; h.dst = tmp; h.dp = tp;
+            art_prof_begin(ctx, "k_gauss3sep");
+            k_gauss3sep<<<pgrid, 256, 0, st>>>(h, 0);
+            G3Args v = g; v.src = tmp; v.sp = tp;
+            k_gauss3sep<<<pgrid, 256, 0, st>>>(v, 1);
+            art_prof_end(ctx);
+            ctx->launches += 2;
+        }
+        ART_CUDA(ctx, cudaGetLastError());
+        return ART_HP_OK;
+    }
+    GArgs a;
+    a.src = src; a.sp = sp; a.dst = dst; a.dp = dp; a.W = W; a.H = H; a.dscr = nullptr; a.dsp = 0;
+    a.big = sigma >= 25.0;
+    double b1, b2, b3, B, M[9];
+    if (!a.big) {
+        const float sigf = (float)sigma;         // gaussHorizontalSse(..., const float sigma)
+        yvv_factors(sigf, b1, b2, b3, B, M);
+        for (int i = 0; i < 9; ++i) {            // L559-563
+            M[i] *= (1.0 + b2 + (b1 - b3) * b3);
+            M[i] /= (1.0 + b1 - b2 + b3) * (1.0 - b1 - b2 - b3);
+        }
+    } else {
+        yvv_factors(sigma, b1, b2, b3, B, M);
+        for (int i = 0; i < 9; ++i) M[i] /= (1.0 + b1 - b2 + b3) * (1.0 + b2 + (b1 - b3) * b3);     // L674-677
+        a.dsp = round_up((size_t)W, 32);
+        int rc = art_reserve(ctx, ctx->d_scratch, a.dsp * (size_t)H * sizeof(double));
+        if (rc) return rc;
+        a.dscr = (double*)ctx->d_scratch.p;
+    }
+    a.c.B = B; a.c.b1 = b1; a.c.b2 = b2; a.c.b3 = b3;
+    a.c.Bf = (float)B; a.c.b1f = (float)b1; a.c.b2f = (float)b2; a.c.b3f = (float)b3;
+    for (int i = 0; i < 9; ++i) { a.c.M[i] = M[i]; a.c.Mf[i] = (float)M[i]; }
+    art_prof_begin(ctx, "k_gauss_h");
+    k_gauss_h<<<(H + 63) / 64, 64, 0, st>>>(a);
+    art_prof_end(ctx);
+    GArgs v = a;
+    v.src = dst; v.sp = dp;                      // vertical runs in place on the horizontal result (L1529-1530)
+    art_prof_begin(ctx, "k_gauss_v");
+    k_gauss_v<<<(W + 127) / 128, 128, 0, st>>>(v);
+    art_prof_end(ctx);
+    ctx->launches += 2;
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}

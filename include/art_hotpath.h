@@ -142,6 +142,19 @@ int art_hp_scale_colors_bayer(art_hp_ctx* ctx, int W, int H, unsigned filters, f
 int art_hp_scale_colors_bayer_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* d_raw, size_t pitch,
                                   const float cblacksom[4], const float scale_mul[4], float chmax[3]);
 
+/* ---- Gaussian blur --------------------------------------------------------- */
+/*
+ * Replaces gaussianBlur(src, dst, W, H, sigma, buffer = nullptr, GAUSS_STANDARD) (rtengine/gauss.h L25,
+ * rtengine/gauss.cc L1387-1574): every sigma branch (copy < 0.25, 3x3 / separable 3-tap < 0.6, Young-van
+ * Vliet recursive filter in float < 25, in double above).  src == dst (the same row table / the same device
+ * pointer) selects the reference's in-place variants.  gausstype: 0 = GAUSS_STANDARD; GAUSS_MULT / GAUSS_DIV
+ * and the box-blur `buffer` variant are not on the hot path and return ART_HP_ERR_UNSUPPORTED.
+ * W, H >= 4.
+ */
+int art_hp_gauss(art_hp_ctx* ctx, float* const* src, float* const* dst, int W, int H, double sigma, int gausstype);
+int art_hp_gauss_dev(art_hp_ctx* ctx, const float* d_src, size_t src_pitch, float* d_dst, size_t dst_pitch,
+                     int W, int H, double sigma, int gausstype);
+
 /* ---- gain / clip / camera->working colour space ------------------------- */
 /*
  * Replaces the per-pixel part of RawImageSource::getImage (rtengine/rawimagesource.cc L943-1025, full

@@ -63,6 +63,9 @@ class _Port:
     def scale_colors_bayer(self, raw, filters, black, mul):
         return _scale_colors(self.lib, "artoracle_scale_colors_bayer", raw, filters, black, mul)
 
+    def gauss(self, src, sigma, inplace=False):
+        return _gauss(self.lib, "artoracle_gauss", src, sigma, inplace, False)
+
     def amaze(self, raw, filters, initial_gain=1.0, border=4):
         raw, H, W, (r, g, b) = self._planes(raw)
         rc = self.lib.artoracle_amaze(W, H, ctypes.c_uint(filters), _fp(raw), ctypes.c_long(W),
@@ -70,6 +73,22 @@ class _Port:
                                       ctypes.c_float(initial_gain), border)
         assert rc == 0
         return r, g, b
+
+
+def _gauss(lib, fname, src, sigma, inplace, extra_arg):
+    src = np.ascontiguousarray(src, dtype=np.float32)
+    H, W = src.shape
+    if inplace:
+        dst = src.copy()
+        args = [_fp(dst), ctypes.c_long(W), _fp(dst), ctypes.c_long(W), W, H, ctypes.c_double(sigma)]
+    else:
+        dst = np.zeros_like(src)
+        args = [_fp(src), ctypes.c_long(W), _fp(dst), ctypes.c_long(W), W, H, ctypes.c_double(sigma)]
+    if extra_arg:
+        args.append(1 if inplace else 0)
+    rc = getattr(lib, fname)(*args)
+    assert rc == 0
+    return dst
 
 
 def _scale_convert(lib, fname, planes, mul, do_clip, mat):
@@ -92,6 +111,9 @@ def _scale_colors(lib, fname, raw, filters, black, mul):
 
 
 class _Ref:
+    def gauss(self, src, sigma, inplace=False):
+        return _gauss(self.lib, "artref_gauss", src, sigma, inplace, True)
+
     def scale_colors_bayer(self, raw, filters, black, mul):
         return _scale_colors(self.lib, "artref_scale_colors_bayer", raw, filters, black, mul)
 

@@ -324,6 +324,37 @@ int artref_max_threads(void) { return omp_get_max_threads(); }
 """
 
 
+SHIM_GAUSS_TU = r"""
+// Shim TU hosting the reference's gauss.cc from its first namespace to the end of the file
+// (its #include lines are replaced: boxblur.h drags StopWatch.h -> settings.h -> procparams.h -> lcms2.h).
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include "rt_math.h"
+#include "opthelper.h"
+#include "alignedbuffer.h"
+#include "gauss.h"
+namespace rtengine {
+// only reached through the `buffer != nullptr` variant (retinex), which the hot path never uses
+template <class T, class A> void boxblur(T** src, A** dst, T* buffer, int radx, int rady, int W, int H) { std::abort(); }
+}
+#include "gauss_body.inc"
+
+extern "C" int artref_gauss(const float* src, long sstride, float* dst, long dstride, int W, int H, double sigma, int inplace)
+{
+    float** d = new float*[H];
+    float** s = inplace ? d : new float*[H];      // the reference tests `src != dst` on the row tables themselves
+    for (int i = 0; i < H; ++i) { d[i] = dst + (long)i * dstride; if (!inplace) s[i] = const_cast<float*>(src) + (long)i * sstride; }
+#pragma omp parallel
+    gaussianBlur(s, d, W, H, sigma);
+    if (!inplace) delete[] s;
+    delete[] d;
+    return 0;
+}
+"""
+
+
 def extract(det):
     sub = os.path.join(SRC, "det" if det else "stock")
     os.makedirs(sub, exist_ok=True)
@@ -357,6 +388,10 @@ def extract(det):
     open(os.path.join(sub, "scalecolors_loop.inc"), "w").write(scl)
     open(os.path.join(sub, "glibmm.h"), "w").write(SHIM_GLIBMM)
     open(os.path.join(sub, "shim.cc"), "w").write(SHIM_TU)
+    gtext = open(os.path.join(RT, "gauss.cc"), encoding="utf-8", errors="replace").read()
+    m = re.search(r"^namespace \{", gtext, flags=re.M)
+    open(os.path.join(sub, "gauss_body.inc"), "w").write(gtext[m.start():])
+    open(os.path.join(sub, "shim_gauss.cc"), "w").write(SHIM_GAUSS_TU)
     return sub
 
 
@@ -364,7 +399,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)
