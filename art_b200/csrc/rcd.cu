@@ -27,7 +27,6 @@ constexpr int SUB = 88;   // output rows/cols per CTA (TN / 2)
 constexpr int HALO = 10;  // dependency reach of one output pixel
 constexpr int RW = SUB + 2 * HALO;   // 108: region rows/cols (max)
 constexpr int PS = 112;              // shared-memory row stride (floats)
-constexpr int NTHREADS = 512;
 constexpr size_t SMEM_BYTES = 4ull * RW * PS * sizeof(float);
 
 __device__ __forceinline__ unsigned fc(unsigned filters, int row, int col)
@@ -52,6 +51,7 @@ struct RcdArgs {
     int tr0;          // first reference tile row of this launch
 };
 
+template <int NTHREADS>
 __global__ void __launch_bounds__(NTHREADS, 1) rcd_kernel(RcdArgs a)
 {
     extern __shared__ __align__(16) float smem[];
@@ -335,10 +335,12 @@ int art_border_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, int bord, co
 int art_rcd_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, const float* raw, size_t rp,
                 float* R, float* G, float* B, size_t op, int row_begin, int row_end)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        ART_CUDA(ctx, cudaFuncSetAttribute(rcd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        attr_set = true;
+    static int nthreads = 0;
+    if (!nthreads) {
+        ART_CUDA(ctx, cudaFuncSetAttribute(rcd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        ART_CUDA(ctx, cudaFuncSetAttribute(rcd_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        const char* e = getenv("ART_HP_RCD_THREADS");
+        nthreads = (e && atoi(e) == 512) ? 512 : 1024;
     }
     const int nth = H / TN + ((H % TN) ? 1 : 0), ntw = W / TN + ((W % TN) ? 1 : 0);   // L86-87
     // reference tile row tr writes image rows [176 tr + 9, 176 tr + 185) (L305-316); bands are cut at 176 k + 9
@@ -348,7 +350,8 @@ int art_rcd_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, const float* ra
     RcdArgs a{raw, rp, R, G, B, op, W, H, filters, ntw, tr_begin};
     dim3 grid(2 * ntw, 2 * (tr_end - tr_begin));
     art_prof_begin(ctx, "rcd_kernel");
-    rcd_kernel<<<grid, NTHREADS, SMEM_BYTES, ctx->stream>>>(a);
+    if (nthreads == 512) rcd_kernel<512><<<grid, 512, SMEM_BYTES, ctx->stream>>>(a);
+    else rcd_kernel<1024><<<grid, 1024, SMEM_BYTES, ctx->stream>>>(a);
     art_prof_end(ctx);
     ctx->launches++;
     ART_CUDA(ctx, cudaGetLastError());
