@@ -67,6 +67,10 @@ def load_library(build_if_missing=True):
         "art_hp_demosaic_bayer": (i, [vp, i, i, i, u, vp, vp, vp, vp, d, i]),
         "art_hp_demosaic_bayer_dev": (i, [vp, i, i, i, u, vp, sz, vp, vp, vp, sz, d, i]),
         "art_hp_border_interpolate2_dev": (i, [vp, i, i, u, i, vp, sz, vp, vp, vp, sz]),
+        "art_hp_boxblur": (i, [vp, vp, vp, i, i, i]),
+        "art_hp_boxblur_dev": (i, [vp, vp, sz, vp, sz, i, i, i]),
+        "art_hp_guided_filter": (i, [vp, i, i, vp, vp, vp, i, ctypes.c_float, i]),
+        "art_hp_guided_filter_dev": (i, [vp, i, i, vp, sz, vp, sz, vp, sz, i, ctypes.c_float, i]),
         "art_hp_gauss": (i, [vp, vp, vp, i, i, d, i]),
         "art_hp_gauss_dev": (i, [vp, vp, sz, vp, sz, i, i, d, i]),
         "art_hp_scale_colors_bayer": (i, [vp, i, i, u, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
@@ -201,6 +205,26 @@ class HotPath:
         """Row-band form: only output rows [row_begin,row_end); pointers address row 0 of the frame."""
         self._check(self.lib.art_hp_demosaic_bayer_rows_dev(self.h, method, W, H, filters, d_raw, raw_pitch, d_r, d_g, d_b,
                                                             out_pitch, float(initial_gain), int(border), row_begin, row_end))
+
+    def boxblur(self, src, radius, dst=None):
+        H, W = src.shape
+        if dst is src:
+            tab = row_table(src)
+            self._check(self.lib.art_hp_boxblur(self.h, tab, tab, int(radius), W, H))
+            return src
+        if dst is None:
+            dst = np.empty_like(src)
+        self._check(self.lib.art_hp_boxblur(self.h, row_table(src), row_table(dst), int(radius), W, H))
+        return dst
+
+    def guided_filter(self, guide, src, r, epsilon, subsampling=0, dst=None):
+        H, W = src.shape
+        if dst is None:
+            dst = np.empty_like(src)
+        gt = row_table(guide)
+        stab = gt if src is guide else row_table(src)
+        self._check(self.lib.art_hp_guided_filter(self.h, W, H, gt, stab, row_table(dst), int(r), float(epsilon), int(subsampling)))
+        return dst
 
     def gauss(self, src, sigma, dst=None, gausstype=0):
         """Host entry.  dst=None -> out of place into a new array; dst is src -> the in-place variants."""

@@ -428,6 +428,72 @@ int art_hp_demosaic_bayer(art_hp_ctx* ctx, int method, int W, int H, unsigned fi
     return ART_HP_OK;
 }
 
+int art_hp_boxblur_dev(art_hp_ctx* ctx, const float* d_src, size_t src_pitch, float* d_dst, size_t dst_pitch, int radius, int W, int H)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_src || !d_dst) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || radius < 0 || src_pitch < (size_t)W || dst_pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d radius %d", W, H, radius);
+    if (radius > 0 && (2 * radius + 1 > W || 2 * radius + 1 > H)) return ctx->fail(ART_HP_ERR_INVALID, "radius %d does not fit %dx%d", radius, W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_boxblur_dev(ctx, d_src, src_pitch, d_dst, dst_pitch, W, H, radius);
+}
+
+int art_hp_boxblur(art_hp_ctx* ctx, float* const* src, float* const* dst, int radius, int W, int H)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!src || !dst) return ctx->fail(ART_HP_ERR_INVALID, "null row table");
+    if (W < 1 || H < 1 || radius < 0) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d radius %d", W, H, radius);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32), plane = pitch * (size_t)H * sizeof(float);
+    int rc;
+    if ((rc = art_reserve(ctx, ctx->d_out[0], plane))) return rc;
+    if ((rc = art_reserve(ctx, ctx->d_out[1], plane))) return rc;
+    Plane in = {src, (float*)ctx->d_out[0].p};
+    if ((rc = transfer(ctx, ctx->stream, &in, 1, W, 0, H, pitch, true))) return rc;
+    float* dd = (src == dst) ? in.dev : (float*)ctx->d_out[1].p;
+    if ((rc = art_hp_boxblur_dev(ctx, in.dev, pitch, dd, pitch, radius, W, H))) return rc;
+    Plane out = {dst, dd};
+    if ((rc = transfer(ctx, ctx->stream, &out, 1, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+int art_hp_guided_filter_dev(art_hp_ctx* ctx, int W, int H, const float* d_guide, size_t guide_pitch,
+                             const float* d_src, size_t src_pitch, float* d_dst, size_t dst_pitch,
+                             int r, float epsilon, int subsampling)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_guide || !d_src || !d_dst) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 8 || H < 8 || r < 1 || guide_pitch < (size_t)W || src_pitch < (size_t)W || dst_pitch < (size_t)W)
+        return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d r %d", W, H, r);
+    if (subsampling > 0 && (W / subsampling < 4 || H / subsampling < 4)) return ctx->fail(ART_HP_ERR_INVALID, "subsampling %d too coarse", subsampling);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_guided_dev(ctx, d_guide, guide_pitch, d_src, src_pitch, d_dst, dst_pitch, W, H, r, epsilon, subsampling);
+}
+
+int art_hp_guided_filter(art_hp_ctx* ctx, int W, int H, float* const* guide, float* const* src, float* const* dst,
+                         int r, float epsilon, int subsampling)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!guide || !src || !dst) return ctx->fail(ART_HP_ERR_INVALID, "null row table");
+    if (W < 8 || H < 8 || r < 1) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d r %d", W, H, r);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32), plane = pitch * (size_t)H * sizeof(float);
+    int rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+    Plane in[2] = {{guide, (float*)ctx->d_out[0].p}, {src, (float*)ctx->d_out[1].p}};
+    const bool same = (guide == src);
+    if ((rc = transfer(ctx, ctx->stream, in, same ? 1 : 2, W, 0, H, pitch, true))) return rc;
+    const float* ds = same ? in[0].dev : in[1].dev;
+    float* dd = (float*)ctx->d_out[2].p;
+    if ((rc = art_hp_guided_filter_dev(ctx, W, H, in[0].dev, pitch, ds, pitch, dd, pitch, r, epsilon, subsampling))) return rc;
+    Plane out = {dst, dd};
+    if ((rc = transfer(ctx, ctx->stream, &out, 1, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
 int art_hp_gauss_dev(art_hp_ctx* ctx, const float* d_src, size_t src_pitch, float* d_dst, size_t dst_pitch,
                      int W, int H, double sigma, int gausstype)
 {

@@ -155,6 +155,24 @@ int art_hp_gauss(art_hp_ctx* ctx, float* const* src, float* const* dst, int W, i
 int art_hp_gauss_dev(art_hp_ctx* ctx, const float* d_src, size_t src_pitch, float* d_dst, size_t dst_pitch,
                      int W, int H, double sigma, int gausstype);
 
+/* ---- box blur / guided filter ----------------------------------------------- */
+/*
+ * art_hp_boxblur*: replaces rtengine::boxblur(float** src, float** dst, int radius, int W, int H, bool multiThread)
+ * (rtengine/boxblur.h L318-556); src == dst selects the in-place use.  Requires 2*radius+1 <= min(W,H).
+ * art_hp_guided_filter*: replaces rtengine::guidedFilter(guide, src, dst, r, epsilon, multithread, subsampling)
+ * (rtengine/guidedfilter.h L26, rtengine/guidedfilter.cc L80-241); subsampling <= 0 selects the reference's
+ * own rule (calculate_subsampling, L58-75).  dst may be the same plane as src (the reference is called that
+ * way by guidedFilterLog, L256).
+ */
+int art_hp_boxblur(art_hp_ctx* ctx, float* const* src, float* const* dst, int radius, int W, int H);
+int art_hp_boxblur_dev(art_hp_ctx* ctx, const float* d_src, size_t src_pitch, float* d_dst, size_t dst_pitch,
+                       int radius, int W, int H);
+int art_hp_guided_filter(art_hp_ctx* ctx, int W, int H, float* const* guide, float* const* src, float* const* dst,
+                         int r, float epsilon, int subsampling);
+int art_hp_guided_filter_dev(art_hp_ctx* ctx, int W, int H, const float* d_guide, size_t guide_pitch,
+                             const float* d_src, size_t src_pitch, float* d_dst, size_t dst_pitch,
+                             int r, float epsilon, int subsampling);
+
 /* ---- gain / clip / camera->working colour space ------------------------- */
 /*
  * Replaces the per-pixel part of RawImageSource::getImage (rtengine/rawimagesource.cc L943-1025, full

@@ -66,6 +66,12 @@ class _Port:
     def gauss(self, src, sigma, inplace=False):
         return _gauss(self.lib, "artoracle_gauss", src, sigma, inplace, False)
 
+    def boxblur(self, src, radius, inplace=False):
+        return _boxblur(self.lib, "artoracle_boxblur", src, radius, inplace, False)
+
+    def guided_filter(self, guide, src, r, eps, subsampling=0):
+        return _guided(self.lib, "artoracle_guided_filter", guide, src, r, eps, subsampling)
+
     def amaze(self, raw, filters, initial_gain=1.0, border=4):
         raw, H, W, (r, g, b) = self._planes(raw)
         rc = self.lib.artoracle_amaze(W, H, ctypes.c_uint(filters), _fp(raw), ctypes.c_long(W),
@@ -91,6 +97,29 @@ def _gauss(lib, fname, src, sigma, inplace, extra_arg):
     return dst
 
 
+def _boxblur(lib, fname, src, radius, inplace, extra_arg):
+    src = np.ascontiguousarray(src, dtype=np.float32)
+    H, W = src.shape
+    dst = src.copy() if inplace else np.zeros_like(src)
+    a = dst if inplace else src
+    args = [_fp(a), ctypes.c_long(W), _fp(dst), ctypes.c_long(W), W, H, int(radius)]
+    if extra_arg:
+        args.append(1 if inplace else 0)
+    rc = getattr(lib, fname)(*args)
+    assert rc == 0
+    return dst
+
+
+def _guided(lib, fname, guide, src, r, eps, subsampling):
+    guide = np.ascontiguousarray(guide, dtype=np.float32)
+    src = np.ascontiguousarray(src, dtype=np.float32)
+    H, W = src.shape
+    dst = np.zeros_like(src)
+    rc = getattr(lib, fname)(_fp(guide), _fp(src), _fp(dst), ctypes.c_long(W), W, H, int(r), ctypes.c_float(eps), int(subsampling))
+    assert rc == 0
+    return dst
+
+
 def _scale_convert(lib, fname, planes, mul, do_clip, mat):
     outs = [np.array(p, dtype=np.float32, order="C", copy=True) for p in planes]
     H, W = outs[0].shape
@@ -111,6 +140,12 @@ def _scale_colors(lib, fname, raw, filters, black, mul):
 
 
 class _Ref:
+    def boxblur(self, src, radius, inplace=False):
+        return _boxblur(self.lib, "artref_boxblur", src, radius, inplace, True)
+
+    def guided_filter(self, guide, src, r, eps, subsampling=0):
+        return _guided(self.lib, "artref_guided_filter", guide, src, r, eps, subsampling)
+
     def gauss(self, src, sigma, inplace=False):
         return _gauss(self.lib, "artref_gauss", src, sigma, inplace, True)
 

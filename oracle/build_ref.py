@@ -355,6 +355,59 @@ extern "C" int artref_gauss(const float* src, long sstride, float* dst, long dst
 """
 
 
+SHIM_GUIDED_TU = r"""
+// Shim TU hosting the reference's boxblur.h body (its include block is replaced: StopWatch.h drags
+// settings.h -> procparams.h -> lcms2.h) and guidedFilter + calculate_subsampling cut from guidedfilter.cc.
+#include <assert.h>
+#include <memory>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <algorithm>
+#include "alignedbuffer.h"
+#include "rt_math.h"
+#include "opthelper.h"
+#include "array2D.h"
+#include "sleef.h"
+#define BENCHFUN
+#include "boxblur_body.inc"
+#include "rescale.h"
+#define DEBUG_DUMP(arr)
+namespace rtengine {
+namespace {
+#include "guided_subsampling.inc"
+}
+#include "guided_body.inc"
+}
+
+namespace {
+struct Tab {
+    float** p;
+    Tab(float* base, long stride, int H) { p = new float*[H]; for (int i = 0; i < H; ++i) p[i] = base + (long)i * stride; }
+    ~Tab() { delete[] p; }
+};
+}
+
+extern "C" int artref_boxblur(const float* src, long sstride, float* dst, long dstride, int W, int H, int radius, int inplace)
+{
+    Tab d(dst, dstride, H);
+    if (inplace) { rtengine::boxblur(d.p, d.p, radius, W, H, true); return 0; }
+    Tab s(const_cast<float*>(src), sstride, H);
+    rtengine::boxblur(s.p, d.p, radius, W, H, true);
+    return 0;
+}
+
+extern "C" int artref_guided_filter(const float* guide, const float* src, float* dst, long stride, int W, int H,
+                                    int r, float epsilon, int subsampling)
+{
+    Tab g(const_cast<float*>(guide), stride, H), s(const_cast<float*>(src), stride, H), d(dst, stride, H);
+    rtengine::array2D<float> G(W, H, g.p, rtengine::ARRAY2D_BYREFERENCE), S(W, H, s.p, rtengine::ARRAY2D_BYREFERENCE), D(W, H, d.p, rtengine::ARRAY2D_BYREFERENCE);
+    rtengine::guidedFilter(G, S, D, r, epsilon, true, subsampling);
+    return 0;
+}
+"""
+
+
 def extract(det):
     sub = os.path.join(SRC, "det" if det else "stock")
     os.makedirs(sub, exist_ok=True)
@@ -392,6 +445,14 @@ def extract(det):
     m = re.search(r"^namespace \{", gtext, flags=re.M)
     open(os.path.join(sub, "gauss_body.inc"), "w").write(gtext[m.start():])
     open(os.path.join(sub, "shim_gauss.cc"), "w").write(SHIM_GAUSS_TU)
+    btext = open(os.path.join(RT, "boxblur.h"), encoding="utf-8", errors="replace").read()
+    m = re.search(r"^namespace rtengine", btext, flags=re.M)
+    e = btext.rindex("#endif")
+    open(os.path.join(sub, "boxblur_body.inc"), "w").write(btext[m.start():e])
+    gf = os.path.join(RT, "guidedfilter.cc")
+    open(os.path.join(sub, "guided_subsampling.inc"), "w").write(cut_function(gf, r"int calculate_subsampling\(int w, int h, int r\)"))
+    open(os.path.join(sub, "guided_body.inc"), "w").write(cut_function(gf, r"void guidedFilter\(const array2D<float> &guide[^)]*\)"))
+    open(os.path.join(sub, "shim_guided.cc"), "w").write(SHIM_GUIDED_TU)
     return sub
 
 
@@ -399,7 +460,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)
