@@ -69,6 +69,9 @@ class _Port:
     def boxblur(self, src, radius, inplace=False):
         return _boxblur(self.lib, "artoracle_boxblur", src, radius, inplace, False)
 
+    def wavelet(self, src, maxlvl, subsamp=1):
+        return Wavelet(self.lib, "artoracle", src, maxlvl, subsamp)
+
     def guided_filter(self, guide, src, r, eps, subsampling=0):
         return _guided(self.lib, "artoracle_guided_filter", guide, src, r, eps, subsampling)
 
@@ -140,6 +143,9 @@ def _scale_colors(lib, fname, raw, filters, black, mul):
 
 
 class _Ref:
+    def wavelet(self, src, maxlvl, subsamp=1):
+        return Wavelet(self.lib, "artref", src, maxlvl, subsamp)
+
     def boxblur(self, src, radius, inplace=False):
         return _boxblur(self.lib, "artref_boxblur", src, radius, inplace, True)
 
@@ -192,6 +198,55 @@ class _Ref:
         self.lib.artref_border_interpolate2(W, H, ctypes.c_uint(filters), bord, _fp(raw), ctypes.c_long(W),
                                             _fp(r), _fp(g), _fp(b), ctypes.c_long(W))
         return r, g, b
+
+
+class Wavelet:
+    """wavelet_decomposition through either checker (prefix 'artref' = reference headers, 'artoracle' = port)."""
+
+    def __init__(self, lib, prefix, src, maxlvl, subsamp=1):
+        self.lib, self.p = lib, prefix
+        self.src = np.ascontiguousarray(src, dtype=np.float32)      # keep alive
+        H, W = self.src.shape
+        f = getattr(lib, prefix + "_wavelet_new")
+        f.restype = ctypes.c_void_p
+        args = [_fp(self.src), W, H, int(maxlvl), int(subsamp)]
+        if prefix == "artref":
+            args.append(0)
+        self.h = ctypes.c_void_p(f(*args))
+        self.shape = (H, W)
+        for name in ("maxlevel", "level_W", "level_H", "level_stride"):
+            getattr(lib, "%s_wavelet_%s" % (prefix, name)).argtypes = [ctypes.c_void_p] + ([ctypes.c_int] if name != "maxlevel" else [])
+        getattr(lib, prefix + "_wavelet_band").restype = ctypes.POINTER(ctypes.c_float)
+        getattr(lib, prefix + "_wavelet_band").argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        getattr(lib, prefix + "_wavelet_reconstruct").argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_float]
+        getattr(lib, prefix + "_wavelet_delete").argtypes = [ctypes.c_void_p]
+
+    def _c(self, name, *a):
+        return getattr(self.lib, "%s_wavelet_%s" % (self.p, name))(self.h, *a)
+
+    def maxlevel(self):
+        return int(self._c("maxlevel"))
+
+    def dims(self, lvl):
+        return int(self._c("level_H", lvl)), int(self._c("level_W", lvl)), int(self._c("level_stride", lvl))
+
+    def band(self, lvl, d):
+        """numpy VIEW of subband d (1..3) of level lvl; d == 0: the final lowpass (dims of the last level)."""
+        h, w, _ = self.dims(lvl if d else self.maxlevel() - 1)
+        ptr = self._c("band", lvl, d)
+        return np.ctypeslib.as_array(ptr, shape=(h, w))
+
+    def reconstruct(self, dst=None, blend=1.0):
+        H, W = self.shape
+        if dst is None:
+            dst = np.zeros((H, W), np.float32)
+        self._c("reconstruct", _fp(dst), ctypes.c_float(blend))
+        return dst
+
+    def close(self):
+        if self.h:
+            self._c("delete")
+            self.h = None
 
 
 _cache = {}

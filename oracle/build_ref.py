@@ -408,6 +408,28 @@ extern "C" int artref_guided_filter(const float* guide, const float* src, float*
 """
 
 
+SHIM_WAVELET_TU = r"""
+// The reference's wavelet headers compile standalone: included unmodified, straight from /root/reference.
+#include <algorithm>
+#include <cstring>
+#include "cplx_wavelet_dec.h"
+#include "cplx_wavelet_dec.cc"
+using rtengine::wavelet_decomposition;
+extern "C" {
+void* artref_wavelet_new(float* src, int W, int H, int maxlvl, int subsamp, int nthreads)
+{ return new wavelet_decomposition(src, W, H, maxlvl, subsamp, 1, nthreads > 0 ? nthreads : 1, 6); }
+int artref_wavelet_maxlevel(void* w) { return ((wavelet_decomposition*)w)->maxlevel(); }
+int artref_wavelet_level_W(void* w, int l) { return ((wavelet_decomposition*)w)->level_W(l); }
+int artref_wavelet_level_H(void* w, int l) { return ((wavelet_decomposition*)w)->level_H(l); }
+int artref_wavelet_level_stride(void* w, int l) { return ((wavelet_decomposition*)w)->level_stride(l); }
+float* artref_wavelet_band(void* w, int l, int dir)
+{ wavelet_decomposition* d = (wavelet_decomposition*)w; return dir == 0 ? d->coeff0 : d->level_coeffs(l)[dir]; }
+void artref_wavelet_reconstruct(void* w, float* dst, float blend) { ((wavelet_decomposition*)w)->reconstruct(dst, blend); }
+void artref_wavelet_delete(void* w) { delete (wavelet_decomposition*)w; }
+}
+"""
+
+
 def extract(det):
     sub = os.path.join(SRC, "det" if det else "stock")
     os.makedirs(sub, exist_ok=True)
@@ -453,6 +475,7 @@ def extract(det):
     open(os.path.join(sub, "guided_subsampling.inc"), "w").write(cut_function(gf, r"int calculate_subsampling\(int w, int h, int r\)"))
     open(os.path.join(sub, "guided_body.inc"), "w").write(cut_function(gf, r"void guidedFilter\(const array2D<float> &guide[^)]*\)"))
     open(os.path.join(sub, "shim_guided.cc"), "w").write(SHIM_GUIDED_TU)
+    open(os.path.join(sub, "shim_wavelet.cc"), "w").write(SHIM_WAVELET_TU)
     return sub
 
 
@@ -460,7 +483,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)
