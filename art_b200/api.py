@@ -67,6 +67,12 @@ def load_library(build_if_missing=True):
         "art_hp_demosaic_bayer": (i, [vp, i, i, i, u, vp, vp, vp, vp, d, i]),
         "art_hp_demosaic_bayer_dev": (i, [vp, i, i, i, u, vp, sz, vp, vp, vp, sz, d, i]),
         "art_hp_border_interpolate2_dev": (i, [vp, i, i, u, i, vp, sz, vp, vp, vp, sz]),
+        "art_hp_wavelet_decompose_dev": (i, [vp, vp, sz, i, i, i, i, ctypes.POINTER(vp)]),
+        "art_hp_wavelet_maxlevel": (i, [vp]),
+        "art_hp_wavelet_level_dims": (i, [vp, i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]),
+        "art_hp_wavelet_band_dev": (vp, [vp, i, i]),
+        "art_hp_wavelet_reconstruct_dev": (i, [vp, vp, sz, ctypes.c_float]),
+        "art_hp_wavelet_destroy": (None, [vp]),
         "art_hp_boxblur": (i, [vp, vp, vp, i, i, i]),
         "art_hp_boxblur_dev": (i, [vp, vp, sz, vp, sz, i, i, i]),
         "art_hp_guided_filter": (i, [vp, i, i, vp, vp, vp, i, ctypes.c_float, i]),
@@ -121,6 +127,32 @@ class PinnedArray:
             self.free()
         except Exception:
             pass
+
+
+class WaveletDev:
+    """Device-resident wavelet_decomposition (mirror of rtengine::wavelet_decomposition's accessors)."""
+
+    def __init__(self, hp, handle, W, H):
+        self.hp, self.h, self.W, self.H = hp, handle, W, H
+
+    def maxlevel(self):
+        return int(self.hp.lib.art_hp_wavelet_maxlevel(self.h))
+
+    def dims(self, lvl):
+        w, h, s = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self.hp._check(self.hp.lib.art_hp_wavelet_level_dims(self.h, lvl, ctypes.byref(w), ctypes.byref(h), ctypes.byref(s)))
+        return h.value, w.value, s.value
+
+    def band_ptr(self, lvl, d):
+        return int(self.hp.lib.art_hp_wavelet_band_dev(self.h, lvl, d) or 0)
+
+    def reconstruct_dev(self, d_dst, pitch, blend=1.0):
+        self.hp._check(self.hp.lib.art_hp_wavelet_reconstruct_dev(self.h, d_dst, pitch, float(blend)))
+
+    def close(self):
+        if self.h:
+            self.hp.lib.art_hp_wavelet_destroy(self.h)
+            self.h = None
 
 
 class HotPath:
@@ -205,6 +237,12 @@ class HotPath:
         """Row-band form: only output rows [row_begin,row_end); pointers address row 0 of the frame."""
         self._check(self.lib.art_hp_demosaic_bayer_rows_dev(self.h, method, W, H, filters, d_raw, raw_pitch, d_r, d_g, d_b,
                                                             out_pitch, float(initial_gain), int(border), row_begin, row_end))
+
+    def wavelet_decompose_dev(self, d_src, pitch, W, H, maxlvl, subsampling=1):
+        """wavelet_decomposition on a device plane; returns a WaveletDev handle object."""
+        h = ctypes.c_void_p()
+        self._check(self.lib.art_hp_wavelet_decompose_dev(self.h, d_src, pitch, W, H, int(maxlvl), int(subsampling), ctypes.byref(h)))
+        return WaveletDev(self, h, W, H)
 
     def boxblur(self, src, radius, dst=None):
         H, W = src.shape

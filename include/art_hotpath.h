@@ -155,6 +155,29 @@ int art_hp_gauss(art_hp_ctx* ctx, float* const* src, float* const* dst, int W, i
 int art_hp_gauss_dev(art_hp_ctx* ctx, const float* d_src, size_t src_pitch, float* d_dst, size_t dst_pitch,
                      int W, int H, double sigma, int gausstype);
 
+/* ---- wavelet decomposition ------------------------------------------------- */
+/*
+ * Replaces rtengine::wavelet_decomposition (rtengine/cplx_wavelet_dec.h L37-95, ctor L97-198, reconstruct
+ * L201-270) as FTblockDN uses it (rtengine/FTblockDN.cc L2296-2438): Daub4Len == 6, skipcrop == 1, `subsampling`
+ * bit l set = level l decimated (bit 0 must be set).  Device-resident: the object owns its subbands in HBM;
+ * callers (the shrink stages) read and write them through art_hp_wavelet_band_dev.
+ *   art_hp_wavelet_decompose_dev   = the constructor (asynchronous on the context's stream)
+ *   art_hp_wavelet_maxlevel        = maxlevel()
+ *   art_hp_wavelet_level_dims      = level_W(), level_H(), level_stride()
+ *   art_hp_wavelet_band_dev        = level_coeffs(level)[dir] for dir 1..3 (dense, width = level_W); dir 0 = coeff0,
+ *                                    the lowpass of the LAST level
+ *   art_hp_wavelet_reconstruct_dev = reconstruct(dst, blend); like the reference it consumes the decomposition and,
+ *                                    for blend != 1, blends into the existing contents of dst
+ */
+typedef struct art_hp_wavelet art_hp_wavelet;
+int    art_hp_wavelet_decompose_dev(art_hp_ctx* ctx, const float* d_src, size_t pitch, int W, int H, int maxlvl,
+                                    int subsampling, art_hp_wavelet** out);
+int    art_hp_wavelet_maxlevel(const art_hp_wavelet* w);
+int    art_hp_wavelet_level_dims(const art_hp_wavelet* w, int level, int* width, int* height, int* stride);
+float* art_hp_wavelet_band_dev(const art_hp_wavelet* w, int level, int dir);
+int    art_hp_wavelet_reconstruct_dev(art_hp_wavelet* w, float* d_dst, size_t pitch, float blend);
+void   art_hp_wavelet_destroy(art_hp_wavelet* w);
+
 /* ---- box blur / guided filter ----------------------------------------------- */
 /*
  * art_hp_boxblur*: replaces rtengine::boxblur(float** src, float** dst, int radius, int W, int H, bool multiThread)
