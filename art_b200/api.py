@@ -72,6 +72,8 @@ def load_library(build_if_missing=True):
         "art_hp_wavelet_level_dims": (i, [vp, i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]),
         "art_hp_wavelet_band_dev": (vp, [vp, i, i]),
         "art_hp_wavelet_reconstruct_dev": (i, [vp, vp, sz, ctypes.c_float]),
+        "art_hp_wavelet_get_band": (i, [vp, i, i, vp]),
+        "art_hp_wavelet_set_band": (i, [vp, i, i, vp]),
         "art_hp_wavelet_destroy": (None, [vp]),
         "art_hp_boxblur": (i, [vp, vp, vp, i, i, i]),
         "art_hp_boxblur_dev": (i, [vp, vp, sz, vp, sz, i, i, i]),
@@ -145,6 +147,17 @@ class WaveletDev:
 
     def band_ptr(self, lvl, d):
         return int(self.hp.lib.art_hp_wavelet_band_dev(self.h, lvl, d) or 0)
+
+    def band(self, lvl, d):
+        """Download subband d (1..3) of level lvl, or the final lowpass (d == 0), as a numpy array."""
+        h, w, _ = self.dims(lvl if d else self.maxlevel() - 1)
+        out = np.empty((h, w), np.float32)
+        self.hp._check(self.hp.lib.art_hp_wavelet_get_band(self.h, lvl, d, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def set_band(self, lvl, d, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float32)
+        self.hp._check(self.hp.lib.art_hp_wavelet_set_band(self.h, lvl, d, arr.ctypes.data_as(ctypes.c_void_p)))
 
     def reconstruct_dev(self, d_dst, pitch, blend=1.0):
         self.hp._check(self.hp.lib.art_hp_wavelet_reconstruct_dev(self.h, d_dst, pitch, float(blend)))

@@ -264,6 +264,37 @@ int art_hp_wavelet_reconstruct_dev(art_hp_wavelet* w, float* d_dst, size_t pitch
     return ART_HP_OK;
 }
 
+static int band_geometry(const art_hp_wavelet* w, int level, int dir, float** p, size_t* n)
+{
+    if (!w || dir < 0 || dir > 3 || level < 0 || level >= w->nlev) return ART_HP_ERR_INVALID;
+    const WLevel& L = w->lev[dir == 0 ? w->nlev - 1 : level];
+    *p = dir == 0 ? w->coeff0 : w->lev[level].band[dir];
+    *n = (size_t)L.w2 * L.h2;
+    return ART_HP_OK;
+}
+
+int art_hp_wavelet_get_band(const art_hp_wavelet* w, int level, int dir, float* host)
+{
+    float* p; size_t n;
+    if (!host || band_geometry(w, level, dir, &p, &n)) return ART_HP_ERR_INVALID;
+    art_hp_ctx* ctx = w->ctx;
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    ART_CUDA(ctx, cudaMemcpyAsync(host, p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+int art_hp_wavelet_set_band(art_hp_wavelet* w, int level, int dir, const float* host)
+{
+    float* p; size_t n;
+    if (!host || band_geometry(w, level, dir, &p, &n)) return ART_HP_ERR_INVALID;
+    art_hp_ctx* ctx = w->ctx;
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    ART_CUDA(ctx, cudaMemcpyAsync(p, host, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
 void art_hp_wavelet_destroy(art_hp_wavelet* w)
 {
     if (!w) return;

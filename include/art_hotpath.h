@@ -176,6 +176,9 @@ int    art_hp_wavelet_maxlevel(const art_hp_wavelet* w);
 int    art_hp_wavelet_level_dims(const art_hp_wavelet* w, int level, int* width, int* height, int* stride);
 float* art_hp_wavelet_band_dev(const art_hp_wavelet* w, int level, int dir);
 int    art_hp_wavelet_reconstruct_dev(art_hp_wavelet* w, float* d_dst, size_t pitch, float blend);
+/* host access to one subband (dense level_W x level_H floats), for callers that keep a stage on the CPU */
+int    art_hp_wavelet_get_band(const art_hp_wavelet* w, int level, int dir, float* host);
+int    art_hp_wavelet_set_band(art_hp_wavelet* w, int level, int dir, const float* host);
 void   art_hp_wavelet_destroy(art_hp_wavelet* w);
 
 /* ---- box blur / guided filter ----------------------------------------------- */
