@@ -48,7 +48,7 @@ def cut_function(path, signature_regex):
     """Return the text of the function whose header matches signature_regex
     (from the header through the matching closing brace)."""
     text = open(path, encoding="utf-8", errors="replace").read()
-    m = re.search(signature_regex, text)
+    m = re.search(signature_regex, text, flags=re.M)
     if not m:
         raise RuntimeError("signature %r not found in %s" % (signature_regex, path))
     i = text.index("{", m.end() - 1)
@@ -430,6 +430,39 @@ void artref_wavelet_delete(void* w) { delete (wavelet_decomposition*)w; }
 """
 
 
+SHIM_SHRINK_TU = r"""
+// Shim TU hosting the reference's wavelet shrinkage: MadRgb, ShrinkAllL, ShrinkAllAB, WaveletDenoiseAllL,
+// WaveletDenoiseAllAB cut from FTblockDN.cc, over the reference's own wavelet headers, boxblur.h body and sleef.
+#include <assert.h>
+#include <memory>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <algorithm>
+#include "alignedbuffer.h"
+#include "rt_math.h"
+#include "opthelper.h"
+#include "sleef.h"
+#include "cplx_wavelet_dec.h"
+#define BENCHFUN
+#include "boxblur_body.inc"
+namespace rtengine {
+namespace {
+int denoiseNestedLevels = 1;
+#include "shrink_body.inc"
+}
+}
+using rtengine::wavelet_decomposition;
+extern "C" {
+float artref_madrgb(float* data, int n) { return rtengine::MadRgb(data, n); }
+int artref_wavelet_denoise_L(void* wL, float* noisevarlum, float* madL /*[8][3]*/, double scale)
+{ return rtengine::WaveletDenoiseAllL(scale, *(wavelet_decomposition*)wL, noisevarlum, (float(*)[3])madL, nullptr, 0) ? 0 : 1; }
+int artref_wavelet_denoise_AB(void* wL, void* wab, float* noisevarchrom, float* madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale)
+{ return rtengine::WaveletDenoiseAllAB(scale, *(wavelet_decomposition*)wL, *(wavelet_decomposition*)wab, noisevarchrom, (float(*)[3])madL, noisevar_ab, useNoiseCCurve != 0, autoch != 0) ? 0 : 1; }
+}
+"""
+
+
 def extract(det):
     sub = os.path.join(SRC, "det" if det else "stock")
     os.makedirs(sub, exist_ok=True)
@@ -476,6 +509,14 @@ def extract(det):
     open(os.path.join(sub, "guided_body.inc"), "w").write(cut_function(gf, r"void guidedFilter\(const array2D<float> &guide[^)]*\)"))
     open(os.path.join(sub, "shim_guided.cc"), "w").write(SHIM_GUIDED_TU)
     open(os.path.join(sub, "shim_wavelet.cc"), "w").write(SHIM_WAVELET_TU)
+    ft = os.path.join(RT, "FTblockDN.cc")
+    parts = [cut_function(ft, r"^float MadRgb\(float \* DataList, const int datalen\)"),
+             cut_function(ft, r"^void ShrinkAllL\(double scale,[^)]*\)"),
+             cut_function(ft, r"^void ShrinkAllAB\(double scale,[^)]*\)"),
+             cut_function(ft, r"^bool WaveletDenoiseAllL\(double scale,[^)]*\)"),
+             cut_function(ft, r"^bool WaveletDenoiseAllAB\(double scale,[^)]*\)")]
+    open(os.path.join(sub, "shrink_body.inc"), "w").write("\n\n".join(parts))
+    open(os.path.join(sub, "shim_shrink.cc"), "w").write(SHIM_SHRINK_TU)
     return sub
 
 
@@ -483,7 +524,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)
