@@ -75,6 +75,9 @@ def load_library(build_if_missing=True):
         "art_hp_wavelet_get_band": (i, [vp, i, i, vp]),
         "art_hp_wavelet_set_band": (i, [vp, i, i, vp]),
         "art_hp_wavelet_destroy": (None, [vp]),
+        "art_hp_wavelet_mad_dev": (i, [vp, vp, vp]),
+        "art_hp_wavelet_denoise_L_dev": (i, [vp, vp, vp, vp, d]),
+        "art_hp_wavelet_denoise_AB_dev": (i, [vp, vp, vp, vp, vp, ctypes.c_float, i, i, d]),
         "art_hp_boxblur": (i, [vp, vp, vp, i, i, i]),
         "art_hp_boxblur_dev": (i, [vp, vp, sz, vp, sz, i, i, i]),
         "art_hp_guided_filter": (i, [vp, i, i, vp, vp, vp, i, ctypes.c_float, i]),
@@ -256,6 +259,16 @@ class HotPath:
         h = ctypes.c_void_p()
         self._check(self.lib.art_hp_wavelet_decompose_dev(self.h, d_src, pitch, W, H, int(maxlvl), int(subsampling), ctypes.byref(h)))
         return WaveletDev(self, h, W, H)
+
+    def wavelet_mad_dev(self, wv, d_madL):
+        self._check(self.lib.art_hp_wavelet_mad_dev(self.h, wv.h, d_madL))
+
+    def wavelet_denoise_L_dev(self, wL, d_noisevarlum, d_madL, scale=1.0):
+        self._check(self.lib.art_hp_wavelet_denoise_L_dev(self.h, wL.h, d_noisevarlum, d_madL, float(scale)))
+
+    def wavelet_denoise_AB_dev(self, wL, wab, d_noisevarchrom, d_madL, noisevar_ab, use_ccurve=False, autoch=False, scale=1.0):
+        self._check(self.lib.art_hp_wavelet_denoise_AB_dev(self.h, wL.h, wab.h, d_noisevarchrom, d_madL, float(noisevar_ab),
+                                                           int(use_ccurve), int(autoch), float(scale)))
 
     def boxblur(self, src, radius, dst=None):
         H, W = src.shape

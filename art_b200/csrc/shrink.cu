@@ -1,0 +1,374 @@
+// FTblockDN wavelet shrinkage for sm_100a.
+//
+// Replaces (reference rtengine/FTblockDN.cc) MadRgb L569-603, ShrinkAllL L638-726, ShrinkAllAB L729-839 and the
+// drivers WaveletDenoiseAllL L1111-1167 (edge == 0) / WaveletDenoiseAllAB L1170-1221 on device-resident
+// wavelet decompositions (wavelet.cu).  Everything stays in HBM: the MAD values live in a small device table
+// that the shrink kernels read, so a whole denoise pass needs no host synchronisation.
+//   * MAD: int32 histogram of |trunc(coeff)| (exact by construction: integer counts), hot low bins privatised in
+//     shared memory, then a one-block prefix scan finds the median bin and interpolates like the reference.
+//   * shrink factor / apply: element-wise; coefficients the reference handles in its 4-wide SSE loops use the
+//     vector xexpf (rtengine/sleefsseavx.h L1326-1345) and the vector expression association, the n % 4 tail
+//     uses the scalar xexpf (rtengine/sleef.h L1247-1266) and the scalar association -- bit-exact.
+//   * the local averaging is the flat boxblur (rtengine/boxblur.h L558-742) with its three column classes.
+// Compiled with -fmad=false.
+#include "ctx.h"
+
+struct WLevel { int w, h, w2, h2, skip, sub; float* band[4]; };
+struct art_hp_wavelet {
+    art_hp_ctx* ctx;
+    int nlev, W, H, subsamp;
+    WLevel lev[10];
+    float* block;
+    float* buf[2];
+    float* coeff0;
+    int consumed;
+};
+
+namespace {
+
+__device__ __forceinline__ float ldexpk4(float x, int q)
+{   // vldexpf, sleefsseavx.h L987-996
+    int m = q >> 31;
+    m = (((m + q) >> 6) - m) << 4;
+    q = q - (m << 2);
+    float u = __int_as_float((m + 0x7f) << 23);
+    x = x * u; x = x * u; x = x * u; x = x * u;
+    u = __int_as_float((q + 0x7f) << 23);
+    return x * u;
+}
+__device__ __forceinline__ float ldexpk2(float x, int q)
+{   // ldexpkf, sleef.h L953-964
+    int m = q >> 31;
+    m = (((m + q) >> 6) - m) << 4;
+    q = q - (m << 2);
+    float u = __int_as_float((m + 0x7f) << 23);
+    u = u * u;
+    x = x * u * u;
+    u = __int_as_float((q + 0x7f) << 23);
+    return x * u;
+}
+constexpr float L2U = 0.693145751953125f, L2L = 1.428606765330187045e-06f;
+constexpr float R_LN2 = 1.442695040888963407359924681001892137426645954152985934135449406931f;
+
+__device__ __forceinline__ float exp_poly(float s)
+{
+    float u = 0.00136324646882712841033936f;
+    u = u * s + 0.00836596917361021041870117f;
+    u = u * s + 0.0416710823774337768554688f;
+    u = u * s + 0.166665524244308471679688f;
+    u = u * s + 0.499999850988388061523438f;
+    return u;
+}
+__device__ __forceinline__ float xexpf_scalar(float d)
+{   // sleef.h L1247-1266
+    if (d <= -104.0f) return 0.0f;
+    const int q = __float2int_rn(d * R_LN2);
+    float s = (float)q * -L2U + d;
+    s = (float)q * -L2L + s;
+    float u = exp_poly(s);
+    u = s * (s * u + 1.f) + 1.f;
+    return ldexpk2(u, q);
+}
+__device__ __forceinline__ float xexpf_vector(float d)
+{   // sleefsseavx.h L1326-1345
+    const int q = __float2int_rn(d * R_LN2);
+    float s = (float)q * -L2U + d;
+    s = (float)q * -L2L + s;
+    float u = exp_poly(s);
+    u = 1.0f + ((s * s) * u + s);
+    u = ldexpk4(u, q);
+    return (-104.f > d) ? 0.f : u;
+}
+
+// ------------------------------------------------------------------ MAD (MadRgb, L569-603)
+constexpr int NB = 65536, HOT = 4096;
+__global__ void __launch_bounds__(512) k_mad_hist(const float* __restrict__ data, int n, int* __restrict__ histo)
+{
+    __shared__ int hot[HOT];
+    for (int i = threadIdx.x; i < HOT; i += blockDim.x) hot[i] = 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * blockDim.x) {
+        int v = abs(__float2int_rz(data[i]));      // abs(static_cast<int>(x))
+        v = v < 65535 ? v : 65535;
+        if (v < HOT) atomicAdd(&hot[v], 1); else atomicAdd(&histo[v], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HOT; i += blockDim.x) if (hot[i]) atomicAdd(&histo[i], hot[i]);
+}
+
+// one block: median bin by prefix scan, then the reference's interpolation; writes SQR(mad) * premul to out[0]
+__global__ void __launch_bounds__(1024) k_mad_median(const int* __restrict__ histo, int n, float* out, int square)
+{
+    __shared__ int part[1024];
+    const int t = threadIdx.x;
+    int s = 0;
+    for (int k = 0; k < NB / 1024; ++k) s += histo[t * (NB / 1024) + k];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        float r = 0.f;
+        if (n > 1) {
+            const int half = n / 2;
+            int count = 0, seg = 0;
+            while (seg < 1024 && count + part[seg] < half) { count += part[seg]; ++seg; }
+            int median = seg * (NB / 1024);
+            // while (count < datalen / 2) { count += histo[median]; ++median; }
+            while (count < half) { count += histo[median]; ++median; }
+            const int count_ = count - histo[median - 1];
+            r = (float)((double)((median - 1) + (half - count_) / ((float)(count - count_))) / 0.6745);
+        }
+        out[0] = square ? r * r : r;
+    }
+}
+
+// ------------------------------------------------------------------ shrink factors
+struct ShArgs {
+    float* c; const float* cL; const float* nv; float* sf; const float* sfd;
+    const float* mad; int n; float lvlmul; float noisevar_ab; int useCCurve;
+    const float* madab;
+};
+
+__global__ void __launch_bounds__(256) k_sf_L(ShArgs a)
+{   // L669-684
+    const float eps = 0.01f;
+    const float levelFactor = a.mad[0] * 5.f / a.lvlmul;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+        const float x = a.c[i];
+        const float mag = x * x;
+        float r;
+        if ((i & ~3) < a.n - 3) {      // handled by a full 4-wide vector in the reference (for (i = 0; i < n - 3; i += 4))
+            const float mad = a.nv[i] * levelFactor;
+            r = mag / (mag + mad * xexpf_vector(-mag / (9.0f * mad)) + eps);
+        } else {
+            r = mag / (mag + levelFactor * a.nv[i] * xexpf_scalar(-mag / (9 * levelFactor * a.nv[i])) + eps);
+        }
+        a.sf[i] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sf_AB(ShArgs a)
+{   // L762-786
+    const float mad_L = a.mad[0];
+    float madab = a.madab[0];
+    madab = a.useCCurve ? madab : madab * a.noisevar_ab;
+    const float rmadLm9 = 1.f / (mad_L * 9.f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+        const float xl = a.cL[i], xab = a.c[i];
+        float r;
+        if ((i & ~3) < a.n - 3) {
+            const float mad_ab = a.nv[i] * madab;
+            const float mag_ab = xab * xab;
+            const float mag_L = (xl * xl) * rmadLm9;
+            r = 1.f - xexpf_vector(-(mag_ab / mad_ab) - (mag_L));
+        } else {
+            const float mag_L = xl * xl, mag_ab = xab * xab;
+            r = (1.f - xexpf_scalar(-(mag_ab / (a.nv[i] * madab)) - (mag_L / (9.f * mad_L))));
+        }
+        a.sf[i] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sf_apply(ShArgs a)
+{   // L692-709 / L791-813
+    const float eps = 0.01f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+        const float s = a.sf[i], d = a.sfd[i], x = a.c[i];
+        a.c[i] = ((i & ~3) < a.n - 3) ? x * (d * d + s * s) / (d + s + eps) : x * ((d * d + s * s) / (d + s + eps));
+    }
+}
+
+// ------------------------------------------------------------------ flat boxblur (boxblur.h L558-742), radx == rady >= 1
+struct FbArgs { const float* x; float* y; int W, H, rad; };
+
+__global__ void __launch_bounds__(64) k_fbox_h(FbArgs a)
+{   // L571-602: thread per row
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= a.H) return;
+    const float* s = a.x + (size_t)row * a.W;
+    float* o = a.y + (size_t)row * a.W;
+    const int rad = a.rad, W = a.W;
+    int len = rad + 1;
+    float t = s[0];
+    for (int j = 1; j <= rad; j++) t += s[j];
+    t = t / len;
+    o[0] = t;
+    for (int col = 1; col <= rad; col++) {
+        t = (t * len + s[col + rad]) / (len + 1);
+        o[col] = t;
+        len++;
+    }
+    const float reclen = 1.f / len;
+    for (int col = rad + 1; col < W - rad; col++) {
+        t = t + ((float)(s[col + rad] - s[col - rad - 1])) * reclen;
+        o[col] = t;
+    }
+    for (int col = W - rad; col < W; col++) {
+        t = (t * len - s[col - rad - 1]) / (len - 1);
+        o[col] = t;
+        len--;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_fbox_v(FbArgs a)
+{   // L614-710: thread per column
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= a.W) return;
+    const int rad = a.rad, W = a.W, H = a.H;
+    const float* tp = a.x + col;
+    float* d = a.y + col;
+    if (col < W - (W % 4)) {
+        float len = (float)(rad + 1);
+        float t = tp[0];
+        for (int i = 1; i <= rad; i++) t = t + tp[(size_t)i * W];
+        t = t / len;
+        d[0] = t;
+        for (int row = 1; row <= rad; row++) {
+            const float lp1 = len + 1.f;
+            t = (t * len + tp[(size_t)(row + rad) * W]) / lp1;
+            d[(size_t)row * W] = t;
+            len = lp1;
+        }
+        const float rlen = 1.f / len;
+        for (int row = rad + 1; row < H - rad; row++) {
+            t = t + (tp[(size_t)(row + rad) * W] - tp[(size_t)(row - rad - 1) * W]) * rlen;
+            d[(size_t)row * W] = t;
+        }
+        for (int row = H - rad; row < H; row++) {
+            const float lm1 = len - 1.f;
+            t = (t * len - tp[(size_t)(row - rad - 1) * W]) / lm1;
+            d[(size_t)row * W] = t;
+            len = lm1;
+        }
+    } else {
+        int len = rad + 1;
+        float t = tp[0] / len;
+        for (int i = 1; i <= rad; i++) t += tp[(size_t)i * W] / len;
+        d[0] = t;
+        for (int row = 1; row <= rad; row++) {
+            t = (t * len + tp[(size_t)(row + rad) * W]) / (len + 1);
+            d[(size_t)row * W] = t;
+            len++;
+        }
+        for (int row = rad + 1; row < H - rad; row++) {
+            t = t + (tp[(size_t)(row + rad) * W] - tp[(size_t)(row - rad - 1) * W]) / len;
+            d[(size_t)row * W] = t;
+        }
+        for (int row = H - rad; row < H; row++) {
+            t = (t * len - tp[(size_t)(row - rad - 1) * W]) / (len - 1);
+            d[(size_t)row * W] = t;
+            len--;
+        }
+    }
+}
+
+int mad_of(art_hp_ctx* ctx, const float* band, int n, int* d_histo, float* d_out, int square)
+{
+    cudaStream_t st = ctx->stream;
+    ART_CUDA(ctx, cudaMemsetAsync(d_histo, 0, NB * sizeof(int), st));
+    art_prof_begin(ctx, "k_mad_hist");
+    k_mad_hist<<<148 * 4, 512, 0, st>>>(band, n, d_histo);
+    art_prof_end(ctx);
+    k_mad_median<<<1, 1024, 0, st>>>(d_histo, n, d_out, square);
+    ctx->launches += 2;
+    return ART_HP_OK;
+}
+
+int blur_radius(int level, double scale) { const int r = (int)((level + 2) / scale); return r > 1 ? r : 1; }
+
+// scratch: [histogram 65536 ints][madab 64 floats][sf n][sfd n][tmp n]
+struct Scratch { int* histo; float* madab; float *sf, *sfd, *tmp; };
+int scratch_for(art_hp_ctx* ctx, size_t n, Scratch* s)
+{
+    const size_t np = round_up(n, 64);
+    int rc = art_reserve(ctx, ctx->d_scratch, NB * sizeof(int) + 256 + 3 * np * sizeof(float));
+    if (rc) return rc;
+    char* p = (char*)ctx->d_scratch.p;
+    s->histo = (int*)p; p += NB * sizeof(int);
+    s->madab = (float*)p; p += 256;
+    s->sf = (float*)p; s->sfd = s->sf + np; s->tmp = s->sfd + np;
+    return ART_HP_OK;
+}
+
+int shrink_band(art_hp_ctx* ctx, const Scratch& s, ShArgs a, int W, int H, int rad, bool ab)
+{
+    cudaStream_t st = ctx->stream;
+    const int grid = std::min((a.n + 255) / 256, 148 * 16);
+    a.sf = s.sf; a.sfd = s.sfd;
+    art_prof_begin(ctx, ab ? "k_sf_AB" : "k_sf_L");
+    if (ab) k_sf_AB<<<grid, 256, 0, st>>>(a); else k_sf_L<<<grid, 256, 0, st>>>(a);
+    art_prof_end(ctx);
+    if (2 * rad + 1 > W || 2 * rad + 1 > H) return ctx->fail(ART_HP_ERR_INVALID, "blur radius %d does not fit a %dx%d subband", rad, W, H);
+    art_prof_begin(ctx, "k_fbox");
+    k_fbox_h<<<(H + 63) / 64, 64, 0, st>>>(FbArgs{s.sf, s.tmp, W, H, rad});
+    k_fbox_v<<<(W + 127) / 128, 128, 0, st>>>(FbArgs{s.tmp, s.sfd, W, H, rad});
+    art_prof_end(ctx);
+    art_prof_begin(ctx, "k_sf_apply");
+    k_sf_apply<<<grid, 256, 0, st>>>(a);
+    art_prof_end(ctx);
+    ctx->launches += 4;
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// madL[lvl][dir-1] = SQR(MadRgb(level_coeffs(lvl)[dir])) for every level (FTblockDN.cc L2311-2320) into a device table
+int art_hp_wavelet_mad_dev(art_hp_ctx* ctx, const art_hp_wavelet* w, float* d_madL)
+{
+    if (!ctx || !w || !d_madL) return ART_HP_ERR_INVALID;
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    Scratch s;
+    int rc = scratch_for(ctx, 64, &s);
+    if (rc) return rc;
+    for (int l = 0; l < w->nlev; ++l)
+        for (int d = 1; d < 4; ++d)
+            if ((rc = mad_of(ctx, w->lev[l].band[d], w->lev[l].w2 * w->lev[l].h2, s.histo, d_madL + 3 * l + (d - 1), 1))) return rc;
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}
+
+int art_hp_wavelet_denoise_L_dev(art_hp_ctx* ctx, art_hp_wavelet* wL, const float* d_noisevarlum, const float* d_madL, double scale)
+{
+    if (!ctx || !wL || !d_noisevarlum || !d_madL || !(scale > 0)) return ART_HP_ERR_INVALID;
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int maxlvl = std::min(wL->nlev, 5);      // L1115
+    Scratch s;
+    int rc = scratch_for(ctx, (size_t)wL->lev[0].w2 * wL->lev[0].h2, &s);
+    if (rc) return rc;
+    for (int l = 0; l < maxlvl; ++l)
+        for (int d = 1; d < 4; ++d) {
+            const WLevel& L = wL->lev[l];
+            ShArgs a{};
+            a.c = L.band[d]; a.nv = d_noisevarlum; a.mad = d_madL + 3 * l + (d - 1); a.n = L.w2 * L.h2; a.lvlmul = (float)(l + 1);
+            if ((rc = shrink_band(ctx, s, a, L.w2, L.h2, blur_radius(l, scale), false))) return rc;
+        }
+    return ART_HP_OK;
+}
+
+int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom,
+                                  const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale)
+{
+    if (!ctx || !wL || !wab || !d_noisevarchrom || !d_madL || !(scale > 0)) return ART_HP_ERR_INVALID;
+    if (wL->nlev != wab->nlev || wL->W != wab->W || wL->H != wab->H) return ctx->fail(ART_HP_ERR_INVALID, "L and ab decompositions differ in shape");
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (autoch && noisevar_ab <= 0.001f) noisevar_ab = 0.02f;     // L737-739
+    Scratch s;
+    int rc = scratch_for(ctx, (size_t)wab->lev[0].w2 * wab->lev[0].h2, &s);
+    if (rc) return rc;
+    for (int l = 0; l < wL->nlev; ++l)
+        for (int d = 1; d < 4; ++d) {
+            const WLevel& L = wab->lev[l];
+            const int n = L.w2 * L.h2;
+            if (!(noisevar_ab > 0.001f)) continue;                   // L761 (MadRgb is computed but unused)
+            if ((rc = mad_of(ctx, L.band[d], n, s.histo, s.madab, 1))) return rc;
+            ShArgs a{};
+            a.c = L.band[d]; a.cL = wL->lev[l].band[d]; a.nv = d_noisevarchrom; a.mad = d_madL + 3 * l + (d - 1); a.n = n;
+            a.noisevar_ab = noisevar_ab; a.useCCurve = useNoiseCCurve; a.madab = s.madab;
+            if ((rc = shrink_band(ctx, s, a, L.w2, L.h2, blur_radius(l, scale), true))) return rc;
+        }
+    return ART_HP_OK;
+}
+
+}  // extern "C"

@@ -181,6 +181,22 @@ int    art_hp_wavelet_get_band(const art_hp_wavelet* w, int level, int dir, floa
 int    art_hp_wavelet_set_band(art_hp_wavelet* w, int level, int dir, const float* host);
 void   art_hp_wavelet_destroy(art_hp_wavelet* w);
 
+/* ---- wavelet shrinkage (FTblockDN) ------------------------------------------ */
+/*
+ * art_hp_wavelet_mad_dev        madL[lvl][dir-1] = SQR(MadRgb(level_coeffs(lvl)[dir], W*H)) for all levels
+ *                               (rtengine/FTblockDN.cc MadRgb L569-603, table fill L2311-2320) into d_madL, a device
+ *                               array of 8*3 floats.
+ * art_hp_wavelet_denoise_L_dev  WaveletDenoiseAllL(scale, L, noisevarlum, madL, nullptr, 0) (L1111-1167 -> ShrinkAllL L638-726)
+ * art_hp_wavelet_denoise_AB_dev WaveletDenoiseAllAB(scale, L, ab, noisevarchrom, madL, noisevar_ab, useNoiseCCurve, autoch)
+ *                               (L1170-1221 -> ShrinkAllAB L729-839)
+ * d_noisevarlum / d_noisevarchrom: device arrays of level_W(0)*level_H(0) floats, as in the reference.
+ * All asynchronous on the context's stream; nothing is copied to the host.
+ */
+int art_hp_wavelet_mad_dev(art_hp_ctx* ctx, const art_hp_wavelet* w, float* d_madL);
+int art_hp_wavelet_denoise_L_dev(art_hp_ctx* ctx, art_hp_wavelet* wL, const float* d_noisevarlum, const float* d_madL, double scale);
+int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom,
+                                  const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale);
+
 /* ---- box blur / guided filter ----------------------------------------------- */
 /*
  * art_hp_boxblur*: replaces rtengine::boxblur(float** src, float** dst, int radius, int W, int H, bool multiThread)
