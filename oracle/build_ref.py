@@ -462,6 +462,56 @@ int artref_wavelet_denoise_AB(void* wL, void* wab, float* noisevarchrom, float* 
 }
 """
 
+SHIM_NLMEANS_TU = r"""
+// Shim TU hosting the reference's NL-means: NLMeans cut from nlmeans.cc, laplacian + detail_mask cut from
+// FTblockDN.cc, over the reference's own array2D.h / LUT.h / rescale.h / sleef.h and the gaussianBlur of shim_gauss.cc.
+#include <assert.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <omp.h>
+#include "array2D.h"
+#include "LUT.h"
+#include "rt_math.h"
+#include "opthelper.h"
+#include "sleef.h"
+#include "gauss.h"
+#include "rescale.h"
+#define BENCHFUN
+#include "boxblur_body.inc"
+namespace rtengine { namespace denoise {
+enum class BlurType { OFF, BOX, GAUSS };
+void detail_mask(const array2D<float> &src, array2D<float> &mask, float scaling, float threshold, float ceiling, float factor, BlurType blur, float blur_radius, bool multithread);
+namespace {
+#include "laplacian_body.inc"
+}
+#include "detail_mask_body.inc"
+#include "nlmeans_body.inc"
+}}
+namespace {
+using rtengine::array2D; using rtengine::ARRAY2D_BYREFERENCE;
+struct Rows { float** r; Rows(float* p, int W, int H) : r(new float*[H]) { for (int i = 0; i < H; ++i) r[i] = p + (size_t)i * W; } ~Rows() { delete[] r; } };
+}
+extern "C" {
+int artref_detail_mask(float* src, float* mask, int W, int H, float scaling, float threshold, float ceiling, float factor, int blur_type, float blur)
+{
+    Rows rs(src, W, H);
+    array2D<float> s(W, H, rs.r, ARRAY2D_BYREFERENCE), m;
+    rtengine::denoise::detail_mask(s, m, scaling, threshold, ceiling, factor, (rtengine::denoise::BlurType)blur_type, blur, true);
+    for (int y = 0; y < H; ++y) memcpy(mask + (size_t)y * W, m[y], sizeof(float) * W);
+    return 0;
+}
+int artref_nlmeans(float* img, int W, int H, float normcoeff, int strength, int detail_thresh, float scale)
+{
+    Rows rs(img, W, H);
+    array2D<float> a(W, H, rs.r, ARRAY2D_BYREFERENCE);
+    rtengine::denoise::NLMeans(a, normcoeff, strength, detail_thresh, scale, true);
+    return 0;
+}
+}
+"""
+
 
 def extract(det):
     sub = os.path.join(SRC, "det" if det else "stock")
@@ -517,6 +567,11 @@ def extract(det):
              cut_function(ft, r"^bool WaveletDenoiseAllAB\(double scale,[^)]*\)")]
     open(os.path.join(sub, "shrink_body.inc"), "w").write("\n\n".join(parts))
     open(os.path.join(sub, "shim_shrink.cc"), "w").write(SHIM_SHRINK_TU)
+    ft = os.path.join(RT, "FTblockDN.cc")
+    open(os.path.join(sub, "laplacian_body.inc"), "w").write(cut_function(ft, r"^void laplacian\(const array2D<float> &src[^)]*\)"))
+    open(os.path.join(sub, "detail_mask_body.inc"), "w").write(cut_function(ft, r"^void detail_mask\(const array2D<float> &src[^)]*\)"))
+    open(os.path.join(sub, "nlmeans_body.inc"), "w").write(cut_function(os.path.join(RT, "nlmeans.cc"), r"^void NLMeans\(array2D<float> &img[^)]*\)"))
+    open(os.path.join(sub, "shim_nlmeans.cc"), "w").write(SHIM_NLMEANS_TU)
     return sub
 
 
@@ -524,7 +579,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)

@@ -22,64 +22,7 @@ int artoracle_wavelet_level_W(void* p, int l);
 int artoracle_wavelet_level_H(void* p, int l);
 float* artoracle_wavelet_band(void* p, int l, int dir);
 
-static inline float i2f(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
-
-static float ldexpk(float x, int q)
-{   /* ldexpkf (sleef.h L953-964) == vldexpf (sleefsseavx.h L987-996): x * u^4 * 2^q' */
-    int m = q >> 31;
-    m = (((m + q) >> 6) - m) << 4;
-    q = q - (m << 2);
-    float u = i2f((int32_t)(m + 0x7f) << 23);
-    /* scalar: u = u*u; x = x*u*u  -- vector: x = x*u*u*u*u.  Powers of two: both exact unless they over/underflow,
-     * which the shrinkage arguments never reach; we follow the caller's form below */
-    x = x * u; x = x * u; x = x * u; x = x * u;
-    u = i2f((int32_t)(q + 0x7f) << 23);
-    return x * u;
-}
-static float ldexpk_scalar(float x, int q)
-{
-    int m = q >> 31;
-    m = (((m + q) >> 6) - m) << 4;
-    q = q - (m << 2);
-    float u = i2f((int32_t)(m + 0x7f) << 23);
-    u = u * u;
-    x = x * u * u;
-    u = i2f((int32_t)(q + 0x7f) << 23);
-    return x * u;
-}
-
-#define L2U 0.693145751953125f
-#define L2L 1.428606765330187045e-06f
-#define R_LN2 1.442695040888963407359924681001892137426645954152985934135449406931f
-
-static float xexpf_scalar(float d)
-{   /* sleef.h L1247-1266 */
-    if (d <= -104.0f) return 0.0f;
-    const int q = (int)lrintf(d * R_LN2);          /* _mm_cvt_ss2si: round to nearest even */
-    float s = (float)q * -L2U + d;
-    s = (float)q * -L2L + s;
-    float u = 0.00136324646882712841033936f;
-    u = u * s + 0.00836596917361021041870117f;
-    u = u * s + 0.0416710823774337768554688f;
-    u = u * s + 0.166665524244308471679688f;
-    u = u * s + 0.499999850988388061523438f;
-    u = s * (s * u + 1.f) + 1.f;
-    return ldexpk_scalar(u, q);
-}
-static float xexpf_vector(float d)
-{   /* sleefsseavx.h L1326-1345 */
-    const int q = (int)lrintf(d * R_LN2);
-    float s = (float)q * -L2U + d;
-    s = (float)q * -L2L + s;
-    float u = 0.00136324646882712841033936f;
-    u = u * s + 0.00836596917361021041870117f;
-    u = u * s + 0.0416710823774337768554688f;
-    u = u * s + 0.166665524244308471679688f;
-    u = u * s + 0.499999850988388061523438f;
-    u = 1.0f + ((s * s) * u + s);
-    u = ldexpk(u, q);
-    return (-104.f > d) ? 0.f : u;
-}
+#include "sleef_port.h"
 
 /* boxblur(T* src, A* dst, A* buffer, radx, rady, W, H), boxblur.h L558-742 (radx == rady == rad >= 1) */
 static void boxblur_flat(const float* src, float* dst, float* temp, int rad, int W, int H)
