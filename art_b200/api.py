@@ -48,7 +48,7 @@ def load_library(build_if_missing=True):
         from . import build as _build
         _build.build()
     lib = ctypes.CDLL(path)
-    vp, i, u, sz, d = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_size_t, ctypes.c_double
+    vp, i, u, sz, d, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_size_t, ctypes.c_double, ctypes.c_float
     sig = {
         "art_hp_abi_version": (i, []),
         "art_hp_device_count": (i, []),
@@ -82,6 +82,10 @@ def load_library(build_if_missing=True):
         "art_hp_boxblur_dev": (i, [vp, vp, sz, vp, sz, i, i, i]),
         "art_hp_guided_filter": (i, [vp, i, i, vp, vp, vp, i, ctypes.c_float, i]),
         "art_hp_guided_filter_dev": (i, [vp, i, i, vp, sz, vp, sz, vp, sz, i, ctypes.c_float, i]),
+        "art_hp_detail_mask": (i, [vp, vp, vp, i, i, f, f, f, f, i, f]),
+        "art_hp_detail_mask_dev": (i, [vp, vp, sz, vp, sz, i, i, f, f, f, f, i, f]),
+        "art_hp_nlmeans": (i, [vp, vp, i, i, f, i, i, f]),
+        "art_hp_nlmeans_dev": (i, [vp, vp, sz, i, i, f, i, i, f]),
         "art_hp_gauss": (i, [vp, vp, vp, i, i, d, i]),
         "art_hp_gauss_dev": (i, [vp, vp, sz, vp, sz, i, i, d, i]),
         "art_hp_scale_colors_bayer": (i, [vp, i, i, u, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
@@ -289,6 +293,27 @@ class HotPath:
         stab = gt if src is guide else row_table(src)
         self._check(self.lib.art_hp_guided_filter(self.h, W, H, gt, stab, row_table(dst), int(r), float(epsilon), int(subsampling)))
         return dst
+
+    def detail_mask(self, src, scaling, threshold, ceiling, factor, blur_type=2, blur=2.0):
+        """denoise::detail_mask on a host (H, W) float32 array; returns the mask."""
+        H, W = src.shape
+        mask = np.empty_like(src)
+        self._check(self.lib.art_hp_detail_mask(self.h, row_table(src), row_table(mask), W, H, scaling, threshold, ceiling, factor,
+                                                int(blur_type), blur))
+        return mask
+
+    def detail_mask_dev(self, d_src, src_pitch, d_mask, mask_pitch, W, H, scaling, threshold, ceiling, factor, blur_type=2, blur=2.0):
+        self._check(self.lib.art_hp_detail_mask_dev(self.h, d_src, src_pitch, d_mask, mask_pitch, W, H, scaling, threshold, ceiling,
+                                                    factor, int(blur_type), blur))
+
+    def nlmeans(self, img, normcoeff, strength, detail_thresh, scale=1.0):
+        """denoise::NLMeans, in place on a host (H, W) float32 array."""
+        H, W = img.shape
+        self._check(self.lib.art_hp_nlmeans(self.h, row_table(img), W, H, normcoeff, int(strength), int(detail_thresh), scale))
+        return img
+
+    def nlmeans_dev(self, d_img, pitch, W, H, normcoeff, strength, detail_thresh, scale=1.0):
+        self._check(self.lib.art_hp_nlmeans_dev(self.h, d_img, pitch, W, H, normcoeff, int(strength), int(detail_thresh), scale))
 
     def gauss(self, src, sigma, dst=None, gausstype=0):
         """Host entry.  dst=None -> out of place into a new array; dst is src -> the in-place variants."""

@@ -205,7 +205,7 @@ void art_hp_destroy(art_hp_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch, &ctx->d_small};
+    DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch, &ctx->d_small, &ctx->d_work};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; ++i) if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -527,6 +527,70 @@ int art_hp_gauss(art_hp_ctx* ctx, float* const* src, float* const* dst, int W, i
     if ((rc = art_gauss_dev(ctx, ds, pitch, dd, pitch, W, H, sigma))) return rc;
     Plane out = {dst, dd};
     if ((rc = transfer(ctx, ctx->stream, &out, 1, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+int art_hp_detail_mask_dev(art_hp_ctx* ctx, const float* d_src, size_t src_pitch, float* d_mask, size_t mask_pitch, int W, int H,
+                           float scaling, float threshold, float ceiling, float factor, int blur_type, float blur)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_src || !d_mask) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || src_pitch < (size_t)W || mask_pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    if (blur_type < 0 || blur_type > 2) return ctx->fail(ART_HP_ERR_INVALID, "blur_type %d (0 off, 1 box, 2 gauss)", blur_type);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = art_reserve(ctx, ctx->d_work, 2 * (size_t)(W / 4 + 1) * (H / 4 + 1) * sizeof(float));
+    if (rc) return rc;
+    return art_detail_mask_dev(ctx, d_src, src_pitch, d_mask, mask_pitch, W, H, scaling, threshold, ceiling, factor, blur_type, blur,
+                               (float*)ctx->d_work.p);
+}
+
+int art_hp_detail_mask(art_hp_ctx* ctx, float* const* src, float* const* mask, int W, int H,
+                       float scaling, float threshold, float ceiling, float factor, int blur_type, float blur)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!src || !mask) return ctx->fail(ART_HP_ERR_INVALID, "null row table");
+    if (W < 1 || H < 1) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    int rc;
+    if ((rc = art_reserve(ctx, ctx->d_out[0], plane))) return rc;
+    if ((rc = art_reserve(ctx, ctx->d_out[1], plane))) return rc;
+    Plane in = {src, (float*)ctx->d_out[0].p};
+    if ((rc = transfer(ctx, ctx->stream, &in, 1, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_hp_detail_mask_dev(ctx, (float*)ctx->d_out[0].p, pitch, (float*)ctx->d_out[1].p, pitch, W, H, scaling, threshold, ceiling,
+                                     factor, blur_type, blur))) return rc;
+    Plane out = {mask, (float*)ctx->d_out[1].p};
+    if ((rc = transfer(ctx, ctx->stream, &out, 1, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+int art_hp_nlmeans_dev(art_hp_ctx* ctx, float* d_img, size_t pitch, int W, int H, float normcoeff, int strength, int detail_thresh, float scale)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_img) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_nlmeans_dev(ctx, d_img, pitch, W, H, normcoeff, strength, detail_thresh, scale);
+}
+
+int art_hp_nlmeans(art_hp_ctx* ctx, float* const* img, int W, int H, float normcoeff, int strength, int detail_thresh, float scale)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!img) return ctx->fail(ART_HP_ERR_INVALID, "null row table");
+    if (W < 1 || H < 1) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    if (!strength) return ART_HP_OK;                         // nlmeans.cc L52-54
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    int rc;
+    if ((rc = art_reserve(ctx, ctx->d_out[0], pitch * (size_t)H * sizeof(float)))) return rc;
+    float* d = (float*)ctx->d_out[0].p;
+    Plane io = {img, d};
+    if ((rc = transfer(ctx, ctx->stream, &io, 1, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_nlmeans_dev(ctx, d, pitch, W, H, normcoeff, strength, detail_thresh, scale))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, &io, 1, W, 0, H, pitch, false))) return rc;
     ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;
 }

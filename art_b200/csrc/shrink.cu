@@ -12,6 +12,7 @@
 //   * the local averaging is the flat boxblur (rtengine/boxblur.h L558-742) with its three column classes.
 // Compiled with -fmad=false.
 #include "ctx.h"
+#include "sleef_dev.cuh"
 
 struct WLevel { int w, h, w2, h2, skip, sub; float* band[4]; };
 struct art_hp_wavelet {
@@ -25,60 +26,8 @@ struct art_hp_wavelet {
 };
 
 namespace {
-
-__device__ __forceinline__ float ldexpk4(float x, int q)
-{   // vldexpf, sleefsseavx.h L987-996
-    int m = q >> 31;
-    m = (((m + q) >> 6) - m) << 4;
-    q = q - (m << 2);
-    float u = __int_as_float((m + 0x7f) << 23);
-    x = x * u; x = x * u; x = x * u; x = x * u;
-    u = __int_as_float((q + 0x7f) << 23);
-    return x * u;
-}
-__device__ __forceinline__ float ldexpk2(float x, int q)
-{   // ldexpkf, sleef.h L953-964
-    int m = q >> 31;
-    m = (((m + q) >> 6) - m) << 4;
-    q = q - (m << 2);
-    float u = __int_as_float((m + 0x7f) << 23);
-    u = u * u;
-    x = x * u * u;
-    u = __int_as_float((q + 0x7f) << 23);
-    return x * u;
-}
-constexpr float L2U = 0.693145751953125f, L2L = 1.428606765330187045e-06f;
-constexpr float R_LN2 = 1.442695040888963407359924681001892137426645954152985934135449406931f;
-
-__device__ __forceinline__ float exp_poly(float s)
-{
-    float u = 0.00136324646882712841033936f;
-    u = u * s + 0.00836596917361021041870117f;
-    u = u * s + 0.0416710823774337768554688f;
-    u = u * s + 0.166665524244308471679688f;
-    u = u * s + 0.499999850988388061523438f;
-    return u;
-}
-__device__ __forceinline__ float xexpf_scalar(float d)
-{   // sleef.h L1247-1266
-    if (d <= -104.0f) return 0.0f;
-    const int q = __float2int_rn(d * R_LN2);
-    float s = (float)q * -L2U + d;
-    s = (float)q * -L2L + s;
-    float u = exp_poly(s);
-    u = s * (s * u + 1.f) + 1.f;
-    return ldexpk2(u, q);
-}
-__device__ __forceinline__ float xexpf_vector(float d)
-{   // sleefsseavx.h L1326-1345
-    const int q = __float2int_rn(d * R_LN2);
-    float s = (float)q * -L2U + d;
-    s = (float)q * -L2L + s;
-    float u = exp_poly(s);
-    u = 1.0f + ((s * s) * u + s);
-    u = ldexpk4(u, q);
-    return (-104.f > d) ? 0.f : u;
-}
+using sleef::xexpf_scalar;
+using sleef::xexpf_vector;
 
 // ------------------------------------------------------------------ MAD (MadRgb, L569-603)
 constexpr int NB = 65536, HOT = 4096;

@@ -197,6 +197,25 @@ int art_hp_wavelet_denoise_L_dev(art_hp_ctx* ctx, art_hp_wavelet* wL, const floa
 int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom,
                                   const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale);
 
+/* ---- detail mask / NL-means --------------------------------------------------- */
+/*
+ * art_hp_detail_mask   rtengine::denoise::detail_mask(src, mask, scaling, threshold, ceiling, factor, blur_type, blur, mt)
+ *                      (rtengine/FTblockDN.cc L1408-1476; laplacian L1366-1403; rtengine/rescale.h rescaleBilinear L53-77).
+ *                      blur_type follows denoise::BlurType (rtengine/ipdenoise.h L81-85): 0 OFF, 1 BOX, 2 GAUSS.
+ * art_hp_nlmeans       rtengine::denoise::NLMeans(img, normcoeff, strength, detail_thresh, scale, mt)
+ *                      (rtengine/nlmeans.cc L50-280), in place on one plane.  strength == 0 returns at once like the
+ *                      reference.  The reference's tile grid (150/136), shift order, 4-wide vector / scalar LUT lookups
+ *                      and flush-to-zero arithmetic are reproduced: results are bit-identical.
+ * The host forms take array2D-style row tables (row i at rows[i], W floats); the _dev forms device planes with a
+ * pitch in floats, asynchronous on the context's stream.
+ */
+int art_hp_detail_mask(art_hp_ctx* ctx, float* const* src, float* const* mask, int W, int H,
+                       float scaling, float threshold, float ceiling, float factor, int blur_type, float blur);
+int art_hp_detail_mask_dev(art_hp_ctx* ctx, const float* d_src, size_t src_pitch, float* d_mask, size_t mask_pitch, int W, int H,
+                           float scaling, float threshold, float ceiling, float factor, int blur_type, float blur);
+int art_hp_nlmeans(art_hp_ctx* ctx, float* const* img, int W, int H, float normcoeff, int strength, int detail_thresh, float scale);
+int art_hp_nlmeans_dev(art_hp_ctx* ctx, float* d_img, size_t pitch, int W, int H, float normcoeff, int strength, int detail_thresh, float scale);
+
 /* ---- box blur / guided filter ----------------------------------------------- */
 /*
  * art_hp_boxblur*: replaces rtengine::boxblur(float** src, float** dst, int radius, int W, int H, bool multiThread)
