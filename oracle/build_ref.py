@@ -483,10 +483,7 @@ SHIM_NLMEANS_TU = r"""
 namespace rtengine { namespace denoise {
 enum class BlurType { OFF, BOX, GAUSS };
 void detail_mask(const array2D<float> &src, array2D<float> &mask, float scaling, float threshold, float ceiling, float factor, BlurType blur, float blur_radius, bool multithread);
-namespace {
-#include "laplacian_body.inc"
-}
-#include "detail_mask_body.inc"
+// laplacian + detail_mask are defined once, in shim_denoise.cc (the whole FTblockDN.cc body)
 #include "nlmeans_body.inc"
 }}
 namespace {
@@ -507,6 +504,181 @@ int artref_nlmeans(float* img, int W, int H, float normcoeff, int strength, int 
     Rows rs(img, W, H);
     array2D<float> a(W, H, rs.r, ARRAY2D_BYREFERENCE);
     rtengine::denoise::NLMeans(a, normcoeff, strength, detail_thresh, scale, true);
+    return 0;
+}
+}
+"""
+
+SHIM_DENOISE_TU = r"""
+// Shim TU hosting the reference's FTblockDN.cc from its `#define TS 64` to the end of the file (RGB_denoise and
+// everything it calls), with the #include block replaced by the minimal stand-ins below: the real headers drag
+// glibmm / lcms2 / fftw3, none of which exist in this image.  Stand-ins written here (not reference code):
+// Imagefloat, LabImage, ProcParams/DenoiseParams, ImProcData, NoiseCurve, ICCStore, Settings/Options, MyMutex, MyTime,
+// and <fftw3.h> = oracle/dct_standin.h.  Color's members used by RGB_denoise are cut from color.h / color.cc.
+#include <assert.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include <omp.h>
+#include "array2D.h"
+#include "LUT.h"
+#include "rt_math.h"
+#include "opthelper.h"
+#include "sleef.h"
+#include "alignedbuffer.h"
+#include "median.h"
+#include "gauss.h"
+#include "rescale.h"
+#include "cplx_wavelet_dec.h"
+#include "dct_standin.h"
+#define BENCHFUN
+#ifndef MAX
+#define MAX(a, b) (((a) > (b)) ? (a) : (b))   /* glib's gmacros.h forms */
+#define MIN(a, b) (((a) < (b)) ? (a) : (b))
+#endif
+#include "boxblur_body.inc"
+
+namespace rtengine {
+
+typedef const double (*TMatrix)[3];
+
+struct Settings { bool verbose; };
+static const Settings artref_settings = {false};
+const Settings* settings = &artref_settings;
+struct Options { int rgbDenoiseThreadLimit; };
+static Options options = {1};                 // one thread inside detail_recovery: its overlap-add races otherwise
+
+class MyMutex { public: class MyLock { public: explicit MyLock(MyMutex&) {} }; };
+static MyMutex artref_mutex;
+MyMutex* fftwMutex = &artref_mutex;
+class MyTime { public: void set() {} int etime(const MyTime&) { return 0; } };
+
+class Imagefloat {
+public:
+    int W, H; float *R, *G, *B; bool own;
+    Imagefloat(int w, int h) : W(w), H(h), R(new float[(size_t)w * h]), G(new float[(size_t)w * h]), B(new float[(size_t)w * h]), own(true) {}
+    Imagefloat(int w, int h, float* r_, float* g_, float* b_) : W(w), H(h), R(r_), G(g_), B(b_), own(false) {}
+    ~Imagefloat() { if (own) { delete[] R; delete[] G; delete[] B; } }
+    int getWidth() const { return W; }
+    int getHeight() const { return H; }
+    float& r(int i, int j) { return R[(size_t)i * W + j]; }
+    float& g(int i, int j) { return G[(size_t)i * W + j]; }
+    float& b(int i, int j) { return B[(size_t)i * W + j]; }
+    void copyData(Imagefloat* d) { memcpy(d->R, R, sizeof(float) * (size_t)W * H); memcpy(d->G, G, sizeof(float) * (size_t)W * H); memcpy(d->B, B, sizeof(float) * (size_t)W * H); }
+};
+
+class LabImage {
+public:
+    int W, H; float* data; float **L, **a, **b;
+    LabImage(int w, int h) : W(w), H(h), data(new float[(size_t)w * h * 3]), L(new float*[h]), a(new float*[h]), b(new float*[h])
+    { for (int i = 0; i < h; ++i) { L[i] = data + (size_t)i * w; a[i] = data + (size_t)(h + i) * w; b[i] = data + (size_t)(2 * h + i) * w; } }
+    ~LabImage() { delete[] data; delete[] L; delete[] a; delete[] b; }
+};
+
+namespace procparams {
+struct DenoiseParams {
+    enum class ChrominanceMethod { MANUAL, AUTOMATIC };
+    enum class ColorSpace { RGB, LAB };
+    bool enabled; ColorSpace colorSpace; bool aggressive; double gamma; double luminance; double luminanceDetail; int luminanceDetailThreshold;
+    ChrominanceMethod chrominanceMethod; double chrominance; double chrominanceRedGreen; double chrominanceBlueYellow;
+};
+struct ICMParams { std::string workingProfile; };
+struct ProcParams { ICMParams icm; };
+}
+using procparams::ProcParams;
+struct ImProcData { const ProcParams* params; double scale; bool multiThread; };
+
+static double artref_wp[3][3], artref_wpi[3][3];
+class ICCStore {
+public:
+    static ICCStore* getInstance() { static ICCStore s; return &s; }
+    TMatrix workingSpaceMatrix(const std::string&) const { return artref_wp; }
+    TMatrix workingSpaceInverseMatrix(const std::string&) const { return artref_wpi; }
+};
+
+class Color {
+public:
+    constexpr static double sRGBGammaCurve = 2.4;
+    constexpr static double eps = 216.0 / 24389.0;
+    constexpr static double MAXVALD = 65535.0; constexpr static float MAXVALF = 65535.f;
+    constexpr static double eps_max = MAXVALF * eps;
+    constexpr static double kappa = 24389.0 / 27.0;
+    constexpr static float D50x = 0.9642f, D50z = 0.8249f;
+    static LUTf cachef, cachefy, denoiseGammaTab, denoiseIGammaTab, igammatab_srgb, gammatab_srgb;
+    static void init()
+    {
+        if (cachef) return;
+        cachef(65536, LUT_CLIP_BELOW); cachefy(65536, LUT_CLIP_BELOW);
+        int i = 0; const int epsmaxint = eps_max;            // color.cc L205-233
+        for (; i <= epsmaxint; i++) { cachef[i] = 327.68 * ((kappa * i / MAXVALF + 16.0) / 116.0); cachefy[i] = 327.68 * (kappa * i / MAXVALF); }
+        for (; i < 65536; i++) { cachef[i] = 327.68 * std::cbrt((double)i / MAXVALF); cachefy[i] = 327.68 * (116.0 * std::cbrt((double)i / MAXVALF) - 16.0); }
+    }
+#include "color_h_members.inc"
+    static float computeXYZ2Lab(float f);
+    static float computeXYZ2LabY(float f);
+    static void gammaf2lut (LUTf &gammacurve, float gamma, float start, float slope, float divisor, float factor);
+    static void rgbxyz (float r, float g, float b, float &x, float &y, float &z, const float xyz_rgb[3][3]);
+    static void XYZ2Lab(float X, float Y, float Z, float &L, float &a, float &b);
+    template <class T> static void rgb2lab(float, float, float, float&, float&, float&, const T[3][3]) { abort(); }   // colorSpace LAB: not on the path
+    template <class T> static void lab2rgb(float, float, float, float&, float&, float&, const T[3][3]) { abort(); }
+};
+LUTf Color::cachef, Color::cachefy, Color::denoiseGammaTab, Color::denoiseIGammaTab, Color::igammatab_srgb, Color::gammatab_srgb;
+#include "color_cc_members.inc"
+
+
+namespace denoise {
+class NoiseCurve {
+public:
+    LUTf lutNoiseCurve; float sum;
+    NoiseCurve() : sum(0.f) {}
+    float getSum() const { return sum; }
+    float operator[](float index) const { return lutNoiseCurve[index]; }
+    operator bool() const { return lutNoiseCurve; }
+};
+enum class Median { TYPE_3X3_SOFT, TYPE_3X3_STRONG, TYPE_5X5_SOFT, TYPE_5X5_STRONG, TYPE_7X7, TYPE_9X9 };
+enum class BlurType { OFF, BOX, GAUSS };
+void detail_mask(const array2D<float> &src, array2D<float> &mask, float scaling, float threshold, float ceiling, float factor, BlurType blur, float blur_radius, bool multithread);
+void Tile_calc(int tilesize, int overlap, int kall, int imwidth, int imheight, int &numtiles_W, int &numtiles_H, int &tilewidth, int &tileheight, int &tileWskip, int &tileHskip);
+}
+}  // namespace rtengine
+
+#include "ftblockdn_body.inc"
+
+using namespace rtengine;
+extern "C" {
+// p: luminance, luminanceDetail, luminanceDetailThreshold, chrominance, chrominanceRedGreen, chrominanceBlueYellow, gamma, scale
+// ccurve: 501-entry NoiseCurve LUT (or null = curve not set), calclum: 3 planes of ((H+1)/2) x ((W+1)/2) (or null)
+int artref_rgb_denoise(float* r, float* g, float* b, int W, int H, const double* p, const double* wp, const double* wpi,
+                       const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* nresi_highresi)
+{
+    Color::init();
+    memcpy(artref_wp, wp, sizeof artref_wp); memcpy(artref_wpi, wpi, sizeof artref_wpi);
+    procparams::DenoiseParams dn;
+    dn.enabled = true; dn.colorSpace = procparams::DenoiseParams::ColorSpace::RGB; dn.aggressive = false;
+    dn.luminance = p[0]; dn.luminanceDetail = p[1]; dn.luminanceDetailThreshold = (int)p[2];
+    dn.chrominanceMethod = procparams::DenoiseParams::ChrominanceMethod::MANUAL;
+    dn.chrominance = p[3]; dn.chrominanceRedGreen = p[4]; dn.chrominanceBlueYellow = p[5]; dn.gamma = p[6];
+    ProcParams pp; pp.icm.workingProfile = "ProPhoto";
+    ImProcData im = {&pp, p[7], true};
+    Imagefloat img(W, H, r, g, b);
+    denoise::NoiseCurve lc, cc;
+    Imagefloat* calclum = nullptr;
+    if (ccurve) {
+        cc.lutNoiseCurve(501); for (int i = 0; i < 501; ++i) cc.lutNoiseCurve[i] = ccurve[i];
+        cc.sum = ccurve_sum;
+    }
+    if (cl_r) {
+        const int w2 = (W + 1) / 2, h2 = (H + 1) / 2;
+        calclum = new Imagefloat(w2, h2);
+        memcpy(calclum->R, cl_r, sizeof(float) * (size_t)w2 * h2); memcpy(calclum->G, cl_g, sizeof(float) * (size_t)w2 * h2); memcpy(calclum->B, cl_b, sizeof(float) * (size_t)w2 * h2);
+    }
+    float nresi = 0.f, highresi = 0.f;
+    denoise::RGB_denoise(im, 0, &img, &img, calclum, nullptr, nullptr, nullptr, true, dn, 0.0, lc, cc, nresi, highresi);
+    if (nresi_highresi) { nresi_highresi[0] = nresi; nresi_highresi[1] = highresi; }
     return 0;
 }
 }
@@ -572,6 +744,22 @@ def extract(det):
     open(os.path.join(sub, "detail_mask_body.inc"), "w").write(cut_function(ft, r"^void detail_mask\(const array2D<float> &src[^)]*\)"))
     open(os.path.join(sub, "nlmeans_body.inc"), "w").write(cut_function(os.path.join(RT, "nlmeans.cc"), r"^void NLMeans\(array2D<float> &img[^)]*\)"))
     open(os.path.join(sub, "shim_nlmeans.cc"), "w").write(SHIM_NLMEANS_TU)
+    fttext = open(ft, encoding="utf-8", errors="replace").read()
+    m = re.search(r"^#define TS 64", fttext, flags=re.M)
+    open(os.path.join(sub, "ftblockdn_body.inc"), "w").write(fttext[m.start():])
+    ch, cc = os.path.join(RT, "color.h"), os.path.join(RT, "color.cc")
+    members = [cut_function(ch, r"static float rgbLuminance\(float r, float g, float b, const T workingspace\[3\]\[3\]\)"),
+               cut_function(ch, r"static void rgb2yuv\(float r, float g, float b, float &Y"),
+               cut_function(ch, r"static void yuv2rgb\(float Y, float u, float v, float &r"),
+               cut_function(ch, r"static inline float gammaf\s*\(float x, float gamma, float start, float slope\)")]
+    open(os.path.join(sub, "color_h_members.inc"), "w").write("\n".join(("template <class T>\n" if "workingspace" in t else "") + t for t in members))
+    ccm = [cut_function(cc, r"^inline float Color::computeXYZ2Lab\(float f\)"), cut_function(cc, r"^inline float Color::computeXYZ2LabY\(float f\)"),
+           cut_function(cc, r"^void Color::gammaf2lut \(LUTf &gammacurve"),
+           cut_function(cc, r"^void Color::rgbxyz \(float r, float g, float b, float &x, float &y, float &z, const float xyz_rgb"),
+           cut_function(cc, r"^void Color::XYZ2Lab\(float X, float Y, float Z, float &L")]
+    open(os.path.join(sub, "color_cc_members.inc"), "w").write("\n".join(ccm))
+    open(os.path.join(sub, "dct_standin.h"), "w").write(open(os.path.join(HERE, "dct_standin.h")).read())
+    open(os.path.join(sub, "shim_denoise.cc"), "w").write(SHIM_DENOISE_TU)
     return sub
 
 
@@ -579,7 +767,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)

@@ -1,0 +1,458 @@
+#define _POSIX_C_SOURCE 200112L
+/*
+ * oracle/denoise_port.c -- CPU restatement of denoise::RGB_denoise for the path ART actually takes.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Restates (reference) rtengine/FTblockDN.cc RGB_denoise L1638-2689 with kall = 0, isRAW = true, colorSpace RGB,
+ * aggressive = false (QUALITY_STANDARD), chrominanceMethod MANUAL, no luminance noise curve, optional chrominance
+ * noise curve (the driver ipdenoise.cc L1140-1150 always sets one), Tile_calc L442-478 (always one tile), and the
+ * pieces it calls: Color::gammaf2lut (color.cc L1128-1170, SSE2 build), Color::gammaf (color.h L1202-1205),
+ * rgb2yuv / yuv2rgb (color.h L782-796), rgbxyz (color.cc L833-838), XYZ2Lab (color.cc L1247-1274, L1382-1399),
+ * Noise_residualAB L607-635, detail_recovery L1479-1635 run by one thread (its overlap-add races otherwise),
+ * RGBtile_denoise L494-525, RGBoutput_tile_row L531-558, boxabsblur (boxblur.h L745-888).
+ * The block DCT is FFTW's in the reference; here it is oracle/dct_standin.h (parity unpinned at that boundary).
+ * Pinned against the reference function compiled in place over the same stand-in (oracle/_ref) in
+ * tests/test_oracle_denoise.py: bit-exact.
+ * Compile with -ffp-contract=off.
+ */
+#include <stdio.h>
+#include "sleef_port.h"
+#include "dct_standin.h"
+
+void* artoracle_wavelet_new(const float* src, int W, int H, int maxlvl, int subsamp);
+int artoracle_wavelet_maxlevel(void* p);
+int artoracle_wavelet_level_W(void* p, int l);
+int artoracle_wavelet_level_H(void* p, int l);
+float* artoracle_wavelet_band(void* p, int l, int dir);
+void artoracle_wavelet_reconstruct(void* p, float* dst, float blend);
+void artoracle_wavelet_delete(void* p);
+float artoracle_madrgb(const float* data, int n);
+int artoracle_wavelet_denoise_L(void* wL, const float* noisevarlum, const float* madL, double scale);
+int artoracle_wavelet_denoise_AB(void* wL, void* wab, const float* noisevarchrom, const float* madL, float noisevar_ab,
+                                 int useNoiseCCurve, int autoch, double scale);
+int artoracle_detail_mask(const float* src, float* mask, int W, int H, float scaling, float threshold, float ceiling, float factor,
+                          int blur_type, float blur);
+
+#define TS 64
+#define OFFSET 25
+#define BLKRAD 1
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+static inline float sqrf(float x) { return x * x; }
+
+/* LUTf(size, LUT_CLIP_BELOW)::operator[](float), LUT.h L437-459 */
+static inline float lut_clip_below(const float* data, int size, float index)
+{
+    int idx = (int)index;
+    if (index < 0.f || !(index == index)) return data[0];
+    else if (index > (float)(size - 2)) idx = size - 2;
+    const float diff = index - (float)idx;
+    const float p1 = data[idx];
+    const float p2 = data[idx + 1] - p1;
+    return p1 + p2 * diff;
+}
+/* LUTf(size) with both clips (the NoiseCurve's LUT) */
+static inline float lut_clip_both(const float* data, int size, float index)
+{
+    int idx = (int)index;
+    if (index < 0.f || !(index == index)) return data[0];
+    else if (index > (float)(size - 2)) return data[size - 1];
+    const float diff = index - (float)idx;
+    const float p1 = data[idx];
+    const float p2 = data[idx + 1] - p1;
+    return p1 + p2 * diff;
+}
+
+/* Color::gammaf2lut, SSE2 build */
+void artoracle_gammaf2lut(float* lut, float gamma, float start, float slope, float divisor, float factor)
+{
+    const float gammav = 1.f / gamma;
+    const float slopev = (slope / divisor) * factor;
+    const float divisorv = xlogf_scalar(divisor);
+    const float comparev = start * divisor;
+    const int border = (int)(start * divisor);
+    const int border1 = border - (border & 3);
+    const int border2 = border1 + 4;
+    int i = 0;
+    for (; i < border1; ++i) lut[i] = (float)i * slopev;
+    for (; i < border2; ++i) {
+        const float iv = (float)i;
+        const float r0 = iv * slopev;
+        const float r1 = xexpf_vector((xlogf_vector(iv) - divisorv) * gammav) * factor;
+        lut[i] = iv <= comparev ? r0 : r1;
+    }
+    for (; i < 65536; ++i) lut[i] = xexpf_nocheck((xlogf_nocheck((float)i) - divisorv) * gammav) * factor;
+}
+static inline float gammaf_(float x, float gamma, float start, float slope)
+{
+    return x <= start ? x * slope : xexpf_scalar(xlogf_scalar(x) / gamma);
+}
+
+/* Color::cachef / cachefy (color.cc L205-233) and computeXYZ2Lab / computeXYZ2LabY (L1247-1274) */
+static float* g_cachef = NULL; static float* g_cachefy = NULL;
+static void init_cachef(void)
+{
+    if (g_cachef) return;
+    g_cachef = (float*)malloc(sizeof(float) * 65536); g_cachefy = (float*)malloc(sizeof(float) * 65536);
+    const double eps = 216.0 / 24389.0, kappa = 24389.0 / 27.0, MAXVALF = 65535.f;
+    const int epsmaxint = (int)(MAXVALF * eps);
+    int i = 0;
+    for (; i <= epsmaxint; i++) { g_cachef[i] = (float)(327.68 * ((kappa * i / MAXVALF + 16.0) / 116.0)); g_cachefy[i] = (float)(327.68 * (kappa * i / MAXVALF)); }
+    for (; i < 65536; i++) { g_cachef[i] = (float)(327.68 * cbrt((double)i / MAXVALF)); g_cachefy[i] = (float)(327.68 * (116.0 * cbrt((double)i / MAXVALF) - 16.0)); }
+}
+const float* artoracle_cachef(int which) { init_cachef(); return which ? g_cachefy : g_cachef; }
+static float computeXYZ2Lab(float f)
+{
+    const double kappa = 24389.0 / 27.0, MAXVALF = 65535.f;
+    if (f != f) return f;
+    if (f < 0.f) return (float)(327.68 * ((kappa * f / MAXVALF + 16.0) / 116.0));
+    else if (f > 65535.f) return 327.68f * xcbrtf_scalar(f / 65535.f);
+    return lut_clip_below(g_cachef, 65536, f);
+}
+static float computeXYZ2LabY(float f)
+{
+    const double kappa = 24389.0 / 27.0, MAXVALF = 65535.f;
+    if (f != f) return f;
+    if (f < 0.f) return (float)(327.68 * (kappa * f / MAXVALF));
+    else if (f > 65535.f) return 327.68f * (116.f * xcbrtf_scalar(f / 65535.f) - 16.f);
+    return lut_clip_below(g_cachefy, 65536, f);
+}
+
+/* boxabsblur(src, dst, 3, 3, 64, 64, temp), boxblur.h L745-888 (W % 4 == 0: all columns in the vector class) */
+static void boxabsblur64(const float* src, float* dst, int rad, float* temp)
+{
+    const int W = TS, H = TS;
+    for (int row = 0; row < H; row++) {
+        int len = rad + 1;
+        float tempval = fabsf(src[row * W + 0]);
+        for (int j = 1; j <= rad; j++) tempval += fabsf(src[row * W + j]);
+        tempval /= len;
+        temp[row * W + 0] = tempval;
+        for (int col = 1; col <= rad; col++) {
+            tempval = (tempval * len + fabsf(src[row * W + col + rad])) / (len + 1);
+            temp[row * W + col] = tempval;
+            len++;
+        }
+        const float rlen = 1.f / (float)len;
+        for (int col = rad + 1; col < W - rad; col++) {
+            tempval = tempval + ((float)(fabsf(src[row * W + col + rad]) - fabsf(src[row * W + col - rad - 1]))) * rlen;
+            temp[row * W + col] = tempval;
+        }
+        for (int col = W - rad; col < W; col++) {
+            tempval = (tempval * len - fabsf(src[row * W + col - rad - 1])) / (len - 1);
+            temp[row * W + col] = tempval;
+            len--;
+        }
+    }
+    for (int col = 0; col < W; col++) {
+        float len = (float)(rad + 1);
+        float t = temp[col];
+        for (int i = 1; i <= rad; i++) t = t + temp[i * W + col];
+        t = t / len;
+        dst[col] = t;
+        for (int row = 1; row <= rad; row++) {
+            const float lp1 = len + 1.f;
+            t = (t * len + temp[(row + rad) * W + col]) / lp1;
+            dst[row * W + col] = t;
+            len = lp1;
+        }
+        const float rlen = 1.f / len;
+        for (int row = rad + 1; row < H - rad; row++) {
+            t = t + (temp[(row + rad) * W + col] - temp[(row - rad - 1) * W + col]) * rlen;
+            dst[row * W + col] = t;
+        }
+        for (int row = H - rad; row < H; row++) {
+            const float lm1 = len - 1.f;
+            t = (t * len - temp[(row - rad - 1) * W + col]) / lm1;
+            dst[row * W + col] = t;
+            len = lm1;
+        }
+    }
+}
+
+static float compute_detail(float d)
+{   /* L1481-1485 */
+    const float a = (float)(((100. - d) * (100. - d)) + 50. * (100. - d)) * TS * 0.5f;
+    return a * a;
+}
+
+/* tilemask_in / tilemask_out, L1833-1849 */
+void artoracle_tilemasks(float* tin, float* tout)
+{
+    const float epsilon = 0.001f / (TS * TS);
+    const int border = imax(2, TS / 16);
+    const double RT_PI = 3.14159265358979323846;
+    for (int i = 0; i < TS; ++i) {
+        const float i1 = (float)abs((i > TS / 2 ? i - TS + 1 : i));
+        const float vmask = (i1 < border ? (float)(sin((RT_PI * i1) / (2 * border)) * sin((RT_PI * i1) / (2 * border))) : 1.0f);
+        const float vmask2 = (i1 < 2 * border ? (float)(sin((RT_PI * i1) / (2 * border)) * sin((RT_PI * i1) / (2 * border))) : 1.0f);
+        for (int j = 0; j < TS; ++j) {
+            const float j1 = (float)abs((j > TS / 2 ? j - TS + 1 : j));
+            const double sj = sin((RT_PI * j1) / (2 * border));
+            tin[i * TS + j] = (float)((vmask * (j1 < border ? sj * sj : (double)1.0f)) + epsilon);
+            tout[i * TS + j] = (float)((vmask2 * (j1 < 2 * border ? sj * sj : (double)1.0f)) + epsilon);
+        }
+    }
+}
+
+/* detail_recovery, L1479-1635, one thread.  L: wavelet-denoised luma (in/out), Lin: luma before reconstruction */
+int artoracle_detail_recovery(float* L, const float* Lin, int width, int height, float params_Ldetail, int detail_thresh,
+                              const float* tin, const float* tout, double scale)
+{
+    const float detail_hi = compute_detail(params_Ldetail);
+    const float detail_lo = compute_detail(0.f);
+    const int numblox_W = (int)ceil(((float)width) / OFFSET) + 2 * BLKRAD;
+    const int numblox_H = (int)ceil(((float)height) / OFFSET) + 2 * BLKRAD;
+    float* Ldetail = (float*)calloc((size_t)width * height, sizeof(float));
+    float* totwt = (float*)calloc((size_t)width * height, sizeof(float));
+    float* mask = NULL;
+    if (detail_thresh > 0) {
+        mask = (float*)malloc(sizeof(float) * (size_t)width * height);
+        float amount = (float)detail_thresh / 100.f;
+        amount = amount < 0.f ? 0.f : amount > 1.f ? 1.f : amount;
+        int rc = artoracle_detail_mask(L, mask, width, height, 65535.f, 25.f, 10000.f, amount, 2, (float)(25.f / scale));
+        if (rc) return rc;
+    }
+    float* Lblox = (float*)fftwf_malloc(sizeof(float) * (size_t)numblox_W * TS * TS);
+    float* fLblox = (float*)fftwf_malloc(sizeof(float) * (size_t)numblox_W * TS * TS);
+    float* detail_factor = (float*)malloc(sizeof(float) * (size_t)numblox_W * TS * TS);
+    float* pBuf = (float*)malloc(sizeof(float) * (size_t)(width + TS + 2 * BLKRAD * OFFSET));
+    float nbrwt[TS * TS], blurbuffer[TS * TS];
+    const int nfwd[2] = {TS, TS};
+    const fftw_r2r_kind fwdkind[2] = {FFTW_REDFT10, FFTW_REDFT10}, bwdkind[2] = {FFTW_REDFT01, FFTW_REDFT01};
+    fftwf_plan pf = fftwf_plan_many_r2r(2, nfwd, numblox_W, Lblox, NULL, 1, TS * TS, fLblox, NULL, 1, TS * TS, fwdkind, 0);
+    fftwf_plan pb = fftwf_plan_many_r2r(2, nfwd, numblox_W, fLblox, NULL, 1, TS * TS, Lblox, NULL, 1, TS * TS, bwdkind, 0);
+    const int blur_rad = imax(1, (int)(3 / scale));
+    const float DCTnorm = 1.0f / (4 * TS * TS);
+
+    for (int vblk = 0; vblk < numblox_H; ++vblk) {
+        const int top = (vblk - BLKRAD) * OFFSET;
+        float* datarow = pBuf + BLKRAD * OFFSET;
+        for (int i = 0; i < TS; ++i) {
+            const int row = top + i;
+            int rr = row;
+            if (row < 0) rr = imin(-row, height - 1);
+            else if (row >= height) rr = imax(0, 2 * height - 2 - row);
+            for (int j = 0; j < width; ++j) datarow[j] = (Lin[(size_t)rr * width + j] - L[(size_t)rr * width + j]);
+            for (int j = -BLKRAD * OFFSET; j < 0; ++j) datarow[j] = datarow[imin(-j, width - 1)];
+            for (int j = width; j < width + TS + BLKRAD * OFFSET; ++j) datarow[j] = datarow[imax(0, 2 * width - 2 - j)];
+            for (int hblk = 0; hblk < numblox_W; ++hblk) {
+                const int left = (hblk - BLKRAD) * OFFSET;
+                const int indx = hblk * TS;
+                if (top + i >= 0 && top + i < height) {
+                    int j;
+                    for (j = 0; j < imin((-left), TS); ++j) {
+                        Lblox[(indx + i) * TS + j] = tin[i * TS + j] * datarow[left + j];
+                        detail_factor[(indx + i) * TS + j] = detail_lo;
+                    }
+                    for (; j < imin(TS, width - left); ++j) {
+                        Lblox[(indx + i) * TS + j] = tin[i * TS + j] * datarow[left + j];
+                        totwt[(size_t)(top + i) * width + left + j] += tin[i * TS + j] * tout[i * TS + j];
+                        detail_factor[(indx + i) * TS + j] = detail_thresh > 0 ? compute_detail(params_Ldetail * mask[(size_t)(top + i) * width + left + j]) : detail_hi;
+                    }
+                    for (; j < TS; ++j) {
+                        Lblox[(indx + i) * TS + j] = tin[i * TS + j] * datarow[left + j];
+                        detail_factor[(indx + i) * TS + j] = detail_lo;
+                    }
+                } else {
+                    for (int j = 0; j < TS; ++j) {
+                        Lblox[(indx + i) * TS + j] = tin[i * TS + j] * datarow[left + j];
+                        detail_factor[(indx + i) * TS + j] = detail_lo;
+                    }
+                }
+            }
+        }
+        fftwf_execute_r2r(pf, Lblox, fLblox);
+        for (int hblk = 0; hblk < numblox_W; ++hblk) {        /* RGBtile_denoise */
+            float* blk = fLblox + (size_t)hblk * TS * TS;
+            boxabsblur64(blk, nbrwt, blur_rad, blurbuffer);
+            for (int n = 0; n < TS * TS; ++n)
+                blk[n] = blk[n] * (1.0f - xexpf_vector(-(nbrwt[n] * nbrwt[n]) / detail_factor[(size_t)hblk * TS * TS + n]));
+        }
+        fftwf_execute_r2r(pb, fLblox, fLblox);
+        {   /* RGBoutput_tile_row */
+            const int nbw = (int)ceil(((float)width) / OFFSET);
+            const int imin_ = imax(0, -top);
+            const int bottom = imin(top + TS, height);
+            const int imax_ = bottom - top;
+            for (int i = imin_; i < imax_; ++i)
+                for (int hblk = 0; hblk < nbw; ++hblk) {
+                    const int left = (hblk - BLKRAD) * OFFSET;
+                    const int right = imin(left + TS, width);
+                    const int jmin = imax(0, -left);
+                    const int jmax = right - left;
+                    const int indx = hblk * TS;
+                    for (int j = jmin; j < jmax; ++j)
+                        Ldetail[(size_t)(top + i) * width + left + j] += tout[i * TS + j] * fLblox[(indx + i) * TS + j] * DCTnorm;
+                }
+        }
+    }
+    for (size_t i = 0; i < (size_t)width * height; ++i) L[i] += Ldetail[i] / totwt[i];
+    fftwf_destroy_plan(pf); fftwf_destroy_plan(pb);
+    fftwf_free(Lblox); fftwf_free(fLblox); free(detail_factor); free(pBuf); free(Ldetail); free(totwt); free(mask);
+    return 0;
+}
+
+/*
+ * p: luminance, luminanceDetail, luminanceDetailThreshold, chrominance, chrominanceRedGreen, chrominanceBlueYellow, gamma, scale
+ * wp: working space matrix (row-major 3x3 double).  ccurve: the NoiseCurve's 501-entry LUT or NULL; calclum: 3 planes of
+ * ((H+1)/2) x ((W+1)/2), needed when ccurve is in use.  out2: nresi, highresi.
+ */
+int artoracle_rgb_denoise(float* r, float* g, float* b, int W, int H, const double* p, const double* wp,
+                          const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* out2)
+{
+    const double luminance = p[0], luminanceDetail = p[1], chrominance = p[3], chromRG = p[4], chromBY = p[5], scale = p[7];
+    const int detail_thresh = (int)p[2];
+    if (luminance == 0 && chrominance == 0 && !ccurve) return 0;
+    init_cachef();
+    const int useNoiseCCurve = (ccurve && ccurve_sum > 5.f);
+    const float noiseluma = (float)luminance;
+    const float noisevarL = (float)(((noiseluma / 125.0) * (1.0 + noiseluma / 25.0)) * ((noiseluma / 125.0) * (1.0 + noiseluma / 25.0)));
+    const int denoiseLuminance = (noisevarL > 0.00001f);
+    float wpi[3][3];
+    for (int i = 0; i < 9; ++i) wpi[i / 3][i % 3] = (float)wp[i];
+    const size_t n = (size_t)W * H;
+    const int w2 = (W + 1) / 2, h2 = (H + 1) / 2;
+    float* ccalc = NULL;
+    if (useNoiseCCurve) {        /* L1706-1770 */
+        ccalc = (float*)malloc(sizeof(float) * (size_t)w2 * h2);
+        const float cn100Precalc = sqrf(1.f + 1.f * (4.f * lut_clip_both(ccurve, 501, 100.f / 60.f)));
+        for (size_t i = 0; i < (size_t)w2 * h2; ++i) {
+            const float RL = cl_r[i], GL = cl_g[i], BL = cl_b[i];
+            const float XL = ((wpi[0][0] * RL + wpi[0][1] * GL + wpi[0][2] * BL));
+            const float YL = ((wpi[1][0] * RL + wpi[1][1] * GL + wpi[1][2] * BL));
+            const float ZL = ((wpi[2][0] * RL + wpi[2][1] * GL + wpi[2][2] * BL));
+            const float x = XL / 0.9642f, z = ZL / 0.8249f, y = YL;
+            const float fx = computeXYZ2Lab(x), fy = computeXYZ2Lab(y), fz = computeXYZ2Lab(z);
+            const float AA = (500.0f * (fx - fy)), BB = (200.0f * (fy - fz));
+            const float cN = sqrtf(sqrf(AA) + sqrf(BB));
+            ccalc[i] = cN > 100 ? sqrf(1.f + 1.f * (4.f * lut_clip_both(ccurve, 501, cN / 60.f))) : cn100Precalc;
+        }
+        (void)computeXYZ2LabY;
+    }
+    if (!(luminance != 0 || chrominance != 0)) { free(ccalc); return 0; }
+
+    const float gam = (float)p[6];
+    const float gamthresh = 0.001f;
+    float* gamcurve = (float*)malloc(sizeof(float) * 65536);
+    float* igamcurve = (float*)malloc(sizeof(float) * 65536);
+    const float gamslope = (float)(exp(log((double)gamthresh) / gam) / gamthresh);
+    artoracle_gammaf2lut(gamcurve, gam, gamthresh, gamslope, 65535.f, 65535.f);
+    const float igam = 1.f / gam;
+    const float igamthresh = gamthresh * gamslope;
+    const float igamslope = 1.f / gamslope;
+    artoracle_gammaf2lut(igamcurve, igam, igamthresh, igamslope, 65535.f, 65535.f);
+    const float gain = powf(2.0f, (float)0.0);
+    const float params_Ldetail = fminf((float)luminanceDetail, 99.9f);
+    float tin[TS * TS], tout[TS * TS];
+    if (denoiseLuminance) artoracle_tilemasks(tin, tout);
+
+    const int width = W, height = H, width2 = (width + 1) / 2;
+    float interm_med = (float)chrominance / 10.0;
+    float intermred = chromRG > 0. ? (float)(chromRG / 10.) : (float)((float)chromRG / 7.0);
+    float intermblue = chromBY > 0. ? (float)(chromBY / 10.) : (float)((float)chromBY / 7.0);
+    float realred = interm_med + intermred;
+    if (realred <= 0.f) realred = 0.001f;
+    float realblue = interm_med + intermblue;
+    if (realblue <= 0.f) realblue = 0.001f;
+    const float noisevarab_r = sqrf(realred), noisevarab_b = sqrf(realblue);
+    const float maxNoiseVarab = fmaxf(noisevarab_b, noisevarab_r);
+
+    float* Lp = (float*)malloc(sizeof(float) * n), * ap = (float*)malloc(sizeof(float) * n), * bp = (float*)malloc(sizeof(float) * n);
+    float* noisevarlum = (float*)malloc(sizeof(float) * (size_t)h2 * w2);
+    float* noisevarchrom = (float*)malloc(sizeof(float) * (size_t)h2 * w2);
+#define APPLY_GAMMA(v) ((gam > 1.f && (v) > 0.f) ? ((v) < 65535.f ? lut_clip_below(gamcurve, 65536, (v)) : (gammaf_((v) / 65535.f, gam, gamthresh, gamslope) * 65535.f)) : (v))
+#define APPLY_IGAMMA(v) ((gam > 1.f && (v) > 0.f) ? ((v) < 65536.f ? lut_clip_below(igamcurve, 65536, (v)) : (gammaf_((v) / 65535.f, igam, igamthresh, igamslope) * 65535.f)) : (v))
+    for (int i = 0; i < height; ++i)
+        for (int j = 0; j < width; ++j) {
+            float X = gain * r[(size_t)i * W + j], Y = gain * g[(size_t)i * W + j], Z = gain * b[(size_t)i * W + j];
+            X = APPLY_GAMMA(X); Y = APPLY_GAMMA(Y); Z = APPLY_GAMMA(Z);
+            const float l = X * wpi[1][0] + Y * wpi[1][1] + Z * wpi[1][2];      /* rgb2yuv */
+            const float u = l - Z, v = X - l;
+            Lp[(size_t)i * W + j] = l; ap[(size_t)i * W + j] = v; bp[(size_t)i * W + j] = u;
+            if (((i | j) & 1) == 0) {
+                noisevarlum[(i >> 1) * width2 + (j >> 1)] = noisevarL;
+                noisevarchrom[(i >> 1) * width2 + (j >> 1)] = useNoiseCCurve ? maxNoiseVarab * ccalc[(size_t)(i >> 1) * w2 + (j >> 1)] : 1.f;
+            }
+        }
+
+    /* wavelet levels, L2246-2293 */
+    int levwav = 5;
+    const float maxreal = fmaxf(realred, realblue);
+    if (maxreal < 8.f) levwav = 5; else if (maxreal < 10.f) levwav = 6; else if (maxreal < 15.f) levwav = 7; else levwav = 8;
+    if (levwav > 8) levwav = 8;
+    levwav = imax(5, (int)(levwav - ceil(log(scale))));
+    const int minsizetile = imin(W, H);
+    int maxlev2 = 8;
+    if (minsizetile < 256) maxlev2 = 7;
+    if (minsizetile < 128) maxlev2 = 6;
+    if (minsizetile < 64) maxlev2 = 5;
+    if (minsizetile < 32) maxlev2 = 4;
+    if (minsizetile < 16) maxlev2 = 3;
+    levwav = imin(maxlev2, levwav);
+
+    void* Ldecomp = artoracle_wavelet_new(Lp, W, H, levwav, 1);
+    float madL[8][3];
+    memset(madL, 0, sizeof madL);
+    const int maxlvl = artoracle_wavelet_maxlevel(Ldecomp);
+    for (int lvl = 0; lvl < maxlvl; ++lvl)
+        for (int dir = 1; dir < 4; ++dir) {
+            const float m = artoracle_madrgb(artoracle_wavelet_band(Ldecomp, lvl, dir), artoracle_wavelet_level_W(Ldecomp, lvl) * artoracle_wavelet_level_H(Ldecomp, lvl));
+            madL[lvl][dir - 1] = m * m;
+        }
+    float chresid = 0.f, chmaxresid = 0.f, chresidtemp, chmaxresidtemp;
+    float* chan[2] = {ap, bp};
+    const float nv[2] = {noisevarab_r, noisevarab_b};
+    float resid2[2], max2[2];
+    for (int c = 0; c < 2; ++c) {
+        void* dec = artoracle_wavelet_new(chan[c], W, H, levwav, 1);
+        artoracle_wavelet_denoise_AB(Ldecomp, dec, noisevarchrom, &madL[0][0], nv[c], useNoiseCCurve, 0, scale);
+        float resid = 0.f, maxresid = 0.f;      /* Noise_residualAB */
+        const int ml = artoracle_wavelet_maxlevel(dec);
+        for (int lvl = 0; lvl < ml; ++lvl)
+            for (int dir = 1; dir < 4; ++dir) {
+                const float m = artoracle_madrgb(artoracle_wavelet_band(dec, lvl, dir), artoracle_wavelet_level_W(dec, lvl) * artoracle_wavelet_level_H(dec, lvl));
+                const float madC = m * m;
+                resid += madC;
+                if (madC > maxresid) maxresid = madC;
+            }
+        resid2[c] = resid; max2[c] = maxresid;
+        artoracle_wavelet_reconstruct(dec, chan[c], 1.f);
+        artoracle_wavelet_delete(dec);
+    }
+    chresidtemp = resid2[0]; chmaxresidtemp = max2[0];
+    chresid = resid2[1]; chmaxresid = max2[1];
+    chresid += chresidtemp; chmaxresid += chmaxresidtemp;
+    chresid = sqrtf(chresid / (6 * (levwav)));
+    if (out2) { out2[1] = chresid + 0.66f * (sqrtf(chmaxresid) - chresid); out2[0] = chresid; }
+
+    float* Lin = NULL;
+    if (denoiseLuminance) {
+        artoracle_wavelet_denoise_L(Ldecomp, noisevarlum, &madL[0][0], scale);
+        Lin = (float*)malloc(sizeof(float) * n);
+        memcpy(Lin, Lp, sizeof(float) * n);
+        artoracle_wavelet_reconstruct(Ldecomp, Lp, 1.f);
+    }
+    artoracle_wavelet_delete(Ldecomp);
+    if (denoiseLuminance) {
+        int rc = artoracle_detail_recovery(Lp, Lin, W, H, params_Ldetail, detail_thresh, tin, tout, scale);
+        if (rc) return rc;
+    }
+    const float newGain = 1.f / gain;
+    const float qhighFactor = 1.0f;
+    for (size_t i = 0; i < n; ++i) {
+        const float c_h = sqrtf(sqrf(ap[i]) + sqrf(bp[i]));
+        if (c_h > 3000.f) {
+            ap[i] *= 1.f + qhighFactor * realred / 100.f;
+            bp[i] *= 1.f + qhighFactor * realblue / 100.f;
+        }
+        /* yuv2rgb(L, b, a): Y, u = b, v = a */
+        const float Yv = Lp[i], u = bp[i], v = ap[i];
+        float Z = Yv - u;
+        float X = v + Yv;
+        float Y = (Yv - X * wpi[1][0] - Z * wpi[1][2]) / wpi[1][1];
+        X = APPLY_IGAMMA(X); Y = APPLY_IGAMMA(Y); Z = APPLY_IGAMMA(Z);
+        r[i] = newGain * X; g[i] = newGain * Y; b[i] = newGain * Z;
+    }
+    free(Lp); free(ap); free(bp); free(Lin); free(noisevarlum); free(noisevarchrom); free(gamcurve); free(igamcurve); free(ccalc);
+    return 0;
+}

@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <string.h>
 
+static inline int32_t f2i(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
 static inline float i2f(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
 
 static inline float ldexpk(float x, int q)
@@ -70,7 +71,6 @@ static inline float xexpf_vector(float d)
 }
 
 
-static inline int32_t f2i(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
 
 static inline int ilogbp1f_(float d)
 {   /* sleef.h L945-951 */
@@ -97,6 +97,68 @@ static inline float xlogf_scalar(float d)
     if (d < 0) x = NAN;
     if (d == 0) x = -INFINITY;
     return x;
+}
+
+/* vector forms used when the reference fills LUTs: sleefsseavx.h xlogf L1232-1255, xlogfNoCheck L1306-1324,
+ * xexpfNoCheck L1347-1363 */
+static inline float xlogf_vcore(float d)
+{
+    const int e = ilogbp1f_(d * 0.7071f);
+    const float m = ldexpk(d, -e);
+    float x = (-1.0f + m) / (1.0f + m);
+    const float x2 = x * x;
+    float t = 0.2371599674224853515625f;
+    t = t * x2 + 0.285279005765914916992188f;
+    t = t * x2 + 0.400005519390106201171875f;
+    t = t * x2 + 0.666666567325592041015625f;
+    t = t * x2 + 2.0f;
+    return x * t + 0.693147180559945286226764f * (float)e;
+}
+static inline float xlogf_nocheck(float d) { return xlogf_vcore(d); }
+static inline float xlogf_vector(float d)
+{
+    float x = xlogf_vcore(d);
+    if (d == INFINITY) x = INFINITY;
+    if (0.f > d) x = NAN;
+    if (d == 0.f) x = -INFINITY;
+    return x;
+}
+static inline float xexpf_nocheck(float d)
+{
+    const int q = (int)lrintf(d * R_LN2);
+    float s = (float)q * -L2U + d;
+    s = (float)q * -L2L + s;
+    float u = 0.00136324646882712841033936f;
+    u = u * s + 0.00836596917361021041870117f;
+    u = u * s + 0.0416710823774337768554688f;
+    u = u * s + 0.166665524244308471679688f;
+    u = u * s + 0.499999850988388061523438f;
+    u = 1.0f + ((s * s) * u + s);
+    return ldexpk(u, q);
+}
+
+/* xcbrtf, sleef.h L966-991 */
+static inline float xcbrtf_scalar(float d)
+{
+    float x, y, q = 1.0f;
+    int e, r;
+    e = ilogbp1f_(d);
+    d = ldexpk_scalar(d, -e);
+    r = (e + 6144) % 3;
+    q = (r == 1) ? 1.2599210498948731647672106f : q;
+    q = (r == 2) ? 1.5874010519681994747517056f : q;
+    q = ldexpk_scalar(q, (e + 6144) / 3 - 2048);
+    q = i2f(f2i(q) ^ (f2i(d) & (int32_t)0x80000000));      /* mulsignf */
+    d = fabsf(d);
+    x = -0.601564466953277587890625f;
+    x = x * d + 2.8208892345428466796875f;
+    x = x * d + -5.532182216644287109375f;
+    x = x * d + 5.898262500762939453125f;
+    x = x * d + -3.8095417022705078125f;
+    x = x * d + 2.2241256237030029296875f;
+    y = d * x * x;
+    y = (y - (2.0f / 3.0f) * y * (y * x - 1.0f)) * q;
+    return y;
 }
 
 /* pow_F(a, b) = xexpf(b * xlogf(a)), sleef.h L29; xlin2log sleef.h L1303-1307 */
