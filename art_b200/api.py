@@ -82,6 +82,8 @@ def load_library(build_if_missing=True):
         "art_hp_boxblur_dev": (i, [vp, vp, sz, vp, sz, i, i, i]),
         "art_hp_guided_filter": (i, [vp, i, i, vp, vp, vp, i, ctypes.c_float, i]),
         "art_hp_guided_filter_dev": (i, [vp, i, i, vp, sz, vp, sz, vp, sz, i, ctypes.c_float, i]),
+        "art_hp_rgb_denoise": (i, [vp, vp, vp, vp, i, i, vp, vp, vp, vp, vp, vp]),
+        "art_hp_rgb_denoise_dev": (i, [vp, vp, vp, vp, sz, i, i, vp, vp, vp, vp, vp, sz, vp]),
         "art_hp_detail_mask": (i, [vp, vp, vp, i, i, f, f, f, f, i, f]),
         "art_hp_detail_mask_dev": (i, [vp, vp, sz, vp, sz, i, i, f, f, f, f, i, f]),
         "art_hp_nlmeans": (i, [vp, vp, i, i, f, i, i, f]),
@@ -136,6 +138,33 @@ class PinnedArray:
             self.free()
         except Exception:
             pass
+
+
+class _DenoiseParamsC(ctypes.Structure):
+    _fields_ = [("luminance", ctypes.c_double), ("luminanceDetail", ctypes.c_double), ("luminanceDetailThreshold", ctypes.c_int),
+                ("chrominance", ctypes.c_double), ("chrominanceRedGreen", ctypes.c_double), ("chrominanceBlueYellow", ctypes.c_double),
+                ("gamma", ctypes.c_double), ("scale", ctypes.c_double), ("colorSpace", ctypes.c_int), ("aggressive", ctypes.c_int),
+                ("chrominanceMethod", ctypes.c_int), ("noiseCCurve", ctypes.c_void_p), ("noiseCCurveSum", ctypes.c_float)]
+
+
+class DenoiseParams:
+    """Mirror of the procparams::DenoiseParams fields RGB_denoise reads (defaults: rtengine/procparams.cc L1901-1918)."""
+
+    def __init__(self, luminance=0.0, luminanceDetail=0.0, luminanceDetailThreshold=0, chrominance=15.0, chrominanceRedGreen=0.0,
+                 chrominanceBlueYellow=0.0, gamma=1.7, scale=1.0, colorSpace=0, aggressive=0, chrominanceMethod=0, noiseCCurve=None):
+        self.__dict__.update(locals())
+        del self.__dict__["self"]
+
+    def c_struct(self):
+        c = _DenoiseParamsC(self.luminance, self.luminanceDetail, int(self.luminanceDetailThreshold), self.chrominance,
+                            self.chrominanceRedGreen, self.chrominanceBlueYellow, self.gamma, self.scale, int(self.colorSpace),
+                            int(self.aggressive), int(self.chrominanceMethod), None, 0.0)
+        if self.noiseCCurve is not None:
+            self._curve = np.ascontiguousarray(self.noiseCCurve, dtype=np.float32)
+            assert self._curve.size == 501
+            c.noiseCCurve = self._curve.ctypes.data
+            c.noiseCCurveSum = float(np.float32(self._curve.sum(dtype=np.float32)))
+        return c
 
 
 class WaveletDev:
@@ -293,6 +322,25 @@ class HotPath:
         stab = gt if src is guide else row_table(src)
         self._check(self.lib.art_hp_guided_filter(self.h, W, H, gt, stab, row_table(dst), int(r), float(epsilon), int(subsampling)))
         return dst
+
+    def rgb_denoise(self, r, g, b, params, wprof, calclum=None, want_residuals=False):
+        """denoise::RGB_denoise in place on three host (H, W) float32 planes.  params: DenoiseParams; calclum: optional
+        three half-resolution planes (needed with the chroma noise curve).  Returns (nresi, highresi) if asked."""
+        H, W = r.shape
+        wp = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(wprof, dtype=np.float64).reshape(9)])
+        res = (ctypes.c_float * 2)() if want_residuals else None
+        cl = [row_table(p) for p in calclum] if calclum is not None else [None, None, None]
+        self._check(self.lib.art_hp_rgb_denoise(self.h, row_table(r), row_table(g), row_table(b), W, H, ctypes.byref(params.c_struct()),
+                                                wp, cl[0], cl[1], cl[2], res))
+        return (float(res[0]), float(res[1])) if want_residuals else None
+
+    def rgb_denoise_dev(self, d_r, d_g, d_b, pitch, W, H, params, wprof, d_calclum=None, calclum_pitch=0, want_residuals=False):
+        wp = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(wprof, dtype=np.float64).reshape(9)])
+        res = (ctypes.c_float * 2)() if want_residuals else None
+        cl = list(d_calclum) if d_calclum is not None else [None, None, None]
+        self._check(self.lib.art_hp_rgb_denoise_dev(self.h, d_r, d_g, d_b, pitch, W, H, ctypes.byref(params.c_struct()), wp,
+                                                    cl[0], cl[1], cl[2], calclum_pitch, res))
+        return (float(res[0]), float(res[1])) if want_residuals else None
 
     def detail_mask(self, src, scaling, threshold, ceiling, factor, blur_type=2, blur=2.0):
         """denoise::detail_mask on a host (H, W) float32 array; returns the mask."""

@@ -205,7 +205,7 @@ void art_hp_destroy(art_hp_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch, &ctx->d_small, &ctx->d_work};
+    DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch, &ctx->d_small, &ctx->d_work, &ctx->d_dn};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; ++i) if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -527,6 +527,60 @@ int art_hp_gauss(art_hp_ctx* ctx, float* const* src, float* const* dst, int W, i
     if ((rc = art_gauss_dev(ctx, ds, pitch, dd, pitch, W, H, sigma))) return rc;
     Plane out = {dst, dd};
     if ((rc = transfer(ctx, ctx->stream, &out, 1, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+static int check_denoise_params(art_hp_ctx* ctx, const art_hp_denoise_params* P, const double* wprof)
+{
+    if (!P || !wprof) return ctx->fail(ART_HP_ERR_INVALID, "null parameters");
+    if (P->colorSpace != 0 || P->aggressive != 0 || P->chrominanceMethod != 0)
+        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "only colorSpace RGB, aggressive off, chrominanceMethod MANUAL are on the hot path");
+    if (!(P->scale > 0) || !(P->gamma > 0)) return ctx->fail(ART_HP_ERR_INVALID, "scale and gamma must be positive");
+    return ART_HP_OK;
+}
+
+int art_hp_rgb_denoise_dev(art_hp_ctx* ctx, float* d_r, float* d_g, float* d_b, size_t pitch, int W, int H,
+                           const art_hp_denoise_params* params, const double wprof[9],
+                           const float* d_cl_r, const float* d_cl_g, const float* d_cl_b, size_t cl_pitch, float* nresi_highresi)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_r || !d_g || !d_b) return ctx->fail(ART_HP_ERR_INVALID, "null plane");
+    if (W < 1 || H < 1 || W > 32767 || H > 32767 || pitch < (size_t)W)        // `short int imheight, imwidth`, FTblockDN.cc L1779
+        return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d (sides are short ints in the reference)", W, H);
+    int rc = check_denoise_params(ctx, params, wprof);
+    if (rc) return rc;
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_rgb_denoise_dev(ctx, d_r, d_g, d_b, pitch, W, H, params, wprof, d_cl_r, d_cl_g, d_cl_b, cl_pitch, nresi_highresi);
+}
+
+int art_hp_rgb_denoise(art_hp_ctx* ctx, float* const* r, float* const* g, float* const* b, int W, int H,
+                       const art_hp_denoise_params* params, const double wprof[9],
+                       float* const* cl_r, float* const* cl_g, float* const* cl_b, float* nresi_highresi)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!r || !g || !b) return ctx->fail(ART_HP_ERR_INVALID, "null row table");
+    if (W < 1 || H < 1 || W > 32767 || H > 32767) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    int rc = check_denoise_params(ctx, params, wprof);
+    if (rc) return rc;
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    for (int c = 0; c < 3; ++c) if ((rc = art_reserve(ctx, ctx->d_out[c], plane))) return rc;
+    float* d[3] = {(float*)ctx->d_out[0].p, (float*)ctx->d_out[1].p, (float*)ctx->d_out[2].p};
+    Plane io[3] = {{r, d[0]}, {g, d[1]}, {b, d[2]}};
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, true))) return rc;
+    const int w2 = (W + 1) / 2, h2 = (H + 1) / 2;
+    const size_t cp = round_up((size_t)w2, 32);
+    float* dc[3] = {nullptr, nullptr, nullptr};
+    if (cl_r && cl_g && cl_b) {
+        if ((rc = art_reserve(ctx, ctx->d_raw, 3 * cp * (size_t)h2 * sizeof(float)))) return rc;
+        for (int c = 0; c < 3; ++c) dc[c] = (float*)ctx->d_raw.p + (size_t)c * cp * h2;
+        Plane cl[3] = {{cl_r, dc[0]}, {cl_g, dc[1]}, {cl_b, dc[2]}};
+        if ((rc = transfer(ctx, ctx->stream, cl, 3, w2, 0, h2, cp, true))) return rc;
+    }
+    if ((rc = art_rgb_denoise_dev(ctx, d[0], d[1], d[2], pitch, W, H, params, wprof, dc[0], dc[1], dc[2], cp, nresi_highresi))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, false))) return rc;
     ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;
 }

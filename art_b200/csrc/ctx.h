@@ -35,7 +35,7 @@ struct art_hp_ctx {
     std::vector<ProfStat> stats;
     std::string err;
     // device scratch, grown on demand and kept across calls
-    DevBuf d_raw, d_out[3], d_scratch, d_small, d_work;
+    DevBuf d_raw, d_out[3], d_scratch, d_small, d_work, d_dn;
     // pinned staging (two halves for double buffering)
     void* h_stage[2] = {nullptr, nullptr};
     size_t h_stage_bytes = 0;
@@ -114,6 +114,9 @@ int art_guided_subsampling(int w, int h, int r);
 // denoise::detail_mask / denoise::NLMeans (nlmeans.cu).  scratch: 2 * (W/4) * (H/4) floats; blur_type 0 off, 1 box, 2 gauss
 int art_detail_mask_dev(art_hp_ctx* ctx, const float* src, size_t sp, float* mask, size_t mp, int W, int H,
                         float scaling, float threshold, float ceiling, float factor, int blur_type, float blur, float* scratch);
+// denoise::RGB_denoise (denoise.cu); planes r/g/b in place, calclum planes optional (needed with the chroma noise curve)
+int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_denoise_params* P,
+                        const double* wprof, const float* cl_r, const float* cl_g, const float* cl_b, size_t cp, float* nresi_highresi);
 int art_nlmeans_dev(art_hp_ctx* ctx, float* img, size_t ip, int W, int H, float normcoeff, int strength, int detail_thresh, float scale);
 int art_guided_dev(art_hp_ctx* ctx, const float* guide, size_t gp, const float* src, size_t sp, float* dst, size_t dp,
                    int W, int H, int r, float epsilon, int subsampling);

@@ -1,0 +1,537 @@
+// denoise::RGB_denoise for sm_100a: the path ART's driver takes (ipdenoise.cc L1165: kall = 0, isRAW = true).
+//
+// Replaces (reference) rtengine/FTblockDN.cc RGB_denoise L1638-2689 (colorSpace RGB, aggressive off, chrominance
+// method MANUAL, Tile_calc L442-478 = one tile), Noise_residualAB L607-635, detail_recovery L1479-1635 with
+// RGBtile_denoise L494-525 / RGBoutput_tile_row L531-558 / boxabsblur (boxblur.h L745-888), Color::gammaf2lut
+// (color.cc L1128-1170), gammaf / rgb2yuv / yuv2rgb (color.h L782-796, L1202-1205), rgbxyz + XYZ2Lab (color.cc L833,
+// L1247-1274, L1382-1399) for the chroma noise curve.  Everything stays in HBM between stages:
+//   k_dn_gamma_lut x2, [k_dn_ccalc], k_dn_split (gamma LUT + YUV + noise-variance maps), wavelet.cu / shrink.cu for
+//   the three decompositions, k_dn_blocks (one CTA per 64x64 DCT block: gather + window, DCT-II, |.| box blur,
+//   shrink, DCT-III -> block store), k_dn_gather (ordered overlap-add + normalise), k_dn_merge (chroma boost, YUV->RGB,
+//   inverse gamma).
+// Bit-exact with the reference except the two block DCTs, which the reference delegates to FFTW (fp32 codelets,
+// absent here) and which run here as fp32 FMA matrix products against cosine tables rounded from double.
+// The reference's detail_recovery overlap-adds block rows from several OpenMP threads without synchronisation; the
+// one-thread order (vblk, then hblk ascending) is the one reproduced.
+// Compiled with -fmad=false; the DCT uses explicit fmaf.
+#include <cmath>
+#include "ctx.h"
+#include "sleef_dev.cuh"
+
+struct art_hp_wavelet;
+
+namespace {
+
+constexpr int TS = 64, OFFSET = 25, BLKRAD = 1;
+
+__device__ __forceinline__ float lut_clip_below(const float* __restrict__ data, int size, float index)
+{   // LUTf(size, LUT_CLIP_BELOW)::operator[](float), LUT.h L437-459
+    int idx = (int)index;
+    if (index < 0.f || !(index == index)) return data[0];
+    else if (index > (float)(size - 2)) idx = size - 2;
+    const float diff = index - (float)idx;
+    const float p1 = data[idx];
+    const float p2 = data[idx + 1] - p1;
+    return p1 + p2 * diff;
+}
+__device__ __forceinline__ float lut_clip_both(const float* __restrict__ data, int size, float index)
+{
+    const int idx = (int)index;
+    if (index < 0.f || !(index == index)) return data[0];
+    else if (index > (float)(size - 2)) return data[size - 1];
+    const float diff = index - (float)idx;
+    const float p1 = data[idx];
+    const float p2 = data[idx + 1] - p1;
+    return p1 + p2 * diff;
+}
+
+// Color::gammaf2lut, SSE2 build (color.cc L1128-1163)
+__global__ void __launch_bounds__(256) k_dn_gamma_lut(float* lut, float gamma, float start, float slope, float divisor, float factor)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 65536) return;
+    const float gammav = 1.f / gamma;
+    const float slopev = (slope / divisor) * factor;
+    const float divisorv = sleef::xlogf_scalar(divisor);
+    const float comparev = start * divisor;
+    const int border = (int)(start * divisor);
+    const int border1 = border - (border & 3);
+    const int border2 = border1 + 4;
+    const float iv = (float)i;
+    float r;
+    if (i < border1) r = iv * slopev;
+    else if (i < border2) r = iv <= comparev ? iv * slopev : sleef::xexpf_vector((sleef::xlogf_vector(iv) - divisorv) * gammav) * factor;
+    else r = sleef::xexpf_nocheck((sleef::xlogf_nocheck(iv) - divisorv) * gammav) * factor;
+    lut[i] = r;
+}
+
+struct Gam { const float* lut; float gam, thresh, slope, top; };     // top: 65535 for the forward curve, 65536 for the inverse (L1813, L1822)
+__device__ __forceinline__ float gammaf_(float x, float gamma, float start, float slope)
+{
+    return x <= start ? x * slope : sleef::xexpf_scalar(sleef::xlogf_scalar(x) / gamma);
+}
+__device__ __forceinline__ float apply_gam(const Gam& g, float outer_gam, float v)
+{   // apply_gamma / apply_igamma, L1809-1826
+    if (outer_gam > 1.f && v > 0.f) v = v < g.top ? lut_clip_below(g.lut, 65536, v) : (gammaf_(v / 65535.f, g.gam, g.thresh, g.slope) * 65535.f);
+    return v;
+}
+
+// chroma noise-curve map on the half-resolution calclum image, L1722-1764
+struct CcArgs { const float *r, *g, *b; size_t cp; int w2, h2; float wp[9]; const float* cachef; const float* curve; float* ccalc; };
+__device__ __forceinline__ float computeXYZ2Lab(const float* cachef, float f)
+{   // color.cc L1247-1259
+    if (f != f) return f;
+    if (f < 0.f) return (float)(327.68 * (((24389.0 / 27.0) * f / (double)65535.f + 16.0) / 116.0));
+    else if (f > 65535.f) return 327.68f * sleef::xcbrtf_scalar(f / 65535.f);
+    return lut_clip_below(cachef, 65536, f);
+}
+__global__ void __launch_bounds__(256) k_dn_ccalc(CcArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.w2) return;
+    const float RL = a.r[(size_t)y * a.cp + x], GL = a.g[(size_t)y * a.cp + x], BL = a.b[(size_t)y * a.cp + x];
+    const float XL = ((a.wp[0] * RL + a.wp[1] * GL + a.wp[2] * BL));
+    const float YL = ((a.wp[3] * RL + a.wp[4] * GL + a.wp[5] * BL));
+    const float ZL = ((a.wp[6] * RL + a.wp[7] * GL + a.wp[8] * BL));
+    const float fx = computeXYZ2Lab(a.cachef, XL / 0.9642f), fy = computeXYZ2Lab(a.cachef, YL), fz = computeXYZ2Lab(a.cachef, ZL / 0.8249f);
+    const float AA = (500.0f * (fx - fy)), BB = (200.0f * (fy - fz));
+    const float cN = sqrtf(AA * AA + BB * BB);
+    const float cn100 = 1.f + 1.f * (4.f * lut_clip_both(a.curve, 501, 100.f / 60.f));
+    const float c = 1.f + 1.f * (4.f * lut_clip_both(a.curve, 501, cN / 60.f));
+    a.ccalc[(size_t)y * a.w2 + x] = cN > 100 ? c * c : cn100 * cn100;
+}
+
+// gamma + rgb2yuv + noise-variance maps, L2079-2126
+struct SplitArgs {
+    const float *r, *g, *b; size_t ip; int W, H;
+    float *L, *a, *bb;            // dense W x H
+    float *nvl, *nvc; const float* ccalc; int w2;
+    Gam gam; float outer_gam, gain, wy0, wy1, wy2, noisevarL, maxNoiseVarab; int useCC;
+};
+__global__ void __launch_bounds__(256) k_dn_split(SplitArgs s)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= s.W) return;
+    const size_t i = (size_t)y * s.ip + x, o = (size_t)y * s.W + x;
+    float X = s.gain * s.r[i], Y = s.gain * s.g[i], Z = s.gain * s.b[i];
+    X = apply_gam(s.gam, s.outer_gam, X); Y = apply_gam(s.gam, s.outer_gam, Y); Z = apply_gam(s.gam, s.outer_gam, Z);
+    const float l = X * s.wy0 + Y * s.wy1 + Z * s.wy2;
+    s.L[o] = l; s.a[o] = X - l; s.bb[o] = l - Z;
+    if (((x | y) & 1) == 0) {
+        const size_t h = (size_t)(y >> 1) * s.w2 + (x >> 1);
+        s.nvl[h] = s.noisevarL;
+        s.nvc[h] = s.useCC ? s.maxNoiseVarab * s.ccalc[h] : 1.f;
+    }
+}
+
+// detail recovery: one CTA per 64x64 block
+struct BlkArgs {
+    const float* Lin; const float* L; const float* mask; int width, height, nbw, nbh;
+    const float *tin, *dctf, *dctb;    // tilemask_in, REDFT10 matrix C[k][j], REDFT01 matrix D[k][j]
+    float* blocks;                     // [nbh][nbw][64][64]
+    float detail_hi, detail_lo, params_Ldetail; int use_mask, blur_rad;
+};
+__device__ __forceinline__ float compute_detail(float d)
+{   // L1481-1485
+    const float a = (float)(((100. - d) * (100. - d)) + 50. * (100. - d)) * TS * 0.5f;
+    return a * a;
+}
+// Out = A * B^T (TRANS_B) or A * B, all 64x64 row-major in shared memory; 256 threads, 4x4 outputs each
+template <bool TRANS_B>
+__device__ __forceinline__ void mm64(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ Out)
+{
+    const int t = threadIdx.x, r0 = (t >> 4) * 4, c0 = (t & 15) * 4;
+    float acc[4][4] = {};
+#pragma unroll 8
+    for (int k = 0; k < TS; ++k) {
+        float av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = A[(r0 + i) * (TS + 1) + k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = TRANS_B ? B[(c0 + j) * (TS + 1) + k] : B[k * (TS + 1) + c0 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Out[(r0 + i) * (TS + 1) + c0 + j] = acc[i][j];
+}
+
+constexpr int BP = TS + 1;      // padded pitch: column walks hit distinct banks
+__global__ void __launch_bounds__(256) k_dn_blocks(BlkArgs a)
+{
+    extern __shared__ float sm[];
+    float* X = sm;                 // data / coefficients
+    float* T = X + TS * BP;        // temp
+    float* C = T + TS * BP;        // forward matrix
+    float* D = C + TS * BP;        // backward matrix
+    const int hblk = blockIdx.x, vblk = blockIdx.y, t = threadIdx.x;
+    const int top = (vblk - BLKRAD) * OFFSET, left = (hblk - BLKRAD) * OFFSET;
+    for (int i = t; i < TS * TS; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        C[r * BP + c] = a.dctf[i];
+        D[r * BP + c] = a.dctb[i];
+        // padded data row (L1547-1567): mirror without repeating the edge, clamped
+        const int row = top + r;
+        int rr = row;
+        if (row < 0) rr = min(-row, a.height - 1);
+        else if (row >= a.height) rr = max(0, 2 * a.height - 2 - row);
+        int col = left + c;
+        if (col < 0) col = min(-col, a.width - 1);
+        else if (col >= a.width) col = max(0, 2 * a.width - 2 - col);
+        const size_t p = (size_t)rr * a.width + col;
+        X[r * BP + c] = a.tin[i] * (a.Lin[p] - a.L[p]);
+    }
+    __syncthreads();
+    mm64<true>(X, C, T);           // along rows: T[i][k] = sum_j C[k][j] X[i][j]
+    __syncthreads();
+    mm64<false>(C, T, X);          // along columns: X[k][x] = sum_j C[k][j] T[j][x]
+    __syncthreads();
+    // boxabsblur (boxblur.h L745-888), W = H = 64: horizontal into T, vertical into C (the forward matrix is done with)
+    const int rad = a.blur_rad;
+    if (t < TS) {
+        const float* s = X + t * BP;
+        float* o = T + t * BP;
+        int len = rad + 1;
+        float v = fabsf(s[0]);
+        for (int j = 1; j <= rad; j++) v += fabsf(s[j]);
+        v /= len;
+        o[0] = v;
+        for (int col = 1; col <= rad; col++) { v = (v * len + fabsf(s[col + rad])) / (len + 1); o[col] = v; len++; }
+        const float rlen = 1.f / (float)len;
+        for (int col = rad + 1; col < TS - rad; col++) { v = v + ((float)(fabsf(s[col + rad]) - fabsf(s[col - rad - 1]))) * rlen; o[col] = v; }
+        for (int col = TS - rad; col < TS; col++) { v = (v * len - fabsf(s[col - rad - 1])) / (len - 1); o[col] = v; len--; }
+    }
+    __syncthreads();
+    if (t < TS) {
+        const float* s = T + t;
+        float* o = C + t;
+        float len = (float)(rad + 1);
+        float v = s[0];
+        for (int i = 1; i <= rad; i++) v = v + s[i * BP];
+        v = v / len;
+        o[0] = v;
+        for (int row = 1; row <= rad; row++) { const float lp1 = len + 1.f; v = (v * len + s[(row + rad) * BP]) / lp1; o[row * BP] = v; len = lp1; }
+        const float rlen = 1.f / len;
+        for (int row = rad + 1; row < TS - rad; row++) { v = v + (s[(row + rad) * BP] - s[(row - rad - 1) * BP]) * rlen; o[row * BP] = v; }
+        for (int row = TS - rad; row < TS; row++) { const float lm1 = len - 1.f; v = (v * len - s[(row - rad - 1) * BP]) / lm1; o[row * BP] = v; len = lm1; }
+    }
+    __syncthreads();
+    // RGBtile_denoise L511-514 with the per-sample detail factor of L1571-1595
+    for (int i = t; i < TS * TS; i += 256) {
+        const int r = i >> 6, c = i & 63;
+        const int row = top + r, col = left + c;
+        float df = a.detail_lo;
+        if (row >= 0 && row < a.height && col >= 0 && col < a.width)
+            df = a.use_mask ? compute_detail(a.params_Ldetail * a.mask[(size_t)row * a.width + col]) : a.detail_hi;
+        const float nb = C[r * BP + c];
+        X[r * BP + c] = X[r * BP + c] * (1.0f - sleef::xexpf_vector(-(nb * nb) / df));
+    }
+    __syncthreads();
+    mm64<true>(X, D, T);
+    __syncthreads();
+    mm64<false>(D, T, X);
+    __syncthreads();
+    float* out = a.blocks + ((size_t)vblk * a.nbw + hblk) * (TS * TS);
+    for (int i = t; i < TS * TS; i += 256) out[i] = X[(i >> 6) * BP + (i & 63)];
+}
+
+// ordered overlap-add (RGBoutput_tile_row L531-558 + totwt L1577) and L += Ldetail / totwt (L1628-1632)
+struct GatherArgs { float* L; const float* blocks; const float *tin, *tout; int width, height, nbw, nbh, nbw_out; };
+__global__ void __launch_bounds__(256) k_dn_gather(GatherArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.width) return;
+    const float DCTnorm = 1.0f / (4 * TS * TS);
+    float det = 0.f, tw = 0.f;
+    // blocks with top <= y < top + 64, top = (vblk - 1) * 25
+    const int v0 = max(0, (y - TS + OFFSET * BLKRAD + OFFSET) / OFFSET), v1 = min(a.nbh - 1, (y + OFFSET * BLKRAD) / OFFSET);
+    const int h0 = max(0, (x - TS + OFFSET * BLKRAD + OFFSET) / OFFSET), h1 = (x + OFFSET * BLKRAD) / OFFSET;
+    for (int vb = v0; vb <= v1; ++vb) {
+        const int i = y - (vb - BLKRAD) * OFFSET;
+        if (i < 0 || i >= TS) continue;
+        for (int hb = h0; hb <= h1; ++hb) {
+            const int j = x - (hb - BLKRAD) * OFFSET;
+            if (j < 0 || j >= TS) continue;
+            const float ti = a.tin[i * TS + j], to = a.tout[i * TS + j];
+            if (hb < a.nbw) tw += ti * to;
+            if (hb < a.nbw_out) det += to * a.blocks[((size_t)vb * a.nbw + hb) * (TS * TS) + i * TS + j] * DCTnorm;
+        }
+    }
+    float* p = a.L + (size_t)y * a.width + x;
+    *p += det / tw;
+}
+
+// chroma boost, yuv2rgb, inverse gamma, L2489-2543
+struct MergeArgs {
+    const float *L, *a, *bb; float *r, *g, *b; size_t op; int W, H;
+    Gam igam; float outer_gam, newGain, w10, w11, w12, realred, realblue, qhighFactor;
+};
+__global__ void __launch_bounds__(256) k_dn_merge(MergeArgs m)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= m.W) return;
+    const size_t i = (size_t)y * m.W + x, o = (size_t)y * m.op + x;
+    float av = m.a[i], bv = m.bb[i];
+    const float c_h = sqrtf(av * av + bv * bv);
+    if (c_h > 3000.f) {
+        av *= 1.f + m.qhighFactor * m.realred / 100.f;
+        bv *= 1.f + m.qhighFactor * m.realblue / 100.f;
+    }
+    const float Yv = m.L[i];
+    float Z = Yv - bv;
+    float X = av + Yv;
+    float Y = (Yv - X * m.w10 - Z * m.w12) / m.w11;
+    X = apply_gam(m.igam, m.outer_gam, X); Y = apply_gam(m.igam, m.outer_gam, Y); Z = apply_gam(m.igam, m.outer_gam, Z);
+    m.r[o] = m.newGain * X; m.g[o] = m.newGain * Y; m.b[o] = m.newGain * Z;
+}
+
+inline float sqrf(float x) { return x * x; }
+
+}  // namespace
+
+extern "C" {
+int art_hp_wavelet_decompose_dev(art_hp_ctx* ctx, const float* d_src, size_t pitch, int W, int H, int maxlvl, int subsampling, art_hp_wavelet** out);
+int art_hp_wavelet_maxlevel(const art_hp_wavelet* w);
+int art_hp_wavelet_level_dims(const art_hp_wavelet* w, int level, int* width, int* height, int* stride);
+float* art_hp_wavelet_band_dev(const art_hp_wavelet* w, int level, int dir);
+int art_hp_wavelet_reconstruct_dev(art_hp_wavelet* w, float* d_dst, size_t pitch, float blend);
+void art_hp_wavelet_destroy(art_hp_wavelet* w);
+int art_hp_wavelet_mad_dev(art_hp_ctx* ctx, const art_hp_wavelet* w, float* d_madL);
+int art_hp_wavelet_denoise_L_dev(art_hp_ctx* ctx, art_hp_wavelet* wL, const float* d_noisevarlum, const float* d_madL, double scale);
+int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom,
+                                  const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale);
+}
+
+// tilemask_in / tilemask_out (L1833-1849) and the two DCT matrices, built on the host in double like the reference
+static void build_tables(float* tin, float* tout, float* dctf, float* dctb)
+{
+    const float epsilon = 0.001f / (TS * TS);
+    const int border = std::max(2, TS / 16);
+    const double RT_PI = 3.14159265358979323846;
+    for (int i = 0; i < TS; ++i) {
+        const float i1 = (float)std::abs((i > TS / 2 ? i - TS + 1 : i));
+        const float vmask = (i1 < border ? (float)(std::sin((RT_PI * i1) / (2 * border)) * std::sin((RT_PI * i1) / (2 * border))) : 1.0f);
+        const float vmask2 = (i1 < 2 * border ? (float)(std::sin((RT_PI * i1) / (2 * border)) * std::sin((RT_PI * i1) / (2 * border))) : 1.0f);
+        for (int j = 0; j < TS; ++j) {
+            const float j1 = (float)std::abs((j > TS / 2 ? j - TS + 1 : j));
+            const double sj = std::sin((RT_PI * j1) / (2 * border));
+            tin[i * TS + j] = (float)((vmask * (j1 < border ? sj * sj : (double)1.0f)) + epsilon);
+            tout[i * TS + j] = (float)((vmask2 * (j1 < 2 * border ? sj * sj : (double)1.0f)) + epsilon);
+        }
+    }
+    for (int k = 0; k < TS; ++k)
+        for (int j = 0; j < TS; ++j) {
+            dctf[k * TS + j] = (float)(2.0 * std::cos(RT_PI * (j + 0.5) * k / TS));                       // REDFT10
+            dctb[k * TS + j] = j == 0 ? 1.0f : (float)(2.0 * std::cos(RT_PI * j * (k + 0.5) / TS));       // REDFT01
+        }
+}
+
+static float host_compute_detail(float d)
+{
+    const float a = static_cast<float>(((100. - d) * (100. - d)) + 50. * (100. - d)) * TS * 0.5f;
+    return a * a;
+}
+
+// noise_residual: MAD^2 of the 3 * nlev bands into d_out[0 .. 3 nlev)
+static int residual_mads(art_hp_ctx* ctx, const art_hp_wavelet* w, float* d_out) { return art_hp_wavelet_mad_dev(ctx, w, d_out); }
+
+int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_denoise_params* P,
+                        const double* wprof, const float* cl_r, const float* cl_g, const float* cl_b, size_t cp, float* nresi_highresi)
+{
+    cudaStream_t st = ctx->stream;
+    const double scale = P->scale;
+    const bool have_curve = P->noiseCCurve != nullptr;
+    if (P->luminance == 0 && P->chrominance == 0 && !have_curve) return ART_HP_OK;          // L1654-1666
+    const bool useCC = have_curve && P->noiseCCurveSum > 5.f;
+    if (useCC && !(cl_r && cl_g && cl_b)) return ctx->fail(ART_HP_ERR_INVALID, "the chroma noise curve needs the half-resolution calclum planes");
+    const float noiseluma = static_cast<float>(P->luminance);
+    const float noisevarL = static_cast<float>(((noiseluma / 125.0) * (1.0 + noiseluma / 25.0)) * ((noiseluma / 125.0) * (1.0 + noiseluma / 25.0)));
+    const bool denoiseLuminance = (noisevarL > 0.00001f);
+    float wp[9];
+    for (int i = 0; i < 9; ++i) wp[i] = static_cast<float>(wprof[i]);
+    if (!(P->luminance != 0 || P->chrominance != 0)) return ART_HP_OK;                      // curve set but both sliders 0: nothing visible happens
+
+    const size_t n = (size_t)W * H;
+    const int w2 = (W + 1) / 2, h2 = (H + 1) / 2;
+    const size_t nh = (size_t)w2 * h2;
+    const int nbw = (int)std::ceil(((float)W) / OFFSET) + 2 * BLKRAD, nbh = (int)std::ceil(((float)H) / OFFSET) + 2 * BLKRAD;
+    const size_t nblk = denoiseLuminance ? (size_t)nbw * nbh * TS * TS : 0;
+    const bool use_mask = denoiseLuminance && P->luminanceDetailThreshold > 0;
+    // work buffer: L, a, b, Lin (n each), [mask n], nvl, nvc, ccalc (nh each), LUTs, tables, small
+    const size_t small_floats = 2 * 65536 + 65536 + 512 + 4 * TS * TS + 64 + 64;
+    size_t floats = round_up(n, 64) * (4 + (use_mask ? 1 : 0)) + round_up(nh, 64) * 3 + small_floats + nblk + 2 * round_up((size_t)(W / 4 + 1) * (H / 4 + 1), 64);
+    int rc = art_reserve(ctx, ctx->d_dn, floats * sizeof(float));
+    if (rc) return rc;
+    float* p = (float*)ctx->d_dn.p;
+    auto take = [&p](size_t k) { float* q = p; p += round_up(k, 64); return q; };
+    float *Lp = take(n), *ap = take(n), *bp = take(n), *Lin = take(n), *mask = use_mask ? take(n) : nullptr;
+    float *nvl = take(nh), *nvc = take(nh), *ccalc = take(nh);
+    float *gamcurve = take(65536), *igamcurve = take(65536), *cachef = take(65536), *curve = take(512);
+    float *tin = take(TS * TS), *tout = take(TS * TS), *dctf = take(TS * TS), *dctb = take(TS * TS);
+    float *madL = take(64), *resid = take(64);
+    float* quarter = take(2 * (size_t)(W / 4 + 1) * (H / 4 + 1));
+    float* blocks = take(nblk);
+
+    // gamma curves, L1779-1806
+    const float gam = static_cast<float>(P->gamma);
+    const float gamthresh = 0.001f;
+    const float gamslope = std::exp(std::log(static_cast<double>(gamthresh)) / gam) / gamthresh;
+    const float igam = 1.f / gam;
+    const float igamthresh = gamthresh * gamslope;
+    const float igamslope = 1.f / gamslope;
+    art_prof_begin(ctx, "k_dn_tables");
+    k_dn_gamma_lut<<<256, 256, 0, st>>>(gamcurve, gam, gamthresh, gamslope, 65535.f, 65535.f);
+    k_dn_gamma_lut<<<256, 256, 0, st>>>(igamcurve, igam, igamthresh, igamslope, 65535.f, 65535.f);
+    art_prof_end(ctx);
+    ctx->launches += 2;
+    const float gain = std::pow(2.0f, float(0.0));
+    const float params_Ldetail = std::min(float(P->luminanceDetail), 99.9f);
+
+    std::vector<float> host(4 * TS * TS);
+    if (denoiseLuminance) {
+        build_tables(host.data(), host.data() + TS * TS, host.data() + 2 * TS * TS, host.data() + 3 * TS * TS);
+        ART_CUDA(ctx, cudaMemcpyAsync(tin, host.data(), sizeof(float) * TS * TS, cudaMemcpyHostToDevice, st));
+        ART_CUDA(ctx, cudaMemcpyAsync(tout, host.data() + TS * TS, sizeof(float) * TS * TS, cudaMemcpyHostToDevice, st));
+        ART_CUDA(ctx, cudaMemcpyAsync(dctf, host.data() + 2 * TS * TS, sizeof(float) * TS * TS, cudaMemcpyHostToDevice, st));
+        ART_CUDA(ctx, cudaMemcpyAsync(dctb, host.data() + 3 * TS * TS, sizeof(float) * TS * TS, cudaMemcpyHostToDevice, st));
+    }
+    std::vector<float> hcache;
+    if (useCC) {       // L1706-1770
+        hcache.resize(65536);
+        const double eps = 216.0 / 24389.0, kappa = 24389.0 / 27.0, MAXVALF = 65535.f;
+        const int epsmaxint = (int)(MAXVALF * eps);
+        int i = 0;
+        for (; i <= epsmaxint; i++) hcache[i] = (float)(327.68 * ((kappa * i / MAXVALF + 16.0) / 116.0));      // color.cc L205-216
+        for (; i < 65536; i++) hcache[i] = (float)(327.68 * std::cbrt((double)i / MAXVALF));
+        ART_CUDA(ctx, cudaMemcpyAsync(cachef, hcache.data(), sizeof(float) * 65536, cudaMemcpyHostToDevice, st));
+        ART_CUDA(ctx, cudaMemcpyAsync(curve, P->noiseCCurve, sizeof(float) * 501, cudaMemcpyHostToDevice, st));
+        CcArgs c{};
+        c.r = cl_r; c.g = cl_g; c.b = cl_b; c.cp = cp; c.w2 = w2; c.h2 = h2; c.cachef = cachef; c.curve = curve; c.ccalc = ccalc;
+        for (int k = 0; k < 9; ++k) c.wp[k] = wp[k];
+        art_prof_begin(ctx, "k_dn_ccalc");
+        k_dn_ccalc<<<dim3((w2 + 255) / 256, h2), 256, 0, st>>>(c);
+        art_prof_end(ctx);
+        ctx->launches += 1;
+    }
+    // the host staging vectors must outlive the copies
+    ART_CUDA(ctx, cudaStreamSynchronize(st));
+
+    // chroma sliders, L2026-2068
+    float interm_med = static_cast<float>(P->chrominance) / 10.0;
+    float intermred = P->chrominanceRedGreen > 0. ? (P->chrominanceRedGreen / 10.) : static_cast<float>(P->chrominanceRedGreen) / 7.0;
+    float intermblue = P->chrominanceBlueYellow > 0. ? (P->chrominanceBlueYellow / 10.) : static_cast<float>(P->chrominanceBlueYellow) / 7.0;
+    float realred = interm_med + intermred;
+    if (realred <= 0.f) realred = 0.001f;
+    float realblue = interm_med + intermblue;
+    if (realblue <= 0.f) realblue = 0.001f;
+    const float noisevarab_r = sqrf(realred), noisevarab_b = sqrf(realblue);
+    const float maxNoiseVarab = std::max(noisevarab_b, noisevarab_r);
+
+    SplitArgs s{};
+    s.r = r; s.g = g; s.b = b; s.ip = ip; s.W = W; s.H = H; s.L = Lp; s.a = ap; s.bb = bp; s.nvl = nvl; s.nvc = nvc; s.ccalc = ccalc; s.w2 = w2;
+    s.gam = Gam{gamcurve, gam, gamthresh, gamslope, 65535.f}; s.outer_gam = gam; s.gain = gain;
+    s.wy0 = wp[3]; s.wy1 = wp[4]; s.wy2 = wp[5]; s.noisevarL = noisevarL; s.maxNoiseVarab = maxNoiseVarab; s.useCC = useCC;
+    const dim3 gfull((W + 255) / 256, H);
+    art_prof_begin(ctx, "k_dn_split");
+    k_dn_split<<<gfull, 256, 0, st>>>(s);
+    art_prof_end(ctx);
+    ctx->launches += 1;
+    ART_CUDA(ctx, cudaGetLastError());
+
+    // wavelet levels, L2246-2293
+    int levwav = 5;
+    const float maxreal = std::max(realred, realblue);
+    if (maxreal < 8.f) levwav = 5; else if (maxreal < 10.f) levwav = 6; else if (maxreal < 15.f) levwav = 7; else levwav = 8;
+    levwav = std::max(5, int(levwav - std::ceil(std::log(scale))));
+    const int minsizetile = std::min(W, H);
+    int maxlev2 = 8;
+    if (minsizetile < 256) maxlev2 = 7;
+    if (minsizetile < 128) maxlev2 = 6;
+    if (minsizetile < 64) maxlev2 = 5;
+    if (minsizetile < 32) maxlev2 = 4;
+    if (minsizetile < 16) maxlev2 = 3;
+    levwav = std::min(maxlev2, levwav);
+
+    art_hp_wavelet* Ldec = nullptr;
+    if ((rc = art_hp_wavelet_decompose_dev(ctx, Lp, W, W, H, levwav, 1, &Ldec))) return rc;
+    ART_CUDA(ctx, cudaMemsetAsync(madL, 0, 64 * sizeof(float), st));
+    if ((rc = art_hp_wavelet_mad_dev(ctx, Ldec, madL))) { art_hp_wavelet_destroy(Ldec); return rc; }
+    float* chan[2] = {ap, bp};
+    const float nv[2] = {noisevarab_r, noisevarab_b};
+    for (int c = 0; c < 2; ++c) {
+        art_hp_wavelet* dec = nullptr;
+        if ((rc = art_hp_wavelet_decompose_dev(ctx, chan[c], W, W, H, levwav, 1, &dec))) { art_hp_wavelet_destroy(Ldec); return rc; }
+        rc = art_hp_wavelet_denoise_AB_dev(ctx, Ldec, dec, nvc, madL, nv[c], useCC, 0, scale);
+        if (!rc && nresi_highresi) rc = residual_mads(ctx, dec, resid + 24 * c);
+        if (!rc) rc = art_hp_wavelet_reconstruct_dev(dec, chan[c], W, 1.f);
+        art_hp_wavelet_destroy(dec);
+        if (rc) { art_hp_wavelet_destroy(Ldec); return rc; }
+    }
+    const int maxlvl = art_hp_wavelet_maxlevel(Ldec);
+    if (denoiseLuminance) {
+        rc = art_hp_wavelet_denoise_L_dev(ctx, Ldec, nvl, madL, scale);
+        if (!rc) {
+            if (cudaMemcpyAsync(Lin, Lp, n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = ctx->fail(ART_HP_ERR_CUDA, "Lin copy failed");
+        }
+        if (!rc) rc = art_hp_wavelet_reconstruct_dev(Ldec, Lp, W, 1.f);
+    }
+    art_hp_wavelet_destroy(Ldec);
+    if (rc) return rc;
+
+    if (denoiseLuminance) {
+        if (use_mask) {
+            const float amount = std::max(0.f, std::min(float(P->luminanceDetailThreshold) / 100.f, 1.f));
+            if ((rc = art_detail_mask_dev(ctx, Lp, W, mask, W, W, H, 65535.f, 25.f, 10000.f, amount, 2, 25.f / scale, quarter))) return rc;
+        }
+        BlkArgs a{};
+        a.Lin = Lin; a.L = Lp; a.mask = mask; a.width = W; a.height = H; a.nbw = nbw; a.nbh = nbh; a.tin = tin; a.dctf = dctf; a.dctb = dctb; a.blocks = blocks;
+        a.detail_hi = host_compute_detail(params_Ldetail); a.detail_lo = host_compute_detail(0.f); a.params_Ldetail = params_Ldetail;
+        a.use_mask = use_mask; a.blur_rad = std::max(1, int(3 / scale));
+        const size_t smem = 4 * (size_t)TS * BP * sizeof(float);
+        static bool attr = false;
+        if (!attr) { ART_CUDA(ctx, cudaFuncSetAttribute(k_dn_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        art_prof_begin(ctx, "k_dn_blocks");
+        k_dn_blocks<<<dim3(nbw, nbh), 256, smem, st>>>(a);
+        art_prof_end(ctx);
+        GatherArgs ga{};
+        ga.L = Lp; ga.blocks = blocks; ga.tin = tin; ga.tout = tout; ga.width = W; ga.height = H; ga.nbw = nbw; ga.nbh = nbh;
+        ga.nbw_out = (int)std::ceil(((float)W) / OFFSET);
+        art_prof_begin(ctx, "k_dn_gather");
+        k_dn_gather<<<gfull, 256, 0, st>>>(ga);
+        art_prof_end(ctx);
+        ctx->launches += 2;
+        ART_CUDA(ctx, cudaGetLastError());
+    }
+
+    MergeArgs m{};
+    m.L = Lp; m.a = ap; m.bb = bp; m.r = r; m.g = g; m.b = b; m.op = ip; m.W = W; m.H = H;
+    m.igam = Gam{igamcurve, igam, igamthresh, igamslope, 65536.f}; m.outer_gam = gam; m.newGain = 1.f / gain;
+    m.w10 = wp[3]; m.w11 = wp[4]; m.w12 = wp[5]; m.realred = realred; m.realblue = realblue; m.qhighFactor = 1.0f;
+    art_prof_begin(ctx, "k_dn_merge");
+    k_dn_merge<<<gfull, 256, 0, st>>>(m);
+    art_prof_end(ctx);
+    ctx->launches += 1;
+    ART_CUDA(ctx, cudaGetLastError());
+
+    if (nresi_highresi) {       // Noise_residualAB + L2398-2404
+        float h[48];
+        ART_CUDA(ctx, cudaMemcpyAsync(h, resid, sizeof h, cudaMemcpyDeviceToHost, st));
+        ART_CUDA(ctx, cudaStreamSynchronize(st));
+        float res[2], mx[2];
+        for (int c = 0; c < 2; ++c) {
+            float rs = 0.f, mr = 0.f;
+            for (int lvl = 0; lvl < maxlvl; ++lvl)
+                for (int d = 0; d < 3; ++d) { const float madC = h[24 * c + 3 * lvl + d]; rs += madC; if (madC > mr) mr = madC; }
+            res[c] = rs; mx[c] = mr;
+        }
+        float chresid = res[1] + res[0], chmaxresid = mx[1] + mx[0];
+        chresid = std::sqrt(chresid / (6 * (levwav)));
+        nresi_highresi[1] = chresid + 0.66f * (std::sqrt(chmaxresid) - chresid);
+        nresi_highresi[0] = chresid;
+    }
+    return ART_HP_OK;
+}

@@ -86,6 +86,60 @@ __device__ __forceinline__ float xlogf_scalar(float d)
     if (d == 0) x = __int_as_float(0xff800000);
     return x;
 }
+// vector forms the reference uses when it fills LUTs: sleefsseavx.h xlogf L1232-1255, xlogfNoCheck L1306-1324,
+// xexpfNoCheck L1347-1363
+__device__ __forceinline__ float xlogf_nocheck(float d)
+{
+    const int e = ilogbp1f(d * 0.7071f);
+    const float m = ldexpk4(d, -e);
+    float x = (-1.0f + m) / (1.0f + m);
+    const float x2 = x * x;
+    float t = 0.2371599674224853515625f;
+    t = t * x2 + 0.285279005765914916992188f;
+    t = t * x2 + 0.400005519390106201171875f;
+    t = t * x2 + 0.666666567325592041015625f;
+    t = t * x2 + 2.0f;
+    return x * t + 0.693147180559945286226764f * (float)e;
+}
+__device__ __forceinline__ float xlogf_vector(float d)
+{
+    float x = xlogf_nocheck(d);
+    if (d == __int_as_float(0x7f800000)) x = __int_as_float(0x7f800000);
+    if (0.f > d) x = __int_as_float(0x7fc00000);
+    if (d == 0.f) x = __int_as_float(0xff800000);
+    return x;
+}
+__device__ __forceinline__ float xexpf_nocheck(float d)
+{
+    const int q = __float2int_rn(d * R_LN2);
+    float s = (float)q * -L2U + d;
+    s = (float)q * -L2L + s;
+    float u = exp_poly(s);
+    u = 1.0f + ((s * s) * u + s);
+    return ldexpk4(u, q);
+}
+__device__ __forceinline__ float xcbrtf_scalar(float d)
+{   // sleef.h L966-991
+    float x, y, q = 1.0f;
+    int e = ilogbp1f(d);
+    d = ldexpk2(d, -e);
+    const int r = (e + 6144) % 3;
+    q = (r == 1) ? 1.2599210498948731647672106f : q;
+    q = (r == 2) ? 1.5874010519681994747517056f : q;
+    q = ldexpk2(q, (e + 6144) / 3 - 2048);
+    q = __int_as_float(__float_as_int(q) ^ (__float_as_int(d) & 0x80000000));
+    d = fabsf(d);
+    x = -0.601564466953277587890625f;
+    x = x * d + 2.8208892345428466796875f;
+    x = x * d + -5.532182216644287109375f;
+    x = x * d + 5.898262500762939453125f;
+    x = x * d + -3.8095417022705078125f;
+    x = x * d + 2.2241256237030029296875f;
+    y = d * x * x;
+    y = (y - (2.0f / 3.0f) * y * (y * x - 1.0f)) * q;
+    return y;
+}
+
 // pow_F(a, b) = xexpf(b * xlogf(a)), sleef.h L29; xlin2log sleef.h L1303-1307
 __device__ __forceinline__ float pow_F_scalar(float a, float b) { return xexpf_scalar(b * xlogf_scalar(a)); }
 __device__ __forceinline__ float xlin2log_scalar(float x, float base) { return xlogf_scalar(x * (base - 1.f) + 1.f) / xlogf_scalar(base); }

@@ -197,6 +197,39 @@ int art_hp_wavelet_denoise_L_dev(art_hp_ctx* ctx, art_hp_wavelet* wL, const floa
 int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom,
                                   const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale);
 
+/* ---- RGB_denoise ------------------------------------------------------------- */
+/*
+ * art_hp_rgb_denoise   rtengine::denoise::RGB_denoise(im, kall = 0, src = dst = img, calclum, ..., isRAW = true, dnparams,
+ *                      expcomp = 0, noiseLCurve (unset), noiseCCurve, nresi, highresi) (rtengine/FTblockDN.cc L1638-2689)
+ *                      as ImProcFunctions::denoise calls it (rtengine/ipdenoise.cc L1165), in place on three planes.
+ * Parameters mirror procparams::DenoiseParams (rtengine/procparams.h) for the fields RGB_denoise reads.  Supported:
+ * colorSpace RGB (0), aggressive off (0), chrominanceMethod MANUAL (0); anything else returns ART_HP_ERR_UNSUPPORTED.
+ * `scale` is ImProcData::scale.  noiseCCurve: the 501-entry LUT NoiseCurve::Set builds (rtengine/ipdenoise.cc L684-705) and
+ * its sum, host pointers, or NULL for "curve not set"; when given, the half-resolution calclum image of
+ * ipdenoise.cc L1119-1131 (3 planes of ((H+1)/2) x ((W+1)/2)) must be supplied too.
+ * wprof: ICCStore::workingSpaceMatrix(params->icm.workingProfile), row-major 3x3 doubles.
+ * nresi_highresi: optional host float[2] receiving nresi, highresi (forces a stream synchronisation).
+ * The block DCT of detail_recovery (L1479-1635) is FFTW's in the reference; here it is an fp32 matrix product on the
+ * GPU -- the one stage whose results are within tolerance instead of bit-identical.
+ */
+typedef struct art_hp_denoise_params {
+    double luminance, luminanceDetail;
+    int luminanceDetailThreshold;
+    double chrominance, chrominanceRedGreen, chrominanceBlueYellow;
+    double gamma;
+    double scale;
+    int colorSpace, aggressive, chrominanceMethod;
+    const float* noiseCCurve;
+    float noiseCCurveSum;
+} art_hp_denoise_params;
+int art_hp_rgb_denoise(art_hp_ctx* ctx, float* const* r, float* const* g, float* const* b, int W, int H,
+                       const art_hp_denoise_params* params, const double wprof[9],
+                       float* const* calclum_r, float* const* calclum_g, float* const* calclum_b, float* nresi_highresi);
+int art_hp_rgb_denoise_dev(art_hp_ctx* ctx, float* d_r, float* d_g, float* d_b, size_t pitch, int W, int H,
+                           const art_hp_denoise_params* params, const double wprof[9],
+                           const float* d_calclum_r, const float* d_calclum_g, const float* d_calclum_b, size_t calclum_pitch,
+                           float* nresi_highresi);
+
 /* ---- detail mask / NL-means --------------------------------------------------- */
 /*
  * art_hp_detail_mask   rtengine::denoise::detail_mask(src, mask, scaling, threshold, ceiling, factor, blur_type, blur, mt)
