@@ -685,6 +685,119 @@ int artref_rgb_denoise(float* r, float* g, float* b, int W, int H, const double*
 """
 
 
+SHIM_FATTAL_TU = r"""
+// Shim TU hosting the reference's tmo_fattal02.cc from `namespace rtengine {` (after its #include block) up to, not
+// including, ImProcFunctions::dynamicRangeCompression, (Median_Denoise comes from shim_denoise.cc = FTblockDN.cc whole).  Stand-ins written
+// here (not reference code): Imagefloat, ProcParams/FattalToneMappingParams, ICCStore, Settings, MyMutex and <fftw3.h> =
+// oracle/dct_standin.h (REDFT00 restated in double: parity unpinned at that boundary, fftw3f is absent here).
+#include <assert.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <algorithm>
+#include <array>
+#include <iostream>
+#include <string>
+#include <vector>
+#include <omp.h>
+#include "array2D.h"
+#include "rt_math.h"
+#include "opthelper.h"
+#include "sleef.h"
+#include "median.h"
+#include "rescale.h"
+#include "dct_standin.h"
+
+namespace rtengine {
+typedef const double (*TMatrix)[3];
+struct Settings { bool verbose; };                 // same stand-ins as shim_denoise.cc, which defines the two globals
+extern const Settings* settings;
+class MyMutex { public: class MyLock { public: explicit MyLock(MyMutex&) {} }; };
+extern MyMutex* fftwMutex;
+
+class Imagefloat {
+public:
+    int W, H; float *R, *G, *B;
+    Imagefloat(int w, int h, float* r_, float* g_, float* b_) : W(w), H(h), R(r_), G(g_), B(b_) {}
+    int getWidth() const { return W; }
+    int getHeight() const { return H; }
+    float& r(int i, int j) { return R[(size_t)i * W + j]; }
+    float& g(int i, int j) { return G[(size_t)i * W + j]; }
+    float& b(int i, int j) { return B[(size_t)i * W + j]; }
+};
+namespace procparams {
+struct FattalToneMappingParams { bool enabled; int threshold; int amount; bool satcontrol; };
+struct ICMParams { std::string workingProfile; };
+struct ProcParams { FattalToneMappingParams fattal; ICMParams icm; };
+}
+using procparams::ProcParams;
+class ImProcFunctions;
+static double artref_fattal_ws[3][3];
+class ICCStore {
+public:
+    static ICCStore* getInstance() { static ICCStore s; return &s; }
+    TMatrix workingSpaceMatrix(const std::string&) const { return artref_fattal_ws; }
+};
+class Color {
+public:
+#include "fattal_color_members.inc"
+};
+namespace denoise {
+enum class Median { TYPE_3X3_SOFT, TYPE_3X3_STRONG, TYPE_5X5_SOFT, TYPE_5X5_STRONG, TYPE_7X7, TYPE_9X9 };
+}
+namespace denoise {   // defined in shim_denoise.cc: the reference's FTblockDN.cc, whole
+void Median_Denoise(float **src, float **dst, float upperBound, const int width, const int height, const Median medianType, const int iterations, const int numThreads, float **buffer);
+void Median_Denoise(float **src, float **dst, const int width, const int height, const Median medianType, const int iterations, const int numThreads, float **buffer);
+}
+}  // namespace rtengine
+
+#include "fattal_body.inc"
+// (fattal_body.inc leaves `namespace rtengine {` open)
+
+extern "C" {
+int artref_fattal(float* r, float* g, float* b, int W, int H, int threshold, int amount, int satcontrol, const double* ws)
+{
+    memcpy(artref_fattal_ws, ws, sizeof artref_fattal_ws);
+    ProcParams pp; pp.fattal.enabled = true; pp.fattal.threshold = threshold; pp.fattal.amount = amount; pp.fattal.satcontrol = satcontrol != 0;
+    pp.icm.workingProfile = "ProPhoto";
+    Imagefloat img(W, H, r, g, b);
+    ToneMapFattal02(&img, nullptr, &pp, true);
+    return 0;
+}
+// the inner operator alone: Y (w x h, contiguous) -> L, the call at tmo_fattal02.cc L1126
+int artref_tmo_fattal02(int w, int h, float* Y, float alfa, float beta, float noise, int detail_level)
+{
+    Array2Df L(w, h);
+    memcpy(L.data(), Y, sizeof(float) * (size_t)w * h);
+    tmo_fattal02(w, h, L, L, alfa, beta, noise, detail_level, true);
+    memcpy(Y, L.data(), sizeof(float) * (size_t)w * h);
+    return 0;
+}
+int artref_median_denoise(float* src, float* dst, float upperBound, int useUpper, int W, int H, int type, int iterations)
+{
+    float** s = new float*[H]; float** d = new float*[H];
+    for (int i = 0; i < H; ++i) { s[i] = src + (size_t)i * W; d[i] = dst + (size_t)i * W; }
+    if (useUpper) denoise::Median_Denoise(s, src == dst ? s : d, upperBound, W, H, (denoise::Median)type, iterations, omp_get_num_procs(), nullptr);
+    else denoise::Median_Denoise(s, src == dst ? s : d, W, H, (denoise::Median)type, iterations, omp_get_num_procs(), nullptr);
+    delete[] s; delete[] d;
+    return 0;
+}
+int artref_find_fast_dim(int dim) { return find_fast_dim(dim); }
+void artref_redft00_2d(int n0, int n1, const float* in, float* out) { artdct_redft00_2d(n0, n1, in, out); }
+void artref_redft00_1d_naive(int n, const double* x, double* y) { artdct_redft00_1d_naive(n, x, y); }
+void artref_redft00_1d(int n, const double* x, double* y)
+{
+    artdct_cplx* tw = artdct_twiddles(2 * (n - 1));
+    artdct_cplx* a = (artdct_cplx*)malloc(sizeof(artdct_cplx) * 2 * n); artdct_cplx* b = (artdct_cplx*)malloc(sizeof(artdct_cplx) * 2 * n);
+    artdct_redft00_1d(n, x, 1, y, 1, tw, a, b);
+    free(tw); free(a); free(b);
+}
+}
+}  // namespace rtengine
+"""
+
+
 def extract(det):
     sub = os.path.join(SRC, "det" if det else "stock")
     os.makedirs(sub, exist_ok=True)
@@ -760,6 +873,15 @@ def extract(det):
     open(os.path.join(sub, "color_cc_members.inc"), "w").write("\n".join(ccm))
     open(os.path.join(sub, "dct_standin.h"), "w").write(open(os.path.join(HERE, "dct_standin.h")).read())
     open(os.path.join(sub, "shim_denoise.cc"), "w").write(SHIM_DENOISE_TU)
+    fat = open(os.path.join(RT, "tmo_fattal02.cc"), encoding="utf-8", errors="replace").read()
+    m0 = re.search(r"^namespace rtengine\s*\{", fat, flags=re.M)
+    m1 = re.search(r"^void ImProcFunctions::dynamicRangeCompression", fat, flags=re.M)
+    body = fat[m0.start():m1.start()]
+    # ToneMapFattal02 sits in the anonymous namespace; the wrapper appended by the shim is in the same TU so it can call it
+    open(os.path.join(sub, "fattal_body.inc"), "w").write(body)
+    open(os.path.join(sub, "fattal_color_members.inc"), "w").write(
+        "template <class T>\n" + cut_function(ch, r"static float rgbLuminance\(float r, float g, float b, const T workingspace\[3\]\[3\]\)"))
+    open(os.path.join(sub, "shim_fattal.cc"), "w").write(SHIM_FATTAL_TU)
     return sub
 
 
@@ -767,7 +889,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)
