@@ -94,6 +94,12 @@ def load_library(build_if_missing=True):
         "art_hp_scale_colors_bayer_dev": (i, [vp, i, i, u, vp, sz, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
         "art_hp_scale_convert": (i, [vp, i, i, vp, vp, vp, ctypes.POINTER(ctypes.c_float), i, ctypes.POINTER(d)]),
         "art_hp_scale_convert_dev": (i, [vp, i, i, vp, vp, vp, sz, ctypes.POINTER(ctypes.c_float), i, ctypes.POINTER(d)]),
+        "art_hp_fattal": (i, [vp, i, i, vp, vp, vp, i, i, i, ctypes.POINTER(d)]),
+        "art_hp_fattal_dev": (i, [vp, i, i, vp, vp, vp, sz, i, i, i, ctypes.POINTER(d)]),
+        "art_hp_fattal_fast_dim": (i, [i]),
+        "art_hp_median_denoise": (i, [vp, vp, vp, i, i, i, i, f]),
+        "art_hp_median_denoise_dev": (i, [vp, vp, sz, vp, sz, i, i, i, i, f]),
+        "art_hp_redft00_2d": (i, [vp, i, i, vp, vp]),
         "art_hp_band_align": (i, [i, ctypes.POINTER(i), ctypes.POINTER(i)]),
         "art_hp_band_halo": (i, [i]),
         "art_hp_demosaic_bayer_rows_dev": (i, [vp, i, i, i, u, vp, sz, vp, vp, vp, sz, d, i, i, i]),
@@ -362,6 +368,32 @@ class HotPath:
 
     def nlmeans_dev(self, d_img, pitch, W, H, normcoeff, strength, detail_thresh, scale=1.0):
         self._check(self.lib.art_hp_nlmeans_dev(self.h, d_img, pitch, W, H, normcoeff, int(strength), int(detail_thresh), scale))
+
+    def fattal(self, r, g, b, threshold, amount, satcontrol, ws):
+        """ImProcFunctions::dynamicRangeCompression (ToneMapFattal02), in place on three host (H, W) float32 planes."""
+        H, W = r.shape
+        wsc = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(ws, dtype=np.float64).reshape(9)])
+        self._check(self.lib.art_hp_fattal(self.h, W, H, row_table(r), row_table(g), row_table(b), int(threshold), int(amount),
+                                           int(bool(satcontrol)), wsc))
+
+    def fattal_dev(self, W, H, d_r, d_g, d_b, pitch, threshold, amount, satcontrol, ws):
+        wsc = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(ws, dtype=np.float64).reshape(9)])
+        self._check(self.lib.art_hp_fattal_dev(self.h, W, H, d_r, d_g, d_b, pitch, int(threshold), int(amount), int(bool(satcontrol)), wsc))
+
+    def median_denoise(self, src, median_type, upper_bound=None, dst=None):
+        """denoise::Median_Denoise, one iteration; upper_bound=None selects the overload without a bound."""
+        H, W = src.shape
+        if dst is None:
+            dst = np.empty_like(src)
+        self._check(self.lib.art_hp_median_denoise(self.h, row_table(src), row_table(dst), W, H, int(median_type),
+                                                   int(upper_bound is not None), float(upper_bound or 0.0)))
+        return dst
+
+    def redft00_2d(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        out = np.empty_like(a)
+        self._check(self.lib.art_hp_redft00_2d(self.h, a.shape[0], a.shape[1], a.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p)))
+        return out
 
     def gauss(self, src, sigma, dst=None, gausstype=0):
         """Host entry.  dst=None -> out of place into a new array; dst is src -> the in-place variants."""

@@ -205,7 +205,7 @@ void art_hp_destroy(art_hp_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch, &ctx->d_small, &ctx->d_work, &ctx->d_dn};
+    DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch, &ctx->d_small, &ctx->d_work, &ctx->d_dn, &ctx->d_fattal};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; ++i) if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -711,6 +711,86 @@ int art_hp_scale_convert(art_hp_ctx* ctx, int W, int H, float* const* red, float
     if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, true))) return rc;
     if ((rc = art_scale_convert_dev(ctx, W, H, io[0].dev, io[1].dev, io[2].dev, pitch, mul, doClip, mat))) return rc;
     if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+int art_hp_fattal_fast_dim(int dim) { return dim > 0 ? art_fattal_fast_dim(dim) : 0; }
+
+int art_hp_fattal_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
+                      int threshold, int amount, int satcontrol, const double ws[9])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_r || !d_g || !d_b || !ws) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 3 || H < 3 || pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d pitch %zu", W, H, pitch);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_fattal_dev(ctx, d_r, d_g, d_b, pitch, W, H, threshold, amount, satcontrol, ws);
+}
+
+int art_hp_fattal(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b,
+                  int threshold, int amount, int satcontrol, const double ws[9])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!r || !g || !b || !ws) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 3 || H < 3) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    int rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+    Plane io[3] = {{r, (float*)ctx->d_out[0].p}, {g, (float*)ctx->d_out[1].p}, {b, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_fattal_dev(ctx, io[0].dev, io[1].dev, io[2].dev, pitch, W, H, threshold, amount, satcontrol, ws))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+int art_hp_median_denoise_dev(art_hp_ctx* ctx, const float* d_src, size_t src_pitch, float* d_dst, size_t dst_pitch, int W, int H,
+                              int median_type, int use_upper, float upper_bound)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_src || !d_dst || d_src == d_dst) return ctx->fail(ART_HP_ERR_INVALID, "null or aliased planes (the device form is out of place)");
+    if (W < 1 || H < 1 || src_pitch < (size_t)W || dst_pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    if (median_type < 0 || median_type > 5) return ctx->fail(ART_HP_ERR_INVALID, "median_type %d", median_type);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_median_dev(ctx, d_src, src_pitch, d_dst, dst_pitch, W, H, median_type, use_upper, upper_bound);
+}
+
+int art_hp_median_denoise(art_hp_ctx* ctx, float* const* src, float* const* dst, int W, int H, int median_type,
+                          int use_upper, float upper_bound)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!src || !dst) return ctx->fail(ART_HP_ERR_INVALID, "null row table");
+    if (W < 1 || H < 1) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    if (median_type < 0 || median_type > 5) return ctx->fail(ART_HP_ERR_INVALID, "median_type %d", median_type);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    int rc;
+    for (int i = 0; i < 2; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+    Plane in = {src, (float*)ctx->d_out[0].p}, out = {dst, (float*)ctx->d_out[1].p};
+    if ((rc = transfer(ctx, ctx->stream, &in, 1, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_median_dev(ctx, in.dev, pitch, out.dev, pitch, W, H, median_type, use_upper, upper_bound))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, &out, 1, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+int art_hp_redft00_2d(art_hp_ctx* ctx, int n0, int n1, const float* in, float* out)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!in || !out || n0 < 3 || n1 < 3) return ctx->fail(ART_HP_ERR_INVALID, "bad arguments");
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(float) * (size_t)n0 * n1;
+    int rc;
+    if ((rc = art_reserve(ctx, ctx->d_out[0], bytes))) return rc;
+    if ((rc = art_reserve(ctx, ctx->d_out[1], bytes))) return rc;
+    ART_CUDA(ctx, cudaMemcpyAsync(ctx->d_out[0].p, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = art_redft00_2d_dev(ctx, (const float*)ctx->d_out[0].p, (float*)ctx->d_out[1].p, n0, n1))) return rc;
+    ART_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out[1].p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;
 }

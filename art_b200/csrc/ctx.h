@@ -35,7 +35,7 @@ struct art_hp_ctx {
     std::vector<ProfStat> stats;
     std::string err;
     // device scratch, grown on demand and kept across calls
-    DevBuf d_raw, d_out[3], d_scratch, d_small, d_work, d_dn;
+    DevBuf d_raw, d_out[3], d_scratch, d_small, d_work, d_dn, d_fattal;
     // pinned staging (two halves for double buffering)
     void* h_stage[2] = {nullptr, nullptr};
     size_t h_stage_bytes = 0;
@@ -120,3 +120,11 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
 int art_nlmeans_dev(art_hp_ctx* ctx, float* img, size_t ip, int W, int H, float normcoeff, int strength, int detail_thresh, float scale);
 int art_guided_dev(art_hp_ctx* ctx, const float* guide, size_t gp, const float* src, size_t sp, float* dst, size_t dp,
                    int W, int H, int r, float epsilon, int subsampling);
+// ToneMapFattal02 (fattal.cu), planes in place; ws = working-space matrix, row-major 3x3
+int art_fattal_dev(art_hp_ctx* ctx, float* R, float* G, float* B, size_t ip, int W, int H, int threshold, int amount, int satcontrol,
+                   const double* ws9);
+int art_fattal_fast_dim(int dim);
+// denoise::Median_Denoise, one iteration, src != dst; type 0..5 = denoise::Median
+int art_median_dev(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, size_t dp, int W, int H, int type, int useUpper, float upper);
+// 2-D REDFT00 of a contiguous n0 x n1 float array (the transform of tmo_fattal02.cc L768-772 alone)
+int art_redft00_2d_dev(art_hp_ctx* ctx, const float* in, float* out, int n0, int n1);

@@ -249,6 +249,37 @@ int art_hp_detail_mask_dev(art_hp_ctx* ctx, const float* d_src, size_t src_pitch
 int art_hp_nlmeans(art_hp_ctx* ctx, float* const* img, int W, int H, float normcoeff, int strength, int detail_thresh, float scale);
 int art_hp_nlmeans_dev(art_hp_ctx* ctx, float* d_img, size_t pitch, int W, int H, float normcoeff, int strength, int detail_thresh, float scale);
 
+/* ---- Fattal tone mapping ----------------------------------------------------- */
+/*
+ * art_hp_fattal        rtengine::ImProcFunctions::dynamicRangeCompression(Imagefloat*) -> ToneMapFattal02
+ *                      (rtengine/tmo_fattal02.cc L1053-1215, L1220-1225; declared rtengine/improcfun.h L147), in place on the
+ *                      three planes of the working-space image.  threshold / amount / satcontrol are
+ *                      procparams::FattalToneMappingParams (rtengine/procparams.h L835-840); ws is
+ *                      ICCStore::workingSpaceMatrix(params->icm.workingProfile), row-major 3x3 doubles.
+ *                      alpha <= 0 or beta <= 0 returns at once, like the reference (L1068-1070).
+ *                      Bit-identical to the reference except for its two external-library calls: the 2-D REDFT00
+ *                      transforms (FFTW there; an fp64 shared-memory FFT here, rounded to float where the reference's plan
+ *                      stores floats) and pow() in calculateFiMatrix (glibc powf there; fp64 pow rounded to float here).
+ *                      Padded sides (find_fast_dim(W) + 1, L1094-1095) above 14337 return ART_HP_ERR_UNSUPPORTED.
+ * art_hp_fattal_fast_dim   find_fast_dim (L1014-1050).
+ * art_hp_median_denoise    denoise::Median_Denoise(src, dst, [upperBound,] W, H, medianType, iterations = 1, ...)
+ *                      (rtengine/FTblockDN.cc L87-445, rtengine/ipdenoise.h L60-75): type 0..5 = denoise::Median
+ *                      {3X3_SOFT, 3X3_STRONG, 5X5_SOFT, 5X5_STRONG, 7X7, 9X9}; use_upper selects the overload that only
+ *                      filters samples <= upper_bound.  src == dst allowed for the host form (the call tone mapping makes).
+ * art_hp_redft00_2d    the transform at tmo_fattal02.cc L768-772 by itself (fftwf_plan_r2r_2d(n0, n1, in, out, REDFT00,
+ *                      REDFT00)), contiguous host arrays; exposed so the transform can be checked against its definition.
+ */
+int art_hp_fattal(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b,
+                  int threshold, int amount, int satcontrol, const double ws[9]);
+int art_hp_fattal_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
+                      int threshold, int amount, int satcontrol, const double ws[9]);
+int art_hp_fattal_fast_dim(int dim);
+int art_hp_median_denoise(art_hp_ctx* ctx, float* const* src, float* const* dst, int W, int H, int median_type,
+                          int use_upper, float upper_bound);
+int art_hp_median_denoise_dev(art_hp_ctx* ctx, const float* d_src, size_t src_pitch, float* d_dst, size_t dst_pitch, int W, int H,
+                              int median_type, int use_upper, float upper_bound);
+int art_hp_redft00_2d(art_hp_ctx* ctx, int n0, int n1, const float* in, float* out);
+
 /* ---- box blur / guided filter ----------------------------------------------- */
 /*
  * art_hp_boxblur*: replaces rtengine::boxblur(float** src, float** dst, int radius, int W, int H, bool multiThread)
