@@ -94,6 +94,8 @@ def load_library(build_if_missing=True):
         "art_hp_scale_colors_bayer_dev": (i, [vp, i, i, u, vp, sz, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
         "art_hp_scale_convert": (i, [vp, i, i, vp, vp, vp, ctypes.POINTER(ctypes.c_float), i, ctypes.POINTER(d)]),
         "art_hp_scale_convert_dev": (i, [vp, i, i, vp, vp, vp, sz, ctypes.POINTER(ctypes.c_float), i, ctypes.POINTER(d)]),
+        "art_hp_develop": (i, [vp, vp, i, i, vp, vp, vp, vp]),
+        "art_hp_develop_dev": (i, [vp, vp, i, i, vp, sz, vp, vp, vp, sz]),
         "art_hp_fattal": (i, [vp, i, i, vp, vp, vp, i, i, i, ctypes.POINTER(d)]),
         "art_hp_fattal_dev": (i, [vp, i, i, vp, vp, vp, sz, i, i, i, ctypes.POINTER(d)]),
         "art_hp_fattal_fast_dim": (i, [i]),
@@ -151,6 +153,47 @@ class _DenoiseParamsC(ctypes.Structure):
                 ("chrominance", ctypes.c_double), ("chrominanceRedGreen", ctypes.c_double), ("chrominanceBlueYellow", ctypes.c_double),
                 ("gamma", ctypes.c_double), ("scale", ctypes.c_double), ("colorSpace", ctypes.c_int), ("aggressive", ctypes.c_int),
                 ("chrominanceMethod", ctypes.c_int), ("noiseCCurve", ctypes.c_void_p), ("noiseCCurveSum", ctypes.c_float)]
+
+
+class _DevelopParamsC(ctypes.Structure):
+    _fields_ = [("method", ctypes.c_int), ("filters", ctypes.c_uint), ("initialGain", ctypes.c_double), ("border", ctypes.c_int),
+                ("mul", ctypes.c_float * 3), ("doClip", ctypes.c_int), ("cam2work", ctypes.POINTER(ctypes.c_double)),
+                ("denoise", ctypes.POINTER(_DenoiseParamsC)), ("nlStrength", ctypes.c_int), ("nlDetail", ctypes.c_int),
+                ("fattal_enabled", ctypes.c_int), ("fattal_threshold", ctypes.c_int), ("fattal_amount", ctypes.c_int),
+                ("fattal_satcontrol", ctypes.c_int), ("wprof", ctypes.POINTER(ctypes.c_double))]
+
+
+class DevelopParams:
+    """Parameters of art_hp_develop: the simpleprocess.cc stages on the hot path (demosaic, gains + matrix, denoise, Fattal)."""
+
+    def __init__(self, method=0, filters=0x94949494, initial_gain=1.0, border=4, mul=(1.0, 1.0, 1.0), do_clip=True, cam2work=None,
+                 denoise=None, nl_strength=0, nl_detail=80, fattal=None, wprof=None):
+        self.__dict__.update(locals())
+        del self.__dict__["self"]
+
+    def c_struct(self):
+        c = _DevelopParamsC()
+        c.method, c.filters, c.initialGain, c.border = int(self.method), int(self.filters), float(self.initial_gain), int(self.border)
+        c.mul = (ctypes.c_float * 3)(*[float(x) for x in self.mul])
+        c.doClip = int(bool(self.do_clip))
+        self._keep = []
+        if self.cam2work is not None:
+            m = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(self.cam2work, dtype=np.float64).reshape(9)])
+            self._keep.append(m)
+            c.cam2work = ctypes.cast(m, ctypes.POINTER(ctypes.c_double))
+        if self.wprof is not None:
+            w = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(self.wprof, dtype=np.float64).reshape(9)])
+            self._keep.append(w)
+            c.wprof = ctypes.cast(w, ctypes.POINTER(ctypes.c_double))
+        if self.denoise is not None:
+            d = self.denoise.c_struct()
+            self._keep.append(d)
+            c.denoise = ctypes.pointer(d)
+        c.nlStrength, c.nlDetail = int(self.nl_strength), int(self.nl_detail)
+        if self.fattal is not None:
+            thr, amt, sat = self.fattal
+            c.fattal_enabled, c.fattal_threshold, c.fattal_amount, c.fattal_satcontrol = 1, int(thr), int(amt), int(bool(sat))
+        return c
 
 
 class DenoiseParams:
@@ -368,6 +411,18 @@ class HotPath:
 
     def nlmeans_dev(self, d_img, pitch, W, H, normcoeff, strength, detail_thresh, scale=1.0):
         self._check(self.lib.art_hp_nlmeans_dev(self.h, d_img, pitch, W, H, normcoeff, int(strength), int(detail_thresh), scale))
+
+    def develop(self, raw, params, red=None, green=None, blue=None):
+        """art_hp_develop on a host (H, W) float32 CFA plane; returns the three developed planes."""
+        H, W = raw.shape
+        out = [p if p is not None else np.empty((H, W), np.float32) for p in (red, green, blue)]
+        c = params.c_struct()
+        self._check(self.lib.art_hp_develop(self.h, ctypes.byref(c), W, H, row_table(raw), row_table(out[0]), row_table(out[1]), row_table(out[2])))
+        return out
+
+    def develop_dev(self, params, W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch):
+        c = params.c_struct()
+        self._check(self.lib.art_hp_develop_dev(self.h, ctypes.byref(c), W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch))
 
     def fattal(self, r, g, b, threshold, amount, satcontrol, ws):
         """ImProcFunctions::dynamicRangeCompression (ToneMapFattal02), in place on three host (H, W) float32 planes."""

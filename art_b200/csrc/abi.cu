@@ -205,7 +205,7 @@ void art_hp_destroy(art_hp_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch, &ctx->d_small, &ctx->d_work, &ctx->d_dn, &ctx->d_fattal};
+    DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch, &ctx->d_small, &ctx->d_work, &ctx->d_dn, &ctx->d_fattal, &ctx->d_small2};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < 2; ++i) if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -791,6 +791,51 @@ int art_hp_redft00_2d(art_hp_ctx* ctx, int n0, int n1, const float* in, float* o
     ART_CUDA(ctx, cudaMemcpyAsync(ctx->d_out[0].p, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = art_redft00_2d_dev(ctx, (const float*)ctx->d_out[0].p, (float*)ctx->d_out[1].p, n0, n1))) return rc;
     ART_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out[1].p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+static int check_develop(art_hp_ctx* ctx, const art_hp_develop_params* p, int W, int H)
+{
+    if (!p) return ctx->fail(ART_HP_ERR_INVALID, "null parameters");
+    if (p->method != ART_HP_BAYER_AMAZE && p->method != ART_HP_BAYER_RCD) return ctx->fail(ART_HP_ERR_INVALID, "unknown demosaic method %d", p->method);
+    if (!rgb_bayer(p->filters)) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "filters 0x%08x is not an RGB Bayer pattern", p->filters);
+    if (W < 32 || H < 32 || W > 32767 || H > 32767) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    if ((p->denoise || p->fattal_enabled) && !p->wprof) return ctx->fail(ART_HP_ERR_INVALID, "wprof is required by denoise and tone mapping");
+    if (p->denoise) { int rc = check_denoise_params(ctx, p->denoise, p->wprof); if (rc) return rc; }
+    return ART_HP_OK;
+}
+
+int art_hp_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, const float* d_raw, size_t raw_pitch,
+                       float* d_r, float* d_g, float* d_b, size_t out_pitch)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_raw || !d_r || !d_g || !d_b) return ctx->fail(ART_HP_ERR_INVALID, "null plane");
+    int rc = check_develop(ctx, params, W, H);
+    if (rc) return rc;
+    if (raw_pitch < (size_t)W || out_pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "pitch smaller than the width");
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_develop_dev(ctx, params, W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch);
+}
+
+int art_hp_develop(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
+                   float* const* r, float* const* g, float* const* b)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!rawData || !r || !g || !b) return ctx->fail(ART_HP_ERR_INVALID, "null row table");
+    int rc = check_develop(ctx, params, W, H);
+    if (rc) return rc;
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    if ((rc = art_reserve(ctx, ctx->d_raw, plane))) return rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+    Plane in = {rawData, (float*)ctx->d_raw.p};
+    Plane out[3] = {{r, (float*)ctx->d_out[0].p}, {g, (float*)ctx->d_out[1].p}, {b, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, &in, 1, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_develop_dev(ctx, params, W, H, in.dev, pitch, out[0].dev, out[1].dev, out[2].dev, pitch))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, out, 3, W, 0, H, pitch, false))) return rc;
     ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;
 }

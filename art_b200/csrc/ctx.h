@@ -35,7 +35,7 @@ struct art_hp_ctx {
     std::vector<ProfStat> stats;
     std::string err;
     // device scratch, grown on demand and kept across calls
-    DevBuf d_raw, d_out[3], d_scratch, d_small, d_work, d_dn, d_fattal;
+    DevBuf d_raw, d_out[3], d_scratch, d_small, d_work, d_dn, d_fattal, d_small2;
     // pinned staging (two halves for double buffering)
     void* h_stage[2] = {nullptr, nullptr};
     size_t h_stage_bytes = 0;
@@ -128,3 +128,8 @@ int art_fattal_fast_dim(int dim);
 int art_median_dev(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, size_t dp, int W, int H, int type, int useUpper, float upper);
 // 2-D REDFT00 of a contiguous n0 x n1 float array (the transform of tmo_fattal02.cc L768-772 alone)
 int art_redft00_2d_dev(art_hp_ctx* ctx, const float* in, float* out, int n0, int n1);
+// develop.cu: ImProcFunctions::denoise (calclum, adjust_params, RGB_denoise, NL-means on Y) and the whole-frame pipeline
+int art_denoise_stage_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_denoise_params* dn,
+                          int nlStrength, int nlDetail, const double* cam2work, const double* wprof);
+int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int W, int H, const float* raw, size_t rp,
+                    float* r, float* g, float* b, size_t op);

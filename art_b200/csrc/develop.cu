@@ -1,0 +1,145 @@
+// The whole-frame path of simpleprocess.cc's normal pipeline, device resident end to end:
+//   RawImageSource::demosaic            (rtengine/simpleprocess.cc L215-222)
+//   RawImageSource::getImage gains + convertColorSpace matrix branch   (L255-259 region; rawimagesource.cc L943-1025, L3184-3213)
+//   ImProcFunctions::denoise            (rtengine/ipdenoise.cc L1096-1189: half-resolution calclum L1119-1131,
+//                                        adjust_params L35-63, RGB_denoise, optional NL-means on Y)
+//   ImProcFunctions::process STAGE_0 -> dynamicRangeCompression        (rtengine/improcfun.cc L580-583)
+// One H2D of the CFA plane, one D2H of the three result planes; everything between stays in HBM on one stream.
+#include "ctx.h"
+
+#include <cmath>
+
+namespace {
+
+// calclum of ipdenoise.cc L1119-1131: every second sample of every second row, then the camera->working matrix
+// (convertColorSpace -> colorSpaceConversion_ matrix branch: double coefficients, float samples, rounded once)
+__global__ void k_calclum(const float* __restrict__ r, const float* __restrict__ g, const float* __restrict__ b, size_t ip, int W, int H,
+                          float* __restrict__ cr, float* __restrict__ cg, float* __restrict__ cb, size_t cp, int do_mat,
+                          double m0, double m1, double m2, double m3, double m4, double m5, double m6, double m7, double m8)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int w2 = (W + 1) / 2, h2 = (H + 1) / 2;
+    if (x >= w2 || y >= h2) return;
+    const size_t i = (size_t)(2 * y) * ip + 2 * x;
+    float vr = r[i], vg = g[i], vb = b[i];
+    if (do_mat) {
+        const double dr = vr, dg = vg, db = vb;
+        vr = (float)(m0 * dr + m1 * dg + m2 * db);
+        vg = (float)(m3 * dr + m4 * dg + m5 * db);
+        vb = (float)(m6 * dr + m7 * dg + m8 * db);
+    }
+    const size_t o = (size_t)y * cp + x;
+    cr[o] = vr; cg[o] = vg; cb[o] = vb;
+}
+
+// Imagefloat::setMode(YUV) / setMode(RGB) around NLMeans (ipdenoise.cc L1173-1177): Color::rgb2yuv / yuv2rgb with the
+// working-space matrix as float (imagefloat.cc rgb_to_yuv / yuv_to_rgb); Y lives in the g plane, u in b, v in r
+__global__ void k_rgb2yuv(float* __restrict__ r, float* __restrict__ g, float* __restrict__ b, size_t ip, int W, int H, float w0, float w1, float w2)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t i = (size_t)y * ip + x;
+    const float R = r[i], G = g[i], B = b[i];
+    const float Y = R * w0 + G * w1 + B * w2;
+    g[i] = Y; b[i] = Y - B; r[i] = R - Y;
+}
+__global__ void k_yuv2rgb(float* __restrict__ r, float* __restrict__ g, float* __restrict__ b, size_t ip, int W, int H, float w0, float w1, float w2)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const size_t i = (size_t)y * ip + x;
+    const float Y = g[i], u = b[i], v = r[i];
+    const float B = Y - u, R = v + Y;
+    const float G = (Y - R * w0 - B * w2) / w1;
+    r[i] = R; g[i] = G; b[i] = B;
+}
+
+double adj_c(double x, double f)
+{   // the lambda of adjust_params, ipdenoise.cc L41-47: SGN, LIM01, intp
+    const int s = (x > 0) - (x < 0);
+    double y = std::fabs(x) / 100.0;
+    y = y < 0.0 ? 0.0 : y > 1.0 ? 1.0 : y;
+    return s * (y * (y * f) + (1.0 - y) * y) * 100.0;
+}
+
+}  // namespace
+
+void art_adjust_denoise_params(art_hp_denoise_params* p)
+{   // adjust_params, ipdenoise.cc L35-63
+    const double scale = p->scale;
+    if (scale <= 1.0) return;
+    const double scale_factor = 1.0 / scale;
+    const double noise_factor_c = std::pow(scale_factor, 0.46);
+    const double noise_factor_l = std::pow(scale_factor, 0.62) * scale_factor;
+    p->luminance = adj_c(p->luminance, noise_factor_l);
+    p->luminanceDetail *= (1.0 + std::pow(1.0 - scale_factor, 2.2));
+    p->chrominance = adj_c(p->chrominance, noise_factor_c);
+    p->chrominanceRedGreen = adj_c(p->chrominanceRedGreen, noise_factor_c);
+    p->chrominanceBlueYellow = adj_c(p->chrominanceBlueYellow, noise_factor_c);
+}
+
+int art_calclum_dev(art_hp_ctx* ctx, const float* r, const float* g, const float* b, size_t ip, int W, int H,
+                    float* cr, float* cg, float* cb, size_t cp, const double* mat)
+{
+    const dim3 blk(32, 8), grid(((W + 1) / 2 + 31) / 32, ((H + 1) / 2 + 7) / 8);
+    static const double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    const double* m = mat ? mat : ident;
+    art_prof_begin(ctx, "k_calclum");
+    k_calclum<<<grid, blk, 0, ctx->stream>>>(r, g, b, ip, W, H, cr, cg, cb, cp, mat != nullptr, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8]);
+    art_prof_end(ctx);
+    ctx->launches++;
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}
+
+// ImProcFunctions::denoise on device planes (exposure compensation 0, the default)
+int art_denoise_stage_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_denoise_params* dn,
+                          int nlStrength, int nlDetail, const double* cam2work, const double* wprof)
+{
+    art_hp_denoise_params P = *dn;
+    art_adjust_denoise_params(&P);
+    const int w2 = (W + 1) / 2, h2 = (H + 1) / 2;
+    const size_t cp = round_up((size_t)w2, 32);
+    float* cl[3] = {nullptr, nullptr, nullptr};
+    int rc;
+    if (P.noiseCCurve) {
+        if ((rc = art_reserve(ctx, ctx->d_small2, 3 * cp * (size_t)h2 * sizeof(float)))) return rc;
+        for (int c = 0; c < 3; ++c) cl[c] = (float*)ctx->d_small2.p + (size_t)c * cp * h2;
+        if ((rc = art_calclum_dev(ctx, r, g, b, ip, W, H, cl[0], cl[1], cl[2], cp, cam2work))) return rc;
+    }
+    if ((rc = art_rgb_denoise_dev(ctx, r, g, b, ip, W, H, &P, wprof, cl[0], cl[1], cl[2], cp, nullptr))) return rc;
+    if (nlStrength) {
+        const dim3 blk(32, 8), grid((W + 31) / 32, (H + 7) / 8);
+        const float w0 = (float)wprof[3], w1 = (float)wprof[4], w2f = (float)wprof[5];
+        art_prof_begin(ctx, "k_rgb2yuv");
+        k_rgb2yuv<<<grid, blk, 0, ctx->stream>>>(r, g, b, ip, W, H, w0, w1, w2f);
+        art_prof_end(ctx);
+        if ((rc = art_nlmeans_dev(ctx, g, ip, W, H, 65535.f, nlStrength, nlDetail, (float)P.scale))) return rc;
+        art_prof_begin(ctx, "k_yuv2rgb");
+        k_yuv2rgb<<<grid, blk, 0, ctx->stream>>>(r, g, b, ip, W, H, w0, w1, w2f);
+        art_prof_end(ctx);
+        ctx->launches += 2;
+    }
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}
+
+int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int W, int H, const float* raw, size_t rp,
+                    float* r, float* g, float* b, size_t op)
+{
+    int rc;
+    if (p->method == ART_HP_BAYER_AMAZE) rc = art_amaze_dev(ctx, W, H, p->filters, raw, rp, r, g, b, op, p->initialGain, p->border, 0, H);
+    else {
+        rc = art_rcd_dev(ctx, W, H, p->filters, raw, rp, r, g, b, op, 0, H);
+        if (!rc) rc = art_border_dev(ctx, W, H, p->filters, 9, raw, rp, r, g, b, op, 0, H);
+    }
+    if (rc) return rc;
+    if ((rc = art_scale_convert_dev(ctx, W, H, r, g, b, op, p->mul, p->doClip, p->cam2work))) return rc;
+    if (p->denoise) {
+        if ((rc = art_denoise_stage_dev(ctx, r, g, b, op, W, H, p->denoise, p->nlStrength, p->nlDetail, p->cam2work, p->wprof))) return rc;
+    }
+    if (p->fattal_enabled) {
+        if ((rc = art_fattal_dev(ctx, r, g, b, op, W, H, p->fattal_threshold, p->fattal_amount, p->fattal_satcontrol, p->wprof))) return rc;
+    }
+    return ART_HP_OK;
+}

@@ -129,83 +129,108 @@ __global__ void __launch_bounds__(256) k_sf_apply(ShArgs a)
 // ------------------------------------------------------------------ flat boxblur (boxblur.h L558-742), radx == rady >= 1
 struct FbArgs { const float* x; float* y; int W, H, rad; };
 
-__global__ void __launch_bounds__(64) k_fbox_h(FbArgs a)
-{   // L571-602: thread per row
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= a.H) return;
-    const float* s = a.x + (size_t)row * a.W;
-    float* o = a.y + (size_t)row * a.W;
-    const int rad = a.rad, W = a.W;
-    int len = rad + 1;
-    float t = s[0];
-    for (int j = 1; j <= rad; j++) t += s[j];
-    t = t / len;
-    o[0] = t;
-    for (int col = 1; col <= rad; col++) {
-        t = (t * len + s[col + rad]) / (len + 1);
-        o[col] = t;
-        len++;
-    }
-    const float reclen = 1.f / len;
-    for (int col = rad + 1; col < W - rad; col++) {
-        t = t + ((float)(s[col + rad] - s[col - rad - 1])) * reclen;
-        o[col] = t;
-    }
-    for (int col = W - rad; col < W; col++) {
-        t = (t * len - s[col - rad - 1]) / (len - 1);
-        o[col] = t;
-        len--;
-    }
-}
+// Both passes are running sums -- t += (x[n + rad] - x[n - rad - 1]) * (1 / len) -- whose fp32 association is part of the
+// result, so a chain (a row for the horizontal pass, a column for the vertical one) is inherently serial.  The work is
+// split so that only the additions are serial: a CTA owns FB_CH chains and walks them in tiles of FB_T steps; all
+// 256 threads load the tile with coalesced reads and form the per-step differences in parallel, FB_CH lanes run the
+// additions out of shared memory, all threads store the tile.  The ramps at both ends of a chain (rad + 1 and rad steps)
+// are done by the chain lanes straight from global memory.
+constexpr int FB_CH = 16, FB_T = 256, FB_NT = 256;
 
-__global__ void __launch_bounds__(128) k_fbox_v(FbArgs a)
-{   // L614-710: thread per column
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= a.W) return;
-    const int rad = a.rad, W = a.W, H = a.H;
-    const float* tp = a.x + col;
-    float* d = a.y + col;
-    if (col < W - (W % 4)) {
-        float len = (float)(rad + 1);
-        float t = tp[0];
-        for (int i = 1; i <= rad; i++) t = t + tp[(size_t)i * W];
-        t = t / len;
-        d[0] = t;
-        for (int row = 1; row <= rad; row++) {
-            const float lp1 = len + 1.f;
-            t = (t * len + tp[(size_t)(row + rad) * W]) / lp1;
-            d[(size_t)row * W] = t;
-            len = lp1;
+template <bool VERT>
+__global__ void __launch_bounds__(FB_NT) k_fbox(FbArgs a)
+{   // horizontal: boxblur.h L571-602; vertical: L614-710 (columns < W - W % 4 follow the 4-/8-wide code, the rest the scalar tail)
+    __shared__ float tile[FB_T][FB_CH + 1];
+    const int W = a.W, H = a.H, rad = a.rad;
+    const int nchains = VERT ? W : H, nsteps = VERT ? H : W;
+    const int chain0 = blockIdx.x * FB_CH;
+    const int tid = threadIdx.x;
+    auto at = [&](int ch, int st) -> size_t { return VERT ? (size_t)st * W + ch : (size_t)ch * W + st; };
+    const bool chain_thread = tid < FB_CH && chain0 + tid < nchains;
+    const int mych = chain0 + tid;
+    const bool scalar_class = VERT && mych >= W - (W % 4);
+    float t = 0.f;
+    const float full = (float)(2 * rad + 1);
+    if (chain_thread) {
+        if (!VERT) {
+            int len = rad + 1;
+            t = a.x[at(mych, 0)];
+            for (int j = 1; j <= rad; j++) t += a.x[at(mych, j)];
+            t = t / len;
+            a.y[at(mych, 0)] = t;
+            for (int st = 1; st <= rad; st++) {
+                t = (t * len + a.x[at(mych, st + rad)]) / (len + 1);
+                a.y[at(mych, st)] = t;
+                len++;
+            }
+        } else if (!scalar_class) {
+            float len = (float)(rad + 1);
+            t = a.x[at(mych, 0)];
+            for (int i = 1; i <= rad; i++) t = t + a.x[at(mych, i)];
+            t = t / len;
+            a.y[at(mych, 0)] = t;
+            for (int st = 1; st <= rad; st++) {
+                const float lp1 = len + 1.f;
+                t = (t * len + a.x[at(mych, st + rad)]) / lp1;
+                a.y[at(mych, st)] = t;
+                len = lp1;
+            }
+        } else {
+            int len = rad + 1;
+            t = a.x[at(mych, 0)] / len;
+            for (int i = 1; i <= rad; i++) t += a.x[at(mych, i)] / len;
+            a.y[at(mych, 0)] = t;
+            for (int st = 1; st <= rad; st++) {
+                t = (t * len + a.x[at(mych, st + rad)]) / (len + 1);
+                a.y[at(mych, st)] = t;
+                len++;
+            }
         }
-        const float rlen = 1.f / len;
-        for (int row = rad + 1; row < H - rad; row++) {
-            t = t + (tp[(size_t)(row + rad) * W] - tp[(size_t)(row - rad - 1) * W]) * rlen;
-            d[(size_t)row * W] = t;
+    }
+    const float rlen = 1.f / full;
+    const int first = rad + 1, last = nsteps - rad;          // main region [first, last)
+    for (int s0 = first; s0 < last; s0 += FB_T) {
+        const int nst = min(FB_T, last - s0);
+        for (int i = tid; i < FB_CH * FB_T; i += FB_NT) {
+            const int cl = VERT ? i % FB_CH : i / FB_T, sl = VERT ? i / FB_CH : i % FB_T;
+            const int ch = chain0 + cl, st = s0 + sl;
+            if (ch < nchains && sl < nst) {
+                const float diff = a.x[at(ch, st + rad)] - a.x[at(ch, st - rad - 1)];
+                tile[sl][cl] = (VERT && ch >= W - (W % 4)) ? diff / (float)(2 * rad + 1) : diff * rlen;
+            }
         }
-        for (int row = H - rad; row < H; row++) {
-            const float lm1 = len - 1.f;
-            t = (t * len - tp[(size_t)(row - rad - 1) * W]) / lm1;
-            d[(size_t)row * W] = t;
-            len = lm1;
+        __syncthreads();
+        if (chain_thread) {
+#pragma unroll 8
+            for (int sl = 0; sl < nst; ++sl) {
+                t = t + tile[sl][tid];
+                tile[sl][tid] = t;
+            }
         }
-    } else {
-        int len = rad + 1;
-        float t = tp[0] / len;
-        for (int i = 1; i <= rad; i++) t += tp[(size_t)i * W] / len;
-        d[0] = t;
-        for (int row = 1; row <= rad; row++) {
-            t = (t * len + tp[(size_t)(row + rad) * W]) / (len + 1);
-            d[(size_t)row * W] = t;
-            len++;
+        __syncthreads();
+        for (int i = tid; i < FB_CH * FB_T; i += FB_NT) {
+            const int cl = VERT ? i % FB_CH : i / FB_T, sl = VERT ? i / FB_CH : i % FB_T;
+            const int ch = chain0 + cl;
+            if (ch < nchains && sl < nst) a.y[at(ch, s0 + sl)] = tile[sl][cl];
         }
-        for (int row = rad + 1; row < H - rad; row++) {
-            t = t + (tp[(size_t)(row + rad) * W] - tp[(size_t)(row - rad - 1) * W]) / len;
-            d[(size_t)row * W] = t;
-        }
-        for (int row = H - rad; row < H; row++) {
-            t = (t * len - tp[(size_t)(row - rad - 1) * W]) / (len - 1);
-            d[(size_t)row * W] = t;
-            len--;
+        __syncthreads();
+    }
+    if (chain_thread) {
+        if (VERT && !scalar_class) {
+            float len = full;
+            for (int st = max(last, first); st < nsteps; st++) {
+                const float lm1 = len - 1.f;
+                t = (t * len - a.x[at(mych, st - rad - 1)]) / lm1;
+                a.y[at(mych, st)] = t;
+                len = lm1;
+            }
+        } else {
+            int len = 2 * rad + 1;
+            for (int st = max(last, first); st < nsteps; st++) {
+                t = (t * len - a.x[at(mych, st - rad - 1)]) / (len - 1);
+                a.y[at(mych, st)] = t;
+                len--;
+            }
         }
     }
 }
@@ -248,8 +273,8 @@ int shrink_band(art_hp_ctx* ctx, const Scratch& s, ShArgs a, int W, int H, int r
     art_prof_end(ctx);
     if (2 * rad + 1 > W || 2 * rad + 1 > H) return ctx->fail(ART_HP_ERR_INVALID, "blur radius %d does not fit a %dx%d subband", rad, W, H);
     art_prof_begin(ctx, "k_fbox");
-    k_fbox_h<<<(H + 63) / 64, 64, 0, st>>>(FbArgs{s.sf, s.tmp, W, H, rad});
-    k_fbox_v<<<(W + 127) / 128, 128, 0, st>>>(FbArgs{s.tmp, s.sfd, W, H, rad});
+    k_fbox<false><<<(H + FB_CH - 1) / FB_CH, FB_NT, 0, st>>>(FbArgs{s.sf, s.tmp, W, H, rad});
+    k_fbox<true><<<(W + FB_CH - 1) / FB_CH, FB_NT, 0, st>>>(FbArgs{s.tmp, s.sfd, W, H, rad});
     art_prof_end(ctx);
     art_prof_begin(ctx, "k_sf_apply");
     k_sf_apply<<<grid, 256, 0, st>>>(a);

@@ -314,6 +314,36 @@ int art_hp_scale_convert_dev(art_hp_ctx* ctx, int W, int H,
                              float* d_red, float* d_green, float* d_blue, size_t pitch,
                              const float mul[3], int doClip, const double mat[9]);
 
+/* ---- whole frame ------------------------------------------------------------------ */
+/*
+ * art_hp_develop       the stages of simpleprocess.cc's normal pipeline that are on the hot path, back to back on the
+ *                      device: imgsrc->demosaic (rtengine/simpleprocess.cc L215-222), imgsrc->getImage gains +
+ *                      convertColorSpace matrix branch, ipf.denoise (rtengine/ipdenoise.cc L1096-1189: half-resolution
+ *                      calclum through the same matrix when a chroma noise curve is given, adjust_params for scale > 1,
+ *                      RGB_denoise, then -- nlStrength != 0, i.e. smoothingEnabled with guidedChromaRadius 0 --
+ *                      NLMeans(Y, 65535, nlStrength, nlDetail, scale) between Imagefloat::setMode(YUV) and setMode(RGB)),
+ *                      and ipf.process(STAGE_0) = dynamicRangeCompression (rtengine/improcfun.cc L580-583).
+ *                      One host->device copy of the CFA plane, one device->host copy of the three planes.
+ *                      denoise == NULL and fattal_enabled == 0 skip their stages, like `enabled = false` does.
+ */
+typedef struct art_hp_develop_params {
+    int method;                 /* ART_HP_BAYER_AMAZE | ART_HP_BAYER_RCD */
+    unsigned filters;
+    double initialGain;
+    int border;
+    float mul[3];               /* rm, gm, bm of getImage (rawimagesource.cc L790-928) */
+    int doClip;
+    const double* cam2work;     /* 9 doubles, row major; NULL = no matrix */
+    const art_hp_denoise_params* denoise;
+    int nlStrength, nlDetail;
+    int fattal_enabled, fattal_threshold, fattal_amount, fattal_satcontrol;
+    const double* wprof;        /* ICCStore::workingSpaceMatrix(workingProfile), 9 doubles */
+} art_hp_develop_params;
+int art_hp_develop(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
+                   float* const* red, float* const* green, float* const* blue);
+int art_hp_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, const float* d_raw, size_t raw_pitch,
+                       float* d_red, float* d_green, float* d_blue, size_t out_pitch);
+
 #ifdef __cplusplus
 }
 #endif

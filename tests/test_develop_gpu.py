@@ -1,0 +1,89 @@
+"""GPU parity for the whole-frame entry art_hp_develop (simpleprocess.cc's hot-path stages back to back) against the same
+chain of oracle functions: AMaZE -> getImage gains + matrix -> ImProcFunctions::denoise (calclum, RGB_denoise[, NL-means on
+Y]) -> dynamicRangeCompression.  Demosaic + gains + matrix + chroma-only denoise are bit-exact; with luminance denoise or
+tone mapping the stages that stand in for FFTW carry the 1e-4 relative tolerance (BASELINE.json north_star)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import art_b200
+import oracle
+from art_b200 import synth
+from art_b200.api import DenoiseParams, DevelopParams
+from test_oracle_denoise import PROPHOTO, noise_ccurve, run as run_denoise
+from test_oracle_fattal import fattal as run_fattal
+
+pytestmark = pytest.mark.gpu
+
+CAM2WORK = np.array([[0.82, 0.15, 0.03], [0.07, 0.96, -0.03], [0.02, -0.10, 1.08]], np.float64)
+MUL = (1.9, 1.0, 1.6)
+
+
+def oracle_chain(raw, dn_params, curve, fattal_p, nl=None):
+    P = oracle.port()
+    r, g, b = P.amaze(raw, synth.RGGB, 1.0, 4)
+    r, g, b = P.scale_convert([r, g, b], MUL, True, CAM2WORK)
+    planes = [r, g, b]
+    if dn_params is not None:
+        cc = None
+        if curve:
+            lut, s = noise_ccurve()
+            cl = P.scale_convert([np.ascontiguousarray(p[::2, ::2]) for p in planes], (1.0, 1.0, 1.0), False, CAM2WORK)
+            cc = (lut, s, cl)
+        planes = run_chain_denoise(P.lib, planes, dn_params, cc)
+    if fattal_p is not None:
+        planes = list(run_fattal(P.lib, "artoracle_fattal", planes, *fattal_p))
+    return planes
+
+
+def run_chain_denoise(lib, planes, params, cc):
+    """artoracle_rgb_denoise with an explicit calclum (test_oracle_denoise.run subsamples the input itself)"""
+    fp = ctypes.POINTER(ctypes.c_float)
+    dp = ctypes.POINTER(ctypes.c_double)
+    H, W = planes[0].shape
+    out = [np.ascontiguousarray(p).copy() for p in planes]
+    p = np.array(params, np.float64)
+    wp = PROPHOTO.copy()
+    res = np.zeros(2, np.float32)
+    args = [out[0].ctypes.data_as(fp), out[1].ctypes.data_as(fp), out[2].ctypes.data_as(fp), W, H, p.ctypes.data_as(dp), wp.ctypes.data_as(dp)]
+    if cc is not None:
+        lut, s, cl = cc
+        cl = [np.ascontiguousarray(c) for c in cl]
+        args += [lut.ctypes.data_as(fp), ctypes.c_float(s), cl[0].ctypes.data_as(fp), cl[1].ctypes.data_as(fp), cl[2].ctypes.data_as(fp)]
+    else:
+        args += [None, ctypes.c_float(0), None, None, None]
+    args.append(res.ctypes.data_as(fp))
+    assert lib.artoracle_rgb_denoise(*args) == 0
+    return out
+
+
+@pytest.mark.parametrize("W,H,dn,curve,fat,exact", [
+    (322, 260, None, False, None, True),
+    (322, 260, (0, 0, 0, 15, 0, 0, 1.7, 1.0), True, None, True),
+    (322, 260, (30, 50, 0, 15, 0, 0, 1.7, 1.0), True, (30, 20, 0), False),
+    (645, 404, (30, 50, 0, 15, 0, 0, 1.7, 1.0), False, (30, 20, 1), False),
+    (301, 407, None, False, (30, 20, 0), False),
+])
+def test_develop_matches_oracle_chain(hot_path, W, H, dn, curve, fat, exact):
+    raw = synth.bayer_frame(W, H, synth.RGGB, seed=W + H)
+    want = oracle_chain(raw, dn, curve, fat)
+    dnp = None
+    if dn is not None:
+        lum, det, thr, chroma, rg, by, gamma, scale = dn
+        dnp = DenoiseParams(luminance=lum, luminanceDetail=det, luminanceDetailThreshold=thr, chrominance=chroma, chrominanceRedGreen=rg,
+                            chrominanceBlueYellow=by, gamma=gamma, scale=scale, noiseCCurve=noise_ccurve()[0] if curve else None)
+    params = DevelopParams(method=art_b200.BAYER_AMAZE, filters=synth.RGGB, mul=MUL, do_clip=True, cam2work=CAM2WORK, denoise=dnp,
+                           fattal=fat, wprof=PROPHOTO)
+    got = hot_path.develop(raw, params)
+    worst = 0.0
+    for x, y, ch in zip(got, want, "RGB"):
+        if exact:
+            assert np.array_equal(x, y), "%s: %d of %d differ" % (ch, int((x != y).sum()), x.size)
+        else:
+            err = np.abs(x - y)
+            lim = 1e-4 * np.abs(y) + 0.02
+            worst = max(worst, float((err / (np.abs(y) + 0.02)).max()))
+            assert (err <= lim).all(), "%s: %d of %d beyond tolerance, worst %g" % (ch, int((err > lim).sum()), x.size, worst)
+    if not exact:
+        print("\n[develop] %dx%d worst relative error %.3g" % (W, H, worst))
