@@ -167,6 +167,37 @@ int art_reserve(art_hp_ctx* ctx, DevBuf& b, size_t bytes)
     return ART_HP_OK;
 }
 
+int art_pool_alloc(art_hp_ctx* ctx, size_t bytes, void** out)
+{
+    PoolBlk* best = nullptr;
+    for (PoolBlk& b : ctx->pool)
+        if (!b.used && b.bytes >= bytes && (!best || b.bytes < best->bytes)) best = &b;
+    if (best) { best->used = true; *out = best->p; return ART_HP_OK; }
+    // no fit: drop the free blocks that are too small (they would only pile up), then allocate
+    for (size_t i = 0; i < ctx->pool.size();) {
+        if (!ctx->pool[i].used) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(ctx->pool[i].p);
+            ctx->pool.erase(ctx->pool.begin() + i);
+        } else ++i;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(ART_HP_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    ctx->pool.push_back(PoolBlk{p, bytes, true});
+    *out = p;
+    return ART_HP_OK;
+}
+
+void art_pool_free(art_hp_ctx* ctx, void* p)
+{
+    for (PoolBlk& b : ctx->pool)
+        if (b.p == p) { b.used = false; return; }
+}
+
 extern "C" {
 
 int art_hp_abi_version(void) { return ART_HP_ABI_VERSION; }
@@ -207,6 +238,8 @@ void art_hp_destroy(art_hp_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch, &ctx->d_small, &ctx->d_work, &ctx->d_dn, &ctx->d_fattal, &ctx->d_small2};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    if (ctx->d_dn_tables.p) cudaFree(ctx->d_dn_tables.p);
+    for (PoolBlk& b : ctx->pool) cudaFree(b.p);
     for (int i = 0; i < 2; ++i) if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

@@ -17,6 +17,8 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+struct PoolBlk { void* p; size_t bytes; bool used; };
+
 struct ProfSpan { const char* name; cudaEvent_t e0, e1; };
 struct ProfStat { std::string name; double ms = 0.0; int calls = 0; };
 
@@ -36,6 +38,11 @@ struct art_hp_ctx {
     std::string err;
     // device scratch, grown on demand and kept across calls
     DevBuf d_raw, d_out[3], d_scratch, d_small, d_work, d_dn, d_fattal, d_small2;
+    // blocks handed to short-lived device objects (wavelet decompositions): reused across calls instead of
+    // cudaMalloc/cudaFree per frame (both synchronise the device and serialise with NVML queries)
+    std::vector<PoolBlk> pool;
+    bool dn_tables_ready = false;        // the constant window / DCT tables of detail_recovery are uploaded once
+    DevBuf d_dn_tables;
     // pinned staging (two halves for double buffering)
     void* h_stage[2] = {nullptr, nullptr};
     size_t h_stage_bytes = 0;
@@ -80,6 +87,9 @@ static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; 
 
 // grow-only device buffer
 int art_reserve(art_hp_ctx* ctx, DevBuf& b, size_t bytes);
+// stream-ordered block pool: work that used a block was queued on ctx->stream, so the next user (same stream) is ordered after it
+int art_pool_alloc(art_hp_ctx* ctx, size_t bytes, void** out);
+void art_pool_free(art_hp_ctx* ctx, void* p);
 
 // kernels (device-resident planes, pitch in floats); each returns an art_hp_status
 // row_begin/row_end: output rows to produce (tile-grid aligned, see art_hp_demosaic_bayer_rows_dev)

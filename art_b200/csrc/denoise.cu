@@ -391,13 +391,19 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
     const float gain = std::pow(2.0f, float(0.0));
     const float params_Ldetail = std::min(float(P->luminanceDetail), 99.9f);
 
-    std::vector<float> host(4 * TS * TS);
     if (denoiseLuminance) {
-        build_tables(host.data(), host.data() + TS * TS, host.data() + 2 * TS * TS, host.data() + 3 * TS * TS);
-        ART_CUDA(ctx, cudaMemcpyAsync(tin, host.data(), sizeof(float) * TS * TS, cudaMemcpyHostToDevice, st));
-        ART_CUDA(ctx, cudaMemcpyAsync(tout, host.data() + TS * TS, sizeof(float) * TS * TS, cudaMemcpyHostToDevice, st));
-        ART_CUDA(ctx, cudaMemcpyAsync(dctf, host.data() + 2 * TS * TS, sizeof(float) * TS * TS, cudaMemcpyHostToDevice, st));
-        ART_CUDA(ctx, cudaMemcpyAsync(dctb, host.data() + 3 * TS * TS, sizeof(float) * TS * TS, cudaMemcpyHostToDevice, st));
+        // the window / DCT tables are constants: built and uploaded once per context
+        int trc = art_reserve(ctx, ctx->d_dn_tables, 4 * TS * TS * sizeof(float));
+        if (trc) return trc;
+        float* tb = (float*)ctx->d_dn_tables.p;
+        if (!ctx->dn_tables_ready) {
+            std::vector<float> host(4 * TS * TS);
+            build_tables(host.data(), host.data() + TS * TS, host.data() + 2 * TS * TS, host.data() + 3 * TS * TS);
+            ART_CUDA(ctx, cudaMemcpyAsync(tb, host.data(), sizeof(float) * 4 * TS * TS, cudaMemcpyHostToDevice, st));
+            ART_CUDA(ctx, cudaStreamSynchronize(st));
+            ctx->dn_tables_ready = true;
+        }
+        tin = tb; tout = tb + TS * TS; dctf = tb + 2 * TS * TS; dctb = tb + 3 * TS * TS;
     }
     std::vector<float> hcache;
     if (useCC) {       // L1706-1770
@@ -417,8 +423,7 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
         art_prof_end(ctx);
         ctx->launches += 1;
     }
-    // the host staging vectors must outlive the copies
-    ART_CUDA(ctx, cudaStreamSynchronize(st));
+    if (useCC) ART_CUDA(ctx, cudaStreamSynchronize(st));        // hcache (a local) must outlive its copy
 
     // chroma sliders, L2026-2068
     float interm_med = static_cast<float>(P->chrominance) / 10.0;

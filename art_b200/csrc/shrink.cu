@@ -272,8 +272,10 @@ int shrink_band(art_hp_ctx* ctx, const Scratch& s, ShArgs a, int W, int H, int r
     if (ab) k_sf_AB<<<grid, 256, 0, st>>>(a); else k_sf_L<<<grid, 256, 0, st>>>(a);
     art_prof_end(ctx);
     if (2 * rad + 1 > W || 2 * rad + 1 > H) return ctx->fail(ART_HP_ERR_INVALID, "blur radius %d does not fit a %dx%d subband", rad, W, H);
-    art_prof_begin(ctx, "k_fbox");
+    art_prof_begin(ctx, "k_fbox_h");
     k_fbox<false><<<(H + FB_CH - 1) / FB_CH, FB_NT, 0, st>>>(FbArgs{s.sf, s.tmp, W, H, rad});
+    art_prof_end(ctx);
+    art_prof_begin(ctx, "k_fbox_v");
     k_fbox<true><<<(W + FB_CH - 1) / FB_CH, FB_NT, 0, st>>>(FbArgs{s.tmp, s.sfd, W, H, rad});
     art_prof_end(ctx);
     art_prof_begin(ctx, "k_sf_apply");

@@ -178,7 +178,7 @@ int art_hp_wavelet_decompose_dev(art_hp_ctx* ctx, const float* d_src, size_t pit
     }
     const size_t nb = round_up((size_t)wv->lev[0].w2 * wv->lev[0].h2, 64);
     total += 2 * nb;
-    if (cudaMalloc(&wv->block, total * sizeof(float)) != cudaSuccess) { cudaGetLastError(); delete wv; return ctx->fail(ART_HP_ERR_NOMEM, "cudaMalloc(%zu) failed", total * sizeof(float)); }
+    { void* blk = nullptr; const int prc = art_pool_alloc(ctx, total * sizeof(float), &blk); if (prc) { delete wv; return prc; } wv->block = (float*)blk; }
     float* p = wv->block;
     for (int l = 0; l < maxlvl; ++l) {
         WLevel& L = wv->lev[l];
@@ -204,7 +204,7 @@ int art_hp_wavelet_decompose_dev(art_hp_ctx* ctx, const float* d_src, size_t pit
     }
     wv->coeff0 = wv->buf[bi ^ 1];
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { cudaFree(wv->block); delete wv; return ctx->fail(ART_HP_ERR_CUDA, "wavelet kernels: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { art_pool_free(ctx, wv->block); delete wv; return ctx->fail(ART_HP_ERR_CUDA, "wavelet kernels: %s", cudaGetErrorString(e)); }
     *out = wv;
     return ART_HP_OK;
 }
@@ -298,9 +298,7 @@ int art_hp_wavelet_set_band(art_hp_wavelet* w, int level, int dir, const float* 
 void art_hp_wavelet_destroy(art_hp_wavelet* w)
 {
     if (!w) return;
-    cudaSetDevice(w->ctx->device);
-    cudaStreamSynchronize(w->ctx->stream);
-    cudaFree(w->block);
+    art_pool_free(w->ctx, w->block);      // stream-ordered reuse: no synchronisation, no cudaFree
     delete w;
 }
 

@@ -1,11 +1,14 @@
 #!/usr/bin/env python3
 """bench.py -- the hot path on synthetic 45 MP Bayer frames, one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--method amaze|rcd]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload develop|amaze|rcd]
 
-A "step" is one pass of the hot path over one frame.  At N=1 the workload is BASELINE.json
-configs[1]: AMaZE demosaic of an 8192x5464 synthetic RGGB frame (the configuration the metric is
-quoted on that fits one GPU).  With N>1 (torchrun, one rank per GPU) every rank develops its own frame
+A "step" is one pass of the hot path over one frame.  The default workload is the one BASELINE.json's
+metric names -- "Mpixel/s end-to-end (demosaic+denoise+tonemap) on 45 MP Bayer": AMaZE demosaic, getImage
+gains + camera->working matrix, RGB_denoise (luminance 30 / detail 50 / chrominance 15) and
+Fattal tone mapping (threshold 30, amount 20) of an 8192x5464 synthetic RGGB frame, i.e. configs[1]'s frame
+run through the stages of the metric (art_hp_develop).  `--workload amaze` is configs[1] alone (demosaic
+only), `--workload rcd` the configs[0]-style case.  With N>1 (torchrun, one rank per GPU) every rank develops its own frame
 -- frames are independent objects, so there is no data-path collective ("scaling": "weak"); the only
 torch.distributed traffic is the barrier and the max-over-ranks of the timed region.
 
@@ -53,11 +56,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--method", default=os.environ.get("ART_BENCH_METHOD", "amaze"), choices=["amaze", "rcd"])
+    ap.add_argument("--workload", default=os.environ.get("ART_BENCH_WORKLOAD", "develop"), choices=["develop", "amaze", "rcd"])
+    ap.add_argument("--method", default=None, choices=["amaze", "rcd"], help="alias: --workload amaze|rcd")
+    ap.add_argument("--cpu-sample", default="2048x1366", help="frame of the bounded CPU sample of the develop workload")
     ap.add_argument("--width", type=int, default=W45)
     ap.add_argument("--height", type=int, default=H45)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.method:
+        a.workload = a.method
+    a.method = "rcd" if a.workload == "rcd" else "amaze"
+    return a
 
 
 def peaks():
@@ -148,6 +157,97 @@ def cpu_reference_runner(method, raw, filters):
         return (lambda: fn(raw, filters)), "port", os.cpu_count() or 1
 
 
+PROPHOTO = [[0.7976749, 0.1351917, 0.0313534], [0.2880402, 0.7118741, 0.0000857], [0.0, 0.0, 0.8252100]]   # iccmatrices.h xyz_prophoto
+CAM2WORK = [[0.82, 0.15, 0.03], [0.07, 0.96, -0.03], [0.02, -0.10, 1.08]]      # a fixed camera->working matrix (synthetic camera)
+MUL = (1.9, 1.0, 1.6)                                                           # rm, gm, bm of getImage for that camera
+DN = dict(luminance=30.0, luminanceDetail=50.0, luminanceDetailThreshold=0, chrominance=15.0, chrominanceRedGreen=0.0,
+          chrominanceBlueYellow=0.0, gamma=1.7, scale=1.0)
+FATTAL = (30, 20, 0)                                                            # threshold, amount, satcontrol (procparams.cc L2074-2079)
+
+# Algorithmic bytes per unit of the develop kernels that can dominate: fp32 planes, each plane a
+# kernel must read or write counted once.  unit = what one launch covers.
+DEVELOP_KERNEL_BYTES = {
+    "k_fbox_h": (8, "subband coefficient"), "k_fbox_v": (8, "subband coefficient"),        # 4 R + 4 W
+    "k_dn_blocks": (4 + 4 * (64.0 / 25.0) ** 2, "pixel"),   # residual read once + the windowed 64x64 blocks (stride 25) written
+    "k_fat_dct_rows": (4 + 8, "padded pixel"), "k_fat_dct_solve": (8 + 8, "padded pixel"), "k_fat_dct_exp": (8 + 4, "padded pixel"),
+    "k_wav_sy_sub": (16 + 4, "pixel"), "k_sf_apply": (12, "subband coefficient"), "k_mad_hist": (4, "subband coefficient"),
+}
+
+
+def find_fast_dim(dim):
+    v = dim - 1
+    for sh in (1, 2, 4, 8, 16):
+        v |= v >> sh
+    d1 = v + 1
+    for d in (d1 // 128 * 65, d1 // 64 * 33, d1 // 512 * 273, d1 // 16 * 9, d1 // 8 * 5, d1 // 16 * 11, d1 // 128 * 91,
+              d1 // 4 * 3, d1 // 64 * 49, d1 // 16 * 13, d1 // 8 * 7, d1):
+        if d >= dim:
+            return d
+    return dim
+
+
+def develop_units(name, W, H):
+    if name in ("k_fbox_h", "k_fbox_v", "k_sf_apply", "k_mad_hist"):
+        return ((W + 1) // 2) * ((H + 1) // 2)
+    if name.startswith("k_fat_dct"):
+        return (find_fast_dim(W) + 1) * (find_fast_dim(H) + 1)
+    return W * H
+
+
+def develop_params(art_b200):
+    from art_b200.api import DenoiseParams, DevelopParams
+    return DevelopParams(method=art_b200.BAYER_AMAZE, filters=0x94949494, initial_gain=1.0, border=4, mul=MUL, do_clip=True,
+                         cam2work=CAM2WORK, denoise=DenoiseParams(**DN), fattal=FATTAL, wprof=PROPHOTO)
+
+
+def cpu_develop_runner(raw, filters):
+    """The same stages through the reference's own functions compiled in place (oracle/_ref, stock build): AMaZE,
+    getImage gains + matrix, RGB_denoise, ToneMapFattal02.  fftw3f is absent from this image, so the two FFTW call sites
+    (64x64 block DCTs, 2-D REDFT00) run the oracle's double-precision stand-in, which is slower than FFTW would be."""
+    import ctypes
+    import numpy as np
+    import oracle
+    ref = oracle.ref(det=False)
+    lib = ref.lib
+    lib.artref_set_denoise_thread_limit(0)        # the reference's default: all OpenMP threads
+    fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+    H, W = raw.shape
+    out = [np.zeros((H, W), np.float32) for _ in range(3)]
+    wp = np.array(PROPHOTO, np.float64)
+    wpi = np.linalg.inv(wp)
+    p = np.array([DN["luminance"], DN["luminanceDetail"], DN["luminanceDetailThreshold"], DN["chrominance"], DN["chrominanceRedGreen"],
+                  DN["chrominanceBlueYellow"], DN["gamma"], DN["scale"]], np.float64)
+    res = np.zeros(2, np.float32)
+
+    def run():
+        ref.amaze(raw, filters, out=out)
+        r, g, b = ref.scale_convert(out, MUL, True, np.array(CAM2WORK, np.float64))
+        assert lib.artref_rgb_denoise(r.ctypes.data_as(fp), g.ctypes.data_as(fp), b.ctypes.data_as(fp), W, H, p.ctypes.data_as(dp),
+                                      wp.ctypes.data_as(dp), wpi.ctypes.data_as(dp), None, ctypes.c_float(0), None, None, None,
+                                      res.ctypes.data_as(fp)) == 0
+        assert lib.artref_fattal(r.ctypes.data_as(fp), g.ctypes.data_as(fp), b.ctypes.data_as(fp), W, H, FATTAL[0], FATTAL[1], FATTAL[2],
+                                 wp.ctypes.data_as(dp)) == 0
+    return run, "reference", os.cpu_count() or 1
+
+
+def time_cpu_develop(sample, filters, budget_s=20.0, max_runs=3):
+    from art_b200 import synth
+    w, h = [int(v) for v in sample.lower().split("x")]
+    raw = synth.bayer_frame(w, h, filters, seed=1002)
+    run, kind, cores = cpu_develop_runner(raw, filters)
+    ts = []
+    t_end = time.perf_counter() + budget_s
+    while len(ts) < max_runs and (not ts or time.perf_counter() < t_end):
+        t0 = time.perf_counter()
+        run()
+        ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    return {"value": w * h / med / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": kind,
+            "sample": "%d runs of the same four stages on a %dx%d frame (%.1f MP, 1/%d of the workload's pixels), median; reference "
+                      "functions compiled in place, OpenMP on %d threads; FFTW call sites run the oracle's fp64 stand-in (fftw3f absent)"
+                      % (len(ts), w, h, w * h / 1e6, round(W45 * H45 / (w * h)), cores)}
+
+
 def time_cpu(method, raw, filters, budget_s=12.0, max_runs=5):
     run, kind, cores = cpu_reference_runner(method, raw, filters)
     run()                                              # warm-up
@@ -171,8 +271,11 @@ def main():
     W, H = args.width, args.height
     from art_b200 import synth
     filters = synth.RGGB
-    workload = "configs[1]: %s demosaic, %dx%d synthetic RGGB (%.2f MP)" % (args.method.upper() if args.method == "rcd" else "AMaZE", W, H, W * H / 1e6)
-    if args.method == "rcd":
+    workload = "configs[1]: AMaZE demosaic, %dx%d synthetic RGGB (%.2f MP)" % (W, H, W * H / 1e6)
+    if args.workload == "develop":
+        workload = ("metric pipeline on configs[1]'s frame: AMaZE demosaic + gains/matrix + RGB_denoise (lum 30, detail 50, chroma 15) + "
+                    "Fattal (30/20), %dx%d synthetic RGGB (%.2f MP), art_hp_develop" % (W, H, W * H / 1e6))
+    if args.workload == "rcd":
         workload = "configs[0]-style: RCD demosaic, %dx%d synthetic RGGB (%.2f MP)" % (W, H, W * H / 1e6)
     config = {"workload": workload, "frame": [W, H], "cfa": "RGGB", "frames_per_step_per_gpu": 1,
               "parallelism": "replicas x%d (independent frames, no collective)" % world,
@@ -181,6 +284,31 @@ def main():
     # ---------------- reference arm: the reference's own CPU code on this box's host cores
     if args.impl == "reference":
         if rank != 0:
+            return 0
+        if args.workload == "develop":
+            # bounded sample: the same four stages on a smaller frame of the same synthetic scene, at most a few steps
+            sw, sh = [int(v) for v in args.cpu_sample.lower().split("x")]
+            raw = synth.bayer_frame(sw, sh, filters, seed=1002)
+            run, kind, cores = cpu_develop_runner(raw, filters)
+            nsteps = max(1, min(args.steps, 3))
+            t0 = time.perf_counter()
+            run()
+            first = time.perf_counter() - t0
+            nwarm = 1 if first < 20 else 0
+            t0 = time.perf_counter()
+            for _ in range(nsteps):
+                run()
+            dt = time.perf_counter() - t0
+            val = nsteps * sw * sh / dt / 1e6
+            cb = {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": kind,
+                  "sample": "%d steps (+%d warm-up) of the four stages on a %dx%d frame (1/%d of the workload's pixels; per-pixel rate "
+                            "reported); reference functions compiled in place, OpenMP on %d threads; FFTW call sites run the oracle's "
+                            "fp64 stand-in (fftw3f absent)" % (nsteps, nwarm + 0, sw, sh, round(W * H / (sw * sh)), cores)}
+            print(json.dumps({"impl": "reference", "metric": "Mpixel/s", "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus,
+                              "steps": nsteps, "warmup": 1, "ms_per_step": dt / nsteps * 1e3,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                              "data": "synthetic", "config": config, "cpu_baseline": cb,
+                              "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
             return 0
         raw = synth.bayer_frame(W, H, filters, seed=1002)
         run, kind, cores = cpu_reference_runner(args.method, raw, filters)
@@ -224,9 +352,14 @@ def main():
     d_raw[:, :W] = torch.from_numpy(raw).cuda()
     d_out = [torch.empty((H, pitch), dtype=torch.float32, device="cuda") for _ in range(3)]
 
+    dparams = develop_params(art_b200) if args.workload == "develop" else None
+
     def step_dev():
-        hp.demosaic_bayer_dev(method, W, H, filters, d_raw.data_ptr(), pitch,
-                              d_out[0].data_ptr(), d_out[1].data_ptr(), d_out[2].data_ptr(), pitch, 1.0, 4)
+        if dparams is not None:
+            hp.develop_dev(dparams, W, H, d_raw.data_ptr(), pitch, d_out[0].data_ptr(), d_out[1].data_ptr(), d_out[2].data_ptr(), pitch)
+        else:
+            hp.demosaic_bayer_dev(method, W, H, filters, d_raw.data_ptr(), pitch,
+                                  d_out[0].data_ptr(), d_out[1].data_ptr(), d_out[2].data_ptr(), pitch, 1.0, 4)
 
     def barrier():
         if dist is not None:
@@ -262,7 +395,10 @@ def main():
     pins[0].array[:] = raw
 
     def step_e2e():
-        hp.demosaic_bayer(method, pins[0].array, filters, pins[1].array, pins[2].array, pins[3].array, 1.0, 4)
+        if dparams is not None:
+            hp.develop(pins[0].array, dparams, pins[1].array, pins[2].array, pins[3].array)
+        else:
+            hp.demosaic_bayer(method, pins[0].array, filters, pins[1].array, pins[2].array, pins[3].array, 1.0, 4)
 
     for _ in range(2):
         step_e2e()
@@ -298,11 +434,17 @@ def main():
 
     if rank == 0:
         peak, how = peaks()
-        step_achieved = BYTES_PER_PX * W * H / (ms_per_step * 1e-3) / 1e9
+        # SURVEY.md 8(d) ideal-fusion bytes per pixel: demosaic 16 (+ wavelet denoise 333 + denoise I/O and DCT 80 + Fattal 160)
+        step_bytes = 16 + 333 + 80 + 160 if args.workload == "develop" else BYTES_PER_PX
+        step_achieved = step_bytes * W * H / (ms_per_step * 1e-3) / 1e9
         per_step = {k: kern[k] * calls[k] for k in kern}                     # ms per step per kernel
         top = max((k for k in per_step if k != "memset_slabs"), key=lambda k: per_step[k])
         share = per_step[top] / sum(per_step.values())
-        if args.method == "rcd":
+        if args.workload == "develop":
+            unit_bytes, unit_name = DEVELOP_KERNEL_BYTES.get(top, (AMAZE_KERNEL_BYTES.get(top), "tile pixel"))
+            ntiles = ((W + 16 + 127) // 128) * ((H + 16 + 127) // 128)
+            units = ntiles * 160 * 160 if unit_name == "tile pixel" else develop_units(top, W, H)
+        elif args.workload == "rcd":
             units, unit_bytes, unit_name = W * H, BYTES_PER_PX, "pixel"
         else:
             ntiles = ((W + 16 + 127) // 128) * ((H + 16 + 127) // 128)
@@ -310,7 +452,7 @@ def main():
         if unit_bytes is None:
             achieved = None
         else:
-            achieved = unit_bytes * units / calls[top] / (kern[top] * 1e-3) / 1e9
+            achieved = unit_bytes * units / (kern[top] * 1e-3) / 1e9      # per launch: bytes one launch moves / its mean duration
         out = {
             "metric": "Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -326,13 +468,14 @@ def main():
                          "note": "dominant kernel by device time; achieved = algorithmic bytes per launch / mean CUDA-event "
                                  "duration of that kernel (events on the launching stream, separate pass of --steps steps)"},
             "step_roofline": {"achieved": step_achieved, "frac": step_achieved / peak, "unit": "GB/s",
-                              "note": "whole step: 16 B per output pixel / ms_per_step (shows the traffic the multi-pass design adds)"},
+                              "bytes_per_pixel": step_bytes,
+                              "note": "whole step: SURVEY.md 8(d) ideal-fusion bytes per pixel / ms_per_step"},
             "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
             "clocks": clocks, "checksum_green_center": checksum,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                out["cpu_baseline"] = time_cpu(args.method, raw, filters)
+                out["cpu_baseline"] = time_cpu_develop(args.cpu_sample, filters) if args.workload == "develop" else time_cpu(args.method, raw, filters)
             except Exception as ex:  # the checker is optional for the number, never for the tests
                 out["cpu_baseline"] = {"value": None, "unit": "Mpixel/s", "cores": 0, "kind": "unavailable", "sample": str(ex)}
         print(json.dumps(out))

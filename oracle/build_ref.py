@@ -650,6 +650,8 @@ void Tile_calc(int tilesize, int overlap, int kall, int imwidth, int imheight, i
 
 using namespace rtengine;
 extern "C" {
+// timing only: 0 = the reference's default (all OpenMP threads inside detail_recovery, whose overlap-add then races); parity tests keep 1
+void artref_set_denoise_thread_limit(int n) { rtengine::options.rgbDenoiseThreadLimit = n; }
 // p: luminance, luminanceDetail, luminanceDetailThreshold, chrominance, chrominanceRedGreen, chrominanceBlueYellow, gamma, scale
 // ccurve: 501-entry NoiseCurve LUT (or null = curve not set), calclum: 3 planes of ((H+1)/2) x ((W+1)/2) (or null)
 int artref_rgb_denoise(float* r, float* g, float* b, int W, int H, const double* p, const double* wp, const double* wpi,
