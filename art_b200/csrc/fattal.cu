@@ -263,12 +263,19 @@ struct FftPlan {
     int N;                      // DCT-I of N + 1 samples = real-even DFT of length 2N = complex FFT of length N
     int nst;
     int radix[MAX_STAGES];
+    int lgr[MAX_STAGES];        // log2(radix) for the power-of-two radices, -1 otherwise
+    int lgM[MAX_STAGES];        // log2(M) of the stage (M = sub-transform length after the stage) when a power of two, else -1
 };
 
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)); }
+
+// shared-memory layout: XOR-fold swizzle of the 16-byte slot index inside aligned groups of 8, so that unit-stride,
+// small-power-of-two-stride (late stages) and digit-reversed (unpacking) accesses all spread over the bank groups
+__device__ __forceinline__ int swg(int i) { return ((i >> 3) ^ (i >> 6) ^ (i >> 9) ^ (i >> 12)) & 7; }      // GF(2)-linear in the bits of i
+__device__ __forceinline__ int sw(int i) { return i ^ swg(i); }
 
 template <int R>
-__device__ __forceinline__ void fft_stage(double2* z, int N, int L, const double2* __restrict__ tw)
+__device__ __forceinline__ void fft_stage(double2* z, int N, int L, int lgM, const double2* __restrict__ tw)
 {   // in-place decimation-in-frequency pass of radix R over sub-transforms of length L; tw[k] = exp(-i pi k / N)
     const int M = L / R;
     const int twstep = 2 * N / L;
@@ -277,12 +284,29 @@ __device__ __forceinline__ void fft_stage(double2* z, int N, int L, const double
 #pragma unroll
         for (int q = 0; q < R; ++q) wr[q] = tw[(2 * N / R) * q];
     }
+    constexpr bool POW2 = (R == 2 || R == 4);
+    int gq[R];                  // swizzle term of q * M: with power-of-two R and M the bit fields of blk, q and j are disjoint
+    if (POW2 && lgM >= 0) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) gq[q] = swg(q << lgM);
+    }
     for (int t = threadIdx.x; t < N / R; t += FFT_THREADS) {
-        const int blk = t / M, j = t - blk * M;
-        double2* p = z + (size_t)blk * L + j;
+        int blk, j;
+        if (lgM >= 0) { blk = t >> lgM; j = t & (M - 1); }
+        else { blk = t / M; j = t - blk * M; }
+        const int base = blk * L + j;
+        int ad[R];
+        if (POW2 && lgM >= 0) {
+            const int gb = swg(base);
+#pragma unroll
+            for (int q = 0; q < R; ++q) ad[q] = (base + (q << lgM)) ^ (gb ^ gq[q]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) ad[q] = sw(base + q * M);
+        }
         double2 x[R], yv[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) x[q] = p[(size_t)q * M];
+        for (int q = 0; q < R; ++q) x[q] = z[ad[q]];
         if (R == 2) {
             yv[0] = make_double2(x[0].x + x[1].x, x[0].y + x[1].y);
             yv[1] = make_double2(x[0].x - x[1].x, x[0].y - x[1].y);
@@ -306,18 +330,18 @@ __device__ __forceinline__ void fft_stage(double2* z, int N, int L, const double
                 yv[pq] = s;
             }
         }
-        p[0] = yv[0];
+        z[ad[0]] = yv[0];
         if (M > 1) {
             const double2 w1 = tw[twstep * j];
             double2 w = w1;
 #pragma unroll
             for (int q = 1; q < R; ++q) {
-                p[(size_t)q * M] = cmul(yv[q], w);
+                z[ad[q]] = cmul(yv[q], w);
                 if (q + 1 < R) w = cmul(w, w1);
             }
         } else {
 #pragma unroll
-            for (int q = 1; q < R; ++q) p[(size_t)q * M] = yv[q];
+            for (int q = 1; q < R; ++q) z[ad[q]] = yv[q];
         }
     }
 }
@@ -328,32 +352,37 @@ __device__ __forceinline__ void fft_inplace(double2* z, const FftPlan& P, const 
     for (int s = 0; s < P.nst; ++s) {
         const int r = P.radix[s];
         switch (r) {
-            case 2: fft_stage<2>(z, P.N, L, tw); break;
-            case 3: fft_stage<3>(z, P.N, L, tw); break;
-            case 4: fft_stage<4>(z, P.N, L, tw); break;
-            case 5: fft_stage<5>(z, P.N, L, tw); break;
-            case 7: fft_stage<7>(z, P.N, L, tw); break;
-            case 11: fft_stage<11>(z, P.N, L, tw); break;
-            default: fft_stage<13>(z, P.N, L, tw); break;
+            case 2: fft_stage<2>(z, P.N, L, P.lgM[s], tw); break;
+            case 3: fft_stage<3>(z, P.N, L, P.lgM[s], tw); break;
+            case 4: fft_stage<4>(z, P.N, L, P.lgM[s], tw); break;
+            case 5: fft_stage<5>(z, P.N, L, P.lgM[s], tw); break;
+            case 7: fft_stage<7>(z, P.N, L, P.lgM[s], tw); break;
+            case 11: fft_stage<11>(z, P.N, L, P.lgM[s], tw); break;
+            default: fft_stage<13>(z, P.N, L, P.lgM[s], tw); break;
         }
         L /= r;
         __syncthreads();
     }
 }
 
-// where output bin k of the in-place transform sits
+// where output bin k of the in-place transform sits (digit reversal over the stage radices); tabulated once per plan
 __device__ __forceinline__ int fft_pos(const FftPlan& P, int k)
 {
     int pos = 0, L = P.N;
     for (int s = 0; s < P.nst; ++s) {
         const int r = P.radix[s];
-        const int M = L / r;
-        const int q = k / r;
-        pos += (k - q * r) * M;
+        int q, d, M;
+        if (P.lgr[s] >= 0) { q = k >> P.lgr[s]; d = k & (r - 1); } else { q = k / r; d = k - q * r; }
+        if (P.lgM[s] >= 0) { M = 1 << P.lgM[s]; pos += d << P.lgM[s]; } else { M = L / r; pos += d * M; }
         k = q;
         L = M;
     }
     return pos;
+}
+__global__ void k_fat_postab(int* tab, FftPlan P)
+{   // tab[k] = swizzled slot of bin k for k in [0, N], bin N aliasing bin 0
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= P.N) tab[k] = sw(fft_pos(P, k == P.N ? 0 : k));
 }
 
 // pack the even extension of x[0..N] (stride 1) into z: z[m] = y[2m] + i y[2m+1], y[j] = x[j <= N ? j : 2N - j]
@@ -362,19 +391,18 @@ __device__ __forceinline__ void dct_pack(double2* z, const T* x, int N)
 {
     for (int m = threadIdx.x; m < N; m += FFT_THREADS) {
         const int a = 2 * m, b = 2 * m + 1;
-        z[m] = make_double2((double)x[a <= N ? a : 2 * N - a], (double)x[b <= N ? b : 2 * N - b]);
+        z[sw(m)] = make_double2((double)x[a <= N ? a : 2 * N - a], (double)x[b <= N ? b : 2 * N - b]);
     }
     __syncthreads();
 }
 
 // Y_k of the real-even sequence from the packed transform: E_k + exp(-i pi k / N) O_k, real part
-__device__ __forceinline__ double dct_unpack(const double2* z, const FftPlan& P, const double2* __restrict__ tw, int k)
+__device__ __forceinline__ double dct_unpack(const double2* z, const FftPlan& P, const double2* __restrict__ tw, const int* __restrict__ postab, int k)
 {
-    const int N = P.N;
-    const double2 zk = z[fft_pos(P, k == N ? 0 : k)];
-    const double2 zc = z[fft_pos(P, k == 0 ? 0 : N - k)];
+    const double2 zk = z[postab[k]];
+    const double2 zc = z[postab[P.N - k]];
     const double2 w = tw[k];
-    return 0.5 * (zk.x + zc.x) + w.x * (0.5 * (zk.y + zc.y)) + w.y * (0.5 * (zk.x - zc.x));
+    return fma(w.y, 0.5 * (zk.x - zc.x), fma(w.x, 0.5 * (zk.y + zc.y), 0.5 * (zk.x + zc.x)));
 }
 
 // MODE 0: float rows -> double rows.            (first half of transform_normal2ev, L781-788)
@@ -385,7 +413,7 @@ __device__ __forceinline__ double dct_unpack(const double2* z, const FftPlan& P,
 template <int MODE>
 __global__ void __launch_bounds__(FFT_THREADS)
 k_fat_dct(const void* in, size_t ipitch, void* out, size_t opitch, int nrows, FftPlan P,
-          const double2* __restrict__ tw, const double* __restrict__ lam_k, const double* __restrict__ lam_row, float factor)
+          const double2* __restrict__ tw, const int* __restrict__ postab, const double* __restrict__ lam_k, const double* __restrict__ lam_row, float factor)
 {
     extern __shared__ double2 z[];
     const int N = P.N;
@@ -395,12 +423,12 @@ k_fat_dct(const void* in, size_t ipitch, void* out, size_t opitch, int nrows, Ff
         fft_inplace(z, P, tw);
         if (MODE == 0) {
             double* o = (double*)out + (size_t)row * opitch;
-            for (int k = threadIdx.x; k <= N; k += FFT_THREADS) o[k] = dct_unpack(z, P, tw, k);
+            for (int k = threadIdx.x; k <= N; k += FFT_THREADS) o[k] = dct_unpack(z, P, tw, postab, k);
         } else if (MODE == 2) {
             float* o = (float*)out + (size_t)row * opitch;
             const int width = N + 1;
             for (int k = threadIdx.x; k <= N; k += FFT_THREADS) {
-                const float v = (float)dct_unpack(z, P, tw, k);
+                const float v = (float)dct_unpack(z, P, tw, postab, k);
                 o[k] = ((k & ~3) < width - 3) ? sleef::xexpf_vector(v) : sleef::xexpf_scalar(v);
             }
         } else {
@@ -409,7 +437,7 @@ k_fat_dct(const void* in, size_t ipitch, void* out, size_t opitch, int nrows, Ff
             const bool xedge = row == 0 || row == nrows - 1;
             const double lx = lam_row[row];
             for (int k = threadIdx.x; k <= N; k += FFT_THREADS) {
-                float t = (float)dct_unpack(z, P, tw, k);
+                float t = (float)dct_unpack(z, P, tw, postab, k);
                 const bool yedge = k == 0 || k == N;
                 t *= factor;
                 if (yedge) t *= 0.5f;
@@ -425,7 +453,7 @@ k_fat_dct(const void* in, size_t ipitch, void* out, size_t opitch, int nrows, Ff
             fft_inplace(z, P, tw);
             double vals[(14336 + FFT_THREADS) / FFT_THREADS];
             int c = 0;
-            for (int k = threadIdx.x; k <= N; k += FFT_THREADS) vals[c++] = dct_unpack(z, P, tw, k);
+            for (int k = threadIdx.x; k <= N; k += FFT_THREADS) vals[c++] = dct_unpack(z, P, tw, postab, k);
             c = 0;
             for (int k = threadIdx.x; k <= N; k += FFT_THREADS) o[k] = vals[c++];
         }
@@ -434,7 +462,7 @@ k_fat_dct(const void* in, size_t ipitch, void* out, size_t opitch, int nrows, Ff
 }
 
 __global__ void __launch_bounds__(FFT_THREADS)
-k_dct_dd(const double* in, size_t ipitch, double* out, size_t opitch, int nrows, FftPlan P, const double2* __restrict__ tw)
+k_dct_dd(const double* in, size_t ipitch, double* out, size_t opitch, int nrows, FftPlan P, const double2* __restrict__ tw, const int* __restrict__ postab)
 {
     extern __shared__ double2 z[];
     const int N = P.N;
@@ -443,7 +471,7 @@ k_dct_dd(const double* in, size_t ipitch, double* out, size_t opitch, int nrows,
         fft_inplace(z, P, tw);
         double vals[(14336 + FFT_THREADS) / FFT_THREADS];
         int c = 0;
-        for (int k = threadIdx.x; k <= N; k += FFT_THREADS) vals[c++] = dct_unpack(z, P, tw, k);
+        for (int k = threadIdx.x; k <= N; k += FFT_THREADS) vals[c++] = dct_unpack(z, P, tw, postab, k);
         c = 0;
         double* o = out + (size_t)row * opitch;
         for (int k = threadIdx.x; k <= N; k += FFT_THREADS) o[k] = vals[c++];
@@ -620,15 +648,18 @@ bool make_plan(int N, FftPlan* P)
 {
     P->N = N; P->nst = 0;
     int n = N;
+    auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
     const int odd[5] = {13, 11, 7, 5, 3};
     for (int f : odd)
         while (n % f == 0) { if (P->nst >= MAX_STAGES) return false; P->radix[P->nst++] = f; n /= f; }
     while (n % 4 == 0) { if (P->nst >= MAX_STAGES) return false; P->radix[P->nst++] = 4; n /= 4; }
     if (n % 2 == 0) { if (P->nst >= MAX_STAGES) return false; P->radix[P->nst++] = 2; n /= 2; }
+    int L = N;
+    for (int s = 0; s < P->nst; ++s) { L /= P->radix[s]; P->lgr[s] = lg(P->radix[s]); P->lgM[s] = lg(L); }
     return n == 1;
 }
 
-struct AxisTables { double2* tw = nullptr; double* lam = nullptr; };
+struct AxisTables { double2* tw = nullptr; double* lam = nullptr; int* postab = nullptr; };
 std::mutex g_tab_mu;
 std::map<std::pair<int, int>, AxisTables> g_tabs;       // (device, n) -> tables; a handful of sizes per process
 
@@ -642,6 +673,10 @@ int axis_tables(art_hp_ctx* ctx, int n, AxisTables* out)
     AxisTables t;
     ART_CUDA(ctx, cudaMalloc(&t.tw, sizeof(double2) * 2 * (size_t)N));
     ART_CUDA(ctx, cudaMalloc(&t.lam, sizeof(double) * (size_t)n));
+    ART_CUDA(ctx, cudaMalloc(&t.postab, sizeof(int) * (size_t)n));
+    FftPlan P;
+    if (!make_plan(N, &P)) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "no FFT plan for length %d", N);
+    k_fat_postab<<<(n + 255) / 256, 256, 0, ctx->stream>>>(t.postab, P);
     k_fat_twiddles<<<(2 * N + 255) / 256, 256, 0, ctx->stream>>>(t.tw, N);
     ctx->launches++;
     std::vector<double> lam(n);
@@ -689,7 +724,7 @@ int art_fattal_dev(art_hp_ctx* ctx, float* R, float* G, float* B, size_t ip, int
     const int N1 = w2 - 1, N0 = h2 - 1;
     FftPlan P1, P0;
     if (!make_plan(N1, &P1) || !make_plan(N0, &P0)) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "no FFT plan for %d x %d", w2, h2);
-    const size_t smem1 = sizeof(double2) * (size_t)N1, smem0 = sizeof(double2) * (size_t)N0;
+    const size_t smem1 = sizeof(double2) * round_up((size_t)N1, 8), smem0 = sizeof(double2) * round_up((size_t)N0, 8);
     if (std::max(smem1, smem0) > 227u * 1024u || std::max(N1, N0) > 14336)
         return ctx->fail(ART_HP_ERR_UNSUPPORTED, "padded side %d exceeds the shared-memory transform (max 14336)", std::max(N1, N0));
     int ww, hh;
@@ -806,14 +841,14 @@ int art_fattal_dev(art_hp_ctx* ctx, float* R, float* G, float* B, size_t ip, int
     };
     const float factor = 1.0f / ((h2 - 1) * (w2 - 1));
     const dim3 tb32(32, 8);
-    FAT_LAUNCH("k_fat_dct_rows", k_fat_dct<0>, dct_grid(smem1, h2), FFT_THREADS, smem1, (const void*)F, (size_t)w2, (void*)A, pa, h2, P1, t1.tw,
+    FAT_LAUNCH("k_fat_dct_rows", k_fat_dct<0>, dct_grid(smem1, h2), FFT_THREADS, smem1, (const void*)F, (size_t)w2, (void*)A, pa, h2, P1, t1.tw, t1.postab,
                (const double*)nullptr, (const double*)nullptr, 0.f);
     FAT_LAUNCH("k_fat_transpose", k_fat_transpose, dim3((w2 + 31) / 32, (h2 + 31) / 32), tb32, 0, A, pa, Bt, pb, h2, w2);
-    FAT_LAUNCH("k_fat_dct_solve", k_fat_dct<1>, dct_grid(smem0, w2), FFT_THREADS, smem0, (const void*)Bt, pb, (void*)Bt, pb, w2, P0, t0.tw,
+    FAT_LAUNCH("k_fat_dct_solve", k_fat_dct<1>, dct_grid(smem0, w2), FFT_THREADS, smem0, (const void*)Bt, pb, (void*)Bt, pb, w2, P0, t0.tw, t0.postab,
                (const double*)t0.lam, (const double*)t1.lam, factor);
     FAT_LAUNCH("k_fat_transpose", k_fat_transpose, dim3((h2 + 31) / 32, (w2 + 31) / 32), tb32, 0, Bt, pb, A, pa, w2, h2);
     float* L = F;      // F is dead once the first row pass has read it
-    FAT_LAUNCH("k_fat_dct_exp", k_fat_dct<2>, dct_grid(smem1, h2), FFT_THREADS, smem1, (const void*)A, pa, (void*)L, (size_t)w2, h2, P1, t1.tw,
+    FAT_LAUNCH("k_fat_dct_exp", k_fat_dct<2>, dct_grid(smem1, h2), FFT_THREADS, smem1, (const void*)A, pa, (void*)L, (size_t)w2, h2, P1, t1.tw, t1.postab,
                (const double*)nullptr, (const double*)nullptr, 0.f);
 
     // median / shadow statistics on 200-px thumbnails, final application (L1129-1213)
@@ -843,10 +878,10 @@ int art_redft00_2d_dev(art_hp_ctx* ctx, const float* in, float* out, int n0, int
     if ((rc = axis_tables(ctx, n0, &t0))) return rc;
     cudaFuncSetAttribute(k_fat_dct<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(k_dct_dd, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    const size_t smem1 = sizeof(double2) * (size_t)(n1 - 1), smem0 = sizeof(double2) * (size_t)(n0 - 1);
-    k_fat_dct<0><<<std::min(n0, ctx->sm_count), FFT_THREADS, smem1, st>>>(in, (size_t)n1, A, pa, n0, P1, t1.tw, nullptr, nullptr, 0.f);
+    const size_t smem1 = sizeof(double2) * round_up((size_t)(n1 - 1), 8), smem0 = sizeof(double2) * round_up((size_t)(n0 - 1), 8);
+    k_fat_dct<0><<<std::min(n0, ctx->sm_count), FFT_THREADS, smem1, st>>>(in, (size_t)n1, A, pa, n0, P1, t1.tw, t1.postab, nullptr, nullptr, 0.f);
     k_fat_transpose<<<dim3((n1 + 31) / 32, (n0 + 31) / 32), dim3(32, 8), 0, st>>>(A, pa, Bt, pb, n0, n1);
-    k_dct_dd<<<std::min(n1, ctx->sm_count), FFT_THREADS, smem0, st>>>(Bt, pb, Bt, pb, n1, P0, t0.tw);
+    k_dct_dd<<<std::min(n1, ctx->sm_count), FFT_THREADS, smem0, st>>>(Bt, pb, Bt, pb, n1, P0, t0.tw, t0.postab);
     k_fat_transpose<<<dim3((n0 + 31) / 32, (n1 + 31) / 32), dim3(32, 8), 0, st>>>(Bt, pb, A, pa, n1, n0);
     k_round<<<dim3((n1 + 31) / 32, (n0 + 7) / 8), dim3(32, 8), 0, st>>>(A, pa, out, n0, n1);
     ctx->launches += 5;
