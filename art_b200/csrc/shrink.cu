@@ -135,7 +135,7 @@ struct FbArgs { const float* x; float* y; int W, H, rad; };
 // 256 threads load the tile with coalesced reads and form the per-step differences in parallel, FB_CH lanes run the
 // additions out of shared memory, all threads store the tile.  The ramps at both ends of a chain (rad + 1 and rad steps)
 // are done by the chain lanes straight from global memory.
-constexpr int FB_CH = 16, FB_T = 256, FB_NT = 256;
+constexpr int FB_CH = 8, FB_T = 256, FB_NT = 256, FB_PER = FB_CH * FB_T / FB_NT;
 
 template <bool VERT>
 __global__ void __launch_bounds__(FB_NT) k_fbox(FbArgs a)
@@ -191,12 +191,23 @@ __global__ void __launch_bounds__(FB_NT) k_fbox(FbArgs a)
     const int first = rad + 1, last = nsteps - rad;          // main region [first, last)
     for (int s0 = first; s0 < last; s0 += FB_T) {
         const int nst = min(FB_T, last - s0);
-        for (int i = tid; i < FB_CH * FB_T; i += FB_NT) {
-            const int cl = VERT ? i % FB_CH : i / FB_T, sl = VERT ? i / FB_CH : i % FB_T;
-            const int ch = chain0 + cl, st = s0 + sl;
-            if (ch < nchains && sl < nst) {
-                const float diff = a.x[at(ch, st + rad)] - a.x[at(ch, st - rad - 1)];
-                tile[sl][cl] = (VERT && ch >= W - (W % 4)) ? diff / (float)(2 * rad + 1) : diff * rlen;
+        {   // all loads of the tile first (FB_PER independent pairs per thread in flight), then the differences
+            float va[FB_PER], vb[FB_PER];
+#pragma unroll
+            for (int u = 0; u < FB_PER; ++u) {
+                const int i = tid + u * FB_NT;
+                const int cl = VERT ? i % FB_CH : i / FB_T, sl = VERT ? i / FB_CH : i % FB_T;
+                const int ch = chain0 + cl, st = s0 + sl;
+                const bool ok = ch < nchains && sl < nst;
+                va[u] = ok ? a.x[at(ch, st + rad)] : 0.f;
+                vb[u] = ok ? a.x[at(ch, st - rad - 1)] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < FB_PER; ++u) {
+                const int i = tid + u * FB_NT;
+                const int cl = VERT ? i % FB_CH : i / FB_T, sl = VERT ? i / FB_CH : i % FB_T;
+                const float diff = va[u] - vb[u];
+                tile[sl][cl] = (VERT && chain0 + cl >= W - (W % 4)) ? diff / (float)(2 * rad + 1) : diff * rlen;
             }
         }
         __syncthreads();
@@ -208,7 +219,9 @@ __global__ void __launch_bounds__(FB_NT) k_fbox(FbArgs a)
             }
         }
         __syncthreads();
-        for (int i = tid; i < FB_CH * FB_T; i += FB_NT) {
+#pragma unroll
+        for (int u = 0; u < FB_PER; ++u) {
+            const int i = tid + u * FB_NT;
             const int cl = VERT ? i % FB_CH : i / FB_T, sl = VERT ? i / FB_CH : i % FB_T;
             const int ch = chain0 + cl;
             if (ch < nchains && sl < nst) a.y[at(ch, s0 + sl)] = tile[sl][cl];
