@@ -800,6 +800,218 @@ void artref_redft00_1d(int n, const double* x, double* y)
 """
 
 
+SHIM_CHAIN_TU = r"""
+// Shim TU hosting the per-pixel colour / curve chain of ImProcFunctions::process: the pixel loops of expcomp
+// (ipexposure.cc), saturationVibrance (ipsaturation.cc), filmlike_clip + Standard / Adobe tone curves (iptonecurve.cc,
+// curves.h), rgbCurves (iprgbcurves.cc), lab_adjustments (iplabadjustments.cc), Imagefloat::rgb_to_lab / lab_to_rgb
+// (imagefloat.cc) and the Color members they call (color.h / color.cc), all cut from the reference at build time.
+// Written here (not reference code): the Imagefloat / Plane stand-in, Color's constants and LUT initialisation
+// (restating color.cc L205-233), the wrappers.  Everything sits in its own namespace so that this Color does not collide
+// with the one in shim_denoise.cc.
+#include <assert.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include <omp.h>
+#include "LUT.h"
+#include "rt_math.h"
+#include "opthelper.h"
+#include "sleef.h"
+
+namespace artref_chain {
+using namespace rtengine;
+typedef const double (*TMatrix)[3];
+
+class Curve { public: virtual ~Curve() {} virtual double getVal(double) const { abort(); } };
+
+class Color {
+public:
+    constexpr static double eps = 216.0 / 24389.0;
+    constexpr static double MAXVALD = 65535.0; constexpr static float MAXVALF = 65535.f;
+    constexpr static double eps_max = MAXVALF * eps;
+    constexpr static double kappa = 24389.0 / 27.0;
+    constexpr static double kappaInv = 27.0 / 24389.0;
+    constexpr static double epsilonExpInv3 = 6.0 / 29.0;
+    constexpr static float kappaInvf = kappaInv;
+    constexpr static float epsilonExpInv3f = epsilonExpInv3;
+    constexpr static float D50x = 0.9642f, D50z = 0.8249f;
+    constexpr static double epskap = 8.0;
+    constexpr static float c1By116 = 1.0 / 116.0;
+    constexpr static float c16By116 = 16.0 / 116.0;
+    static LUTf cachef, cachefy;
+    static void init()
+    {
+        if (cachef) return;
+        cachef(65536, LUT_CLIP_BELOW); cachefy(65536, LUT_CLIP_BELOW);
+        int i = 0; const int epsmaxint = eps_max;            // color.cc L205-233
+        for (; i <= epsmaxint; i++) { cachef[i] = 327.68 * ((kappa * i / MAXVALF + 16.0) / 116.0); cachefy[i] = 327.68 * (kappa * i / MAXVALF); }
+        for (; i < 65536; i++) { cachef[i] = 327.68 * std::cbrt((double)i / MAXVALF); cachefy[i] = 327.68 * (116.0 * std::cbrt((double)i / MAXVALF) - 16.0); }
+    }
+#include "chain_color_h.inc"
+    static float computeXYZ2Lab(float f);
+    static float computeXYZ2LabY(float f);
+    static void rgbxyz (float r, float g, float b, float &x, float &y, float &z, const float xyz_rgb[3][3]);
+    static void rgbxyz (vfloat r, vfloat g, vfloat b, vfloat &x, vfloat &y, vfloat &z, const vfloat xyz_rgb[3][3]);
+    static void xyz2rgb (float x, float y, float z, float &r, float &g, float &b, const float rgb_xyz[3][3]);
+    static void xyz2rgb (vfloat x, vfloat y, vfloat z, vfloat &r, vfloat &g, vfloat &b, const vfloat rgb_xyz[3][3]);
+    static void XYZ2Lab(float X, float Y, float Z, float &L, float &a, float &b);
+    static void XYZ2Lab(vfloat X, vfloat Y, vfloat Z, vfloat &L, vfloat &a, vfloat &b);
+    static void Lab2XYZ(float L, float a, float b, float &x, float &y, float &z);
+    static void Lab2XYZ(vfloat L, vfloat a, vfloat b, vfloat &x, vfloat &y, vfloat &z);
+    static void filmlike_clip(float *r, float *g, float *b, float Lmax);
+};
+LUTf Color::cachef, Color::cachefy;
+#include "chain_color_cc.inc"
+
+// stand-in for PlanarPtr / Imagefloat: rows 16-byte aligned like the reference's allocation (iimage.h L653-673)
+struct Plane {
+    float* base; int stride; float** ptrs;
+    float& operator()(int y, int x) { return base[(size_t)y * stride + x]; }
+    float* operator()(int y) { return base + (size_t)y * stride; }
+};
+class Imagefloat {
+public:
+    int width, height; Plane r, g, b;
+    float ws_[3][3], iws_[3][3]; vfloat vws_[3][3], viws_[3][3];
+    Imagefloat(int w, int h, const float* R, const float* G, const float* B, const double* ws, const double* iws) : width(w), height(h)
+    {
+        const int st = (w + 3) / 4 * 4;
+        Plane* pl[3] = {&r, &g, &b}; const float* src[3] = {R, G, B};
+        for (int c = 0; c < 3; ++c) {
+            void* p = nullptr; if (posix_memalign(&p, 64, sizeof(float) * (size_t)st * h)) abort();
+            pl[c]->base = (float*)p; pl[c]->stride = st; pl[c]->ptrs = new float*[h];
+            for (int y = 0; y < h; ++y) { pl[c]->ptrs[y] = pl[c]->base + (size_t)y * st; memcpy(pl[c]->ptrs[y], src[c] + (size_t)y * w, sizeof(float) * w); }
+        }
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {      // get_ws(), imagefloat.cc L595-617
+            ws_[i][j] = float(ws[3 * i + j]); iws_[i][j] = float(iws ? iws[3 * i + j] : 0.0);
+            vws_[i][j] = F2V(float(ws[3 * i + j])); viws_[i][j] = F2V(float(iws ? iws[3 * i + j] : 0.0));
+        }
+    }
+    ~Imagefloat() { Plane* pl[3] = {&r, &g, &b}; for (int c = 0; c < 3; ++c) { free(pl[c]->base); delete[] pl[c]->ptrs; } }
+    void store(float* R, float* G, float* B) { Plane* pl[3] = {&r, &g, &b}; float* dst[3] = {R, G, B};
+        for (int c = 0; c < 3; ++c) for (int y = 0; y < height; ++y) memcpy(dst[c] + (size_t)y * width, pl[c]->ptrs[y], sizeof(float) * width); }
+    int getWidth() const { return width; }
+    int getHeight() const { return height; }
+    void get_ws() {}
+    void rgb_to_lab(bool multithread);
+    inline void rgb_to_lab(int y, int x, float &L, float &a, float &b);
+    void lab_to_rgb(bool multithread);
+};
+#include "chain_imagefloat.inc"
+
+namespace curves {
+#include "chain_setlutval.inc"
+}
+class ToneCurve { public: LUTf lutToneCurve; float whitecoeff; float whitept; const Curve* curve; ToneCurve() : whitecoeff(1.f), whitept(65535.f), curve(nullptr) {} };
+class StandardToneCurve : public ToneCurve { public: void Apply(float& r, float& g, float& b) const; };
+class AdobeToneCurve : public ToneCurve { void RGBTone(float& r, float& g, float& b) const; public: void Apply(float& r, float& g, float& b) const; };
+#include "chain_tonecurves.inc"
+
+namespace {
+#include "chain_iptonecurve.inc"
+#include "chain_vibrance.inc"
+}
+
+extern "C" {
+int artref_chain_expcomp(float* R, float* G, float* B, int W, int H, float exp_scale, float black)
+{
+    Imagefloat im(W, H, R, G, B, (const double[9]){1,0,0,0,1,0,0,0,1}, nullptr);
+    Imagefloat* img = &im;
+    const bool multiThread = true;
+    vfloat exp_scalev = F2V(exp_scale);
+    vfloat blackv = F2V(black);
+    float **chan[3] = { img->r.ptrs, img->g.ptrs, img->b.ptrs };
+#pragma omp parallel for if (multiThread)
+#include "chain_expcomp_loop.inc"
+    im.store(R, G, B);
+    return 0;
+}
+int artref_chain_saturation(float* R, float* G, float* B, int W, int H, int sat, int vibr, const double* wsd)
+{
+    Imagefloat im(W, H, R, G, B, wsd, nullptr);
+    Imagefloat* rgb = &im;
+    const bool multiThread = true;
+    double wsm[3][3]; memcpy(wsm, wsd, sizeof wsm);
+    TMatrix ws = wsm;
+    const float saturation = 1.f + sat / 100.f;
+    const float vibrance = 1.f - vibr / 1000.f;
+    const float noise = pow_F(2.f, -16.f);
+    const bool vib = vibr;
+#pragma omp parallel for if (multiThread)
+#include "chain_saturation_loop.inc"
+    im.store(R, G, B);
+    return 0;
+}
+// mode 0 = ToneCurveParams::TcMode::STD, 1 = FILMLIKE; lut = ToneCurve::lutToneCurve (65536 entries); whitept = 1
+int artref_chain_tonecurve(float* R, float* G, float* B, int W, int H, int mode, const float* lut, float whitept)
+{
+    Imagefloat im(W, H, R, G, B, (const double[9]){1,0,0,0,1,0,0,0,1}, nullptr);
+    filmlike_clip(&im, whitept, true);
+    if (mode == 0) {
+        StandardToneCurve c; c.lutToneCurve(65536); for (int i = 0; i < 65536; ++i) c.lutToneCurve[i] = lut[i];
+        c.whitecoeff = whitept; c.whitept = 65535.f * whitept;
+        apply(c, &im, W, H, true);
+    } else {
+        AdobeToneCurve c; c.lutToneCurve(65536); for (int i = 0; i < 65536; ++i) c.lutToneCurve[i] = lut[i];
+        c.whitecoeff = whitept; c.whitept = 65535.f * whitept;
+        apply(c, &im, W, H, true);
+    }
+    im.store(R, G, B);
+    return 0;
+}
+int artref_chain_rgbcurves(float* R, float* G, float* B, int W, int H, const float* rc, const float* gc, const float* bc)
+{
+    Imagefloat im(W, H, R, G, B, (const double[9]){1,0,0,0,1,0,0,0,1}, nullptr);
+    Imagefloat* img = &im;
+    const bool multiThread = true;
+    LUTf rCurve, gCurve, bCurve;
+    if (rc) { rCurve(65536, 0); for (int i = 0; i < 65536; ++i) rCurve[i] = rc[i]; }
+    if (gc) { gCurve(65536, 0); for (int i = 0; i < 65536; ++i) gCurve[i] = gc[i]; }
+    if (bc) { bCurve(65536, 0); for (int i = 0; i < 65536; ++i) bCurve[i] = bc[i]; }
+    if (rCurve || gCurve || bCurve) {
+#pragma omp parallel for if (multiThread)
+#include "chain_rgbcurves_loop.inc"
+    }
+    im.store(R, G, B);
+    return 0;
+}
+// labAdjustments: setMode(LAB), lab_adjustments' pixel loop, setMode(RGB); lcurve 32770, acurve / bcurve 65536 entries
+int artref_chain_lab(float* R, float* G, float* B, int W, int H, const float* lc, const float* ac, const float* bc, float chroma,
+                     const double* wsd, const double* iwsd)
+{
+    Color::init();
+    Imagefloat im(W, H, R, G, B, wsd, iwsd);
+    Imagefloat* img = &im;
+    const bool multiThread = true;
+    im.rgb_to_lab(true);
+    LUTf lcurve, acurve, bcurve;
+    lcurve(32770, 0); acurve(65536); bcurve(65536);
+    for (int i = 0; i < 32770; ++i) lcurve[i] = lc[i];
+    for (int i = 0; i < 65536; ++i) { acurve[i] = ac[i]; bcurve[i] = bc[i]; }
+    const vfloat chromav = F2V(chroma);
+    const vfloat v32768 = F2V(32768.f);
+#pragma omp parallel for if (multiThread)
+#include "chain_lab_loop.inc"
+    im.lab_to_rgb(true);
+    im.store(R, G, B);
+    return 0;
+}
+int artref_chain_rgb2lab(float* R, float* G, float* B, int W, int H, const double* wsd, const double* iwsd, int back)
+{
+    Color::init();
+    Imagefloat im(W, H, R, G, B, wsd, iwsd);
+    if (back) im.lab_to_rgb(true); else im.rgb_to_lab(true);
+    im.store(R, G, B);
+    return 0;
+}
+}
+}  // namespace artref_chain
+"""
+
+
 def extract(det):
     sub = os.path.join(SRC, "det" if det else "stock")
     os.makedirs(sub, exist_ok=True)
@@ -884,6 +1096,58 @@ def extract(det):
     open(os.path.join(sub, "fattal_color_members.inc"), "w").write(
         "template <class T>\n" + cut_function(ch, r"static float rgbLuminance\(float r, float g, float b, const T workingspace\[3\]\[3\]\)"))
     open(os.path.join(sub, "shim_fattal.cc"), "w").write(SHIM_FATTAL_TU)
+    # ---- colour / curve chain
+    def block_after(path, anchor):
+        return cut_block(path, anchor)
+    ipx = os.path.join(RT, "ipexposure.cc")
+    open(os.path.join(sub, "chain_expcomp_loop.inc"), "w").write(
+        block_after(ipx, r"for \(int y = 0; y < H; \+\+y\) \{(?=\s*int x = 0;\s*#ifdef __SSE2__\s*for \(; x < W - 3; x \+= 4\) \{\s*for \(int c = 0; c < 3; \+\+c\))"))
+    ips = os.path.join(RT, "ipsaturation.cc")
+    open(os.path.join(sub, "chain_vibrance.inc"), "w").write(cut_function(ips, r"^float apply_vibrance\(float x, float vib\)"))
+    open(os.path.join(sub, "chain_saturation_loop.inc"), "w").write(
+        block_after(ips, r"for \(int i = 0; i < H; \+\+i\) \{(?=\s*for \(int j = 0; j < W; \+\+j\) \{\s*float &r = rgb->r\(i, j\);)"))
+    ipr = os.path.join(RT, "iprgbcurves.cc")
+    open(os.path.join(sub, "chain_rgbcurves_loop.inc"), "w").write(
+        block_after(ipr, r"for \(int y = 0; y < H; \+\+y\) \{(?=\s*int x = 0;\s*#ifdef __SSE2__\s*for \(; x < W-3; x \+= 4\) \{\s*if \(rCurve\))"))
+    ipl = os.path.join(RT, "iplabadjustments.cc")
+    open(os.path.join(sub, "chain_lab_loop.inc"), "w").write(
+        block_after(ipl, r"for \(int y = 0; y < H; \+\+y\) \{(?=\s*int x = 0;\s*#ifdef __SSE2__\s*for \(; x < W-3; x \+= 4\) \{\s*vfloat L = LVF)"))
+    ipt = os.path.join(RT, "iptonecurve.cc")
+    open(os.path.join(sub, "chain_iptonecurve.inc"), "w").write(
+        "template <class Curve>\n" + cut_function(ipt, r"^inline void apply\(const Curve &c, Imagefloat \*rgb, int W, int H, bool multithread\)") + "\n" +
+        cut_function(ipt, r"^void filmlike_clip\(Imagefloat \*rgb, float whitept, bool multithread\)"))
+    cvh = os.path.join(RT, "curves.h")
+    open(os.path.join(sub, "chain_setlutval.inc"), "w").write(cut_function(cvh, r"^inline void setLutVal\(const LUTf &lut, const Curve \*curve, float &val\)"))
+    open(os.path.join(sub, "chain_tonecurves.inc"), "w").write("\n".join([
+        cut_function(cvh, r"^inline void StandardToneCurve::Apply \(float& r, float& g, float& b\) const"),
+        cut_function(cvh, r"^inline void AdobeToneCurve::RGBTone \(float& r, float& g, float& b\) const"),
+        cut_function(cvh, r"^inline void AdobeToneCurve::Apply \(float& ir, float& ig, float& ib\) const")]))
+    imf = os.path.join(RT, "imagefloat.cc")
+    open(os.path.join(sub, "chain_imagefloat.inc"), "w").write("\n".join([
+        cut_function(imf, r"^inline void Imagefloat::rgb_to_lab\(int y, int x, float &L, float &a, float &b\)"),
+        cut_function(imf, r"^void Imagefloat::rgb_to_lab\(bool multithread\)"),
+        cut_function(imf, r"^void Imagefloat::lab_to_rgb\(bool multithread\)")]))
+    hm = [cut_function(ch, r"static float rgbLuminance\(float r, float g, float b, const T workingspace\[3\]\[3\]\)"),
+          cut_function(ch, r"static inline float f2xyz\(float f\)"),
+          cut_function(ch, r"static inline vfloat f2xyz\(vfloat f\)"),
+          cut_function(ch, r"static void rgb2lab\(float R, float G, float B, float &l, float &a, float &b, const T ws\[3\]\[3\]\)"),
+          cut_function(ch, r"static void lab2rgb\(float l, float a, float b, float &R, float &G, float &B, const T iws\[3\]\[3\]\)"),
+          cut_function(ch, r"static void rgb2lab\(vfloat R, vfloat G, vfloat B, vfloat &l, vfloat &a, vfloat &b, const vfloat ws\[3\]\[3\]\)"),
+          cut_function(ch, r"static void lab2rgb\(vfloat l, vfloat a, vfloat b, vfloat &R, vfloat &G, vfloat &B, const vfloat iws\[3\]\[3\]\)")]
+    open(os.path.join(sub, "chain_color_h.inc"), "w").write("\n".join(("template <class T>\n" if "const T " in t else "") + t for t in hm))
+    ccf = [cut_function(cc, r"^inline float Color::computeXYZ2Lab\(float f\)"), cut_function(cc, r"^inline float Color::computeXYZ2LabY\(float f\)"),
+           cut_function(cc, r"^void Color::rgbxyz \(float r, float g, float b, float &x, float &y, float &z, const float xyz_rgb"),
+           cut_function(cc, r"^void Color::rgbxyz \(vfloat r, vfloat g, vfloat b, vfloat &x, vfloat &y, vfloat &z, const vfloat xyz_rgb"),
+           cut_function(cc, r"^void Color::xyz2rgb \(float x, float y, float z, float &r, float &g, float &b, const float rgb_xyz"),
+           cut_function(cc, r"^void Color::xyz2rgb \(vfloat x, vfloat y, vfloat z, vfloat &r, vfloat &g, vfloat &b, const vfloat rgb_xyz"),
+           cut_function(cc, r"^void Color::XYZ2Lab\(float X, float Y, float Z, float &L"),
+           cut_function(cc, r"^void Color::XYZ2Lab\(vfloat X, vfloat Y, vfloat Z, vfloat &L"),
+           cut_function(cc, r"^void Color::Lab2XYZ\(float L, float a, float b, float &x, float &y, float &z\)"),
+           cut_function(cc, r"^void Color::Lab2XYZ\(vfloat L, vfloat a, vfloat b, vfloat &x, vfloat &y, vfloat &z\)"),
+           cut_function(cc, r"^inline void filmlike_clip_rgb_tone\(float \*r, float \*g, float \*b, const float L\)"),
+           cut_function(cc, r"^void Color::filmlike_clip\(float \*r, float \*g, float \*b, float Lmax\)")]
+    open(os.path.join(sub, "chain_color_cc.inc"), "w").write("\n".join(ccf))
+    open(os.path.join(sub, "shim_chain.cc"), "w").write(SHIM_CHAIN_TU)
     return sub
 
 
@@ -891,7 +1155,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)

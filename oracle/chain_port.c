@@ -1,0 +1,325 @@
+/*
+ * oracle/chain_port.c -- plain-C restatement of the per-pixel colour / curve chain of ImProcFunctions::process.
+ * TEST INFRASTRUCTURE ONLY: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use it.
+ *
+ * Follows reference rtengine/: ipexposure.cc expcomp L29-73; ipsaturation.cc apply_vibrance L29-38, saturationVibrance
+ * L44-83; iptonecurve.cc filmlike_clip L214-231, apply L34-45; curves.h setLutVal L223-230, StandardToneCurve::Apply
+ * L360-368, AdobeToneCurve::Apply / RGBTone L425-472; iprgbcurves.cc rgbCurves pixel loop L113-146; iplabadjustments.cc
+ * lab_adjustments pixel loop L252-283; imagefloat.cc rgb_to_lab L841-878, lab_to_rgb L949-972; color.cc rgbxyz / xyz2rgb
+ * L833-894, Lab2XYZ L1203-1245, computeXYZ2Lab(Y) L1247-1275, XYZ2Lab L1382-1437, filmlike_clip L6650-6688; color.h f2xyz
+ * L767-781, rgbLuminance L203-207; LUT.h operator[](float) L437-459 and operator[](vfloat) L349-377.
+ *
+ * The reference processes every row in groups of four pixels with SSE2 and the remaining W % 4 pixels with scalar code;
+ * the two paths differ (LUT interpolation a*hi + (1-a)*lo versus lo + (hi-lo)*a, Lab2XYZ's Y branch, a whole group
+ * taking the scalar Lab route when one of its four pixels is out of range).  A pixel x is in a group iff
+ * (x & ~3) + 4 <= W.  Pinned bit-exact against the reference code compiled in place (tests/test_oracle_chain.py).
+ * Compile with -ffp-contract=off.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "sleef_port.h"
+
+static inline float maxr(float a, float b) { return a < b ? b : a; }        /* rt_math.h max */
+static inline float minr(float a, float b) { return b < a ? b : a; }        /* rt_math.h min */
+static inline float vmaxf_(float a, float b) { return a > b ? a : b; }      /* _mm_max_ps(a, b) */
+static inline float vminf_(float a, float b) { return a < b ? a : b; }      /* _mm_min_ps(a, b) */
+static inline float vclampf_(float v, float lo, float hi) { return vmaxf_(vminf_(hi, v), lo); }
+static inline int in_group(int x, int W) { return (x & ~3) + 4 <= W; }
+
+/* ---- LUT.h ---- */
+#define CLIP_BELOW 1
+#define CLIP_ABOVE 2
+static inline float lut_s(const float* data, int size, int clip, float index)
+{
+    int idx = (int)index;
+    if (index < 0.f || !(index == index)) {
+        if (clip & CLIP_BELOW) return data[0];
+        idx = 0;
+    } else if (index > (float)(size - 2)) {
+        if (clip & CLIP_ABOVE) return data[size - 1];
+        idx = size - 2;
+    }
+    const float diff = index - (float)idx;
+    const float p1 = data[idx];
+    const float p2 = data[idx + 1] - p1;
+    return p1 + p2 * diff;
+}
+static inline float lut_v(const float* data, int size, float index)
+{
+    const int idx = (int)vclampf_(index, 0.f, (float)(size - 2));
+    const float lower = data[idx], upper = data[idx + 1];
+    const float diff = vclampf_(index, 0.f, (float)(size - 1)) - (float)idx;
+    return diff * upper + (1.f - diff) * lower;
+}
+
+/* ---- expcomp ---- */
+int artoracle_chain_expcomp(float* R, float* G, float* B, int W, int H, float exp_scale, float black)
+{
+    float* ch[3] = {R, G, B};
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x)
+            for (int c = 0; c < 3; ++c) {
+                float* v = ch[c] + (size_t)y * W + x;
+                const float t = *v * exp_scale - black;
+                *v = in_group(x, W) ? vmaxf_(t, 0.f) : maxr(t, 0.f);
+            }
+    return 0;
+}
+
+/* ---- saturationVibrance ---- */
+static inline float lum_d(float r, float g, float b, const double* ws) { return (float)(r * ws[3] + g * ws[4] + b * ws[5]); }
+static inline float apply_vibrance(float x, float vib, float noise)
+{
+    const float ax = fabsf(x / 65535.f);
+    if (ax > noise) {
+        const float sgn = (float)((0.f < x) - (x < 0.f));
+        return sgn * pow_F_scalar(ax, vib) * 65535.f;
+    }
+    return x;
+}
+int artoracle_chain_saturation(float* R, float* G, float* B, int W, int H, int sat, int vibr, const double* ws)
+{
+    const float saturation = 1.f + sat / 100.f;
+    const float vibrance = 1.f - vibr / 1000.f;
+    const float noise = pow_F_scalar(2.f, -16.f);
+    for (size_t i = 0; i < (size_t)W * H; ++i) {
+        const float r = R[i], g = G[i], b = B[i];
+        const float l = lum_d(r, g, b, ws);
+        float rl = r - l, gl = g - l, bl = b - l;
+        if (vibr) { rl = apply_vibrance(rl, vibrance, noise); gl = apply_vibrance(gl, vibrance, noise); bl = apply_vibrance(bl, vibrance, noise); }
+        R[i] = maxr(l + saturation * rl, noise);
+        G[i] = maxr(l + saturation * gl, noise);
+        B[i] = maxr(l + saturation * bl, noise);
+    }
+    return 0;
+}
+
+/* ---- tone curve: filmlike_clip, then StandardToneCurve (mode 0) or AdobeToneCurve (mode 1) ---- */
+static inline void clip_tone(float* r, float* g, float* b, float L)
+{
+    const float r_ = *r > L ? L : *r;
+    const float b_ = *b > L ? L : *b;
+    const float g_ = b_ + ((r_ - b_) * (*g - *b) / (*r - *b));
+    *r = r_; *g = g_; *b = b_;
+}
+static void filmlike_clip(float* r, float* g, float* b, float L)
+{
+    if (*r >= *g) {
+        if (*g > *b) clip_tone(r, g, b, L);
+        else if (*b > *r) clip_tone(b, r, g, L);
+        else if (*b > *g) clip_tone(r, b, g, L);
+        else { *r = *r > L ? L : *r; *g = *g > L ? L : *g; *b = *g; }
+    } else {
+        if (*r >= *b) clip_tone(g, r, b, L);
+        else if (*b > *g) clip_tone(b, g, r, L);
+        else clip_tone(g, b, r, L);
+    }
+}
+static inline void set_lut_val(const float* lut, float* val)
+{   /* curves.h L223-230; values above 65535 would go through Curve::getVal on the host -- not reachable with whitept == 1 */
+    *val = lut_s(lut, 65536, CLIP_BELOW | CLIP_ABOVE, maxr(*val, 0.f));
+}
+static inline void rgb_tone(const float* lut, float* r, float* g, float* b)
+{
+    const float rold = *r, gold = *g, bold = *b;
+    set_lut_val(lut, r);
+    set_lut_val(lut, b);
+    *g = *b + ((*r - *b) * (gold - bold) / (rold - bold));
+}
+int artoracle_chain_tonecurve(float* R, float* G, float* B, int W, int H, int mode, const float* lut, float whitept)
+{
+    if (whitept != 1.f) return 1;
+    const float Lmax = 65535.f * whitept;
+    for (size_t i = 0; i < (size_t)W * H; ++i) {
+        filmlike_clip(&R[i], &G[i], &B[i], Lmax);
+        if (mode == 0) {
+            set_lut_val(lut, &R[i]); set_lut_val(lut, &G[i]); set_lut_val(lut, &B[i]);
+        } else {
+            float r = maxr(0.f, minr(R[i], Lmax)), g = maxr(0.f, minr(G[i], Lmax)), b = maxr(0.f, minr(B[i], Lmax));
+            if (r >= g) {
+                if (g > b) rgb_tone(lut, &r, &g, &b);
+                else if (b > r) rgb_tone(lut, &b, &r, &g);
+                else if (b > g) rgb_tone(lut, &r, &b, &g);
+                else { set_lut_val(lut, &r); set_lut_val(lut, &g); b = g; }
+            } else {
+                if (r >= b) rgb_tone(lut, &g, &r, &b);
+                else if (b > g) rgb_tone(lut, &b, &g, &r);
+                else rgb_tone(lut, &g, &b, &r);
+            }
+            R[i] = r; G[i] = g; B[i] = b;
+        }
+    }
+    return 0;
+}
+
+/* ---- rgbCurves: LUTs built with flags 0 (no clipping) ---- */
+int artoracle_chain_rgbcurves(float* R, float* G, float* B, int W, int H, const float* rc, const float* gc, const float* bc)
+{
+    float* ch[3] = {R, G, B};
+    const float* cv[3] = {rc, gc, bc};
+    for (int c = 0; c < 3; ++c) {
+        if (!cv[c]) continue;
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                float* v = ch[c] + (size_t)y * W + x;
+                *v = in_group(x, W) ? lut_v(cv[c], 65536, *v) : lut_s(cv[c], 65536, 0, *v);
+            }
+    }
+    return 0;
+}
+
+/* ---- Lab ---- */
+static float g_cachef[65536], g_cachefy[65536];
+static int g_cache_ready = 0;
+static void cache_init(void)
+{   /* color.cc L205-233 */
+    if (g_cache_ready) return;
+    const double eps = 216.0 / 24389.0, kappa = 24389.0 / 27.0, MAXVALF = 65535.f;
+    const int epsmaxint = (int)(MAXVALF * eps);
+    int i = 0;
+    for (; i <= epsmaxint; i++) { g_cachef[i] = (float)(327.68 * ((kappa * i / MAXVALF + 16.0) / 116.0)); g_cachefy[i] = (float)(327.68 * (kappa * i / MAXVALF)); }
+    for (; i < 65536; i++) { g_cachef[i] = (float)(327.68 * cbrt((double)i / MAXVALF)); g_cachefy[i] = (float)(327.68 * (116.0 * cbrt((double)i / MAXVALF) - 16.0)); }
+    g_cache_ready = 1;
+}
+#define D50X 0.9642f
+#define D50Z 0.8249f
+static inline float xyz2lab_f(float f)
+{
+    const double kappa = 24389.0 / 27.0;
+    if (f != f) return f;
+    if (f < 0.f) return (float)(327.68 * ((kappa * f / 65535.f + 16.0) / 116.0));
+    else if (f > 65535.f) return 327.68f * xcbrtf_scalar(f / 65535.f);
+    return lut_s(g_cachef, 65536, CLIP_BELOW, f);
+}
+static inline float xyz2lab_fy(float f)
+{
+    const double kappa = 24389.0 / 27.0;
+    if (f != f) return f;
+    if (f < 0.f) return (float)(327.68 * (kappa * f / 65535.f));
+    else if (f > 65535.f) return 327.68f * (116.f * xcbrtf_scalar(f / 65535.f) - 16.f);
+    return lut_s(g_cachefy, 65536, CLIP_BELOW, f);
+}
+static inline void xyz2lab_scalar(float x, float y, float z, float* L, float* a, float* b)
+{
+    const float fx = xyz2lab_f(x), fy = xyz2lab_f(y), fz = xyz2lab_f(z);
+    *L = xyz2lab_fy(y);
+    *a = 500.0f * (fx - fy);
+    *b = 200.0f * (fy - fz);
+}
+static inline float f2xyz_f(float f)
+{
+    const float epsilonExpInv3f = (float)(6.0 / 29.0), kappaInvf = (float)(27.0 / 24389.0);
+    return (f > epsilonExpInv3f) ? f * f * f : (116.f * f - 16.f) * kappaInvf;
+}
+
+/* one row of Imagefloat::rgb_to_lab: r <- a, g <- L, b <- b */
+static void row_rgb_to_lab(float* r, float* g, float* b, int W, const float ws[9])
+{
+    int x = 0;
+    for (; x < W - 3; x += 4) {
+        float X[4], Y[4], Z[4];
+        int slow = 0;
+        for (int k = 0; k < 4; ++k) {
+            const float rv = r[x + k], gv = g[x + k], bv = b[x + k];
+            X[k] = ws[0] * rv + ws[1] * gv + ws[2] * bv;
+            Y[k] = ws[3] * rv + ws[4] * gv + ws[5] * bv;
+            Z[k] = ws[6] * rv + ws[7] * gv + ws[8] * bv;
+            X[k] = X[k] / D50X;
+            Z[k] = Z[k] / D50Z;
+            const float mx = vmaxf_(X[k], vmaxf_(Y[k], Z[k])), mn = vminf_(X[k], vminf_(Y[k], Z[k]));
+            if (mx > 65535.f || mn < 0.f) slow = 1;
+        }
+        for (int k = 0; k < 4; ++k) {
+            float L, a, bb;
+            if (slow) xyz2lab_scalar(X[k], Y[k], Z[k], &L, &a, &bb);
+            else {
+                const float fx = lut_v(g_cachef, 65536, X[k]), fy = lut_v(g_cachef, 65536, Y[k]), fz = lut_v(g_cachef, 65536, Z[k]);
+                L = lut_v(g_cachefy, 65536, Y[k]);
+                a = 500.f * (fx - fy);
+                bb = 200.f * (fy - fz);
+            }
+            g[x + k] = L; r[x + k] = a; b[x + k] = bb;
+        }
+    }
+    for (; x < W; ++x) {
+        const float rv = r[x], gv = g[x], bv = b[x];
+        const float X = ws[0] * rv + ws[1] * gv + ws[2] * bv;
+        const float Y = ws[3] * rv + ws[4] * gv + ws[5] * bv;
+        const float Z = ws[6] * rv + ws[7] * gv + ws[8] * bv;
+        float L, a, bb;
+        xyz2lab_scalar(X / D50X, Y, Z / D50Z, &L, &a, &bb);
+        g[x] = L; r[x] = a; b[x] = bb;
+    }
+}
+
+static void row_lab_to_rgb(float* r, float* g, float* b, int W, const float iws[9])
+{
+    const float c1By116 = (float)(1.0 / 116.0), c16By116 = (float)(16.0 / 116.0);
+    const double kappa = 24389.0 / 27.0;
+    for (int x = 0; x < W; ++x) {
+        const float L = g[x], a = r[x], bb = b[x];
+        float X, Y, Z;
+        if (in_group(x, W)) {       /* Lab2XYZ(vfloat...) */
+            const float Lq = L / 327.68f, aq = a / 327.68f, bq = bb / 327.68f;
+            const float fy = c1By116 * Lq + c16By116;
+            const float fx = 0.002f * aq + fy;
+            const float fz = fy - (0.005f * bq);
+            X = 65535.f * f2xyz_f(fx) * D50X;
+            Z = 65535.f * f2xyz_f(fz) * D50Z;
+            const float res1 = fy * fy * fy;
+            const float res2 = Lq / (float)kappa;
+            Y = (Lq > (float)8.0) ? res1 : res2;
+            Y *= 65535.f;
+        } else {                    /* Lab2XYZ(float...) */
+            const float LL = L / 327.68f, aa = a / 327.68f, b2 = bb / 327.68f;
+            const float fy = (c1By116 * LL) + c16By116;
+            const float fx = (0.002f * aa) + fy;
+            const float fz = fy - (0.005f * b2);
+            X = 65535.0f * f2xyz_f(fx) * D50X;
+            Z = 65535.0f * f2xyz_f(fz) * D50Z;
+            Y = ((double)LL > 8.0) ? 65535.0f * fy * fy * fy : (float)(65535.0f * LL / kappa);
+        }
+        r[x] = iws[0] * X + iws[1] * Y + iws[2] * Z;
+        g[x] = iws[3] * X + iws[4] * Y + iws[5] * Z;
+        b[x] = iws[6] * X + iws[7] * Y + iws[8] * Z;
+    }
+}
+
+int artoracle_chain_rgb2lab(float* R, float* G, float* B, int W, int H, const double* wsd, const double* iwsd, int back)
+{
+    cache_init();
+    float ws[9], iws[9];
+    for (int i = 0; i < 9; ++i) { ws[i] = (float)wsd[i]; iws[i] = (float)(iwsd ? iwsd[i] : 0.0); }
+    for (int y = 0; y < H; ++y) {
+        if (back) row_lab_to_rgb(R + (size_t)y * W, G + (size_t)y * W, B + (size_t)y * W, W, iws);
+        else row_rgb_to_lab(R + (size_t)y * W, G + (size_t)y * W, B + (size_t)y * W, W, ws);
+    }
+    return 0;
+}
+
+/* labAdjustments: setMode(LAB), lab_adjustments' loop, setMode(RGB) */
+int artoracle_chain_lab(float* R, float* G, float* B, int W, int H, const float* lc, const float* ac, const float* bc, float chroma,
+                        const double* wsd, const double* iwsd)
+{
+    cache_init();
+    float ws[9], iws[9];
+    for (int i = 0; i < 9; ++i) { ws[i] = (float)wsd[i]; iws[i] = (float)iwsd[i]; }
+    for (int y = 0; y < H; ++y) {
+        float *r = R + (size_t)y * W, *g = G + (size_t)y * W, *b = B + (size_t)y * W;
+        row_rgb_to_lab(r, g, b, W, ws);
+        for (int x = 0; x < W; ++x) {
+            if (in_group(x, W)) {
+                g[x] = lut_v(lc, 32770, g[x]);
+                r[x] = (lut_v(ac, 65536, r[x] + 32768.f) - 32768.f) * chroma;
+                b[x] = (lut_v(bc, 65536, b[x] + 32768.f) - 32768.f) * chroma;
+            } else {
+                g[x] = lut_s(lc, 32770, 0, g[x]);
+                r[x] = (lut_s(ac, 65536, CLIP_BELOW | CLIP_ABOVE, r[x] + 32768.f) - 32768.f) * chroma;
+                b[x] = (lut_s(bc, 65536, CLIP_BELOW | CLIP_ABOVE, b[x] + 32768.f) - 32768.f) * chroma;
+            }
+        }
+        row_lab_to_rgb(r, g, b, W, iws);
+    }
+    return 0;
+}

@@ -1,0 +1,115 @@
+"""Pin the colour / curve chain oracle (oracle/chain_port.c) against the reference's own pixel loops compiled in place
+(oracle/_ref, shim_chain.cc): expcomp, saturationVibrance, filmlike_clip + Standard / Adobe tone curves, rgbCurves,
+labAdjustments between Imagefloat::setMode(LAB) and setMode(RGB).  Bit-exact, including the 4-wide SSE2 groups versus the
+scalar row tails, out-of-range pixels that push a whole group onto the scalar Lab route, and LUT extrapolation."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+
+needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built and /root/reference absent")
+fp = ctypes.POINTER(ctypes.c_float)
+dp = ctypes.POINTER(ctypes.c_double)
+F = ctypes.c_float
+PROPHOTO = np.array([[0.7976749, 0.1351917, 0.0313534], [0.2880402, 0.7118741, 0.0000857], [0.0, 0.0, 0.8252100]], np.float64)
+PROPHOTO_INV = np.array([[1.3459433, -0.2556075, -0.0511118], [-0.5445989, 1.5081673, 0.0205351], [0.0, 0.0, 1.2118128]], np.float64)
+SIZES = [(64, 8), (67, 5), (5, 9), (3, 3), (130, 17)]
+
+
+def image(H, W, seed, wild=True):
+    """working-space RGB with in-range values, some negatives / overrange samples and exact ties between channels"""
+    rng = np.random.default_rng(seed)
+    planes = [rng.uniform(0, 65535, (H, W)).astype(np.float32) for _ in range(3)]
+    if wild:
+        m = rng.random((H, W))
+        for p in planes:
+            p[m < 0.03] *= -0.2
+            p[(m > 0.95)] *= 1.7
+        planes[1][m > 0.9] = planes[0][m > 0.9]            # r == g
+        planes[2][(m > 0.8) & (m < 0.85)] = planes[1][(m > 0.8) & (m < 0.85)]   # g == b
+        planes[0][:, : W // 5] *= 1e-3                       # deep shadows
+    return planes
+
+
+def curve_lut(n=65536, gamma=0.8, top=65535.0, seed=0):
+    x = np.arange(n, dtype=np.float64) / (n - 1)
+    y = x ** gamma * (1 + 0.05 * np.sin(7 * x + seed))
+    return (np.clip(y, 0, None) * top).astype(np.float32)
+
+
+def call(lib, name, planes, *args):
+    out = [np.ascontiguousarray(p).copy() for p in planes]
+    H, W = out[0].shape
+    rc = getattr(lib, name)(out[0].ctypes.data_as(fp), out[1].ctypes.data_as(fp), out[2].ctypes.data_as(fp), W, H, *args)
+    assert rc == 0
+    return out
+
+
+def same(a, b):
+    for x, y, ch in zip(a, b, "RGB"):
+        eq = (x == y) | (np.isnan(x) & np.isnan(y))
+        assert eq.all(), "%s: %d of %d differ, first at %s: %r vs %r" % (ch, int((~eq).sum()), x.size, np.argwhere(~eq)[0], x[~eq][0], y[~eq][0])
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("ev,black", [(0.0, 0.0), (1.3, 0.01), (-0.7, -0.02)])
+def test_expcomp(W, H, ev, black):
+    planes = image(H, W, W + H)
+    args = (F(np.float32(2.0 ** ev)), F(np.float32(black * 2000.0)))
+    same(call(oracle.port().lib, "artoracle_chain_expcomp", planes, *args), call(oracle.ref().lib, "artref_chain_expcomp", planes, *args))
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("sat,vib", [(30, 0), (0, 40), (-50, -30), (100, 100)])
+def test_saturation(W, H, sat, vib):
+    planes = image(H, W, W * 3 + H)
+    args = (sat, vib, PROPHOTO.ctypes.data_as(dp))
+    same(call(oracle.port().lib, "artoracle_chain_saturation", planes, *args), call(oracle.ref().lib, "artref_chain_saturation", planes, *args))
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_tonecurve(W, H, mode):
+    planes = image(H, W, W * 5 + H)
+    lut = curve_lut(gamma=0.6, seed=mode)
+    args = (mode, lut.ctypes.data_as(fp), F(1.0))
+    same(call(oracle.port().lib, "artoracle_chain_tonecurve", planes, *args), call(oracle.ref().lib, "artref_chain_tonecurve", planes, *args))
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("which", [(1, 1, 1), (1, 0, 0), (0, 1, 1)])
+def test_rgbcurves(W, H, which):
+    planes = image(H, W, W * 7 + H)
+    luts = [curve_lut(gamma=0.7 + 0.2 * i, seed=i) if w else None for i, w in enumerate(which)]
+    args = tuple(l.ctypes.data_as(fp) if l is not None else None for l in luts)
+    same(call(oracle.port().lib, "artoracle_chain_rgbcurves", planes, *args), call(oracle.ref().lib, "artref_chain_rgbcurves", planes, *args))
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("wild", [False, True])
+def test_rgb2lab_and_back(W, H, wild):
+    planes = image(H, W, W * 11 + H, wild)
+    args = (PROPHOTO.ctypes.data_as(dp), PROPHOTO_INV.ctypes.data_as(dp))
+    a = call(oracle.port().lib, "artoracle_chain_rgb2lab", planes, *args, 0)
+    b = call(oracle.ref().lib, "artref_chain_rgb2lab", planes, *args, 0)
+    same(a, b)
+    same(call(oracle.port().lib, "artoracle_chain_rgb2lab", a, *args, 1), call(oracle.ref().lib, "artref_chain_rgb2lab", b, *args, 1))
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("chroma", [1.0, 1.35, 0.4])
+def test_lab_adjustments(W, H, chroma):
+    planes = image(H, W, W * 13 + H)
+    lc = np.concatenate([curve_lut(32768, 0.85, 32767.0), np.array([32768.0, 32769.0], np.float32)]).astype(np.float32)
+    ac = curve_lut(65536, 1.1, 65535.0, 1)
+    bc = curve_lut(65536, 0.9, 65535.0, 2)
+    args = (lc.ctypes.data_as(fp), ac.ctypes.data_as(fp), bc.ctypes.data_as(fp), F(chroma), PROPHOTO.ctypes.data_as(dp), PROPHOTO_INV.ctypes.data_as(dp))
+    same(call(oracle.port().lib, "artoracle_chain_lab", planes, *args), call(oracle.ref().lib, "artref_chain_lab", planes, *args))
