@@ -99,6 +99,8 @@ def load_library(build_if_missing=True):
         "art_hp_fattal": (i, [vp, i, i, vp, vp, vp, i, i, i, ctypes.POINTER(d)]),
         "art_hp_fattal_dev": (i, [vp, i, i, vp, vp, vp, sz, i, i, i, ctypes.POINTER(d)]),
         "art_hp_fattal_fast_dim": (i, [i]),
+        "art_hp_color_chain": (i, [vp, i, i, vp, vp, vp, vp]),
+        "art_hp_color_chain_dev": (i, [vp, i, i, vp, vp, vp, sz, vp]),
         "art_hp_median_denoise": (i, [vp, vp, vp, i, i, i, i, f]),
         "art_hp_median_denoise_dev": (i, [vp, vp, sz, vp, sz, i, i, i, i, f]),
         "art_hp_redft00_2d": (i, [vp, i, i, vp, vp]),
@@ -161,6 +163,63 @@ class _DevelopParamsC(ctypes.Structure):
                 ("denoise", ctypes.POINTER(_DenoiseParamsC)), ("nlStrength", ctypes.c_int), ("nlDetail", ctypes.c_int),
                 ("fattal_enabled", ctypes.c_int), ("fattal_threshold", ctypes.c_int), ("fattal_amount", ctypes.c_int),
                 ("fattal_satcontrol", ctypes.c_int), ("wprof", ctypes.POINTER(ctypes.c_double))]
+
+
+class _ChainParamsC(ctypes.Structure):
+    _fp, _dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+    _fields_ = [("exposure_enabled", ctypes.c_int), ("exp_scale", ctypes.c_float), ("black", ctypes.c_float),
+                ("saturation_enabled", ctypes.c_int), ("saturation", ctypes.c_int), ("vibrance", ctypes.c_int),
+                ("tonecurve_mode", ctypes.c_int), ("tonecurve_lut", _fp),
+                ("rcurve", _fp), ("gcurve", _fp), ("bcurve", _fp),
+                ("lab_enabled", ctypes.c_int), ("lab_lcurve", _fp), ("lab_acurve", _fp), ("lab_bcurve", _fp), ("lab_chroma", ctypes.c_float),
+                ("ws", _dp), ("iws", _dp)]
+
+
+class ChainParams:
+    """Parameters of art_hp_color_chain: the per-pixel stages of ImProcFunctions::process (improcfun.cc L567-641).
+    exposure = (expcomp EV, black) as in procparams::ExposureParams; saturation = (saturation, vibrance) integers;
+    tonecurve = (mode, 65536-entry LUT); rgbcurves = three LUTs or None each; lab = (L LUT of 32770, a LUT, b LUT, chroma)."""
+
+    def __init__(self, exposure=None, saturation=None, tonecurve=None, rgbcurves=None, lab=None, ws=None, iws=None):
+        self.__dict__.update(locals())
+        del self.__dict__["self"]
+
+    def c_struct(self):
+        c = _ChainParamsC()
+        self._keep = []
+        fp = ctypes.POINTER(ctypes.c_float)
+
+        def lut(a, n):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            assert a.size == n, "LUT of %d entries expected, got %d" % (n, a.size)
+            self._keep.append(a)
+            return a.ctypes.data_as(fp)
+
+        def mat(m):
+            if m is None:
+                return None
+            v = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(m, dtype=np.float64).reshape(9)])
+            self._keep.append(v)
+            return ctypes.cast(v, ctypes.POINTER(ctypes.c_double))
+
+        if self.exposure is not None:
+            ev, black = self.exposure
+            # ipexposure.cc L33-34: exp_scale = pow(2.f, expcomp), black = params black * 2000.f
+            c.exposure_enabled, c.exp_scale, c.black = 1, float(np.float32(2.0) ** np.float32(ev)), float(np.float32(black) * np.float32(2000.0))
+        if self.saturation is not None:
+            c.saturation_enabled, c.saturation, c.vibrance = 1, int(self.saturation[0]), int(self.saturation[1])
+        if self.tonecurve is not None:
+            c.tonecurve_mode, c.tonecurve_lut = int(self.tonecurve[0]), lut(self.tonecurve[1], 65536)
+        if self.rgbcurves is not None:
+            c.rcurve, c.gcurve, c.bcurve = [lut(x, 65536) for x in self.rgbcurves]
+        if self.lab is not None:
+            c.lab_enabled = 1
+            c.lab_lcurve, c.lab_acurve, c.lab_bcurve = lut(self.lab[0], 32770), lut(self.lab[1], 65536), lut(self.lab[2], 65536)
+            c.lab_chroma = float(self.lab[3])
+        c.ws, c.iws = mat(self.ws), mat(self.iws)
+        return c
 
 
 class DevelopParams:
@@ -423,6 +482,16 @@ class HotPath:
     def develop_dev(self, params, W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch):
         c = params.c_struct()
         self._check(self.lib.art_hp_develop_dev(self.h, ctypes.byref(c), W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch))
+
+    def color_chain(self, r, g, b, params):
+        """The fused per-pixel chain of ImProcFunctions::process, in place on three host (H, W) float32 planes."""
+        H, W = r.shape
+        c = params.c_struct()
+        self._check(self.lib.art_hp_color_chain(self.h, W, H, row_table(r), row_table(g), row_table(b), ctypes.byref(c)))
+
+    def color_chain_dev(self, W, H, d_r, d_g, d_b, pitch, params):
+        c = params.c_struct()
+        self._check(self.lib.art_hp_color_chain_dev(self.h, W, H, d_r, d_g, d_b, pitch, ctypes.byref(c)))
 
     def fattal(self, r, g, b, threshold, amount, satcontrol, ws):
         """ImProcFunctions::dynamicRangeCompression (ToneMapFattal02), in place on three host (H, W) float32 planes."""

@@ -38,12 +38,18 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    objs = []
+    from concurrent.futures import ThreadPoolExecutor
+    hdrs = glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        [os.path.join(HERE, "..", "include", "art_hotpath.h"), __file__]
+    objs, jobs = [], []
     for src in sources():
         obj = src[:-3] + ".o"
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
-        subprocess.check_call(cmd)
         objs.append(obj)
+        # per-object staleness: a translation unit is recompiled when it or any header is newer than its object
+        if force or verbose or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in [src] + hdrs):
+            jobs.append([NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        list(ex.map(subprocess.check_call, jobs))
     subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ccbin", "/usr/bin/g++"])
     return LIB
 

@@ -44,6 +44,11 @@ struct art_hp_ctx {
     bool dn_tables_ready = false;        // the constant window / DCT tables of detail_recovery are uploaded once
     DevBuf d_dn_tables;
     // pinned staging (two halves for double buffering)
+    // colour chain: device LUT slots, their pinned staging and the event that says the staging may be rewritten
+    DevBuf d_chain;
+    void* h_chain = nullptr;
+    cudaEvent_t ev_chain = nullptr;
+    bool chain_cache_ready = false;
     void* h_stage[2] = {nullptr, nullptr};
     size_t h_stage_bytes = 0;
 
@@ -138,6 +143,8 @@ int art_fattal_fast_dim(int dim);
 int art_median_dev(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, size_t dp, int W, int H, int type, int useUpper, float upper);
 // 2-D REDFT00 of a contiguous n0 x n1 float array (the transform of tmo_fattal02.cc L768-772 alone)
 int art_redft00_2d_dev(art_hp_ctx* ctx, const float* in, float* out, int n0, int n1);
+// ImProcFunctions::process per-pixel chain (chain.cu), planes in place
+int art_chain_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch, const art_hp_chain_params* p);
 // develop.cu: ImProcFunctions::denoise (calclum, adjust_params, RGB_denoise, NL-means on Y) and the whole-frame pipeline
 int art_denoise_stage_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_denoise_params* dn,
                           int nlStrength, int nlDetail, const double* cam2work, const double* wprof);

@@ -314,6 +314,35 @@ int art_hp_scale_convert_dev(art_hp_ctx* ctx, int W, int H,
                              float* d_red, float* d_green, float* d_blue, size_t pitch,
                              const float mul[3], int doClip, const double mat[9]);
 
+/* ---- per-pixel colour / curve chain ------------------------------------------------ */
+/*
+ * art_hp_color_chain   the per-pixel stages of ImProcFunctions::process (rtengine/improcfun.cc L567-641) fused into one pass,
+ *                      in the reference's order: STAGE_1 exposure = expcomp (rtengine/ipexposure.cc L29-73: the caller passes
+ *                      exp_scale = pow(2, expcomp) and black = params black * 2000, L33-34); STAGE_3 saturationVibrance
+ *                      (rtengine/ipsaturation.cc L44-83), toneCurve (rtengine/iptonecurve.cc L553-716 for its per-pixel LUT
+ *                      branch: filmlike_clip then StandardToneCurve::Apply [tonecurve_mode 0] or AdobeToneCurve::Apply [1],
+ *                      rtengine/curves.h L360-368, L425-472, white point 1), rgbCurves (rtengine/iprgbcurves.cc L113-146) and
+ *                      labAdjustments (rtengine/iplabadjustments.cc L252-283 between Imagefloat::setMode(LAB) and the
+ *                      setMode(RGB) of the next stage, rtengine/imagefloat.cc L841-878, L949-972).
+ *                      Curves stay host-built (rtengine/curves.cc) and are passed by pointer as the LUT<float> data they fill:
+ *                      65536 floats each, lab_lcurve 32770.  A NULL LUT / a zero `*_enabled` skips that stage like the
+ *                      reference's `enabled == false` / identity-curve early-outs.  In place on three planes.
+ *                      Bit-identical to the reference's SSE2 build, 4-pixel groups and scalar row tails included.
+ */
+typedef struct art_hp_chain_params {
+    int   exposure_enabled;  float exp_scale, black;
+    int   saturation_enabled, saturation, vibrance;      /* procparams::SaturationParams, integers as in the GUI */
+    int   tonecurve_mode;    const float* tonecurve_lut;  /* 0 = STD, 1 = FILMLIKE; NULL = no tone curve */
+    const float *rcurve, *gcurve, *bcurve;                /* rgbCurves LUTs, each may be NULL */
+    int   lab_enabled;       const float *lab_lcurve, *lab_acurve, *lab_bcurve;  float lab_chroma;
+    const double* ws;        /* ICCStore::workingSpaceMatrix, 9 doubles (saturation luminance, rgb -> Lab) */
+    const double* iws;       /* ICCStore::workingSpaceInverseMatrix, 9 doubles (Lab -> rgb) */
+} art_hp_chain_params;
+int art_hp_color_chain(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b,
+                       const art_hp_chain_params* params);
+int art_hp_color_chain_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
+                           const art_hp_chain_params* params);
+
 /* ---- whole frame ------------------------------------------------------------------ */
 /*
  * art_hp_develop       the stages of simpleprocess.cc's normal pipeline that are on the hot path, back to back on the

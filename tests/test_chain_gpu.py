@@ -1,0 +1,100 @@
+"""GPU parity for the fused per-pixel colour / curve chain (art_hp_color_chain = the per-pixel stages of
+ImProcFunctions::process) through the C-ABI against the oracle port, which test_oracle_chain.py pins bit-exact to the
+reference's own loops compiled in place.  The oracle applies the stages one after the other as the reference does (one
+full pass each); the GPU applies them in one pass.  Bit-exact, SSE2 groups and scalar row tails included."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+from art_b200.api import ChainParams
+from test_oracle_chain import F, PROPHOTO, PROPHOTO_INV, call, curve_lut, dp, fp, image, same
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(64, 8), (67, 5), (5, 9), (3, 3), (130, 17), (1021, 300)]
+
+
+def lab_luts():
+    lc = np.concatenate([curve_lut(32768, 0.85, 32767.0), np.array([32768.0, 32769.0], np.float32)]).astype(np.float32)
+    return lc, curve_lut(65536, 1.1, 65535.0, 1), curve_lut(65536, 0.9, 65535.0, 2)
+
+
+def oracle_chain(planes, exposure=None, saturation=None, tonecurve=None, rgbcurves=None, lab=None):
+    lib = oracle.port().lib
+    out = planes
+    if exposure is not None:
+        ev, black = exposure
+        out = call(lib, "artoracle_chain_expcomp", out, F(np.float32(2.0) ** np.float32(ev)), F(np.float32(black) * np.float32(2000.0)))
+    if saturation is not None and (saturation[0] or saturation[1]):
+        out = call(lib, "artoracle_chain_saturation", out, saturation[0], saturation[1], PROPHOTO.ctypes.data_as(dp))
+    if tonecurve is not None:
+        out = call(lib, "artoracle_chain_tonecurve", out, tonecurve[0], tonecurve[1].ctypes.data_as(fp), F(1.0))
+    if rgbcurves is not None:
+        out = call(lib, "artoracle_chain_rgbcurves", out, *[c.ctypes.data_as(fp) if c is not None else None for c in rgbcurves])
+    if lab is not None:
+        out = call(lib, "artoracle_chain_lab", out, lab[0].ctypes.data_as(fp), lab[1].ctypes.data_as(fp), lab[2].ctypes.data_as(fp), F(lab[3]),
+                   PROPHOTO.ctypes.data_as(dp), PROPHOTO_INV.ctypes.data_as(dp))
+    return out
+
+
+def gpu_chain(hp, planes, **kw):
+    out = [np.ascontiguousarray(p).copy() for p in planes]
+    hp.color_chain(out[0], out[1], out[2], ChainParams(ws=PROPHOTO, iws=PROPHOTO_INV, **kw))
+    return out
+
+
+STAGES = {
+    "exposure": dict(exposure=(1.3, 0.01)),
+    "exposure_neg": dict(exposure=(-0.7, -0.02)),
+    "saturation": dict(saturation=(30, 0)),
+    "vibrance": dict(saturation=(-50, -30)),
+    "satvib": dict(saturation=(100, 100)),
+    "tone_std": dict(tonecurve=(0, curve_lut(gamma=0.6, seed=0))),
+    "tone_film": dict(tonecurve=(1, curve_lut(gamma=0.6, seed=1))),
+    "rgbcurves": dict(rgbcurves=[curve_lut(gamma=0.7, seed=0), None, curve_lut(gamma=1.1, seed=2)]),
+    "lab": dict(lab=lab_luts() + (1.35,)),
+    "lab_lowchroma": dict(lab=lab_luts() + (0.4,)),
+}
+STAGES["all_std"] = dict(STAGES["exposure"], **STAGES["satvib"], **STAGES["tone_std"], **STAGES["rgbcurves"], **STAGES["lab"])
+STAGES["all_film"] = dict(STAGES["exposure_neg"], **STAGES["saturation"], **STAGES["tone_film"],
+                          rgbcurves=[curve_lut(gamma=0.9, seed=i) for i in range(3)], **STAGES["lab_lowchroma"])
+
+
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("name", sorted(STAGES))
+def test_chain_matches_oracle(hot_path, W, H, name):
+    planes = image(H, W, W * 17 + H)
+    same(gpu_chain(hot_path, planes, **STAGES[name]), oracle_chain(planes, **STAGES[name]))
+
+
+def test_chain_in_range_image(hot_path):
+    planes = image(240, 516, 7, wild=False)
+    same(gpu_chain(hot_path, planes, **STAGES["all_std"]), oracle_chain(planes, **STAGES["all_std"]))
+
+
+def test_chain_nothing_enabled_is_identity(hot_path):
+    planes = image(33, 70, 3)
+    same(gpu_chain(hot_path, planes), planes)
+
+
+def test_chain_device_form_with_pitch(hot_path):
+    torch = pytest.importorskip("torch")
+    W, H, pitch = 203, 41, 224
+    planes = image(H, W, 99)
+    dev = [torch.zeros((H, pitch), dtype=torch.float32, device="cuda") for _ in range(3)]
+    for d, p in zip(dev, planes):
+        d[:, :W] = torch.from_numpy(p).cuda()
+    torch.cuda.synchronize()
+    hot_path.color_chain_dev(W, H, dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), pitch,
+                             ChainParams(ws=PROPHOTO, iws=PROPHOTO_INV, **STAGES["all_film"]))
+    hot_path.sync()
+    same([d[:, :W].cpu().numpy() for d in dev], oracle_chain(planes, **STAGES["all_film"]))
+
+
+def test_chain_rejects_missing_matrix(hot_path):
+    import art_b200
+    planes = image(8, 8, 1)
+    with pytest.raises(art_b200.HotPathError):
+        hot_path.color_chain(planes[0], planes[1], planes[2], ChainParams(saturation=(10, 0)))
