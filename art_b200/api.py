@@ -99,6 +99,8 @@ def load_library(build_if_missing=True):
         "art_hp_fattal": (i, [vp, i, i, vp, vp, vp, i, i, i, ctypes.POINTER(d)]),
         "art_hp_fattal_dev": (i, [vp, i, i, vp, vp, vp, sz, i, i, i, ctypes.POINTER(d)]),
         "art_hp_fattal_fast_dim": (i, [i]),
+        "art_hp_sharpen_usm": (i, [vp, i, i, vp, vp, vp, vp, ctypes.POINTER(d)]),
+        "art_hp_sharpen_usm_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, ctypes.POINTER(d)]),
         "art_hp_color_chain": (i, [vp, i, i, vp, vp, vp, vp]),
         "art_hp_color_chain_dev": (i, [vp, i, i, vp, vp, vp, sz, vp]),
         "art_hp_median_denoise": (i, [vp, vp, vp, i, i, i, i, f]),
@@ -162,7 +164,26 @@ class _DevelopParamsC(ctypes.Structure):
                 ("mul", ctypes.c_float * 3), ("doClip", ctypes.c_int), ("cam2work", ctypes.POINTER(ctypes.c_double)),
                 ("denoise", ctypes.POINTER(_DenoiseParamsC)), ("nlStrength", ctypes.c_int), ("nlDetail", ctypes.c_int),
                 ("fattal_enabled", ctypes.c_int), ("fattal_threshold", ctypes.c_int), ("fattal_amount", ctypes.c_int),
-                ("fattal_satcontrol", ctypes.c_int), ("wprof", ctypes.POINTER(ctypes.c_double))]
+                ("fattal_satcontrol", ctypes.c_int), ("wprof", ctypes.POINTER(ctypes.c_double)),
+                ("sharpen", ctypes.c_void_p), ("chain", ctypes.c_void_p)]
+
+
+class _SharpenParamsC(ctypes.Structure):
+    _fields_ = [("contrast", ctypes.c_double), ("radius", ctypes.c_double), ("amount", ctypes.c_int), ("threshold", ctypes.c_int * 4),
+                ("edgesonly", ctypes.c_int), ("halocontrol", ctypes.c_int), ("halocontrol_amount", ctypes.c_int), ("scale", ctypes.c_double)]
+
+
+class SharpenParams:
+    """Mirror of procparams::SharpeningParams for method "usm" (defaults: rtengine/procparams.cc L1756-1776)."""
+
+    def __init__(self, contrast=20.0, radius=0.5, amount=200, threshold=(20, 80, 2000, 1200), edgesonly=False, halocontrol=False,
+                 halocontrol_amount=85, scale=1.0):
+        self.__dict__.update(locals())
+        del self.__dict__["self"]
+
+    def c_struct(self):
+        return _SharpenParamsC(float(self.contrast), float(self.radius), int(self.amount), (ctypes.c_int * 4)(*[int(t) for t in self.threshold]),
+                               int(bool(self.edgesonly)), int(bool(self.halocontrol)), int(self.halocontrol_amount), float(self.scale))
 
 
 class _ChainParamsC(ctypes.Structure):
@@ -226,7 +247,7 @@ class DevelopParams:
     """Parameters of art_hp_develop: the simpleprocess.cc stages on the hot path (demosaic, gains + matrix, denoise, Fattal)."""
 
     def __init__(self, method=0, filters=0x94949494, initial_gain=1.0, border=4, mul=(1.0, 1.0, 1.0), do_clip=True, cam2work=None,
-                 denoise=None, nl_strength=0, nl_detail=80, fattal=None, wprof=None):
+                 denoise=None, nl_strength=0, nl_detail=80, fattal=None, wprof=None, sharpen=None, chain=None):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
@@ -252,6 +273,15 @@ class DevelopParams:
         if self.fattal is not None:
             thr, amt, sat = self.fattal
             c.fattal_enabled, c.fattal_threshold, c.fattal_amount, c.fattal_satcontrol = 1, int(thr), int(amt), int(bool(sat))
+        if self.sharpen is not None:
+            sc = self.sharpen.c_struct()
+            self._keep.append(sc)
+            c.sharpen = ctypes.addressof(sc)
+        if self.chain is not None:
+            self._keep.append(self.chain)
+            cc = self.chain.c_struct()
+            self._keep.append(cc)
+            c.chain = ctypes.addressof(cc)
         return c
 
 
@@ -482,6 +512,18 @@ class HotPath:
     def develop_dev(self, params, W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch):
         c = params.c_struct()
         self._check(self.lib.art_hp_develop_dev(self.h, ctypes.byref(c), W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch))
+
+    def sharpen_usm(self, r, g, b, params, ws):
+        """ImProcFunctions::sharpening with method "usm", in place on three host (H, W) float32 planes."""
+        H, W = r.shape
+        wsc = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(ws, dtype=np.float64).reshape(9)])
+        c = params.c_struct()
+        self._check(self.lib.art_hp_sharpen_usm(self.h, W, H, row_table(r), row_table(g), row_table(b), ctypes.byref(c), wsc))
+
+    def sharpen_usm_dev(self, W, H, d_r, d_g, d_b, pitch, params, ws):
+        wsc = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(ws, dtype=np.float64).reshape(9)])
+        c = params.c_struct()
+        self._check(self.lib.art_hp_sharpen_usm_dev(self.h, W, H, d_r, d_g, d_b, pitch, ctypes.byref(c), wsc))
 
     def color_chain(self, r, g, b, params):
         """The fused per-pixel chain of ImProcFunctions::process, in place on three host (H, W) float32 planes."""

@@ -240,6 +240,7 @@ void art_hp_destroy(art_hp_ctx* ctx)
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_dn_tables.p) cudaFree(ctx->d_dn_tables.p);
     if (ctx->d_chain.p) cudaFree(ctx->d_chain.p);
+    if (ctx->d_usm_tables.p) cudaFree(ctx->d_usm_tables.p);
     if (ctx->h_chain) cudaFreeHost(ctx->h_chain);
     if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
     for (PoolBlk& b : ctx->pool) cudaFree(b.p);
@@ -808,6 +809,39 @@ int art_hp_color_chain(art_hp_ctx* ctx, int W, int H, float* const* r, float* co
     Plane io[3] = {{r, (float*)ctx->d_out[0].p}, {g, (float*)ctx->d_out[1].p}, {b, (float*)ctx->d_out[2].p}};
     if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, true))) return rc;
     if ((rc = art_chain_dev(ctx, W, H, io[0].dev, io[1].dev, io[2].dev, pitch, params))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+int art_hp_sharpen_usm_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
+                           const art_hp_sharpen_params* params, const double ws[9])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_r || !d_g || !d_b || !params || !ws) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    if (params->contrast < 0 || params->radius < 0) return ctx->fail(ART_HP_ERR_INVALID, "negative contrast or radius");
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_usm_dev(ctx, d_r, d_g, d_b, pitch, W, H, params, ws);
+}
+
+int art_hp_sharpen_usm(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b,
+                       const art_hp_sharpen_params* params, const double ws[9])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!r || !g || !b || !params || !ws) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    if (params->contrast < 0 || params->radius < 0) return ctx->fail(ART_HP_ERR_INVALID, "negative contrast or radius");
+    if (params->amount < 1 || W < 8 || H < 8) return ART_HP_OK;
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    int rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+    Plane io[3] = {{r, (float*)ctx->d_out[0].p}, {g, (float*)ctx->d_out[1].p}, {b, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_usm_dev(ctx, io[0].dev, io[1].dev, io[2].dev, pitch, W, H, params, ws))) return rc;
     if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, false))) return rc;
     ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;

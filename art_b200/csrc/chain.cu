@@ -25,7 +25,7 @@ namespace {
 struct ChainArgs {
     float *r, *g, *b; size_t pitch; int W, H;
     int do_exp; float exp_scale, black;
-    int do_sat, vib_on; float saturation, vibrance, noise; double wy0, wy1, wy2;
+    int do_sat, vib_on; float saturation, vibrance, noise, wy0, wy1, wy2;
     int tc_mode; const float* tc_lut; float Lmax;
     const float *rc, *gc, *bc;
     int do_lab; const float *lc, *ac, *bcl; float chroma; const float *cachef, *cachefy;
@@ -137,7 +137,7 @@ __device__ __forceinline__ void rgb_stages(const ChainArgs& a, float& r, float& 
         b = VEC ? vmaxf_(tb, 0.f) : maxr(tb, 0.f);
     }
     if (a.do_sat) {
-        const float l = (float)((double)r * a.wy0 + (double)g * a.wy1 + (double)b * a.wy2);
+        const float l = r * a.wy0 + g * a.wy1 + b * a.wy2;      // rgbLuminance over the float TMatrix (iccstore.h L38)
         float rl = r - l, gl = g - l, bl = b - l;
         if (a.vib_on) { rl = apply_vibrance(rl, a.vibrance, a.noise); gl = apply_vibrance(gl, a.vibrance, a.noise); bl = apply_vibrance(bl, a.vibrance, a.noise); }
         r = maxr(l + a.saturation * rl, a.noise);
@@ -328,7 +328,7 @@ int art_chain_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, s
     if ((a.do_sat || a.do_lab) && !p->ws) return ctx->fail(ART_HP_ERR_INVALID, "ws is required by saturation and Lab stages");
     if (a.do_lab && (!p->iws || !p->lab_lcurve || !p->lab_acurve || !p->lab_bcurve)) return ctx->fail(ART_HP_ERR_INVALID, "Lab stage needs iws and the three curves");
     if (a.tc_mode > 1) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "tone curve mode %d", a.tc_mode);
-    if (p->ws) { a.wy0 = p->ws[3]; a.wy1 = p->ws[4]; a.wy2 = p->ws[5]; for (int i = 0; i < 9; ++i) a.ws[i] = (float)p->ws[i]; }
+    if (p->ws) { a.wy0 = (float)p->ws[3]; a.wy1 = (float)p->ws[4]; a.wy2 = (float)p->ws[5]; for (int i = 0; i < 9; ++i) a.ws[i] = (float)p->ws[i]; }
     if (p->iws) for (int i = 0; i < 9; ++i) a.iws[i] = (float)p->iws[i];
     ART_CUDA(ctx, cudaEventRecord(ctx->ev_chain, st));
     const dim3 blk(64, 1), grid(((W + 3) / 4 + 63) / 64, std::min(H, 148 * 16));

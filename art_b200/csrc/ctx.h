@@ -49,6 +49,8 @@ struct art_hp_ctx {
     void* h_chain = nullptr;
     cudaEvent_t ev_chain = nullptr;
     bool chain_cache_ready = false;
+    DevBuf d_usm_tables;                 // apply_gamma's two 65536-entry LUTs (gamma 1/3 and 3), built once on the device
+    bool usm_tables_ready = false;
     void* h_stage[2] = {nullptr, nullptr};
     size_t h_stage_bytes = 0;
 
@@ -145,6 +147,8 @@ int art_median_dev(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, siz
 int art_redft00_2d_dev(art_hp_ctx* ctx, const float* in, float* out, int n0, int n1);
 // ImProcFunctions::process per-pixel chain (chain.cu), planes in place
 int art_chain_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch, const art_hp_chain_params* p);
+// doSharpening, "usm" route (usm.cu), planes in place
+int art_usm_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_sharpen_params* p, const double* ws9);
 // develop.cu: ImProcFunctions::denoise (calclum, adjust_params, RGB_denoise, NL-means on Y) and the whole-frame pipeline
 int art_denoise_stage_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_denoise_params* dn,
                           int nlStrength, int nlDetail, const double* cam2work, const double* wprof);

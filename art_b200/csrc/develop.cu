@@ -141,5 +141,21 @@ int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int W, int 
     if (p->fattal_enabled) {
         if ((rc = art_fattal_dev(ctx, r, g, b, op, W, H, p->fattal_threshold, p->fattal_amount, p->fattal_satcontrol, p->wprof))) return rc;
     }
+    // ipf.process(STAGE_1 .. STAGE_3), improcfun.cc L584-625: exposure | sharpening | saturationVibrance, toneCurve, rgbCurves, labAdjustments
+    const bool sharpen = p->sharpen && p->sharpen->amount >= 1;
+    if (p->chain && sharpen && p->chain->exposure_enabled) {
+        art_hp_chain_params e{};
+        e.exposure_enabled = 1; e.exp_scale = p->chain->exp_scale; e.black = p->chain->black;
+        if ((rc = art_chain_dev(ctx, W, H, r, g, b, op, &e))) return rc;
+    }
+    if (sharpen) {
+        if (!p->wprof) return ctx->fail(ART_HP_ERR_INVALID, "sharpening needs wprof");
+        if ((rc = art_usm_dev(ctx, r, g, b, op, W, H, p->sharpen, p->wprof))) return rc;
+    }
+    if (p->chain) {
+        art_hp_chain_params c = *p->chain;
+        if (sharpen) c.exposure_enabled = 0;
+        if ((rc = art_chain_dev(ctx, W, H, r, g, b, op, &c))) return rc;
+    }
     return ART_HP_OK;
 }

@@ -30,11 +30,11 @@ __device__ __forceinline__ float fmaxr(float a, float b) { return a < b ? b : a;
 // ------------------------------------------------------------------------------------------------------------------
 // luminance, median, nearest + log
 // ------------------------------------------------------------------------------------------------------------------
-struct Ws3 { double y0, y1, y2; };
+struct Ws3 { float y0, y1, y2; };
 
 __device__ __forceinline__ float luminance(float r, float g, float b, const Ws3 ws)
-{   // Color::rgbLuminance(r, g, b, TMatrix), color.h L203-207: float * double products summed in double
-    return (float)((double)r * ws.y0 + (double)g * ws.y1 + (double)b * ws.y2);
+{   // Color::rgbLuminance(r, g, b, TMatrix), color.h L203-207; TMatrix holds floats (iccstore.h L38): float arithmetic
+    return r * ws.y0 + g * ws.y1 + b * ws.y2;
 }
 
 __global__ void k_fat_lum(const float* __restrict__ R, const float* __restrict__ G, const float* __restrict__ B, size_t ip,
@@ -776,7 +776,7 @@ int art_fattal_dev(art_hp_ctx* ctx, float* R, float* G, float* B, size_t ip, int
     if ((rc = axis_tables(ctx, w2, &t1))) return rc;
     if ((rc = axis_tables(ctx, h2, &t0))) return rc;
 
-    const Ws3 ws = {ws9[3], ws9[4], ws9[5]};
+    const Ws3 ws = {(float)ws9[3], (float)ws9[4], (float)ws9[5]};
     const dim3 b(32, 8);
 #define FAT_LAUNCH(name, kern, grid, block, smem, ...)              \
     do {                                                            \

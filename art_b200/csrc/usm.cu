@@ -1,0 +1,182 @@
+// Unsharp-mask sharpening: the "usm" route of ImProcFunctions::doSharpening (reference rtengine/ipsharpen.cc L711-790).
+//
+//   k_usm_lum      get_luminance (rt_algo.cc L942-956) fused with apply_gamma<false>(Y, 1, 3) (ipsharpen.cc L46-78) of the
+//                  copy unsharp_mask works on: reads R, G, B once, writes Y and gamma(Y)
+//   k_usm_contrast buildBlendMask's contrast sigmoid (rt_algo.cc L416-476): 4-pixel SSE2 groups from column 2 use the vector
+//                  xexpf, the row tails the scalar one; the replicated two-pixel border is the clamped interior sample
+//   art_gauss_dev  gaussianBlur(blend, blend, sigma = 2 / sqrt(scale)) in place and gaussianBlur(Y', b2, radius / scale)
+//   k_usm_apply    unsharp_mask's threshold loop (L270-283, Threshold<int>::multiply in double, procparams.h L476-502),
+//                  apply_gamma<true>, and multiply(rgb, YY, Y) (rt_algo.cc L958-975): reads Y', b2, blend, Y, R, G, B, writes R, G, B
+//
+// Algorithmic bytes per pixel: 12 + 8 (lum) + 4 + 4 (contrast) + 28 + 12 (apply) + the two Gaussians (8 each at the 3x3 / one
+// IIR sweep pair) ~ 84-110 B/px (~110).  All kernels are streaming: HBM-bound.
+// Bit-identical to the reference's SSE2 build (no FMA contraction, IEEE division and sqrt).
+#include "ctx.h"
+#include "sleef_dev.cuh"
+
+namespace {
+
+__device__ __forceinline__ float maxr(float a, float b) { return a < b ? b : a; }
+__device__ __forceinline__ float minr(float a, float b) { return b < a ? b : a; }
+
+__device__ __forceinline__ float lut_clip(const float* __restrict__ data, float index)
+{   // LUT.h L437-459, 65536 entries, LUT_CLIP_BELOW | LUT_CLIP_ABOVE
+    if (index < 0.f || !(index == index)) return data[0];
+    if (index > 65534.f) return data[65535];
+    const int idx = (int)index;
+    const float diff = index - (float)idx;
+    const float p1 = data[idx];
+    const float p2 = data[idx + 1] - p1;
+    return p1 + p2 * diff;
+}
+
+__device__ __forceinline__ float gamma_apply(const float* __restrict__ glut, float l, float gamma)
+{   // ipsharpen.cc L66-74, pivot 1
+    if (l >= 0.f && l < 65536.f) return lut_clip(glut, l);
+    l = sleef::pow_F_scalar(maxr(l / 65535.f, 1e-18f), gamma) * 1.f;
+    return l * 65535.f;
+}
+
+// glut of apply_gamma<false> (slot 0, gamma 1/3) and apply_gamma<true> (slot 1, gamma 3), L56-62
+__global__ void k_usm_tables(float* __restrict__ t)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 65536) return;
+    const float d = 65535.f * 1.f;
+    const float gf = 1.f / 3.f, gr = 3.f;
+    float a = 0.f, b = 0.f;
+    if (i) {
+        a = sleef::pow_F_scalar((float)i / d, gf) * 1.f; a *= 65535.f;
+        b = sleef::pow_F_scalar((float)i / d, gr) * 1.f; b *= 65535.f;
+    }
+    t[i] = a;
+    t[65536 + i] = b;
+}
+
+__global__ void __launch_bounds__(256) k_usm_lum(const float* __restrict__ R, const float* __restrict__ G, const float* __restrict__ B, size_t ip,
+                                                 float* __restrict__ Y, float* __restrict__ YY, size_t yp, int W, int H,
+                                                 float w0, float w1, float w2, const float* __restrict__ glut)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const size_t i = (size_t)y * ip + x, o = (size_t)y * yp + x;
+        const float l = R[i] * w0 + G[i] * w1 + B[i] * w2;       // Color::rgbLuminance over the float TMatrix
+        Y[o] = l;
+        YY[o] = gamma_apply(glut, l, 1.f / 3.f);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_usm_contrast(const float* __restrict__ L, size_t lp, float* __restrict__ blend, size_t bp, int W, int H,
+                                                      float cpar, float s_scale, float amount, float scale)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const float thr = sleef::pow_F_scalar(cpar, 1.2f) * s_scale;   // doSharpening L727, same sleef steps as the reference's pow_F
+    const int i = min(max(x, 2), W - 3);                        // left / right border columns copy column 2 / W-3
+    const bool vec = 2 + ((i - 2) & ~3) < W - 5;                // the 4-wide loop `for (i = 2; i < W - 5; i += 4)` covers this column
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const int j = min(max(y, 2), H - 3);                    // upper / lower border rows copy row 2 / H-3
+        const float* row = L + (size_t)j * lp;
+        const float a = row[i + 1] - row[i - 1], b = row[i + lp] - row[i - (ptrdiff_t)lp];
+        const float c = row[i + 2] - row[i - 2], d = row[i + 2 * lp] - row[i - 2 * (ptrdiff_t)lp];
+        const float contrast = sqrtf(a * a + b * b + c * c + d * d) * scale;
+        const float arg = 16.f - 16.f * contrast / thr;
+        const float e = vec ? sleef::xexpf_vector(arg) : sleef::xexpf_scalar(arg);
+        blend[(size_t)y * bp + x] = amount * (1.f / (1.f + e));
+    }
+}
+
+__global__ void k_usm_fill(float* __restrict__ p, size_t pp, int W, int H, float v)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) p[(size_t)y * pp + x] = v;
+}
+
+struct Thr { double bl, tl, br, tr; };
+
+__device__ __forceinline__ float threshold_multiply(const Thr t, float x, float y_max)
+{   // Threshold<int>(bl, tl, br, tr, false)::multiply<float, float, float>, procparams.h L476-502
+    const double val = x;
+    if (val == t.br && t.br == t.tr) return y_max;
+    if (val >= t.br) return 0.f;
+    if (val > t.tr) return (float)((double)y_max * (1.0 - (val - t.tr) / (t.br - t.tr)));
+    if (val >= t.tl) return y_max;
+    if (val > t.bl) return (float)((double)y_max * (val - t.bl) / (t.tl - t.bl));
+    return 0.f;
+}
+
+__global__ void __launch_bounds__(256) k_usm_apply(float* __restrict__ R, float* __restrict__ G, float* __restrict__ B, size_t ip,
+                                                   const float* __restrict__ Y, const float* __restrict__ YY, const float* __restrict__ b2,
+                                                   const float* __restrict__ blend, size_t yp, int W, int H, int amount, Thr thr,
+                                                   const float* __restrict__ glut_rev)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const size_t i = (size_t)y * ip + x, o = (size_t)y * yp + x;
+        const float yy = YY[o], bl = blend[o], den = Y[o];
+        const float diff = yy - b2[o];
+        const float delta = threshold_multiply(thr, minr(fabsf(diff), 2000.f), amount * diff * 0.01f);
+        float v = bl * (yy + delta) + (1.f - bl) * yy;           // intp(blend, Y + delta, Y)
+        v = gamma_apply(glut_rev, v, 3.f);
+        if (den > 0.f) {
+            const float f = v / den;
+            R[i] *= f; G[i] *= f; B[i] *= f;
+        }
+    }
+}
+
+}  // namespace
+
+int art_usm_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_sharpen_params* p, const double* ws9)
+{
+    if (p->amount < 1 || W < 8 || H < 8) return ART_HP_OK;      // doSharpening L716-718
+    if (p->halocontrol || p->edgesonly) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "halo control / edges-only sharpening are not on the hot path");
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if (!ctx->usm_tables_ready) {
+        if ((rc = art_reserve(ctx, ctx->d_usm_tables, 2 * 65536 * sizeof(float)))) return rc;
+        k_usm_tables<<<256, 256, 0, st>>>((float*)ctx->d_usm_tables.p);
+        ctx->launches++;
+        ctx->usm_tables_ready = true;
+    }
+    const float* glut = (const float*)ctx->d_usm_tables.p;
+    const size_t yp = round_up((size_t)W, 32);
+    float* planes = nullptr;
+    if ((rc = art_pool_alloc(ctx, 4 * yp * (size_t)H * sizeof(float), (void**)&planes))) return rc;
+    float *Y = planes, *YY = Y + yp * H, *b2 = YY + yp * H, *blend = b2 + yp * H;
+    const dim3 blk(256), grid((W + 255) / 256, std::min(H, 148 * 8));
+
+    art_prof_begin(ctx, "k_usm_lum");
+    k_usm_lum<<<grid, blk, 0, st>>>(r, g, b, ip, Y, YY, yp, W, H, (float)ws9[3], (float)ws9[4], (float)ws9[5], glut);
+    art_prof_end(ctx);
+    ctx->launches++;
+
+    const double scale = p->scale > 0 ? p->scale : 1.0;
+    const float s_scale = (float)std::sqrt(scale);
+    // contrastThreshold = pow_F(contrast / 100.f, 1.2f) * s_scale (L727) is zero exactly when contrast is: exp(1.2 * log(0)) = 0
+    if (p->contrast == 0.0) {     // rt_algo.cc L417-422
+        art_prof_begin(ctx, "k_usm_fill");
+        k_usm_fill<<<grid, blk, 0, st>>>(blend, yp, W, H, 1.f);
+        art_prof_end(ctx);
+        ctx->launches++;
+    } else {
+        art_prof_begin(ctx, "k_usm_contrast");
+        k_usm_contrast<<<grid, blk, 0, st>>>(Y, yp, blend, yp, W, H, (float)(p->contrast / 100.f), s_scale, 1.f, 0.0625f / 327.68f * 1.f);
+        art_prof_end(ctx);
+        ctx->launches++;
+        if ((rc = art_gauss_dev(ctx, blend, yp, blend, yp, W, H, (double)(2.f / s_scale)))) { art_pool_free(ctx, planes); return rc; }
+    }
+    if ((rc = art_gauss_dev(ctx, YY, yp, b2, yp, W, H, p->radius / scale))) { art_pool_free(ctx, planes); return rc; }
+
+    const Thr thr{(double)p->threshold[0], (double)p->threshold[1], (double)p->threshold[2], (double)p->threshold[3]};
+    art_prof_begin(ctx, "k_usm_apply");
+    k_usm_apply<<<grid, blk, 0, st>>>(r, g, b, ip, Y, YY, b2, blend, yp, W, H, p->amount, thr, glut + 65536);
+    art_prof_end(ctx);
+    ctx->launches++;
+    ART_CUDA(ctx, cudaGetLastError());
+    art_pool_free(ctx, planes);
+    return ART_HP_OK;
+}

@@ -343,6 +343,35 @@ int art_hp_color_chain(art_hp_ctx* ctx, int W, int H, float* const* r, float* co
 int art_hp_color_chain_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
                            const art_hp_chain_params* params);
 
+/* ---- sharpening ------------------------------------------------------------------- */
+/*
+ * art_hp_sharpen_usm   ImProcFunctions::sharpening -> doSharpening (rtengine/ipsharpen.cc L711-790; declared
+ *                      rtengine/improcfun.h) for SharpeningParams::method == "usm", in place on the three planes of the
+ *                      working-space image: get_luminance (rtengine/rt_algo.cc L942-956), buildBlendMask with
+ *                      autoContrast = false (L315-496), unsharp_mask (ipsharpen.cc L232-312: apply_gamma 3,
+ *                      gaussianBlur(radius / scale), Threshold<int>::multiply, rtengine/procparams.h L445-503), multiply
+ *                      (rt_algo.cc L958-975).  Fields are procparams::SharpeningParams (rtengine/procparams.h L669-693,
+ *                      defaults rtengine/procparams.cc L1756-1776); threshold = {bottom_left, top_left, bottom_right,
+ *                      top_right}; scale = ImProcFunctions::scale (1 for full-resolution output); ws =
+ *                      ICCStore::workingSpaceMatrix.  amount < 1 or an image under 8x8 returns untouched, like the
+ *                      reference (L716-718).  edgesonly / halocontrol return ART_HP_ERR_UNSUPPORTED.  Bit-identical to the
+ *                      reference's SSE2 build.
+ */
+typedef struct art_hp_sharpen_params {
+    double contrast;            /* 20 */
+    double radius;              /* 0.5 */
+    int    amount;              /* 200 */
+    int    threshold[4];        /* 20, 80, 2000, 1200 */
+    int    edgesonly;           /* must be 0 */
+    int    halocontrol;         /* must be 0 */
+    int    halocontrol_amount;
+    double scale;               /* 1 */
+} art_hp_sharpen_params;
+int art_hp_sharpen_usm(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b,
+                       const art_hp_sharpen_params* params, const double ws[9]);
+int art_hp_sharpen_usm_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
+                           const art_hp_sharpen_params* params, const double ws[9]);
+
 /* ---- whole frame ------------------------------------------------------------------ */
 /*
  * art_hp_develop       the stages of simpleprocess.cc's normal pipeline that are on the hot path, back to back on the
@@ -351,7 +380,8 @@ int art_hp_color_chain_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g
  *                      calclum through the same matrix when a chroma noise curve is given, adjust_params for scale > 1,
  *                      RGB_denoise, then -- nlStrength != 0, i.e. smoothingEnabled with guidedChromaRadius 0 --
  *                      NLMeans(Y, 65535, nlStrength, nlDetail, scale) between Imagefloat::setMode(YUV) and setMode(RGB)),
- *                      and ipf.process(STAGE_0) = dynamicRangeCompression (rtengine/improcfun.cc L580-583).
+ *                      ipf.process(STAGE_0) = dynamicRangeCompression (rtengine/improcfun.cc L580-583), and the per-pixel /
+ *                      sharpening steps of STAGE_1..3 (see `sharpen` and `chain` below).
  *                      One host->device copy of the CFA plane, one device->host copy of the three planes.
  *                      denoise == NULL and fattal_enabled == 0 skip their stages, like `enabled = false` does.
  */
@@ -367,6 +397,11 @@ typedef struct art_hp_develop_params {
     int nlStrength, nlDetail;
     int fattal_enabled, fattal_threshold, fattal_amount, fattal_satcontrol;
     const double* wprof;        /* ICCStore::workingSpaceMatrix(workingProfile), 9 doubles */
+    /* ipf.process(STAGE_1..3) (rtengine/improcfun.cc L584-625): exposure, then sharpening ("usm"), then saturationVibrance,
+     * toneCurve, rgbCurves, labAdjustments.  Both may be NULL.  Without sharpening the whole chain is one fused pass; with it
+     * the exposure stage runs before the sharpening and the rest after, in the reference's order. */
+    const art_hp_sharpen_params* sharpen;
+    const art_hp_chain_params* chain;
 } art_hp_develop_params;
 int art_hp_develop(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
                    float* const* red, float* const* green, float* const* blue);

@@ -544,7 +544,7 @@ SHIM_DENOISE_TU = r"""
 
 namespace rtengine {
 
-typedef const double (*TMatrix)[3];
+typedef const float (*TMatrix)[3];      // iccstore.h L38
 
 struct Settings { bool verbose; };
 static const Settings artref_settings = {false};
@@ -592,7 +592,7 @@ struct ProcParams { ICMParams icm; };
 using procparams::ProcParams;
 struct ImProcData { const ProcParams* params; double scale; bool multiThread; };
 
-static double artref_wp[3][3], artref_wpi[3][3];
+static float artref_wp[3][3], artref_wpi[3][3];     // iccmatrices.h holds float constants
 class ICCStore {
 public:
     static ICCStore* getInstance() { static ICCStore s; return &s; }
@@ -658,7 +658,7 @@ int artref_rgb_denoise(float* r, float* g, float* b, int W, int H, const double*
                        const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* nresi_highresi)
 {
     Color::init();
-    memcpy(artref_wp, wp, sizeof artref_wp); memcpy(artref_wpi, wpi, sizeof artref_wpi);
+    for (int i = 0; i < 9; ++i) { (&artref_wp[0][0])[i] = (float)((const double*)wp)[i]; (&artref_wpi[0][0])[i] = (float)((const double*)wpi)[i]; }
     procparams::DenoiseParams dn;
     dn.enabled = true; dn.colorSpace = procparams::DenoiseParams::ColorSpace::RGB; dn.aggressive = false;
     dn.luminance = p[0]; dn.luminanceDetail = p[1]; dn.luminanceDetailThreshold = (int)p[2];
@@ -712,7 +712,7 @@ SHIM_FATTAL_TU = r"""
 #include "dct_standin.h"
 
 namespace rtengine {
-typedef const double (*TMatrix)[3];
+typedef const float (*TMatrix)[3];      // iccstore.h L38
 struct Settings { bool verbose; };                 // same stand-ins as shim_denoise.cc, which defines the two globals
 extern const Settings* settings;
 class MyMutex { public: class MyLock { public: explicit MyLock(MyMutex&) {} }; };
@@ -735,7 +735,7 @@ struct ProcParams { FattalToneMappingParams fattal; ICMParams icm; };
 }
 using procparams::ProcParams;
 class ImProcFunctions;
-static double artref_fattal_ws[3][3];
+static float artref_fattal_ws[3][3];
 class ICCStore {
 public:
     static ICCStore* getInstance() { static ICCStore s; return &s; }
@@ -760,7 +760,7 @@ void Median_Denoise(float **src, float **dst, const int width, const int height,
 extern "C" {
 int artref_fattal(float* r, float* g, float* b, int W, int H, int threshold, int amount, int satcontrol, const double* ws)
 {
-    memcpy(artref_fattal_ws, ws, sizeof artref_fattal_ws);
+    for (int i = 0; i < 9; ++i) (&artref_fattal_ws[0][0])[i] = (float)((const double*)ws)[i];
     ProcParams pp; pp.fattal.enabled = true; pp.fattal.threshold = threshold; pp.fattal.amount = amount; pp.fattal.satcontrol = satcontrol != 0;
     pp.icm.workingProfile = "ProPhoto";
     Imagefloat img(W, H, r, g, b);
@@ -823,7 +823,7 @@ SHIM_CHAIN_TU = r"""
 
 namespace artref_chain {
 using namespace rtengine;
-typedef const double (*TMatrix)[3];
+typedef const float (*TMatrix)[3];      // iccstore.h L38
 
 class Curve { public: virtual ~Curve() {} virtual double getVal(double) const { abort(); } };
 
@@ -934,7 +934,7 @@ int artref_chain_saturation(float* R, float* G, float* B, int W, int H, int sat,
     Imagefloat im(W, H, R, G, B, wsd, nullptr);
     Imagefloat* rgb = &im;
     const bool multiThread = true;
-    double wsm[3][3]; memcpy(wsm, wsd, sizeof wsm);
+    float wsm[3][3]; for (int i = 0; i < 9; ++i) (&wsm[0][0])[i] = (float)wsd[i];
     TMatrix ws = wsm;
     const float saturation = 1.f + sat / 100.f;
     const float vibrance = 1.f - vibr / 1000.f;
@@ -1009,6 +1009,82 @@ int artref_chain_rgb2lab(float* R, float* G, float* B, int W, int H, const doubl
 }
 }
 }  // namespace artref_chain
+"""
+
+
+SHIM_USM_TU = r"""
+// Shim TU hosting the reference's unsharp-mask sharpening: apply_gamma, sharpenHaloCtrl, unsharp_mask cut from ipsharpen.cc;
+// calcBlendFactor, tileAverage, tileVariance, calcContrastThreshold, buildBlendMask, get_luminance, multiply cut from
+// rt_algo.cc; Threshold<T> cut from procparams.h; Color::rgbLuminance cut from color.h; gaussianBlur from shim_gauss.cc.
+// Written here (not reference code): the Imagefloat / SharpeningParams stand-ins, the bilateral stub (edgesonly is never
+// set) and the wrapper, which restates the "usm" route of ImProcFunctions::doSharpening (ipsharpen.cc L711-790).
+#include <assert.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <memory>
+#include <type_traits>
+#include <vector>
+#include <omp.h>
+#include "array2D.h"
+#include "jaggedarray.h"
+#include "LUT.h"
+#include "rt_math.h"
+#include "opthelper.h"
+#include "sleef.h"
+#include "gauss.h"
+#define BENCHFUN
+namespace artref_usm {
+using namespace rtengine;
+typedef const float (*TMatrix)[3];      // iccstore.h L38
+class Color { public:
+template <class T>
+#include "usm_rgblum.inc"
+};
+#include "usm_threshold.inc"
+;
+struct SharpeningParams { double contrast, radius; int amount; Threshold<int> threshold; bool edgesonly; double edges_radius; int edges_tolerance;
+                          bool halocontrol; int halocontrol_amount;
+                          SharpeningParams() : contrast(20.0), radius(0.5), amount(200), threshold(20, 80, 2000, 1200, false), edgesonly(false), edges_radius(1.9),
+                                               edges_tolerance(1800), halocontrol(false), halocontrol_amount(85) {} };
+template <class T, class A> void bilateral(T**, T**, T**, int, int, double, double, bool) { abort(); }
+struct Chan { float* base; int W; float& operator()(int y, int x) const { return base[(size_t)y * W + x]; } };
+class Imagefloat { public: int width, height; Chan r, g, b; int getWidth() const { return width; } int getHeight() const { return height; } };
+namespace {
+#include "usm_rtalgo_anon.inc"
+}
+#include "usm_rtalgo.inc"
+namespace {
+#include "usm_ipsharpen.inc"
+}
+
+extern "C" int artref_usm(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double radius, int amount,
+                          const int* thr, int halocontrol, int halocontrol_amount, float* blend_out)
+{
+    if (amount < 1 || W < 8 || H < 8) return 0;                    // doSharpening L716-718
+    const bool multiThread = true;
+    Imagefloat im{W, H, {R, W}, {G, W}, {B, W}};
+    Imagefloat* rgb = &im;
+    SharpeningParams sharpenParam;
+    sharpenParam.contrast = contrast_p; sharpenParam.radius = radius; sharpenParam.amount = amount;
+    sharpenParam.threshold = Threshold<int>(thr[0], thr[1], thr[2], thr[3], false);
+    sharpenParam.halocontrol = halocontrol != 0; sharpenParam.halocontrol_amount = halocontrol_amount;
+    float wsm[3][3]; for (int i = 0; i < 9; ++i) (&wsm[0][0])[i] = (float)wsd[i];
+    TMatrix ws = wsm;
+    array2D<float> Y(ARRAY2D_ALIGNED);
+    get_luminance(rgb, Y, ws, multiThread);
+    float s_scale = std::sqrt(scale);
+    float contrast = pow_F(sharpenParam.contrast / 100.f, 1.2f) * s_scale;
+    JaggedArray<float> blend(W, H);
+    buildBlendMask(Y, blend, W, H, contrast, 1.f, false, 2.f / s_scale, 1.f);
+    if (blend_out) for (int y = 0; y < H; ++y) memcpy(blend_out + (size_t)y * W, blend[y], sizeof(float) * W);
+    array2D<float> YY(W, H, Y, ARRAY2D_ALIGNED);
+    unsharp_mask(YY, blend, W, H, sharpenParam, scale, multiThread);
+    multiply(rgb, YY, Y, multiThread);
+    return 0;
+}
+}  // namespace artref_usm
 """
 
 
@@ -1148,6 +1224,28 @@ def extract(det):
            cut_function(cc, r"^void Color::filmlike_clip\(float \*r, float \*g, float \*b, float Lmax\)")]
     open(os.path.join(sub, "chain_color_cc.inc"), "w").write("\n".join(ccf))
     open(os.path.join(sub, "shim_chain.cc"), "w").write(SHIM_CHAIN_TU)
+
+    # USM sharpening (ipsharpen.cc, rt_algo.cc)
+    ra = os.path.join(RT, "rt_algo.cc")
+    ish = os.path.join(RT, "ipsharpen.cc")
+    open(os.path.join(sub, "usm_rgblum.inc"), "w").write(
+        cut_function(os.path.join(RT, "color.h"), r"static float rgbLuminance\(float r, float g, float b, const T workingspace\[3\]\[3\]\)"))
+    open(os.path.join(sub, "usm_threshold.inc"), "w").write(cut_function(os.path.join(RT, "procparams.h"), r"^template<typename T>\nclass Threshold final"))
+    anon = [cut_function(ra, r"^float calcBlendFactor\(float val, float threshold\)"),
+            cut_function(ra, r"^vfloat calcBlendFactor\(vfloat valv, vfloat thresholdv\)"),
+            cut_function(ra, r"^float tileAverage\(float \*\*data[^)]*\)"),
+            cut_function(ra, r"^float tileVariance\(float \*\*data[^)]*\)"),
+            cut_function(ra, r"^float calcContrastThreshold\(float\*\* luminance[^)]*\)")]
+    open(os.path.join(sub, "usm_rtalgo_anon.inc"), "w").write("\n\n".join(anon))
+    pub = [cut_function(ra, r"^void buildBlendMask\(float\*\* luminance[^)]*\)"),
+           cut_function(ra, r"^void get_luminance\(const Imagefloat \*src[^)]*\)"),
+           cut_function(ra, r"^void multiply\(Imagefloat \*img[^)]*\)")]
+    open(os.path.join(sub, "usm_rtalgo.inc"), "w").write("\n\n".join(pub))
+    ips = ["template <bool reverse>\n" + cut_function(ish, r"^void apply_gamma\(float \*\*Y[^)]*\)"),
+           cut_function(ish, r"^void sharpenHaloCtrl\(float\*\* luminance[^)]*\)"),
+           cut_function(ish, r"^void unsharp_mask\(float \*\*Y[^)]*\)")]
+    open(os.path.join(sub, "usm_ipsharpen.inc"), "w").write("\n\n".join(ips))
+    open(os.path.join(sub, "shim_usm.cc"), "w").write(SHIM_USM_TU)
     return sub
 
 
@@ -1155,7 +1253,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)

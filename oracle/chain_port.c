@@ -68,7 +68,11 @@ int artoracle_chain_expcomp(float* R, float* G, float* B, int W, int H, float ex
 }
 
 /* ---- saturationVibrance ---- */
-static inline float lum_d(float r, float g, float b, const double* ws) { return (float)(r * ws[3] + g * ws[4] + b * ws[5]); }
+static inline float lum_d(float r, float g, float b, const double* ws)
+{   /* Color::rgbLuminance(r, g, b, TMatrix), color.h L203-207; TMatrix is const float (*)[3] (iccstore.h L38): float arithmetic */
+    const float w0 = (float)ws[3], w1 = (float)ws[4], w2 = (float)ws[5];
+    return r * w0 + g * w1 + b * w2;
+}
 static inline float apply_vibrance(float x, float vib, float noise)
 {
     const float ax = fabsf(x / 65535.f);

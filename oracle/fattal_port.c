@@ -336,7 +336,9 @@ int artoracle_find_fast_dim(int dim)
 
 static inline float fat_luminance(float r, float g, float b, const double* ws)
 {
-    return (float)(r * ws[3] + g * ws[4] + b * ws[5]);
+    /* Color::rgbLuminance(r, g, b, TMatrix), color.h L203-207; TMatrix is const float (*)[3] (iccstore.h L38): float arithmetic */
+    const float w0 = (float)ws[3], w1 = (float)ws[4], w2 = (float)ws[5];
+    return r * w0 + g * w1 + b * w2;
 }
 
 /* ToneMapFattal02 L1053-1215; planes contiguous W x H, in place; ws = working-space matrix, row-major 3x3 */

@@ -10,7 +10,7 @@ import pytest
 import art_b200
 import oracle
 from art_b200 import synth
-from art_b200.api import DenoiseParams, DevelopParams
+from art_b200.api import ChainParams, DenoiseParams, DevelopParams, SharpenParams
 from test_oracle_denoise import PROPHOTO, noise_ccurve, run as run_denoise
 from test_oracle_fattal import fattal as run_fattal
 
@@ -87,3 +87,49 @@ def test_develop_matches_oracle_chain(hot_path, W, H, dn, curve, fat, exact):
             assert (err <= lim).all(), "%s: %d of %d beyond tolerance, worst %g" % (ch, int((err > lim).sum()), x.size, worst)
     if not exact:
         print("\n[develop] %dx%d worst relative error %.3g" % (W, H, worst))
+
+
+def finishing_stages(planes, sharpen, chain_kw):
+    """oracle: ipf.process(STAGE_1..3) = exposure | sharpening (usm) | saturationVibrance, toneCurve, rgbCurves, labAdjustments"""
+    from test_chain_gpu import oracle_chain as colour_chain
+    from test_oracle_usm import run as run_usm
+    kw = dict(chain_kw)
+    exposure = kw.pop("exposure", None)
+    if exposure is not None:
+        planes = colour_chain(planes, exposure=exposure)
+    if sharpen is not None:
+        planes, _ = run_usm(oracle.port().lib, "artoracle_usm", planes, **sharpen)
+    return colour_chain(planes, **kw)
+
+
+@pytest.mark.parametrize("W,H,dn,fat,sharpen,exact", [
+    (322, 260, (0, 0, 0, 15, 0, 0, 1.7, 1.0), None, dict(), True),
+    (323, 261, None, None, None, True),
+    (322, 260, (30, 50, 0, 15, 0, 0, 1.7, 1.0), (30, 20, 0), dict(radius=0.5, amount=200), False),
+])
+def test_develop_with_finishing_stages(hot_path, W, H, dn, fat, sharpen, exact):
+    from test_chain_gpu import STAGES
+    from test_oracle_chain import PROPHOTO_INV
+    raw = synth.bayer_frame(W, H, synth.RGGB, seed=W + H)
+    chain_kw = STAGES["all_std"]
+    want = finishing_stages(oracle_chain(raw, dn, False, fat), sharpen, chain_kw)
+    dnp = None
+    if dn is not None:
+        lum, det, thr, chroma, rg, by, gamma, scale = dn
+        dnp = DenoiseParams(luminance=lum, luminanceDetail=det, luminanceDetailThreshold=thr, chrominance=chroma, chrominanceRedGreen=rg,
+                            chrominanceBlueYellow=by, gamma=gamma, scale=scale)
+    params = DevelopParams(method=art_b200.BAYER_AMAZE, filters=synth.RGGB, mul=MUL, do_clip=True, cam2work=CAM2WORK, denoise=dnp, fattal=fat,
+                           wprof=PROPHOTO, sharpen=SharpenParams(**sharpen) if sharpen is not None else None,
+                           chain=ChainParams(ws=PROPHOTO, iws=PROPHOTO_INV, **chain_kw))
+    got = hot_path.develop(raw, params)
+    worst = 0.0
+    for x, y, ch in zip(got, want, "RGB"):
+        if exact:
+            assert np.array_equal(x, y), "%s: %d of %d differ" % (ch, int((x != y).sum()), x.size)
+        else:
+            err = np.abs(x - y)
+            lim = 1e-4 * np.abs(y) + 0.05
+            worst = max(worst, float((err / (np.abs(y) + 0.05)).max()))
+            assert (err <= lim).mean() > 0.9999, "%s: %d of %d beyond tolerance, worst %g" % (ch, int((err > lim).sum()), x.size, worst)
+    if not exact:
+        print("\n[develop+finishing] %dx%d worst relative error %.3g" % (W, H, worst))

@@ -1,0 +1,79 @@
+"""Pin the unsharp-mask oracle (oracle/usm_port.c) against the reference's own functions compiled in place (oracle/_ref,
+shim_usm.cc: apply_gamma, unsharp_mask, buildBlendMask, get_luminance, multiply, Threshold<int>::multiply, gaussianBlur).
+Bit-exact on the blend mask and on the sharpened planes, SSE2 groups versus scalar row tails included."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+
+needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built and /root/reference absent")
+fp = ctypes.POINTER(ctypes.c_float)
+dp = ctypes.POINTER(ctypes.c_double)
+ip = ctypes.POINTER(ctypes.c_int)
+D = ctypes.c_double
+PROPHOTO = np.array([[0.7976749, 0.1351917, 0.0313534], [0.2880402, 0.7118741, 0.0000857], [0.0, 0.0, 0.8252100]], np.float64)
+DEFAULT_THR = (20, 80, 2000, 1200)      # procparams.cc L1761
+SIZES = [(64, 48), (67, 35), (9, 8), (8, 11), (130, 77), (301, 203)]
+
+
+def scene(W, H, seed, wild=False):
+    """working-space RGB: smooth gradients + edges + texture + noise, so that the blend mask spans ]0, 1]"""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    base = 8000 + 20000 * (0.5 + 0.5 * np.sin(xx / 17.0 + yy / 29.0)) + 15000 * (xx > W * 0.6) + 9000 * (yy > H * 0.35)
+    tex = 2500 * np.sin(xx * 1.3) * np.sin(yy * 0.9) * (xx < W * 0.4)
+    planes = []
+    for c, gain in enumerate((0.9, 1.0, 0.7)):
+        p = (base * gain + tex + rng.normal(0, 150, (H, W))).astype(np.float32)
+        planes.append(np.clip(p, 1.0, 65535.0).astype(np.float32))
+    if wild:
+        m = rng.random((H, W))
+        for p in planes:
+            p[m < 0.02] = 0.0                       # luminance 0: multiply() leaves the pixel alone
+            p[m > 0.985] *= 1.6                     # above 65535: apply_gamma's pow_F branch
+        planes[0][(m > 0.5) & (m < 0.51)] = -40.0   # negative luminance contributions
+    return planes
+
+
+def run(lib, name, planes, scale=1.0, contrast=20.0, radius=0.5, amount=200, thr=DEFAULT_THR, halo=0, halo_amount=85):
+    out = [np.ascontiguousarray(p).copy() for p in planes]
+    H, W = out[0].shape
+    blend = np.zeros((H, W), np.float32)
+    t = (ctypes.c_int * 4)(*thr)
+    rc = getattr(lib, name)(out[0].ctypes.data_as(fp), out[1].ctypes.data_as(fp), out[2].ctypes.data_as(fp), W, H, PROPHOTO.ctypes.data_as(dp),
+                            D(scale), D(contrast), D(radius), int(amount), t, int(halo), int(halo_amount), blend.ctypes.data_as(fp))
+    assert rc == 0
+    return out, blend
+
+
+def same(a, b, what="RGB"):
+    for x, y, ch in zip(a, b, what):
+        eq = (x == y) | (np.isnan(x) & np.isnan(y))
+        assert eq.all(), "%s: %d of %d differ, first at %s: %r vs %r" % (ch, int((~eq).sum()), x.size, np.argwhere(~eq)[0], x[~eq][0], y[~eq][0])
+
+
+CASES = [dict(), dict(radius=0.9, amount=350), dict(contrast=0.0), dict(contrast=55.0, radius=2.4, amount=80, thr=(10, 40, 1500, 600)),
+         dict(radius=0.2), dict(scale=2.0, radius=1.5), dict(amount=0)]
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("wild", [False, True])
+def test_usm(W, H, case, wild):
+    planes = scene(W, H, W * 3 + H + case, wild)
+    a, ba = run(oracle.port().lib, "artoracle_usm", planes, **CASES[case])
+    b, bb = run(oracle.ref().lib, "artref_usm", planes, **CASES[case])
+    same([ba], [bb], ["blend"])
+    same(a, b)
+    if CASES[case].get("amount", 200) >= 1:
+        assert any((x != y).any() for x, y in zip(a, planes)), "sharpening changed nothing"
+
+
+@needs_ref
+def test_blend_mask_spans_range():
+    planes = scene(301, 203, 5)
+    _, blend = run(oracle.ref().lib, "artref_usm", planes)
+    assert blend.min() < 0.05 and blend.max() > 0.95

@@ -1,0 +1,57 @@
+"""GPU parity for unsharp-mask sharpening (art_hp_sharpen_usm = ImProcFunctions::sharpening, method "usm") through the C-ABI
+against the oracle port, which test_oracle_usm.py pins bit-exact to the reference functions compiled in place.  Bit-exact."""
+import numpy as np
+import pytest
+
+import oracle
+from art_b200.api import SharpenParams
+from test_oracle_usm import CASES, PROPHOTO, SIZES, run, same, scene
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu(hp, planes, **kw):
+    out = [np.ascontiguousarray(p).copy() for p in planes]
+    kw = dict(kw)
+    if "thr" in kw:
+        kw["threshold"] = kw.pop("thr")
+    hp.sharpen_usm(out[0], out[1], out[2], SharpenParams(**kw), PROPHOTO)
+    return out
+
+
+@pytest.mark.parametrize("W,H", SIZES + [(1023, 517)])
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("wild", [False, True])
+def test_usm_matches_oracle(hot_path, W, H, case, wild):
+    planes = scene(W, H, W * 3 + H + case, wild)
+    want, _ = run(oracle.port().lib, "artoracle_usm", planes, **CASES[case])
+    same(gpu(hot_path, planes, **CASES[case]), want)
+
+
+def test_usm_too_small_or_disabled_is_identity(hot_path):
+    planes = scene(7, 40, 1)
+    same(gpu(hot_path, planes), planes)
+    planes = scene(64, 40, 2)
+    same(gpu(hot_path, planes, amount=0), planes)
+
+
+def test_usm_rejects_halo_control(hot_path):
+    import art_b200
+    planes = scene(64, 40, 3)
+    with pytest.raises(art_b200.HotPathError) as e:
+        gpu(hot_path, planes, halocontrol=True)
+    assert e.value.code == 5
+
+
+def test_usm_device_form_with_pitch(hot_path):
+    torch = pytest.importorskip("torch")
+    W, H, pitch = 203, 141, 224
+    planes = scene(W, H, 9)
+    dev = [torch.zeros((H, pitch), dtype=torch.float32, device="cuda") for _ in range(3)]
+    for d, p in zip(dev, planes):
+        d[:, :W] = torch.from_numpy(p).cuda()
+    torch.cuda.synchronize()
+    hot_path.sharpen_usm_dev(W, H, dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), pitch, SharpenParams(radius=0.9, amount=300), PROPHOTO)
+    hot_path.sync()
+    want, _ = run(oracle.port().lib, "artoracle_usm", planes, radius=0.9, amount=300)
+    same([d[:, :W].cpu().numpy() for d in dev], want)
