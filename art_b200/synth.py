@@ -64,6 +64,31 @@ def bayer_frame(width, height, filters=RGGB, seed=1001, noise_a=4.0, noise_b=100
     return out
 
 
+# X-Trans 6x6 colour matrix (0 R, 1 G, 2 B), the layout dcraw reports for Fuji X-Trans sensors (passed explicitly);
+# `xtrans_matrix(dy, dx)` gives the same pattern read from another origin (different camera crops start elsewhere in the 6x6 cell)
+XTRANS = ((1, 1, 0, 1, 1, 2), (1, 1, 2, 1, 1, 0), (2, 0, 1, 0, 2, 1), (1, 1, 2, 1, 1, 0), (1, 1, 0, 1, 1, 2), (0, 2, 1, 2, 0, 1))
+# camera RGB -> sRGB, 3x4 as RawImage::getRgbCam returns it: a fixed identity-ish matrix (rows sum to 1)
+XTRANS_RGB_CAM = ((1.62, -0.48, -0.14, 0.0), (-0.21, 1.45, -0.24, 0.0), (0.02, -0.52, 1.50, 0.0))
+
+
+def xtrans_matrix(dy=0, dx=0):
+    return np.array([[XTRANS[(r + dy) % 6][(c + dx) % 6] for c in range(6)] for r in range(6)], dtype=np.int32)
+
+
+def xtrans_frame(width, height, xtrans=None, seed=1004, noise_a=4.0, noise_b=100.0):
+    """X-Trans CFA plane from the same scene as bayer_frame (the Bayer frame supplies the radiance, re-mosaicked 6x6)."""
+    xt = np.asarray(xtrans if xtrans is not None else XTRANS, dtype=np.int32)
+    rng = np.random.default_rng(seed)
+    gains = np.array([0.6, 1.0, 0.7], dtype=np.float32)
+    # bayer_frame with an all-green "CFA" (filters 0x55555555 -> colour 1 everywhere, gain 1) and no noise is the radiance itself
+    rad = bayer_frame(width, height, 0x55555555, seed=seed, noise_a=0.0, noise_b=0.0)
+    cmap = xt[np.arange(height)[:, None] % 6, np.arange(width)[None, :] % 6]
+    blk = rad * gains[cmap]
+    sigma = np.sqrt(noise_a * blk + noise_b, dtype=np.float32)
+    blk = blk + sigma * rng.standard_normal(blk.shape, dtype=np.float32)
+    return np.clip(np.rint(blk), 0.0, 65535.0).astype(np.float32)
+
+
 def random_frame(width, height, seed=7, lo=0.0, hi=65535.0):
     """Uniform integer noise -- the harshest input for direction-select parity."""
     rng = np.random.default_rng(seed)

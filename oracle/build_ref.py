@@ -1088,6 +1088,72 @@ extern "C" int artref_usm(float* R, float* G, float* B, int W, int H, const doub
 """
 
 
+SHIM_XTRANS_TU = r"""
+// Shim TU hosting the reference's X-Trans demosaic: the xyz_rgb / d65_white constants, RawImageSource::cielab,
+// xtransborder_interpolate and xtrans_interpolate (Markesteijn) cut from xtrans_demosaic.cc at build time, inside a stand-in
+// class holding only the members those bodies touch.  ARTREF_DET clears the per-thread tile buffer at the start of every tile.
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <algorithm>
+#include <omp.h>
+#include "glibmm.h"
+#include "array2D.h"
+#include "LUT.h"
+#include "rt_math.h"
+#include "opthelper.h"
+#define M(x) Glib::ustring(x)
+#ifndef MIN
+#define MIN(a, b) ((a) < (b) ? (a) : (b))
+#define MAX(a, b) ((a) > (b) ? (a) : (b))
+#endif
+#define LIM(x, lo, hi) rtengine::LIM(x, lo, hi)
+#define SQR(x) rtengine::SQR(x)
+namespace artref_xt {
+using namespace rtengine;
+typedef unsigned short ushort;
+struct ProgressListener { void setProgressStr(const Glib::ustring&) {} void setProgress(double) {} };
+struct StopWatch { StopWatch(const char*) {} };
+struct Color { constexpr static double eps = 216.0 / 24389.0; constexpr static double kappa = 24389.0 / 27.0; };   // color.h
+struct RawImage {
+    int xt[6][6]; float cam[3][4];
+    void getXtransMatrix(int m[6][6]) const { memcpy(m, xt, sizeof xt); }
+    void getRgbCam(float m[3][4]) const { memcpy(m, cam, sizeof cam); }
+};
+struct RawImageSource {
+    int W, H; RawImage* ri; ProgressListener* plistener;
+    array2D<float> rawData, red, green, blue;
+    RawImageSource(int w, int h, RawImage* r_, float** raw, float** r, float** g, float** b)
+        : W(w), H(h), ri(r_), plistener(nullptr), rawData(w, h, raw, ARRAY2D_BYREFERENCE), red(w, h, r, ARRAY2D_BYREFERENCE),
+          green(w, h, g, ARRAY2D_BYREFERENCE), blue(w, h, b, ARRAY2D_BYREFERENCE) {}
+    void cielab(const float (*rgb)[3], float* l, float* a, float* b, const int width, const int height, const int labWidth, const float xyz_cam[3][3]);
+    void xtransborder_interpolate(int border, array2D<float>& red, array2D<float>& green, array2D<float>& blue);
+    void xtrans_interpolate(const int passes, const bool useCieLab);
+};
+#include "xtrans_body.inc"
+}  // namespace artref_xt
+
+extern "C" int artref_xtrans(int W, int H, const int* xtrans36, const float* rgb_cam12, int passes, int useCieLab, const float* raw,
+                             float* r, float* g, float* b, int border_only, int nthreads)
+{
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+    float **rr = new float*[H], **gr = new float*[H], **br = new float*[H], **wr = new float*[H];
+    for (int i = 0; i < H; ++i) { rr[i] = r + (size_t)i * W; gr[i] = g + (size_t)i * W; br[i] = b + (size_t)i * W; wr[i] = const_cast<float*>(raw) + (size_t)i * W; }
+    artref_xt::RawImage ri;
+    memcpy(ri.xt, xtrans36, sizeof ri.xt); memcpy(ri.cam, rgb_cam12, sizeof ri.cam);
+    artref_xt::RawImageSource src(W, H, &ri, wr, rr, gr, br);
+    if (border_only) src.xtransborder_interpolate(border_only, src.red, src.green, src.blue);
+    else src.xtrans_interpolate(passes, useCieLab != 0);
+    delete[] rr; delete[] gr; delete[] br; delete[] wr;
+    return 0;
+}
+"""
+
+
 def extract(det):
     sub = os.path.join(SRC, "det" if det else "stock")
     os.makedirs(sub, exist_ok=True)
@@ -1246,6 +1312,24 @@ def extract(det):
            cut_function(ish, r"^void unsharp_mask\(float \*\*Y[^)]*\)")]
     open(os.path.join(sub, "usm_ipsharpen.inc"), "w").write("\n\n".join(ips))
     open(os.path.join(sub, "shim_usm.cc"), "w").write(SHIM_USM_TU)
+
+    # X-Trans demosaic (xtrans_demosaic.cc): constants + cielab + border + Markesteijn
+    xt = os.path.join(RT, "xtrans_demosaic.cc")
+    xtext = open(xt, encoding="utf-8", errors="replace").read()
+    m0 = re.search(r"^const float xyz_rgb\[3\]\[3\]", xtext, flags=re.M)
+    m1 = re.search(r"^void RawImageSource::cielab", xtext, flags=re.M)
+    body = [xtext[m0.start():m1.start()],
+            cut_function(xt, r"^void RawImageSource::cielab \([^)]*\)"),
+            "#define fcol(row,col) xtrans[(row)%6][(col)%6]\n#define isgreen(row,col) (xtrans[(row)%3][(col)%3]&1)\n",
+            cut_function(xt, r"^void RawImageSource::xtransborder_interpolate \([^)]*\)"),
+            "#define CLIP(x) (x)\n",
+            cut_function(xt, r"^void RawImageSource::xtrans_interpolate\(const int passes, const bool useCieLab\)"),
+            "#undef CLIP\n#undef fcol\n#undef isgreen\n"]
+    if det:
+        body[5] = insert_before(body[5], r"int mrow = MIN \(top \+ ts, height - 3\);",
+                                "memset(buffer, 0, (ts * ts * (ndir * 4 + 3) + 128) * sizeof(float));\n                ")
+    open(os.path.join(sub, "xtrans_body.inc"), "w").write("\n".join(body))
+    open(os.path.join(sub, "shim_xtrans.cc"), "w").write(SHIM_XTRANS_TU)
     return sub
 
 
@@ -1253,7 +1337,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)
