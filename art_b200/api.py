@@ -99,6 +99,8 @@ def load_library(build_if_missing=True):
         "art_hp_fattal": (i, [vp, i, i, vp, vp, vp, i, i, i, ctypes.POINTER(d)]),
         "art_hp_fattal_dev": (i, [vp, i, i, vp, vp, vp, sz, i, i, i, ctypes.POINTER(d)]),
         "art_hp_fattal_fast_dim": (i, [i]),
+        "art_hp_demosaic_xtrans": (i, [vp, i, i, i, i, ctypes.POINTER(i), ctypes.POINTER(f), vp, vp, vp, vp]),
+        "art_hp_demosaic_xtrans_dev": (i, [vp, i, i, i, i, ctypes.POINTER(i), ctypes.POINTER(f), vp, sz, vp, vp, vp, sz]),
         "art_hp_sharpen_usm": (i, [vp, i, i, vp, vp, vp, vp, ctypes.POINTER(d)]),
         "art_hp_sharpen_usm_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, ctypes.POINTER(d)]),
         "art_hp_color_chain": (i, [vp, i, i, vp, vp, vp, vp]),
@@ -512,6 +514,23 @@ class HotPath:
     def develop_dev(self, params, W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch):
         c = params.c_struct()
         self._check(self.lib.art_hp_develop_dev(self.h, ctypes.byref(c), W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch))
+
+    def demosaic_xtrans(self, raw, xtrans, rgb_cam, passes=3, use_cielab=True, out=None):
+        """RawImageSource::xtrans_interpolate(passes, useCieLab) on a host (H, W) float32 X-Trans CFA plane.
+        xtrans: 6x6 colours (0 R, 1 G, 2 B) as RawImage::getXtransMatrix; rgb_cam: 3x4 as RawImage::getRgbCam."""
+        H, W = raw.shape
+        out = out if out is not None else [np.empty((H, W), np.float32) for _ in range(3)]
+        xt = (ctypes.c_int * 36)(*[int(v) for v in np.asarray(xtrans).reshape(36)])
+        cam = (ctypes.c_float * 12)(*[float(v) for v in np.asarray(rgb_cam, dtype=np.float32).reshape(12)])
+        self._check(self.lib.art_hp_demosaic_xtrans(self.h, int(passes), int(bool(use_cielab)), W, H, xt, cam, row_table(raw),
+                                                    row_table(out[0]), row_table(out[1]), row_table(out[2])))
+        return out
+
+    def demosaic_xtrans_dev(self, W, H, xtrans, rgb_cam, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch, passes=3, use_cielab=True):
+        xt = (ctypes.c_int * 36)(*[int(v) for v in np.asarray(xtrans).reshape(36)])
+        cam = (ctypes.c_float * 12)(*[float(v) for v in np.asarray(rgb_cam, dtype=np.float32).reshape(12)])
+        self._check(self.lib.art_hp_demosaic_xtrans_dev(self.h, int(passes), int(bool(use_cielab)), W, H, xt, cam, d_raw, raw_pitch,
+                                                        d_r, d_g, d_b, out_pitch))
 
     def sharpen_usm(self, r, g, b, params, ws):
         """ImProcFunctions::sharpening with method "usm", in place on three host (H, W) float32 planes."""

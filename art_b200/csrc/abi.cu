@@ -241,6 +241,7 @@ void art_hp_destroy(art_hp_ctx* ctx)
     if (ctx->d_dn_tables.p) cudaFree(ctx->d_dn_tables.p);
     if (ctx->d_chain.p) cudaFree(ctx->d_chain.p);
     if (ctx->d_usm_tables.p) cudaFree(ctx->d_usm_tables.p);
+    if (ctx->d_xt_cbrt.p) cudaFree(ctx->d_xt_cbrt.p);
     if (ctx->h_chain) cudaFreeHost(ctx->h_chain);
     if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
     for (PoolBlk& b : ctx->pool) cudaFree(b.p);
@@ -843,6 +844,53 @@ int art_hp_sharpen_usm(art_hp_ctx* ctx, int W, int H, float* const* r, float* co
     if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, true))) return rc;
     if ((rc = art_usm_dev(ctx, io[0].dev, io[1].dev, io[2].dev, pitch, W, H, params, ws))) return rc;
     if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+static int xtrans_check(art_hp_ctx* ctx, int passes, int W, int H, const int* xtrans)
+{
+    if (passes != 1 && passes != 3) return ctx->fail(ART_HP_ERR_INVALID, "passes must be 1 or 3, got %d", passes);
+    if (W < 23 || H < 23 || W > 16380 || H > 65536) return ctx->fail(ART_HP_ERR_INVALID, "frame %dx%d out of range", W, H);
+    int n[3] = {0, 0, 0};
+    for (int i = 0; i < 36; ++i) {
+        if (xtrans[i] < 0 || xtrans[i] > 2) return ctx->fail(ART_HP_ERR_INVALID, "xtrans[%d] = %d is not a colour", i, xtrans[i]);
+        n[xtrans[i]]++;
+    }
+    if (n[1] != 20 || n[0] != 8 || n[2] != 8) return ctx->fail(ART_HP_ERR_INVALID, "not an X-Trans matrix (%d R, %d G, %d B)", n[0], n[1], n[2]);
+    return ART_HP_OK;
+}
+
+int art_hp_demosaic_xtrans_dev(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, const int xtrans[36], const float rgb_cam[12],
+                               const float* d_raw, size_t raw_pitch, float* d_red, float* d_green, float* d_blue, size_t out_pitch)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!xtrans || !rgb_cam || !d_raw || !d_red || !d_green || !d_blue) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    int rc = xtrans_check(ctx, passes, W, H, xtrans);
+    if (rc) return rc;
+    if (raw_pitch < (size_t)W || out_pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "pitch smaller than the width");
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_xtrans_dev(ctx, passes, useCieLab != 0, W, H, xtrans, rgb_cam, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch);
+}
+
+int art_hp_demosaic_xtrans(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, const int xtrans[36], const float rgb_cam[12],
+                           float* const* rawData, float* const* red, float* const* green, float* const* blue)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!xtrans || !rgb_cam || !rawData || !red || !green || !blue) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    int rc = xtrans_check(ctx, passes, W, H, xtrans);
+    if (rc) return rc;
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    if ((rc = art_reserve(ctx, ctx->d_raw, plane))) return rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+    Plane in = {rawData, (float*)ctx->d_raw.p};
+    Plane out[3] = {{red, (float*)ctx->d_out[0].p}, {green, (float*)ctx->d_out[1].p}, {blue, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, &in, 1, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_xtrans_dev(ctx, passes, useCieLab != 0, W, H, xtrans, rgb_cam, in.dev, pitch, out[0].dev, out[1].dev, out[2].dev, pitch))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, out, 3, W, 0, H, pitch, false))) return rc;
     ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;
 }

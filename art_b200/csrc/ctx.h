@@ -51,6 +51,8 @@ struct art_hp_ctx {
     bool chain_cache_ready = false;
     DevBuf d_usm_tables;                 // apply_gamma's two 65536-entry LUTs (gamma 1/3 and 3), built once on the device
     bool usm_tables_ready = false;
+    DevBuf d_xt_cbrt;                    // cielab's 0x14000-entry cube-root LUT of the X-Trans demosaic
+    bool xt_cbrt_ready = false;
     void* h_stage[2] = {nullptr, nullptr};
     size_t h_stage_bytes = 0;
 
@@ -115,6 +117,9 @@ int art_amaze_dev_banded(art_hp_ctx* ctx, int W, int H, unsigned filters, const 
                          float* R, float* G, float* B, size_t op, double initialGain, int border,
                          int band_tile_rows, art_band_cb cb, void* user, int row_begin, int row_end);
 
+// xtrans_interpolate(passes, useCieLab) + xtransborder_interpolate (xtrans.cu); xtrans36 = 6x6 colours, rgb_cam12 = 3x4
+int art_xtrans_dev(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, const int* xtrans36, const float* rgb_cam12,
+                   const float* raw, size_t rp, float* R, float* G, float* B, size_t op);
 // getImage gain/clip + colorSpaceConversion_ matrix branch, in place on device planes
 int art_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch,
                           const float mul[3], int doClip, const double* mat);

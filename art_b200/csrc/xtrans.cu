@@ -1,0 +1,486 @@
+// X-Trans demosaic (Markesteijn, 1 or 3 passes): RawImageSource::xtrans_interpolate, cielab and xtransborder_interpolate
+// (reference rtengine/xtrans_demosaic.cc L42-116, L122-173, L181-969).
+//
+// Design.  The reference grid is kept (tiles of 114 from (3, 3), stride 98): a tile's intermediate planes are 1.0 MB
+// (1-pass) / 1.8 MB (3-pass), far beyond shared memory, so every resident CTA owns one tile slab in HBM / L2 with exactly
+// the reference's buffer layout and walks the tiles of the frame (persistent grid, static striding).  Each step of the
+// algorithm is a data-parallel loop over the tile's pixels followed by a CTA barrier; which sites a step visits, with which
+// hexagon / colour / direction plane, is computed per pixel instead of with the reference's running column toggles
+// (the test-suite's CPU restatement is organised the same way and is pinned bit-exact to the reference).
+//
+// The layout has to be the reference's because its sub-buffers alias (homo and the green min/max table over lab, homosum
+// over drv) and the 5x5 homogeneity sums next to the image border read homo bytes that the homogeneity step never wrote,
+// i.e. bytes of Lab / YPbPr floats and of min/max floats; those sums may pass 255, where the reference's 16-wide SSE2 path
+// saturates and its scalar tail wraps.  The slab is cleared at the start of every tile: the canonical ("det") reference.
+//
+// Algorithmic bytes: 4 B read + 12 B written per pixel = 16 B/px.  The kernel is L2 / latency bound, not
+// HBM bound: ~35 slab planes are rewritten per tile.
+#include "ctx.h"
+
+#include <cfloat>
+#include <cmath>
+
+namespace {
+
+constexpr int TS = 114, TSH = TS / 2;
+constexpr int XT_THREADS = 512;
+constexpr int CBRT_N = 0x14000;
+
+struct XtArgs {
+    const float* raw; size_t rp;
+    float *R, *G, *B; size_t op;
+    int W, H, passes, ndir, useCieLab;
+    int ntx, nty;
+    float* slabs; size_t slab_floats;
+    const float* cbrt;
+    float xyz_cam[9];
+    signed char hexv[3][3][8], hexh[3][3][8];      // allhex as (v, h) pairs: image offset h + v * rp, tile offset h + v * TS
+    unsigned char xt[6][6];
+    unsigned char rshift[3];
+    int sgrow, sgcol;
+};
+
+__device__ __forceinline__ int fcol(const XtArgs& a, int row, int col) { return a.xt[row % 6][col % 6]; }
+__device__ __forceinline__ bool isgreen(const XtArgs& a, int row, int col) { return a.xt[row % 3][col % 3] & 1; }
+__device__ __forceinline__ float limf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ float sqrf(float v) { return v * v; }
+__device__ __forceinline__ float lut_i(const float* __restrict__ t, int idx) { return t[idx < 0 ? 0 : (idx > CBRT_N - 1 ? CBRT_N - 1 : idx)]; }
+
+// rgb[d][r][c][ch] of the slab
+#define RGB(d, r, c, ch) rgb[(((size_t)(d) * TS + (r)) * TS + (c)) * 3 + (ch)]
+
+__global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
+{
+    const int tid = threadIdx.x;
+    const int ndir = a.ndir, W = a.W, H = a.H;
+    float* const buffer = a.slabs + (size_t)blockIdx.x * a.slab_floats;
+    float* const lab = buffer + TS * TS * (ndir * 3);                 // [3][TS-8][TS-8]
+    float* const drv = buffer + TS * TS * (ndir * 3 + 3);             // [ndir][TS-10][TS-10]
+    unsigned char* const homo = reinterpret_cast<unsigned char*>(lab);       // [ndir][TS][TS]
+    float2* const gmm = reinterpret_cast<float2*>(lab);                      // [TS][TSH] {min, max}
+    unsigned char* const homosum = reinterpret_cast<unsigned char*>(drv);    // [ndir][TS][TS]
+    constexpr int LW = TS - 8, DW = TS - 10;
+    constexpr int LAB_VEC_COLS = (LW - 3 + 3) / 4 * 4;               // columns covered by `for (j = 0; j < labWidth - 3; j += 4)`
+
+    for (int t = blockIdx.x; t < a.ntx * a.nty; t += gridDim.x) {
+        const int top = 3 + (t / a.ntx) * (TS - 16), left = 3 + (t % a.ntx) * (TS - 16);
+        int mrow = min(top + TS, H - 3), mcol = min(left + TS, W - 3);
+        const int rows = mrow - top, cols = mcol - left;
+        float* rgb = buffer;
+
+        {   // the canonical reference clears its tile buffer
+            float4* b4 = reinterpret_cast<float4*>(buffer);
+            const int n4 = (int)(a.slab_floats / 4);
+            for (int i = tid; i < n4; i += XT_THREADS) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+
+        // mosaic into rgb[0..3]; green min / max (L319-408) and green along the four directions (L421-475) at non-green sites
+        for (int i = tid; i < rows * cols; i += XT_THREADS) {
+            const int r = i / cols, c = i - r * cols, row = top + r, col = left + c;
+            const float* pix = a.raw + (size_t)row * a.rp + col;
+            const int f = fcol(a, row, col);
+            const float v = pix[0];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) RGB(d, r, c, f) = v;
+            if (f == 1) continue;
+            int src = col;
+            const bool rs = a.rshift[row % 3];
+            if (!rs && !isgreen(a, row, col + 5) && col - 1 >= left) src = col - 1;      // second pixel of a horizontal pair
+            float mn = FLT_MAX, mx = 0.f;
+            {
+                const signed char* hv = a.hexv[row % 3][src % 3];
+                const signed char* hh = a.hexh[row % 3][src % 3];
+                const float* sp = a.raw + (size_t)row * a.rp + src;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const float val = sp[hh[k] + (ptrdiff_t)hv[k] * (ptrdiff_t)a.rp];
+                    mn = mn < val ? mn : val;
+                    mx = mx > val ? mx : val;
+                }
+            }
+            gmm[r * TSH + (c >> 1)] = make_float2(mn, mx);
+            const signed char* hv = a.hexv[row % 3][col % 3];
+            const signed char* hh = a.hexh[row % 3][col % 3];
+            ptrdiff_t hex[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) hex[k] = hh[k] + (ptrdiff_t)hv[k] * (ptrdiff_t)a.rp;
+            float color[4];
+            color[0] = 0.6796875f * (pix[hex[1]] + pix[hex[0]]) - 0.1796875f * (pix[2 * hex[1]] + pix[2 * hex[0]]);
+            color[1] = 0.87109375f * pix[hex[3]] + pix[hex[2]] * 0.12890625f + 0.359375f * (pix[0] - pix[-hex[2]]);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                color[2 + k] = 0.640625f * pix[hex[4 + k]] + 0.359375f * pix[-2 * hex[4 + k]] +
+                               0.12890625f * (2.f * pix[0] - pix[3 * hex[4 + k]] - pix[-3 * hex[4 + k]]);
+            const int flip = rs ? 0 : 1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) RGB(k ^ flip, r, c, 1) = limf(color[k], mn, mx);
+        }
+        __syncthreads();
+
+        for (int pass = 0; pass < a.passes; ++pass) {
+            if (pass == 1) {        // memcpy(rgb += 4, buffer, 4 * sizeof *rgb), L479-481
+                const float4* s4 = reinterpret_cast<const float4*>(buffer);
+                float4* d4 = reinterpret_cast<float4*>(buffer + (size_t)4 * TS * TS * 3);
+                for (int i = tid; i < 4 * TS * TS * 3 / 4; i += XT_THREADS) d4[i] = s4[i];
+                rgb = buffer + (size_t)4 * TS * TS * 3;
+                __syncthreads();
+            }
+            if (pass) {             // recalculate green from interpolated values of closer pixels, L483-522
+                const int nr = rows - 4, nc = cols - 4;
+                for (int i = tid; i < nr * nc; i += XT_THREADS) {
+                    const int r = 2 + i / nc, c = 2 + i % nc, row = top + r, col = left + c;
+                    const int f = fcol(a, row, col);
+                    if (f == 1) continue;
+                    const signed char* hv = a.hexv[row % 3][col % 3];
+                    const signed char* hh = a.hexh[row % 3][col % 3];
+                    const int flip = a.rshift[row % 3] ? 0 : 1;
+                    const float2 mm = gmm[r * TSH + (c >> 1)];
+#pragma unroll
+                    for (int d = 3; d < 6; ++d) {
+                        float* rix = &RGB((d - 2) ^ flip, r, c, 0);
+                        const int hx = (hh[d] + hv[d] * TS) * 3;
+                        const float val = 0.33333333f * (rix[-2 * hx + 1] + 2 * (rix[hx + 1] - rix[hx + f]) - rix[-2 * hx + f]) + rix[f];
+                        rix[1] = limf(val, mm.x, mm.y);
+                    }
+                }
+                __syncthreads();
+            }
+            {   // red and blue for solitary green pixels, L524-561
+                const int row0 = (top - a.sgrow + 4) / 3 * 3 + a.sgrow, col0 = (left - a.sgcol + 4) / 3 * 3 + a.sgcol;
+                const int nr = row0 < mrow - 2 ? (mrow - 2 - row0 + 2) / 3 : 0, nc = col0 < mcol - 2 ? (mcol - 2 - col0 + 2) / 3 : 0;
+                for (int i = tid; i < nr * nc; i += XT_THREADS) {
+                    const int row = row0 + 3 * (i / nc), col = col0 + 3 * (i % nc);
+                    int h = fcol(a, row, col + 1);
+                    float* rix = &RGB(0, row - top, col - left, 0);
+                    float diff[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    float color[3][6];
+                    int o1 = 1;
+#pragma unroll
+                    for (int d = 0; d < 6; ++d) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int o = (o1 << c) * 3;
+                            const float g = rix[1] + rix[1] - rix[o + 1] - rix[-o + 1];
+                            color[h][d] = g + rix[o + h] + rix[-o + h];
+                            if (d > 1) diff[d] += sqrf(rix[o + 1] - rix[-o + 1] - rix[o + h] + rix[-o + h]) + sqrf(g);
+                            h ^= 2;
+                        }
+                        if (d > 2 && (d & 1))
+                            if (diff[d - 1] < diff[d]) { color[0][d] = color[0][d - 1]; color[2][d] = color[2][d - 1]; }
+                        if ((d & 1) || d < 2) {
+                            rix[0] = 0.5f * color[0][d];
+                            rix[2] = 0.5f * color[2][d];
+                            rix += TS * TS * 3;
+                        }
+                        o1 ^= TS ^ 1;
+                        h ^= 2;
+                    }
+                }
+                __syncthreads();
+            }
+            {   // red for blue pixels and vice versa, L563-603
+                const int nr = rows - 6, nc = cols - 6;
+                for (int i = tid; i < nr * nc; i += XT_THREADS) {
+                    const int r = 3 + i / nc, c = 3 + i % nc, row = top + r, col = left + c;
+                    const int fc = fcol(a, row, col);
+                    if (fc == 1) continue;
+                    const int f = 2 - fc;
+                    const int cs = ((row - a.sgrow) % 3) ? TS : 1;
+                    const int hs = 3 * (cs ^ TS ^ 1);
+                    const int co = cs * 3, ho = hs * 3;
+                    float* rix = &RGB(0, r, c, 0);
+#pragma unroll
+                    for (int d = 0; d < 4; ++d, rix += TS * TS * 3) {
+                        const bool usec = d > 1 || ((d ^ cs) & 1) ||
+                                          ((fabsf(rix[1] - rix[co + 1]) + fabsf(rix[1] - rix[-co + 1])) < 2.f * (fabsf(rix[1] - rix[ho + 1]) + fabsf(rix[1] - rix[-ho + 1])));
+                        const int io = usec ? co : ho;
+                        rix[f] = rix[1] + 0.5f * (rix[io + f] + rix[-io + f] - rix[io + 1] - rix[-io + 1]);
+                    }
+                }
+                __syncthreads();
+            }
+            {   // red and blue for the 2x2 blocks of green, L605-650
+                const int nr = rows - 4, nc = cols - 4;
+                for (int i = tid; i < nr * nc; i += XT_THREADS) {
+                    const int r = 2 + i / nc, c = 2 + i % nc, row = top + r, col = left + c;
+                    if (!((row - a.sgrow) % 3) || !((col - a.sgcol) % 3)) continue;
+                    const signed char* hv = a.hexv[row % 3][col % 3];
+                    const signed char* hh = a.hexh[row % 3][col % 3];
+                    float* rix = &RGB(0, r, c, 0);
+                    for (int d = 0; d < ndir; d += 2, rix += TS * TS * 3) {
+                        const int h0 = hh[d] + hv[d] * TS, h1 = hh[d + 1] + hv[d + 1] * TS;
+                        const float* p0 = rix + h0 * 3;
+                        const float* p1 = rix + h1 * 3;
+                        if (h0 + h1) {
+                            const float g = 3 * rix[1] - 2 * p0[1] - p1[1];
+                            rix[0] = (g + 2 * p0[0] + p1[0]) * 0.33333333f;
+                            rix[2] = (g + 2 * p0[2] + p1[2]) * 0.33333333f;
+                        } else {
+                            const float g = 2 * rix[1] - p0[1] - p1[1];
+                            rix[0] = (g + p0[0] + p1[0]) * 0.5f;
+                            rix[2] = (g + p0[2] + p1[2]) * 0.5f;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+
+        rgb = buffer;
+        mrow = rows;
+        mcol = cols;
+
+        // derivatives of every direction plane in CIELab (L657-683) or YPbPr (L684-741)
+        for (int d = 0; d < ndir; ++d) {
+            if (a.useCieLab) {          // cielab(&rgb[d][4][4], lab, ts, mrow - 8, ts - 8, xyz_cam), L65-116
+                const int n = (mrow - 8) * LW;
+                for (int i = tid; i < n; i += XT_THREADS) {
+                    const int r = i / LW, c = i - r * LW;
+                    const float* p = &RGB(d, 4 + r, 4 + c, 0);
+                    float fx, fy, fz;
+                    if (c < LAB_VEC_COLS) {
+                        // 4-wide SSE2 groups (j < labWidth - 3): index rounded to nearest even by _mm_cvtps_epi32
+                        const float X = p[0] * a.xyz_cam[0] + p[1] * a.xyz_cam[1] + p[2] * a.xyz_cam[2];
+                        const float Y = p[0] * a.xyz_cam[3] + p[1] * a.xyz_cam[4] + p[2] * a.xyz_cam[5];
+                        const float Z = p[0] * a.xyz_cam[6] + p[1] * a.xyz_cam[7] + p[2] * a.xyz_cam[8];
+                        fx = lut_i(a.cbrt, __float2int_rn(X)); fy = lut_i(a.cbrt, __float2int_rn(Y)); fz = lut_i(a.cbrt, __float2int_rn(Z));
+                        lab[i] = 116.f * fy - 16.f;
+                    } else {            // scalar tail: 0.5 added first, index truncated
+                        float x0 = 0.5f, x1 = 0.5f, x2 = 0.5f;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            x0 += a.xyz_cam[k] * p[k]; x1 += a.xyz_cam[3 + k] * p[k]; x2 += a.xyz_cam[6 + k] * p[k];
+                        }
+                        fx = lut_i(a.cbrt, (int)x0); fy = lut_i(a.cbrt, (int)x1); fz = lut_i(a.cbrt, (int)x2);
+                        lab[i] = 116 * fy - 16;
+                    }
+                    lab[LW * LW + i] = 500.f * (fx - fy);
+                    lab[2 * LW * LW + i] = 200.f * (fy - fz);
+                }
+            } else {
+                const int nr = mrow - 8, nc = mcol - 8;
+                for (int i = tid; i < nr * nc; i += XT_THREADS) {
+                    const int r = i / nc, c = i % nc;
+                    const float* p = &RGB(d, 4 + r, 4 + c, 0);
+                    const float y = 0.2627f * p[0] + 0.6780f * p[1] + 0.0593f * p[2];
+                    lab[r * LW + c] = y;
+                    lab[LW * LW + r * LW + c] = (p[2] - y) * 0.56433f;
+                    lab[2 * LW * LW + r * LW + c] = (p[0] - y) * 0.67815f;
+                }
+            }
+            __syncthreads();
+            {
+                const int dd = d & 3;
+                const int f = dd == 0 ? 1 : (dd == 1 ? TS : (dd == 2 ? TS + 1 : TS - 1)) - (dd == 0 ? 0 : 8);
+                const int nr = mrow - 10, nc = mcol - 10;
+                for (int i = tid; i < nr * nc; i += XT_THREADS) {
+                    const int r = 5 + i / nc, c = 5 + i % nc;
+                    const float* l = lab + (r - 4) * LW + (c - 4);
+                    const float* aa = l + LW * LW;
+                    const float* bb = aa + LW * LW;
+                    float v;
+                    if (a.useCieLab) {
+                        const float g = 2 * l[0] - l[f] - l[-f];
+                        v = sqrf(g) + sqrf((2 * aa[0] - aa[f] - aa[-f] + g * 2.1551724f)) + sqrf((2 * bb[0] - bb[f] - bb[-f] - g * 0.86206896f));
+                    } else {
+                        v = sqrf(2 * l[0] - l[f] - l[-f]) + sqrf(2 * aa[0] - aa[f] - aa[-f]) + sqrf(2 * bb[0] - bb[f] - bb[-f]);
+                    }
+                    drv[(size_t)d * DW * DW + (r - 5) * DW + (c - 5)] = v;
+                }
+            }
+            __syncthreads();
+        }
+
+        {   // homogeneity maps, L743-811
+            const int nr = mrow - 12, nc = mcol - 12;
+            for (int i = tid; i < nr * nc; i += XT_THREADS) {
+                const int r = 6 + i / nc, c = 6 + i % nc;
+                const float* dp = drv + (r - 5) * DW + (c - 5);
+                float tr = dp[0] < dp[DW * DW] ? dp[0] : dp[DW * DW];
+                for (int d = 2; d < ndir; ++d) tr = dp[(size_t)d * DW * DW] < tr ? dp[(size_t)d * DW * DW] : tr;
+                tr *= 8;
+                for (int d = 0; d < ndir; ++d) {
+                    const float* q = dp + (size_t)d * DW * DW;
+                    int cnt = 0;
+#pragma unroll
+                    for (int v = -1; v <= 1; ++v)
+#pragma unroll
+                        for (int h = -1; h <= 1; ++h) cnt += q[v * DW + h] <= tr ? 1 : 0;
+                    homo[(size_t)d * TS * TS + r * TS + c] = (unsigned char)cnt;
+                }
+            }
+        }
+        __syncthreads();
+
+        if (H - top < TS + 4) mrow = H - top + 2;
+        if (W - left < TS + 4) mcol = W - left + 2;
+        const int startrow = min(top, 8), startcol = min(left, 8);
+
+        {   // 5x5 sums of the homogeneity maps, L822-868: saturating 16-wide groups, wrapping scalar tail on the last row
+            const int nr = mrow - 8 - startrow, nc = mcol - 8 - startcol;
+            const int n = nr > 0 && nc > 0 ? nr * nc : 0;
+            for (int i = tid; i < n * ndir; i += XT_THREADS) {
+                const int d = i / n, j = i - d * n;
+                const int r = startrow + j / nc, c = startcol + j % nc;
+                const int endcol = r < mrow - 9 ? mcol - 8 : mcol - 23;
+                const int vec_end = endcol > startcol ? startcol + (endcol - startcol + 15) / 16 * 16 : startcol;
+                const unsigned char* base = homo + (size_t)d * TS * TS + r * TS + c;
+                int sum = 0;
+#pragma unroll
+                for (int v = -2; v <= 2; ++v)
+#pragma unroll
+                    for (int h = -2; h <= 2; ++h) sum += base[v * TS + h];
+                homosum[(size_t)d * TS * TS + r * TS + c] = (unsigned char)(c < vec_end ? min(sum, 255) : sum);
+            }
+        }
+        __syncthreads();
+
+        {   // maximum minus an eighth (L870-911) and the average of the most homogeneous directions (L914-949)
+            const int nr = mrow - 8 - startrow, nc = mcol - 8 - startcol;
+            const int n = nr > 0 && nc > 0 ? nr * nc : 0;
+            for (int i = tid; i < n; i += XT_THREADS) {
+                const int r = startrow + i / nc, c = startcol + i % nc;
+                unsigned char hm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                const unsigned char* hs = homosum + r * TS + c;
+                unsigned char maxval = hs[0];
+                for (int d = 1; d < ndir; ++d) { const unsigned char v = hs[(size_t)d * TS * TS]; maxval = maxval < v ? v : maxval; }
+                maxval -= maxval >> 3;
+#pragma unroll
+                for (int d = 0; d < 4; ++d) hm[d] = hs[(size_t)d * TS * TS];
+                for (int d = 4; d < ndir; ++d) {
+                    hm[d] = hs[(size_t)d * TS * TS];
+                    if (hm[d - 4] < hm[d]) hm[d - 4] = 0;
+                    else if (hm[d - 4] > hm[d]) hm[d] = 0;
+                }
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (int d = 0; d < ndir; ++d)
+                    if (hm[d] >= maxval) {
+                        const float* p = &RGB(d, r, c, 0);
+                        a0 += p[0]; a1 += p[1]; a2 += p[2];
+                        a3 += 1.f;
+                    }
+                const size_t o = (size_t)(r + top) * a.op + c + left;
+                const float vr = a0 / a3, vg = a1 / a3, vb = a2 / a3;
+                a.R[o] = 0.f < vr ? vr : 0.f;
+                a.G[o] = 0.f < vg ? vg : 0.f;
+                a.B[o] = 0.f < vb ? vb : 0.f;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// xtransborder_interpolate, L122-173: one thread per pixel of the outer ring
+__global__ void k_xtrans_border(const XtArgs a, int border)
+{
+    const int W = a.W, H = a.H;
+    const long ring_top = (long)border * W, side = (long)(H - 2 * border) * 2 * border;
+    const long n = 2 * ring_top + side;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int row, col;
+    if (i < ring_top) { row = (int)(i / W); col = (int)(i % W); }
+    else if (i < ring_top + side) {
+        const long j = i - ring_top;
+        row = border + (int)(j / (2 * border));
+        const int k = (int)(j % (2 * border));
+        col = k < border ? k : W - 2 * border + k;
+    } else { const long j = i - ring_top - side; row = H - border + (int)(j / W); col = (int)(j % W); }
+    float sum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int y = max(0, row - 1), v = row == 0 ? 0 : -1; y <= min(row + 1, H - 1); ++y, ++v)
+        for (int x = max(0, col - 1), h = col == 0 ? 0 : -1; x <= min(col + 1, W - 1); ++x, ++h) {
+            const float w = (v == 0 && h == 0) ? 0.f : ((v == 0 || h == 0) ? 0.5f : 0.25f);
+            const int f = a.xt[y % 6][x % 6];
+            sum[f] += a.raw[(size_t)y * a.rp + x] * w;
+            sum[f + 3] += w;
+        }
+    const size_t o = (size_t)row * a.op + col;
+    const float p = a.raw[(size_t)row * a.rp + col];
+    switch (a.xt[row % 6][col % 6]) {
+    case 0: a.R[o] = p; a.G[o] = sum[1] / sum[4]; a.B[o] = sum[2] / sum[5]; break;
+    case 1:
+        if (sum[3] == 0.f) { a.R[o] = p; a.G[o] = p; a.B[o] = p; }
+        else { a.R[o] = sum[0] / sum[3]; a.G[o] = p; a.B[o] = sum[2] / sum[5]; }
+        break;
+    default: a.R[o] = sum[0] / sum[3]; a.G[o] = sum[1] / sum[4]; a.B[o] = p;
+    }
+}
+
+}  // namespace
+
+int art_xtrans_dev(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, const int* xtrans36, const float* rgb_cam12,
+                   const float* raw, size_t rp, float* R, float* G, float* B, size_t op)
+{
+    static const short orth[12] = {1, 0, 0, 1, -1, 0, 0, -1, 1, 0, 0, 1};
+    static const short patt[2][16] = {{0, 1, 0, -1, 2, 0, -1, 0, 1, 1, 1, -1, 0, 0, 0, 0}, {0, 1, 0, -2, 1, 0, -2, 0, 1, 1, -2, -2, 1, -1, -1, 1}};
+    static const float xyz_rgb[3][3] = {{0.412453, 0.357580, 0.180423}, {0.212671, 0.715160, 0.072169}, {0.019334, 0.119193, 0.950227}};
+    static const float d65_white[3] = {0.950456, 1, 1.088754};
+    cudaStream_t st = ctx->stream;
+    XtArgs a{};
+    a.raw = raw; a.rp = rp; a.R = R; a.G = G; a.B = B; a.op = op; a.W = W; a.H = H;
+    a.passes = passes; a.ndir = 4 << (passes > 1); a.useCieLab = useCieLab;
+    for (int i = 0; i < 36; ++i) a.xt[i / 6][i % 6] = (unsigned char)xtrans36[i];
+    for (int i = 0; i < 3; i++)          // L224-232, float arithmetic
+        for (int j = 0; j < 3; j++) {
+            float s = 0;
+            for (int k = 0; k < 3; k++) s += xyz_rgb[i][k] * rgb_cam12[k * 4 + j] / d65_white[i];
+            a.xyz_cam[i * 3 + j] = s;
+        }
+    auto green = [&](int r, int c) { return a.xt[r % 3][c % 3] & 1; };
+    for (int row = 0; row < 3; row++)    // L235-266
+        for (int col = 0; col < 3; col++) {
+            const int gint = green(row, col);
+            for (int ng = 0, d = 0; d < 10; d += 2) {
+                if (green(row + orth[d] + 6, col + orth[d + 2] + 6)) ng = 0; else ng++;
+                if (ng == 4) { a.sgrow = row; a.sgcol = col; }
+                if (ng == gint + 1)
+                    for (int c = 0; c < 8; c++) {
+                        a.hexv[row][col][c ^ (gint * 2 & d)] = (signed char)(orth[d] * patt[gint][c * 2] + orth[d + 1] * patt[gint][c * 2 + 1]);
+                        a.hexh[row][col][c ^ (gint * 2 & d)] = (signed char)(orth[d + 2] * patt[gint][c * 2] + orth[d + 3] * patt[gint][c * 2 + 1]);
+                    }
+            }
+        }
+    for (int row = 0; row < 3; row++) {  // L280-291
+        int greencount = 0;
+        for (int col = 0; col < 3; col++) greencount += green(row, col);
+        a.rshift[row] = (greencount == 2);
+    }
+    int rc;
+    if (!ctx->xt_cbrt_ready) {           // cielab's cbrt LUT, L44-63 (host libm cbrt, as in the reference)
+        if ((rc = art_reserve(ctx, ctx->d_xt_cbrt, CBRT_N * sizeof(float)))) return rc;
+        std::vector<float> t(CBRT_N);
+        const double eps = 216.0 / 24389.0, kappa = 24389.0 / 27.0;
+        for (int i = 0; i < CBRT_N; i++) {
+            const double r = i / 65535.0;
+            t[i] = (float)(r > eps ? std::cbrt(r) : (kappa * r + 16.0) / 116.0);
+        }
+        ART_CUDA(ctx, cudaMemcpyAsync(ctx->d_xt_cbrt.p, t.data(), CBRT_N * sizeof(float), cudaMemcpyHostToDevice, st));
+        ART_CUDA(ctx, cudaStreamSynchronize(st));      // t goes out of scope
+        ctx->xt_cbrt_ready = true;
+    }
+    a.cbrt = (const float*)ctx->d_xt_cbrt.p;
+    a.nty = H - 19 > 3 ? (H - 19 - 3 + (TS - 16) - 1) / (TS - 16) : 0;
+    a.ntx = W - 19 > 3 ? (W - 19 - 3 + (TS - 16) - 1) / (TS - 16) : 0;
+    const int ntiles = a.ntx * a.nty;
+    if (ntiles > 0) {
+        a.slab_floats = round_up((size_t)TS * TS * (a.ndir * 4 + 3) + 128, 32);
+        const int grid = std::min(ntiles, ctx->sm_count * 2);
+        if ((rc = art_reserve(ctx, ctx->d_scratch, (size_t)grid * a.slab_floats * sizeof(float)))) return rc;
+        a.slabs = (float*)ctx->d_scratch.p;
+        art_prof_begin(ctx, "k_xtrans");
+        k_xtrans<<<grid, XT_THREADS, 0, st>>>(a);
+        art_prof_end(ctx);
+        ctx->launches++;
+    }
+    const int border = passes > 1 ? 8 : 11;
+    {
+        const long n = 2L * border * W + (long)std::max(0, H - 2 * border) * 2 * border;
+        art_prof_begin(ctx, "k_xtrans_border");
+        k_xtrans_border<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, border);
+        art_prof_end(ctx);
+        ctx->launches++;
+    }
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}

@@ -108,6 +108,20 @@ int art_hp_demosaic_bayer_dev(art_hp_ctx* ctx, int method, int W, int H, unsigne
                               float* d_red, float* d_green, float* d_blue, size_t out_pitch,
                               double initialGain, int border);
 
+/*
+ * art_hp_demosaic_xtrans   replaces RawImageSource::xtrans_interpolate(passes, useCieLab) including its closing
+ *                      xtransborder_interpolate(passes > 1 ? 8 : 11) (rtengine/xtrans_demosaic.cc L181-969, L122-173, cielab
+ *                      L42-116; dispatch rtengine/rawimagesource.cc L1916-1924: "1-pass" = (1, false), "3-pass (best)" =
+ *                      (3, true)).  xtrans = RawImage::getXtransMatrix (0 R, 1 G, 2 B), rgb_cam = RawImage::getRgbCam.
+ *                      passes must be 1 or 3; 23 <= W <= 16380 (the reference keeps its hexagon offsets in shorts), H >= 23.
+ *                      Bit-identical to the reference with its per-thread tile buffer cleared per tile (the stock
+ *                      reference reads the previous tile's bytes near the image border and is schedule dependent there).
+ */
+int art_hp_demosaic_xtrans(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, const int xtrans[36], const float rgb_cam[12],
+                           float* const* rawData, float* const* red, float* const* green, float* const* blue);
+int art_hp_demosaic_xtrans_dev(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, const int xtrans[36], const float rgb_cam[12],
+                               const float* d_raw, size_t raw_pitch, float* d_red, float* d_green, float* d_blue, size_t out_pitch);
+
 /* Row-band form for sharding one frame across GPUs: computes only the output
  * rows [row_begin, row_end) of the full W x H frame.  Bands must be cut on the method's reference tile
  * grid so that results are identical to the full-frame call: art_hp_band_align(method) gives the period P
