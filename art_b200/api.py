@@ -96,6 +96,9 @@ def load_library(build_if_missing=True):
         "art_hp_scale_convert_dev": (i, [vp, i, i, vp, vp, vp, sz, ctypes.POINTER(ctypes.c_float), i, ctypes.POINTER(d)]),
         "art_hp_develop": (i, [vp, vp, i, i, vp, vp, vp, vp]),
         "art_hp_develop_dev": (i, [vp, vp, i, i, vp, sz, vp, vp, vp, sz]),
+        "art_hp_develop_submit": (i, [vp, vp, i, i, vp, vp, vp, vp]),
+        "art_hp_develop_wait": (i, [vp]),
+        "art_hp_develop_pending": (i, [vp]),
         "art_hp_fattal": (i, [vp, i, i, vp, vp, vp, i, i, i, ctypes.POINTER(d)]),
         "art_hp_fattal_dev": (i, [vp, i, i, vp, vp, vp, sz, i, i, i, ctypes.POINTER(d)]),
         "art_hp_fattal_fast_dim": (i, [i]),
@@ -120,12 +123,21 @@ def load_library(build_if_missing=True):
     return lib
 
 
+_row_tables = {}
+
+
 def row_table(a):
     """H row pointers into a 2-D float32 array (what rtengine::array2D<float> holds)."""
     assert a.dtype == np.float32 and a.ndim == 2 and a.strides[1] == 4
     H = a.shape[0]
     base = a.ctypes.data
-    tbl = (ctypes.c_void_p * H)(*[base + r * a.strides[0] for r in range(H)])
+    key = (base, H, a.strides[0])
+    tbl = _row_tables.get(key)
+    if tbl is None:      # a table only depends on (base, H, stride): frames that reuse their buffers reuse their tables
+        if len(_row_tables) >= 64:
+            _row_tables.clear()
+        tbl = (ctypes.c_void_p * H)(*[base + r * a.strides[0] for r in range(H)])
+        _row_tables[key] = tbl
     return tbl
 
 
@@ -510,6 +522,18 @@ class HotPath:
         c = params.c_struct()
         self._check(self.lib.art_hp_develop(self.h, ctypes.byref(c), W, H, row_table(raw), row_table(out[0]), row_table(out[1]), row_table(out[2])))
         return out
+
+    def develop_submit(self, raw, params, red, green, blue):
+        """Queue one frame (pinned planes, see HotPath.pinned) and return; develop_wait() collects the oldest queued frame."""
+        H, W = raw.shape
+        c = params.c_struct()
+        self._check(self.lib.art_hp_develop_submit(self.h, ctypes.byref(c), W, H, row_table(raw), row_table(red), row_table(green), row_table(blue)))
+
+    def develop_wait(self):
+        self._check(self.lib.art_hp_develop_wait(self.h))
+
+    def develop_pending(self):
+        return int(self.lib.art_hp_develop_pending(self.h))
 
     def develop_dev(self, params, W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch):
         c = params.c_struct()

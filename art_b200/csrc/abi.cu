@@ -242,6 +242,13 @@ void art_hp_destroy(art_hp_ctx* ctx)
     if (ctx->d_chain.p) cudaFree(ctx->d_chain.p);
     if (ctx->d_usm_tables.p) cudaFree(ctx->d_usm_tables.p);
     if (ctx->d_xt_cbrt.p) cudaFree(ctx->d_xt_cbrt.p);
+    for (auto& q : ctx->q) {
+        if (q.raw.p) cudaFree(q.raw.p);
+        for (DevBuf& o : q.out) if (o.p) cudaFree(o.p);
+        if (q.up) cudaEventDestroy(q.up);
+        if (q.done) cudaEventDestroy(q.done);
+        if (q.down) cudaEventDestroy(q.down);
+    }
     if (ctx->h_chain) cudaFreeHost(ctx->h_chain);
     if (ctx->ev_chain) cudaEventDestroy(ctx->ev_chain);
     for (PoolBlk& b : ctx->pool) cudaFree(b.p);
@@ -987,5 +994,60 @@ int art_hp_develop(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, 
     ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;
 }
+
+// Batch-queue form: the copies of frame k overlap the kernels of frames k-1 / k+1 (three streams, two frames in flight).
+int art_hp_develop_submit(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
+                          float* const* r, float* const* g, float* const* b)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!rawData || !r || !g || !b) return ctx->fail(ART_HP_ERR_INVALID, "null row table");
+    int rc = check_develop(ctx, params, W, H);
+    if (rc) return rc;
+    if (ctx->q_submitted - ctx->q_collected >= 2) return ctx->fail(ART_HP_ERR_INVALID, "two frames are already in flight: call art_hp_develop_wait first");
+    ptrdiff_t st[4];
+    float* const* tabs[4] = {rawData, r, g, b};
+    for (int i = 0; i < 4; ++i)
+        if (!constant_stride(tabs[i], H, &st[i]) || !is_pinned(tabs[i][0]))
+            return ctx->fail(ART_HP_ERR_UNSUPPORTED, "the batch queue needs pinned, constant-stride planes (art_hp_host_alloc); use art_hp_develop otherwise");
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    art_hp_ctx::QSlot& q = ctx->q[ctx->q_submitted & 1];
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    if ((rc = art_reserve(ctx, q.raw, plane))) return rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, q.out[i], plane))) return rc;
+    if (!q.up) {
+        ART_CUDA(ctx, cudaEventCreateWithFlags(&q.up, cudaEventDisableTiming));
+        ART_CUDA(ctx, cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
+        ART_CUDA(ctx, cudaEventCreateWithFlags(&q.down, cudaEventDisableTiming));
+    }
+    const size_t wbytes = (size_t)W * sizeof(float);
+    // the slot's previous frame (k-2) has been collected, so its planes are free; the upload runs beside frame k-1's kernels
+    ART_CUDA(ctx, cudaMemcpy2DAsync(q.raw.p, pitch * sizeof(float), rawData[0], (H > 1 ? (size_t)st[0] : (size_t)W) * sizeof(float), wbytes, H,
+                                    cudaMemcpyHostToDevice, ctx->copy_stream));
+    ART_CUDA(ctx, cudaEventRecord(q.up, ctx->copy_stream));
+    ART_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, q.up, 0));
+    if ((rc = art_develop_dev(ctx, params, W, H, (const float*)q.raw.p, pitch, (float*)q.out[0].p, (float*)q.out[1].p, (float*)q.out[2].p, pitch))) return rc;
+    ART_CUDA(ctx, cudaEventRecord(q.done, ctx->stream));
+    ART_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, q.done, 0));
+    for (int i = 0; i < 3; ++i)
+        ART_CUDA(ctx, cudaMemcpy2DAsync(tabs[i + 1][0], (H > 1 ? (size_t)st[i + 1] : (size_t)W) * sizeof(float), q.out[i].p, pitch * sizeof(float), wbytes, H,
+                                        cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    ART_CUDA(ctx, cudaEventRecord(q.down, ctx->d2h_stream));
+    ctx->q_submitted++;
+    return ART_HP_OK;
+}
+
+int art_hp_develop_wait(art_hp_ctx* ctx)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (ctx->q_submitted == ctx->q_collected) return ctx->fail(ART_HP_ERR_INVALID, "no frame in flight");
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    ART_CUDA(ctx, cudaEventSynchronize(ctx->q[ctx->q_collected & 1].down));
+    ctx->q_collected++;
+    return ART_HP_OK;
+}
+
+int art_hp_develop_pending(const art_hp_ctx* ctx) { return ctx ? (int)(ctx->q_submitted - ctx->q_collected) : 0; }
 
 }  // extern "C"

@@ -53,6 +53,10 @@ struct art_hp_ctx {
     bool usm_tables_ready = false;
     DevBuf d_xt_cbrt;                    // cielab's 0x14000-entry cube-root LUT of the X-Trans demosaic
     bool xt_cbrt_ready = false;
+    // batch queue (art_hp_develop_submit / _wait): two frames in flight, each with its own raw + output planes
+    struct QSlot { DevBuf raw, out[3]; cudaEvent_t up = nullptr, done = nullptr, down = nullptr; };
+    QSlot q[2];
+    unsigned long long q_submitted = 0, q_collected = 0;
     void* h_stage[2] = {nullptr, nullptr};
     size_t h_stage_bytes = 0;
 

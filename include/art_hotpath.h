@@ -421,6 +421,19 @@ int art_hp_develop(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, 
                    float* const* red, float* const* green, float* const* blue);
 int art_hp_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, const float* d_raw, size_t raw_pitch,
                        float* d_red, float* d_green, float* d_blue, size_t out_pitch);
+/*
+ * Batch-queue form of art_hp_develop, for the loop of rtgui/batchqueue.cc (BatchQueue::startProcessing ->
+ * rtengine::startBatchProcessing, one job after the other, L586-676): art_hp_develop_submit queues one frame -- upload, kernels,
+ * download on three streams -- and returns; art_hp_develop_wait blocks until the OLDEST queued frame's planes are in host
+ * memory.  At most two frames are in flight, so a caller alternates submit(k), wait() [collects k-1] and the copies of one
+ * frame overlap the kernels of its neighbours.  Planes must be pinned (art_hp_host_alloc) with a constant row stride and must
+ * stay untouched until the frame is collected; otherwise ART_HP_ERR_UNSUPPORTED is returned and art_hp_develop is the call
+ * to make.  Results are identical to art_hp_develop.  `params` is consumed before submit returns.
+ */
+int art_hp_develop_submit(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
+                          float* const* red, float* const* green, float* const* blue);
+int art_hp_develop_wait(art_hp_ctx* ctx);
+int art_hp_develop_pending(const art_hp_ctx* ctx);
 
 #ifdef __cplusplus
 }

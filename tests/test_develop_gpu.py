@@ -133,3 +133,34 @@ def test_develop_with_finishing_stages(hot_path, W, H, dn, fat, sharpen, exact):
             assert (err <= lim).mean() > 0.9999, "%s: %d of %d beyond tolerance, worst %g" % (ch, int((err > lim).sum()), x.size, worst)
     if not exact:
         print("\n[develop+finishing] %dx%d worst relative error %.3g" % (W, H, worst))
+
+
+def test_batch_queue_matches_synchronous_develop(hot_path):
+    """art_hp_develop_submit / _wait (two frames in flight, copies overlapping the neighbours' kernels) == art_hp_develop"""
+    W, H = 322, 260
+    dnp = DenoiseParams(luminance=30, luminanceDetail=50, chrominance=15, gamma=1.7)
+    params = DevelopParams(method=art_b200.BAYER_AMAZE, filters=synth.RGGB, mul=MUL, do_clip=True, cam2work=CAM2WORK, denoise=dnp,
+                           fattal=(30, 20, 0), wprof=PROPHOTO)
+    frames = [synth.bayer_frame(W, H, synth.RGGB, seed=100 + k) for k in range(5)]
+    want = [hot_path.develop(f, params) for f in frames]
+    pins = [[hot_path.pinned(H, W) for _ in range(4)] for _ in range(2)]
+    got = []
+    for k, f in enumerate(frames):
+        slot = pins[k & 1]
+        if k >= 2:
+            hot_path.develop_wait()                      # frame k-2 leaves this slot's planes
+            got.append([p.array.copy() for p in slot[1:]])
+        slot[0].array[:] = f
+        hot_path.develop_submit(slot[0].array, params, slot[1].array, slot[2].array, slot[3].array)
+        assert 1 <= hot_path.develop_pending() <= 2
+    for k in (3, 4):
+        hot_path.develop_wait()
+        got.append([p.array.copy() for p in pins[k & 1][1:]])
+    assert hot_path.develop_pending() == 0
+    for g, w in zip(got, want):
+        for x, y in zip(g, w):
+            assert np.array_equal(x, y)
+    with pytest.raises(art_b200.HotPathError):
+        hot_path.develop_wait()                          # nothing in flight
+    with pytest.raises(art_b200.HotPathError):           # pageable planes are refused, not silently staged
+        hot_path.develop_submit(frames[0], params, *[np.empty((H, W), np.float32) for _ in range(3)])
