@@ -10,10 +10,10 @@
 //   shrink, DCT-III -> block store), k_dn_gather (ordered overlap-add + normalise), k_dn_merge (chroma boost, YUV->RGB,
 //   inverse gamma).
 // Bit-exact with the reference except the two block DCTs, which the reference delegates to FFTW (fp32 codelets,
-// absent here) and which run here as fp32 FMA matrix products against cosine tables rounded from double.
+// absent here) and which run here as 3xTF32 tensor-core matrix products (fp32 accuracy) against cosine tables rounded from double.
 // The reference's detail_recovery overlap-adds block rows from several OpenMP threads without synchronisation; the
 // one-thread order (vblk, then hblk ascending) is the one reproduced.
-// Compiled with -fmad=false; the DCT uses explicit fmaf.
+// Compiled with -fmad=false; the DCT runs on the tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split).
 #include <cmath>
 #include "ctx.h"
 #include "sleef_dev.cuh"
@@ -136,44 +136,72 @@ __device__ __forceinline__ float compute_detail(float d)
     const float a = (float)(((100. - d) * (100. - d)) + 50. * (100. - d)) * TS * 0.5f;
     return a * a;
 }
-// Out = A * B^T (TRANS_B) or A * B, all 64x64 row-major in shared memory; 256 threads, 4x4 outputs each
-template <bool TRANS_B>
+// 64x64x64 products on the tensor cores: mma.sync m16n8k8 TF32 with the 3xTF32 split (x = big + small, both TF32;
+// acc += small_a * big_b + big_a * small_b + big_a * big_b with fp32 accumulation), which keeps the products at fp32
+// accuracy.  8 warps: warp w owns rows 16 * (w & 3) .. +16 and columns 32 * (w >> 2) .. +32 (four n-tiles).
+// Out[m][n] = sum_k A(m, k) * B(k, n);  A(m, k) = A[m * PA + k];  B(k, n) = TRANS_B ? B[n * PB + k] : B[k * PB + n].
+// Pitches are chosen so that every fragment load is bank-conflict free: 68 (== 4 mod 32) where a fragment walks
+// (row g, column t), 72 (== 8 mod 32) where it walks (row t, column g).
+constexpr int PX = 68, PT = 72, PC = 68;
+__device__ __forceinline__ unsigned f2tf32(float x) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void split_tf32(float x, unsigned& big, unsigned& small)
+{
+    big = f2tf32(x);
+    small = f2tf32(x - __uint_as_float(big));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <bool TRANS_B, int PA, int PB, int PO>
 __device__ __forceinline__ void mm64(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ Out)
 {
-    const int t = threadIdx.x, r0 = (t >> 4) * 4, c0 = (t & 15) * 4;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int m0 = (w & 3) * 16, nbase = (w >> 2) * 32;
     float acc[4][4] = {};
-#pragma unroll 8
-    for (int k = 0; k < TS; ++k) {
-        float av[4], bv[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) av[i] = A[(r0 + i) * (TS + 1) + k];
+    for (int k0 = 0; k0 < TS; k0 += 8) {
+        unsigned ab[4], as[4];
+        split_tf32(A[(m0 + g) * PA + k0 + t], ab[0], as[0]);
+        split_tf32(A[(m0 + g + 8) * PA + k0 + t], ab[1], as[1]);
+        split_tf32(A[(m0 + g) * PA + k0 + t + 4], ab[2], as[2]);
+        split_tf32(A[(m0 + g + 8) * PA + k0 + t + 4], ab[3], as[3]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bv[j] = TRANS_B ? B[(c0 + j) * (TS + 1) + k] : B[k * (TS + 1) + c0 + j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int nt = 0; nt < 4; ++nt) {
+            const int n = nbase + nt * 8 + g;
+            unsigned bb[2], bs[2];
+            split_tf32(TRANS_B ? B[n * PB + k0 + t] : B[(k0 + t) * PB + n], bb[0], bs[0]);
+            split_tf32(TRANS_B ? B[n * PB + k0 + t + 4] : B[(k0 + t + 4) * PB + n], bb[1], bs[1]);
+            mma_tf32(acc[nt], as, bb);
+            mma_tf32(acc[nt], ab, bs);
+            mma_tf32(acc[nt], ab, bb);
+        }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) Out[(r0 + i) * (TS + 1) + c0 + j] = acc[i][j];
+    for (int nt = 0; nt < 4; ++nt) {
+        const int n = nbase + nt * 8 + 2 * t;
+        Out[(m0 + g) * PO + n] = acc[nt][0];
+        Out[(m0 + g) * PO + n + 1] = acc[nt][1];
+        Out[(m0 + g + 8) * PO + n] = acc[nt][2];
+        Out[(m0 + g + 8) * PO + n + 1] = acc[nt][3];
+    }
 }
 
-constexpr int BP = TS + 1;      // padded pitch: column walks hit distinct banks
 __global__ void __launch_bounds__(256) k_dn_blocks(BlkArgs a)
 {
     extern __shared__ float sm[];
     float* X = sm;                 // data / coefficients
-    float* T = X + TS * BP;        // temp
-    float* C = T + TS * BP;        // forward matrix
-    float* D = C + TS * BP;        // backward matrix
+    float* T = X + TS * PX;        // temp
+    float* C = T + TS * PT;        // forward matrix
+    float* D = C + TS * PC;        // backward matrix
     const int hblk = blockIdx.x, vblk = blockIdx.y, t = threadIdx.x;
     const int top = (vblk - BLKRAD) * OFFSET, left = (hblk - BLKRAD) * OFFSET;
     for (int i = t; i < TS * TS; i += 256) {
         const int r = i >> 6, c = i & 63;
-        C[r * BP + c] = a.dctf[i];
-        D[r * BP + c] = a.dctb[i];
+        C[r * PC + c] = a.dctf[i];
+        D[r * PC + c] = a.dctb[i];
         // padded data row (L1547-1567): mirror without repeating the edge, clamped
         const int row = top + r;
         int rr = row;
@@ -183,18 +211,18 @@ __global__ void __launch_bounds__(256) k_dn_blocks(BlkArgs a)
         if (col < 0) col = min(-col, a.width - 1);
         else if (col >= a.width) col = max(0, 2 * a.width - 2 - col);
         const size_t p = (size_t)rr * a.width + col;
-        X[r * BP + c] = a.tin[i] * (a.Lin[p] - a.L[p]);
+        X[r * PX + c] = a.tin[i] * (a.Lin[p] - a.L[p]);
     }
     __syncthreads();
-    mm64<true>(X, C, T);           // along rows: T[i][k] = sum_j C[k][j] X[i][j]
+    mm64<true, PX, PC, PT>(X, C, T);       // along rows: T[i][k] = sum_j C[k][j] X[i][j]
     __syncthreads();
-    mm64<false>(C, T, X);          // along columns: X[k][x] = sum_j C[k][j] T[j][x]
+    mm64<false, PC, PT, PX>(C, T, X);      // along columns: X[k][x] = sum_j C[k][j] T[j][x]
     __syncthreads();
     // boxabsblur (boxblur.h L745-888), W = H = 64: horizontal into T, vertical into C (the forward matrix is done with)
     const int rad = a.blur_rad;
     if (t < TS) {
-        const float* s = X + t * BP;
-        float* o = T + t * BP;
+        const float* s = X + t * PX;
+        float* o = T + t * PT;
         int len = rad + 1;
         float v = fabsf(s[0]);
         for (int j = 1; j <= rad; j++) v += fabsf(s[j]);
@@ -211,13 +239,13 @@ __global__ void __launch_bounds__(256) k_dn_blocks(BlkArgs a)
         float* o = C + t;
         float len = (float)(rad + 1);
         float v = s[0];
-        for (int i = 1; i <= rad; i++) v = v + s[i * BP];
+        for (int i = 1; i <= rad; i++) v = v + s[i * PT];
         v = v / len;
         o[0] = v;
-        for (int row = 1; row <= rad; row++) { const float lp1 = len + 1.f; v = (v * len + s[(row + rad) * BP]) / lp1; o[row * BP] = v; len = lp1; }
+        for (int row = 1; row <= rad; row++) { const float lp1 = len + 1.f; v = (v * len + s[(row + rad) * PT]) / lp1; o[row * PC] = v; len = lp1; }
         const float rlen = 1.f / len;
-        for (int row = rad + 1; row < TS - rad; row++) { v = v + (s[(row + rad) * BP] - s[(row - rad - 1) * BP]) * rlen; o[row * BP] = v; }
-        for (int row = TS - rad; row < TS; row++) { const float lm1 = len - 1.f; v = (v * len - s[(row - rad - 1) * BP]) / lm1; o[row * BP] = v; len = lm1; }
+        for (int row = rad + 1; row < TS - rad; row++) { v = v + (s[(row + rad) * PT] - s[(row - rad - 1) * PT]) * rlen; o[row * PC] = v; }
+        for (int row = TS - rad; row < TS; row++) { const float lm1 = len - 1.f; v = (v * len - s[(row - rad - 1) * PT]) / lm1; o[row * PC] = v; len = lm1; }
     }
     __syncthreads();
     // RGBtile_denoise L511-514 with the per-sample detail factor of L1571-1595
@@ -227,16 +255,16 @@ __global__ void __launch_bounds__(256) k_dn_blocks(BlkArgs a)
         float df = a.detail_lo;
         if (row >= 0 && row < a.height && col >= 0 && col < a.width)
             df = a.use_mask ? compute_detail(a.params_Ldetail * a.mask[(size_t)row * a.width + col]) : a.detail_hi;
-        const float nb = C[r * BP + c];
-        X[r * BP + c] = X[r * BP + c] * (1.0f - sleef::xexpf_vector(-(nb * nb) / df));
+        const float nb = C[r * PC + c];
+        X[r * PX + c] = X[r * PX + c] * (1.0f - sleef::xexpf_vector(-(nb * nb) / df));
     }
     __syncthreads();
-    mm64<true>(X, D, T);
+    mm64<true, PX, PC, PT>(X, D, T);
     __syncthreads();
-    mm64<false>(D, T, X);
+    mm64<false, PC, PT, PX>(D, T, X);
     __syncthreads();
     float* out = a.blocks + ((size_t)vblk * a.nbw + hblk) * (TS * TS);
-    for (int i = t; i < TS * TS; i += 256) out[i] = X[(i >> 6) * BP + (i & 63)];
+    for (int i = t; i < TS * TS; i += 256) out[i] = X[(i >> 6) * PX + (i & 63)];
 }
 
 // ordered overlap-add (RGBoutput_tile_row L531-558 + totwt L1577) and L += Ldetail / totwt (L1628-1632)
@@ -496,7 +524,7 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
         a.Lin = Lin; a.L = Lp; a.mask = mask; a.width = W; a.height = H; a.nbw = nbw; a.nbh = nbh; a.tin = tin; a.dctf = dctf; a.dctb = dctb; a.blocks = blocks;
         a.detail_hi = host_compute_detail(params_Ldetail); a.detail_lo = host_compute_detail(0.f); a.params_Ldetail = params_Ldetail;
         a.use_mask = use_mask; a.blur_rad = std::max(1, int(3 / scale));
-        const size_t smem = 4 * (size_t)TS * BP * sizeof(float);
+        const size_t smem = (size_t)TS * (PX + PT + 2 * PC) * sizeof(float);
         static bool attr = false;
         if (!attr) { ART_CUDA(ctx, cudaFuncSetAttribute(k_dn_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
         art_prof_begin(ctx, "k_dn_blocks");

@@ -3,8 +3,8 @@
 // attenuation helpers (L157-417), the DCT Poisson solver (L731-950) and denoise::Median_Denoise
 // (rtengine/FTblockDN.cc L87-445).
 //
-// Everything is restated operation by operation (fp32 association, the double-promoted products at L593-594, L902 and in
-// rgbLuminance, the vector / scalar sleef lanes of the xlogf and xexpf row loops) and is bit-identical to the reference
+// Everything is restated operation by operation (fp32 association, the double-promoted products at L593-594 and L902, the
+// float rgbLuminance over the float TMatrix, the vector / scalar sleef lanes of the xlogf and xexpf row loops) and is bit-identical to the reference
 // compiled in place, with two documented exceptions:
 //   * the two 2-D REDFT00 transforms are FFTW calls in the reference (fftw3f is an external library).  Here they are an
 //     fp64 mixed-radix FFT in shared memory (one CTA per row, in-place decimation in frequency, real-even unpacking),

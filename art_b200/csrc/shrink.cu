@@ -262,19 +262,52 @@ int mad_of(art_hp_ctx* ctx, const float* band, int n, int* d_histo, float* d_out
 
 int blur_radius(int level, double scale) { const int r = (int)((level + 2) / scale); return r > 1 ? r : 1; }
 
-// scratch: [histogram 65536 ints][madab 64 floats][sf n][sfd n][tmp n]
+// scratch, one set per lane: [histogram 65536 ints][madab 64 floats][sf n][sfd n][tmp n]
 struct Scratch { int* histo; float* madab; float *sf, *sfd, *tmp; };
-int scratch_for(art_hp_ctx* ctx, size_t n, Scratch* s)
+int scratch_for(art_hp_ctx* ctx, size_t n, Scratch s[3])
 {
     const size_t np = round_up(n, 64);
-    int rc = art_reserve(ctx, ctx->d_scratch, NB * sizeof(int) + 256 + 3 * np * sizeof(float));
+    const size_t one = round_up(NB * sizeof(int) + 256 + 3 * np * sizeof(float), 256);
+    int rc = art_reserve(ctx, ctx->d_scratch, 3 * one);
     if (rc) return rc;
-    char* p = (char*)ctx->d_scratch.p;
-    s->histo = (int*)p; p += NB * sizeof(int);
-    s->madab = (float*)p; p += 256;
-    s->sf = (float*)p; s->sfd = s->sf + np; s->tmp = s->sfd + np;
+    for (int i = 0; i < 3; ++i) {
+        char* p = (char*)ctx->d_scratch.p + i * one;
+        s[i].histo = (int*)p; p += NB * sizeof(int);
+        s[i].madab = (float*)p; p += 256;
+        s[i].sf = (float*)p; s[i].sfd = s[i].sf + np; s[i].tmp = s[i].sfd + np;
+    }
     return ART_HP_OK;
 }
+
+// Fork the context's stream into three lanes (one per wavelet direction) and join them again.  Between the two calls
+// `ctx->stream` is pointed at a lane with lane_of(): every helper queues on ctx->stream, so nothing else changes.
+struct Lanes {
+    art_hp_ctx* ctx; cudaStream_t main;
+    int begin(art_hp_ctx* c)
+    {
+        ctx = c; main = c->stream;
+        if (!c->lane[0]) {
+            for (int i = 0; i < 3; ++i) {
+                ART_CUDA(c, cudaStreamCreateWithFlags(&c->lane[i], cudaStreamNonBlocking));
+                ART_CUDA(c, cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+            }
+            ART_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        }
+        ART_CUDA(c, cudaEventRecord(c->ev_fork, main));
+        for (int i = 0; i < 3; ++i) ART_CUDA(c, cudaStreamWaitEvent(c->lane[i], c->ev_fork, 0));
+        return ART_HP_OK;
+    }
+    void lane_of(int i) { ctx->stream = ctx->lane[i]; }
+    int end()
+    {
+        ctx->stream = main;
+        for (int i = 0; i < 3; ++i) {
+            ART_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ctx->lane[i]));
+            ART_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[i], 0));
+        }
+        return ART_HP_OK;
+    }
+};
 
 int shrink_band(art_hp_ctx* ctx, const Scratch& s, ShArgs a, int W, int H, int rad, bool ab)
 {
@@ -308,12 +341,18 @@ int art_hp_wavelet_mad_dev(art_hp_ctx* ctx, const art_hp_wavelet* w, float* d_ma
 {
     if (!ctx || !w || !d_madL) return ART_HP_ERR_INVALID;
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
-    Scratch s;
-    int rc = scratch_for(ctx, 64, &s);
+    Scratch s[3];
+    int rc = scratch_for(ctx, 64, s);
     if (rc) return rc;
-    for (int l = 0; l < w->nlev; ++l)
-        for (int d = 1; d < 4; ++d)
-            if ((rc = mad_of(ctx, w->lev[l].band[d], w->lev[l].w2 * w->lev[l].h2, s.histo, d_madL + 3 * l + (d - 1), 1))) return rc;
+    Lanes lanes;
+    if ((rc = lanes.begin(ctx))) return rc;
+    for (int l = 0; l < w->nlev && !rc; ++l)
+        for (int d = 1; d < 4 && !rc; ++d) {
+            lanes.lane_of(d - 1);
+            rc = mad_of(ctx, w->lev[l].band[d], w->lev[l].w2 * w->lev[l].h2, s[d - 1].histo, d_madL + 3 * l + (d - 1), 1);
+        }
+    const int rc2 = lanes.end();
+    if (rc || rc2) return rc ? rc : rc2;
     ART_CUDA(ctx, cudaGetLastError());
     return ART_HP_OK;
 }
@@ -323,17 +362,21 @@ int art_hp_wavelet_denoise_L_dev(art_hp_ctx* ctx, art_hp_wavelet* wL, const floa
     if (!ctx || !wL || !d_noisevarlum || !d_madL || !(scale > 0)) return ART_HP_ERR_INVALID;
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
     const int maxlvl = std::min(wL->nlev, 5);      // L1115
-    Scratch s;
-    int rc = scratch_for(ctx, (size_t)wL->lev[0].w2 * wL->lev[0].h2, &s);
+    Scratch s[3];
+    int rc = scratch_for(ctx, (size_t)wL->lev[0].w2 * wL->lev[0].h2, s);
     if (rc) return rc;
-    for (int l = 0; l < maxlvl; ++l)
-        for (int d = 1; d < 4; ++d) {
+    Lanes lanes;
+    if ((rc = lanes.begin(ctx))) return rc;
+    for (int l = 0; l < maxlvl && !rc; ++l)
+        for (int d = 1; d < 4 && !rc; ++d) {
             const WLevel& L = wL->lev[l];
             ShArgs a{};
             a.c = L.band[d]; a.nv = d_noisevarlum; a.mad = d_madL + 3 * l + (d - 1); a.n = L.w2 * L.h2; a.lvlmul = (float)(l + 1);
-            if ((rc = shrink_band(ctx, s, a, L.w2, L.h2, blur_radius(l, scale), false))) return rc;
+            lanes.lane_of(d - 1);
+            rc = shrink_band(ctx, s[d - 1], a, L.w2, L.h2, blur_radius(l, scale), false);
         }
-    return ART_HP_OK;
+    const int rc2 = lanes.end();
+    return rc ? rc : rc2;
 }
 
 int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom,
@@ -343,21 +386,26 @@ int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art
     if (wL->nlev != wab->nlev || wL->W != wab->W || wL->H != wab->H) return ctx->fail(ART_HP_ERR_INVALID, "L and ab decompositions differ in shape");
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
     if (autoch && noisevar_ab <= 0.001f) noisevar_ab = 0.02f;     // L737-739
-    Scratch s;
-    int rc = scratch_for(ctx, (size_t)wab->lev[0].w2 * wab->lev[0].h2, &s);
+    Scratch s[3];
+    int rc = scratch_for(ctx, (size_t)wab->lev[0].w2 * wab->lev[0].h2, s);
     if (rc) return rc;
-    for (int l = 0; l < wL->nlev; ++l)
-        for (int d = 1; d < 4; ++d) {
+    Lanes lanes;
+    if ((rc = lanes.begin(ctx))) return rc;
+    for (int l = 0; l < wL->nlev && !rc; ++l)
+        for (int d = 1; d < 4 && !rc; ++d) {
             const WLevel& L = wab->lev[l];
             const int n = L.w2 * L.h2;
             if (!(noisevar_ab > 0.001f)) continue;                   // L761 (MadRgb is computed but unused)
-            if ((rc = mad_of(ctx, L.band[d], n, s.histo, s.madab, 1))) return rc;
+            lanes.lane_of(d - 1);
+            const Scratch& sc = s[d - 1];
+            if ((rc = mad_of(ctx, L.band[d], n, sc.histo, sc.madab, 1))) break;
             ShArgs a{};
             a.c = L.band[d]; a.cL = wL->lev[l].band[d]; a.nv = d_noisevarchrom; a.mad = d_madL + 3 * l + (d - 1); a.n = n;
-            a.noisevar_ab = noisevar_ab; a.useCCurve = useNoiseCCurve; a.madab = s.madab;
-            if ((rc = shrink_band(ctx, s, a, L.w2, L.h2, blur_radius(l, scale), true))) return rc;
+            a.noisevar_ab = noisevar_ab; a.useCCurve = useNoiseCCurve; a.madab = sc.madab;
+            rc = shrink_band(ctx, sc, a, L.w2, L.h2, blur_radius(l, scale), true);
         }
-    return ART_HP_OK;
+    const int rc2 = lanes.end();
+    return rc ? rc : rc2;
 }
 
 }  // extern "C"

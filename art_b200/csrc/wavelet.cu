@@ -134,6 +134,65 @@ __global__ void __launch_bounds__(256) k_wav_sy_sub(SyArgs a)
     }
 }
 
+
+// The same synthesis for tap spacing 1 (level 0, the only decimated level FTblockDN uses), one thread per 2x2 output quad:
+// the two output columns (rows) of a quad draw on source columns (rows) m-1 .. m+2, so the quad shares its 4 x 4 x 4 loads and
+// its horizontal stage; every output is still the reference's expression, term for term.
+__global__ void __launch_bounds__(256) k_wav_sy_sub_quad(SyArgs a)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * m >= a.dw) return;
+    const float srcFactor = 1.f - a.blend;
+    int col[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) col[k] = max(0, min(m - 1 + k, a.sw - 1));
+    const bool has_x1 = 2 * m + 1 < a.dw;
+    for (int n = blockIdx.y; 2 * n < a.dh; n += gridDim.y) {
+        float tl[4][2], th[4][2];            // horizontal stage of source rows n-1 .. n+2 for the even / odd output column
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const size_t r = (size_t)max(0, min(n - 1 + k, a.sh - 1)) * a.sw;
+            float lo[4], b1[4], b2[4], b3[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { lo[q] = a.lo[r + col[q]]; b1[q] = a.b1[r + col[q]]; b2[q] = a.b2[r + col[q]]; b3[q] = a.b3[r + col[q]]; }
+            // x = 2m: i_src = m + 1, taps j = 1, 3, 5 on columns m+1, m, m-1;  x = 2m + 1: i_src = m + 2, taps j = 0, 2, 4 on m+2, m+1, m
+            float t = 0.f;
+            t += ((c_anal[0][4] * lo[2] + c_anal[1][4] * b1[2])); t += ((c_anal[0][2] * lo[1] + c_anal[1][2] * b1[1])); t += ((c_anal[0][0] * lo[0] + c_anal[1][0] * b1[0]));
+            tl[k][0] = t;
+            t = 0.f;
+            t += ((c_anal[0][5] * lo[3] + c_anal[1][5] * b1[3])); t += ((c_anal[0][3] * lo[2] + c_anal[1][3] * b1[2])); t += ((c_anal[0][1] * lo[1] + c_anal[1][1] * b1[1]));
+            tl[k][1] = t;
+            t = 0.f;
+            t += ((c_anal[0][4] * b2[2] + c_anal[1][4] * b3[2])); t += ((c_anal[0][2] * b2[1] + c_anal[1][2] * b3[1])); t += ((c_anal[0][0] * b2[0] + c_anal[1][0] * b3[0]));
+            th[k][0] = t;
+            t = 0.f;
+            t += ((c_anal[0][5] * b2[3] + c_anal[1][5] * b3[3])); t += ((c_anal[0][3] * b2[2] + c_anal[1][3] * b3[2])); t += ((c_anal[0][1] * b2[1] + c_anal[1][1] * b3[1]));
+            th[k][1] = t;
+        }
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+            const int y = 2 * n + py;
+            if (y >= a.dh) break;
+            float* d = a.dst + (size_t)y * a.dp + 2 * m;
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                if (px && !has_x1) break;
+                float tot = 0.f;
+                if (py == 0) {          // y = 2n: i_src = n + 1, taps j = 1, 3, 5 on rows n+1, n, n-1
+                    tot += ((c_anal[0][4] * tl[2][px] + c_anal[1][4] * th[2][px]));
+                    tot += ((c_anal[0][2] * tl[1][px] + c_anal[1][2] * th[1][px]));
+                    tot += ((c_anal[0][0] * tl[0][px] + c_anal[1][0] * th[0][px]));
+                } else {                // y = 2n + 1: i_src = n + 2, taps j = 0, 2, 4 on rows n+2, n+1, n
+                    tot += ((c_anal[0][5] * tl[3][px] + c_anal[1][5] * th[3][px]));
+                    tot += ((c_anal[0][3] * tl[2][px] + c_anal[1][3] * th[2][px]));
+                    tot += ((c_anal[0][1] * tl[1][px] + c_anal[1][1] * th[1][px]));
+                }
+                d[px] = d[px] * srcFactor + a.blend * 4.f * tot;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 struct WLevel { int w, h, w2, h2, skip, sub; float* band[4]; };
@@ -253,7 +312,10 @@ int art_hp_wavelet_reconstruct_dev(art_hp_wavelet* w, float* d_dst, size_t pitch
                 // start from a copy so that dst * (1 - blend) reads the same values
                 ART_CUDA(ctx, cudaMemcpyAsync(other, cur, (size_t)L.w2 * L.h2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
             }
-            k_wav_sy_sub<<<grid, 256, 0, st>>>(a);
+            if (a.skip == 1) {
+                const dim3 qgrid(((L.w + 1) / 2 + 255) / 256, std::min((L.h + 1) / 2, 148 * 8));
+                k_wav_sy_sub_quad<<<qgrid, 256, 0, st>>>(a);
+            } else k_wav_sy_sub<<<grid, 256, 0, st>>>(a);
         } else k_wav_sy_haar<<<grid, 256, 0, st>>>(a);
         art_prof_end(ctx);
         ctx->launches++;
