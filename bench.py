@@ -170,7 +170,8 @@ DEVELOP_KERNEL_BYTES = {
     "k_fbox_h": (8, "subband coefficient"), "k_fbox_v": (8, "subband coefficient"),        # 4 R + 4 W
     "k_dn_blocks": (4 + 4 * (64.0 / 25.0) ** 2, "pixel"),   # residual read once + the windowed 64x64 blocks (stride 25) written
     "k_fat_dct_rows": (4 + 8, "padded pixel"), "k_fat_dct_solve": (8 + 8, "padded pixel"), "k_fat_dct_exp": (8 + 4, "padded pixel"),
-    "k_wav_sy_sub": (16 + 4, "pixel"), "k_sf_apply": (12, "subband coefficient"), "k_mad_hist": (4, "subband coefficient"),
+    "k_wav_sy_sub": (16 + 4, "pixel"), "k_sf_apply": (12 + 4, "subband coefficient"), "k_mad_hist": (4, "subband coefficient"),
+    "k_sf_L": (8 + 4, "subband coefficient"), "k_sf_AB": (12 + 4, "subband coefficient"),
 }
 
 
@@ -187,11 +188,32 @@ def find_fast_dim(dim):
 
 
 def develop_units(name, W, H):
-    if name in ("k_fbox_h", "k_fbox_v", "k_sf_apply", "k_mad_hist"):
+    if name in ("k_fbox_h", "k_fbox_v", "k_sf_apply", "k_mad_hist", "k_sf_L", "k_sf_AB"):
         return ((W + 1) // 2) * ((H + 1) // 2)
     if name.startswith("k_fat_dct"):
         return (find_fast_dim(W) + 1) * (find_fast_dim(H) + 1)
     return W * H
+
+
+def roofline_top(per_step, kern, calls, W, H, peak, n=6):
+    """The same algorithmic-bytes / CUDA-event-time figure for the n largest kernels of the step (the wavelet-shrink kernels of
+    the three directions run on three concurrent streams, so their per-launch times include each other's interference)."""
+    out = []
+    ntiles = ((W + 16 + 127) // 128) * ((H + 16 + 127) // 128)
+    for k in sorted(per_step, key=lambda k: -per_step[k])[:n]:
+        ub = DEVELOP_KERNEL_BYTES.get(k)
+        if ub is not None:
+            units = develop_units(k, W, H)
+            b = ub[0]
+        elif k in AMAZE_KERNEL_BYTES:
+            units, b = ntiles * 160 * 160, AMAZE_KERNEL_BYTES[k]
+        else:
+            out.append({"kernel": k, "ms_per_step": round(per_step[k], 4), "launches_per_step": calls[k], "achieved_GBps": None, "frac": None})
+            continue
+        ach = b * units / (kern[k] * 1e-3) / 1e9
+        out.append({"kernel": k, "ms_per_step": round(per_step[k], 4), "launches_per_step": calls[k], "achieved_GBps": round(ach, 1),
+                    "frac": round(ach / peak, 4)})
+    return out
 
 
 def develop_params(art_b200):
@@ -491,6 +513,7 @@ def main():
             "step_roofline": {"achieved": step_achieved, "frac": step_achieved / peak, "unit": "GB/s",
                               "bytes_per_pixel": step_bytes,
                               "note": "whole step: SURVEY.md 8(d) ideal-fusion bytes per pixel / ms_per_step"},
+            "roofline_top": roofline_top(per_step, kern, calls, W, H, peak) if args.workload == "develop" else None,
             "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
             "clocks": clocks, "checksum_green_center": checksum,
         }
