@@ -360,7 +360,20 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the first communicator is created; stdout carries the ONE JSON line, so the
+        # banner is sent to stderr: fd 1 points at fd 2 until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            t = torch.zeros(1, device="cuda")
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     hp = art_b200.HotPath(local)
     method = art_b200.BAYER_RCD if args.method == "rcd" else art_b200.BAYER_AMAZE
     raw = synth.bayer_frame(W, H, filters, seed=1002 + rank)
