@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(256) k_dn_split(SplitArgs s)
 struct BlkArgs {
     const float* Lin; const float* L; const float* mask; int width, height, nbw, nbh;
     const float *tin, *dctf, *dctb;    // tilemask_in, REDFT10 matrix C[k][j], REDFT01 matrix D[k][j]
+    const float *tin_p, *dctf_p, *dctb_p;   // the same three with the shared-memory pitches PT / PC / PC (bulk-copy sources)
     float* blocks;                     // [nbh][nbw][64][64]
     float detail_hi, detail_lo, params_Ldetail; int use_mask, blur_rad;
 };
@@ -189,29 +190,66 @@ __device__ __forceinline__ void mm64(const float* __restrict__ A, const float* _
     }
 }
 
+// bulk asynchronous copies (the TMA engine's 1-D form) completing on an mbarrier
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
 __global__ void __launch_bounds__(256) k_dn_blocks(BlkArgs a)
 {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(128) float sm[];
+    __shared__ __align__(8) unsigned long long mbar;
     float* X = sm;                 // data / coefficients
     float* T = X + TS * PX;        // temp
     float* C = T + TS * PT;        // forward matrix
     float* D = C + TS * PC;        // backward matrix
     const int hblk = blockIdx.x, vblk = blockIdx.y, t = threadIdx.x;
     const int top = (vblk - BLKRAD) * OFFSET, left = (hblk - BLKRAD) * OFFSET;
-    for (int i = t; i < TS * TS; i += 256) {
-        const int r = i >> 6, c = i & 63;
-        C[r * PC + c] = a.dctf[i];
-        D[r * PC + c] = a.dctb[i];
-        // padded data row (L1547-1567): mirror without repeating the edge, clamped
-        const int row = top + r;
+    const unsigned bar = smem_u32(&mbar);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (t == 0) {
+        // the window (into T, the matmul temp) and the two DCT matrices, stored in global memory with their shared-memory
+        // pitches: three bulk copies by the copy engine instead of 48 scalar loads per thread
+        constexpr unsigned BT = TS * PT * sizeof(float), BC = TS * PC * sizeof(float);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(BT + 2 * BC) : "memory");
+        bulk_g2s(T, a.tin_p, BT, bar);
+        bulk_g2s(C, a.dctf_p, BC, bar);
+        bulk_g2s(D, a.dctb_p, BC, bar);
+    }
+    // gather the residual while the copies fly.  padded data (L1547-1567): mirror without repeating the edge, clamped
+    const int c = t & 63, r0 = t >> 6;
+    int col = left + c;
+    if (col < 0) col = min(-col, a.width - 1);
+    else if (col >= a.width) col = max(0, 2 * a.width - 2 - col);
+    float res[TS * TS / 256];
+#pragma unroll
+    for (int k = 0; k < TS * TS / 256; ++k) {
+        const int row = top + r0 + 4 * k;
         int rr = row;
         if (row < 0) rr = min(-row, a.height - 1);
         else if (row >= a.height) rr = max(0, 2 * a.height - 2 - row);
-        int col = left + c;
-        if (col < 0) col = min(-col, a.width - 1);
-        else if (col >= a.width) col = max(0, 2 * a.width - 2 - col);
         const size_t p = (size_t)rr * a.width + col;
-        X[r * PX + c] = a.tin[i] * (a.Lin[p] - a.L[p]);
+        res[k] = a.Lin[p] - a.L[p];
+    }
+    while (!mbar_try_wait(bar, 0)) { }
+#pragma unroll
+    for (int k = 0; k < TS * TS / 256; ++k) {
+        const int r = r0 + 4 * k;
+        X[r * PX + c] = T[r * PT + c] * res[k];
     }
     __syncthreads();
     mm64<true, PX, PC, PT>(X, C, T);       // along rows: T[i][k] = sum_j C[k][j] X[i][j]
@@ -249,14 +287,18 @@ __global__ void __launch_bounds__(256) k_dn_blocks(BlkArgs a)
     }
     __syncthreads();
     // RGBtile_denoise L511-514 with the per-sample detail factor of L1571-1595
-    for (int i = t; i < TS * TS; i += 256) {
-        const int r = i >> 6, c = i & 63;
-        const int row = top + r, col = left + c;
-        float df = a.detail_lo;
-        if (row >= 0 && row < a.height && col >= 0 && col < a.width)
-            df = a.use_mask ? compute_detail(a.params_Ldetail * a.mask[(size_t)row * a.width + col]) : a.detail_hi;
-        const float nb = C[r * PC + c];
-        X[r * PX + c] = X[r * PX + c] * (1.0f - sleef::xexpf_vector(-(nb * nb) / df));
+    {
+        const int icol = left + c;
+        const bool col_in = icol >= 0 && icol < a.width;
+#pragma unroll 4
+        for (int k = 0; k < TS * TS / 256; ++k) {
+            const int r = r0 + 4 * k, row = top + r;
+            float df = a.detail_lo;
+            if (col_in && row >= 0 && row < a.height)
+                df = a.use_mask ? compute_detail(a.params_Ldetail * a.mask[(size_t)row * a.width + icol]) : a.detail_hi;
+            const float nb = C[r * PC + c];
+            X[r * PX + c] = X[r * PX + c] * (1.0f - sleef::xexpf_vector(-(nb * nb) / df));
+        }
     }
     __syncthreads();
     mm64<true, PX, PC, PT>(X, D, T);
@@ -421,13 +463,21 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
 
     if (denoiseLuminance) {
         // the window / DCT tables are constants: built and uploaded once per context
-        int trc = art_reserve(ctx, ctx->d_dn_tables, 4 * TS * TS * sizeof(float));
+        constexpr size_t NT = 4 * TS * TS + TS * PT + 2 * TS * PC;     // dense tables + pitched copies for the bulk loads
+        int trc = art_reserve(ctx, ctx->d_dn_tables, NT * sizeof(float));
         if (trc) return trc;
         float* tb = (float*)ctx->d_dn_tables.p;
         if (!ctx->dn_tables_ready) {
-            std::vector<float> host(4 * TS * TS);
+            std::vector<float> host(NT, 0.f);
             build_tables(host.data(), host.data() + TS * TS, host.data() + 2 * TS * TS, host.data() + 3 * TS * TS);
-            ART_CUDA(ctx, cudaMemcpyAsync(tb, host.data(), sizeof(float) * 4 * TS * TS, cudaMemcpyHostToDevice, st));
+            float* tp = host.data() + 4 * TS * TS;
+            for (int r = 0; r < TS; ++r)
+                for (int c = 0; c < TS; ++c) {
+                    tp[r * PT + c] = host[r * TS + c];
+                    tp[TS * PT + r * PC + c] = host[2 * TS * TS + r * TS + c];
+                    tp[TS * PT + TS * PC + r * PC + c] = host[3 * TS * TS + r * TS + c];
+                }
+            ART_CUDA(ctx, cudaMemcpyAsync(tb, host.data(), sizeof(float) * NT, cudaMemcpyHostToDevice, st));
             ART_CUDA(ctx, cudaStreamSynchronize(st));
             ctx->dn_tables_ready = true;
         }
@@ -522,6 +572,7 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
         }
         BlkArgs a{};
         a.Lin = Lin; a.L = Lp; a.mask = mask; a.width = W; a.height = H; a.nbw = nbw; a.nbh = nbh; a.tin = tin; a.dctf = dctf; a.dctb = dctb; a.blocks = blocks;
+        a.tin_p = tin + 4 * TS * TS; a.dctf_p = a.tin_p + TS * PT; a.dctb_p = a.dctf_p + TS * PC;
         a.detail_hi = host_compute_detail(params_Ldetail); a.detail_lo = host_compute_detail(0.f); a.params_Ldetail = params_Ldetail;
         a.use_mask = use_mask; a.blur_rad = std::max(1, int(3 / scale));
         const size_t smem = (size_t)TS * (PX + PT + 2 * PC) * sizeof(float);
