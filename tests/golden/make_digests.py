@@ -1,0 +1,96 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/digests.json: SHA-256 of what the REFERENCE (oracle/_ref/libartref_det.so, the reference's own function
+bodies compiled where they lie under /root/reference) returns for seeded inputs, for the ports whose outputs are too many to
+commit as planes: X-Trans demosaic, unsharp mask, the colour / curve chain, Fattal tone mapping, RGB_denoise.
+
+Run in the build container (needs /root/reference):  python tests/golden/make_digests.py
+tests/test_oracle_golden_digests.py recomputes the same inputs, runs the plain-C port and compares digests -- that test needs
+neither /root/reference nor oracle/_ref.  The FFTW call sites of Fattal and RGB_denoise run the same double-precision stand-in on
+both sides (fftw3f is absent), so those two digests pin everything around the transforms, not the transforms themselves."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def digest(planes):
+    h = hashlib.sha256()
+    for p in planes:
+        h.update(np.ascontiguousarray(p, dtype=np.float32).tobytes())
+    return h.hexdigest()
+
+
+def cases(which):
+    """name -> callable returning the output planes; `which` is "ref" or "port"."""
+    import oracle
+    from art_b200 import synth
+    import test_oracle_xtrans as tx
+    import test_oracle_usm as tu
+    import test_oracle_chain as tc
+    import test_oracle_fattal as tf
+    import test_oracle_denoise as td
+    import test_chain_gpu as tcg
+    ref = which == "ref"
+    lib = oracle.ref().lib if ref else oracle.port().lib
+    pre = "artref_" if ref else "artoracle_"
+    out = {}
+    for passes, lab, dy, dx, W, H in [(3, 1, 0, 0, 233, 217), (1, 0, 2, 5, 131, 140), (3, 0, 4, 1, 120, 125)]:
+        def f(passes=passes, lab=lab, dy=dy, dx=dx, W=W, H=H):
+            xt = synth.xtrans_matrix(dy, dx)
+            raw = synth.xtrans_frame(W, H, xt, seed=W + dy)
+            return tx.ref_xtrans(raw, xt, passes, lab) if ref else tx.port_xtrans(raw, xt, passes, lab)
+        out["xtrans_p%d_lab%d_o%d%d_%dx%d" % (passes, lab, dy, dx, W, H)] = f
+    for k, kw in enumerate([dict(), dict(radius=0.9, amount=350), dict(contrast=55.0, radius=2.4, amount=80, thr=(10, 40, 1500, 600))]):
+        def f(k=k, kw=kw):
+            return tu.run(lib, pre + "usm", tu.scene(301, 203, 40 + k, wild=bool(k & 1)), **kw)[0]
+        out["usm_case%d_301x203" % k] = f
+    for name in ("all_std", "all_film"):
+        def f(name=name):
+            planes = tc.image(77, 130, 5)
+            if not ref:
+                return tcg.oracle_chain(planes, **tcg.STAGES[name])
+            # the same sequence through the reference's loops
+            kw = dict(tcg.STAGES[name])
+            o = planes
+            if "exposure" in kw:
+                ev, black = kw["exposure"]
+                o = tc.call(lib, "artref_chain_expcomp", o, tc.F(np.float32(2.0) ** np.float32(ev)), tc.F(np.float32(black) * np.float32(2000.0)))
+            if "saturation" in kw and (kw["saturation"][0] or kw["saturation"][1]):
+                o = tc.call(lib, "artref_chain_saturation", o, kw["saturation"][0], kw["saturation"][1], tc.PROPHOTO.ctypes.data_as(tc.dp))
+            if "tonecurve" in kw:
+                o = tc.call(lib, "artref_chain_tonecurve", o, kw["tonecurve"][0], kw["tonecurve"][1].ctypes.data_as(tc.fp), tc.F(1.0))
+            if "rgbcurves" in kw:
+                o = tc.call(lib, "artref_chain_rgbcurves", o, *[c.ctypes.data_as(tc.fp) if c is not None else None for c in kw["rgbcurves"]])
+            if "lab" in kw:
+                lab = kw["lab"]
+                o = tc.call(lib, "artref_chain_lab", o, lab[0].ctypes.data_as(tc.fp), lab[1].ctypes.data_as(tc.fp), lab[2].ctypes.data_as(tc.fp), tc.F(lab[3]),
+                            tc.PROPHOTO.ctypes.data_as(tc.dp), tc.PROPHOTO_INV.ctypes.data_as(tc.dp))
+            return o
+        out["chain_%s_130x77" % name] = f
+
+    def f():
+        return tf.fattal(lib, pre + "fattal", tf.scene(203, 301, 7), 30, 20, 1)
+    out["fattal_301x203_30_20_sat"] = f
+
+    def f():
+        planes = td.rgb_frame(200, 264, seed=21)
+        return td.run(lib, pre + "rgb_denoise", planes, (30, 50, 0, 15, 0, 0, 1.7, 1.0), td.noise_ccurve(), with_inverse=ref)[0]
+    out["rgb_denoise_264x200_lum30_curve"] = f
+    return out
+
+
+def main():
+    d = {name: digest(fn()) for name, fn in cases("ref").items()}
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "digests.json")
+    json.dump(d, open(path, "w"), indent=1, sort_keys=True)
+    print("wrote", path, len(d), "digests")
+
+
+if __name__ == "__main__":
+    main()

@@ -57,3 +57,33 @@ def test_product_does_not_reference_oracle():
     assert not bad, bad
     out = subprocess.check_output(["ldd", art_b200.lib_path()], text=True)
     assert "artoracle" not in out and "artref" not in out
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The Python mirror's ctypes structures have the size and field offsets the C compiler gives the header's structs."""
+    import ctypes
+    pairs = {
+        "art_hp_denoise_params": (api._DenoiseParamsC, ["luminance", "luminanceDetail", "luminanceDetailThreshold", "chrominance", "gamma", "scale",
+                                                         "colorSpace", "noiseCCurve", "noiseCCurveSum"]),
+        "art_hp_develop_params": (api._DevelopParamsC, ["method", "filters", "initialGain", "border", "mul", "doClip", "cam2work", "denoise",
+                                                         "nlStrength", "fattal_enabled", "fattal_satcontrol", "wprof", "sharpen", "chain"]),
+        "art_hp_chain_params": (api._ChainParamsC, ["exposure_enabled", "exp_scale", "black", "saturation_enabled", "vibrance", "tonecurve_mode",
+                                                     "tonecurve_lut", "rcurve", "bcurve", "lab_enabled", "lab_lcurve", "lab_bcurve", "lab_chroma", "ws", "iws"]),
+        "art_hp_sharpen_params": (api._SharpenParamsC, ["contrast", "radius", "amount", "threshold", "edgesonly", "halocontrol", "halocontrol_amount", "scale"]),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "art_hotpath.h"', 'int main(void){']
+    for s, (_, fields) in pairs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (s, s))
+        for f in fields:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (s, f, s, f))
+    lines.append('return 0;}')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(art_b200.lib_path()), "..", "include")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for s, (cls, fields) in pairs.items():
+        assert int(out[s]) == ctypes.sizeof(cls), s
+        for f in fields:
+            assert int(out["%s.%s" % (s, f)]) == getattr(cls, f).offset, (s, f)
