@@ -242,7 +242,7 @@ void art_hp_destroy(art_hp_ctx* ctx)
     if (ctx->d_chain.p) cudaFree(ctx->d_chain.p);
     if (ctx->d_usm_tables.p) cudaFree(ctx->d_usm_tables.p);
     if (ctx->d_xt_cbrt.p) cudaFree(ctx->d_xt_cbrt.p);
-    for (int i = 0; i < 3; ++i) { if (ctx->lane[i]) cudaStreamDestroy(ctx->lane[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
+    for (int i = 0; i < art_hp_ctx::NLANES; ++i) { if (ctx->lane[i]) cudaStreamDestroy(ctx->lane[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (auto& q : ctx->q) {
         if (q.raw.p) cudaFree(q.raw.p);

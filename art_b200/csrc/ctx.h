@@ -57,10 +57,11 @@ struct art_hp_ctx {
     struct QSlot { DevBuf raw, out[3]; cudaEvent_t up = nullptr, done = nullptr, down = nullptr; };
     QSlot q[2];
     unsigned long long q_submitted = 0, q_collected = 0;
-    // three side streams for work that is independent per wavelet direction (shrink.cu): the flat box blurs are serial
-    // recurrences along a line, so one subband cannot fill the GPU -- three directions run side by side
-    cudaStream_t lane[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    // side streams for work that is independent per wavelet subband (shrink.cu): the flat box blurs are serial recurrences
+    // along a line, so one subband cannot fill the GPU -- the subbands of a channel run side by side
+    static constexpr int NLANES = 15;    // one per (level, direction) of a 5-level decomposition
+    cudaStream_t lane[NLANES] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[NLANES] = {};
     void* h_stage[2] = {nullptr, nullptr};
     size_t h_stage_bytes = 0;
 

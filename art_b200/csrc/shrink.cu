@@ -264,13 +264,14 @@ int blur_radius(int level, double scale) { const int r = (int)((level + 2) / sca
 
 // scratch, one set per lane: [histogram 65536 ints][madab 64 floats][sf n][sfd n][tmp n]
 struct Scratch { int* histo; float* madab; float *sf, *sfd, *tmp; };
-int scratch_for(art_hp_ctx* ctx, size_t n, Scratch s[3])
+constexpr int NL = art_hp_ctx::NLANES;
+int scratch_for(art_hp_ctx* ctx, size_t n, Scratch s[NL])
 {
     const size_t np = round_up(n, 64);
     const size_t one = round_up(NB * sizeof(int) + 256 + 3 * np * sizeof(float), 256);
-    int rc = art_reserve(ctx, ctx->d_scratch, 3 * one);
+    int rc = art_reserve(ctx, ctx->d_scratch, NL * one);
     if (rc) return rc;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < NL; ++i) {
         char* p = (char*)ctx->d_scratch.p + i * one;
         s[i].histo = (int*)p; p += NB * sizeof(int);
         s[i].madab = (float*)p; p += 256;
@@ -279,7 +280,7 @@ int scratch_for(art_hp_ctx* ctx, size_t n, Scratch s[3])
     return ART_HP_OK;
 }
 
-// Fork the context's stream into three lanes (one per wavelet direction) and join them again.  Between the two calls
+// Fork the context's stream into NL lanes (one per subband of a channel) and join them again.  Between the two calls
 // `ctx->stream` is pointed at a lane with lane_of(): every helper queues on ctx->stream, so nothing else changes.
 struct Lanes {
     art_hp_ctx* ctx; cudaStream_t main;
@@ -287,21 +288,21 @@ struct Lanes {
     {
         ctx = c; main = c->stream;
         if (!c->lane[0]) {
-            for (int i = 0; i < 3; ++i) {
+            for (int i = 0; i < NL; ++i) {
                 ART_CUDA(c, cudaStreamCreateWithFlags(&c->lane[i], cudaStreamNonBlocking));
                 ART_CUDA(c, cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
             }
             ART_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         }
         ART_CUDA(c, cudaEventRecord(c->ev_fork, main));
-        for (int i = 0; i < 3; ++i) ART_CUDA(c, cudaStreamWaitEvent(c->lane[i], c->ev_fork, 0));
+        for (int i = 0; i < NL; ++i) ART_CUDA(c, cudaStreamWaitEvent(c->lane[i], c->ev_fork, 0));
         return ART_HP_OK;
     }
     void lane_of(int i) { ctx->stream = ctx->lane[i]; }
     int end()
     {
         ctx->stream = main;
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < NL; ++i) {
             ART_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ctx->lane[i]));
             ART_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[i], 0));
         }
@@ -341,15 +342,16 @@ int art_hp_wavelet_mad_dev(art_hp_ctx* ctx, const art_hp_wavelet* w, float* d_ma
 {
     if (!ctx || !w || !d_madL) return ART_HP_ERR_INVALID;
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
-    Scratch s[3];
+    Scratch s[NL];
     int rc = scratch_for(ctx, 64, s);
     if (rc) return rc;
     Lanes lanes;
     if ((rc = lanes.begin(ctx))) return rc;
     for (int l = 0; l < w->nlev && !rc; ++l)
         for (int d = 1; d < 4 && !rc; ++d) {
-            lanes.lane_of(d - 1);
-            rc = mad_of(ctx, w->lev[l].band[d], w->lev[l].w2 * w->lev[l].h2, s[d - 1].histo, d_madL + 3 * l + (d - 1), 1);
+            const int ln = (3 * l + d - 1) % NL;
+            lanes.lane_of(ln);
+            rc = mad_of(ctx, w->lev[l].band[d], w->lev[l].w2 * w->lev[l].h2, s[ln].histo, d_madL + 3 * l + (d - 1), 1);
         }
     const int rc2 = lanes.end();
     if (rc || rc2) return rc ? rc : rc2;
@@ -362,7 +364,7 @@ int art_hp_wavelet_denoise_L_dev(art_hp_ctx* ctx, art_hp_wavelet* wL, const floa
     if (!ctx || !wL || !d_noisevarlum || !d_madL || !(scale > 0)) return ART_HP_ERR_INVALID;
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
     const int maxlvl = std::min(wL->nlev, 5);      // L1115
-    Scratch s[3];
+    Scratch s[NL];
     int rc = scratch_for(ctx, (size_t)wL->lev[0].w2 * wL->lev[0].h2, s);
     if (rc) return rc;
     Lanes lanes;
@@ -372,8 +374,9 @@ int art_hp_wavelet_denoise_L_dev(art_hp_ctx* ctx, art_hp_wavelet* wL, const floa
             const WLevel& L = wL->lev[l];
             ShArgs a{};
             a.c = L.band[d]; a.nv = d_noisevarlum; a.mad = d_madL + 3 * l + (d - 1); a.n = L.w2 * L.h2; a.lvlmul = (float)(l + 1);
-            lanes.lane_of(d - 1);
-            rc = shrink_band(ctx, s[d - 1], a, L.w2, L.h2, blur_radius(l, scale), false);
+            const int ln = (3 * l + d - 1) % NL;
+            lanes.lane_of(ln);
+            rc = shrink_band(ctx, s[ln], a, L.w2, L.h2, blur_radius(l, scale), false);
         }
     const int rc2 = lanes.end();
     return rc ? rc : rc2;
@@ -386,7 +389,7 @@ int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art
     if (wL->nlev != wab->nlev || wL->W != wab->W || wL->H != wab->H) return ctx->fail(ART_HP_ERR_INVALID, "L and ab decompositions differ in shape");
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
     if (autoch && noisevar_ab <= 0.001f) noisevar_ab = 0.02f;     // L737-739
-    Scratch s[3];
+    Scratch s[NL];
     int rc = scratch_for(ctx, (size_t)wab->lev[0].w2 * wab->lev[0].h2, s);
     if (rc) return rc;
     Lanes lanes;
@@ -396,8 +399,9 @@ int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art
             const WLevel& L = wab->lev[l];
             const int n = L.w2 * L.h2;
             if (!(noisevar_ab > 0.001f)) continue;                   // L761 (MadRgb is computed but unused)
-            lanes.lane_of(d - 1);
-            const Scratch& sc = s[d - 1];
+            const int ln = (3 * l + d - 1) % NL;
+            lanes.lane_of(ln);
+            const Scratch& sc = s[ln];
             if ((rc = mad_of(ctx, L.band[d], n, sc.histo, sc.madab, 1))) break;
             ShArgs a{};
             a.c = L.band[d]; a.cL = wL->lev[l].band[d]; a.nv = d_noisevarchrom; a.mad = d_madL + 3 * l + (d - 1); a.n = n;
