@@ -211,8 +211,8 @@ __global__ void __launch_bounds__(256) k_dn_blocks(BlkArgs a)
     __shared__ __align__(8) unsigned long long mbar;
     float* X = sm;                 // data / coefficients
     float* T = X + TS * PX;        // temp
-    float* C = T + TS * PT;        // forward matrix
-    float* D = C + TS * PC;        // backward matrix
+    float* C = T + TS * PT;        // forward matrix, then the blur's intermediate, then the backward matrix
+    float* D = C;                  // (three buffers = 53 KB: four CTAs per SM)
     const int hblk = blockIdx.x, vblk = blockIdx.y, t = threadIdx.x;
     const int top = (vblk - BLKRAD) * OFFSET, left = (hblk - BLKRAD) * OFFSET;
     const unsigned bar = smem_u32(&mbar);
@@ -225,10 +225,9 @@ __global__ void __launch_bounds__(256) k_dn_blocks(BlkArgs a)
         // the window (into T, the matmul temp) and the two DCT matrices, stored in global memory with their shared-memory
         // pitches: three bulk copies by the copy engine instead of 48 scalar loads per thread
         constexpr unsigned BT = TS * PT * sizeof(float), BC = TS * PC * sizeof(float);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(BT + 2 * BC) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(BT + BC) : "memory");
         bulk_g2s(T, a.tin_p, BT, bar);
         bulk_g2s(C, a.dctf_p, BC, bar);
-        bulk_g2s(D, a.dctb_p, BC, bar);
     }
     // gather the residual while the copies fly.  padded data (L1547-1567): mirror without repeating the edge, clamped
     const int c = t & 63, r0 = t >> 6;
@@ -256,11 +255,11 @@ __global__ void __launch_bounds__(256) k_dn_blocks(BlkArgs a)
     __syncthreads();
     mm64<false, PC, PT, PX>(C, T, X);      // along columns: X[k][x] = sum_j C[k][j] T[j][x]
     __syncthreads();
-    // boxabsblur (boxblur.h L745-888), W = H = 64: horizontal into T, vertical into C (the forward matrix is done with)
+    // boxabsblur (boxblur.h L745-888), W = H = 64: horizontal into C (the forward matrix is done with), vertical into T
     const int rad = a.blur_rad;
     if (t < TS) {
         const float* s = X + t * PX;
-        float* o = T + t * PT;
+        float* o = C + t * PC;
         int len = rad + 1;
         float v = fabsf(s[0]);
         for (int j = 1; j <= rad; j++) v += fabsf(s[j]);
@@ -273,19 +272,25 @@ __global__ void __launch_bounds__(256) k_dn_blocks(BlkArgs a)
     }
     __syncthreads();
     if (t < TS) {
-        const float* s = T + t;
-        float* o = C + t;
+        const float* s = C + t;
+        float* o = T + t;
         float len = (float)(rad + 1);
         float v = s[0];
-        for (int i = 1; i <= rad; i++) v = v + s[i * PT];
+        for (int i = 1; i <= rad; i++) v = v + s[i * PC];
         v = v / len;
         o[0] = v;
-        for (int row = 1; row <= rad; row++) { const float lp1 = len + 1.f; v = (v * len + s[(row + rad) * PT]) / lp1; o[row * PC] = v; len = lp1; }
+        for (int row = 1; row <= rad; row++) { const float lp1 = len + 1.f; v = (v * len + s[(row + rad) * PC]) / lp1; o[row * PT] = v; len = lp1; }
         const float rlen = 1.f / len;
-        for (int row = rad + 1; row < TS - rad; row++) { v = v + (s[(row + rad) * PT] - s[(row - rad - 1) * PT]) * rlen; o[row * PC] = v; }
-        for (int row = TS - rad; row < TS; row++) { const float lm1 = len - 1.f; v = (v * len - s[(row - rad - 1) * PT]) / lm1; o[row * PC] = v; len = lm1; }
+        for (int row = rad + 1; row < TS - rad; row++) { v = v + (s[(row + rad) * PC] - s[(row - rad - 1) * PC]) * rlen; o[row * PT] = v; }
+        for (int row = TS - rad; row < TS; row++) { const float lm1 = len - 1.f; v = (v * len - s[(row - rad - 1) * PC]) / lm1; o[row * PT] = v; len = lm1; }
     }
     __syncthreads();
+    if (t == 0) {       // the blur's intermediate is consumed: the backward matrix streams into its place while the shrink loop runs
+        constexpr unsigned BC = TS * PC * sizeof(float);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy accesses to C are ordered before the async write
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(BC) : "memory");
+        bulk_g2s(D, a.dctb_p, BC, bar);
+    }
     // RGBtile_denoise L511-514 with the per-sample detail factor of L1571-1595
     {
         const int icol = left + c;
@@ -296,11 +301,12 @@ __global__ void __launch_bounds__(256) k_dn_blocks(BlkArgs a)
             float df = a.detail_lo;
             if (col_in && row >= 0 && row < a.height)
                 df = a.use_mask ? compute_detail(a.params_Ldetail * a.mask[(size_t)row * a.width + icol]) : a.detail_hi;
-            const float nb = C[r * PC + c];
+            const float nb = T[r * PT + c];
             X[r * PX + c] = X[r * PX + c] * (1.0f - sleef::xexpf_vector(-(nb * nb) / df));
         }
     }
     __syncthreads();
+    while (!mbar_try_wait(bar, 1)) { }
     mm64<true, PX, PC, PT>(X, D, T);
     __syncthreads();
     mm64<false, PC, PT, PX>(D, T, X);
@@ -575,7 +581,7 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
         a.tin_p = tin + 4 * TS * TS; a.dctf_p = a.tin_p + TS * PT; a.dctb_p = a.dctf_p + TS * PC;
         a.detail_hi = host_compute_detail(params_Ldetail); a.detail_lo = host_compute_detail(0.f); a.params_Ldetail = params_Ldetail;
         a.use_mask = use_mask; a.blur_rad = std::max(1, int(3 / scale));
-        const size_t smem = (size_t)TS * (PX + PT + 2 * PC) * sizeof(float);
+        const size_t smem = (size_t)TS * (PX + PT + PC) * sizeof(float);
         static bool attr = false;
         if (!attr) { ART_CUDA(ctx, cudaFuncSetAttribute(k_dn_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
         art_prof_begin(ctx, "k_dn_blocks");

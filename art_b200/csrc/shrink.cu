@@ -283,10 +283,12 @@ int scratch_for(art_hp_ctx* ctx, size_t n, Scratch s[NL])
 // Fork the context's stream into NL lanes (one per subband of a channel) and join them again.  Between the two calls
 // `ctx->stream` is pointed at a lane with lane_of(): every helper queues on ctx->stream, so nothing else changes.
 struct Lanes {
-    art_hp_ctx* ctx; cudaStream_t main;
+    art_hp_ctx* ctx; cudaStream_t main; bool serial;
     int begin(art_hp_ctx* c)
     {
         ctx = c; main = c->stream;
+        serial = c->profiling;       // per-kernel timing (art_hp_profile_*) wants every launch alone on the stream its events are on
+        if (serial) return ART_HP_OK;
         if (!c->lane[0]) {
             for (int i = 0; i < NL; ++i) {
                 ART_CUDA(c, cudaStreamCreateWithFlags(&c->lane[i], cudaStreamNonBlocking));
@@ -298,10 +300,11 @@ struct Lanes {
         for (int i = 0; i < NL; ++i) ART_CUDA(c, cudaStreamWaitEvent(c->lane[i], c->ev_fork, 0));
         return ART_HP_OK;
     }
-    void lane_of(int i) { ctx->stream = ctx->lane[i]; }
+    void lane_of(int i) { if (!serial) ctx->stream = ctx->lane[i]; }
     int end()
     {
         ctx->stream = main;
+        if (serial) return ART_HP_OK;
         for (int i = 0; i < NL; ++i) {
             ART_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ctx->lane[i]));
             ART_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[i], 0));
