@@ -7,9 +7,10 @@ bound to the library with ctypes.  There is no CPU fallback: importing works
 anywhere (so the ABI can be inspected), computing without a GPU raises.
 """
 from .api import (HotPath, HotPathError, lib_path, load_library, ABI_SYMBOLS,  # noqa: F401
-                  BAYER_AMAZE, BAYER_RCD)
+                  BAYER_AMAZE, BAYER_RCD, XTRANS_3PASS, XTRANS_1PASS)
 from .rawimagesource import RawImageSource  # noqa: F401
+from .batchqueue import BatchQueue  # noqa: F401
 from . import synth  # noqa: F401
 
-__all__ = ["HotPath", "HotPathError", "RawImageSource", "lib_path", "load_library",
-           "ABI_SYMBOLS", "BAYER_AMAZE", "BAYER_RCD", "synth"]
+__all__ = ["HotPath", "HotPathError", "RawImageSource", "BatchQueue", "lib_path", "load_library",
+           "ABI_SYMBOLS", "BAYER_AMAZE", "BAYER_RCD", "XTRANS_3PASS", "XTRANS_1PASS", "synth"]

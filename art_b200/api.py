@@ -10,6 +10,8 @@ HEADER = os.path.join(HERE, "..", "include", "art_hotpath.h")
 
 BAYER_AMAZE = 0
 BAYER_RCD = 1
+XTRANS_3PASS = 2     # art_hp_develop only
+XTRANS_1PASS = 3
 
 _c_float_p = ctypes.POINTER(ctypes.c_float)
 _c_float_pp = ctypes.POINTER(_c_float_p)
@@ -179,7 +181,8 @@ class _DevelopParamsC(ctypes.Structure):
                 ("denoise", ctypes.POINTER(_DenoiseParamsC)), ("nlStrength", ctypes.c_int), ("nlDetail", ctypes.c_int),
                 ("fattal_enabled", ctypes.c_int), ("fattal_threshold", ctypes.c_int), ("fattal_amount", ctypes.c_int),
                 ("fattal_satcontrol", ctypes.c_int), ("wprof", ctypes.POINTER(ctypes.c_double)),
-                ("sharpen", ctypes.c_void_p), ("chain", ctypes.c_void_p)]
+                ("sharpen", ctypes.c_void_p), ("chain", ctypes.c_void_p),
+                ("xtrans", ctypes.POINTER(ctypes.c_int)), ("rgb_cam", ctypes.POINTER(ctypes.c_float))]
 
 
 class _SharpenParamsC(ctypes.Structure):
@@ -261,7 +264,7 @@ class DevelopParams:
     """Parameters of art_hp_develop: the simpleprocess.cc stages on the hot path (demosaic, gains + matrix, denoise, Fattal)."""
 
     def __init__(self, method=0, filters=0x94949494, initial_gain=1.0, border=4, mul=(1.0, 1.0, 1.0), do_clip=True, cam2work=None,
-                 denoise=None, nl_strength=0, nl_detail=80, fattal=None, wprof=None, sharpen=None, chain=None):
+                 denoise=None, nl_strength=0, nl_detail=80, fattal=None, wprof=None, sharpen=None, chain=None, xtrans=None, rgb_cam=None):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
@@ -287,6 +290,12 @@ class DevelopParams:
         if self.fattal is not None:
             thr, amt, sat = self.fattal
             c.fattal_enabled, c.fattal_threshold, c.fattal_amount, c.fattal_satcontrol = 1, int(thr), int(amt), int(bool(sat))
+        if self.xtrans is not None:
+            xt = (ctypes.c_int * 36)(*[int(v) for v in np.asarray(self.xtrans).reshape(36)])
+            cam = (ctypes.c_float * 12)(*[float(v) for v in np.asarray(self.rgb_cam, dtype=np.float32).reshape(12)])
+            self._keep += [xt, cam]
+            c.xtrans = ctypes.cast(xt, ctypes.POINTER(ctypes.c_int))
+            c.rgb_cam = ctypes.cast(cam, ctypes.POINTER(ctypes.c_float))
         if self.sharpen is not None:
             sc = self.sharpen.c_struct()
             self._keep.append(sc)

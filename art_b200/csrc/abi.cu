@@ -955,8 +955,14 @@ int art_hp_redft00_2d(art_hp_ctx* ctx, int n0, int n1, const float* in, float* o
 static int check_develop(art_hp_ctx* ctx, const art_hp_develop_params* p, int W, int H)
 {
     if (!p) return ctx->fail(ART_HP_ERR_INVALID, "null parameters");
-    if (p->method != ART_HP_BAYER_AMAZE && p->method != ART_HP_BAYER_RCD) return ctx->fail(ART_HP_ERR_INVALID, "unknown demosaic method %d", p->method);
-    if (!rgb_bayer(p->filters)) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "filters 0x%08x is not an RGB Bayer pattern", p->filters);
+    if (p->method == ART_HP_XTRANS_3PASS || p->method == ART_HP_XTRANS_1PASS) {
+        if (!p->xtrans || !p->rgb_cam) return ctx->fail(ART_HP_ERR_INVALID, "X-Trans methods need xtrans and rgb_cam");
+        int rc = xtrans_check(ctx, p->method == ART_HP_XTRANS_3PASS ? 3 : 1, W, H, p->xtrans);
+        if (rc) return rc;
+    } else {
+        if (p->method != ART_HP_BAYER_AMAZE && p->method != ART_HP_BAYER_RCD) return ctx->fail(ART_HP_ERR_INVALID, "unknown demosaic method %d", p->method);
+        if (!rgb_bayer(p->filters)) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "filters 0x%08x is not an RGB Bayer pattern", p->filters);
+    }
     if (W < 32 || H < 32 || W > 32767 || H > 32767) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
     if ((p->denoise || p->fattal_enabled) && !p->wprof) return ctx->fail(ART_HP_ERR_INVALID, "wprof is required by denoise and tone mapping");
     if (p->denoise) { int rc = check_denoise_params(ctx, p->denoise, p->wprof); if (rc) return rc; }

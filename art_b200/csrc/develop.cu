@@ -128,7 +128,9 @@ int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int W, int 
                     float* r, float* g, float* b, size_t op)
 {
     int rc;
-    if (p->method == ART_HP_BAYER_AMAZE) rc = art_amaze_dev(ctx, W, H, p->filters, raw, rp, r, g, b, op, p->initialGain, p->border, 0, H);
+    if (p->method == ART_HP_XTRANS_3PASS || p->method == ART_HP_XTRANS_1PASS)
+        rc = art_xtrans_dev(ctx, p->method == ART_HP_XTRANS_3PASS ? 3 : 1, p->method == ART_HP_XTRANS_3PASS, W, H, p->xtrans, p->rgb_cam, raw, rp, r, g, b, op);
+    else if (p->method == ART_HP_BAYER_AMAZE) rc = art_amaze_dev(ctx, W, H, p->filters, raw, rp, r, g, b, op, p->initialGain, p->border, 0, H);
     else {
         rc = art_rcd_dev(ctx, W, H, p->filters, raw, rp, r, g, b, op, 0, H);
         if (!rc) rc = art_border_dev(ctx, W, H, p->filters, 9, raw, rp, r, g, b, op, 0, H);

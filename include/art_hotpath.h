@@ -47,7 +47,10 @@ typedef enum art_hp_status {
  * rtengine/rawimagesource.cc L1872-1924) */
 typedef enum art_hp_bayer_method {
     ART_HP_BAYER_AMAZE = 0,      /* RawImageSource::amaze_demosaic_RT, rtengine/amaze_demosaic_RT.cc L41-1595 */
-    ART_HP_BAYER_RCD = 1         /* RawImageSource::rcd_demosaic,      rtengine/rcd_demosaic.cc L51-347   */
+    ART_HP_BAYER_RCD = 1,        /* RawImageSource::rcd_demosaic,      rtengine/rcd_demosaic.cc L51-347   */
+    /* art_hp_develop only: RawImageSource::xtrans_interpolate(3, true) / (1, false), rtengine/rawimagesource.cc L1920-1924 */
+    ART_HP_XTRANS_3PASS = 2,
+    ART_HP_XTRANS_1PASS = 3
 } art_hp_bayer_method;
 
 typedef struct art_hp_ctx art_hp_ctx;
@@ -400,7 +403,7 @@ int art_hp_sharpen_usm_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g
  *                      denoise == NULL and fattal_enabled == 0 skip their stages, like `enabled = false` does.
  */
 typedef struct art_hp_develop_params {
-    int method;                 /* ART_HP_BAYER_AMAZE | ART_HP_BAYER_RCD */
+    int method;                 /* ART_HP_BAYER_AMAZE | ART_HP_BAYER_RCD | ART_HP_XTRANS_3PASS | ART_HP_XTRANS_1PASS */
     unsigned filters;
     double initialGain;
     int border;
@@ -416,6 +419,10 @@ typedef struct art_hp_develop_params {
      * the exposure stage runs before the sharpening and the rest after, in the reference's order. */
     const art_hp_sharpen_params* sharpen;
     const art_hp_chain_params* chain;
+    /* method == ART_HP_XTRANS_*: RawImage::getXtransMatrix (36 ints) and RawImage::getRgbCam (12 floats); `filters`, `initialGain`
+     * and `border` are not used */
+    const int* xtrans;
+    const float* rgb_cam;
 } art_hp_develop_params;
 int art_hp_develop(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
                    float* const* red, float* const* green, float* const* blue);

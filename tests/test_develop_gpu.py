@@ -196,3 +196,55 @@ def test_full_pipeline_at_100mp_properties(hot_path):
     small = hot_path.demosaic_bayer(art_b200.BAYER_AMAZE, crop, synth.RGGB, initial_gain=1.0, border=4)
     for x, y in zip(big, small):
         assert np.array_equal(x[:768 - 16, :1024 - 16], y[:768 - 16, :1024 - 16])
+
+
+def test_batchqueue_mirror_shards_and_orders_jobs(hot_path):
+    """art_b200.BatchQueue (the reference's batch loop over the batch entry): every rank's share comes back in order and equals
+    the synchronous call; the two ranks of a world of 2 cover all jobs once."""
+    W, H = 260, 228
+    params = DevelopParams(method=art_b200.BAYER_RCD, filters=synth.RGGB, mul=MUL, do_clip=True, cam2work=CAM2WORK, fattal=(30, 20, 0), wprof=PROPHOTO)
+    jobs = [synth.bayer_frame(W, H, synth.RGGB, seed=300 + k) for k in range(7)]
+    seen = []
+    for rank in range(2):
+        order = []
+        for j, planes in art_b200.BatchQueue(hot_path, jobs, params, rank=rank, world=2):
+            want = hot_path.develop(jobs[j], params)
+            for x, y in zip(planes, want):
+                assert np.array_equal(x, y)
+            order.append(j)
+        assert order == list(range(rank, 7, 2))
+        seen += order
+    assert sorted(seen) == list(range(7))
+
+
+def test_develop_xtrans_with_nlmeans_matches_oracle_chain(hot_path):
+    """BASELINE configs[3] in one call: X-Trans 3-pass demosaic -> gains / matrix -> ImProcFunctions::denoise with chroma-only
+    RGB_denoise and NL-means on Y (setMode(YUV) / NLMeans / setMode(RGB)).  No FFTW-backed stage is reached: bit-exact."""
+    import ctypes
+    from test_oracle_xtrans import CAM, port_xtrans
+    fp = ctypes.POINTER(ctypes.c_float)
+    W, H = 322, 268
+    xt = synth.xtrans_matrix(1, 3)
+    raw = synth.xtrans_frame(W, H, xt, seed=77)
+    P = oracle.port()
+    planes = port_xtrans(raw, xt, 3, 1)
+    planes = P.scale_convert(planes, MUL, True, CAM2WORK)
+    dn = (0, 0, 0, 15, 0, 0, 1.7, 1.0)
+    planes = run_chain_denoise(P.lib, planes, dn, None)
+    # Imagefloat::setMode(YUV): Y = rgbLuminance over the float working-space matrix, u = Y - b, v = r - Y; NLMeans on Y; back
+    w0, w1, w2 = [np.float32(v) for v in PROPHOTO[1]]
+    r, g, b = planes
+    Y = (r * w0 + g * w1) + b * w2
+    u, v = Y - b, r - Y
+    Yd = np.ascontiguousarray(Y).copy()
+    assert P.lib.artoracle_nlmeans(Yd.ctypes.data_as(fp), W, H, ctypes.c_float(65535.0), 50, 80, ctypes.c_float(1.0)) == 0
+    rb = v + Yd
+    bb = Yd - u
+    gb = (Yd - w0 * rb - w2 * bb) / w1
+    want = [rb, gb, bb]
+    dnp = DenoiseParams(luminance=0, luminanceDetail=0, chrominance=15, gamma=1.7)
+    params = DevelopParams(method=art_b200.XTRANS_3PASS, mul=MUL, do_clip=True, cam2work=CAM2WORK, denoise=dnp, nl_strength=50, nl_detail=80,
+                           wprof=PROPHOTO, xtrans=xt, rgb_cam=CAM)
+    got = hot_path.develop(raw, params)
+    for x, y, ch in zip(got, want, "RGB"):
+        assert np.array_equal(x, y), "%s: %d of %d differ, max %g" % (ch, int((x != y).sum()), x.size, float(np.abs(x - y).max()))
