@@ -1,29 +1,36 @@
 // X-Trans demosaic (Markesteijn, 1 or 3 passes): RawImageSource::xtrans_interpolate, cielab and xtransborder_interpolate
 // (reference rtengine/xtrans_demosaic.cc L42-116, L122-173, L181-969).
 //
-// Design.  The reference grid is kept (tiles of 114 from (3, 3), stride 98): a tile's intermediate planes are 1.0 MB
-// (1-pass) / 1.8 MB (3-pass), far beyond shared memory, so every resident CTA owns one tile slab in HBM / L2 with exactly
-// the reference's buffer layout and walks the tiles of the frame (persistent grid, static striding).  Each step of the
-// algorithm is a data-parallel loop over the tile's pixels followed by a CTA barrier; which sites a step visits, with which
-// hexagon / colour / direction plane, is computed per pixel instead of with the reference's running column toggles
-// (the test-suite's CPU restatement is organised the same way and is pinned bit-exact to the reference).
+// Design.  The reference grid is kept (tiles of 114 from (3, 3), stride 98).  One persistent 1024-thread CTA per SM walks the
+// tiles of the frame (static striding) and owns (a) a tile slab in HBM / L2 with exactly the reference's buffer layout and (b)
+// 208 KB of shared memory holding ONE direction plane (114 x 114 x 3 floats) plus the green min/max table.  The direction planes
+// of a pass never read each other, so a plane is loaded once, all passes and all their steps run on it in shared memory, it is
+// stored as direction p (pass 0) and p + 4 (passes 1-2), and its CIELab / YPbPr conversion (in place) and derivative are taken
+// before the next plane comes in.  Every step is a data-parallel loop over the tile followed by a CTA barrier; which sites a step
+// visits, with which hexagon / colour / direction plane, is computed per pixel instead of with the reference's running column
+// toggles (the test-suite's CPU restatement is organised the same way and is pinned bit-exact to the reference).  The small
+// per-sensor tables are indexed differently in every lane and therefore live in shared memory, not in the constant bank.
 //
 // The layout has to be the reference's because its sub-buffers alias (homo and the green min/max table over lab, homosum
 // over drv) and the 5x5 homogeneity sums next to the image border read homo bytes that the homogeneity step never wrote,
 // i.e. bytes of Lab / YPbPr floats and of min/max floats; those sums may pass 255, where the reference's 16-wide SSE2 path
 // saturates and its scalar tail wraps.  The slab is cleared at the start of every tile: the canonical ("det") reference.
 //
-// Algorithmic bytes: 4 B read + 12 B written per pixel = 16 B/px.  The kernel is L2 / latency bound, not
-// HBM bound: ~35 slab planes are rewritten per tile.
+// Algorithmic bytes: 4 B read + 12 B written per pixel = 16 B/px.  The kernel is latency / L2 bound, not HBM
+// bound.  Phase times at 6240 x 4160, 3-pass CIELab (tools/xtrans_phase_probe.py): mosaic + first greens 1.1 ms, passes 4.2 ms,
+// Lab + derivatives 4.9 ms (three cube-root LUT gathers per pixel and direction into a 327 KB table that no longer fits beside
+// 208 KB of shared memory in L1), homogeneity maps / 5x5 sums / selection 2.9 ms.
 #include "ctx.h"
 
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
 constexpr int TS = 114, TSH = TS / 2;
-constexpr int XT_THREADS = 512;
+constexpr int XT_THREADS = 1024;
+constexpr size_t XT_SMEM = ((size_t)TS * TS * 3 + (size_t)TS * TSH * 2) * sizeof(float);     // one direction plane + the green min/max table
 constexpr int CBRT_N = 0x14000;
 
 struct XtArgs {
@@ -38,10 +45,18 @@ struct XtArgs {
     unsigned char xt[6][6];
     unsigned char rshift[3];
     int sgrow, sgcol;
+    int stop;       // tools only (ART_XT_STOP): leave every tile after phase `stop` (0 = run everything)
 };
 
-__device__ __forceinline__ int fcol(const XtArgs& a, int row, int col) { return a.xt[row % 6][col % 6]; }
-__device__ __forceinline__ bool isgreen(const XtArgs& a, int row, int col) { return a.xt[row % 3][col % 3] & 1; }
+// The small per-sensor tables are indexed by (row % 3, col % 3) / (row % 6, col % 6), i.e. with a different index in every lane:
+// from kernel parameters (constant bank) such loads serialise per distinct address, so the kernel keeps a copy in shared memory.
+struct XtTab {
+    unsigned char xt[6][6];
+    unsigned char rshift[3];
+    signed char hexv[3][3][8], hexh[3][3][8];
+};
+__device__ __forceinline__ int fcol(const XtTab& a, int row, int col) { return a.xt[row % 6][col % 6]; }
+__device__ __forceinline__ bool isgreen(const XtTab& a, int row, int col) { return a.xt[row % 3][col % 3] & 1; }
 __device__ __forceinline__ float limf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 __device__ __forceinline__ float sqrf(float v) { return v * v; }
 __device__ __forceinline__ float lut_i(const float* __restrict__ t, int idx) { return t[idx < 0 ? 0 : (idx > CBRT_N - 1 ? CBRT_N - 1 : idx)]; }
@@ -51,7 +66,13 @@ __device__ __forceinline__ float lut_i(const float* __restrict__ t, int idx) { r
 
 __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
 {
+    extern __shared__ __align__(16) float xsm[];
+    __shared__ XtTab tb;
     const int tid = threadIdx.x;
+    if (tid < 36) tb.xt[tid / 6][tid % 6] = a.xt[tid / 6][tid % 6];
+    if (tid < 3) tb.rshift[tid] = a.rshift[tid];
+    if (tid < 72) { (&tb.hexv[0][0][0])[tid] = (&a.hexv[0][0][0])[tid]; (&tb.hexh[0][0][0])[tid] = (&a.hexh[0][0][0])[tid]; }
+    __syncthreads();
     const int ndir = a.ndir, W = a.W, H = a.H;
     float* const buffer = a.slabs + (size_t)blockIdx.x * a.slab_floats;
     float* const lab = buffer + TS * TS * (ndir * 3);                 // [3][TS-8][TS-8]
@@ -68,10 +89,12 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
         const int rows = mrow - top, cols = mcol - left;
         float* rgb = buffer;
 
-        {   // the canonical reference clears its tile buffer
+        {   // the canonical reference clears its tile buffer; what is read before it is written are the four mosaic planes
+            // (channels the mosaic does not fill, rows / columns the passes do not reach) and the lab area (as homo bytes)
             float4* b4 = reinterpret_cast<float4*>(buffer);
-            const int n4 = (int)(a.slab_floats / 4);
-            for (int i = tid; i < n4; i += XT_THREADS) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = tid; i < 4 * TS * TS * 3 / 4; i += XT_THREADS) b4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4* l4 = reinterpret_cast<float4*>(lab);
+            for (int i = tid; i < 3 * LW * LW / 4; i += XT_THREADS) l4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
 
@@ -79,18 +102,18 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
         for (int i = tid; i < rows * cols; i += XT_THREADS) {
             const int r = i / cols, c = i - r * cols, row = top + r, col = left + c;
             const float* pix = a.raw + (size_t)row * a.rp + col;
-            const int f = fcol(a, row, col);
+            const int f = fcol(tb, row, col);
             const float v = pix[0];
 #pragma unroll
             for (int d = 0; d < 4; ++d) RGB(d, r, c, f) = v;
             if (f == 1) continue;
             int src = col;
-            const bool rs = a.rshift[row % 3];
-            if (!rs && !isgreen(a, row, col + 5) && col - 1 >= left) src = col - 1;      // second pixel of a horizontal pair
+            const bool rs = tb.rshift[row % 3];
+            if (!rs && !isgreen(tb, row, col + 5) && col - 1 >= left) src = col - 1;      // second pixel of a horizontal pair
             float mn = FLT_MAX, mx = 0.f;
             {
-                const signed char* hv = a.hexv[row % 3][src % 3];
-                const signed char* hh = a.hexh[row % 3][src % 3];
+                const signed char* hv = tb.hexv[row % 3][src % 3];
+                const signed char* hh = tb.hexh[row % 3][src % 3];
                 const float* sp = a.raw + (size_t)row * a.rp + src;
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
@@ -100,8 +123,8 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
                 }
             }
             gmm[r * TSH + (c >> 1)] = make_float2(mn, mx);
-            const signed char* hv = a.hexv[row % 3][col % 3];
-            const signed char* hh = a.hexh[row % 3][col % 3];
+            const signed char* hv = tb.hexv[row % 3][col % 3];
+            const signed char* hh = tb.hexh[row % 3][col % 3];
             ptrdiff_t hex[6];
 #pragma unroll
             for (int k = 0; k < 6; ++k) hex[k] = hh[k] + (ptrdiff_t)hv[k] * (ptrdiff_t)a.rp;
@@ -118,180 +141,206 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
         }
         __syncthreads();
 
-        for (int pass = 0; pass < a.passes; ++pass) {
-            if (pass == 1) {        // memcpy(rgb += 4, buffer, 4 * sizeof *rgb), L479-481
-                const float4* s4 = reinterpret_cast<const float4*>(buffer);
-                float4* d4 = reinterpret_cast<float4*>(buffer + (size_t)4 * TS * TS * 3);
-                for (int i = tid; i < 4 * TS * TS * 3 / 4; i += XT_THREADS) d4[i] = s4[i];
-                rgb = buffer + (size_t)4 * TS * TS * 3;
-                __syncthreads();
+        if (a.stop == 1) { __syncthreads(); continue; }
+        // ---- the passes, ONE DIRECTION PLANE AT A TIME IN SHARED MEMORY.  The four planes a pass works on never read each other
+        // (the solitary-green step carries values from direction d-1 to d only within a plane), and passes 1 and 2 start from
+        // pass 0's planes (`memcpy(rgb += 4, buffer, ...)`, L479-481): plane p is loaded once, pass 0 runs and is stored as
+        // direction p, passes 1-2 run on the same shared-memory copy and are stored as direction p + 4.
+        {
+            float* const plane = xsm;                                              // [TS][TS][3]
+            float2* const sgmm = reinterpret_cast<float2*>(xsm + TS * TS * 3);     // [TS][TSH]
+            if (a.passes > 1) {
+                const float4* s4 = reinterpret_cast<const float4*>(gmm);
+                float4* d4 = reinterpret_cast<float4*>(sgmm);
+                for (int i = tid; i < TS * TSH * 2 / 4; i += XT_THREADS) d4[i] = s4[i];
             }
-            if (pass) {             // recalculate green from interpolated values of closer pixels, L483-522
-                const int nr = rows - 4, nc = cols - 4;
-                for (int i = tid; i < nr * nc; i += XT_THREADS) {
-                    const int r = 2 + i / nc, c = 2 + i % nc, row = top + r, col = left + c;
-                    const int f = fcol(a, row, col);
-                    if (f == 1) continue;
-                    const signed char* hv = a.hexv[row % 3][col % 3];
-                    const signed char* hh = a.hexh[row % 3][col % 3];
-                    const int flip = a.rshift[row % 3] ? 0 : 1;
-                    const float2 mm = gmm[r * TSH + (c >> 1)];
-#pragma unroll
-                    for (int d = 3; d < 6; ++d) {
-                        float* rix = &RGB((d - 2) ^ flip, r, c, 0);
-                        const int hx = (hh[d] + hv[d] * TS) * 3;
-                        const float val = 0.33333333f * (rix[-2 * hx + 1] + 2 * (rix[hx + 1] - rix[hx + f]) - rix[-2 * hx + f]) + rix[f];
-                        rix[1] = limf(val, mm.x, mm.y);
-                    }
-                }
-                __syncthreads();
-            }
-            {   // red and blue for solitary green pixels, L524-561
-                const int row0 = (top - a.sgrow + 4) / 3 * 3 + a.sgrow, col0 = (left - a.sgcol + 4) / 3 * 3 + a.sgcol;
-                const int nr = row0 < mrow - 2 ? (mrow - 2 - row0 + 2) / 3 : 0, nc = col0 < mcol - 2 ? (mcol - 2 - col0 + 2) / 3 : 0;
-                for (int i = tid; i < nr * nc; i += XT_THREADS) {
-                    const int row = row0 + 3 * (i / nc), col = col0 + 3 * (i % nc);
-                    int h = fcol(a, row, col + 1);
-                    float* rix = &RGB(0, row - top, col - left, 0);
-                    float diff[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    float color[3][6];
-                    int o1 = 1;
-#pragma unroll
-                    for (int d = 0; d < 6; ++d) {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const int o = (o1 << c) * 3;
-                            const float g = rix[1] + rix[1] - rix[o + 1] - rix[-o + 1];
-                            color[h][d] = g + rix[o + h] + rix[-o + h];
-                            if (d > 1) diff[d] += sqrf(rix[o + 1] - rix[-o + 1] - rix[o + h] + rix[-o + h]) + sqrf(g);
-                            h ^= 2;
+            const int sol_row0 = (top - a.sgrow + 4) / 3 * 3 + a.sgrow, sol_col0 = (left - a.sgcol + 4) / 3 * 3 + a.sgcol;
+            const int sol_nr = sol_row0 < mrow - 2 ? (mrow - 2 - sol_row0 + 2) / 3 : 0, sol_nc = sol_col0 < mcol - 2 ? (mcol - 2 - sol_col0 + 2) / 3 : 0;
+            // Derivatives of the direction plane held in shared memory, in CIELab (L657-683; cielab L65-116) or YPbPr (L684-741).
+            // The conversion is done in place over the plane's own pixels; the lab buffer in the slab is written for the LAST
+            // direction only: nothing but its final content is ever read (as homo bytes next to the image border).
+            auto labdrv = [&](int dd) {
+                if (a.useCieLab) {
+                    const int n = (rows - 8) * LW;
+                    for (int i = tid; i < n; i += XT_THREADS) {
+                        const int r = i / LW, c = i - r * LW;
+                        float* px = plane + ((4 + r) * TS + 4 + c) * 3;
+                        const float p0 = px[0], p1 = px[1], p2 = px[2];
+                        float fx, fy, fz, L;
+                        if (c < LAB_VEC_COLS) {     // 4-wide SSE2 groups (j < labWidth - 3): index rounded to nearest even by _mm_cvtps_epi32
+                            const float X = p0 * a.xyz_cam[0] + p1 * a.xyz_cam[1] + p2 * a.xyz_cam[2];
+                            const float Y = p0 * a.xyz_cam[3] + p1 * a.xyz_cam[4] + p2 * a.xyz_cam[5];
+                            const float Z = p0 * a.xyz_cam[6] + p1 * a.xyz_cam[7] + p2 * a.xyz_cam[8];
+                            fx = lut_i(a.cbrt, __float2int_rn(X)); fy = lut_i(a.cbrt, __float2int_rn(Y)); fz = lut_i(a.cbrt, __float2int_rn(Z));
+                            L = 116.f * fy - 16.f;
+                        } else {                    // scalar tail: 0.5 added first, index truncated
+                            float x0 = 0.5f, x1 = 0.5f, x2 = 0.5f;
+                            x0 += a.xyz_cam[0] * p0; x1 += a.xyz_cam[3] * p0; x2 += a.xyz_cam[6] * p0;
+                            x0 += a.xyz_cam[1] * p1; x1 += a.xyz_cam[4] * p1; x2 += a.xyz_cam[7] * p1;
+                            x0 += a.xyz_cam[2] * p2; x1 += a.xyz_cam[5] * p2; x2 += a.xyz_cam[8] * p2;
+                            fx = lut_i(a.cbrt, (int)x0); fy = lut_i(a.cbrt, (int)x1); fz = lut_i(a.cbrt, (int)x2);
+                            L = 116 * fy - 16;
                         }
-                        if (d > 2 && (d & 1))
-                            if (diff[d - 1] < diff[d]) { color[0][d] = color[0][d - 1]; color[2][d] = color[2][d - 1]; }
-                        if ((d & 1) || d < 2) {
-                            rix[0] = 0.5f * color[0][d];
-                            rix[2] = 0.5f * color[2][d];
-                            rix += TS * TS * 3;
-                        }
-                        o1 ^= TS ^ 1;
-                        h ^= 2;
+                        px[0] = L; px[1] = 500.f * (fx - fy); px[2] = 200.f * (fy - fz);
+                    }
+                } else {
+                    const int nr = rows - 8, nc = cols - 8;
+                    for (int i = tid; i < nr * nc; i += XT_THREADS) {
+                        const int r = i / nc, c = i % nc;
+                        float* px = plane + ((4 + r) * TS + 4 + c) * 3;
+                        const float p0 = px[0], p1 = px[1], p2 = px[2];
+                        const float y = 0.2627f * p0 + 0.6780f * p1 + 0.0593f * p2;
+                        px[0] = y; px[1] = (p2 - y) * 0.56433f; px[2] = (p0 - y) * 0.67815f;
                     }
                 }
                 __syncthreads();
-            }
-            {   // red for blue pixels and vice versa, L563-603
-                const int nr = rows - 6, nc = cols - 6;
-                for (int i = tid; i < nr * nc; i += XT_THREADS) {
-                    const int r = 3 + i / nc, c = 3 + i % nc, row = top + r, col = left + c;
-                    const int fc = fcol(a, row, col);
-                    if (fc == 1) continue;
-                    const int f = 2 - fc;
-                    const int cs = ((row - a.sgrow) % 3) ? TS : 1;
-                    const int hs = 3 * (cs ^ TS ^ 1);
-                    const int co = cs * 3, ho = hs * 3;
-                    float* rix = &RGB(0, r, c, 0);
-#pragma unroll
-                    for (int d = 0; d < 4; ++d, rix += TS * TS * 3) {
-                        const bool usec = d > 1 || ((d ^ cs) & 1) ||
-                                          ((fabsf(rix[1] - rix[co + 1]) + fabsf(rix[1] - rix[-co + 1])) < 2.f * (fabsf(rix[1] - rix[ho + 1]) + fabsf(rix[1] - rix[-ho + 1])));
-                        const int io = usec ? co : ho;
-                        rix[f] = rix[1] + 0.5f * (rix[io + f] + rix[-io + f] - rix[io + 1] - rix[-io + 1]);
-                    }
-                }
-                __syncthreads();
-            }
-            {   // red and blue for the 2x2 blocks of green, L605-650
-                const int nr = rows - 4, nc = cols - 4;
-                for (int i = tid; i < nr * nc; i += XT_THREADS) {
-                    const int r = 2 + i / nc, c = 2 + i % nc, row = top + r, col = left + c;
-                    if (!((row - a.sgrow) % 3) || !((col - a.sgcol) % 3)) continue;
-                    const signed char* hv = a.hexv[row % 3][col % 3];
-                    const signed char* hh = a.hexh[row % 3][col % 3];
-                    float* rix = &RGB(0, r, c, 0);
-                    for (int d = 0; d < ndir; d += 2, rix += TS * TS * 3) {
-                        const int h0 = hh[d] + hv[d] * TS, h1 = hh[d + 1] + hv[d + 1] * TS;
-                        const float* p0 = rix + h0 * 3;
-                        const float* p1 = rix + h1 * 3;
-                        if (h0 + h1) {
-                            const float g = 3 * rix[1] - 2 * p0[1] - p1[1];
-                            rix[0] = (g + 2 * p0[0] + p1[0]) * 0.33333333f;
-                            rix[2] = (g + 2 * p0[2] + p1[2]) * 0.33333333f;
+                {
+                    const int q = dd & 3;           // dir[d & 3] = {1, ts, ts + 1, ts - 1} as a (row, column) step
+                    const int fo = (q == 0 ? 1 : (q == 1 ? TS : (q == 2 ? TS + 1 : TS - 1))) * 3;
+                    const int nr = rows - 10, nc = cols - 10;
+                    for (int i = tid; i < nr * nc; i += XT_THREADS) {
+                        const int r = 5 + i / nc, c = 5 + i % nc;
+                        const float* l = plane + (r * TS + c) * 3;
+                        float v;
+                        if (a.useCieLab) {
+                            const float g = 2 * l[0] - l[fo] - l[-fo];
+                            v = sqrf(g) + sqrf((2 * l[1] - l[fo + 1] - l[-fo + 1] + g * 2.1551724f)) + sqrf((2 * l[2] - l[fo + 2] - l[-fo + 2] - g * 0.86206896f));
                         } else {
-                            const float g = 2 * rix[1] - p0[1] - p1[1];
-                            rix[0] = (g + p0[0] + p1[0]) * 0.5f;
-                            rix[2] = (g + p0[2] + p1[2]) * 0.5f;
+                            v = sqrf(2 * l[0] - l[fo] - l[-fo]) + sqrf(2 * l[1] - l[fo + 1] - l[-fo + 1]) + sqrf(2 * l[2] - l[fo + 2] - l[-fo + 2]);
                         }
+                        drv[(size_t)dd * DW * DW + (r - 5) * DW + (c - 5)] = v;
+                    }
+                }
+                if (dd == ndir - 1) {               // the lab buffer's final content
+                    const int nr = rows - 8, nc = a.useCieLab ? LW : cols - 8;
+                    for (int i = tid; i < nr * nc; i += XT_THREADS) {
+                        const int r = i / nc, c = i % nc;
+                        const float* px = plane + ((4 + r) * TS + 4 + c) * 3;
+                        lab[r * LW + c] = px[0]; lab[LW * LW + r * LW + c] = px[1]; lab[2 * LW * LW + r * LW + c] = px[2];
                     }
                 }
                 __syncthreads();
+            };
+            for (int p = 0; p < 4; ++p) {
+                {
+                    const float4* s4 = reinterpret_cast<const float4*>(buffer + (size_t)p * TS * TS * 3);
+                    float4* d4 = reinterpret_cast<float4*>(plane);
+                    for (int i = tid; i < TS * TS * 3 / 4; i += XT_THREADS) d4[i] = s4[i];
+                }
+                __syncthreads();
+                for (int pass = 0; pass < a.passes; ++pass) {
+                    if (pass) {             // recalculate green from interpolated values of closer pixels, L483-522
+                        const int nr = rows - 4, nc = cols - 4;
+                        for (int i = tid; i < nr * nc; i += XT_THREADS) {
+                            const int r = 2 + i / nc, c = 2 + i % nc, row = top + r, col = left + c;
+                            const int f = fcol(tb, row, col);
+                            if (f == 1) continue;
+                            const int q = p ^ (tb.rshift[row % 3] ? 0 : 1);          // plane (d - 2) ^ flip == p  <=>  d = q + 2, d in 3 .. 5
+                            if (q == 0) continue;
+                            const int d = q + 2;
+                            const int hx = (tb.hexh[row % 3][col % 3][d] + tb.hexv[row % 3][col % 3][d] * TS) * 3;
+                            const float2 mm = sgmm[r * TSH + (c >> 1)];
+                            float* rix = plane + (r * TS + c) * 3;
+                            const float val = 0.33333333f * (rix[-2 * hx + 1] + 2 * (rix[hx + 1] - rix[hx + f]) - rix[-2 * hx + f]) + rix[f];
+                            rix[1] = limf(val, mm.x, mm.y);
+                        }
+                        __syncthreads();
+                    }
+                    // red and blue for solitary green pixels, L524-561: plane 0 <- d = 0, plane 1 <- d = 1, plane 2 <- d = 2, 3, plane 3 <- d = 4, 5
+                    for (int i = tid; i < sol_nr * sol_nc; i += XT_THREADS) {
+                        const int row = sol_row0 + 3 * (i / sol_nc), col = sol_col0 + 3 * (i % sol_nc);
+                        const int h0 = fcol(tb, row, col + 1);
+                        float* rix = plane + ((row - top) * TS + (col - left)) * 3;
+                        const int dfirst = p < 2 ? p : 2 * p - 2, dlast = p < 2 ? p : 2 * p - 1;
+                        float color[3][2], diff[2] = {0.f, 0.f};
+                        for (int d = dfirst; d <= dlast; ++d) {
+                            const int k = d - dfirst;
+                            int h = h0 ^ ((d & 1) << 1);
+                            const int o1 = (d & 1) ? TS : 1;
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                const int o = (o1 << c) * 3;
+                                const float g = rix[1] + rix[1] - rix[o + 1] - rix[-o + 1];
+                                color[h][k] = g + rix[o + h] + rix[-o + h];
+                                if (d > 1) diff[k] += sqrf(rix[o + 1] - rix[-o + 1] - rix[o + h] + rix[-o + h]) + sqrf(g);
+                                h ^= 2;
+                            }
+                            if (d > 2 && (d & 1))
+                                if (diff[0] < diff[1]) { color[0][1] = color[0][0]; color[2][1] = color[2][0]; }
+                            if ((d & 1) || d < 2) {
+                                rix[0] = 0.5f * color[0][k];
+                                rix[2] = 0.5f * color[2][k];
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    {   // red for blue pixels and vice versa, L563-603
+                        const int nr = rows - 6, nc = cols - 6;
+                        for (int i = tid; i < nr * nc; i += XT_THREADS) {
+                            const int r = 3 + i / nc, c = 3 + i % nc, row = top + r, col = left + c;
+                            const int fc = fcol(tb, row, col);
+                            if (fc == 1) continue;
+                            const int f = 2 - fc;
+                            const int cs = ((row - a.sgrow) % 3) ? TS : 1;
+                            const int hs = 3 * (cs ^ TS ^ 1);
+                            const int co = cs * 3, ho = hs * 3;
+                            float* rix = plane + (r * TS + c) * 3;
+                            const bool usec = p > 1 || ((p ^ cs) & 1) ||
+                                              ((fabsf(rix[1] - rix[co + 1]) + fabsf(rix[1] - rix[-co + 1])) < 2.f * (fabsf(rix[1] - rix[ho + 1]) + fabsf(rix[1] - rix[-ho + 1])));
+                            const int io = usec ? co : ho;
+                            rix[f] = rix[1] + 0.5f * (rix[io + f] + rix[-io + f] - rix[io + 1] - rix[-io + 1]);
+                        }
+                    }
+                    __syncthreads();
+                    if (2 * p < ndir) {     // red and blue for the 2x2 blocks of green, L605-650: `for (d = 0; d < ndir; d += 2)` reaches planes d / 2
+                        const int nr = rows - 4, nc = cols - 4;
+                        for (int i = tid; i < nr * nc; i += XT_THREADS) {
+                            const int r = 2 + i / nc, c = 2 + i % nc, row = top + r, col = left + c;
+                            if (!((row - a.sgrow) % 3) || !((col - a.sgcol) % 3)) continue;
+                            const signed char* hv = tb.hexv[row % 3][col % 3];
+                            const signed char* hh = tb.hexh[row % 3][col % 3];
+                            float* rix = plane + (r * TS + c) * 3;
+                            const int d = 2 * p;
+                            const int h0 = hh[d] + hv[d] * TS, h1 = hh[d + 1] + hv[d + 1] * TS;
+                            const float* p0 = rix + h0 * 3;
+                            const float* p1 = rix + h1 * 3;
+                            if (h0 + h1) {
+                                const float g = 3 * rix[1] - 2 * p0[1] - p1[1];
+                                rix[0] = (g + 2 * p0[0] + p1[0]) * 0.33333333f;
+                                rix[2] = (g + 2 * p0[2] + p1[2]) * 0.33333333f;
+                            } else {
+                                const float g = 2 * rix[1] - p0[1] - p1[1];
+                                rix[0] = (g + p0[0] + p1[0]) * 0.5f;
+                                rix[2] = (g + p0[2] + p1[2]) * 0.5f;
+                            }
+                        }
+                        __syncthreads();
+                    }
+                    if (pass == 0 || pass == a.passes - 1) {
+                        float4* d4 = reinterpret_cast<float4*>(buffer + (size_t)(pass == 0 ? p : p + 4) * TS * TS * 3);
+                        const float4* s4 = reinterpret_cast<const float4*>(plane);
+                        for (int i = tid; i < TS * TS * 3 / 4; i += XT_THREADS) d4[i] = s4[i];
+                        __syncthreads();
+                    }
+                }
+                if (a.stop == 2) continue;
+                if (a.passes > 1) {         // shared memory holds direction p + 4; direction p comes back from the slab afterwards
+                    labdrv(p + 4);
+                    const float4* s4 = reinterpret_cast<const float4*>(buffer + (size_t)p * TS * TS * 3);
+                    float4* d4 = reinterpret_cast<float4*>(plane);
+                    for (int i = tid; i < TS * TS * 3 / 4; i += XT_THREADS) d4[i] = s4[i];
+                    __syncthreads();
+                }
+                labdrv(p);
             }
         }
 
         rgb = buffer;
         mrow = rows;
         mcol = cols;
+        if (a.stop == 2) { __syncthreads(); continue; }
 
-        // derivatives of every direction plane in CIELab (L657-683) or YPbPr (L684-741)
-        for (int d = 0; d < ndir; ++d) {
-            if (a.useCieLab) {          // cielab(&rgb[d][4][4], lab, ts, mrow - 8, ts - 8, xyz_cam), L65-116
-                const int n = (mrow - 8) * LW;
-                for (int i = tid; i < n; i += XT_THREADS) {
-                    const int r = i / LW, c = i - r * LW;
-                    const float* p = &RGB(d, 4 + r, 4 + c, 0);
-                    float fx, fy, fz;
-                    if (c < LAB_VEC_COLS) {
-                        // 4-wide SSE2 groups (j < labWidth - 3): index rounded to nearest even by _mm_cvtps_epi32
-                        const float X = p[0] * a.xyz_cam[0] + p[1] * a.xyz_cam[1] + p[2] * a.xyz_cam[2];
-                        const float Y = p[0] * a.xyz_cam[3] + p[1] * a.xyz_cam[4] + p[2] * a.xyz_cam[5];
-                        const float Z = p[0] * a.xyz_cam[6] + p[1] * a.xyz_cam[7] + p[2] * a.xyz_cam[8];
-                        fx = lut_i(a.cbrt, __float2int_rn(X)); fy = lut_i(a.cbrt, __float2int_rn(Y)); fz = lut_i(a.cbrt, __float2int_rn(Z));
-                        lab[i] = 116.f * fy - 16.f;
-                    } else {            // scalar tail: 0.5 added first, index truncated
-                        float x0 = 0.5f, x1 = 0.5f, x2 = 0.5f;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            x0 += a.xyz_cam[k] * p[k]; x1 += a.xyz_cam[3 + k] * p[k]; x2 += a.xyz_cam[6 + k] * p[k];
-                        }
-                        fx = lut_i(a.cbrt, (int)x0); fy = lut_i(a.cbrt, (int)x1); fz = lut_i(a.cbrt, (int)x2);
-                        lab[i] = 116 * fy - 16;
-                    }
-                    lab[LW * LW + i] = 500.f * (fx - fy);
-                    lab[2 * LW * LW + i] = 200.f * (fy - fz);
-                }
-            } else {
-                const int nr = mrow - 8, nc = mcol - 8;
-                for (int i = tid; i < nr * nc; i += XT_THREADS) {
-                    const int r = i / nc, c = i % nc;
-                    const float* p = &RGB(d, 4 + r, 4 + c, 0);
-                    const float y = 0.2627f * p[0] + 0.6780f * p[1] + 0.0593f * p[2];
-                    lab[r * LW + c] = y;
-                    lab[LW * LW + r * LW + c] = (p[2] - y) * 0.56433f;
-                    lab[2 * LW * LW + r * LW + c] = (p[0] - y) * 0.67815f;
-                }
-            }
-            __syncthreads();
-            {
-                const int dd = d & 3;
-                const int f = dd == 0 ? 1 : (dd == 1 ? TS : (dd == 2 ? TS + 1 : TS - 1)) - (dd == 0 ? 0 : 8);
-                const int nr = mrow - 10, nc = mcol - 10;
-                for (int i = tid; i < nr * nc; i += XT_THREADS) {
-                    const int r = 5 + i / nc, c = 5 + i % nc;
-                    const float* l = lab + (r - 4) * LW + (c - 4);
-                    const float* aa = l + LW * LW;
-                    const float* bb = aa + LW * LW;
-                    float v;
-                    if (a.useCieLab) {
-                        const float g = 2 * l[0] - l[f] - l[-f];
-                        v = sqrf(g) + sqrf((2 * aa[0] - aa[f] - aa[-f] + g * 2.1551724f)) + sqrf((2 * bb[0] - bb[f] - bb[-f] - g * 0.86206896f));
-                    } else {
-                        v = sqrf(2 * l[0] - l[f] - l[-f]) + sqrf(2 * aa[0] - aa[f] - aa[-f]) + sqrf(2 * bb[0] - bb[f] - bb[-f]);
-                    }
-                    drv[(size_t)d * DW * DW + (r - 5) * DW + (c - 5)] = v;
-                }
-            }
-            __syncthreads();
-        }
-
+        if (a.stop == 3) { __syncthreads(); continue; }
         {   // homogeneity maps, L743-811
             const int nr = mrow - 12, nc = mcol - 12;
             for (int i = tid; i < nr * nc; i += XT_THREADS) {
@@ -313,6 +362,7 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
         }
         __syncthreads();
 
+        if (a.stop == 4) { __syncthreads(); continue; }
         if (H - top < TS + 4) mrow = H - top + 2;
         if (W - left < TS + 4) mcol = W - left + 2;
         const int startrow = min(top, 8), startcol = min(left, 8);
@@ -336,6 +386,7 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
         }
         __syncthreads();
 
+        if (a.stop == 5) { __syncthreads(); continue; }
         {   // maximum minus an eighth (L870-911) and the average of the most homogeneous directions (L914-949)
             const int nr = mrow - 8 - startrow, nc = mcol - 8 - startcol;
             const int n = nr > 0 && nc > 0 ? nr * nc : 0;
@@ -420,6 +471,7 @@ int art_xtrans_dev(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, con
     XtArgs a{};
     a.raw = raw; a.rp = rp; a.R = R; a.G = G; a.B = B; a.op = op; a.W = W; a.H = H;
     a.passes = passes; a.ndir = 4 << (passes > 1); a.useCieLab = useCieLab;
+    { const char* e = getenv("ART_XT_STOP"); a.stop = e ? atoi(e) : 0; }
     for (int i = 0; i < 36; ++i) a.xt[i / 6][i % 6] = (unsigned char)xtrans36[i];
     for (int i = 0; i < 3; i++)          // L224-232, float arithmetic
         for (int j = 0; j < 3; j++) {
@@ -465,11 +517,13 @@ int art_xtrans_dev(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, con
     const int ntiles = a.ntx * a.nty;
     if (ntiles > 0) {
         a.slab_floats = round_up((size_t)TS * TS * (a.ndir * 4 + 3) + 128, 32);
-        const int grid = std::min(ntiles, ctx->sm_count * 2);
+        const int grid = std::min(ntiles, ctx->sm_count);       // one 1024-thread CTA (208 KB of shared memory) per SM
+        static bool attr = false;
+        if (!attr) { ART_CUDA(ctx, cudaFuncSetAttribute(k_xtrans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XT_SMEM)); attr = true; }
         if ((rc = art_reserve(ctx, ctx->d_scratch, (size_t)grid * a.slab_floats * sizeof(float)))) return rc;
         a.slabs = (float*)ctx->d_scratch.p;
         art_prof_begin(ctx, "k_xtrans");
-        k_xtrans<<<grid, XT_THREADS, 0, st>>>(a);
+        k_xtrans<<<grid, XT_THREADS, XT_SMEM, st>>>(a);
         art_prof_end(ctx);
         ctx->launches++;
     }
