@@ -369,6 +369,11 @@ inline float sqrf(float x) { return x * x; }
 
 }  // namespace
 
+// shrink.cu, internal forms: `uniform` != nullptr says the noise-variance map is that one value everywhere
+int art_wavelet_denoise_L(art_hp_ctx* ctx, art_hp_wavelet* wL, const float* d_noisevarlum, const float* uniform, const float* d_madL, double scale);
+int art_wavelet_denoise_AB(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom, const float* uniform,
+                           const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale);
+
 extern "C" {
 int art_hp_wavelet_decompose_dev(art_hp_ctx* ctx, const float* d_src, size_t pitch, int W, int H, int maxlvl, int subsampling, art_hp_wavelet** out);
 int art_hp_wavelet_maxlevel(const art_hp_wavelet* w);
@@ -554,7 +559,10 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
     for (int c = 0; c < 2; ++c) {
         art_hp_wavelet* dec = nullptr;
         if ((rc = art_hp_wavelet_decompose_dev(ctx, chan[c], W, W, H, levwav, 1, &dec))) { art_hp_wavelet_destroy(Ldec); return rc; }
-        rc = art_hp_wavelet_denoise_AB_dev(ctx, Ldec, dec, nvc, madL, nv[c], useCC, 0, scale);
+        {   // without the chroma noise curve the chroma variance map is 1 everywhere (L2098-2100): passed as a value, not read
+            const float one = 1.f;
+            rc = art_wavelet_denoise_AB(ctx, Ldec, dec, nvc, useCC ? nullptr : &one, madL, nv[c], useCC, 0, scale);
+        }
         if (!rc && nresi_highresi) rc = residual_mads(ctx, dec, resid + 24 * c);
         if (!rc) rc = art_hp_wavelet_reconstruct_dev(dec, chan[c], W, 1.f);
         art_hp_wavelet_destroy(dec);
@@ -562,7 +570,7 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
     }
     const int maxlvl = art_hp_wavelet_maxlevel(Ldec);
     if (denoiseLuminance) {
-        rc = art_hp_wavelet_denoise_L_dev(ctx, Ldec, nvl, madL, scale);
+        rc = art_wavelet_denoise_L(ctx, Ldec, nvl, &noisevarL, madL, scale);       // the luminance variance map is noisevarL everywhere (L2097)
         if (!rc) {
             if (cudaMemcpyAsync(Lin, Lp, n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = ctx->fail(ART_HP_ERR_CUDA, "Lin copy failed");
         }

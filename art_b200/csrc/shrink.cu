@@ -75,6 +75,7 @@ struct ShArgs {
     float* c; const float* cL; const float* nv; float* sf; const float* sfd;
     const float* mad; int n; float lvlmul; float noisevar_ab; int useCCurve;
     const float* madab;
+    int nv_uniform; float nv_value;      // the noise-variance map holds one value everywhere: it is passed instead of read
 };
 
 __global__ void __launch_bounds__(256) k_sf_L(ShArgs a)
@@ -83,13 +84,14 @@ __global__ void __launch_bounds__(256) k_sf_L(ShArgs a)
     const float levelFactor = a.mad[0] * 5.f / a.lvlmul;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
         const float x = a.c[i];
+        const float nvi = a.nv_uniform ? a.nv_value : a.nv[i];
         const float mag = x * x;
         float r;
         if ((i & ~3) < a.n - 3) {      // handled by a full 4-wide vector in the reference (for (i = 0; i < n - 3; i += 4))
-            const float mad = a.nv[i] * levelFactor;
+            const float mad = nvi * levelFactor;
             r = mag / (mag + mad * xexpf_vector(-mag / (9.0f * mad)) + eps);
         } else {
-            r = mag / (mag + levelFactor * a.nv[i] * xexpf_scalar(-mag / (9 * levelFactor * a.nv[i])) + eps);
+            r = mag / (mag + levelFactor * nvi * xexpf_scalar(-mag / (9 * levelFactor * nvi)) + eps);
         }
         a.sf[i] = r;
     }
@@ -103,15 +105,16 @@ __global__ void __launch_bounds__(256) k_sf_AB(ShArgs a)
     const float rmadLm9 = 1.f / (mad_L * 9.f);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
         const float xl = a.cL[i], xab = a.c[i];
+        const float nvi = a.nv_uniform ? a.nv_value : a.nv[i];
         float r;
         if ((i & ~3) < a.n - 3) {
-            const float mad_ab = a.nv[i] * madab;
+            const float mad_ab = nvi * madab;
             const float mag_ab = xab * xab;
             const float mag_L = (xl * xl) * rmadLm9;
             r = 1.f - xexpf_vector(-(mag_ab / mad_ab) - (mag_L));
         } else {
             const float mag_L = xl * xl, mag_ab = xab * xab;
-            r = (1.f - xexpf_scalar(-(mag_ab / (a.nv[i] * madab)) - (mag_L / (9.f * mad_L))));
+            r = (1.f - xexpf_scalar(-(mag_ab / (nvi * madab)) - (mag_L / (9.f * mad_L))));
         }
         a.sf[i] = r;
     }
@@ -362,9 +365,26 @@ int art_hp_wavelet_mad_dev(art_hp_ctx* ctx, const art_hp_wavelet* w, float* d_ma
     return ART_HP_OK;
 }
 
+}  // extern "C"
+
+// internal forms: `uniform` != nullptr says the noise-variance map is that one value everywhere (the map pointer is then unused)
+int art_wavelet_denoise_L(art_hp_ctx* ctx, art_hp_wavelet* wL, const float* d_noisevarlum, const float* uniform, const float* d_madL, double scale);
+int art_wavelet_denoise_AB(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom, const float* uniform,
+                           const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale);
+
+extern "C" {
+
 int art_hp_wavelet_denoise_L_dev(art_hp_ctx* ctx, art_hp_wavelet* wL, const float* d_noisevarlum, const float* d_madL, double scale)
 {
-    if (!ctx || !wL || !d_noisevarlum || !d_madL || !(scale > 0)) return ART_HP_ERR_INVALID;
+    if (!d_noisevarlum) return ART_HP_ERR_INVALID;
+    return art_wavelet_denoise_L(ctx, wL, d_noisevarlum, nullptr, d_madL, scale);
+}
+
+}  // extern "C"
+
+int art_wavelet_denoise_L(art_hp_ctx* ctx, art_hp_wavelet* wL, const float* d_noisevarlum, const float* uniform, const float* d_madL, double scale)
+{
+    if (!ctx || !wL || (!d_noisevarlum && !uniform) || !d_madL || !(scale > 0)) return ART_HP_ERR_INVALID;
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
     const int maxlvl = std::min(wL->nlev, 5);      // L1115
     Scratch s[NL];
@@ -377,6 +397,7 @@ int art_hp_wavelet_denoise_L_dev(art_hp_ctx* ctx, art_hp_wavelet* wL, const floa
             const WLevel& L = wL->lev[l];
             ShArgs a{};
             a.c = L.band[d]; a.nv = d_noisevarlum; a.mad = d_madL + 3 * l + (d - 1); a.n = L.w2 * L.h2; a.lvlmul = (float)(l + 1);
+            a.nv_uniform = uniform != nullptr; a.nv_value = uniform ? *uniform : 0.f;
             const int ln = (3 * l + d - 1) % NL;
             lanes.lane_of(ln);
             rc = shrink_band(ctx, s[ln], a, L.w2, L.h2, blur_radius(l, scale), false);
@@ -385,10 +406,17 @@ int art_hp_wavelet_denoise_L_dev(art_hp_ctx* ctx, art_hp_wavelet* wL, const floa
     return rc ? rc : rc2;
 }
 
-int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom,
-                                  const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale)
+extern "C" int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom,
+                                             const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale)
 {
-    if (!ctx || !wL || !wab || !d_noisevarchrom || !d_madL || !(scale > 0)) return ART_HP_ERR_INVALID;
+    if (!d_noisevarchrom) return ART_HP_ERR_INVALID;
+    return art_wavelet_denoise_AB(ctx, wL, wab, d_noisevarchrom, nullptr, d_madL, noisevar_ab, useNoiseCCurve, autoch, scale);
+}
+
+int art_wavelet_denoise_AB(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom, const float* uniform,
+                           const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale)
+{
+    if (!ctx || !wL || !wab || (!d_noisevarchrom && !uniform) || !d_madL || !(scale > 0)) return ART_HP_ERR_INVALID;
     if (wL->nlev != wab->nlev || wL->W != wab->W || wL->H != wab->H) return ctx->fail(ART_HP_ERR_INVALID, "L and ab decompositions differ in shape");
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
     if (autoch && noisevar_ab <= 0.001f) noisevar_ab = 0.02f;     // L737-739
@@ -409,10 +437,9 @@ int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art
             ShArgs a{};
             a.c = L.band[d]; a.cL = wL->lev[l].band[d]; a.nv = d_noisevarchrom; a.mad = d_madL + 3 * l + (d - 1); a.n = n;
             a.noisevar_ab = noisevar_ab; a.useCCurve = useNoiseCCurve; a.madab = sc.madab;
+            a.nv_uniform = uniform != nullptr; a.nv_value = uniform ? *uniform : 0.f;
             rc = shrink_band(ctx, sc, a, L.w2, L.h2, blur_radius(l, scale), true);
         }
     const int rc2 = lanes.end();
     return rc ? rc : rc2;
 }
-
-}  // extern "C"
