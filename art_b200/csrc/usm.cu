@@ -128,12 +128,67 @@ __global__ void __launch_bounds__(256) k_usm_apply(float* __restrict__ R, float*
     }
 }
 
+// unsharp_mask with halo control: sharpenHaloCtrl (ipsharpen.cc L80-141) over a copy of the gamma-encoded luminance, then the same
+// tail as k_usm_apply.  The reference slides a two-entry max / min queue along each row (both entries start at 0); here every
+// pixel recomputes the three 3x3-window statistics of columns j-2, j-1, j from the 5x5 neighbourhood it holds in registers.
+__global__ void __launch_bounds__(256) k_usm_apply_halo(float* __restrict__ R, float* __restrict__ G, float* __restrict__ B, size_t ip,
+                                                        const float* __restrict__ Y, const float* __restrict__ YY, const float* __restrict__ b2,
+                                                        const float* __restrict__ blend, size_t yp, int W, int H, int amount, int halo_amount, Thr thr,
+                                                        const float* __restrict__ glut_rev)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const float scl = (100.f - halo_amount) * 0.01f;
+    const float sharpFac = amount * 0.01f;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const size_t i = (size_t)y * ip + x, o = (size_t)y * yp + x;
+        const float labL = YY[o], den = Y[o];
+        float v = labL;
+        if (y >= 2 && y < H - 2 && x >= 2 && x < W - 2) {
+            // nL[y-2 .. y+2][x-2 .. x+2]; columns left of 0 are never used (their windows belong to j < 2, which count as 0)
+            float n[5][5];
+#pragma unroll
+            for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 5; ++dx) n[dy][dx] = YY[o + (ptrdiff_t)(dy - 2) * (ptrdiff_t)yp + (dx - 2)];
+            float mx[3], mn[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {           // window statistics of column j = x - 2 + k (columns k .. k + 2 of n)
+                float np[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q)         // rows q .. q + 2 of n: np1 (rows y-2..y), np2, np3
+                    np[q] = 2.f * (n[q][k] + n[q][k + 1] + n[q][k + 2] + n[q + 1][k] + n[q + 1][k + 1] + n[q + 1][k + 2] + n[q + 2][k] + n[q + 2][k + 1] + n[q + 2][k + 2]) / 27.f +
+                            n[q + 1][k + 1] / 3.f;
+                mx[k] = maxr(maxr(np[0], np[1]), np[2]);
+                mn[k] = minr(minr(np[0], np[1]), np[2]);
+            }
+            const float max1 = x - 2 >= 2 ? mx[0] : 0.f, max2 = x - 1 >= 2 ? mx[1] : 0.f;
+            const float min1 = x - 2 >= 2 ? mn[0] : 0.f, min2 = x - 1 >= 2 ? mn[1] : 0.f;
+            float max_ = maxr(maxr(max1, max2), mx[2]), min_ = minr(minr(min1, min2), mn[2]);
+            if (max_ < labL) max_ = labL;
+            if (min_ > labL) min_ = labL;
+            const float diff = labL - b2[o];
+            const float delta = threshold_multiply(thr, minr(fabsf(diff), 2000.f), sharpFac * diff);
+            float newL = labL + delta;
+            if (newL > max_) newL = max_ + (newL - max_) * scl;
+            else if (newL < min_) newL = min_ - (min_ - newL) * scl;
+            const float bl = blend[o];
+            v = bl * newL + (1.f - bl) * labL;
+        }
+        v = gamma_apply(glut_rev, v, 3.f);
+        if (den > 0.f) {
+            const float f = v / den;
+            R[i] *= f; G[i] *= f; B[i] *= f;
+        }
+    }
+}
+
 }  // namespace
 
 int art_usm_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_sharpen_params* p, const double* ws9)
 {
     if (p->amount < 1 || W < 8 || H < 8) return ART_HP_OK;      // doSharpening L716-718
-    if (p->halocontrol || p->edgesonly) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "halo control / edges-only sharpening are not on the hot path");
+    if (p->edgesonly) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "edges-only sharpening (bilateral pre-filter) is not on the hot path");
     cudaStream_t st = ctx->stream;
     int rc;
     if (!ctx->usm_tables_ready) {
@@ -173,7 +228,8 @@ int art_usm_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W,
 
     const Thr thr{(double)p->threshold[0], (double)p->threshold[1], (double)p->threshold[2], (double)p->threshold[3]};
     art_prof_begin(ctx, "k_usm_apply");
-    k_usm_apply<<<grid, blk, 0, st>>>(r, g, b, ip, Y, YY, b2, blend, yp, W, H, p->amount, thr, glut + 65536);
+    if (p->halocontrol) k_usm_apply_halo<<<grid, blk, 0, st>>>(r, g, b, ip, Y, YY, b2, blend, yp, W, H, p->amount, p->halocontrol_amount, thr, glut + 65536);
+    else k_usm_apply<<<grid, blk, 0, st>>>(r, g, b, ip, Y, YY, b2, blend, yp, W, H, p->amount, thr, glut + 65536);
     art_prof_end(ctx);
     ctx->launches++;
     ART_CUDA(ctx, cudaGetLastError());

@@ -371,7 +371,7 @@ int art_hp_color_chain_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g
  *                      defaults rtengine/procparams.cc L1756-1776); threshold = {bottom_left, top_left, bottom_right,
  *                      top_right}; scale = ImProcFunctions::scale (1 for full-resolution output); ws =
  *                      ICCStore::workingSpaceMatrix.  amount < 1 or an image under 8x8 returns untouched, like the
- *                      reference (L716-718).  edgesonly / halocontrol return ART_HP_ERR_UNSUPPORTED.  Bit-identical to the
+ *                      reference (L716-718).  halocontrol runs sharpenHaloCtrl (L80-141); edgesonly returns ART_HP_ERR_UNSUPPORTED.  Bit-identical to the
  *                      reference's SSE2 build.
  */
 typedef struct art_hp_sharpen_params {
@@ -380,7 +380,7 @@ typedef struct art_hp_sharpen_params {
     int    amount;              /* 200 */
     int    threshold[4];        /* 20, 80, 2000, 1200 */
     int    edgesonly;           /* must be 0 */
-    int    halocontrol;         /* must be 0 */
+    int    halocontrol;         /* 0 | 1 */
     int    halocontrol_amount;
     double scale;               /* 1 */
 } art_hp_sharpen_params;

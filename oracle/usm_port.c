@@ -3,7 +3,7 @@
  * TEST INFRASTRUCTURE ONLY: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use it.
  *
  * Follows reference rtengine/: ipsharpen.cc ImProcFunctions::doSharpening L711-790 ("usm" route), apply_gamma L46-78,
- * unsharp_mask L232-312 (edgesonly == false, halocontrol == false); rt_algo.cc calcBlendFactor L47-63, buildBlendMask
+ * sharpenHaloCtrl L80-141, unsharp_mask L232-312 (edgesonly == false); rt_algo.cc calcBlendFactor L47-63, buildBlendMask
  * L315-496 (autoContrast == false), get_luminance L942-956, multiply L958-975; procparams.h Threshold<T>::multiply
  * L445-503; color.h rgbLuminance L203-207; LUT.h operator[](float) L437-459; gauss.cc through oracle/gauss_port.c.
  *
@@ -109,9 +109,7 @@ int artoracle_blend_mask(const float* lum, float* blend, int W, int H, float con
 int artoracle_usm(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double radius, int amount,
                   const int* thr, int halocontrol, int halocontrol_amount, float* blend_out)
 {
-    (void)halocontrol_amount;
     if (amount < 1 || W < 8 || H < 8) return 0;
-    if (halocontrol) return 1;
     const size_t n = (size_t)W * H;
     const float w0 = (float)wsd[3], w1 = (float)wsd[4], w2 = (float)wsd[5];
     float* Y = (float*)malloc(sizeof(float) * n);
@@ -127,10 +125,41 @@ int artoracle_usm(float* R, float* G, float* B, int W, int H, const double* wsd,
     /* unsharp_mask */
     apply_gamma(YY, n, 3.f, 0);
     if (!rc) rc = artoracle_gauss(YY, W, b2, W, W, H, radius / scale);
-    for (size_t k = 0; k < n; ++k) {
-        const float diff = YY[k] - b2[k];
-        const float delta = threshold_multiply(thr, minr(fabsf(diff), 2000.f), amount * diff * 0.01f);
-        YY[k] = blend[k] * (YY[k] + delta) + (1.f - blend[k]) * YY[k];
+    if (!halocontrol) {
+        for (size_t k = 0; k < n; ++k) {
+            const float diff = YY[k] - b2[k];
+            const float delta = threshold_multiply(thr, minr(fabsf(diff), 2000.f), amount * diff * 0.01f);
+            YY[k] = blend[k] * (YY[k] + delta) + (1.f - blend[k]) * YY[k];
+        }
+    } else {        /* sharpenHaloCtrl(Y, b2, labCopy, blend, ...), L80-141: base is a copy of Y taken before the loop (L289-299) */
+        const float scl = (100.f - halocontrol_amount) * 0.01f;
+        const float sharpFac = amount * 0.01f;
+        float* nL = (float*)malloc(sizeof(float) * n);
+        memcpy(nL, YY, sizeof(float) * n);
+#define NL(i, j) nL[(size_t)(i) * W + (j)]
+        for (int i = 2; i < H - 2; i++) {
+            float max1 = 0, max2 = 0, min1 = 0, min2 = 0;
+            for (int j = 2; j < W - 2; j++) {
+                const float np1 = 2.f * (NL(i - 2, j) + NL(i - 2, j + 1) + NL(i - 2, j + 2) + NL(i - 1, j) + NL(i - 1, j + 1) + NL(i - 1, j + 2) + NL(i, j) + NL(i, j + 1) + NL(i, j + 2)) / 27.f + NL(i - 1, j + 1) / 3.f;
+                const float np2 = 2.f * (NL(i - 1, j) + NL(i - 1, j + 1) + NL(i - 1, j + 2) + NL(i, j) + NL(i, j + 1) + NL(i, j + 2) + NL(i + 1, j) + NL(i + 1, j + 1) + NL(i + 1, j + 2)) / 27.f + NL(i, j + 1) / 3.f;
+                const float np3 = 2.f * (NL(i, j) + NL(i, j + 1) + NL(i, j + 2) + NL(i + 1, j) + NL(i + 1, j + 1) + NL(i + 1, j + 2) + NL(i + 2, j) + NL(i + 2, j + 1) + NL(i + 2, j + 2)) / 27.f + NL(i + 1, j + 1) / 3.f;
+                const float maxn = maxr(maxr(np1, np2), np3), minn = minr(minr(np1, np2), np3);       /* rt_math.h variadic max / min */
+                float max_ = maxr(maxr(max1, max2), maxn), min_ = minr(minr(min1, min2), minn);
+                max1 = max2; max2 = maxn; min1 = min2; min2 = minn;
+                const float labL = YY[(size_t)i * W + j];
+                if (max_ < labL) max_ = labL;
+                if (min_ > labL) min_ = labL;
+                const float diff = NL(i, j) - b2[(size_t)i * W + j];
+                const float delta = threshold_multiply(thr, minr(fabsf(diff), 2000.f), sharpFac * diff);
+                float newL = labL + delta;
+                if (newL > max_) newL = max_ + (newL - max_) * scl;
+                else if (newL < min_) newL = min_ - (min_ - newL) * scl;
+                const float bl = blend[(size_t)i * W + j];
+                YY[(size_t)i * W + j] = bl * newL + (1.f - bl) * YY[(size_t)i * W + j];
+            }
+        }
+#undef NL
+        free(nL);
     }
     apply_gamma(YY, n, 3.f, 1);
     /* multiply(rgb, YY, Y) */

@@ -55,7 +55,8 @@ def same(a, b, what="RGB"):
 
 
 CASES = [dict(), dict(radius=0.9, amount=350), dict(contrast=0.0), dict(contrast=55.0, radius=2.4, amount=80, thr=(10, 40, 1500, 600)),
-         dict(radius=0.2), dict(scale=2.0, radius=1.5), dict(amount=0)]
+         dict(radius=0.2), dict(scale=2.0, radius=1.5), dict(amount=0), dict(halo=1), dict(halo=1, halo_amount=30, radius=1.2, amount=400),
+         dict(halo=1, halo_amount=100, contrast=0.0)]
 
 
 @needs_ref

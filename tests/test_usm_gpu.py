@@ -15,6 +15,10 @@ def gpu(hp, planes, **kw):
     kw = dict(kw)
     if "thr" in kw:
         kw["threshold"] = kw.pop("thr")
+    if "halo" in kw:
+        kw["halocontrol"] = bool(kw.pop("halo"))
+    if "halo_amount" in kw:
+        kw["halocontrol_amount"] = kw.pop("halo_amount")
     hp.sharpen_usm(out[0], out[1], out[2], SharpenParams(**kw), PROPHOTO)
     return out
 
@@ -35,11 +39,11 @@ def test_usm_too_small_or_disabled_is_identity(hot_path):
     same(gpu(hot_path, planes, amount=0), planes)
 
 
-def test_usm_rejects_halo_control(hot_path):
+def test_usm_rejects_edges_only(hot_path):
     import art_b200
     planes = scene(64, 40, 3)
     with pytest.raises(art_b200.HotPathError) as e:
-        gpu(hot_path, planes, halocontrol=True)
+        gpu(hot_path, planes, edgesonly=True)
     assert e.value.code == 5
 
 
