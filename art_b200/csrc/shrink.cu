@@ -138,7 +138,7 @@ struct FbArgs { const float* x; float* y; int W, H, rad; };
 // 256 threads load the tile with coalesced reads and form the per-step differences in parallel, FB_CH lanes run the
 // additions out of shared memory, all threads store the tile.  The ramps at both ends of a chain (rad + 1 and rad steps)
 // are done by the chain lanes straight from global memory.
-constexpr int FB_CH = 8, FB_T = 256, FB_NT = 256, FB_PER = FB_CH * FB_T / FB_NT;
+constexpr int FB_CH = 32, FB_T = 64, FB_NT = 256, FB_PER = FB_CH * FB_T / FB_NT;
 
 template <bool VERT>
 __global__ void __launch_bounds__(FB_NT) k_fbox(FbArgs a)
