@@ -138,11 +138,13 @@ struct FbArgs { const float* x; float* y; int W, H, rad; };
 // 256 threads load the tile with coalesced reads and form the per-step differences in parallel, FB_CH lanes run the
 // additions out of shared memory, all threads store the tile.  The ramps at both ends of a chain (rad + 1 and rad steps)
 // are done by the chain lanes straight from global memory.
-constexpr int FB_CH = 32, FB_T = 64, FB_NT = 256, FB_PER = FB_CH * FB_T / FB_NT;
+// horizontal pass: 8 rows x 256 steps per tile (342 CTAs per 45 MP subband); vertical pass: 32 columns x 64 steps (128-byte segments)
+constexpr int FB_NT = 256, FB_CH_H = 8, FB_T_H = 256, FB_CH_V = 32, FB_T_V = 64;
 
 template <bool VERT>
 __global__ void __launch_bounds__(FB_NT) k_fbox(FbArgs a)
-{   // horizontal: boxblur.h L571-602; vertical: L614-710 (columns < W - W % 4 follow the 4-/8-wide code, the rest the scalar tail)
+{
+    constexpr int FB_CH = VERT ? FB_CH_V : FB_CH_H, FB_T = VERT ? FB_T_V : FB_T_H, FB_PER = FB_CH * FB_T / FB_NT;   // horizontal: boxblur.h L571-602; vertical: L614-710 (columns < W - W % 4 follow the 4-/8-wide code, the rest the scalar tail)
     __shared__ float tile[FB_T][FB_CH + 1];
     const int W = a.W, H = a.H, rad = a.rad;
     const int nchains = VERT ? W : H, nsteps = VERT ? H : W;
@@ -326,10 +328,10 @@ int shrink_band(art_hp_ctx* ctx, const Scratch& s, ShArgs a, int W, int H, int r
     art_prof_end(ctx);
     if (2 * rad + 1 > W || 2 * rad + 1 > H) return ctx->fail(ART_HP_ERR_INVALID, "blur radius %d does not fit a %dx%d subband", rad, W, H);
     art_prof_begin(ctx, "k_fbox_h");
-    k_fbox<false><<<(H + FB_CH - 1) / FB_CH, FB_NT, 0, st>>>(FbArgs{s.sf, s.tmp, W, H, rad});
+    k_fbox<false><<<(H + FB_CH_H - 1) / FB_CH_H, FB_NT, 0, st>>>(FbArgs{s.sf, s.tmp, W, H, rad});
     art_prof_end(ctx);
     art_prof_begin(ctx, "k_fbox_v");
-    k_fbox<true><<<(W + FB_CH - 1) / FB_CH, FB_NT, 0, st>>>(FbArgs{s.tmp, s.sfd, W, H, rad});
+    k_fbox<true><<<(W + FB_CH_V - 1) / FB_CH_V, FB_NT, 0, st>>>(FbArgs{s.tmp, s.sfd, W, H, rad});
     art_prof_end(ctx);
     art_prof_begin(ctx, "k_sf_apply");
     k_sf_apply<<<grid, 256, 0, st>>>(a);
