@@ -79,7 +79,6 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
     float* const drv = buffer + TS * TS * (ndir * 3 + 3);             // [ndir][TS-10][TS-10]
     unsigned char* const homo = reinterpret_cast<unsigned char*>(lab);       // [ndir][TS][TS]
     float2* const gmm = reinterpret_cast<float2*>(lab);                      // [TS][TSH] {min, max}
-    unsigned char* const homosum = reinterpret_cast<unsigned char*>(drv);    // [ndir][TS][TS]
     constexpr int LW = TS - 8, DW = TS - 10;
     constexpr int LAB_VEC_COLS = (LW - 3 + 3) / 4 * 4;               // columns covered by `for (j = 0; j < labWidth - 3; j += 4)`
 
@@ -341,6 +340,17 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
         if (a.stop == 2) { __syncthreads(); continue; }
 
         if (a.stop == 3) { __syncthreads(); continue; }
+        // The homogeneity maps and their 5x5 sums live in shared memory (2 x ndir x 114 x 114 bytes: exactly the space the direction
+        // plane and the min/max table used).  The maps are seeded with the bytes of the slab's lab area, which is what the
+        // reference's `homo` alias holds wherever the homogeneity step does not write.
+        unsigned char* const shomo = reinterpret_cast<unsigned char*>(xsm);
+        unsigned char* const shsum = shomo + (size_t)ndir * TS * TS;
+        {
+            const uint4* s4 = reinterpret_cast<const uint4*>(homo);
+            uint4* d4 = reinterpret_cast<uint4*>(shomo);
+            for (int i = tid; i < ndir * TS * TS / 16; i += XT_THREADS) d4[i] = s4[i];
+        }
+        __syncthreads();
         {   // homogeneity maps, L743-811
             const int nr = mrow - 12, nc = mcol - 12;
             for (int i = tid; i < nr * nc; i += XT_THREADS) {
@@ -356,7 +366,7 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
                     for (int v = -1; v <= 1; ++v)
 #pragma unroll
                         for (int h = -1; h <= 1; ++h) cnt += q[v * DW + h] <= tr ? 1 : 0;
-                    homo[(size_t)d * TS * TS + r * TS + c] = (unsigned char)cnt;
+                    shomo[(size_t)d * TS * TS + r * TS + c] = (unsigned char)cnt;
                 }
             }
         }
@@ -375,13 +385,13 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
                 const int r = startrow + j / nc, c = startcol + j % nc;
                 const int endcol = r < mrow - 9 ? mcol - 8 : mcol - 23;
                 const int vec_end = endcol > startcol ? startcol + (endcol - startcol + 15) / 16 * 16 : startcol;
-                const unsigned char* base = homo + (size_t)d * TS * TS + r * TS + c;
+                const unsigned char* base = shomo + (size_t)d * TS * TS + r * TS + c;
                 int sum = 0;
 #pragma unroll
                 for (int v = -2; v <= 2; ++v)
 #pragma unroll
                     for (int h = -2; h <= 2; ++h) sum += base[v * TS + h];
-                homosum[(size_t)d * TS * TS + r * TS + c] = (unsigned char)(c < vec_end ? min(sum, 255) : sum);
+                shsum[(size_t)d * TS * TS + r * TS + c] = (unsigned char)(c < vec_end ? min(sum, 255) : sum);
             }
         }
         __syncthreads();
@@ -393,7 +403,7 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
             for (int i = tid; i < n; i += XT_THREADS) {
                 const int r = startrow + i / nc, c = startcol + i % nc;
                 unsigned char hm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                const unsigned char* hs = homosum + r * TS + c;
+                const unsigned char* hs = shsum + r * TS + c;
                 unsigned char maxval = hs[0];
                 for (int d = 1; d < ndir; ++d) { const unsigned char v = hs[(size_t)d * TS * TS]; maxval = maxval < v ? v : maxval; }
                 maxval -= maxval >> 3;
