@@ -61,6 +61,12 @@ __device__ __forceinline__ float limf(float v, float lo, float hi) { return v < 
 __device__ __forceinline__ float sqrf(float v) { return v * v; }
 __device__ __forceinline__ float lut_i(const float* __restrict__ t, int idx) { return t[idx < 0 ? 0 : (idx > CBRT_N - 1 ? CBRT_N - 1 : idx)]; }
 
+// for (ri, ci) over an NR x NC rectangle, thread-strided in row-major order, without a division per iteration
+#define XT_FOR2(ri, ci, NR, NC)                                                                                                   \
+    for (int nr_ = (NR), nc_ = (NC), ok_ = (nr_ > 0 && nc_ > 0), ri = ok_ ? tid / nc_ : nr_, ci = ok_ ? tid % nc_ : 0,             \
+             dr_ = ok_ ? XT_THREADS / nc_ : 0, dc_ = ok_ ? XT_THREADS % nc_ : 0;                                                  \
+         ri < nr_; ci += dc_, ri += dr_ + (ci >= nc_), ci -= (ci >= nc_) ? nc_ : 0)
+
 // rgb[d][r][c][ch] of the slab
 #define RGB(d, r, c, ch) rgb[(((size_t)(d) * TS + (r)) * TS + (c)) * 3 + (ch)]
 
@@ -98,8 +104,8 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
         __syncthreads();
 
         // mosaic into rgb[0..3]; green min / max (L319-408) and green along the four directions (L421-475) at non-green sites
-        for (int i = tid; i < rows * cols; i += XT_THREADS) {
-            const int r = i / cols, c = i - r * cols, row = top + r, col = left + c;
+        XT_FOR2(r, c, rows, cols) {
+            const int row = top + r, col = left + c;
             const float* pix = a.raw + (size_t)row * a.rp + col;
             const int f = fcol(tb, row, col);
             const float v = pix[0];
@@ -184,8 +190,7 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
                     }
                 } else {
                     const int nr = rows - 8, nc = cols - 8;
-                    for (int i = tid; i < nr * nc; i += XT_THREADS) {
-                        const int r = i / nc, c = i % nc;
+                    XT_FOR2(r, c, nr, nc) {
                         float* px = plane + ((4 + r) * TS + 4 + c) * 3;
                         const float p0 = px[0], p1 = px[1], p2 = px[2];
                         const float y = 0.2627f * p0 + 0.6780f * p1 + 0.0593f * p2;
@@ -197,8 +202,8 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
                     const int q = dd & 3;           // dir[d & 3] = {1, ts, ts + 1, ts - 1} as a (row, column) step
                     const int fo = (q == 0 ? 1 : (q == 1 ? TS : (q == 2 ? TS + 1 : TS - 1))) * 3;
                     const int nr = rows - 10, nc = cols - 10;
-                    for (int i = tid; i < nr * nc; i += XT_THREADS) {
-                        const int r = 5 + i / nc, c = 5 + i % nc;
+                    XT_FOR2(ri, ci, nr, nc) {
+                        const int r = 5 + ri, c = 5 + ci;
                         const float* l = plane + (r * TS + c) * 3;
                         float v;
                         if (a.useCieLab) {
@@ -212,8 +217,7 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
                 }
                 if (dd == ndir - 1) {               // the lab buffer's final content
                     const int nr = rows - 8, nc = a.useCieLab ? LW : cols - 8;
-                    for (int i = tid; i < nr * nc; i += XT_THREADS) {
-                        const int r = i / nc, c = i % nc;
+                    XT_FOR2(r, c, nr, nc) {
                         const float* px = plane + ((4 + r) * TS + 4 + c) * 3;
                         lab[r * LW + c] = px[0]; lab[LW * LW + r * LW + c] = px[1]; lab[2 * LW * LW + r * LW + c] = px[2];
                     }
@@ -230,8 +234,8 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
                 for (int pass = 0; pass < a.passes; ++pass) {
                     if (pass) {             // recalculate green from interpolated values of closer pixels, L483-522
                         const int nr = rows - 4, nc = cols - 4;
-                        for (int i = tid; i < nr * nc; i += XT_THREADS) {
-                            const int r = 2 + i / nc, c = 2 + i % nc, row = top + r, col = left + c;
+                        XT_FOR2(ri, ci, nr, nc) {
+                            const int r = 2 + ri, c = 2 + ci, row = top + r, col = left + c;
                             const int f = fcol(tb, row, col);
                             if (f == 1) continue;
                             const int q = p ^ (tb.rshift[row % 3] ? 0 : 1);          // plane (d - 2) ^ flip == p  <=>  d = q + 2, d in 3 .. 5
@@ -246,8 +250,8 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
                         __syncthreads();
                     }
                     // red and blue for solitary green pixels, L524-561: plane 0 <- d = 0, plane 1 <- d = 1, plane 2 <- d = 2, 3, plane 3 <- d = 4, 5
-                    for (int i = tid; i < sol_nr * sol_nc; i += XT_THREADS) {
-                        const int row = sol_row0 + 3 * (i / sol_nc), col = sol_col0 + 3 * (i % sol_nc);
+                    XT_FOR2(ri, ci, sol_nr, sol_nc) {
+                        const int row = sol_row0 + 3 * ri, col = sol_col0 + 3 * ci;
                         const int h0 = fcol(tb, row, col + 1);
                         float* rix = plane + ((row - top) * TS + (col - left)) * 3;
                         const int dfirst = p < 2 ? p : 2 * p - 2, dlast = p < 2 ? p : 2 * p - 1;
@@ -275,8 +279,8 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
                     __syncthreads();
                     {   // red for blue pixels and vice versa, L563-603
                         const int nr = rows - 6, nc = cols - 6;
-                        for (int i = tid; i < nr * nc; i += XT_THREADS) {
-                            const int r = 3 + i / nc, c = 3 + i % nc, row = top + r, col = left + c;
+                        XT_FOR2(ri, ci, nr, nc) {
+                            const int r = 3 + ri, c = 3 + ci, row = top + r, col = left + c;
                             const int fc = fcol(tb, row, col);
                             if (fc == 1) continue;
                             const int f = 2 - fc;
@@ -293,8 +297,8 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
                     __syncthreads();
                     if (2 * p < ndir) {     // red and blue for the 2x2 blocks of green, L605-650: `for (d = 0; d < ndir; d += 2)` reaches planes d / 2
                         const int nr = rows - 4, nc = cols - 4;
-                        for (int i = tid; i < nr * nc; i += XT_THREADS) {
-                            const int r = 2 + i / nc, c = 2 + i % nc, row = top + r, col = left + c;
+                        XT_FOR2(ri, ci, nr, nc) {
+                            const int r = 2 + ri, c = 2 + ci, row = top + r, col = left + c;
                             if (!((row - a.sgrow) % 3) || !((col - a.sgcol) % 3)) continue;
                             const signed char* hv = tb.hexv[row % 3][col % 3];
                             const signed char* hh = tb.hexh[row % 3][col % 3];
@@ -353,8 +357,8 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
         __syncthreads();
         {   // homogeneity maps, L743-811
             const int nr = mrow - 12, nc = mcol - 12;
-            for (int i = tid; i < nr * nc; i += XT_THREADS) {
-                const int r = 6 + i / nc, c = 6 + i % nc;
+            XT_FOR2(ri, ci, nr, nc) {
+                const int r = 6 + ri, c = 6 + ci;
                 const float* dp = drv + (r - 5) * DW + (c - 5);
                 float tr = dp[0] < dp[DW * DW] ? dp[0] : dp[DW * DW];
                 for (int d = 2; d < ndir; ++d) tr = dp[(size_t)d * DW * DW] < tr ? dp[(size_t)d * DW * DW] : tr;
@@ -399,9 +403,8 @@ __global__ void __launch_bounds__(XT_THREADS) k_xtrans(const XtArgs a)
         if (a.stop == 5) { __syncthreads(); continue; }
         {   // maximum minus an eighth (L870-911) and the average of the most homogeneous directions (L914-949)
             const int nr = mrow - 8 - startrow, nc = mcol - 8 - startcol;
-            const int n = nr > 0 && nc > 0 ? nr * nc : 0;
-            for (int i = tid; i < n; i += XT_THREADS) {
-                const int r = startrow + i / nc, c = startcol + i % nc;
+            XT_FOR2(ri, ci, nr, nc) {
+                const int r = startrow + ri, c = startcol + ci;
                 unsigned char hm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 const unsigned char* hs = shsum + r * TS + c;
                 unsigned char maxval = hs[0];
