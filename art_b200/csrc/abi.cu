@@ -581,8 +581,8 @@ int art_hp_gauss(art_hp_ctx* ctx, float* const* src, float* const* dst, int W, i
 static int check_denoise_params(art_hp_ctx* ctx, const art_hp_denoise_params* P, const double* wprof)
 {
     if (!P || !wprof) return ctx->fail(ART_HP_ERR_INVALID, "null parameters");
-    if (P->colorSpace != 0 || P->aggressive != 0 || P->chrominanceMethod != 0)
-        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "only colorSpace RGB, aggressive off, chrominanceMethod MANUAL are on the hot path");
+    if (P->colorSpace != 0 || P->chrominanceMethod != 0)
+        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "only colorSpace RGB and chrominanceMethod MANUAL are on the hot path");
     if (!(P->scale > 0) || !(P->gamma > 0)) return ctx->fail(ART_HP_ERR_INVALID, "scale and gamma must be positive");
     return ART_HP_OK;
 }

@@ -1,6 +1,6 @@
 // denoise::RGB_denoise for sm_100a: the path ART's driver takes (ipdenoise.cc L1165: kall = 0, isRAW = true).
 //
-// Replaces (reference) rtengine/FTblockDN.cc RGB_denoise L1638-2689 (colorSpace RGB, aggressive off, chrominance
+// Replaces (reference) rtengine/FTblockDN.cc RGB_denoise L1638-2689 (colorSpace RGB, standard and aggressive quality, chrominance
 // method MANUAL, Tile_calc L442-478 = one tile), Noise_residualAB L607-635, detail_recovery L1479-1635 with
 // RGBtile_denoise L494-525 / RGBoutput_tile_row L531-558 / boxabsblur (boxblur.h L745-888), Color::gammaf2lut
 // (color.cc L1128-1170), gammaf / rgb2yuv / yuv2rgb (color.h L782-796, L1202-1205), rgbxyz + XYZ2Lab (color.cc L833,
@@ -372,7 +372,7 @@ inline float sqrf(float x) { return x * x; }
 // shrink.cu, internal forms: `uniform` != nullptr says the noise-variance map is that one value everywhere
 int art_wavelet_denoise_L(art_hp_ctx* ctx, art_hp_wavelet* wL, const float* d_noisevarlum, const float* uniform, const float* d_madL, double scale);
 int art_wavelet_denoise_AB(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom, const float* uniform,
-                           const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale);
+                           const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale, int bishrink = 0);
 
 extern "C" {
 int art_hp_wavelet_decompose_dev(art_hp_ctx* ctx, const float* d_src, size_t pitch, int W, int H, int maxlvl, int subsampling, art_hp_wavelet** out);
@@ -540,6 +540,9 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
     int levwav = 5;
     const float maxreal = std::max(realred, realblue);
     if (maxreal < 8.f) levwav = 5; else if (maxreal < 10.f) levwav = 6; else if (maxreal < 15.f) levwav = 7; else levwav = 8;
+    const bool aggressive = P->aggressive != 0;         // nrQuality == QUALITY_HIGH, L1671
+    if (aggressive) levwav += 2;                         // L2260-2262
+    if (levwav > 8) levwav = 8;
     levwav = std::max(5, int(levwav - std::ceil(std::log(scale))));
     const int minsizetile = std::min(W, H);
     int maxlev2 = 8;
@@ -561,7 +564,9 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
         if ((rc = art_hp_wavelet_decompose_dev(ctx, chan[c], W, W, H, levwav, 1, &dec))) { art_hp_wavelet_destroy(Ldec); return rc; }
         {   // without the chroma noise curve the chroma variance map is 1 everywhere (L2098-2100): passed as a value, not read
             const float one = 1.f;
-            rc = art_wavelet_denoise_AB(ctx, Ldec, dec, nvc, useCC ? nullptr : &one, madL, nv[c], useCC, 0, scale);
+            // QUALITY_HIGH: WaveletDenoiseAll_BiShrinkAB and then WaveletDenoiseAllAB as well (L2339-2349)
+            if (aggressive) rc = art_wavelet_denoise_AB(ctx, Ldec, dec, nvc, useCC ? nullptr : &one, madL, nv[c], useCC, 0, scale, 1);
+            if (!rc) rc = art_wavelet_denoise_AB(ctx, Ldec, dec, nvc, useCC ? nullptr : &one, madL, nv[c], useCC, 0, scale, 0);
         }
         if (!rc && nresi_highresi) rc = residual_mads(ctx, dec, resid + 24 * c);
         if (!rc) rc = art_hp_wavelet_reconstruct_dev(dec, chan[c], W, 1.f);
@@ -570,7 +575,9 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
     }
     const int maxlvl = art_hp_wavelet_maxlevel(Ldec);
     if (denoiseLuminance) {
-        rc = art_wavelet_denoise_L(ctx, Ldec, nvl, &noisevarL, madL, scale);       // the luminance variance map is noisevarL everywhere (L2097)
+        // QUALITY_HIGH: WaveletDenoiseAll_BiShrinkL (the same computation as WaveletDenoiseAllL) and then WaveletDenoiseAllL (L2412-2421)
+        if (aggressive) rc = art_wavelet_denoise_L(ctx, Ldec, nvl, &noisevarL, madL, scale);
+        if (!rc) rc = art_wavelet_denoise_L(ctx, Ldec, nvl, &noisevarL, madL, scale);       // the luminance variance map is noisevarL everywhere (L2097)
         if (!rc) {
             if (cudaMemcpyAsync(Lin, Lp, n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = ctx->fail(ART_HP_ERR_CUDA, "Lin copy failed");
         }
@@ -608,7 +615,7 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
     MergeArgs m{};
     m.L = Lp; m.a = ap; m.bb = bp; m.r = r; m.g = g; m.b = b; m.op = ip; m.W = W; m.H = H;
     m.igam = Gam{igamcurve, igam, igamthresh, igamslope, 65536.f}; m.outer_gam = gam; m.newGain = 1.f / gain;
-    m.w10 = wp[3]; m.w11 = wp[4]; m.w12 = wp[5]; m.realred = realred; m.realblue = realblue; m.qhighFactor = 1.0f;
+    m.w10 = wp[3]; m.w11 = wp[4]; m.w12 = wp[5]; m.realred = realred; m.realblue = realblue; m.qhighFactor = aggressive ? 1.f / static_cast<float>(0.9) : 1.0f;
     art_prof_begin(ctx, "k_dn_merge");
     k_dn_merge<<<gfull, 256, 0, st>>>(m);
     art_prof_end(ctx);

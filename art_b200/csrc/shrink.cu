@@ -120,6 +120,31 @@ __global__ void __launch_bounds__(256) k_sf_AB(ShArgs a)
     }
 }
 
+// WaveletDenoiseAll_BiShrinkAB's "simple" shrinkage of the levels below the coarsest one (L1046-1087): in place, no local averaging,
+// the factor squared, mad_abr = (useNoiseCCurve ? noisevar_ab : SQR(noisevar_ab)) * madab
+__global__ void __launch_bounds__(256) k_sf_AB_simple(ShArgs a)
+{
+    const float mad_L = a.mad[0];
+    const float madab = a.madab[0];
+    const float mad_abr = a.useCCurve ? a.noisevar_ab * madab : (a.noisevar_ab * a.noisevar_ab) * madab;
+    const float rmadLm9 = 1.f / (mad_L * 9.f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+        const float xl = a.cL[i], xab = a.c[i];
+        const float nvi = a.nv_uniform ? a.nv_value : a.nv[i];
+        if ((i & ~3) < a.n - 3) {
+            const float mad_ab = nvi * mad_abr;
+            const float mag_ab = xab * xab;
+            const float mag_L = (xl * xl) * rmadLm9;
+            const float f = 1.f - xexpf_vector(-(mag_ab / mad_ab) - (mag_L));
+            a.c[i] = xab * (f * f);
+        } else {
+            const float mag_L = xl * xl, mag_ab = xab * xab;
+            const float f = 1.f - xexpf_scalar(-(mag_ab / (nvi * mad_abr)) - (mag_L / (9.f * mad_L)));
+            a.c[i] = xab * (f * f);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_sf_apply(ShArgs a)
 {   // L692-709 / L791-813
     const float eps = 0.01f;
@@ -372,7 +397,7 @@ int art_hp_wavelet_mad_dev(art_hp_ctx* ctx, const art_hp_wavelet* w, float* d_ma
 // internal forms: `uniform` != nullptr says the noise-variance map is that one value everywhere (the map pointer is then unused)
 int art_wavelet_denoise_L(art_hp_ctx* ctx, art_hp_wavelet* wL, const float* d_noisevarlum, const float* uniform, const float* d_madL, double scale);
 int art_wavelet_denoise_AB(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom, const float* uniform,
-                           const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale);
+                           const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale, int bishrink = 0);
 
 extern "C" {
 
@@ -412,11 +437,13 @@ extern "C" int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavel
                                              const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale)
 {
     if (!d_noisevarchrom) return ART_HP_ERR_INVALID;
-    return art_wavelet_denoise_AB(ctx, wL, wab, d_noisevarchrom, nullptr, d_madL, noisevar_ab, useNoiseCCurve, autoch, scale);
+    return art_wavelet_denoise_AB(ctx, wL, wab, d_noisevarchrom, nullptr, d_madL, noisevar_ab, useNoiseCCurve, autoch, scale, 0);
 }
 
+// bishrink != 0: WaveletDenoiseAll_BiShrinkAB (L976-1108) instead of WaveletDenoiseAllAB: the coarsest level goes through ShrinkAllAB
+// as usual (its MAD is the same whether computed up front or now), every finer level through the simple shrinkage
 int art_wavelet_denoise_AB(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom, const float* uniform,
-                           const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale)
+                           const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale, int bishrink)
 {
     if (!ctx || !wL || !wab || (!d_noisevarchrom && !uniform) || !d_madL || !(scale > 0)) return ART_HP_ERR_INVALID;
     if (wL->nlev != wab->nlev || wL->W != wab->W || wL->H != wab->H) return ctx->fail(ART_HP_ERR_INVALID, "L and ab decompositions differ in shape");
@@ -440,6 +467,13 @@ int art_wavelet_denoise_AB(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wav
             a.c = L.band[d]; a.cL = wL->lev[l].band[d]; a.nv = d_noisevarchrom; a.mad = d_madL + 3 * l + (d - 1); a.n = n;
             a.noisevar_ab = noisevar_ab; a.useCCurve = useNoiseCCurve; a.madab = sc.madab;
             a.nv_uniform = uniform != nullptr; a.nv_value = uniform ? *uniform : 0.f;
+            if (bishrink && l != wL->nlev - 1) {
+                art_prof_begin(ctx, "k_sf_AB_simple");
+                k_sf_AB_simple<<<std::min((n + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(a);
+                art_prof_end(ctx);
+                ctx->launches++;
+                continue;
+            }
             rc = shrink_band(ctx, sc, a, L.w2, L.h2, blur_radius(l, scale), true);
         }
     const int rc2 = lanes.end();

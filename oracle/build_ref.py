@@ -654,13 +654,13 @@ extern "C" {
 void artref_set_denoise_thread_limit(int n) { rtengine::options.rgbDenoiseThreadLimit = n; }
 // p: luminance, luminanceDetail, luminanceDetailThreshold, chrominance, chrominanceRedGreen, chrominanceBlueYellow, gamma, scale
 // ccurve: 501-entry NoiseCurve LUT (or null = curve not set), calclum: 3 planes of ((H+1)/2) x ((W+1)/2) (or null)
-int artref_rgb_denoise(float* r, float* g, float* b, int W, int H, const double* p, const double* wp, const double* wpi,
-                       const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* nresi_highresi)
+int artref_rgb_denoise_ex(float* r, float* g, float* b, int W, int H, const double* p, const double* wp, const double* wpi,
+                       const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* nresi_highresi, int aggressive)
 {
     Color::init();
     for (int i = 0; i < 9; ++i) { (&artref_wp[0][0])[i] = (float)((const double*)wp)[i]; (&artref_wpi[0][0])[i] = (float)((const double*)wpi)[i]; }
     procparams::DenoiseParams dn;
-    dn.enabled = true; dn.colorSpace = procparams::DenoiseParams::ColorSpace::RGB; dn.aggressive = false;
+    dn.enabled = true; dn.colorSpace = procparams::DenoiseParams::ColorSpace::RGB; dn.aggressive = aggressive != 0;
     dn.luminance = p[0]; dn.luminanceDetail = p[1]; dn.luminanceDetailThreshold = (int)p[2];
     dn.chrominanceMethod = procparams::DenoiseParams::ChrominanceMethod::MANUAL;
     dn.chrominance = p[3]; dn.chrominanceRedGreen = p[4]; dn.chrominanceBlueYellow = p[5]; dn.gamma = p[6];
@@ -682,6 +682,11 @@ int artref_rgb_denoise(float* r, float* g, float* b, int W, int H, const double*
     denoise::RGB_denoise(im, 0, &img, &img, calclum, nullptr, nullptr, nullptr, true, dn, 0.0, lc, cc, nresi, highresi);
     if (nresi_highresi) { nresi_highresi[0] = nresi; nresi_highresi[1] = highresi; }
     return 0;
+}
+int artref_rgb_denoise(float* r, float* g, float* b, int W, int H, const double* p, const double* wp, const double* wpi,
+                       const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* nresi_highresi)
+{
+    return artref_rgb_denoise_ex(r, g, b, W, H, p, wp, wpi, ccurve, ccurve_sum, cl_r, cl_g, cl_b, nresi_highresi, 0);
 }
 }
 """

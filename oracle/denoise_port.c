@@ -297,8 +297,20 @@ int artoracle_detail_recovery(float* L, const float* Lin, int width, int height,
  * wp: working space matrix (row-major 3x3 double).  ccurve: the NoiseCurve's 501-entry LUT or NULL; calclum: 3 planes of
  * ((H+1)/2) x ((W+1)/2), needed when ccurve is in use.  out2: nresi, highresi.
  */
+int artoracle_wavelet_denoise_AB_bishrink(void* wL, void* wab, const float* noisevarchrom, const float* madL, float noisevar_ab,
+                                          int useNoiseCCurve, int autoch, double scale);
+int artoracle_rgb_denoise_ex(float* r, float* g, float* b, int W, int H, const double* p, const double* wp,
+                             const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* out2, int aggressive);
 int artoracle_rgb_denoise(float* r, float* g, float* b, int W, int H, const double* p, const double* wp,
                           const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* out2)
+{
+    return artoracle_rgb_denoise_ex(r, g, b, W, H, p, wp, ccurve, ccurve_sum, cl_r, cl_g, cl_b, out2, 0);
+}
+/* aggressive = DenoiseParams::aggressive: nrQuality QUALITY_HIGH (L1671-1672): two more wavelet levels (L2260-2262), BiShrink for the
+ * chroma channels and the luminance FOLLOWED by the standard shrinkage (L2339-2349, L2376-2386, L2412-2421; WaveletDenoiseAll_BiShrinkL
+ * computes exactly what WaveletDenoiseAllL does, so the luminance is simply shrunk twice), qhighFactor 1 / 0.9 */
+int artoracle_rgb_denoise_ex(float* r, float* g, float* b, int W, int H, const double* p, const double* wp,
+                             const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* out2, int aggressive)
 {
     const double luminance = p[0], luminanceDetail = p[1], chrominance = p[3], chromRG = p[4], chromBY = p[5], scale = p[7];
     const int detail_thresh = (int)p[2];
@@ -379,6 +391,7 @@ int artoracle_rgb_denoise(float* r, float* g, float* b, int W, int H, const doub
     int levwav = 5;
     const float maxreal = fmaxf(realred, realblue);
     if (maxreal < 8.f) levwav = 5; else if (maxreal < 10.f) levwav = 6; else if (maxreal < 15.f) levwav = 7; else levwav = 8;
+    if (aggressive) levwav += 2;
     if (levwav > 8) levwav = 8;
     levwav = imax(5, (int)(levwav - ceil(log(scale))));
     const int minsizetile = imin(W, H);
@@ -405,6 +418,8 @@ int artoracle_rgb_denoise(float* r, float* g, float* b, int W, int H, const doub
     float resid2[2], max2[2];
     for (int c = 0; c < 2; ++c) {
         void* dec = artoracle_wavelet_new(chan[c], W, H, levwav, 1);
+        /* QUALITY_HIGH runs BiShrink and THEN the standard shrinkage (L2339-2349) */
+        if (aggressive) artoracle_wavelet_denoise_AB_bishrink(Ldecomp, dec, noisevarchrom, &madL[0][0], nv[c], useNoiseCCurve, 0, scale);
         artoracle_wavelet_denoise_AB(Ldecomp, dec, noisevarchrom, &madL[0][0], nv[c], useNoiseCCurve, 0, scale);
         float resid = 0.f, maxresid = 0.f;      /* Noise_residualAB */
         const int ml = artoracle_wavelet_maxlevel(dec);
@@ -427,6 +442,8 @@ int artoracle_rgb_denoise(float* r, float* g, float* b, int W, int H, const doub
 
     float* Lin = NULL;
     if (denoiseLuminance) {
+        /* QUALITY_HIGH: WaveletDenoiseAll_BiShrinkL (the same computation as WaveletDenoiseAllL) and then WaveletDenoiseAllL again, L2412-2421 */
+        if (aggressive) artoracle_wavelet_denoise_L(Ldecomp, noisevarlum, &madL[0][0], scale);
         artoracle_wavelet_denoise_L(Ldecomp, noisevarlum, &madL[0][0], scale);
         Lin = (float*)malloc(sizeof(float) * n);
         memcpy(Lin, Lp, sizeof(float) * n);
@@ -438,7 +455,7 @@ int artoracle_rgb_denoise(float* r, float* g, float* b, int W, int H, const doub
         if (rc) return rc;
     }
     const float newGain = 1.f / gain;
-    const float qhighFactor = 1.0f;
+    const float qhighFactor = aggressive ? 1.f / (float)0.9 : 1.0f;
     for (size_t i = 0; i < n; ++i) {
         const float c_h = sqrtf(sqrf(ap[i]) + sqrf(bp[i]));
         if (c_h > 3000.f) {

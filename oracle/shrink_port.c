@@ -203,6 +203,52 @@ int artoracle_wavelet_denoise_L(void* wL, const float* noisevarlum, const float*
     return 0;
 }
 
+/* WaveletDenoiseAll_BiShrinkAB, L976-1108 (QUALITY_HIGH = DenoiseParams::aggressive): the MADs of every band first, then the
+ * coarsest level through ShrinkAllAB (with those MADs) and every finer level through the "simple" shrinkage, which has no local
+ * averaging and squares (1 - exp(.)); note SQR(noisevar_ab) where ShrinkAllAB has noisevar_ab. */
+int artoracle_wavelet_denoise_AB_bishrink(void* wL, void* wab, const float* noisevarchrom, const float* madL, float noisevar_ab,
+                                          int useNoiseCCurve, int autoch, double scale)
+{
+    const int maxlvl = artoracle_wavelet_maxlevel(wL);
+    if (autoch && noisevar_ab <= 0.001f) noisevar_ab = 0.02f;
+    float** b = shrink_buffers(wL, maxlvl);
+    for (int lvl = maxlvl - 1; lvl >= 0; lvl--)
+        for (int dir = 1; dir < 4; ++dir) {
+            if (lvl == maxlvl - 1) {       /* ShrinkAllAB recomputes nothing else: the band's MAD is the same before and after the others shrink */
+                shrink_AB(wL, wab, b, lvl, dir, noisevarchrom, noisevar_ab, useNoiseCCurve, autoch, madL + 3 * lvl, scale);
+                continue;
+            }
+            const int W = artoracle_wavelet_level_W(wab, lvl), H = artoracle_wavelet_level_H(wab, lvl), n = W * H;
+            const float* cL = artoracle_wavelet_band(wL, lvl, dir);
+            float* cab = artoracle_wavelet_band(wab, lvl, dir);
+            float madab = artoracle_madrgb(cab, n);
+            madab = madab * madab;
+            const float mad_Lr = madL[3 * lvl + dir - 1];
+            const float mad_abr = useNoiseCCurve ? noisevar_ab * madab : (noisevar_ab * noisevar_ab) * madab;
+            if (!(noisevar_ab > 0.001f)) continue;
+            const float rmad_Lm9 = 1.f / (mad_Lr * 9.f);
+            int i;
+            for (i = 0; i < n - 3; i += 4)
+                for (int l = 0; l < 4; ++l) {
+                    const float mad_ab = noisevarchrom[i + l] * mad_abr;
+                    const float t = cab[i + l];
+                    float mag_L = cL[i + l];
+                    const float mag_ab = t * t;
+                    mag_L = (mag_L * mag_L) * rmad_Lm9;
+                    const float f = 1.f - xexpf_vector(-(mag_ab / mad_ab) - (mag_L));
+                    cab[i + l] = t * (f * f);
+                }
+            for (; i < n; ++i) {
+                const float mag_L = cL[i] * cL[i], mag_ab = cab[i] * cab[i];
+                const float f = 1.f - xexpf_scalar(-(mag_ab / (noisevarchrom[i] * mad_abr)) - (mag_L / (9.f * mad_Lr)));
+                cab[i] *= f * f;
+            }
+        }
+    for (int k = 0; k < 3; ++k) free(b[k]);
+    free(b);
+    return 0;
+}
+
 int artoracle_wavelet_denoise_AB(void* wL, void* wab, const float* noisevarchrom, const float* madL, float noisevar_ab,
                                  int useNoiseCCurve, int autoch, double scale)
 {

@@ -39,7 +39,7 @@ def calclum_of(planes):
     return [np.ascontiguousarray(p[::2, ::2]) for p in planes]
 
 
-def run(lib, fname, planes, params, ccurve=None, with_inverse=False):
+def run(lib, fname, planes, params, ccurve=None, with_inverse=False, aggressive=None):
     H, W = planes[0].shape
     out = [p.copy() for p in planes]
     p = np.array(params, np.float64)
@@ -56,6 +56,8 @@ def run(lib, fname, planes, params, ccurve=None, with_inverse=False):
     else:
         args += [None, F(0), None, None, None]
     args.append(res.ctypes.data_as(fp))
+    if aggressive is not None:          # the *_ex entries: DenoiseParams::aggressive
+        args.append(int(aggressive))
     assert getattr(lib, fname)(*args) == 0
     return out, res
 
@@ -83,6 +85,22 @@ def test_rgb_denoise(W, H, params, curve, hot):
         assert np.array_equal(x, y), "%s: %d of %d differ, max %g" % (name, int((x != y).sum()), x.size, float(np.abs(x - y).max()))
     assert np.array_equal(ra, rb), (ra, rb)
     assert not np.array_equal(b[1], planes[1])
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H,params,curve,hot", CASES)
+def test_rgb_denoise_aggressive(W, H, params, curve, hot):
+    """DenoiseParams::aggressive (QUALITY_HIGH): two more wavelet levels, BiShrink for the chroma channels, qhighFactor 1 / 0.9"""
+    planes = rgb_frame(H, W, seed=W * 5 + H, hot=hot)
+    cc = noise_ccurve() if curve else None
+    a, ra = run(oracle.port().lib, "artoracle_rgb_denoise_ex", planes, params, cc, aggressive=1)
+    b, rb = run(oracle.ref().lib, "artref_rgb_denoise_ex", planes, params, cc, with_inverse=True, aggressive=1)
+    for name, x, y in zip("rgb", a, b):
+        assert np.isfinite(y).all()
+        assert np.array_equal(x, y), "%s: %d of %d differ, max %g" % (name, int((x != y).sum()), x.size, float(np.abs(x - y).max()))
+    assert np.array_equal(ra, rb), (ra, rb)
+    std, _ = run(oracle.ref().lib, "artref_rgb_denoise", planes, params, cc, with_inverse=True)
+    assert any(not np.array_equal(x, y) for x, y in zip(b, std)), "aggressive mode changed nothing"
 
 
 @needs_ref
