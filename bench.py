@@ -48,10 +48,10 @@ AMAZE_KERNEL_BYTES = {
 NCU_TRAFFIC = {"k_dirinterp": 0.974235e9 + 1.551996e9, "k_rbdiag": 0.854833e9 + 0.355250e9, "k_grad": 0.282756e9 + 0.768683e9,
                "k_write": 0.565864e9 + 0.500666e9, "k_vcd": 1.110983e9 + 0.500444e9, "k_split": 0.081761e9 + 0.071985e9,
                "rcd_kernel": 181.060608e6 + 475.030528e6,
-               # profiles/r1_develop_ncu_full.csv (isolated replay, cold L2: writes stay in the 126 MB L2 within the kernel's window)
-               "k_dn_blocks": 358.285056e6 + 1.138656e6, "k_fbox_h": 44.786176e6 + 5.1264e6, "k_fbox_v": 44.808704e6 + 7.129088e6,
-               "k_sf_apply": 134.28992e6 + 19.197184e6, "k_sf_AB": 134.29248e6 + 24.803072e6, "k_mad_hist": 44.784384e6,
-               "k_fat_dct_solve": 370.600192e6 + 0.325564e6, "k_fat_dct_rows": 184.990464e6 + 0.316937e6, "k_fat_dct_exp": 370.19008e6 + 0.154872e6}
+               # profiles/r1_develop_ncu_full.csv (isolated replays, cold L2; a 45 MB plane written by a shrink kernel can stay in the 126 MB L2)
+               "k_dn_blocks": 358.347e6 + 1137.494e6, "k_fbox_h": 44.786e6 + 3.397e6, "k_fbox_v": 44.808e6 + 6.248e6,
+               "k_sf_apply": 134.296e6 + 18.761e6, "k_sf_AB": 89.535e6 + 18.726e6, "k_mad_hist": 44.784e6, "k_wav_sy_sub": 358.56e6 + 137.405e6,
+               "k_fat_dct_rows": 184.989e6 + 316.294e6, "k_fat_dct_solve": 370.647e6 + 327.235e6, "k_fat_dct_exp": 370.152e6 + 156.166e6}
 
 
 def parse():
