@@ -616,6 +616,8 @@ public:
         int i = 0; const int epsmaxint = eps_max;            // color.cc L205-233
         for (; i <= epsmaxint; i++) { cachef[i] = 327.68 * ((kappa * i / MAXVALF + 16.0) / 116.0); cachefy[i] = 327.68 * (kappa * i / MAXVALF); }
         for (; i < 65536; i++) { cachef[i] = 327.68 * std::cbrt((double)i / MAXVALF); cachefy[i] = 327.68 * (116.0 * std::cbrt((double)i / MAXVALF) - 16.0); }
+        denoiseGammaTab(65536, 0); denoiseIGammaTab(65536, 0);          // color.cc L188-189, L278-292
+        for (int k = 0; k < 65536; k++) { denoiseGammaTab[k] = 65535.0 * gamma55 (k / 65535.0); denoiseIGammaTab[k] = 65535.0 * igamma55 (k / 65535.0); }
     }
 #include "color_h_members.inc"
     static float computeXYZ2Lab(float f);
@@ -623,8 +625,16 @@ public:
     static void gammaf2lut (LUTf &gammacurve, float gamma, float start, float slope, float divisor, float factor);
     static void rgbxyz (float r, float g, float b, float &x, float &y, float &z, const float xyz_rgb[3][3]);
     static void XYZ2Lab(float X, float Y, float Z, float &L, float &a, float &b);
-    template <class T> static void rgb2lab(float, float, float, float&, float&, float&, const T[3][3]) { abort(); }   // colorSpace LAB: not on the path
-    template <class T> static void lab2rgb(float, float, float, float&, float&, float&, const T[3][3]) { abort(); }
+    constexpr static double kappaInv = 27.0 / 24389.0;
+    constexpr static double epsilonExpInv3 = 6.0 / 29.0;
+    constexpr static float kappaInvf = kappaInv;
+    constexpr static float epsilonExpInv3f = epsilonExpInv3;
+    constexpr static double epskap = 8.0;
+    constexpr static float c1By116 = 1.0 / 116.0;
+    constexpr static float c16By116 = 16.0 / 116.0;
+    static void xyz2rgb (float x, float y, float z, float &r, float &g, float &b, const float rgb_xyz[3][3]);
+    static void Lab2XYZ(float L, float a, float b, float &x, float &y, float &z);
+#include "color_h_lab_members.inc"
 };
 LUTf Color::cachef, Color::cachefy, Color::denoiseGammaTab, Color::denoiseIGammaTab, Color::igammatab_srgb, Color::gammatab_srgb;
 #include "color_cc_members.inc"
@@ -654,13 +664,13 @@ extern "C" {
 void artref_set_denoise_thread_limit(int n) { rtengine::options.rgbDenoiseThreadLimit = n; }
 // p: luminance, luminanceDetail, luminanceDetailThreshold, chrominance, chrominanceRedGreen, chrominanceBlueYellow, gamma, scale
 // ccurve: 501-entry NoiseCurve LUT (or null = curve not set), calclum: 3 planes of ((H+1)/2) x ((W+1)/2) (or null)
-int artref_rgb_denoise_ex(float* r, float* g, float* b, int W, int H, const double* p, const double* wp, const double* wpi,
-                       const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* nresi_highresi, int aggressive)
+int artref_rgb_denoise_ex2(float* r, float* g, float* b, int W, int H, const double* p, const double* wp, const double* wpi,
+                       const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* nresi_highresi, int aggressive, int lab_mode)
 {
     Color::init();
     for (int i = 0; i < 9; ++i) { (&artref_wp[0][0])[i] = (float)((const double*)wp)[i]; (&artref_wpi[0][0])[i] = (float)((const double*)wpi)[i]; }
     procparams::DenoiseParams dn;
-    dn.enabled = true; dn.colorSpace = procparams::DenoiseParams::ColorSpace::RGB; dn.aggressive = aggressive != 0;
+    dn.enabled = true; dn.colorSpace = lab_mode ? procparams::DenoiseParams::ColorSpace::LAB : procparams::DenoiseParams::ColorSpace::RGB; dn.aggressive = aggressive != 0;
     dn.luminance = p[0]; dn.luminanceDetail = p[1]; dn.luminanceDetailThreshold = (int)p[2];
     dn.chrominanceMethod = procparams::DenoiseParams::ChrominanceMethod::MANUAL;
     dn.chrominance = p[3]; dn.chrominanceRedGreen = p[4]; dn.chrominanceBlueYellow = p[5]; dn.gamma = p[6];
@@ -682,6 +692,11 @@ int artref_rgb_denoise_ex(float* r, float* g, float* b, int W, int H, const doub
     denoise::RGB_denoise(im, 0, &img, &img, calclum, nullptr, nullptr, nullptr, true, dn, 0.0, lc, cc, nresi, highresi);
     if (nresi_highresi) { nresi_highresi[0] = nresi; nresi_highresi[1] = highresi; }
     return 0;
+}
+int artref_rgb_denoise_ex(float* r, float* g, float* b, int W, int H, const double* p, const double* wp, const double* wpi,
+                       const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* nresi_highresi, int aggressive)
+{
+    return artref_rgb_denoise_ex2(r, g, b, W, H, p, wp, wpi, ccurve, ccurve_sum, cl_r, cl_g, cl_b, nresi_highresi, aggressive, 0);
 }
 int artref_rgb_denoise(float* r, float* g, float* b, int W, int H, const double* p, const double* wp, const double* wpi,
                        const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* nresi_highresi)
@@ -1226,11 +1241,18 @@ def extract(det):
                cut_function(ch, r"static void rgb2yuv\(float r, float g, float b, float &Y"),
                cut_function(ch, r"static void yuv2rgb\(float Y, float u, float v, float &r"),
                cut_function(ch, r"static inline float gammaf\s*\(float x, float gamma, float start, float slope\)")]
+    labm = ["template <class T>\n" + cut_function(ch, r"static void rgb2lab\(float R, float G, float B, float &l, float &a, float &b, const T ws\[3\]\[3\]\)"),
+            "template <class T>\n" + cut_function(ch, r"static void lab2rgb\(float l, float a, float b, float &R, float &G, float &B, const T iws\[3\]\[3\]\)"),
+            cut_function(ch, r"static inline float f2xyz\(float f\)"),
+            cut_function(ch, r"static inline double gamma55\(double x\)"), cut_function(ch, r"static inline double igamma55\(double x\)")]
+    open(os.path.join(sub, "color_h_lab_members.inc"), "w").write("\n".join(labm))
     open(os.path.join(sub, "color_h_members.inc"), "w").write("\n".join(("template <class T>\n" if "workingspace" in t else "") + t for t in members))
     ccm = [cut_function(cc, r"^inline float Color::computeXYZ2Lab\(float f\)"), cut_function(cc, r"^inline float Color::computeXYZ2LabY\(float f\)"),
            cut_function(cc, r"^void Color::gammaf2lut \(LUTf &gammacurve"),
            cut_function(cc, r"^void Color::rgbxyz \(float r, float g, float b, float &x, float &y, float &z, const float xyz_rgb"),
-           cut_function(cc, r"^void Color::XYZ2Lab\(float X, float Y, float Z, float &L")]
+           cut_function(cc, r"^void Color::XYZ2Lab\(float X, float Y, float Z, float &L"),
+           cut_function(cc, r"^void Color::xyz2rgb \(float x, float y, float z, float &r, float &g, float &b, const float rgb_xyz"),
+           cut_function(cc, r"^void Color::Lab2XYZ\(float L, float a, float b, float &x, float &y, float &z\)")]
     open(os.path.join(sub, "color_cc_members.inc"), "w").write("\n".join(ccm))
     open(os.path.join(sub, "dct_standin.h"), "w").write(open(os.path.join(HERE, "dct_standin.h")).read())
     open(os.path.join(sub, "shim_denoise.cc"), "w").write(SHIM_DENOISE_TU)

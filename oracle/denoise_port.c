@@ -301,6 +301,8 @@ int artoracle_wavelet_denoise_AB_bishrink(void* wL, void* wab, const float* nois
                                           int useNoiseCCurve, int autoch, double scale);
 int artoracle_rgb_denoise_ex(float* r, float* g, float* b, int W, int H, const double* p, const double* wp,
                              const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* out2, int aggressive);
+int artoracle_rgb_denoise_ex2(float* r, float* g, float* b, int W, int H, const double* p, const double* wp, const double* wp_inverse,
+                              const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* out2, int aggressive, int lab_mode);
 int artoracle_rgb_denoise(float* r, float* g, float* b, int W, int H, const double* p, const double* wp,
                           const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* out2)
 {
@@ -312,6 +314,46 @@ int artoracle_rgb_denoise(float* r, float* g, float* b, int W, int H, const doub
 int artoracle_rgb_denoise_ex(float* r, float* g, float* b, int W, int H, const double* p, const double* wp,
                              const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* out2, int aggressive)
 {
+    return artoracle_rgb_denoise_ex2(r, g, b, W, H, p, wp, NULL, ccurve, ccurve_sum, cl_r, cl_g, cl_b, out2, aggressive, 0);
+}
+/* Color::denoiseGammaTab / denoiseIGammaTab (color.cc L188-189, L278-292; gamma55 / igamma55 color.h L1155-1169): LUTf(65536, 0) */
+static float *g_dn_gamma = NULL, *g_dn_igamma = NULL;
+static void init_dn_tabs(void)
+{
+    if (g_dn_gamma) return;
+    float* a = (float*)malloc(sizeof(float) * 65536); float* b = (float*)malloc(sizeof(float) * 65536);
+    for (int i = 0; i < 65536; i++) {
+        const double x = i / 65535.0;
+        a[i] = (float)(65535.0 * (x <= 0.013189 ? x * 10.0 : 1.593503 * exp(log(x) / 5.5) - 0.593503));
+        b[i] = (float)(65535.0 * (x <= 0.131889 ? x / 10.0 : exp(log((x + 0.593503) / 1.593503) * 5.5)));
+    }
+    g_dn_gamma = a; g_dn_igamma = b;
+}
+const float* artoracle_denoise_gamma_tab(int inverse) { init_dn_tabs(); return inverse ? g_dn_igamma : g_dn_gamma; }
+static inline float lut_noclip(const float* data, int size, float index)
+{   /* LUT.h L437-459 with flags 0: extrapolates at both ends */
+    int idx = (int)index;
+    if (index < 0.f || !(index == index)) idx = 0;
+    else if (index > (float)(size - 2)) idx = size - 2;
+    const float diff = index - (float)idx;
+    const float p1 = data[idx];
+    const float p2 = data[idx + 1] - p1;
+    return p1 + p2 * diff;
+}
+static inline float f2xyz_(float f)
+{   /* color.h L767-770 */
+    const float epsilonExpInv3f = (float)(6.0 / 29.0), kappaInvf = (float)(27.0 / 24389.0);
+    return (f > epsilonExpInv3f) ? f * f * f : (116.f * f - 16.f) * kappaInvf;
+}
+/* lab_mode = DenoiseParams::ColorSpace::LAB (L1996): the samples go through denoiseIGammaTab before the gamma curve and through Color::rgb2lab
+ * instead of rgb2yuv (L2093-2118); on the way out Color::lab2rgb with the inverse working-space matrix and denoiseGammaTab (L2519-2538) */
+int artoracle_rgb_denoise_ex2(float* r, float* g, float* b, int W, int H, const double* p, const double* wp, const double* wp_inverse,
+                              const float* ccurve, float ccurve_sum, const float* cl_r, const float* cl_g, const float* cl_b, float* out2, int aggressive, int lab_mode)
+{
+    if (lab_mode && !wp_inverse) return 1;
+    float wpinv[3][3] = {{0}};
+    if (wp_inverse) for (int i = 0; i < 9; ++i) wpinv[i / 3][i % 3] = (float)wp_inverse[i];
+    if (lab_mode) init_dn_tabs();
     const double luminance = p[0], luminanceDetail = p[1], chrominance = p[3], chromRG = p[4], chromBY = p[5], scale = p[7];
     const int detail_thresh = (int)p[2];
     if (luminance == 0 && chrominance == 0 && !ccurve) return 0;
@@ -377,9 +419,17 @@ int artoracle_rgb_denoise_ex(float* r, float* g, float* b, int W, int H, const d
     for (int i = 0; i < height; ++i)
         for (int j = 0; j < width; ++j) {
             float X = gain * r[(size_t)i * W + j], Y = gain * g[(size_t)i * W + j], Z = gain * b[(size_t)i * W + j];
+            if (lab_mode) { X = lut_noclip(g_dn_igamma, 65536, X); Y = lut_noclip(g_dn_igamma, 65536, Y); Z = lut_noclip(g_dn_igamma, 65536, Z); }
             X = APPLY_GAMMA(X); Y = APPLY_GAMMA(Y); Z = APPLY_GAMMA(Z);
-            const float l = X * wpi[1][0] + Y * wpi[1][1] + Z * wpi[1][2];      /* rgb2yuv */
-            const float u = l - Z, v = X - l;
+            float l, u, v;
+            if (lab_mode) {     /* Color::rgb2lab(X, Y, Z, l, v, u, wpi): rgbxyz + XYZ2Lab (color.cc L833-838, L1382-1399) */
+                const float x = (wpi[0][0] * X + wpi[0][1] * Y + wpi[0][2] * Z), y = (wpi[1][0] * X + wpi[1][1] * Y + wpi[1][2] * Z), z = (wpi[2][0] * X + wpi[2][1] * Y + wpi[2][2] * Z);
+                const float fx = computeXYZ2Lab(x / 0.9642f), fy = computeXYZ2Lab(y), fz = computeXYZ2Lab(z / 0.8249f);
+                l = computeXYZ2LabY(y); v = 500.0f * (fx - fy); u = 200.0f * (fy - fz);
+            } else {
+                l = X * wpi[1][0] + Y * wpi[1][1] + Z * wpi[1][2];      /* rgb2yuv */
+                u = l - Z; v = X - l;
+            }
             Lp[(size_t)i * W + j] = l; ap[(size_t)i * W + j] = v; bp[(size_t)i * W + j] = u;
             if (((i | j) & 1) == 0) {
                 noisevarlum[(i >> 1) * width2 + (j >> 1)] = noisevarL;
@@ -464,10 +514,27 @@ int artoracle_rgb_denoise_ex(float* r, float* g, float* b, int W, int H, const d
         }
         /* yuv2rgb(L, b, a): Y, u = b, v = a */
         const float Yv = Lp[i], u = bp[i], v = ap[i];
-        float Z = Yv - u;
-        float X = v + Yv;
-        float Y = (Yv - X * wpi[1][0] - Z * wpi[1][2]) / wpi[1][1];
+        float X, Y, Z;
+        if (lab_mode) {     /* Color::lab2rgb(L, a, b, X, Y, Z, wpi_inverse): Lab2XYZ (color.cc L1203-1214) + xyz2rgb (L880-885) */
+            const float c1By116 = (float)(1.0 / 116.0), c16By116 = (float)(16.0 / 116.0);
+            const double kappa = 24389.0 / 27.0;
+            const float LL = Yv / 327.68f, aa = v / 327.68f, bb = u / 327.68f;
+            const float fy = (c1By116 * LL) + c16By116;
+            const float fx = (0.002f * aa) + fy;
+            const float fz = fy - (0.005f * bb);
+            const float x = 65535.0f * f2xyz_(fx) * 0.9642f;
+            const float z = 65535.0f * f2xyz_(fz) * 0.8249f;
+            const float y = ((double)LL > 8.0) ? 65535.0f * fy * fy * fy : (float)(65535.0f * LL / kappa);
+            X = (wpinv[0][0] * x + wpinv[0][1] * y + wpinv[0][2] * z);
+            Y = (wpinv[1][0] * x + wpinv[1][1] * y + wpinv[1][2] * z);
+            Z = (wpinv[2][0] * x + wpinv[2][1] * y + wpinv[2][2] * z);
+        } else {
+            Z = Yv - u;
+            X = v + Yv;
+            Y = (Yv - X * wpi[1][0] - Z * wpi[1][2]) / wpi[1][1];
+        }
         X = APPLY_IGAMMA(X); Y = APPLY_IGAMMA(Y); Z = APPLY_IGAMMA(Z);
+        if (lab_mode) { X = lut_noclip(g_dn_gamma, 65536, X); Y = lut_noclip(g_dn_gamma, 65536, Y); Z = lut_noclip(g_dn_gamma, 65536, Z); }
         r[i] = newGain * X; g[i] = newGain * Y; b[i] = newGain * Z;
     }
     free(Lp); free(ap); free(bp); free(Lin); free(noisevarlum); free(noisevarchrom); free(gamcurve); free(igamcurve); free(ccalc);

@@ -39,12 +39,15 @@ def calclum_of(planes):
     return [np.ascontiguousarray(p[::2, ::2]) for p in planes]
 
 
-def run(lib, fname, planes, params, ccurve=None, with_inverse=False, aggressive=None):
+PROPHOTO_INV = np.array([[1.3459433, -0.2556075, -0.0511118], [-0.5445989, 1.5081673, 0.0205351], [0.0, 0.0, 1.2118128]], np.float64)   # iccmatrices.h prophoto_xyz
+
+
+def run(lib, fname, planes, params, ccurve=None, with_inverse=False, aggressive=None, lab=None):
     H, W = planes[0].shape
     out = [p.copy() for p in planes]
     p = np.array(params, np.float64)
     wp = PROPHOTO.copy()
-    wpi = np.linalg.inv(wp)
+    wpi = PROPHOTO_INV.copy() if lab is not None else np.linalg.inv(wp)
     res = np.zeros(2, np.float32)
     args = [out[0].ctypes.data_as(fp), out[1].ctypes.data_as(fp), out[2].ctypes.data_as(fp), W, H, p.ctypes.data_as(dp), wp.ctypes.data_as(dp)]
     if with_inverse:
@@ -58,6 +61,8 @@ def run(lib, fname, planes, params, ccurve=None, with_inverse=False, aggressive=
     args.append(res.ctypes.data_as(fp))
     if aggressive is not None:          # the *_ex entries: DenoiseParams::aggressive
         args.append(int(aggressive))
+    if lab is not None:                 # the *_ex2 entries: DenoiseParams::colorSpace == LAB
+        args.append(int(lab))
     assert getattr(lib, fname)(*args) == 0
     return out, res
 
@@ -101,6 +106,23 @@ def test_rgb_denoise_aggressive(W, H, params, curve, hot):
     assert np.array_equal(ra, rb), (ra, rb)
     std, _ = run(oracle.ref().lib, "artref_rgb_denoise", planes, params, cc, with_inverse=True)
     assert any(not np.array_equal(x, y) for x, y in zip(b, std)), "aggressive mode changed nothing"
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H,params,curve,hot", CASES)
+@pytest.mark.parametrize("aggressive", [0, 1])
+def test_rgb_denoise_lab_colour_space(W, H, params, curve, hot, aggressive):
+    """DenoiseParams::colorSpace == LAB: denoiseIGammaTab + Color::rgb2lab on the way in, Color::lab2rgb + denoiseGammaTab on the way out"""
+    planes = rgb_frame(H, W, seed=W * 3 + H, hot=hot)
+    cc = noise_ccurve() if curve else None
+    a, ra = run(oracle.port().lib, "artoracle_rgb_denoise_ex2", planes, params, cc, with_inverse=True, aggressive=aggressive, lab=1)
+    b, rb = run(oracle.ref().lib, "artref_rgb_denoise_ex2", planes, params, cc, with_inverse=True, aggressive=aggressive, lab=1)
+    for name, x, y in zip("rgb", a, b):
+        assert np.isfinite(y).all()
+        assert np.array_equal(x, y), "%s: %d of %d differ, max %g" % (name, int((x != y).sum()), x.size, float(np.abs(x - y).max()))
+    assert np.array_equal(ra, rb), (ra, rb)
+    std, _ = run(oracle.ref().lib, "artref_rgb_denoise_ex", planes, params, cc, with_inverse=True, aggressive=aggressive)
+    assert any(not np.array_equal(x, y) for x, y in zip(b, std)), "the colour space changed nothing"
 
 
 @needs_ref
