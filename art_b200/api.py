@@ -172,7 +172,8 @@ class _DenoiseParamsC(ctypes.Structure):
     _fields_ = [("luminance", ctypes.c_double), ("luminanceDetail", ctypes.c_double), ("luminanceDetailThreshold", ctypes.c_int),
                 ("chrominance", ctypes.c_double), ("chrominanceRedGreen", ctypes.c_double), ("chrominanceBlueYellow", ctypes.c_double),
                 ("gamma", ctypes.c_double), ("scale", ctypes.c_double), ("colorSpace", ctypes.c_int), ("aggressive", ctypes.c_int),
-                ("chrominanceMethod", ctypes.c_int), ("noiseCCurve", ctypes.c_void_p), ("noiseCCurveSum", ctypes.c_float)]
+                ("chrominanceMethod", ctypes.c_int), ("noiseCCurve", ctypes.c_void_p), ("noiseCCurveSum", ctypes.c_float),
+                ("wprof_inverse", ctypes.POINTER(ctypes.c_double))]
 
 
 class _DevelopParamsC(ctypes.Structure):
@@ -312,14 +313,18 @@ class DenoiseParams:
     """Mirror of the procparams::DenoiseParams fields RGB_denoise reads (defaults: rtengine/procparams.cc L1901-1918)."""
 
     def __init__(self, luminance=0.0, luminanceDetail=0.0, luminanceDetailThreshold=0, chrominance=15.0, chrominanceRedGreen=0.0,
-                 chrominanceBlueYellow=0.0, gamma=1.7, scale=1.0, colorSpace=0, aggressive=0, chrominanceMethod=0, noiseCCurve=None):
+                 chrominanceBlueYellow=0.0, gamma=1.7, scale=1.0, colorSpace=0, aggressive=0, chrominanceMethod=0, noiseCCurve=None,
+                 wprof_inverse=None):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
     def c_struct(self):
         c = _DenoiseParamsC(self.luminance, self.luminanceDetail, int(self.luminanceDetailThreshold), self.chrominance,
                             self.chrominanceRedGreen, self.chrominanceBlueYellow, self.gamma, self.scale, int(self.colorSpace),
-                            int(self.aggressive), int(self.chrominanceMethod), None, 0.0)
+                            int(self.aggressive), int(self.chrominanceMethod), None, 0.0, None)
+        if self.wprof_inverse is not None:      # needed by colorSpace 1 (LAB)
+            self._wpi = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(self.wprof_inverse, dtype=np.float64).reshape(9)])
+            c.wprof_inverse = ctypes.cast(self._wpi, ctypes.POINTER(ctypes.c_double))
         if self.noiseCCurve is not None:
             self._curve = np.ascontiguousarray(self.noiseCCurve, dtype=np.float32)
             assert self._curve.size == 501

@@ -239,6 +239,7 @@ void art_hp_destroy(art_hp_ctx* ctx)
     DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch, &ctx->d_small, &ctx->d_work, &ctx->d_dn, &ctx->d_fattal, &ctx->d_small2};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_dn_tables.p) cudaFree(ctx->d_dn_tables.p);
+    if (ctx->d_dn_labtabs.p) cudaFree(ctx->d_dn_labtabs.p);
     if (ctx->d_chain.p) cudaFree(ctx->d_chain.p);
     if (ctx->d_usm_tables.p) cudaFree(ctx->d_usm_tables.p);
     if (ctx->d_xt_cbrt.p) cudaFree(ctx->d_xt_cbrt.p);
@@ -581,8 +582,9 @@ int art_hp_gauss(art_hp_ctx* ctx, float* const* src, float* const* dst, int W, i
 static int check_denoise_params(art_hp_ctx* ctx, const art_hp_denoise_params* P, const double* wprof)
 {
     if (!P || !wprof) return ctx->fail(ART_HP_ERR_INVALID, "null parameters");
-    if (P->colorSpace != 0 || P->chrominanceMethod != 0)
-        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "only colorSpace RGB and chrominanceMethod MANUAL are on the hot path");
+    if ((P->colorSpace != 0 && P->colorSpace != 1) || P->chrominanceMethod != 0)
+        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "only chrominanceMethod MANUAL is on the hot path");
+    if (P->colorSpace == 1 && !P->wprof_inverse) return ctx->fail(ART_HP_ERR_INVALID, "colorSpace LAB needs wprof_inverse");
     if (!(P->scale > 0) || !(P->gamma > 0)) return ctx->fail(ART_HP_ERR_INVALID, "scale and gamma must be positive");
     return ART_HP_OK;
 }

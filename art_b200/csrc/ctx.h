@@ -43,6 +43,8 @@ struct art_hp_ctx {
     std::vector<PoolBlk> pool;
     bool dn_tables_ready = false;        // the constant window / DCT tables of detail_recovery are uploaded once
     DevBuf d_dn_tables;
+    DevBuf d_dn_labtabs;                 // colorSpace LAB: denoiseIGammaTab, denoiseGammaTab, cachef, cachefy
+    bool dn_labtabs_ready = false;
     // pinned staging (two halves for double buffering)
     // colour chain: device LUT slots, their pinned staging and the event that says the staging may be rewritten
     DevBuf d_chain;

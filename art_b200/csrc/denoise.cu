@@ -1,6 +1,6 @@
 // denoise::RGB_denoise for sm_100a: the path ART's driver takes (ipdenoise.cc L1165: kall = 0, isRAW = true).
 //
-// Replaces (reference) rtengine/FTblockDN.cc RGB_denoise L1638-2689 (colorSpace RGB, standard and aggressive quality, chrominance
+// Replaces (reference) rtengine/FTblockDN.cc RGB_denoise L1638-2689 (colorSpace RGB and LAB, standard and aggressive quality, chrominance
 // method MANUAL, Tile_calc L442-478 = one tile), Noise_residualAB L607-635, detail_recovery L1479-1635 with
 // RGBtile_denoise L494-525 / RGBoutput_tile_row L531-558 / boxabsblur (boxblur.h L745-888), Color::gammaf2lut
 // (color.cc L1128-1170), gammaf / rgb2yuv / yuv2rgb (color.h L782-796, L1202-1205), rgbxyz + XYZ2Lab (color.cc L833,
@@ -85,6 +85,31 @@ __device__ __forceinline__ float computeXYZ2Lab(const float* cachef, float f)
     else if (f > 65535.f) return 327.68f * sleef::xcbrtf_scalar(f / 65535.f);
     return lut_clip_below(cachef, 65536, f);
 }
+__device__ __forceinline__ float computeXYZ2LabY(const float* cachefy, float f)
+{   // color.cc L1262-1274
+    if (f != f) return f;
+    if (f < 0.f) return (float)(327.68 * ((24389.0 / 27.0) * f / (double)65535.f));
+    else if (f > 65535.f) return 327.68f * (116.f * sleef::xcbrtf_scalar(f / 65535.f) - 16.f);
+    return lut_clip_below(cachefy, 65536, f);
+}
+__device__ __forceinline__ float lut_noclip(const float* __restrict__ data, int size, float index)
+{   // LUTf(size, 0)::operator[](float), LUT.h L437-459: extrapolates at both ends
+    int idx = (int)index;
+    if (index < 0.f || !(index == index)) idx = 0;
+    else if (index > (float)(size - 2)) idx = size - 2;
+    const float diff = index - (float)idx;
+    const float p1 = data[idx];
+    const float p2 = data[idx + 1] - p1;
+    return p1 + p2 * diff;
+}
+// DenoiseParams::ColorSpace::LAB: Color::denoiseIGammaTab / denoiseGammaTab, cachef / cachefy, working-space matrix and its inverse
+struct LabTabs { int on; const float *dn_igamma, *dn_gamma, *cachef, *cachefy; float wp[9], iwp[9]; };
+__device__ __forceinline__ float f2xyz(float f)
+{   // color.h L767-770
+    const float epsilonExpInv3f = (float)(6.0 / 29.0), kappaInvf = (float)(27.0 / 24389.0);
+    return (f > epsilonExpInv3f) ? f * f * f : (116.f * f - 16.f) * kappaInvf;
+}
+
 __global__ void __launch_bounds__(256) k_dn_ccalc(CcArgs a)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -107,6 +132,7 @@ struct SplitArgs {
     float *L, *a, *bb;            // dense W x H
     float *nvl, *nvc; const float* ccalc; int w2;
     Gam gam; float outer_gam, gain, wy0, wy1, wy2, noisevarL, maxNoiseVarab; int useCC;
+    LabTabs lab;
 };
 __global__ void __launch_bounds__(256) k_dn_split(SplitArgs s)
 {
@@ -114,9 +140,17 @@ __global__ void __launch_bounds__(256) k_dn_split(SplitArgs s)
     if (x >= s.W) return;
     const size_t i = (size_t)y * s.ip + x, o = (size_t)y * s.W + x;
     float X = s.gain * s.r[i], Y = s.gain * s.g[i], Z = s.gain * s.b[i];
+    if (s.lab.on) { X = lut_noclip(s.lab.dn_igamma, 65536, X); Y = lut_noclip(s.lab.dn_igamma, 65536, Y); Z = lut_noclip(s.lab.dn_igamma, 65536, Z); }   // L2093-2097
     X = apply_gam(s.gam, s.outer_gam, X); Y = apply_gam(s.gam, s.outer_gam, Y); Z = apply_gam(s.gam, s.outer_gam, Z);
-    const float l = X * s.wy0 + Y * s.wy1 + Z * s.wy2;
-    s.L[o] = l; s.a[o] = X - l; s.bb[o] = l - Z;
+    if (s.lab.on) {     // Color::rgb2lab(X, Y, Z, l, v, u, wpi): rgbxyz (color.cc L833-838) + XYZ2Lab (L1382-1399)
+        const float* w = s.lab.wp;
+        const float x = (w[0] * X + w[1] * Y + w[2] * Z), y = (w[3] * X + w[4] * Y + w[5] * Z), z = (w[6] * X + w[7] * Y + w[8] * Z);
+        const float fx = computeXYZ2Lab(s.lab.cachef, x / 0.9642f), fy = computeXYZ2Lab(s.lab.cachef, y), fz = computeXYZ2Lab(s.lab.cachef, z / 0.8249f);
+        s.L[o] = computeXYZ2LabY(s.lab.cachefy, y); s.a[o] = 500.0f * (fx - fy); s.bb[o] = 200.0f * (fy - fz);
+    } else {
+        const float l = X * s.wy0 + Y * s.wy1 + Z * s.wy2;
+        s.L[o] = l; s.a[o] = X - l; s.bb[o] = l - Z;
+    }
     if (((x | y) & 1) == 0) {
         const size_t h = (size_t)(y >> 1) * s.w2 + (x >> 1);
         s.nvl[h] = s.noisevarL;
@@ -345,6 +379,7 @@ __global__ void __launch_bounds__(256) k_dn_gather(GatherArgs a)
 struct MergeArgs {
     const float *L, *a, *bb; float *r, *g, *b; size_t op; int W, H;
     Gam igam; float outer_gam, newGain, w10, w11, w12, realred, realblue, qhighFactor;
+    LabTabs lab;
 };
 __global__ void __launch_bounds__(256) k_dn_merge(MergeArgs m)
 {
@@ -358,10 +393,25 @@ __global__ void __launch_bounds__(256) k_dn_merge(MergeArgs m)
         bv *= 1.f + m.qhighFactor * m.realblue / 100.f;
     }
     const float Yv = m.L[i];
-    float Z = Yv - bv;
-    float X = av + Yv;
-    float Y = (Yv - X * m.w10 - Z * m.w12) / m.w11;
+    float X, Y, Z;
+    if (m.lab.on) {     // Color::lab2rgb(L, a, b, X, Y, Z, wpi_inverse): Lab2XYZ (color.cc L1203-1214) + xyz2rgb (L880-885)
+        const float c1By116 = (float)(1.0 / 116.0), c16By116 = (float)(16.0 / 116.0);
+        const float LL = Yv / 327.68f, aa = av / 327.68f, b2 = bv / 327.68f;
+        const float fy = (c1By116 * LL) + c16By116;
+        const float fx = (0.002f * aa) + fy;
+        const float fz = fy - (0.005f * b2);
+        const float x = 65535.0f * f2xyz(fx) * 0.9642f;
+        const float z = 65535.0f * f2xyz(fz) * 0.8249f;
+        const float y = ((double)LL > 8.0) ? 65535.0f * fy * fy * fy : (float)((double)(65535.0f * LL) / (24389.0 / 27.0));
+        const float* w = m.lab.iwp;
+        X = (w[0] * x + w[1] * y + w[2] * z); Y = (w[3] * x + w[4] * y + w[5] * z); Z = (w[6] * x + w[7] * y + w[8] * z);
+    } else {
+        Z = Yv - bv;
+        X = av + Yv;
+        Y = (Yv - X * m.w10 - Z * m.w12) / m.w11;
+    }
     X = apply_gam(m.igam, m.outer_gam, X); Y = apply_gam(m.igam, m.outer_gam, Y); Z = apply_gam(m.igam, m.outer_gam, Z);
+    if (m.lab.on) { X = lut_noclip(m.lab.dn_gamma, 65536, X); Y = lut_noclip(m.lab.dn_gamma, 65536, Y); Z = lut_noclip(m.lab.dn_gamma, 65536, Z); }   // L2533-2537
     m.r[o] = m.newGain * X; m.g[o] = m.newGain * Y; m.b[o] = m.newGain * Z;
 }
 
@@ -494,6 +544,30 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
         }
         tin = tb; tout = tb + TS * TS; dctf = tb + 2 * TS * TS; dctb = tb + 3 * TS * TS;
     }
+    LabTabs labt{};
+    if (P->colorSpace == 1) {      // DenoiseParams::ColorSpace::LAB
+        if (!P->wprof_inverse) return ctx->fail(ART_HP_ERR_INVALID, "colorSpace LAB needs wprof_inverse");
+        int lrc = art_reserve(ctx, ctx->d_dn_labtabs, 4 * 65536 * sizeof(float));
+        if (lrc) return lrc;
+        float* lt = (float*)ctx->d_dn_labtabs.p;
+        if (!ctx->dn_labtabs_ready) {      // color.cc L188-189, L205-233, L278-292 (host libm, as in the reference)
+            std::vector<float> h(4 * 65536);
+            const double eps = 216.0 / 24389.0, kappa = 24389.0 / 27.0, MAXVALF = 65535.f;
+            const int epsmaxint = (int)(MAXVALF * eps);
+            for (int i = 0; i < 65536; i++) {
+                const double x = i / 65535.0;
+                h[i] = (float)(65535.0 * (x <= 0.131889 ? x / 10.0 : std::exp(std::log((x + 0.593503) / 1.593503) * 5.5)));           // denoiseIGammaTab
+                h[65536 + i] = (float)(65535.0 * (x <= 0.013189 ? x * 10.0 : 1.593503 * std::exp(std::log(x) / 5.5) - 0.593503));   // denoiseGammaTab
+                if (i <= epsmaxint) { h[2 * 65536 + i] = (float)(327.68 * ((kappa * i / MAXVALF + 16.0) / 116.0)); h[3 * 65536 + i] = (float)(327.68 * (kappa * i / MAXVALF)); }
+                else { h[2 * 65536 + i] = (float)(327.68 * std::cbrt((double)i / MAXVALF)); h[3 * 65536 + i] = (float)(327.68 * (116.0 * std::cbrt((double)i / MAXVALF) - 16.0)); }
+            }
+            ART_CUDA(ctx, cudaMemcpyAsync(lt, h.data(), sizeof(float) * 4 * 65536, cudaMemcpyHostToDevice, st));
+            ART_CUDA(ctx, cudaStreamSynchronize(st));
+            ctx->dn_labtabs_ready = true;
+        }
+        labt.on = 1; labt.dn_igamma = lt; labt.dn_gamma = lt + 65536; labt.cachef = lt + 2 * 65536; labt.cachefy = lt + 3 * 65536;
+        for (int i = 0; i < 9; ++i) { labt.wp[i] = wp[i]; labt.iwp[i] = static_cast<float>(P->wprof_inverse[i]); }
+    }
     std::vector<float> hcache;
     if (useCC) {       // L1706-1770
         hcache.resize(65536);
@@ -528,7 +602,7 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
     SplitArgs s{};
     s.r = r; s.g = g; s.b = b; s.ip = ip; s.W = W; s.H = H; s.L = Lp; s.a = ap; s.bb = bp; s.nvl = nvl; s.nvc = nvc; s.ccalc = ccalc; s.w2 = w2;
     s.gam = Gam{gamcurve, gam, gamthresh, gamslope, 65535.f}; s.outer_gam = gam; s.gain = gain;
-    s.wy0 = wp[3]; s.wy1 = wp[4]; s.wy2 = wp[5]; s.noisevarL = noisevarL; s.maxNoiseVarab = maxNoiseVarab; s.useCC = useCC;
+    s.wy0 = wp[3]; s.wy1 = wp[4]; s.wy2 = wp[5]; s.noisevarL = noisevarL; s.maxNoiseVarab = maxNoiseVarab; s.useCC = useCC; s.lab = labt;
     const dim3 gfull((W + 255) / 256, H);
     art_prof_begin(ctx, "k_dn_split");
     k_dn_split<<<gfull, 256, 0, st>>>(s);
@@ -615,7 +689,7 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
     MergeArgs m{};
     m.L = Lp; m.a = ap; m.bb = bp; m.r = r; m.g = g; m.b = b; m.op = ip; m.W = W; m.H = H;
     m.igam = Gam{igamcurve, igam, igamthresh, igamslope, 65536.f}; m.outer_gam = gam; m.newGain = 1.f / gain;
-    m.w10 = wp[3]; m.w11 = wp[4]; m.w12 = wp[5]; m.realred = realred; m.realblue = realblue; m.qhighFactor = aggressive ? 1.f / static_cast<float>(0.9) : 1.0f;
+    m.lab = labt; m.w10 = wp[3]; m.w11 = wp[4]; m.w12 = wp[5]; m.realred = realred; m.realblue = realblue; m.qhighFactor = aggressive ? 1.f / static_cast<float>(0.9) : 1.0f;
     art_prof_begin(ctx, "k_dn_merge");
     k_dn_merge<<<gfull, 256, 0, st>>>(m);
     art_prof_end(ctx);

@@ -220,7 +220,7 @@ int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art
  *                      expcomp = 0, noiseLCurve (unset), noiseCCurve, nresi, highresi) (rtengine/FTblockDN.cc L1638-2689)
  *                      as ImProcFunctions::denoise calls it (rtengine/ipdenoise.cc L1165), in place on three planes.
  * Parameters mirror procparams::DenoiseParams (rtengine/procparams.h) for the fields RGB_denoise reads.  Supported:
- * colorSpace RGB (0), aggressive 0 | 1 (QUALITY_STANDARD | QUALITY_HIGH, FTblockDN.cc L1671), chrominanceMethod MANUAL (0); anything else returns ART_HP_ERR_UNSUPPORTED.
+ * colorSpace RGB (0) | LAB (1), aggressive 0 | 1 (QUALITY_STANDARD | QUALITY_HIGH, FTblockDN.cc L1671), chrominanceMethod MANUAL (0); anything else returns ART_HP_ERR_UNSUPPORTED.
  * `scale` is ImProcData::scale.  noiseCCurve: the 501-entry LUT NoiseCurve::Set builds (rtengine/ipdenoise.cc L684-705) and
  * its sum, host pointers, or NULL for "curve not set"; when given, the half-resolution calclum image of
  * ipdenoise.cc L1119-1131 (3 planes of ((H+1)/2) x ((W+1)/2)) must be supplied too.
@@ -238,6 +238,7 @@ typedef struct art_hp_denoise_params {
     int colorSpace, aggressive, chrominanceMethod;
     const float* noiseCCurve;
     float noiseCCurveSum;
+    const double* wprof_inverse;    /* ICCStore::workingSpaceInverseMatrix, 9 doubles: needed when colorSpace == 1 (LAB), else may be NULL */
 } art_hp_denoise_params;
 int art_hp_rgb_denoise(art_hp_ctx* ctx, float* const* r, float* const* g, float* const* b, int W, int H,
                        const art_hp_denoise_params* params, const double wprof[9],
