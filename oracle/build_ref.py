@@ -1104,6 +1104,33 @@ extern "C" int artref_usm(float* R, float* G, float* B, int W, int H, const doub
     multiply(rgb, YY, Y, multiThread);
     return 0;
 }
+
+// the "rld" route of doSharpening (ipsharpen.cc L747-771 without the corner boost): markImpulse(Y, 2), deconvsharpening(copy of Y), multiply
+extern "C" int artref_rld(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double deconvradius,
+                          int deconvamount, float* impulse_out)
+{
+    if (W < 8 || H < 8) return 0;
+    const bool multiThread = true;
+    Imagefloat im{W, H, {R, W}, {G, W}, {B, W}};
+    Imagefloat* rgb = &im;
+    float wsm[3][3]; for (int i = 0; i < 9; ++i) (&wsm[0][0])[i] = (float)wsd[i];
+    TMatrix ws = wsm;
+    array2D<float> Y(ARRAY2D_ALIGNED);
+    get_luminance(rgb, Y, ws, multiThread);
+    float s_scale = std::sqrt(scale);
+    float contrast = pow_F(contrast_p / 100.f, 1.2f) * s_scale;
+    JaggedArray<float> blend(W, H);
+    buildBlendMask(Y, blend, W, H, contrast, 1.f, false, 2.f / s_scale, 1.f);
+    JaggedArray<char> impulse(W, H);
+    markImpulse(W, H, Y, impulse, 2.f);
+    if (impulse_out) for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) impulse_out[(size_t)y * W + x] = impulse[y][x];
+    array2D<float> YY(W, H, Y, ARRAY2D_ALIGNED);
+    double sigma = deconvradius / scale;
+    float amount = deconvamount / 100.f;
+    deconvsharpening(YY, blend, impulse, W, H, sigma, amount, multiThread);
+    multiply(rgb, YY, Y, multiThread);
+    return 0;
+}
 }  // namespace artref_usm
 """
 
@@ -1330,12 +1357,14 @@ def extract(det):
             cut_function(ra, r"^float tileVariance\(float \*\*data[^)]*\)"),
             cut_function(ra, r"^float calcContrastThreshold\(float\*\* luminance[^)]*\)")]
     open(os.path.join(sub, "usm_rtalgo_anon.inc"), "w").write("\n\n".join(anon))
-    pub = [cut_function(ra, r"^void buildBlendMask\(float\*\* luminance[^)]*\)"),
+    pub = [cut_function(ra, r"^void markImpulse\(int width, int height, float \*\*const src, char \*\*impulse, float thresh\)"),
+           cut_function(ra, r"^void buildBlendMask\(float\*\* luminance[^)]*\)"),
            cut_function(ra, r"^void get_luminance\(const Imagefloat \*src[^)]*\)"),
            cut_function(ra, r"^void multiply\(Imagefloat \*img[^)]*\)")]
     open(os.path.join(sub, "usm_rtalgo.inc"), "w").write("\n\n".join(pub))
     ips = ["template <bool reverse>\n" + cut_function(ish, r"^void apply_gamma\(float \*\*Y[^)]*\)"),
            cut_function(ish, r"^void sharpenHaloCtrl\(float\*\* luminance[^)]*\)"),
+           cut_function(ish, r"^void deconvsharpening\(float \*\*luminance, float \*\*blend, char \*\*impulse[^)]*\)"),
            cut_function(ish, r"^void unsharp_mask\(float \*\*Y[^)]*\)")]
     open(os.path.join(sub, "usm_ipsharpen.inc"), "w").write("\n\n".join(ips))
     open(os.path.join(sub, "shim_usm.cc"), "w").write(SHIM_USM_TU)

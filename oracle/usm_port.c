@@ -171,3 +171,193 @@ int artoracle_usm(float* R, float* G, float* B, int W, int H, const double* wsd,
     free(Y); free(YY); free(b2); free(blend);
     return rc;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * "rld" route of doSharpening (ipsharpen.cc L747-771, no corner boost): markImpulse (rt_algo.cc L497-591), deconvsharpening
+ * (ipsharpen.cc L144-230) over gaussianBlur's GAUSS_DIV / GAUSS_MULT forms for sigma <= 1.15: gauss3x3div / mult (gauss.cc L177-274),
+ * gauss5x5div / mult (L331-378, L415-443), gauss7x7div / mult (L276-329, L380-413), kernels L52-92, dispatch L1444-1511.
+ * ------------------------------------------------------------------------------------------------------------------------- */
+#define S_(i, j) src[(size_t)(i) * W + (j)]
+#define D_(i, j) dst[(size_t)(i) * W + (j)]
+#define V_(i, j) divb[(size_t)(i) * W + (j)]
+
+static void kernel5(float sigma, float k[5][5])
+{   /* compute5x5kernel, L73-92 */
+    const double temp = -2.f * (sigma * sigma);
+    float sum = 0.f;
+    for (int i = -2; i <= 2; ++i)
+        for (int j = -2; j <= 2; ++j) {
+            if ((i * i + j * j) <= (3.0 * 0.84) * (3.0 * 0.84)) { k[i + 2][j + 2] = (float)exp((i * i + j * j) / temp); sum += k[i + 2][j + 2]; }
+            else k[i + 2][j + 2] = 0.f;
+        }
+    for (int i = 0; i < 5; ++i) for (int j = 0; j < 5; ++j) k[i][j] /= sum;
+}
+static void kernel7(float sigma, float k[7][7])
+{   /* compute7x7kernel, L52-71 */
+    const double temp = -2.f * (sigma * sigma);
+    float sum = 0.f;
+    for (int i = -3; i <= 3; ++i)
+        for (int j = -3; j <= 3; ++j) {
+            if ((i * i + j * j) <= (3.0 * 1.15) * (3.0 * 1.15)) { k[i + 3][j + 3] = (float)exp((i * i + j * j) / temp); sum += k[i + 3][j + 3]; }
+            else k[i + 3][j + 3] = 0.f;
+        }
+    for (int i = 0; i < 7; ++i) for (int j = 0; j < 7; ++j) k[i][j] /= sum;
+}
+static inline float conv5(const float* src, int W, int i, int j, const float k[5][5])
+{
+    const float c21 = k[0][1], c20 = k[0][2], c11 = k[1][1], c10 = k[1][2], c00 = k[2][2];
+    return c21 * (S_(i - 2, j - 1) + S_(i - 2, j + 1) + S_(i - 1, j - 2) + S_(i - 1, j + 2) + S_(i + 1, j - 2) + S_(i + 1, j + 2) + S_(i + 2, j - 1) + S_(i + 2, j + 1)) +
+           c20 * (S_(i - 2, j) + S_(i, j - 2) + S_(i, j + 2) + S_(i + 2, j)) +
+           c11 * (S_(i - 1, j - 1) + S_(i - 1, j + 1) + S_(i + 1, j - 1) + S_(i + 1, j + 1)) +
+           c10 * (S_(i - 1, j) + S_(i, j - 1) + S_(i, j + 1) + S_(i + 1, j)) +
+           c00 * S_(i, j);
+}
+static inline float conv7(const float* src, int W, int i, int j, const float k[7][7])
+{   /* note `src[i - 2][j + 1] * c21` inside the c21 group: as written in the reference (L302, L402) */
+    const float c31 = k[0][2], c30 = k[0][3], c22 = k[1][1], c21 = k[1][2], c20 = k[1][3], c11 = k[2][2], c10 = k[2][3], c00 = k[3][3];
+    return c31 * (S_(i - 3, j - 1) + S_(i - 3, j + 1) + S_(i - 1, j - 3) + S_(i - 1, j + 3) + S_(i + 1, j - 3) + S_(i + 1, j + 3) + S_(i + 3, j - 1) + S_(i + 3, j + 1)) +
+           c30 * (S_(i - 3, j) + S_(i, j - 3) + S_(i, j + 3) + S_(i + 3, j)) +
+           c22 * (S_(i - 2, j - 2) + S_(i - 2, j + 2) + S_(i + 2, j - 2) + S_(i + 2, j + 2)) +
+           c21 * (S_(i - 2, j - 1) + S_(i - 2, j + 1) * c21 + S_(i - 1, j - 2) + S_(i - 1, j + 2) + S_(i + 1, j - 2) + S_(i + 1, j + 2) + S_(i + 2, j - 1) + S_(i + 2, j + 1)) +
+           c20 * (S_(i - 2, j) + S_(i, j - 2) + S_(i, j + 2) + S_(i + 2, j)) +
+           c11 * (S_(i - 1, j - 1) + S_(i - 1, j + 1) + S_(i + 1, j - 1) + S_(i + 1, j + 1)) +
+           c10 * (S_(i - 1, j) + S_(i, j - 1) + S_(i, j + 1) + S_(i + 1, j)) +
+           c00 * S_(i, j);
+}
+/* the 3x3 forms: value of the (bordered) 3x3 blur at (i, j) */
+static inline float conv3(const float* src, int W, int H, int i, int j, float c0, float c1, float c2, float b0, float b1)
+{
+    const int top = (i == 0 || i == H - 1), side = (j == 0 || j == W - 1);
+    if (top && side) return S_(i, j);
+    if (top) return b1 * (S_(i, j - 1) + S_(i, j + 1)) + b0 * S_(i, j);
+    if (side) return b1 * (S_(i - 1, j) + S_(i + 1, j)) + b0 * S_(i, j);
+    return c2 * (S_(i - 1, j - 1) + S_(i - 1, j + 1) + S_(i + 1, j - 1) + S_(i + 1, j + 1)) + c1 * (S_(i - 1, j) + S_(i, j - 1) + S_(i, j + 1) + S_(i + 1, j)) + c0 * S_(i, j);
+}
+/* gaussianBlur(src, dst, W, H, sigma, nullptr, GAUSS_DIV, divb) / (..., GAUSS_MULT) for 0.25 <= sigma <= 1.15, src != dst; 1 = unsupported sigma */
+static int gauss_divmult(const float* src, float* dst, const float* divb, int W, int H, double sigma, int mult)
+{
+    if (sigma < 0.25) {        /* GAUSS_SKIP: plain copy whatever the type (L1436-1443) */
+        memcpy(dst, src, sizeof(float) * (size_t)W * H);
+        return 0;
+    }
+    if (sigma < 0.6) {
+        double c0 = 1.0, c1 = exp(-0.5 * ((1.0 / sigma) * (1.0 / sigma))), c2 = exp(-((1.0 / sigma) * (1.0 / sigma)));
+        const double sum = c0 + 4.0 * (c1 + c2);
+        c0 /= sum; c1 /= sum; c2 /= sum;
+        double b1 = exp(-1.0 / (2.0 * sigma * sigma));
+        const double bsum = 2.0 * b1 + 1.0;
+        b1 /= bsum;
+        const double b0 = 1.0 / bsum;
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < W; ++j) {
+                const float t = conv3(src, W, H, i, j, (float)c0, (float)c1, (float)c2, (float)b0, (float)b1);
+                if (mult) D_(i, j) *= t;
+                else D_(i, j) = maxr(V_(i, j) / (t > 0.f ? t : 1.f), 0.f);
+            }
+        return 0;
+    }
+    if (sigma <= 0.84) {
+        float k[5][5];
+        kernel5((float)sigma, k);
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < W; ++j) {
+                const int inner = i >= 2 && i < H - 2 && j >= 2 && j < W - 2;
+                if (mult) { if (inner) D_(i, j) *= conv5(src, W, i, j, k); }
+                else D_(i, j) = inner ? V_(i, j) / maxr(conv5(src, W, i, j, k), 0.00001f) : 1.f;
+            }
+        return 0;
+    }
+    if (sigma <= 1.15) {
+        float k[7][7];
+        kernel7((float)sigma, k);
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < W; ++j) {
+                const int inner = i >= 3 && i < H - 3 && j >= 3 && j < W - 3;
+                if (mult) { if (inner) D_(i, j) *= conv7(src, W, i, j, k); }
+                else D_(i, j) = inner ? V_(i, j) / maxr(conv7(src, W, i, j, k), 0.00001f) : 1.f;
+            }
+        return 0;
+    }
+    return 1;
+}
+#undef S_
+#undef D_
+#undef V_
+
+/* markImpulse(width, height, src, impulse, thresh), rt_algo.cc L497-591: the SSE2 and scalar forms agree (same summation order per pixel;
+ * the sum contains hpfabs itself, so it cannot round below it and the sign test equals the comparison) */
+int artoracle_mark_impulse(const float* src, unsigned char* impulse, int W, int H, float thresh)
+{
+    float* lpf = (float*)malloc(sizeof(float) * (size_t)W * H);
+    int rc = artoracle_gauss(src, W, lpf, W, W, H, (double)maxr(2.f, thresh - 1.f));
+    const float impthr = maxr(1.f, 5.5f - thresh);
+    const float impthrDiv24 = impthr / 24.0f;
+    for (int i = 0; i < H && !rc; i++)
+        for (int j = 0; j < W; j++) {
+            const float hpfabs = fabsf(src[(size_t)i * W + j] - lpf[(size_t)i * W + j]);
+            float hfnbrave = 0;
+            for (int i1 = i - 2 > 0 ? i - 2 : 0; i1 <= (i + 2 < H - 1 ? i + 2 : H - 1); i1++)
+                for (int j1 = j - 2 > 0 ? j - 2 : 0; j1 <= (j + 2 < W - 1 ? j + 2 : W - 1); j1++)
+                    hfnbrave += fabsf(src[(size_t)i1 * W + j1] - lpf[(size_t)i1 * W + j1]);
+            impulse[(size_t)i * W + j] = (hpfabs > ((hfnbrave - hpfabs) * impthrDiv24));
+        }
+    free(lpf);
+    return rc;
+}
+
+/* deconvsharpening(luminance, blend, impulse, W, H, sigma, amount), ipsharpen.cc L144-230 */
+static int deconv(float* lum, const float* blend, const unsigned char* impulse, int W, int H, double sigma, float amount)
+{
+    if (amount <= 0) return 0;
+    if (sigma < 0.2f) return 0;
+    if (sigma > 1.15) return 1;
+    const size_t n = (size_t)W * H;
+    const int maxiter = 20;
+    const float delta_factor = 0.2f, offset = 1000.f;
+    float* tmp = (float*)malloc(sizeof(float) * n); float* tmpI = (float*)malloc(sizeof(float) * n); float* out = (float*)malloc(sizeof(float) * n);
+    for (size_t k = 0; k < n; ++k) { lum[k] += offset; tmpI[k] = maxr(lum[k], 0.f); out[k] = NAN; }
+#define GET_OUTPUT(k) ((tmpI[k] != tmpI[k]) ? lum[k] : ({ const float b_ = impulse[k] ? 0.f : blend[k] * amount; b_ * maxr(tmpI[k], 0.0f) + (1.f - b_) * lum[k]; }))
+    for (int it = 0; it < maxiter; it++) {
+        gauss_divmult(tmpI, tmp, lum, W, H, sigma, 0);
+        gauss_divmult(tmp, tmpI, NULL, W, H, sigma, 1);
+        for (size_t k = 0; k < n; ++k)
+            if (out[k] != out[k]) {
+                const float l = lum[k];
+                const float delta = l * delta_factor;
+                if (fabsf(tmpI[k] - l) > delta) out[k] = GET_OUTPUT(k);
+            }
+    }
+    for (size_t k = 0; k < n; ++k) {
+        float l = out[k];
+        if (l != l) l = GET_OUTPUT(k);
+        lum[k] = maxr(l - offset, 0.f);
+    }
+#undef GET_OUTPUT
+    free(tmp); free(tmpI); free(out);
+    return 0;
+}
+
+int artoracle_rld(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double deconvradius,
+                  int deconvamount, float* impulse_out)
+{
+    if (W < 8 || H < 8) return 0;
+    const size_t n = (size_t)W * H;
+    const float w0 = (float)wsd[3], w1 = (float)wsd[4], w2 = (float)wsd[5];
+    float* Y = (float*)malloc(sizeof(float) * n); float* YY = (float*)malloc(sizeof(float) * n); float* blend = (float*)malloc(sizeof(float) * n);
+    unsigned char* impulse = (unsigned char*)malloc(n);
+    for (size_t k = 0; k < n; ++k) Y[k] = R[k] * w0 + G[k] * w1 + B[k] * w2;
+    const float s_scale = (float)sqrt(scale);
+    const float contrast = pow_F_scalar((float)(contrast_p / 100.f), 1.2f) * s_scale;
+    int rc = artoracle_blend_mask(Y, blend, W, H, contrast, 1.f, 2.f / s_scale);
+    if (!rc) rc = artoracle_mark_impulse(Y, impulse, W, H, 2.f);
+    if (impulse_out) for (size_t k = 0; k < n; ++k) impulse_out[k] = impulse[k];
+    memcpy(YY, Y, sizeof(float) * n);
+    if (!rc) rc = deconv(YY, blend, impulse, W, H, deconvradius / scale, deconvamount / 100.f);
+    for (size_t k = 0; k < n && !rc; ++k)
+        if (Y[k] > 0.f) {
+            const float f = YY[k] / Y[k];
+            R[k] *= f; G[k] *= f; B[k] *= f;
+        }
+    free(Y); free(YY); free(blend); free(impulse);
+    return rc;
+}

@@ -78,3 +78,39 @@ def test_blend_mask_spans_range():
     planes = scene(301, 203, 5)
     _, blend = run(oracle.ref().lib, "artref_usm", planes)
     assert blend.min() < 0.05 and blend.max() > 0.95
+
+
+# ---- "rld" (RL deconvolution) route: markImpulse + deconvsharpening over gaussianBlur's GAUSS_DIV / GAUSS_MULT forms
+def run_rld(lib, name, planes, scale=1.0, contrast=20.0, radius=0.75, amount=100):
+    out = [np.ascontiguousarray(p).copy() for p in planes]
+    H, W = out[0].shape
+    imp = np.zeros((H, W), np.float32)
+    rc = getattr(lib, name)(out[0].ctypes.data_as(fp), out[1].ctypes.data_as(fp), out[2].ctypes.data_as(fp), W, H, PROPHOTO.ctypes.data_as(dp),
+                            D(scale), D(contrast), D(radius), int(amount), imp.ctypes.data_as(fp))
+    assert rc == 0
+    return out, imp
+
+
+RLD_CASES = [dict(), dict(radius=0.5, amount=60), dict(radius=1.0, amount=150), dict(radius=0.84), dict(radius=1.15, contrast=0.0),
+             dict(radius=0.3), dict(radius=0.22), dict(amount=0), dict(scale=2.0, radius=1.5)]
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("case", range(len(RLD_CASES)))
+@pytest.mark.parametrize("wild", [False, True])
+def test_rld(W, H, case, wild):
+    planes = scene(W, H, W * 7 + H + case, wild)
+    a, ia = run_rld(oracle.port().lib, "artoracle_rld", planes, **RLD_CASES[case])
+    b, ib = run_rld(oracle.ref().lib, "artref_rld", planes, **RLD_CASES[case])
+    same([ia], [ib], ["impulse"])
+    same(a, b)
+
+
+@needs_ref
+def test_rld_changes_the_image_and_marks_impulses():
+    planes = scene(301, 203, 5)
+    planes[1][50, 60] += 20000.0            # an isolated spike
+    out, imp = run_rld(oracle.ref().lib, "artref_rld", planes)
+    assert imp[50, 60] == 1 and 0 < imp.mean() < 0.2
+    assert any((x != y).any() for x, y in zip(out, planes))
