@@ -183,11 +183,241 @@ __global__ void __launch_bounds__(256) k_usm_apply_halo(float* __restrict__ R, f
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// "rld": RL-deconvolution sharpening, doSharpening L747-771 without the corner boost: markImpulse (rt_algo.cc L497-591),
+// deconvsharpening (ipsharpen.cc L144-230) over gaussianBlur's GAUSS_DIV / GAUSS_MULT forms for sigma <= 1.15 (gauss.cc L177-443:
+// 3x3 with its border rules, 5x5, 7x7 with the `* c21` slip of L302 / L402 kept), multiply.  20 iterations x 2 stencil passes.
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rld_copy_lum(const float* __restrict__ R, const float* __restrict__ G, const float* __restrict__ B, size_t ip,
+                                                      float* __restrict__ Y, size_t yp, int W, int H, float w0, float w1, float w2)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const size_t i = (size_t)y * ip + x;
+        Y[(size_t)y * yp + x] = R[i] * w0 + G[i] * w1 + B[i] * w2;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_rld_impulse(const float* __restrict__ src, const float* __restrict__ lpf, size_t yp, unsigned char* __restrict__ imp,
+                                                     int W, int H, float impthrDiv24)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const float hpfabs = fabsf(src[(size_t)y * yp + x] - lpf[(size_t)y * yp + x]);
+        float hfnbrave = 0.f;
+        for (int i1 = max(0, y - 2); i1 <= min(y + 2, H - 1); i1++)
+            for (int j1 = max(0, x - 2); j1 <= min(x + 2, W - 1); j1++)
+                hfnbrave += fabsf(src[(size_t)i1 * yp + j1] - lpf[(size_t)i1 * yp + j1]);
+        imp[(size_t)y * yp + x] = hpfabs > ((hfnbrave - hpfabs) * impthrDiv24);
+    }
+}
+
+struct RldK { int size; float c[8]; float c3[5]; };      // 5x5: c21 c20 c11 c10 c00; 7x7: c31 c30 c22 c21 c20 c11 c10 c00; 3x3: c0 c1 c2 b0 b1
+
+__device__ __forceinline__ float rld_conv(const RldK& k, const float* __restrict__ s, ptrdiff_t p, int W, int H, int x, int y, bool& inner)
+{
+#define S(dy, dx) s[(dy) * p + (dx)]
+    if (k.size == 3) {
+        inner = true;
+        const bool top = (y == 0 || y == H - 1), side = (x == 0 || x == W - 1);
+        if (top && side) return S(0, 0);
+        if (top) return k.c3[4] * (S(0, -1) + S(0, 1)) + k.c3[3] * S(0, 0);
+        if (side) return k.c3[4] * (S(-1, 0) + S(1, 0)) + k.c3[3] * S(0, 0);
+        return k.c3[2] * (S(-1, -1) + S(-1, 1) + S(1, -1) + S(1, 1)) + k.c3[1] * (S(-1, 0) + S(0, -1) + S(0, 1) + S(1, 0)) + k.c3[0] * S(0, 0);
+    }
+    if (k.size == 5) {
+        inner = y >= 2 && y < H - 2 && x >= 2 && x < W - 2;
+        if (!inner) return 0.f;
+        return k.c[0] * (S(-2, -1) + S(-2, 1) + S(-1, -2) + S(-1, 2) + S(1, -2) + S(1, 2) + S(2, -1) + S(2, 1)) +
+               k.c[1] * (S(-2, 0) + S(0, -2) + S(0, 2) + S(2, 0)) +
+               k.c[2] * (S(-1, -1) + S(-1, 1) + S(1, -1) + S(1, 1)) +
+               k.c[3] * (S(-1, 0) + S(0, -1) + S(0, 1) + S(1, 0)) +
+               k.c[4] * S(0, 0);
+    }
+    inner = y >= 3 && y < H - 3 && x >= 3 && x < W - 3;
+    if (!inner) return 0.f;
+    const float c31 = k.c[0], c30 = k.c[1], c22 = k.c[2], c21 = k.c[3], c20 = k.c[4], c11 = k.c[5], c10 = k.c[6], c00 = k.c[7];
+    return c31 * (S(-3, -1) + S(-3, 1) + S(-1, -3) + S(-1, 3) + S(1, -3) + S(1, 3) + S(3, -1) + S(3, 1)) +
+           c30 * (S(-3, 0) + S(0, -3) + S(0, 3) + S(3, 0)) +
+           c22 * (S(-2, -2) + S(-2, 2) + S(2, -2) + S(2, 2)) +
+           c21 * (S(-2, -1) + S(-2, 1) * c21 + S(-1, -2) + S(-1, 2) + S(1, -2) + S(1, 2) + S(2, -1) + S(2, 1)) +
+           c20 * (S(-2, 0) + S(0, -2) + S(0, 2) + S(2, 0)) +
+           c11 * (S(-1, -1) + S(-1, 1) + S(1, -1) + S(1, 1)) +
+           c10 * (S(-1, 0) + S(0, -1) + S(0, 1) + S(1, 0)) +
+           c00 * S(0, 0);
+#undef S
+}
+
+__global__ void __launch_bounds__(256) k_rld_init(const float* __restrict__ Y, float* __restrict__ lum, float* __restrict__ tmpI, float* __restrict__ out,
+                                                  size_t yp, int W, int H)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const size_t o = (size_t)y * yp + x;
+        const float l = Y[o] + 1000.f;
+        lum[o] = l;
+        tmpI[o] = maxr(l, 0.f);
+        out[o] = __int_as_float(0x7fc00000);
+    }
+}
+
+// gaussianBlur(tmpI, tmp, sigma, nullptr, GAUSS_DIV, luminance)
+__global__ void __launch_bounds__(256) k_rld_div(RldK k, const float* __restrict__ tmpI, const float* __restrict__ lum, float* __restrict__ tmp, size_t yp, int W, int H)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const size_t o = (size_t)y * yp + x;
+        bool inner;
+        const float t = rld_conv(k, tmpI + o, (ptrdiff_t)yp, W, H, x, y, inner);
+        if (k.size == 3) tmp[o] = maxr(lum[o] / (t > 0.f ? t : 1.f), 0.f);
+        else tmp[o] = inner ? lum[o] / maxr(t, 0.00001f) : 1.f;          // std::max(val, 0.00001f)
+    }
+}
+
+// gaussianBlur(tmp, tmpI, sigma, nullptr, GAUSS_MULT) fused with check_stop (L189-199) of the same pixel
+__global__ void __launch_bounds__(256) k_rld_mult(RldK k, const float* __restrict__ tmp, float* __restrict__ tmpI, const float* __restrict__ lum, float* __restrict__ out,
+                                                  const unsigned char* __restrict__ imp, const float* __restrict__ blend, float amount, size_t yp, int W, int H)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const size_t o = (size_t)y * yp + x;
+        bool inner;
+        const float t = rld_conv(k, tmp + o, (ptrdiff_t)yp, W, H, x, y, inner);
+        float v = tmpI[o];
+        if (inner) { v = v * t; tmpI[o] = v; }
+        const float cur = out[o];
+        if (cur != cur) {
+            const float l = lum[o];
+            const float delta = l * 0.2f;
+            if (fabsf(v - l) > delta) {
+                float res;
+                if (v != v) res = l;
+                else { const float bb = imp[o] ? 0.f : blend[o] * amount; res = bb * maxr(v, 0.0f) + (1.f - bb) * l; }
+                out[o] = res;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_rld_final(float* __restrict__ R, float* __restrict__ G, float* __restrict__ B, size_t ip, const float* __restrict__ Y,
+                                                   const float* __restrict__ out, const float* __restrict__ tmpI, const float* __restrict__ lum,
+                                                   const unsigned char* __restrict__ imp, const float* __restrict__ blend, float amount, size_t yp, int W, int H)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const size_t i = (size_t)y * ip + x, o = (size_t)y * yp + x;
+        float l = out[o];
+        if (l != l) {
+            const float v = tmpI[o], lu = lum[o];
+            if (v != v) l = lu;
+            else { const float bb = imp[o] ? 0.f : blend[o] * amount; l = bb * maxr(v, 0.0f) + (1.f - bb) * lu; }
+        }
+        const float yy = maxr(l - 1000.f, 0.f), den = Y[o];
+        if (den > 0.f) {
+            const float f = yy / den;
+            R[i] *= f; G[i] *= f; B[i] *= f;
+        }
+    }
+}
+
 }  // namespace
+
+static int rld_kernel(double sigma, RldK* k)
+{   // the coefficient set gaussianBlurImpl would use for GAUSS_DIV / GAUSS_MULT at this sigma (gauss.cc L1444-1511, L52-92); 0.25 <= sigma <= 1.15
+    if (sigma < 0.6) {
+        double c0 = 1.0, c1 = std::exp(-0.5 * ((1.0 / sigma) * (1.0 / sigma))), c2 = std::exp(-((1.0 / sigma) * (1.0 / sigma)));
+        const double sum = c0 + 4.0 * (c1 + c2);
+        c0 /= sum; c1 /= sum; c2 /= sum;
+        double b1 = std::exp(-1.0 / (2.0 * sigma * sigma));
+        const double bsum = 2.0 * b1 + 1.0;
+        b1 /= bsum;
+        k->size = 3; k->c3[0] = (float)c0; k->c3[1] = (float)c1; k->c3[2] = (float)c2; k->c3[3] = (float)(1.0 / bsum); k->c3[4] = (float)b1;
+        return 0;
+    }
+    const int half = sigma <= 0.84 ? 2 : 3;
+    const double lim = half == 2 ? (3.0 * 0.84) * (3.0 * 0.84) : (3.0 * 1.15) * (3.0 * 1.15);
+    const float sg = (float)sigma;
+    const double temp = -2.f * (sg * sg);
+    float kk[7][7], sum = 0.f;
+    for (int i = -half; i <= half; ++i)
+        for (int j = -half; j <= half; ++j) {
+            if ((i * i + j * j) <= lim) { kk[i + half][j + half] = (float)std::exp((i * i + j * j) / temp); sum += kk[i + half][j + half]; }
+            else kk[i + half][j + half] = 0.f;
+        }
+    for (int i = 0; i <= 2 * half; ++i) for (int j = 0; j <= 2 * half; ++j) kk[i][j] /= sum;
+    if (half == 2) { k->size = 5; k->c[0] = kk[0][1]; k->c[1] = kk[0][2]; k->c[2] = kk[1][1]; k->c[3] = kk[1][2]; k->c[4] = kk[2][2]; }
+    else { k->size = 7; k->c[0] = kk[0][2]; k->c[1] = kk[0][3]; k->c[2] = kk[1][1]; k->c[3] = kk[1][2]; k->c[4] = kk[1][3]; k->c[5] = kk[2][2]; k->c[6] = kk[2][3]; k->c[7] = kk[3][3]; }
+    return 0;
+}
+
+static int art_rld_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_sharpen_params* p, const double* ws9)
+{
+    const double scale = p->scale > 0 ? p->scale : 1.0;
+    const double sigma = p->deconvradius / scale;
+    const float amount = p->deconvamount / 100.f;
+    if (p->deconvCornerBoost / scale > 0.01f) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "rld corner boost is not on the hot path");
+    if (amount > 0 && !(sigma < 0.2f) && sigma > 1.15) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "rld with sigma %.3f > 1.15 (recursive GAUSS_DIV / GAUSS_MULT forms) is not on the hot path", sigma);
+    if (amount <= 0 || sigma < 0.2f) return ART_HP_OK;           // deconvsharpening returns at once (L146-155): multiply() then scales by exactly 1
+    cudaStream_t st = ctx->stream;
+    int rc;
+    const size_t yp = round_up((size_t)W, 32), pl = yp * (size_t)H;
+    float* planes = nullptr;
+    if ((rc = art_pool_alloc(ctx, (6 * pl + pl / 4 + 64) * sizeof(float), (void**)&planes))) return rc;
+    float *Y = planes, *blend = Y + pl, *lum = blend + pl, *tmp = lum + pl, *tmpI = tmp + pl, *out = tmpI + pl;
+    unsigned char* imp = reinterpret_cast<unsigned char*>(out + pl);
+    const dim3 blk(256), grid((W + 255) / 256, std::min(H, 148 * 8));
+    art_prof_begin(ctx, "k_rld_copy_lum");
+    k_rld_copy_lum<<<grid, blk, 0, st>>>(r, g, b, ip, Y, yp, W, H, (float)ws9[3], (float)ws9[4], (float)ws9[5]);
+    art_prof_end(ctx);
+    const float s_scale = (float)std::sqrt(scale);
+    if (p->contrast == 0.0) {
+        k_usm_fill<<<grid, blk, 0, st>>>(blend, yp, W, H, 1.f);
+    } else {
+        k_usm_contrast<<<grid, blk, 0, st>>>(Y, yp, blend, yp, W, H, (float)(p->contrast / 100.f), s_scale, 1.f, 0.0625f / 327.68f * 1.f);
+        if ((rc = art_gauss_dev(ctx, blend, yp, blend, yp, W, H, (double)(2.f / s_scale)))) { art_pool_free(ctx, planes); return rc; }
+    }
+    // markImpulse(W, H, Y, impulse, 2.f): lpf = gaussianBlur(Y, max(2, thresh - 1)) into tmp
+    if ((rc = art_gauss_dev(ctx, Y, yp, tmp, yp, W, H, 2.0))) { art_pool_free(ctx, planes); return rc; }
+    art_prof_begin(ctx, "k_rld_impulse");
+    k_rld_impulse<<<grid, blk, 0, st>>>(Y, tmp, yp, imp, W, H, 3.5f / 24.0f);
+    art_prof_end(ctx);
+    k_rld_init<<<grid, blk, 0, st>>>(Y, lum, tmpI, out, yp, W, H);
+    ctx->launches += 5;
+    RldK k{};
+    if (sigma < 0.25) {      // GAUSS_SKIP: both blurs are plain copies, tmpI stays max(lum, 0) through all 20 iterations; check_stop never fires
+        // (|tmpI - l| = 0 for l >= 0; for l < 0, |0 - l| = -l > 0.2 l): handled by the generic kernels with an identity "3x3" kernel
+        k.size = 3; k.c3[0] = 1.f; k.c3[1] = 0.f; k.c3[2] = 0.f; k.c3[3] = 1.f; k.c3[4] = 0.f;
+        art_pool_free(ctx, planes);
+        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "rld with 0.2 <= sigma < 0.25 (GAUSS_SKIP copies) is not on the hot path");
+    }
+    rld_kernel(sigma, &k);
+    art_prof_begin(ctx, "k_rld_iterations");
+    for (int it = 0; it < 20; ++it) {
+        k_rld_div<<<grid, blk, 0, st>>>(k, tmpI, lum, tmp, yp, W, H);
+        k_rld_mult<<<grid, blk, 0, st>>>(k, tmp, tmpI, lum, out, imp, blend, amount, yp, W, H);
+    }
+    art_prof_end(ctx);
+    art_prof_begin(ctx, "k_rld_final");
+    k_rld_final<<<grid, blk, 0, st>>>(r, g, b, ip, Y, out, tmpI, lum, imp, blend, amount, yp, W, H);
+    art_prof_end(ctx);
+    ctx->launches += 41;
+    ART_CUDA(ctx, cudaGetLastError());
+    art_pool_free(ctx, planes);
+    return ART_HP_OK;
+}
 
 int art_usm_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_sharpen_params* p, const double* ws9)
 {
     if (p->amount < 1 || W < 8 || H < 8) return ART_HP_OK;      // doSharpening L716-718
+    if (p->method == 1) return art_rld_dev(ctx, r, g, b, ip, W, H, p, ws9);
+    if (p->method != 0) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "sharpening method %d (psf) is not on the hot path", p->method);
     if (p->edgesonly) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "edges-only sharpening (bilateral pre-filter) is not on the hot path");
     cudaStream_t st = ctx->stream;
     int rc;

@@ -372,7 +372,7 @@ int art_hp_color_chain_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g
  *                      defaults rtengine/procparams.cc L1756-1776); threshold = {bottom_left, top_left, bottom_right,
  *                      top_right}; scale = ImProcFunctions::scale (1 for full-resolution output); ws =
  *                      ICCStore::workingSpaceMatrix.  amount < 1 or an image under 8x8 returns untouched, like the
- *                      reference (L716-718).  halocontrol runs sharpenHaloCtrl (L80-141); edgesonly returns ART_HP_ERR_UNSUPPORTED.  Bit-identical to the
+ *                      reference (L716-718).  method 1 selects the "rld" route (the reference's default method).  halocontrol runs sharpenHaloCtrl (L80-141); edgesonly returns ART_HP_ERR_UNSUPPORTED.  Bit-identical to the
  *                      reference's SSE2 build.
  */
 typedef struct art_hp_sharpen_params {
@@ -384,6 +384,10 @@ typedef struct art_hp_sharpen_params {
     int    halocontrol;         /* 0 | 1 */
     int    halocontrol_amount;
     double scale;               /* 1 */
+    int    method;              /* 0 = "usm", 1 = "rld" (RL deconvolution: markImpulse + deconvsharpening, ipsharpen.cc L144-230, L747-771) */
+    double deconvradius;        /* 0.75; rld is on the hot path for 0.25 <= deconvradius / scale <= 1.15 (3x3 / 5x5 / 7x7 GAUSS_DIV / GAUSS_MULT) */
+    int    deconvamount;        /* 100 */
+    double deconvCornerBoost;   /* must be 0 */
 } art_hp_sharpen_params;
 int art_hp_sharpen_usm(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b,
                        const art_hp_sharpen_params* params, const double ws[9]);
