@@ -305,23 +305,51 @@ __global__ void __launch_bounds__(256) k_rld_mult(RldK k, const float* __restric
     }
 }
 
-__global__ void __launch_bounds__(256) k_rld_final(float* __restrict__ R, float* __restrict__ G, float* __restrict__ B, size_t ip, const float* __restrict__ Y,
-                                                   const float* __restrict__ out, const float* __restrict__ tmpI, const float* __restrict__ lum,
+__global__ void __launch_bounds__(256) k_rld_final(float* __restrict__ YY, const float* __restrict__ out, const float* __restrict__ tmpI, const float* __restrict__ lum,
                                                    const unsigned char* __restrict__ imp, const float* __restrict__ blend, float amount, size_t yp, int W, int H)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= W) return;
     for (int y = blockIdx.y; y < H; y += gridDim.y) {
-        const size_t i = (size_t)y * ip + x, o = (size_t)y * yp + x;
+        const size_t o = (size_t)y * yp + x;
         float l = out[o];
         if (l != l) {
             const float v = tmpI[o], lu = lum[o];
             if (v != v) l = lu;
             else { const float bb = imp[o] ? 0.f : blend[o] * amount; l = bb * maxr(v, 0.0f) + (1.f - bb) * lu; }
         }
-        const float yy = maxr(l - 1000.f, 0.f), den = Y[o];
+        YY[o] = maxr(l - 1000.f, 0.f);
+    }
+}
+
+// YY = intp(CornerBoostMask(x, y), YY2, YY), ipsharpen.cc L313-338, L762-771
+__global__ void __launch_bounds__(256) k_rld_corner_mix(float* __restrict__ YY, const float* __restrict__ YY2, size_t yp, int W, int H,
+                                                        int ox, int oy, int w2, int h2, float r2, float sg)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const size_t o = (size_t)y * yp + x;
+        const int xx = x + ox - w2, yy = y + oy - h2;
+        const float distance = sqrtf((float)(xx * xx + yy * yy));
+        const float d = maxr(distance - r2, 0.f);
+        const float e = sleef::xexpf_scalar((-(d * d)) / sg);
+        const float m = 1.f - maxr(0.f, minr(e, 1.f));
+        YY[o] = m * YY2[o] + (1.f - m) * YY[o];
+    }
+}
+
+// multiply(rgb, YY, Y), rt_algo.cc L958-975
+__global__ void __launch_bounds__(256) k_rld_multiply(float* __restrict__ R, float* __restrict__ G, float* __restrict__ B, size_t ip,
+                                                      const float* __restrict__ YY, const float* __restrict__ Y, size_t yp, int W, int H)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const size_t i = (size_t)y * ip + x, o = (size_t)y * yp + x;
+        const float den = Y[o];
         if (den > 0.f) {
-            const float f = yy / den;
+            const float f = YY[o] / den;
             R[i] *= f; G[i] *= f; B[i] *= f;
         }
     }
@@ -357,21 +385,50 @@ static int rld_kernel(double sigma, RldK* k)
     return 0;
 }
 
+// deconvsharpening(YY = copy of Y, blend, impulse, sigma, amount) into the plane YY
+static int rld_deconv(art_hp_ctx* ctx, const float* Y, const float* blend, const unsigned char* imp, double sigma, float amount,
+                      float* YY, float* lum, float* tmp, float* tmpI, float* out, size_t yp, int W, int H)
+{
+    cudaStream_t st = ctx->stream;
+    const dim3 blk(256), grid((W + 255) / 256, std::min(H, 148 * 8));
+    if (amount <= 0 || sigma < 0.2f) {       // returns at once (L146-155): the copy of Y stays as it is
+        ART_CUDA(ctx, cudaMemcpyAsync(YY, Y, yp * (size_t)H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return ART_HP_OK;
+    }
+    RldK k{};
+    rld_kernel(sigma, &k);
+    k_rld_init<<<grid, blk, 0, st>>>(Y, lum, tmpI, out, yp, W, H);
+    art_prof_begin(ctx, "k_rld_iterations");
+    for (int it = 0; it < 20; ++it) {
+        k_rld_div<<<grid, blk, 0, st>>>(k, tmpI, lum, tmp, yp, W, H);
+        k_rld_mult<<<grid, blk, 0, st>>>(k, tmp, tmpI, lum, out, imp, blend, amount, yp, W, H);
+    }
+    art_prof_end(ctx);
+    art_prof_begin(ctx, "k_rld_final");
+    k_rld_final<<<grid, blk, 0, st>>>(YY, out, tmpI, lum, imp, blend, amount, yp, W, H);
+    art_prof_end(ctx);
+    ctx->launches += 42;
+    return ART_HP_OK;
+}
+
 static int art_rld_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_sharpen_params* p, const double* ws9)
 {
     const double scale = p->scale > 0 ? p->scale : 1.0;
     const double sigma = p->deconvradius / scale;
     const float amount = p->deconvamount / 100.f;
-    if (p->deconvCornerBoost / scale > 0.01f) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "rld corner boost is not on the hot path");
-    if (amount > 0 && !(sigma < 0.2f) && sigma > 1.15) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "rld with sigma %.3f > 1.15 (recursive GAUSS_DIV / GAUSS_MULT forms) is not on the hot path", sigma);
-    if (amount <= 0 || sigma < 0.2f) return ART_HP_OK;           // deconvsharpening returns at once (L146-155): multiply() then scales by exactly 1
+    const float delta = (float)(p->deconvCornerBoost / scale);
+    const bool boost = delta > 0.01f;
+    auto unsupported = [&](double sg) { return amount > 0 && !(sg < 0.2f) && (sg > 1.15 || sg < 0.25); };
+    if (unsupported(sigma) || (boost && unsupported(sigma + delta)))
+        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "rld is on the hot path for 0.25 <= sigma <= 1.15 (3x3 / 5x5 / 7x7 GAUSS_DIV / GAUSS_MULT forms), got %.3f", boost ? sigma + delta : sigma);
+    if (!boost && (amount <= 0 || sigma < 0.2f)) return ART_HP_OK;           // deconvsharpening returns at once: multiply() then scales by exactly 1
     cudaStream_t st = ctx->stream;
     int rc;
     const size_t yp = round_up((size_t)W, 32), pl = yp * (size_t)H;
     float* planes = nullptr;
-    if ((rc = art_pool_alloc(ctx, (6 * pl + pl / 4 + 64) * sizeof(float), (void**)&planes))) return rc;
-    float *Y = planes, *blend = Y + pl, *lum = blend + pl, *tmp = lum + pl, *tmpI = tmp + pl, *out = tmpI + pl;
-    unsigned char* imp = reinterpret_cast<unsigned char*>(out + pl);
+    if ((rc = art_pool_alloc(ctx, (8 * pl + pl / 4 + 64) * sizeof(float), (void**)&planes))) return rc;
+    float *Y = planes, *blend = Y + pl, *lum = blend + pl, *tmp = lum + pl, *tmpI = tmp + pl, *out = tmpI + pl, *YY = out + pl, *YY2 = YY + pl;
+    unsigned char* imp = reinterpret_cast<unsigned char*>(YY2 + pl);
     const dim3 blk(256), grid((W + 255) / 256, std::min(H, 148 * 8));
     art_prof_begin(ctx, "k_rld_copy_lum");
     k_rld_copy_lum<<<grid, blk, 0, st>>>(r, g, b, ip, Y, yp, W, H, (float)ws9[3], (float)ws9[4], (float)ws9[5]);
@@ -388,26 +445,26 @@ static int art_rld_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip,
     art_prof_begin(ctx, "k_rld_impulse");
     k_rld_impulse<<<grid, blk, 0, st>>>(Y, tmp, yp, imp, W, H, 3.5f / 24.0f);
     art_prof_end(ctx);
-    k_rld_init<<<grid, blk, 0, st>>>(Y, lum, tmpI, out, yp, W, H);
-    ctx->launches += 5;
-    RldK k{};
-    if (sigma < 0.25) {      // GAUSS_SKIP: both blurs are plain copies, tmpI stays max(lum, 0) through all 20 iterations; check_stop never fires
-        // (|tmpI - l| = 0 for l >= 0; for l < 0, |0 - l| = -l > 0.2 l): handled by the generic kernels with an identity "3x3" kernel
-        k.size = 3; k.c3[0] = 1.f; k.c3[1] = 0.f; k.c3[2] = 0.f; k.c3[3] = 1.f; k.c3[4] = 0.f;
-        art_pool_free(ctx, planes);
-        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "rld with 0.2 <= sigma < 0.25 (GAUSS_SKIP copies) is not on the hot path");
+    ctx->launches += 4;
+    if ((rc = rld_deconv(ctx, Y, blend, imp, sigma, amount, YY, lum, tmp, tmpI, out, yp, W, H))) { art_pool_free(ctx, planes); return rc; }
+    if (boost) {        // doSharpening L757-771
+        if ((rc = rld_deconv(ctx, Y, blend, imp, sigma + delta, amount, YY2, lum, tmp, tmpI, out, yp, W, H))) { art_pool_free(ctx, planes); return rc; }
+        const int fw = p->full_width > 0 ? p->full_width : W, fh = p->full_height > 0 ? p->full_height : H;
+        const int w2 = fw / 2, h2 = fh / 2;
+        const float radius = (float)std::max(w2, h2);
+        const float lat = float(p->deconvCornerLatitude) / 150.f;
+        const float lim = lat < 0.f ? 0.f : (lat > 1.f ? 1.f : lat);
+        const float r2 = (radius - radius * lim) / 2.f;
+        const float sg = 2.f * ((radius * 0.3f) * (radius * 0.3f));
+        art_prof_begin(ctx, "k_rld_corner_mix");
+        k_rld_corner_mix<<<grid, blk, 0, st>>>(YY, YY2, yp, W, H, p->offset_x, p->offset_y, w2, h2, r2, sg);
+        art_prof_end(ctx);
+        ctx->launches++;
     }
-    rld_kernel(sigma, &k);
-    art_prof_begin(ctx, "k_rld_iterations");
-    for (int it = 0; it < 20; ++it) {
-        k_rld_div<<<grid, blk, 0, st>>>(k, tmpI, lum, tmp, yp, W, H);
-        k_rld_mult<<<grid, blk, 0, st>>>(k, tmp, tmpI, lum, out, imp, blend, amount, yp, W, H);
-    }
+    art_prof_begin(ctx, "k_rld_multiply");
+    k_rld_multiply<<<grid, blk, 0, st>>>(r, g, b, ip, YY, Y, yp, W, H);
     art_prof_end(ctx);
-    art_prof_begin(ctx, "k_rld_final");
-    k_rld_final<<<grid, blk, 0, st>>>(r, g, b, ip, Y, out, tmpI, lum, imp, blend, amount, yp, W, H);
-    art_prof_end(ctx);
-    ctx->launches += 41;
+    ctx->launches++;
     ART_CUDA(ctx, cudaGetLastError());
     art_pool_free(ctx, planes);
     return ART_HP_OK;

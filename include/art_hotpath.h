@@ -387,7 +387,9 @@ typedef struct art_hp_sharpen_params {
     int    method;              /* 0 = "usm", 1 = "rld" (RL deconvolution: markImpulse + deconvsharpening, ipsharpen.cc L144-230, L747-771) */
     double deconvradius;        /* 0.75; rld is on the hot path for 0.25 <= deconvradius / scale <= 1.15 (3x3 / 5x5 / 7x7 GAUSS_DIV / GAUSS_MULT) */
     int    deconvamount;        /* 100 */
-    double deconvCornerBoost;   /* must be 0 */
+    double deconvCornerBoost;   /* 0; > 0.01 * scale mixes a second deconvolution (radius + boost) in towards the corners (CornerBoostMask, L313-338) */
+    int    deconvCornerLatitude;            /* 25 */
+    int    offset_x, offset_y, full_width, full_height;   /* ImProcFunctions' viewport (improcfun.h L227-230); full_* <= 0 means the image itself */
 } art_hp_sharpen_params;
 int art_hp_sharpen_usm(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b,
                        const art_hp_sharpen_params* params, const double ws[9]);

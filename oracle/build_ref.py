@@ -1106,8 +1106,18 @@ extern "C" int artref_usm(float* R, float* G, float* B, int W, int H, const doub
 }
 
 // the "rld" route of doSharpening (ipsharpen.cc L747-771 without the corner boost): markImpulse(Y, 2), deconvsharpening(copy of Y), multiply
+extern "C" int artref_rld_ex(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double deconvradius,
+                             int deconvamount, float* impulse_out, double deconvCornerBoost, int deconvCornerLatitude, int offset_x, int offset_y,
+                             int full_width, int full_height);
 extern "C" int artref_rld(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double deconvradius,
                           int deconvamount, float* impulse_out)
+{
+    return artref_rld_ex(R, G, B, W, H, wsd, scale, contrast_p, deconvradius, deconvamount, impulse_out, 0.0, 25, 0, 0, 0, 0);
+}
+// doSharpening L753-771 with the corner boost: two deconvolutions (sigma, sigma + delta) mixed by CornerBoostMask
+extern "C" int artref_rld_ex(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double deconvradius,
+                             int deconvamount, float* impulse_out, double deconvCornerBoost, int deconvCornerLatitude, int offset_x, int offset_y,
+                             int full_width, int full_height)
 {
     if (W < 8 || H < 8) return 0;
     const bool multiThread = true;
@@ -1127,7 +1137,23 @@ extern "C" int artref_rld(float* R, float* G, float* B, int W, int H, const doub
     array2D<float> YY(W, H, Y, ARRAY2D_ALIGNED);
     double sigma = deconvradius / scale;
     float amount = deconvamount / 100.f;
-    deconvsharpening(YY, blend, impulse, W, H, sigma, amount, multiThread);
+    float delta = deconvCornerBoost / scale;
+    if (delta > 0.01f) {
+        array2D<float> YY2(W, H, Y, ARRAY2D_ALIGNED);
+        deconvsharpening(YY, blend, impulse, W, H, sigma, amount, multiThread);
+        deconvsharpening(YY2, blend, impulse, W, H, sigma + delta, amount, multiThread);
+        int fw = full_width > 0 ? full_width : W;
+        int fh = full_height > 0 ? full_height : H;
+        CornerBoostMask mask(offset_x, offset_y, fw, fh, deconvCornerLatitude);
+        for (int y = 0; y < H; ++y) {
+            for (int x = 0; x < W; ++x) {
+                float blend = mask(x, y);
+                YY[y][x] = intp(blend, YY2[y][x], YY[y][x]);
+            }
+        }
+    } else {
+        deconvsharpening(YY, blend, impulse, W, H, sigma, amount, multiThread);
+    }
     multiply(rgb, YY, Y, multiThread);
     return 0;
 }
@@ -1365,6 +1391,7 @@ def extract(det):
     ips = ["template <bool reverse>\n" + cut_function(ish, r"^void apply_gamma\(float \*\*Y[^)]*\)"),
            cut_function(ish, r"^void sharpenHaloCtrl\(float\*\* luminance[^)]*\)"),
            cut_function(ish, r"^void deconvsharpening\(float \*\*luminance, float \*\*blend, char \*\*impulse[^)]*\)"),
+           cut_function(ish, r"^class CornerBoostMask ") + ";",
            cut_function(ish, r"^void unsharp_mask\(float \*\*Y[^)]*\)")]
     open(os.path.join(sub, "usm_ipsharpen.inc"), "w").write("\n\n".join(ips))
     open(os.path.join(sub, "shim_usm.cc"), "w").write(SHIM_USM_TU)

@@ -337,8 +337,25 @@ static int deconv(float* lum, const float* blend, const unsigned char* impulse, 
     return 0;
 }
 
-int artoracle_rld(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double deconvradius,
-                  int deconvamount, float* impulse_out)
+/* CornerBoostMask, ipsharpen.cc L313-338 */
+static float corner_mask(int x, int y, int ox, int oy, int width, int height, int latitude)
+{
+    const int w2 = width / 2, h2 = height / 2;
+    const float radius = (float)(w2 > h2 ? w2 : h2);
+    const float lat = (float)latitude / 150.f;
+    const float lim = maxr(0.f, minr(lat, 1.f));                                  /* LIM01 */
+    const float r2 = (radius - radius * lim) / 2.f;
+    const float sg = 2.f * ((radius * 0.3f) * (radius * 0.3f));
+    const int xx = x + ox - w2, yy = y + oy - h2;
+    const float distance = sqrtf((float)(xx * xx + yy * yy));
+    const float d = maxr(distance - r2, 0.f);
+    const float e = xexpf_scalar((-(d * d)) / sg);
+    return 1.f - maxr(0.f, minr(e, 1.f));
+}
+
+int artoracle_rld_ex(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double deconvradius,
+                     int deconvamount, float* impulse_out, double deconvCornerBoost, int deconvCornerLatitude, int offset_x, int offset_y,
+                     int full_width, int full_height)
 {
     if (W < 8 || H < 8) return 0;
     const size_t n = (size_t)W * H;
@@ -352,7 +369,23 @@ int artoracle_rld(float* R, float* G, float* B, int W, int H, const double* wsd,
     if (!rc) rc = artoracle_mark_impulse(Y, impulse, W, H, 2.f);
     if (impulse_out) for (size_t k = 0; k < n; ++k) impulse_out[k] = impulse[k];
     memcpy(YY, Y, sizeof(float) * n);
-    if (!rc) rc = deconv(YY, blend, impulse, W, H, deconvradius / scale, deconvamount / 100.f);
+    const double sigma = deconvradius / scale;
+    const float amount = deconvamount / 100.f;
+    const float delta = (float)(deconvCornerBoost / scale);
+    if (delta > 0.01f) {       /* doSharpening L757-771 */
+        float* YY2 = (float*)malloc(sizeof(float) * n);
+        memcpy(YY2, Y, sizeof(float) * n);
+        if (!rc) rc = deconv(YY, blend, impulse, W, H, sigma, amount);
+        if (!rc) rc = deconv(YY2, blend, impulse, W, H, sigma + delta, amount);
+        const int fw = full_width > 0 ? full_width : W, fh = full_height > 0 ? full_height : H;
+        for (int y = 0; y < H && !rc; ++y)
+            for (int x = 0; x < W; ++x) {
+                const float m = corner_mask(x, y, offset_x, offset_y, fw, fh, deconvCornerLatitude);
+                const size_t k = (size_t)y * W + x;
+                YY[k] = m * YY2[k] + (1.f - m) * YY[k];
+            }
+        free(YY2);
+    } else if (!rc) rc = deconv(YY, blend, impulse, W, H, sigma, amount);
     for (size_t k = 0; k < n && !rc; ++k)
         if (Y[k] > 0.f) {
             const float f = YY[k] / Y[k];
@@ -360,4 +393,10 @@ int artoracle_rld(float* R, float* G, float* B, int W, int H, const double* wsd,
         }
     free(Y); free(YY); free(blend); free(impulse);
     return rc;
+}
+
+int artoracle_rld(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double deconvradius,
+                  int deconvamount, float* impulse_out)
+{
+    return artoracle_rld_ex(R, G, B, W, H, wsd, scale, contrast_p, deconvradius, deconvamount, impulse_out, 0.0, 25, 0, 0, 0, 0);
 }

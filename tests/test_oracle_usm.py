@@ -114,3 +114,24 @@ def test_rld_changes_the_image_and_marks_impulses():
     out, imp = run_rld(oracle.ref().lib, "artref_rld", planes)
     assert imp[50, 60] == 1 and 0 < imp.mean() < 0.2
     assert any((x != y).any() for x, y in zip(out, planes))
+
+
+def run_rld_ex(lib, name, planes, boost, latitude=25, ox=0, oy=0, fw=0, fh=0, scale=1.0, contrast=20.0, radius=0.75, amount=100):
+    out = [np.ascontiguousarray(p).copy() for p in planes]
+    H, W = out[0].shape
+    rc = getattr(lib, name)(out[0].ctypes.data_as(fp), out[1].ctypes.data_as(fp), out[2].ctypes.data_as(fp), W, H, PROPHOTO.ctypes.data_as(dp),
+                            D(scale), D(contrast), D(radius), int(amount), None, D(boost), int(latitude), int(ox), int(oy), int(fw), int(fh))
+    assert rc == 0
+    return out
+
+
+BOOST_CASES = [dict(boost=0.2), dict(boost=0.35, latitude=60, radius=0.6), dict(boost=0.3, latitude=0, ox=40, oy=25, fw=600, fh=420),
+               dict(boost=0.25, latitude=200), dict(boost=0.005)]
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", [(64, 48), (301, 203), (130, 77)])
+@pytest.mark.parametrize("case", range(len(BOOST_CASES)))
+def test_rld_corner_boost(W, H, case):
+    planes = scene(W, H, W * 11 + H + case, wild=bool(case & 1))
+    same(run_rld_ex(oracle.port().lib, "artoracle_rld_ex", planes, **BOOST_CASES[case]), run_rld_ex(oracle.ref().lib, "artref_rld_ex", planes, **BOOST_CASES[case]))

@@ -68,7 +68,8 @@ from test_oracle_usm import RLD_CASES, run_rld  # noqa: E402
 def gpu_rld(hp, planes, **kw):
     out = [np.ascontiguousarray(p).copy() for p in planes]
     p = SharpenParams(method="rld", contrast=kw.get("contrast", 20.0), deconvradius=kw.get("radius", 0.75), deconvamount=kw.get("amount", 100),
-                      scale=kw.get("scale", 1.0))
+                      scale=kw.get("scale", 1.0), deconvCornerBoost=kw.get("boost", 0.0), deconvCornerLatitude=kw.get("latitude", 25),
+                      offset_x=kw.get("ox", 0), offset_y=kw.get("oy", 0), full_width=kw.get("fw", 0), full_height=kw.get("fh", 0))
     hp.sharpen_usm(out[0], out[1], out[2], p, PROPHOTO)
     return out
 
@@ -88,3 +89,13 @@ def test_rld_rejects_large_sigma(hot_path):
     with pytest.raises(art_b200.HotPathError) as e:
         gpu_rld(hot_path, planes, radius=2.0)
     assert e.value.code == 5
+
+
+from test_oracle_usm import BOOST_CASES, run_rld_ex  # noqa: E402
+
+
+@pytest.mark.parametrize("W,H", [(64, 48), (301, 203), (130, 77), (1023, 517)])
+@pytest.mark.parametrize("case", range(len(BOOST_CASES)))
+def test_rld_corner_boost_matches_oracle(hot_path, W, H, case):
+    planes = scene(W, H, W * 11 + H + case, wild=bool(case & 1))
+    same(gpu_rld(hot_path, planes, **BOOST_CASES[case]), run_rld_ex(oracle.port().lib, "artoracle_rld_ex", planes, **BOOST_CASES[case]))
