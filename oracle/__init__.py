@@ -66,6 +66,9 @@ class _Port:
     def gauss(self, src, sigma, inplace=False):
         return _gauss(self.lib, "artoracle_gauss", src, sigma, inplace, False)
 
+    def gauss_iir(self, src, dst, divb, sigma, kind):
+        return _gauss_iir(self.lib, False, src, dst, divb, sigma, kind)
+
     def boxblur(self, src, radius, inplace=False):
         return _boxblur(self.lib, "artoracle_boxblur", src, radius, inplace, False)
 
@@ -82,6 +85,23 @@ class _Port:
                                       ctypes.c_float(initial_gain), border)
         assert rc == 0
         return r, g, b
+
+
+def _gauss_iir(lib, ref, src, dst, divb, sigma, kind):
+    """GAUSS_MULT ("mult": dst *= blur(src), src blurred horizontally in place) / GAUSS_DIV ("div": dst = divb / blur(src)) of the
+    recursive branch; returns (src_after, dst)."""
+    s = np.array(src, dtype=np.float32, order="C", copy=True)
+    d = np.array(dst, dtype=np.float32, order="C", copy=True)
+    H, W = s.shape
+    t = 1 if kind == "mult" else 2
+    v = None if divb is None else np.ascontiguousarray(divb, dtype=np.float32)
+    vp = _fp(v) if v is not None else None
+    if ref:
+        rc = lib.artref_gauss_ex(_fp(s), _fp(d), vp, W, H, ctypes.c_double(sigma), t)
+    else:
+        rc = lib.artoracle_gauss_iir(_fp(s), ctypes.c_long(W), _fp(d), ctypes.c_long(W), vp, ctypes.c_long(W), W, H, ctypes.c_double(sigma), t)
+    assert rc == 0
+    return s, d
 
 
 def _gauss(lib, fname, src, sigma, inplace, extra_arg):
@@ -154,6 +174,9 @@ class _Ref:
 
     def gauss(self, src, sigma, inplace=False):
         return _gauss(self.lib, "artref_gauss", src, sigma, inplace, True)
+
+    def gauss_iir(self, src, dst, divb, sigma, kind):
+        return _gauss_iir(self.lib, True, src, dst, divb, sigma, kind)
 
     def scale_colors_bayer(self, raw, filters, black, mul):
         return _scale_colors(self.lib, "artref_scale_colors_bayer", raw, filters, black, mul)

@@ -352,6 +352,20 @@ extern "C" int artref_gauss(const float* src, long sstride, float* dst, long dst
     delete[] d;
     return 0;
 }
+
+// gaussianBlur(src, dst, W, H, sigma, nullptr, GAUSS_MULT (type 1) / GAUSS_DIV (type 2), divb); contiguous planes, src != dst.
+// GAUSS_MULT blurs src in place on the way (gauss.cc L1496).
+extern "C" int artref_gauss_ex(float* src, float* dst, float* divb, int W, int H, double sigma, int type)
+{
+    float** s = new float*[H];
+    float** d = new float*[H];
+    float** v = new float*[H];
+    for (int i = 0; i < H; ++i) { s[i] = src + (long)i * W; d[i] = dst + (long)i * W; v[i] = divb ? divb + (long)i * W : nullptr; }
+#pragma omp parallel
+    gaussianBlur(s, d, W, H, sigma, nullptr, type == 1 ? GAUSS_MULT : GAUSS_DIV, v);
+    delete[] s; delete[] d; delete[] v;
+    return 0;
+}
 """
 
 

@@ -13,6 +13,8 @@
  *                           columns) use the scalar loop, which computes in double with double coefficients and
  *                           rounds to float on every store to the float scratch
  *   sigma >= 25             gaussHorizontal (L669-713) + gaussVertical (L1148-1225): everything in double
+ * artoracle_gauss_iir: the recursive branch of GAUSS_MULT / GAUSS_DIV (L1490-1511: gaussHorizontalSse + gaussVerticalSsemult L860-999 /
+ * gaussVerticalSsediv L1002-1144), the forms deconvsharpening reaches above sigma 1.15.
  * Pinned bit-exact against the reference's own gauss.cc compiled in place (oracle/_ref) in tests/test_oracle_gauss.py.
  * Compile with -ffp-contract=off.
  */
@@ -239,6 +241,64 @@ int artoracle_gauss(const float* src, long ss, float* dst, long ds, int W, int H
 #pragma omp for
             for (int i = 0; i < W; i++) yvv_line_double(dst + i, ds, dst + i, ds, H, t, B, b1, b2, b3, M);
             free(t);
+        }
+    }
+    return fail;
+}
+
+/* gaussianBlur(src, dst, W, H, sigma, nullptr, type, divb) in the recursive branch, 0.6 <= sigma < 25, src != dst (strides in floats):
+ *   type 1  GAUSS_MULT  gaussHorizontalSse(src, src) IN PLACE (L1496), then dst *= vertical(src)             (L860-999)
+ *   type 2  GAUSS_DIV   gaussHorizontalSse(src, dst), then dst = divb / (v > 0 ? v : 1) with v = vertical(dst) (L1002-1144):
+ *                       clamped at 0 by vmaxf for rows < H-3 of the 8-column groups (the three boundary rows L1078-1091 are
+ *                       stored unclamped) and by rtengine::max on every row of the W%8 remainder columns (L1139-1141) */
+int artoracle_gauss_iir(float* src, long ss, float* dst, long ds, const float* divb, long vs, int W, int H, double sigma, int type)
+{
+    if (W < 4 || H < 4 || !(sigma >= 0.6) || sigma >= 25.0 || (type != 1 && type != 2) || (type == 2 && !divb)) return 1;
+    double b1, b2, b3, B, M[3][3];
+    const float sigf = (float)sigma;
+    yvv_factors(sigf, &b1, &b2, &b3, &B, M);
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            M[i][j] *= (1.0 + b2 + (b1 - b3) * b3);
+            M[i][j] /= (1.0 + b1 - b2 + b3) * (1.0 - b1 - b2 - b3);
+        }
+    float Mf[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Mf[i][j] = (float)M[i][j];
+    const float Bf = (float)B, b1f = (float)b1, b2f = (float)b2, b3f = (float)b3;
+    const int n = W > H ? W : H;
+    float* hp = type == 1 ? src : dst;              /* plane holding the horizontal result */
+    const long hs = type == 1 ? ss : ds;
+    int fail = 0;
+#pragma omp parallel
+    {
+        float* tmp = (float*)malloc(sizeof(float) * (size_t)n * 2);
+        if (!tmp) {
+#pragma omp atomic write
+            fail = 1;
+        } else {
+            float* col = tmp + n;
+#pragma omp for
+            for (int i = 0; i < H; i++) {
+                if (i < H - (H % 4)) yvv_line_float(src + (long)i * ss, 1, hp + (long)i * hs, 1, W, tmp, Bf, b1f, b2f, b3f, Mf, 0);
+                else yvv_line_mixed(src + (long)i * ss, 1, hp + (long)i * hs, 1, W, tmp, B, b1, b2, b3, M);
+            }
+#pragma omp for
+            for (int i = 0; i < W; i++) {
+                const int vec = i < W - (W % 8);
+                if (vec) yvv_line_float(hp + i, hs, col, 1, H, tmp, Bf, b1f, b2f, b3f, Mf, 1);
+                else yvv_line_mixed(hp + i, hs, col, 1, H, tmp, B, b1, b2, b3, M);
+                for (int j = 0; j < H; j++) {
+                    float* o = dst + (long)j * ds + i;
+                    if (type == 1) *o = *o * col[j];
+                    else {
+                        float q = divb[(long)j * vs + i] / (col[j] > 0.f ? col[j] : 1.f);
+                        if (!vec) q = q < 0.f ? 0.f : q;                    /* rtengine::max(q, 0.f) */
+                        else if (j < H - 3) q = q > 0.f ? q : 0.f;          /* vmaxf(q, ZEROV) */
+                        *o = q;
+                    }
+                }
+            }
+            free(tmp);
         }
     }
     return fail;

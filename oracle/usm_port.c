@@ -17,6 +17,7 @@
 #include "sleef_port.h"
 
 int artoracle_gauss(const float* src, long ss, float* dst, long ds, int W, int H, double sigma);
+int artoracle_gauss_iir(float* src, long ss, float* dst, long ds, const float* divb, long vs, int W, int H, double sigma, int type);
 
 static inline float maxr(float a, float b) { return a < b ? b : a; }
 static inline float minr(float a, float b) { return b < a ? b : a; }
@@ -174,8 +175,9 @@ int artoracle_usm(float* R, float* G, float* B, int W, int H, const double* wsd,
 
 /* ---------------------------------------------------------------------------------------------------------------------------
  * "rld" route of doSharpening (ipsharpen.cc L747-771, no corner boost): markImpulse (rt_algo.cc L497-591), deconvsharpening
- * (ipsharpen.cc L144-230) over gaussianBlur's GAUSS_DIV / GAUSS_MULT forms for sigma <= 1.15: gauss3x3div / mult (gauss.cc L177-274),
- * gauss5x5div / mult (L331-378, L415-443), gauss7x7div / mult (L276-329, L380-413), kernels L52-92, dispatch L1444-1511.
+ * (ipsharpen.cc L144-230) over gaussianBlur's GAUSS_DIV / GAUSS_MULT forms: gauss3x3div / mult (gauss.cc L177-274), gauss5x5div / mult (L331-378,
+ * L415-443), gauss7x7div / mult (L276-329, L380-413), kernels L52-92, dispatch L1444-1511; above sigma 1.15 the recursive forms
+ * (artoracle_gauss_iir in gauss_port.c).
  * ------------------------------------------------------------------------------------------------------------------------- */
 #define S_(i, j) src[(size_t)(i) * W + (j)]
 #define D_(i, j) dst[(size_t)(i) * W + (j)]
@@ -233,7 +235,7 @@ static inline float conv3(const float* src, int W, int H, int i, int j, float c0
     if (side) return b1 * (S_(i - 1, j) + S_(i + 1, j)) + b0 * S_(i, j);
     return c2 * (S_(i - 1, j - 1) + S_(i - 1, j + 1) + S_(i + 1, j - 1) + S_(i + 1, j + 1)) + c1 * (S_(i - 1, j) + S_(i, j - 1) + S_(i, j + 1) + S_(i + 1, j)) + c0 * S_(i, j);
 }
-/* gaussianBlur(src, dst, W, H, sigma, nullptr, GAUSS_DIV, divb) / (..., GAUSS_MULT) for 0.25 <= sigma <= 1.15, src != dst; 1 = unsupported sigma */
+/* gaussianBlur(src, dst, W, H, sigma, nullptr, GAUSS_DIV, divb) / (..., GAUSS_MULT), src != dst; 1 = unsupported sigma (>= 25) */
 static int gauss_divmult(const float* src, float* dst, const float* divb, int W, int H, double sigma, int mult)
 {
     if (sigma < 0.25) {        /* GAUSS_SKIP: plain copy whatever the type (L1436-1443) */
@@ -278,7 +280,8 @@ static int gauss_divmult(const float* src, float* dst, const float* divb, int W,
             }
         return 0;
     }
-    return 1;
+    /* recursive forms (gauss.cc L1490-1511); GAUSS_MULT blurs its source plane in place on the way */
+    return artoracle_gauss_iir((float*)src, W, dst, W, divb, W, W, H, sigma, mult ? 1 : 2);
 }
 #undef S_
 #undef D_
@@ -310,7 +313,7 @@ static int deconv(float* lum, const float* blend, const unsigned char* impulse, 
 {
     if (amount <= 0) return 0;
     if (sigma < 0.2f) return 0;
-    if (sigma > 1.15) return 1;
+    if (sigma >= 25.0 || (sigma > 1.15 && (W < 4 || H < 4))) return 1;
     const size_t n = (size_t)W * H;
     const int maxiter = 20;
     const float delta_factor = 0.2f, offset = 1000.f;

@@ -92,7 +92,8 @@ def run_rld(lib, name, planes, scale=1.0, contrast=20.0, radius=0.75, amount=100
 
 
 RLD_CASES = [dict(), dict(radius=0.5, amount=60), dict(radius=1.0, amount=150), dict(radius=0.84), dict(radius=1.15, contrast=0.0),
-             dict(radius=0.3), dict(radius=0.22), dict(amount=0), dict(scale=2.0, radius=1.5)]
+             dict(radius=0.3), dict(radius=0.22), dict(amount=0), dict(scale=2.0, radius=1.5),
+             dict(radius=1.2), dict(radius=1.8, amount=70), dict(radius=2.5, contrast=5.0)]        # recursive GAUSS_DIV / GAUSS_MULT
 
 
 @needs_ref
@@ -126,7 +127,7 @@ def run_rld_ex(lib, name, planes, boost, latitude=25, ox=0, oy=0, fw=0, fh=0, sc
 
 
 BOOST_CASES = [dict(boost=0.2), dict(boost=0.35, latitude=60, radius=0.6), dict(boost=0.3, latitude=0, ox=40, oy=25, fw=600, fh=420),
-               dict(boost=0.25, latitude=200), dict(boost=0.005)]
+               dict(boost=0.25, latitude=200), dict(boost=0.005), dict(boost=0.4, radius=1.0), dict(boost=0.5, radius=1.4)]
 
 
 @needs_ref
