@@ -139,6 +139,7 @@ int art_scale_colors_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float*
                          const float black[4], const float mul[4], int* d_chmax_bits);
 // gaussianBlur, GAUSS_STANDARD (src == dst allowed)
 int art_gauss_dev(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, size_t dp, int W, int H, double sigma);
+int art_gauss_divmult_dev(art_hp_ctx* ctx, float* src, size_t sp, float* dst, size_t dp, const float* div, size_t vp, int W, int H, double sigma, int type);
 // rtengine::boxblur(float**, float**, radius, W, H) and rtengine::guidedFilter (src == dst allowed for boxblur;
 // for the guided filter dst may alias src but not guide... both are read before dst is written only in the
 // final pass, pixel by pixel, so dst may alias either)

@@ -13,6 +13,9 @@
 // 32-column tiles that are transposed through shared memory, so global traffic stays coalesced while each
 // lane runs its own row's recurrence.  The causal pass stores its output in the destination plane (float)
 // or in a double scratch plane (sigma >= 25), the anticausal pass sweeps back over it.
+// GAUSS_MULT / GAUSS_DIV in the recursive branch (L1490-1511: gaussVerticalSsemult L860-999, gaussVerticalSsediv L1002-1144, the forms
+// deconvsharpening reaches above sigma 1.15) are the same recurrence with another store: dst *= v, or dst = div / (v > 0 ? v : 1)
+// clamped at 0 (not on the three boundary rows of the 8-column groups, L1078-1091) -- an epilogue of the vertical kernel.
 // Compiled with -fmad=false: bit-identical to the reference build.
 #include "ctx.h"
 
@@ -135,11 +138,14 @@ struct GArgs {
     double* dscr; size_t dsp;       // double scratch plane (sigma >= 25), pitch in doubles
     int W, H;
     int big;                        // 1: all-double form
+    float* cs; size_t csp;          // vertical pass: plane that takes the causal output (dst; the source plane for GAUSS_MULT)
+    const float* div; size_t vp;    // GAUSS_DIV numerator
     Coef c;
 };
 
 // ------------------------------------------------------------------ vertical pass: thread per column
-template <int MODE>
+// EPI 0: dst = v; 1 (GAUSS_MULT): dst *= v; 2 (GAUSS_DIV): dst = div / (v > 0 ? v : 1), clamped at 0
+template <int MODE, int EPI>
 __device__ __forceinline__ void vline(const GArgs& a, int col)
 {
     using T = typename Acc<MODE>::T;
@@ -147,7 +153,21 @@ __device__ __forceinline__ void vline(const GArgs& a, int col)
     const int H = a.H;
     const float* x = a.src + col;
     float* y = a.dst + col;
+    float* cs = a.cs + col;
+    const float* e = EPI == 1 ? y : (EPI == 2 ? a.div + col : nullptr);      // second operand of the epilogue
+    const size_t ep = EPI == 1 ? a.dp : a.vp;
     double* d = MODE == 2 ? a.dscr + col : nullptr;
+    auto emit = [&](int j, float v, float ev, bool boundary_row) {
+        float* o = y + (size_t)j * a.dp;
+        if (EPI == 0) *o = v;
+        else if (EPI == 1) *o = ev * v;
+        else {
+            float q = ev / (v > 0.f ? v : 1.f);
+            if (MODE == 1) q = q < 0.f ? 0.f : q;                  // rtengine::max(q, 0.f), every row (L1139-1141)
+            else if (!boundary_row) q = q > 0.f ? q : 0.f;         // vmaxf(q, ZEROV), rows < H-3 only (L1103-1104)
+            *o = q;
+        }
+    };
     // causal sweep; the input of row j+PF is loaded before the output of row j is stored (in-place safe)
     constexpr int PF = 8;
     float q[PF];
@@ -167,41 +187,49 @@ __device__ __forceinline__ void vline(const GArgs& a, int col)
                 else if (j == 1) t = L.second(a.c, xv);
                 else if (j == 2) t = L.third(a.c, xv);
                 else t = L.fwd(a.c, xv);
-                if (MODE == 2) d[(size_t)j * a.dsp] = t; else y[(size_t)j * a.dp] = (float)t;
+                if (MODE == 2) d[(size_t)j * a.dsp] = t; else cs[(size_t)j * a.csp] = (float)t;
                 xl = xv;
             }
         }
     }
     T o1, o2, o3;
     L.boundary(a.c, xl, o1, o2, o3);
-    y[(size_t)(H - 1) * a.dp] = (float)o1;
-    y[(size_t)(H - 2) * a.dp] = (float)o2;
-    y[(size_t)(H - 3) * a.dp] = (float)o3;
+    emit(H - 1, (float)o1, EPI ? e[(size_t)(H - 1) * ep] : 0.f, true);
+    emit(H - 2, (float)o2, EPI ? e[(size_t)(H - 2) * ep] : 0.f, true);
+    emit(H - 3, (float)o3, EPI ? e[(size_t)(H - 3) * ep] : 0.f, true);
     // anticausal sweep over the stored causal output
     T p[PF];
+    float pe[PF];
     #pragma unroll
-    for (int k = 0; k < PF; ++k) { const int j = H - 4 - k; p[k] = (j >= 0) ? (MODE == 2 ? (T)d[(size_t)j * a.dsp] : (T)y[(size_t)j * a.dp]) : (T)0; }
+    for (int k = 0; k < PF; ++k) {
+        const int j = H - 4 - k;
+        p[k] = (j >= 0) ? (MODE == 2 ? (T)d[(size_t)j * a.dsp] : (T)cs[(size_t)j * a.csp]) : (T)0;
+        pe[k] = (EPI && j >= 0) ? e[(size_t)j * ep] : 0.f;
+    }
     for (int j0 = H - 4; j0 >= 0; j0 -= PF) {
         #pragma unroll
         for (int k = 0; k < PF; ++k) {
             const int j = j0 - k;
             if (j >= 0) {
                 const T t = p[k];
+                const float ev = pe[k];
                 const int jn = j - PF;
-                p[k] = (jn >= 0) ? (MODE == 2 ? (T)d[(size_t)jn * a.dsp] : (T)y[(size_t)jn * a.dp]) : (T)0;
-                y[(size_t)j * a.dp] = (float)L.bwd(a.c, t);
+                p[k] = (jn >= 0) ? (MODE == 2 ? (T)d[(size_t)jn * a.dsp] : (T)cs[(size_t)jn * a.csp]) : (T)0;
+                pe[k] = (EPI && jn >= 0) ? e[(size_t)jn * ep] : 0.f;
+                emit(j, (float)L.bwd(a.c, t), ev, false);
             }
         }
     }
 }
 
+template <int EPI>
 __global__ void __launch_bounds__(128) k_gauss_v(GArgs a)
 {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= a.W) return;
-    if (a.big) vline<2>(a, col);
-    else if (col < a.W - (a.W % 8)) vline<0>(a, col);       // 8-column vector groups (L750)
-    else vline<1>(a, col);                                  // scalar remainder (L843)
+    if (a.big) vline<2, EPI>(a, col);
+    else if (col < a.W - (a.W % 8)) vline<0, EPI>(a, col);  // 8-column vector groups (L750)
+    else vline<1, EPI>(a, col);                             // scalar remainder (L843)
 }
 
 // ------------------------------------------------------------------ horizontal pass: warp per 32 rows
@@ -375,6 +403,7 @@ int art_gauss_dev(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, size
     }
     GArgs a;
     a.src = src; a.sp = sp; a.dst = dst; a.dp = dp; a.W = W; a.H = H; a.dscr = nullptr; a.dsp = 0;
+    a.cs = dst; a.csp = dp; a.div = nullptr; a.vp = 0;
     a.big = sigma >= 25.0;
     double b1, b2, b3, B, M[9];
     if (!a.big) {
@@ -401,7 +430,44 @@ int art_gauss_dev(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, size
     GArgs v = a;
     v.src = dst; v.sp = dp;                      // vertical runs in place on the horizontal result (L1529-1530)
     art_prof_begin(ctx, "k_gauss_v");
-    k_gauss_v<<<(W + 127) / 128, 128, 0, st>>>(v);
+    k_gauss_v<0><<<(W + 127) / 128, 128, 0, st>>>(v);
+    art_prof_end(ctx);
+    ctx->launches += 2;
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}
+
+// gaussianBlur(src, dst, W, H, sigma, nullptr, GAUSS_MULT (type 1) / GAUSS_DIV (type 2), div) in the recursive branch (L1490-1511),
+// 0.6 <= sigma < 25, src != dst.  GAUSS_MULT filters src horizontally IN PLACE like the reference (L1496) and then keeps the
+// vertical pass's causal output there; GAUSS_DIV leaves src alone.
+int art_gauss_divmult_dev(art_hp_ctx* ctx, float* src, size_t sp, float* dst, size_t dp, const float* div, size_t vp, int W, int H, double sigma, int type)
+{
+    if (!(sigma >= 0.6) || sigma >= 25.0 || W < 4 || H < 4 || src == dst || (type != 1 && type != 2) || (type == 2 && !div))
+        return ctx->fail(ART_HP_ERR_INVALID, "recursive GAUSS_MULT / GAUSS_DIV: needs 0.6 <= sigma < 25, W, H >= 4, src != dst (got sigma %.3f, %dx%d, type %d)", sigma, W, H, type);
+    cudaStream_t st = ctx->stream;
+    GArgs a;
+    a.W = W; a.H = H; a.dscr = nullptr; a.dsp = 0; a.big = 0;
+    double b1, b2, b3, B, M[9];
+    const float sigf = (float)sigma;
+    yvv_factors(sigf, b1, b2, b3, B, M);
+    for (int i = 0; i < 9; ++i) {
+        M[i] *= (1.0 + b2 + (b1 - b3) * b3);
+        M[i] /= (1.0 + b1 - b2 + b3) * (1.0 - b1 - b2 - b3);
+    }
+    a.c.B = B; a.c.b1 = b1; a.c.b2 = b2; a.c.b3 = b3;
+    a.c.Bf = (float)B; a.c.b1f = (float)b1; a.c.b2f = (float)b2; a.c.b3f = (float)b3;
+    for (int i = 0; i < 9; ++i) { a.c.M[i] = M[i]; a.c.Mf[i] = (float)M[i]; }
+    float* hp = type == 1 ? src : dst;                // plane holding the horizontal result
+    const size_t hpp = type == 1 ? sp : dp;
+    a.src = src; a.sp = sp; a.dst = hp; a.dp = hpp; a.cs = hp; a.csp = hpp; a.div = nullptr; a.vp = 0;
+    art_prof_begin(ctx, "k_gauss_h");
+    k_gauss_h<<<(H + 63) / 64, 64, 0, st>>>(a);
+    art_prof_end(ctx);
+    GArgs v = a;
+    v.src = hp; v.sp = hpp; v.cs = hp; v.csp = hpp; v.dst = dst; v.dp = dp; v.div = div; v.vp = vp;
+    art_prof_begin(ctx, "k_gauss_v");
+    if (type == 1) k_gauss_v<1><<<(W + 127) / 128, 128, 0, st>>>(v);
+    else k_gauss_v<2><<<(W + 127) / 128, 128, 0, st>>>(v);
     art_prof_end(ctx);
     ctx->launches += 2;
     ART_CUDA(ctx, cudaGetLastError());

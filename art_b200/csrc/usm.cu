@@ -220,6 +220,7 @@ struct RldK { int size; float c[8]; float c3[5]; };      // 5x5: c21 c20 c11 c10
 __device__ __forceinline__ float rld_conv(const RldK& k, const float* __restrict__ s, ptrdiff_t p, int W, int H, int x, int y, bool& inner)
 {
 #define S(dy, dx) s[(dy) * p + (dx)]
+    if (k.size == 0) { inner = false; return 0.f; }          // recursive forms: the blur ran in art_gauss_divmult_dev
     if (k.size == 3) {
         inner = true;
         const bool top = (y == 0 || y == H - 1), side = (x == 0 || x == W - 1);
@@ -396,18 +397,31 @@ static int rld_deconv(art_hp_ctx* ctx, const float* Y, const float* blend, const
         return ART_HP_OK;
     }
     RldK k{};
-    rld_kernel(sigma, &k);
     k_rld_init<<<grid, blk, 0, st>>>(Y, lum, tmpI, out, yp, W, H);
-    art_prof_begin(ctx, "k_rld_iterations");
-    for (int it = 0; it < 20; ++it) {
-        k_rld_div<<<grid, blk, 0, st>>>(k, tmpI, lum, tmp, yp, W, H);
-        k_rld_mult<<<grid, blk, 0, st>>>(k, tmp, tmpI, lum, out, imp, blend, amount, yp, W, H);
+    if (sigma > 1.15) {        // gauss.cc L1490-1511: recursive GAUSS_DIV / GAUSS_MULT, then check_stop alone (k.size == 0)
+        for (int it = 0; it < 20; ++it) {
+            int rc;
+            if ((rc = art_gauss_divmult_dev(ctx, tmpI, yp, tmp, yp, lum, yp, W, H, sigma, 2))) return rc;
+            if ((rc = art_gauss_divmult_dev(ctx, tmp, yp, tmpI, yp, nullptr, 0, W, H, sigma, 1))) return rc;
+            art_prof_begin(ctx, "k_rld_check");
+            k_rld_mult<<<grid, blk, 0, st>>>(k, tmp, tmpI, lum, out, imp, blend, amount, yp, W, H);
+            art_prof_end(ctx);
+        }
+        ctx->launches += 20;
+    } else {
+        rld_kernel(sigma, &k);
+        art_prof_begin(ctx, "k_rld_iterations");
+        for (int it = 0; it < 20; ++it) {
+            k_rld_div<<<grid, blk, 0, st>>>(k, tmpI, lum, tmp, yp, W, H);
+            k_rld_mult<<<grid, blk, 0, st>>>(k, tmp, tmpI, lum, out, imp, blend, amount, yp, W, H);
+        }
+        art_prof_end(ctx);
+        ctx->launches += 40;
     }
-    art_prof_end(ctx);
     art_prof_begin(ctx, "k_rld_final");
     k_rld_final<<<grid, blk, 0, st>>>(YY, out, tmpI, lum, imp, blend, amount, yp, W, H);
     art_prof_end(ctx);
-    ctx->launches += 42;
+    ctx->launches += 2;
     return ART_HP_OK;
 }
 
@@ -418,9 +432,9 @@ static int art_rld_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip,
     const float amount = p->deconvamount / 100.f;
     const float delta = (float)(p->deconvCornerBoost / scale);
     const bool boost = delta > 0.01f;
-    auto unsupported = [&](double sg) { return amount > 0 && !(sg < 0.2f) && (sg > 1.15 || sg < 0.25); };
+    auto unsupported = [&](double sg) { return amount > 0 && !(sg < 0.2f) && (sg >= 25.0 || sg < 0.25 || (sg > 1.15 && (W < 4 || H < 4))); };
     if (unsupported(sigma) || (boost && unsupported(sigma + delta)))
-        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "rld is on the hot path for 0.25 <= sigma <= 1.15 (3x3 / 5x5 / 7x7 GAUSS_DIV / GAUSS_MULT forms), got %.3f", boost ? sigma + delta : sigma);
+        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "rld is on the hot path for 0.25 <= sigma < 25 (3x3 / 5x5 / 7x7 and recursive GAUSS_DIV / GAUSS_MULT forms; the recursive ones need W, H >= 4), got %.3f", boost ? sigma + delta : sigma);
     if (!boost && (amount <= 0 || sigma < 0.2f)) return ART_HP_OK;           // deconvsharpening returns at once: multiply() then scales by exactly 1
     cudaStream_t st = ctx->stream;
     int rc;

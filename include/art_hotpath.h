@@ -385,7 +385,7 @@ typedef struct art_hp_sharpen_params {
     int    halocontrol_amount;
     double scale;               /* 1 */
     int    method;              /* 0 = "usm", 1 = "rld" (RL deconvolution: markImpulse + deconvsharpening, ipsharpen.cc L144-230, L747-771) */
-    double deconvradius;        /* 0.75; rld is on the hot path for 0.25 <= deconvradius / scale <= 1.15 (3x3 / 5x5 / 7x7 GAUSS_DIV / GAUSS_MULT) */
+    double deconvradius;        /* 0.75; rld is on the hot path for 0.25 <= deconvradius / scale < 25 (3x3 / 5x5 / 7x7 and recursive GAUSS_DIV / GAUSS_MULT) */
     int    deconvamount;        /* 100 */
     double deconvCornerBoost;   /* 0; > 0.01 * scale mixes a second deconvolution (radius + boost) in towards the corners (CornerBoostMask, L313-338) */
     int    deconvCornerLatitude;            /* 25 */

@@ -87,7 +87,7 @@ def test_rld_rejects_large_sigma(hot_path):
     import art_b200
     planes = scene(64, 40, 3)
     with pytest.raises(art_b200.HotPathError) as e:
-        gpu_rld(hot_path, planes, radius=2.0)
+        gpu_rld(hot_path, planes, radius=30.0)       # sigma >= 25 would take gaussianBlur's all-double branch
     assert e.value.code == 5
 
 
