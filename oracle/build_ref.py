@@ -1050,8 +1050,9 @@ SHIM_USM_TU = r"""
 // Shim TU hosting the reference's unsharp-mask sharpening: apply_gamma, sharpenHaloCtrl, unsharp_mask cut from ipsharpen.cc;
 // calcBlendFactor, tileAverage, tileVariance, calcContrastThreshold, buildBlendMask, get_luminance, multiply cut from
 // rt_algo.cc; Threshold<T> cut from procparams.h; Color::rgbLuminance cut from color.h; gaussianBlur from shim_gauss.cc.
-// Written here (not reference code): the Imagefloat / SharpeningParams stand-ins, the bilateral stub (edgesonly is never
-// set) and the wrapper, which restates the "usm" route of ImProcFunctions::doSharpening (ipsharpen.cc L711-790).
+// bilateral<T, A> and its 21 fixed-kernel variants cut from bilateral2.h (from its ELEM macro to the end of the dispatcher).
+// Written here (not reference code): the Imagefloat / SharpeningParams stand-ins and the wrapper, which restates the "usm"
+// route of ImProcFunctions::doSharpening (ipsharpen.cc L711-790).
 #include <assert.h>
 #include <math.h>
 #include <stdlib.h>
@@ -1082,7 +1083,7 @@ struct SharpeningParams { double contrast, radius; int amount; Threshold<int> th
                           bool halocontrol; int halocontrol_amount;
                           SharpeningParams() : contrast(20.0), radius(0.5), amount(200), threshold(20, 80, 2000, 1200, false), edgesonly(false), edges_radius(1.9),
                                                edges_tolerance(1800), halocontrol(false), halocontrol_amount(85) {} };
-template <class T, class A> void bilateral(T**, T**, T**, int, int, double, double, bool) { abort(); }
+#include "usm_bilateral.inc"
 struct Chan { float* base; int W; float& operator()(int y, int x) const { return base[(size_t)y * W + x]; } };
 class Imagefloat { public: int width, height; Chan r, g, b; int getWidth() const { return width; } int getHeight() const { return height; } };
 namespace {
@@ -1093,8 +1094,15 @@ namespace {
 #include "usm_ipsharpen.inc"
 }
 
+extern "C" int artref_usm_ex(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double radius, int amount,
+                             const int* thr, int halocontrol, int halocontrol_amount, float* blend_out, int edgesonly, double edges_radius, int edges_tolerance);
 extern "C" int artref_usm(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double radius, int amount,
                           const int* thr, int halocontrol, int halocontrol_amount, float* blend_out)
+{
+    return artref_usm_ex(R, G, B, W, H, wsd, scale, contrast_p, radius, amount, thr, halocontrol, halocontrol_amount, blend_out, 0, 1.9, 1800);
+}
+extern "C" int artref_usm_ex(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double radius, int amount,
+                             const int* thr, int halocontrol, int halocontrol_amount, float* blend_out, int edgesonly, double edges_radius, int edges_tolerance)
 {
     if (amount < 1 || W < 8 || H < 8) return 0;                    // doSharpening L716-718
     const bool multiThread = true;
@@ -1104,6 +1112,7 @@ extern "C" int artref_usm(float* R, float* G, float* B, int W, int H, const doub
     sharpenParam.contrast = contrast_p; sharpenParam.radius = radius; sharpenParam.amount = amount;
     sharpenParam.threshold = Threshold<int>(thr[0], thr[1], thr[2], thr[3], false);
     sharpenParam.halocontrol = halocontrol != 0; sharpenParam.halocontrol_amount = halocontrol_amount;
+    sharpenParam.edgesonly = edgesonly != 0; sharpenParam.edges_radius = edges_radius; sharpenParam.edges_tolerance = edges_tolerance;
     float wsm[3][3]; for (int i = 0; i < 9; ++i) (&wsm[0][0])[i] = (float)wsd[i];
     TMatrix ws = wsm;
     array2D<float> Y(ARRAY2D_ALIGNED);
@@ -1408,6 +1417,10 @@ def extract(det):
            cut_function(ish, r"^class CornerBoostMask ") + ";",
            cut_function(ish, r"^void unsharp_mask\(float \*\*Y[^)]*\)")]
     open(os.path.join(sub, "usm_ipsharpen.inc"), "w").write("\n\n".join(ips))
+    btext = open(os.path.join(RT, "bilateral2.h"), encoding="utf-8", errors="replace").read()
+    b0 = re.search(r"^#define ELEM\(a,b\)", btext, flags=re.M)
+    b1 = re.search(r"^// START OF EXPERIMENTAL CODE", btext, flags=re.M)
+    open(os.path.join(sub, "usm_bilateral.inc"), "w").write(btext[b0.start():b1.start()])
     open(os.path.join(sub, "shim_usm.cc"), "w").write(SHIM_USM_TU)
 
     # X-Trans demosaic (xtrans_demosaic.cc): constants + cielab + border + Markesteijn

@@ -106,9 +106,96 @@ int artoracle_blend_mask(const float* lum, float* blend, int W, int H, float con
     return artoracle_gauss(blend, W, blend, W, W, H, (double)blur_radius);
 }
 
+
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * bilateral<float, float>(src, dst, buffer, W, H, sigma, sens), bilateral2.h L38-547: 21 fixed integer kernels (3x3 .. 11x11, one per
+ * 0.1 step of sigma) weighted by a range LUT ec[d + 65536] = exp(-d^2 / (2 sens^2)) * scale, read with LUTf's interpolating
+ * float index; each sum runs row-major over src[i - a][j - b], a, b = -h .. h, in float; the h-pixel border is copied.
+ * Rows: {LUT scale, half width h, quarter kernel (h + 1) x (h + 1), row-major, corner first} -- the BL_BEGIN / BL_OPERn arguments.
+ * ------------------------------------------------------------------------------------------------------------------------- */
+typedef struct { int scale, half; int q[36]; } bl_kernel;
+static const bl_kernel BL_KERNELS[21] = {
+    {318, 1, {1, 7, 7, 55}},                                                                                  /* sigma 0.5, L151-164 */
+    {768, 1, {1, 4, 4, 16}},
+    {366, 2, {0, 0, 1, 0, 8, 21, 1, 21, 59}},
+    {753, 2, {0, 0, 1, 0, 5, 10, 1, 10, 23}},
+    {595, 2, {0, 1, 2, 1, 6, 12, 2, 12, 22}},
+    {910, 2, {0, 1, 2, 1, 4, 7, 2, 7, 12}},                                                                   /* 1.0 */
+    {209, 3, {0, 0, 1, 1, 0, 2, 5, 8, 1, 5, 18, 27, 1, 8, 27, 41}},
+    {322, 3, {0, 0, 1, 1, 0, 1, 4, 6, 1, 4, 11, 16, 1, 6, 16, 23}},
+    {336, 3, {0, 0, 1, 1, 0, 2, 4, 6, 1, 4, 11, 14, 1, 6, 14, 19}},
+    {195, 3, {0, 1, 2, 3, 1, 4, 8, 10, 2, 8, 17, 21, 3, 10, 21, 28}},
+    {132, 4, {0, 0, 0, 1, 1, 0, 1, 2, 4, 5, 0, 2, 6, 12, 14, 1, 4, 12, 22, 28, 1, 5, 14, 28, 35}},            /* 1.5 */
+    {180, 4, {0, 0, 0, 1, 1, 0, 1, 2, 3, 4, 0, 2, 5, 9, 10, 1, 3, 9, 15, 19, 1, 4, 10, 19, 23}},
+    {195, 4, {0, 0, 1, 1, 1, 0, 1, 2, 3, 4, 1, 2, 5, 8, 9, 1, 3, 8, 13, 16, 1, 4, 9, 16, 19}},
+    {151, 4, {0, 0, 1, 2, 2, 0, 1, 3, 5, 5, 1, 3, 6, 10, 12, 2, 5, 10, 16, 19, 2, 5, 12, 19, 22}},
+    {151, 4, {0, 0, 1, 2, 2, 0, 1, 3, 4, 5, 1, 3, 5, 8, 9, 2, 4, 8, 12, 14, 2, 5, 9, 14, 16}},
+    {116, 5, {0, 0, 0, 1, 1, 1, 0, 0, 1, 2, 3, 3, 0, 1, 2, 4, 7, 7, 1, 2, 4, 8, 12, 14, 1, 3, 7, 12, 18, 20, 1, 3, 7, 14, 20, 23}},   /* 2.0 */
+    {127, 5, {0, 0, 0, 1, 1, 1, 0, 0, 1, 2, 3, 3, 0, 1, 2, 4, 6, 7, 1, 2, 4, 8, 11, 12, 1, 3, 6, 11, 15, 17, 1, 3, 7, 12, 17, 19}},
+    {109, 5, {0, 0, 0, 1, 1, 2, 0, 1, 2, 3, 3, 4, 1, 2, 3, 5, 7, 8, 1, 3, 5, 9, 12, 13, 1, 3, 7, 12, 16, 18, 2, 4, 8, 13, 18, 20}},
+    {132, 5, {0, 0, 1, 1, 1, 1, 0, 1, 1, 2, 3, 3, 1, 1, 3, 5, 6, 7, 1, 2, 5, 7, 10, 11, 1, 3, 6, 10, 13, 14, 1, 3, 7, 11, 14, 16}},
+    {156, 5, {0, 0, 1, 1, 1, 1, 0, 1, 1, 2, 3, 3, 1, 1, 3, 4, 5, 6, 1, 2, 4, 6, 8, 9, 1, 3, 5, 8, 10, 11, 1, 3, 6, 9, 11, 12}},
+    {173, 5, {0, 0, 1, 1, 1, 1, 0, 1, 1, 2, 3, 3, 1, 1, 2, 4, 5, 5, 1, 2, 4, 5, 7, 7, 1, 3, 5, 7, 9, 9, 1, 3, 5, 7, 9, 10}},           /* 2.5 */
+};
+/* the dispatcher's thresholds (L487-547): kernel k serves sigma < BL_LIMITS[k], the last one everything above */
+static const double BL_LIMITS[20] = {0.55, 0.65, 0.75, 0.85, 0.95, 1.05, 1.15, 1.25, 1.35, 1.45, 1.55, 1.65, 1.75, 1.85, 1.95, 2.05, 2.15, 2.25, 2.35, 2.45};
+
+static inline float bl_lut(const float* ec, float index)
+{   /* LUTf::operator[](float), LUT.h L437-459: 0x20000 entries, clipped both ways */
+    if (index < 0.f || !(index == index)) return ec[0];
+    if (index > 131070.f) return ec[131071];
+    const int idx = (int)index;
+    const float diff = index - (float)idx;
+    const float p1 = ec[idx];
+    const float p2 = ec[idx + 1] - p1;
+    return p1 + p2 * diff;
+}
+
+int artoracle_bilateral(const float* src, float* dst, int W, int H, double sigma, double sens)
+{
+    if (sigma < 0.45) { memcpy(dst, src, sizeof(float) * (size_t)W * H); return 0; }
+    int kx = 0;
+    while (kx < 20 && !(sigma < BL_LIMITS[kx])) kx++;
+    const bl_kernel* K = &BL_KERNELS[kx];
+    const int h = K->half, hw = h + 1;
+    float* ec = (float*)malloc(sizeof(float) * 0x20000);
+    if (!ec) return 1;
+    const double scale = K->scale;
+    for (int i = 0; i < 0x20000; i++) ec[i] = (exp(-(double)(i - 0x10000) * (double)(i - 0x10000) / (2.0 * sens * sens)) * scale);
+#pragma omp parallel for
+    for (int i = 0; i < H; i++)
+        for (int j = 0; j < W; j++) {
+            const size_t o = (size_t)i * W + j;
+            if (i < h || j < h || i >= H - h || j >= W - h) { dst[o] = src[o]; continue; }
+            const float c = src[o];
+            float v = 0.f, den = 0.f;
+            int first = 1;
+            for (int a = -h; a <= h; a++)
+                for (int b = -h; b <= h; b++) {
+                    const float coef = (float)K->q[(h - abs(a)) * hw + (h - abs(b))];
+                    const float s = src[(size_t)(i - a) * W + (j - b)];
+                    const float e = bl_lut(ec, s - c + 65536.0f);
+                    const float tv = coef * (s * e), td = coef * e;
+                    if (first) { v = tv; den = td; first = 0; }
+                    else { v = v + tv; den = den + td; }
+                }
+            dst[o] = v / den;
+        }
+    free(ec);
+    return 0;
+}
+
 /* thr = Threshold<int> {bottom_left, top_left, bottom_right, top_right}; blend_out (optional) receives the blend mask */
+int artoracle_usm_ex(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double radius, int amount,
+                     const int* thr, int halocontrol, int halocontrol_amount, float* blend_out, int edgesonly, double edges_radius, int edges_tolerance);
 int artoracle_usm(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double radius, int amount,
                   const int* thr, int halocontrol, int halocontrol_amount, float* blend_out)
+{
+    return artoracle_usm_ex(R, G, B, W, H, wsd, scale, contrast_p, radius, amount, thr, halocontrol, halocontrol_amount, blend_out, 0, 1.9, 1800);
+}
+/* edgesonly (unsharp_mask L239-262): the difference image is taken on a bilateral-filtered copy (base = b3), the blur of that copy */
+int artoracle_usm_ex(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double radius, int amount,
+                     const int* thr, int halocontrol, int halocontrol_amount, float* blend_out, int edgesonly, double edges_radius, int edges_tolerance)
 {
     if (amount < 1 || W < 8 || H < 8) return 0;
     const size_t n = (size_t)W * H;
@@ -125,10 +212,15 @@ int artoracle_usm(float* R, float* G, float* B, int W, int H, const double* wsd,
     memcpy(YY, Y, sizeof(float) * n);
     /* unsharp_mask */
     apply_gamma(YY, n, 3.f, 0);
-    if (!rc) rc = artoracle_gauss(YY, W, b2, W, W, H, radius / scale);
+    float* base = YY;
+    if (edgesonly) {
+        base = (float*)malloc(sizeof(float) * n);
+        if (!rc) rc = artoracle_bilateral(YY, base, W, H, edges_radius / scale, (double)edges_tolerance);
+    }
+    if (!rc) rc = artoracle_gauss(base, W, b2, W, W, H, radius / scale);
     if (!halocontrol) {
         for (size_t k = 0; k < n; ++k) {
-            const float diff = YY[k] - b2[k];
+            const float diff = base[k] - b2[k];
             const float delta = threshold_multiply(thr, minr(fabsf(diff), 2000.f), amount * diff * 0.01f);
             YY[k] = blend[k] * (YY[k] + delta) + (1.f - blend[k]) * YY[k];
         }
@@ -136,7 +228,7 @@ int artoracle_usm(float* R, float* G, float* B, int W, int H, const double* wsd,
         const float scl = (100.f - halocontrol_amount) * 0.01f;
         const float sharpFac = amount * 0.01f;
         float* nL = (float*)malloc(sizeof(float) * n);
-        memcpy(nL, YY, sizeof(float) * n);
+        memcpy(nL, base, sizeof(float) * n);        /* edgesonly passes b3 itself (L302) */
 #define NL(i, j) nL[(size_t)(i) * W + (j)]
         for (int i = 2; i < H - 2; i++) {
             float max1 = 0, max2 = 0, min1 = 0, min2 = 0;
@@ -162,6 +254,7 @@ int artoracle_usm(float* R, float* G, float* B, int W, int H, const double* wsd,
 #undef NL
         free(nL);
     }
+    if (edgesonly) free(base);
     apply_gamma(YY, n, 3.f, 1);
     /* multiply(rgb, YY, Y) */
     for (size_t k = 0; k < n; ++k)

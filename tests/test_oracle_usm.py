@@ -136,3 +136,37 @@ BOOST_CASES = [dict(boost=0.2), dict(boost=0.35, latitude=60, radius=0.6), dict(
 def test_rld_corner_boost(W, H, case):
     planes = scene(W, H, W * 11 + H + case, wild=bool(case & 1))
     same(run_rld_ex(oracle.port().lib, "artoracle_rld_ex", planes, **BOOST_CASES[case]), run_rld_ex(oracle.ref().lib, "artref_rld_ex", planes, **BOOST_CASES[case]))
+
+
+# ---- edgesonly: the difference image is taken on a bilateral-filtered copy (bilateral2.h)
+def run_edges(lib, name, planes, edges_radius=1.9, edges_tolerance=1800, scale=1.0, contrast=20.0, radius=0.5, amount=200, thr=DEFAULT_THR, halo=0, halo_amount=85):
+    out = [np.ascontiguousarray(p).copy() for p in planes]
+    H, W = out[0].shape
+    t = (ctypes.c_int * 4)(*thr)
+    rc = getattr(lib, name)(out[0].ctypes.data_as(fp), out[1].ctypes.data_as(fp), out[2].ctypes.data_as(fp), W, H, PROPHOTO.ctypes.data_as(dp),
+                            D(scale), D(contrast), D(radius), int(amount), t, int(halo), int(halo_amount), None, 1, D(edges_radius), int(edges_tolerance))
+    assert rc == 0
+    return out
+
+
+# one case per bilateral kernel (sigma 0.5 .. 2.5 in 0.1 steps; below 0.45 is a copy), thresholds hit on both sides, plus the other switches
+EDGES_CASES = [dict(edges_radius=0.4 + 0.1 * k) for k in range(0, 23)] + [
+    dict(edges_radius=0.45), dict(edges_radius=0.55), dict(edges_radius=2.45), dict(edges_radius=3.7),
+    dict(edges_tolerance=10), dict(edges_tolerance=10000, radius=1.4), dict(scale=2.0, edges_radius=2.5),
+    dict(halo=1), dict(halo=1, halo_amount=20, edges_radius=1.0, edges_tolerance=400, amount=500)]
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", [(64, 48), (9, 8), (12, 11), (130, 77)])
+@pytest.mark.parametrize("case", range(len(EDGES_CASES)))
+def test_usm_edgesonly(W, H, case):
+    planes = scene(W, H, W * 5 + H + case, wild=bool(case % 3 == 1))
+    same(run_edges(oracle.port().lib, "artoracle_usm_ex", planes, **EDGES_CASES[case]), run_edges(oracle.ref().lib, "artref_usm_ex", planes, **EDGES_CASES[case]))
+
+
+@needs_ref
+def test_usm_edgesonly_differs_from_plain():
+    planes = scene(130, 77, 9)
+    a = run_edges(oracle.port().lib, "artoracle_usm_ex", planes)
+    b, _ = run(oracle.port().lib, "artoracle_usm", planes)
+    assert any((x != y).any() for x, y in zip(a, b))
