@@ -191,15 +191,15 @@ class _SharpenParamsC(ctypes.Structure):
                 ("edgesonly", ctypes.c_int), ("halocontrol", ctypes.c_int), ("halocontrol_amount", ctypes.c_int), ("scale", ctypes.c_double),
                 ("method", ctypes.c_int), ("deconvradius", ctypes.c_double), ("deconvamount", ctypes.c_int), ("deconvCornerBoost", ctypes.c_double),
                 ("deconvCornerLatitude", ctypes.c_int), ("offset_x", ctypes.c_int), ("offset_y", ctypes.c_int), ("full_width", ctypes.c_int),
-                ("full_height", ctypes.c_int)]
+                ("full_height", ctypes.c_int), ("edges_radius", ctypes.c_double), ("edges_tolerance", ctypes.c_int)]
 
 
 class SharpenParams:
-    """Mirror of procparams::SharpeningParams for method "usm" (defaults: rtengine/procparams.cc L1756-1776)."""
+    """Mirror of procparams::SharpeningParams for methods "usm" and "rld" (defaults: rtengine/procparams.cc L1756-1776)."""
 
     def __init__(self, contrast=20.0, radius=0.5, amount=200, threshold=(20, 80, 2000, 1200), edgesonly=False, halocontrol=False,
                  halocontrol_amount=85, scale=1.0, method="usm", deconvradius=0.75, deconvamount=100, deconvCornerBoost=0.0,
-                 deconvCornerLatitude=25, offset_x=0, offset_y=0, full_width=0, full_height=0):
+                 deconvCornerLatitude=25, offset_x=0, offset_y=0, full_width=0, full_height=0, edges_radius=1.9, edges_tolerance=1800):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
@@ -207,7 +207,8 @@ class SharpenParams:
         return _SharpenParamsC(float(self.contrast), float(self.radius), int(self.amount), (ctypes.c_int * 4)(*[int(t) for t in self.threshold]),
                                int(bool(self.edgesonly)), int(bool(self.halocontrol)), int(self.halocontrol_amount), float(self.scale),
                                {"usm": 0, "rld": 1, "psf": 2}[self.method], float(self.deconvradius), int(self.deconvamount), float(self.deconvCornerBoost),
-                               int(self.deconvCornerLatitude), int(self.offset_x), int(self.offset_y), int(self.full_width), int(self.full_height))
+                               int(self.deconvCornerLatitude), int(self.offset_x), int(self.offset_y), int(self.full_width), int(self.full_height),
+                               float(self.edges_radius), int(self.edges_tolerance))
 
 
 class _ChainParamsC(ctypes.Structure):

@@ -242,6 +242,7 @@ void art_hp_destroy(art_hp_ctx* ctx)
     if (ctx->d_dn_labtabs.p) cudaFree(ctx->d_dn_labtabs.p);
     if (ctx->d_chain.p) cudaFree(ctx->d_chain.p);
     if (ctx->d_usm_tables.p) cudaFree(ctx->d_usm_tables.p);
+    if (ctx->d_bl_lut.p) cudaFree(ctx->d_bl_lut.p);
     if (ctx->d_xt_cbrt.p) cudaFree(ctx->d_xt_cbrt.p);
     for (int i = 0; i < art_hp_ctx::NLANES; ++i) { if (ctx->lane[i]) cudaStreamDestroy(ctx->lane[i]); if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);

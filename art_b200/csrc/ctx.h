@@ -53,6 +53,8 @@ struct art_hp_ctx {
     bool chain_cache_ready = false;
     DevBuf d_usm_tables;                 // apply_gamma's two 65536-entry LUTs (gamma 1/3 and 3), built once on the device
     bool usm_tables_ready = false;
+    DevBuf d_bl_lut;                     // edges-only sharpening: the bilateral filter's range LUT (0x20000 floats), host-built
+    int bl_lut_scale = 0, bl_lut_sens = 0;
     DevBuf d_xt_cbrt;                    // cielab's 0x14000-entry cube-root LUT of the X-Trans demosaic
     bool xt_cbrt_ready = false;
     // batch queue (art_hp_develop_submit / _wait): two frames in flight, each with its own raw + output planes

@@ -12,6 +12,8 @@
 // IIR sweep pair) ~ 84-110 B/px (~110).  All kernels are streaming: HBM-bound.
 // Bit-identical to the reference's SSE2 build (no FMA contraction, IEEE division and sqrt).
 #include "ctx.h"
+
+#include <vector>
 #include "sleef_dev.cuh"
 
 namespace {
@@ -108,7 +110,7 @@ __device__ __forceinline__ float threshold_multiply(const Thr t, float x, float 
 }
 
 __global__ void __launch_bounds__(256) k_usm_apply(float* __restrict__ R, float* __restrict__ G, float* __restrict__ B, size_t ip,
-                                                   const float* __restrict__ Y, const float* __restrict__ YY, const float* __restrict__ b2,
+                                                   const float* __restrict__ Y, const float* __restrict__ YY, const float* base, const float* __restrict__ b2,
                                                    const float* __restrict__ blend, size_t yp, int W, int H, int amount, Thr thr,
                                                    const float* __restrict__ glut_rev)
 {
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(256) k_usm_apply(float* __restrict__ R, float*
     for (int y = blockIdx.y; y < H; y += gridDim.y) {
         const size_t i = (size_t)y * ip + x, o = (size_t)y * yp + x;
         const float yy = YY[o], bl = blend[o], den = Y[o];
-        const float diff = yy - b2[o];
+        const float diff = base[o] - b2[o];                      // base: YY itself, or its bilateral-filtered copy (edgesonly, L263-265)
         const float delta = threshold_multiply(thr, minr(fabsf(diff), 2000.f), amount * diff * 0.01f);
         float v = bl * (yy + delta) + (1.f - bl) * yy;           // intp(blend, Y + delta, Y)
         v = gamma_apply(glut_rev, v, 3.f);
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(256) k_usm_apply(float* __restrict__ R, float*
 // tail as k_usm_apply.  The reference slides a two-entry max / min queue along each row (both entries start at 0); here every
 // pixel recomputes the three 3x3-window statistics of columns j-2, j-1, j from the 5x5 neighbourhood it holds in registers.
 __global__ void __launch_bounds__(256) k_usm_apply_halo(float* __restrict__ R, float* __restrict__ G, float* __restrict__ B, size_t ip,
-                                                        const float* __restrict__ Y, const float* __restrict__ YY, const float* __restrict__ b2,
+                                                        const float* __restrict__ Y, const float* __restrict__ YY, const float* base, const float* __restrict__ b2,
                                                         const float* __restrict__ blend, size_t yp, int W, int H, int amount, int halo_amount, Thr thr,
                                                         const float* __restrict__ glut_rev)
 {
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(256) k_usm_apply_halo(float* __restrict__ R, f
 #pragma unroll
             for (int dy = 0; dy < 5; ++dy)
 #pragma unroll
-                for (int dx = 0; dx < 5; ++dx) n[dy][dx] = YY[o + (ptrdiff_t)(dy - 2) * (ptrdiff_t)yp + (dx - 2)];
+                for (int dx = 0; dx < 5; ++dx) n[dy][dx] = base[o + (ptrdiff_t)(dy - 2) * (ptrdiff_t)yp + (dx - 2)];
             float mx[3], mn[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {           // window statistics of column j = x - 2 + k (columns k .. k + 2 of n)
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(256) k_usm_apply_halo(float* __restrict__ R, f
             float max_ = maxr(maxr(max1, max2), mx[2]), min_ = minr(minr(min1, min2), mn[2]);
             if (max_ < labL) max_ = labL;
             if (min_ > labL) min_ = labL;
-            const float diff = labL - b2[o];
+            const float diff = n[2][2] - b2[o];
             const float delta = threshold_multiply(thr, minr(fabsf(diff), 2000.f), sharpFac * diff);
             float newL = labL + delta;
             if (newL > max_) newL = max_ + (newL - max_) * scl;
@@ -183,6 +185,52 @@ __global__ void __launch_bounds__(256) k_usm_apply_halo(float* __restrict__ R, f
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// edgesonly: bilateral<float, float> (bilateral2.h L38-547).  One of 21 fixed integer kernels (3x3 .. 11x11, chosen by sigma in 0.1
+// steps) weighted by a range LUT ec[d + 65536] = exp(-d^2 / (2 sens^2)) * scale that is read with LUTf's interpolating float index;
+// numerator and denominator are summed in float, row-major over src[i - a][j - b], a, b = -h .. h; the h-pixel border is copied.
+// ---------------------------------------------------------------------------------------------------------------------------
+struct BlK { int half; float q[36]; };       // quarter kernel (h + 1) x (h + 1), row-major, corner first: the BL_OPERn arguments
+
+__device__ __forceinline__ float bl_lut(const float* __restrict__ ec, float index)
+{   // LUT.h L437-459, 0x20000 entries, LUT_CLIP_BELOW | LUT_CLIP_ABOVE
+    if (index < 0.f || !(index == index)) return ec[0];
+    if (index > 131070.f) return ec[131071];
+    const int idx = (int)index;
+    const float diff = index - (float)idx;
+    const float p1 = ec[idx];
+    const float p2 = ec[idx + 1] - p1;
+    return p1 + p2 * diff;
+}
+
+__global__ void __launch_bounds__(256) k_usm_bilateral(BlK k, const float* __restrict__ src, float* __restrict__ dst, size_t yp, int W, int H,
+                                                       const float* __restrict__ ec)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    const int h = k.half, hw = h + 1;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const size_t o = (size_t)y * yp + x;
+        if (y < h || x < h || y >= H - h || x >= W - h) { dst[o] = src[o]; continue; }        // BL_END, L52-57
+        const float c = src[o];
+        float v = 0.f, den = 0.f;
+        bool first = true;
+        for (int a = -h; a <= h; ++a) {
+            const float* row = src + o - (ptrdiff_t)a * (ptrdiff_t)yp;
+            const float* qr = k.q + (h - abs(a)) * hw;
+            for (int b = -h; b <= h; ++b) {
+                const float coef = qr[h - abs(b)];
+                const float s = row[-b];
+                const float e = bl_lut(ec, s - c + 65536.0f);
+                const float tv = coef * (s * e), td = coef * e;
+                if (first) { v = tv; den = td; first = false; }
+                else { v = v + tv; den = den + td; }
+            }
+        }
+        dst[o] = v / den;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // "rld": RL-deconvolution sharpening, doSharpening L747-771 without the corner boost: markImpulse (rt_algo.cc L497-591),
@@ -484,12 +532,73 @@ static int art_rld_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip,
     return ART_HP_OK;
 }
 
+// the BL_BEGIN / BL_OPERn arguments of bilateral05 .. bilateral25 (bilateral2.h L151-484): LUT scale, half width, quarter kernel
+struct BlKernel { int scale, half; int q[36]; };
+static const BlKernel BL_KERNELS[21] = {
+    {318, 1, {1, 7, 7, 55}},
+    {768, 1, {1, 4, 4, 16}},
+    {366, 2, {0, 0, 1, 0, 8, 21, 1, 21, 59}},
+    {753, 2, {0, 0, 1, 0, 5, 10, 1, 10, 23}},
+    {595, 2, {0, 1, 2, 1, 6, 12, 2, 12, 22}},
+    {910, 2, {0, 1, 2, 1, 4, 7, 2, 7, 12}},
+    {209, 3, {0, 0, 1, 1, 0, 2, 5, 8, 1, 5, 18, 27, 1, 8, 27, 41}},
+    {322, 3, {0, 0, 1, 1, 0, 1, 4, 6, 1, 4, 11, 16, 1, 6, 16, 23}},
+    {336, 3, {0, 0, 1, 1, 0, 2, 4, 6, 1, 4, 11, 14, 1, 6, 14, 19}},
+    {195, 3, {0, 1, 2, 3, 1, 4, 8, 10, 2, 8, 17, 21, 3, 10, 21, 28}},
+    {132, 4, {0, 0, 0, 1, 1, 0, 1, 2, 4, 5, 0, 2, 6, 12, 14, 1, 4, 12, 22, 28, 1, 5, 14, 28, 35}},
+    {180, 4, {0, 0, 0, 1, 1, 0, 1, 2, 3, 4, 0, 2, 5, 9, 10, 1, 3, 9, 15, 19, 1, 4, 10, 19, 23}},
+    {195, 4, {0, 0, 1, 1, 1, 0, 1, 2, 3, 4, 1, 2, 5, 8, 9, 1, 3, 8, 13, 16, 1, 4, 9, 16, 19}},
+    {151, 4, {0, 0, 1, 2, 2, 0, 1, 3, 5, 5, 1, 3, 6, 10, 12, 2, 5, 10, 16, 19, 2, 5, 12, 19, 22}},
+    {151, 4, {0, 0, 1, 2, 2, 0, 1, 3, 4, 5, 1, 3, 5, 8, 9, 2, 4, 8, 12, 14, 2, 5, 9, 14, 16}},
+    {116, 5, {0, 0, 0, 1, 1, 1, 0, 0, 1, 2, 3, 3, 0, 1, 2, 4, 7, 7, 1, 2, 4, 8, 12, 14, 1, 3, 7, 12, 18, 20, 1, 3, 7, 14, 20, 23}},
+    {127, 5, {0, 0, 0, 1, 1, 1, 0, 0, 1, 2, 3, 3, 0, 1, 2, 4, 6, 7, 1, 2, 4, 8, 11, 12, 1, 3, 6, 11, 15, 17, 1, 3, 7, 12, 17, 19}},
+    {109, 5, {0, 0, 0, 1, 1, 2, 0, 1, 2, 3, 3, 4, 1, 2, 3, 5, 7, 8, 1, 3, 5, 9, 12, 13, 1, 3, 7, 12, 16, 18, 2, 4, 8, 13, 18, 20}},
+    {132, 5, {0, 0, 1, 1, 1, 1, 0, 1, 1, 2, 3, 3, 1, 1, 3, 5, 6, 7, 1, 2, 5, 7, 10, 11, 1, 3, 6, 10, 13, 14, 1, 3, 7, 11, 14, 16}},
+    {156, 5, {0, 0, 1, 1, 1, 1, 0, 1, 1, 2, 3, 3, 1, 1, 3, 4, 5, 6, 1, 2, 4, 6, 8, 9, 1, 3, 5, 8, 10, 11, 1, 3, 6, 9, 11, 12}},
+    {173, 5, {0, 0, 1, 1, 1, 1, 0, 1, 1, 2, 3, 3, 1, 1, 2, 4, 5, 5, 1, 2, 4, 5, 7, 7, 1, 3, 5, 7, 9, 9, 1, 3, 5, 7, 9, 10}},
+};
+// kernel k serves sigma < BL_LIMITS[k] (the dispatcher, L487-547), the last one everything above
+static const double BL_LIMITS[20] = {0.55, 0.65, 0.75, 0.85, 0.95, 1.05, 1.15, 1.25, 1.35, 1.45, 1.55, 1.65, 1.75, 1.85, 1.95, 2.05, 2.15, 2.25, 2.35, 2.45};
+
+// bilateral<float, float>(src, dst, buffer, W, H, sigma, sens): src -> dst, planes of pitch yp
+static int usm_bilateral(art_hp_ctx* ctx, const float* src, float* dst, size_t yp, int W, int H, double sigma, int sens)
+{
+    cudaStream_t st = ctx->stream;
+    if (sigma < 0.45) {         // L490-497
+        ART_CUDA(ctx, cudaMemcpyAsync(dst, src, yp * (size_t)H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return ART_HP_OK;
+    }
+    int kx = 0;
+    while (kx < 20 && !(sigma < BL_LIMITS[kx])) kx++;
+    const BlKernel& K = BL_KERNELS[kx];
+    int rc = art_reserve(ctx, ctx->d_bl_lut, 0x20000 * sizeof(float));
+    if (rc) return rc;
+    if (ctx->bl_lut_scale != K.scale || ctx->bl_lut_sens != sens) {     // BL_BEGIN, L42-45: host libm exp in double, as the reference
+        std::vector<float> ec(0x20000);
+        const double scale = K.scale, s = sens;
+        for (int i = 0; i < 0x20000; i++) ec[i] = (float)(std::exp(-(double)(i - 0x10000) * (double)(i - 0x10000) / (2.0 * s * s)) * scale);
+        ART_CUDA(ctx, cudaMemcpyAsync(ctx->d_bl_lut.p, ec.data(), 0x20000 * sizeof(float), cudaMemcpyHostToDevice, st));
+        ART_CUDA(ctx, cudaStreamSynchronize(st));       // pageable source: keep it alive until the copy has run
+        ctx->bl_lut_scale = K.scale; ctx->bl_lut_sens = sens;
+    }
+    BlK k{};
+    k.half = K.half;
+    for (int i = 0; i < (K.half + 1) * (K.half + 1); ++i) k.q[i] = (float)K.q[i];
+    const dim3 blk(256), grid((W + 255) / 256, std::min(H, 148 * 8));
+    art_prof_begin(ctx, "k_usm_bilateral");
+    k_usm_bilateral<<<grid, blk, 0, st>>>(k, src, dst, yp, W, H, (const float*)ctx->d_bl_lut.p);
+    art_prof_end(ctx);
+    ctx->launches++;
+    return ART_HP_OK;
+}
+
 int art_usm_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_sharpen_params* p, const double* ws9)
 {
     if (p->amount < 1 || W < 8 || H < 8) return ART_HP_OK;      // doSharpening L716-718
     if (p->method == 1) return art_rld_dev(ctx, r, g, b, ip, W, H, p, ws9);
     if (p->method != 0) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "sharpening method %d (psf) is not on the hot path", p->method);
-    if (p->edgesonly) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "edges-only sharpening (bilateral pre-filter) is not on the hot path");
+    if (p->edgesonly && p->edges_tolerance < 1) return ctx->fail(ART_HP_ERR_INVALID, "edges_tolerance must be >= 1, got %d", p->edges_tolerance);
+    if (p->edgesonly && !(p->edges_radius >= 0)) return ctx->fail(ART_HP_ERR_INVALID, "negative edges_radius");
     cudaStream_t st = ctx->stream;
     int rc;
     if (!ctx->usm_tables_ready) {
@@ -501,8 +610,9 @@ int art_usm_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W,
     const float* glut = (const float*)ctx->d_usm_tables.p;
     const size_t yp = round_up((size_t)W, 32);
     float* planes = nullptr;
-    if ((rc = art_pool_alloc(ctx, 4 * yp * (size_t)H * sizeof(float), (void**)&planes))) return rc;
+    if ((rc = art_pool_alloc(ctx, (p->edgesonly ? 5 : 4) * yp * (size_t)H * sizeof(float), (void**)&planes))) return rc;
     float *Y = planes, *YY = Y + yp * H, *b2 = YY + yp * H, *blend = b2 + yp * H;
+    float* base = p->edgesonly ? blend + yp * H : YY;           // b3 of unsharp_mask (L239-262)
     const dim3 blk(256), grid((W + 255) / 256, std::min(H, 148 * 8));
 
     art_prof_begin(ctx, "k_usm_lum");
@@ -525,12 +635,13 @@ int art_usm_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W,
         ctx->launches++;
         if ((rc = art_gauss_dev(ctx, blend, yp, blend, yp, W, H, (double)(2.f / s_scale)))) { art_pool_free(ctx, planes); return rc; }
     }
-    if ((rc = art_gauss_dev(ctx, YY, yp, b2, yp, W, H, p->radius / scale))) { art_pool_free(ctx, planes); return rc; }
+    if (p->edgesonly && (rc = usm_bilateral(ctx, YY, base, yp, W, H, p->edges_radius / scale, p->edges_tolerance))) { art_pool_free(ctx, planes); return rc; }
+    if ((rc = art_gauss_dev(ctx, base, yp, b2, yp, W, H, p->radius / scale))) { art_pool_free(ctx, planes); return rc; }
 
     const Thr thr{(double)p->threshold[0], (double)p->threshold[1], (double)p->threshold[2], (double)p->threshold[3]};
     art_prof_begin(ctx, "k_usm_apply");
-    if (p->halocontrol) k_usm_apply_halo<<<grid, blk, 0, st>>>(r, g, b, ip, Y, YY, b2, blend, yp, W, H, p->amount, p->halocontrol_amount, thr, glut + 65536);
-    else k_usm_apply<<<grid, blk, 0, st>>>(r, g, b, ip, Y, YY, b2, blend, yp, W, H, p->amount, thr, glut + 65536);
+    if (p->halocontrol) k_usm_apply_halo<<<grid, blk, 0, st>>>(r, g, b, ip, Y, YY, base, b2, blend, yp, W, H, p->amount, p->halocontrol_amount, thr, glut + 65536);
+    else k_usm_apply<<<grid, blk, 0, st>>>(r, g, b, ip, Y, YY, base, b2, blend, yp, W, H, p->amount, thr, glut + 65536);
     art_prof_end(ctx);
     ctx->launches++;
     ART_CUDA(ctx, cudaGetLastError());

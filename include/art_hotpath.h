@@ -372,7 +372,7 @@ int art_hp_color_chain_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g
  *                      defaults rtengine/procparams.cc L1756-1776); threshold = {bottom_left, top_left, bottom_right,
  *                      top_right}; scale = ImProcFunctions::scale (1 for full-resolution output); ws =
  *                      ICCStore::workingSpaceMatrix.  amount < 1 or an image under 8x8 returns untouched, like the
- *                      reference (L716-718).  method 1 selects the "rld" route (the reference's default method).  halocontrol runs sharpenHaloCtrl (L80-141); edgesonly returns ART_HP_ERR_UNSUPPORTED.  Bit-identical to the
+ *                      reference (L716-718).  method 1 selects the "rld" route (the reference's default method).  halocontrol runs sharpenHaloCtrl (L80-141); edgesonly takes the difference image on a bilateral-filtered copy (bilateral<float, float>, rtengine/bilateral2.h L38-547).  Bit-identical to the
  *                      reference's SSE2 build.
  */
 typedef struct art_hp_sharpen_params {
@@ -380,7 +380,7 @@ typedef struct art_hp_sharpen_params {
     double radius;              /* 0.5 */
     int    amount;              /* 200 */
     int    threshold[4];        /* 20, 80, 2000, 1200 */
-    int    edgesonly;           /* must be 0 */
+    int    edgesonly;           /* 0 | 1 */
     int    halocontrol;         /* 0 | 1 */
     int    halocontrol_amount;
     double scale;               /* 1 */
@@ -390,6 +390,8 @@ typedef struct art_hp_sharpen_params {
     double deconvCornerBoost;   /* 0; > 0.01 * scale mixes a second deconvolution (radius + boost) in towards the corners (CornerBoostMask, L313-338) */
     int    deconvCornerLatitude;            /* 25 */
     int    offset_x, offset_y, full_width, full_height;   /* ImProcFunctions' viewport (improcfun.h L227-230); full_* <= 0 means the image itself */
+    double edges_radius;        /* 1.9; edgesonly: bilateral sigma = edges_radius / scale */
+    int    edges_tolerance;     /* 1800; edgesonly: range sigma of the bilateral filter, >= 1 */
 } art_hp_sharpen_params;
 int art_hp_sharpen_usm(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b,
                        const art_hp_sharpen_params* params, const double ws[9]);

@@ -69,7 +69,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
                                                          "nlStrength", "fattal_enabled", "fattal_satcontrol", "wprof", "sharpen", "chain", "xtrans", "rgb_cam"]),
         "art_hp_chain_params": (api._ChainParamsC, ["exposure_enabled", "exp_scale", "black", "saturation_enabled", "vibrance", "tonecurve_mode",
                                                      "tonecurve_lut", "rcurve", "bcurve", "lab_enabled", "lab_lcurve", "lab_bcurve", "lab_chroma", "ws", "iws"]),
-        "art_hp_sharpen_params": (api._SharpenParamsC, ["contrast", "radius", "amount", "threshold", "edgesonly", "halocontrol", "halocontrol_amount", "scale", "method", "deconvradius", "deconvamount", "deconvCornerBoost", "deconvCornerLatitude", "offset_x", "full_height"]),
+        "art_hp_sharpen_params": (api._SharpenParamsC, ["contrast", "radius", "amount", "threshold", "edgesonly", "halocontrol", "halocontrol_amount", "scale", "method", "deconvradius", "deconvamount", "deconvCornerBoost", "deconvCornerLatitude", "offset_x", "full_height", "edges_radius", "edges_tolerance"]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "art_hotpath.h"', 'int main(void){']
     for s, (_, fields) in pairs.items():

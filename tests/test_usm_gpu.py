@@ -39,12 +39,25 @@ def test_usm_too_small_or_disabled_is_identity(hot_path):
     same(gpu(hot_path, planes, amount=0), planes)
 
 
-def test_usm_rejects_edges_only(hot_path):
+def test_usm_rejects_bad_edges_tolerance(hot_path):
     import art_b200
     planes = scene(64, 40, 3)
     with pytest.raises(art_b200.HotPathError) as e:
-        gpu(hot_path, planes, edgesonly=True)
-    assert e.value.code == 5
+        gpu(hot_path, planes, edgesonly=True, edges_tolerance=0)
+    assert e.value.code == 1
+
+
+from test_oracle_usm import EDGES_CASES, run_edges  # noqa: E402
+
+
+@pytest.mark.parametrize("W,H", [(64, 48), (9, 8), (12, 11), (130, 77), (1023, 517)])
+@pytest.mark.parametrize("case", range(len(EDGES_CASES)))
+def test_usm_edgesonly_matches_oracle(hot_path, W, H, case):
+    """edgesonly: every one of bilateral2.h's 21 kernels, the copy below sigma 0.45, both sides of the dispatch thresholds, range
+    sigma extremes, with and without halo control; the range LUT is rebuilt when (kernel scale, tolerance) changes between calls."""
+    planes = scene(W, H, W * 5 + H + case, wild=bool(case % 3 == 1))
+    want = run_edges(oracle.port().lib, "artoracle_usm_ex", planes, **EDGES_CASES[case])
+    same(gpu(hot_path, planes, edgesonly=True, **EDGES_CASES[case]), want)
 
 
 def test_usm_device_form_with_pitch(hot_path):
