@@ -601,7 +601,7 @@ struct DenoiseParams {
     ChrominanceMethod chrominanceMethod; double chrominance; double chrominanceRedGreen; double chrominanceBlueYellow;
 };
 struct ICMParams { std::string workingProfile; };
-struct ProcParams { ICMParams icm; };
+struct ProcParams { ICMParams icm; DenoiseParams denoise; };
 }
 using procparams::ProcParams;
 struct ImProcData { const ProcParams* params; double scale; bool multiThread; };
@@ -672,8 +672,62 @@ void Tile_calc(int tilesize, int overlap, int kall, int imwidth, int imheight, i
 
 #include "ftblockdn_body.inc"
 
+// calcautodn_info, RGB_denoise_infoGamCurve, RGB_denoise_info cut from ipdenoise.cc (the AUTOMATIC chroma estimator)
+namespace rtengine { namespace {
+#include "ipdenoise_info.inc"
+} }
+
 using namespace rtengine;
 extern "C" {
+// RGB_denoise_info over one crop (isRAW); out[15] = chaut, Nb, redaut, blueaut, maxredaut, maxblueaut, minredaut, minblueaut, chromina,
+// sigma, lumema, sigma_L, redyel, skinc, nsknc, read as the initial values and written back
+int artref_denoise_info(const float* r, const float* g, const float* b, int W, int H, const float* cr, const float* cg, const float* cb,
+                        double gamma, int aggressive, double scale, double expcomp, const double* wp, float* out)
+{
+    Color::init();
+    for (int i = 0; i < 9; ++i) { (&artref_wp[0][0])[i] = (float)wp[i]; }
+    procparams::DenoiseParams dn;
+    dn.enabled = true; dn.colorSpace = procparams::DenoiseParams::ColorSpace::RGB; dn.aggressive = aggressive != 0;
+    dn.chrominanceMethod = procparams::DenoiseParams::ChrominanceMethod::AUTOMATIC; dn.gamma = gamma;
+    dn.luminance = 0; dn.luminanceDetail = 0; dn.luminanceDetailThreshold = 0; dn.chrominance = 15; dn.chrominanceRedGreen = 0; dn.chrominanceBlueYellow = 0;
+    ProcParams pp; pp.icm.workingProfile = "ProPhoto"; pp.denoise = dn;
+    ImProcData im = {&pp, scale, true};
+    Imagefloat src(W, H, const_cast<float*>(r), const_cast<float*>(g), const_cast<float*>(b));
+    Imagefloat provicalc((W + 1) / 2, (H + 1) / 2, const_cast<float*>(cr), const_cast<float*>(cg), const_cast<float*>(cb));
+    LUTf gamcurve(65536, 0);
+    float gam, gamthresh, gamslope;
+    RGB_denoise_infoGamCurve(dn, true, gamcurve, gam, gamthresh, gamslope);
+    float chaut = out[0], redaut = out[2], blueaut = out[3], maxredaut = out[4], maxblueaut = out[5], minredaut = out[6], minblueaut = out[7],
+          chromina = out[8], sigma = out[9], lumema = out[10], sigma_L = out[11], redyel = out[12], skinc = out[13], nsknc = out[14];
+    int nb = (int)out[1];
+    RGB_denoise_info(im, &src, &provicalc, true, gamcurve, gam, gamthresh, gamslope, dn, expcomp, chaut, nb, redaut, blueaut, maxredaut, maxblueaut,
+                     minredaut, minblueaut, chromina, sigma, lumema, sigma_L, redyel, skinc, nsknc);
+    out[0] = chaut; out[1] = (float)nb; out[2] = redaut; out[3] = blueaut; out[4] = maxredaut; out[5] = maxblueaut; out[6] = minredaut; out[7] = minblueaut;
+    out[8] = chromina; out[9] = sigma; out[10] = lumema; out[11] = sigma_L; out[12] = redyel; out[13] = skinc; out[14] = nsknc;
+    return 0;
+}
+// the nine-crop combination of ImProcFunctions::denoiseComputeParams (ipdenoise.cc, from `float chM = 0.f;` to the store assignments), cut in place
+int artref_denoise_auto_params(const float* stats, int isRAW_, int aggressive, float* out3)
+{
+    struct Src { bool raw; bool isRAW() const { return raw; } } src_{isRAW_ != 0};
+    Src* imgsrc = &src_;
+    struct { float ch_M[9], max_r[9], max_b[9]; double chrominance, chrominanceRedGreen, chrominanceBlueYellow; } store;
+    ProcParams pp; pp.denoise.aggressive = aggressive != 0;
+    const ProcParams* params = &pp;
+    float min_b[9], min_r[9], lumL[9], chromC[9], ry[9], sk[9], pcsk[9];
+    int Nb[9];
+    const float pondcorrec = 1.0f;
+    for (int k = 0; k < 9; ++k) {
+        const float* s = stats + 15 * k;
+        Nb[k] = (int)s[1]; store.ch_M[k] = pondcorrec * s[0]; store.max_r[k] = pondcorrec * s[4]; store.max_b[k] = pondcorrec * s[5];
+        min_r[k] = pondcorrec * s[6]; min_b[k] = pondcorrec * s[7]; lumL[k] = s[10]; chromC[k] = s[8]; ry[k] = s[12]; sk[k] = s[13]; pcsk[k] = s[14];
+    }
+    float autoNR = 10, autoNRmax = 40, lowdenoise = 1.f;
+    int levaut = 0;
+#include "ipdenoise_combine.inc"
+    out3[0] = (float)store.chrominance; out3[1] = (float)store.chrominanceRedGreen; out3[2] = (float)store.chrominanceBlueYellow;
+    return 0;
+}
 // timing only: 0 = the reference's default (all OpenMP threads inside detail_recovery, whose overlap-add then races); parity tests keep 1
 void artref_set_denoise_thread_limit(int n) { rtengine::options.rgbDenoiseThreadLimit = n; }
 // p: luminance, luminanceDetail, luminanceDetailThreshold, chrominance, chrominanceRedGreen, chrominanceBlueYellow, gamma, scale
@@ -1316,7 +1370,8 @@ def extract(det):
     members = [cut_function(ch, r"static float rgbLuminance\(float r, float g, float b, const T workingspace\[3\]\[3\]\)"),
                cut_function(ch, r"static void rgb2yuv\(float r, float g, float b, float &Y"),
                cut_function(ch, r"static void yuv2rgb\(float Y, float u, float v, float &r"),
-               cut_function(ch, r"static inline float gammaf\s*\(float x, float gamma, float start, float slope\)")]
+               cut_function(ch, r"static inline float gammaf\s*\(float x, float gamma, float start, float slope\)"),
+               cut_function(ch, r"static inline float gammanf\s*\(float x, float gamma\)")]
     labm = ["template <class T>\n" + cut_function(ch, r"static void rgb2lab\(float R, float G, float B, float &l, float &a, float &b, const T ws\[3\]\[3\]\)"),
             "template <class T>\n" + cut_function(ch, r"static void lab2rgb\(float l, float a, float b, float &R, float &G, float &B, const T iws\[3\]\[3\]\)"),
             cut_function(ch, r"static inline float f2xyz\(float f\)"),
@@ -1331,6 +1386,15 @@ def extract(det):
            cut_function(cc, r"^void Color::Lab2XYZ\(float L, float a, float b, float &x, float &y, float &z\)")]
     open(os.path.join(sub, "color_cc_members.inc"), "w").write("\n".join(ccm))
     open(os.path.join(sub, "dct_standin.h"), "w").write(open(os.path.join(HERE, "dct_standin.h")).read())
+    ipd = os.path.join(RT, "ipdenoise.cc")
+    info = [cut_function(ipd, r"^void calcautodn_info\(const ProcParams \*params[^)]*\)"),
+            cut_function(ipd, r"^void RGB_denoise_infoGamCurve\(const procparams::DenoiseParams & dnparams[^)]*\)"),
+            cut_function(ipd, r"^void RGB_denoise_info\(ImProcData &im[^)]*\)")]
+    open(os.path.join(sub, "ipdenoise_info.inc"), "w").write("\n\n".join(info))
+    iptext = open(ipd, encoding="utf-8", errors="replace").read()
+    c0 = re.search(r"^        float chM = 0\.f;", iptext, flags=re.M)
+    c1 = re.search(r"^        store\.chrominanceBlueYellow = maxb;\n", iptext, flags=re.M)
+    open(os.path.join(sub, "ipdenoise_combine.inc"), "w").write(iptext[c0.start():c1.end()])
     open(os.path.join(sub, "shim_denoise.cc"), "w").write(SHIM_DENOISE_TU)
     fat = open(os.path.join(RT, "tmo_fattal02.cc"), encoding="utf-8", errors="replace").read()
     m0 = re.search(r"^namespace rtengine\s*\{", fat, flags=re.M)

@@ -540,3 +540,240 @@ int artoracle_rgb_denoise_ex2(float* r, float* g, float* b, int W, int H, const 
     free(Lp); free(ap); free(bp); free(Lin); free(noisevarlum); free(noisevarchrom); free(gamcurve); free(igamcurve); free(ccalc);
     return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * Automatic chroma estimator (DenoiseParams::ChrominanceMethod::AUTOMATIC, the reference's default): RGB_denoise_info
+ * (ipdenoise.cc L227-669) over one crop, WaveletDenoiseAll_info / ShrinkAll_info (FTblockDN.cc L1227-1364), calcautodn_info
+ * (ipdenoise.cc L66-206) and the nine-crop combination of ImProcFunctions::denoiseComputeParams (L964-1075).
+ * ------------------------------------------------------------------------------------------------------------------------- */
+static inline float mulsignf_(float x, float y)
+{
+    union { float f; uint32_t u; } a, b;
+    a.f = x; b.f = y;
+    a.u ^= (b.u & 0x80000000u);
+    return a.f;
+}
+static float atan2kf_(float y, float x)
+{   /* sleef.h L1155-1177; the SSE form (sleefsseavx.h L1168-1197) evaluates the same products and sums */
+    float s, t, u, q = 0.f;
+    if (x < 0) { x = -x; q = -2.f; }
+    if (y > x) { t = x; x = y; y = -t; q += 1.f; }
+    s = y / x;
+    t = s * s;
+    u = 0.00282363896258175373077393f;
+    u = u * t + -0.0159569028764963150024414f;
+    u = u * t + 0.0425049886107444763183594f;
+    u = u * t + -0.0748900920152664184570312f;
+    u = u * t + 0.106347933411598205566406f;
+    u = u * t + -0.142027363181114196777344f;
+    u = u * t + 0.199926957488059997558594f;
+    u = u * t + -0.333331018686294555664062f;
+    t = u * t;
+    t = t * s + s;
+    return q * (float)(3.14159265358979323846 / 2.0) + t;
+}
+static float xatan2f_(float y, float x)
+{   /* sleef.h L1179-1188 */
+    const float PI_F = (float)3.14159265358979323846;
+    float r = atan2kf_(fabsf(y), x);
+    r = mulsignf_(r, x);
+    if (isinf(x) || x == 0) r = PI_F / 2 - (isinf(x) ? (copysignf(1.f, x) * (float)(PI_F * .5f)) : 0);
+    if (isinf(y)) r = PI_F / 2 - (isinf(x) ? (copysignf(1.f, x) * (float)(PI_F * .25f)) : 0);
+    if (y == 0) r = (copysignf(1.f, x) == -1 ? PI_F : 0);
+    return (x != x) || (y != y) ? NAN : mulsignf_(r, y);
+}
+
+/* src: the crop (W x H); calc: the crop's even pixels converted to the working space (provicalc, (H+1)/2 x (W+1)/2).
+ * out[15] = chaut, Nb, redaut, blueaut, maxredaut, maxblueaut, minredaut, minblueaut, chromina, sigma, lumema, sigma_L, redyel, skinc, nsknc
+ * (entries the reference leaves untouched keep the caller's values).  Returns 2 when the crop is too small for levwav wavelet levels. */
+int artoracle_denoise_info(const float* r, const float* g, const float* b, int W, int H, const float* cr, const float* cg, const float* cb,
+                           double gamma, int aggressive, double scale, double expcomp, const double* wp9, float* out)
+{
+    init_cachef();
+    const int wid = (W + 1) / 2, hei = (H + 1) / 2;
+    float wp[3][3];
+    for (int i = 0; i < 9; ++i) wp[i / 3][i % 3] = (float)wp9[i];
+    const size_t n2 = (size_t)wid * hei, n = (size_t)W * H;
+    float* lumcalc = (float*)malloc(sizeof(float) * n2); float* acalc = (float*)malloc(sizeof(float) * n2); float* bcalc = (float*)malloc(sizeof(float) * n2);
+    for (size_t k = 0; k < n2; ++k) {       /* L271-287: Color::rgbxyz + Color::XYZ2Lab */
+        const float RL = cr[k], GL = cg[k], BL = cb[k];
+        const float XL = ((wp[0][0] * RL + wp[0][1] * GL + wp[0][2] * BL));
+        const float YL = ((wp[1][0] * RL + wp[1][1] * GL + wp[1][2] * BL));
+        const float ZL = ((wp[2][0] * RL + wp[2][1] * GL + wp[2][2] * BL));
+        const float x = XL / 0.9642f, z = ZL / 0.8249f, y = YL;
+        const float fx = computeXYZ2Lab(x), fy = computeXYZ2Lab(y), fz = computeXYZ2Lab(z);
+        lumcalc[k] = computeXYZ2LabY(y);
+        acalc[k] = (500.0f * (fx - fy));
+        bcalc[k] = (200.0f * (fy - fz));
+    }
+    /* RGB_denoise_infoGamCurve, L209-225 (isRAW) */
+    const float gam = (float)gamma;
+    const float gamthresh = 0.001f;
+    const float gamslope = (float)(exp(log((double)gamthresh) / gam) / gamthresh);
+    float* gamcurve = (float*)malloc(sizeof(float) * 65536);
+    artoracle_gammaf2lut(gamcurve, gam, gamthresh, gamslope, 65535.f, 32768.f);
+    const float gain = powf(2.0f, (float)expcomp);      /* L293 */
+
+    /* the whole crop is one tile (Tile_calc with kall == 0, L311); isRAW branch L390-474 */
+    float* nvlum = (float*)malloc(sizeof(float) * n2); float* nvchrom = (float*)malloc(sizeof(float) * n2); float* nvhue = (float*)malloc(sizeof(float) * n2);
+    for (size_t k = 0; k < n2; ++k) {
+        const float aN = acalc[k], bN = bcalc[k];
+        float cN = sqrtf(sqrf(aN) + sqrf(bN));
+        nvhue[k] = xatan2f_(bN, aN);
+        if (cN < 100.f) cN = 100.f;
+        nvchrom[k] = cN;
+        float Llum = lumcalc[k];
+        Llum = Llum < 2.f ? 2.f : Llum;
+        Llum = Llum > 32768.f ? 32768.f : Llum;
+        nvlum[k] = Llum;
+    }
+    float* la = (float*)malloc(sizeof(float) * n); float* lb = (float*)malloc(sizeof(float) * n);
+    for (size_t k = 0; k < n; ++k) {
+        float X = gain * r[k], Y = gain * g[k], Z = gain * b[k];
+        X = X < 65535.f ? lut_noclip(gamcurve, 65536, X) : (gammaf_(X / 65535.f, gam, gamthresh, gamslope) * 32768.f);
+        Y = Y < 65535.f ? lut_noclip(gamcurve, 65536, Y) : (gammaf_(Y / 65535.f, gam, gamthresh, gamslope) * 32768.f);
+        Z = Z < 65535.f ? lut_noclip(gamcurve, 65536, Z) : (gammaf_(Z / 65535.f, gam, gamthresh, gamslope) * 32768.f);
+        const float l = X * wp[1][0] + Y * wp[1][1] + Z * wp[1][2];      /* Color::rgb2yuv */
+        la[k] = X - l;          /* labdn->a = v */
+        lb[k] = l - Z;          /* labdn->b = u */
+    }
+    const int schoice = aggressive ? 2 : 0;
+    const int levwav = imax(2, (int)(5 - ceil(log(scale))));
+    void* adec = artoracle_wavelet_new(la, W, H, levwav, 1);
+    void* bdec = artoracle_wavelet_new(lb, W, H, levwav, 1);
+    int rc = 0;
+    if (artoracle_wavelet_maxlevel(adec) < levwav) rc = 2;
+    /* WaveletDenoiseAll_info -> ShrinkAll_info, FTblockDN.cc L1227-1364 */
+    float chau = 0.f, chred = 0.f, chblue = 0.f, maxchred = 0.f, maxchblue = 0.f, minchred = 100000000.f, minchblue = 100000000.f;
+    int nb = 0;
+    for (int lvl = 0; lvl < levwav && !rc; ++lvl) {
+        const int W_ab = artoracle_wavelet_level_W(adec, lvl), H_ab = artoracle_wavelet_level_H(adec, lvl);
+        if (lvl == 1) {
+            float chro = 0.f, dev = 0.f, devL = 0.f, lume = 0.f, red_yel = 0.f, skin_c = 0.f;
+            int nc = 0, nL = 0, nry = 0, nsk = 0;
+            for (int i = 0; i < H_ab; ++i)
+                for (int j = 0; j < W_ab; ++j) {
+                    const float c = nvchrom[(size_t)i * wid + j], h = nvhue[(size_t)i * wid + j], l = nvlum[(size_t)i * wid + j];
+                    chro += c;
+                    ++nc;
+                    dev += sqrf(c - (chro / nc));
+                    if (h > -0.8f && h < 2.0f && c > 10000.f) { red_yel += c; ++nry; }
+                    if (h > 0.f && h < 1.6f && c < 10000.f) { skin_c += c; ++nsk; }
+                    lume += l;
+                    ++nL;
+                    devL += sqrf(l - (lume / nL));
+                }
+            if (nc > 0) { out[8] = chro / nc; out[9] = sqrtf(dev / nc); out[14] = (float)nsk / (float)nc; }
+            else out[14] = (float)nsk;
+            if (nL > 0) { out[10] = lume / nL; out[11] = sqrtf(devL / nL); }
+            if (nry > 0) out[12] = red_yel / nry;
+            if (nsk > 0) out[13] = skin_c / nsk;
+        }
+        const float reduc = (schoice == 2) ? (float)0.9 : 1.f;
+        for (int dir = 1; dir < 4; ++dir) {
+            const float ma = artoracle_madrgb(artoracle_wavelet_band(adec, lvl, dir), W_ab * H_ab);
+            const float mada = ma * ma;
+            chred += mada;
+            if (mada > maxchred) maxchred = mada;
+            if (mada < minchred) minchred = mada;
+            out[4] = sqrtf(reduc * maxchred);
+            out[6] = sqrtf(reduc * minchred);
+            const float mb = artoracle_madrgb(artoracle_wavelet_band(bdec, lvl, dir), W_ab * H_ab);
+            const float madb = mb * mb;
+            chblue += madb;
+            if (madb > maxchblue) maxchblue = madb;
+            if (madb < minchblue) minchblue = madb;
+            out[5] = sqrtf(reduc * maxchblue);
+            out[7] = sqrtf(reduc * minchblue);
+            chau += (mada + madb);
+            ++nb;
+            out[0] = sqrtf(reduc * chau / (nb + nb));
+            out[2] = sqrtf(reduc * chred / nb);
+            out[3] = sqrtf(reduc * chblue / nb);
+            out[1] = (float)nb;
+        }
+    }
+    artoracle_wavelet_delete(adec); artoracle_wavelet_delete(bdec);
+    free(lumcalc); free(acalc); free(bcalc); free(gamcurve); free(nvlum); free(nvchrom); free(nvhue); free(la); free(lb);
+    return rc;
+}
+
+/* calcautodn_info, ipdenoise.cc L66-206 */
+static void calcautodn_info_(int aggressive, float* chaut, float* delta, int Nb, int levaut, float maxmax, float lumema, float chromina, int mode, int lissage,
+                             float redyel, float skinc, float nsknc)
+{
+    float reducdelta = 1.f;
+    if (aggressive) reducdelta = (float)0.9;
+    float c = (*chaut * Nb - maxmax) / (Nb - 1);
+    if ((redyel > 5000.f || skinc > 1000.f) && nsknc < 0.4f && chromina > 3000.f) c *= 0.45f;
+    else if ((redyel > 12000.f || skinc > 1200.f) && nsknc < 0.3f && chromina > 3000.f) c *= 0.3f;
+    if (mode == 0 || mode == 2) {
+        if (chromina > 10000.f) c *= 0.7f; else if (chromina > 6000.f) c *= 0.9f; else if (chromina < 3000.f) c *= 1.2f; else if (chromina < 2000.f) c *= 1.5f;
+        if (lumema < 2500.f) c *= 1.3f; else if (lumema < 5000.f) c *= 1.2f; else if (lumema > 20000.f) c *= 0.9f;
+    } else if (mode == 1) {
+        if (chromina > 10000.f) c *= 0.8f; else if (chromina > 6000.f) c *= 0.9f; else if (chromina < 3000.f) c *= 1.5f; else if (chromina < 2000.f) c *= 2.2f;
+        if (lumema < 2500.f) c *= 1.2f; else if (lumema < 5000.f) c *= 1.1f; else if (lumema > 20000.f) c *= 0.9f;
+    }
+    if (levaut == 0 && c > 300.f) c = 0.714286f * c + 85.71428f;
+    float d = maxmax - c;
+    d *= reducdelta;
+    if (lissage == 1 || lissage == 2) {
+        if (c < 200.f && d < 200.f) d *= 0.95f; else if (c < 200.f && d < 400.f) d *= 0.5f; else if (c < 200.f && d >= 400.f) d = 200.f;
+        else if (c < 400.f && d < 400.f) d *= 0.4f; else if (c < 400.f && d >= 400.f) d = 120.f;
+        else if (c < 550.f) d *= 0.15f; else if (c < 650.f) d *= 0.1f; else d *= 0.07f;
+        if (mode == 0 || mode == 2) { if (chromina < 6000.f) d *= 1.4f; if (lumema < 5000.f) d *= 1.4f; }
+        else if (mode == 1) { if (chromina < 6000.f) d *= 1.2f; if (lumema < 5000.f) d *= 1.2f; }
+    }
+    if (lissage == 0) {
+        if (c < 200.f && d < 200.f) d *= 0.95f; else if (c < 200.f && d < 400.f) d *= 0.7f; else if (c < 200.f && d >= 400.f) d = 280.f;
+        else if (c < 400.f && d < 400.f) d *= 0.6f; else if (c < 400.f && d >= 400.f) d = 200.f;
+        else if (c < 550.f) d *= 0.3f; else if (c < 650.f) d *= 0.2f; else d *= 0.15f;
+        if (mode == 0 || mode == 2) { if (chromina < 6000.f) d *= 1.4f; if (lumema < 5000.f) d *= 1.4f; }
+        else if (mode == 1) { if (chromina < 6000.f) d *= 1.2f; if (lumema < 5000.f) d *= 1.2f; }
+    }
+    *chaut = c; *delta = d;
+}
+
+/* The nine-crop combination of denoiseComputeParams (L964-1075).  stats: 9 x 15 floats in artoracle_denoise_info's layout, crop k = hcr * 3 + wcr.
+ * out3 = store.chrominance, store.chrominanceRedGreen, store.chrominanceBlueYellow (before chrominanceAutoFactor). */
+int artoracle_denoise_auto_params(const float* stats, int isRAW, int aggressive, float* out3)
+{
+    const float autoNR = 10, autoNRmax = 40, lowdenoise = 1.f, adjustr = 1.f;
+    const int levaut = 0, mode = 1, lissage = 0;
+    float ch_M[9], max_r[9], max_b[9], min_r[9], min_b[9], delta[9];
+    float Max_R[9] = {0}, Max_B[9] = {0}, Min_R[9], Min_B[9];
+    const float multip = isRAW ? 1.f : 2.f;
+    for (int k = 0; k < 9; ++k) {
+        const float* s = stats + 15 * k;
+        ch_M[k] = 1.0f * s[0]; max_r[k] = 1.0f * s[4]; max_b[k] = 1.0f * s[5]; min_r[k] = 1.0f * s[6]; min_b[k] = 1.0f * s[7];
+        const float maxmax = max_r[k] > max_b[k] ? max_r[k] : max_b[k];       /* rtengine::max(a, b) */
+        calcautodn_info_(aggressive, &ch_M[k], &delta[k], (int)s[1], levaut, maxmax, s[10], s[8], mode, lissage, s[12], s[13], s[14]);
+    }
+    for (int k = 0; k < 9; ++k) {
+        if (max_r[k] > max_b[k]) {
+            Max_R[k] = (delta[k]) / ((autoNRmax * multip * adjustr * lowdenoise) / 2.f);
+            Min_B[k] = -(ch_M[k] - min_b[k]) / (autoNRmax * multip * adjustr * lowdenoise);
+            Max_B[k] = 0.f; Min_R[k] = 0.f;
+        } else {
+            Max_B[k] = (delta[k]) / ((autoNRmax * multip * adjustr * lowdenoise) / 2.f);
+            Min_R[k] = -(ch_M[k] - min_r[k]) / (autoNRmax * multip * adjustr * lowdenoise);
+            Min_B[k] = 0.f; Max_R[k] = 0.f;
+        }
+    }
+    float chM = 0.f, MaxR = 0.f, MaxB = 0.f, MinR = 100000000000.f, MinB = 100000000000.f, maxr, maxb;
+    float MaxRMoy = 0.f, MaxBMoy = 0.f, MinRMoy = 0.f, MinBMoy = 0.f;
+    for (int k = 0; k < 9; ++k) {
+        chM += ch_M[k]; MaxBMoy += Max_B[k]; MaxRMoy += Max_R[k]; MinRMoy += Min_R[k]; MinBMoy += Min_B[k];
+        if (Max_R[k] > MaxR) MaxR = Max_R[k];
+        if (Max_B[k] > MaxB) MaxB = Max_B[k];
+        if (Min_R[k] < MinR) MinR = Min_R[k];
+        if (Min_B[k] < MinB) MinB = Min_B[k];
+    }
+    chM /= 9; MaxBMoy /= 9; MaxRMoy /= 9; MinBMoy /= 9; MinRMoy /= 9;
+    if (MaxR > MaxB) { maxr = MaxRMoy + (MaxR - MaxRMoy) * 0.66f; maxb = MinBMoy + (MinB - MinBMoy) * 0.66f; }
+    else { maxb = MaxBMoy + (MaxB - MaxBMoy) * 0.66f; maxr = MinRMoy + (MinR - MinRMoy) * 0.66f; }
+    out3[0] = chM / (autoNR * multip * adjustr);
+    out3[1] = maxr;
+    out3[2] = maxb;
+    return 0;
+}
