@@ -369,6 +369,52 @@ extern "C" int artref_gauss_ex(float* src, float* dst, float* divb, int W, int H
 """
 
 
+SHIM_RESIZE_TU = r"""
+// Shim TU hosting the reference's Lanczos resampler: Lanc and ImProcFunctions::Lanczos cut from ipresize.cc.
+// Written here (not reference code): the Imagefloat / ImProcFunctions stand-ins (setMode / assignMode are no-ops: the Lab round
+// trip around the resampler is not part of this unit) and the wrapper.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <omp.h>
+#include "rt_math.h"
+#include "opthelper.h"
+#include "sleef.h"
+#include "alignedbuffer.h"
+namespace rtengine {
+struct ResizePlane { float** ptrs; };
+class Imagefloat {
+public:
+    enum class Mode { RGB, XYZ, YUV, LAB };
+    int W, H; ResizePlane r, g, b;
+    int getWidth() const { return W; }
+    int getHeight() const { return H; }
+    Mode mode() const { return Mode::LAB; }
+    void setMode(Mode, bool) {}
+    void assignMode(Mode) {}
+};
+class ImProcFunctions { public: bool multiThread; void Lanczos(Imagefloat *src, Imagefloat *dst, float scale); };
+namespace {
+#include "resize_lanc.inc"
+}
+#include "resize_lanczos.inc"
+}
+extern "C" int artref_lanczos(const float* s0, const float* s1, const float* s2, int sW, int sH, float* d0, float* d1, float* d2, int dW, int dH, float scale)
+{
+    using namespace rtengine;
+    auto rows = [](const float* p, int W, int H) { float** t = new float*[H]; for (int i = 0; i < H; ++i) t[i] = const_cast<float*>(p) + (size_t)i * W; return t; };
+    // the reference reads g / r / b as L / a / b; plane k of the wrapper goes to the same slot on both sides
+    Imagefloat src{sW, sH, {rows(s1, sW, sH)}, {rows(s0, sW, sH)}, {rows(s2, sW, sH)}};
+    Imagefloat dst{dW, dH, {rows(d1, dW, dH)}, {rows(d0, dW, dH)}, {rows(d2, dW, dH)}};
+    ImProcFunctions ipf; ipf.multiThread = true;
+    ipf.Lanczos(&src, &dst, scale);
+    delete[] src.r.ptrs; delete[] src.g.ptrs; delete[] src.b.ptrs; delete[] dst.r.ptrs; delete[] dst.g.ptrs; delete[] dst.b.ptrs;
+    return 0;
+}
+"""
+
+
 SHIM_GUIDED_TU = r"""
 // Shim TU hosting the reference's boxblur.h body (its include block is replaced: StopWatch.h drags
 // settings.h -> procparams.h -> lcms2.h) and guidedFilter + calculate_subsampling cut from guidedfilter.cc.
@@ -1487,6 +1533,11 @@ def extract(det):
     open(os.path.join(sub, "usm_bilateral.inc"), "w").write(btext[b0.start():b1.start()])
     open(os.path.join(sub, "shim_usm.cc"), "w").write(SHIM_USM_TU)
 
+    rz = os.path.join(RT, "ipresize.cc")
+    open(os.path.join(sub, "resize_lanc.inc"), "w").write(cut_function(rz, r"^inline float Lanc\(float x, float a\)"))
+    open(os.path.join(sub, "resize_lanczos.inc"), "w").write(cut_function(rz, r"^void ImProcFunctions::Lanczos\(Imagefloat \*src, Imagefloat \*dst, float scale\)"))
+    open(os.path.join(sub, "shim_resize.cc"), "w").write(SHIM_RESIZE_TU)
+
     # X-Trans demosaic (xtrans_demosaic.cc): constants + cielab + border + Markesteijn
     xt = os.path.join(RT, "xtrans_demosaic.cc")
     xtext = open(xt, encoding="utf-8", errors="replace").read()
@@ -1511,7 +1562,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), os.path.join(sub, "shim_resize.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)
