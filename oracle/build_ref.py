@@ -415,6 +415,70 @@ extern "C" int artref_lanczos(const float* s0, const float* s1, const float* s2,
 """
 
 
+SHIM_GREENEQ_TU = r"""
+// Shim TU hosting the reference's green equilibration: RawImageSource::green_equilibrate_global and ::green_equilibrate cut from
+// green_equil_RT.cc.  Written here (not reference code): the RawImageSource stand-in (W, H, border, FC, the threshold functor's
+// interface as rawimagesource.h L205-212 declares it) and the wrappers.
+#include <math.h>
+#include <cmath>
+#include <stdlib.h>
+#include <string.h>
+#include <omp.h>
+#include "array2D.h"
+#include "rt_math.h"
+#include "opthelper.h"
+namespace rtengine {
+struct RawImageSource {
+    int W, H, border; unsigned filters;
+    class GreenEqulibrateThreshold {
+    public:
+        explicit GreenEqulibrateThreshold(float thresh): thresh_(thresh) {}
+        virtual ~GreenEqulibrateThreshold() {}
+        virtual float operator()(int row, int column) const { return thresh_; }
+    protected:
+        const float thresh_;
+    };
+    unsigned FC(int row, int col) const { return (filters >> ((((row) << 1 & 14) + ((col) & 1)) << 1) & 3); }
+    void green_equilibrate_global(array2D<float> &rawData);
+    void green_equilibrate(const GreenEqulibrateThreshold &greenthresh, array2D<float> &rawData);
+};
+#include "greeneq_body.inc"
+}
+namespace {
+struct MapThreshold : rtengine::RawImageSource::GreenEqulibrateThreshold {
+    const float* map; int W;
+    MapThreshold(const float* m, int w) : GreenEqulibrateThreshold(0.f), map(m), W(w) {}
+    float operator()(int row, int column) const override { return map[(size_t)row * W + column]; }
+};
+}
+extern "C" int artref_green_equilibrate_global(float* raw, int W, int H, unsigned filters, int border)
+{
+    float** rows = new float*[H];
+    for (int i = 0; i < H; ++i) rows[i] = raw + (size_t)i * W;
+    {
+        rtengine::array2D<float> rd(W, H, rows, rtengine::ARRAY2D_BYREFERENCE);
+        rtengine::RawImageSource s{W, H, border, filters};
+        s.green_equilibrate_global(rd);
+    }
+    delete[] rows;
+    return 0;
+}
+extern "C" int artref_green_equilibrate(float* raw, int W, int H, unsigned filters, float thresh, const float* thresh_map)
+{
+    float** rows = new float*[H];
+    for (int i = 0; i < H; ++i) rows[i] = raw + (size_t)i * W;
+    {
+        rtengine::array2D<float> rd(W, H, rows, rtengine::ARRAY2D_BYREFERENCE);
+        rtengine::RawImageSource s{W, H, 4, filters};
+        if (thresh_map) { MapThreshold t(thresh_map, W); s.green_equilibrate(t, rd); }
+        else { rtengine::RawImageSource::GreenEqulibrateThreshold t(thresh); s.green_equilibrate(t, rd); }
+    }
+    delete[] rows;
+    return 0;
+}
+"""
+
+
 SHIM_GUIDED_TU = r"""
 // Shim TU hosting the reference's boxblur.h body (its include block is replaced: StopWatch.h drags
 // settings.h -> procparams.h -> lcms2.h) and guidedFilter + calculate_subsampling cut from guidedfilter.cc.
@@ -1533,6 +1597,11 @@ def extract(det):
     open(os.path.join(sub, "usm_bilateral.inc"), "w").write(btext[b0.start():b1.start()])
     open(os.path.join(sub, "shim_usm.cc"), "w").write(SHIM_USM_TU)
 
+    ge = os.path.join(RT, "green_equil_RT.cc")
+    open(os.path.join(sub, "greeneq_body.inc"), "w").write(
+        cut_function(ge, r"^void RawImageSource::green_equilibrate_global\(array2D<float> &rawData\)") + "\n\n" +
+        cut_function(ge, r"^void RawImageSource::green_equilibrate\(const GreenEqulibrateThreshold &thresh, array2D<float> &rawData\)"))
+    open(os.path.join(sub, "shim_greeneq.cc"), "w").write(SHIM_GREENEQ_TU)
     rz = os.path.join(RT, "ipresize.cc")
     open(os.path.join(sub, "resize_lanc.inc"), "w").write(cut_function(rz, r"^inline float Lanc\(float x, float a\)"))
     open(os.path.join(sub, "resize_lanczos.inc"), "w").write(cut_function(rz, r"^void ImProcFunctions::Lanczos\(Imagefloat \*src, Imagefloat \*dst, float scale\)"))
@@ -1562,7 +1631,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), os.path.join(sub, "shim_resize.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), os.path.join(sub, "shim_resize.cc"), os.path.join(sub, "shim_greeneq.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)
