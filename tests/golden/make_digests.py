@@ -82,6 +82,51 @@ def cases(which):
         planes = td.rgb_frame(200, 264, seed=21)
         return td.run(lib, pre + "rgb_denoise", planes, (30, 50, 0, 15, 0, 0, 1.7, 1.0), td.noise_ccurve(), with_inverse=ref)[0]
     out["rgb_denoise_264x200_lum30_curve"] = f
+
+    # later additions: rld (recursive GAUSS_DIV / GAUSS_MULT above sigma 1.15, corner boost), edges-only unsharp mask, recursive div / mult,
+    # the automatic chroma estimator, the Lanczos resampler, green equilibration
+    import test_oracle_denoise_auto as tda
+    import test_oracle_resize as tr
+    import test_oracle_greeneq as tg
+    for k, kw in enumerate([dict(radius=0.75), dict(radius=1.8, amount=70)]):
+        def f(k=k, kw=kw):
+            return tu.run_rld(lib, pre + "rld", tu.scene(301, 203, 60 + k), **kw)[0]
+        out["rld_case%d_301x203" % k] = f
+
+    def f():
+        return tu.run_rld_ex(lib, pre + "rld_ex", tu.scene(130, 77, 71, wild=True), boost=0.5, radius=1.0)
+    out["rld_boost_130x77"] = f
+    for k, kw in enumerate([dict(edges_radius=0.9, edges_tolerance=400), dict(edges_radius=2.2, halo=1)]):
+        def f(k=k, kw=kw):
+            return tu.run_edges(lib, pre + "usm_ex", tu.scene(130, 77, 80 + k), **kw)
+        out["usm_edges_case%d_130x77" % k] = f
+    for kind in ("mult", "div"):
+        def f(kind=kind):
+            import test_oracle_gauss as tgs
+            src = tgs.image(53, 67, seed=120) - 9000.0
+            dst = np.random.default_rng(5).uniform(-2.0, 3.0, size=(53, 67)).astype(np.float32)
+            divb = (tgs.image(53, 67, seed=7) - 3000.0).astype(np.float32)
+            return list((oracle.ref() if ref else oracle.port()).gauss_iir(src, dst, divb, 2.5, kind))
+        out["gauss_iir_%s_67x53" % kind] = f
+
+    def f():
+        rows = [tda.info(lib, pre + "denoise_info", tda.crop(200 + 8 * k, 260 - 6 * k, 31 + k, k % 3), aggressive=k & 1) for k in range(9)]
+        stats = np.ascontiguousarray(np.stack(rows), dtype=np.float32)
+        return [stats, tda.auto(lib, pre + "denoise_auto_params", stats, 1, 0), tda.auto(lib, pre + "denoise_auto_params", stats, 0, 1)]
+    out["denoise_auto_9crops"] = f
+
+    def f():
+        return tr.lanczos(lib, pre + "lanczos", tr.planes3(131, 203, 9), 156, 101, 0.77)
+    out["lanczos_203x131_0.77"] = f
+
+    def f():
+        raw = tg.mosaic(203, 301, 17)
+        import ctypes
+        a = raw.copy()
+        getattr(lib, pre + "green_equilibrate_global")(a.ctypes.data_as(tg.fp), 301, 203, ctypes.c_uint(0x94949494), 4)
+        getattr(lib, pre + "green_equilibrate")(a.ctypes.data_as(tg.fp), 301, 203, ctypes.c_uint(0x94949494), ctypes.c_float(0.05), None)
+        return [a]
+    out["greeneq_301x203_rggb"] = f
     return out
 
 
