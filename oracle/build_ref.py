@@ -479,6 +479,47 @@ extern "C" int artref_green_equilibrate(float* raw, int W, int H, unsigned filte
 """
 
 
+SHIM_PACK_TU = r"""
+// Shim TU hosting the reference's output packing: Imagefloat::getScanline cut from imagefloat.cc, over the reference's own rt_math.h
+// and halffloat.h.  Written here (not reference code): the Imagefloat stand-in (planar accessors) and the wrapper.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "rt_math.h"
+#include "halffloat.h"
+namespace rtengine {
+class Imagefloat {
+public:
+    const float *R, *G, *B; int width, height; const void* data;
+    float r(int row, int col) const { return R[(size_t)row * width + col]; }
+    float g(int row, int col) const { return G[(size_t)row * width + col]; }
+    float b(int row, int col) const { return B[(size_t)row * width + col]; }
+    void getScanline (int row, unsigned char* buffer, int bps, bool isFloat) const;
+};
+#include "pack_getscanline.inc"
+}
+extern "C" int artref_scanlines(const float* r, const float* g, const float* b, int W, int H, int bps, int is_float, void* out)
+{
+    rtengine::Imagefloat im{r, g, b, W, H, r};
+    const size_t rowbytes = (size_t)W * 3 * (bps / 8);
+    for (int row = 0; row < H; ++row) im.getScanline(row, (unsigned char*)out + rowbytes * row, bps, is_float != 0);
+    return 0;
+}
+extern "C" unsigned short artref_float_to_half(float f) { return rtengine::DNG_FloatToHalf(f); }
+// the whole float range in one call: number of bit patterns in [lo, hi) where `fn` (the port under test) disagrees with DNG_FloatToHalf
+extern "C" long long artref_float_to_half_mismatches(unsigned lo, unsigned hi, unsigned short (*fn)(float))
+{
+    long long bad = 0;
+#pragma omp parallel for reduction(+: bad) schedule(static)
+    for (long long u = lo; u < (long long)hi; ++u) {
+        uint32_t v = (uint32_t)u; float f; memcpy(&f, &v, 4);
+        if (rtengine::DNG_FloatToHalf(f) != fn(f)) ++bad;
+    }
+    return bad;
+}
+"""
+
+
 SHIM_GUIDED_TU = r"""
 // Shim TU hosting the reference's boxblur.h body (its include block is replaced: StopWatch.h drags
 // settings.h -> procparams.h -> lcms2.h) and guidedFilter + calculate_subsampling cut from guidedfilter.cc.
@@ -1597,6 +1638,9 @@ def extract(det):
     open(os.path.join(sub, "usm_bilateral.inc"), "w").write(btext[b0.start():b1.start()])
     open(os.path.join(sub, "shim_usm.cc"), "w").write(SHIM_USM_TU)
 
+    open(os.path.join(sub, "pack_getscanline.inc"), "w").write(
+        cut_function(os.path.join(RT, "imagefloat.cc"), r"^void Imagefloat::getScanline \(int row, unsigned char\* buffer, int bps, bool isFloat\) const"))
+    open(os.path.join(sub, "shim_pack.cc"), "w").write(SHIM_PACK_TU)
     ge = os.path.join(RT, "green_equil_RT.cc")
     open(os.path.join(sub, "greeneq_body.inc"), "w").write(
         cut_function(ge, r"^void RawImageSource::green_equilibrate_global\(array2D<float> &rawData\)") + "\n\n" +
@@ -1631,7 +1675,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), os.path.join(sub, "shim_resize.cc"), os.path.join(sub, "shim_greeneq.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), os.path.join(sub, "shim_resize.cc"), os.path.join(sub, "shim_greeneq.cc"), os.path.join(sub, "shim_pack.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)
