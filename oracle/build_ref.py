@@ -427,6 +427,7 @@ SHIM_GREENEQ_TU = r"""
 #include "array2D.h"
 #include "rt_math.h"
 #include "opthelper.h"
+#define RawImageSource RawImageSourceGreenEq       /* other shim TUs define their own stand-in of this name: keep the inline members apart */
 namespace rtengine {
 struct RawImageSource {
     int W, H, border; unsigned filters;
@@ -516,6 +517,44 @@ extern "C" long long artref_float_to_half_mismatches(unsigned lo, unsigned hi, u
         if (rtengine::DNG_FloatToHalf(f) != fn(f)) ++bad;
     }
     return bad;
+}
+"""
+
+
+SHIM_BILINEAR_TU = r"""
+// Shim TU hosting the reference's blended bilinear demosaic: RawImageSource::bayer_bilinear_demosaic(blend, ...) cut from
+// bayer_bilinear_demosaic.cc.  Written here (not reference code): the RawImageSource stand-in and the wrapper.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <omp.h>
+#include "glibmm.h"
+#include "array2D.h"
+#include "rt_math.h"
+#define M(x) Glib::ustring(x)
+#define RawImageSource RawImageSourceBilinear       /* other shim TUs define their own stand-in of this name: keep the inline members apart */
+namespace rtengine {
+struct BlProgress { void setProgressStr(const Glib::ustring&) {} void setProgress(double) {} };
+struct RawImageSource {
+    int W, H; unsigned filters; BlProgress* plistener;
+    unsigned FC(int row, int col) const { return (filters >> ((((row) << 1 & 14) + ((col) & 1)) << 1) & 3); }
+    void bayer_bilinear_demosaic(const float* const * blend, const array2D<float> &rawData, array2D<float> &red, array2D<float> &green, array2D<float> &blue);
+};
+}
+using namespace rtengine;
+#include "bilinear_body.inc"
+extern "C" int artref_bilinear_blend(const float* raw, const float* blend, int W, int H, unsigned filters, float* red, float* green, float* blue)
+{
+    auto rows = [&](const float* p) { float** t = new float*[H]; for (int i = 0; i < H; ++i) t[i] = const_cast<float*>(p) + (size_t)i * W; return t; };
+    float **rr = rows(raw), **bl = rows(blend), **r = rows(red), **g = rows(green), **b = rows(blue);
+    {
+        array2D<float> rd(W, H, rr, ARRAY2D_BYREFERENCE), R(W, H, r, ARRAY2D_BYREFERENCE), G(W, H, g, ARRAY2D_BYREFERENCE), B(W, H, b, ARRAY2D_BYREFERENCE);
+        RawImageSource s{W, H, filters, nullptr};
+        s.bayer_bilinear_demosaic(bl, rd, R, G, B);
+    }
+    delete[] rr; delete[] bl; delete[] r; delete[] g; delete[] b;
+    return 0;
 }
 """
 
@@ -790,6 +829,7 @@ public:
     static void gammaf2lut (LUTf &gammacurve, float gamma, float start, float slope, float divisor, float factor);
     static void rgbxyz (float r, float g, float b, float &x, float &y, float &z, const float xyz_rgb[3][3]);
     static void XYZ2Lab(float X, float Y, float Z, float &L, float &a, float &b);
+    static void RGB2L(float *R, float *G, float *B, float *L, const float wp[3][3], int width);
     constexpr static double kappaInv = 27.0 / 24389.0;
     constexpr static double epsilonExpInv3 = 6.0 / 29.0;
     constexpr static float kappaInvf = kappaInv;
@@ -855,6 +895,15 @@ int artref_denoise_info(const float* r, const float* g, const float* b, int W, i
                      minredaut, minblueaut, chromina, sigma, lumema, sigma_L, redyel, skinc, nsknc);
     out[0] = chaut; out[1] = (float)nb; out[2] = redaut; out[3] = blueaut; out[4] = maxredaut; out[5] = maxblueaut; out[6] = minredaut; out[7] = minblueaut;
     out[8] = chromina; out[9] = sigma; out[10] = lumema; out[11] = sigma_L; out[12] = redyel; out[13] = skinc; out[14] = nsknc;
+    return 0;
+}
+// Color::RGB2L row by row, as dual_demosaic_RT.cc L101-106 calls it
+int artref_rgb2l(const float* R, const float* G, const float* B, float* L, int W, int H, const float* wp9)
+{
+    Color::init();
+    float wp[3][3]; for (int i = 0; i < 9; ++i) (&wp[0][0])[i] = wp9[i];
+    for (int i = 0; i < H; ++i)
+        Color::RGB2L(const_cast<float*>(R) + (size_t)i * W, const_cast<float*>(G) + (size_t)i * W, const_cast<float*>(B) + (size_t)i * W, L + (size_t)i * W, wp, W);
     return 0;
 }
 // the nine-crop combination of ImProcFunctions::denoiseComputeParams (ipdenoise.cc, from `float chM = 0.f;` to the store assignments), cut in place
@@ -1333,6 +1382,18 @@ extern "C" int artref_usm_ex(float* R, float* G, float* B, int W, int H, const d
     return 0;
 }
 
+// buildBlendMask(luminance, blend, W, H, contrastThreshold, amount, false, blur_radius, 1.f) on contiguous planes
+extern "C" int artref_blend_mask(const float* lum, float* blend_out, int W, int H, float contrastThreshold, float amount, float blur_radius)
+{
+    float** l = new float*[H];
+    for (int y = 0; y < H; ++y) l[y] = const_cast<float*>(lum) + (size_t)y * W;
+    JaggedArray<float> blend(W, H);
+    buildBlendMask(l, blend, W, H, contrastThreshold, amount, false, blur_radius, 1.f);
+    for (int y = 0; y < H; ++y) memcpy(blend_out + (size_t)y * W, blend[y], sizeof(float) * W);
+    delete[] l;
+    return 0;
+}
+
 // the "rld" route of doSharpening (ipsharpen.cc L747-771 without the corner boost): markImpulse(Y, 2), deconvsharpening(copy of Y), multiply
 extern "C" int artref_rld_ex(float* R, float* G, float* B, int W, int H, const double* wsd, double scale, double contrast_p, double deconvradius,
                              int deconvamount, float* impulse_out, double deconvCornerBoost, int deconvCornerLatitude, int offset_x, int offset_y,
@@ -1534,7 +1595,8 @@ def extract(det):
            cut_function(cc, r"^void Color::rgbxyz \(float r, float g, float b, float &x, float &y, float &z, const float xyz_rgb"),
            cut_function(cc, r"^void Color::XYZ2Lab\(float X, float Y, float Z, float &L"),
            cut_function(cc, r"^void Color::xyz2rgb \(float x, float y, float z, float &r, float &g, float &b, const float rgb_xyz"),
-           cut_function(cc, r"^void Color::Lab2XYZ\(float L, float a, float b, float &x, float &y, float &z\)")]
+           cut_function(cc, r"^void Color::Lab2XYZ\(float L, float a, float b, float &x, float &y, float &z\)"),
+           cut_function(cc, r"^void Color::RGB2L\(float \*R, float \*G, float \*B, float \*L, const float wp\[3\]\[3\], int width\)")]
     open(os.path.join(sub, "color_cc_members.inc"), "w").write("\n".join(ccm))
     open(os.path.join(sub, "dct_standin.h"), "w").write(open(os.path.join(HERE, "dct_standin.h")).read())
     ipd = os.path.join(RT, "ipdenoise.cc")
@@ -1641,6 +1703,9 @@ def extract(det):
     open(os.path.join(sub, "pack_getscanline.inc"), "w").write(
         cut_function(os.path.join(RT, "imagefloat.cc"), r"^void Imagefloat::getScanline \(int row, unsigned char\* buffer, int bps, bool isFloat\) const"))
     open(os.path.join(sub, "shim_pack.cc"), "w").write(SHIM_PACK_TU)
+    open(os.path.join(sub, "bilinear_body.inc"), "w").write(
+        cut_function(os.path.join(RT, "bayer_bilinear_demosaic.cc"), r"^void RawImageSource::bayer_bilinear_demosaic\(const float\* const \* blend[^)]*\)"))
+    open(os.path.join(sub, "shim_bilinear.cc"), "w").write(SHIM_BILINEAR_TU)
     ge = os.path.join(RT, "green_equil_RT.cc")
     open(os.path.join(sub, "greeneq_body.inc"), "w").write(
         cut_function(ge, r"^void RawImageSource::green_equilibrate_global\(array2D<float> &rawData\)") + "\n\n" +
@@ -1675,7 +1740,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), os.path.join(sub, "shim_resize.cc"), os.path.join(sub, "shim_greeneq.cc"), os.path.join(sub, "shim_pack.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), os.path.join(sub, "shim_resize.cc"), os.path.join(sub, "shim_greeneq.cc"), os.path.join(sub, "shim_pack.cc"), os.path.join(sub, "shim_bilinear.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)

@@ -777,3 +777,6 @@ int artoracle_denoise_auto_params(const float* stats, int isRAW, int aggressive,
     out3[2] = maxb;
     return 0;
 }
+
+/* Color::computeXYZ2LabY for other ports (color.cc L1262-1274) */
+float artoracle_xyz2laby(float f) { init_cachef(); return computeXYZ2LabY(f); }
