@@ -1382,13 +1382,18 @@ extern "C" int artref_usm_ex(float* R, float* G, float* B, int W, int H, const d
     return 0;
 }
 
-// buildBlendMask(luminance, blend, W, H, contrastThreshold, amount, false, blur_radius, 1.f) on contiguous planes
+// buildBlendMask(luminance, blend, W, H, contrastThreshold, amount, autoContrast, blur_radius, 1.f) on contiguous planes; the threshold is in / out
+extern "C" int artref_blend_mask_ex(const float* lum, float* blend_out, int W, int H, float* contrastThreshold, float amount, int autoContrast, float blur_radius);
 extern "C" int artref_blend_mask(const float* lum, float* blend_out, int W, int H, float contrastThreshold, float amount, float blur_radius)
+{
+    return artref_blend_mask_ex(lum, blend_out, W, H, &contrastThreshold, amount, 0, blur_radius);
+}
+extern "C" int artref_blend_mask_ex(const float* lum, float* blend_out, int W, int H, float* contrastThreshold, float amount, int autoContrast, float blur_radius)
 {
     float** l = new float*[H];
     for (int y = 0; y < H; ++y) l[y] = const_cast<float*>(lum) + (size_t)y * W;
     JaggedArray<float> blend(W, H);
-    buildBlendMask(l, blend, W, H, contrastThreshold, amount, false, blur_radius, 1.f);
+    buildBlendMask(l, blend, W, H, *contrastThreshold, amount, autoContrast != 0, blur_radius, 1.f);
     for (int y = 0; y < H; ++y) memcpy(blend_out + (size_t)y * W, blend[y], sizeof(float) * W);
     delete[] l;
     return 0;

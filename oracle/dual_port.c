@@ -3,7 +3,7 @@
  * TEST INFRASTRUCTURE ONLY.
  *
  * Restates the part of RawImageSource::dual_demosaic_RT (reference rtengine/dual_demosaic_RT.cc L39-152) that follows the first
- * demosaicer (AMaZE / RCD, restated in amaze_port.c / rcd_port.c) for Method::AMAZEBILINEAR / RCDBILINEAR with autoContrast off:
+ * demosaicer (AMaZE / RCD, restated in amaze_port.c / rcd_port.c) for Method::AMAZEBILINEAR / RCDBILINEAR  (autoContrast: usm_port.c's artoracle_auto_contrast_threshold):
  *   Color::RGB2L          (color.cc L1343-1380)  L of the demosaiced frame through the sRGB -> XYZ row of L95-99; SSE2 groups of four
  *                         read cachefy with the vector LUT form (LUT.h L349-377) unless one of the four Y is outside [0, 65535],
  *                         then (and in the row tail) each goes through computeXYZ2LabY
@@ -20,6 +20,7 @@
 const float* artoracle_cachef(int which);
 float artoracle_xyz2laby(float f);
 int artoracle_blend_mask(const float* lum, float* blend, int W, int H, float contrastThreshold, float amount, float blur_radius);
+float artoracle_auto_contrast_threshold(const float* lum, int W, int H, float contrastThreshold, float luminance_factor);
 
 static inline unsigned fc_(unsigned filters, int row, int col) { return (filters >> ((((row) << 1 & 14) + ((col) & 1)) << 1) & 3); }
 static inline float vclampf_(float v, float lo, float hi) { const float m = v > lo ? v : lo; return m < hi ? m : hi; }     /* minps(maxps(v, lo), hi): NaN -> lo */
@@ -78,17 +79,26 @@ int artoracle_bilinear_blend(const float* raw, const float* blend, int W, int H,
     return 0;
 }
 
-/* dual_demosaic_RT after the first demosaicer: red / green / blue hold its result on entry.  contrast in percent (> 0). */
+/* dual_demosaic_RT after the first demosaicer: red / green / blue hold its result on entry.  *contrast in percent, in / out (L108-112):
+ * with auto_contrast the threshold comes from the frame (usm_port.c: artoracle_auto_contrast_threshold; needs W, H >= 80). */
+int artoracle_dual_bilinear_ex(const float* raw, int W, int H, unsigned filters, float* red, float* green, float* blue, double* contrast, int auto_contrast, float* blend_out);
 int artoracle_dual_bilinear(const float* raw, int W, int H, unsigned filters, float* red, float* green, float* blue, double contrast, float* blend_out)
 {
+    return artoracle_dual_bilinear_ex(raw, W, H, filters, red, green, blue, &contrast, 0, blend_out);
+}
+int artoracle_dual_bilinear_ex(const float* raw, int W, int H, unsigned filters, float* red, float* green, float* blue, double* contrast, int auto_contrast, float* blend_out)
+{
+    if (auto_contrast && (W < 80 || H < 80)) return 1;
     static const float xyz_rgb[9] = {0.412453, 0.357580, 0.180423, 0.212671, 0.715160, 0.072169, 0.019334, 0.119193, 0.950227};
     const size_t n = (size_t)W * H;
     float* L = (float*)malloc(sizeof(float) * n);
     float* blend = (float*)malloc(sizeof(float) * n);
     if (!L || !blend) { free(L); free(blend); return 1; }
     artoracle_rgb2l(red, green, blue, L, W, H, xyz_rgb);
-    const float contrastf = contrast / 100.0;
+    float contrastf = *contrast / 100.0;
+    if (auto_contrast) contrastf = artoracle_auto_contrast_threshold(L, W, H, contrastf, 1.f);
     int rc = artoracle_blend_mask(L, blend, W, H, contrastf, 1.f, 2.f);
+    *contrast = contrastf * 100.f;
     if (!rc) rc = artoracle_bilinear_blend(raw, blend, W, H, filters, red, green, blue);
     if (blend_out) memcpy(blend_out, blend, sizeof(float) * n);
     free(L); free(blend);

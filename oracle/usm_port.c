@@ -108,6 +108,102 @@ int artoracle_blend_mask(const float* lum, float* blend, int W, int H, float con
 
 
 /* ---------------------------------------------------------------------------------------------------------------------------
+ * buildBlendMask's automatic contrast threshold (rt_algo.cc L317-414: tileAverage L65-86, tileVariance L88-110, calcContrastThreshold
+ * L112-170).  Pass 0 looks for the flattest 80x80 tile on an 80-pixel grid, pass 1 for the flattest 40x40 tile on a 10-pixel grid and
+ * then around it pixel by pixel; the threshold is the smallest c / 100 for which the blend factors of that tile sum to <= 1 % of it.
+ * The SSE2 loops keep four lane sums (columns 0..3 mod 4 of each group) beside the scalar tail's sum; vhadd adds lanes (0 + 2) + (1 + 3).
+ * ------------------------------------------------------------------------------------------------------------------------- */
+static float tile_average(const float* d, int W, int tileY, int tileX, int ts)
+{
+    float avg = 0.f, v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int y = tileY; y < tileY + ts; ++y) {
+        int x = tileX;
+        for (; x < tileX + ts - 3; x += 4) for (int k = 0; k < 4; ++k) v[k] += d[(size_t)y * W + x + k];
+        for (; x < tileX + ts; ++x) avg += d[(size_t)y * W + x];
+    }
+    avg += (v[0] + v[2]) + (v[1] + v[3]);
+    return avg / (float)(ts * ts);
+}
+static float tile_variance(const float* d, int W, int tileY, int tileX, int ts, float avg)
+{
+    float var = 0.f, v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int y = tileY; y < tileY + ts; ++y) {
+        int x = tileX;
+        for (; x < tileX + ts - 3; x += 4) for (int k = 0; k < 4; ++k) { const float t = d[(size_t)y * W + x + k] - avg; v[k] += t * t; }
+        for (; x < tileX + ts; ++x) { const float t = d[(size_t)y * W + x] - avg; var += t * t; }
+    }
+    var += (v[0] + v[2]) + (v[1] + v[3]);
+    return var / ((float)(ts * ts) * avg);
+}
+static float calc_contrast_threshold(const float* lum, int W, int tileY, int tileX, int ts, float factor)
+{
+    const float scale = 0.0625f / 327.68f * factor;
+    const int n = ts - 4;
+    float* bl = (float*)malloc(sizeof(float) * (size_t)n * n);
+#define L(j, i) lum[(size_t)(j) * W + (i)]
+    for (int j = tileY + 2; j < tileY + ts - 2; ++j)
+        for (int i = tileX + 2; i < tileX + ts - 2; ++i) {
+            const float a = L(j, i + 1) - L(j, i - 1), b = L(j + 1, i) - L(j - 1, i), c = L(j, i + 2) - L(j, i - 2), d = L(j + 2, i) - L(j - 2, i);
+            bl[(size_t)(j - tileY - 2) * n + (i - tileX - 2)] = sqrtf(a * a + b * b + c * c + d * d) * scale;
+        }
+#undef L
+    const float limit = (float)(n * n) / 100.f;
+    int c;
+    for (c = 1; c < 100; ++c) {
+        const float thr = c / 100.f;
+        float sum = 0.f, v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < n; ++j) {
+            int i = 0;
+            for (; i < ts - 7; i += 4) for (int k = 0; k < 4; ++k) v[k] += 1.f / (1.f + xexpf_vector(16.f - 16.f * bl[(size_t)j * n + i + k] / thr));
+            for (; i < n; ++i) sum += 1.f / (1.f + xexpf_scalar(16.f - 16.f * bl[(size_t)j * n + i] / thr));
+        }
+        sum += (v[0] + v[2]) + (v[1] + v[3]);
+        if (sum <= limit) break;
+    }
+    free(bl);
+    return c / 100.f;
+}
+static float tile_score(const float* lum, int W, int tileY, int tileX, int ts, float minLum, float maxLum)
+{
+    const float avg = tile_average(lum, W, tileY, tileX, ts);
+    if (avg < minLum || avg > maxLum) return INFINITY;
+    const float v = tile_variance(lum, W, tileY, tileX, ts, avg);
+    return v < 0.5f ? INFINITY : v;
+}
+/* the autoContrast block of buildBlendMask: returns the threshold (the caller's value when neither pass assigns one); needs W, H >= 80 */
+float artoracle_auto_contrast_threshold(const float* lum, int W, int H, float contrastThreshold, float luminance_factor)
+{
+    const float minLum = 2000.f / luminance_factor, maxLum = 20000.f / luminance_factor;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ts = 80 / (pass + 1);
+        const int skip = pass == 0 ? ts : ts / 4;
+        const int ntw = W / skip - 3 * pass, nth = H / skip - 3 * pass;
+        float minvar = INFINITY;
+        int minI = 0, minJ = 0;
+        for (int i = 0; i < nth; ++i)
+            for (int j = 0; j < ntw; ++j) {
+                const float v = tile_score(lum, W, i * skip, j * skip, ts, minLum, maxLum);
+                if (v < minvar) { minvar = v; minI = i; minJ = j; }
+            }
+        if (minvar <= 1.f || pass == 1) {
+            const int minY = skip * minI, minX = skip * minJ;
+            if (pass == 0) return calc_contrast_threshold(lum, W, minY, minX, ts, luminance_factor);
+            const int y0 = minY - skip > 0 ? minY - skip : 0, x0 = minX - skip > 0 ? minX - skip : 0;
+            const int y1 = minY + skip < H - ts ? minY + skip : H - ts, x1 = minX + skip < W - ts ? minX + skip : W - ts;
+            float mv = INFINITY;
+            int mi = 0, mj = 0;
+            for (int i = 0; i < y1 - y0 + 1; ++i)
+                for (int j = 0; j < x1 - x0 + 1; ++j) {
+                    const float v = tile_score(lum, W, y0 + i, x0 + j, ts, minLum, maxLum);
+                    if (v < mv) { mv = v; mi = i; mj = j; }
+                }
+            contrastThreshold = mv <= 8.f ? calc_contrast_threshold(lum, W, y0 + mi, x0 + mj, ts, luminance_factor) : 0.f;
+        }
+    }
+    return contrastThreshold;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------------------
  * bilateral<float, float>(src, dst, buffer, W, H, sigma, sens), bilateral2.h L38-547: 21 fixed integer kernels (3x3 .. 11x11, one per
  * 0.1 step of sigma) weighted by a range LUT ec[d + 65536] = exp(-d^2 / (2 sens^2)) * scale, read with LUTf's interpolating
  * float index; each sum runs row-major over src[i - a][j - b], a, b = -h .. h, in float; the h-pixel border is copied.

@@ -71,3 +71,68 @@ def test_dual_bilinear(filters, W, H, contrast, first):
         assert np.array_equal(x, y), "%s: %d differ" % (ch, int((x != y).sum()))
     assert 0.0 < gb.min() <= gb.max() <= 1.001          # the blurred sigmoid
     assert any((x != p).any() for x, p in zip(got, planes))
+
+
+def lum_scene(W, H, seed, kind):
+    """L-like plane: texture + flat patches in the accepted luminance range.  kind 0: a very flat patch (pass 0 finds it); 1: only
+    moderately flat patches (pass 1 + the fine scan); 2: everything busy or out of range (threshold 0)."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:H, 0:W].astype(np.float32)
+    img = 9000 + 5000 * np.sin(0.21 * x) * np.cos(0.17 * y) + rng.normal(0, 900, (H, W))
+    if kind == 0:
+        ph, pw = min(170, H - H // 4), min(170, W - W // 3)
+        img[H // 4: H // 4 + ph, W // 3: W // 3 + pw] = 8000 + rng.normal(0, 80, (ph, pw))
+    elif kind == 1:
+        img[H // 2: H // 2 + 47, W // 5: W // 5 + 52] = 6000 + rng.normal(0, 170, (47, 52))
+    else:
+        img[: H // 2] = 30000 + rng.normal(0, 10, (H // 2, W))
+    return np.ascontiguousarray(img, dtype=np.float32)
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", [(400, 300), (333, 251), (163, 170)])
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_auto_contrast_threshold(W, H, kind):
+    lum = lum_scene(W, H, W + kind, kind)
+    f = oracle.port().lib.artoracle_auto_contrast_threshold
+    f.restype = ctypes.c_float
+    got = f(P(lum), W, H, F(0.2), F(1.0))
+    thr = ctypes.c_float(0.2)
+    blend = np.zeros((H, W), np.float32)
+    assert oracle.ref().lib.artref_blend_mask_ex(P(lum), P(blend), W, H, ctypes.byref(thr), F(1.0), 1, F(2.0)) == 0
+    assert got == thr.value, (got, thr.value)
+    if kind == 2:
+        assert got == 0.0
+    else:
+        assert 0.0 < got < 1.0
+    # and the mask built with that threshold is the one the reference built
+    mine = np.zeros((H, W), np.float32)
+    assert oracle.port().lib.artoracle_blend_mask(P(lum), P(mine), W, H, F(got), F(1.0), F(2.0)) == 0
+    assert np.array_equal(mine, blend)
+
+
+@needs_ref
+@pytest.mark.parametrize("filters", [0x94949494, 0x49494949])
+@pytest.mark.parametrize("W,H", [(301, 203), (640, 427)])
+def test_dual_bilinear_auto_contrast(filters, W, H):
+    """autoContrast (the reference's default for the dual methods): the threshold comes from the flattest tile of the frame's L."""
+    raw = synth.bayer_frame(W, H, filters, seed=W)
+    planes = list(oracle.port().amaze(raw, filters))
+    lib = oracle.port().lib
+    r, g, b = [p.copy() for p in planes]
+    c = ctypes.c_double(20.0)
+    blend = np.zeros((H, W), np.float32)
+    assert lib.artoracle_dual_bilinear_ex(P(raw), W, H, ctypes.c_uint(filters), P(r), P(g), P(b), ctypes.byref(c), 1, P(blend)) == 0
+    # the reference's pieces, chained as dual_demosaic_RT.cc L101-127 chains them
+    rl = oracle.ref().lib
+    rr, rg, rb = [p.copy() for p in planes]
+    L = np.zeros((H, W), np.float32)
+    rl.artref_rgb2l(P(rr), P(rg), P(rb), P(L), W, H, P(XYZ_RGB))
+    thr = ctypes.c_float(np.float32(20.0 / 100.0))
+    rblend = np.zeros((H, W), np.float32)
+    rl.artref_blend_mask_ex(P(L), P(rblend), W, H, ctypes.byref(thr), F(1.0), 1, F(2.0))
+    rl.artref_bilinear_blend(P(raw), P(rblend), W, H, ctypes.c_uint(filters), P(rr), P(rg), P(rb))
+    assert c.value == float(np.float32(thr.value) * np.float32(100.0))
+    assert np.array_equal(blend, rblend)
+    for x, y in zip((r, g, b), (rr, rg, rb)):
+        assert np.array_equal(x, y)
