@@ -1500,6 +1500,7 @@ struct RawImageSource {
     void cielab(const float (*rgb)[3], float* l, float* a, float* b, const int width, const int height, const int labWidth, const float xyz_cam[3][3]);
     void xtransborder_interpolate(int border, array2D<float>& red, array2D<float>& green, array2D<float>& blue);
     void xtrans_interpolate(const int passes, const bool useCieLab);
+    void fast_xtrans_interpolate_blend (const float* const * blend, const array2D<float> &rawData, array2D<float> &red, array2D<float> &green, array2D<float> &blue);
 };
 #include "xtrans_body.inc"
 }  // namespace artref_xt
@@ -1516,6 +1517,18 @@ extern "C" int artref_xtrans(int W, int H, const int* xtrans36, const float* rgb
     if (border_only) src.xtransborder_interpolate(border_only, src.red, src.green, src.blue);
     else src.xtrans_interpolate(passes, useCieLab != 0);
     delete[] rr; delete[] gr; delete[] br; delete[] wr;
+    return 0;
+}
+// fast_xtrans_interpolate_blend(blend, rawData, red, green, blue): the second half of the dual demosaic on X-Trans (dual_demosaic_RT.cc L151)
+extern "C" int artref_xtrans_fast_blend(int W, int H, const int* xtrans36, const float* raw, const float* blend, float* r, float* g, float* b)
+{
+    float **rr = new float*[H], **gr = new float*[H], **br = new float*[H], **wr = new float*[H], **bl = new float*[H];
+    for (int i = 0; i < H; ++i) { rr[i] = r + (size_t)i * W; gr[i] = g + (size_t)i * W; br[i] = b + (size_t)i * W; wr[i] = const_cast<float*>(raw) + (size_t)i * W; bl[i] = const_cast<float*>(blend) + (size_t)i * W; }
+    artref_xt::RawImage ri;
+    memcpy(ri.xt, xtrans36, sizeof ri.xt); memset(ri.cam, 0, sizeof ri.cam);
+    artref_xt::RawImageSource src(W, H, &ri, wr, rr, gr, br);
+    src.fast_xtrans_interpolate_blend(bl, src.rawData, src.red, src.green, src.blue);
+    delete[] rr; delete[] gr; delete[] br; delete[] wr; delete[] bl;
     return 0;
 }
 """
@@ -1732,7 +1745,9 @@ def extract(det):
             cut_function(xt, r"^void RawImageSource::xtransborder_interpolate \([^)]*\)"),
             "#define CLIP(x) (x)\n",
             cut_function(xt, r"^void RawImageSource::xtrans_interpolate\(const int passes, const bool useCieLab\)"),
-            "#undef CLIP\n#undef fcol\n#undef isgreen\n"]
+            "#undef CLIP\n",
+            cut_function(xt, r"^void RawImageSource::fast_xtrans_interpolate_blend \(const float\* const \* blend[^)]*\)"),
+            "#undef fcol\n#undef isgreen\n"]
     if det:
         body[5] = insert_before(body[5], r"int mrow = MIN \(top \+ ts, height - 3\);",
                                 "memset(buffer, 0, (ts * ts * (ndir * 4 + 3) + 128) * sizeof(float));\n                ")

@@ -104,3 +104,37 @@ int artoracle_dual_bilinear_ex(const float* raw, int W, int H, unsigned filters,
     free(L); free(blend);
     return rc;
 }
+
+/* fast_xtrans_interpolate_blend(blend, rawData, red, green, blue), xtrans_demosaic.cc L1033-1092: the dual demosaic's flat-region
+ * demosaicer on X-Trans: 3x3 weighted sums per colour, mixed with the first demosaicer's planes by intp(blend, first, fast); the
+ * 8-pixel border keeps the first demosaicer's values */
+int artoracle_xtrans_fast_blend(int W, int H, const int* xtrans36, const float* raw, const float* blend, float* red, float* green, float* blue)
+{
+    static const float weight[3][3] = {{0.25f, 0.5f, 0.25f}, {0.5f, 0.f, 0.5f}, {0.25f, 0.5f, 0.25f}};
+#define FCOL(r, c) xtrans36[((r) % 6) * 6 + ((c) % 6)]
+#define INTP(a, b, c) ((a) * (b) + (1.f - (a)) * (c))
+    for (int row = 8; row < H - 8; ++row)
+        for (int col = 8; col < W - 8; ++col) {
+            float sum[3] = {0.f, 0.f, 0.f};
+            for (int v = -1; v <= 1; v++)
+                for (int h = -1; h <= 1; h++) sum[FCOL(row + v, col + h)] += raw[(size_t)(row + v) * W + (col + h)] * weight[v + 1][h + 1];
+            const size_t o = (size_t)row * W + col;
+            const float bl = blend[o], x = raw[o];
+            switch (FCOL(row, col)) {
+            case 0:
+                red[o] = INTP(bl, red[o], x); green[o] = INTP(bl, green[o], sum[1] * 0.5f); blue[o] = INTP(bl, blue[o], sum[2]);
+                break;
+            case 1:
+                green[o] = INTP(bl, green[o], x);
+                if (FCOL(row, col - 1) == FCOL(row, col + 1)) { red[o] = INTP(bl, red[o], sum[0]); blue[o] = INTP(bl, blue[o], sum[2]); }
+                else { red[o] = INTP(bl, red[o], sum[0] * 1.3333333f); blue[o] = INTP(bl, blue[o], sum[2] * 1.3333333f); }
+                break;
+            case 2:
+                red[o] = INTP(bl, red[o], sum[0]); green[o] = INTP(bl, green[o], sum[1] * 0.5f); blue[o] = INTP(bl, blue[o], x);
+                break;
+            }
+        }
+#undef FCOL
+#undef INTP
+    return 0;
+}

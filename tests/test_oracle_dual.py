@@ -136,3 +136,27 @@ def test_dual_bilinear_auto_contrast(filters, W, H):
     assert np.array_equal(blend, rblend)
     for x, y in zip((r, g, b), (rr, rg, rb)):
         assert np.array_equal(x, y)
+
+
+@needs_ref
+@pytest.mark.parametrize("dy,dx", [(0, 0), (2, 5), (4, 1)])
+@pytest.mark.parametrize("W,H", [(64, 48), (67, 53), (131, 140), (17, 40)])
+def test_xtrans_fast_blend(dy, dx, W, H):
+    """The X-Trans half of the dual demosaic: fast_xtrans_interpolate_blend over arbitrary first-demosaicer planes and blend mask."""
+    xt = np.ascontiguousarray(synth.xtrans_matrix(dy, dx), np.int32)
+    raw = synth.xtrans_frame(W, H, xt, seed=W + dy)
+    rng = np.random.default_rng(H + dx)
+    planes = [np.ascontiguousarray(rng.uniform(0, 65535, (H, W)), dtype=np.float32) for _ in range(3)]
+    blend = np.ascontiguousarray(rng.uniform(0, 1, (H, W)), dtype=np.float32)
+    blend[::5, ::3] = 1.0
+    blend[1::7, ::2] = 0.0
+    ip = ctypes.POINTER(ctypes.c_int)
+    a = [p.copy() for p in planes]
+    b = [p.copy() for p in planes]
+    assert oracle.port().lib.artoracle_xtrans_fast_blend(W, H, xt.ctypes.data_as(ip), P(raw), P(blend), P(a[0]), P(a[1]), P(a[2])) == 0
+    assert oracle.ref().lib.artref_xtrans_fast_blend(W, H, xt.ctypes.data_as(ip), P(raw), P(blend), P(b[0]), P(b[1]), P(b[2])) == 0
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    if W > 16 and H > 16:
+        assert any((x != p).any() for x, p in zip(a, planes))
+        assert all(np.array_equal(x[:8], p[:8]) and np.array_equal(x[:, :8], p[:, :8]) for x, p in zip(a, planes))
