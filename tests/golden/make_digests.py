@@ -127,6 +127,40 @@ def cases(which):
         getattr(lib, pre + "green_equilibrate")(a.ctypes.data_as(tg.fp), 301, 203, ctypes.c_uint(0x94949494), ctypes.c_float(0.05), None)
         return [a]
     out["greeneq_301x203_rggb"] = f
+
+    import test_oracle_dual as tdu
+    import test_oracle_pack as tp
+
+    def f():
+        raw = synth.bayer_frame(301, 203, 0x94949494, seed=31)
+        planes = list(oracle.port().amaze(raw, 0x94949494))       # the first demosaicer's planes are an input here (AMaZE has its own pins)
+        if ref:
+            o, blend, _ = tdu.ref_chain(raw, 0x94949494, planes, 20.0)
+        else:
+            o, blend = tdu.port_chain(raw, 0x94949494, planes, 20.0)
+        return o + [blend]
+    out["dual_amaze_bilinear_301x203_c20"] = f
+
+    def f():
+        lum = tdu.lum_scene(333, 251, 334, 1)
+        import ctypes
+        if ref:
+            thr = ctypes.c_float(0.2)
+            blend = np.zeros_like(lum)
+            lib.artref_blend_mask_ex(tdu.P(lum), tdu.P(blend), 333, 251, ctypes.byref(thr), tdu.F(1.0), 1, tdu.F(2.0))
+            return [np.array([thr.value], np.float32), blend]
+        fn = lib.artoracle_auto_contrast_threshold
+        fn.restype = ctypes.c_float
+        t = fn(tdu.P(lum), 333, 251, tdu.F(0.2), tdu.F(1.0))
+        blend = np.zeros_like(lum)
+        lib.artoracle_blend_mask(tdu.P(lum), tdu.P(blend), 333, 251, tdu.F(t), tdu.F(1.0), tdu.F(2.0))
+        return [np.array([t], np.float32), blend]
+    out["auto_contrast_333x251"] = f
+
+    def f():
+        planes = tp.frame(35, 67, 102)
+        return [tp.scan(lib, pre + "scanlines", planes, bps, fl).view(np.uint8).astype(np.float32) for bps, fl in ((8, 0), (16, 0), (16, 1))]
+    out["scanlines_67x35"] = f
     return out
 
 
