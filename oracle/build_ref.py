@@ -559,6 +559,67 @@ extern "C" int artref_bilinear_blend(const float* raw, const float* blend, int W
 """
 
 
+SHIM_VNG4_TU = r"""
+// Shim TU hosting the reference's VNG4 demosaic: vng4interpolate_row_redblue and RawImageSource::vng4_demosaic cut from
+// vng4_demosaic_RT.cc, border_interpolate2 from demosaic_algos.cc.  Written here (not reference code): the RawImage / RawImageSource /
+// RAWParams stand-ins and the wrapper.
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <omp.h>
+#include "glibmm.h"
+#include "array2D.h"
+#include "rt_math.h"
+#include "opthelper.h"
+#define M(x) Glib::ustring(x)
+#define BENCHFUN
+#define RawImageSource RawImageSourceVNG4       /* other shim TUs define their own stand-in of this name: keep the inline members apart */
+namespace rtengine {
+struct RAWParams { struct BayerSensor { enum class Method { VNG4 }; static Glib::ustring getMethodString(Method) { return Glib::ustring("vng4"); } }; };
+struct VngProgress { void setProgressStr(const Glib::ustring&) {} void setProgress(double) {} };
+struct RawImage {
+    unsigned filters, prefilters;
+    unsigned FC(unsigned row, unsigned col) const { return (filters >> ((((row) << 1 & 14) + ((col) & 1)) << 1) & 3); }
+    bool ISGREEN(unsigned row, unsigned col) const { return FC(row, col) == 1; }
+    bool ISBLUE(unsigned row, unsigned col) const { return FC(row, col) == 2; }
+};
+struct RawImageSource {
+    int W, H; RawImage* ri; VngProgress* plistener;
+    unsigned FC(int row, int col) const { return ri->FC(row, col); }
+    void vng4_demosaic (const array2D<float> &rawData, array2D<float> &red, array2D<float> &green, array2D<float> &blue);
+    void border_interpolate2(int winw, int winh, int lborders, const array2D<float> &rawData, array2D<float> &red, array2D<float> &green, array2D<float> &blue);
+};
+#include "border_body.inc"
+}
+namespace {
+using namespace rtengine;
+#include "vng4_rowrb.inc"
+}
+namespace rtengine {
+#define fc(row,col) (prefilters >> ((((row) << 1 & 14) + ((col) & 1)) << 1) & 3)
+#include "vng4_body.inc"
+#undef fc
+}
+extern "C" int artref_vng4(int W, int H, unsigned prefilters, const float* raw, float* red, float* green, float* blue, int nthreads)
+{
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+    auto rows = [&](const float* p) { float** t = new float*[H]; for (int i = 0; i < H; ++i) t[i] = const_cast<float*>(p) + (size_t)i * W; return t; };
+    float **rr = rows(raw), **r = rows(red), **g = rows(green), **b = rows(blue);
+    {
+        rtengine::array2D<float> rd(W, H, rr, rtengine::ARRAY2D_BYREFERENCE), R(W, H, r, rtengine::ARRAY2D_BYREFERENCE), G(W, H, g, rtengine::ARRAY2D_BYREFERENCE), B(W, H, b, rtengine::ARRAY2D_BYREFERENCE);
+        rtengine::RawImage ri{prefilters & ~((prefilters & 0x55555555u) << 1), prefilters};
+        rtengine::RawImageSource s{W, H, &ri, nullptr};
+        s.vng4_demosaic(rd, R, G, B);
+    }
+    delete[] rr; delete[] r; delete[] g; delete[] b;
+    return 0;
+}
+"""
+
+
 SHIM_GUIDED_TU = r"""
 // Shim TU hosting the reference's boxblur.h body (its include block is replaced: StopWatch.h drags
 // settings.h -> procparams.h -> lcms2.h) and guidedFilter + calculate_subsampling cut from guidedfilter.cc.
@@ -1724,6 +1785,10 @@ def extract(det):
     open(os.path.join(sub, "bilinear_body.inc"), "w").write(
         cut_function(os.path.join(RT, "bayer_bilinear_demosaic.cc"), r"^void RawImageSource::bayer_bilinear_demosaic\(const float\* const \* blend[^)]*\)"))
     open(os.path.join(sub, "shim_bilinear.cc"), "w").write(SHIM_BILINEAR_TU)
+    vg = os.path.join(RT, "vng4_demosaic_RT.cc")
+    open(os.path.join(sub, "vng4_rowrb.inc"), "w").write(cut_function(vg, r"^inline void vng4interpolate_row_redblue \(const RawImage \*ri[^)]*\)"))
+    open(os.path.join(sub, "vng4_body.inc"), "w").write(cut_function(vg, r"^void RawImageSource::vng4_demosaic \(const array2D<float> &rawData[^)]*\)"))
+    open(os.path.join(sub, "shim_vng4.cc"), "w").write(SHIM_VNG4_TU)
     ge = os.path.join(RT, "green_equil_RT.cc")
     open(os.path.join(sub, "greeneq_body.inc"), "w").write(
         cut_function(ge, r"^void RawImageSource::green_equilibrate_global\(array2D<float> &rawData\)") + "\n\n" +
@@ -1760,7 +1825,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), os.path.join(sub, "shim_resize.cc"), os.path.join(sub, "shim_greeneq.cc"), os.path.join(sub, "shim_pack.cc"), os.path.join(sub, "shim_bilinear.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), os.path.join(sub, "shim_resize.cc"), os.path.join(sub, "shim_greeneq.cc"), os.path.join(sub, "shim_pack.cc"), os.path.join(sub, "shim_bilinear.cc"), os.path.join(sub, "shim_vng4.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)

@@ -138,3 +138,30 @@ int artoracle_xtrans_fast_blend(int W, int H, const int* xtrans36, const float* 
 #undef INTP
     return 0;
 }
+
+/* dual_demosaic_RT for Method::AMAZEVNG4 / RCDVNG4 (L128-147) after the first demosaicer: the flat-region planes come from VNG4 (vng4_port.c) */
+int artoracle_vng4(int W, int H, unsigned prefilters, const float* raw, float* red, float* green, float* blue);
+int artoracle_dual_vng4(const float* raw, int W, int H, unsigned prefilters, float* red, float* green, float* blue, double* contrast, int auto_contrast, float* blend_out)
+{
+    static const float xyz_rgb[9] = {0.412453, 0.357580, 0.180423, 0.212671, 0.715160, 0.072169, 0.019334, 0.119193, 0.950227};
+    if (auto_contrast && (W < 80 || H < 80)) return 1;
+    const size_t n = (size_t)W * H;
+    float* L = (float*)malloc(sizeof(float) * n * 5);
+    if (!L) return 1;
+    float *blend = L + n, *tr = blend + n, *tg = tr + n, *tb = tg + n;
+    artoracle_rgb2l(red, green, blue, L, W, H, xyz_rgb);
+    float contrastf = *contrast / 100.0;
+    if (auto_contrast) contrastf = artoracle_auto_contrast_threshold(L, W, H, contrastf, 1.f);
+    int rc = artoracle_blend_mask(L, blend, W, H, contrastf, 1.f, 2.f);
+    *contrast = contrastf * 100.f;
+    if (!rc) rc = artoracle_vng4(W, H, prefilters, raw, tr, tg, tb);
+    if (!rc)
+        for (size_t k = 0; k < n; ++k) {
+            red[k] = blend[k] * red[k] + (1.f - blend[k]) * tr[k];
+            green[k] = blend[k] * green[k] + (1.f - blend[k]) * tg[k];
+            blue[k] = blend[k] * blue[k] + (1.f - blend[k]) * tb[k];
+        }
+    if (blend_out) memcpy(blend_out, blend, sizeof(float) * n);
+    free(L);
+    return rc;
+}

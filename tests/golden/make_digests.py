@@ -158,6 +158,12 @@ def cases(which):
     out["auto_contrast_333x251"] = f
 
     def f():
+        import test_oracle_vng4 as tv
+        raw = synth.bayer_frame(130, 77, 0x61616161, seed=9)
+        return tv.vng4(lib, pre + "vng4", raw, 0xe1e1e1e1, *([1] if ref else []))
+    out["vng4_130x77_grbg"] = f
+
+    def f():
         planes = tp.frame(35, 67, 102)
         return [tp.scan(lib, pre + "scanlines", planes, bps, fl).view(np.uint8).astype(np.float32) for bps, fl in ((8, 0), (16, 0), (16, 1))]
     out["scanlines_67x35"] = f

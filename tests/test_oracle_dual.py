@@ -160,3 +160,30 @@ def test_xtrans_fast_blend(dy, dx, W, H):
     if W > 16 and H > 16:
         assert any((x != p).any() for x, p in zip(a, planes))
         assert all(np.array_equal(x[:8], p[:8]) and np.array_equal(x[:, :8], p[:, :8]) for x, p in zip(a, planes))
+
+
+@needs_ref
+@pytest.mark.parametrize("filters,pf", [(0x94949494, 0xb4b4b4b4), (0x61616161, 0xe1e1e1e1)])
+@pytest.mark.parametrize("auto", [0, 1])
+def test_dual_vng4(filters, pf, auto):
+    """AMAZEVNG4: the flat-region planes come from VNG4; chained from the reference's own pieces as dual_demosaic_RT.cc L101-147 chains them."""
+    W, H = 301, 203
+    raw = synth.bayer_frame(W, H, filters, seed=77)
+    planes = list(oracle.port().amaze(raw, filters))
+    r, g, b = [p.copy() for p in planes]
+    c = ctypes.c_double(20.0)
+    blend = np.zeros((H, W), np.float32)
+    assert oracle.port().lib.artoracle_dual_vng4(P(raw), W, H, ctypes.c_uint(pf), P(r), P(g), P(b), ctypes.byref(c), auto, P(blend)) == 0
+    rl = oracle.ref().lib
+    L = np.zeros((H, W), np.float32)
+    rl.artref_rgb2l(P(planes[0]), P(planes[1]), P(planes[2]), P(L), W, H, P(XYZ_RGB))
+    thr = ctypes.c_float(np.float32(0.2))
+    rblend = np.zeros((H, W), np.float32)
+    rl.artref_blend_mask_ex(P(L), P(rblend), W, H, ctypes.byref(thr), F(1.0), auto, F(2.0))
+    tmp = [np.zeros((H, W), np.float32) for _ in range(3)]
+    rl.artref_vng4(W, H, ctypes.c_uint(pf), P(raw), P(tmp[0]), P(tmp[1]), P(tmp[2]), 0)
+    assert np.array_equal(blend, rblend)
+    one = np.float32(1.0)
+    for mine, first, flat in zip((r, g, b), planes, tmp):
+        want = rblend * first + (one - rblend) * flat           # intp(blend, first, flat), float32 throughout
+        assert np.array_equal(mine, want)

@@ -1,0 +1,60 @@
+"""Pin the VNG4 oracle (oracle/vng4_port.c) against the reference's own RawImageSource::vng4_demosaic compiled in place (oracle/_ref).
+Bit-exact over the four Bayer phases (four-colour `prefilters`), ragged sizes, one and many reference threads (row chunking)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+from art_b200 import synth
+
+needs_ref = pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built and /root/reference absent")
+fp = ctypes.POINTER(ctypes.c_float)
+# four-colour patterns (the second green of each 2x2 is colour 3): RGGB, BGGR, GRBG, GBRG
+PREFILTERS = {0x94949494: 0xb4b4b4b4, 0x16161616: 0x1e1e1e1e, 0x61616161: 0xe1e1e1e1, 0x49494949: 0x4b4b4b4b}
+
+
+def collapse(pf):
+    return pf & ~((pf & 0x55555555) << 1) & 0xffffffff
+
+
+def vng4(lib, name, raw, pf, *extra):
+    H, W = raw.shape
+    out = [np.zeros((H, W), np.float32) for _ in range(3)]
+    rc = getattr(lib, name)(W, H, ctypes.c_uint(pf), raw.ctypes.data_as(fp), *[o.ctypes.data_as(fp) for o in out], *extra)
+    assert rc == 0
+    return out
+
+
+def test_prefilters_collapse_to_the_three_colour_patterns():
+    for f, pf in PREFILTERS.items():
+        assert collapse(pf) == f
+
+
+@needs_ref
+@pytest.mark.parametrize("filters", sorted(PREFILTERS))
+@pytest.mark.parametrize("W,H", [(64, 48), (67, 53), (130, 77), (33, 95), (8, 8), (301, 203)])
+@pytest.mark.parametrize("threads", [1, 5])
+def test_port_matches_reference(filters, W, H, threads):
+    raw = synth.bayer_frame(W, H, filters, seed=W * 3 + H)
+    raw[H // 3, W // 2] = 0.0                       # the clamps at 0
+    raw[H // 2: H // 2 + 3, 2: 9] = 65535.0
+    pf = PREFILTERS[filters]
+    got = vng4(oracle.port().lib, "artoracle_vng4", raw, pf)
+    want = vng4(oracle.ref().lib, "artref_vng4", raw, pf, threads)
+    for g, w, ch in zip(got, want, "RGB"):
+        n = int((g != w).sum())
+        assert n == 0, "%s: %d of %d differ, first at %s" % (ch, n, g.size, np.argwhere(g != w)[0])
+
+
+@needs_ref
+def test_vng4_keeps_native_red_blue_and_is_smooth_in_flat_areas():
+    f = 0x94949494
+    raw = np.full((40, 60), 1000.0, np.float32)
+    out = vng4(oracle.port().lib, "artoracle_vng4", raw, PREFILTERS[f])
+    for p in out:
+        assert np.allclose(p[4:-4, 4:-4], 1000.0, rtol=1e-6)
+    raw = synth.bayer_frame(60, 40, f, seed=3)
+    r, g, b = vng4(oracle.port().lib, "artoracle_vng4", raw, PREFILTERS[f])
+    assert np.array_equal(r[4:-4:2, 4:-4:2], raw[4:-4:2, 4:-4:2])           # red sites of RGGB keep their sample
+    assert np.array_equal(b[5:-4:2, 5:-4:2], raw[5:-4:2, 5:-4:2])
