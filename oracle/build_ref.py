@@ -620,6 +620,27 @@ extern "C" int artref_vng4(int W, int H, unsigned prefilters, const float* raw, 
 """
 
 
+SHIM_HLBLEND_TU = r"""
+// Shim TU hosting the reference's "Blend" highlight reconstruction: RawImageSource::HLRecovery_blend cut from rawimagesource.cc.
+// Written here (not reference code): the class stand-in and the wrapper.
+#include <cmath>
+#include <cstdlib>
+#include <algorithm>
+#include "rt_math.h"
+#define RawImageSource RawImageSourceHL       /* other shim TUs define their own stand-in of this name */
+namespace rtengine {
+struct RawImageSource { static void HLRecovery_blend(float* rin, float* gin, float* bin, int width, float maxval, float* hlmax); };
+#include "hlblend_body.inc"
+}
+extern "C" int artref_hl_blend(float* rin, float* gin, float* bin, int width, float maxval, const float* hlmax)
+{
+    float h[3] = {hlmax[0], hlmax[1], hlmax[2]};
+    rtengine::RawImageSource::HLRecovery_blend(rin, gin, bin, width, maxval, h);
+    return 0;
+}
+"""
+
+
 SHIM_GUIDED_TU = r"""
 // Shim TU hosting the reference's boxblur.h body (its include block is replaced: StopWatch.h drags
 // settings.h -> procparams.h -> lcms2.h) and guidedFilter + calculate_subsampling cut from guidedfilter.cc.
@@ -1785,6 +1806,9 @@ def extract(det):
     open(os.path.join(sub, "bilinear_body.inc"), "w").write(
         cut_function(os.path.join(RT, "bayer_bilinear_demosaic.cc"), r"^void RawImageSource::bayer_bilinear_demosaic\(const float\* const \* blend[^)]*\)"))
     open(os.path.join(sub, "shim_bilinear.cc"), "w").write(SHIM_BILINEAR_TU)
+    open(os.path.join(sub, "hlblend_body.inc"), "w").write(
+        cut_function(os.path.join(RT, "rawimagesource.cc"), r"^void RawImageSource::HLRecovery_blend\(float\* rin, float\* gin, float\* bin, int width, float maxval, float\* hlmax\)"))
+    open(os.path.join(sub, "shim_hlblend.cc"), "w").write(SHIM_HLBLEND_TU)
     vg = os.path.join(RT, "vng4_demosaic_RT.cc")
     open(os.path.join(sub, "vng4_rowrb.inc"), "w").write(cut_function(vg, r"^inline void vng4interpolate_row_redblue \(const RawImage \*ri[^)]*\)"))
     open(os.path.join(sub, "vng4_body.inc"), "w").write(cut_function(vg, r"^void RawImageSource::vng4_demosaic \(const array2D<float> &rawData[^)]*\)"))
@@ -1825,7 +1849,7 @@ def build(det):
     sub = extract(det)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), os.path.join(sub, "shim_resize.cc"), os.path.join(sub, "shim_greeneq.cc"), os.path.join(sub, "shim_pack.cc"), os.path.join(sub, "shim_bilinear.cc"), os.path.join(sub, "shim_vng4.cc"), "-o", lib]
+           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), os.path.join(sub, "shim_resize.cc"), os.path.join(sub, "shim_greeneq.cc"), os.path.join(sub, "shim_pack.cc"), os.path.join(sub, "shim_bilinear.cc"), os.path.join(sub, "shim_vng4.cc"), os.path.join(sub, "shim_hlblend.cc"), "-o", lib]
     if det:
         cmd.insert(1, "-DARTREF_DET")
     subprocess.check_call(cmd)

@@ -8,6 +8,7 @@
  * Pinned against oracle/_ref (the reference's own CLIP and its own matrix loop) in
  * tests/test_oracle_pointwise.py: bit-exact.
  */
+#include <math.h>
 #include <stddef.h>
 
 static inline float clip65535_(float a)
@@ -56,5 +57,58 @@ int artoracle_scale_colors_bayer(int W, int H, unsigned filters, float* raw, lon
             mx[c] = mx[c] < val ? val : mx[c];
         }
     chmax[0] = mx[0]; chmax[1] = mx[1]; chmax[2] = mx[2];
+    return 0;
+}
+
+/* RawImageSource::HLRecovery_blend (rawimagesource.cc L3613-3747; hlRecovery L3752-3755 calls it with maxval 65535), the "Blend" highlight
+ * reconstruction getImage applies per line (L1014): clipped pixels get their chroma (in an opponent space) scaled to the unclipped
+ * estimate's, faded in above half the lowest clip point; the tail mixes float and double arithmetic (double literals). */
+static inline float hl_min(float a, float b) { return b < a ? b : a; }      /* rtengine::min */
+int artoracle_hl_blend(float* rin, float* gin, float* bin, int width, float maxval, const float* hlmax)
+{
+    static const float trans[3][3] = {{1, 1, 1}, {1.7320508, -1.7320508, 0}, {-1, -1, 2}};
+    static const float itrans[3][3] = {{1, 0.8660254, -0.5}, {1, -0.8660254, -0.5}, {1, 0, 1}};
+    const float minpt = hl_min(hl_min(hlmax[0], hlmax[1]), hlmax[2]);
+    const float maxave = (hlmax[0] + hlmax[1] + hlmax[2]) / 3;
+    const float clipthresh = 0.95, fixthresh = 0.5;
+    float clip[3];
+    for (int c = 0; c < 3; c++) clip[c] = hl_min(maxave, hlmax[c]);
+    const float clippt = clipthresh * maxval;
+    const float fixpt = fixthresh * minpt;
+    for (int col = 0; col < width; col++) {
+        float rgb[3], cam[2][3], lab[2][3], sum[2], chratio, lratio = 0;
+        float L, C, H;
+        rgb[0] = rin[col]; rgb[1] = gin[col]; rgb[2] = bin[col];
+        int c;
+        for (c = 0; c < 3; c++) if (rgb[c] > clippt) break;
+        if (c == 3) continue;
+        for (c = 0; c < 3; c++) { lratio += hl_min(rgb[c], clip[c]); cam[0][c] = rgb[c]; cam[1][c] = hl_min(cam[0][c], maxval); }
+        for (int i = 0; i < 2; i++) {
+            for (c = 0; c < 3; c++) {
+                lab[i][c] = 0;
+                for (int j = 0; j < 3; j++) lab[i][c] += trans[c][j] * cam[i][j];
+            }
+            sum[i] = 0;
+            for (c = 1; c < 3; c++) sum[i] += lab[i][c] * lab[i][c];
+        }
+        chratio = sqrtf(sum[1] / sum[0]);
+        for (c = 1; c < 3; c++) lab[0][c] *= chratio;
+        for (c = 0; c < 3; c++) {
+            cam[0][c] = 0;
+            for (int j = 0; j < 3; j++) cam[0][c] += itrans[c][j] * lab[0][j];
+        }
+        for (c = 0; c < 3; c++) rgb[c] = cam[0][c] / 3;
+        if (rin[col] > fixpt) { const float t = (hl_min(clip[0], rin[col]) - fixpt) / (clip[0] - fixpt), f = t * t; rin[col] = hl_min(maxave, f * rgb[0] + (1 - f) * rin[col]); }
+        if (gin[col] > fixpt) { const float t = (hl_min(clip[1], gin[col]) - fixpt) / (clip[1] - fixpt), f = t * t; gin[col] = hl_min(maxave, f * rgb[1] + (1 - f) * gin[col]); }
+        if (bin[col] > fixpt) { const float t = (hl_min(clip[2], bin[col]) - fixpt) / (clip[2] - fixpt), f = t * t; bin[col] = hl_min(maxave, f * rgb[2] + (1 - f) * bin[col]); }
+        const float tot = (rin[col] + gin[col] + bin[col]);
+        lratio /= tot;
+        L = tot / 3 / lratio;
+        C = lratio * 1.732050808 * (rin[col] - gin[col]);
+        H = lratio * (2 * bin[col] - rin[col] - gin[col]);
+        rin[col] = L - H / 6.0 + C / 3.464101615;
+        gin[col] = L - H / 6.0 - C / 3.464101615;
+        bin[col] = L + H / 3.0;
+    }
     return 0;
 }
