@@ -664,6 +664,47 @@ namespace {
 #include "guided_subsampling.inc"
 }
 #include "guided_body.inc"
+// guidedFilterLog (guidedfilter.cc L243-263), guided_smoothing (ipsmoothing.cc L334-409) over the Color members it calls (color.h)
+void guidedFilterLog(const array2D<float> &guide, float base, array2D<float> &chan, int r, float eps, bool multithread, int subsampling=0);    // guidedfilter.h
+void guidedFilterLog(float base, array2D<float> &chan, int r, float eps, bool multithread, int subsampling=0);
+#include "guided_log.inc"
+#include "guided_log2.inc"
+typedef const float (*TMatrix)[3];      // iccstore.h L38
+class Color { public:
+template <class T>
+#include "gs_rgblum.inc"
+template <class T>
+#include "gs_rgb2yuv.inc"
+template <class T>
+#include "gs_yuv2rgb.inc"
+};
+namespace {
+enum class Channel { L, C, LC };        // ipsmoothing.cc L327-331
+#include "guided_smoothing.inc"
+}
+// denoise::denoiseGuidedSmoothing (ipsmoothing.cc L875-897) with Imagefloat::normalizeFloatTo1 / To65535 (imagefloat.cc L396-438: x *= factor)
+void artref_gs(float* R, float* G, float* B, int W, int H, const float ws[3][3], int guidedChromaRadius, double scale)
+{
+    if (guidedChromaRadius == 0) return;
+    const size_t n = (size_t)W * H;
+    const float down = 1.f / 65535.f, up = 65535.f;
+    for (size_t k = 0; k < n; ++k) { R[k] *= down; G[k] *= down; B[k] *= down; }
+    float **r = new float*[H], **g = new float*[H], **b = new float*[H];
+    for (int i = 0; i < H; ++i) { r[i] = R + (size_t)i * W; g[i] = G + (size_t)i * W; b[i] = B + (size_t)i * W; }
+    {
+        array2D<float> aR(W, H, r, ARRAY2D_BYREFERENCE), aG(W, H, g, ARRAY2D_BYREFERENCE), aB(W, H, b, ARRAY2D_BYREFERENCE);
+        TMatrix wsm = ws, iws = ws;
+        guided_smoothing(aR, aG, aB, wsm, iws, Channel::C, guidedChromaRadius, 0.001f, scale, true);
+    }
+    delete[] r; delete[] g; delete[] b;
+    for (size_t k = 0; k < n; ++k) { R[k] *= up; G[k] *= up; B[k] *= up; }
+}
+}
+extern "C" int artref_denoise_guided_smoothing(float* R, float* G, float* B, int W, int H, const double* ws9, int guidedChromaRadius, double scale)
+{
+    float ws[3][3]; for (int i = 0; i < 9; ++i) (&ws[0][0])[i] = (float)ws9[i];
+    rtengine::artref_gs(R, G, B, W, H, ws, guidedChromaRadius, scale);
+    return 0;
 }
 
 namespace {
@@ -1660,6 +1701,13 @@ def extract(det):
     gf = os.path.join(RT, "guidedfilter.cc")
     open(os.path.join(sub, "guided_subsampling.inc"), "w").write(cut_function(gf, r"int calculate_subsampling\(int w, int h, int r\)"))
     open(os.path.join(sub, "guided_body.inc"), "w").write(cut_function(gf, r"void guidedFilter\(const array2D<float> &guide[^)]*\)"))
+    open(os.path.join(sub, "guided_log.inc"), "w").write(cut_function(gf, r"^void guidedFilterLog\(const array2D<float> &guide, float base[^)]*\)"))
+    open(os.path.join(sub, "guided_log2.inc"), "w").write(cut_function(gf, r"^void guidedFilterLog\(float base, array2D<float> &chan[^)]*\)"))
+    open(os.path.join(sub, "guided_smoothing.inc"), "w").write(cut_function(os.path.join(RT, "ipsmoothing.cc"), r"^void guided_smoothing\(array2D<float> &R[^)]*\)"))
+    chh = os.path.join(RT, "color.h")
+    open(os.path.join(sub, "gs_rgblum.inc"), "w").write(cut_function(chh, r"static float rgbLuminance\(float r, float g, float b, const T workingspace\[3\]\[3\]\)"))
+    open(os.path.join(sub, "gs_rgb2yuv.inc"), "w").write(cut_function(chh, r"static void rgb2yuv\(float r, float g, float b, float &Y"))
+    open(os.path.join(sub, "gs_yuv2rgb.inc"), "w").write(cut_function(chh, r"static void yuv2rgb\(float Y, float u, float v, float &r"))
     open(os.path.join(sub, "shim_guided.cc"), "w").write(SHIM_GUIDED_TU)
     open(os.path.join(sub, "shim_wavelet.cc"), "w").write(SHIM_WAVELET_TU)
     ft = os.path.join(RT, "FTblockDN.cc")

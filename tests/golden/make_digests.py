@@ -164,6 +164,17 @@ def cases(which):
     out["vng4_130x77_grbg"] = f
 
     def f():
+        import test_oracle_smoothing as tsm
+        return tsm.run(lib, pre + "denoise_guided_smoothing", td.rgb_frame(200, 264, seed=4, noise=2500.0), 3, 1.0)
+    out["guided_smoothing_264x200_r3"] = f
+
+    def f():
+        import test_oracle_hlblend as thl
+        hl = (124000.0, 65535.0, 98000.0)
+        return thl.run(lib, pre + "hl_blend", thl.line(4001, 5, hl), hl)
+    out["hl_blend_4001"] = f
+
+    def f():
         planes = tp.frame(35, 67, 102)
         return [tp.scan(lib, pre + "scanlines", planes, bps, fl).view(np.uint8).astype(np.float32) for bps, fl in ((8, 0), (16, 0), (16, 1))]
     out["scanlines_67x35"] = f
