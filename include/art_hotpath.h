@@ -410,6 +410,10 @@ int art_hp_sharpen_usm_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g
  *                      sharpening steps of STAGE_1..3 (see `sharpen` and `chain` below).
  *                      One host->device copy of the CFA plane, one device->host copy of the three planes.
  *                      denoise == NULL and fattal_enabled == 0 skip their stages, like `enabled = false` does.
+ *                      NOT reproduced yet: for exposure.expcomp > 0 ImProcFunctions::denoise brackets RGB_denoise .. NLMeans between
+ *                      expcomp(+ecomp) and expcomp(-ecomp) (ipdenoise.cc L1155-1163, L1181-1184), and with smoothingEnabled and
+ *                      guidedChromaRadius != 0 it runs denoiseGuidedSmoothing before NLMeans (L1171-1172).  The denoise stage of
+ *                      this entry matches the reference for expcomp <= 0 (or exposure disabled) and guidedChromaRadius == 0.
  */
 typedef struct art_hp_develop_params {
     int method;                 /* ART_HP_BAYER_AMAZE | ART_HP_BAYER_RCD | ART_HP_XTRANS_3PASS | ART_HP_XTRANS_1PASS */
