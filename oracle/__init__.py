@@ -30,7 +30,9 @@ def build(force=False):
     if force or not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs):
         subprocess.check_call(["make", "-C", HERE, "-s", "-B", "libartoracle.so"])
     ref_lib = os.path.join(HERE, "_ref", "libartref_det.so")
-    if os.path.isdir("/root/reference/rtengine") and (force or not os.path.exists(ref_lib)):
+    recipes = [os.path.join(HERE, "build_ref.py"), os.path.join(HERE, "build_ref_tone.py")]
+    if os.path.isdir("/root/reference/rtengine") and (force or not os.path.exists(ref_lib) or
+                                                       any(os.path.getmtime(r) > os.path.getmtime(ref_lib) for r in recipes)):
         subprocess.check_call(["python3", os.path.join(HERE, "build_ref.py")])
 
 

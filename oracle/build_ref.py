@@ -1895,12 +1895,18 @@ def extract(det):
 
 def build(det):
     sub = extract(det)
+    import build_ref_tone
+    build_ref_tone.extract(sub)
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
-    cmd = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-           "-I", sub, "-I", RT, os.path.join(sub, "shim.cc"), os.path.join(sub, "shim_gauss.cc"), os.path.join(sub, "shim_guided.cc"), os.path.join(sub, "shim_wavelet.cc"), os.path.join(sub, "shim_shrink.cc"), os.path.join(sub, "shim_nlmeans.cc"), os.path.join(sub, "shim_denoise.cc"), os.path.join(sub, "shim_fattal.cc"), os.path.join(sub, "shim_chain.cc"), os.path.join(sub, "shim_usm.cc"), os.path.join(sub, "shim_xtrans.cc"), os.path.join(sub, "shim_resize.cc"), os.path.join(sub, "shim_greeneq.cc"), os.path.join(sub, "shim_pack.cc"), os.path.join(sub, "shim_bilinear.cc"), os.path.join(sub, "shim_vng4.cc"), os.path.join(sub, "shim_hlblend.cc"), "-o", lib]
-    if det:
-        cmd.insert(1, "-DARTREF_DET")
-    subprocess.check_call(cmd)
+    tus = ["shim.cc", "shim_gauss.cc", "shim_guided.cc", "shim_wavelet.cc", "shim_shrink.cc", "shim_nlmeans.cc", "shim_denoise.cc", "shim_fattal.cc",
+           "shim_chain.cc", "shim_usm.cc", "shim_xtrans.cc", "shim_resize.cc", "shim_greeneq.cc", "shim_pack.cc", "shim_bilinear.cc", "shim_vng4.cc",
+           "shim_hlblend.cc", "shim_tone.cc"]
+    base = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-w", "-I", sub, "-I", RT] + (["-DARTREF_DET"] if det else [])
+    from concurrent.futures import ThreadPoolExecutor
+    objs = [os.path.join(sub, t[:-3] + ".o") for t in tus]
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:      # one object per translation unit, side by side
+        list(ex.map(subprocess.check_call, [base + ["-c", os.path.join(sub, t), "-o", o] for t, o in zip(tus, objs)]))
+    subprocess.check_call(["g++", "-shared", "-fopenmp", "-o", lib] + objs)
     return lib
 
 

@@ -1,0 +1,307 @@
+"""oracle/_ref, tone-curve translation unit (used by build_ref.py).  TEST INFRASTRUCTURE ONLY.
+
+Hosts the reference's DEFAULT tone-curve path -- ToneCurveParams::TcMode::NEUTRAL, procparams.cc L1585 -- compiled from the
+sources where they lie:
+  curves.h            class Curve, DiagonalCurve, FlatCurve, curves::setLutVal
+  curves.cc           Curve::{Curve, AddPolygons, fillDyByDx, fillHash, ...}, ToneCurve::Set, NeutralToneCurve::BatchApply
+  diagonalcurves.cc   everything (DiagonalCurve)
+  flatcurves.cc       everything (FlatCurve)
+  iptonecurve.cc      ContrastCurve, expand_range, satcurve_lut, SatCurveRemap, apply_satcurve, DoubleCurve and the curve
+                      assembly of ImProcFunctions::toneCurve (the `expand` / `adjust` lambdas, L601-650)
+  color.cc / color.h  XYZ_D50_to_D65, XYZ_D65_to_D50, PQ, PQ_inv, xyz2jzazbz, jzazbz2xyz, yuv2hsl, hsl2yuv, filmlike_clip, the
+                      rgb2jzczhz / jzczhz2rgb family, rgbxyz, xyz2rgb
+Written here (not reference code): the Color table initialisation restating color.cc L236-256, L322-326, the ApplyState
+constructor body without ICCStore (matrices come in as arguments) and the C wrappers.
+"""
+import os
+import re
+
+from build_ref import RT, cut_function
+
+SHIM_TONE_TU = r"""
+#include <assert.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include <omp.h>
+#include "LUT.h"
+#include "rt_math.h"
+#include "opthelper.h"
+#include "sleef.h"
+#include "linalgebra.h"
+#include "iccmatrices.h"
+
+enum DiagonalCurveType { DCT_Empty = -1, DCT_Linear, DCT_Spline, DCT_Parametric, DCT_NURBS, DCT_CatmullRom, DCT_Unchanged };   // rtgui/mydiagonalcurve.h L31-40
+enum FlatCurveType { FCT_Empty = -1, FCT_Linear, FCT_MinMaxCPoints, FCT_Unchanged };                                           // rtgui/myflatcurve.h L29-36
+#define CURVES_MIN_POLY_POINTS 1000                                                                                            // rtgui/mycurve.h
+
+namespace artref_tone {
+using namespace rtengine;
+typedef const float (*TMatrix)[3];      // iccstore.h L38
+struct Settings { int verbose; };
+static const Settings settings_ = {0};
+static const Settings* settings = &settings_;
+
+namespace {
+typedef Vec3f A3;
+#include "tone_color_anon.inc"
+}
+
+class Color {
+public:
+    constexpr static double sRGBGammaCurve = 2.4;
+    static LUTf gamma2curve, igammatab_srgb, gammatab_srgb, jzazbz_pq_, jzazbz_pq_inv_;
+#include "tone_color_h.inc"
+    static void init()
+    {   // color.cc L236-256, L322-326
+        if (gammatab_srgb) return;
+        const int maxindex = 65536;
+        igammatab_srgb(maxindex, 0); gammatab_srgb(maxindex, 0); jzazbz_pq_(maxindex, 0); jzazbz_pq_inv_(maxindex, 0);
+        for (int i = 0; i < maxindex; i++) gammatab_srgb[i] = gamma2(i / 65535.0);
+        gammatab_srgb *= 65535.f;
+        gamma2curve.share(gammatab_srgb, LUT_CLIP_BELOW | LUT_CLIP_ABOVE);
+        for (int i = 0; i < maxindex; i++) igammatab_srgb[i] = igamma2(i / 65535.0);
+        igammatab_srgb *= 65535.f;
+        for (int i = 0; i < maxindex; ++i) { jzazbz_pq_[i] = PQ(float(i) / 65535.f); jzazbz_pq_inv_[i] = PQ_inv(float(i) / 65535.f); }
+    }
+    static void rgbxyz (float r, float g, float b, float &x, float &y, float &z, const float xyz_rgb[3][3]);
+    static void xyz2rgb (float x, float y, float z, float &r, float &g, float &b, const float rgb_xyz[3][3]);
+    static void filmlike_clip(float *r, float *g, float *b, float Lmax);
+    static void yuv2hsl(float u, float v, float &h, float &s);
+    static void hsl2yuv(float h, float s, float &u, float &v);
+    static void xyz2jzazbz(float X, float Y, float Z, float &Jz, float &az, float &bz);
+    static void jzazbz2xyz(float Jz, float az, float bz, float &X, float &Y, float &Z);
+};
+LUTf Color::gamma2curve, Color::igammatab_srgb, Color::gammatab_srgb, Color::jzazbz_pq_, Color::jzazbz_pq_inv_;
+#include "tone_color_cc.inc"
+
+#include "tone_curve_classes.inc"
+#include "tone_curve_base.inc"
+namespace { inline double CLIPD(double d) { return std::max(d, 0.0); } }
+#include "tone_diag.inc"
+#include "tone_flat.inc"
+
+namespace curves {
+#include "tone_setlutval.inc"
+}
+class ToneCurve { public: LUTf lutToneCurve; float whitecoeff; float whitept; const Curve* curve; ToneCurve() : whitecoeff(1.f), whitept(65535.f), curve(nullptr) {}
+    void Set(const Curve &pCurve, float whitecoeff=1.f); };
+#include "tone_toneset.inc"
+class NeutralToneCurve: public ToneCurve {
+public:
+    struct ApplyState {
+        const Curve *basecurve;
+        float ws[3][3];
+        float iws[3][3];
+        Mat33<float> to_work;
+        Mat33<float> to_out;
+        float rhue, bhue, yhue, rrange, brange, yrange;
+        // the constructor of curves.cc L854-888 with the matrices ICCStore would return passed in; om = nullptr is the
+        // "no matrix for this output profile" branch (identity)
+        ApplyState(const float work[3][3], const float iwork[3][3], const float (*om_)[3], const Curve* base)
+        {
+            basecurve = base;
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { ws[i][j] = work[i][j]; iws[i][j] = iwork[i][j]; }
+            if (om_) {
+                Mat33<float> om(om_);
+                auto iom = inverse(om);
+                to_out = dot_product(iom, Mat33<float>(work));
+                to_work = dot_product(Mat33<float>(iwork), om);
+            } else { to_out = identity<float>(); to_work = identity<float>(); }
+            float j, c;
+            const auto hws = xyz_rec2020;
+            Color::rgb2jzczhz(1, 0, 0, j, c, rhue, hws);
+            Color::rgb2jzczhz(0, 0, 1, j, c, bhue, hws);
+            Color::rgb2jzczhz(1, 1, 0, j, c, yhue, hws);
+            float ohue;
+            Color::rgb2jzczhz(1, 0.5, 0, j, c, ohue, hws);
+            yrange = std::abs(ohue - yhue) * 0.8f;
+            rrange = std::abs(ohue - rhue);
+            brange = rrange;
+        }
+    };
+    void BatchApply(const size_t start, const size_t end, float *r, float *g, float *b, const ApplyState &state) const;
+};
+#include "tone_batchapply.inc"
+
+struct Plane { float* base; int W; float& operator()(int y, int x) { return base[(size_t)y * W + x]; } };
+struct Imagefloat { int width, height; Plane r, g, b; int getWidth() const { return width; } int getHeight() const { return height; } };
+struct WsHolder { const float (*ws)[3]; const float (*iws)[3]; };
+static WsHolder g_ws;
+struct ICCStore { static ICCStore* getInstance() { static ICCStore s; return &s; }
+    TMatrix workingSpaceMatrix(const std::string&) { return g_ws.ws; } TMatrix workingSpaceInverseMatrix(const std::string&) { return g_ws.iws; } };
+namespace Glib { typedef std::string ustring; }
+
+namespace {
+#include "tone_iptonecurve.inc"
+}
+
+// the curve assembly of ImProcFunctions::toneCurve for one (possibly contrast-prefixed) curve pair, iptonecurve.cc L596-650
+struct Built {
+    std::unique_ptr<Curve> ccurve; std::unique_ptr<DiagonalCurve> t1, t2; std::unique_ptr<DoubleCurve> d, dc; Curve* tcurve;
+};
+static void build(Built& B, const double* c1, int n1, const double* c2, int n2, int contrast, float whitept, double scale, double pivot_gray)
+{
+    struct { struct { std::vector<double> curve, curve2; } toneCurve; } P; auto* params = &P;
+    P.toneCurve.curve.assign(c1, c1 + n1); P.toneCurve.curve2.assign(c2, c2 + n2);
+    if (contrast) {        // get_contrast_curve, L335-349 (pivot_gray = logenc.enabled ? targetGray / 100 : 0.18)
+        const double pivot = pivot_gray / whitept;
+        const double c = std::pow(std::abs(contrast) / 100.0, 1.5) * 16.0;
+        const double b = contrast > 0 ? (1 + c) : 1.0 / (1 + c);
+        const double a = std::log((std::exp(std::log(b) * pivot) - 1) / (b - 1)) / std::log(pivot);
+        B.ccurve.reset(new ContrastCurve(a, b, whitept));
+    }
+#include "tone_assembly.inc"
+    B.t2.reset(new DiagonalCurve(adjust(params->toneCurve.curve2), CURVES_MIN_POLY_POINTS / max(int(scale), 1)));
+    B.t1.reset(new DiagonalCurve(adjust(params->toneCurve.curve), CURVES_MIN_POLY_POINTS / max(int(scale), 1)));
+    B.d.reset(new DoubleCurve(*B.t1, *B.t2));
+    B.tcurve = B.d.get();
+    if (B.ccurve) { B.dc.reset(new DoubleCurve(*B.ccurve, *B.d)); B.tcurve = B.dc.get(); }
+}
+
+struct PolyPeek : public DiagonalCurve { using DiagonalCurve::poly_x; using DiagonalCurve::poly_y; using DiagonalCurve::kind; };
+
+extern "C" {
+// LUT of ToneCurve::Set for the single-curve case (curveMode == curveMode2): lut[65536]; which = 0 the whole chain, 1 curve 1
+// alone, 2 curve 2 alone, 3 the contrast curve alone (the two-curve mode's separate passes); returns 1 when that curve is
+// the identity (the reference then skips the pass), else 0
+int artref_tone_build_lut(const double* c1, int n1, const double* c2, int n2, int contrast, float whitept, double scale, int which, float* lut)
+{
+    Color::init();
+    Built B; build(B, c1, n1, c2, n2, contrast, whitept, scale, 0.18);
+    const Curve* c = which == 0 ? B.tcurve : which == 1 ? (Curve*)B.t1.get() : which == 2 ? (Curve*)B.t2.get() : (Curve*)B.ccurve.get();
+    if (!c) return 1;
+    ToneCurve tc; tc.Set(*c, whitept);
+    for (int i = 0; i < 65536; ++i) lut[i] = tc.lutToneCurve[i];
+    return c->isIdentity() ? 1 : 0;
+}
+// the polyline DiagonalCurve::getVal(DCT_CatmullRom) searches (which = 1 | 2); returns the point count (0 = identity curve), fills up to cap
+int artref_tone_polyline(const double* c1, int n1, const double* c2, int n2, float whitept, double scale, int which, double* px, double* py, int cap)
+{
+    Color::init();
+    Built B; build(B, c1, n1, c2, n2, 0, whitept, scale, 0.18);
+    const PolyPeek* p = static_cast<const PolyPeek*>(which == 1 ? B.t1.get() : B.t2.get());
+    if (p->kind == DCT_Empty) return 0;
+    const int n = (int)p->poly_x.size();
+    for (int i = 0; i < n && i < cap; ++i) { px[i] = p->poly_x[i]; py[i] = p->poly_y[i]; }
+    return n;
+}
+// contrast curve parameters a, b of get_contrast_curve
+int artref_tone_contrast_ab(int contrast, float whitept, double* ab)
+{
+    const double pivot = 0.18 / whitept;
+    const double c = std::pow(std::abs(contrast) / 100.0, 1.5) * 16.0;
+    const double b = contrast > 0 ? (1 + c) : 1.0 / (1 + c);
+    ab[0] = std::log((std::exp(std::log(b) * pivot) - 1) / (b - 1)) / std::log(pivot); ab[1] = b;
+    return 0;
+}
+double artref_tone_curve_eval(const double* c1, int n1, const double* c2, int n2, int contrast, float whitept, double scale, double t)
+{
+    Color::init();
+    Built B; build(B, c1, n1, c2, n2, contrast, whitept, scale, 0.18);
+    return B.tcurve->getVal(t);
+}
+// apply_tc(NEUTRAL) over the whole single-curve chain: R, G, B in place.  om9: the output profile's matrix or NULL
+int artref_tone_neutral(float* R, float* G, float* B_, int W, int H, const double* c1, int n1, const double* c2, int n2, int contrast, float whitept, double scale,
+                        const float* ws9, const float* iws9, const float* om9)
+{
+    Color::init();
+    Built B; build(B, c1, n1, c2, n2, contrast, whitept, scale, 0.18);
+    NeutralToneCurve tc; tc.Set(*B.tcurve, whitept);
+    NeutralToneCurve::ApplyState state((const float (*)[3])ws9, (const float (*)[3])iws9, (const float (*)[3])om9, nullptr);
+#pragma omp parallel for
+    for (int y = 0; y < H; ++y) tc.BatchApply(0, W, R + (size_t)y * W, G + (size_t)y * W, B_ + (size_t)y * W, state);
+    return 0;
+}
+// satcurve_lut: the 65536-entry table apply_satcurve reads at white point 1
+int artref_tone_satlut(const double* sc, int ns, double scale, float* lut)
+{
+    Color::init();
+    std::vector<double> pts(sc, sc + ns);
+    const FlatCurve satlcurve(pts, false, CURVES_MIN_POLY_POINTS / max(int(scale), 1));
+    if (satlcurve.isIdentity()) return 1;
+    LUTf sat; satcurve_lut(satlcurve, sat, 1.f);
+    for (int i = 0; i < 65536; ++i) lut[i] = sat[i];
+    return 0;
+}
+// apply_satcurve (white point 1 or not; saturation2 = sc2)
+int artref_tone_satcurve(float* R, float* G, float* B_, int W, int H, const double* sc, int ns, const double* sc2, int ns2, float whitept, double scale,
+                         const float* ws9, const float* iws9)
+{
+    Color::init();
+    std::vector<double> pts(sc, sc + ns), pts2(sc2, sc2 + ns2);
+    const FlatCurve satlcurve(pts, false, CURVES_MIN_POLY_POINTS / max(int(scale), 1));
+    const DiagonalCurve satccurve(pts2);
+    if (satlcurve.isIdentity() && satccurve.isIdentity()) return 1;
+    g_ws.ws = (const float (*)[3])ws9; g_ws.iws = (const float (*)[3])iws9;
+    Imagefloat im{W, H, {R, W}, {G, W}, {B_, W}};
+    apply_satcurve(&im, satlcurve, satccurve, "", whitept, true);
+    return 0;
+}
+int artref_tone_tables(float* pq, float* pq_inv, float* gamma2curve)
+{
+    Color::init();
+    for (int i = 0; i < 65536; ++i) { if (pq) pq[i] = Color::jzazbz_pq_[i]; if (pq_inv) pq_inv[i] = Color::jzazbz_pq_inv_[i]; if (gamma2curve) gamma2curve[i] = Color::gamma2curve[i]; }
+    return 0;
+}
+}
+}  // namespace artref_tone
+"""
+
+
+def between(text, start_regex, end_regex):
+    m0 = re.search(start_regex, text, flags=re.M)
+    if not m0:
+        raise RuntimeError("anchor %r not found" % start_regex)
+    m1 = re.search(end_regex, text[m0.start():], flags=re.M)
+    if not m1:
+        raise RuntimeError("anchor %r not found" % end_regex)
+    return text[m0.start(): m0.start() + m1.start()]
+
+
+def extract(sub):
+    rd = lambda p: open(p, encoding="utf-8", errors="replace").read()
+    cc, ch = os.path.join(RT, "color.cc"), os.path.join(RT, "color.h")
+    cvh, cvc = os.path.join(RT, "curves.h"), os.path.join(RT, "curves.cc")
+    ipt = os.path.join(RT, "iptonecurve.cc")
+    w = lambda name, text: open(os.path.join(sub, name), "w").write(text)
+    w("tone_color_anon.inc", "\n".join([
+        cut_function(cc, r"^void XYZ_D50_to_D65\(float &X, float &Y, float &Z\)"),
+        cut_function(cc, r"^void XYZ_D65_to_D50\(float &X, float &Y, float &Z\)"),
+        cut_function(cc, r"^float PQ\(float X\)"), cut_function(cc, r"^float PQ_inv\(float X\)"),
+        cut_function(cc, r"^inline void filmlike_clip_rgb_tone\(float \*r, float \*g, float \*b, const float L\)")]))
+    htext = rd(ch)
+    w("tone_color_h.inc", "\n".join([
+        cut_function(ch, r"static inline double gamma2\(double x\)"), cut_function(ch, r"static inline double igamma2\(double x\)"),
+        between(htext, r"^    template <class T>\n    static void rgb2jzazbz\(", r"^    static void xyz2oklab\(")]))
+    w("tone_color_cc.inc", "\n".join([
+        cut_function(cc, r"^void Color::rgbxyz \(float r, float g, float b, float &x, float &y, float &z, const float xyz_rgb"),
+        cut_function(cc, r"^void Color::xyz2rgb \(float x, float y, float z, float &r, float &g, float &b, const float rgb_xyz"),
+        cut_function(cc, r"^void Color::filmlike_clip\(float \*r, float \*g, float \*b, float Lmax\)"),
+        cut_function(cc, r"^void Color::yuv2hsl\(float u, float v, float &h, float &s\)"),
+        cut_function(cc, r"^void Color::hsl2yuv\(float h, float s, float &u, float &v\)"),
+        cut_function(cc, r"^void Color::xyz2jzazbz\(float X, float Y, float Z, float &Jz, float &az, float &bz\)"),
+        cut_function(cc, r"^void Color::jzazbz2xyz\(float Jz, float az, float bz, float &X, float &Y, float &Z\)")]))
+    w("tone_curve_classes.inc", between(rd(cvh), r"^class Curve \{", r"^namespace curves \{"))
+    w("tone_curve_base.inc", between(rd(cvc), r"^Curve::Curve \(\)", r"^void ToneCurve::Reset\(\)"))
+    w("tone_diag.inc", between(rd(os.path.join(RT, "diagonalcurves.cc")), r"^DiagonalCurve::DiagonalCurve\(", r"^\} // namespace rtengine"))
+    ftext = rd(os.path.join(RT, "flatcurves.cc"))
+    w("tone_flat.inc", ftext[re.search(r"^FlatCurve::FlatCurve \(", ftext, flags=re.M).start(): ftext.rindex("}")])
+    w("tone_setlutval.inc", cut_function(cvh, r"^inline void setLutVal\(const LUTf &lut, const Curve \*curve, float &val\)"))
+    w("tone_toneset.inc", cut_function(cvc, r"^void ToneCurve::Set\(const Curve &pCurve, float whitecoeff\)"))
+    w("tone_batchapply.inc", cut_function(cvc, r"^void NeutralToneCurve::BatchApply\("))
+    w("tone_iptonecurve.inc", "\n".join([
+        cut_function(ipt, r"^class ContrastCurve: public Curve") + ";",
+        cut_function(ipt, r"^float expand_range\(float whitept, float x\)"),
+        cut_function(ipt, r"^void satcurve_lut\(const FlatCurve &curve, LUTf &sat, float whitept\)"),
+        cut_function(ipt, r"^class SatCurveRemap") + ";",
+        cut_function(ipt, r"^void apply_satcurve\(Imagefloat \*rgb, const FlatCurve &curve"),
+        cut_function(ipt, r"^class DoubleCurve: public Curve") + ";"]))
+    w("tone_assembly.inc", between(rd(ipt), r"^        const auto expand =", r"^        DiagonalCurve tcurve2\("))
+    w("shim_tone.cc", SHIM_TONE_TU)
+    return os.path.join(sub, "shim_tone.cc")
