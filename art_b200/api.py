@@ -211,6 +211,12 @@ class SharpenParams:
                                float(self.edges_radius), int(self.edges_tolerance))
 
 
+class _CurveStageC(ctypes.Structure):      # art_hp_curve_stage
+    _dp = ctypes.POINTER(ctypes.c_double)
+    _fields_ = [("kind", ctypes.c_int), ("poly_x", _dp), ("poly_y", _dp), ("n", ctypes.c_int),
+                ("a", ctypes.c_double), ("b", ctypes.c_double), ("w", ctypes.c_double)]
+
+
 class _ChainParamsC(ctypes.Structure):
     _fp, _dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
     _fields_ = [("exposure_enabled", ctypes.c_int), ("exp_scale", ctypes.c_float), ("black", ctypes.c_float),
@@ -218,15 +224,21 @@ class _ChainParamsC(ctypes.Structure):
                 ("tonecurve_mode", ctypes.c_int), ("tonecurve_lut", _fp),
                 ("rcurve", _fp), ("gcurve", _fp), ("bcurve", _fp),
                 ("lab_enabled", ctypes.c_int), ("lab_lcurve", _fp), ("lab_acurve", _fp), ("lab_bcurve", _fp), ("lab_chroma", ctypes.c_float),
-                ("ws", _dp), ("iws", _dp)]
+                ("ws", _dp), ("iws", _dp),
+                ("tonecurve_whitept", ctypes.c_float), ("tonecurve_stages", ctypes.POINTER(_CurveStageC)), ("tonecurve_nstages", ctypes.c_int),
+                ("neutral_to_out", _fp), ("neutral_to_work", _fp), ("satcurve_lut", _fp)]
 
 
 class ChainParams:
     """Parameters of art_hp_color_chain: the per-pixel stages of ImProcFunctions::process (improcfun.cc L567-641).
     exposure = (expcomp EV, black) as in procparams::ExposureParams; saturation = (saturation, vibrance) integers;
-    tonecurve = (mode, 65536-entry LUT); rgbcurves = three LUTs or None each; lab = (L LUT of 32770, a LUT, b LUT, chroma)."""
+    tonecurve = (mode, 65536-entry LUT) with mode 0 STD, 1 FILMLIKE, 2 NEUTRAL (ToneCurveParams::TcMode, the reference default);
+    whitept = ToneCurve::whitecoeff; stages = the Curve::getVal chain above the LUT as (kind, poly_x, poly_y, a, b, w) tuples
+    (art_hp_curve_stage); to_out / to_work = NeutralToneCurve::ApplyState's 3x3 float matrices or None; satcurve = apply_satcurve's
+    65536-entry table; rgbcurves = three LUTs or None each; lab = (L LUT of 32770, a LUT, b LUT, chroma)."""
 
-    def __init__(self, exposure=None, saturation=None, tonecurve=None, rgbcurves=None, lab=None, ws=None, iws=None):
+    def __init__(self, exposure=None, saturation=None, tonecurve=None, rgbcurves=None, lab=None, ws=None, iws=None,
+                 whitept=1.0, stages=None, to_out=None, to_work=None, satcurve=None):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
@@ -265,6 +277,25 @@ class ChainParams:
             c.lab_lcurve, c.lab_acurve, c.lab_bcurve = lut(self.lab[0], 32770), lut(self.lab[1], 65536), lut(self.lab[2], 65536)
             c.lab_chroma = float(self.lab[3])
         c.ws, c.iws = mat(self.ws), mat(self.iws)
+        c.tonecurve_whitept = float(self.whitept)
+        if self.stages:
+            arr = (_CurveStageC * len(self.stages))()
+            dp = ctypes.POINTER(ctypes.c_double)
+            for i, (kind, px, py, ca, cb, cw) in enumerate(self.stages):
+                arr[i].kind = int(kind)
+                if int(kind) == 1:
+                    px, py = np.ascontiguousarray(px, np.float64), np.ascontiguousarray(py, np.float64)
+                    self._keep += [px, py]
+                    arr[i].poly_x, arr[i].poly_y, arr[i].n = px.ctypes.data_as(dp), py.ctypes.data_as(dp), int(px.size)
+                arr[i].a, arr[i].b, arr[i].w = float(ca), float(cb), float(cw)
+            self._keep.append(arr)
+            c.tonecurve_stages, c.tonecurve_nstages = arr, len(self.stages)
+        for name, m in (("neutral_to_out", self.to_out), ("neutral_to_work", self.to_work)):
+            if m is not None:
+                v = np.ascontiguousarray(m, np.float32).reshape(9)
+                self._keep.append(v)
+                setattr(c, name, v.ctypes.data_as(fp))
+        c.satcurve_lut = lut(self.satcurve, 65536)
         return c
 
 

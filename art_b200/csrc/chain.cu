@@ -26,7 +26,10 @@ struct ChainArgs {
     float *r, *g, *b; size_t pitch; int W, H;
     int do_exp; float exp_scale, black;
     int do_sat, vib_on; float saturation, vibrance, noise, wy0, wy1, wy2;
-    int tc_mode; const float* tc_lut; float Lmax;
+    int tc_mode; const float* tc_lut; float Lmax, whitecoeff;
+    const art_hp_curve_stage* stages; int nstages;           // device copies (poly arrays in device memory)
+    const float *pq, *pq_inv, *satlut, *hues;                 // jzazbz_pq_, jzazbz_pq_inv_ (color.cc L322-326), satcurve_lut's table, ApplyState's hue constants
+    float to_out[9], to_work[9];
     const float *rc, *gc, *bc;
     int do_lab; const float *lc, *ac, *bcl; float chroma; const float *cachef, *cachefy;
     float ws[9], iws[9];
@@ -94,15 +97,6 @@ __device__ __forceinline__ void filmlike_clip(float& r, float& g, float& b, floa
         else clip_tone(g, b, r, L);
     }
 }
-__device__ __forceinline__ void set_lut_val(const float* __restrict__ lut, float& v) { v = lut_s(lut, 65536, CLIP_BELOW | CLIP_ABOVE, maxr(v, 0.f)); }
-__device__ __forceinline__ void rgb_tone(const float* __restrict__ lut, float& r, float& g, float& b)
-{   // curves.h L462-472
-    const float rold = r, gold = g, bold = b;
-    set_lut_val(lut, r);
-    set_lut_val(lut, b);
-    g = b + ((r - b) * (gold - bold) / (rold - bold));
-}
-
 constexpr float D50X = 0.9642f, D50Z = 0.8249f;
 __device__ __forceinline__ float xyz2lab_f(const float* __restrict__ cachef, float f)
 {   // Color::computeXYZ2Lab, color.cc L1247-1259
@@ -126,6 +120,208 @@ __device__ __forceinline__ float f2xyz(float f)
     return (f > epsilonExpInv3f) ? f * f * f : (116.f * f - 16.f) * kappaInvf;
 }
 
+
+// ---- the reference's default tone curve: NeutralToneCurve::BatchApply (curves.cc L891-1037) and apply_satcurve (iptonecurve.cc L398-441) ----
+__device__ __forceinline__ float powf_cr(float a, float b) { return (float)pow((double)a, (double)b); }   // glibc powf is correctly rounded but for rare ties
+__device__ __forceinline__ float pq_fn(float X)
+{   // color.cc L67-74
+    X = X < 1e-10f ? 1e-10f : X;
+    const float XX = powf_cr(X * 1e-4f, 0.1593017578125f);
+    return powf_cr((0.8359375f + 18.8515625f * XX) / (1 + 18.6875f * XX), 134.034375f);
+}
+__device__ __forceinline__ float pq_inv_fn(float X)
+{   // color.cc L77-84
+    X = X < 1e-10f ? 1e-10f : X;
+    const float XX = powf_cr(X, 7.460772656268214e-03f);
+    return 1e4f * powf_cr((0.8359375f - XX) / (18.6875f * XX - 18.8515625f), 6.277394636015326f);
+}
+__device__ __forceinline__ void mat3(const float* m, float a, float b, float c, float& x, float& y, float& z)
+{
+    x = m[0] * a + m[1] * b + m[2] * c;
+    y = m[3] * a + m[4] * b + m[5] * c;
+    z = m[6] * a + m[7] * b + m[8] * c;
+}
+__device__ __forceinline__ void xyz2jzazbz(const float* __restrict__ pq, float X, float Y, float Z, float& Jz, float& az, float& bz)
+{   // color.cc L6706-6722, XYZ_D50_to_D65 L37-49
+    const float x = 0.9555766f * X + -0.0230393f * Y + 0.0631636f * Z;
+    const float y = -0.0282895f * X + 1.0099416f * Y + 0.0210077f * Z;
+    const float z = 0.0122982f * X + -0.0204830f * Y + 1.3299098f * Z;
+    const float l = 0.674207838f * x + 0.382799340f * y - 0.047570458f * z;
+    const float m = 0.149284160f * x + 0.739628340f * y + 0.083327300f * z;
+    const float s = 0.070941080f * x + 0.174768000f * y + 0.670970020f * z;
+    const float Lp = (l >= 0.f && l <= 1.f) ? lut_s(pq, 65536, 0, l * 65535.f) : pq_fn(l);
+    const float Mp = (m >= 0.f && m <= 1.f) ? lut_s(pq, 65536, 0, m * 65535.f) : pq_fn(m);
+    const float Sp = (s >= 0.f && s <= 1.f) ? lut_s(pq, 65536, 0, s * 65535.f) : pq_fn(s);
+    const float Iz = 0.5f * (Lp + Mp);
+    az = 3.524000f * Lp - 4.066708f * Mp + 0.542708f * Sp;
+    bz = 0.199076f * Lp + 1.096799f * Mp - 1.295875f * Sp;
+    Jz = (0.44f * Iz) / (1.f - 0.56f * Iz) - 1.6295499532821566e-11f;
+}
+__device__ __forceinline__ void jzazbz2xyz(const float* __restrict__ pqi, float Jz, float az, float bz, float& X, float& Y, float& Z)
+{   // color.cc L6724-6742, XYZ_D65_to_D50 L52-64
+    Jz = Jz + 1.6295499532821566e-11f;
+    const float Iz = Jz / (0.44f + 0.56f * Jz);
+    const float l = Iz + 1.386050432715393e-1f * az + 5.804731615611869e-2f * bz;
+    const float m = Iz - 1.386050432715393e-1f * az - 5.804731615611891e-2f * bz;
+    const float s = Iz - 9.601924202631895e-2f * az - 8.118918960560390e-1f * bz;
+    const float L = (l >= 0.f && l <= 1.f) ? lut_s(pqi, 65536, 0, l * 65535.f) : pq_inv_fn(l);
+    const float M = (m >= 0.f && m <= 1.f) ? lut_s(pqi, 65536, 0, m * 65535.f) : pq_inv_fn(m);
+    const float S = (s >= 0.f && s <= 1.f) ? lut_s(pqi, 65536, 0, s * 65535.f) : pq_inv_fn(s);
+    const float x = +1.661373055774069e+00f * L - 9.145230923250668e-01f * M + 2.313620767186147e-01f * S;
+    const float y = -3.250758740427037e-01f * L + 1.571847038366936e+00f * M - 2.182538318672940e-01f * S;
+    const float z = -9.098281098284756e-02f * L - 3.127282905230740e-01f * M + 1.522766561305260e+00f * S;
+    X = 1.0478112f * x + 0.0228866f * y + -0.0501270f * z;
+    Y = 0.0295424f * x + 0.9904844f * y + -0.0170491f * z;
+    Z = -0.0092345f * x + 0.0150436f * y + 0.7521316f * z;
+}
+__device__ __forceinline__ void rgb2jzczhz(const float* __restrict__ pq, const float* ws, float R, float G, float B, float& Jz, float& cz, float& hz)
+{   // color.h L1791-1796; jzazbz2jzch = yuv2hsl(bz, az, h, c), color.cc L6691-6695
+    float X, Y, Z, az, bz;
+    mat3(ws, R, G, B, X, Y, Z);
+    xyz2jzazbz(pq, X, Y, Z, Jz, az, bz);
+    cz = sqrtf(bz * bz + az * az);
+    hz = sleef::xatan2f(bz, az);
+}
+__device__ __forceinline__ void jzczhz2rgb(const float* __restrict__ pqi, const float* iws, float Jz, float cz, float hz, float& R, float& G, float& B)
+{   // color.h L1799-1804; jzch2jzazbz = hsl2yuv(h, c, bz, az), color.cc L6698-6703
+    float sn, cs, X, Y, Z;
+    sleef::xsincosf(hz, sn, cs);
+    jzazbz2xyz(pqi, Jz, cz * cs, cz * sn, X, Y, Z);
+    mat3(iws, X, Y, Z, R, G, B);
+}
+// Curve::getVal of the composed curve above the LUT, stage by stage (see art_hp_curve_stage)
+__device__ __noinline__ double curve_eval(const art_hp_curve_stage* __restrict__ st, int n, double t)
+{
+    for (int s = 0; s < n; ++s) {
+        if (st[s].kind == 1) {
+            const double* __restrict__ px = st[s].poly_x; const int np = st[s].n;
+            int lo = 0, hi = np;
+            while (lo < hi) { const int mid = (lo + hi) / 2; if (px[mid] < t) lo = mid + 1; else hi = mid; }
+            if (lo == np) { t = st[s].poly_y[np - 1]; continue; }
+            int d = lo;
+            if (lo + 1 < np && t - px[lo] > px[lo + 1] - t) ++d;
+            const double v = st[s].poly_y[d];
+            t = v < 0.0 ? 0.0 : v;
+        } else if (st[s].kind == 2) {
+            const double w = st[s].w;
+            double x = w < t ? w : t;
+            x = x < 0.0 ? 0.0 : x;
+            const double p = pow(x / w, st[s].a);
+            t = log(p * (st[s].b - 1.0) + 1.0) / log(st[s].b) * w;
+        }
+    }
+    return t;
+}
+// curves::setLutVal, curves.h L224-231
+__device__ __forceinline__ void set_lut_val_c(const ChainArgs& a, float& v)
+{
+    if (v <= 65535.f || !a.nstages) v = lut_s(a.tc_lut, 65536, CLIP_BELOW | CLIP_ABOVE, maxr(v, 0.f));
+    else v = (float)(curve_eval(a.stages, a.nstages, (double)(v / 65535.f)) * 65535.f);
+}
+__device__ __forceinline__ void rgb_tone(const ChainArgs& a, float& r, float& g, float& b)
+{   // curves.h L462-472
+    const float rold = r, gold = g, bold = b;
+    set_lut_val_c(a, r);
+    set_lut_val_c(a, b);
+    g = b + ((r - b) * (gold - bold) / (rold - bold));
+}
+__device__ __forceinline__ float lim01(float a) { const float m = 1.f < a ? 1.f : a; return 0.f < m ? m : 0.f; }
+__device__ __forceinline__ float gauss_hue(float x, float b, float c) { return sleef::xexpf_scalar(-((x - b) * (x - b)) / (2 * (c * c))); }
+
+__device__ __noinline__ void neutral_tone(const ChainArgs& a, float& R, float& G, float& B)
+{
+    const float th[3] = {0.85f, 0.75f, 0.95f};
+    const float dl[3] = {1.1f, 1.2f, 1.5f};
+    const float PI_F_180 = (float)(3.14159265358979323846 / 180.0);
+    const float whitept = 65535.f * a.whitecoeff;
+    float rgb[3], jl, jc, jh;
+    rgb[0] = R / 65535.f; rgb[0] = rgb[0] < 0.f ? 0.f : rgb[0];
+    rgb[1] = G / 65535.f; rgb[1] = rgb[1] < 0.f ? 0.f : rgb[1];
+    rgb[2] = B / 65535.f; rgb[2] = rgb[2] < 0.f ? 0.f : rgb[2];
+    rgb2jzczhz(a.pq, a.ws, rgb[0], rgb[1], rgb[2], jl, jc, jh);
+    const float ilum = jl;
+    float hue = jh;
+    const float iY = (rgb[0] + rgb[1] + rgb[2]) / 3.f;
+    {
+        float x = 0.f, y = 0.f, z = 0.f;
+        x += a.to_out[0] * rgb[0]; x += a.to_out[1] * rgb[1]; x += a.to_out[2] * rgb[2];
+        y += a.to_out[3] * rgb[0]; y += a.to_out[4] * rgb[1]; y += a.to_out[5] * rgb[2];
+        z += a.to_out[6] * rgb[0]; z += a.to_out[7] * rgb[1]; z += a.to_out[8] * rgb[2];
+        rgb[0] = x; rgb[1] = y; rgb[2] = z;
+    }
+    float ac = rgb[0] < rgb[1] ? rgb[1] : rgb[0];
+    ac = ac < rgb[2] ? rgb[2] : ac;
+    const float aac = fabsf(ac);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float d = ac != 0.f ? (ac - rgb[k]) / aac : 0.f;
+        const float s = (1.f - th[k]) / sqrtf(dl[k] - 1.f);
+        const float cd = d < th[k] ? d : s * sqrtf(d - th[k] + (s * s) / 4.0f) - s * sqrtf((s * s) / 4.0f) + th[k];
+        rgb[k] = ac - cd * aac;
+    }
+    {
+        float x = 0.f, y = 0.f, z = 0.f;
+        x += a.to_work[0] * rgb[0]; x += a.to_work[1] * rgb[1]; x += a.to_work[2] * rgb[2];
+        y += a.to_work[3] * rgb[0]; y += a.to_work[4] * rgb[1]; y += a.to_work[5] * rgb[2];
+        z += a.to_work[6] * rgb[0]; z += a.to_work[7] * rgb[1]; z += a.to_work[8] * rgb[2];
+        rgb[0] = x; rgb[1] = y; rgb[2] = z;
+    }
+    const float oY = (rgb[0] + rgb[1] + rgb[2]) / 3.f;
+    if (oY > 0.f) {
+        const float f = iY / oY;
+        rgb[0] *= f; rgb[1] *= f; rgb[2] *= f;
+        filmlike_clip(rgb[0], rgb[1], rgb[2], whitept);       // Lmax = ToneCurve::whitept = 65535 * whitecoeff on [0, 1] data, as the reference has it
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float nt = rgb[j] * 65535.f;
+        set_lut_val_c(a, nt);
+        rgb[j] = nt / 65535.f;
+    }
+    rgb2jzczhz(a.pq, a.ws, rgb[0], rgb[1], rgb[2], jl, jc, jh);
+    const float rhue = a.hues[0], bhue = a.hues[1], yhue = a.hues[2], rrange = a.hues[3], brange = a.hues[4], yrange = a.hues[5];
+    float hue_shift = 15.f * PI_F_180 * gauss_hue(hue, rhue, rrange);
+    hue_shift += -5.f * PI_F_180 * gauss_hue(hue, bhue, brange);
+    hue_shift *= lim01((rgb[0] + rgb[1] + rgb[2]) / (3.f * a.whitecoeff));
+    hue += hue_shift;
+    float sat = jc;
+    {
+        const float olum = jl;
+        float ccf = ilum > 1e-5f ? (1.f - (lim01((olum / ilum) - 1.f) * 0.2f)) : 1.f;
+        ccf = lim01(ccf + 0.5f * gauss_hue(hue, yhue, yrange));
+        sat *= ccf;
+    }
+    jzczhz2rgb(a.pq_inv, a.iws, jl, sat, hue, rgb[0], rgb[1], rgb[2]);
+    float v;
+    v = rgb[0] * 65535.f; v = whitept < v ? whitept : v; R = 0.f < v ? v : 0.f;
+    v = rgb[1] * 65535.f; v = whitept < v ? whitept : v; G = 0.f < v ? v : 0.f;
+    v = rgb[2] * 65535.f; v = whitept < v ? whitept : v; B = 0.f < v ? v : 0.f;
+}
+__device__ __noinline__ void sat_curve(const ChainArgs& a, float& R, float& G, float& B)
+{
+    float X, Y, Z, Jz, az, bz;
+    mat3(a.ws, R / 65535.f, G / 65535.f, B / 65535.f, X, Y, Z);
+    xyz2jzazbz(a.pq, X, Y, Z, Jz, az, bz);
+    float cz = sqrtf(bz * bz + az * az);
+    const float hz = sleef::xatan2f(bz, az);
+    cz *= lut_s(a.satlut, 65536, CLIP_BELOW, Y * 65535.f);
+    float r, g, b;
+    jzczhz2rgb(a.pq_inv, a.iws, Jz, cz, hz, r, g, b);
+    R = r * 65535.f; G = g * 65535.f; B = b * 65535.f;
+}
+// ApplyState's hue constants (curves.cc L877-887), computed once with the same device arithmetic
+__global__ void k_tone_hues(const float* __restrict__ pq, float* __restrict__ out)
+{
+    const float rec2020[9] = {0.6734241f, 0.1656411f, 0.1251286f, 0.2790177f, 0.6753402f, 0.0456377f, -0.0019300f, 0.0299784f, 0.7973330f};
+    float j, c, rh, bh, yh, oh;
+    rgb2jzczhz(pq, rec2020, 1.f, 0.f, 0.f, j, c, rh);
+    rgb2jzczhz(pq, rec2020, 0.f, 0.f, 1.f, j, c, bh);
+    rgb2jzczhz(pq, rec2020, 1.f, 1.f, 0.f, j, c, yh);
+    rgb2jzczhz(pq, rec2020, 1.f, 0.5f, 0.f, j, c, oh);
+    out[0] = rh; out[1] = bh; out[2] = yh;
+    out[3] = fabsf(oh - rh); out[4] = out[3]; out[5] = fabsf(oh - yh) * 0.8f;
+}
+
 // everything before the Lab stage, one pixel; VEC = the pixel sits in a 4-wide SSE2 group of the reference's row loops
 template <bool VEC>
 __device__ __forceinline__ void rgb_stages(const ChainArgs& a, float& r, float& g, float& b)
@@ -144,23 +340,26 @@ __device__ __forceinline__ void rgb_stages(const ChainArgs& a, float& r, float& 
         g = maxr(l + a.saturation * gl, a.noise);
         b = maxr(l + a.saturation * bl, a.noise);
     }
-    if (a.tc_mode >= 0) {
+    if (a.tc_mode == 2) {
+        neutral_tone(a, r, g, b);
+    } else if (a.tc_mode >= 0) {
         filmlike_clip(r, g, b, a.Lmax);
-        if (a.tc_mode == 0) { set_lut_val(a.tc_lut, r); set_lut_val(a.tc_lut, g); set_lut_val(a.tc_lut, b); }
+        if (a.tc_mode == 0) { set_lut_val_c(a, r); set_lut_val_c(a, g); set_lut_val_c(a, b); }
         else {
             r = maxr(0.f, minr(r, a.Lmax)); g = maxr(0.f, minr(g, a.Lmax)); b = maxr(0.f, minr(b, a.Lmax));
             if (r >= g) {
-                if (g > b) rgb_tone(a.tc_lut, r, g, b);
-                else if (b > r) rgb_tone(a.tc_lut, b, r, g);
-                else if (b > g) rgb_tone(a.tc_lut, r, b, g);
-                else { set_lut_val(a.tc_lut, r); set_lut_val(a.tc_lut, g); b = g; }
+                if (g > b) rgb_tone(a, r, g, b);
+                else if (b > r) rgb_tone(a, b, r, g);
+                else if (b > g) rgb_tone(a, r, b, g);
+                else { set_lut_val_c(a, r); set_lut_val_c(a, g); b = g; }
             } else {
-                if (r >= b) rgb_tone(a.tc_lut, g, r, b);
-                else if (b > g) rgb_tone(a.tc_lut, b, g, r);
-                else rgb_tone(a.tc_lut, g, b, r);
+                if (r >= b) rgb_tone(a, g, r, b);
+                else if (b > g) rgb_tone(a, b, g, r);
+                else rgb_tone(a, g, b, r);
             }
         }
     }
+    if (a.satlut) sat_curve(a, r, g, b);
     if (a.rc) r = VEC ? lut_v(a.rc, 65536, r) : lut_s(a.rc, 65536, 0, r);
     if (a.gc) g = VEC ? lut_v(a.gc, 65536, g) : lut_s(a.gc, 65536, 0, g);
     if (a.bc) b = VEC ? lut_v(a.bc, 65536, b) : lut_s(a.bc, 65536, 0, b);
@@ -272,52 +471,88 @@ __global__ void __launch_bounds__(256) k_chain(ChainArgs A)
 
 }  // namespace
 
-// LUT slots in the context's device / pinned staging: 0 tone curve, 1-3 rgb curves, 4 L curve, 5-6 a / b curves, 7-8 cachef / cachefy
+// LUT slots in the context's device / pinned staging: 0 tone curve, 1-3 rgb curves, 4 L curve, 5-6 a / b curves, 7-8 cachef / cachefy,
+// 9-10 jzazbz_pq_ / jzazbz_pq_inv_, 11 the saturation curve's table, 12 ApplyState's hue constants (device-computed)
 constexpr size_t LUT_SLOT = 65536 + 64;
+constexpr int N_SLOTS = 13;
+constexpr int STAGE_SLOTS = 4;     // pinned staging only: the curve stages above the LUT when they fit (1 MB), else a pageable copy
 
 int art_chain_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch, const art_hp_chain_params* p)
 {
+    // every check comes before the first upload: a rejected call leaves the staging buffer and its event untouched
     if ((pitch & 3) || (reinterpret_cast<uintptr_t>(r) & 15) || (reinterpret_cast<uintptr_t>(g) & 15) || (reinterpret_cast<uintptr_t>(b) & 15))
         return ctx->fail(ART_HP_ERR_INVALID, "planes must be 16-byte aligned with a pitch that is a multiple of 4 floats");
+    const int do_sat = p->saturation_enabled && (p->saturation || p->vibrance);
+    const int tc_mode = p->tonecurve_lut ? p->tonecurve_mode : -1;
+    const bool jz = tc_mode == 2 || p->satcurve_lut;
+    if ((do_sat || p->lab_enabled || jz) && !p->ws) return ctx->fail(ART_HP_ERR_INVALID, "ws is required by the saturation, NEUTRAL tone curve and Lab stages");
+    if (jz && !p->iws) return ctx->fail(ART_HP_ERR_INVALID, "the NEUTRAL tone curve and the saturation curve need iws");
+    if (p->lab_enabled && (!p->iws || !p->lab_lcurve || !p->lab_acurve || !p->lab_bcurve)) return ctx->fail(ART_HP_ERR_INVALID, "Lab stage needs iws and the three curves");
+    if (tc_mode > 2) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "tone curve mode %d", tc_mode);
+    const float whitecoeff = p->tonecurve_whitept > 0.f ? p->tonecurve_whitept : 1.f;
+    const int nstages = (tc_mode >= 0 && p->tonecurve_stages) ? p->tonecurve_nstages : 0;
+    if (nstages < 0 || nstages > 4) return ctx->fail(ART_HP_ERR_INVALID, "tonecurve_nstages %d (0..4)", nstages);
+    for (int i = 0; i < nstages; ++i) {
+        const art_hp_curve_stage& st = p->tonecurve_stages[i];
+        if (st.kind < 0 || st.kind > 2) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "curve stage kind %d", st.kind);
+        if (st.kind == 1 && (st.n < 1 || !st.poly_x || !st.poly_y)) return ctx->fail(ART_HP_ERR_INVALID, "curve stage %d: empty polyline", i);
+        if (st.kind == 2 && !(st.w > 0.0 && st.b > 0.0 && st.b != 1.0)) return ctx->fail(ART_HP_ERR_INVALID, "curve stage %d: contrast curve parameters", i);
+    }
     cudaStream_t st = ctx->stream;
-    int rc = art_reserve(ctx, ctx->d_chain, 9 * LUT_SLOT * sizeof(float));
+    int rc = art_reserve(ctx, ctx->d_chain, N_SLOTS * LUT_SLOT * sizeof(float));
     if (rc) return rc;
     float* d = (float*)ctx->d_chain.p;
     if (!ctx->h_chain) {
-        ART_CUDA(ctx, cudaMallocHost(&ctx->h_chain, 9 * LUT_SLOT * sizeof(float)));
+        ART_CUDA(ctx, cudaMallocHost(&ctx->h_chain, (N_SLOTS + STAGE_SLOTS) * LUT_SLOT * sizeof(float)));
         ART_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chain, cudaEventDisableTiming));
     } else {
         ART_CUDA(ctx, cudaEventSynchronize(ctx->ev_chain));        // the previous call's uploads left the staging buffer
     }
     float* h = (float*)ctx->h_chain;
-    if (!ctx->chain_cache_ready) {      // Color::cachef / cachefy, color.cc L205-233 (host libm cbrt, as in the reference)
-        float* cf = h + 7 * LUT_SLOT; float* cfy = h + 8 * LUT_SLOT;
+    cudaError_t up_err = cudaSuccess;
+    if (!ctx->chain_cache_ready) {      // Color::cachef / cachefy, color.cc L205-233 (host libm cbrt, as in the reference); jzazbz_pq_ / _inv_, L322-326 (host powf)
+        float* cf = h + 7 * LUT_SLOT; float* cfy = h + 8 * LUT_SLOT; float* pq = h + 9 * LUT_SLOT; float* pqi = h + 10 * LUT_SLOT;
         const double eps = 216.0 / 24389.0, kappa = 24389.0 / 27.0, MAXVALF = 65535.f;
         const int epsmaxint = (int)(MAXVALF * eps);
         int i = 0;
         for (; i <= epsmaxint; i++) { cf[i] = (float)(327.68 * ((kappa * i / MAXVALF + 16.0) / 116.0)); cfy[i] = (float)(327.68 * (kappa * i / MAXVALF)); }
         for (; i < 65536; i++) { cf[i] = (float)(327.68 * std::cbrt((double)i / MAXVALF)); cfy[i] = (float)(327.68 * (116.0 * std::cbrt((double)i / MAXVALF) - 16.0)); }
         cf[65536] = cf[65535]; cfy[65536] = cfy[65535];
-        ART_CUDA(ctx, cudaMemcpyAsync(d + 7 * LUT_SLOT, cf, 2 * LUT_SLOT * sizeof(float), cudaMemcpyHostToDevice, st));
-        ctx->chain_cache_ready = true;
+        for (i = 0; i < 65536; ++i) {
+            float X = (float)i / 65535.f;
+            X = std::max(X, 1e-10f);
+            const float XX = std::pow(X * 1e-4f, 0.1593017578125f);
+            pq[i] = std::pow((0.8359375f + 18.8515625f * XX) / (1 + 18.6875f * XX), 134.034375f);
+            const float XI = std::pow(X, 7.460772656268214e-03f);
+            pqi[i] = 1e4f * std::pow((0.8359375f - XI) / (18.6875f * XI - 18.8515625f), 6.277394636015326f);
+        }
+        pq[65536] = pq[65535]; pqi[65536] = pqi[65535];
+        up_err = cudaMemcpyAsync(d + 7 * LUT_SLOT, cf, 4 * LUT_SLOT * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (up_err == cudaSuccess) {
+            k_tone_hues<<<1, 1, 0, st>>>(d + 9 * LUT_SLOT, d + 12 * LUT_SLOT);
+            ctx->launches++;
+            ctx->chain_cache_ready = true;
+        }
     }
     auto up = [&](int slot, const float* src, int n) -> const float* {
         if (!src) return nullptr;
         memcpy(h + slot * LUT_SLOT, src, sizeof(float) * n);
         h[slot * LUT_SLOT + n] = src[n - 1];       // LUT<T> allocates s + 3 entries; data[size] is touched (times a zero weight) at the top index
-        cudaMemcpyAsync(d + slot * LUT_SLOT, h + slot * LUT_SLOT, sizeof(float) * (n + 1), cudaMemcpyHostToDevice, st);
+        const cudaError_t e = cudaMemcpyAsync(d + slot * LUT_SLOT, h + slot * LUT_SLOT, sizeof(float) * (n + 1), cudaMemcpyHostToDevice, st);
+        if (up_err == cudaSuccess) up_err = e;
         return d + slot * LUT_SLOT;
     };
     ChainArgs a{};
     a.r = r; a.g = g; a.b = b; a.pitch = pitch; a.W = W; a.H = H;
     a.do_exp = p->exposure_enabled; a.exp_scale = p->exp_scale; a.black = p->black;
-    a.do_sat = p->saturation_enabled && (p->saturation || p->vibrance);
+    a.do_sat = do_sat;
     a.vib_on = p->vibrance != 0;
     a.saturation = 1.f + p->saturation / 100.f;
     a.vibrance = 1.f - p->vibrance / 1000.f;
-    a.tc_mode = p->tonecurve_lut ? p->tonecurve_mode : -1;
+    a.tc_mode = tc_mode;
     a.tc_lut = up(0, p->tonecurve_lut, 65536);
-    a.Lmax = 65535.f * 1.f;
+    a.whitecoeff = whitecoeff;
+    a.Lmax = 65535.f * whitecoeff;
     a.rc = up(1, p->rcurve, 65536); a.gc = up(2, p->gcurve, 65536); a.bc = up(3, p->bcurve, 65536);
     a.do_lab = p->lab_enabled;
     if (a.do_lab) {
@@ -325,12 +560,49 @@ int art_chain_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, s
         a.chroma = p->lab_chroma;
         a.cachef = d + 7 * LUT_SLOT; a.cachefy = d + 8 * LUT_SLOT;
     }
-    if ((a.do_sat || a.do_lab) && !p->ws) return ctx->fail(ART_HP_ERR_INVALID, "ws is required by saturation and Lab stages");
-    if (a.do_lab && (!p->iws || !p->lab_lcurve || !p->lab_acurve || !p->lab_bcurve)) return ctx->fail(ART_HP_ERR_INVALID, "Lab stage needs iws and the three curves");
-    if (a.tc_mode > 1) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "tone curve mode %d", a.tc_mode);
+    a.pq = d + 9 * LUT_SLOT; a.pq_inv = d + 10 * LUT_SLOT; a.hues = d + 12 * LUT_SLOT;
+    a.satlut = up(11, p->satcurve_lut, 65536);
+    static const float ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int i = 0; i < 9; ++i) { a.to_out[i] = p->neutral_to_out ? p->neutral_to_out[i] : ident[i]; a.to_work[i] = p->neutral_to_work ? p->neutral_to_work[i] : ident[i]; }
     if (p->ws) { a.wy0 = (float)p->ws[3]; a.wy1 = (float)p->ws[4]; a.wy2 = (float)p->ws[5]; for (int i = 0; i < 9; ++i) a.ws[i] = (float)p->ws[i]; }
     if (p->iws) for (int i = 0; i < 9; ++i) a.iws[i] = (float)p->iws[i];
-    ART_CUDA(ctx, cudaEventRecord(ctx->ev_chain, st));
+    ART_CUDA(ctx, cudaEventRecord(ctx->ev_chain, st));        // recorded on every path that queued an upload
+    if (up_err != cudaSuccess) return ctx->fail(ART_HP_ERR_CUDA, "curve upload failed: %s", cudaGetErrorString(up_err));
+    if (nstages) {
+        // the stages above the LUT: descriptors + polylines in one device block.  Only samples above 65535 read them; when a
+        // polyline ends at or below 1 (white point 1) every such sample lies beyond it and the last point alone decides
+        size_t doubles = 0;
+        int keep[4];
+        for (int i = 0; i < nstages; ++i) {
+            const art_hp_curve_stage& s = p->tonecurve_stages[i];
+            keep[i] = s.kind != 1 ? 0 : (i == 0 && s.poly_x[s.n - 1] <= 1.0) ? 1 : s.n;
+            doubles += 2 * (size_t)keep[i];
+        }
+        const size_t hdr = round_up(4 * sizeof(art_hp_curve_stage), 256);
+        if ((rc = art_reserve(ctx, ctx->d_chain_stages, hdr + doubles * sizeof(double)))) return rc;
+        const size_t total = hdr + doubles * sizeof(double);
+        char* hbase;
+        if (total <= STAGE_SLOTS * LUT_SLOT * sizeof(float)) hbase = reinterpret_cast<char*>(h + N_SLOTS * LUT_SLOT);     // pinned, guarded by ev_chain (re-recorded below)
+        else { ctx->h_chain_stages.assign(total, 0); hbase = ctx->h_chain_stages.data(); }       // pageable: cudaMemcpyAsync stages it before returning
+        memset(hbase, 0, hdr);
+        art_hp_curve_stage* hd = reinterpret_cast<art_hp_curve_stage*>(hbase);
+        double* hp = reinterpret_cast<double*>(hbase + hdr);
+        double* dp = reinterpret_cast<double*>((char*)ctx->d_chain_stages.p + hdr);
+        size_t off = 0;
+        for (int i = 0; i < nstages; ++i) {
+            hd[i] = p->tonecurve_stages[i];
+            if (hd[i].kind == 1) {
+                const int n = keep[i], skip = hd[i].n - n;
+                memcpy(hp + off, hd[i].poly_x + skip, n * sizeof(double)); hd[i].poly_x = dp + off; off += n;
+                memcpy(hp + off, p->tonecurve_stages[i].poly_y + skip, n * sizeof(double)); hd[i].poly_y = dp + off; off += n;
+                hd[i].n = n;
+            }
+        }
+        ART_CUDA(ctx, cudaMemcpyAsync(ctx->d_chain_stages.p, hbase, total, cudaMemcpyHostToDevice, st));
+        ART_CUDA(ctx, cudaEventRecord(ctx->ev_chain, st));
+        a.stages = reinterpret_cast<const art_hp_curve_stage*>(ctx->d_chain_stages.p);
+        a.nstages = nstages;
+    }
     const dim3 blk(64, 1), grid(((W + 3) / 4 + 63) / 64, std::min(H, 148 * 16));
     art_prof_begin(ctx, "k_chain");
     k_chain<<<grid, blk, 0, st>>>(a);

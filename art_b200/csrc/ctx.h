@@ -51,6 +51,8 @@ struct art_hp_ctx {
     void* h_chain = nullptr;
     cudaEvent_t ev_chain = nullptr;
     bool chain_cache_ready = false;
+    DevBuf d_chain_stages;               // Curve::getVal stages above the tone-curve LUT (descriptors + polylines)
+    std::vector<char> h_chain_stages;
     DevBuf d_usm_tables;                 // apply_gamma's two 65536-entry LUTs (gamma 1/3 and 3), built once on the device
     bool usm_tables_ready = false;
     DevBuf d_bl_lut;                     // edges-only sharpening: the bilateral filter's range LUT (0x20000 floats), host-built

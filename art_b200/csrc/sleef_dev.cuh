@@ -144,4 +144,63 @@ __device__ __forceinline__ float xcbrtf_scalar(float d)
 __device__ __forceinline__ float pow_F_scalar(float a, float b) { return xexpf_scalar(b * xlogf_scalar(a)); }
 __device__ __forceinline__ float xlin2log_scalar(float x, float base) { return xlogf_scalar(x * (base - 1.f) + 1.f) / xlogf_scalar(base); }
 
+// xlog2lin, sleef.h L1309-1313
+__device__ __forceinline__ float xlog2lin_scalar(float x, float base) { return (pow_F_scalar(base, x) - 1.f) / (base - 1.f); }
+
+__device__ __forceinline__ float mulsignf(float x, float y) { return __int_as_float(__float_as_int(x) ^ (__float_as_int(y) & 0x80000000)); }
+__device__ __forceinline__ float atan2kf(float y, float x)
+{   // sleef.h L1155-1177
+    float s, t, u, q = 0.f;
+    if (x < 0) { x = -x; q = -2.f; }
+    if (y > x) { t = x; x = y; y = -t; q += 1.f; }
+    s = y / x;
+    t = s * s;
+    u = 0.00282363896258175373077393f;
+    u = u * t + -0.0159569028764963150024414f;
+    u = u * t + 0.0425049886107444763183594f;
+    u = u * t + -0.0748900920152664184570312f;
+    u = u * t + 0.106347933411598205566406f;
+    u = u * t + -0.142027363181114196777344f;
+    u = u * t + 0.199926957488059997558594f;
+    u = u * t + -0.333331018686294555664062f;
+    t = u * t;
+    t = t * s + s;
+    return q * (float)(3.14159265358979323846 / 2.0) + t;
+}
+__device__ __forceinline__ float xatan2f(float y, float x)
+{   // sleef.h L1179-1188
+    const float PI_F = (float)3.14159265358979323846;
+    float r = atan2kf(fabsf(y), x);
+    r = mulsignf(r, x);
+    if (isinf(x) || x == 0) r = PI_F / 2 - (isinf(x) ? (copysignf(1.f, x) * (float)(PI_F * .5f)) : 0);
+    if (isinf(y)) r = PI_F / 2 - (isinf(x) ? (copysignf(1.f, x) * (float)(PI_F * .25f)) : 0);
+    if (y == 0) r = (copysignf(1.f, x) == -1 ? PI_F : 0);
+    return (x != x) || (y != y) ? __int_as_float(0x7fc00000) : mulsignf(r, y);
+}
+__device__ __forceinline__ void xsincosf(float d, float& sn, float& cs)
+{   // sleef.h L1048-1052 -> sleefsseavx.h L1051-1101 (an SSE2 build routes the scalar call through the vector form)
+    const float A = 0.78515625f * 2, B = 0.00024127960205078125f * 2, C = 6.3329935073852539062e-07f * 2, D = 4.9604681473525147339e-10f * 2;
+    const int q = __float2int_rn(d * (float)(2.0 / 3.14159265358979323846));
+    float u = (float)q, s = d, t, rx, ry;
+    s = u * -A + s; s = u * -B + s; s = u * -C + s; s = u * -D + s;
+    t = s;
+    s = s * s;
+    u = -0.000195169282960705459117889f;
+    u = u * s + 0.00833215750753879547119141f;
+    u = u * s + -0.166666537523269653320312f;
+    u = (u * s) * t;
+    rx = t + u;
+    u = -2.71811842367242206819355e-07f;
+    u = u * s + 2.47990446951007470488548e-05f;
+    u = u * s + -0.00138888787478208541870117f;
+    u = u * s + 0.0416666641831398010253906f;
+    u = u * s + -0.5f;
+    ry = 1.f + s * u;
+    float x = (q & 1) == 0 ? rx : ry, y = (q & 1) == 0 ? ry : rx;
+    if ((q & 2) == 2) x = -x;
+    if (((q + 1) & 2) == 2) y = -y;
+    if (isinf(d)) { x = __int_as_float(0x7fc00000); y = x; }
+    sn = x; cs = y;
+}
+
 }  // namespace sleef

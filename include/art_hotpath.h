@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ART_HP_ABI_VERSION 1
+#define ART_HP_ABI_VERSION 2
 
 typedef enum art_hp_status {
     ART_HP_OK = 0,
@@ -339,7 +339,9 @@ int art_hp_scale_convert_dev(art_hp_ctx* ctx, int W, int H,
  *                      exp_scale = pow(2, expcomp) and black = params black * 2000, L33-34); STAGE_3 saturationVibrance
  *                      (rtengine/ipsaturation.cc L44-83), toneCurve (rtengine/iptonecurve.cc L553-716 for its per-pixel LUT
  *                      branch: filmlike_clip then StandardToneCurve::Apply [tonecurve_mode 0] or AdobeToneCurve::Apply [1],
- *                      rtengine/curves.h L360-368, L425-472, white point 1), rgbCurves (rtengine/iprgbcurves.cc L113-146) and
+ *                      rtengine/curves.h L360-368, L425-472; or, tonecurve_mode 2, the reference's default single NEUTRAL curve:
+ *                      NeutralToneCurve::BatchApply, rtengine/curves.cc L891-1037, base curve LINEAR, no filmlike_clip pass before
+ *                      it, iptonecurve.cc L581-589; then apply_satcurve, L398-441), rgbCurves (rtengine/iprgbcurves.cc L113-146) and
  *                      labAdjustments (rtengine/iplabadjustments.cc L252-283 between Imagefloat::setMode(LAB) and the
  *                      setMode(RGB) of the next stage, rtengine/imagefloat.cc L841-878, L949-972).
  *                      Curves stay host-built (rtengine/curves.cc) and are passed by pointer as the LUT<float> data they fill:
@@ -347,14 +349,38 @@ int art_hp_scale_convert_dev(art_hp_ctx* ctx, int W, int H,
  *                      reference's `enabled == false` / identity-curve early-outs.  In place on three planes.
  *                      Bit-identical to the reference's SSE2 build, 4-pixel groups and scalar row tails included.
  */
+/* One stage of the Curve::getVal chain the reference composes with DoubleCurve (rtengine/iptonecurve.cc L525-551, L652-658).
+ * curves::setLutVal (rtengine/curves.h L224-231) reads the 65536-entry LUT for samples <= 65535 and calls Curve::getVal above
+ * it -- and NeutralToneCurve::BatchApply never clips (its filmlike_clip runs with Lmax = 65535 * whitecoeff on [0, 1] data,
+ * rtengine/curves.cc L893, L989), so over-range samples take that branch even at white point 1.  The curve objects stay
+ * host-built; a stage is what one of them evaluates:
+ *   kind 0  identity (DiagonalCurve of kind DCT_Empty)
+ *   kind 1  DiagonalCurve::getVal for DCT_CatmullRom (rtengine/diagonalcurves.cc L511-522) -- the kind every tone curve has
+ *           after ImProcFunctions::toneCurve's `adjust` (iptonecurve.cc L604-650): nearest point of the polyline poly_x / poly_y
+ *           (n doubles each, the curve's own members), the last y above the last x
+ *   kind 2  ContrastCurve::getVal (iptonecurve.cc L104-121): lin2log(pow(LIM(x, 0, w) / w, a), b) * w */
+typedef struct art_hp_curve_stage {
+    int kind;
+    const double* poly_x; const double* poly_y; int n;
+    double a, b, w;
+} art_hp_curve_stage;
+
 typedef struct art_hp_chain_params {
     int   exposure_enabled;  float exp_scale, black;
     int   saturation_enabled, saturation, vibrance;      /* procparams::SaturationParams, integers as in the GUI */
-    int   tonecurve_mode;    const float* tonecurve_lut;  /* 0 = STD, 1 = FILMLIKE; NULL = no tone curve */
+    int   tonecurve_mode;    const float* tonecurve_lut;  /* 0 = STD, 1 = FILMLIKE, 2 = NEUTRAL (the reference default); NULL = no tone curve */
     const float *rcurve, *gcurve, *bcurve;                /* rgbCurves LUTs, each may be NULL */
     int   lab_enabled;       const float *lab_lcurve, *lab_acurve, *lab_bcurve;  float lab_chroma;
     const double* ws;        /* ICCStore::workingSpaceMatrix, 9 doubles (saturation luminance, rgb -> Lab) */
     const double* iws;       /* ICCStore::workingSpaceInverseMatrix, 9 doubles (Lab -> rgb) */
+    /* ---- ABI version 2 ---- */
+    float tonecurve_whitept;                              /* ToneCurve::whitecoeff (params->toneCurve.whitePoint when hasWhitePoint()); 0 reads as 1 */
+    const art_hp_curve_stage* tonecurve_stages;           /* the curve above the LUT, applied first to last; NULL / 0 = `curve == nullptr` (LUT only) */
+    int   tonecurve_nstages;
+    const float *neutral_to_out, *neutral_to_work;        /* NeutralToneCurve::ApplyState::to_out / to_work (curves.cc L866-875), 9 floats each;
+                                                             NULL = identity (no matrix for the output profile) */
+    const float* satcurve_lut;                            /* apply_satcurve's table (satcurve_lut, iptonecurve.cc L365-374), 65536 floats; NULL = identity
+                                                             saturation curve.  White point 1 and identity `saturation2` only */
 } art_hp_chain_params;
 int art_hp_color_chain(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b,
                        const art_hp_chain_params* params);

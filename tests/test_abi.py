@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, "declared in include/art_hotpath.h but not exported: %s" % missing
     for s in api.ABI_SYMBOLS:
         assert getattr(lib, s) is not None
-    assert lib.art_hp_abi_version() == 1
+    assert lib.art_hp_abi_version() == 2
 
 
 def test_header_is_plain_c():
@@ -68,7 +68,9 @@ def test_ctypes_structs_match_the_header(tmp_path):
         "art_hp_develop_params": (api._DevelopParamsC, ["method", "filters", "initialGain", "border", "mul", "doClip", "cam2work", "denoise",
                                                          "nlStrength", "fattal_enabled", "fattal_satcontrol", "wprof", "sharpen", "chain", "xtrans", "rgb_cam"]),
         "art_hp_chain_params": (api._ChainParamsC, ["exposure_enabled", "exp_scale", "black", "saturation_enabled", "vibrance", "tonecurve_mode",
-                                                     "tonecurve_lut", "rcurve", "bcurve", "lab_enabled", "lab_lcurve", "lab_bcurve", "lab_chroma", "ws", "iws"]),
+                                                     "tonecurve_lut", "rcurve", "bcurve", "lab_enabled", "lab_lcurve", "lab_bcurve", "lab_chroma", "ws", "iws",
+                                                     "tonecurve_whitept", "tonecurve_stages", "tonecurve_nstages", "neutral_to_out", "neutral_to_work", "satcurve_lut"]),
+        "art_hp_curve_stage": (api._CurveStageC, ["kind", "poly_x", "poly_y", "n", "a", "b", "w"]),
         "art_hp_sharpen_params": (api._SharpenParamsC, ["contrast", "radius", "amount", "threshold", "edgesonly", "halocontrol", "halocontrol_amount", "scale", "method", "deconvradius", "deconvamount", "deconvCornerBoost", "deconvCornerLatitude", "offset_x", "full_height", "edges_radius", "edges_tolerance"]),
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "art_hotpath.h"', 'int main(void){']
