@@ -99,6 +99,9 @@ def load_library(build_if_missing=True):
         "art_hp_develop": (i, [vp, vp, i, i, vp, vp, vp, vp]),
         "art_hp_develop_dev": (i, [vp, vp, i, i, vp, sz, vp, vp, vp, sz]),
         "art_hp_develop_submit": (i, [vp, vp, i, i, vp, vp, vp, vp]),
+        "art_hp_develop_size": (i, [vp, i, i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]),
+        "art_hp_denoise_guided_smoothing": (i, [vp, i, i, vp, vp, vp, vp, i, d]),
+        "art_hp_denoise_guided_smoothing_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, i, d]),
         "art_hp_develop_wait": (i, [vp]),
         "art_hp_develop_pending": (i, [vp]),
         "art_hp_fattal": (i, [vp, i, i, vp, vp, vp, i, i, i, ctypes.POINTER(d)]),
@@ -183,7 +186,8 @@ class _DevelopParamsC(ctypes.Structure):
                 ("fattal_enabled", ctypes.c_int), ("fattal_threshold", ctypes.c_int), ("fattal_amount", ctypes.c_int),
                 ("fattal_satcontrol", ctypes.c_int), ("wprof", ctypes.POINTER(ctypes.c_double)),
                 ("sharpen", ctypes.c_void_p), ("chain", ctypes.c_void_p),
-                ("xtrans", ctypes.POINTER(ctypes.c_int)), ("rgb_cam", ctypes.POINTER(ctypes.c_float))]
+                ("xtrans", ctypes.POINTER(ctypes.c_int)), ("rgb_cam", ctypes.POINTER(ctypes.c_float)),
+                ("full_frame", ctypes.c_int), ("guidedChromaRadius", ctypes.c_int), ("denoise_expcomp", ctypes.c_double)]
 
 
 class _SharpenParamsC(ctypes.Structure):
@@ -300,12 +304,21 @@ class ChainParams:
 
 
 class DevelopParams:
-    """Parameters of art_hp_develop: the simpleprocess.cc stages on the hot path (demosaic, gains + matrix, denoise, Fattal)."""
+    """Parameters of art_hp_develop: the simpleprocess.cc stages on the hot path (demosaic, gains + matrix, denoise, Fattal, sharpening,
+    the colour chain).  Like the reference the frame is cropped by the raw border after the demosaic (4 px for Bayer, 7 for X-Trans)
+    unless full_frame; guided_chroma_radius / nl_strength are DenoiseParams' smoothing fields (0 unless smoothingEnabled);
+    denoise_expcomp = the exposure compensation ImProcFunctions::denoise brackets its stage with when positive."""
 
     def __init__(self, method=0, filters=0x94949494, initial_gain=1.0, border=4, mul=(1.0, 1.0, 1.0), do_clip=True, cam2work=None,
-                 denoise=None, nl_strength=0, nl_detail=80, fattal=None, wprof=None, sharpen=None, chain=None, xtrans=None, rgb_cam=None):
+                 denoise=None, nl_strength=0, nl_detail=80, fattal=None, wprof=None, sharpen=None, chain=None, xtrans=None, rgb_cam=None,
+                 full_frame=False, guided_chroma_radius=0, denoise_expcomp=0.0):
         self.__dict__.update(locals())
         del self.__dict__["self"]
+
+    def out_shape(self, H, W):
+        """(rows, columns) of the developed planes for an (H, W) raw frame"""
+        b = 0 if self.full_frame else (7 if self.method in (2, 3) else max(int(self.border), 0))
+        return H - 2 * b, W - 2 * b
 
     def c_struct(self):
         c = _DevelopParamsC()
@@ -326,6 +339,7 @@ class DevelopParams:
             self._keep.append(d)
             c.denoise = ctypes.pointer(d)
         c.nlStrength, c.nlDetail = int(self.nl_strength), int(self.nl_detail)
+        c.full_frame, c.guidedChromaRadius, c.denoise_expcomp = int(bool(self.full_frame)), int(self.guided_chroma_radius), float(self.denoise_expcomp)
         if self.fattal is not None:
             thr, amt, sat = self.fattal
             c.fattal_enabled, c.fattal_threshold, c.fattal_amount, c.fattal_satcontrol = 1, int(thr), int(amt), int(bool(sat))
@@ -570,7 +584,8 @@ class HotPath:
     def develop(self, raw, params, red=None, green=None, blue=None):
         """art_hp_develop on a host (H, W) float32 CFA plane; returns the three developed planes."""
         H, W = raw.shape
-        out = [p if p is not None else np.empty((H, W), np.float32) for p in (red, green, blue)]
+        out = [p if p is not None else np.empty(params.out_shape(H, W), np.float32) for p in (red, green, blue)]
+        assert all(p.shape == params.out_shape(H, W) for p in out), "output planes must be %s" % (params.out_shape(H, W),)
         c = params.c_struct()
         self._check(self.lib.art_hp_develop(self.h, ctypes.byref(c), W, H, row_table(raw), row_table(out[0]), row_table(out[1]), row_table(out[2])))
         return out
@@ -629,6 +644,12 @@ class HotPath:
     def color_chain_dev(self, W, H, d_r, d_g, d_b, pitch, params):
         c = params.c_struct()
         self._check(self.lib.art_hp_color_chain_dev(self.h, W, H, d_r, d_g, d_b, pitch, ctypes.byref(c)))
+
+    def denoise_guided_smoothing(self, r, g, b, ws, guided_chroma_radius=3, scale=1.0):
+        """denoise::denoiseGuidedSmoothing, in place on three host (H, W) float32 planes."""
+        H, W = r.shape
+        wsc = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(ws, dtype=np.float64).reshape(9)])
+        self._check(self.lib.art_hp_denoise_guided_smoothing(self.h, W, H, row_table(r), row_table(g), row_table(b), wsc, int(guided_chroma_radius), float(scale)))
 
     def fattal(self, r, g, b, threshold, amount, satcontrol, ws):
         """ImProcFunctions::dynamicRangeCompression (ToneMapFattal02), in place on three host (H, W) float32 planes."""

@@ -12,16 +12,19 @@ from . import dist as adist
 class BatchQueue:
     """`jobs`: a sequence of callables (or arrays) giving each job's (H, W) float32 CFA plane; `params`: DevelopParams (one for all
     jobs or one per job).  Iterating yields (job_index, [red, green, blue]) in submission order; the yielded planes are views of
-    the queue's pinned buffers and are valid until the next-but-one iteration (copy them out, as the reference saves the file)."""
+    the queue's pinned buffers and are valid only until the next iteration -- resuming the generator writes the next raw frame into
+    the same slot and queues kernels that overwrite its planes (copy them out, as the reference saves the file)."""
 
     def __init__(self, hot_path, jobs, params, rank=0, world=1):
         self.hp, self.jobs, self.params = hot_path, jobs, params
         self.mine = adist.frames_for_rank(len(jobs), rank, world)
         self._slots = None
 
-    def _slot(self, k, H, W):
-        if self._slots is None or self._slots[0][0].array.shape != (H, W):
-            self._slots = [[self.hp.pinned(H, W) for _ in range(4)] for _ in range(2)]
+    def _slot(self, k, H, W, params):
+        Ho, Wo = params.out_shape(H, W)
+        if self._slots is None or self._slots[0][0].array.shape != (H, W) or self._slots[0][1].array.shape != (Ho, Wo):
+            # frames in flight keep their own slots alive through `inflight`; new shapes get new buffers
+            self._slots = [[self.hp.pinned(H, W)] + [self.hp.pinned(Ho, Wo) for _ in range(3)] for _ in range(2)]
         return self._slots[k & 1]
 
     def _params_of(self, j):
@@ -37,7 +40,7 @@ class BatchQueue:
                 self.hp.develop_wait()
                 done = inflight.pop(0)
                 yield done[0], [p.array for p in done[1][1:]]
-            slot = self._slot(k, H, W)
+            slot = self._slot(k, H, W, self._params_of(j))
             slot[0].array[:] = raw
             self.hp.develop_submit(slot[0].array, self._params_of(j), slot[1].array, slot[2].array, slot[3].array)
             inflight.append((j, slot))

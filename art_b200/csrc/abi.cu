@@ -236,7 +236,8 @@ void art_hp_destroy(art_hp_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch, &ctx->d_small, &ctx->d_work, &ctx->d_dn, &ctx->d_fattal, &ctx->d_small2};
+    DevBuf* bufs[] = {&ctx->d_raw, &ctx->d_out[0], &ctx->d_out[1], &ctx->d_out[2], &ctx->d_scratch, &ctx->d_small, &ctx->d_work, &ctx->d_dn, &ctx->d_fattal, &ctx->d_small2, &ctx->d_dm[0], &ctx->d_dm[1], &ctx->d_dm[2], &ctx->d_chain_stages};
+    if (ctx->d_nlm_dbg) cudaFree(ctx->d_nlm_dbg);
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (ctx->d_dn_tables.p) cudaFree(ctx->d_dn_tables.p);
     if (ctx->d_dn_labtabs.p) cudaFree(ctx->d_dn_labtabs.p);
@@ -797,6 +798,47 @@ int art_hp_fattal(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* 
     return ART_HP_OK;
 }
 
+int art_hp_develop_size(const art_hp_develop_params* params, int W, int H, int* out_w, int* out_h, int* border)
+{
+    if (!params) return ART_HP_ERR_INVALID;
+    int bd, Wo, Ho;
+    art_develop_geometry(params, W, H, &bd, &Wo, &Ho);
+    if (out_w) *out_w = Wo;
+    if (out_h) *out_h = Ho;
+    if (border) *border = bd;
+    return ART_HP_OK;
+}
+
+int art_hp_denoise_guided_smoothing_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
+                                        const double ws[9], int guidedChromaRadius, double scale)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_r || !d_g || !d_b || !ws) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || pitch < (size_t)W || guidedChromaRadius < 0) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d or radius %d", W, H, guidedChromaRadius);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_guided_smoothing_dev(ctx, d_r, d_g, d_b, pitch, W, H, ws, guidedChromaRadius, scale);
+}
+
+int art_hp_denoise_guided_smoothing(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b,
+                                    const double ws[9], int guidedChromaRadius, double scale)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!r || !g || !b || !ws) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || guidedChromaRadius < 0) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d or radius %d", W, H, guidedChromaRadius);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    int rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+    Plane io[3] = {{r, (float*)ctx->d_out[0].p}, {g, (float*)ctx->d_out[1].p}, {b, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_guided_smoothing_dev(ctx, io[0].dev, io[1].dev, io[2].dev, pitch, W, H, ws, guidedChromaRadius, scale))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
 int art_hp_color_chain_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
                            const art_hp_chain_params* params)
 {
@@ -967,6 +1009,12 @@ static int check_develop(art_hp_ctx* ctx, const art_hp_develop_params* p, int W,
         if (!rgb_bayer(p->filters)) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "filters 0x%08x is not an RGB Bayer pattern", p->filters);
     }
     if (W < 32 || H < 32 || W > 32767 || H > 32767) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    {
+        int bd, Wo, Ho;
+        art_develop_geometry(p, W, H, &bd, &Wo, &Ho);
+        if (Wo < 24 || Ho < 24) return ctx->fail(ART_HP_ERR_INVALID, "frame %dx%d is too small for a border of %d", W, H, bd);
+    }
+    if (p->guidedChromaRadius < 0) return ctx->fail(ART_HP_ERR_INVALID, "guidedChromaRadius %d", p->guidedChromaRadius);
     if ((p->denoise || p->fattal_enabled) && !p->wprof) return ctx->fail(ART_HP_ERR_INVALID, "wprof is required by denoise and tone mapping");
     if (p->denoise) { int rc = check_denoise_params(ctx, p->denoise, p->wprof); if (rc) return rc; }
     return ART_HP_OK;
@@ -979,7 +1027,11 @@ int art_hp_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* params, int
     if (!d_raw || !d_r || !d_g || !d_b) return ctx->fail(ART_HP_ERR_INVALID, "null plane");
     int rc = check_develop(ctx, params, W, H);
     if (rc) return rc;
-    if (raw_pitch < (size_t)W || out_pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "pitch smaller than the width");
+    int bd, Wo, Ho;
+    art_develop_geometry(params, W, H, &bd, &Wo, &Ho);
+    if (raw_pitch < (size_t)W || out_pitch < (size_t)Wo) return ctx->fail(ART_HP_ERR_INVALID, "pitch smaller than the width");
+    if (params->chain && ((out_pitch & 3) || ((reinterpret_cast<uintptr_t>(d_r) | reinterpret_cast<uintptr_t>(d_g) | reinterpret_cast<uintptr_t>(d_b)) & 15)))
+        return ctx->fail(ART_HP_ERR_INVALID, "the colour chain needs 16-byte aligned output planes with a pitch that is a multiple of 4 floats");
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
     return art_develop_dev(ctx, params, W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch);
 }
@@ -992,16 +1044,17 @@ int art_hp_develop(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, 
     int rc = check_develop(ctx, params, W, H);
     if (rc) return rc;
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t pitch = round_up((size_t)W, 32);
-    const size_t plane = pitch * (size_t)H * sizeof(float);
-    if ((rc = art_reserve(ctx, ctx->d_raw, plane))) return rc;
+    int bd, Wo, Ho;
+    art_develop_geometry(params, W, H, &bd, &Wo, &Ho);
+    const size_t pitch = round_up((size_t)W, 32), opitch = round_up((size_t)Wo, 32);
+    if ((rc = art_reserve(ctx, ctx->d_raw, pitch * (size_t)H * sizeof(float)))) return rc;
     for (int i = 0; i < 3; ++i)
-        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+        if ((rc = art_reserve(ctx, ctx->d_out[i], opitch * (size_t)Ho * sizeof(float)))) return rc;
     Plane in = {rawData, (float*)ctx->d_raw.p};
     Plane out[3] = {{r, (float*)ctx->d_out[0].p}, {g, (float*)ctx->d_out[1].p}, {b, (float*)ctx->d_out[2].p}};
     if ((rc = transfer(ctx, ctx->stream, &in, 1, W, 0, H, pitch, true))) return rc;
-    if ((rc = art_develop_dev(ctx, params, W, H, in.dev, pitch, out[0].dev, out[1].dev, out[2].dev, pitch))) return rc;
-    if ((rc = transfer(ctx, ctx->stream, out, 3, W, 0, H, pitch, false))) return rc;
+    if ((rc = art_develop_dev(ctx, params, W, H, in.dev, pitch, out[0].dev, out[1].dev, out[2].dev, opitch))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, out, 3, Wo, 0, Ho, opitch, false))) return rc;
     ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;
 }
@@ -1015,18 +1068,19 @@ int art_hp_develop_submit(art_hp_ctx* ctx, const art_hp_develop_params* params, 
     int rc = check_develop(ctx, params, W, H);
     if (rc) return rc;
     if (ctx->q_submitted - ctx->q_collected >= 2) return ctx->fail(ART_HP_ERR_INVALID, "two frames are already in flight: call art_hp_develop_wait first");
+    int bd, Wo, Ho;
+    art_develop_geometry(params, W, H, &bd, &Wo, &Ho);
     ptrdiff_t st[4];
     float* const* tabs[4] = {rawData, r, g, b};
     for (int i = 0; i < 4; ++i)
-        if (!constant_stride(tabs[i], H, &st[i]) || !is_pinned(tabs[i][0]))
+        if (!constant_stride(tabs[i], i ? Ho : H, &st[i]) || !is_pinned(tabs[i][0]))
             return ctx->fail(ART_HP_ERR_UNSUPPORTED, "the batch queue needs pinned, constant-stride planes (art_hp_host_alloc); use art_hp_develop otherwise");
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
     art_hp_ctx::QSlot& q = ctx->q[ctx->q_submitted & 1];
-    const size_t pitch = round_up((size_t)W, 32);
-    const size_t plane = pitch * (size_t)H * sizeof(float);
-    if ((rc = art_reserve(ctx, q.raw, plane))) return rc;
+    const size_t pitch = round_up((size_t)W, 32), opitch = round_up((size_t)Wo, 32);
+    if ((rc = art_reserve(ctx, q.raw, pitch * (size_t)H * sizeof(float)))) return rc;
     for (int i = 0; i < 3; ++i)
-        if ((rc = art_reserve(ctx, q.out[i], plane))) return rc;
+        if ((rc = art_reserve(ctx, q.out[i], opitch * (size_t)Ho * sizeof(float)))) return rc;
     if (!q.up) {
         ART_CUDA(ctx, cudaEventCreateWithFlags(&q.up, cudaEventDisableTiming));
         ART_CUDA(ctx, cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
@@ -1038,11 +1092,11 @@ int art_hp_develop_submit(art_hp_ctx* ctx, const art_hp_develop_params* params, 
                                     cudaMemcpyHostToDevice, ctx->copy_stream));
     ART_CUDA(ctx, cudaEventRecord(q.up, ctx->copy_stream));
     ART_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, q.up, 0));
-    if ((rc = art_develop_dev(ctx, params, W, H, (const float*)q.raw.p, pitch, (float*)q.out[0].p, (float*)q.out[1].p, (float*)q.out[2].p, pitch))) return rc;
+    if ((rc = art_develop_dev(ctx, params, W, H, (const float*)q.raw.p, pitch, (float*)q.out[0].p, (float*)q.out[1].p, (float*)q.out[2].p, opitch))) return rc;
     ART_CUDA(ctx, cudaEventRecord(q.done, ctx->stream));
     ART_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, q.done, 0));
     for (int i = 0; i < 3; ++i)
-        ART_CUDA(ctx, cudaMemcpy2DAsync(tabs[i + 1][0], (H > 1 ? (size_t)st[i + 1] : (size_t)W) * sizeof(float), q.out[i].p, pitch * sizeof(float), wbytes, H,
+        ART_CUDA(ctx, cudaMemcpy2DAsync(tabs[i + 1][0], (size_t)st[i + 1] * sizeof(float), q.out[i].p, opitch * sizeof(float), (size_t)Wo * sizeof(float), Ho,
                                         cudaMemcpyDeviceToHost, ctx->d2h_stream));
     ART_CUDA(ctx, cudaEventRecord(q.down, ctx->d2h_stream));
     ctx->q_submitted++;

@@ -31,12 +31,17 @@ struct art_hp_ctx {
     cudaStream_t d2h_stream = nullptr;   // device->host copies that overlap compute (other DMA engine)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long launches = 0;
+    // cudaFuncSetAttribute is per device: the opt-ins to > 48 KB of dynamic shared memory are remembered per context, not per process
+    enum { ATTR_RCD = 1, ATTR_XTRANS = 2, ATTR_DN_BLOCKS = 4, ATTR_NLM = 8, ATTR_FATTAL = 16, ATTR_DN_TC = 32, ATTR_SHRINK = 64, ATTR_AMAZE = 128 };
+    unsigned attrs_set = 0;
+    void* d_nlm_dbg = nullptr;
     // optional per-kernel timing (art_hp_profile_*): CUDA events around every launch
     bool profiling = false;
     std::vector<ProfSpan> spans;
     std::vector<ProfStat> stats;
     std::string err;
     // device scratch, grown on demand and kept across calls
+    DevBuf d_dm[3];                      // art_hp_develop: the demosaiced W x H planes the cropped getImage stage reads
     DevBuf d_raw, d_out[3], d_scratch, d_small, d_work, d_dn, d_fattal, d_small2;
     // blocks handed to short-lived device objects (wavelet decompositions): reused across calls instead of
     // cudaMalloc/cudaFree per frame (both synchronise the device and serialise with NVML queries)
@@ -138,6 +143,10 @@ int art_xtrans_dev(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, con
 // getImage gain/clip + colorSpaceConversion_ matrix branch, in place on device planes
 int art_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch,
                           const float mul[3], int doClip, const double* mat);
+int art_scale_convert_crop_dev(art_hp_ctx* ctx, int W, int H, const float* sr, const float* sg, const float* sb, size_t sp,
+                               float* r, float* g, float* b, size_t pitch, const float mul[3], int doClip, const double* mat);
+// denoise::denoiseGuidedSmoothing (smoothing.cu), planes in place
+int art_guided_smoothing_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const double* ws9, int guidedChromaRadius, double scale);
 // scaleColors (Bayer): in place; d_chmax_bits = 3 device ints receiving the float bit patterns of chmax[0..2]
 int art_scale_colors_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* raw, size_t pitch,
                          const float black[4], const float mul[4], int* d_chmax_bits);
@@ -172,6 +181,8 @@ int art_chain_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, s
 int art_usm_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_sharpen_params* p, const double* ws9);
 // develop.cu: ImProcFunctions::denoise (calclum, adjust_params, RGB_denoise, NL-means on Y) and the whole-frame pipeline
 int art_denoise_stage_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_denoise_params* dn,
-                          int nlStrength, int nlDetail, const double* cam2work, const double* wprof);
+                          int nlStrength, int nlDetail, int guidedChromaRadius, double ecomp, const double* cam2work, const double* wprof);
+// output size of art_hp_develop for a W x H raw frame
+void art_develop_geometry(const art_hp_develop_params* p, int W, int H, int* b, int* Wo, int* Ho);
 int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int W, int H, const float* raw, size_t rp,
                     float* r, float* g, float* b, size_t op);

@@ -671,8 +671,10 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
         a.detail_hi = host_compute_detail(params_Ldetail); a.detail_lo = host_compute_detail(0.f); a.params_Ldetail = params_Ldetail;
         a.use_mask = use_mask; a.blur_rad = std::max(1, int(3 / scale));
         const size_t smem = (size_t)TS * (PX + PT + PC) * sizeof(float);
-        static bool attr = false;
-        if (!attr) { ART_CUDA(ctx, cudaFuncSetAttribute(k_dn_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        if (!(ctx->attrs_set & art_hp_ctx::ATTR_DN_BLOCKS)) {
+            ART_CUDA(ctx, cudaFuncSetAttribute(k_dn_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->attrs_set |= art_hp_ctx::ATTR_DN_BLOCKS;
+        }
         art_prof_begin(ctx, "k_dn_blocks");
         k_dn_blocks<<<dim3(nbw, nbh), 256, smem, st>>>(a);
         art_prof_end(ctx);

@@ -92,12 +92,19 @@ int art_calclum_dev(art_hp_ctx* ctx, const float* r, const float* g, const float
     return ART_HP_OK;
 }
 
-// ImProcFunctions::denoise on device planes (exposure compensation 0, the default)
+// ImProcFunctions::denoise on device planes (ipdenoise.cc L1096-1189).  ecomp = params->exposure.enabled ? expcomp : 0: when
+// positive the stage runs between expcomp(+ecomp) and expcomp(-ecomp) (L1155-1163, L1181-1184; ExposureParams() has black 0).
+// guidedChromaRadius / nlStrength are 0 unless smoothingEnabled (L1170-1178).
 int art_denoise_stage_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_denoise_params* dn,
-                          int nlStrength, int nlDetail, const double* cam2work, const double* wprof)
+                          int nlStrength, int nlDetail, int guidedChromaRadius, double ecomp, const double* cam2work, const double* wprof)
 {
     art_hp_denoise_params P = *dn;
     art_adjust_denoise_params(&P);
+    auto bracket = [&](double ev) -> int {       // expcomp, ipexposure.cc L29-73: exp_scale = pow(2.f, expcomp) evaluated in double, stored to float
+        art_hp_chain_params e{};
+        e.exposure_enabled = 1; e.exp_scale = (float)std::pow(2.0, ev); e.black = 0.f;
+        return art_chain_dev(ctx, W, H, r, g, b, ip, &e);
+    };
     const int w2 = (W + 1) / 2, h2 = (H + 1) / 2;
     const size_t cp = round_up((size_t)w2, 32);
     float* cl[3] = {nullptr, nullptr, nullptr};
@@ -107,7 +114,9 @@ int art_denoise_stage_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t 
         for (int c = 0; c < 3; ++c) cl[c] = (float*)ctx->d_small2.p + (size_t)c * cp * h2;
         if ((rc = art_calclum_dev(ctx, r, g, b, ip, W, H, cl[0], cl[1], cl[2], cp, cam2work))) return rc;
     }
+    if (ecomp > 0 && (rc = bracket(ecomp))) return rc;
     if ((rc = art_rgb_denoise_dev(ctx, r, g, b, ip, W, H, &P, wprof, cl[0], cl[1], cl[2], cp, nullptr))) return rc;
+    if (guidedChromaRadius && (rc = art_guided_smoothing_dev(ctx, r, g, b, ip, W, H, wprof, guidedChromaRadius, dn->scale > 0 ? dn->scale : 1.0))) return rc;
     if (nlStrength) {
         const dim3 blk(32, 8), grid((W + 31) / 32, (H + 7) / 8);
         const float w0 = (float)wprof[3], w1 = (float)wprof[4], w2f = (float)wprof[5];
@@ -120,25 +129,45 @@ int art_denoise_stage_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t 
         art_prof_end(ctx);
         ctx->launches += 2;
     }
+    if (ecomp > 0 && (rc = bracket(-ecomp))) return rc;
     ART_CUDA(ctx, cudaGetLastError());
     return ART_HP_OK;
 }
 
-int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int W, int H, const float* raw, size_t rp,
+void art_develop_geometry(const art_hp_develop_params* p, int W, int H, int* b, int* Wo, int* Ho)
+{   // RawImageSource::border: 4 for Bayer sensors (the caller's value), 7 for X-Trans (rawimagesource.cc L1345-1352, computeFullSize L1163-1175)
+    const bool xt = p->method == ART_HP_XTRANS_3PASS || p->method == ART_HP_XTRANS_1PASS;
+    const int bd = p->full_frame ? 0 : (xt ? 7 : (p->border > 0 ? p->border : 0));
+    *b = bd; *Wo = W - 2 * bd; *Ho = H - 2 * bd;
+}
+
+int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr, int Hr, const float* raw, size_t rp,
                     float* r, float* g, float* b, size_t op)
 {
-    int rc;
-    if (p->method == ART_HP_XTRANS_3PASS || p->method == ART_HP_XTRANS_1PASS)
-        rc = art_xtrans_dev(ctx, p->method == ART_HP_XTRANS_3PASS ? 3 : 1, p->method == ART_HP_XTRANS_3PASS, W, H, p->xtrans, p->rgb_cam, raw, rp, r, g, b, op);
-    else if (p->method == ART_HP_BAYER_AMAZE) rc = art_amaze_dev(ctx, W, H, p->filters, raw, rp, r, g, b, op, p->initialGain, p->border, 0, H);
-    else {
-        rc = art_rcd_dev(ctx, W, H, p->filters, raw, rp, r, g, b, op, 0, H);
-        if (!rc) rc = art_border_dev(ctx, W, H, p->filters, 9, raw, rp, r, g, b, op, 0, H);
+    int rc, bd, W, H;
+    art_develop_geometry(p, Wr, Hr, &bd, &W, &H);
+    // with a border the demosaicer writes context-owned W x H planes and getImage's stage crops them into the caller's planes
+    float* dm[3] = {r, g, b};
+    size_t dmp = op;
+    if (bd) {
+        dmp = round_up((size_t)Wr, 32);
+        for (int c = 0; c < 3; ++c) {
+            if ((rc = art_reserve(ctx, ctx->d_dm[c], dmp * (size_t)Hr * sizeof(float)))) return rc;
+            dm[c] = (float*)ctx->d_dm[c].p;
+        }
     }
+    if (p->method == ART_HP_XTRANS_3PASS || p->method == ART_HP_XTRANS_1PASS)
+        rc = art_xtrans_dev(ctx, p->method == ART_HP_XTRANS_3PASS ? 3 : 1, p->method == ART_HP_XTRANS_3PASS, Wr, Hr, p->xtrans, p->rgb_cam, raw, rp, dm[0], dm[1], dm[2], dmp);
+    else if (p->method == ART_HP_BAYER_AMAZE) rc = art_amaze_dev(ctx, Wr, Hr, p->filters, raw, rp, dm[0], dm[1], dm[2], dmp, p->initialGain, p->border, 0, Hr);
+    else rc = art_rcd_dev(ctx, Wr, Hr, p->filters, raw, rp, dm[0], dm[1], dm[2], dmp, 0, Hr);      // ends with its own border_interpolate2(9)
     if (rc) return rc;
-    if ((rc = art_scale_convert_dev(ctx, W, H, r, g, b, op, p->mul, p->doClip, p->cam2work))) return rc;
+    if (bd) {
+        const size_t off = (size_t)bd * dmp + bd;
+        rc = art_scale_convert_crop_dev(ctx, W, H, dm[0] + off, dm[1] + off, dm[2] + off, dmp, r, g, b, op, p->mul, p->doClip, p->cam2work);
+    } else rc = art_scale_convert_dev(ctx, W, H, r, g, b, op, p->mul, p->doClip, p->cam2work);
+    if (rc) return rc;
     if (p->denoise) {
-        if ((rc = art_denoise_stage_dev(ctx, r, g, b, op, W, H, p->denoise, p->nlStrength, p->nlDetail, p->cam2work, p->wprof))) return rc;
+        if ((rc = art_denoise_stage_dev(ctx, r, g, b, op, W, H, p->denoise, p->nlStrength, p->nlDetail, p->guidedChromaRadius, p->denoise_expcomp, p->cam2work, p->wprof))) return rc;
     }
     if (p->fattal_enabled) {
         if ((rc = art_fattal_dev(ctx, r, g, b, op, W, H, p->fattal_threshold, p->fattal_amount, p->fattal_satcontrol, p->wprof))) return rc;

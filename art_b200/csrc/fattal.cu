@@ -828,12 +828,11 @@ int art_fattal_dev(art_hp_ctx* ctx, float* R, float* G, float* B, size_t ip, int
     else FAT_LAUNCH("k_fat_div", k_fat_div<false>, grid2(w2, h2, b), b, 0, Hl, fi[0], sw, sh, F, w2, h2);
 
     // Poisson solve (L869-950) and exponentiation (L647-664)
-    static bool attr_done[3] = {false, false, false};
-    if (!attr_done[0]) {
+    if (!(ctx->attrs_set & art_hp_ctx::ATTR_FATTAL)) {
         cudaFuncSetAttribute(k_fat_dct<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(k_fat_dct<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(k_fat_dct<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done[0] = true;
+        ctx->attrs_set |= art_hp_ctx::ATTR_FATTAL;
     }
     auto dct_grid = [&](size_t smem, int rows) {
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200u * 1024u) / std::max<size_t>(smem, 1)));

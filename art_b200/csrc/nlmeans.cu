@@ -312,15 +312,13 @@ int art_nlmeans_dev(art_hp_ctx* ctx, float* img, size_t ip, int W, int H, float 
     a.ntx = int(std::ceil(float(WW) / stepsz));
     const int nty = int(std::ceil(float(HH) / stepsz));
     const size_t smem = (size_t)TS * TS * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attrs_set & art_hp_ctx::ATTR_NLM)) {
         ART_CUDA(ctx, cudaFuncSetAttribute(k_nlm_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        ctx->attrs_set |= art_hp_ctx::ATTR_NLM;
     }
-    static long long* d_dbg = nullptr;
     if (getenv("ART_HP_NLM_PHASES")) {
-        if (!d_dbg) ART_CUDA(ctx, cudaMalloc(&d_dbg, 3 * sizeof(long long)));
-        a.dbg = d_dbg;
+        if (!ctx->d_nlm_dbg) ART_CUDA(ctx, cudaMalloc(&ctx->d_nlm_dbg, 3 * sizeof(long long)));
+        a.dbg = (long long*)ctx->d_nlm_dbg;
     }
     art_prof_begin(ctx, "k_nlm_tile");
     k_nlm_tile<<<a.ntx * nty, NT, smem, st>>>(a);
@@ -329,7 +327,7 @@ int art_nlmeans_dev(art_hp_ctx* ctx, float* img, size_t ip, int W, int H, float 
     ART_CUDA(ctx, cudaGetLastError());
     if (a.dbg) {
         long long h[3];
-        ART_CUDA(ctx, cudaMemcpyAsync(h, d_dbg, sizeof h, cudaMemcpyDeviceToHost, st));
+        ART_CUDA(ctx, cudaMemcpyAsync(h, a.dbg, sizeof h, cudaMemcpyDeviceToHost, st));
         ART_CUDA(ctx, cudaStreamSynchronize(st));
         fprintf(stderr, "[nlm phases, CTA 0, clocks] scores %lld  integral %lld  weights %lld\n", h[0], h[1], h[2]);
     }

@@ -73,6 +73,22 @@ __global__ void __launch_bounds__(256) k_scale_convert_scalar(ScArgs a)
     }
 }
 
+// out-of-place form for art_hp_develop: getImage reads the demosaiced planes from (border, border) and writes a
+// (W - 2 border) x (H - 2 border) image (rawimagesource.cc L943-1025 with sx1 = sy1 = border, transformRect L664-700)
+struct ScCropArgs { const float *sr, *sg, *sb; size_t sp; ScArgs d; };
+__global__ void __launch_bounds__(256) k_scale_convert_crop(ScCropArgs c)
+{
+    const ScArgs& a = c.d;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.W) return;
+    for (int y = blockIdx.y; y < a.H; y += gridDim.y) {
+        const size_t i = (size_t)y * c.sp + x, o = (size_t)y * a.pitch + x;
+        float r = c.sr[i], g = c.sg[i], b = c.sb[i];
+        sc_pixel(a, r, g, b);
+        a.r[o] = r; a.g[o] = g; a.b[o] = b;
+    }
+}
+
 // scaleColors, Bayer branch (rawimagesource.cc L2731-2772): black subtraction + per-CFA-channel scaling in
 // place, and the per-colour maxima chmax[] (max is exact under any association, so a tree reduce is fine;
 // values are >= 0, hence atomicMax on the int bit pattern orders them correctly).
@@ -151,6 +167,25 @@ int art_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, flo
         art_prof_begin(ctx, "k_scale_convert_scalar");
         k_scale_convert_scalar<<<grid, 256, 0, ctx->stream>>>(a);
     }
+    art_prof_end(ctx);
+    ctx->launches++;
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}
+
+int art_scale_convert_crop_dev(art_hp_ctx* ctx, int W, int H, const float* sr, const float* sg, const float* sb, size_t sp,
+                               float* r, float* g, float* b, size_t pitch, const float mul[3], int doClip, const double* mat)
+{
+    ScCropArgs c;
+    c.sr = sr; c.sg = sg; c.sb = sb; c.sp = sp;
+    ScArgs& a = c.d;
+    a.r = r; a.g = g; a.b = b; a.pitch = pitch; a.W = W; a.H = H;
+    for (int i = 0; i < 3; ++i) a.mul[i] = mul[i];
+    a.do_clip = doClip; a.do_mat = mat != nullptr;
+    for (int i = 0; i < 9; ++i) a.mat[i] = mat ? mat[i] : 0.0;
+    dim3 grid((W + 255) / 256, std::min(H, 148 * 8));
+    art_prof_begin(ctx, "k_scale_convert_crop");
+    k_scale_convert_crop<<<grid, 256, 0, ctx->stream>>>(c);
     art_prof_end(ctx);
     ctx->launches++;
     ART_CUDA(ctx, cudaGetLastError());

@@ -335,13 +335,13 @@ int art_border_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, int bord, co
 int art_rcd_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, const float* raw, size_t rp,
                 float* R, float* G, float* B, size_t op, int row_begin, int row_end)
 {
-    static int nthreads = 0;
-    if (!nthreads) {
+    if (!(ctx->attrs_set & art_hp_ctx::ATTR_RCD)) {
         ART_CUDA(ctx, cudaFuncSetAttribute(rcd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         ART_CUDA(ctx, cudaFuncSetAttribute(rcd_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        const char* e = getenv("ART_HP_RCD_THREADS");
-        nthreads = (e && atoi(e) == 512) ? 512 : 1024;
+        ctx->attrs_set |= art_hp_ctx::ATTR_RCD;
     }
+    const char* e = getenv("ART_HP_RCD_THREADS");
+    const int nthreads = (e && atoi(e) == 512) ? 512 : 1024;
     const int nth = H / TN + ((H % TN) ? 1 : 0), ntw = W / TN + ((W % TN) ? 1 : 0);   // L86-87
     // reference tile row tr writes image rows [176 tr + 9, 176 tr + 185) (L305-316); bands are cut at 176 k + 9
     const int tr_begin = row_begin <= TB ? 0 : (row_begin - TB) / TN;

@@ -531,8 +531,10 @@ int art_xtrans_dev(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, con
     if (ntiles > 0) {
         a.slab_floats = round_up((size_t)TS * TS * (a.ndir * 4 + 3) + 128, 32);
         const int grid = std::min(ntiles, ctx->sm_count);       // one 1024-thread CTA (208 KB of shared memory) per SM
-        static bool attr = false;
-        if (!attr) { ART_CUDA(ctx, cudaFuncSetAttribute(k_xtrans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XT_SMEM)); attr = true; }
+        if (!(ctx->attrs_set & art_hp_ctx::ATTR_XTRANS)) {
+            ART_CUDA(ctx, cudaFuncSetAttribute(k_xtrans, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XT_SMEM));
+            ctx->attrs_set |= art_hp_ctx::ATTR_XTRANS;
+        }
         if ((rc = art_reserve(ctx, ctx->d_scratch, (size_t)grid * a.slab_floats * sizeof(float)))) return rc;
         a.slabs = (float*)ctx->d_scratch.p;
         art_prof_begin(ctx, "k_xtrans");

@@ -226,6 +226,20 @@ def develop_params(art_b200):
                          cam2work=CAM2WORK, denoise=DenoiseParams(**DN), fattal=FATTAL, wprof=PROPHOTO)
 
 
+def use_all_host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the reference arm is the reference's OpenMP code on ALL host
+    threads of the box, so the count is set explicitly (environment for a libgomp not loaded yet, omp_set_num_threads for one that is)."""
+    import ctypes
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def cpu_develop_runner(raw, filters):
     """The same stages through the reference's own functions compiled in place (oracle/_ref, stock build): AMaZE,
     getImage gains + matrix, RGB_denoise, ToneMapFattal02.  fftw3f is absent from this image, so the two FFTW call sites
@@ -233,12 +247,15 @@ def cpu_develop_runner(raw, filters):
     import ctypes
     import numpy as np
     import oracle
+    ncores = use_all_host_threads()
     ref = oracle.ref(det=False)
+    use_all_host_threads()
     lib = ref.lib
     lib.artref_set_denoise_thread_limit(0)        # the reference's default: all OpenMP threads
     fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
-    H, W = raw.shape
-    out = [np.zeros((H, W), np.float32) for _ in range(3)]
+    Hr, Wr = raw.shape
+    H, W = Hr - 8, Wr - 8                         # getImage crops the demosaiced frame by RawImageSource::border (4)
+    out = [np.zeros((Hr, Wr), np.float32) for _ in range(3)]
     wp = np.array(PROPHOTO, np.float64)
     wpi = np.linalg.inv(wp)
     p = np.array([DN["luminance"], DN["luminanceDetail"], DN["luminanceDetailThreshold"], DN["chrominance"], DN["chrominanceRedGreen"],
@@ -246,14 +263,14 @@ def cpu_develop_runner(raw, filters):
     res = np.zeros(2, np.float32)
 
     def run():
-        ref.amaze(raw, filters, out=out)
-        r, g, b = ref.scale_convert(out, MUL, True, np.array(CAM2WORK, np.float64))
+        ref.amaze(raw, filters, nthreads=ncores, out=out)
+        r, g, b = ref.scale_convert([np.ascontiguousarray(p[4:-4, 4:-4]) for p in out], MUL, True, np.array(CAM2WORK, np.float64))
         assert lib.artref_rgb_denoise(r.ctypes.data_as(fp), g.ctypes.data_as(fp), b.ctypes.data_as(fp), W, H, p.ctypes.data_as(dp),
                                       wp.ctypes.data_as(dp), wpi.ctypes.data_as(dp), None, ctypes.c_float(0), None, None, None,
                                       res.ctypes.data_as(fp)) == 0
         assert lib.artref_fattal(r.ctypes.data_as(fp), g.ctypes.data_as(fp), b.ctypes.data_as(fp), W, H, FATTAL[0], FATTAL[1], FATTAL[2],
                                  wp.ctypes.data_as(dp)) == 0
-    return run, "reference", os.cpu_count() or 1
+    return run, "reference", ncores
 
 
 def time_cpu_develop(sample, filters, budget_s=20.0, max_runs=3):
@@ -311,6 +328,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        use_all_host_threads()
         if args.workload == "develop":
             # bounded sample: the same four stages on a smaller frame of the same synthetic scene, at most a few steps
             sw, sh = [int(v) for v in args.cpu_sample.lower().split("x")]
@@ -433,7 +451,8 @@ def main():
     #      batch-queue form (art_hp_develop_submit / _wait, what a batch of files calls): every step uploads its own CFA plane
     #      and downloads its own three planes; the copies of frame k overlap the kernels of frames k-1 / k+1.
     nslots = 2 if dparams is not None else 1
-    pins = [[hp.pinned(H, W) for _ in range(4)] for _ in range(nslots)]
+    Ho, Wo = dparams.out_shape(H, W) if dparams is not None else (H, W)
+    pins = [[hp.pinned(H, W)] + [hp.pinned(Ho, Wo) for _ in range(3)] for _ in range(nslots)]
     for sl in pins:
         sl[0].array[:] = raw
 
@@ -475,7 +494,7 @@ def main():
         e2e_latency_ms = (time.perf_counter() - t0) * 1e3
     pins = pins[0]
     clocks = sampler.stop() if sampler else None
-    checksum = float(pins[2].array[H // 2, W // 2])
+    checksum = float(pins[2].array[Ho // 2, Wo // 2])
 
     # ---- per-kernel device time (CUDA events around every launch, on the launching stream), outside
     #      the timed regions above so the extra events do not perturb `value`
@@ -514,7 +533,7 @@ def main():
             "metric": "Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": W * H * 4, "d2h_bytes_per_step": W * H * 12,
+            "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": W * H * 4, "d2h_bytes_per_step": Wo * Ho * 12,
                     "steps": e2e_steps, "host_memory": "pinned (art_hp_host_alloc)", "single_frame_latency_ms": e2e_latency_ms,
                     "call": ("art_hp_develop_submit / art_hp_develop_wait: two frames in flight, every frame uploaded and downloaded "
                              "inside the timed region (host wall clock from the first submit to the last frame in host memory)")

@@ -316,6 +316,18 @@ int art_hp_guided_filter_dev(art_hp_ctx* ctx, int W, int H, const float* d_guide
                              const float* d_src, size_t src_pitch, float* d_dst, size_t dst_pitch,
                              int r, float epsilon, int subsampling);
 
+/*
+ * art_hp_denoise_guided_smoothing   rtengine::denoise::denoiseGuidedSmoothing(im, rgb) (rtengine/ipsmoothing.cc L875-897; guided_smoothing
+ *                      L334-409 with Channel::C, guidedFilterLog rtengine/guidedfilter.cc L243-263), in place on the three planes of the
+ *                      working-space image: chroma smoothing guided by the log luminance, the input luminance kept.
+ *                      guidedChromaRadius = params->denoise.guidedChromaRadius (0 returns at once, like the reference), scale =
+ *                      ImProcData::scale, ws = ICCStore::workingSpaceMatrix.  Bit-identical to the reference's SSE2 build.
+ */
+int art_hp_denoise_guided_smoothing(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b,
+                                    const double ws[9], int guidedChromaRadius, double scale);
+int art_hp_denoise_guided_smoothing_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
+                                        const double ws[9], int guidedChromaRadius, double scale);
+
 /* ---- gain / clip / camera->working colour space ------------------------- */
 /*
  * Replaces the per-pixel part of RawImageSource::getImage (rtengine/rawimagesource.cc L943-1025, full
@@ -436,10 +448,14 @@ int art_hp_sharpen_usm_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g
  *                      sharpening steps of STAGE_1..3 (see `sharpen` and `chain` below).
  *                      One host->device copy of the CFA plane, one device->host copy of the three planes.
  *                      denoise == NULL and fattal_enabled == 0 skip their stages, like `enabled = false` does.
- *                      NOT reproduced yet: for exposure.expcomp > 0 ImProcFunctions::denoise brackets RGB_denoise .. NLMeans between
- *                      expcomp(+ecomp) and expcomp(-ecomp) (ipdenoise.cc L1155-1163, L1181-1184), and with smoothingEnabled and
- *                      guidedChromaRadius != 0 it runs denoiseGuidedSmoothing before NLMeans (L1171-1172).  The denoise stage of
- *                      this entry matches the reference for expcomp <= 0 (or exposure disabled) and guidedChromaRadius == 0.
+ *                      Geometry: like the reference, the frame is cropped by RawImageSource::border after the demosaic --
+ *                      getImage reads from (border, border) and every later stage sees (W - 2 border) x (H - 2 border)
+ *                      (rtengine/rawimagesource.cc transformRect L664-700, computeFullSize L1163-1175; border = `border` for Bayer
+ *                      sensors, i.e. 4, and 7 for X-Trans).  red / green / blue are therefore tables of H - 2 border rows of
+ *                      W - 2 border floats; art_hp_develop_size gives the numbers.  full_frame = 1 keeps W x H (no crop).
+ *                      ImProcFunctions::denoise is reproduced with its expcomp(+ecomp) / expcomp(-ecomp) bracket
+ *                      (ipdenoise.cc L1155-1163, L1181-1184: denoise_expcomp) and denoiseGuidedSmoothing (L1171-1172:
+ *                      guidedChromaRadius).
  */
 typedef struct art_hp_develop_params {
     int method;                 /* ART_HP_BAYER_AMAZE | ART_HP_BAYER_RCD | ART_HP_XTRANS_3PASS | ART_HP_XTRANS_1PASS */
@@ -462,7 +478,14 @@ typedef struct art_hp_develop_params {
      * and `border` are not used */
     const int* xtrans;
     const float* rgb_cam;
+    /* ---- ABI version 2 ---- */
+    int full_frame;             /* 0 = the reference's geometry (crop by the border, see above); 1 = outputs are W x H */
+    int guidedChromaRadius;     /* params->denoise.smoothingEnabled ? guidedChromaRadius : 0 (default 3): denoiseGuidedSmoothing between
+                                   RGB_denoise and NLMeans; likewise nlStrength above is 0 unless smoothingEnabled */
+    double denoise_expcomp;     /* params->exposure.enabled ? params->exposure.expcomp : 0; > 0 brackets the denoise stage */
 } art_hp_develop_params;
+/* output size of art_hp_develop for a W x H raw frame: *out_w = W - 2 b, *out_h = H - 2 b, b = the border it crops (0 with full_frame) */
+int art_hp_develop_size(const art_hp_develop_params* params, int W, int H, int* out_w, int* out_h, int* border);
 int art_hp_develop(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
                    float* const* red, float* const* green, float* const* blue);
 int art_hp_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, const float* d_raw, size_t raw_pitch,

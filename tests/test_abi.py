@@ -66,7 +66,8 @@ def test_ctypes_structs_match_the_header(tmp_path):
         "art_hp_denoise_params": (api._DenoiseParamsC, ["luminance", "luminanceDetail", "luminanceDetailThreshold", "chrominance", "gamma", "scale",
                                                          "colorSpace", "noiseCCurve", "noiseCCurveSum", "wprof_inverse"]),
         "art_hp_develop_params": (api._DevelopParamsC, ["method", "filters", "initialGain", "border", "mul", "doClip", "cam2work", "denoise",
-                                                         "nlStrength", "fattal_enabled", "fattal_satcontrol", "wprof", "sharpen", "chain", "xtrans", "rgb_cam"]),
+                                                         "nlStrength", "fattal_enabled", "fattal_satcontrol", "wprof", "sharpen", "chain", "xtrans", "rgb_cam",
+                                                         "full_frame", "guidedChromaRadius", "denoise_expcomp"]),
         "art_hp_chain_params": (api._ChainParamsC, ["exposure_enabled", "exp_scale", "black", "saturation_enabled", "vibrance", "tonecurve_mode",
                                                      "tonecurve_lut", "rcurve", "bcurve", "lab_enabled", "lab_lcurve", "lab_bcurve", "lab_chroma", "ws", "iws",
                                                      "tonecurve_whitept", "tonecurve_stages", "tonecurve_nstages", "neutral_to_out", "neutral_to_work", "satcurve_lut"]),

@@ -20,18 +20,67 @@ CAM2WORK = np.array([[0.82, 0.15, 0.03], [0.07, 0.96, -0.03], [0.02, -0.10, 1.08
 MUL = (1.9, 1.0, 1.6)
 
 
-def oracle_chain(raw, dn_params, curve, fattal_p, nl=None):
+def crop(planes, b):
+    """RawImageSource::getImage reads the demosaiced planes from (border, border): every later stage sees the cropped frame"""
+    return [np.ascontiguousarray(p[b:p.shape[0] - b, b:p.shape[1] - b]) for p in planes] if b else list(planes)
+
+
+def guided_smoothing(planes, radius, scale=1.0):
+    fp = ctypes.POINTER(ctypes.c_float)
+    dp = ctypes.POINTER(ctypes.c_double)
+    out = [np.ascontiguousarray(p).copy() for p in planes]
+    H, W = out[0].shape
+    ws = PROPHOTO.copy()
+    assert oracle.port().lib.artoracle_denoise_guided_smoothing(out[0].ctypes.data_as(fp), out[1].ctypes.data_as(fp), out[2].ctypes.data_as(fp), W, H,
+                                                                ws.ctypes.data_as(dp), int(radius), ctypes.c_double(scale)) == 0
+    return out
+
+
+def expcomp(planes, ev):
+    """ImProcFunctions::expcomp with ExposureParams() defaults but expcomp (black 0): exp_scale = pow(2.f, ev) evaluated in double"""
+    fp = ctypes.POINTER(ctypes.c_float)
+    out = [np.ascontiguousarray(p).copy() for p in planes]
+    H, W = out[0].shape
+    assert oracle.port().lib.artoracle_chain_expcomp(out[0].ctypes.data_as(fp), out[1].ctypes.data_as(fp), out[2].ctypes.data_as(fp), W, H,
+                                                     ctypes.c_float(np.float32(2.0 ** ev)), ctypes.c_float(0.0)) == 0
+    return out
+
+
+def adjust_params(dn, scale):
+    """adjust_params, ipdenoise.cc L35-63 (double arithmetic on the host): what ImProcFunctions::denoise hands to RGB_denoise at scale > 1"""
+    if scale <= 1.0:
+        return tuple(dn)
+    lum, det, thr, chroma, rg, by, gamma, sc = dn
+
+    def c(x, f):
+        s = (x > 0) - (x < 0)
+        y = min(max(abs(x) / 100.0, 0.0), 1.0)
+        return s * (y * (y * f) + (1.0 - y) * y) * 100.0
+    sf = 1.0 / scale
+    nc, nl = sf ** 0.46, sf ** 0.62 * sf
+    return (c(lum, nl), det * (1.0 + (1.0 - sf) ** 2.2), thr, c(chroma, nc), c(rg, nc), c(by, nc), gamma, sc)
+
+
+def oracle_chain(raw, dn_params, curve, fattal_p, nl=None, border=4, guided=0, ecomp=0.0):
     P = oracle.port()
-    r, g, b = P.amaze(raw, synth.RGGB, 1.0, 4)
+    r, g, b = crop(P.amaze(raw, synth.RGGB, 1.0, 4), border)
     r, g, b = P.scale_convert([r, g, b], MUL, True, CAM2WORK)
     planes = [r, g, b]
+    if dn_params is not None and ecomp > 0:
+        planes = expcomp(planes, ecomp)
     if dn_params is not None:
         cc = None
         if curve:
             lut, s = noise_ccurve()
             cl = P.scale_convert([np.ascontiguousarray(p[::2, ::2]) for p in planes], (1.0, 1.0, 1.0), False, CAM2WORK)
             cc = (lut, s, cl)
-        planes = run_chain_denoise(P.lib, planes, dn_params, cc)
+        if ecomp > 0:       # calclum is taken BEFORE the bracket's first expcomp (ipdenoise.cc L1119-1131 vs L1161-1163)
+            assert cc is None
+        planes = run_chain_denoise(P.lib, planes, adjust_params(dn_params, dn_params[7]), cc)
+        if guided:
+            planes = guided_smoothing(planes, guided, dn_params[7])
+        if ecomp > 0:
+            planes = expcomp(planes, -ecomp)
     if fattal_p is not None:
         planes = list(run_fattal(P.lib, "artoracle_fattal", planes, *fattal_p))
     return planes
@@ -58,24 +107,30 @@ def run_chain_denoise(lib, planes, params, cc):
     return out
 
 
-@pytest.mark.parametrize("W,H,dn,curve,fat,exact", [
-    (322, 260, None, False, None, True),
-    (322, 260, (0, 0, 0, 15, 0, 0, 1.7, 1.0), True, None, True),
-    (322, 260, (30, 50, 0, 15, 0, 0, 1.7, 1.0), True, (30, 20, 0), False),
-    (645, 404, (30, 50, 0, 15, 0, 0, 1.7, 1.0), False, (30, 20, 1), False),
-    (301, 407, None, False, (30, 20, 0), False),
+@pytest.mark.parametrize("W,H,dn,curve,fat,exact,full,guided,ecomp", [
+    (322, 260, None, False, None, True, False, 0, 0.0),
+    (322, 260, None, False, None, True, True, 0, 0.0),
+    (322, 260, (0, 0, 0, 15, 0, 0, 1.7, 1.0), True, None, True, False, 0, 0.0),
+    (322, 260, (0, 0, 0, 15, 0, 0, 1.7, 1.0), False, None, True, False, 3, 0.0),          # denoiseGuidedSmoothing, the default radius
+    (322, 260, (0, 0, 0, 15, 0, 0, 1.7, 1.0), False, None, True, False, 3, 0.7),          # ... inside the expcomp(+/-) bracket
+    (645, 404, (0, 0, 0, 15, 0, 0, 1.7, 2.0), False, None, True, False, 5, 0.0),          # preview scale 2: radius round(5 / 2), adjusted parameters
+    (322, 260, (30, 50, 0, 15, 0, 0, 1.7, 1.0), True, (30, 20, 0), False, False, 0, 0.0),
+    (645, 404, (30, 50, 0, 15, 0, 0, 1.7, 1.0), False, (30, 20, 1), False, False, 3, 0.5),
+    (645, 404, (30, 50, 0, 15, 0, 0, 1.7, 1.0), False, (30, 20, 1), False, True, 0, 0.0),
+    (301, 407, None, False, (30, 20, 0), False, False, 0, 0.0),
 ])
-def test_develop_matches_oracle_chain(hot_path, W, H, dn, curve, fat, exact):
+def test_develop_matches_oracle_chain(hot_path, W, H, dn, curve, fat, exact, full, guided, ecomp):
     raw = synth.bayer_frame(W, H, synth.RGGB, seed=W + H)
-    want = oracle_chain(raw, dn, curve, fat)
+    want = oracle_chain(raw, dn, curve, fat, border=0 if full else 4, guided=guided, ecomp=ecomp)
     dnp = None
     if dn is not None:
         lum, det, thr, chroma, rg, by, gamma, scale = dn
         dnp = DenoiseParams(luminance=lum, luminanceDetail=det, luminanceDetailThreshold=thr, chrominance=chroma, chrominanceRedGreen=rg,
                             chrominanceBlueYellow=by, gamma=gamma, scale=scale, noiseCCurve=noise_ccurve()[0] if curve else None)
     params = DevelopParams(method=art_b200.BAYER_AMAZE, filters=synth.RGGB, mul=MUL, do_clip=True, cam2work=CAM2WORK, denoise=dnp,
-                           fattal=fat, wprof=PROPHOTO)
+                           fattal=fat, wprof=PROPHOTO, full_frame=full, guided_chroma_radius=guided, denoise_expcomp=ecomp)
     got = hot_path.develop(raw, params)
+    assert got[0].shape == ((H, W) if full else (H - 8, W - 8))
     worst = 0.0
     for x, y, ch in zip(got, want, "RGB"):
         if exact:
@@ -128,9 +183,9 @@ def test_develop_with_finishing_stages(hot_path, W, H, dn, fat, sharpen, exact):
             assert np.array_equal(x, y), "%s: %d of %d differ" % (ch, int((x != y).sum()), x.size)
         else:
             err = np.abs(x - y)
-            lim = 1e-4 * np.abs(y) + 0.05
-            worst = max(worst, float((err / (np.abs(y) + 0.05)).max()))
-            assert (err <= lim).mean() > 0.9999, "%s: %d of %d beyond tolerance, worst %g" % (ch, int((err > lim).sum()), x.size, worst)
+            lim = 1e-4 * np.abs(y) + 0.02
+            worst = max(worst, float((err / (np.abs(y) + 0.02)).max()))
+            assert (err <= lim).all(), "%s: %d of %d beyond tolerance, worst %g" % (ch, int((err > lim).sum()), x.size, worst)
     if not exact:
         print("\n[develop+finishing] %dx%d worst relative error %.3g" % (W, H, worst))
 
@@ -143,7 +198,7 @@ def test_batch_queue_matches_synchronous_develop(hot_path):
                            fattal=(30, 20, 0), wprof=PROPHOTO)
     frames = [synth.bayer_frame(W, H, synth.RGGB, seed=100 + k) for k in range(5)]
     want = [hot_path.develop(f, params) for f in frames]
-    pins = [[hot_path.pinned(H, W) for _ in range(4)] for _ in range(2)]
+    pins = [[hot_path.pinned(H, W)] + [hot_path.pinned(H - 8, W - 8) for _ in range(3)] for _ in range(2)]
     got = []
     for k, f in enumerate(frames):
         slot = pins[k & 1]
@@ -163,7 +218,7 @@ def test_batch_queue_matches_synchronous_develop(hot_path):
     with pytest.raises(art_b200.HotPathError):
         hot_path.develop_wait()                          # nothing in flight
     with pytest.raises(art_b200.HotPathError):           # pageable planes are refused, not silently staged
-        hot_path.develop_submit(frames[0], params, *[np.empty((H, W), np.float32) for _ in range(3)])
+        hot_path.develop_submit(frames[0], params, *[np.empty((H - 8, W - 8), np.float32) for _ in range(3)])
 
 
 def test_full_pipeline_at_100mp_properties(hot_path):
@@ -178,7 +233,7 @@ def test_full_pipeline_at_100mp_properties(hot_path):
     dnp = DenoiseParams(luminance=30, luminanceDetail=50, chrominance=15, gamma=1.7)
     params = DevelopParams(method=art_b200.BAYER_AMAZE, filters=synth.RGGB, mul=MUL, do_clip=True, cam2work=CAM2WORK, denoise=dnp,
                            fattal=(30, 20, 0), wprof=PROPHOTO, sharpen=SharpenParams(), chain=ChainParams(ws=PROPHOTO, iws=PROPHOTO_INV, **STAGES["all_std"]))
-    pins = [[hot_path.pinned(H, W) for _ in range(4)] for _ in range(2)]
+    pins = [[hot_path.pinned(H, W)] + [hot_path.pinned(H - 8, W - 8) for _ in range(3)] for _ in range(2)]
     for sl in pins:
         sl[0].array[:] = raw
         hot_path.develop_submit(sl[0].array, params, sl[1].array, sl[2].array, sl[3].array)
@@ -227,8 +282,9 @@ def test_develop_xtrans_with_nlmeans_matches_oracle_chain(hot_path):
     xt = synth.xtrans_matrix(1, 3)
     raw = synth.xtrans_frame(W, H, xt, seed=77)
     P = oracle.port()
-    planes = port_xtrans(raw, xt, 3, 1)
+    planes = crop(port_xtrans(raw, xt, 3, 1), 7)            # RawImageSource::border is 7 for X-Trans sensors
     planes = P.scale_convert(planes, MUL, True, CAM2WORK)
+    H, W = planes[0].shape
     dn = (0, 0, 0, 15, 0, 0, 1.7, 1.0)
     planes = run_chain_denoise(P.lib, planes, dn, None)
     # Imagefloat::setMode(YUV): Y = rgbLuminance over the float working-space matrix, u = Y - b, v = r - Y; NLMeans on Y; back
