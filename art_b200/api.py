@@ -99,6 +99,8 @@ def load_library(build_if_missing=True):
         "art_hp_develop": (i, [vp, vp, i, i, vp, vp, vp, vp]),
         "art_hp_develop_dev": (i, [vp, vp, i, i, vp, sz, vp, vp, vp, sz]),
         "art_hp_develop_submit": (i, [vp, vp, i, i, vp, vp, vp, vp]),
+        "art_hp_denoise_compute_params": (i, [vp, i, i, vp, vp, vp, vp, i, vp, vp, d, i, vp, vp]),
+        "art_hp_denoise_compute_params_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, i, vp, vp, d, i, vp, vp]),
         "art_hp_develop_size": (i, [vp, i, i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]),
         "art_hp_denoise_guided_smoothing": (i, [vp, i, i, vp, vp, vp, vp, i, d]),
         "art_hp_denoise_guided_smoothing_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, i, d]),
@@ -176,7 +178,7 @@ class _DenoiseParamsC(ctypes.Structure):
                 ("chrominance", ctypes.c_double), ("chrominanceRedGreen", ctypes.c_double), ("chrominanceBlueYellow", ctypes.c_double),
                 ("gamma", ctypes.c_double), ("scale", ctypes.c_double), ("colorSpace", ctypes.c_int), ("aggressive", ctypes.c_int),
                 ("chrominanceMethod", ctypes.c_int), ("noiseCCurve", ctypes.c_void_p), ("noiseCCurveSum", ctypes.c_float),
-                ("wprof_inverse", ctypes.POINTER(ctypes.c_double))]
+                ("wprof_inverse", ctypes.POINTER(ctypes.c_double)), ("chrominanceAutoFactor", ctypes.c_double)]
 
 
 class _DevelopParamsC(ctypes.Structure):
@@ -366,14 +368,14 @@ class DenoiseParams:
 
     def __init__(self, luminance=0.0, luminanceDetail=0.0, luminanceDetailThreshold=0, chrominance=15.0, chrominanceRedGreen=0.0,
                  chrominanceBlueYellow=0.0, gamma=1.7, scale=1.0, colorSpace=0, aggressive=0, chrominanceMethod=0, noiseCCurve=None,
-                 wprof_inverse=None):
+                 wprof_inverse=None, chrominanceAutoFactor=1.0):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
     def c_struct(self):
         c = _DenoiseParamsC(self.luminance, self.luminanceDetail, int(self.luminanceDetailThreshold), self.chrominance,
                             self.chrominanceRedGreen, self.chrominanceBlueYellow, self.gamma, self.scale, int(self.colorSpace),
-                            int(self.aggressive), int(self.chrominanceMethod), None, 0.0, None)
+                            int(self.aggressive), int(self.chrominanceMethod), None, 0.0, None, float(self.chrominanceAutoFactor))
         if self.wprof_inverse is not None:      # needed by colorSpace 1 (LAB)
             self._wpi = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(self.wprof_inverse, dtype=np.float64).reshape(9)])
             c.wprof_inverse = ctypes.cast(self._wpi, ctypes.POINTER(ctypes.c_double))
@@ -644,6 +646,20 @@ class HotPath:
     def color_chain_dev(self, W, H, d_r, d_g, d_b, pitch, params):
         c = params.c_struct()
         self._check(self.lib.art_hp_color_chain_dev(self.h, W, H, d_r, d_g, d_b, pitch, ctypes.byref(c)))
+
+    def denoise_compute_params(self, r, g, b, mul, do_clip, cam2work, wprof, gamma=1.7, aggressive=0):
+        """ImProcFunctions::denoiseComputeParams (AUTOMATIC chroma) on the demosaiced camera-space planes; returns
+        (chrominance, chrominanceRedGreen, chrominanceBlueYellow) as float32 and the 9 x 15 per-crop statistics."""
+        H, W = r.shape
+        m = (ctypes.c_float * 3)(*[float(x) for x in mul])
+        c2w = None if cam2work is None else (ctypes.c_double * 9)(*[float(x) for x in np.asarray(cam2work, dtype=np.float64).reshape(9)])
+        wp = (ctypes.c_double * 9)(*[float(x) for x in np.asarray(wprof, dtype=np.float64).reshape(9)])
+        out3 = np.zeros(3, np.float32)
+        stats = np.zeros((9, 15), np.float32)
+        self._check(self.lib.art_hp_denoise_compute_params(self.h, W, H, row_table(r), row_table(g), row_table(b), m, int(bool(do_clip)), c2w, wp,
+                                                           float(gamma), int(aggressive), out3.ctypes.data_as(ctypes.c_void_p),
+                                                           stats.ctypes.data_as(ctypes.c_void_p)))
+        return out3, stats
 
     def denoise_guided_smoothing(self, r, g, b, ws, guided_chroma_radius=3, scale=1.0):
         """denoise::denoiseGuidedSmoothing, in place on three host (H, W) float32 planes."""

@@ -581,11 +581,12 @@ int art_hp_gauss(art_hp_ctx* ctx, float* const* src, float* const* dst, int W, i
     return ART_HP_OK;
 }
 
-static int check_denoise_params(art_hp_ctx* ctx, const art_hp_denoise_params* P, const double* wprof)
+static int check_denoise_params(art_hp_ctx* ctx, const art_hp_denoise_params* P, const double* wprof, bool allow_auto = false)
 {
     if (!P || !wprof) return ctx->fail(ART_HP_ERR_INVALID, "null parameters");
-    if ((P->colorSpace != 0 && P->colorSpace != 1) || P->chrominanceMethod != 0)
-        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "only chrominanceMethod MANUAL is on the hot path");
+    if (P->colorSpace != 0 && P->colorSpace != 1) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "colorSpace %d", P->colorSpace);
+    if (P->chrominanceMethod != 0 && !(allow_auto && P->chrominanceMethod == 1))
+        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "chrominanceMethod %d: AUTOMATIC needs the camera-space frame (art_hp_develop / art_hp_denoise_compute_params)", P->chrominanceMethod);
     if (P->colorSpace == 1 && !P->wprof_inverse) return ctx->fail(ART_HP_ERR_INVALID, "colorSpace LAB needs wprof_inverse");
     if (!(P->scale > 0) || !(P->gamma > 0)) return ctx->fail(ART_HP_ERR_INVALID, "scale and gamma must be positive");
     return ART_HP_OK;
@@ -796,6 +797,37 @@ int art_hp_fattal(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* 
     if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, false))) return rc;
     ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;
+}
+
+int art_hp_denoise_compute_params_dev(art_hp_ctx* ctx, int W, int H, const float* d_r, const float* d_g, const float* d_b, size_t pitch,
+                                      const float mul[3], int doClip, const double cam2work[9], const double wprof[9], double gamma, int aggressive,
+                                      float out3[3], float* stats)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_r || !d_g || !d_b || !mul || !wprof || !out3) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 256 || H < 256 || W > 32767 || H > 32767 || pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    if (!(gamma > 0)) return ctx->fail(ART_HP_ERR_INVALID, "gamma must be positive");
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_denoise_auto_chroma_dev(ctx, d_r, d_g, d_b, pitch, W, H, mul, doClip, cam2work, wprof, gamma, aggressive, out3, stats);
+}
+
+int art_hp_denoise_compute_params(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b,
+                                  const float mul[3], int doClip, const double cam2work[9], const double wprof[9], double gamma, int aggressive,
+                                  float out3[3], float* stats)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!r || !g || !b || !mul || !wprof || !out3) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 256 || H < 256 || W > 32767 || H > 32767) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    if (!(gamma > 0)) return ctx->fail(ART_HP_ERR_INVALID, "gamma must be positive");
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    int rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+    Plane io[3] = {{r, (float*)ctx->d_out[0].p}, {g, (float*)ctx->d_out[1].p}, {b, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, true))) return rc;
+    return art_denoise_auto_chroma_dev(ctx, io[0].dev, io[1].dev, io[2].dev, pitch, W, H, mul, doClip, cam2work, wprof, gamma, aggressive, out3, stats);
 }
 
 int art_hp_develop_size(const art_hp_develop_params* params, int W, int H, int* out_w, int* out_h, int* border)
@@ -1016,7 +1048,7 @@ static int check_develop(art_hp_ctx* ctx, const art_hp_develop_params* p, int W,
     }
     if (p->guidedChromaRadius < 0) return ctx->fail(ART_HP_ERR_INVALID, "guidedChromaRadius %d", p->guidedChromaRadius);
     if ((p->denoise || p->fattal_enabled) && !p->wprof) return ctx->fail(ART_HP_ERR_INVALID, "wprof is required by denoise and tone mapping");
-    if (p->denoise) { int rc = check_denoise_params(ctx, p->denoise, p->wprof); if (rc) return rc; }
+    if (p->denoise) { int rc = check_denoise_params(ctx, p->denoise, p->wprof, true); if (rc) return rc; }
     return ART_HP_OK;
 }
 

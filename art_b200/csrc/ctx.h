@@ -56,6 +56,8 @@ struct art_hp_ctx {
     void* h_chain = nullptr;
     cudaEvent_t ev_chain = nullptr;
     bool chain_cache_ready = false;
+    std::vector<float> h_auto_tabs;      // automatic chroma: cachef / cachefy, built once
+    cudaEvent_t ev_auto = nullptr;
     DevBuf d_chain_stages;               // Curve::getVal stages above the tone-curve LUT (descriptors + polylines)
     std::vector<char> h_chain_stages;
     DevBuf d_usm_tables;                 // apply_gamma's two 65536-entry LUTs (gamma 1/3 and 3), built once on the device
@@ -182,6 +184,12 @@ int art_usm_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W,
 // develop.cu: ImProcFunctions::denoise (calclum, adjust_params, RGB_denoise, NL-means on Y) and the whole-frame pipeline
 int art_denoise_stage_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_denoise_params* dn,
                           int nlStrength, int nlDetail, int guidedChromaRadius, double ecomp, const double* cam2work, const double* wprof);
+// ImProcFunctions::denoiseComputeParams for the AUTOMATIC chroma method (denoise.cu): r / g / b = the demosaiced camera-space planes at the frame's
+// origin (after the border crop); out3 = store.chrominance, chrominanceRedGreen, chrominanceBlueYellow; stats_out (optional) = 9 x 15 per-crop values.
+// Synchronises the stream (the result decides RGB_denoise's wavelet depth).
+int art_denoise_auto_chroma_dev(art_hp_ctx* ctx, const float* r, const float* g, const float* b, size_t ip, int widIm, int heiIm,
+                                const float mul[3], int doClip, const double* cam2work, const double* wprof, double gamma, int aggressive,
+                                float out3[3], float* stats_out);
 // output size of art_hp_develop for a W x H raw frame
 void art_develop_geometry(const art_hp_develop_params* p, int W, int H, int* b, int* Wo, int* Ho);
 int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int W, int H, const float* raw, size_t rp,

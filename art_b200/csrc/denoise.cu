@@ -716,3 +716,366 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
     }
     return ART_HP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Automatic chroma estimator: ImProcFunctions::denoiseComputeParams for DenoiseParams::ChrominanceMethod::AUTOMATIC, the reference's
+// default (rtengine/ipdenoise.cc L800-1093; procparams.cc L1909).  Nine crops of HALF the frame's width and height (Tile_calc returns
+// one tile, so crW = widIm / 2, crH = heiIm / 2: L866-877, FTblockDN.cc L442-480) at 50 px from the corners / centred, each through
+// RGB_denoise_info (ipdenoise.cc L227-669): getImage (gain / clip, camera space) -> gamma LUT + rgb2yuv -> two 5-level wavelet
+// decompositions -> WaveletDenoiseAll_info / ShrinkAll_info (FTblockDN.cc L1227-1364): the MAD of every subband and, on level 1, running
+// statistics of the crop's half-resolution chroma / hue / luminance maps (provicalc through the camera->working matrix, XYZ2Lab).
+// Those statistics are float sums in raster order whose terms depend on the running mean (`dev += SQR(c - chro / nc)`), so the order is
+// part of the result: k_auto_stats keeps it -- per crop one CTA streams the maps through shared memory; two lanes carry the running sums
+// (one dependent add per element), all threads form the terms, two more lanes add them, pipelined one chunk apart.
+// The scalar tail (calcautodn_info L66-206 and the nine-crop combination L964-1075) is ~200 flops and runs on the host after one
+// download of 9 x (30 MADs + 10 sums): the number of wavelet levels of RGB_denoise depends on the result, so the host has to see it.
+namespace {
+
+struct AutoPrepArgs {
+    const float *r, *g, *b; size_t ip;          // demosaiced planes, camera space, addressed at the crop's origin
+    int W, H, wid;                               // crop size, half-resolution width
+    float mul[3]; int do_clip, do_mat; double mat[9];
+    float wp[9]; const float *cachef, *cachefy, *gamcurve;
+    float gam, gamthresh, gamslope, gain;
+    float *la, *lb;                              // dense W x H
+    float *nvc, *nvh, *nvl;                      // dense wid x hei
+};
+
+__device__ __forceinline__ float clip65535_dn(float a) { const float m = a < 65535.f ? a : 65535.f; return 0.f < m ? m : 0.f; }
+
+__global__ void __launch_bounds__(256) k_auto_prep(AutoPrepArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.W) return;
+    for (int y = blockIdx.y; y < a.H; y += gridDim.y) {
+        const size_t i = (size_t)y * a.ip + x;
+        float R = a.r[i] * a.mul[0], G = a.g[i] * a.mul[1], B = a.b[i] * a.mul[2];          // getImage, rawimagesource.cc L943-1025
+        if (a.do_clip) { R = clip65535_dn(R); G = clip65535_dn(G); B = clip65535_dn(B); }
+        if (!((x | y) & 1)) {      // provicalc: the even pixels through convertColorSpace's matrix, then Lab (ipdenoise.cc L271-287, L390-420)
+            float RL = R, GL = G, BL = B;
+            if (a.do_mat) {
+                const double dr = R, dg = G, db = B;
+                RL = (float)(a.mat[0] * dr + a.mat[1] * dg + a.mat[2] * db);
+                GL = (float)(a.mat[3] * dr + a.mat[4] * dg + a.mat[5] * db);
+                BL = (float)(a.mat[6] * dr + a.mat[7] * dg + a.mat[8] * db);
+            }
+            const float XL = ((a.wp[0] * RL + a.wp[1] * GL + a.wp[2] * BL));
+            const float YL = ((a.wp[3] * RL + a.wp[4] * GL + a.wp[5] * BL));
+            const float ZL = ((a.wp[6] * RL + a.wp[7] * GL + a.wp[8] * BL));
+            const float fx = computeXYZ2Lab(a.cachef, XL / 0.9642f), fy = computeXYZ2Lab(a.cachef, YL), fz = computeXYZ2Lab(a.cachef, ZL / 0.8249f);
+            const float aN = (500.0f * (fx - fy)), bN = (200.0f * (fy - fz));
+            float cN = sqrtf(aN * aN + bN * bN);
+            const size_t o = (size_t)(y >> 1) * a.wid + (x >> 1);
+            a.nvh[o] = sleef::xatan2f(bN, aN);
+            if (cN < 100.f) cN = 100.f;
+            a.nvc[o] = cN;
+            float Llum = computeXYZ2LabY(a.cachefy, YL);
+            Llum = Llum < 2.f ? 2.f : Llum;
+            Llum = Llum > 32768.f ? 32768.f : Llum;
+            a.nvl[o] = Llum;
+        }
+        float X = a.gain * R, Y = a.gain * G, Z = a.gain * B;                                  // ipdenoise.cc L430-447
+        X = X < 65535.f ? lut_noclip(a.gamcurve, 65536, X) : (gammaf_(X / 65535.f, a.gam, a.gamthresh, a.gamslope) * 32768.f);
+        Y = Y < 65535.f ? lut_noclip(a.gamcurve, 65536, Y) : (gammaf_(Y / 65535.f, a.gam, a.gamthresh, a.gamslope) * 32768.f);
+        Z = Z < 65535.f ? lut_noclip(a.gamcurve, 65536, Z) : (gammaf_(Z / 65535.f, a.gam, a.gamthresh, a.gamslope) * 32768.f);
+        const float l = X * a.wp[3] + Y * a.wp[4] + Z * a.wp[5];
+        const size_t o = (size_t)y * a.W + x;
+        a.la[o] = X - l;
+        a.lb[o] = l - Z;
+    }
+}
+
+// ShrinkAll_info's level-1 statistics (FTblockDN.cc L1262-1316) over rows [0, Hab) x columns [0, Wab) of maps with row stride `wid`.
+// out: chro, dev, lume, devL, red_yel, skin_c, then nc, nry, nsk as floats (counts are exact below 2^24; nc is passed back as an int too)
+struct AutoStatsArgs { const float *nvc, *nvh, *nvl; int wid, Wab, Hab; float* out; int* out_n; };
+constexpr int AS_CHUNK = 1024, AS_THREADS = 256;      // 10 arrays x 1024 floats = 40 KB of static shared memory
+
+__global__ void __launch_bounds__(AS_THREADS) k_auto_stats(const AutoStatsArgs* __restrict__ crops)
+{
+    const AutoStatsArgs a = crops[blockIdx.x];
+    __shared__ float sc[2][AS_CHUNK], sh[2][AS_CHUNK], sl[2][AS_CHUNK];       // chroma, hue, luminance of a chunk (double buffered)
+    __shared__ float tdev[2][AS_CHUNK], tdevL[2][AS_CHUNK];                   // the terms SQR(x - running mean)
+    const long long total = (long long)a.Wab * a.Hab;
+    const int nchunks = (int)((total + AS_CHUNK - 1) / AS_CHUNK);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float chro = 0.f, lume = 0.f, dev = 0.f, devL = 0.f, red_yel = 0.f, skin_c = 0.f;     // live in lane 0 of warps 0..3
+    int nry = 0, nsk = 0;
+    auto load = [&](int c, int buf) {
+        const long long base = (long long)c * AS_CHUNK;
+        for (int k = tid; k < AS_CHUNK; k += AS_THREADS) {
+            const long long e = base + k;
+            if (e < total) {
+                const int i = (int)(e / a.Wab), j = (int)(e - (long long)i * a.Wab);
+                const size_t o = (size_t)i * a.wid + j;
+                sc[buf][k] = a.nvc[o]; sh[buf][k] = a.nvh[o]; sl[buf][k] = a.nvl[o];
+            }
+        }
+    };
+    if (nchunks > 0) load(0, 0);
+    __syncthreads();
+    // iteration c: lanes run the serial sums of chunk c while the other threads fetch chunk c + 1; then everybody forms chunk c's terms;
+    // the term sums of chunk c run in iteration c + 1 beside the running sums of chunk c + 1
+    for (int c = 0; c <= nchunks; ++c) {
+        const int buf = c & 1;
+        const int cnt = c < nchunks ? (int)min((long long)AS_CHUNK, total - (long long)c * AS_CHUNK) : 0;
+        const int pcnt = c > 0 ? (int)min((long long)AS_CHUNK, total - (long long)(c - 1) * AS_CHUNK) : 0;
+        if (lane == 0) {
+            if (warp == 0) {          // chro += c: the running sum after each element goes where the term will be formed (the mean's numerator)
+#pragma unroll 8
+                for (int k = 0; k < cnt; ++k) { chro += sc[buf][k]; tdev[buf][k] = chro; }
+            } else if (warp == 1) {
+#pragma unroll 8
+                for (int k = 0; k < cnt; ++k) { lume += sl[buf][k]; tdevL[buf][k] = lume; }
+            } else if (warp == 2) {
+                for (int k = 0; k < cnt; ++k) {
+                    const float cv = sc[buf][k], hv = sh[buf][k];
+                    if (hv > -0.8f && hv < 2.0f && cv > 10000.f) { red_yel += cv; ++nry; }
+                    if (hv > 0.f && hv < 1.6f && cv < 10000.f) { skin_c += cv; ++nsk; }
+                }
+            } else if (warp == 3) {
+#pragma unroll 8
+                for (int k = 0; k < pcnt; ++k) dev += tdev[buf ^ 1][k];
+            } else if (warp == 4) {
+#pragma unroll 8
+                for (int k = 0; k < pcnt; ++k) devL += tdevL[buf ^ 1][k];
+            }
+        }
+        if (warp >= 5 && c + 1 < nchunks) {
+            // warps 5..7 fetch the next chunk into the other buffer's inputs: its terms (tdev[buf ^ 1]) are still being summed by warps
+            // 3 / 4, but its inputs sc / sh / sl were consumed in the previous iteration
+            const long long base = (long long)(c + 1) * AS_CHUNK;
+            for (int k = tid - 160; k < AS_CHUNK; k += AS_THREADS - 160) {
+                const long long e = base + k;
+                if (e < total) {
+                    const int i = (int)(e / a.Wab), j = (int)(e - (long long)i * a.Wab);
+                    const size_t o = (size_t)i * a.wid + j;
+                    sc[buf ^ 1][k] = a.nvc[o]; sh[buf ^ 1][k] = a.nvh[o]; sl[buf ^ 1][k] = a.nvl[o];
+                }
+            }
+        }
+        __syncthreads();
+        // terms of chunk c: SQR(x - sum / n) with n = elements so far (float(sum) / int, L1268 / L1288: the int is converted to float)
+        const long long base = (long long)c * AS_CHUNK;
+        for (int k = tid; k < cnt; k += AS_THREADS) {
+            const float n = (float)(int)(base + k + 1);
+            const float d1 = sc[buf][k] - (tdev[buf][k] / n), d2 = sl[buf][k] - (tdevL[buf][k] / n);
+            tdev[buf][k] = d1 * d1; tdevL[buf][k] = d2 * d2;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { a.out[0] = chro; a.out_n[0] = (int)total; }
+    if (tid == 32) a.out[2] = lume;
+    if (tid == 64) { a.out[4] = red_yel; a.out[5] = skin_c; a.out_n[1] = nry; a.out_n[2] = nsk; }
+    if (tid == 96) a.out[1] = dev;
+    if (tid == 128) a.out[3] = devL;
+}
+
+// calcautodn_info, ipdenoise.cc L66-206 (mode 1, lissage 0, levaut 0 as denoiseComputeParams calls it; the other branches are kept)
+void calcautodn_info_host(bool aggressive, float& chaut, float& delta, int Nb, int levaut, float maxmax, float lumema, float chromina, int mode, int lissage,
+                          float redyel, float skinc, float nsknc)
+{
+    float reducdelta = 1.f;
+    if (aggressive) reducdelta = static_cast<float>(0.9);
+    chaut = (chaut * Nb - maxmax) / (Nb - 1);
+    if ((redyel > 5000.f || skinc > 1000.f) && nsknc < 0.4f && chromina > 3000.f) chaut *= 0.45f;
+    else if ((redyel > 12000.f || skinc > 1200.f) && nsknc < 0.3f && chromina > 3000.f) chaut *= 0.3f;
+    if (mode == 0 || mode == 2) {
+        if (chromina > 10000.f) chaut *= 0.7f; else if (chromina > 6000.f) chaut *= 0.9f; else if (chromina < 3000.f) chaut *= 1.2f; else if (chromina < 2000.f) chaut *= 1.5f;
+        if (lumema < 2500.f) chaut *= 1.3f; else if (lumema < 5000.f) chaut *= 1.2f; else if (lumema > 20000.f) chaut *= 0.9f;
+    } else if (mode == 1) {
+        if (chromina > 10000.f) chaut *= 0.8f; else if (chromina > 6000.f) chaut *= 0.9f; else if (chromina < 3000.f) chaut *= 1.5f; else if (chromina < 2000.f) chaut *= 2.2f;
+        if (lumema < 2500.f) chaut *= 1.2f; else if (lumema < 5000.f) chaut *= 1.1f; else if (lumema > 20000.f) chaut *= 0.9f;
+    }
+    if (levaut == 0 && chaut > 300.f) chaut = 0.714286f * chaut + 85.71428f;
+    delta = maxmax - chaut;
+    delta *= reducdelta;
+    if (lissage == 1 || lissage == 2) {
+        if (chaut < 200.f && delta < 200.f) delta *= 0.95f; else if (chaut < 200.f && delta < 400.f) delta *= 0.5f; else if (chaut < 200.f && delta >= 400.f) delta = 200.f;
+        else if (chaut < 400.f && delta < 400.f) delta *= 0.4f; else if (chaut < 400.f && delta >= 400.f) delta = 120.f;
+        else if (chaut < 550.f) delta *= 0.15f; else if (chaut < 650.f) delta *= 0.1f; else delta *= 0.07f;
+        if (mode == 0 || mode == 2) { if (chromina < 6000.f) delta *= 1.4f; if (lumema < 5000.f) delta *= 1.4f; }
+        else if (mode == 1) { if (chromina < 6000.f) delta *= 1.2f; if (lumema < 5000.f) delta *= 1.2f; }
+    }
+    if (lissage == 0) {
+        if (chaut < 200.f && delta < 200.f) delta *= 0.95f; else if (chaut < 200.f && delta < 400.f) delta *= 0.7f; else if (chaut < 200.f && delta >= 400.f) delta = 280.f;
+        else if (chaut < 400.f && delta < 400.f) delta *= 0.6f; else if (chaut < 400.f && delta >= 400.f) delta = 200.f;
+        else if (chaut < 550.f) delta *= 0.3f; else if (chaut < 650.f) delta *= 0.2f; else delta *= 0.15f;
+        if (mode == 0 || mode == 2) { if (chromina < 6000.f) delta *= 1.4f; if (lumema < 5000.f) delta *= 1.4f; }
+        else if (mode == 1) { if (chromina < 6000.f) delta *= 1.2f; if (lumema < 5000.f) delta *= 1.2f; }
+    }
+}
+
+}  // namespace
+
+int art_denoise_auto_chroma_dev(art_hp_ctx* ctx, const float* r, const float* g, const float* b, size_t ip, int widIm, int heiIm,
+                                const float mul[3], int doClip, const double* cam2work, const double* wprof, double gamma, int aggressive,
+                                float out3[3], float* stats_out)
+{
+    cudaStream_t st = ctx->stream;
+    const int crW = widIm / 2, crH = heiIm / 2;                    // L866-877 with Tile_calc's single tile
+    const int levwav = 5;                                           // max(2, 5 - ceil(log(scale))) at RGB_denoise_info's scale 1 (L935, L449)
+    if (crW < 128 || crH < 128)
+        return ctx->fail(ART_HP_ERR_UNSUPPORTED, "automatic chroma needs a frame of at least 256 x 256 after the border crop (got %dx%d)", widIm, heiIm);
+    const int wid = (crW + 1) / 2, hei = (crH + 1) / 2;
+    const size_t n = (size_t)crW * crH, nh = (size_t)wid * hei;
+    // scratch: la, lb (one crop at a time), nine sets of half-resolution maps, LUTs, results
+    const size_t floats = 2 * round_up(n, 64) + 27 * round_up(nh, 64) + 3 * 65536 + 9 * 64 + 9 * 16 + 1024;
+    void* blk = nullptr;
+    int rc = art_pool_alloc(ctx, floats * sizeof(float), &blk);
+    if (rc) return rc;
+    float* p = (float*)blk;
+    auto take = [&p](size_t k) { float* q = p; p += round_up(k, 64); return q; };
+    float *la = take(n), *lb = take(n);
+    float* maps = take(27 * round_up(nh, 64));
+    float *cachef = take(65536), *cachefy = take(65536), *gamcurve = take(65536);
+    float* mads = take(9 * 64);                                     // per crop: a[8][3] at 0, b[8][3] at 24 (art_hp_wavelet_mad_dev's layout)
+    float* sums = take(9 * 16);                                     // per crop: 6 floats + 3 ints
+    AutoStatsArgs* d_crops = reinterpret_cast<AutoStatsArgs*>(take(512));
+    auto done = [&](int code) { art_pool_free(ctx, blk); return code; };
+
+    {   // Color::cachef / cachefy, color.cc L205-233 (host libm cbrt, as in the reference)
+        std::vector<float>& h = ctx->h_auto_tabs;
+        if (h.empty()) {
+            h.resize(2 * 65536);
+            const double eps = 216.0 / 24389.0, kappa = 24389.0 / 27.0, MAXVALF = 65535.f;
+            const int epsmaxint = (int)(MAXVALF * eps);
+            int i = 0;
+            for (; i <= epsmaxint; i++) { h[i] = (float)(327.68 * ((kappa * i / MAXVALF + 16.0) / 116.0)); h[65536 + i] = (float)(327.68 * (kappa * i / MAXVALF)); }
+            for (; i < 65536; i++) { h[i] = (float)(327.68 * std::cbrt((double)i / MAXVALF)); h[65536 + i] = (float)(327.68 * (116.0 * std::cbrt((double)i / MAXVALF) - 16.0)); }
+        }
+        if (cudaMemcpyAsync(cachef, h.data(), sizeof(float) * 2 * 65536, cudaMemcpyHostToDevice, st) != cudaSuccess) return done(ctx->fail(ART_HP_ERR_CUDA, "table upload failed"));
+    }
+    // RGB_denoise_infoGamCurve, L209-225 (isRAW)
+    const float gam = static_cast<float>(gamma);
+    const float gamthresh = 0.001f;
+    const float gamslope = std::exp(std::log(static_cast<double>(gamthresh)) / gam) / gamthresh;
+    k_dn_gamma_lut<<<256, 256, 0, st>>>(gamcurve, gam, gamthresh, gamslope, 65535.f, 32768.f);
+    ctx->launches++;
+    const float gain = std::pow(2.0f, float(std::log(5.f) / std::log(2.f)));      // expcomp = log(5) / log(2), L939 -> L293
+    if (cudaMemsetAsync(mads, 0, 9 * 64 * sizeof(float), st) != cudaSuccess) return done(ctx->fail(ART_HP_ERR_CUDA, "memset failed"));
+
+    const int begW = 50, begH = 50;
+    const int coordW[3] = {begW, widIm / 2 - crW / 2, widIm - crW - begW};
+    const int coordH[3] = {begH, heiIm / 2 - crH / 2, heiIm - crH - begH};
+    AutoStatsArgs hc[9];
+    if (!ctx->ev_auto) { if (cudaEventCreateWithFlags(&ctx->ev_auto, cudaEventDisableTiming) != cudaSuccess) return done(ctx->fail(ART_HP_ERR_CUDA, "event")); }
+    for (int wcr = 0; wcr < 3 && !rc; ++wcr)
+        for (int hcr = 0; hcr < 3 && !rc; ++hcr) {
+            const int k = hcr * 3 + wcr;
+            const size_t org = (size_t)coordH[hcr] * ip + coordW[wcr];
+            AutoPrepArgs a{};
+            a.r = r + org; a.g = g + org; a.b = b + org; a.ip = ip; a.W = crW; a.H = crH; a.wid = wid;
+            for (int i = 0; i < 3; ++i) a.mul[i] = mul[i];
+            a.do_clip = doClip; a.do_mat = cam2work != nullptr;
+            for (int i = 0; i < 9; ++i) { a.mat[i] = cam2work ? cam2work[i] : 0.0; a.wp[i] = static_cast<float>(wprof[i]); }
+            a.cachef = cachef; a.cachefy = cachefy; a.gamcurve = gamcurve; a.gam = gam; a.gamthresh = gamthresh; a.gamslope = gamslope; a.gain = gain;
+            a.la = la; a.lb = lb;
+            a.nvc = maps + (size_t)(3 * k) * round_up(nh, 64); a.nvh = a.nvc + round_up(nh, 64); a.nvl = a.nvh + round_up(nh, 64);
+            art_prof_begin(ctx, "k_auto_prep");
+            k_auto_prep<<<dim3((crW + 255) / 256, std::min(crH, 148 * 4)), 256, 0, st>>>(a);
+            art_prof_end(ctx);
+            ctx->launches++;
+            art_hp_wavelet *adec = nullptr, *bdec = nullptr;
+            if ((rc = art_hp_wavelet_decompose_dev(ctx, la, crW, crW, crH, levwav, 1, &adec))) break;
+            if (art_hp_wavelet_maxlevel(adec) < levwav) { art_hp_wavelet_destroy(adec); rc = ctx->fail(ART_HP_ERR_UNSUPPORTED, "crop %dx%d is too small for %d wavelet levels", crW, crH, levwav); break; }
+            int Wab = 0, Hab = 0, stride = 0;
+            art_hp_wavelet_level_dims(adec, 1, &Wab, &Hab, &stride);
+            hc[k] = AutoStatsArgs{a.nvc, a.nvh, a.nvl, wid, Wab, Hab, sums + 16 * k, reinterpret_cast<int*>(sums + 16 * k + 8)};
+            rc = art_hp_wavelet_mad_dev(ctx, adec, mads + 64 * k);
+            art_hp_wavelet_destroy(adec);
+            if (rc) break;
+            if ((rc = art_hp_wavelet_decompose_dev(ctx, lb, crW, crW, crH, levwav, 1, &bdec))) break;
+            rc = art_hp_wavelet_mad_dev(ctx, bdec, mads + 64 * k + 24);
+            art_hp_wavelet_destroy(bdec);
+        }
+    if (rc) return done(rc);
+    // the nine serial statistics run side by side, one CTA each
+    if (cudaMemcpyAsync(d_crops, hc, sizeof hc, cudaMemcpyHostToDevice, st) != cudaSuccess) return done(ctx->fail(ART_HP_ERR_CUDA, "upload failed"));
+    art_prof_begin(ctx, "k_auto_stats");
+    k_auto_stats<<<9, AS_THREADS, 0, st>>>(d_crops);
+    art_prof_end(ctx);
+    ctx->launches++;
+    float hm[9 * 64], hs[9 * 16];
+    if (cudaMemcpyAsync(hm, mads, sizeof hm, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaMemcpyAsync(hs, sums, sizeof hs, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+        return done(ctx->fail(ART_HP_ERR_CUDA, "automatic chroma: download failed: %s", cudaGetErrorString(cudaGetLastError())));
+    art_pool_free(ctx, blk);
+
+    // ShrinkAll_info's scalar part per crop, then calcautodn_info and the nine-crop combination
+    const float reduc = aggressive ? static_cast<float>(0.9) : 1.f;
+    float ch_M[9], max_r[9], max_b[9], min_r[9], min_b[9], lumL[9], chromC[9], ry[9], sk[9], pcsk[9], delta[9];
+    int Nb[9];
+    for (int k = 0; k < 9; ++k) {
+        const float* ma = hm + 64 * k; const float* mb = ma + 24;
+        const float* s = hs + 16 * k; const int* sn = reinterpret_cast<const int*>(s + 8);
+        float chromina = 0.f, sigma = 0.f, lumema = 0.f, sigma_L = 0.f, redyel = 0.f, skinc = 0.f, nsknc = 0.f;
+        const int nc = sn[0], nry = sn[1], nsk = sn[2], nL = nc;
+        if (nc > 0) { chromina = s[0] / nc; sigma = std::sqrt(s[1] / nc); nsknc = (float)nsk / (float)nc; } else nsknc = (float)nsk;
+        if (nL > 0) { lumema = s[2] / nL; sigma_L = std::sqrt(s[3] / nL); }
+        if (nry > 0) redyel = s[4] / nry;
+        if (nsk > 0) skinc = s[5] / nsk;
+        float chau = 0.f, chred = 0.f, chblue = 0.f, maxchred = 0.f, maxchblue = 0.f, minchred = 100000000.f, minchblue = 100000000.f;
+        float chaut = 0.f, redaut = 0.f, blueaut = 0.f, maxredaut = 0.f, maxblueaut = 0.f, minredaut = 0.f, minblueaut = 0.f;
+        int nb = 0;
+        for (int lvl = 0; lvl < levwav; ++lvl)
+            for (int dir = 0; dir < 3; ++dir) {
+                const float mada = ma[3 * lvl + dir], madb = mb[3 * lvl + dir];
+                chred += mada;
+                if (mada > maxchred) maxchred = mada;
+                if (mada < minchred) minchred = mada;
+                maxredaut = std::sqrt(reduc * maxchred);
+                minredaut = std::sqrt(reduc * minchred);
+                chblue += madb;
+                if (madb > maxchblue) maxchblue = madb;
+                if (madb < minchblue) minchblue = madb;
+                maxblueaut = std::sqrt(reduc * maxchblue);
+                minblueaut = std::sqrt(reduc * minchblue);
+                chau += (mada + madb);
+                ++nb;
+                chaut = std::sqrt(reduc * chau / (nb + nb));
+                redaut = std::sqrt(reduc * chred / nb);
+                blueaut = std::sqrt(reduc * chblue / nb);
+            }
+        Nb[k] = nb; ch_M[k] = 1.0f * chaut; max_r[k] = 1.0f * maxredaut; max_b[k] = 1.0f * maxblueaut; min_r[k] = 1.0f * minredaut; min_b[k] = 1.0f * minblueaut;
+        lumL[k] = lumema; chromC[k] = chromina; ry[k] = redyel; sk[k] = skinc; pcsk[k] = nsknc;
+        if (stats_out) {
+            float* o = stats_out + 15 * k;
+            o[0] = chaut; o[1] = (float)nb; o[2] = redaut; o[3] = blueaut; o[4] = maxredaut; o[5] = maxblueaut; o[6] = minredaut; o[7] = minblueaut;
+            o[8] = chromina; o[9] = sigma; o[10] = lumema; o[11] = sigma_L; o[12] = redyel; o[13] = skinc; o[14] = nsknc;
+        }
+    }
+    const float autoNR = 10, autoNRmax = 40, lowdenoise = 1.f, adjustr = 1.f, multip = 1.f;      // isRAW
+    const int levaut = 0, mode = 1, lissage = 0;
+    float Max_R[9] = {0}, Max_B[9] = {0}, Min_R[9], Min_B[9];
+    for (int k = 0; k < 9; ++k) {
+        const float maxmax = max_r[k] < max_b[k] ? max_b[k] : max_r[k];
+        calcautodn_info_host(aggressive != 0, ch_M[k], delta[k], Nb[k], levaut, maxmax, lumL[k], chromC[k], mode, lissage, ry[k], sk[k], pcsk[k]);
+    }
+    for (int k = 0; k < 9; ++k) {
+        if (max_r[k] > max_b[k]) {
+            Max_R[k] = (delta[k]) / ((autoNRmax * multip * adjustr * lowdenoise) / 2.f);
+            Min_B[k] = -(ch_M[k] - min_b[k]) / (autoNRmax * multip * adjustr * lowdenoise);
+            Max_B[k] = 0.f; Min_R[k] = 0.f;
+        } else {
+            Max_B[k] = (delta[k]) / ((autoNRmax * multip * adjustr * lowdenoise) / 2.f);
+            Min_R[k] = -(ch_M[k] - min_r[k]) / (autoNRmax * multip * adjustr * lowdenoise);
+            Min_B[k] = 0.f; Max_R[k] = 0.f;
+        }
+    }
+    float chM = 0.f, MaxR = 0.f, MaxB = 0.f, MinR = 100000000000.f, MinB = 100000000000.f, maxr, maxb;
+    float MaxRMoy = 0.f, MaxBMoy = 0.f, MinRMoy = 0.f, MinBMoy = 0.f;
+    for (int k = 0; k < 9; ++k) {
+        chM += ch_M[k]; MaxBMoy += Max_B[k]; MaxRMoy += Max_R[k]; MinRMoy += Min_R[k]; MinBMoy += Min_B[k];
+        if (Max_R[k] > MaxR) MaxR = Max_R[k];
+        if (Max_B[k] > MaxB) MaxB = Max_B[k];
+        if (Min_R[k] < MinR) MinR = Min_R[k];
+        if (Min_B[k] < MinB) MinB = Min_B[k];
+    }
+    chM /= 9; MaxBMoy /= 9; MaxRMoy /= 9; MinBMoy /= 9; MinRMoy /= 9;
+    if (MaxR > MaxB) { maxr = MaxRMoy + (MaxR - MaxRMoy) * 0.66f; maxb = MinBMoy + (MinB - MinBMoy) * 0.66f; }
+    else { maxb = MaxBMoy + (MaxB - MaxBMoy) * 0.66f; maxr = MinRMoy + (MinR - MinRMoy) * 0.66f; }
+    out3[0] = chM / (autoNR * multip * adjustr);
+    out3[1] = maxr;
+    out3[2] = maxb;
+    return ART_HP_OK;
+}

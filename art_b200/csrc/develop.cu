@@ -161,13 +161,30 @@ int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr, int
     else if (p->method == ART_HP_BAYER_AMAZE) rc = art_amaze_dev(ctx, Wr, Hr, p->filters, raw, rp, dm[0], dm[1], dm[2], dmp, p->initialGain, p->border, 0, Hr);
     else rc = art_rcd_dev(ctx, Wr, Hr, p->filters, raw, rp, dm[0], dm[1], dm[2], dmp, 0, Hr);      // ends with its own border_interpolate2(9)
     if (rc) return rc;
+    // simpleprocess.cc L254-256: denoiseComputeParams measures the demosaiced frame (camera space, through getImage per crop) before
+    // getImage converts it; the estimate replaces the chroma sliders of this frame's denoise parameters
+    art_hp_denoise_params dn_resolved;
+    const art_hp_denoise_params* dn = p->denoise;
+    if (dn && dn->chrominanceMethod == 1) {
+        float est[3];
+        const size_t off0 = (size_t)bd * dmp + bd;
+        if ((rc = art_denoise_auto_chroma_dev(ctx, dm[0] + off0, dm[1] + off0, dm[2] + off0, dmp, W, H, p->mul, p->doClip, p->cam2work, p->wprof,
+                                              dn->gamma, dn->aggressive, est, nullptr))) return rc;
+        dn_resolved = *dn;
+        const double f = dn->chrominanceAutoFactor > 0 ? dn->chrominanceAutoFactor : 1.0;
+        dn_resolved.chrominance = est[0] * f;                  // float * double, as `store.chrominance * dnparams.chrominanceAutoFactor` (L1064-1066)
+        dn_resolved.chrominanceRedGreen = est[1] * f;
+        dn_resolved.chrominanceBlueYellow = est[2] * f;
+        dn_resolved.chrominanceMethod = 0;
+        dn = &dn_resolved;
+    }
     if (bd) {
         const size_t off = (size_t)bd * dmp + bd;
         rc = art_scale_convert_crop_dev(ctx, W, H, dm[0] + off, dm[1] + off, dm[2] + off, dmp, r, g, b, op, p->mul, p->doClip, p->cam2work);
     } else rc = art_scale_convert_dev(ctx, W, H, r, g, b, op, p->mul, p->doClip, p->cam2work);
     if (rc) return rc;
-    if (p->denoise) {
-        if ((rc = art_denoise_stage_dev(ctx, r, g, b, op, W, H, p->denoise, p->nlStrength, p->nlDetail, p->guidedChromaRadius, p->denoise_expcomp, p->cam2work, p->wprof))) return rc;
+    if (dn) {
+        if ((rc = art_denoise_stage_dev(ctx, r, g, b, op, W, H, dn, p->nlStrength, p->nlDetail, p->guidedChromaRadius, p->denoise_expcomp, p->cam2work, p->wprof))) return rc;
     }
     if (p->fattal_enabled) {
         if ((rc = art_fattal_dev(ctx, r, g, b, op, W, H, p->fattal_threshold, p->fattal_amount, p->fattal_satcontrol, p->wprof))) return rc;

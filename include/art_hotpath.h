@@ -220,7 +220,9 @@ int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art
  *                      expcomp = 0, noiseLCurve (unset), noiseCCurve, nresi, highresi) (rtengine/FTblockDN.cc L1638-2689)
  *                      as ImProcFunctions::denoise calls it (rtengine/ipdenoise.cc L1165), in place on three planes.
  * Parameters mirror procparams::DenoiseParams (rtengine/procparams.h) for the fields RGB_denoise reads.  Supported:
- * colorSpace RGB (0) | LAB (1), aggressive 0 | 1 (QUALITY_STANDARD | QUALITY_HIGH, FTblockDN.cc L1671), chrominanceMethod MANUAL (0); anything else returns ART_HP_ERR_UNSUPPORTED.
+ * colorSpace RGB (0) | LAB (1), aggressive 0 | 1 (QUALITY_STANDARD | QUALITY_HIGH, FTblockDN.cc L1671), chrominanceMethod MANUAL (0); AUTOMATIC (1)
+ * needs the camera-space frame and is resolved by art_hp_develop (or by the caller through art_hp_denoise_compute_params below): here it
+ * returns ART_HP_ERR_UNSUPPORTED, like anything else.
  * `scale` is ImProcData::scale.  noiseCCurve: the 501-entry LUT NoiseCurve::Set builds (rtengine/ipdenoise.cc L684-705) and
  * its sum, host pointers, or NULL for "curve not set"; when given, the half-resolution calclum image of
  * ipdenoise.cc L1119-1131 (3 planes of ((H+1)/2) x ((W+1)/2)) must be supplied too.
@@ -239,6 +241,8 @@ typedef struct art_hp_denoise_params {
     const float* noiseCCurve;
     float noiseCCurveSum;
     const double* wprof_inverse;    /* ICCStore::workingSpaceInverseMatrix, 9 doubles: needed when colorSpace == 1 (LAB), else may be NULL */
+    /* ---- ABI version 2 ---- */
+    double chrominanceAutoFactor;   /* chrominanceMethod == 1 (AUTOMATIC, the reference default): the estimate is multiplied by it; 0 reads as 1 */
 } art_hp_denoise_params;
 int art_hp_rgb_denoise(art_hp_ctx* ctx, float* const* r, float* const* g, float* const* b, int W, int H,
                        const art_hp_denoise_params* params, const double wprof[9],
@@ -247,6 +251,26 @@ int art_hp_rgb_denoise_dev(art_hp_ctx* ctx, float* d_r, float* d_g, float* d_b, 
                            const art_hp_denoise_params* params, const double wprof[9],
                            const float* d_calclum_r, const float* d_calclum_g, const float* d_calclum_b, size_t calclum_pitch,
                            float* nresi_highresi);
+
+/*
+ * art_hp_denoise_compute_params   ImProcFunctions::denoiseComputeParams for DenoiseParams::ChrominanceMethod::AUTOMATIC -- the reference's default
+ *                      (rtengine/ipdenoise.cc L800-1093; RGB_denoise_info L227-669, calcautodn_info L66-206, WaveletDenoiseAll_info /
+ *                      ShrinkAll_info rtengine/FTblockDN.cc L1227-1364): nine crops of half the frame each are measured (wavelet MADs,
+ *                      chroma / hue / luminance statistics in the reference's summation order) and combined into
+ *                      out3 = DenoiseInfoStore::chrominance, chrominanceRedGreen, chrominanceBlueYellow (the caller multiplies by
+ *                      chrominanceAutoFactor as L1064-1066 do).  red / green / blue: the DEMOSAICED planes in camera space, W x H = the size
+ *                      getFullSize reports (after the raw border crop); mul / doClip / cam2work as in art_hp_scale_convert (getImage and
+ *                      convertColorSpace run inside, per crop, as in the reference); wprof = ICCStore::workingSpaceMatrix; gamma / aggressive =
+ *                      DenoiseParams'.  stats (optional): 9 x 15 floats, crop k = hcr * 3 + wcr: chaut, Nb, redaut, blueaut, maxredaut,
+ *                      maxblueaut, minredaut, minblueaut, chromina, sigma, lumema, sigma_L, redyel, skinc, nsknc.  W, H >= 256.
+ *                      Bit-identical to the reference.  Synchronises the context's stream.
+ */
+int art_hp_denoise_compute_params(art_hp_ctx* ctx, int W, int H, float* const* red, float* const* green, float* const* blue,
+                                  const float mul[3], int doClip, const double cam2work[9], const double wprof[9], double gamma, int aggressive,
+                                  float out3[3], float* stats);
+int art_hp_denoise_compute_params_dev(art_hp_ctx* ctx, int W, int H, const float* d_red, const float* d_green, const float* d_blue, size_t pitch,
+                                      const float mul[3], int doClip, const double cam2work[9], const double wprof[9], double gamma, int aggressive,
+                                      float out3[3], float* stats);
 
 /* ---- detail mask / NL-means --------------------------------------------------- */
 /*
@@ -453,6 +477,8 @@ int art_hp_sharpen_usm_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g
  *                      (rtengine/rawimagesource.cc transformRect L664-700, computeFullSize L1163-1175; border = `border` for Bayer
  *                      sensors, i.e. 4, and 7 for X-Trans).  red / green / blue are therefore tables of H - 2 border rows of
  *                      W - 2 border floats; art_hp_develop_size gives the numbers.  full_frame = 1 keeps W x H (no crop).
+ *                      denoise->chrominanceMethod AUTOMATIC (the reference default) runs denoiseComputeParams on the demosaiced frame first
+ *                      (simpleprocess.cc L254-256) -- one stream synchronisation, as its result sets RGB_denoise's wavelet depth.
  *                      ImProcFunctions::denoise is reproduced with its expcomp(+ecomp) / expcomp(-ecomp) bracket
  *                      (ipdenoise.cc L1155-1163, L1181-1184: denoise_expcomp) and denoiseGuidedSmoothing (L1171-1172:
  *                      guidedChromaRadius).

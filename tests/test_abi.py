@@ -64,7 +64,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
     import ctypes
     pairs = {
         "art_hp_denoise_params": (api._DenoiseParamsC, ["luminance", "luminanceDetail", "luminanceDetailThreshold", "chrominance", "gamma", "scale",
-                                                         "colorSpace", "noiseCCurve", "noiseCCurveSum", "wprof_inverse"]),
+                                                         "colorSpace", "noiseCCurve", "noiseCCurveSum", "wprof_inverse", "chrominanceAutoFactor"]),
         "art_hp_develop_params": (api._DevelopParamsC, ["method", "filters", "initialGain", "border", "mul", "doClip", "cam2work", "denoise",
                                                          "nlStrength", "fattal_enabled", "fattal_satcontrol", "wprof", "sharpen", "chain", "xtrans", "rgb_cam",
                                                          "full_frame", "guidedChromaRadius", "denoise_expcomp"]),

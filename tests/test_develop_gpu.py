@@ -132,14 +132,21 @@ def test_develop_matches_oracle_chain(hot_path, W, H, dn, curve, fat, exact, ful
     got = hot_path.develop(raw, params)
     assert got[0].shape == ((H, W) if full else (H - 8, W - 8))
     worst = 0.0
+    # The chroma transfer of denoiseGuidedSmoothing rebuilds R and B as Y +- chroma and G as (Y - w0 R - w2 B) / w1: a channel that is
+    # small next to its pixel's luminance carries the luminance's rounding differences, so behind a tolerance stage (the block DCT)
+    # the 1e-4 is taken against the pixel's largest channel, not the channel's own value.
+    scale_ref = np.maximum.reduce([np.abs(y) for y in want]) if (guided and not exact) else None
     for x, y, ch in zip(got, want, "RGB"):
         if exact:
             assert np.array_equal(x, y), "%s: %d of %d differ" % (ch, int((x != y).sum()), x.size)
         else:
             err = np.abs(x - y)
-            lim = 1e-4 * np.abs(y) + 0.02
-            worst = max(worst, float((err / (np.abs(y) + 0.02)).max()))
-            assert (err <= lim).all(), "%s: %d of %d beyond tolerance, worst %g" % (ch, int((err > lim).sum()), x.size, worst)
+            mag = scale_ref if scale_ref is not None else np.abs(y)
+            lim = 1e-4 * mag + 0.02
+            worst = max(worst, float((err / (mag + 0.02)).max()))
+            bad = err > lim
+            assert not bad.any(), "%s: %d of %d beyond tolerance, worst %g; first offenders (got, want, pixel scale): %s" % (
+                ch, int(bad.sum()), x.size, worst, [(float(x[i, j]), float(y[i, j]), float(mag[i, j])) for i, j in np.argwhere(bad)[:4]])
     if not exact:
         print("\n[develop] %dx%d worst relative error %.3g" % (W, H, worst))
 
