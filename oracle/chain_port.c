@@ -121,7 +121,7 @@ static void filmlike_clip(float* r, float* g, float* b, float L)
     }
 }
 static inline void set_lut_val(const float* lut, float* val)
-{   /* curves.h L223-230; values above 65535 would go through Curve::getVal on the host -- not reachable with whitept == 1 */
+{   /* curves.h L223-230 with `curve == nullptr` (the LUT serves every sample, clipped above); the Curve::getVal branch is tone_port.c's */
     *val = lut_s(lut, 65536, CLIP_BELOW | CLIP_ABOVE, maxr(*val, 0.f));
 }
 static inline void rgb_tone(const float* lut, float* r, float* g, float* b)
@@ -133,7 +133,6 @@ static inline void rgb_tone(const float* lut, float* r, float* g, float* b)
 }
 int artoracle_chain_tonecurve(float* R, float* G, float* B, int W, int H, int mode, const float* lut, float whitept)
 {
-    if (whitept != 1.f) return 1;
     const float Lmax = 65535.f * whitept;
     for (size_t i = 0; i < (size_t)W * H; ++i) {
         filmlike_clip(&R[i], &G[i], &B[i], Lmax);

@@ -74,10 +74,11 @@ def test_saturation(W, H, sat, vib):
 @needs_ref
 @pytest.mark.parametrize("W,H", SIZES)
 @pytest.mark.parametrize("mode", [0, 1])
-def test_tonecurve(W, H, mode):
+@pytest.mark.parametrize("whitept", [1.0, 2.0])
+def test_tonecurve(W, H, mode, whitept):
     planes = image(H, W, W * 5 + H)
     lut = curve_lut(gamma=0.6, seed=mode)
-    args = (mode, lut.ctypes.data_as(fp), F(1.0))
+    args = (mode, lut.ctypes.data_as(fp), F(whitept))
     same(call(oracle.port().lib, "artoracle_chain_tonecurve", planes, *args), call(oracle.ref().lib, "artref_chain_tonecurve", planes, *args))
 
 
