@@ -5,11 +5,13 @@
 // wavelet decompositions (wavelet.cu).  Everything stays in HBM: the MAD values live in a small device table
 // that the shrink kernels read, so a whole denoise pass needs no host synchronisation.
 //   * MAD: int32 histogram of |trunc(coeff)| (exact by construction: integer counts), hot low bins privatised in
-//     shared memory, then a one-block prefix scan finds the median bin and interpolates like the reference.
+//     shared memory, then a one-block prefix scan finds the median bin and interpolates like the reference; every
+//     subband of a decomposition in one launch pair (grid.y = subband).
 //   * shrink factor / apply: element-wise; coefficients the reference handles in its 4-wide SSE loops use the
 //     vector xexpf (rtengine/sleefsseavx.h L1326-1345) and the vector expression association, the n % 4 tail
 //     uses the scalar xexpf (rtengine/sleef.h L1247-1266) and the scalar association -- bit-exact.
-//   * the local averaging is the flat boxblur (rtengine/boxblur.h L558-742) with its three column classes.
+//   * the local averaging is the flat boxblur (rtengine/boxblur.h L558-742) with its three column classes, fused with the
+//     shrink factor (horizontal pass) and the apply step (vertical pass); all subbands of a channel run in one grid.
 // Compiled with -fmad=false.
 #include "ctx.h"
 #include "sleef_dev.cuh"
@@ -31,45 +33,6 @@ using sleef::xexpf_vector;
 
 // ------------------------------------------------------------------ MAD (MadRgb, L569-603)
 constexpr int NB = 65536, HOT = 4096;
-__global__ void __launch_bounds__(512) k_mad_hist(const float* __restrict__ data, int n, int* __restrict__ histo)
-{
-    __shared__ int hot[HOT];
-    for (int i = threadIdx.x; i < HOT; i += blockDim.x) hot[i] = 0;
-    __syncthreads();
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += (size_t)gridDim.x * blockDim.x) {
-        int v = abs(__float2int_rz(data[i]));      // abs(static_cast<int>(x))
-        v = v < 65535 ? v : 65535;
-        if (v < HOT) atomicAdd(&hot[v], 1); else atomicAdd(&histo[v], 1);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < HOT; i += blockDim.x) if (hot[i]) atomicAdd(&histo[i], hot[i]);
-}
-
-// one block: median bin by prefix scan, then the reference's interpolation; writes SQR(mad) * premul to out[0]
-__global__ void __launch_bounds__(1024) k_mad_median(const int* __restrict__ histo, int n, float* out, int square)
-{
-    __shared__ int part[1024];
-    const int t = threadIdx.x;
-    int s = 0;
-    for (int k = 0; k < NB / 1024; ++k) s += histo[t * (NB / 1024) + k];
-    part[t] = s;
-    __syncthreads();
-    if (t == 0) {
-        float r = 0.f;
-        if (n > 1) {
-            const int half = n / 2;
-            int count = 0, seg = 0;
-            while (seg < 1024 && count + part[seg] < half) { count += part[seg]; ++seg; }
-            int median = seg * (NB / 1024);
-            // while (count < datalen / 2) { count += histo[median]; ++median; }
-            while (count < half) { count += histo[median]; ++median; }
-            const int count_ = count - histo[median - 1];
-            r = (float)((double)((median - 1) + (half - count_) / ((float)(count - count_))) / 0.6745);
-        }
-        out[0] = square ? r * r : r;
-    }
-}
-
 // ------------------------------------------------------------------ shrink factors
 struct ShArgs {
     float* c; const float* cL; const float* nv; float* sf; const float* sfd;
@@ -77,48 +40,6 @@ struct ShArgs {
     const float* madab;
     int nv_uniform; float nv_value;      // the noise-variance map holds one value everywhere: it is passed instead of read
 };
-
-__global__ void __launch_bounds__(256) k_sf_L(ShArgs a)
-{   // L669-684
-    const float eps = 0.01f;
-    const float levelFactor = a.mad[0] * 5.f / a.lvlmul;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
-        const float x = a.c[i];
-        const float nvi = a.nv_uniform ? a.nv_value : a.nv[i];
-        const float mag = x * x;
-        float r;
-        if ((i & ~3) < a.n - 3) {      // handled by a full 4-wide vector in the reference (for (i = 0; i < n - 3; i += 4))
-            const float mad = nvi * levelFactor;
-            r = mag / (mag + mad * xexpf_vector(-mag / (9.0f * mad)) + eps);
-        } else {
-            r = mag / (mag + levelFactor * nvi * xexpf_scalar(-mag / (9 * levelFactor * nvi)) + eps);
-        }
-        a.sf[i] = r;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_sf_AB(ShArgs a)
-{   // L762-786
-    const float mad_L = a.mad[0];
-    float madab = a.madab[0];
-    madab = a.useCCurve ? madab : madab * a.noisevar_ab;
-    const float rmadLm9 = 1.f / (mad_L * 9.f);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
-        const float xl = a.cL[i], xab = a.c[i];
-        const float nvi = a.nv_uniform ? a.nv_value : a.nv[i];
-        float r;
-        if ((i & ~3) < a.n - 3) {
-            const float mad_ab = nvi * madab;
-            const float mag_ab = xab * xab;
-            const float mag_L = (xl * xl) * rmadLm9;
-            r = 1.f - xexpf_vector(-(mag_ab / mad_ab) - (mag_L));
-        } else {
-            const float mag_L = xl * xl, mag_ab = xab * xab;
-            r = (1.f - xexpf_scalar(-(mag_ab / (nvi * madab)) - (mag_L / (9.f * mad_L))));
-        }
-        a.sf[i] = r;
-    }
-}
 
 // WaveletDenoiseAll_BiShrinkAB's "simple" shrinkage of the levels below the coarsest one (L1046-1087): in place, no local averaging,
 // the factor squared, mad_abr = (useNoiseCCurve ? noisevar_ab : SQR(noisevar_ab)) * madab
@@ -145,223 +66,356 @@ __global__ void __launch_bounds__(256) k_sf_AB_simple(ShArgs a)
     }
 }
 
-__global__ void __launch_bounds__(256) k_sf_apply(ShArgs a)
-{   // L692-709 / L791-813
-    const float eps = 0.01f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
-        const float s = a.sf[i], d = a.sfd[i], x = a.c[i];
-        a.c[i] = ((i & ~3) < a.n - 3) ? x * (d * d + s * s) / (d + s + eps) : x * ((d * d + s * s) / (d + s + eps));
+// ------------------------------------------------------------------ batched shrinkage: every subband of a channel in one launch
+// The local averaging is two running sums per subband (rows, then columns) whose fp32 association is part of the result, so a chain
+// is serial -- but a channel has 15 subbands x (2732 rows | 4096 columns) of them at 45 MP, enough to fill the chip when they all run
+// in ONE grid with one chain per thread:
+//   k_shrink_sf the shrink factor sf (ShrinkAllL L669-684 / ShrinkAllAB L762-786), element-wise at full occupancy (two IEEE divisions
+//               and one sleef exp per coefficient: the arithmetic-heavy part stays out of the latency-bound chain kernels)
+//   k_shrink_h  the horizontal pass of the flat boxblur (boxblur.h L571-602), one chain per lane through shared-memory transposes
+//   k_shrink_v  the vertical pass (boxblur.h L614-710, three column classes) fused with the apply step (L692-709 / L791-813): one
+//               thread per column marching down the subband with eight rows of loads in flight, the blurred value never stored.
+// Per coefficient: 4 (+4 L coefficient) B read, 8 B written; then 12 B read (+4 B trailing sample from L2), 4 B written.
+struct ShJob { float* c; const float* cL; const float* madL; const float* madab; float* sf; float* tmp; int W, H, rad; float lvlmul; };
+constexpr int SH_MAXJOBS = 24;
+struct ShBatch {
+    ShJob job[SH_MAXJOBS]; int njobs;
+    int unit0[SH_MAXJOBS + 1];            // first work unit of each job (prefix sums), per kernel
+    const float* nv; int nv_uniform; float nv_value; float noisevar_ab; int useCCurve, ab;
+};
+constexpr int SH_ROWS = 16, SH_RING = 64, SH_RP = SH_RING + 1, SH_SP = 33, SH_WARPS = 16;
+constexpr size_t SH_SMEM = (size_t)SH_WARPS * SH_ROWS * (SH_RP + SH_SP) * sizeof(float);
+
+__device__ __forceinline__ float sf_value(const ShBatch& b, const ShJob& j, float levelFactor, float madab, float rmadLm9, float mad_L, size_t i, size_t n)
+{
+    const float nvi = b.nv_uniform ? b.nv_value : b.nv[i];
+    const bool vec = (i & ~(size_t)3) + 3 < n;           // handled by a full 4-wide vector in the reference (for (i = 0; i < n - 3; i += 4))
+    if (!b.ab) {
+        const float eps = 0.01f;
+        const float x = j.c[i];
+        const float mag = x * x;
+        if (vec) {
+            const float mad = nvi * levelFactor;
+            return mag / (mag + mad * xexpf_vector(-mag / (9.0f * mad)) + eps);
+        }
+        return mag / (mag + levelFactor * nvi * xexpf_scalar(-mag / (9 * levelFactor * nvi)) + eps);
+    }
+    const float xl = j.cL[i], xab = j.c[i];
+    if (vec) {
+        const float mad_ab = nvi * madab;
+        const float mag_ab = xab * xab;
+        const float mag_L = (xl * xl) * rmadLm9;
+        return 1.f - xexpf_vector(-(mag_ab / mad_ab) - (mag_L));
+    }
+    const float mag_L = xl * xl, mag_ab = xab * xab;
+    return (1.f - xexpf_scalar(-(mag_ab / (nvi * madab)) - (mag_L / (9.f * mad_L))));
+}
+
+// shrink factors of every subband of the batch: element-wise, grid.y = subband
+__global__ void __launch_bounds__(256) k_shrink_sf(const __grid_constant__ ShBatch b)
+{
+    const ShJob& j = b.job[blockIdx.y];
+    const size_t n = (size_t)j.W * j.H;
+    const float mad_L = j.madL[0];
+    const float levelFactor = b.ab ? 0.f : mad_L * 5.f / j.lvlmul;
+    float madab = b.ab ? j.madab[0] : 0.f;
+    if (b.ab) madab = b.useCCurve ? madab : madab * b.noisevar_ab;
+    const float rmadLm9 = 1.f / (mad_L * 9.f);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = sf_value(b, j, levelFactor, madab, rmadLm9, mad_L, i + k * stride, n);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) j.sf[i + k * stride] = v[k];
+    }
+    for (; i < n; i += stride) j.sf[i] = sf_value(b, j, levelFactor, madab, rmadLm9, mad_L, i, n);
+}
+
+// horizontal pass of the flat boxblur over sf -> tmp (boxblur.h L571-602).  A warp owns SH_ROWS rows of one subband and streams along
+// them in 32-column tiles: coalesced row segments into registers (the next tile's loads are in flight while this one is processed), the
+// samples parked in a 64-column shared-memory ring, the per-step increments (x[n + rad] - x[n - rad - 1]) / len formed by all lanes, then
+// lane r walks row r's chain -- one dependent add per step -- and the sums leave through the same transposing tile.
+__global__ void __launch_bounds__(SH_WARPS * 32) k_shrink_h(const __grid_constant__ ShBatch b)
+{
+    extern __shared__ float shm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* ring = shm + (size_t)warp * SH_ROWS * (SH_RP + SH_SP);
+    float* dt = ring + SH_ROWS * SH_RP;
+    const int total = b.unit0[b.njobs];
+    for (int u = blockIdx.x * SH_WARPS + warp; u < total; u += gridDim.x * SH_WARPS) {
+        int ji = 0;
+        while (u >= b.unit0[ji + 1]) ++ji;
+        const ShJob& j = b.job[ji];
+        const int W = j.W, H = j.H, rad = j.rad;
+        const int row0 = (u - b.unit0[ji]) * SH_ROWS, nrows = min(SH_ROWS, H - row0);
+        const float* __restrict__ src = j.sf + (size_t)row0 * W;
+        float* __restrict__ dst = j.tmp + (size_t)row0 * W;
+        const int ntiles = (W + 31) / 32;
+        const bool chain = lane < nrows;
+        float t = 0.f;
+        int len = rad + 1;
+        const float rlen = 1.f / (float)(2 * rad + 1);
+        float nxt[SH_ROWS];
+#pragma unroll
+        for (int r = 0; r < SH_ROWS; ++r) nxt[r] = (r < nrows && lane < W) ? src[(size_t)r * W + lane] : 0.f;
+        // iteration T consumes tile T and produces the output positions p = 32 T - rad + k, k = 0..31; one more iteration drains the ramp-down
+        for (int T = 0; T <= ntiles; ++T) {
+            const int col = 32 * T + lane;
+            if (T < ntiles) {
+                float cur[SH_ROWS];
+#pragma unroll
+                for (int r = 0; r < SH_ROWS; ++r) cur[r] = nxt[r];
+                if (T + 1 < ntiles) {
+                    const int ncol = col + 32;
+#pragma unroll
+                    for (int r = 0; r < SH_ROWS; ++r) nxt[r] = (r < nrows && ncol < W) ? src[(size_t)r * W + ncol] : 0.f;
+                }
+#pragma unroll
+                for (int r = 0; r < SH_ROWS; ++r) ring[r * SH_RP + (col & (SH_RING - 1))] = cur[r];
+                __syncwarp();
+                const int tc = (col - 2 * rad - 1) & (SH_RING - 1);
+#pragma unroll
+                for (int r = 0; r < SH_ROWS; ++r) dt[r * SH_SP + lane] = (cur[r] - ring[r * SH_RP + tc]) * rlen;      // increment of position col - rad
+            }
+            __syncwarp();
+            const int base = 32 * T - rad;
+            if (chain) {
+                const float* x = ring + lane * SH_RP;
+                float* o = dt + lane * SH_SP;
+                const int k_main0 = max(0, rad + 1 - base), k_main1 = min(32, W - rad - base);      // main region rad < p < W - rad
+                const int k_first = max(0, -base), k_last = min(32, W - base);
+                for (int k = k_first; k < min(k_main0, k_last); ++k) {      // p <= rad: the first sample and the ramp-up
+                    const int p = base + k;
+                    if (p == 0) {
+                        t = x[0];
+                        for (int q = 1; q <= rad; q++) t += x[q];
+                        t = t / len;
+                    } else {
+                        t = (t * len + x[(p + rad) & (SH_RING - 1)]) / (len + 1);
+                        len++;
+                    }
+                    o[k] = t;
+                }
+#pragma unroll 4
+                for (int k = max(k_main0, k_first); k < k_main1; ++k) { t = t + o[k]; o[k] = t; }
+                for (int k = max(max(k_main1, k_main0), k_first); k < k_last; ++k) {        // p >= W - rad: the ramp-down
+                    const int p = base + k;
+                    t = (t * len - x[(p - rad - 1) & (SH_RING - 1)]) / (len - 1);
+                    len--;
+                    o[k] = t;
+                }
+            }
+            __syncwarp();
+            const int p = base + lane;
+            if (p >= 0 && p < W) {
+#pragma unroll
+                for (int r = 0; r < SH_ROWS; ++r) if (r < nrows) dst[(size_t)r * W + p] = dt[r * SH_SP + lane];
+            }
+            __syncwarp();
+        }
     }
 }
 
-// ------------------------------------------------------------------ flat boxblur (boxblur.h L558-742), radx == rady >= 1
-struct FbArgs { const float* x; float* y; int W, H, rad; };
-
-// Both passes are running sums -- t += (x[n + rad] - x[n - rad - 1]) * (1 / len) -- whose fp32 association is part of the
-// result, so a chain (a row for the horizontal pass, a column for the vertical one) is inherently serial.  The work is
-// split so that only the additions are serial: a CTA owns FB_CH chains and walks them in tiles of FB_T steps; all
-// 256 threads load the tile with coalesced reads and form the per-step differences in parallel, FB_CH lanes run the
-// additions out of shared memory, all threads store the tile.  The ramps at both ends of a chain (rad + 1 and rad steps)
-// are done by the chain lanes straight from global memory.
-// horizontal pass: 8 rows x 256 steps per tile (342 CTAs per 45 MP subband); vertical pass: 32 columns x 64 steps (128-byte segments)
-constexpr int FB_NT = 256, FB_CH_H = 8, FB_T_H = 256, FB_CH_V = 32, FB_T_V = 64;
-
-template <bool VERT>
-__global__ void __launch_bounds__(FB_NT) k_fbox(FbArgs a)
+constexpr int SV_THREADS = 128, SV_UNROLL = 8;
+__global__ void __launch_bounds__(SV_THREADS) k_shrink_v(const __grid_constant__ ShBatch b)
 {
-    constexpr int FB_CH = VERT ? FB_CH_V : FB_CH_H, FB_T = VERT ? FB_T_V : FB_T_H, FB_PER = FB_CH * FB_T / FB_NT;   // horizontal: boxblur.h L571-602; vertical: L614-710 (columns < W - W % 4 follow the 4-/8-wide code, the rest the scalar tail)
-    __shared__ float tile[FB_T][FB_CH + 1];
-    const int W = a.W, H = a.H, rad = a.rad;
-    const int nchains = VERT ? W : H, nsteps = VERT ? H : W;
-    const int chain0 = blockIdx.x * FB_CH;
-    const int tid = threadIdx.x;
-    auto at = [&](int ch, int st) -> size_t { return VERT ? (size_t)st * W + ch : (size_t)ch * W + st; };
-    const bool chain_thread = tid < FB_CH && chain0 + tid < nchains;
-    const int mych = chain0 + tid;
-    const bool scalar_class = VERT && mych >= W - (W % 4);
-    float t = 0.f;
-    const float full = (float)(2 * rad + 1);
-    if (chain_thread) {
-        if (!VERT) {
-            int len = rad + 1;
-            t = a.x[at(mych, 0)];
-            for (int j = 1; j <= rad; j++) t += a.x[at(mych, j)];
-            t = t / len;
-            a.y[at(mych, 0)] = t;
-            for (int st = 1; st <= rad; st++) {
-                t = (t * len + a.x[at(mych, st + rad)]) / (len + 1);
-                a.y[at(mych, st)] = t;
-                len++;
-            }
-        } else if (!scalar_class) {
+    const int total = b.unit0[b.njobs];        // units of 32 columns
+    const int lane = threadIdx.x & 31;
+    for (int u = blockIdx.x * (SV_THREADS / 32) + (threadIdx.x >> 5); u < total; u += gridDim.x * (SV_THREADS / 32)) {
+        int ji = 0;
+        while (u >= b.unit0[ji + 1]) ++ji;
+        const ShJob& j = b.job[ji];
+        const int W = j.W, H = j.H, rad = j.rad;
+        const int col = (u - b.unit0[ji]) * 32 + lane;
+        if (col >= W) continue;
+        const size_t n = (size_t)W * H;
+        const float* __restrict__ x = j.tmp + col;
+        const float* __restrict__ sfp = j.sf + col;
+        float* __restrict__ cp = j.c + col;
+        const bool scalar_class = col >= W - (W % 4);       // boxblur.h L614-710: the W % 4 tail columns divide, the vector columns multiply by 1 / len
+        const float eps = 0.01f;
+        auto emit = [&](int row, float d, float s, float xc) {
+            const size_t i = (size_t)row * W + col;
+            cp[(size_t)row * W] = ((i & ~(size_t)3) + 3 < n) ? xc * (d * d + s * s) / (d + s + eps) : xc * ((d * d + s * s) / (d + s + eps));
+        };
+        float t;
+        const float full = (float)(2 * rad + 1);
+        // first row and the ramp-up
+        if (!scalar_class) {
             float len = (float)(rad + 1);
-            t = a.x[at(mych, 0)];
-            for (int i = 1; i <= rad; i++) t = t + a.x[at(mych, i)];
+            t = x[0];
+            for (int i = 1; i <= rad; i++) t = t + x[(size_t)i * W];
             t = t / len;
-            a.y[at(mych, 0)] = t;
+            emit(0, t, sfp[0], cp[0]);
             for (int st = 1; st <= rad; st++) {
                 const float lp1 = len + 1.f;
-                t = (t * len + a.x[at(mych, st + rad)]) / lp1;
-                a.y[at(mych, st)] = t;
+                t = (t * len + x[(size_t)(st + rad) * W]) / lp1;
+                emit(st, t, sfp[(size_t)st * W], cp[(size_t)st * W]);
                 len = lp1;
             }
         } else {
             int len = rad + 1;
-            t = a.x[at(mych, 0)] / len;
-            for (int i = 1; i <= rad; i++) t += a.x[at(mych, i)] / len;
-            a.y[at(mych, 0)] = t;
+            t = x[0] / len;
+            for (int i = 1; i <= rad; i++) t += x[(size_t)i * W] / len;
+            emit(0, t, sfp[0], cp[0]);
             for (int st = 1; st <= rad; st++) {
-                t = (t * len + a.x[at(mych, st + rad)]) / (len + 1);
-                a.y[at(mych, st)] = t;
+                t = (t * len + x[(size_t)(st + rad) * W]) / (len + 1);
+                emit(st, t, sfp[(size_t)st * W], cp[(size_t)st * W]);
                 len++;
             }
         }
-    }
-    const float rlen = 1.f / full;
-    const int first = rad + 1, last = nsteps - rad;          // main region [first, last)
-    for (int s0 = first; s0 < last; s0 += FB_T) {
-        const int nst = min(FB_T, last - s0);
-        {   // all loads of the tile first (FB_PER independent pairs per thread in flight), then the differences
-            float va[FB_PER], vb[FB_PER];
+        const float rlen = 1.f / full;
+        const int first = rad + 1, last = H - rad;
+        int st = first;
+        for (; st + SV_UNROLL <= last; st += SV_UNROLL) {
+            float lead[SV_UNROLL], trail[SV_UNROLL], sv[SV_UNROLL], cv[SV_UNROLL];
 #pragma unroll
-            for (int u = 0; u < FB_PER; ++u) {
-                const int i = tid + u * FB_NT;
-                const int cl = VERT ? i % FB_CH : i / FB_T, sl = VERT ? i / FB_CH : i % FB_T;
-                const int ch = chain0 + cl, st = s0 + sl;
-                const bool ok = ch < nchains && sl < nst;
-                va[u] = ok ? a.x[at(ch, st + rad)] : 0.f;
-                vb[u] = ok ? a.x[at(ch, st - rad - 1)] : 0.f;
+            for (int k = 0; k < SV_UNROLL; ++k) {
+                lead[k] = x[(size_t)(st + k + rad) * W];
+                trail[k] = x[(size_t)(st + k - rad - 1) * W];
+                sv[k] = sfp[(size_t)(st + k) * W];
+                cv[k] = cp[(size_t)(st + k) * W];
             }
 #pragma unroll
-            for (int u = 0; u < FB_PER; ++u) {
-                const int i = tid + u * FB_NT;
-                const int cl = VERT ? i % FB_CH : i / FB_T, sl = VERT ? i / FB_CH : i % FB_T;
-                const float diff = va[u] - vb[u];
-                tile[sl][cl] = (VERT && chain0 + cl >= W - (W % 4)) ? diff / (float)(2 * rad + 1) : diff * rlen;
+            for (int k = 0; k < SV_UNROLL; ++k) {
+                const float diff = lead[k] - trail[k];
+                t = t + (scalar_class ? diff / full : diff * rlen);
+                emit(st + k, t, sv[k], cv[k]);
             }
         }
-        __syncthreads();
-        if (chain_thread) {
-#pragma unroll 8
-            for (int sl = 0; sl < nst; ++sl) {
-                t = t + tile[sl][tid];
-                tile[sl][tid] = t;
-            }
+        for (; st < last; ++st) {
+            const float diff = x[(size_t)(st + rad) * W] - x[(size_t)(st - rad - 1) * W];
+            t = t + (scalar_class ? diff / full : diff * rlen);
+            emit(st, t, sfp[(size_t)st * W], cp[(size_t)st * W]);
         }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < FB_PER; ++u) {
-            const int i = tid + u * FB_NT;
-            const int cl = VERT ? i % FB_CH : i / FB_T, sl = VERT ? i / FB_CH : i % FB_T;
-            const int ch = chain0 + cl;
-            if (ch < nchains && sl < nst) a.y[at(ch, s0 + sl)] = tile[sl][cl];
-        }
-        __syncthreads();
-    }
-    if (chain_thread) {
-        if (VERT && !scalar_class) {
+        if (!scalar_class) {
             float len = full;
-            for (int st = max(last, first); st < nsteps; st++) {
+            for (st = max(last, first); st < H; st++) {
                 const float lm1 = len - 1.f;
-                t = (t * len - a.x[at(mych, st - rad - 1)]) / lm1;
-                a.y[at(mych, st)] = t;
+                t = (t * len - x[(size_t)(st - rad - 1) * W]) / lm1;
+                emit(st, t, sfp[(size_t)st * W], cp[(size_t)st * W]);
                 len = lm1;
             }
         } else {
             int len = 2 * rad + 1;
-            for (int st = max(last, first); st < nsteps; st++) {
-                t = (t * len - a.x[at(mych, st - rad - 1)]) / (len - 1);
-                a.y[at(mych, st)] = t;
+            for (st = max(last, first); st < H; st++) {
+                t = (t * len - x[(size_t)(st - rad - 1) * W]) / (len - 1);
+                emit(st, t, sfp[(size_t)st * W], cp[(size_t)st * W]);
                 len--;
             }
         }
     }
 }
 
-int mad_of(art_hp_ctx* ctx, const float* band, int n, int* d_histo, float* d_out, int square)
+// MadRgb of several subbands at once: grid.y = subband
+struct MadBatch { const float* band[SH_MAXJOBS]; int n[SH_MAXJOBS]; float* out[SH_MAXJOBS]; int njobs, square; };
+__global__ void __launch_bounds__(512) k_mad_hist_all(const __grid_constant__ MadBatch mb, int* __restrict__ histo)
 {
-    cudaStream_t st = ctx->stream;
-    ART_CUDA(ctx, cudaMemsetAsync(d_histo, 0, NB * sizeof(int), st));
-    art_prof_begin(ctx, "k_mad_hist");
-    k_mad_hist<<<148 * 4, 512, 0, st>>>(band, n, d_histo);
-    art_prof_end(ctx);
-    k_mad_median<<<1, 1024, 0, st>>>(d_histo, n, d_out, square);
-    ctx->launches += 2;
-    return ART_HP_OK;
+    __shared__ int hot[HOT];
+    const int jb = blockIdx.y;
+    const float* __restrict__ data = mb.band[jb];
+    const size_t n = (size_t)mb.n[jb];
+    int* __restrict__ h = histo + (size_t)jb * NB;
+    for (int i = threadIdx.x; i < HOT; i += blockDim.x) hot[i] = 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int v = abs(__float2int_rz(data[i]));      // abs(static_cast<int>(x))
+        v = v < 65535 ? v : 65535;
+        if (v < HOT) atomicAdd(&hot[v], 1); else atomicAdd(&h[v], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HOT; i += blockDim.x) if (hot[i]) atomicAdd(&h[i], hot[i]);
+}
+__global__ void __launch_bounds__(1024) k_mad_median_all(const __grid_constant__ MadBatch mb, const int* __restrict__ histo_all)
+{
+    __shared__ int part[1024];
+    const int jb = blockIdx.x;
+    const int* __restrict__ histo = histo_all + (size_t)jb * NB;
+    const int n = mb.n[jb];
+    const int t = threadIdx.x;
+    int s = 0;
+    for (int k = 0; k < NB / 1024; ++k) s += histo[t * (NB / 1024) + k];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        float r = 0.f;
+        if (n > 1) {
+            const int half = n / 2;
+            int count = 0, seg = 0;
+            while (seg < 1024 && count + part[seg] < half) { count += part[seg]; ++seg; }
+            int median = seg * (NB / 1024);
+            while (count < half) { count += histo[median]; ++median; }
+            const int count_ = count - histo[median - 1];
+            r = (float)((double)((median - 1) + (half - count_) / ((float)(count - count_))) / 0.6745);
+        }
+        mb.out[jb][0] = mb.square ? r * r : r;
+    }
 }
 
 int blur_radius(int level, double scale) { const int r = (int)((level + 2) / scale); return r > 1 ? r : 1; }
 
-// scratch, one set per lane: [histogram 65536 ints][madab 64 floats][sf n][sfd n][tmp n]
-struct Scratch { int* histo; float* madab; float *sf, *sfd, *tmp; };
-constexpr int NL = art_hp_ctx::NLANES;
-int scratch_for(art_hp_ctx* ctx, size_t n, Scratch s[NL])
+// scratch of the batched path: [njobs histograms][njobs x (sf, tmp) planes]
+struct BatchScratch { int* histo; float* planes; size_t np; };
+int batch_scratch(art_hp_ctx* ctx, int njobs, size_t n, bool planes, BatchScratch& s)
 {
-    const size_t np = round_up(n, 64);
-    const size_t one = round_up(NB * sizeof(int) + 256 + 3 * np * sizeof(float), 256);
-    int rc = art_reserve(ctx, ctx->d_scratch, NL * one);
+    s.np = round_up(n, 64);
+    const size_t hb = round_up((size_t)njobs * NB * sizeof(int), 256);
+    int rc = art_reserve(ctx, ctx->d_scratch, hb + (planes ? 2 * (size_t)njobs * s.np * sizeof(float) : 0));
     if (rc) return rc;
-    for (int i = 0; i < NL; ++i) {
-        char* p = (char*)ctx->d_scratch.p + i * one;
-        s[i].histo = (int*)p; p += NB * sizeof(int);
-        s[i].madab = (float*)p; p += 256;
-        s[i].sf = (float*)p; s[i].sfd = s[i].sf + np; s[i].tmp = s[i].sfd + np;
-    }
+    s.histo = (int*)ctx->d_scratch.p;
+    s.planes = (float*)((char*)ctx->d_scratch.p + hb);
     return ART_HP_OK;
 }
 
-// Fork the context's stream into NL lanes (one per subband of a channel) and join them again.  Between the two calls
-// `ctx->stream` is pointed at a lane with lane_of(): every helper queues on ctx->stream, so nothing else changes.
-struct Lanes {
-    art_hp_ctx* ctx; cudaStream_t main; bool serial;
-    int begin(art_hp_ctx* c)
-    {
-        ctx = c; main = c->stream;
-        serial = c->profiling;       // per-kernel timing (art_hp_profile_*) wants every launch alone on the stream its events are on
-        if (serial) return ART_HP_OK;
-        if (!c->lane[0]) {
-            for (int i = 0; i < NL; ++i) {
-                ART_CUDA(c, cudaStreamCreateWithFlags(&c->lane[i], cudaStreamNonBlocking));
-                ART_CUDA(c, cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
-            }
-            ART_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        }
-        ART_CUDA(c, cudaEventRecord(c->ev_fork, main));
-        for (int i = 0; i < NL; ++i) ART_CUDA(c, cudaStreamWaitEvent(c->lane[i], c->ev_fork, 0));
-        return ART_HP_OK;
-    }
-    void lane_of(int i) { if (!serial) ctx->stream = ctx->lane[i]; }
-    int end()
-    {
-        ctx->stream = main;
-        if (serial) return ART_HP_OK;
-        for (int i = 0; i < NL; ++i) {
-            ART_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ctx->lane[i]));
-            ART_CUDA(ctx, cudaStreamWaitEvent(main, ctx->ev_join[i], 0));
-        }
-        return ART_HP_OK;
-    }
-};
-
-int shrink_band(art_hp_ctx* ctx, const Scratch& s, ShArgs a, int W, int H, int rad, bool ab)
+int mad_batch(art_hp_ctx* ctx, const MadBatch& mb, int* histo)
 {
+    if (mb.njobs == 0) return ART_HP_OK;
     cudaStream_t st = ctx->stream;
-    const int grid = std::min((a.n + 255) / 256, 148 * 16);
-    a.sf = s.sf; a.sfd = s.sfd;
-    art_prof_begin(ctx, ab ? "k_sf_AB" : "k_sf_L");
-    if (ab) k_sf_AB<<<grid, 256, 0, st>>>(a); else k_sf_L<<<grid, 256, 0, st>>>(a);
+    ART_CUDA(ctx, cudaMemsetAsync(histo, 0, (size_t)mb.njobs * NB * sizeof(int), st));
+    art_prof_begin(ctx, "k_mad_hist_all");
+    k_mad_hist_all<<<dim3(std::max(1, 148 * 4 / mb.njobs), mb.njobs), 512, 0, st>>>(mb, histo);
     art_prof_end(ctx);
-    if (2 * rad + 1 > W || 2 * rad + 1 > H) return ctx->fail(ART_HP_ERR_INVALID, "blur radius %d does not fit a %dx%d subband", rad, W, H);
-    art_prof_begin(ctx, "k_fbox_h");
-    k_fbox<false><<<(H + FB_CH_H - 1) / FB_CH_H, FB_NT, 0, st>>>(FbArgs{s.sf, s.tmp, W, H, rad});
+    art_prof_begin(ctx, "k_mad_median_all");
+    k_mad_median_all<<<mb.njobs, 1024, 0, st>>>(mb, histo);
     art_prof_end(ctx);
-    art_prof_begin(ctx, "k_fbox_v");
-    k_fbox<true><<<(W + FB_CH_V - 1) / FB_CH_V, FB_NT, 0, st>>>(FbArgs{s.tmp, s.sfd, W, H, rad});
+    ctx->launches += 2;
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}
+
+int shrink_batch(art_hp_ctx* ctx, ShBatch& b)
+{
+    if (b.njobs == 0) return ART_HP_OK;
+    cudaStream_t st = ctx->stream;
+    if (!(ctx->attrs_set & art_hp_ctx::ATTR_SHRINK)) {
+        ART_CUDA(ctx, cudaFuncSetAttribute(k_shrink_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SH_SMEM));
+        ctx->attrs_set |= art_hp_ctx::ATTR_SHRINK;
+    }
+    b.unit0[0] = 0;
+    for (int i = 0; i < b.njobs; ++i) {
+        const ShJob& j = b.job[i];
+        if (j.rad > 15) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "blur radius %d above 15 (the horizontal pass keeps 2 rad + 1 <= 32 samples behind the tile)", j.rad);
+        if (2 * j.rad + 1 > j.W || 2 * j.rad + 1 > j.H) return ctx->fail(ART_HP_ERR_INVALID, "blur radius %d does not fit a %dx%d subband", j.rad, j.W, j.H);
+        b.unit0[i + 1] = b.unit0[i] + (j.H + SH_ROWS - 1) / SH_ROWS;
+    }
+    {
+        size_t nmax = 0;
+        for (int i = 0; i < b.njobs; ++i) nmax = std::max(nmax, (size_t)b.job[i].W * b.job[i].H);
+        const int gx = (int)std::min<size_t>((nmax + 1023) / 1024, (size_t)std::max(1, ctx->sm_count * 8 / b.njobs));
+        art_prof_begin(ctx, "k_shrink_sf");
+        k_shrink_sf<<<dim3(gx, b.njobs), 256, 0, st>>>(b);
+        art_prof_end(ctx);
+    }
+    art_prof_begin(ctx, "k_shrink_h");
+    k_shrink_h<<<std::min((b.unit0[b.njobs] + SH_WARPS - 1) / SH_WARPS, ctx->sm_count), SH_WARPS * 32, SH_SMEM, st>>>(b);
     art_prof_end(ctx);
-    art_prof_begin(ctx, "k_sf_apply");
-    k_sf_apply<<<grid, 256, 0, st>>>(a);
+    for (int i = 0; i < b.njobs; ++i) b.unit0[i + 1] = b.unit0[i] + (b.job[i].W + 31) / 32;
+    art_prof_begin(ctx, "k_shrink_v");
+    k_shrink_v<<<std::min((b.unit0[b.njobs] + SV_THREADS / 32 - 1) / (SV_THREADS / 32), ctx->sm_count * 8), SV_THREADS, 0, st>>>(b);
     art_prof_end(ctx);
-    ctx->launches += 4;
+    ctx->launches += 3;
     ART_CUDA(ctx, cudaGetLastError());
     return ART_HP_OK;
 }
@@ -375,21 +429,18 @@ int art_hp_wavelet_mad_dev(art_hp_ctx* ctx, const art_hp_wavelet* w, float* d_ma
 {
     if (!ctx || !w || !d_madL) return ART_HP_ERR_INVALID;
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
-    Scratch s[NL];
-    int rc = scratch_for(ctx, 64, s);
+    if (3 * w->nlev > SH_MAXJOBS) return ctx->fail(ART_HP_ERR_INVALID, "too many wavelet levels (%d)", w->nlev);
+    BatchScratch bs;
+    int rc = batch_scratch(ctx, 3 * w->nlev, 0, false, bs);
     if (rc) return rc;
-    Lanes lanes;
-    if ((rc = lanes.begin(ctx))) return rc;
-    for (int l = 0; l < w->nlev && !rc; ++l)
-        for (int d = 1; d < 4 && !rc; ++d) {
-            const int ln = (3 * l + d - 1) % NL;
-            lanes.lane_of(ln);
-            rc = mad_of(ctx, w->lev[l].band[d], w->lev[l].w2 * w->lev[l].h2, s[ln].histo, d_madL + 3 * l + (d - 1), 1);
+    MadBatch mb{};
+    mb.square = 1;
+    for (int l = 0; l < w->nlev; ++l)
+        for (int d = 1; d < 4; ++d) {
+            mb.band[mb.njobs] = w->lev[l].band[d]; mb.n[mb.njobs] = w->lev[l].w2 * w->lev[l].h2; mb.out[mb.njobs] = d_madL + 3 * l + (d - 1);
+            mb.njobs++;
         }
-    const int rc2 = lanes.end();
-    if (rc || rc2) return rc ? rc : rc2;
-    ART_CUDA(ctx, cudaGetLastError());
-    return ART_HP_OK;
+    return mad_batch(ctx, mb, bs.histo);
 }
 
 }  // extern "C"
@@ -414,23 +465,21 @@ int art_wavelet_denoise_L(art_hp_ctx* ctx, art_hp_wavelet* wL, const float* d_no
     if (!ctx || !wL || (!d_noisevarlum && !uniform) || !d_madL || !(scale > 0)) return ART_HP_ERR_INVALID;
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
     const int maxlvl = std::min(wL->nlev, 5);      // L1115
-    Scratch s[NL];
-    int rc = scratch_for(ctx, (size_t)wL->lev[0].w2 * wL->lev[0].h2, s);
+    BatchScratch bs;
+    int rc = batch_scratch(ctx, 3 * maxlvl, (size_t)wL->lev[0].w2 * wL->lev[0].h2, true, bs);
     if (rc) return rc;
-    Lanes lanes;
-    if ((rc = lanes.begin(ctx))) return rc;
-    for (int l = 0; l < maxlvl && !rc; ++l)
-        for (int d = 1; d < 4 && !rc; ++d) {
+    ShBatch b{};
+    b.nv = d_noisevarlum; b.nv_uniform = uniform != nullptr; b.nv_value = uniform ? *uniform : 0.f; b.ab = 0;
+    for (int l = 0; l < maxlvl; ++l)
+        for (int d = 1; d < 4; ++d) {
             const WLevel& L = wL->lev[l];
-            ShArgs a{};
-            a.c = L.band[d]; a.nv = d_noisevarlum; a.mad = d_madL + 3 * l + (d - 1); a.n = L.w2 * L.h2; a.lvlmul = (float)(l + 1);
-            a.nv_uniform = uniform != nullptr; a.nv_value = uniform ? *uniform : 0.f;
-            const int ln = (3 * l + d - 1) % NL;
-            lanes.lane_of(ln);
-            rc = shrink_band(ctx, s[ln], a, L.w2, L.h2, blur_radius(l, scale), false);
+            ShJob& j = b.job[b.njobs];
+            j.c = L.band[d]; j.cL = nullptr; j.madL = d_madL + 3 * l + (d - 1); j.madab = nullptr;
+            j.sf = bs.planes + (size_t)(2 * b.njobs) * bs.np; j.tmp = j.sf + bs.np;
+            j.W = L.w2; j.H = L.h2; j.rad = blur_radius(l, scale); j.lvlmul = (float)(l + 1);
+            b.njobs++;
         }
-    const int rc2 = lanes.end();
-    return rc ? rc : rc2;
+    return shrink_batch(ctx, b);
 }
 
 extern "C" int art_hp_wavelet_denoise_AB_dev(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom,
@@ -449,33 +498,49 @@ int art_wavelet_denoise_AB(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wav
     if (wL->nlev != wab->nlev || wL->W != wab->W || wL->H != wab->H) return ctx->fail(ART_HP_ERR_INVALID, "L and ab decompositions differ in shape");
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
     if (autoch && noisevar_ab <= 0.001f) noisevar_ab = 0.02f;     // L737-739
-    Scratch s[NL];
-    int rc = scratch_for(ctx, (size_t)wab->lev[0].w2 * wab->lev[0].h2, s);
+    if (!(noisevar_ab > 0.001f)) return ART_HP_OK;                // L761 (MadRgb is computed but unused)
+    if (3 * wL->nlev > SH_MAXJOBS) return ctx->fail(ART_HP_ERR_INVALID, "too many wavelet levels (%d)", wL->nlev);
+    const int nj = 3 * wL->nlev;
+    BatchScratch bs;
+    int rc = batch_scratch(ctx, nj, (size_t)wab->lev[0].w2 * wab->lev[0].h2, true, bs);
     if (rc) return rc;
-    Lanes lanes;
-    if ((rc = lanes.begin(ctx))) return rc;
-    for (int l = 0; l < wL->nlev && !rc; ++l)
-        for (int d = 1; d < 4 && !rc; ++d) {
+    // MadRgb of every ab subband: njobs floats kept behind the L table's 24 entries? no -- in the context's small buffer
+    if ((rc = art_reserve(ctx, ctx->d_small, 64 * sizeof(float)))) return rc;
+    float* madab = (float*)ctx->d_small.p;
+    MadBatch mb{};
+    mb.square = 1;
+    for (int l = 0; l < wL->nlev; ++l)
+        for (int d = 1; d < 4; ++d) {
             const WLevel& L = wab->lev[l];
-            const int n = L.w2 * L.h2;
-            if (!(noisevar_ab > 0.001f)) continue;                   // L761 (MadRgb is computed but unused)
-            const int ln = (3 * l + d - 1) % NL;
-            lanes.lane_of(ln);
-            const Scratch& sc = s[ln];
-            if ((rc = mad_of(ctx, L.band[d], n, sc.histo, sc.madab, 1))) break;
-            ShArgs a{};
-            a.c = L.band[d]; a.cL = wL->lev[l].band[d]; a.nv = d_noisevarchrom; a.mad = d_madL + 3 * l + (d - 1); a.n = n;
-            a.noisevar_ab = noisevar_ab; a.useCCurve = useNoiseCCurve; a.madab = sc.madab;
-            a.nv_uniform = uniform != nullptr; a.nv_value = uniform ? *uniform : 0.f;
+            mb.band[mb.njobs] = L.band[d]; mb.n[mb.njobs] = L.w2 * L.h2; mb.out[mb.njobs] = madab + mb.njobs;
+            mb.njobs++;
+        }
+    if ((rc = mad_batch(ctx, mb, bs.histo))) return rc;
+    ShBatch b{};
+    b.nv = d_noisevarchrom; b.nv_uniform = uniform != nullptr; b.nv_value = uniform ? *uniform : 0.f; b.ab = 1;
+    b.noisevar_ab = noisevar_ab; b.useCCurve = useNoiseCCurve;
+    for (int l = 0; l < wL->nlev; ++l)
+        for (int d = 1; d < 4; ++d) {
+            const WLevel& L = wab->lev[l];
+            const int idx = 3 * l + (d - 1);
             if (bishrink && l != wL->nlev - 1) {
+                // WaveletDenoiseAll_BiShrinkAB's "simple" shrinkage of the finer levels (L1046-1087): element-wise, in place
+                ShArgs a{};
+                a.c = L.band[d]; a.cL = wL->lev[l].band[d]; a.nv = d_noisevarchrom; a.mad = d_madL + idx; a.n = L.w2 * L.h2;
+                a.noisevar_ab = noisevar_ab; a.useCCurve = useNoiseCCurve; a.madab = madab + idx;
+                a.nv_uniform = uniform != nullptr; a.nv_value = uniform ? *uniform : 0.f;
                 art_prof_begin(ctx, "k_sf_AB_simple");
-                k_sf_AB_simple<<<std::min((n + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(a);
+                k_sf_AB_simple<<<std::min((a.n + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(a);
                 art_prof_end(ctx);
                 ctx->launches++;
                 continue;
             }
-            rc = shrink_band(ctx, sc, a, L.w2, L.h2, blur_radius(l, scale), true);
+            ShJob& j = b.job[b.njobs];
+            j.c = L.band[d]; j.cL = wL->lev[l].band[d]; j.madL = d_madL + idx; j.madab = madab + idx;
+            j.sf = bs.planes + (size_t)(2 * b.njobs) * bs.np; j.tmp = j.sf + bs.np;
+            j.W = L.w2; j.H = L.h2; j.rad = blur_radius(l, scale); j.lvlmul = 0.f;
+            b.njobs++;
         }
-    const int rc2 = lanes.end();
-    return rc ? rc : rc2;
+    ART_CUDA(ctx, cudaGetLastError());
+    return shrink_batch(ctx, b);
 }
