@@ -104,6 +104,9 @@ def load_library(build_if_missing=True):
         "art_hp_develop_size": (i, [vp, i, i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]),
         "art_hp_denoise_guided_smoothing": (i, [vp, i, i, vp, vp, vp, vp, i, d]),
         "art_hp_denoise_guided_smoothing_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, i, d]),
+        "art_hp_develop_submit_packed": (i, [vp, vp, i, i, vp, i, i, vp, sz]),
+        "art_hp_scanlines": (i, [vp, i, i, vp, vp, vp, i, i, vp, sz]),
+        "art_hp_scanlines_dev": (i, [vp, i, i, vp, vp, vp, sz, i, i, vp, sz]),
         "art_hp_develop_wait": (i, [vp]),
         "art_hp_develop_pending": (i, [vp]),
         "art_hp_fattal": (i, [vp, i, i, vp, vp, vp, i, i, i, ctypes.POINTER(d)]),
@@ -149,16 +152,16 @@ def row_table(a):
 
 
 class PinnedArray:
-    """A float32 (H, W) numpy view over art_hp_host_alloc'ed (pinned) memory."""
+    """An (H, W) numpy view (float32 unless `dtype` says otherwise) over art_hp_host_alloc'ed (pinned) memory."""
 
-    def __init__(self, lib, H, W):
+    def __init__(self, lib, H, W, dtype=np.float32):
         self._lib = lib
-        n = H * W * 4
+        n = H * W * np.dtype(dtype).itemsize
         self.ptr = lib.art_hp_host_alloc(n)
         if not self.ptr:
             raise MemoryError("art_hp_host_alloc(%d)" % n)
-        buf = (ctypes.c_float * (H * W)).from_address(self.ptr)
-        self.array = np.frombuffer(buf, dtype=np.float32).reshape(H, W)
+        buf = (ctypes.c_ubyte * n).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(H, W)
 
     def free(self):
         if self.ptr:
@@ -477,8 +480,8 @@ class HotPath:
             out[name.value.decode()] = (ms.value, calls.value)
         return out
 
-    def pinned(self, H, W):
-        return PinnedArray(self.lib, H, W)
+    def pinned(self, H, W, dtype=np.float32):
+        return PinnedArray(self.lib, H, W, dtype)
 
     # -- demosaic ----------------------------------------------------------
     def demosaic_bayer(self, method, raw, filters, red=None, green=None, blue=None, initial_gain=1.0, border=4):
@@ -597,6 +600,23 @@ class HotPath:
         H, W = raw.shape
         c = params.c_struct()
         self._check(self.lib.art_hp_develop_submit(self.h, ctypes.byref(c), W, H, row_table(raw), row_table(red), row_table(green), row_table(blue)))
+
+    def develop_submit_packed(self, raw, params, out, bps=16, is_float=False):
+        """Queue one frame whose result leaves as interleaved scanlines (Imagefloat::getScanline on the device): `out` is a pinned
+        (H_out, 3 * W_out) array of uint16 / uint8 / float32 (see HotPath.pinned_bytes)."""
+        H, W = raw.shape
+        c = params.c_struct()
+        self._check(self.lib.art_hp_develop_submit_packed(self.h, ctypes.byref(c), W, H, row_table(raw), int(bps), int(bool(is_float)),
+                                                          out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
+
+    def scanlines(self, r, g, b, bps=16, is_float=False):
+        """Imagefloat::getScanline for every row: three host (H, W) float32 planes -> (H, 3 W) interleaved samples."""
+        H, W = r.shape
+        dt = {(8, False): np.uint8, (16, False): np.uint16, (16, True): np.uint16, (32, True): np.float32}[(int(bps), bool(is_float))]
+        out = np.zeros((H, 3 * W), dt)
+        self._check(self.lib.art_hp_scanlines(self.h, W, H, row_table(r), row_table(g), row_table(b), int(bps), int(bool(is_float)),
+                                              out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
+        return out
 
     def develop_wait(self):
         self._check(self.lib.art_hp_develop_wait(self.h))

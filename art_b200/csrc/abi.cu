@@ -250,6 +250,7 @@ void art_hp_destroy(art_hp_ctx* ctx)
     for (auto& q : ctx->q) {
         if (q.raw.p) cudaFree(q.raw.p);
         for (DevBuf& o : q.out) if (o.p) cudaFree(o.p);
+        if (q.packed.p) cudaFree(q.packed.p);
         if (q.up) cudaEventDestroy(q.up);
         if (q.done) cudaEventDestroy(q.done);
         if (q.down) cudaEventDestroy(q.down);
@@ -1092,27 +1093,36 @@ int art_hp_develop(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, 
 }
 
 // Batch-queue form: the copies of frame k overlap the kernels of frames k-1 / k+1 (three streams, two frames in flight).
-int art_hp_develop_submit(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
-                          float* const* r, float* const* g, float* const* b)
+// packed_out != nullptr: the frame leaves as interleaved scanlines (pack.cu) instead of three float planes.
+static int develop_submit(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
+                          float* const* r, float* const* g, float* const* b, int bps, int is_float, void* packed_out, size_t packed_stride)
 {
     if (!ctx) return ART_HP_ERR_INVALID;
-    if (!rawData || !r || !g || !b) return ctx->fail(ART_HP_ERR_INVALID, "null row table");
+    if (!rawData || (!packed_out && (!r || !g || !b))) return ctx->fail(ART_HP_ERR_INVALID, "null row table");
     int rc = check_develop(ctx, params, W, H);
     if (rc) return rc;
     if (ctx->q_submitted - ctx->q_collected >= 2) return ctx->fail(ART_HP_ERR_INVALID, "two frames are already in flight: call art_hp_develop_wait first");
     int bd, Wo, Ho;
     art_develop_geometry(params, W, H, &bd, &Wo, &Ho);
-    ptrdiff_t st[4];
+    ptrdiff_t st[4] = {0, 0, 0, 0};
     float* const* tabs[4] = {rawData, r, g, b};
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < (packed_out ? 1 : 4); ++i)
         if (!constant_stride(tabs[i], i ? Ho : H, &st[i]) || !is_pinned(tabs[i][0]))
             return ctx->fail(ART_HP_ERR_UNSUPPORTED, "the batch queue needs pinned, constant-stride planes (art_hp_host_alloc); use art_hp_develop otherwise");
+    size_t row_bytes = 0;
+    if (packed_out) {
+        if (art_scanline_mode(bps, is_float) < 0) return ctx->fail(ART_HP_ERR_INVALID, "bps %d / isFloat %d is not a format of Imagefloat::getScanline", bps, is_float);
+        row_bytes = (size_t)Wo * 3 * (bps / 8);
+        if (packed_stride < row_bytes || !is_pinned(packed_out)) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "the packed output must be pinned with rows of at least %zu bytes", row_bytes);
+    }
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
     art_hp_ctx::QSlot& q = ctx->q[ctx->q_submitted & 1];
     const size_t pitch = round_up((size_t)W, 32), opitch = round_up((size_t)Wo, 32);
     if ((rc = art_reserve(ctx, q.raw, pitch * (size_t)H * sizeof(float)))) return rc;
     for (int i = 0; i < 3; ++i)
         if ((rc = art_reserve(ctx, q.out[i], opitch * (size_t)Ho * sizeof(float)))) return rc;
+    const size_t dpitch = round_up(row_bytes, 128);
+    if (packed_out && (rc = art_reserve(ctx, q.packed, dpitch * (size_t)Ho))) return rc;
     if (!q.up) {
         ART_CUDA(ctx, cudaEventCreateWithFlags(&q.up, cudaEventDisableTiming));
         ART_CUDA(ctx, cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
@@ -1125,13 +1135,66 @@ int art_hp_develop_submit(art_hp_ctx* ctx, const art_hp_develop_params* params, 
     ART_CUDA(ctx, cudaEventRecord(q.up, ctx->copy_stream));
     ART_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, q.up, 0));
     if ((rc = art_develop_dev(ctx, params, W, H, (const float*)q.raw.p, pitch, (float*)q.out[0].p, (float*)q.out[1].p, (float*)q.out[2].p, opitch))) return rc;
+    if (packed_out && (rc = art_scanlines_dev(ctx, Wo, Ho, (const float*)q.out[0].p, (const float*)q.out[1].p, (const float*)q.out[2].p, opitch, bps, is_float,
+                                              q.packed.p, dpitch))) return rc;
     ART_CUDA(ctx, cudaEventRecord(q.done, ctx->stream));
     ART_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, q.done, 0));
-    for (int i = 0; i < 3; ++i)
-        ART_CUDA(ctx, cudaMemcpy2DAsync(tabs[i + 1][0], (size_t)st[i + 1] * sizeof(float), q.out[i].p, opitch * sizeof(float), (size_t)Wo * sizeof(float), Ho,
-                                        cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    if (packed_out) {
+        ART_CUDA(ctx, cudaMemcpy2DAsync(packed_out, packed_stride, q.packed.p, dpitch, row_bytes, Ho, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    } else {
+        for (int i = 0; i < 3; ++i)
+            ART_CUDA(ctx, cudaMemcpy2DAsync(tabs[i + 1][0], (size_t)st[i + 1] * sizeof(float), q.out[i].p, opitch * sizeof(float), (size_t)Wo * sizeof(float), Ho,
+                                            cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    }
     ART_CUDA(ctx, cudaEventRecord(q.down, ctx->d2h_stream));
     ctx->q_submitted++;
+    return ART_HP_OK;
+}
+
+int art_hp_develop_submit(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
+                          float* const* r, float* const* g, float* const* b)
+{
+    return develop_submit(ctx, params, W, H, rawData, r, g, b, 0, 0, nullptr, 0);
+}
+
+int art_hp_develop_submit_packed(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
+                                 int bps, int isFloat, void* out, size_t out_stride_bytes)
+{
+    if (ctx && !out) return ctx->fail(ART_HP_ERR_INVALID, "null output");
+    return develop_submit(ctx, params, W, H, rawData, nullptr, nullptr, nullptr, bps, isFloat, out, out_stride_bytes);
+}
+
+int art_hp_scanlines_dev(art_hp_ctx* ctx, int W, int H, const float* d_r, const float* d_g, const float* d_b, size_t pitch, int bps, int isFloat,
+                         void* d_out, size_t out_stride_bytes)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_r || !d_g || !d_b || !d_out) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_scanlines_dev(ctx, W, H, d_r, d_g, d_b, pitch, bps, isFloat, d_out, out_stride_bytes);
+}
+
+int art_hp_scanlines(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b, int bps, int isFloat,
+                     void* out, size_t out_stride_bytes)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!r || !g || !b || !out) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    if (art_scanline_mode(bps, isFloat) < 0) return ctx->fail(ART_HP_ERR_INVALID, "bps %d / isFloat %d is not a format of Imagefloat::getScanline", bps, isFloat);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    const size_t row_bytes = (size_t)W * 3 * (bps / 8), dpitch = round_up(row_bytes, 128);
+    if (out_stride_bytes < row_bytes) return ctx->fail(ART_HP_ERR_INVALID, "output rows need %zu bytes", row_bytes);
+    int rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+    if ((rc = art_reserve(ctx, ctx->d_raw, dpitch * (size_t)H))) return rc;
+    Plane io[3] = {{r, (float*)ctx->d_out[0].p}, {g, (float*)ctx->d_out[1].p}, {b, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_scanlines_dev(ctx, W, H, io[0].dev, io[1].dev, io[2].dev, pitch, bps, isFloat, ctx->d_raw.p, dpitch))) return rc;
+    ART_CUDA(ctx, cudaMemcpy2DAsync(out, out_stride_bytes, ctx->d_raw.p, dpitch, row_bytes, H, cudaMemcpyDeviceToHost, ctx->stream));
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;
 }
 

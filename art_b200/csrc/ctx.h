@@ -67,7 +67,7 @@ struct art_hp_ctx {
     DevBuf d_xt_cbrt;                    // cielab's 0x14000-entry cube-root LUT of the X-Trans demosaic
     bool xt_cbrt_ready = false;
     // batch queue (art_hp_develop_submit / _wait): two frames in flight, each with its own raw + output planes
-    struct QSlot { DevBuf raw, out[3]; cudaEvent_t up = nullptr, done = nullptr, down = nullptr; };
+    struct QSlot { DevBuf raw, out[3], packed; cudaEvent_t up = nullptr, done = nullptr, down = nullptr; };
     QSlot q[2];
     unsigned long long q_submitted = 0, q_collected = 0;
     // side streams for work that is independent per wavelet subband (shrink.cu): the flat box blurs are serial recurrences
@@ -190,6 +190,10 @@ int art_denoise_stage_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t 
 int art_denoise_auto_chroma_dev(art_hp_ctx* ctx, const float* r, const float* g, const float* b, size_t ip, int widIm, int heiIm,
                                 const float mul[3], int doClip, const double* cam2work, const double* wprof, double gamma, int aggressive,
                                 float out3[3], float* stats_out);
+// Imagefloat::getScanline for every row (pack.cu): planar float -> interleaved 16-bit / 8-bit / float / half rows
+int art_scanline_mode(int bps, int is_float);
+int art_scanlines_dev(art_hp_ctx* ctx, int W, int H, const float* r, const float* g, const float* b, size_t ip, int bps, int is_float,
+                      void* out, size_t stride_bytes);
 // output size of art_hp_develop for a W x H raw frame
 void art_develop_geometry(const art_hp_develop_params* p, int W, int H, int* b, int* Wo, int* Ho);
 int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int W, int H, const float* raw, size_t rp,

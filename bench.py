@@ -1,24 +1,26 @@
 #!/usr/bin/env python3
-"""bench.py -- the hot path on synthetic 45 MP Bayer frames, one process per GPU.
+"""bench.py -- the hot path on synthetic Bayer / X-Trans frames, one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload develop|amaze|rcd]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload develop|c2|c3|c4|amaze|rcd]
 
-A "step" is one pass of the hot path over one frame.  The default workload is the one BASELINE.json's
-metric names -- "Mpixel/s end-to-end (demosaic+denoise+tonemap) on 45 MP Bayer": AMaZE demosaic, getImage
-gains + camera->working matrix, RGB_denoise (luminance 30 / detail 50 / chrominance 15) and
-Fattal tone mapping (threshold 30, amount 20) of an 8192x5464 synthetic RGGB frame, i.e. configs[1]'s frame
-run through the stages of the metric (art_hp_develop).  `--workload amaze` is configs[1] alone (demosaic
-only), `--workload rcd` the configs[0]-style case.  With N>1 (torchrun, one rank per GPU) every rank develops its own frame
--- frames are independent objects, so there is no data-path collective ("scaling": "weak"); the only
-torch.distributed traffic is the barrier and the max-over-ranks of the timed region.
+A "step" is one pass of the hot path over one frame.  Workloads (BASELINE.json `configs`):
+  develop  the metric -- "Mpixel/s end-to-end (demosaic+denoise+tonemap) on 45 MP Bayer": AMaZE, getImage gains + camera->working matrix (with
+           the reference's border crop), RGB_denoise (luminance 30 / detail 50 / chrominance 15), Fattal (30 / 20) of an
+           8192x5464 RGGB frame = configs[1]'s frame through the stages of the metric (art_hp_develop).  The default.
+  c2       configs[2]: AMaZE + RGB_denoise + unsharp mask (radius 0.5, amount 200), 8192x5464
+  c3       configs[3]: X-Trans 3-pass + chroma RGB_denoise + NL-means (50 / 80), 6240x4160
+  c4       configs[4]: AMaZE + RGB_denoise + Fattal + the default colour chain (NEUTRAL film curve, saturation curve), 12288x8192
+  amaze    configs[1] alone (demosaic only);  rcd  the configs[0]-style case
+With N>1 (torchrun, one rank per GPU) every rank develops its own frames -- frames are independent objects (the batch queue), so there is no
+data-path collective ("scaling": "weak"); torch.distributed carries the barrier and the max-over-ranks of the timed region only.
 
 Printed JSON (rank 0, one line): the driver contract plus
   roofline     dominant kernel: algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json
-  cpu_baseline the reference's own code (oracle/_ref, kind "reference") or our C restatement
-               (kind "port") timed on this box's host cores on a bounded sample
-  e2e          the same metric through the host-buffer C-ABI call (art_hp_demosaic_bayer):
-               pinned host planes in, pinned host planes out, both copies inside the timed region
+  cpu_baseline the reference's own code (oracle/_ref, kind "reference") timed on this box's host cores on a bounded sample
+  e2e          the same metric through the host-buffer C-ABI batch-queue call: pinned host planes in, the developed frame out in the
+               reference's 16-bit wire format (Imagefloat::getScanline on the device), both copies inside the timed region
   clocks       nvidia-smi samples taken during the timed region
+`--impl reference`: the reference's own functions (oracle/_ref) on ALL host threads, the full frame of the workload per step.
 """
 import argparse
 import json
@@ -60,16 +62,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("ART_BENCH_WORKLOAD", "develop"), choices=["develop", "amaze", "rcd"])
+    ap.add_argument("--workload", default=os.environ.get("ART_BENCH_WORKLOAD", "develop"), choices=["develop", "c2", "c3", "c4", "amaze", "rcd"])
     ap.add_argument("--method", default=None, choices=["amaze", "rcd"], help="alias: --workload amaze|rcd")
-    ap.add_argument("--cpu-sample", default="2048x1366", help="frame of the bounded CPU sample of the develop workload")
-    ap.add_argument("--width", type=int, default=W45)
-    ap.add_argument("--height", type=int, default=H45)
+    ap.add_argument("--cpu-sample", default="2048x1366", help="frame of the bounded CPU sample (cpu_baseline leg of our arm)")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="reference arm: seconds of CPU work the timed steps may take")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.method:
         a.workload = a.method
     a.method = "rcd" if a.workload == "rcd" else "amaze"
+    dw, dh = {"c3": (6240, 4160), "c4": (12288, 8192)}.get(a.workload, (W45, H45))
+    a.width, a.height = a.width or dw, a.height or dh
     return a
 
 
@@ -162,23 +167,64 @@ def cpu_reference_runner(method, raw, filters):
 
 
 PROPHOTO = [[0.7976749, 0.1351917, 0.0313534], [0.2880402, 0.7118741, 0.0000857], [0.0, 0.0, 0.8252100]]   # iccmatrices.h xyz_prophoto
+PROPHOTO_INV = [[1.3459433, -0.2556075, -0.0511118], [-0.5445989, 1.5081673, 0.0205351], [0.0, 0.0, 1.2118128]]
 CAM2WORK = [[0.82, 0.15, 0.03], [0.07, 0.96, -0.03], [0.02, -0.10, 1.08]]      # a fixed camera->working matrix (synthetic camera)
 MUL = (1.9, 1.0, 1.6)                                                           # rm, gm, bm of getImage for that camera
 DN = dict(luminance=30.0, luminanceDetail=50.0, luminanceDetailThreshold=0, chrominance=15.0, chrominanceRedGreen=0.0,
           chrominanceBlueYellow=0.0, gamma=1.7, scale=1.0)
+DN_CHROMA = dict(DN, luminance=0.0, luminanceDetail=0.0)
 FATTAL = (30, 20, 0)                                                            # threshold, amount, satcontrol (procparams.cc L2074-2079)
-
-# Algorithmic bytes per unit of the develop kernels that can dominate: fp32 planes, each plane a
-# kernel must read or write counted once.  unit = what one launch covers.
-DEVELOP_KERNEL_BYTES = {
-    "k_fbox_h": (8, "subband coefficient"), "k_fbox_v": (8, "subband coefficient"),        # 4 R + 4 W
-    "k_dn_blocks": (4 + 4 * (64.0 / 25.0) ** 2, "pixel"),   # residual read once + the windowed 64x64 blocks (stride 25) written
-    "k_fat_dct_rows": (4 + 8, "padded pixel"), "k_fat_dct_solve": (8 + 8, "padded pixel"), "k_fat_dct_exp": (8 + 4, "padded pixel"),
-    "k_wav_sy_sub": (16 + 4, "pixel"), "k_sf_apply": (12 + 4, "subband coefficient"), "k_mad_hist": (4, "subband coefficient"),
-    "k_sf_L": (8 + 4, "subband coefficient"), "k_sf_AB": (12 + 4, "subband coefficient"),
-}
+PIPELINES = ("develop", "c2", "c3", "c4")
+FILM_CURVE = [1, 0, 0, 0.11, 0.09, 0.32, 0.47, 0.66, 0.87, 1, 1]               # rtdata/profiles/Standard Film Curve.arp
+FILM_SAT = [1, 0, 0.48, 0.34, 0.35, 1, 0.48, 0.35, 0.35]
 
 
+def workload_text(wl, W, H):
+    mp = W * H / 1e6
+    return {
+        "develop": "metric pipeline on configs[1]'s frame: AMaZE demosaic + gains/matrix (border crop 4) + RGB_denoise (lum 30, detail 50, chroma 15) + "
+                   "Fattal (30/20), %dx%d synthetic RGGB (%.2f MP), art_hp_develop" % (W, H, mp),
+        "c2": "configs[2]: AMaZE + gains/matrix + RGB_denoise (lum 30, detail 50, chroma 15) + unsharp mask (radius 0.5, amount 200), %dx%d synthetic RGGB "
+              "(%.2f MP), art_hp_develop" % (W, H, mp),
+        "c3": "configs[3]: X-Trans 3-pass demosaic + gains/matrix (border crop 7) + chroma RGB_denoise (15) + NL-means (50/80), %dx%d synthetic X-Trans "
+              "(%.2f MP), art_hp_develop" % (W, H, mp),
+        "c4": "configs[4]: AMaZE + gains/matrix + RGB_denoise + Fattal (30/20) + default colour chain (NEUTRAL Standard Film Curve, saturation curve), %dx%d "
+              "synthetic RGGB (%.2f MP), art_hp_develop" % (W, H, mp),
+        "amaze": "configs[1]: AMaZE demosaic, %dx%d synthetic RGGB (%.2f MP)" % (W, H, mp),
+        "rcd": "configs[0]-style: RCD demosaic, %dx%d synthetic RGGB (%.2f MP)" % (W, H, mp),
+    }[wl]
+
+
+def make_raw(wl, W, H, seed):
+    from art_b200 import synth
+    if wl == "c3":
+        return synth.xtrans_frame(W, H, synth.xtrans_matrix(1, 3), seed=seed)
+    return synth.bayer_frame(W, H, synth.RGGB, seed=seed)
+
+
+def develop_params(art_b200, wl):
+    """DevelopParams of a pipeline workload (our arm).  The c4 tone curve comes from the committed golden fixture (the reference's own
+    curve objects evaluated once, tests/golden/make_tone_golden.py): curves stay host-built, the hot path takes LUTs."""
+    import numpy as np
+    from art_b200 import synth
+    from art_b200.api import ChainParams, DenoiseParams, DevelopParams, SharpenParams
+    kw = dict(mul=MUL, do_clip=True, cam2work=CAM2WORK, wprof=PROPHOTO)
+    if wl == "c3":
+        return DevelopParams(method=art_b200.XTRANS_3PASS, xtrans=synth.xtrans_matrix(1, 3), rgb_cam=np.array(synth.XTRANS_RGB_CAM, np.float32),
+                             denoise=DenoiseParams(**DN_CHROMA), nl_strength=50, nl_detail=80, **kw)
+    kw.update(method=art_b200.BAYER_AMAZE, filters=0x94949494, initial_gain=1.0, border=4, denoise=DenoiseParams(**DN))
+    if wl == "c2":
+        return DevelopParams(sharpen=SharpenParams(radius=0.5, amount=200), **kw)
+    if wl == "c4":
+        z = np.load(os.path.join(ROOT, "tests", "golden", "tone_film.npz"))
+        stages = [(1, z["poly_last"][:1], z["poly_last"][1:], 0, 0, 0), (0, None, None, 0, 0, 0)]
+        return DevelopParams(fattal=FATTAL, chain=ChainParams(ws=PROPHOTO, iws=PROPHOTO_INV, tonecurve=(2, z["lut"]), stages=stages, satcurve=z["satlut"]), **kw)
+    return DevelopParams(fattal=FATTAL, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------------------- roofline bookkeeping
+# Algorithmic bytes per unit of the kernels that can dominate (DESIGN.md section 11): fp32 planes, each plane a kernel must read or write
+# counted once.  unit = what one LAUNCH covers.
 def find_fast_dim(dim):
     v = dim - 1
     for sh in (1, 2, 4, 8, 16):
@@ -191,46 +237,55 @@ def find_fast_dim(dim):
     return dim
 
 
-def develop_units(name, W, H):
-    if name in ("k_fbox_h", "k_fbox_v", "k_sf_apply", "k_mad_hist", "k_sf_L", "k_sf_AB"):
-        return ((W + 1) // 2) * ((H + 1) // 2)
-    if name.startswith("k_fat_dct"):
-        return (find_fast_dim(W) + 1) * (find_fast_dim(H) + 1)
-    return W * H
+def kernel_bytes(name, Wr, Hr, W, H, nlev=5):
+    """(algorithmic bytes per launch, description) or None.  Wr x Hr: raw frame; W x H: the developed (cropped) frame."""
+    px, sub = W * H, ((W + 1) // 2) * ((H + 1) // 2)
+    ntiles = ((Wr + 16 + 127) // 128) * ((Hr + 16 + 127) // 128)
+    pad = (find_fast_dim(W) + 1) * (find_fast_dim(H) + 1)
+    nsub = 3 * nlev
+    table = {
+        # shrink stage: one launch = all 15 subbands of one channel; sf: read c (+ L coefficient for a / b), write sf -> (8 + 12 + 12) / 3 on average
+        "k_shrink_sf": ((32.0 / 3.0) * sub * nsub, "15 subbands of a channel: coefficient (+ L coefficient for a, b) read, sf written"),
+        "k_shrink_h": (8.0 * sub * nsub, "15 subbands: sf read, row sums written"),
+        "k_shrink_v": (16.0 * sub * nsub, "15 subbands: row sums, sf, coefficient read, coefficient written"),
+        "k_mad_hist_all": (4.0 * sub * nsub, "15 subbands read once"),
+        "k_dn_blocks": ((4 + 4 * (64.0 / 25.0) ** 2) * px, "residual read once + the windowed 64x64 blocks (stride 25) written"),
+        "k_dn_gather": ((4 * (64.0 / 25.0) ** 2 + 8) * px, "blocks read, L read and written"),
+        "k_dn_split": (24.0 * px, "3 planes read, 3 written"), "k_dn_merge": (24.0 * px, "3 planes read, 3 written"),
+        "k_fat_dct_rows": (12.0 * pad, "padded plane: 4 read, 8 written"), "k_fat_dct_solve": (16.0 * pad, "8 read, 8 written"),
+        "k_fat_dct_exp": (12.0 * pad, "8 read, 4 written"),
+        "k_wav_sy_sub": (20.0 * px, "4 quarter-size planes read, 1 full written"), "k_wav_an_sub": (20.0 * px, "1 full plane read, 4 quarter-size written"),
+        "k_wav_sy_haar": (20.0 * sub, "4 planes read, 1 written"), "k_wav_an_haar": (20.0 * sub, "1 plane read, 4 written"),
+        "k_chain": (24.0 * px, "3 planes read, 3 written"), "k_scale_convert_crop": (24.0 * px, "3 planes read, 3 written"),
+        "k_scanlines": (18.0 * px, "3 float planes read, 6 B/px written"),
+        "k_nlm_tile": (44.0 * px, "SURVEY.md 8(d)"), "k_xtrans": (16.0 * Wr * Hr, "4 B read, 12 B written per pixel"),
+        "rcd_kernel": (16.0 * Wr * Hr, "4 B read, 12 B written per pixel"),
+    }
+    if name in table:
+        return table[name]
+    if name in AMAZE_KERNEL_BYTES:
+        return AMAZE_KERNEL_BYTES[name] * ntiles * 160 * 160, "tile pixels x planes per pass"
+    return None
 
 
-def roofline_top(per_step, kern, calls, W, H, peak, n=6):
-    """The same algorithmic-bytes / CUDA-event-time figure for the n largest kernels of the step (the wavelet-shrink kernels of
-    the three directions run on three concurrent streams, so their per-launch times include each other's interference)."""
+def roofline_top(per_step, kern, calls, geo, peak, n=8):
     out = []
-    ntiles = ((W + 16 + 127) // 128) * ((H + 16 + 127) // 128)
     for k in sorted(per_step, key=lambda k: -per_step[k])[:n]:
-        ub = DEVELOP_KERNEL_BYTES.get(k)
-        if ub is not None:
-            units = develop_units(k, W, H)
-            b = ub[0]
-        elif k in AMAZE_KERNEL_BYTES:
-            units, b = ntiles * 160 * 160, AMAZE_KERNEL_BYTES[k]
-        else:
-            out.append({"kernel": k, "ms_per_step": round(per_step[k], 4), "launches_per_step": calls[k], "achieved_GBps": None, "frac": None})
-            continue
-        ach = b * units / (kern[k] * 1e-3) / 1e9
-        out.append({"kernel": k, "ms_per_step": round(per_step[k], 4), "launches_per_step": calls[k], "achieved_GBps": round(ach, 1),
-                    "frac": round(ach / peak, 4)})
+        kb = kernel_bytes(k, *geo)
+        e = {"kernel": k, "ms_per_step": round(per_step[k], 4), "launches_per_step": calls[k], "achieved_GBps": None, "frac": None}
+        if kb is not None:
+            ach = kb[0] / (kern[k] * 1e-3) / 1e9
+            e.update(achieved_GBps=round(ach, 1), frac=round(ach / peak, 4), traffic=NCU_TRAFFIC.get(k))
+        out.append(e)
     return out
 
 
-def develop_params(art_b200):
-    from art_b200.api import DenoiseParams, DevelopParams
-    return DevelopParams(method=art_b200.BAYER_AMAZE, filters=0x94949494, initial_gain=1.0, border=4, mul=MUL, do_clip=True,
-                         cam2work=CAM2WORK, denoise=DenoiseParams(**DN), fattal=FATTAL, wprof=PROPHOTO)
-
-
-def use_all_host_threads():
+# ---------------------------------------------------------------------------------------------------------------- host-side placement
+def use_all_host_threads(n=None):
     """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the reference arm is the reference's OpenMP code on ALL host
     threads of the box, so the count is set explicitly (environment for a libgomp not loaded yet, omp_set_num_threads for one that is)."""
     import ctypes
-    n = os.cpu_count() or 1
+    n = n or len(os.sched_getaffinity(0)) or os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(n)
     os.environ.pop("OMP_THREAD_LIMIT", None)
     try:
@@ -240,13 +295,41 @@ def use_all_host_threads():
     return n
 
 
-def cpu_develop_runner(raw, filters):
-    """The same stages through the reference's own functions compiled in place (oracle/_ref, stock build): AMaZE,
-    getImage gains + matrix, RGB_denoise, ToneMapFattal02.  fftw3f is absent from this image, so the two FFTW call sites
-    (64x64 block DCTs, 2-D REDFT00) run the oracle's double-precision stand-in, which is slower than FFTW would be."""
+def pin_rank_near_gpu(local, world):
+    """One process per GPU: keep the rank's threads (and, by first touch, its pinned host buffers) on the CPUs of its GPU's NUMA node, and
+    give every rank of that node its own slice of them, so eight ranks do not stack on the same cores.  Returns a description."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (dom, bus, dev)
+        node = int(open(path + "/numa_node").read())
+        cl = open(path + "/local_cpulist").read().strip()
+        cpus = []
+        for part in cl.split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        cpus = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not cpus:
+            return {"numa_node": node, "pinned": False}
+        per = max(1, len(cpus) // max(1, world))
+        mine = cpus[(local * per) % len(cpus):][:per] or cpus
+        os.sched_setaffinity(0, mine)
+        return {"numa_node": node, "pinned": True, "cpus": "%d-%d" % (mine[0], mine[-1]), "ncpus": len(mine)}
+    except Exception as ex:       # placement is an optimisation, never a requirement
+        return {"pinned": False, "why": str(ex)[:120]}
+
+
+# ---------------------------------------------------------------------------------------------------------------- the reference on the host
+def cpu_pipeline_runner(wl, raw):
+    """The workload's stages through the reference's OWN functions compiled in place (oracle/_ref, stock build), OpenMP on all host
+    threads.  fftw3f is absent from this image, so the two FFTW call sites (64x64 block DCTs, 2-D REDFT00) run the oracle's double-precision
+    stand-in, which is slower than FFTW would be.  Returns (callable, kind, threads)."""
     import ctypes
     import numpy as np
     import oracle
+    from art_b200 import synth
     ncores = use_all_host_threads()
     ref = oracle.ref(det=False)
     use_all_host_threads()
@@ -254,30 +337,59 @@ def cpu_develop_runner(raw, filters):
     lib.artref_set_denoise_thread_limit(0)        # the reference's default: all OpenMP threads
     fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
     Hr, Wr = raw.shape
-    H, W = Hr - 8, Wr - 8                         # getImage crops the demosaiced frame by RawImageSource::border (4)
+    bd = 7 if wl == "c3" else 4                   # getImage crops the demosaiced frame by RawImageSource::border
+    H, W = Hr - 2 * bd, Wr - 2 * bd
     out = [np.zeros((Hr, Wr), np.float32) for _ in range(3)]
     wp = np.array(PROPHOTO, np.float64)
     wpi = np.linalg.inv(wp)
-    p = np.array([DN["luminance"], DN["luminanceDetail"], DN["luminanceDetailThreshold"], DN["chrominance"], DN["chrominanceRedGreen"],
-                  DN["chrominanceBlueYellow"], DN["gamma"], DN["scale"]], np.float64)
+    dn = DN_CHROMA if wl == "c3" else DN
+    p = np.array([dn["luminance"], dn["luminanceDetail"], dn["luminanceDetailThreshold"], dn["chrominance"], dn["chrominanceRedGreen"],
+                  dn["chrominanceBlueYellow"], dn["gamma"], dn["scale"]], np.float64)
     res = np.zeros(2, np.float32)
+    xt = np.ascontiguousarray(synth.xtrans_matrix(1, 3), np.int32)
+    cam = np.array(synth.XTRANS_RGB_CAM, np.float32)
+    c1, c2, sat = np.array(FILM_CURVE, np.float64), np.array([0.0]), np.array(FILM_SAT, np.float64)
+    wsf, iwsf = np.array(PROPHOTO, np.float32), np.array(PROPHOTO_INV, np.float32)
+    thr = (ctypes.c_int * 4)(20, 80, 2000, 1200)
+    P3 = lambda pl: [x.ctypes.data_as(fp) for x in pl]
 
     def run():
-        ref.amaze(raw, filters, nthreads=ncores, out=out)
-        r, g, b = ref.scale_convert([np.ascontiguousarray(p[4:-4, 4:-4]) for p in out], MUL, True, np.array(CAM2WORK, np.float64))
+        if wl == "c3":
+            assert lib.artref_xtrans(Wr, Hr, xt.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), cam.ctypes.data_as(fp), 3, 1, raw.ctypes.data_as(fp), *P3(out), 0, ncores) == 0
+        else:
+            ref.amaze(raw, synth.RGGB, nthreads=ncores, out=out)
+        r, g, b = ref.scale_convert([np.ascontiguousarray(q[bd:Hr - bd, bd:Wr - bd]) for q in out], MUL, True, np.array(CAM2WORK, np.float64))
         assert lib.artref_rgb_denoise(r.ctypes.data_as(fp), g.ctypes.data_as(fp), b.ctypes.data_as(fp), W, H, p.ctypes.data_as(dp),
                                       wp.ctypes.data_as(dp), wpi.ctypes.data_as(dp), None, ctypes.c_float(0), None, None, None,
                                       res.ctypes.data_as(fp)) == 0
-        assert lib.artref_fattal(r.ctypes.data_as(fp), g.ctypes.data_as(fp), b.ctypes.data_as(fp), W, H, FATTAL[0], FATTAL[1], FATTAL[2],
-                                 wp.ctypes.data_as(dp)) == 0
+        if wl == "c3":       # Imagefloat::setMode(YUV) / NLMeans on Y / setMode(RGB), ipdenoise.cc L1173-1177
+            w0, w1, w2 = [np.float32(v) for v in PROPHOTO[1]]
+            Y = (r * w0 + g * w1) + b * w2
+            u, v = Y - b, r - Y
+            Y = np.ascontiguousarray(Y)
+            assert lib.artref_nlmeans(Y.ctypes.data_as(fp), W, H, ctypes.c_float(65535.0), 50, 80, ctypes.c_float(1.0)) == 0
+            r = v + Y
+            b = Y - u
+            g = (Y - w0 * r - w2 * b) / w1
+        if wl in ("develop", "c4"):
+            assert lib.artref_fattal(r.ctypes.data_as(fp), g.ctypes.data_as(fp), b.ctypes.data_as(fp), W, H, FATTAL[0], FATTAL[1], FATTAL[2],
+                                     wp.ctypes.data_as(dp)) == 0
+        if wl == "c2":
+            assert lib.artref_usm(r.ctypes.data_as(fp), g.ctypes.data_as(fp), b.ctypes.data_as(fp), W, H, wp.ctypes.data_as(dp), ctypes.c_double(1.0),
+                                  ctypes.c_double(20.0), ctypes.c_double(0.5), 200, thr, 0, 85, None) == 0
+        if wl == "c4":
+            assert lib.artref_tone_neutral(r.ctypes.data_as(fp), g.ctypes.data_as(fp), b.ctypes.data_as(fp), W, H, c1.ctypes.data_as(dp), len(c1),
+                                           c2.ctypes.data_as(dp), len(c2), 0, ctypes.c_float(1.0), ctypes.c_double(1.0), wsf.ctypes.data_as(fp),
+                                           iwsf.ctypes.data_as(fp), None) == 0
+            lib.artref_tone_satcurve(r.ctypes.data_as(fp), g.ctypes.data_as(fp), b.ctypes.data_as(fp), W, H, sat.ctypes.data_as(dp), len(sat),
+                                     c2.ctypes.data_as(dp), 1, ctypes.c_float(1.0), ctypes.c_double(1.0), wsf.ctypes.data_as(fp), iwsf.ctypes.data_as(fp))
     return run, "reference", ncores
 
 
-def time_cpu_develop(sample, filters, budget_s=20.0, max_runs=3):
-    from art_b200 import synth
+def time_cpu_pipeline(wl, sample, seed, budget_s=20.0, max_runs=3):
     w, h = [int(v) for v in sample.lower().split("x")]
-    raw = synth.bayer_frame(w, h, filters, seed=1002)
-    run, kind, cores = cpu_develop_runner(raw, filters)
+    raw = make_raw(wl, w, h, seed)
+    run, kind, cores = cpu_pipeline_runner(wl, raw)
     ts = []
     t_end = time.perf_counter() + budget_s
     while len(ts) < max_runs and (not ts or time.perf_counter() < t_end):
@@ -286,9 +398,9 @@ def time_cpu_develop(sample, filters, budget_s=20.0, max_runs=3):
         ts.append(time.perf_counter() - t0)
     med = statistics.median(ts)
     return {"value": w * h / med / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": kind,
-            "sample": "%d runs of the same four stages on a %dx%d frame (%.1f MP, 1/%d of the workload's pixels), median; reference "
-                      "functions compiled in place, OpenMP on %d threads; FFTW call sites run the oracle's fp64 stand-in (fftw3f absent)"
-                      % (len(ts), w, h, w * h / 1e6, round(W45 * H45 / (w * h)), cores)}
+            "sample": "%d runs of the workload's stages on a %dx%d frame of the same synthetic scene (%.1f MP), median; reference functions compiled in "
+                      "place, OpenMP on %d threads; FFTW call sites run the oracle's fp64 stand-in (fftw3f absent); the reference arm "
+                      "(--impl reference) times the full frame" % (len(ts), w, h, w * h / 1e6, cores)}
 
 
 def time_cpu(method, raw, filters, budget_s=12.0, max_runs=5):
@@ -306,79 +418,68 @@ def time_cpu(method, raw, filters, budget_s=12.0, max_runs=5):
             "sample": "%d full %dx%d frames after warm-up, median; OpenMP threads = %d (faster of all/half)" % (len(ts), W, H, cores)}
 
 
+def reference_arm(args, config, W, H):
+    """The reference's own CPU implementation of the workload on all host threads, the full frame per step.  Steps are bounded by
+    --ref-budget seconds of CPU work (stated in the line); rank 0 alone runs it."""
+    from art_b200 import synth
+    wl = args.workload
+    raw = make_raw(wl, W, H, 1002)
+    if wl in PIPELINES:
+        run, kind, cores = cpu_pipeline_runner(wl, raw)
+    else:
+        run, kind, cores = cpu_reference_runner(args.method, raw, synth.RGGB)
+    t0 = time.perf_counter()
+    run()                                                       # warm-up (page faults, OpenMP team start-up)
+    first = time.perf_counter() - t0
+    nsteps = max(1, min(args.steps, int(args.ref_budget / max(first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        run()
+    dt = time.perf_counter() - t0
+    val = nsteps * W * H / dt / 1e6
+    cb = {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": kind,
+          "sample": "%d timed steps (1 warm-up) of the FULL %dx%d frame through the reference's own functions compiled in place; OpenMP on %d threads "
+                    "(set explicitly: torchrun exports OMP_NUM_THREADS=1); steps bounded by %.0f s of CPU work%s"
+                    % (nsteps, W, H, cores, args.ref_budget,
+                       "; FFTW call sites run the oracle's fp64 stand-in (fftw3f absent)" if wl in PIPELINES else "")}
+    print(json.dumps({"impl": "reference", "metric": "Mpixel/s", "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus,
+                      "steps": nsteps, "warmup": 1, "ms_per_step": dt / nsteps * 1e3,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "config": config, "cpu_baseline": cb,
+                      "note": "one CPU pipeline on the box's host threads; it does not multiply with --gpus",
+                      "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    return 0
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     W, H = args.width, args.height
+    wl = args.workload
+    pipeline = wl in PIPELINES
     from art_b200 import synth
     filters = synth.RGGB
-    workload = "configs[1]: AMaZE demosaic, %dx%d synthetic RGGB (%.2f MP)" % (W, H, W * H / 1e6)
-    if args.workload == "develop":
-        workload = ("metric pipeline on configs[1]'s frame: AMaZE demosaic + gains/matrix + RGB_denoise (lum 30, detail 50, chroma 15) + "
-                    "Fattal (30/20), %dx%d synthetic RGGB (%.2f MP), art_hp_develop" % (W, H, W * H / 1e6))
-    if args.workload == "rcd":
-        workload = "configs[0]-style: RCD demosaic, %dx%d synthetic RGGB (%.2f MP)" % (W, H, W * H / 1e6)
-    config = {"workload": workload, "frame": [W, H], "cfa": "RGGB", "frames_per_step_per_gpu": 1,
+    config = {"workload": workload_text(wl, W, H), "frame": [W, H], "cfa": "X-Trans" if wl == "c3" else "RGGB", "frames_per_step_per_gpu": 1,
               "parallelism": "replicas x%d (independent frames, no collective)" % world,
               "l2": "per-step working set %.0f MB > 126 MB L2 (inputs larger than L2; no flush needed)" % (W * H * 16 / 1e6)}
 
-    # ---------------- reference arm: the reference's own CPU code on this box's host cores
     if args.impl == "reference":
         if rank != 0:
             return 0
         use_all_host_threads()
-        if args.workload == "develop":
-            # bounded sample: the same four stages on a smaller frame of the same synthetic scene, at most a few steps
-            sw, sh = [int(v) for v in args.cpu_sample.lower().split("x")]
-            raw = synth.bayer_frame(sw, sh, filters, seed=1002)
-            run, kind, cores = cpu_develop_runner(raw, filters)
-            nsteps = max(1, min(args.steps, 3))
-            t0 = time.perf_counter()
-            run()
-            first = time.perf_counter() - t0
-            nwarm = 1 if first < 20 else 0
-            t0 = time.perf_counter()
-            for _ in range(nsteps):
-                run()
-            dt = time.perf_counter() - t0
-            val = nsteps * sw * sh / dt / 1e6
-            cb = {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": kind,
-                  "sample": "%d steps (+%d warm-up) of the four stages on a %dx%d frame (1/%d of the workload's pixels; per-pixel rate "
-                            "reported); reference functions compiled in place, OpenMP on %d threads; FFTW call sites run the oracle's "
-                            "fp64 stand-in (fftw3f absent)" % (nsteps, nwarm + 0, sw, sh, round(W * H / (sw * sh)), cores)}
-            print(json.dumps({"impl": "reference", "metric": "Mpixel/s", "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus,
-                              "steps": nsteps, "warmup": 1, "ms_per_step": dt / nsteps * 1e3,
-                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                              "data": "synthetic", "config": config, "cpu_baseline": cb,
-                              "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-            return 0
-        raw = synth.bayer_frame(W, H, filters, seed=1002)
-        run, kind, cores = cpu_reference_runner(args.method, raw, filters)
-        for _ in range(max(1, min(args.warmup, 2))):
-            run()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            run()
-        dt = time.perf_counter() - t0
-        val = args.steps * W * H / dt / 1e6
-        cb = {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": kind,
-              "sample": "%d full %dx%d frames (this run's steps); OpenMP threads = %d (faster of all/half)" % (args.steps, W, H, cores)}
-        print(json.dumps({"impl": "reference", "metric": "Mpixel/s", "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "config": config, "cpu_baseline": cb,
-                          "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return 0
+        return reference_arm(args, config, W, H)
 
     # ---------------- our arm
+    import numpy as np
     import torch
     import art_b200
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device; the hot path has no CPU fallback"}))
         return 2
     torch.cuda.set_device(local)
+    placement = pin_rank_near_gpu(local, world) if world > 1 else {"pinned": False, "why": "single rank"}
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -398,7 +499,7 @@ def main():
             os.close(saved)
     hp = art_b200.HotPath(local)
     method = art_b200.BAYER_RCD if args.method == "rcd" else art_b200.BAYER_AMAZE
-    raw = synth.bayer_frame(W, H, filters, seed=1002 + rank)
+    raw = make_raw(wl, W, H, 1002 + rank)
 
     # a real (non-default) stream: the library launches on it and the timing events are recorded on it
     stream = torch.cuda.Stream()
@@ -409,11 +510,13 @@ def main():
     d_raw[:, :W] = torch.from_numpy(raw).cuda()
     d_out = [torch.empty((H, pitch), dtype=torch.float32, device="cuda") for _ in range(3)]
 
-    dparams = develop_params(art_b200) if args.workload == "develop" else None
+    dparams = develop_params(art_b200, wl) if pipeline else None
+    Ho, Wo = dparams.out_shape(H, W) if pipeline else (H, W)
+    opitch = (Wo + 31) // 32 * 32
 
     def step_dev():
         if dparams is not None:
-            hp.develop_dev(dparams, W, H, d_raw.data_ptr(), pitch, d_out[0].data_ptr(), d_out[1].data_ptr(), d_out[2].data_ptr(), pitch)
+            hp.develop_dev(dparams, W, H, d_raw.data_ptr(), pitch, d_out[0].data_ptr(), d_out[1].data_ptr(), d_out[2].data_ptr(), opitch)
         else:
             hp.demosaic_bayer_dev(method, W, H, filters, d_raw.data_ptr(), pitch,
                                   d_out[0].data_ptr(), d_out[1].data_ptr(), d_out[2].data_ptr(), pitch, 1.0, 4)
@@ -447,42 +550,46 @@ def main():
     ms_per_step = ms / args.steps
     value = world * W * H / (ms_per_step * 1e-3) / 1e6
 
-    # ---- e2e: host-buffer C-ABI call, pinned planes, copies inside the timed region.  The develop workload goes through the
-    #      batch-queue form (art_hp_develop_submit / _wait, what a batch of files calls): every step uploads its own CFA plane
-    #      and downloads its own three planes; the copies of frame k overlap the kernels of frames k-1 / k+1.
-    nslots = 2 if dparams is not None else 1
-    Ho, Wo = dparams.out_shape(H, W) if dparams is not None else (H, W)
-    pins = [[hp.pinned(H, W)] + [hp.pinned(Ho, Wo) for _ in range(3)] for _ in range(nslots)]
-    for sl in pins:
-        sl[0].array[:] = raw
-
-    def run_e2e(n):
+    # ---- e2e: the host-buffer C-ABI call, pinned buffers, copies inside the timed region.  Pipelines go through the batch-queue form (what a
+    #      batch of files calls): every step uploads its own CFA plane and downloads its own developed frame; the copies of frame k overlap the
+    #      kernels of frames k-1 / k+1.  `packed`: the frame leaves as 16-bit interleaved scanlines (Imagefloat::getScanline on the device, the
+    #      format the reference's writers take: 6 B/px over PCIe); `planes`: three float planes (12 B/px), reported beside it.
+    def run_e2e(n, mode):
         if dparams is None:
-            p = pins[0]
             for _ in range(n):
-                hp.demosaic_bayer(method, p[0].array, filters, p[1].array, p[2].array, p[3].array, 1.0, 4)
+                hp.demosaic_bayer(method, pins[0][0].array, filters, pins[0][1].array, pins[0][2].array, pins[0][3].array, 1.0, 4)
             return
         for k in range(n):
             if k >= 2:
                 hp.develop_wait()
-            p = pins[k & 1]
-            hp.develop_submit(p[0].array, dparams, p[1].array, p[2].array, p[3].array)
+            sl = pins[k & 1]
+            if mode == "packed":
+                hp.develop_submit_packed(sl[0].array, dparams, packed[k & 1].array, 16, False)
+            else:
+                hp.develop_submit(sl[0].array, dparams, sl[1].array, sl[2].array, sl[3].array)
         while hp.develop_pending():
             hp.develop_wait()
 
-    run_e2e(3)
-    barrier()
+    nslots = 2 if pipeline else 1
+    pins = [[hp.pinned(H, W)] + [hp.pinned(Ho, Wo) for _ in range(3)] for _ in range(nslots)]
+    packed = [hp.pinned(Ho, 3 * Wo, np.uint16) for _ in range(nslots)] if pipeline else None
+    for sl in pins:
+        sl[0].array[:] = raw
     e2e_steps = min(max(20, args.steps), 50)      # the pipeline fills and drains once (one upload + one download not hidden): amortised over >= 20 frames
-    t0 = time.perf_counter()
-    run_e2e(e2e_steps)                     # returns when the last frame's planes are in host memory
-    wall = time.perf_counter() - t0
-    barrier()
-    ms2 = wall * 1e3
-    if dist is not None:
-        t = torch.tensor([ms2], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms2 = float(t.item())
-    e2e_val = world * W * H / (ms2 / e2e_steps * 1e-3) / 1e6
+    e2e = {}
+    for mode in (("packed", "planes") if pipeline else ("planes",)):
+        run_e2e(3, mode)
+        barrier()
+        t0 = time.perf_counter()
+        run_e2e(e2e_steps, mode)               # returns when the last frame is in host memory
+        wall = time.perf_counter() - t0
+        barrier()
+        ms2 = wall * 1e3
+        if dist is not None:
+            t = torch.tensor([ms2], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = float(t.item())
+        e2e[mode] = world * W * H / (ms2 / e2e_steps * 1e-3) / 1e6
     # one synchronous call (upload, kernels, download back to back): the latency of a single frame
     p = pins[0]
     for rep in range(2):                   # the first call allocates the synchronous entry's own device planes
@@ -492,13 +599,12 @@ def main():
         else:
             hp.demosaic_bayer(method, p[0].array, filters, p[1].array, p[2].array, p[3].array, 1.0, 4)
         e2e_latency_ms = (time.perf_counter() - t0) * 1e3
-    pins = pins[0]
     clocks = sampler.stop() if sampler else None
-    checksum = float(pins[2].array[Ho // 2, Wo // 2])
+    checksum = float(p[2].array[Ho // 2, Wo // 2])
 
     # ---- per-kernel device time (CUDA events around every launch, on the launching stream), outside
     #      the timed regions above so the extra events do not perturb `value`
-    kern = {}
+    kern, calls = {}, {}
     if rank == 0:
         hp.profile_enable(True)
         for _ in range(args.steps):
@@ -510,52 +616,48 @@ def main():
 
     if rank == 0:
         peak, how = peaks()
-        # SURVEY.md 8(d) ideal-fusion bytes per pixel: demosaic 16 (+ wavelet denoise 333 + denoise I/O and DCT 80 + Fattal 160)
-        step_bytes = 16 + 333 + 80 + 160 if args.workload == "develop" else BYTES_PER_PX
+        geo = (W, H, Wo, Ho)
+        # SURVEY.md 8(d) ideal-fusion bytes per pixel of the workload
+        step_bytes = {"develop": 16 + 333 + 80 + 160, "c2": 16 + 333 + 80 + 110, "c3": 16 + 24 + 232 + 44, "c4": 16 + 333 + 80 + 160 + 24}.get(wl, BYTES_PER_PX)
         step_achieved = step_bytes * W * H / (ms_per_step * 1e-3) / 1e9
         per_step = {k: kern[k] * calls[k] for k in kern}                     # ms per step per kernel
         top = max((k for k in per_step if k != "memset_slabs"), key=lambda k: per_step[k])
         share = per_step[top] / sum(per_step.values())
-        if args.workload == "develop":
-            unit_bytes, unit_name = DEVELOP_KERNEL_BYTES.get(top, (AMAZE_KERNEL_BYTES.get(top), "tile pixel"))
-            ntiles = ((W + 16 + 127) // 128) * ((H + 16 + 127) // 128)
-            units = ntiles * 160 * 160 if unit_name == "tile pixel" else develop_units(top, W, H)
-        elif args.workload == "rcd":
-            units, unit_bytes, unit_name = W * H, BYTES_PER_PX, "pixel"
-        else:
-            ntiles = ((W + 16 + 127) // 128) * ((H + 16 + 127) // 128)
-            units, unit_bytes, unit_name = ntiles * 160 * 160, AMAZE_KERNEL_BYTES.get(top), "tile pixel"
-        if unit_bytes is None:
-            achieved = None
-        else:
-            achieved = unit_bytes * units / (kern[top] * 1e-3) / 1e9      # per launch: bytes one launch moves / its mean duration
+        kb = kernel_bytes(top, *geo)
+        achieved = kb[0] / (kern[top] * 1e-3) / 1e9 if kb else None          # per launch: bytes one launch moves / its mean duration
+        pipe_e2e = e2e.get("packed", e2e.get("planes"))
         out = {
             "metric": "Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": W * H * 4, "d2h_bytes_per_step": Wo * Ho * 12,
+            "e2e": {"value": pipe_e2e, "unit": "Mpixel/s", "h2d_bytes_per_step": W * H * 4, "d2h_bytes_per_step": Wo * Ho * (6 if pipeline else 12),
                     "steps": e2e_steps, "host_memory": "pinned (art_hp_host_alloc)", "single_frame_latency_ms": e2e_latency_ms,
-                    "call": ("art_hp_develop_submit / art_hp_develop_wait: two frames in flight, every frame uploaded and downloaded "
-                             "inside the timed region (host wall clock from the first submit to the last frame in host memory)")
-                    if dparams is not None else "art_hp_demosaic_bayer (synchronous, banded copy/compute overlap inside the call)"},
+                    "float_planes_value": e2e.get("planes"), "float_planes_d2h_bytes_per_step": Wo * Ho * 12,
+                    "placement": placement,
+                    "call": ("art_hp_develop_submit_packed / art_hp_develop_wait: two frames in flight, every frame uploaded (float CFA plane) and "
+                             "downloaded (16-bit interleaved scanlines, Imagefloat::getScanline on the device) inside the timed region (host wall clock "
+                             "from the first submit to the last frame in host memory); float_planes_value = the same through art_hp_develop_submit "
+                             "(three float planes out)")
+                    if pipeline else "art_hp_demosaic_bayer (synchronous, banded copy/compute overlap inside the call)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
                          "traffic": NCU_TRAFFIC.get(top), "peak_source": how,
                          "kernel_ms": kern[top], "launches_per_step": calls[top], "share_of_step": share,
-                         "algorithmic_bytes_per_unit": unit_bytes, "unit_name": unit_name, "units_per_step": units,
+                         "algorithmic_bytes_per_launch": kb[0] if kb else None, "what": kb[1] if kb else None,
                          "note": "dominant kernel by device time; achieved = algorithmic bytes per launch / mean CUDA-event "
                                  "duration of that kernel (events on the launching stream, separate pass of --steps steps)"},
             "step_roofline": {"achieved": step_achieved, "frac": step_achieved / peak, "unit": "GB/s",
                               "bytes_per_pixel": step_bytes,
                               "note": "whole step: SURVEY.md 8(d) ideal-fusion bytes per pixel / ms_per_step"},
-            "roofline_top": roofline_top(per_step, kern, calls, W, H, peak) if args.workload == "develop" else None,
+            "roofline_top": roofline_top(per_step, kern, calls, geo, peak) if pipeline else None,
             "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+            "kernels_ms_sum": round(sum(per_step.values()), 4),
             "clocks": clocks, "checksum_green_center": checksum,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                out["cpu_baseline"] = time_cpu_develop(args.cpu_sample, filters) if args.workload == "develop" else time_cpu(args.method, raw, filters)
+                out["cpu_baseline"] = time_cpu_pipeline(wl, args.cpu_sample, 1002) if pipeline else time_cpu(args.method, raw, filters)
             except Exception as ex:  # the checker is optional for the number, never for the tests
                 out["cpu_baseline"] = {"value": None, "unit": "Mpixel/s", "cores": 0, "kind": "unavailable", "sample": str(ex)}
         print(json.dumps(out))

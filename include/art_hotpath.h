@@ -460,6 +460,18 @@ int art_hp_sharpen_usm(art_hp_ctx* ctx, int W, int H, float* const* r, float* co
 int art_hp_sharpen_usm_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
                            const art_hp_sharpen_params* params, const double ws[9]);
 
+/* ---- output packing --------------------------------------------------------------- */
+/*
+ * art_hp_scanlines     Imagefloat::getScanline(row, buffer, bps, isFloat) for row = 0 .. H - 1 (rtengine/imagefloat.cc L125-169; CLIP and
+ *                      uint16ToUint8Rounded rtengine/rt_math.h L97-100, L144-147; DNG_FloatToHalf rtengine/halffloat.h L9-47): planar float
+ *                      RGB in [0, 65535] to interleaved rows, row `y` at out + y * out_stride_bytes.  (bps, isFloat) in {(16, 0), (8, 0),
+ *                      (32, 1), (16, 1)}.  Bit-identical to the reference.
+ */
+int art_hp_scanlines(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b, int bps, int isFloat,
+                     void* out, size_t out_stride_bytes);
+int art_hp_scanlines_dev(art_hp_ctx* ctx, int W, int H, const float* d_r, const float* d_g, const float* d_b, size_t pitch, int bps, int isFloat,
+                         void* d_out, size_t out_stride_bytes);
+
 /* ---- whole frame ------------------------------------------------------------------ */
 /*
  * art_hp_develop       the stages of simpleprocess.cc's normal pipeline that are on the hot path, back to back on the
@@ -527,6 +539,12 @@ int art_hp_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* params, int
  */
 int art_hp_develop_submit(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
                           float* const* red, float* const* green, float* const* blue);
+/* The same, with the developed frame leaving in the reference's wire format: Imagefloat::getScanline(row, buffer, bps, isFloat)
+ * (rtengine/imagefloat.cc L125-169) runs on the device for every row and `out` -- pinned, H_out rows of 3 * W_out samples at
+ * out_stride_bytes -- receives interleaved RGB: bps 16 / 8 integer (clamped; truncated / rounded), bps 32 / 16 float (v / 65535; half).
+ * 6 (or 3) bytes per pixel cross PCIe instead of 12. */
+int art_hp_develop_submit_packed(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
+                                 int bps, int isFloat, void* out, size_t out_stride_bytes);
 int art_hp_develop_wait(art_hp_ctx* ctx);
 int art_hp_develop_pending(const art_hp_ctx* ctx);
 
