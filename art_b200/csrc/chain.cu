@@ -228,7 +228,7 @@ __device__ __forceinline__ void rgb_tone(const ChainArgs& a, float& r, float& g,
 __device__ __forceinline__ float lim01(float a) { const float m = 1.f < a ? 1.f : a; return 0.f < m ? m : 0.f; }
 __device__ __forceinline__ float gauss_hue(float x, float b, float c) { return sleef::xexpf_scalar(-((x - b) * (x - b)) / (2 * (c * c))); }
 
-__device__ __noinline__ void neutral_tone(const ChainArgs& a, float& R, float& G, float& B)
+__device__ __forceinline__ void neutral_tone(const ChainArgs& a, float& R, float& G, float& B)
 {
     const float th[3] = {0.85f, 0.75f, 0.95f};
     const float dl[3] = {1.1f, 1.2f, 1.5f};
@@ -297,7 +297,7 @@ __device__ __noinline__ void neutral_tone(const ChainArgs& a, float& R, float& G
     v = rgb[1] * 65535.f; v = whitept < v ? whitept : v; G = 0.f < v ? v : 0.f;
     v = rgb[2] * 65535.f; v = whitept < v ? whitept : v; B = 0.f < v ? v : 0.f;
 }
-__device__ __noinline__ void sat_curve(const ChainArgs& a, float& R, float& G, float& B)
+__device__ __forceinline__ void sat_curve(const ChainArgs& a, float& R, float& G, float& B)
 {
     float X, Y, Z, Jz, az, bz;
     mat3(a.ws, R / 65535.f, G / 65535.f, B / 65535.f, X, Y, Z);

@@ -37,6 +37,13 @@ __device__ __forceinline__ unsigned short float_to_half(float f)
     return (unsigned short)(sign | ((unsigned)ee << 10) | (m >> 13));
 }
 
+// v / 65535.f as an x86 SSE division gives it: a NaN operand comes back quieted with its payload (the GPU would return the canonical NaN,
+// and DNG_FloatToHalf keeps the top mantissa bits)
+__device__ __forceinline__ float div65535(float v)
+{
+    return (v != v) ? __uint_as_float(__float_as_uint(v) | 0x00400000u) : v / 65535.f;
+}
+
 struct PackArgs { const float *r, *g, *b; size_t ip; int W, H; unsigned char* out; size_t stride; };
 
 // MODE 0: 16-bit integer, 1: 8-bit integer, 2: float32, 3: half.  One thread per pixel; a warp covers 32 consecutive pixels of a row.
@@ -54,8 +61,8 @@ __global__ void __launch_bounds__(256) k_scanlines(PackArgs a)
             const size_t ix = (size_t)x * 3 + c;
             if (MODE == 0) reinterpret_cast<unsigned short*>(row)[ix] = (unsigned short)clipf(v[c]);
             else if (MODE == 1) { const unsigned k = (unsigned short)clipf(v[c]); row[ix] = (unsigned char)(((k + 128) - ((k + 128) >> 8)) >> 8); }
-            else if (MODE == 2) reinterpret_cast<float*>(row)[ix] = v[c] / 65535.f;
-            else reinterpret_cast<unsigned short*>(row)[ix] = float_to_half(v[c] / 65535.f);
+            else if (MODE == 2) reinterpret_cast<float*>(row)[ix] = div65535(v[c]);
+            else reinterpret_cast<unsigned short*>(row)[ix] = float_to_half(div65535(v[c]));
         }
     }
 }

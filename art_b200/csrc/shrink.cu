@@ -409,7 +409,7 @@ int shrink_batch(art_hp_ctx* ctx, ShBatch& b)
         art_prof_end(ctx);
     }
     art_prof_begin(ctx, "k_shrink_h");
-    k_shrink_h<<<std::min((b.unit0[b.njobs] + SH_WARPS - 1) / SH_WARPS, ctx->sm_count), SH_WARPS * 32, SH_SMEM, st>>>(b);
+    k_shrink_h<<<std::min((b.unit0[b.njobs] + SH_WARPS - 1) / SH_WARPS, 2 * ctx->sm_count), SH_WARPS * 32, SH_SMEM, st>>>(b);     // 100 KB of shared memory: two CTAs per SM, all row groups of a 45 MP channel resident at once
     art_prof_end(ctx);
     for (int i = 0; i < b.njobs; ++i) b.unit0[i + 1] = b.unit0[i] + (b.job[i].W + 31) / 32;
     art_prof_begin(ctx, "k_shrink_v");
