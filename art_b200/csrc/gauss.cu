@@ -169,7 +169,7 @@ __device__ __forceinline__ void vline(const GArgs& a, int col)
         }
     };
     // causal sweep; the input of row j+PF is loaded before the output of row j is stored (in-place safe)
-    constexpr int PF = 8;
+    constexpr int PF = 24;      // rows in flight per column: a frame has only W chains (1-2 warps per SM), so the memory latency is hidden by depth, not by occupancy
     float q[PF];
     #pragma unroll
     for (int k = 0; k < PF; ++k) q[k] = (k < H) ? x[(size_t)k * a.sp] : 0.f;
@@ -242,10 +242,19 @@ __device__ __forceinline__ void hline(const GArgs& a, int row0, int lane, float 
     const int nrows = min(32, a.H - row0);
     const bool mine = lane < nrows;
     float xl = 0.f;
-    // causal sweep, tile by tile
+    // causal sweep, tile by tile: the next tile's 32 row segments are loaded into registers before this tile's serial chain runs
+    float nxt[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) nxt[r] = (r < nrows && lane < W) ? a.src[(size_t)(row0 + r) * a.sp + lane] : 0.f;
     for (int c0 = 0; c0 < W; c0 += 32) {
         const int nc = min(32, W - c0);
-        for (int r = 0; r < nrows; ++r) if (lane < nc) tile[r][lane] = a.src[(size_t)(row0 + r) * a.sp + c0 + lane];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) tile[r][lane] = nxt[r];
+        if (c0 + 32 < W) {
+            const int cn = c0 + 32 + lane;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) nxt[r] = (r < nrows && cn < W) ? a.src[(size_t)(row0 + r) * a.sp + cn] : 0.f;
+        }
         __syncwarp();
         if (mine)
             for (int k = 0; k < nc; ++k) {
@@ -271,13 +280,27 @@ __device__ __forceinline__ void hline(const GArgs& a, int row0, int lane, float 
     if (mine) L.boundary(a.c, xl, o1, o2, o3);
     // anticausal sweep: tiles from the right; the last three columns come from the boundary step
     const int ntile = (W + 31) / 32;
+    if (MODE != 2) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int cn = (ntile - 1) * 32 + lane;
+            nxt[r] = (r < nrows && cn < W) ? a.dst[(size_t)(row0 + r) * a.dp + cn] : 0.f;
+        }
+    }
     for (int tix = ntile - 1; tix >= 0; --tix) {
         const int c0 = tix * 32, nc = min(32, W - c0);
-        for (int r = 0; r < nrows; ++r)
-            if (lane < nc) {
-                if (MODE == 2) dtile[r][lane] = a.dscr[(size_t)(row0 + r) * a.dsp + c0 + lane];
-                else tile[r][lane] = a.dst[(size_t)(row0 + r) * a.dp + c0 + lane];
+        if (MODE == 2) {
+            for (int r = 0; r < nrows; ++r)
+                if (lane < nc) dtile[r][lane] = a.dscr[(size_t)(row0 + r) * a.dsp + c0 + lane];
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) tile[r][lane] = nxt[r];
+            if (tix > 0) {
+                const int cn = c0 - 32 + lane;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) nxt[r] = (r < nrows) ? a.dst[(size_t)(row0 + r) * a.dp + cn] : 0.f;
             }
+        }
         __syncwarp();
         if (mine)
             for (int k = nc - 1; k >= 0; --k) {

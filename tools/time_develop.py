@@ -11,7 +11,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import art_b200  # noqa: E402
 from art_b200 import synth  # noqa: E402
-from art_b200.api import DenoiseParams, DevelopParams  # noqa: E402
+from art_b200.api import DenoiseParams, DevelopParams, SharpenParams  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--width", type=int, default=8192)
@@ -21,6 +21,7 @@ ap.add_argument("--no-denoise", action="store_true")
 ap.add_argument("--no-fattal", action="store_true")
 ap.add_argument("--nl", type=int, default=0)
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--usm", action="store_true", help="add the unsharp mask of configs[2]")
 args = ap.parse_args()
 W, H = args.width, args.height
 PROPHOTO = np.array([[0.7976749, 0.1351917, 0.0313534], [0.2880402, 0.7118741, 0.0000857], [0.0, 0.0, 0.8252100]], np.float64)
@@ -33,7 +34,8 @@ d_raw[:, :W] = torch.from_numpy(raw).cuda()
 outs = [torch.empty((H, pitch), dtype=torch.float32, device="cuda") for _ in range(3)]
 dn = None if args.no_denoise else DenoiseParams(luminance=30, luminanceDetail=50, chrominance=15)
 params = DevelopParams(method=art_b200.BAYER_AMAZE, filters=synth.RGGB, mul=(1.9, 1.0, 1.6), do_clip=True, cam2work=CAM2WORK, denoise=dn,
-                       nl_strength=args.nl, fattal=None if args.no_fattal else (30, 20, 0), wprof=PROPHOTO)
+                       nl_strength=args.nl, fattal=None if args.no_fattal else (30, 20, 0), wprof=PROPHOTO,
+                       sharpen=SharpenParams(radius=0.5, amount=200) if args.usm else None)
 
 
 def step():
