@@ -171,18 +171,23 @@ __device__ __forceinline__ float compute_detail(float d)
     const float a = (float)(((100. - d) * (100. - d)) + 50. * (100. - d)) * TS * 0.5f;
     return a * a;
 }
-// 64x64x64 products on the tensor cores: mma.sync m16n8k8 TF32 with the 3xTF32 split (x = big + small, both TF32;
+// 64x64x64 products on the tensor cores: mma.sync m16n8k8 TF32 with the 3xTF32 split (x = big + small;
 // acc += small_a * big_b + big_a * small_b + big_a * big_b with fp32 accumulation), which keeps the products at fp32
 // accuracy.  8 warps: warp w owns rows 16 * (w & 3) .. +16 and columns 32 * (w >> 2) .. +32 (four n-tiles).
 // Out[m][n] = sum_k A(m, k) * B(k, n);  A(m, k) = A[m * PA + k];  B(k, n) = TRANS_B ? B[n * PB + k] : B[k * PB + n].
 // Pitches are chosen so that every fragment load is bank-conflict free: 68 (== 4 mod 32) where a fragment walks
 // (row g, column t), 72 (== 8 mod 32) where it walks (row t, column g).
 constexpr int PX = 68, PT = 72, PC = 68;
-__device__ __forceinline__ unsigned f2tf32(float x) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+// x = big + small, both rounded to TF32 (10 mantissa bits) to nearest by integer arithmetic on the bit pattern: add half an ulp of the kept
+// field, clear the 13 dropped bits.  x - big is exact in fp32.  (cvt.rna.tf32.f32 is emulated with a dozen integer instructions per value
+// on sm_100a -- ncu showed FSETP / SEL / LOP3 / IMAD at 60 % of this kernel's instructions; its handling of NaN / infinity is not needed
+// for image residuals.  Plain truncation is cheaper still but biased: its error adds up coherently over the 64-term sums and came out 4x
+// worse on the final image.)
+__device__ __forceinline__ unsigned rn_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void split_tf32(float x, unsigned& big, unsigned& small)
 {
-    big = f2tf32(x);
-    small = f2tf32(x - __uint_as_float(big));
+    big = rn_tf32(x);
+    small = rn_tf32(x - __uint_as_float(big));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2])
 {

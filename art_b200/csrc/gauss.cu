@@ -145,8 +145,9 @@ struct GArgs {
 
 // ------------------------------------------------------------------ vertical pass: thread per column
 // EPI 0: dst = v; 1 (GAUSS_MULT): dst *= v; 2 (GAUSS_DIV): dst = div / (v > 0 ? v : 1), clamped at 0
+constexpr int VR = 96, VT = 64;       // rows of a column in flight (cp.async ring depth), threads per CTA; 2 rings x 96 rows x 64 threads x 4 B = 48 KB of dynamic shared memory
 template <int MODE, int EPI>
-__device__ __forceinline__ void vline(const GArgs& a, int col)
+__device__ __forceinline__ void vline(const GArgs& a, int col, float* vring)
 {
     using T = typename Acc<MODE>::T;
     Line<MODE> L;
@@ -168,8 +169,63 @@ __device__ __forceinline__ void vline(const GArgs& a, int col)
             *o = q;
         }
     };
-    // causal sweep; the input of row j+PF is loaded before the output of row j is stored (in-place safe)
-    constexpr int PF = 24;      // rows in flight per column: a frame has only W chains (1-2 warps per SM), so the memory latency is hidden by depth, not by occupancy
+    if (MODE != 2) {
+        // A frame has only W chains (one or two warps per SM), so the memory latency has to be hidden by depth: every thread keeps
+        // VR - 1 rows of its column in flight through cp.async into a private shared-memory ring (ncu, register prefetch of 24 rows:
+        // 6 % occupancy, 90 % of the issue slots idle waiting for the loads).  The input of row j + VR - 1 is read before the output
+        // of row j is stored: in-place safe, as before.
+        float* ring = vring + threadIdx.x;                 // slot s of this thread: ring[s * blockDim.x]
+        const unsigned rbase = (unsigned)__cvta_generic_to_shared(ring);
+        const unsigned rstep = blockDim.x * sizeof(float);
+        auto fetch = [&](const float* g, int slot, bool ok) {
+            if (ok) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(rbase + slot * rstep), "l"(g) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int k = 0; k < VR - 1; ++k) fetch(x + (size_t)k * a.sp, k, k < H);
+        float xl = 0.f;
+        for (int j = 0; j < H; ++j) {
+            const int jn = j + VR - 1;
+            fetch(x + (size_t)jn * a.sp, jn % VR, jn < H);
+            asm volatile("cp.async.wait_group %0;" :: "n"(VR - 1) : "memory");
+            const float xv = ring[(j % VR) * blockDim.x];
+            T t;
+            if (j == 0) t = L.first(a.c, xv);
+            else if (j == 1) t = L.second(a.c, xv);
+            else if (j == 2) t = L.third(a.c, xv);
+            else t = L.fwd(a.c, xv);
+            cs[(size_t)j * a.csp] = (float)t;
+            xl = xv;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        T o1, o2, o3;
+        L.boundary(a.c, xl, o1, o2, o3);
+        emit(H - 1, (float)o1, EPI ? e[(size_t)(H - 1) * ep] : 0.f, true);
+        emit(H - 2, (float)o2, EPI ? e[(size_t)(H - 2) * ep] : 0.f, true);
+        emit(H - 3, (float)o3, EPI ? e[(size_t)(H - 3) * ep] : 0.f, true);
+        // anticausal sweep over the stored causal output (rows H-4 .. 0); the epilogue operand rides in a second ring
+        float* ring2 = ring + VR * blockDim.x;
+        const unsigned r2base = rbase + VR * rstep;
+        auto fetch2 = [&](int j, int slot) {
+            if (j >= 0) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(rbase + slot * rstep), "l"(cs + (size_t)j * a.csp) : "memory");
+                if (EPI) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(r2base + slot * rstep), "l"(e + (size_t)j * ep) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int k = 0; k < VR - 1; ++k) fetch2(H - 4 - k, k);
+        int it = 0;
+        for (int j = H - 4; j >= 0; --j, ++it) {
+            fetch2(j - (VR - 1), (it + VR - 1) % VR);
+            asm volatile("cp.async.wait_group %0;" :: "n"(VR - 1) : "memory");
+            const T t = (T)ring[(it % VR) * blockDim.x];
+            const float ev = EPI ? ring2[(it % VR) * blockDim.x] : 0.f;
+            emit(j, (float)L.bwd(a.c, t), ev, false);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return;
+    }
+    // all-double form (sigma >= 25): register prefetch; the input of row j+PF is loaded before the output of row j is stored (in-place safe)
+    constexpr int PF = 8;
     float q[PF];
     #pragma unroll
     for (int k = 0; k < PF; ++k) q[k] = (k < H) ? x[(size_t)k * a.sp] : 0.f;
@@ -223,13 +279,14 @@ __device__ __forceinline__ void vline(const GArgs& a, int col)
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(128) k_gauss_v(GArgs a)
+__global__ void __launch_bounds__(VT) k_gauss_v(GArgs a)
 {
+    extern __shared__ float vring[];
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= a.W) return;
-    if (a.big) vline<2, EPI>(a, col);
-    else if (col < a.W - (a.W % 8)) vline<0, EPI>(a, col);  // 8-column vector groups (L750)
-    else vline<1, EPI>(a, col);                             // scalar remainder (L843)
+    if (a.big) vline<2, EPI>(a, col, vring);
+    else if (col < a.W - (a.W % 8)) vline<0, EPI>(a, col, vring);  // 8-column vector groups (L750)
+    else vline<1, EPI>(a, col, vring);                             // scalar remainder (L843)
 }
 
 // ------------------------------------------------------------------ horizontal pass: warp per 32 rows
@@ -453,7 +510,7 @@ int art_gauss_dev(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, size
     GArgs v = a;
     v.src = dst; v.sp = dp;                      // vertical runs in place on the horizontal result (L1529-1530)
     art_prof_begin(ctx, "k_gauss_v");
-    k_gauss_v<0><<<(W + 127) / 128, 128, 0, st>>>(v);
+    k_gauss_v<0><<<(W + VT - 1) / VT, VT, 2 * VR * VT * sizeof(float), st>>>(v);
     art_prof_end(ctx);
     ctx->launches += 2;
     ART_CUDA(ctx, cudaGetLastError());
@@ -489,8 +546,8 @@ int art_gauss_divmult_dev(art_hp_ctx* ctx, float* src, size_t sp, float* dst, si
     GArgs v = a;
     v.src = hp; v.sp = hpp; v.cs = hp; v.csp = hpp; v.dst = dst; v.dp = dp; v.div = div; v.vp = vp;
     art_prof_begin(ctx, "k_gauss_v");
-    if (type == 1) k_gauss_v<1><<<(W + 127) / 128, 128, 0, st>>>(v);
-    else k_gauss_v<2><<<(W + 127) / 128, 128, 0, st>>>(v);
+    if (type == 1) k_gauss_v<1><<<(W + VT - 1) / VT, VT, 2 * VR * VT * sizeof(float), st>>>(v);
+    else k_gauss_v<2><<<(W + VT - 1) / VT, VT, 2 * VR * VT * sizeof(float), st>>>(v);
     art_prof_end(ctx);
     ctx->launches += 2;
     ART_CUDA(ctx, cudaGetLastError());
