@@ -313,18 +313,34 @@ __device__ __forceinline__ void hline(const GArgs& a, int row0, int lane, float 
             for (int r = 0; r < 32; ++r) nxt[r] = (r < nrows && cn < W) ? a.src[(size_t)(row0 + r) * a.sp + cn] : 0.f;
         }
         __syncwarp();
-        if (mine)
-            for (int k = 0; k < nc; ++k) {
-                const int j = c0 + k;
-                const float xv = tile[lane][k];
-                T t;
-                if (j == 0) t = L.first(a.c, xv);
-                else if (j == 1) t = L.second(a.c, xv);
-                else if (j == 2) t = L.third(a.c, xv);
-                else t = L.fwd(a.c, xv);
-                if (MODE == 2) dtile[lane][k] = t; else tile[lane][k] = (float)t;
-                xl = xv;
+        if (mine) {
+            if (MODE != 2 && nc == 32) {
+                // the lane's 32 samples into registers first: the recurrence then runs on registers, its shared-memory loads off the dependency chain
+                float xr[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) xr[k] = tile[lane][k];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    T t;
+                    if (k < 3 && c0 == 0) t = k == 0 ? L.first(a.c, xr[k]) : k == 1 ? L.second(a.c, xr[k]) : L.third(a.c, xr[k]);
+                    else t = L.fwd(a.c, xr[k]);
+                    tile[lane][k] = (float)t;
+                }
+                xl = xr[31];
+            } else {
+                for (int k = 0; k < nc; ++k) {
+                    const int j = c0 + k;
+                    const float xv = tile[lane][k];
+                    T t;
+                    if (j == 0) t = L.first(a.c, xv);
+                    else if (j == 1) t = L.second(a.c, xv);
+                    else if (j == 2) t = L.third(a.c, xv);
+                    else t = L.fwd(a.c, xv);
+                    if (MODE == 2) dtile[lane][k] = t; else tile[lane][k] = (float)t;
+                    xl = xv;
+                }
             }
+        }
         __syncwarp();
         for (int r = 0; r < nrows; ++r)
             if (lane < nc) {
@@ -359,16 +375,25 @@ __device__ __forceinline__ void hline(const GArgs& a, int row0, int lane, float 
             }
         }
         __syncwarp();
-        if (mine)
-            for (int k = nc - 1; k >= 0; --k) {
-                const int j = c0 + k;
-                T v;
-                if (j == W - 1) v = o1;
-                else if (j == W - 2) v = o2;
-                else if (j == W - 3) v = o3;
-                else v = L.bwd(a.c, MODE == 2 ? (T)dtile[lane][k] : (T)tile[lane][k]);
-                tile[lane][k] = (float)v;
+        if (mine) {
+            if (MODE != 2 && nc == 32 && c0 + 32 <= W - 3) {
+                float xr[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) xr[k] = tile[lane][k];
+#pragma unroll
+                for (int k = 31; k >= 0; --k) tile[lane][k] = (float)L.bwd(a.c, (T)xr[k]);
+            } else {
+                for (int k = nc - 1; k >= 0; --k) {
+                    const int j = c0 + k;
+                    T v;
+                    if (j == W - 1) v = o1;
+                    else if (j == W - 2) v = o2;
+                    else if (j == W - 3) v = o3;
+                    else v = L.bwd(a.c, MODE == 2 ? (T)dtile[lane][k] : (T)tile[lane][k]);
+                    tile[lane][k] = (float)v;
+                }
             }
+        }
         __syncwarp();
         for (int r = 0; r < nrows; ++r) if (lane < nc) a.dst[(size_t)(row0 + r) * a.dp + c0 + lane] = tile[r][lane];
         __syncwarp();
