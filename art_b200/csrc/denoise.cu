@@ -16,6 +16,7 @@
 // Compiled with -fmad=false; the DCT runs on the tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split).
 #include <cmath>
 #include "ctx.h"
+#include "dn_blocks.h"
 #include "sleef_dev.cuh"
 
 struct art_hp_wavelet;
@@ -532,7 +533,8 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
 
     if (denoiseLuminance) {
         // the window / DCT tables are constants: built and uploaded once per context
-        constexpr size_t NT = 4 * TS * TS + TS * PT + 2 * TS * PC;     // dense tables + pitched copies for the bulk loads
+        constexpr size_t NT0 = 4 * TS * TS + TS * PT + 2 * TS * PC;    // dense tables + pitched copies for the bulk loads
+        constexpr size_t NT = NT0 + DN_SPLIT_WORDS;                     // + the pre-split tcgen05 operand images of the two DCT matrices
         int trc = art_reserve(ctx, ctx->d_dn_tables, NT * sizeof(float));
         if (trc) return trc;
         float* tb = (float*)ctx->d_dn_tables.p;
@@ -546,6 +548,7 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
                     tp[TS * PT + r * PC + c] = host[2 * TS * TS + r * TS + c];
                     tp[TS * PT + TS * PC + r * PC + c] = host[3 * TS * TS + r * TS + c];
                 }
+            art_dn_blocks_split_tables(host.data() + 2 * TS * TS, host.data() + 3 * TS * TS, reinterpret_cast<unsigned*>(host.data() + NT0));
             ART_CUDA(ctx, cudaMemcpyAsync(tb, host.data(), sizeof(float) * NT, cudaMemcpyHostToDevice, st));
             ART_CUDA(ctx, cudaStreamSynchronize(st));
             ctx->dn_tables_ready = true;
@@ -679,12 +682,20 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
         a.detail_hi = host_compute_detail(params_Ldetail); a.detail_lo = host_compute_detail(0.f); a.params_Ldetail = params_Ldetail;
         a.use_mask = use_mask; a.blur_rad = std::max(1, int(3 / scale));
         const size_t smem = (size_t)TS * (PX + PT + PC) * sizeof(float);
-        if (!(ctx->attrs_set & art_hp_ctx::ATTR_DN_BLOCKS)) {
+        if (!(ctx->attrs_set & art_hp_ctx::ATTR_DN_BLOCKS_LEGACY)) {
             ART_CUDA(ctx, cudaFuncSetAttribute(k_dn_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ctx->attrs_set |= art_hp_ctx::ATTR_DN_BLOCKS;
+            ctx->attrs_set |= art_hp_ctx::ATTR_DN_BLOCKS_LEGACY;
         }
+        static const bool legacy = getenv("ART_HP_DN_BLOCKS_LEGACY") != nullptr;
         art_prof_begin(ctx, "k_dn_blocks");
-        k_dn_blocks<<<dim3(nbw, nbh), 256, smem, st>>>(a);
+        if (legacy) k_dn_blocks<<<dim3(nbw, nbh), 256, smem, st>>>(a);
+        else {
+            DnBlocksArgs b{};
+            b.Lin = Lin; b.L = Lp; b.mask = mask; b.width = W; b.height = H; b.nbw = nbw; b.nbh = nbh; b.tin = tin;
+            b.fwd_split = reinterpret_cast<const unsigned*>(a.dctb_p + TS * PC); b.bwd_split = b.fwd_split + DN_SPLIT_WORDS / 2;
+            b.blocks = blocks; b.detail_hi = a.detail_hi; b.detail_lo = a.detail_lo; b.params_Ldetail = params_Ldetail; b.use_mask = use_mask; b.blur_rad = a.blur_rad;
+            if ((rc = art_dn_blocks_launch(ctx, b))) return rc;
+        }
         art_prof_end(ctx);
         GatherArgs ga{};
         ga.L = Lp; ga.blocks = blocks; ga.tin = tin; ga.tout = tout; ga.width = W; ga.height = H; ga.nbw = nbw; ga.nbh = nbh;
