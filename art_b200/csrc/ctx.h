@@ -32,7 +32,7 @@ struct art_hp_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long launches = 0;
     // cudaFuncSetAttribute is per device: the opt-ins to > 48 KB of dynamic shared memory are remembered per context, not per process
-    enum { ATTR_RCD = 1, ATTR_XTRANS = 2, ATTR_DN_BLOCKS = 4, ATTR_NLM = 8, ATTR_FATTAL = 16, ATTR_DN_TC = 32, ATTR_SHRINK = 64, ATTR_AMAZE = 128, ATTR_DN_BLOCKS_LEGACY = 256 };
+    enum { ATTR_RCD = 1, ATTR_XTRANS = 2, ATTR_DN_BLOCKS = 4, ATTR_NLM = 8, ATTR_FATTAL = 16, ATTR_DN_TC = 32, ATTR_SHRINK = 64, ATTR_AMAZE = 128 };
     unsigned attrs_set = 0;
     void* d_nlm_dbg = nullptr;
     // optional per-kernel timing (art_hp_profile_*): CUDA events around every launch

@@ -6,14 +6,14 @@
 // (color.cc L1128-1170), gammaf / rgb2yuv / yuv2rgb (color.h L782-796, L1202-1205), rgbxyz + XYZ2Lab (color.cc L833,
 // L1247-1274, L1382-1399) for the chroma noise curve.  Everything stays in HBM between stages:
 //   k_dn_gamma_lut x2, [k_dn_ccalc], k_dn_split (gamma LUT + YUV + noise-variance maps), wavelet.cu / shrink.cu for
-//   the three decompositions, k_dn_blocks (one CTA per 64x64 DCT block: gather + window, DCT-II, |.| box blur,
-//   shrink, DCT-III -> block store), k_dn_gather (ordered overlap-add + normalise), k_dn_merge (chroma boost, YUV->RGB,
+//   the three decompositions, k_dn_blocks5 (dn_blocks.cu: pairs of 64x64 DCT blocks on tcgen05 -- gather + window, DCT-II,
+//   |.| box blur, shrink, DCT-III -> block store), k_dn_gather (ordered overlap-add + normalise), k_dn_merge (chroma boost, YUV->RGB,
 //   inverse gamma).
 // Bit-exact with the reference except the two block DCTs, which the reference delegates to FFTW (fp32 codelets,
-// absent here) and which run here as 3xTF32 tensor-core matrix products (fp32 accuracy) against cosine tables rounded from double.
+// absent here) and which run here as 3xTF32 tcgen05 matrix products (fp32 accuracy) against cosine tables rounded from double.
 // The reference's detail_recovery overlap-adds block rows from several OpenMP threads without synchronisation; the
 // one-thread order (vblk, then hblk ascending) is the one reproduced.
-// Compiled with -fmad=false; the DCT runs on the tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split).
+// Compiled with -fmad=false.
 #include <cmath>
 #include "ctx.h"
 #include "dn_blocks.h"
@@ -157,205 +157,6 @@ __global__ void __launch_bounds__(256) k_dn_split(SplitArgs s)
         s.nvl[h] = s.noisevarL;
         s.nvc[h] = s.useCC ? s.maxNoiseVarab * s.ccalc[h] : 1.f;
     }
-}
-
-// detail recovery: one CTA per 64x64 block
-struct BlkArgs {
-    const float* Lin; const float* L; const float* mask; int width, height, nbw, nbh;
-    const float *tin, *dctf, *dctb;    // tilemask_in, REDFT10 matrix C[k][j], REDFT01 matrix D[k][j]
-    const float *tin_p, *dctf_p, *dctb_p;   // the same three with the shared-memory pitches PT / PC / PC (bulk-copy sources)
-    float* blocks;                     // [nbh][nbw][64][64]
-    float detail_hi, detail_lo, params_Ldetail; int use_mask, blur_rad;
-};
-__device__ __forceinline__ float compute_detail(float d)
-{   // L1481-1485
-    const float a = (float)(((100. - d) * (100. - d)) + 50. * (100. - d)) * TS * 0.5f;
-    return a * a;
-}
-// 64x64x64 products on the tensor cores: mma.sync m16n8k8 TF32 with the 3xTF32 split (x = big + small;
-// acc += small_a * big_b + big_a * small_b + big_a * big_b with fp32 accumulation), which keeps the products at fp32
-// accuracy.  8 warps: warp w owns rows 16 * (w & 3) .. +16 and columns 32 * (w >> 2) .. +32 (four n-tiles).
-// Out[m][n] = sum_k A(m, k) * B(k, n);  A(m, k) = A[m * PA + k];  B(k, n) = TRANS_B ? B[n * PB + k] : B[k * PB + n].
-// Pitches are chosen so that every fragment load is bank-conflict free: 68 (== 4 mod 32) where a fragment walks
-// (row g, column t), 72 (== 8 mod 32) where it walks (row t, column g).
-constexpr int PX = 68, PT = 72, PC = 68;
-// x = big + small, both rounded to TF32 (10 mantissa bits) to nearest by integer arithmetic on the bit pattern: add half an ulp of the kept
-// field, clear the 13 dropped bits.  x - big is exact in fp32.  (cvt.rna.tf32.f32 is emulated with a dozen integer instructions per value
-// on sm_100a -- ncu showed FSETP / SEL / LOP3 / IMAD at 60 % of this kernel's instructions; its handling of NaN / infinity is not needed
-// for image residuals.  Plain truncation is cheaper still but biased: its error adds up coherently over the 64-term sums and came out 4x
-// worse on the final image.)
-__device__ __forceinline__ unsigned rn_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
-__device__ __forceinline__ void split_tf32(float x, unsigned& big, unsigned& small)
-{
-    big = rn_tf32(x);
-    small = rn_tf32(x - __uint_as_float(big));
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2])
-{
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-template <bool TRANS_B, int PA, int PB, int PO>
-__device__ __forceinline__ void mm64(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ Out)
-{
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    const int m0 = (w & 3) * 16, nbase = (w >> 2) * 32;
-    float acc[4][4] = {};
-#pragma unroll
-    for (int k0 = 0; k0 < TS; k0 += 8) {
-        unsigned ab[4], as[4];
-        split_tf32(A[(m0 + g) * PA + k0 + t], ab[0], as[0]);
-        split_tf32(A[(m0 + g + 8) * PA + k0 + t], ab[1], as[1]);
-        split_tf32(A[(m0 + g) * PA + k0 + t + 4], ab[2], as[2]);
-        split_tf32(A[(m0 + g + 8) * PA + k0 + t + 4], ab[3], as[3]);
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            const int n = nbase + nt * 8 + g;
-            unsigned bb[2], bs[2];
-            split_tf32(TRANS_B ? B[n * PB + k0 + t] : B[(k0 + t) * PB + n], bb[0], bs[0]);
-            split_tf32(TRANS_B ? B[n * PB + k0 + t + 4] : B[(k0 + t + 4) * PB + n], bb[1], bs[1]);
-            mma_tf32(acc[nt], as, bb);
-            mma_tf32(acc[nt], ab, bs);
-            mma_tf32(acc[nt], ab, bb);
-        }
-    }
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-        const int n = nbase + nt * 8 + 2 * t;
-        Out[(m0 + g) * PO + n] = acc[nt][0];
-        Out[(m0 + g) * PO + n + 1] = acc[nt][1];
-        Out[(m0 + g + 8) * PO + n] = acc[nt][2];
-        Out[(m0 + g + 8) * PO + n + 1] = acc[nt][3];
-    }
-}
-
-// bulk asynchronous copies (the TMA engine's 1-D form) completing on an mbarrier
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity)
-{
-    unsigned ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-
-__global__ void __launch_bounds__(256) k_dn_blocks(BlkArgs a)
-{
-    extern __shared__ __align__(128) float sm[];
-    __shared__ __align__(8) unsigned long long mbar;
-    float* X = sm;                 // data / coefficients
-    float* T = X + TS * PX;        // temp
-    float* C = T + TS * PT;        // forward matrix, then the blur's intermediate, then the backward matrix
-    float* D = C;                  // (three buffers = 53 KB: four CTAs per SM)
-    const int hblk = blockIdx.x, vblk = blockIdx.y, t = threadIdx.x;
-    const int top = (vblk - BLKRAD) * OFFSET, left = (hblk - BLKRAD) * OFFSET;
-    const unsigned bar = smem_u32(&mbar);
-    if (t == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (t == 0) {
-        // the window (into T, the matmul temp) and the two DCT matrices, stored in global memory with their shared-memory
-        // pitches: three bulk copies by the copy engine instead of 48 scalar loads per thread
-        constexpr unsigned BT = TS * PT * sizeof(float), BC = TS * PC * sizeof(float);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(BT + BC) : "memory");
-        bulk_g2s(T, a.tin_p, BT, bar);
-        bulk_g2s(C, a.dctf_p, BC, bar);
-    }
-    // gather the residual while the copies fly.  padded data (L1547-1567): mirror without repeating the edge, clamped
-    const int c = t & 63, r0 = t >> 6;
-    int col = left + c;
-    if (col < 0) col = min(-col, a.width - 1);
-    else if (col >= a.width) col = max(0, 2 * a.width - 2 - col);
-    float res[TS * TS / 256];
-#pragma unroll
-    for (int k = 0; k < TS * TS / 256; ++k) {
-        const int row = top + r0 + 4 * k;
-        int rr = row;
-        if (row < 0) rr = min(-row, a.height - 1);
-        else if (row >= a.height) rr = max(0, 2 * a.height - 2 - row);
-        const size_t p = (size_t)rr * a.width + col;
-        res[k] = a.Lin[p] - a.L[p];
-    }
-    while (!mbar_try_wait(bar, 0)) { }
-#pragma unroll
-    for (int k = 0; k < TS * TS / 256; ++k) {
-        const int r = r0 + 4 * k;
-        X[r * PX + c] = T[r * PT + c] * res[k];
-    }
-    __syncthreads();
-    mm64<true, PX, PC, PT>(X, C, T);       // along rows: T[i][k] = sum_j C[k][j] X[i][j]
-    __syncthreads();
-    mm64<false, PC, PT, PX>(C, T, X);      // along columns: X[k][x] = sum_j C[k][j] T[j][x]
-    __syncthreads();
-    // boxabsblur (boxblur.h L745-888), W = H = 64: horizontal into C (the forward matrix is done with), vertical into T
-    const int rad = a.blur_rad;
-    if (t < TS) {
-        const float* s = X + t * PX;
-        float* o = C + t * PC;
-        int len = rad + 1;
-        float v = fabsf(s[0]);
-        for (int j = 1; j <= rad; j++) v += fabsf(s[j]);
-        v /= len;
-        o[0] = v;
-        for (int col = 1; col <= rad; col++) { v = (v * len + fabsf(s[col + rad])) / (len + 1); o[col] = v; len++; }
-        const float rlen = 1.f / (float)len;
-        for (int col = rad + 1; col < TS - rad; col++) { v = v + ((float)(fabsf(s[col + rad]) - fabsf(s[col - rad - 1]))) * rlen; o[col] = v; }
-        for (int col = TS - rad; col < TS; col++) { v = (v * len - fabsf(s[col - rad - 1])) / (len - 1); o[col] = v; len--; }
-    }
-    __syncthreads();
-    if (t < TS) {
-        const float* s = C + t;
-        float* o = T + t;
-        float len = (float)(rad + 1);
-        float v = s[0];
-        for (int i = 1; i <= rad; i++) v = v + s[i * PC];
-        v = v / len;
-        o[0] = v;
-        for (int row = 1; row <= rad; row++) { const float lp1 = len + 1.f; v = (v * len + s[(row + rad) * PC]) / lp1; o[row * PT] = v; len = lp1; }
-        const float rlen = 1.f / len;
-        for (int row = rad + 1; row < TS - rad; row++) { v = v + (s[(row + rad) * PC] - s[(row - rad - 1) * PC]) * rlen; o[row * PT] = v; }
-        for (int row = TS - rad; row < TS; row++) { const float lm1 = len - 1.f; v = (v * len - s[(row - rad - 1) * PC]) / lm1; o[row * PT] = v; len = lm1; }
-    }
-    __syncthreads();
-    if (t == 0) {       // the blur's intermediate is consumed: the backward matrix streams into its place while the shrink loop runs
-        constexpr unsigned BC = TS * PC * sizeof(float);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy accesses to C are ordered before the async write
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(BC) : "memory");
-        bulk_g2s(D, a.dctb_p, BC, bar);
-    }
-    // RGBtile_denoise L511-514 with the per-sample detail factor of L1571-1595.  The coefficients already differ from the reference's in
-    // their last bits (fp32 matrix product here, FFTW there), so this factor is evaluated with the fast reciprocal / exponential
-    // (2 ulp, ~1e-7 of the factor) instead of the reference's sleef exp and IEEE division: a sixth of the instructions.
-    {
-        const int icol = left + c;
-        const bool col_in = icol >= 0 && icol < a.width;
-        const float inv_hi = -1.4426950408889634f / a.detail_hi, inv_lo = -1.4426950408889634f / a.detail_lo;      // exp(x) = 2^(x log2 e)
-#pragma unroll 4
-        for (int k = 0; k < TS * TS / 256; ++k) {
-            const int r = r0 + 4 * k, row = top + r;
-            float idf = inv_lo;
-            if (col_in && row >= 0 && row < a.height)
-                idf = a.use_mask ? __fdividef(-1.4426950408889634f, compute_detail(a.params_Ldetail * a.mask[(size_t)row * a.width + icol])) : inv_hi;
-            const float nb = T[r * PT + c];
-            X[r * PX + c] = X[r * PX + c] * (1.0f - exp2f((nb * nb) * idf));
-        }
-    }
-    __syncthreads();
-    while (!mbar_try_wait(bar, 1)) { }
-    mm64<true, PX, PC, PT>(X, D, T);
-    __syncthreads();
-    mm64<false, PC, PT, PX>(D, T, X);
-    __syncthreads();
-    float* out = a.blocks + ((size_t)vblk * a.nbw + hblk) * (TS * TS);
-    for (int i = t; i < TS * TS; i += 256) out[i] = X[(i >> 6) * PX + (i & 63)];
 }
 
 // ordered overlap-add (RGBoutput_tile_row L531-558 + totwt L1577) and L += Ldetail / totwt (L1628-1632)
@@ -533,7 +334,7 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
 
     if (denoiseLuminance) {
         // the window / DCT tables are constants: built and uploaded once per context
-        constexpr size_t NT0 = 4 * TS * TS + TS * PT + 2 * TS * PC;    // dense tables + pitched copies for the bulk loads
+        constexpr size_t NT0 = 4 * TS * TS;                             // tilemask_in, tilemask_out, REDFT10 and REDFT01 matrices, dense
         constexpr size_t NT = NT0 + DN_SPLIT_WORDS;                     // + the pre-split tcgen05 operand images of the two DCT matrices
         int trc = art_reserve(ctx, ctx->d_dn_tables, NT * sizeof(float));
         if (trc) return trc;
@@ -541,13 +342,6 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
         if (!ctx->dn_tables_ready) {
             std::vector<float> host(NT, 0.f);
             build_tables(host.data(), host.data() + TS * TS, host.data() + 2 * TS * TS, host.data() + 3 * TS * TS);
-            float* tp = host.data() + 4 * TS * TS;
-            for (int r = 0; r < TS; ++r)
-                for (int c = 0; c < TS; ++c) {
-                    tp[r * PT + c] = host[r * TS + c];
-                    tp[TS * PT + r * PC + c] = host[2 * TS * TS + r * TS + c];
-                    tp[TS * PT + TS * PC + r * PC + c] = host[3 * TS * TS + r * TS + c];
-                }
             art_dn_blocks_split_tables(host.data() + 2 * TS * TS, host.data() + 3 * TS * TS, reinterpret_cast<unsigned*>(host.data() + NT0));
             ART_CUDA(ctx, cudaMemcpyAsync(tb, host.data(), sizeof(float) * NT, cudaMemcpyHostToDevice, st));
             ART_CUDA(ctx, cudaStreamSynchronize(st));
@@ -676,27 +470,15 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
             const float amount = std::max(0.f, std::min(float(P->luminanceDetailThreshold) / 100.f, 1.f));
             if ((rc = art_detail_mask_dev(ctx, Lp, W, mask, W, W, H, 65535.f, 25.f, 10000.f, amount, 2, 25.f / scale, quarter))) return rc;
         }
-        BlkArgs a{};
-        a.Lin = Lin; a.L = Lp; a.mask = mask; a.width = W; a.height = H; a.nbw = nbw; a.nbh = nbh; a.tin = tin; a.dctf = dctf; a.dctb = dctb; a.blocks = blocks;
-        a.tin_p = tin + 4 * TS * TS; a.dctf_p = a.tin_p + TS * PT; a.dctb_p = a.dctf_p + TS * PC;
-        a.detail_hi = host_compute_detail(params_Ldetail); a.detail_lo = host_compute_detail(0.f); a.params_Ldetail = params_Ldetail;
-        a.use_mask = use_mask; a.blur_rad = std::max(1, int(3 / scale));
-        const size_t smem = (size_t)TS * (PX + PT + PC) * sizeof(float);
-        if (!(ctx->attrs_set & art_hp_ctx::ATTR_DN_BLOCKS_LEGACY)) {
-            ART_CUDA(ctx, cudaFuncSetAttribute(k_dn_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ctx->attrs_set |= art_hp_ctx::ATTR_DN_BLOCKS_LEGACY;
-        }
-        static const bool legacy = getenv("ART_HP_DN_BLOCKS_LEGACY") != nullptr;
+        DnBlocksArgs b{};
+        b.Lin = Lin; b.L = Lp; b.mask = mask; b.width = W; b.height = H; b.nbw = nbw; b.nbh = nbh; b.tin = tin;
+        b.fwd_split = reinterpret_cast<const unsigned*>(tin + 4 * TS * TS); b.bwd_split = b.fwd_split + DN_SPLIT_WORDS / 2;
+        b.blocks = blocks; b.detail_hi = host_compute_detail(params_Ldetail); b.detail_lo = host_compute_detail(0.f); b.params_Ldetail = params_Ldetail;
+        b.use_mask = use_mask; b.blur_rad = std::max(1, int(3 / scale));
         art_prof_begin(ctx, "k_dn_blocks");
-        if (legacy) k_dn_blocks<<<dim3(nbw, nbh), 256, smem, st>>>(a);
-        else {
-            DnBlocksArgs b{};
-            b.Lin = Lin; b.L = Lp; b.mask = mask; b.width = W; b.height = H; b.nbw = nbw; b.nbh = nbh; b.tin = tin;
-            b.fwd_split = reinterpret_cast<const unsigned*>(a.dctb_p + TS * PC); b.bwd_split = b.fwd_split + DN_SPLIT_WORDS / 2;
-            b.blocks = blocks; b.detail_hi = a.detail_hi; b.detail_lo = a.detail_lo; b.params_Ldetail = params_Ldetail; b.use_mask = use_mask; b.blur_rad = a.blur_rad;
-            if ((rc = art_dn_blocks_launch(ctx, b))) return rc;
-        }
+        rc = art_dn_blocks_launch(ctx, b);
         art_prof_end(ctx);
+        if (rc) return rc;
         GatherArgs ga{};
         ga.L = Lp; ga.blocks = blocks; ga.tin = tin; ga.tout = tout; ga.width = W; ga.height = H; ga.nbw = nbw; ga.nbh = nbh;
         ga.nbw_out = (int)std::ceil(((float)W) / OFFSET);

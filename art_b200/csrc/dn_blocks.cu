@@ -5,11 +5,12 @@
 // L494-525 (boxabsblur of |coefficients|, boxblur.h L745-888, and the shrink factor), fftwf REDFT01 (L1614).  The overlap-add
 // (RGBoutput_tile_row L531-558) stays in k_dn_gather (denoise.cu), in the reference's one-thread order.
 //
-// One persistent CTA (128 threads, two per SM) handles PAIRS of horizontally adjacent blocks stacked into M = 128, so each of the four
+// One persistent CTA (256 threads, two per SM) handles PAIRS of horizontally adjacent blocks stacked into M = 128, so each of the four
 // 64^3 products of a block pair is a 128 x 64 x 64 tcgen05.mma.kind::tf32 with the accumulator in TMEM.  fp32 accuracy comes
 // from the 3xTF32 split (x = big + small; small * big + big * small + big * big, fp32 accumulation): every operand is split
 // ONCE, when it is written to shared memory (the mma.sync version re-split per fragment load, which was 5 of every 7
-// instructions of its products).  Thread t owns TMEM lane t = row t of every product's result, i.e. (block t / 64, index t % 64).
+// instructions of its products).  Threads t and t + 128 share TMEM lane t = row t of every product's result, i.e. (block t / 64,
+// index t % 64), and take 32 of its 64 columns each.
 //
 // The chain is arranged so that the moving operand is always A and every hand-over is the same transposing write:
 //   product 1  T [i][k'] = sum_j  X[i][j]  C[k'][j]      A(row = i,  K = j)  written by the gather thread of column j
@@ -42,32 +43,47 @@ __device__ __forceinline__ float compute_detail(float d)
     return a * a;
 }
 
+// 2^x, x <= 0, by the special-function unit (results below 2^-126 flush to zero: the factor is then 1 either way)
+__device__ __forceinline__ float ex2_fast(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // element (row = blk * 64 + m, K = q): koff carries the thread's (blk, q) part
 __device__ __forceinline__ void put(unsigned char* big, unsigned char* small, unsigned koff, int m, float v)
 {
-    unsigned b, s;
-    umma::split_tf32(v, b, s);
+    // big = v truncated to TF32 (what the tensor core would read anyway), small = the exact remainder rounded to nearest: the only
+    // rounding of the pair is the small part's (2^-22 of v, unbiased)
+    const unsigned b = __float_as_uint(v) & 0xffffe000u;
+    const unsigned s = umma::rn_tf32(v - __uint_as_float(b));
     const unsigned off = koff + (m & 7) * 16 + (m >> 3) * A_SBO;
     *reinterpret_cast<unsigned*>(big + off) = b;
     *reinterpret_cast<unsigned*>(small + off) = s;
 }
 
-// this thread's 64 accumulator columns
-__device__ __forceinline__ void ld64(unsigned taddr, float (&v)[64])
+// 32 accumulator columns of this thread's lane
+__device__ __forceinline__ void ld32(unsigned taddr, float (&v)[32])
 {
-    unsigned r0[16], r1[16], r2[16], r3[16];
+    unsigned r0[16], r1[16];
     umma::tmem_ld16_nowait(taddr, r0);
     umma::tmem_ld16_nowait(taddr + 16, r1);
-    umma::tmem_ld16_nowait(taddr + 32, r2);
-    umma::tmem_ld16_nowait(taddr + 48, r3);
     umma::wait_ld();
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         v[i] = __uint_as_float(r0[i]);
         v[16 + i] = __uint_as_float(r1[i]);
-        v[32 + i] = __uint_as_float(r2[i]);
-        v[48 + i] = __uint_as_float(r3[i]);
     }
+}
+
+// The CTA waits for its product: one thread on the mbarrier, the others at the hardware barrier (no issue slots spent spinning)
+__device__ __forceinline__ void mma_done(unsigned bar, unsigned& parity)
+{
+    if (threadIdx.x == 0) umma::mbar_wait(bar, parity);
+    parity ^= 1;
+    __syncthreads();
+    umma::fence_after_sync();
 }
 
 // 24 instructions: three passes (small * big, big * small, big * big) of eight K steps
@@ -87,27 +103,47 @@ __device__ __forceinline__ void issue_product(unsigned tmem, unsigned a_big, uns
     umma::mma_commit(bar);
 }
 
-// one pass of boxabsblur (boxblur.h L745-888) over a 64-vector (the |.| already taken), same expressions in both directions
+// One pass of boxabsblur (boxblur.h L745-888) over a 64-vector (the |.| already taken), same expressions in both directions, cut
+// in two halves of 32 outputs so that two threads share a line.  The lower half is the reference's running mean as it stands; the
+// upper half restarts the running mean at element 32 from the 2 RAD + 1 samples under the window (the same value up to the
+// rounding the running form has accumulated by then, ~1e-7 relative) and finishes with the reference's shrinking window.
+// lo: s[j] = sample j, j = 0 .. 31 + RAD.   hi: s[j] = sample 31 - RAD + j, j = 0 .. 32 + RAD.
 template <int RAD>
-__device__ __forceinline__ void box64(const float (&s)[64], float (&o)[64])
+__device__ __forceinline__ void box_lo(const float (&s)[32 + RAD], float (&o)[32])
 {
-    float len = (float)(RAD + 1);
     float v = s[0];
 #pragma unroll
     for (int j = 1; j <= RAD; ++j) v = v + s[j];
-    v = v / len;
+    v = v * (1.f / (float)(RAD + 1));         // the window lengths are compile-time constants: reciprocals, not IEEE divisions
     o[0] = v;
 #pragma unroll
-    for (int c = 1; c <= RAD; ++c) { const float lp1 = len + 1.f; v = (v * len + s[c + RAD]) / lp1; o[c] = v; len = lp1; }
-    const float rlen = 1.f / len;
+    for (int c = 1; c <= RAD; ++c) { v = (v * (float)(RAD + c) + s[c + RAD]) * (1.f / (float)(RAD + c + 1)); o[c] = v; }
+    constexpr float rlen = 1.f / (float)(2 * RAD + 1);
 #pragma unroll
-    for (int c = RAD + 1; c < TS - RAD; ++c) { v = v + (s[c + RAD] - s[c - RAD - 1]) * rlen; o[c] = v; }
+    for (int c = RAD + 1; c < 32; ++c) { v = v + (s[c + RAD] - s[c - RAD - 1]) * rlen; o[c] = v; }
+}
+template <int RAD>
+__device__ __forceinline__ void box_hi(const float (&s)[33 + RAD], float (&o)[32])
+{
+    constexpr int B = 31 - RAD;              // sample index of s[0]
+    constexpr float rlen = 1.f / (float)(2 * RAD + 1);
+    float v = s[32 - RAD - B];
 #pragma unroll
-    for (int c = TS - RAD; c < TS; ++c) { const float lm1 = len - 1.f; v = (v * len - s[c - RAD - 1]) / lm1; o[c] = v; len = lm1; }
+    for (int j = 33 - RAD; j <= 32 + RAD; ++j) v = v + s[j - B];
+    v = v * rlen;
+    o[0] = v;
+#pragma unroll
+    for (int c = 33; c < TS - RAD; ++c) { v = v + (s[c + RAD - B] - s[c - RAD - 1 - B]) * rlen; o[c - 32] = v; }
+#pragma unroll
+    for (int c = TS - RAD; c < TS; ++c) {          // window length TS - 1 - c + RAD + 1 shrinking from 2 RAD + 1
+        const int len = TS - c + RAD + 1;
+        v = (v * (float)len - s[c - RAD - 1 - B]) * (1.f / (float)(len - 1));
+        o[c - 32] = v;
+    }
 }
 
 template <int RAD>
-__global__ void __launch_bounds__(128, 2) k_dn_blocks5(DnBlocksArgs a, int npw, int npairs)
+__global__ void __launch_bounds__(256, 2) k_dn_blocks5(DnBlocksArgs a, int npw, int npairs)
 {
     extern __shared__ __align__(128) unsigned char sm[];
     __shared__ __align__(8) unsigned long long bars[2];
@@ -116,7 +152,8 @@ __global__ void __launch_bounds__(128, 2) k_dn_blocks5(DnBlocksArgs a, int npw, 
     unsigned char* a_small = sm + A_BYTES;
     unsigned char* b_big = sm + 2 * A_BYTES;
     float* S = reinterpret_cast<float*>(a_big);
-    const int t = threadIdx.x, blk = t >> 6, q = t & 63;
+    // thread = (row owner r = TMEM lane, half hh of the 64 columns); r = (block of the pair, index q)
+    const int t = threadIdx.x, r = t & 127, hh = t >> 7, blk = r >> 6, q = r & 63, c0 = 32 * hh;
     const unsigned bar_b = umma::smem_addr(&bars[0]), bar_m = umma::smem_addr(&bars[1]);
     const unsigned sa_big = umma::smem_addr(a_big), sa_small = umma::smem_addr(a_small);
     const unsigned sb_big = umma::smem_addr(b_big), sb_small = sb_big + B_BYTES;
@@ -130,9 +167,10 @@ __global__ void __launch_bounds__(128, 2) k_dn_blocks5(DnBlocksArgs a, int npw, 
     __syncthreads();
     umma::fence_after_sync();
     const unsigned tmem = tmem_slot;
-    const unsigned tm = tmem + ((unsigned)(((t >> 5) & 3) * 32) << 16);       // this warp's lane quadrant
+    const unsigned tm = tmem + ((unsigned)(((t >> 5) & 3) * 32) << 16) + (unsigned)c0;       // this warp's lane quadrant, this thread's column half
     unsigned par_m = 0, par_b = 0;
-    const unsigned koff = (unsigned)blk * 8 * A_SBO + (unsigned)(q >> 2) * A_LBO + (unsigned)(q & 3) * 4;
+    // operand element (row = blk * 64 + m, K = q) for m = c0 + u: everything but u in koff
+    const unsigned koff = (unsigned)(blk * 8 + 4 * hh) * A_SBO + (unsigned)(q >> 2) * A_LBO + (unsigned)(q & 3) * 4;
     const float inv_hi = -1.4426950408889634f / a.detail_hi, inv_lo = -1.4426950408889634f / a.detail_lo;      // exp(x) = 2^(x log2 e)
     if (t == 0 && (int)blockIdx.x < npairs) {
         umma::mbar_expect_tx(bar_b, 2 * B_BYTES);
@@ -144,29 +182,46 @@ __global__ void __launch_bounds__(128, 2) k_dn_blocks5(DnBlocksArgs a, int npw, 
         const bool valid = hblk < a.nbw;         // an odd block count leaves the last pair half empty: computed, not stored
         const int top = (vblk - BLKRAD) * OFFSET, left = (hblk - BLKRAD) * OFFSET;
 
-        // ---- phase 0: residual x window for column q of the block (L1547-1567: mirror without repeating the edge, clamped)
+        // ---- phase 0: residual x window, column q of the block, rows c0 .. c0 + 31 (L1547-1567: mirror without repeating the edge, clamped)
         {
             int col = left + q;
             if (col < 0) col = min(-col, a.width - 1);
             else if (col >= a.width) col = max(0, 2 * a.width - 2 - col);
-            // sixteen rows of loads in flight before the first use (the row mirror is branch-free so that the loads can be batched)
-#pragma unroll 1
-            for (int i0 = 0; i0 < TS; i0 += 16) {
-                float lin[16], lo[16], win[16];
+            // sixteen rows of loads in flight before the first use; blocks that do not touch the frame's top / bottom (all but two block rows)
+            // walk the column by pointer, the others mirror each row (branch-free, so that the loads still batch)
+            const float* wp = a.tin + c0 * TS + q;
+            if (top >= 0 && top + TS <= a.height) {
+                const float* pl = a.Lin + (size_t)(top + c0) * a.width + col;
+                const float* po = a.L + (size_t)(top + c0) * a.width + col;
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const int row = top + i0 + u;
-                    const int below = min(-row, a.height - 1), above = max(0, 2 * a.height - 2 - row);
-                    const int rr = row < 0 ? below : (row >= a.height ? above : row);
-                    const size_t p = (size_t)rr * a.width + col;
-                    lin[u] = __ldg(a.Lin + p);
-                    lo[u] = __ldg(a.L + p);
-                    win[u] = __ldg(a.tin + (i0 + u) * TS + q);
+                for (int i0 = 0; i0 < 32; i0 += 16) {
+                    float lin[16], lo[16], win[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        lin[u] = __ldg(pl + (size_t)(i0 + u) * a.width);
+                        lo[u] = __ldg(po + (size_t)(i0 + u) * a.width);
+                        win[u] = __ldg(wp + (i0 + u) * TS);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) put(a_big, a_small, koff, i0 + u, win[u] * (lin[u] - lo[u]));
                 }
-                unsigned char* pb = a_big + (i0 >> 3) * A_SBO;
-                unsigned char* ps = a_small + (i0 >> 3) * A_SBO;
+            } else {
 #pragma unroll
-                for (int u = 0; u < 16; ++u) put(pb, ps, koff, u, win[u] * (lin[u] - lo[u]));
+                for (int i0 = 0; i0 < 32; i0 += 16) {
+                    float lin[16], lo[16], win[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const int row = top + c0 + i0 + u;
+                        const int below = min(-row, a.height - 1), above = max(0, 2 * a.height - 2 - row);
+                        const int rr = row < 0 ? below : (row >= a.height ? above : row);
+                        const size_t p = (size_t)rr * a.width + col;
+                        lin[u] = __ldg(a.Lin + p);
+                        lo[u] = __ldg(a.L + p);
+                        win[u] = __ldg(wp + (i0 + u) * TS);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) put(a_big, a_small, koff, i0 + u, win[u] * (lin[u] - lo[u]));
+                }
             }
         }
         // ---- product 1 (needs the forward matrices)
@@ -178,14 +233,13 @@ __global__ void __launch_bounds__(128, 2) k_dn_blocks5(DnBlocksArgs a, int npw, 
             umma::fence_after_sync();
             issue_product(tmem, sa_big, sa_small, sb_big, sb_small, bar_m);
         }
-        umma::mbar_wait(bar_m, par_m); par_m ^= 1;
-        umma::fence_after_sync();
+        mma_done(bar_m, par_m);
         // ---- phase 1: row i = q of T, transposed into the operand of product 2
         {
-            float v[64];
-            ld64(tm, v);
+            float v[32];
+            ld32(tm, v);
 #pragma unroll
-            for (int n = 0; n < TS; ++n) put(a_big, a_small, koff, n, v[n]);
+            for (int n = 0; n < 32; ++n) put(a_big, a_small, koff, n, v[n]);
         }
         umma::fence_before_sync();
         umma::fence_async_smem();
@@ -194,51 +248,75 @@ __global__ void __launch_bounds__(128, 2) k_dn_blocks5(DnBlocksArgs a, int npw, 
             umma::fence_after_sync();
             issue_product(tmem, sa_big, sa_small, sb_big, sb_small, bar_m);
         }
-        umma::mbar_wait(bar_m, par_m); par_m ^= 1;
-        umma::fence_after_sync();
+        mma_done(bar_m, par_m);
         if (t == 0) {       // the forward matrices are consumed: the backward ones stream in under the blur
             umma::mbar_expect_tx(bar_b, 2 * B_BYTES);
             umma::bulk_g2s(sb_big, a.bwd_split, 2 * B_BYTES, bar_b);
         }
-        // ---- phase 2: this thread holds Y[k][k' = q] for all k.  boxabsblur: along k' (threads) through the scratch, then along k (registers)
+        // ---- phase 2: this thread holds Y[k][k' = q] for k = c0 .. c0 + 31.  boxabsblur: along k' (threads) through the scratch, then along k (registers)
         {
             float* srow = S + (size_t)(blk * TS + q) * SP;       // scratch row q of this block: element k
             float* scol = S + (size_t)(blk * TS) * SP + q;       // scratch column q: element k' at stride SP
             {
-                float y[64];
-                ld64(tm, y);
+                float y[32];
+                ld32(tm, y);
 #pragma unroll
-                for (int k = 0; k < TS; ++k) srow[k] = fabsf(y[k]);
+                for (int k = 0; k < 32; ++k) srow[c0 + k] = fabsf(y[k]);
             }
             __syncthreads();
-            {   // as the owner of coefficient row k = q: the horizontal pass, in place
-                float s[64], h[64];
+            {   // as the owner of coefficient row k = q: the horizontal pass over k' = c0 .. c0 + 31, in place
+                float h[32];
+                if (hh == 0) {
+                    float s[32 + RAD];
 #pragma unroll
-                for (int c = 0; c < TS; ++c) s[c] = scol[c * SP];
-                box64<RAD>(s, h);
+                    for (int c = 0; c < 32 + RAD; ++c) s[c] = scol[c * SP];
+                    box_lo<RAD>(s, h);
+                } else {
+                    float s[33 + RAD];
 #pragma unroll
-                for (int c = 0; c < TS; ++c) scol[c * SP] = h[c];
+                    for (int c = 0; c < 33 + RAD; ++c) s[c] = scol[(31 - RAD + c) * SP];
+                    box_hi<RAD>(s, h);
+                }
+                __syncthreads();        // every window is read before any element is replaced
+#pragma unroll
+                for (int c = 0; c < 32; ++c) scol[(c0 + c) * SP] = h[c];
             }
             __syncthreads();
-            float h[64];
+            float nb[32];
+            if (hh == 0) {
+                float s[32 + RAD];
 #pragma unroll
-            for (int k = 0; k < TS; ++k) h[k] = srow[k];
+                for (int k = 0; k < 32 + RAD; ++k) s[k] = srow[k];
+                box_lo<RAD>(s, nb);       // the vertical pass
+            } else {
+                float s[33 + RAD];
+#pragma unroll
+                for (int k = 0; k < 33 + RAD; ++k) s[k] = srow[31 - RAD + k];
+                box_hi<RAD>(s, nb);
+            }
             __syncthreads();         // the scratch (= the big operand buffer) is free again
-            float nb[64];
-            box64<RAD>(h, nb);       // the vertical pass
-            float y[64];
-            ld64(tm, y);
+            float y[32];
+            ld32(tm, y);
             // RGBtile_denoise L511-514 with the per-sample detail factor of L1571-1595.  The coefficients already differ from the reference's in
             // their last bits (tensor-core products here, FFTW there), so the factor uses the fast reciprocal / exp2 instead of sleef exp + IEEE division.
             const int icol = left + q;
             const bool col_in = valid && icol >= 0 && icol < a.width;
+            if (!a.use_mask) {
 #pragma unroll
-            for (int k = 0; k < TS; ++k) {
-                const int row = top + k;
-                float idf = inv_lo;
-                if (col_in && row >= 0 && row < a.height)
-                    idf = a.use_mask ? __fdividef(-1.4426950408889634f, compute_detail(a.params_Ldetail * a.mask[(size_t)row * a.width + icol])) : inv_hi;
-                put(a_big, a_small, koff, k, y[k] * (1.0f - exp2f((nb[k] * nb[k]) * idf)));
+                for (int k = 0; k < 32; ++k) {
+                    const int row = top + c0 + k;
+                    const float idf = (col_in && row >= 0 && row < a.height) ? inv_hi : inv_lo;
+                    put(a_big, a_small, koff, k, y[k] * (1.0f - ex2_fast((nb[k] * nb[k]) * idf)));
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const int row = top + c0 + k;
+                    float idf = inv_lo;
+                    if (col_in && row >= 0 && row < a.height)
+                        idf = __fdividef(-1.4426950408889634f, compute_detail(a.params_Ldetail * __ldg(a.mask + (size_t)row * a.width + icol)));
+                    put(a_big, a_small, koff, k, y[k] * (1.0f - ex2_fast((nb[k] * nb[k]) * idf)));
+                }
             }
         }
         // ---- product 3 (needs the backward matrices)
@@ -250,14 +328,13 @@ __global__ void __launch_bounds__(128, 2) k_dn_blocks5(DnBlocksArgs a, int npw, 
             umma::fence_after_sync();
             issue_product(tmem, sa_big, sa_small, sb_big, sb_small, bar_m);
         }
-        umma::mbar_wait(bar_m, par_m); par_m ^= 1;
-        umma::fence_after_sync();
+        mma_done(bar_m, par_m);
         // ---- phase 3: row k = q of U, transposed into the operand of product 4
         {
-            float v[64];
-            ld64(tm, v);
+            float v[32];
+            ld32(tm, v);
 #pragma unroll
-            for (int n = 0; n < TS; ++n) put(a_big, a_small, koff, n, v[n]);
+            for (int n = 0; n < 32; ++n) put(a_big, a_small, koff, n, v[n]);
         }
         umma::fence_before_sync();
         umma::fence_async_smem();
@@ -266,20 +343,19 @@ __global__ void __launch_bounds__(128, 2) k_dn_blocks5(DnBlocksArgs a, int npw, 
             umma::fence_after_sync();
             issue_product(tmem, sa_big, sa_small, sb_big, sb_small, bar_m);
         }
-        umma::mbar_wait(bar_m, par_m); par_m ^= 1;
-        umma::fence_after_sync();
+        mma_done(bar_m, par_m);
         if (t == 0 && pair + (int)gridDim.x < npairs) {       // forward matrices for the next pair
             umma::mbar_expect_tx(bar_b, 2 * B_BYTES);
             umma::bulk_g2s(sb_big, a.fwd_split, 2 * B_BYTES, bar_b);
         }
-        // ---- phase 4: this thread holds Z[y][x = q] for all y: rows of 32 consecutive floats per warp
+        // ---- phase 4: this thread holds Z[y][x = q] for y = c0 .. c0 + 31: rows of 32 consecutive floats per warp
         {
-            float z[64];
-            ld64(tm, z);
+            float z[32];
+            ld32(tm, z);
             if (valid) {
-                float* out = a.blocks + ((size_t)vblk * a.nbw + hblk) * (TS * TS) + q;
+                float* out = a.blocks + ((size_t)vblk * a.nbw + hblk) * (TS * TS) + (size_t)c0 * TS + q;
 #pragma unroll
-                for (int y = 0; y < TS; ++y) out[y * TS] = z[y];
+                for (int y = 0; y < 32; ++y) out[y * TS] = z[y];
             }
         }
     }
@@ -324,9 +400,9 @@ int art_dn_blocks_launch(art_hp_ctx* ctx, const DnBlocksArgs& a)
         ctx->attrs_set |= art_hp_ctx::ATTR_DN_BLOCKS;
     }
     switch (a.blur_rad) {
-    case 1: k_dn_blocks5<1><<<grid, 128, SMEM_BYTES, ctx->stream>>>(a, npw, npairs); break;
-    case 2: k_dn_blocks5<2><<<grid, 128, SMEM_BYTES, ctx->stream>>>(a, npw, npairs); break;
-    case 3: k_dn_blocks5<3><<<grid, 128, SMEM_BYTES, ctx->stream>>>(a, npw, npairs); break;
+    case 1: k_dn_blocks5<1><<<grid, 256, SMEM_BYTES, ctx->stream>>>(a, npw, npairs); break;
+    case 2: k_dn_blocks5<2><<<grid, 256, SMEM_BYTES, ctx->stream>>>(a, npw, npairs); break;
+    case 3: k_dn_blocks5<3><<<grid, 256, SMEM_BYTES, ctx->stream>>>(a, npw, npairs); break;
     default: return ctx->fail(ART_HP_ERR_INVALID, "detail recovery: blur radius %d outside 1..3", a.blur_rad);
     }
     ART_CUDA(ctx, cudaGetLastError());
