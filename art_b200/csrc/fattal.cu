@@ -265,6 +265,11 @@ struct FftPlan {
     int radix[MAX_STAGES];
     int lgr[MAX_STAGES];        // log2(radix) for the power-of-two radices, -1 otherwise
     int lgM[MAX_STAGES];        // log2(M) of the stage (M = sub-transform length after the stage) when a power of two, else -1
+    // execution list: one entry per trip through shared memory.  op = the stage's radix, or 16 for two consecutive radix-4 stages fused
+    // (fft_stage44); oplg = log2(M) after the entry's last stage (or -1)
+    int nops;
+    int op[MAX_STAGES];
+    int oplg[MAX_STAGES];
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x)); }
@@ -346,19 +351,84 @@ __device__ __forceinline__ void fft_stage(double2* z, int N, int L, int lgM, con
     }
 }
 
+// Two consecutive radix-4 passes (sub-transform lengths L and L / 4, both powers of two) in one trip through shared memory: the
+// thread owns the 16 points {base + (4 a + b) L / 16} and keeps them in registers between the passes.  Operation for
+// operation what fft_stage<4> computes twice (same butterflies, same twiddle products in the same order), so the
+// transform's bits do not change; the number of shared-memory passes and CTA barriers of the power-of-two part halves.
+__device__ __forceinline__ void radix4(const double2 (&x)[4], double2 (&y)[4])
+{
+    const double2 a = make_double2(x[0].x + x[2].x, x[0].y + x[2].y), b = make_double2(x[0].x - x[2].x, x[0].y - x[2].y);
+    const double2 c = make_double2(x[1].x + x[3].x, x[1].y + x[3].y), d = make_double2(x[1].x - x[3].x, x[1].y - x[3].y);
+    y[0] = make_double2(a.x + c.x, a.y + c.y);
+    y[2] = make_double2(a.x - c.x, a.y - c.y);
+    y[1] = make_double2(b.x + d.y, b.y - d.x);
+    y[3] = make_double2(b.x - d.y, b.y + d.x);
+}
+__device__ __forceinline__ void fft_stage44(double2* z, int N, int L, int lgM16, const double2* __restrict__ tw)
+{
+    const int M16 = 1 << lgM16;
+    const int tws1 = 2 * N / L, tws2 = 4 * tws1;
+    int gq[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) gq[q] = swg(q << lgM16);
+    for (int t = threadIdx.x; t < N / 16; t += FFT_THREADS) {
+        const int j = t & (M16 - 1);
+        const int base = ((t >> lgM16) << (lgM16 + 4)) + j;
+        const int gb = swg(base);
+        double2 x[4][4];            // [a][b]
+#pragma unroll
+        for (int q = 0; q < 16; ++q) x[q >> 2][q & 3] = z[(base + (q << lgM16)) ^ (gb ^ gq[q])];
+        // pass 1: radix 4 over a for each b, twiddles exp(-2 pi i d (b M16 + j) / L)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const double2 in[4] = {x[0][b], x[1][b], x[2][b], x[3][b]};
+            double2 y[4];
+            radix4(in, y);
+            const double2 w1 = tw[tws1 * ((b << lgM16) + j)];
+            double2 w = w1;
+            x[0][b] = y[0];
+#pragma unroll
+            for (int d = 1; d < 4; ++d) {
+                x[d][b] = cmul(y[d], w);
+                if (d + 1 < 4) w = cmul(w, w1);
+            }
+        }
+        // pass 2: radix 4 over b for each d, twiddles exp(-2 pi i f j / (L / 4))
+        const double2 w1 = tw[tws2 * j];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            double2 y[4];
+            radix4(x[d], y);
+            z[(base + ((4 * d) << lgM16)) ^ (gb ^ gq[4 * d])] = y[0];
+            if (M16 > 1) {
+                double2 w = w1;
+#pragma unroll
+                for (int f = 1; f < 4; ++f) {
+                    z[(base + ((4 * d + f) << lgM16)) ^ (gb ^ gq[4 * d + f])] = cmul(y[f], w);
+                    if (f + 1 < 4) w = cmul(w, w1);
+                }
+            } else {
+#pragma unroll
+                for (int f = 1; f < 4; ++f) z[(base + ((4 * d + f) << lgM16)) ^ (gb ^ gq[4 * d + f])] = y[f];
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void fft_inplace(double2* z, const FftPlan& P, const double2* __restrict__ tw)
 {
     int L = P.N;
-    for (int s = 0; s < P.nst; ++s) {
-        const int r = P.radix[s];
+    for (int s = 0; s < P.nops; ++s) {
+        const int r = P.op[s];
         switch (r) {
-            case 2: fft_stage<2>(z, P.N, L, P.lgM[s], tw); break;
-            case 3: fft_stage<3>(z, P.N, L, P.lgM[s], tw); break;
-            case 4: fft_stage<4>(z, P.N, L, P.lgM[s], tw); break;
-            case 5: fft_stage<5>(z, P.N, L, P.lgM[s], tw); break;
-            case 7: fft_stage<7>(z, P.N, L, P.lgM[s], tw); break;
-            case 11: fft_stage<11>(z, P.N, L, P.lgM[s], tw); break;
-            default: fft_stage<13>(z, P.N, L, P.lgM[s], tw); break;
+            case 2: fft_stage<2>(z, P.N, L, P.oplg[s], tw); break;
+            case 3: fft_stage<3>(z, P.N, L, P.oplg[s], tw); break;
+            case 4: fft_stage<4>(z, P.N, L, P.oplg[s], tw); break;
+            case 5: fft_stage<5>(z, P.N, L, P.oplg[s], tw); break;
+            case 7: fft_stage<7>(z, P.N, L, P.oplg[s], tw); break;
+            case 11: fft_stage<11>(z, P.N, L, P.oplg[s], tw); break;
+            case 16: fft_stage44(z, P.N, L, P.oplg[s], tw); break;
+            default: fft_stage<13>(z, P.N, L, P.oplg[s], tw); break;
         }
         L /= r;
         __syncthreads();
@@ -656,6 +726,11 @@ bool make_plan(int N, FftPlan* P)
     if (n % 2 == 0) { if (P->nst >= MAX_STAGES) return false; P->radix[P->nst++] = 2; n /= 2; }
     int L = N;
     for (int s = 0; s < P->nst; ++s) { L /= P->radix[s]; P->lgr[s] = lg(P->radix[s]); P->lgM[s] = lg(L); }
+    P->nops = 0;
+    for (int s = 0; s < P->nst; ++s) {
+        if (P->radix[s] == 4 && s + 1 < P->nst && P->radix[s + 1] == 4 && P->lgM[s + 1] >= 0) { P->op[P->nops] = 16; P->oplg[P->nops++] = P->lgM[s + 1]; ++s; }
+        else { P->op[P->nops] = P->radix[s]; P->oplg[P->nops++] = P->lgM[s]; }
+    }
     return n == 1;
 }
 
