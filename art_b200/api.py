@@ -102,6 +102,12 @@ def load_library(build_if_missing=True):
         "art_hp_denoise_compute_params": (i, [vp, i, i, vp, vp, vp, vp, i, vp, vp, d, i, vp, vp]),
         "art_hp_denoise_compute_params_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, i, vp, vp, d, i, vp, vp]),
         "art_hp_develop_size": (i, [vp, i, i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]),
+        "art_hp_band_plan_rows": (i, [vp, i, i, i, i, i, vp]),
+        "art_hp_set_allreduce": (i, [vp, vp, vp]),
+        "art_hp_comm_unique_id": (i, [vp]),
+        "art_hp_comm_init": (i, [vp, vp, i, i]),
+        "art_hp_comm_destroy": (i, [vp]),
+        "art_hp_develop_band_dev": (i, [vp, vp, i, i, vp, sz, vp, vp, vp, sz, vp]),
         "art_hp_denoise_guided_smoothing": (i, [vp, i, i, vp, vp, vp, vp, i, d]),
         "art_hp_denoise_guided_smoothing_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, i, d]),
         "art_hp_develop_submit_packed": (i, [vp, vp, i, i, vp, i, i, vp, sz]),
@@ -182,6 +188,29 @@ class _DenoiseParamsC(ctypes.Structure):
                 ("gamma", ctypes.c_double), ("scale", ctypes.c_double), ("colorSpace", ctypes.c_int), ("aggressive", ctypes.c_int),
                 ("chrominanceMethod", ctypes.c_int), ("noiseCCurve", ctypes.c_void_p), ("noiseCCurveSum", ctypes.c_float),
                 ("wprof_inverse", ctypes.POINTER(ctypes.c_double)), ("chrominanceAutoFactor", ctypes.c_double)]
+
+
+class BandPlan(ctypes.Structure):
+    """art_hp_band_plan: the rows of one rank when a frame is split across GPUs (all in rows; see include/art_hotpath.h)."""
+    _fields_ = [("own_begin", ctypes.c_int), ("own_end", ctypes.c_int), ("band_begin", ctypes.c_int), ("band_end", ctypes.c_int),
+                ("dm_begin", ctypes.c_int), ("dm_end", ctypes.c_int), ("raw_begin", ctypes.c_int), ("raw_end", ctypes.c_int)]
+
+    def __repr__(self):
+        return "BandPlan(own=[%d,%d) band=[%d,%d) dm=[%d,%d) raw=[%d,%d))" % (self.own_begin, self.own_end, self.band_begin, self.band_end,
+                                                                             self.dm_begin, self.dm_end, self.raw_begin, self.raw_end)
+
+
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
+
+
+def band_plan(params, W, H, own_begin, own_end, halo=200):
+    """Rows of a rank that delivers rows [own_begin, own_end) of the developed frame of a W x H raw frame (no GPU needed)."""
+    c = params.c_struct()
+    plan = BandPlan()
+    rc = load_library().art_hp_band_plan_rows(ctypes.byref(c), W, H, int(own_begin), int(own_end), int(halo), ctypes.byref(plan))
+    if rc:
+        raise HotPathError(rc, "art_hp_band_plan_rows(own=[%d,%d), halo=%d) on a %dx%d frame" % (own_begin, own_end, halo, W, H))
+    return plan
 
 
 class _DevelopParamsC(ctypes.Structure):
@@ -627,6 +656,37 @@ class HotPath:
     def develop_dev(self, params, W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch):
         c = params.c_struct()
         self._check(self.lib.art_hp_develop_dev(self.h, ctypes.byref(c), W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch))
+
+    # ---- one frame across GPUs (ABI version 3) ----
+    def band_plan(self, params, W, H, own_begin, own_end, halo=200):
+        return band_plan(params, W, H, own_begin, own_end, halo)
+
+    def set_allreduce(self, fn):
+        """fn(d_buf: int, count: int, stream: int) -> int sums `count` int32 at device address d_buf over the ranks, in place, on the stream."""
+        if fn is None:
+            self._allreduce_cb = None
+            self._check(self.lib.art_hp_set_allreduce(self.h, None, None))
+            return
+        self._allreduce_cb = ALLREDUCE_FN(lambda user, buf, count, stream: int(fn(int(buf or 0), int(count), int(stream or 0)) or 0))
+        self._check(self.lib.art_hp_set_allreduce(self.h, ctypes.cast(self._allreduce_cb, ctypes.c_void_p), None))
+
+    def comm_unique_id(self):
+        buf = (ctypes.c_ubyte * 128)()
+        rc = self.lib.art_hp_comm_unique_id(buf)
+        if rc:
+            raise HotPathError(rc, "NCCL is not available (libnccl.so.2)")
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, nranks):
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self.lib.art_hp_comm_init(self.h, buf, int(rank), int(nranks)))
+
+    def comm_destroy(self):
+        self._check(self.lib.art_hp_comm_destroy(self.h))
+
+    def develop_band_dev(self, params, W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch, plan):
+        c = params.c_struct()
+        self._check(self.lib.art_hp_develop_band_dev(self.h, ctypes.byref(c), W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch, ctypes.byref(plan)))
 
     def demosaic_xtrans(self, raw, xtrans, rgb_cam, passes=3, use_cielab=True, out=None):
         """RawImageSource::xtrans_interpolate(passes, useCieLab) on a host (H, W) float32 X-Trans CFA plane.

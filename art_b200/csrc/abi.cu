@@ -233,6 +233,7 @@ int art_hp_create(art_hp_ctx** out, int device_id)
 
 void art_hp_destroy(art_hp_ctx* ctx)
 {
+    if (ctx) art_hp_comm_destroy(ctx);
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -1067,6 +1068,28 @@ int art_hp_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* params, int
         return ctx->fail(ART_HP_ERR_INVALID, "the colour chain needs 16-byte aligned output planes with a pitch that is a multiple of 4 floats");
     ART_CUDA(ctx, cudaSetDevice(ctx->device));
     return art_develop_dev(ctx, params, W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch);
+}
+
+int art_hp_band_plan_rows(const art_hp_develop_params* params, int W, int H, int own_begin, int own_end, int halo, art_hp_band_plan* plan)
+{
+    if (!params || !plan || W < 32 || H < 32) return ART_HP_ERR_INVALID;
+    return art_band_plan(params, W, H, own_begin, own_end, halo, plan);
+}
+
+int art_hp_develop_band_dev(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, const float* d_raw, size_t raw_pitch,
+                            float* d_r, float* d_g, float* d_b, size_t out_pitch, const art_hp_band_plan* plan)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_raw || !d_r || !d_g || !d_b || !plan) return ctx->fail(ART_HP_ERR_INVALID, "null plane or plan");
+    int rc = check_develop(ctx, params, W, H);
+    if (rc) return rc;
+    int bd, Wo, Ho;
+    art_develop_geometry(params, W, H, &bd, &Wo, &Ho);
+    if (raw_pitch < (size_t)W || out_pitch < (size_t)Wo) return ctx->fail(ART_HP_ERR_INVALID, "pitch smaller than the width");
+    if (params->chain && ((out_pitch & 3) || ((reinterpret_cast<uintptr_t>(d_r) | reinterpret_cast<uintptr_t>(d_g) | reinterpret_cast<uintptr_t>(d_b)) & 15)))
+        return ctx->fail(ART_HP_ERR_INVALID, "the colour chain needs 16-byte aligned output planes with a pitch that is a multiple of 4 floats");
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_develop_band_dev(ctx, params, W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch, plan);
 }
 
 int art_hp_develop(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,

@@ -77,6 +77,14 @@ struct art_hp_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[NLANES] = {};
     void* h_stage[2] = {nullptr, nullptr};
     size_t h_stage_bytes = 0;
+    // one frame across GPUs (art_hp_develop_band_dev): the planes the stages see are a row band of the frame; `own0 .. own1` are the
+    // band-local rows this rank owns (whole-frame statistics count only those), H_full the frame's height after the border crop
+    struct Band { bool active = false; int own0 = 0, own1 = 0, H_full = 0; } band;
+    // sum of an int32 device buffer over the ranks sharing the frame, queued on `stream`: ncclAllReduce (art_hp_comm_init) or the caller's hook
+    art_hp_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
+    void* nccl_comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
 
     int fail(int code, const char* fmt, ...)
     {
@@ -198,3 +206,8 @@ int art_scanlines_dev(art_hp_ctx* ctx, int W, int H, const float* r, const float
 void art_develop_geometry(const art_hp_develop_params* p, int W, int H, int* b, int* Wo, int* Ho);
 int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int W, int H, const float* raw, size_t rp,
                     float* r, float* g, float* b, size_t op);
+// one frame across GPUs: geometry of a rank's band and the band pipeline (develop.cu); the collective (comm.cu)
+int art_band_plan(const art_hp_develop_params* p, int W, int H, int own_begin, int own_end, int halo, art_hp_band_plan* out);
+int art_develop_band_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int W, int H, const float* raw, size_t rp,
+                         float* r, float* g, float* b, size_t op, const art_hp_band_plan* plan);
+int art_allreduce_i32(art_hp_ctx* ctx, int* d_buf, size_t count);

@@ -286,6 +286,7 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
     cudaStream_t st = ctx->stream;
     const double scale = P->scale;
     const bool have_curve = P->noiseCCurve != nullptr;
+    if (ctx->band.active && nresi_highresi) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "residual statistics are whole-frame: not available on a row band");
     if (P->luminance == 0 && P->chrominance == 0 && !have_curve) return ART_HP_OK;          // L1654-1666
     const bool useCC = have_curve && P->noiseCCurveSum > 5.f;
     if (useCC && !(cl_r && cl_g && cl_b)) return ctx->fail(ART_HP_ERR_INVALID, "the chroma noise curve needs the half-resolution calclum planes");
@@ -423,7 +424,7 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
     if (aggressive) levwav += 2;                         // L2260-2262
     if (levwav > 8) levwav = 8;
     levwav = std::max(5, int(levwav - std::ceil(std::log(scale))));
-    const int minsizetile = std::min(W, H);
+    const int minsizetile = std::min(W, ctx->band.active ? ctx->band.H_full : H);      // a row band follows its frame's wavelet depth
     int maxlev2 = 8;
     if (minsizetile < 256) maxlev2 = 7;
     if (minsizetile < 128) maxlev2 = 6;

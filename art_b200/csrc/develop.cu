@@ -207,3 +207,93 @@ int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr, int
     }
     return ART_HP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// One frame across GPUs: a rank's row band (include/art_hotpath.h, ABI version 3)
+// ---------------------------------------------------------------------------------------------------------------------------
+int art_band_plan(const art_hp_develop_params* p, int Wr, int Hr, int own_begin, int own_end, int halo, art_hp_band_plan* out)
+{
+    int bd, W, H, P = 0, O = 0;
+    art_develop_geometry(p, Wr, Hr, &bd, &W, &H);
+    if (art_hp_band_align(p->method, &P, &O)) return ART_HP_ERR_UNSUPPORTED;
+    if (own_begin < 0 || own_end > H || own_begin >= own_end || (own_begin & 1) || ((own_end & 1) && own_end != H) || halo < 150) return ART_HP_ERR_INVALID;
+    art_hp_band_plan b{};
+    b.own_begin = own_begin; b.own_end = own_end;
+    b.band_begin = own_begin - halo > 0 ? (own_begin - halo) / 50 * 50 : 0;       // 2: decimated wavelet level; 25: the DCT block grid
+    b.band_end = std::min(H, own_end + halo);
+    // demosaiced rows [band_begin + bd, band_end + bd) of the raw frame, widened to the method's tile grid
+    const int lo = b.band_begin + bd, hi = b.band_end + bd;
+    b.dm_begin = lo <= O + P ? 0 : O + (lo - O) / P * P;
+    b.dm_end = O + (hi - O + P - 1) / P * P;
+    if (b.dm_end >= Hr || b.dm_end <= O) b.dm_end = Hr;
+    const int dh = art_hp_band_halo(p->method);
+    b.raw_begin = std::max(0, b.dm_begin - dh);
+    b.raw_end = std::min(Hr, b.dm_end + dh);
+    if (b.dm_begin == 0) b.raw_end = std::max(b.raw_end, std::min(Hr, 33));         // the mirrored rows at the frame's top / bottom (dist.row_bands)
+    if (b.dm_end == Hr) b.raw_begin = std::min(b.raw_begin, std::max(0, Hr - 17));
+    *out = b;
+    return ART_HP_OK;
+}
+
+int art_develop_band_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr, int Hr, const float* raw, size_t rp,
+                         float* r, float* g, float* b, size_t op, const art_hp_band_plan* plan)
+{
+    int rc, bd, W, H;
+    art_develop_geometry(p, Wr, Hr, &bd, &W, &H);
+    if (p->method != ART_HP_BAYER_AMAZE && p->method != ART_HP_BAYER_RCD) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: Bayer methods only");
+    if (p->fattal_enabled) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: Fattal's Poisson solve is a transform of the whole frame");
+    if (p->denoise && p->denoise->chrominanceMethod == 1) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: the automatic chroma estimator measures crops of the whole frame");
+    if (p->nlStrength) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: NL-means is not split");
+    if (p->denoise && p->denoise->aggressive) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: the aggressive (twice shrunk) mode is not split");
+    {
+        const art_hp_band_plan& q = *plan;
+        int P = 0, O = 0;
+        art_hp_band_align(p->method, &P, &O);
+        auto aligned = [&](int row, int edge) { return row == edge || (row > O && row < Hr && (row - O) % P == 0); };
+        const bool ok = q.own_begin >= 0 && q.own_begin < q.own_end && q.own_end <= H && !(q.own_begin & 1) && (!(q.own_end & 1) || q.own_end == H) &&
+                        q.band_begin >= 0 && q.band_begin % 50 == 0 && q.band_begin <= q.own_begin && q.band_end >= q.own_end && q.band_end <= H &&
+                        (q.band_begin == 0 || q.own_begin - q.band_begin >= 150) && (q.band_end == H || q.band_end - q.own_end >= 150) &&
+                        aligned(q.dm_begin, 0) && aligned(q.dm_end, Hr) && q.dm_begin <= q.band_begin + bd && q.dm_end >= q.band_end + bd;
+        if (!ok) return ctx->fail(ART_HP_ERR_INVALID, "inconsistent band plan: own [%d,%d) band [%d,%d) demosaic [%d,%d) of %d rows", q.own_begin, q.own_end,
+                                  q.band_begin, q.band_end, q.dm_begin, q.dm_end, H);
+    }
+    // demosaic on the frame's tile grid into context-owned full-frame planes (only the band's rows are touched)
+    const size_t dmp = round_up((size_t)Wr, 32);
+    float* dm[3];
+    for (int c = 0; c < 3; ++c) {
+        if ((rc = art_reserve(ctx, ctx->d_dm[c], dmp * (size_t)Hr * sizeof(float)))) return rc;
+        dm[c] = (float*)ctx->d_dm[c].p;
+    }
+    if (p->method == ART_HP_BAYER_AMAZE) rc = art_amaze_dev(ctx, Wr, Hr, p->filters, raw, rp, dm[0], dm[1], dm[2], dmp, p->initialGain, p->border, plan->dm_begin, plan->dm_end);
+    else rc = art_rcd_dev(ctx, Wr, Hr, p->filters, raw, rp, dm[0], dm[1], dm[2], dmp, plan->dm_begin, plan->dm_end);
+    if (rc) return rc;
+    // from here on the band is a frame of Hb rows whose first row is row band_begin of the developed frame
+    const int y0 = plan->band_begin, Hb = plan->band_end - plan->band_begin;
+    const size_t off = (size_t)(y0 + bd) * dmp + bd, oo = (size_t)y0 * op;
+    float *br = r + oo, *bg = g + oo, *bb = b + oo;
+    if ((rc = art_scale_convert_crop_dev(ctx, W, Hb, dm[0] + off, dm[1] + off, dm[2] + off, dmp, br, bg, bb, op, p->mul, p->doClip, p->cam2work))) return rc;
+    ctx->band.active = true;
+    ctx->band.own0 = plan->own_begin - y0; ctx->band.own1 = plan->own_end - y0; ctx->band.H_full = H;
+    rc = ART_HP_OK;
+    if (p->denoise)
+        rc = art_denoise_stage_dev(ctx, br, bg, bb, op, W, Hb, p->denoise, 0, 0, p->guidedChromaRadius, p->denoise_expcomp, p->cam2work, p->wprof);
+    ctx->band.active = false;
+    if (rc) return rc;
+    const bool sharpen = p->sharpen && p->sharpen->amount >= 1;
+    if (p->chain && sharpen && p->chain->exposure_enabled) {
+        art_hp_chain_params e{};
+        e.exposure_enabled = 1; e.exp_scale = p->chain->exp_scale; e.black = p->chain->black;
+        if ((rc = art_chain_dev(ctx, W, Hb, br, bg, bb, op, &e))) return rc;
+    }
+    if (sharpen) {
+        if (!p->wprof) return ctx->fail(ART_HP_ERR_INVALID, "sharpening needs wprof");
+        art_hp_sharpen_params sp = *p->sharpen;
+        if ((rc = art_usm_dev(ctx, br, bg, bb, op, W, Hb, &sp, p->wprof))) return rc;
+    }
+    if (p->chain) {
+        art_hp_chain_params c = *p->chain;
+        if (sharpen) c.exposure_enabled = 0;
+        if ((rc = art_chain_dev(ctx, W, Hb, br, bg, bb, op, &c))) return rc;
+    }
+    return ART_HP_OK;
+}

@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(SV_THREADS) k_shrink_v(const __grid_constant__
 }
 
 // MadRgb of several subbands at once: grid.y = subband
-struct MadBatch { const float* band[SH_MAXJOBS]; int n[SH_MAXJOBS]; float* out[SH_MAXJOBS]; int njobs, square; };
+struct MadBatch { const float* band[SH_MAXJOBS]; int n[SH_MAXJOBS]; int w[SH_MAXJOBS]; float* out[SH_MAXJOBS]; int njobs, square; };      // w = row length of the subband
 __global__ void __launch_bounds__(512) k_mad_hist_all(const __grid_constant__ MadBatch mb, int* __restrict__ histo)
 {
     __shared__ int hot[HOT];
@@ -374,11 +374,29 @@ int mad_batch(art_hp_ctx* ctx, const MadBatch& mb, int* histo)
     if (mb.njobs == 0) return ART_HP_OK;
     cudaStream_t st = ctx->stream;
     ART_CUDA(ctx, cudaMemsetAsync(histo, 0, (size_t)mb.njobs * NB * sizeof(int), st));
+    // One frame across GPUs: MadRgb is a statistic of the whole subband.  The int32 histograms are exact, so each rank counts the
+    // coefficient rows it owns, the histograms are summed over the ranks and every rank takes the median of the frame's counts:
+    // the same bits as the single-GPU frame wherever the coefficients are.  (Subbands are decimated once: subband row = image row / 2.)
+    MadBatch hist = mb, med = mb;
+    if (ctx->band.active) {
+        for (int j = 0; j < mb.njobs; ++j) {
+            const int r0 = ctx->band.own0 >> 1, r1 = (ctx->band.own1 + 1) >> 1;
+            hist.band[j] = mb.band[j] + (size_t)r0 * mb.w[j];
+            hist.n[j] = (r1 - r0) * mb.w[j];
+            med.n[j] = ((ctx->band.H_full + 1) >> 1) * mb.w[j];
+        }
+    }
     art_prof_begin(ctx, "k_mad_hist_all");
-    k_mad_hist_all<<<dim3(std::max(1, 148 * 4 / mb.njobs), mb.njobs), 512, 0, st>>>(mb, histo);
+    k_mad_hist_all<<<dim3(std::max(1, 148 * 4 / mb.njobs), mb.njobs), 512, 0, st>>>(hist, histo);
     art_prof_end(ctx);
+    if (ctx->band.active) {
+        art_prof_begin(ctx, "allreduce_mad_hist");
+        const int arc = art_allreduce_i32(ctx, histo, (size_t)mb.njobs * NB);
+        art_prof_end(ctx);
+        if (arc) return arc;
+    }
     art_prof_begin(ctx, "k_mad_median_all");
-    k_mad_median_all<<<mb.njobs, 1024, 0, st>>>(mb, histo);
+    k_mad_median_all<<<mb.njobs, 1024, 0, st>>>(med, histo);
     art_prof_end(ctx);
     ctx->launches += 2;
     ART_CUDA(ctx, cudaGetLastError());
@@ -437,7 +455,7 @@ int art_hp_wavelet_mad_dev(art_hp_ctx* ctx, const art_hp_wavelet* w, float* d_ma
     mb.square = 1;
     for (int l = 0; l < w->nlev; ++l)
         for (int d = 1; d < 4; ++d) {
-            mb.band[mb.njobs] = w->lev[l].band[d]; mb.n[mb.njobs] = w->lev[l].w2 * w->lev[l].h2; mb.out[mb.njobs] = d_madL + 3 * l + (d - 1);
+            mb.band[mb.njobs] = w->lev[l].band[d]; mb.n[mb.njobs] = w->lev[l].w2 * w->lev[l].h2; mb.w[mb.njobs] = w->lev[l].w2; mb.out[mb.njobs] = d_madL + 3 * l + (d - 1);
             mb.njobs++;
         }
     return mad_batch(ctx, mb, bs.histo);
@@ -512,7 +530,7 @@ int art_wavelet_denoise_AB(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wav
     for (int l = 0; l < wL->nlev; ++l)
         for (int d = 1; d < 4; ++d) {
             const WLevel& L = wab->lev[l];
-            mb.band[mb.njobs] = L.band[d]; mb.n[mb.njobs] = L.w2 * L.h2; mb.out[mb.njobs] = madab + mb.njobs;
+            mb.band[mb.njobs] = L.band[d]; mb.n[mb.njobs] = L.w2 * L.h2; mb.w[mb.njobs] = L.w2; mb.out[mb.njobs] = madab + mb.njobs;
             mb.njobs++;
         }
     if ((rc = mad_batch(ctx, mb, bs.histo))) return rc;

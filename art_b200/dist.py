@@ -4,8 +4,9 @@ Two ways to use N GPUs:
   * replicas -- independent frames, one per rank at a time (the batch queue): `frames_for_rank`;
   * row bands -- one frame cut on the method's reference tile grid: `row_bands` gives every rank its
     output rows and the raw rows it must hold (band + halo + the mirror rows at the frame edges).
-No tensor ever moves between ranks for demosaic; torch.distributed is used only for the barrier and
-for reducing the timing (`max_over_ranks`).
+  * one developed frame per box -- `frame_bands` + HotPath.band_plan / develop_band_dev: every rank develops a band (+ halo) of the
+    same frame; the only exchange is the int32 all-reduce of the wavelet subbands' MAD histograms (NCCL, inside the library).
+torch.distributed is used for the barrier, for reducing the timing (`max_over_ranks`) and to hand the NCCL unique id to the ranks.
 """
 from . import api
 
@@ -51,6 +52,15 @@ def row_bands(H, world, method):
             lo = min(lo, max(0, H - 17))
         bands.append({"out": (r0, r1), "need": (lo, hi)})
     return bands
+
+
+def frame_bands(H, world, align=2):
+    """One developed frame of H rows cut into `world` contiguous bands of owned rows, boundaries on multiples of `align`
+    (2: subband rows of the once-decimated wavelet levels must not straddle two ranks).  Returns [(begin, end)] per rank; ranks beyond the
+    number of cells get an empty band (begin == end)."""
+    cells = max(1, H // align)
+    cuts = [min(H, (cells * k // world) * align) for k in range(world)] + [H]
+    return [(cuts[k], cuts[k + 1]) for k in range(world)]
 
 
 def max_over_ranks(value, dist=None, device="cpu"):

@@ -13,6 +13,10 @@ A "step" is one pass of the hot path over one frame.  Workloads (BASELINE.json `
   amaze    configs[1] alone (demosaic only);  rcd  the configs[0]-style case
 With N>1 (torchrun, one rank per GPU) every rank develops its own frames -- frames are independent objects (the batch queue), so there is no
 data-path collective ("scaling": "weak"); torch.distributed carries the barrier and the max-over-ranks of the timed region only.
+`--split frame --workload c2` (configs[2]) instead cuts ONE frame into row bands, one per rank (art_hp_develop_band_dev): each rank demosaics its
+band on the frame's tile grid, carries `--halo` redundant rows either side through RGB_denoise and the unsharp mask, and the ranks exchange one thing,
+the int32 MAD histograms of the wavelet subbands (ncclAllReduce inside the library, three per frame): "scaling": "strong", value = the frame's
+pixels / the slowest rank's time.
 
 Printed JSON (rank 0, one line): the driver contract plus
   roofline     dominant kernel: algorithmic bytes / CUDA-event time, against MEASURED_PEAKS.json
@@ -69,6 +73,10 @@ def parse():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--ref-budget", type=float, default=150.0, help="reference arm: seconds of CPU work the timed steps may take")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split", default=os.environ.get("ART_BENCH_SPLIT", "replicas"), choices=["replicas", "frame"],
+                    help="N > 1: replicas = one frame per rank (weak scaling, the default); frame = ONE frame cut into row bands across the ranks "
+                         "(strong scaling, configs[2]: ncclAllReduce of the MAD histograms inside the library; workload c2)")
+    ap.add_argument("--halo", type=int, default=200, help="--split frame: rows of redundant halo either side of a band")
     a = ap.parse_args()
     if a.method:
         a.workload = a.method
@@ -451,6 +459,152 @@ def reference_arm(args, config, W, H):
     return 0
 
 
+def frame_split_arm(args, hp, dist, rank, world, local, W, H, wl, config, placement):
+    """ONE frame across the ranks (configs[2]).  Every rank holds the same synthetic frame on the host, uploads the raw rows its band plan names,
+    develops its band and downloads the rows it owns.  Device-resident `value`: band kernels only; `e2e`: upload + kernels + download per step."""
+    import numpy as np
+    import torch
+    import art_b200
+    from art_b200 import dist as adist
+    if wl != "c2":
+        print(json.dumps({"error": "--split frame is configs[2]: use --workload c2 (Fattal's solve and NL-means are not split)"}))
+        return 2
+    params = develop_params(art_b200, wl)
+    Ho, Wo = params.out_shape(H, W)
+    own = adist.frame_bands(Ho, world)[rank]
+    plan = hp.band_plan(params, W, H, own[0], own[1], args.halo)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    hp.set_stream(stream.cuda_stream)
+    # the library's own communicator: rank 0 makes the id, torch.distributed hands it round
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(hp.comm_unique_id()), dtype=torch.uint8))
+    if dist is not None:
+        dist.broadcast(idt, 0)
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)                      # NCCL's banner goes to stderr, stdout carries the ONE JSON line
+    try:
+        hp.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    raw = make_raw(wl, W, H, 1002)     # the SAME frame on every rank
+    pitch = (W + 31) // 32 * 32
+    opitch = (Wo + 31) // 32 * 32
+    h_raw = torch.from_numpy(raw).pin_memory()
+    d_raw = torch.full((H, pitch), float("nan"), dtype=torch.float32, device="cuda")
+    d_out = [torch.zeros((Ho, opitch), dtype=torch.float32, device="cuda") for _ in range(3)]
+    h_out = [torch.zeros((own[1] - own[0], Wo), dtype=torch.float32).pin_memory() for _ in range(3)]
+
+    def upload():
+        d_raw[plan.raw_begin:plan.raw_end, :W].copy_(h_raw[plan.raw_begin:plan.raw_end], non_blocking=True)
+
+    def step_dev():
+        hp.develop_band_dev(params, W, H, d_raw.data_ptr(), pitch, d_out[0].data_ptr(), d_out[1].data_ptr(), d_out[2].data_ptr(), opitch, plan)
+
+    def download():
+        for c in range(3):
+            h_out[c].copy_(d_out[c][own[0]:own[1], :Wo], non_blocking=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ms(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    upload()
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    l0 = hp.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    ms_per_step = max_ms(e0.elapsed_time(e1)) / args.steps
+    launches = hp.launch_count() - l0
+    # e2e: upload of the band's raw rows, kernels, download of the owned rows, every step, host wall clock
+    for _ in range(2):
+        upload(); step_dev(); download()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        upload(); step_dev(); download()
+        torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max_ms(wall) / args.steps
+    clocks = sampler.stop() if sampler else None
+    # check: the owned rows against this rank's own single-GPU development of the whole frame
+    whole = [torch.zeros((Ho, opitch), dtype=torch.float32, device="cuda") for _ in range(3)]
+    d_full = torch.zeros((H, pitch), dtype=torch.float32, device="cuda")
+    d_full[:, :W] = torch.from_numpy(raw).cuda()
+    hp.develop_dev(params, W, H, d_full.data_ptr(), pitch, whole[0].data_ptr(), whole[1].data_ptr(), whole[2].data_ptr(), opitch)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for c in range(3):
+        a, b = d_out[c][own[0]:own[1], :Wo], whole[c][own[0]:own[1], :Wo]
+        worst = max(worst, float(((a - b).abs() / (b.abs() + 65.535)).max().item()))      # relative, floored at 0.1 % of the 0..65535 scale
+    worst = max_ms(worst)
+    # per-kernel device time of the band; every rank runs the pass (the all-reduces inside the step must match up), rank 0's is reported
+    hp.profile_enable(True)
+    for _ in range(args.steps):
+        step_dev()
+    prof = hp.profile_collect()
+    hp.profile_enable(False)
+    kern = {k: v[0] / args.steps for k, v in prof.items()}
+    barrier()
+    hp.comm_destroy()
+    if rank == 0:
+        peak, how = peaks()
+        rows = plan.band_end - plan.band_begin
+        step_bytes = 16 + 333 + 80 + 110
+        step_achieved = step_bytes * W * H / (ms_per_step * 1e-3) / 1e9
+        top = max(kern, key=lambda k: kern[k])
+        config = dict(config)
+        config["parallelism"] = ("row bands x%d of ONE frame: %d owned + up to %d halo rows per rank, demosaic on the frame's tile grid; collective = ncclAllReduce(int32, sum) "
+                                 "of the wavelet subbands' MAD histograms (3 x 15 x 65536 counters per frame), inside the library" % (world, own[1] - own[0], 2 * args.halo))
+        out = {"metric": "Mpixel/s", "value": W * H / (ms_per_step * 1e-3) / 1e6, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+               "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic", "config": config,
+               "e2e": {"value": W * H / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": (plan.raw_end - plan.raw_begin) * W * 4,
+                       "d2h_bytes_per_step": (own[1] - own[0]) * Wo * 12, "steps": args.steps, "host_memory": "pinned", "placement": placement,
+                       "call": "per rank and step: upload of the band's raw rows, art_hp_develop_band_dev, download of the owned rows (float planes); bytes are rank 0's"},
+               "gpu_launches": int(launches),
+               "split": {"rank0_plan": repr(plan), "band_rows_rank0": rows, "owned_rows_rank0": own[1] - own[0],
+                         "redundant_rows_fraction_rank0": 1.0 - (own[1] - own[0]) / rows,
+                         "max_relative_difference_from_single_gpu_frame": worst,
+                         "note": "difference measured on every rank's owned rows against its own art_hp_develop_dev of the whole frame, max over ranks; "
+                                 "|a - b| / (|b| + 0.1 % of full scale)"},
+               "roofline": {"bound": "hbm", "kernel": top, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": how,
+                            "kernel_ms": kern[top], "note": "rank 0's band; see the single-GPU line of the same workload for per-kernel roofline fractions"},
+               "step_roofline": {"achieved": step_achieved, "frac": step_achieved / peak, "unit": "GB/s", "bytes_per_pixel": step_bytes,
+                                 "note": "whole frame over all ranks: SURVEY.md 8(d) ideal-fusion bytes per pixel / ms_per_step / n_gpus peaks", "n_gpus": world},
+               "kernels_ms_per_step": {k: round(v, 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1])},
+               "clocks": clocks}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -498,6 +652,8 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     hp = art_b200.HotPath(local)
+    if args.split == "frame":
+        return frame_split_arm(args, hp, dist, rank, world, local, W, H, wl, config, placement)
     method = art_b200.BAYER_RCD if args.method == "rcd" else art_b200.BAYER_AMAZE
     raw = make_raw(wl, W, H, 1002 + rank)
 

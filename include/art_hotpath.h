@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ART_HP_ABI_VERSION 2
+#define ART_HP_ABI_VERSION 3
 
 typedef enum art_hp_status {
     ART_HP_OK = 0,
@@ -547,6 +547,47 @@ int art_hp_develop_submit_packed(art_hp_ctx* ctx, const art_hp_develop_params* p
                                  int bps, int isFloat, void* out, size_t out_stride_bytes);
 int art_hp_develop_wait(art_hp_ctx* ctx);
 int art_hp_develop_pending(const art_hp_ctx* ctx);
+
+/* ---- ABI version 3: ONE frame across the GPUs of a box (row bands; SURVEY.md section 8e, BASELINE.json configs[2]) --------------
+ *
+ * Every rank (one process and one context per GPU) develops a band of rows of the same frame.  The reference has no
+ * counterpart: its frame lives in one address space and OpenMP threads share it.  What a band needs from the rest of the frame:
+ *   - demosaic: raw rows within the method's tile halo (art_hp_band_halo) -- the band is demosaiced on the frame's own
+ *     tile grid (art_hp_demosaic_bayer_rows_dev), bit-identical to the whole frame;
+ *   - getImage gains / matrix, colour chain: nothing (per pixel);
+ *   - RGB_denoise: MadRgb of every wavelet subband is a whole-frame statistic -- each rank histograms the coefficient rows
+ *     it owns and the int32 histograms are SUMMED OVER THE RANKS (one ncclAllReduce per decomposition, 15 x 65536
+ *     counters), so every rank shrinks with the frame's MAD; everything else in the stage (wavelet filters, box blurs,
+ *     64 x 64 DCT blocks anchored at the frame origin, unsharp mask) has a bounded reach, and the band carries `halo`
+ *     extra rows either side that are computed and thrown away.  The band's first row is a multiple of 50 (2: the
+ *     decimated wavelet level; 25: the DCT block grid), so the band's grids coincide with the frame's.
+ * The result on the owned rows equals the single-GPU frame up to the rounding of the box blurs' running sums, which restart
+ * at the band's first row (~1e-7 relative; tests hold 1e-5) -- within north_star's 1e-4, not bit-identical.
+ * Not available on a band (ART_HP_ERR_UNSUPPORTED): Fattal tone mapping (a global 2-D transform), the automatic chroma
+ * estimator (crops of the whole frame), NL-means, X-Trans, RCD.
+ */
+typedef struct art_hp_band_plan {
+    int own_begin, own_end;      /* rows of the developed frame (after the border crop) this rank delivers; even or the frame's end */
+    int band_begin, band_end;    /* rows it computes: own rows + halo, band_begin a multiple of 50, clipped to the frame */
+    int dm_begin, dm_end;        /* rows of the raw frame it demosaics (on the method's tile grid) */
+    int raw_begin, raw_end;      /* rows of the raw frame it reads (dm rows + the demosaic halo; at the frame's top / bottom also the
+                                    rows the demosaicer mirrors) */
+} art_hp_band_plan;
+/* rows for a rank that owns [own_begin, own_end) of the developed frame of a W x H raw frame; halo >= 150 (200 is a good value) */
+int art_hp_band_plan_rows(const art_hp_develop_params* params, int W, int H, int own_begin, int own_end, int halo, art_hp_band_plan* plan);
+/* The collective: sum an int32 device buffer in place over the ranks that share the frame, ordered on `cuda_stream`.  Either
+ * art_hp_comm_init (ncclAllReduce on the context's stream; libnccl.so.2 is loaded on first use) or a caller's own function. */
+typedef int (*art_hp_allreduce_fn)(void* user, int* d_buf, size_t count, void* cuda_stream);
+int art_hp_set_allreduce(art_hp_ctx* ctx, art_hp_allreduce_fn fn, void* user);
+int art_hp_comm_unique_id(unsigned char id[128]);                                /* rank 0 makes it, every rank gets a copy */
+int art_hp_comm_init(art_hp_ctx* ctx, const unsigned char id[128], int rank, int nranks);
+int art_hp_comm_destroy(art_hp_ctx* ctx);
+/* d_raw / d_red / ... are the addresses of ROW 0 of the raw frame and of the developed frame (as for
+ * art_hp_demosaic_bayer_rows_dev); raw rows [raw_begin, raw_end) must be valid, rows
+ * [band_begin, band_end) of the outputs are written and rows [own_begin, own_end) are the result.  Every rank of the
+ * communicator must make the call (the all-reduces match up). */
+int art_hp_develop_band_dev(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, const float* d_raw, size_t raw_pitch,
+                            float* d_red, float* d_green, float* d_blue, size_t out_pitch, const art_hp_band_plan* plan);
 
 #ifdef __cplusplus
 }

@@ -84,3 +84,74 @@ def test_row_bands_partition(H, world, method):
     for b in bands:
         if b["out"][1] > b["out"][0]:
             assert 0 <= b["need"][0] <= b["out"][0] and b["out"][1] <= b["need"][1] <= H
+
+
+# ---- one frame across GPUs: frame bands, band plans, and the MAD histogram all-reduce (ABI version 3) ----
+def _band_params():
+    import numpy as np
+    from art_b200.api import DenoiseParams, DevelopParams
+    from art_b200 import synth
+    return DevelopParams(method=art_b200.BAYER_AMAZE, filters=synth.RGGB, mul=(1.9, 1.0, 1.6), do_clip=True, cam2work=np.eye(3),
+                         denoise=DenoiseParams(luminance=30, luminanceDetail=50, chrominance=15), fattal=None, wprof=np.eye(3))
+
+
+@pytest.mark.parametrize("H", [600, 1600, 5456, 8184])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_frame_bands_and_plans(H, world):
+    from art_b200 import api
+    params = _band_params()
+    Hr, Wr = H + 8, 648                     # raw frame: the developed frame + the 4-pixel border either side
+    bands = adist.frame_bands(H, world)
+    assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == H
+    for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
+        assert a1 == b0 and a1 % 2 == 0
+    for b0, b1 in bands:
+        if b1 <= b0:
+            continue
+        p = api.band_plan(params, Wr, Hr, b0, b1, 200)
+        assert (p.own_begin, p.own_end) == (b0, b1)
+        assert p.band_begin % 50 == 0 and 0 <= p.band_begin <= b0 and b1 <= p.band_end <= H
+        assert p.band_begin == 0 or b0 - p.band_begin >= 200          # at least the halo, rounded down to the block / decimation grid
+        assert p.band_end == H or p.band_end - b1 == 200
+        assert p.dm_begin % 128 == 0 and (p.dm_end % 128 == 0 or p.dm_end == Hr)            # AMaZE's tile grid
+        assert p.dm_begin <= p.band_begin + 4 and p.dm_end >= p.band_end + 4
+        assert 0 <= p.raw_begin <= max(0, p.dm_begin - 16) and min(Hr, p.dm_end + 16) <= p.raw_end <= Hr
+    with pytest.raises(art_b200.HotPathError):
+        api.band_plan(params, Wr, Hr, 1, H, 200)                      # an odd first row would split a subband row between two ranks
+    with pytest.raises(art_b200.HotPathError):
+        api.band_plan(params, Wr, Hr, 0, H, 10)                       # a halo shorter than the stages' reach
+
+
+def _mad_worker(rank, world, port, q):
+    """MadRgb over ranks: int32 histograms of the owned coefficient rows, summed with all_reduce, give the whole subband's median bin."""
+    import numpy as np
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        H, W = 1000, 37
+        coeff = (rng.standard_normal((H // 2, W)) * 300).astype(np.float32)        # a once-decimated subband of the frame, same on every rank
+        b0, b1 = adist.frame_bands(H, world)[rank]
+        own = coeff[b0 // 2:(b1 + 1) // 2]
+        v = np.minimum(np.abs(own.astype(np.int32)), 65535)
+        h = torch.from_numpy(np.bincount(v.ravel(), minlength=65536).astype(np.int32))
+        dist.all_reduce(h)
+        whole = np.bincount(np.minimum(np.abs(coeff.astype(np.int32)), 65535).ravel(), minlength=65536)
+        q.put((rank, bool((h.numpy() == whole).all()), int(h.sum()) == coeff.size))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_mad_histograms():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(same and count for _, same, count in res)
