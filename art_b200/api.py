@@ -221,7 +221,8 @@ class _DevelopParamsC(ctypes.Structure):
                 ("fattal_satcontrol", ctypes.c_int), ("wprof", ctypes.POINTER(ctypes.c_double)),
                 ("sharpen", ctypes.c_void_p), ("chain", ctypes.c_void_p),
                 ("xtrans", ctypes.POINTER(ctypes.c_int)), ("rgb_cam", ctypes.POINTER(ctypes.c_float)),
-                ("full_frame", ctypes.c_int), ("guidedChromaRadius", ctypes.c_int), ("denoise_expcomp", ctypes.c_double)]
+                ("full_frame", ctypes.c_int), ("guidedChromaRadius", ctypes.c_int), ("denoise_expcomp", ctypes.c_double),
+                ("tran", ctypes.c_int), ("hr_blend", ctypes.c_int), ("hlmax", ctypes.c_float * 3)]
 
 
 class _SharpenParamsC(ctypes.Structure):
@@ -345,14 +346,14 @@ class DevelopParams:
 
     def __init__(self, method=0, filters=0x94949494, initial_gain=1.0, border=4, mul=(1.0, 1.0, 1.0), do_clip=True, cam2work=None,
                  denoise=None, nl_strength=0, nl_detail=80, fattal=None, wprof=None, sharpen=None, chain=None, xtrans=None, rgb_cam=None,
-                 full_frame=False, guided_chroma_radius=0, denoise_expcomp=0.0):
+                 full_frame=False, guided_chroma_radius=0, denoise_expcomp=0.0, tran=0, hr_blend=False, hlmax=(65535.0, 65535.0, 65535.0)):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
     def out_shape(self, H, W):
         """(rows, columns) of the developed planes for an (H, W) raw frame"""
         b = 0 if self.full_frame else (7 if self.method in (2, 3) else max(int(self.border), 0))
-        return H - 2 * b, W - 2 * b
+        return (W - 2 * b, H - 2 * b) if int(self.tran) & 1 else (H - 2 * b, W - 2 * b)       # TR_R90 / TR_R270 turn the frame
 
     def c_struct(self):
         c = _DevelopParamsC()
@@ -374,6 +375,8 @@ class DevelopParams:
             c.denoise = ctypes.pointer(d)
         c.nlStrength, c.nlDetail = int(self.nl_strength), int(self.nl_detail)
         c.full_frame, c.guidedChromaRadius, c.denoise_expcomp = int(bool(self.full_frame)), int(self.guided_chroma_radius), float(self.denoise_expcomp)
+        c.tran, c.hr_blend = int(self.tran), int(bool(self.hr_blend))
+        c.hlmax = (ctypes.c_float * 3)(*[float(x) for x in self.hlmax])
         if self.fattal is not None:
             thr, amt, sat = self.fattal
             c.fattal_enabled, c.fattal_threshold, c.fattal_amount, c.fattal_satcontrol = 1, int(thr), int(amt), int(bool(sat))

@@ -1049,6 +1049,8 @@ static int check_develop(art_hp_ctx* ctx, const art_hp_develop_params* p, int W,
         if (Wo < 24 || Ho < 24) return ctx->fail(ART_HP_ERR_INVALID, "frame %dx%d is too small for a border of %d", W, H, bd);
     }
     if (p->guidedChromaRadius < 0) return ctx->fail(ART_HP_ERR_INVALID, "guidedChromaRadius %d", p->guidedChromaRadius);
+    if (p->tran < 0 || p->tran > 15) return ctx->fail(ART_HP_ERR_INVALID, "tran %d is not a combination of TR_R90 / R180 / R270, TR_VFLIP, TR_HFLIP", p->tran);
+    if (p->hr_blend && !(p->hlmax[0] > 0 && p->hlmax[1] > 0 && p->hlmax[2] > 0)) return ctx->fail(ART_HP_ERR_INVALID, "hr_blend needs positive hlmax");
     if ((p->denoise || p->fattal_enabled) && !p->wprof) return ctx->fail(ART_HP_ERR_INVALID, "wprof is required by denoise and tone mapping");
     if (p->denoise) { int rc = check_denoise_params(ctx, p->denoise, p->wprof, true); if (rc) return rc; }
     return ART_HP_OK;

@@ -154,7 +154,8 @@ int art_xtrans_dev(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, con
 int art_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch,
                           const float mul[3], int doClip, const double* mat);
 int art_scale_convert_crop_dev(art_hp_ctx* ctx, int W, int H, const float* sr, const float* sg, const float* sb, size_t sp,
-                               float* r, float* g, float* b, size_t pitch, const float mul[3], int doClip, const double* mat);
+                               float* r, float* g, float* b, size_t pitch, const float mul[3], int doClip, const double* mat,
+                               int tran = 0, int hr_blend = 0, const float* hlmax = nullptr);
 // denoise::denoiseGuidedSmoothing (smoothing.cu), planes in place
 int art_guided_smoothing_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const double* ws9, int guidedChromaRadius, double scale);
 // scaleColors (Bayer): in place; d_chmax_bits = 3 device ints receiving the float bit patterns of chmax[0..2]

@@ -139,6 +139,7 @@ void art_develop_geometry(const art_hp_develop_params* p, int W, int H, int* b, 
     const bool xt = p->method == ART_HP_XTRANS_3PASS || p->method == ART_HP_XTRANS_1PASS;
     const int bd = p->full_frame ? 0 : (xt ? 7 : (p->border > 0 ? p->border : 0));
     *b = bd; *Wo = W - 2 * bd; *Ho = H - 2 * bd;
+    if (p->tran & 1) std::swap(*Wo, *Ho);          // TR_R90 / TR_R270: the developed frame is turned
 }
 
 int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr, int Hr, const float* raw, size_t rp,
@@ -146,10 +147,11 @@ int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr, int
 {
     int rc, bd, W, H;
     art_develop_geometry(p, Wr, Hr, &bd, &W, &H);
-    // with a border the demosaicer writes context-owned W x H planes and getImage's stage crops them into the caller's planes
+    const bool oop = bd || p->tran || p->hr_blend;        // getImage's stage runs out of place: crop, coarse transform, highlight reconstruction
+    // then the demosaicer writes context-owned planes and getImage's stage crops / turns them into the caller's planes
     float* dm[3] = {r, g, b};
     size_t dmp = op;
-    if (bd) {
+    if (oop) {
         dmp = round_up((size_t)Wr, 32);
         for (int c = 0; c < 3; ++c) {
             if ((rc = art_reserve(ctx, ctx->d_dm[c], dmp * (size_t)Hr * sizeof(float)))) return rc;
@@ -168,6 +170,7 @@ int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr, int
     if (dn && dn->chrominanceMethod == 1) {
         float est[3];
         const size_t off0 = (size_t)bd * dmp + bd;
+        if (p->tran) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "the automatic chroma estimator with a coarse transform: its crops are cut from the turned frame (pass the estimate, chrominanceMethod 0)");
         if ((rc = art_denoise_auto_chroma_dev(ctx, dm[0] + off0, dm[1] + off0, dm[2] + off0, dmp, W, H, p->mul, p->doClip, p->cam2work, p->wprof,
                                               dn->gamma, dn->aggressive, est, nullptr))) return rc;
         dn_resolved = *dn;
@@ -178,9 +181,11 @@ int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr, int
         dn_resolved.chrominanceMethod = 0;
         dn = &dn_resolved;
     }
-    if (bd) {
+    if (oop) {
         const size_t off = (size_t)bd * dmp + bd;
-        rc = art_scale_convert_crop_dev(ctx, W, H, dm[0] + off, dm[1] + off, dm[2] + off, dmp, r, g, b, op, p->mul, p->doClip, p->cam2work);
+        const int sw = Wr - 2 * bd, sh = Hr - 2 * bd;       // the source lines (imwidth x imheight); W x H is the turned frame
+        rc = art_scale_convert_crop_dev(ctx, sw, sh, dm[0] + off, dm[1] + off, dm[2] + off, dmp, r, g, b, op, p->mul, p->doClip, p->cam2work,
+                                        p->tran, p->hr_blend, p->hlmax);
     } else rc = art_scale_convert_dev(ctx, W, H, r, g, b, op, p->mul, p->doClip, p->cam2work);
     if (rc) return rc;
     if (dn) {
@@ -241,6 +246,7 @@ int art_develop_band_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr
     int rc, bd, W, H;
     art_develop_geometry(p, Wr, Hr, &bd, &W, &H);
     if (p->method != ART_HP_BAYER_AMAZE && p->method != ART_HP_BAYER_RCD) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: Bayer methods only");
+    if (p->tran) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: the coarse transform is not split (rows of the turned frame are columns of the raw frame)");
     if (p->fattal_enabled) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: Fattal's Poisson solve is a transform of the whole frame");
     if (p->denoise && p->denoise->chrominanceMethod == 1) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: the automatic chroma estimator measures crops of the whole frame");
     if (p->nlStrength) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: NL-means is not split");
@@ -271,7 +277,8 @@ int art_develop_band_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr
     const int y0 = plan->band_begin, Hb = plan->band_end - plan->band_begin;
     const size_t off = (size_t)(y0 + bd) * dmp + bd, oo = (size_t)y0 * op;
     float *br = r + oo, *bg = g + oo, *bb = b + oo;
-    if ((rc = art_scale_convert_crop_dev(ctx, W, Hb, dm[0] + off, dm[1] + off, dm[2] + off, dmp, br, bg, bb, op, p->mul, p->doClip, p->cam2work))) return rc;
+    if ((rc = art_scale_convert_crop_dev(ctx, W, Hb, dm[0] + off, dm[1] + off, dm[2] + off, dmp, br, bg, bb, op, p->mul, p->doClip, p->cam2work,
+                                         0, p->hr_blend, p->hlmax))) return rc;
     ctx->band.active = true;
     ctx->band.own0 = plan->own_begin - y0; ctx->band.own1 = plan->own_end - y0; ctx->band.H_full = H;
     rc = ART_HP_OK;

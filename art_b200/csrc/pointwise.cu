@@ -73,18 +73,86 @@ __global__ void __launch_bounds__(256) k_scale_convert_scalar(ScArgs a)
     }
 }
 
+// RawImageSource::HLRecovery_blend for one pixel (rawimagesource.cc L3613-3747; hlRecovery calls it with maxval 65535): clipped pixels get their
+// chroma (in an opponent space) scaled to the unclipped estimate's, faded in above half the lowest clip point.  The tail mixes float variables with
+// double literals, so those expressions are evaluated in double and rounded once, as in the reference.
+struct HlArgs { float clip[3], maxave, clippt, fixpt, maxval; };
+__device__ __forceinline__ float hl_min(float a, float b) { return b < a ? b : a; }      // rtengine::min
+__device__ __forceinline__ void hl_blend_pixel(const HlArgs& h, float& rin, float& gin, float& bin)
+{
+    const float trans[3][3] = {{1, 1, 1}, {1.7320508f, -1.7320508f, 0}, {-1, -1, 2}};
+    const float itrans[3][3] = {{1, 0.8660254f, -0.5f}, {1, -0.8660254f, -0.5f}, {1, 0, 1}};
+    float rgb[3] = {rin, gin, bin};
+    if (!(rgb[0] > h.clippt) && !(rgb[1] > h.clippt) && !(rgb[2] > h.clippt)) return;
+    float cam[2][3], lab[2][3], sum[2], lratio = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { lratio += hl_min(rgb[c], h.clip[c]); cam[0][c] = rgb[c]; cam[1][c] = hl_min(cam[0][c], h.maxval); }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            lab[i][c] = 0;
+#pragma unroll
+            for (int j = 0; j < 3; j++) lab[i][c] += trans[c][j] * cam[i][j];
+        }
+        sum[i] = 0;
+#pragma unroll
+        for (int c = 1; c < 3; c++) sum[i] += lab[i][c] * lab[i][c];
+    }
+    const float chratio = sqrtf(sum[1] / sum[0]);
+    lab[0][1] *= chratio; lab[0][2] *= chratio;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        cam[0][c] = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) cam[0][c] += itrans[c][j] * lab[0][j];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) rgb[c] = cam[0][c] / 3;
+    if (rin > h.fixpt) { const float t = (hl_min(h.clip[0], rin) - h.fixpt) / (h.clip[0] - h.fixpt), f = t * t; rin = hl_min(h.maxave, f * rgb[0] + (1 - f) * rin); }
+    if (gin > h.fixpt) { const float t = (hl_min(h.clip[1], gin) - h.fixpt) / (h.clip[1] - h.fixpt), f = t * t; gin = hl_min(h.maxave, f * rgb[1] + (1 - f) * gin); }
+    if (bin > h.fixpt) { const float t = (hl_min(h.clip[2], bin) - h.fixpt) / (h.clip[2] - h.fixpt), f = t * t; bin = hl_min(h.maxave, f * rgb[2] + (1 - f) * bin); }
+    const float tot = (rin + gin + bin);
+    lratio /= tot;
+    const float L = tot / 3 / lratio;
+    const float C = lratio * 1.732050808 * (rin - gin);
+    const float H = lratio * (2 * bin - rin - gin);
+    rin = L - H / 6.0 + C / 3.464101615;
+    gin = L - H / 6.0 - C / 3.464101615;
+    bin = L + H / 3.0;
+}
+
 // out-of-place form for art_hp_develop: getImage reads the demosaiced planes from (border, border) and writes a
-// (W - 2 border) x (H - 2 border) image (rawimagesource.cc L943-1025 with sx1 = sy1 = border, transformRect L664-700)
-struct ScCropArgs { const float *sr, *sg, *sb; size_t sp; ScArgs d; };
+// (W - 2 border) x (H - 2 border) image (rawimagesource.cc L943-1025 with sx1 = sy1 = border, transformRect L664-700): gains / clip, the optional
+// "Blend" highlight reconstruction, the coarse rotation of rotateLine (L57-87) and the mirrors (L1079-1086) as the store's address, then the matrix.
+// W / H below are the SOURCE line geometry (imwidth / imheight); a quarter turn writes an H-wide, W-high image.
+struct ScCropArgs { const float *sr, *sg, *sb; size_t sp; ScArgs d; int tran, hr; HlArgs hl; };
 __global__ void __launch_bounds__(256) k_scale_convert_crop(ScCropArgs c)
 {
     const ScArgs& a = c.d;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= a.W) return;
+    const int rot = c.tran & 3, ow = (rot & 1) ? a.H : a.W, oh = (rot & 1) ? a.W : a.H;
     for (int y = blockIdx.y; y < a.H; y += gridDim.y) {
-        const size_t i = (size_t)y * c.sp + x, o = (size_t)y * a.pitch + x;
+        const size_t i = (size_t)y * c.sp + x;
         float r = c.sr[i], g = c.sg[i], b = c.sb[i];
-        sc_pixel(a, r, g, b);
+        r *= a.mul[0]; g *= a.mul[1]; b *= a.mul[2];
+        if (a.do_clip) { r = clip65535(r); g = clip65535(g); b = clip65535(b); }
+        if (c.hr) hl_blend_pixel(c.hl, r, g, b);
+        if (a.do_mat) {
+            const double dr = r, dg = g, db = b;
+            const float nr = (float)(a.mat[0] * dr + a.mat[1] * dg + a.mat[2] * db);
+            const float ng = (float)(a.mat[3] * dr + a.mat[4] * dg + a.mat[5] * db);
+            const float nb = (float)(a.mat[6] * dr + a.mat[7] * dg + a.mat[8] * db);
+            r = nr; g = ng; b = nb;
+        }
+        int row = y, col = x;
+        if (rot == 2) { row = a.H - 1 - y; col = a.W - 1 - x; }
+        else if (rot == 1) { row = x; col = a.H - 1 - y; }
+        else if (rot == 3) { row = a.W - 1 - x; col = y; }
+        if (c.tran & 8) col = ow - 1 - col;
+        if (c.tran & 4) row = oh - 1 - row;
+        const size_t o = (size_t)row * a.pitch + col;
         a.r[o] = r; a.g[o] = g; a.b[o] = b;
     }
 }
@@ -174,10 +242,21 @@ int art_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, flo
 }
 
 int art_scale_convert_crop_dev(art_hp_ctx* ctx, int W, int H, const float* sr, const float* sg, const float* sb, size_t sp,
-                               float* r, float* g, float* b, size_t pitch, const float mul[3], int doClip, const double* mat)
+                               float* r, float* g, float* b, size_t pitch, const float mul[3], int doClip, const double* mat,
+                               int tran, int hr_blend, const float* hlmax)
 {
     ScCropArgs c;
     c.sr = sr; c.sg = sg; c.sb = sb; c.sp = sp;
+    c.tran = tran; c.hr = hr_blend && hlmax;
+    if (c.hr) {       // the line constants of HLRecovery_blend (L3623-3640), maxval = 65535
+        const float minpt = std::min(std::min(hlmax[0], hlmax[1]), hlmax[2]);
+        c.hl.maxave = (hlmax[0] + hlmax[1] + hlmax[2]) / 3;
+        for (int k = 0; k < 3; ++k) c.hl.clip[k] = std::min(c.hl.maxave, hlmax[k]);
+        const float clipthresh = 0.95, fixthresh = 0.5;
+        c.hl.maxval = 65535.0f;
+        c.hl.clippt = clipthresh * c.hl.maxval;
+        c.hl.fixpt = fixthresh * minpt;
+    } else c.hl = HlArgs{};
     ScArgs& a = c.d;
     a.r = r; a.g = g; a.b = b; a.pitch = pitch; a.W = W; a.H = H;
     for (int i = 0; i < 3; ++i) a.mul[i] = mul[i];

@@ -355,7 +355,7 @@ int art_hp_denoise_guided_smoothing_dev(art_hp_ctx* ctx, int W, int H, float* d_
 /* ---- gain / clip / camera->working colour space ------------------------- */
 /*
  * Replaces the per-pixel part of RawImageSource::getImage (rtengine/rawimagesource.cc L943-1025, full
- * resolution i.e. skip == 1, no flips: `x *= mul[c]; if (doClip) x = CLIP(x)`) followed by the matrix
+ * resolution i.e. skip == 1, no flips -- art_hp_develop's `tran` / `hr_blend` cover those: `x *= mul[c]; if (doClip) x = CLIP(x)`) followed by the matrix
  * branch of RawImageSource::colorSpaceConversion_ (L3184-3213): mat = workingSpaceInverse * camMatrix, row
  * major double[9], applied as (float)(m0*r + m1*g + m2*b) in double.  mat == NULL skips the matrix.
  * In place on three planes.  The caller computes mul[] (rm,gm,bm, L790-928) and mat exactly as the
@@ -521,6 +521,13 @@ typedef struct art_hp_develop_params {
     int guidedChromaRadius;     /* params->denoise.smoothingEnabled ? guidedChromaRadius : 0 (default 3): denoiseGuidedSmoothing between
                                    RGB_denoise and NLMeans; likewise nlStrength above is 0 unless smoothingEnabled */
     double denoise_expcomp;     /* params->exposure.enabled ? params->exposure.expcomp : 0; > 0 brackets the denoise stage */
+    /* ---- ABI version 3: the rest of RawImageSource::getImage (rtengine/rawimagesource.cc L781-1104, a standard CCD at skip == 1) ---- */
+    int tran;                   /* coarse transform: TR_R90 1 | TR_R180 2 | TR_R270 3, | TR_VFLIP 4, | TR_HFLIP 8 (iimage.h L34-40): transLineStandard ->
+                                   rotateLine per line (L57-95), then hflip / vflip (L1079-1086).  The quarter turns swap the output's width and height
+                                   (art_hp_develop_size reports it); every later stage sees the turned frame, as in the reference */
+    int hr_blend;               /* 1 = ExposureParams::HR_BLEND: hlRecovery -> HLRecovery_blend on every line after the gains (L1013-1015, L3613-3755);
+                                   the reference then leaves doClip off (L882) -- the caller passes doClip as it computed it */
+    float hlmax[3];             /* clmax[c] * {rm, gm, bm} (L916-918), used by hr_blend */
 } art_hp_develop_params;
 /* output size of art_hp_develop for a W x H raw frame: *out_w = W - 2 b, *out_h = H - 2 b, b = the border it crops (0 with full_frame) */
 int art_hp_develop_size(const art_hp_develop_params* params, int W, int H, int* out_w, int* out_h, int* border);

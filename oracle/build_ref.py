@@ -641,6 +641,68 @@ extern "C" int artref_hl_blend(float* rin, float* gin, float* bin, int width, fl
 """
 
 
+SHIM_GETIMAGE_TU = r"""
+// Shim TU hosting the geometry half of RawImageSource::getImage: rotateLine (the coarse rotation of transLineStandard) cut from rawimagesource.cc,
+// over a stand-in of PlanarPtr<float>.  Written here (not reference code): the stand-in, the line loop around it (getImage L943-1025 at skip == 1
+// with the reference's own CLIP and, through artref_hl_blend, its own HLRecovery_blend) and the two mirror loops of PlanarRGBData::hflip / vflip
+// (iimage.h L868-915: swap column j with width - 1 - j, row i with height - 1 - i).
+#include <cmath>
+#include <cstdlib>
+#include <algorithm>
+#include <vector>
+#include "rt_math.h"
+#define TR_NONE 0
+#define TR_R90 1
+#define TR_R180 2
+#define TR_R270 3
+#define TR_VFLIP 4
+#define TR_HFLIP 8
+#define TR_ROT 3
+namespace rtengine {
+template <class T> struct PlanarPtr {
+    T* base; long stride;
+    T& operator()(int row, int col) { return base[(long)row * stride + col]; }
+};
+}
+namespace {
+#include "getimage_rotateline.inc"
+}
+extern "C" int artref_hl_blend(float* rin, float* gin, float* bin, int width, float maxval, const float* hlmax);
+extern "C" int artref_getimage(int W, int H, const float* r, const float* g, const float* b, long stride, const float* mul, int doClip,
+                               int doHr, const float* hlmax, int tran, float* outr, float* outg, float* outb, long ostride)
+{
+    const bool swap = (tran & TR_ROT) == TR_R90 || (tran & TR_ROT) == TR_R270;
+    const int ow = swap ? H : W, oh = swap ? W : H;
+    rtengine::PlanarPtr<float> pr{outr, ostride}, pg{outg, ostride}, pb{outb, ostride};
+    std::vector<float> lr(W), lg(W), lb(W);
+    const float rm = mul[0], gm = mul[1], bm = mul[2];
+    for (int i = 0; i < H; ++i) {
+        for (int j = 0; j < W; ++j) {
+            float rtot = r[(long)i * stride + j], gtot = g[(long)i * stride + j], btot = b[(long)i * stride + j];
+            rtot *= rm; gtot *= gm; btot *= bm;
+            if (doClip) { rtot = rtengine::CLIP(rtot); gtot = rtengine::CLIP(gtot); btot = rtengine::CLIP(btot); }
+            lr[j] = rtot; lg[j] = gtot; lb[j] = btot;
+        }
+        if (doHr) artref_hl_blend(lr.data(), lg.data(), lb.data(), W, 65535.0f, hlmax);
+        rotateLine(lr.data(), pr, tran, i, W, H);
+        rotateLine(lg.data(), pg, tran, i, W, H);
+        rotateLine(lb.data(), pb, tran, i, W, H);
+    }
+    float* planes[3] = {outr, outg, outb};
+    for (int c = 0; c < 3; ++c) {
+        float* v = planes[c];
+        if (tran & TR_HFLIP)
+            for (int i = 0; i < oh; i++)
+                for (int j = 0; j < ow / 2; j++) std::swap(v[(long)i * ostride + j], v[(long)i * ostride + ow - 1 - j]);
+        if (tran & TR_VFLIP)
+            for (int i = 0; i < oh / 2; i++)
+                for (int j = 0; j < ow; j++) std::swap(v[(long)i * ostride + j], v[(long)(oh - 1 - i) * ostride + j]);
+    }
+    return 0;
+}
+"""
+
+
 SHIM_GUIDED_TU = r"""
 // Shim TU hosting the reference's boxblur.h body (its include block is replaced: StopWatch.h drags
 // settings.h -> procparams.h -> lcms2.h) and guidedFilter + calculate_subsampling cut from guidedfilter.cc.
@@ -1857,6 +1919,9 @@ def extract(det):
     open(os.path.join(sub, "hlblend_body.inc"), "w").write(
         cut_function(os.path.join(RT, "rawimagesource.cc"), r"^void RawImageSource::HLRecovery_blend\(float\* rin, float\* gin, float\* bin, int width, float maxval, float\* hlmax\)"))
     open(os.path.join(sub, "shim_hlblend.cc"), "w").write(SHIM_HLBLEND_TU)
+    open(os.path.join(sub, "getimage_rotateline.inc"), "w").write(
+        cut_function(os.path.join(RT, "rawimagesource.cc"), r"^void rotateLine \(const float\* const line, rtengine::PlanarPtr<float> &channel, const int tran, const int i, const int w, const int h\)"))
+    open(os.path.join(sub, "shim_getimage.cc"), "w").write(SHIM_GETIMAGE_TU)
     vg = os.path.join(RT, "vng4_demosaic_RT.cc")
     open(os.path.join(sub, "vng4_rowrb.inc"), "w").write(cut_function(vg, r"^inline void vng4interpolate_row_redblue \(const RawImage \*ri[^)]*\)"))
     open(os.path.join(sub, "vng4_body.inc"), "w").write(cut_function(vg, r"^void RawImageSource::vng4_demosaic \(const array2D<float> &rawData[^)]*\)"))
@@ -1900,7 +1965,7 @@ def build(det):
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     tus = ["shim.cc", "shim_gauss.cc", "shim_guided.cc", "shim_wavelet.cc", "shim_shrink.cc", "shim_nlmeans.cc", "shim_denoise.cc", "shim_fattal.cc",
            "shim_chain.cc", "shim_usm.cc", "shim_xtrans.cc", "shim_resize.cc", "shim_greeneq.cc", "shim_pack.cc", "shim_bilinear.cc", "shim_vng4.cc",
-           "shim_hlblend.cc", "shim_tone.cc"]
+           "shim_hlblend.cc", "shim_getimage.cc", "shim_tone.cc"]
     base = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-w", "-I", sub, "-I", RT] + (["-DARTREF_DET"] if det else [])
     from concurrent.futures import ThreadPoolExecutor
     objs = [os.path.join(sub, t[:-3] + ".o") for t in tus]

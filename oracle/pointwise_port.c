@@ -10,6 +10,7 @@
  */
 #include <math.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 static inline float clip65535_(float a)
 {   /* LIM(a, 0.f, 65535.f) = max(0, min(a, 65535)), rt_math.h L84-101 */
@@ -110,5 +111,44 @@ int artoracle_hl_blend(float* rin, float* gin, float* bin, int width, float maxv
         gin[col] = L - H / 6.0 - C / 3.464101615;
         bin[col] = L + H / 3.0;
     }
+    return 0;
+}
+
+/* RawImageSource::getImage at skip == 1 for a standard CCD (rawimagesource.cc L943-1025, L1079-1086): per source line the gains / clip, the optional
+ * "Blend" highlight reconstruction (hlRecovery, L1014), the coarse rotation of transLineStandard -> rotateLine (L57-87) into the output image, and after
+ * the loop the horizontal / vertical mirror (PlanarRGBData::hflip / vflip, iimage.h L868-915).  tran = TR_R90 1 | TR_R180 2 | TR_R270 3 | TR_VFLIP 4 | TR_HFLIP 8.
+ * Output: W x H, or H wide and W high for the quarter turns.  Pinned against the reference's own rotateLine / CLIP / HLRecovery_blend in
+ * tests/test_oracle_getimage.py. */
+int artoracle_getimage(int W, int H, const float* r, const float* g, const float* b, long stride, const float* mul, int doClip,
+                       int doHr, const float* hlmax, int tran, float* outr, float* outg, float* outb, long ostride)
+{
+    const int rot = tran & 3, swap = rot == 1 || rot == 3;
+    const int ow = swap ? H : W, oh = swap ? W : H;
+    float* lr = (float*)malloc(sizeof(float) * (size_t)W * 3);
+    if (!lr) return 1;
+    float *lg = lr + W, *lb = lg + W;
+    for (int i = 0; i < H; ++i) {
+        for (int j = 0; j < W; ++j) {
+            const size_t k = (size_t)i * stride + j;
+            float x = r[k] * mul[0], y = g[k] * mul[1], z = b[k] * mul[2];
+            if (doClip) { x = clip65535_(x); y = clip65535_(y); z = clip65535_(z); }
+            lr[j] = x; lg[j] = y; lb[j] = z;
+        }
+        if (doHr) artoracle_hl_blend(lr, lg, lb, W, 65535.0f, hlmax);
+        for (int j = 0; j < W; ++j) {
+            int row, col;
+            switch (rot) {
+            case 2: row = H - 1 - i; col = W - 1 - j; break;      /* channel(h - 1 - i, w - 1 - j) = line[j] */
+            case 1: row = j; col = H - 1 - i; break;              /* channel(j, h - 1 - i) */
+            case 3: row = W - 1 - j; col = i; break;              /* channel(w - 1 - j, i) */
+            default: row = i; col = j;
+            }
+            if (tran & 8) col = ow - 1 - col;                     /* hflip, then vflip: both are involutions on disjoint axes */
+            if (tran & 4) row = oh - 1 - row;
+            const size_t o = (size_t)row * ostride + col;
+            outr[o] = lr[j]; outg[o] = lg[j]; outb[o] = lb[j];
+        }
+    }
+    free(lr);
     return 0;
 }

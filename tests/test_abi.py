@@ -67,7 +67,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
                                                          "colorSpace", "noiseCCurve", "noiseCCurveSum", "wprof_inverse", "chrominanceAutoFactor"]),
         "art_hp_develop_params": (api._DevelopParamsC, ["method", "filters", "initialGain", "border", "mul", "doClip", "cam2work", "denoise",
                                                          "nlStrength", "fattal_enabled", "fattal_satcontrol", "wprof", "sharpen", "chain", "xtrans", "rgb_cam",
-                                                         "full_frame", "guidedChromaRadius", "denoise_expcomp"]),
+                                                         "full_frame", "guidedChromaRadius", "denoise_expcomp", "tran", "hr_blend", "hlmax"]),
         "art_hp_chain_params": (api._ChainParamsC, ["exposure_enabled", "exp_scale", "black", "saturation_enabled", "vibrance", "tonecurve_mode",
                                                      "tonecurve_lut", "rcurve", "bcurve", "lab_enabled", "lab_lcurve", "lab_bcurve", "lab_chroma", "ws", "iws",
                                                      "tonecurve_whitept", "tonecurve_stages", "tonecurve_nstages", "neutral_to_out", "neutral_to_work", "satcurve_lut"]),
