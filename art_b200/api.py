@@ -102,6 +102,10 @@ def load_library(build_if_missing=True):
         "art_hp_denoise_compute_params": (i, [vp, i, i, vp, vp, vp, vp, i, vp, vp, d, i, vp, vp]),
         "art_hp_denoise_compute_params_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, i, vp, vp, d, i, vp, vp]),
         "art_hp_develop_size": (i, [vp, i, i, ctypes.POINTER(i), ctypes.POINTER(i), ctypes.POINTER(i)]),
+        "art_hp_green_equilibrate_global": (i, [vp, i, i, u, vp, i]),
+        "art_hp_green_equilibrate_global_dev": (i, [vp, i, i, u, vp, sz, i]),
+        "art_hp_green_equilibrate": (i, [vp, i, i, u, vp, f, vp]),
+        "art_hp_green_equilibrate_dev": (i, [vp, i, i, u, vp, sz, f, vp, sz]),
         "art_hp_band_plan_rows": (i, [vp, i, i, i, i, i, vp]),
         "art_hp_set_allreduce": (i, [vp, vp, vp]),
         "art_hp_comm_unique_id": (i, [vp]),
@@ -659,6 +663,18 @@ class HotPath:
     def develop_dev(self, params, W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch):
         c = params.c_struct()
         self._check(self.lib.art_hp_develop_dev(self.h, ctypes.byref(c), W, H, d_raw, raw_pitch, d_r, d_g, d_b, out_pitch))
+
+    # ---- preprocess: green equilibration (green_equil_RT.cc), in place on a host (H, W) float32 Bayer plane ----
+    def green_equilibrate_global(self, raw, filters, border=4):
+        H, W = raw.shape
+        self._check(self.lib.art_hp_green_equilibrate_global(self.h, W, H, int(filters), row_table(raw), int(border)))
+        return raw
+
+    def green_equilibrate(self, raw, filters, thresh, thresh_map=None):
+        H, W = raw.shape
+        self._check(self.lib.art_hp_green_equilibrate(self.h, W, H, int(filters), row_table(raw), float(thresh),
+                                                      row_table(thresh_map) if thresh_map is not None else None))
+        return raw
 
     # ---- one frame across GPUs (ABI version 3) ----
     def band_plan(self, params, W, H, own_begin, own_end, halo=200):

@@ -739,6 +739,63 @@ int art_hp_scale_colors_bayer(art_hp_ctx* ctx, int W, int H, unsigned filters, f
     return ART_HP_OK;
 }
 
+int art_hp_green_equilibrate_global_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* d_raw, size_t pitch, int border)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_raw) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 2 || H < 2 || pitch < (size_t)W || border < 0) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d pitch %zu border %d", W, H, pitch, border);
+    if (!rgb_bayer(filters)) return ctx->fail(ART_HP_ERR_INVALID, "filters=0x%08x is not an RGB Bayer pattern", filters);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_green_equilibrate_global_dev(ctx, W, H, filters, d_raw, pitch, border);
+}
+
+int art_hp_green_equilibrate_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* d_raw, size_t pitch, float thresh,
+                                 const float* d_thresh_map, size_t map_pitch)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_raw) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 2 || H < 2 || pitch < (size_t)W || (d_thresh_map && map_pitch < (size_t)W)) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d pitch %zu", W, H, pitch);
+    if (!rgb_bayer(filters)) return ctx->fail(ART_HP_ERR_INVALID, "filters=0x%08x is not an RGB Bayer pattern", filters);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_green_equilibrate_dev(ctx, W, H, filters, d_raw, pitch, thresh, d_thresh_map, map_pitch);
+}
+
+static int green_eq_host(art_hp_ctx* ctx, int W, int H, unsigned filters, float* const* rawData, int global, int border, float thresh, const float* const* thresh_map)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!rawData) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 2 || H < 2) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    int rc;
+    if ((rc = art_reserve(ctx, ctx->d_raw, pitch * (size_t)H * sizeof(float)))) return rc;
+    Plane io = {rawData, (float*)ctx->d_raw.p};
+    if ((rc = transfer(ctx, ctx->stream, &io, 1, W, 0, H, pitch, true))) return rc;
+    if (global) rc = art_hp_green_equilibrate_global_dev(ctx, W, H, filters, io.dev, pitch, border);
+    else {
+        float* dmap = nullptr;
+        if (thresh_map) {
+            if ((rc = art_reserve(ctx, ctx->d_out[0], pitch * (size_t)H * sizeof(float)))) return rc;
+            Plane mp = {const_cast<float* const*>(thresh_map), (float*)ctx->d_out[0].p};
+            if ((rc = transfer(ctx, ctx->stream, &mp, 1, W, 0, H, pitch, true))) return rc;
+            dmap = mp.dev;
+        }
+        rc = art_hp_green_equilibrate_dev(ctx, W, H, filters, io.dev, pitch, thresh, dmap, pitch);
+    }
+    if (rc) return rc;
+    if ((rc = transfer(ctx, ctx->stream, &io, 1, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+int art_hp_green_equilibrate_global(art_hp_ctx* ctx, int W, int H, unsigned filters, float* const* rawData, int border)
+{
+    return green_eq_host(ctx, W, H, filters, rawData, 1, border, 0.f, nullptr);
+}
+int art_hp_green_equilibrate(art_hp_ctx* ctx, int W, int H, unsigned filters, float* const* rawData, float thresh, const float* const* thresh_map)
+{
+    return green_eq_host(ctx, W, H, filters, rawData, 0, 0, thresh, thresh_map);
+}
+
 int art_hp_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* d_red, float* d_green, float* d_blue, size_t pitch,
                              const float mul[3], int doClip, const double mat[9])
 {

@@ -161,6 +161,9 @@ int art_guided_smoothing_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size
 // scaleColors (Bayer): in place; d_chmax_bits = 3 device ints receiving the float bit patterns of chmax[0..2]
 int art_scale_colors_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* raw, size_t pitch,
                          const float black[4], const float mul[4], int* d_chmax_bits);
+// green_equil_RT.cc (greeneq.cu): global and local green equilibration of the Bayer plane, in place
+int art_green_equilibrate_global_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* raw, size_t pitch, int border);
+int art_green_equilibrate_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* raw, size_t pitch, float thresh, const float* thresh_map, size_t map_pitch);
 // gaussianBlur, GAUSS_STANDARD (src == dst allowed)
 int art_gauss_dev(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, size_t dp, int W, int H, double sigma);
 int art_gauss_divmult_dev(art_hp_ctx* ctx, float* src, size_t sp, float* dst, size_t dp, const float* div, size_t vp, int W, int H, double sigma, int type);

@@ -352,6 +352,23 @@ int art_hp_denoise_guided_smoothing(art_hp_ctx* ctx, int W, int H, float* const*
 int art_hp_denoise_guided_smoothing_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
                                         const double ws[9], int guidedChromaRadius, double scale);
 
+/*
+ * Bayer green equilibration (preprocess; RawImageSource::preprocess calls them when raw.bayersensor.greenthresh > 0, rtengine/rawimagesource.cc
+ * L1720-1745), on the rawData plane in place, before the demosaic:
+ *   art_hp_green_equilibrate_global   RawImageSource::green_equilibrate_global (rtengine/green_equil_RT.cc L37-89): both green phases scaled to their
+ *                      common mean over the frame less `border`.  The row sums are added in row order (the reference's OpenMP reduction
+ *                      moves with the schedule in the last bits; its one-thread order is the one reproduced).
+ *   art_hp_green_equilibrate          RawImageSource::green_equilibrate(thresh, rawData) (L92-250): thresh = the constant of
+ *                      GreenEqulibrateThreshold (0.01 * greenthresh); thresh_map (optional, W x H floats at map_pitch) stands for a derived
+ *                      threshold class (per-pixel values, e.g. the PDAF-lines one).
+ * Bit-identical to the reference's SSE2 build.
+ */
+int art_hp_green_equilibrate_global(art_hp_ctx* ctx, int W, int H, unsigned filters, float* const* rawData, int border);
+int art_hp_green_equilibrate_global_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* d_raw, size_t pitch, int border);
+int art_hp_green_equilibrate(art_hp_ctx* ctx, int W, int H, unsigned filters, float* const* rawData, float thresh, const float* const* thresh_map);
+int art_hp_green_equilibrate_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* d_raw, size_t pitch, float thresh,
+                                 const float* d_thresh_map, size_t map_pitch);
+
 /* ---- gain / clip / camera->working colour space ------------------------- */
 /*
  * Replaces the per-pixel part of RawImageSource::getImage (rtengine/rawimagesource.cc L943-1025, full
