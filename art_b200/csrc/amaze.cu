@@ -319,6 +319,28 @@ __global__ void __launch_bounds__(TS * 2) k_vcd(AmzArgs a)
     float xm = vcd[i - v2];               // rows 2,3 are never updated: "new" == old there
     float x = vcd[i];
     float altm = vcdalt[i - v2], alt = vcdalt[i];
+    // Only `xm` is carried from row to row: the operands of VCD_U rows are fetched together (the loads of a row never
+    // alias a store of this thread's earlier rows: stores go to vcd[i] / cddiffsq[i], loads to vcd[i + v2] and read-only planes).
+    constexpr int VCD_U = 8;
+    for (; rr + 2 * (VCD_U - 1) < g.rr1 - 4; rr += 2 * VCD_U, i += v2 * VCD_U) {
+        float xp[VCD_U], ap[VCD_U], c0[VCD_U], cu[VCD_U], cd[VCD_U], hh[VCD_U];
+        #pragma unroll
+        for (int k = 0; k < VCD_U; ++k) {
+            const int ik = i + k * v2;
+            xp[k] = vcd[ik + v2]; ap[k] = vcdalt[ik + v2];
+            c0[k] = cfa[ik]; cu[k] = cfa[ik - v1]; cd[k] = cfa[ik + v1];
+            hh[k] = hcd[ik];
+        }
+        #pragma unroll
+        for (int k = 0; k < VCD_U; ++k) {
+            const int ik = i + k * v2;
+            const float sgn = (fc(a.filters, rr + 2 * k, cc) & 1) ? -1.f : 1.f;
+            const float nv = bound_lane(x, xm, xp[k], alt, altm, ap[k], c0[k], cu[k], cd[k], sgn, a.clip_pt);
+            vcd[ik] = nv;
+            cddiffsq[ik] = sq(nv - hh[k]);
+            xm = nv; x = xp[k]; altm = alt; alt = ap[k];
+        }
+    }
     for (; rr < g.rr1 - 4; rr += 2, i += v2) {
         const float xp = vcd[i + v2], altp = vcdalt[i + v2];
         const float sgn = (fc(a.filters, rr, cc) & 1) ? -1.f : 1.f;
@@ -517,37 +539,55 @@ __global__ void __launch_bounds__(128) k_rowrec(AmzArgs a)
     float* cur = rows[w][1];
     float* next = rows[w][2];
     for (int h = lane; h < TSH; h += 32) { prev[h] = buf[(rf - 1) * TSH + h]; cur[h] = buf[rf * TSH + h]; }
+    // the old values of the rows below are fetched RR_PF rows ahead of the row being decided (a row is only ever written by its own
+    // step, so a value fetched early is the value the step would have read); only the decided row travels through shared memory
+    constexpr int RR_PF = 6;
+    const int rend = g.rr1 - rf;
+    float q[RR_PF][3];
+    auto fetch = [&](int row, float (&dst)[3]) {
+        #pragma unroll
+        for (int m = 0; m < 3; ++m) { const int h = lane + 32 * m; dst[m] = (row < TS && h < TSH) ? buf[row * TSH + h] : 0.f; }
+    };
+    #pragma unroll
+    for (int k = 0; k < RR_PF; ++k) fetch(rf + 1 + k, q[k]);
     __syncwarp();
-    for (int rr = rf; rr < g.rr1 - rf; ++rr) {
-        for (int h = lane; h < TSH; h += 32) next[h] = buf[(rr + 1) * TSH + h];
-        __syncwarp();
-        const int p = fc(a.filters, rr, 2) & 1;
-        float nv[3];
-        bool act[3];
+    for (int rr0 = rf; rr0 < rend; rr0 += RR_PF) {
         #pragma unroll
-        for (int m = 0; m < 3; ++m) {
-            const int j = lane + 32 * m;                 // site number in the row
-            const int cc = rf + p + 2 * j;
-            act[m] = PMWT ? ((rf + p + 8 * (j >> 2)) < g.cc1 - rf && cc < TS) : (cc < g.cc1 - rf);
-            nv[m] = 0.f;
-            if (act[m]) {
-                // diagonal neighbours: row above (new) and row below (old), columns cc-1 and cc+1
-                const int hl = (cc - 1) >> 1, hr = (cc + 1) >> 1;
-                const float alt = 0.25f * (prev[hl] + prev[hr] + next[hl] + next[hr]);
-                const float x = cur[cc >> 1];
-                nv[m] = fabsf(0.5f - x) < fabsf(0.5f - alt) ? alt : x;
+        for (int k = 0; k < RR_PF; ++k) {
+            const int rr = rr0 + k;
+            if (rr >= rend) break;
+            #pragma unroll
+            for (int m = 0; m < 3; ++m) { const int h = lane + 32 * m; if (h < TSH) next[h] = q[k][m]; }
+            fetch(rr + 1 + RR_PF, q[k]);
+            __syncwarp();
+            const int p = fc(a.filters, rr, 2) & 1;
+            float nv[3];
+            bool act[3];
+            #pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const int j = lane + 32 * m;                 // site number in the row
+                const int cc = rf + p + 2 * j;
+                act[m] = PMWT ? ((rf + p + 8 * (j >> 2)) < g.cc1 - rf && cc < TS) : (cc < g.cc1 - rf);
+                nv[m] = 0.f;
+                if (act[m]) {
+                    // diagonal neighbours: row above (new) and row below (old), columns cc-1 and cc+1
+                    const int hl = (cc - 1) >> 1, hr = (cc + 1) >> 1;
+                    const float alt = 0.25f * (prev[hl] + prev[hr] + next[hl] + next[hr]);
+                    const float x = cur[cc >> 1];
+                    nv[m] = fabsf(0.5f - x) < fabsf(0.5f - alt) ? alt : x;
+                }
             }
+            __syncwarp();
+            #pragma unroll
+            for (int m = 0; m < 3; ++m)
+                if (act[m]) {
+                    const int cc = rf + p + 2 * (lane + 32 * m);
+                    cur[cc >> 1] = nv[m];
+                    buf[(rr * TS + cc) >> 1] = nv[m];
+                }
+            __syncwarp();
+            float* tmp = prev; prev = cur; cur = next; next = tmp;
         }
-        __syncwarp();
-        #pragma unroll
-        for (int m = 0; m < 3; ++m)
-            if (act[m]) {
-                const int cc = rf + p + 2 * (lane + 32 * m);
-                cur[cc >> 1] = nv[m];
-                buf[(rr * TS + cc) >> 1] = nv[m];
-            }
-        __syncwarp();
-        float* tmp = prev; prev = cur; cur = next; next = tmp;
     }
 }
 
@@ -844,6 +884,10 @@ static int amaze_band(art_hp_ctx* ctx, AmzArgs a, int stop_after)
         ctx->launches++;                                               \
         if (++pass == stop_after) { ART_CUDA(ctx, cudaGetLastError()); return ART_HP_OK; } \
     } while (0)
+    // The oracle's deterministic variant zeroes a tile's scratch before the tile starts.  Clearing less is not safe: which sub-buffers
+    // are read before the tile has written them (lanes overrunning a vector loop, cells read under an aliased name) depends on the
+    // tile geometry AND the data (a poisoning sweep of the oracle found delhvsqsum, vcd .. cddiffsq, nyquist always, dginth and cfa
+    // for some frames), so the whole slab is cleared.
     art_prof_begin(ctx, "memset_slabs");
     ART_CUDA(ctx, cudaMemsetAsync(a.slabs, 0, (size_t)nt * SLAB_BYTES, st));
     art_prof_end(ctx);
