@@ -116,6 +116,14 @@ def load_library(build_if_missing=True):
         "art_hp_denoise_guided_smoothing_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, i, d]),
         "art_hp_develop_submit_packed": (i, [vp, vp, i, i, vp, i, i, vp, sz]),
         "art_hp_scanlines": (i, [vp, i, i, vp, vp, vp, i, i, vp, sz]),
+        "art_hp_demosaic_vng4": (i, [vp, i, i, u, vp, vp, vp, vp]),
+        "art_hp_demosaic_vng4_dev": (i, [vp, i, i, u, vp, sz, vp, vp, vp, sz]),
+        "art_hp_dual_demosaic_bayer": (i, [vp, i, i, i, i, u, u, vp, vp, vp, vp, d, i, vp, i]),
+        "art_hp_dual_demosaic_bayer_dev": (i, [vp, i, i, i, i, u, u, vp, sz, vp, vp, vp, sz, d, i, d, i, vp]),
+        "art_hp_dual_demosaic_xtrans": (i, [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, i]),
+        "art_hp_dual_demosaic_xtrans_dev": (i, [vp, i, i, i, i, vp, vp, vp, sz, vp, vp, vp, sz, d, i, vp]),
+        "art_hp_resize_lanczos": (i, [vp, i, i, vp, vp, vp, i, i, vp, vp, vp, f]),
+        "art_hp_resize_lanczos_dev": (i, [vp, i, i, vp, vp, vp, sz, i, i, vp, vp, vp, sz, f]),
         "art_hp_scanlines_dev": (i, [vp, i, i, vp, vp, vp, sz, i, i, vp, sz]),
         "art_hp_develop_wait": (i, [vp]),
         "art_hp_develop_pending": (i, [vp]),
@@ -653,6 +661,45 @@ class HotPath:
         self._check(self.lib.art_hp_scanlines(self.h, W, H, row_table(r), row_table(g), row_table(b), int(bps), int(bool(is_float)),
                                               out.ctypes.data_as(ctypes.c_void_p), out.strides[0]))
         return out
+
+    # ---- dual demosaic (dual_demosaic_RT.cc) and its flat-region demosaicer VNG4 (vng4_demosaic_RT.cc) ----
+    def demosaic_vng4(self, raw, prefilters):
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        H, W = raw.shape
+        out = [np.zeros((H, W), np.float32) for _ in range(3)]
+        self._check(self.lib.art_hp_demosaic_vng4(self.h, W, H, int(prefilters), row_table(raw), *[row_table(o) for o in out]))
+        return out
+
+    def dual_demosaic_bayer(self, method, second, raw, filters, prefilters=0, contrast=20.0, auto_contrast=True, initial_gain=1.0, border=4):
+        """Returns ((r, g, b), contrast): contrast is the percent value dual_demosaic_RT hands back (the automatic threshold x 100)."""
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        H, W = raw.shape
+        out = [np.zeros((H, W), np.float32) for _ in range(3)]
+        c = ctypes.c_double(float(contrast))
+        self._check(self.lib.art_hp_dual_demosaic_bayer(self.h, int(method), int(second), W, H, int(filters), int(prefilters), row_table(raw),
+                                                        *[row_table(o) for o in out], float(initial_gain), int(border), ctypes.byref(c), int(bool(auto_contrast))))
+        return out, c.value
+
+    def dual_demosaic_xtrans(self, raw, xtrans, rgb_cam, passes=3, use_cielab=True, contrast=20.0, auto_contrast=True):
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        H, W = raw.shape
+        out = [np.zeros((H, W), np.float32) for _ in range(3)]
+        xt = np.ascontiguousarray(xtrans, dtype=np.int32)
+        cam = np.ascontiguousarray(rgb_cam, dtype=np.float32)
+        c = ctypes.c_double(float(contrast))
+        self._check(self.lib.art_hp_dual_demosaic_xtrans(self.h, int(passes), int(bool(use_cielab)), W, H, xt.ctypes.data_as(ctypes.c_void_p),
+                                                         cam.ctypes.data_as(ctypes.c_void_p), row_table(raw), *[row_table(o) for o in out],
+                                                         ctypes.byref(c), int(bool(auto_contrast))))
+        return out, c.value
+
+    def resize_lanczos(self, planes, scale, size=None):
+        """ImProcFunctions::Lanczos on three host (H, W) float32 planes; size = (dH, dW), by default resizeScale's int(n * scale + 0.5)."""
+        sH, sW = planes[0].shape
+        dH, dW = size if size is not None else (max(1, int(sH * scale + 0.5)), max(1, int(sW * scale + 0.5)))
+        src = [np.ascontiguousarray(p, dtype=np.float32) for p in planes]
+        dst = [np.zeros((dH, dW), np.float32) for _ in range(3)]
+        self._check(self.lib.art_hp_resize_lanczos(self.h, sW, sH, *[row_table(p) for p in src], dW, dH, *[row_table(p) for p in dst], float(scale)))
+        return dst
 
     def develop_wait(self):
         self._check(self.lib.art_hp_develop_wait(self.h))

@@ -2,6 +2,8 @@
 // The compute lives in rcd.cu / amaze.cu / ...; this file holds no pixel arithmetic.
 #include "ctx.h"
 
+#include <functional>
+
 #include <algorithm>
 #include <thread>
 #include <utility>
@@ -796,6 +798,40 @@ int art_hp_green_equilibrate(art_hp_ctx* ctx, int W, int H, unsigned filters, fl
     return green_eq_host(ctx, W, H, filters, rawData, 0, 0, thresh, thresh_map);
 }
 
+int art_hp_resize_lanczos_dev(art_hp_ctx* ctx, int sW, int sH, const float* d_s0, const float* d_s1, const float* d_s2, size_t src_pitch,
+                              int dW, int dH, float* d_d0, float* d_d1, float* d_d2, size_t dst_pitch, float scale)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_s0 || !d_s1 || !d_s2 || !d_d0 || !d_d1 || !d_d2) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (sW < 1 || sH < 1 || dW < 1 || dH < 1 || src_pitch < (size_t)sW || dst_pitch < (size_t)dW || !(scale > 0.f))
+        return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d -> %dx%d, scale %g", sW, sH, dW, dH, (double)scale);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_lanczos_dev(ctx, d_s0, d_s1, d_s2, src_pitch, sW, sH, d_d0, d_d1, d_d2, dst_pitch, dW, dH, scale);
+}
+
+int art_hp_resize_lanczos(art_hp_ctx* ctx, int sW, int sH, float* const* s0, float* const* s1, float* const* s2,
+                          int dW, int dH, float* const* d0, float* const* d1, float* const* d2, float scale)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!s0 || !s1 || !s2 || !d0 || !d1 || !d2) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (sW < 1 || sH < 1 || dW < 1 || dH < 1 || !(scale > 0.f))
+        return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d -> %dx%d, scale %g", sW, sH, dW, dH, (double)scale);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t sp = round_up((size_t)sW, 32), dp = round_up((size_t)dW, 32);
+    int rc;
+    for (int i = 0; i < 3; ++i) {
+        if ((rc = art_reserve(ctx, ctx->d_dm[i], sp * (size_t)sH * sizeof(float)))) return rc;
+        if ((rc = art_reserve(ctx, ctx->d_out[i], dp * (size_t)dH * sizeof(float)))) return rc;
+    }
+    Plane in[3] = {{s0, (float*)ctx->d_dm[0].p}, {s1, (float*)ctx->d_dm[1].p}, {s2, (float*)ctx->d_dm[2].p}};
+    Plane out[3] = {{d0, (float*)ctx->d_out[0].p}, {d1, (float*)ctx->d_out[1].p}, {d2, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, in, 3, sW, 0, sH, sp, true))) return rc;
+    if ((rc = art_lanczos_dev(ctx, in[0].dev, in[1].dev, in[2].dev, sp, sW, sH, out[0].dev, out[1].dev, out[2].dev, dp, dW, dH, scale))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, out, 3, dW, 0, dH, dp, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
 int art_hp_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* d_red, float* d_green, float* d_blue, size_t pitch,
                              const float mul[3], int doClip, const double mat[9])
 {
@@ -1038,6 +1074,136 @@ int art_hp_demosaic_xtrans(art_hp_ctx* ctx, int passes, int useCieLab, int W, in
     if ((rc = transfer(ctx, ctx->stream, out, 3, W, 0, H, pitch, false))) return rc;
     ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;
+}
+
+// ---- dual demosaic (dual.cu)
+static int vng4_check(art_hp_ctx* ctx, int W, int H, unsigned prefilters)
+{
+    if (W < 8 || H < 8 || W > 65536 || H > 65535) return ctx->fail(ART_HP_ERR_INVALID, "frame %dx%d out of range", W, H);
+    const unsigned filters = prefilters & ~((prefilters & 0x55555555u) << 1);
+    if (!rgb_bayer(filters)) return ctx->fail(ART_HP_ERR_INVALID, "prefilters=0x%08x does not collapse to an RGB Bayer pattern", prefilters);
+    return ART_HP_OK;
+}
+
+int art_hp_demosaic_vng4_dev(art_hp_ctx* ctx, int W, int H, unsigned prefilters, const float* d_raw, size_t raw_pitch,
+                             float* d_red, float* d_green, float* d_blue, size_t out_pitch)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_raw || !d_red || !d_green || !d_blue) return ctx->fail(ART_HP_ERR_INVALID, "null plane pointer");
+    int rc = vng4_check(ctx, W, H, prefilters);
+    if (rc) return rc;
+    if (raw_pitch < (size_t)W || out_pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "pitch smaller than width");
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_vng4_dev(ctx, W, H, prefilters, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch);
+}
+
+static int dual_check(art_hp_ctx* ctx, int W, int H, double contrast, int autoContrast)
+{
+    if (!(contrast >= 0.0)) return ctx->fail(ART_HP_ERR_INVALID, "contrast must be >= 0");
+    if (autoContrast && (W < 80 || H < 80)) return ctx->fail(ART_HP_ERR_INVALID, "the automatic contrast threshold needs a frame of at least 80x80, got %dx%d", W, H);
+    return ART_HP_OK;
+}
+
+int art_hp_dual_demosaic_bayer_dev(art_hp_ctx* ctx, int method, int second, int W, int H, unsigned filters, unsigned prefilters,
+                                   const float* d_raw, size_t raw_pitch, float* d_red, float* d_green, float* d_blue, size_t out_pitch,
+                                   double initialGain, int border, double contrast, int autoContrast, float* d_threshold_out)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (second != ART_HP_DUAL_BILINEAR && second != ART_HP_DUAL_VNG4) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "unknown flat-region demosaicer %d", second);
+    int rc = dual_check(ctx, W, H, contrast, autoContrast);
+    if (rc) return rc;
+    if (second == ART_HP_DUAL_VNG4) {
+        if ((rc = vng4_check(ctx, W, H, prefilters))) return rc;
+        if ((prefilters & ~((prefilters & 0x55555555u) << 1)) != filters) return ctx->fail(ART_HP_ERR_INVALID, "prefilters=0x%08x is not the four-colour form of filters=0x%08x", prefilters, filters);
+    }
+    if ((rc = art_hp_demosaic_bayer_dev(ctx, method, W, H, filters, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch, initialGain, border))) return rc;
+    if (contrast == 0.0 && !autoContrast) {       // dual_demosaic_RT.cc L43-71: the first demosaicer alone
+        if (d_threshold_out) ART_CUDA(ctx, cudaMemsetAsync(d_threshold_out, 0, sizeof(float), ctx->stream));
+        return ART_HP_OK;
+    }
+    return art_dual_blend_dev(ctx, second, W, H, second == ART_HP_DUAL_VNG4 ? prefilters : filters, nullptr, d_raw, raw_pitch,
+                              d_red, d_green, d_blue, out_pitch, contrast, autoContrast, d_threshold_out);
+}
+
+int art_hp_dual_demosaic_xtrans_dev(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, const int xtrans[36], const float rgb_cam[12],
+                                    const float* d_raw, size_t raw_pitch, float* d_red, float* d_green, float* d_blue, size_t out_pitch,
+                                    double contrast, int autoContrast, float* d_threshold_out)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    int rc = dual_check(ctx, W, H, contrast, autoContrast);
+    if (rc) return rc;
+    if ((rc = art_hp_demosaic_xtrans_dev(ctx, passes, useCieLab, W, H, xtrans, rgb_cam, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch))) return rc;
+    if (contrast == 0.0 && !autoContrast) {
+        if (d_threshold_out) ART_CUDA(ctx, cudaMemsetAsync(d_threshold_out, 0, sizeof(float), ctx->stream));
+        return ART_HP_OK;
+    }
+    return art_dual_blend_dev(ctx, 2, W, H, 0, xtrans, d_raw, raw_pitch, d_red, d_green, d_blue, out_pitch, contrast, autoContrast, d_threshold_out);
+}
+
+// host entries: upload the raw plane, run `stage` on the device planes, download the frame, read the threshold back
+typedef std::function<int(float*, size_t, float*, float*, float*, int*)> DualStage;       // sets *blended when the blend step ran
+static int dual_host(art_hp_ctx* ctx, int W, int H, const float* const* rawData, float* const* red, float* const* green, float* const* blue,
+                     double* contrast, const DualStage& stage)
+{
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    int rc;
+    if ((rc = art_reserve(ctx, ctx->d_raw, plane))) return rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+    Plane in = {rawData, (float*)ctx->d_raw.p};
+    Plane out[3] = {{red, (float*)ctx->d_out[0].p}, {green, (float*)ctx->d_out[1].p}, {blue, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, &in, 1, W, 0, H, pitch, true))) return rc;
+    int blended = 0;
+    if ((rc = stage(in.dev, pitch, out[0].dev, out[1].dev, out[2].dev, &blended))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, out, 3, W, 0, H, pitch, false))) return rc;
+    float thr = 0.f;
+    if (contrast && blended) ART_CUDA(ctx, cudaMemcpyAsync(&thr, art_dual_threshold_slot(ctx), sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (contrast) *contrast = thr * 100.f;           // dual_demosaic_RT.cc L112: contrast = contrastf * 100.f
+    return ART_HP_OK;
+}
+
+int art_hp_demosaic_vng4(art_hp_ctx* ctx, int W, int H, unsigned prefilters, const float* const* rawData,
+                         float* const* red, float* const* green, float* const* blue)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!rawData || !red || !green || !blue) return ctx->fail(ART_HP_ERR_INVALID, "null row table");
+    int rc = vng4_check(ctx, W, H, prefilters);
+    if (rc) return rc;
+    return dual_host(ctx, W, H, rawData, red, green, blue, nullptr, [&](float* raw, size_t p, float* r, float* g, float* b, int*) {
+        return art_vng4_dev(ctx, W, H, prefilters, raw, p, r, g, b, p);
+    });
+}
+
+int art_hp_dual_demosaic_bayer(art_hp_ctx* ctx, int method, int second, int W, int H, unsigned filters, unsigned prefilters,
+                               const float* const* rawData, float* const* red, float* const* green, float* const* blue,
+                               double initialGain, int border, double* contrast, int autoContrast)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!rawData || !red || !green || !blue || !contrast) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 32 || H < 32 || W > 65536 || H > 65535) return ctx->fail(ART_HP_ERR_INVALID, "frame %dx%d out of range", W, H);
+    const double c0 = *contrast;
+    return dual_host(ctx, W, H, rawData, red, green, blue, contrast, [&](float* raw, size_t p, float* r, float* g, float* b, int* blended) {
+        *blended = c0 != 0.0 || autoContrast;
+        return art_hp_dual_demosaic_bayer_dev(ctx, method, second, W, H, filters, prefilters, raw, p, r, g, b, p, initialGain, border, c0, autoContrast, nullptr);
+    });
+}
+
+int art_hp_dual_demosaic_xtrans(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, const int xtrans[36], const float rgb_cam[12],
+                                const float* const* rawData, float* const* red, float* const* green, float* const* blue,
+                                double* contrast, int autoContrast)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!xtrans || !rgb_cam || !rawData || !red || !green || !blue || !contrast) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    int rc = xtrans_check(ctx, passes, W, H, xtrans);
+    if (rc) return rc;
+    const double c0 = *contrast;
+    return dual_host(ctx, W, H, rawData, red, green, blue, contrast, [&](float* raw, size_t p, float* r, float* g, float* b, int* blended) {
+        *blended = c0 != 0.0 || autoContrast;
+        return art_hp_dual_demosaic_xtrans_dev(ctx, passes, useCieLab, W, H, xtrans, rgb_cam, raw, p, r, g, b, p, c0, autoContrast, nullptr);
+    });
 }
 
 int art_hp_median_denoise_dev(art_hp_ctx* ctx, const float* d_src, size_t src_pitch, float* d_dst, size_t dst_pitch, int W, int H,

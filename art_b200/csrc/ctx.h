@@ -65,6 +65,9 @@ struct art_hp_ctx {
     DevBuf d_bl_lut;                     // edges-only sharpening: the bilateral filter's range LUT (0x20000 floats), host-built
     int bl_lut_scale = 0, bl_lut_sens = 0;
     DevBuf d_xt_cbrt;                    // cielab's 0x14000-entry cube-root LUT of the X-Trans demosaic
+    DevBuf d_dual_tabs;                  // dual demosaic: cachefy, VNG4's gradient programs, the automatic threshold's state
+    bool dual_tabs_ready = false, dual_prog_ready = false;
+    unsigned dual_prog_filters = 0;
     bool xt_cbrt_ready = false;
     // batch queue (art_hp_develop_submit / _wait): two frames in flight, each with its own raw + output planes
     struct QSlot { DevBuf raw, out[3], packed; cudaEvent_t up = nullptr, done = nullptr, down = nullptr; };
@@ -161,6 +164,14 @@ int art_guided_smoothing_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size
 // scaleColors (Bayer): in place; d_chmax_bits = 3 device ints receiving the float bit patterns of chmax[0..2]
 int art_scale_colors_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* raw, size_t pitch,
                          const float black[4], const float mul[4], int* d_chmax_bits);
+// vng4_demosaic_RT.cc / dual_demosaic_RT.cc (dual.cu).  second: 0 bilinear (cfa = filters), 1 VNG4 (cfa = prefilters), 2 fast X-Trans (xtrans36)
+int art_vng4_dev(art_hp_ctx* ctx, int W, int H, unsigned prefilters, const float* raw, size_t rp, float* R, float* G, float* B, size_t op);
+const float* art_dual_threshold_slot(art_hp_ctx* ctx);
+int art_dual_blend_dev(art_hp_ctx* ctx, int second, int W, int H, unsigned cfa, const int* xtrans36, const float* raw, size_t rp,
+                       float* R, float* G, float* B, size_t op, double contrast, int auto_contrast, float* d_threshold_out);
+// ipresize.cc (resize.cu): ImProcFunctions::Lanczos on three planes
+int art_lanczos_dev(art_hp_ctx* ctx, const float* s0, const float* s1, const float* s2, size_t sp, int sW, int sH,
+                    float* d0, float* d1, float* d2, size_t dp, int dW, int dH, float scale);
 // green_equil_RT.cc (greeneq.cu): global and local green equilibration of the Bayer plane, in place
 int art_green_equilibrate_global_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* raw, size_t pitch, int border);
 int art_green_equilibrate_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* raw, size_t pitch, float thresh, const float* thresh_map, size_t map_pitch);

@@ -489,6 +489,60 @@ int art_hp_scanlines(art_hp_ctx* ctx, int W, int H, float* const* r, float* cons
 int art_hp_scanlines_dev(art_hp_ctx* ctx, int W, int H, const float* d_r, const float* d_g, const float* d_b, size_t pitch, int bps, int isFloat,
                          void* d_out, size_t out_stride_bytes);
 
+/* ---- dual demosaic ----------------------------------------------------------------- */
+/*
+ * art_hp_demosaic_vng4        RawImageSource::vng4_demosaic(rawData, red, green, blue) (rtengine/vng4_demosaic_RT.cc L32-397): the four-colour
+ *                             VNG demosaic the dual methods use in flat regions.  prefilters = RawImage::prefilters, the CFA with the
+ *                             second green of each 2x2 as colour 3 (RGGB: 0xb4b4b4b4).  W, H >= 8.  Bit-identical to the reference run on
+ *                             one thread (on several threads the stock function races with its own border pass in rows / columns 3 and
+ *                             n - 4 of its row chunks).
+ * art_hp_dual_demosaic_bayer  RawImageSource::dual_demosaic_RT(isBayer = true, ...) (rtengine/dual_demosaic_RT.cc L39-152) for
+ *                             Method::AMAZEBILINEAR / AMAZEVNG4 / RCDBILINEAR / RCDVNG4: the first demosaicer (method = ART_HP_BAYER_AMAZE |
+ *                             ART_HP_BAYER_RCD), Color::RGB2L of its frame (rtengine/color.cc L1343-1380), buildBlendMask(L, blend, W, H,
+ *                             contrast / 100, 1, autoContrast) (rtengine/rt_algo.cc L317-494, blur radius 2) and the flat-region demosaicer
+ *                             mixed in by intp(blend, first, flat): second = ART_HP_DUAL_BILINEAR (bayer_bilinear_demosaic(blend, ...),
+ *                             rtengine/bayer_bilinear_demosaic.cc L33-75) or ART_HP_DUAL_VNG4.  *contrast is in percent, in / out as in the
+ *                             reference (L108-112): with autoContrast != 0 (the reference default, procparams.cc L2928) it returns the
+ *                             threshold buildBlendMask chose from the flattest tile of the frame (W, H >= 80 then).  contrast == 0 without
+ *                             autoContrast is the first demosaicer alone (L43-71).  Bit-identical to the reference.
+ * art_hp_dual_demosaic_xtrans the same for X-Trans (isBayer = false): xtrans_interpolate(passes, useCieLab) (FOUR_PASS: 3, true; TWO_PASS:
+ *                             1, false) and fast_xtrans_interpolate_blend (rtengine/xtrans_demosaic.cc L1033-1092).
+ * The _dev forms take the threshold by value and, optionally, a device float that receives the threshold used (contrast / 100): they do not
+ * synchronise, the automatic search runs as a chain of small kernels on the context's stream.
+ */
+#define ART_HP_DUAL_BILINEAR 0
+#define ART_HP_DUAL_VNG4     1
+int art_hp_demosaic_vng4(art_hp_ctx* ctx, int W, int H, unsigned prefilters, const float* const* rawData,
+                         float* const* red, float* const* green, float* const* blue);
+int art_hp_demosaic_vng4_dev(art_hp_ctx* ctx, int W, int H, unsigned prefilters, const float* d_raw, size_t raw_pitch,
+                             float* d_red, float* d_green, float* d_blue, size_t out_pitch);
+int art_hp_dual_demosaic_bayer(art_hp_ctx* ctx, int method, int second, int W, int H, unsigned filters, unsigned prefilters,
+                               const float* const* rawData, float* const* red, float* const* green, float* const* blue,
+                               double initialGain, int border, double* contrast, int autoContrast);
+int art_hp_dual_demosaic_bayer_dev(art_hp_ctx* ctx, int method, int second, int W, int H, unsigned filters, unsigned prefilters,
+                                   const float* d_raw, size_t raw_pitch, float* d_red, float* d_green, float* d_blue, size_t out_pitch,
+                                   double initialGain, int border, double contrast, int autoContrast, float* d_threshold_out);
+int art_hp_dual_demosaic_xtrans(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, const int xtrans[36], const float rgb_cam[12],
+                                const float* const* rawData, float* const* red, float* const* green, float* const* blue,
+                                double* contrast, int autoContrast);
+int art_hp_dual_demosaic_xtrans_dev(art_hp_ctx* ctx, int passes, int useCieLab, int W, int H, const int xtrans[36], const float rgb_cam[12],
+                                    const float* d_raw, size_t raw_pitch, float* d_red, float* d_green, float* d_blue, size_t out_pitch,
+                                    double contrast, int autoContrast, float* d_threshold_out);
+
+/* ---- resize ------------------------------------------------------------------------ */
+/*
+ * art_hp_resize_lanczos   ImProcFunctions::Lanczos(src, dst, scale) (rtengine/ipresize.cc L38-207; called by ImProcFunctions::resize L365-394
+ *                         with the destination size of resizeScale L230-362, int(w * scale + 0.5)): three planes sW x sH -> dW x dH, 3 lobes,
+ *                         int(6 / min(scale, 1)) + 1 taps.  The reference runs it between src->setMode(LAB) and dst->setMode(mode): those
+ *                         per-pixel conversions are not part of this entry (all three planes are resampled alike, as the reference does with
+ *                         its L / a / b slots).  Bit-identical to the reference on the same planes.  ART_HP_ERR_UNSUPPORTED below a scale of
+ *                         about 0.001 (the taps of one output pixel no longer fit a shared-memory line).
+ */
+int art_hp_resize_lanczos(art_hp_ctx* ctx, int sW, int sH, float* const* s0, float* const* s1, float* const* s2,
+                          int dW, int dH, float* const* d0, float* const* d1, float* const* d2, float scale);
+int art_hp_resize_lanczos_dev(art_hp_ctx* ctx, int sW, int sH, const float* d_s0, const float* d_s1, const float* d_s2, size_t src_pitch,
+                              int dW, int dH, float* d_d0, float* d_d1, float* d_d2, size_t dst_pitch, float scale);
+
 /* ---- whole frame ------------------------------------------------------------------ */
 /*
  * art_hp_develop       the stages of simpleprocess.cc's normal pipeline that are on the hot path, back to back on the

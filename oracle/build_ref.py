@@ -1402,6 +1402,18 @@ int artref_chain_expcomp(float* R, float* G, float* B, int W, int H, float exp_s
     im.store(R, G, B);
     return 0;
 }
+int artref_chmixer(float* R, float* G, float* B, int W, int H, const float* m)
+{
+    Imagefloat im(W, H, R, G, B, (const double[9]){1,0,0,0,1,0,0,0,1}, nullptr);
+    Imagefloat* img = &im;
+    const bool multiThread = true;
+    const float RR = m[0], RG = m[1], RB = m[2], GR = m[3], GG = m[4], GB = m[5], BR = m[6], BG = m[7], BB = m[8];
+    vfloat vRR = F2V(RR), vRG = F2V(RG), vRB = F2V(RB), vGR = F2V(GR), vGG = F2V(GG), vGB = F2V(GB), vBR = F2V(BR), vBG = F2V(BG), vBB = F2V(BB);
+#pragma omp parallel for if (multiThread)
+#include "chain_chmixer_loop.inc"
+    im.store(R, G, B);
+    return 0;
+}
 int artref_chain_saturation(float* R, float* G, float* B, int W, int H, int sat, int vibr, const double* wsd)
 {
     Imagefloat im(W, H, R, G, B, wsd, nullptr);
@@ -1834,6 +1846,9 @@ def extract(det):
     ipx = os.path.join(RT, "ipexposure.cc")
     open(os.path.join(sub, "chain_expcomp_loop.inc"), "w").write(
         block_after(ipx, r"for \(int y = 0; y < H; \+\+y\) \{(?=\s*int x = 0;\s*#ifdef __SSE2__\s*for \(; x < W - 3; x \+= 4\) \{\s*for \(int c = 0; c < 3; \+\+c\))"))
+    ipm = os.path.join(RT, "ipchmixer.cc")
+    open(os.path.join(sub, "chain_chmixer_loop.inc"), "w").write(
+        block_after(ipm, r"for \(int y = 0; y < img->getHeight\(\); \+\+y\) \{(?=\s*int x = 0;\s*#ifdef __SSE2__\s*for \(; x < img->getWidth\(\)-3; x \+= 4\) \{\s*vfloat r = LVF\(img->r\(y, x\)\);)"))
     ips = os.path.join(RT, "ipsaturation.cc")
     open(os.path.join(sub, "chain_vibrance.inc"), "w").write(cut_function(ips, r"^float apply_vibrance\(float x, float vib\)"))
     open(os.path.join(sub, "chain_saturation_loop.inc"), "w").write(

@@ -67,6 +67,23 @@ int artoracle_chain_expcomp(float* R, float* G, float* B, int W, int H, float ex
     return 0;
 }
 
+/* ---- channelMixer (ipchmixer.cc L152-232), the per-pixel loop: m = RR RG RB / GR GG GB / BR BG BB (RGB_MATRIX: the per-mille sliders / 1000.f;
+ * PRIMARIES_CHROMA: get_mixer_matrix's result).  SSE2 groups clamp with _mm_max_ps (NaN -> 0), the row tail with rt_math.h max (NaN stays). ---- */
+int artoracle_chmixer(float* R, float* G, float* B, int W, int H, const float* m)
+{
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const size_t o = (size_t)y * W + x;
+            const float r = R[o], g = G[o], b = B[o];
+            const float rmix = (r * m[0] + g * m[1] + b * m[2]);
+            const float gmix = (r * m[3] + g * m[4] + b * m[5]);
+            const float bmix = (r * m[6] + g * m[7] + b * m[8]);
+            if (in_group(x, W)) { R[o] = vmaxf_(rmix, 0.f); G[o] = vmaxf_(gmix, 0.f); B[o] = vmaxf_(bmix, 0.f); }
+            else { R[o] = maxr(rmix, 0.f); G[o] = maxr(gmix, 0.f); B[o] = maxr(bmix, 0.f); }
+        }
+    return 0;
+}
+
 /* ---- saturationVibrance ---- */
 static inline float lum_d(float r, float g, float b, const double* ws)
 {   /* Color::rgbLuminance(r, g, b, TMatrix), color.h L203-207; TMatrix is const float (*)[3] (iccstore.h L38): float arithmetic */

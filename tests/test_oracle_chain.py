@@ -62,6 +62,20 @@ def test_expcomp(W, H, ev, black):
     same(call(oracle.port().lib, "artoracle_chain_expcomp", planes, *args), call(oracle.ref().lib, "artref_chain_expcomp", planes, *args))
 
 
+MIXERS = [(1000, 0, 0, 0, 1000, 0, 0, 0, 1000), (800, 300, -100, -50, 1100, -50, 20, -400, 1380), (-200, 600, 600, 333, 333, 334, 0, 0, -1000)]
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("mixer", MIXERS)
+def test_channel_mixer(W, H, mixer):
+    """ImProcFunctions::channelMixer's loop (ipchmixer.cc L200-230), RGB_MATRIX coefficients float(v) / 1000.f; NaN samples show the two clamps."""
+    planes = image(H, W, W * 5 + H)
+    planes[0][H // 2, ::3] = np.nan
+    m = (np.array(mixer, np.float32) / np.float32(1000.0)).astype(np.float32)
+    same(call(oracle.port().lib, "artoracle_chmixer", planes, m.ctypes.data_as(fp)), call(oracle.ref().lib, "artref_chmixer", planes, m.ctypes.data_as(fp)))
+
+
 @needs_ref
 @pytest.mark.parametrize("W,H", SIZES)
 @pytest.mark.parametrize("sat,vib", [(30, 0), (0, 40), (-50, -30), (100, 100)])
