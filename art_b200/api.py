@@ -94,6 +94,8 @@ def load_library(build_if_missing=True):
         "art_hp_gauss_dev": (i, [vp, vp, sz, vp, sz, i, i, d, i]),
         "art_hp_scale_colors_bayer": (i, [vp, i, i, u, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
         "art_hp_scale_colors_bayer_dev": (i, [vp, i, i, u, vp, sz, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+        "art_hp_scale_colors_xtrans": (i, [vp, i, i, vp, vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+        "art_hp_scale_colors_xtrans_dev": (i, [vp, i, i, vp, vp, sz, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
         "art_hp_scale_convert": (i, [vp, i, i, vp, vp, vp, ctypes.POINTER(ctypes.c_float), i, ctypes.POINTER(d)]),
         "art_hp_scale_convert_dev": (i, [vp, i, i, vp, vp, vp, sz, ctypes.POINTER(ctypes.c_float), i, ctypes.POINTER(d)]),
         "art_hp_develop": (i, [vp, vp, i, i, vp, vp, vp, vp]),
@@ -122,6 +124,12 @@ def load_library(build_if_missing=True):
         "art_hp_dual_demosaic_bayer_dev": (i, [vp, i, i, i, i, u, u, vp, sz, vp, vp, vp, sz, d, i, d, i, vp]),
         "art_hp_dual_demosaic_xtrans": (i, [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, i]),
         "art_hp_dual_demosaic_xtrans_dev": (i, [vp, i, i, i, i, vp, vp, vp, sz, vp, vp, vp, sz, d, i, vp]),
+        "art_hp_channel_mixer": (i, [vp, i, i, vp, vp, vp, vp]),
+        "art_hp_channel_mixer_dev": (i, [vp, i, i, vp, vp, vp, sz, vp]),
+        "art_hp_find_hot_dead_pixels": (i, [vp, i, i, vp, vp, f, i, i, vp, sz, ctypes.POINTER(i)]),
+        "art_hp_find_hot_dead_pixels_dev": (i, [vp, i, i, vp, vp, sz, f, i, i, vp, sz, ctypes.POINTER(i)]),
+        "art_hp_interpolate_bad_pixels_bayer": (i, [vp, i, i, u, vp, vp, sz, ctypes.POINTER(i)]),
+        "art_hp_interpolate_bad_pixels_bayer_dev": (i, [vp, i, i, u, vp, sz, vp, sz, ctypes.POINTER(i)]),
         "art_hp_resize_lanczos": (i, [vp, i, i, vp, vp, vp, i, i, vp, vp, vp, f]),
         "art_hp_resize_lanczos_dev": (i, [vp, i, i, vp, vp, vp, sz, i, i, vp, vp, vp, sz, f]),
         "art_hp_scanlines_dev": (i, [vp, i, i, vp, vp, vp, sz, i, i, vp, sz]),
@@ -692,6 +700,35 @@ class HotPath:
                                                          ctypes.byref(c), int(bool(auto_contrast))))
         return out, c.value
 
+    def channel_mixer(self, r, g, b, matrix):
+        """ImProcFunctions::channelMixer's loop in place on three host (H, W) float32 planes; matrix = 9 floats (RGB_MATRIX: sliders / 1000.f)."""
+        H, W = r.shape
+        m = np.ascontiguousarray(matrix, dtype=np.float32).reshape(9)
+        self._check(self.lib.art_hp_channel_mixer(self.h, W, H, row_table(r), row_table(g), row_table(b), m.ctypes.data_as(ctypes.c_void_p)))
+        return r, g, b
+
+    # ---- preprocess: hot / dead pixel filter (badpixels.cc) ----
+    def find_hot_dead_pixels(self, raw, thresh=100.0, hot=True, dead=True, xtrans=None, bad_map=None):
+        """findHotDeadPixels on a host (H, W) float32 CFA plane; returns (map, count), map = (H, W) uint8 with the new marks OR-ed into bad_map."""
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        H, W = raw.shape
+        m = np.zeros((H, W), np.uint8) if bad_map is None else np.ascontiguousarray(bad_map, dtype=np.uint8).copy()
+        xt = None if xtrans is None else np.ascontiguousarray(xtrans, dtype=np.int32)
+        n = ctypes.c_int(0)
+        self._check(self.lib.art_hp_find_hot_dead_pixels(self.h, W, H, None if xt is None else xt.ctypes.data_as(ctypes.c_void_p), row_table(raw),
+                                                         float(thresh), int(bool(hot)), int(bool(dead)), m.ctypes.data_as(ctypes.c_void_p), m.strides[0],
+                                                         ctypes.byref(n)))
+        return m, n.value
+
+    def interpolate_bad_pixels_bayer(self, raw, filters, bad_map):
+        """interpolateBadPixelsBayer in place on a host (H, W) float32 Bayer plane; returns the number of pixels interpolated."""
+        H, W = raw.shape
+        m = np.ascontiguousarray(bad_map, dtype=np.uint8)
+        n = ctypes.c_int(0)
+        self._check(self.lib.art_hp_interpolate_bad_pixels_bayer(self.h, W, H, int(filters), row_table(raw), m.ctypes.data_as(ctypes.c_void_p), m.strides[0],
+                                                                 ctypes.byref(n)))
+        return n.value
+
     def resize_lanczos(self, planes, scale, size=None):
         """ImProcFunctions::Lanczos on three host (H, W) float32 planes; size = (dH, dW), by default resizeScale's int(n * scale + 0.5)."""
         sH, sW = planes[0].shape
@@ -862,6 +899,16 @@ class HotPath:
         mu = (ctypes.c_float * 4)(*[float(x) for x in scale_mul])
         ch = (ctypes.c_float * 3)()
         self._check(self.lib.art_hp_scale_colors_bayer(self.h, W, H, filters, tab, bl, mu, ch))
+        return [float(ch[0]), float(ch[1]), float(ch[2])]
+
+    def scale_colors_xtrans(self, raw, xtrans, cblacksom, scale_mul):
+        """scaleColors' X-Trans branch, in place on a (H, W) float32 array; returns chmax[3]."""
+        H, W = raw.shape
+        xt = np.ascontiguousarray(xtrans, dtype=np.int32)
+        bl = (ctypes.c_float * 3)(*[float(x) for x in cblacksom[:3]])
+        mu = (ctypes.c_float * 3)(*[float(x) for x in scale_mul[:3]])
+        ch = (ctypes.c_float * 3)()
+        self._check(self.lib.art_hp_scale_colors_xtrans(self.h, W, H, xt.ctypes.data_as(ctypes.c_void_p), row_table(raw), bl, mu, ch))
         return [float(ch[0]), float(ch[1]), float(ch[2])]
 
     def scale_colors_bayer_dev(self, W, H, filters, d_raw, pitch, cblacksom, scale_mul):

@@ -741,6 +741,43 @@ int art_hp_scale_colors_bayer(art_hp_ctx* ctx, int W, int H, unsigned filters, f
     return ART_HP_OK;
 }
 
+int art_hp_scale_colors_xtrans_dev(art_hp_ctx* ctx, int W, int H, const int xtrans[36], float* d_raw, size_t pitch,
+                                   const float cblacksom[3], const float scale_mul[3], float chmax[3])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!xtrans || !d_raw || !cblacksom || !scale_mul || !chmax) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d pitch %zu", W, H, pitch);
+    for (int i = 0; i < 36; ++i)
+        if (xtrans[i] < 0 || xtrans[i] > 2) return ctx->fail(ART_HP_ERR_INVALID, "xtrans[%d] = %d is not a colour", i, xtrans[i]);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = art_reserve(ctx, ctx->d_small, 256);
+    if (rc) return rc;
+    if ((rc = art_scale_colors_xtrans_dev(ctx, W, H, xtrans, d_raw, pitch, cblacksom, scale_mul, (int*)ctx->d_small.p))) return rc;
+    int bits[3];
+    ART_CUDA(ctx, cudaMemcpyAsync(bits, ctx->d_small.p, sizeof bits, cudaMemcpyDeviceToHost, ctx->stream));
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 3; ++i) memcpy(&chmax[i], &bits[i], sizeof(float));
+    return ART_HP_OK;
+}
+
+int art_hp_scale_colors_xtrans(art_hp_ctx* ctx, int W, int H, const int xtrans[36], float* const* rawData,
+                               const float cblacksom[3], const float scale_mul[3], float chmax[3])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!xtrans || !rawData || !cblacksom || !scale_mul || !chmax) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    int rc;
+    if ((rc = art_reserve(ctx, ctx->d_raw, pitch * (size_t)H * sizeof(float)))) return rc;
+    Plane io = {rawData, (float*)ctx->d_raw.p};
+    if ((rc = transfer(ctx, ctx->stream, &io, 1, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_hp_scale_colors_xtrans_dev(ctx, W, H, xtrans, io.dev, pitch, cblacksom, scale_mul, chmax))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, &io, 1, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
 int art_hp_green_equilibrate_global_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* d_raw, size_t pitch, int border)
 {
     if (!ctx) return ART_HP_ERR_INVALID;
@@ -1072,6 +1109,111 @@ int art_hp_demosaic_xtrans(art_hp_ctx* ctx, int passes, int useCieLab, int W, in
     if ((rc = transfer(ctx, ctx->stream, &in, 1, W, 0, H, pitch, true))) return rc;
     if ((rc = art_xtrans_dev(ctx, passes, useCieLab != 0, W, H, xtrans, rgb_cam, in.dev, pitch, out[0].dev, out[1].dev, out[2].dev, pitch))) return rc;
     if ((rc = transfer(ctx, ctx->stream, out, 3, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+// ---- hot / dead pixel filter (badpixels.cu)
+static int read_count(art_hp_ctx* ctx, const int* d_count, int* count)
+{
+    int n = 0;
+    ART_CUDA(ctx, cudaMemcpyAsync(&n, d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (count) *count = n;
+    return ART_HP_OK;
+}
+
+int art_hp_find_hot_dead_pixels_dev(art_hp_ctx* ctx, int W, int H, const int* xtrans, const float* d_raw, size_t raw_pitch, float thresh,
+                                    int findHotPixels, int findDeadPixels, unsigned char* d_map, size_t map_pitch, int* count)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_raw || !d_map) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || H > 65535 || raw_pitch < (size_t)W || map_pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    if (xtrans)
+        for (int i = 0; i < 36; ++i)
+            if (xtrans[i] < 0 || xtrans[i] > 2) return ctx->fail(ART_HP_ERR_INVALID, "xtrans[%d] = %d is not a colour", i, xtrans[i]);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = art_reserve(ctx, ctx->d_small2, 256);
+    if (rc) return rc;
+    if ((rc = art_find_hot_dead_dev(ctx, W, H, xtrans, d_raw, raw_pitch, thresh, findHotPixels != 0, findDeadPixels != 0, d_map, map_pitch, (int*)ctx->d_small2.p))) return rc;
+    return read_count(ctx, (const int*)ctx->d_small2.p, count);
+}
+
+int art_hp_interpolate_bad_pixels_bayer_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* d_raw, size_t raw_pitch,
+                                            const unsigned char* d_map, size_t map_pitch, int* count)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_raw || !d_map) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || H > 65535 || raw_pitch < (size_t)W || map_pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = art_reserve(ctx, ctx->d_small2, 256);
+    if (rc) return rc;
+    if ((rc = art_interpolate_bad_bayer_dev(ctx, W, H, filters, d_raw, raw_pitch, d_map, map_pitch, (int*)ctx->d_small2.p))) return rc;
+    return read_count(ctx, (const int*)ctx->d_small2.p, count);
+}
+
+// host forms: the raw plane and the byte map travel to the device and back (the map through d_out[0], one byte per pixel)
+static int badpix_host(art_hp_ctx* ctx, int W, int H, const int* xtrans, unsigned filters, const float* const* rawData, float thresh, int hot, int dead,
+                       unsigned char* map, size_t map_stride, int* count, bool interpolate)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!rawData || !map) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || H > 65535 || map_stride < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32), mp = round_up((size_t)W, 128);
+    int rc;
+    if ((rc = art_reserve(ctx, ctx->d_raw, pitch * (size_t)H * sizeof(float)))) return rc;
+    if ((rc = art_reserve(ctx, ctx->d_out[0], mp * (size_t)H))) return rc;
+    Plane io = {rawData, (float*)ctx->d_raw.p};
+    unsigned char* d_map = (unsigned char*)ctx->d_out[0].p;
+    if ((rc = transfer(ctx, ctx->stream, &io, 1, W, 0, H, pitch, true))) return rc;
+    ART_CUDA(ctx, cudaMemcpy2DAsync(d_map, mp, map, map_stride, (size_t)W, (size_t)H, cudaMemcpyHostToDevice, ctx->stream));
+    if (interpolate) {
+        if ((rc = art_hp_interpolate_bad_pixels_bayer_dev(ctx, W, H, filters, io.dev, pitch, d_map, mp, count))) return rc;
+        if ((rc = transfer(ctx, ctx->stream, &io, 1, W, 0, H, pitch, false))) return rc;
+    } else {
+        if ((rc = art_hp_find_hot_dead_pixels_dev(ctx, W, H, xtrans, io.dev, pitch, thresh, hot, dead, d_map, mp, count))) return rc;
+        ART_CUDA(ctx, cudaMemcpy2DAsync(map, map_stride, d_map, mp, (size_t)W, (size_t)H, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+int art_hp_find_hot_dead_pixels(art_hp_ctx* ctx, int W, int H, const int* xtrans, const float* const* rawData, float thresh,
+                                int findHotPixels, int findDeadPixels, unsigned char* map, size_t map_stride, int* count)
+{
+    return badpix_host(ctx, W, H, xtrans, 0u, rawData, thresh, findHotPixels, findDeadPixels, map, map_stride, count, false);
+}
+
+int art_hp_interpolate_bad_pixels_bayer(art_hp_ctx* ctx, int W, int H, unsigned filters, float* const* rawData,
+                                        const unsigned char* map, size_t map_stride, int* count)
+{
+    return badpix_host(ctx, W, H, nullptr, filters, rawData, 0.f, 0, 0, const_cast<unsigned char*>(map), map_stride, count, true);
+}
+
+int art_hp_channel_mixer_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch, const float matrix[9])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_r || !d_g || !d_b || !matrix) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_channel_mixer_dev(ctx, W, H, d_r, d_g, d_b, pitch, matrix);
+}
+
+int art_hp_channel_mixer(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b, const float matrix[9])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!r || !g || !b || !matrix) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    int rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], pitch * (size_t)H * sizeof(float)))) return rc;
+    Plane io[3] = {{r, (float*)ctx->d_out[0].p}, {g, (float*)ctx->d_out[1].p}, {b, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_channel_mixer_dev(ctx, W, H, io[0].dev, io[1].dev, io[2].dev, pitch, matrix))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, false))) return rc;
     ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ART_HP_OK;
 }

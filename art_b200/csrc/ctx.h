@@ -169,6 +169,15 @@ int art_vng4_dev(art_hp_ctx* ctx, int W, int H, unsigned prefilters, const float
 const float* art_dual_threshold_slot(art_hp_ctx* ctx);
 int art_dual_blend_dev(art_hp_ctx* ctx, int second, int W, int H, unsigned cfa, const int* xtrans36, const float* raw, size_t rp,
                        float* R, float* G, float* B, size_t op, double contrast, int auto_contrast, float* d_threshold_out);
+// ImProcFunctions::channelMixer's loop (pointwise.cu), planes in place; m = RR RG RB / GR GG GB / BR BG BB
+int art_channel_mixer_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch, const float m[9]);
+int art_scale_colors_xtrans_dev(art_hp_ctx* ctx, int W, int H, const int* xtrans36, float* raw, size_t pitch,
+                                const float black[3], const float mul[3], int* d_chmax_bits);
+// badpixels.cc (badpixels.cu): findHotDeadPixels (xtrans36 == nullptr: Bayer) into a byte map (bad pixels OR-ed in), interpolateBadPixelsBayer;
+// d_count = one device int receiving the number of pixels marked / interpolated
+int art_find_hot_dead_dev(art_hp_ctx* ctx, int W, int H, const int* xtrans36, const float* raw, size_t rp, float thresh, int hot, int dead,
+                          unsigned char* map, size_t mp, int* d_count);
+int art_interpolate_bad_bayer_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* raw, size_t rp, const unsigned char* map, size_t mp, int* d_count);
 // ipresize.cc (resize.cu): ImProcFunctions::Lanczos on three planes
 int art_lanczos_dev(art_hp_ctx* ctx, const float* s0, const float* s1, const float* s2, size_t sp, int sW, int sH,
                     float* d0, float* d1, float* d2, size_t dp, int dW, int dH, float scale);

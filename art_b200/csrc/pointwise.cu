@@ -198,6 +198,33 @@ __global__ void __launch_bounds__(256) k_scale_colors(ScaleColorsArgs a)
     }
 }
 
+// scaleColors, X-Trans branch (rawimagesource.cc L2795-2826): c = XTRANSFC(row, col)
+struct ScaleColorsXtArgs { float* raw; size_t pitch; int W, H; int xt[36]; float black[3], mul[3]; int* chmax_bits; };
+__global__ void __launch_bounds__(256) k_scale_colors_xtrans(const __grid_constant__ ScaleColorsXtArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    float mx[3] = {0.f, 0.f, 0.f};
+    if (x < a.W) {
+        for (int y = blockIdx.y; y < a.H; y += gridDim.y) {
+            const int c = a.xt[(y % 6) * 6 + (x % 6)];
+            float* p = a.raw + (size_t)y * a.pitch + x;
+            const float d = *p - (c == 0 ? a.black[0] : c == 1 ? a.black[1] : a.black[2]);
+            const float val = (0.f < d ? d : 0.f) * (c == 0 ? a.mul[0] : c == 1 ? a.mul[1] : a.mul[2]);
+            *p = val;
+            mx[0] = (c == 0 && mx[0] < val) ? val : mx[0];
+            mx[1] = (c == 1 && mx[1] < val) ? val : mx[1];
+            mx[2] = (c == 2 && mx[2] < val) ? val : mx[2];
+        }
+    }
+    #pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = mx[k];
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const float w = __shfl_xor_sync(0xffffffffu, v, o); v = v < w ? w : v; }
+        if ((threadIdx.x & 31) == 0 && v > 0.f) atomicMax(a.chmax_bits + k, __float_as_int(v));
+    }
+}
+
 }  // namespace
 
 int art_scale_colors_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* raw, size_t pitch,
@@ -265,6 +292,56 @@ int art_scale_convert_crop_dev(art_hp_ctx* ctx, int W, int H, const float* sr, c
     dim3 grid((W + 255) / 256, std::min(H, 148 * 8));
     art_prof_begin(ctx, "k_scale_convert_crop");
     k_scale_convert_crop<<<grid, 256, 0, ctx->stream>>>(c);
+    art_prof_end(ctx);
+    ctx->launches++;
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}
+
+// ------------------------------------------------------------------ ImProcFunctions::channelMixer (ipchmixer.cc L152-232), the per-pixel loop
+namespace {
+struct MixArgs { float* r; float* g; float* b; size_t pitch; int W, H; float m[9]; };
+__global__ void __launch_bounds__(256) k_channel_mixer(MixArgs a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.W) return;
+    const bool vec = (x & ~3) + 4 <= a.W;        // the SSE2 loop `for (; x < W - 3; x += 4)` clamps with _mm_max_ps (NaN -> 0), the tail with rt_math.h max
+    for (int y = blockIdx.y; y < a.H; y += gridDim.y) {
+        const size_t o = (size_t)y * a.pitch + x;
+        const float r = a.r[o], g = a.g[o], b = a.b[o];
+        const float rmix = (r * a.m[0] + g * a.m[1] + b * a.m[2]);
+        const float gmix = (r * a.m[3] + g * a.m[4] + b * a.m[5]);
+        const float bmix = (r * a.m[6] + g * a.m[7] + b * a.m[8]);
+        a.r[o] = vec ? (rmix > 0.f ? rmix : 0.f) : (rmix < 0.f ? 0.f : rmix);
+        a.g[o] = vec ? (gmix > 0.f ? gmix : 0.f) : (gmix < 0.f ? 0.f : gmix);
+        a.b[o] = vec ? (bmix > 0.f ? bmix : 0.f) : (bmix < 0.f ? 0.f : bmix);
+    }
+}
+}  // namespace
+
+int art_channel_mixer_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch, const float m[9])
+{
+    MixArgs a;
+    a.r = r; a.g = g; a.b = b; a.pitch = pitch; a.W = W; a.H = H;
+    for (int i = 0; i < 9; ++i) a.m[i] = m[i];
+    art_prof_begin(ctx, "k_channel_mixer");
+    k_channel_mixer<<<dim3((W + 255) / 256, std::min(H, 148 * 8)), 256, 0, ctx->stream>>>(a);
+    art_prof_end(ctx);
+    ctx->launches++;
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}
+
+int art_scale_colors_xtrans_dev(art_hp_ctx* ctx, int W, int H, const int* xtrans36, float* raw, size_t pitch,
+                                const float black[3], const float mul[3], int* d_chmax_bits)
+{
+    ScaleColorsXtArgs a;
+    a.raw = raw; a.pitch = pitch; a.W = W; a.H = H; a.chmax_bits = d_chmax_bits;
+    for (int i = 0; i < 36; ++i) a.xt[i] = xtrans36[i];
+    for (int i = 0; i < 3; ++i) { a.black[i] = black[i]; a.mul[i] = mul[i]; }
+    ART_CUDA(ctx, cudaMemsetAsync(d_chmax_bits, 0, 3 * sizeof(int), ctx->stream));
+    art_prof_begin(ctx, "k_scale_colors_xtrans");
+    k_scale_colors_xtrans<<<dim3((W + 255) / 256, std::min(H, 148 * 4)), 256, 0, ctx->stream>>>(a);
     art_prof_end(ctx);
     ctx->launches++;
     ART_CUDA(ctx, cudaGetLastError());

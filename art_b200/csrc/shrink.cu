@@ -83,7 +83,7 @@ struct ShBatch {
     int unit0[SH_MAXJOBS + 1];            // first work unit of each job (prefix sums), per kernel
     const float* nv; int nv_uniform; float nv_value; float noisevar_ab; int useCCurve, ab;
 };
-constexpr int SH_ROWS = 16, SH_RING = 64, SH_RP = SH_RING + 1, SH_SP = 33, SH_WARPS = 16;
+constexpr int SH_ROWS = 32, SH_RING = 64, SH_RP = SH_RING + 1, SH_SP = 36, SH_WARPS = 8;      // SH_SP: 16-byte aligned rows, conflict-free 128-bit reads by 8 lanes
 constexpr size_t SH_SMEM = (size_t)SH_WARPS * SH_ROWS * (SH_RP + SH_SP) * sizeof(float);
 
 __device__ __forceinline__ float sf_value(const ShBatch& b, const ShJob& j, float levelFactor, float madab, float rmadLm9, float mad_L, size_t i, size_t n)
@@ -133,18 +133,20 @@ __global__ void __launch_bounds__(256) k_shrink_sf(const __grid_constant__ ShBat
     for (; i < n; i += stride) j.sf[i] = sf_value(b, j, levelFactor, madab, rmadLm9, mad_L, i, n);
 }
 
-// horizontal pass of the flat boxblur over sf -> tmp (boxblur.h L571-602).  A warp owns SH_ROWS rows of one subband and streams along
+// horizontal pass of the flat boxblur over sf -> tmp (boxblur.h L571-602).  A warp owns SH_ROWS = 32 rows of one subband and streams along
 // them in 32-column tiles: coalesced row segments into registers (the next tile's loads are in flight while this one is processed), the
 // samples parked in a 64-column shared-memory ring, the per-step increments (x[n + rad] - x[n - rad - 1]) / len formed by all lanes, then
-// lane r walks row r's chain -- one dependent add per step -- and the sums leave through the same transposing tile.
+// lane r walks row r's chain -- one dependent add per step, every lane of the warp busy, four steps per 128-bit shared-memory access -- and
+// the sums leave through the same transposing tile.  Units are dealt to CTAs round-robin so that a launch with fewer units than warp
+// slots still spreads over every SM.
 __global__ void __launch_bounds__(SH_WARPS * 32) k_shrink_h(const __grid_constant__ ShBatch b)
 {
-    extern __shared__ float shm[];
+    extern __shared__ __align__(16) float shm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* ring = shm + (size_t)warp * SH_ROWS * (SH_RP + SH_SP);
     float* dt = ring + SH_ROWS * SH_RP;
     const int total = b.unit0[b.njobs];
-    for (int u = blockIdx.x * SH_WARPS + warp; u < total; u += gridDim.x * SH_WARPS) {
+    for (int u = warp * gridDim.x + blockIdx.x; u < total; u += gridDim.x * SH_WARPS) {
         int ji = 0;
         while (u >= b.unit0[ji + 1]) ++ji;
         const ShJob& j = b.job[ji];
@@ -198,8 +200,19 @@ __global__ void __launch_bounds__(SH_WARPS * 32) k_shrink_h(const __grid_constan
                     }
                     o[k] = t;
                 }
-#pragma unroll 4
-                for (int k = max(k_main0, k_first); k < k_main1; ++k) { t = t + o[k]; o[k] = t; }
+                {
+                    int k = max(k_main0, k_first);
+                    for (; k < k_main1 && (k & 3); ++k) { t = t + o[k]; o[k] = t; }
+                    for (; k + 4 <= k_main1; k += 4) {
+                        float4 v = *reinterpret_cast<float4*>(o + k);
+                        t = t + v.x; v.x = t;
+                        t = t + v.y; v.y = t;
+                        t = t + v.z; v.z = t;
+                        t = t + v.w; v.w = t;
+                        *reinterpret_cast<float4*>(o + k) = v;
+                    }
+                    for (; k < k_main1; ++k) { t = t + o[k]; o[k] = t; }
+                }
                 for (int k = max(max(k_main1, k_main0), k_first); k < k_last; ++k) {        // p >= W - rad: the ramp-down
                     const int p = base + k;
                     t = (t * len - x[(p - rad - 1) & (SH_RING - 1)]) / (len - 1);
@@ -427,7 +440,7 @@ int shrink_batch(art_hp_ctx* ctx, ShBatch& b)
         art_prof_end(ctx);
     }
     art_prof_begin(ctx, "k_shrink_h");
-    k_shrink_h<<<std::min((b.unit0[b.njobs] + SH_WARPS - 1) / SH_WARPS, 2 * ctx->sm_count), SH_WARPS * 32, SH_SMEM, st>>>(b);     // 100 KB of shared memory: two CTAs per SM, all row groups of a 45 MP channel resident at once
+    k_shrink_h<<<std::min(b.unit0[b.njobs], 2 * ctx->sm_count), SH_WARPS * 32, SH_SMEM, st>>>(b);     // 101 KB of shared memory: two CTAs per SM; units dealt round-robin over the CTAs
     art_prof_end(ctx);
     for (int i = 0; i < b.njobs; ++i) b.unit0[i + 1] = b.unit0[i] + (b.job[i].W + 31) / 32;
     art_prof_begin(ctx, "k_shrink_v");

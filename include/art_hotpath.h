@@ -158,6 +158,11 @@ int art_hp_scale_colors_bayer(art_hp_ctx* ctx, int W, int H, unsigned filters, f
                               const float cblacksom[4], const float scale_mul[4], float chmax[3]);
 int art_hp_scale_colors_bayer_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* d_raw, size_t pitch,
                                   const float cblacksom[4], const float scale_mul[4], float chmax[3]);
+/* The X-Trans branch (L2795-2826): c = XTRANSFC(row, col) = xtrans[row % 6][col % 6], cblacksom / scale_mul per colour. */
+int art_hp_scale_colors_xtrans(art_hp_ctx* ctx, int W, int H, const int xtrans[36], float* const* rawData,
+                               const float cblacksom[3], const float scale_mul[3], float chmax[3]);
+int art_hp_scale_colors_xtrans_dev(art_hp_ctx* ctx, int W, int H, const int xtrans[36], float* d_raw, size_t pitch,
+                                   const float cblacksom[3], const float scale_mul[3], float chmax[3]);
 
 /* ---- Gaussian blur --------------------------------------------------------- */
 /*
@@ -488,6 +493,42 @@ int art_hp_scanlines(art_hp_ctx* ctx, int W, int H, float* const* r, float* cons
                      void* out, size_t out_stride_bytes);
 int art_hp_scanlines_dev(art_hp_ctx* ctx, int W, int H, const float* d_r, const float* d_g, const float* d_b, size_t pitch, int bps, int isFloat,
                          void* d_out, size_t out_stride_bytes);
+
+/* ---- hot / dead pixel filter ------------------------------------------------------- */
+/*
+ * art_hp_find_hot_dead_pixels        RawImageSource::findHotDeadPixels(bpMap, thresh, findHotPixels, findDeadPixels) (rtengine/badpixels.cc
+ *                                    L477-627; called by RawImageSource::preprocess, rtengine/rawimagesource.cc L1394-1420, with
+ *                                    raw.hotdeadpix_thresh): a sample is bad when it deviates from the median of its same-colour
+ *                                    neighbourhood by more than varthresh x the mean deviation around it.  xtrans = NULL: Bayer (any 2x2
+ *                                    CFA: only the distance-2 neighbours are used), else the 6x6 X-Trans matrix.  `map` plays PixelsMap: H
+ *                                    rows of W bytes, row y at map + y * map_stride, non-zero = bad; bad pixels found are OR-ed in (the caller
+ *                                    pre-fills it with the bad pixels it knows from its files, as the reference does).  *count = pixels
+ *                                    marked by this call (the return value of the reference function).
+ * art_hp_interpolate_bad_pixels_bayer  RawImageSource::interpolateBadPixelsBayer(bitmapBads, rawData) (L66-180), in place; *count = pixels
+ *                                    interpolated.
+ * Bit-identical to the reference (for findHotDeadPixels: whenever each of its OpenMP threads owns at least two rows; below that the stock
+ * function depends on its thread count).  interpolateBadPixelsXtrans (L288-475) reads pixels its own loop may already have rewritten and is
+ * not reproduced.
+ */
+int art_hp_find_hot_dead_pixels(art_hp_ctx* ctx, int W, int H, const int* xtrans, const float* const* rawData, float thresh,
+                                int findHotPixels, int findDeadPixels, unsigned char* map, size_t map_stride, int* count);
+int art_hp_find_hot_dead_pixels_dev(art_hp_ctx* ctx, int W, int H, const int* xtrans, const float* d_raw, size_t raw_pitch, float thresh,
+                                    int findHotPixels, int findDeadPixels, unsigned char* d_map, size_t map_pitch, int* count);
+int art_hp_interpolate_bad_pixels_bayer(art_hp_ctx* ctx, int W, int H, unsigned filters, float* const* rawData,
+                                        const unsigned char* map, size_t map_stride, int* count);
+int art_hp_interpolate_bad_pixels_bayer_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* d_raw, size_t raw_pitch,
+                                            const unsigned char* d_map, size_t map_pitch, int* count);
+
+/* ---- channel mixer ----------------------------------------------------------------- */
+/*
+ * art_hp_channel_mixer   the per-pixel loop of ImProcFunctions::channelMixer (rtengine/ipchmixer.cc L152-232), in place on linear RGB planes:
+ *                        out = max(M rgb, 0), M row-major RR RG RB / GR GG GB / BR BG BB in float.  ChannelMixerParams::RGB_MATRIX: M[i] =
+ *                        float(slider[i]) / 1000.f (L156-164); PRIMARIES_CHROMA: the caller passes get_mixer_matrix's result (L33-149: host
+ *                        colour science on the working profile, not part of the hot path).  Bit-identical to the reference, including its two
+ *                        clamps (SSE2 groups of four turn NaN into 0, the row tail keeps it).
+ */
+int art_hp_channel_mixer(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b, const float matrix[9]);
+int art_hp_channel_mixer_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch, const float matrix[9]);
 
 /* ---- dual demosaic ----------------------------------------------------------------- */
 /*

@@ -217,6 +217,16 @@ void ref_scalecolors_bayer(int winx, int winy, int winw, int winh, unsigned filt
 #include "scalecolors_loop.inc"
 }
 
+// ---- scaleColors, X-Trans branch (rawimagesource.cc L2807-2815): the reference's own row/col loop
+struct RiXtShim { const int* xt; int XTRANSFC(int row, int col) const { return xt[(row % 6) * 6 + (col % 6)]; } };      // rawimage.h: xtrans[(row) % 6][(col) % 6]
+void ref_scalecolors_xtrans(int winx, int winy, int winw, int winh, const int* xtrans36, float** rawData,
+                            const float* cblacksom, const float* scale_mul, float* tmpchmax)
+{
+    RiXtShim ri_{xtrans36}; RiXtShim* ri = &ri_;
+    using std::max;
+#include "scalecolors_xtrans_loop.inc"
+}
+
 void ref_matrix_convert(ImShim* im, double mat[3][3], bool multithread)
 {
     (void)multithread;
@@ -304,6 +314,18 @@ int artref_scale_colors_bayer(int W, int H, unsigned filters, float* raw, long s
     for (int i = 0; i < H; ++i) rows[i] = raw + (long)i * stride;
     float t[3] = {0.f, 0.f, 0.f};
     rtengine::ref_scalecolors_bayer(0, 0, W, H, filters, rows, cblacksom, scale_mul, t);
+    chmax[0] = t[0]; chmax[1] = t[1]; chmax[2] = t[2];
+    delete[] rows;
+    return 0;
+}
+
+int artref_scale_colors_xtrans(int W, int H, const int* xtrans36, float* raw, long stride,
+                               const float* cblacksom, const float* scale_mul, float* chmax)
+{
+    float** rows = new float*[H];
+    for (int i = 0; i < H; ++i) rows[i] = raw + (long)i * stride;
+    float t[3] = {0.f, 0.f, 0.f};
+    rtengine::ref_scalecolors_xtrans(0, 0, W, H, xtrans36, rows, cblacksom, scale_mul, t);
     chmax[0] = t[0]; chmax[1] = t[1]; chmax[2] = t[2];
     delete[] rows;
     return 0;
@@ -476,6 +498,76 @@ extern "C" int artref_green_equilibrate(float* raw, int W, int H, unsigned filte
     }
     delete[] rows;
     return 0;
+}
+"""
+
+
+SHIM_BADPIX_TU = r"""
+// Shim TU hosting the reference's hot / dead pixel filter: the helpers of badpixels.cc's anonymous namespace, RawImageSource::findHotDeadPixels
+// and ::interpolateBadPixelsBayer cut from badpixels.cc, over the reference's own median.h and pixelsmap.h.  Written here (not reference
+// code): the RawImageSource / RawImage stand-ins and the wrappers (byte maps in and out).
+#include <math.h>
+#include <cmath>
+#include <array>
+#include <stdlib.h>
+#include <string.h>
+#include <omp.h>
+#include "array2D.h"
+#include "rt_math.h"
+#include "opthelper.h"
+#include "median.h"
+#include "pixelsmap.h"
+#define BENCHFUN
+#define RawImageSource RawImageSourceBadPix       /* other shim TUs define their own stand-in of this name: keep the inline members apart */
+namespace rtengine {
+enum { ST_BAYER_ = 1, ST_FUJI_XTRANS = 2 };
+struct RawImageBadPix {
+    int sensor; const int* xt;
+    int getSensorType() const { return sensor; }
+    unsigned XTRANSFC(int row, int col) const { return (unsigned)xt[(row % 6) * 6 + (col % 6)]; }     // rawimage.h: xtrans[(row) % 6][(col) % 6]
+};
+struct RawImageSource {
+    int W, H; unsigned filters; RawImageBadPix* ri; array2D<float>& rawData;
+    unsigned FC(int row, int col) const { return (filters >> ((((row) << 1 & 14) + ((col) & 1)) << 1) & 3); }
+    int interpolateBadPixelsBayer(const PixelsMap &bitmapBads, array2D<float> &rawData);
+    int findHotDeadPixels(PixelsMap &bpMap, const float thresh, const bool findHotPixels, const bool findDeadPixels) const;
+};
+#include "badpix_body.inc"
+}
+extern "C" int artref_find_hot_dead(float* raw, int W, int H, const int* xtrans36, float thresh, int hot, int dead, unsigned char* map, int nthreads)
+{
+    float** rows = new float*[H];
+    for (int i = 0; i < H; ++i) rows[i] = raw + (size_t)i * W;
+    int n = 0;
+    {
+        rtengine::array2D<float> rd(W, H, rows, rtengine::ARRAY2D_BYREFERENCE);
+        rtengine::RawImageBadPix ri{xtrans36 ? (int)rtengine::ST_FUJI_XTRANS : (int)rtengine::ST_BAYER_, xtrans36};
+        rtengine::RawImageSource s{W, H, 0u, &ri, rd};
+        rtengine::PixelsMap pm(W, H);
+        const int old = omp_get_max_threads();
+        if (nthreads > 0) omp_set_num_threads(nthreads);
+        n = s.findHotDeadPixels(pm, thresh, hot != 0, dead != 0);
+        omp_set_num_threads(old);
+        for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) if (pm.get(x, y)) map[(size_t)y * W + x] = 1;
+    }
+    delete[] rows;
+    return n;
+}
+extern "C" int artref_interpolate_bad_bayer(float* raw, int W, int H, unsigned filters, const unsigned char* map)
+{
+    float** rows = new float*[H];
+    for (int i = 0; i < H; ++i) rows[i] = raw + (size_t)i * W;
+    int n = 0;
+    {
+        rtengine::array2D<float> rd(W, H, rows, rtengine::ARRAY2D_BYREFERENCE);
+        rtengine::RawImageBadPix ri{(int)rtengine::ST_BAYER_, nullptr};
+        rtengine::RawImageSource s{W, H, filters, &ri, rd};
+        rtengine::PixelsMap pm(W, H);
+        for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) if (map[(size_t)y * W + x]) pm.set(x, y);
+        n = s.interpolateBadPixelsBayer(pm, rd);
+    }
+    delete[] rows;
+    return n;
 }
 """
 
@@ -1762,6 +1854,9 @@ def extract(det):
     scl = cut_block(os.path.join(RT, "rawimagesource.cc"),
                     r"for \(int row = winy; row < winy \+ winh; row \+\+\)\s*\{(?=\s*for \(int col = winx; col < winx \+ winw; col\+\+\) \{\s*const int c  = FC\(row, col\);)")
     open(os.path.join(sub, "scalecolors_loop.inc"), "w").write(scl)
+    sclx = cut_block(os.path.join(RT, "rawimagesource.cc"),
+                     r"for \(int row = winy; row < winy \+ winh; row \+\+\)\s*\{(?=\s*for \(int col = winx; col < winx \+ winw; col\+\+\) \{\s*const int c = ri->XTRANSFC\(row, col\);)")
+    open(os.path.join(sub, "scalecolors_xtrans_loop.inc"), "w").write(sclx)
     open(os.path.join(sub, "glibmm.h"), "w").write(SHIM_GLIBMM)
     open(os.path.join(sub, "shim.cc"), "w").write(SHIM_TU)
     gtext = open(os.path.join(RT, "gauss.cc"), encoding="utf-8", errors="replace").read()
@@ -1946,6 +2041,15 @@ def extract(det):
         cut_function(ge, r"^void RawImageSource::green_equilibrate_global\(array2D<float> &rawData\)") + "\n\n" +
         cut_function(ge, r"^void RawImageSource::green_equilibrate\(const GreenEqulibrateThreshold &thresh, array2D<float> &rawData\)"))
     open(os.path.join(sub, "shim_greeneq.cc"), "w").write(SHIM_GREENEQ_TU)
+    bp = os.path.join(RT, "badpixels.cc")
+    bptext = open(bp, encoding="utf-8", errors="replace").read()
+    a0 = re.search(r"^namespace \{", bptext, flags=re.M)
+    a1 = re.search(r"^\} // namespace", bptext, flags=re.M)
+    open(os.path.join(sub, "badpix_body.inc"), "w").write(
+        bptext[a0.start():a1.end()] + "\n\n" +
+        cut_function(bp, r"^int RawImageSource::interpolateBadPixelsBayer\(const PixelsMap &bitmapBads, array2D<float> &rawData\)") + "\n\n" +
+        cut_function(bp, r"^int RawImageSource::findHotDeadPixels\(PixelsMap &bpMap, const float thresh, const bool findHotPixels, const bool findDeadPixels\) const"))
+    open(os.path.join(sub, "shim_badpix.cc"), "w").write(SHIM_BADPIX_TU)
     rz = os.path.join(RT, "ipresize.cc")
     open(os.path.join(sub, "resize_lanc.inc"), "w").write(cut_function(rz, r"^inline float Lanc\(float x, float a\)"))
     open(os.path.join(sub, "resize_lanczos.inc"), "w").write(cut_function(rz, r"^void ImProcFunctions::Lanczos\(Imagefloat \*src, Imagefloat \*dst, float scale\)"))
@@ -1980,7 +2084,7 @@ def build(det):
     lib = os.path.join(OUT, "libartref_det.so" if det else "libartref.so")
     tus = ["shim.cc", "shim_gauss.cc", "shim_guided.cc", "shim_wavelet.cc", "shim_shrink.cc", "shim_nlmeans.cc", "shim_denoise.cc", "shim_fattal.cc",
            "shim_chain.cc", "shim_usm.cc", "shim_xtrans.cc", "shim_resize.cc", "shim_greeneq.cc", "shim_pack.cc", "shim_bilinear.cc", "shim_vng4.cc",
-           "shim_hlblend.cc", "shim_getimage.cc", "shim_tone.cc"]
+           "shim_hlblend.cc", "shim_getimage.cc", "shim_tone.cc", "shim_badpix.cc"]
     base = ["g++", "-std=c++11", "-O3", "-fopenmp", "-ffp-contract=off", "-fPIC", "-w", "-I", sub, "-I", RT] + (["-DARTREF_DET"] if det else [])
     from concurrent.futures import ThreadPoolExecutor
     objs = [os.path.join(sub, t[:-3] + ".o") for t in tus]

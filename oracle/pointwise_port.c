@@ -61,6 +61,23 @@ int artoracle_scale_colors_bayer(int W, int H, unsigned filters, float* raw, lon
     return 0;
 }
 
+/* RawImageSource::scaleColors, X-Trans branch (rawimagesource.cc L2795-2826): c = XTRANSFC(row, col) = xtrans[row % 6][col % 6] */
+int artoracle_scale_colors_xtrans(int W, int H, const int* xtrans36, float* raw, long stride,
+                                  const float* cblacksom, const float* scale_mul, float* chmax)
+{
+    float mx[3] = {0.f, 0.f, 0.f};
+    for (int row = 0; row < H; ++row)
+        for (int col = 0; col < W; ++col) {
+            const int c = xtrans36[(row % 6) * 6 + (col % 6)];
+            const float d = raw[(size_t)row * stride + col] - cblacksom[c];
+            const float val = (0.f < d ? d : 0.f) * scale_mul[c];
+            raw[(size_t)row * stride + col] = val;
+            mx[c] = mx[c] < val ? val : mx[c];
+        }
+    chmax[0] = mx[0]; chmax[1] = mx[1]; chmax[2] = mx[2];
+    return 0;
+}
+
 /* RawImageSource::HLRecovery_blend (rawimagesource.cc L3613-3747; hlRecovery L3752-3755 calls it with maxval 65535), the "Blend" highlight
  * reconstruction getImage applies per line (L1014): clipped pixels get their chroma (in an opponent space) scaled to the unclipped
  * estimate's, faded in above half the lowest clip point; the tail mixes float and double arithmetic (double literals). */

@@ -98,3 +98,22 @@ def test_chain_rejects_missing_matrix(hot_path):
     planes = image(8, 8, 1)
     with pytest.raises(art_b200.HotPathError):
         hot_path.color_chain(planes[0], planes[1], planes[2], ChainParams(saturation=(10, 0)))
+
+
+@pytest.mark.parametrize("W,H", [(64, 48), (67, 35), (301, 203), (1021, 77)])
+@pytest.mark.parametrize("mixer", [(1000, 0, 0, 0, 1000, 0, 0, 0, 1000), (800, 300, -100, -50, 1100, -50, 20, -400, 1380), (-200, 600, 600, 333, 333, 334, 0, 0, -1000)])
+def test_channel_mixer_matches_oracle(hot_path, W, H, mixer):
+    """art_hp_channel_mixer = ImProcFunctions::channelMixer's loop (ipchmixer.cc L200-230); the oracle is pinned to it in test_oracle_chain.py.
+    Bit-exact, NaN samples included (the vector groups clamp them to 0, the row tail keeps them)."""
+    import ctypes
+    import oracle
+    rng = np.random.default_rng(W + H)
+    planes = [np.ascontiguousarray(rng.uniform(-3000, 70000, (H, W)), dtype=np.float32) for _ in range(3)]
+    planes[0][H // 2, ::3] = np.nan
+    m = (np.array(mixer, np.float32) / np.float32(1000.0)).astype(np.float32)
+    fp = ctypes.POINTER(ctypes.c_float)
+    want = [p.copy() for p in planes]
+    assert oracle.port().lib.artoracle_chmixer(*[p.ctypes.data_as(fp) for p in want], W, H, m.ctypes.data_as(fp)) == 0
+    got = hot_path.channel_mixer(*[p.copy() for p in planes], m)
+    for g, w in zip(got, want):
+        assert ((g == w) | (np.isnan(g) & np.isnan(w))).all()

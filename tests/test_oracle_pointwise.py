@@ -52,3 +52,31 @@ def test_scale_colors_port_matches_reference(pattern):
     got, gmax = oracle.port().scale_colors_bayer(raw, f, black, mul)
     want, wmax = oracle.ref().scale_colors_bayer(raw, f, black, mul)
     assert np.array_equal(got, want) and gmax == wmax
+
+
+def scale_colors_xtrans(lib, name, raw, xt, black, mul):
+    import ctypes
+    out = np.array(raw, dtype=np.float32, order="C", copy=True)
+    H, W = out.shape
+    x = np.ascontiguousarray(xt, dtype=np.int32)
+    bl = (ctypes.c_float * 4)(*[float(v) for v in black])
+    mu = (ctypes.c_float * 4)(*[float(v) for v in mul])
+    ch = (ctypes.c_float * 3)()
+    assert getattr(lib, name)(W, H, x.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                              ctypes.c_long(W), bl, mu, ch) == 0
+    return out, [float(ch[0]), float(ch[1]), float(ch[2])]
+
+
+@needs_ref
+@pytest.mark.parametrize("dy,dx", [(0, 0), (2, 5), (4, 1)])
+def test_scale_colors_xtrans_port_matches_reference(dy, dx):
+    """scaleColors' X-Trans branch (rawimagesource.cc L2795-2826) against the reference's own loop."""
+    from art_b200 import synth
+    xt = synth.xtrans_matrix(dy, dx)
+    rng = np.random.default_rng(12 + dy)
+    raw = rng.integers(0, 16384, size=(75, 103)).astype(np.float32)
+    black = (1023.0, 1024.5, 1022.0, 0.0)
+    mul = (7.9, 4.0625, 6.3321, 0.0)
+    got, gmax = scale_colors_xtrans(oracle.port().lib, "artoracle_scale_colors_xtrans", raw, xt, black, mul)
+    want, wmax = scale_colors_xtrans(oracle.ref().lib, "artref_scale_colors_xtrans", raw, xt, black, mul)
+    assert np.array_equal(got, want) and gmax == wmax

@@ -80,3 +80,20 @@ def test_scale_colors_bayer(hot_path, pattern, W, H):
     got = raw.copy()
     gmax = hot_path.scale_colors_bayer(got, f, black, mul)
     assert np.array_equal(got, want) and gmax == wmax
+
+
+@pytest.mark.parametrize("dy,dx", [(0, 0), (2, 5), (4, 1)])
+@pytest.mark.parametrize("W,H", [(640, 480), (333, 77), (6240, 417)])
+def test_scale_colors_xtrans(hot_path, dy, dx, W, H):
+    """scaleColors' X-Trans branch (rawimagesource.cc L2795-2826) through the C-ABI against the oracle (pinned in test_oracle_pointwise.py)."""
+    from art_b200 import synth
+    from test_oracle_pointwise import scale_colors_xtrans
+    xt = synth.xtrans_matrix(dy, dx)
+    rng = np.random.default_rng(W + dy)
+    raw = rng.integers(0, 16384, size=(H, W)).astype(np.float32)
+    black = (1023.0, 1024.5, 1022.0)
+    mul = (7.9, 4.0625, 6.3321)
+    want, wmax = scale_colors_xtrans(oracle.port().lib, "artoracle_scale_colors_xtrans", raw, xt, black + (0.0,), mul + (0.0,))
+    got = raw.copy()
+    gmax = hot_path.scale_colors_xtrans(got, xt, black, mul)
+    assert np.array_equal(got, want) and gmax == wmax
