@@ -231,6 +231,9 @@ inline float sqrf(float x) { return x * x; }
 
 // shrink.cu, internal forms: `uniform` != nullptr says the noise-variance map is that one value everywhere
 int art_wavelet_denoise_L(art_hp_ctx* ctx, art_hp_wavelet* wL, const float* d_noisevarlum, const float* uniform, const float* d_madL, double scale);
+int art_wavelet_denoise_LAB(art_hp_ctx* ctx, art_hp_wavelet* wL, art_hp_wavelet* wa, art_hp_wavelet* wb, const float* d_noisevarchrom, const float* uniform_c,
+                            float noisevar_a, float noisevar_b, int useNoiseCCurve, const float* d_noisevarlum, const float* uniform_l,
+                            const float* d_madL, double scale, int with_L);
 int art_wavelet_denoise_AB(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wavelet* wab, const float* d_noisevarchrom, const float* uniform,
                            const float* d_madL, float noisevar_ab, int useNoiseCCurve, int autoch, double scale, int bishrink = 0);
 
@@ -439,6 +442,28 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
     if ((rc = art_hp_wavelet_mad_dev(ctx, Ldec, madL))) { art_hp_wavelet_destroy(Ldec); return rc; }
     float* chan[2] = {ap, bp};
     const float nv[2] = {noisevarab_r, noisevarab_b};
+    // The standard quality runs the shrinkage of a, b and L as one batch (shrink.cu: art_wavelet_denoise_LAB); ART_HP_SHRINK_MERGE = 0 restores the
+    // channel-by-channel order of the reference (same bits either way), 1 merges a and b only.
+    static const int merge_mode = [] { const char* e = getenv("ART_HP_SHRINK_MERGE"); return e ? atoi(e) : 2; }();
+    const int maxlvl = art_hp_wavelet_maxlevel(Ldec);
+    (void)maxlvl;
+    if (!aggressive && merge_mode > 0) {
+        art_hp_wavelet* dec[2] = {nullptr, nullptr};
+        for (int c = 0; c < 2 && !rc; ++c) rc = art_hp_wavelet_decompose_dev(ctx, chan[c], W, W, H, levwav, 1, &dec[c]);
+        const float one = 1.f;
+        const bool with_L = denoiseLuminance && merge_mode > 1;
+        if (!rc) rc = art_wavelet_denoise_LAB(ctx, Ldec, dec[0], dec[1], nvc, useCC ? nullptr : &one, nv[0], nv[1], useCC, nvl, &noisevarL, madL, scale, with_L);
+        for (int c = 0; c < 2; ++c) {
+            if (!rc && nresi_highresi) rc = residual_mads(ctx, dec[c], resid + 24 * c);
+            if (!rc) rc = art_hp_wavelet_reconstruct_dev(dec[c], chan[c], W, 1.f);
+            if (dec[c]) art_hp_wavelet_destroy(dec[c]);
+        }
+        if (!rc && denoiseLuminance) {
+            if (!with_L) rc = art_wavelet_denoise_L(ctx, Ldec, nvl, &noisevarL, madL, scale);
+            if (!rc && cudaMemcpyAsync(Lin, Lp, n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = ctx->fail(ART_HP_ERR_CUDA, "Lin copy failed");
+            if (!rc) rc = art_hp_wavelet_reconstruct_dev(Ldec, Lp, W, 1.f);
+        }
+    } else {
     for (int c = 0; c < 2; ++c) {
         art_hp_wavelet* dec = nullptr;
         if ((rc = art_hp_wavelet_decompose_dev(ctx, chan[c], W, W, H, levwav, 1, &dec))) { art_hp_wavelet_destroy(Ldec); return rc; }
@@ -453,7 +478,6 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
         art_hp_wavelet_destroy(dec);
         if (rc) { art_hp_wavelet_destroy(Ldec); return rc; }
     }
-    const int maxlvl = art_hp_wavelet_maxlevel(Ldec);
     if (denoiseLuminance) {
         // QUALITY_HIGH: WaveletDenoiseAll_BiShrinkL (the same computation as WaveletDenoiseAllL) and then WaveletDenoiseAllL (L2412-2421)
         if (aggressive) rc = art_wavelet_denoise_L(ctx, Ldec, nvl, &noisevarL, madL, scale);
@@ -462,6 +486,7 @@ int art_rgb_denoise_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip
             if (cudaMemcpyAsync(Lin, Lp, n * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) rc = ctx->fail(ART_HP_ERR_CUDA, "Lin copy failed");
         }
         if (!rc) rc = art_hp_wavelet_reconstruct_dev(Ldec, Lp, W, 1.f);
+    }
     }
     art_hp_wavelet_destroy(Ldec);
     if (rc) return rc;

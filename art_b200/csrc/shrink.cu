@@ -76,21 +76,26 @@ __global__ void __launch_bounds__(256) k_sf_AB_simple(ShArgs a)
 //   k_shrink_v  the vertical pass (boxblur.h L614-710, three column classes) fused with the apply step (L692-709 / L791-813): one
 //               thread per column marching down the subband with eight rows of loads in flight, the blurred value never stored.
 // Per coefficient: 4 (+4 L coefficient) B read, 8 B written; then 12 B read (+4 B trailing sample from L2), 4 B written.
-struct ShJob { float* c; const float* cL; const float* madL; const float* madab; float* sf; float* tmp; int W, H, rad; float lvlmul; };
-constexpr int SH_MAXJOBS = 24;
+// A job is one subband; the jobs of a batch may belong to different channels (a, b and L of a frame run in one grid: the chroma factors
+// read the luminance coefficients in the first kernel, the luminance coefficients are only rewritten in the last one).
+struct ShJob {
+    float* c; const float* cL; const float* madL; const float* madab; float* sf; float* tmp; int W, H, rad; float lvlmul;
+    const float* nv; float nv_value; float noisevar_ab; int nv_uniform, useCCurve, ab;      // the noise-variance map (or its one value), chroma parameters
+};
+constexpr int SH_MAXJOBS = 64;          // 2 x 3 x 8 chroma + 3 x 5 luminance subbands
 struct ShBatch {
     ShJob job[SH_MAXJOBS]; int njobs;
     int unit0[SH_MAXJOBS + 1];            // first work unit of each job (prefix sums), per kernel
-    const float* nv; int nv_uniform; float nv_value; float noisevar_ab; int useCCurve, ab;
 };
 constexpr int SH_ROWS = 32, SH_RING = 64, SH_RP = SH_RING + 1, SH_SP = 36, SH_WARPS = 8;      // SH_SP: 16-byte aligned rows, conflict-free 128-bit reads by 8 lanes
 constexpr size_t SH_SMEM = (size_t)SH_WARPS * SH_ROWS * (SH_RP + SH_SP) * sizeof(float);
 
-__device__ __forceinline__ float sf_value(const ShBatch& b, const ShJob& j, float levelFactor, float madab, float rmadLm9, float mad_L, size_t i, size_t n)
+struct SfJob { const float* c; const float* cL; const float* nv; float nv_value; bool nv_uniform, ab; };      // the fields the inner loop reads, in registers
+__device__ __forceinline__ float sf_value(const SfJob& j, float levelFactor, float madab, float rmadLm9, float mad_L, size_t i, size_t n)
 {
-    const float nvi = b.nv_uniform ? b.nv_value : b.nv[i];
+    const float nvi = j.nv_uniform ? j.nv_value : j.nv[i];
     const bool vec = (i & ~(size_t)3) + 3 < n;           // handled by a full 4-wide vector in the reference (for (i = 0; i < n - 3; i += 4))
-    if (!b.ab) {
+    if (!j.ab) {
         const float eps = 0.01f;
         const float x = j.c[i];
         const float mag = x * x;
@@ -114,23 +119,25 @@ __device__ __forceinline__ float sf_value(const ShBatch& b, const ShJob& j, floa
 // shrink factors of every subband of the batch: element-wise, grid.y = subband
 __global__ void __launch_bounds__(256) k_shrink_sf(const __grid_constant__ ShBatch b)
 {
-    const ShJob& j = b.job[blockIdx.y];
-    const size_t n = (size_t)j.W * j.H;
-    const float mad_L = j.madL[0];
-    const float levelFactor = b.ab ? 0.f : mad_L * 5.f / j.lvlmul;
-    float madab = b.ab ? j.madab[0] : 0.f;
-    if (b.ab) madab = b.useCCurve ? madab : madab * b.noisevar_ab;
+    const ShJob& jb = b.job[blockIdx.y];
+    const SfJob j{jb.c, jb.cL, jb.nv, jb.nv_value, jb.nv_uniform != 0, jb.ab != 0};
+    float* __restrict__ sf = jb.sf;
+    const size_t n = (size_t)jb.W * jb.H;
+    const float mad_L = jb.madL[0];
+    const float levelFactor = j.ab ? 0.f : mad_L * 5.f / jb.lvlmul;
+    float madab = j.ab ? jb.madab[0] : 0.f;
+    if (j.ab) madab = jb.useCCurve ? madab : madab * jb.noisevar_ab;
     const float rmadLm9 = 1.f / (mad_L * 9.f);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + 3 * stride < n; i += 4 * stride) {
         float v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = sf_value(b, j, levelFactor, madab, rmadLm9, mad_L, i + k * stride, n);
+        for (int k = 0; k < 4; ++k) v[k] = sf_value(j, levelFactor, madab, rmadLm9, mad_L, i + k * stride, n);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) j.sf[i + k * stride] = v[k];
+        for (int k = 0; k < 4; ++k) sf[i + k * stride] = v[k];
     }
-    for (; i < n; i += stride) j.sf[i] = sf_value(b, j, levelFactor, madab, rmadLm9, mad_L, i, n);
+    for (; i < n; i += stride) sf[i] = sf_value(j, levelFactor, madab, rmadLm9, mad_L, i, n);
 }
 
 // horizontal pass of the flat boxblur over sf -> tmp (boxblur.h L571-602).  A warp owns SH_ROWS = 32 rows of one subband and streams along
@@ -444,7 +451,7 @@ int shrink_batch(art_hp_ctx* ctx, ShBatch& b)
     art_prof_end(ctx);
     for (int i = 0; i < b.njobs; ++i) b.unit0[i + 1] = b.unit0[i] + (b.job[i].W + 31) / 32;
     art_prof_begin(ctx, "k_shrink_v");
-    k_shrink_v<<<std::min((b.unit0[b.njobs] + SV_THREADS / 32 - 1) / (SV_THREADS / 32), ctx->sm_count * 8), SV_THREADS, 0, st>>>(b);
+    k_shrink_v<<<std::min((b.unit0[b.njobs] + SV_THREADS / 32 - 1) / (SV_THREADS / 32), ctx->sm_count * 16), SV_THREADS, 0, st>>>(b);      // one unit per warp up to 9.5 k units: the scheduler hands the tail out CTA by CTA
     art_prof_end(ctx);
     ctx->launches += 3;
     ART_CUDA(ctx, cudaGetLastError());
@@ -500,7 +507,6 @@ int art_wavelet_denoise_L(art_hp_ctx* ctx, art_hp_wavelet* wL, const float* d_no
     int rc = batch_scratch(ctx, 3 * maxlvl, (size_t)wL->lev[0].w2 * wL->lev[0].h2, true, bs);
     if (rc) return rc;
     ShBatch b{};
-    b.nv = d_noisevarlum; b.nv_uniform = uniform != nullptr; b.nv_value = uniform ? *uniform : 0.f; b.ab = 0;
     for (int l = 0; l < maxlvl; ++l)
         for (int d = 1; d < 4; ++d) {
             const WLevel& L = wL->lev[l];
@@ -508,6 +514,7 @@ int art_wavelet_denoise_L(art_hp_ctx* ctx, art_hp_wavelet* wL, const float* d_no
             j.c = L.band[d]; j.cL = nullptr; j.madL = d_madL + 3 * l + (d - 1); j.madab = nullptr;
             j.sf = bs.planes + (size_t)(2 * b.njobs) * bs.np; j.tmp = j.sf + bs.np;
             j.W = L.w2; j.H = L.h2; j.rad = blur_radius(l, scale); j.lvlmul = (float)(l + 1);
+            j.nv = d_noisevarlum; j.nv_uniform = uniform != nullptr; j.nv_value = uniform ? *uniform : 0.f; j.ab = 0;
             b.njobs++;
         }
     return shrink_batch(ctx, b);
@@ -548,8 +555,6 @@ int art_wavelet_denoise_AB(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wav
         }
     if ((rc = mad_batch(ctx, mb, bs.histo))) return rc;
     ShBatch b{};
-    b.nv = d_noisevarchrom; b.nv_uniform = uniform != nullptr; b.nv_value = uniform ? *uniform : 0.f; b.ab = 1;
-    b.noisevar_ab = noisevar_ab; b.useCCurve = useNoiseCCurve;
     for (int l = 0; l < wL->nlev; ++l)
         for (int d = 1; d < 4; ++d) {
             const WLevel& L = wab->lev[l];
@@ -570,8 +575,67 @@ int art_wavelet_denoise_AB(art_hp_ctx* ctx, const art_hp_wavelet* wL, art_hp_wav
             j.c = L.band[d]; j.cL = wL->lev[l].band[d]; j.madL = d_madL + idx; j.madab = madab + idx;
             j.sf = bs.planes + (size_t)(2 * b.njobs) * bs.np; j.tmp = j.sf + bs.np;
             j.W = L.w2; j.H = L.h2; j.rad = blur_radius(l, scale); j.lvlmul = 0.f;
+            j.nv = d_noisevarchrom; j.nv_uniform = uniform != nullptr; j.nv_value = uniform ? *uniform : 0.f; j.ab = 1;
+            j.noisevar_ab = noisevar_ab; j.useCCurve = useNoiseCCurve;
             b.njobs++;
         }
     ART_CUDA(ctx, cudaGetLastError());
+    return shrink_batch(ctx, b);
+}
+
+// WaveletDenoiseAllAB of both chroma channels and (with_L) WaveletDenoiseAllL of the luminance in ONE batch: the MAD of the 2 x 15 chroma
+// subbands in one launch pair, then sf / horizontal / vertical over up to 45 subbands.  Same arithmetic as the per-channel calls (the chroma
+// factors read the luminance coefficients in k_shrink_sf, the luminance coefficients change in k_shrink_v only); what changes is the number
+// of chains in flight: 61 k column chains per channel leave an SM with 13 warps, three channels fill it.
+int art_wavelet_denoise_LAB(art_hp_ctx* ctx, art_hp_wavelet* wL, art_hp_wavelet* wa, art_hp_wavelet* wb, const float* d_noisevarchrom, const float* uniform_c,
+                            float noisevar_a, float noisevar_b, int useNoiseCCurve, const float* d_noisevarlum, const float* uniform_l,
+                            const float* d_madL, double scale, int with_L)
+{
+    if (!ctx || !wL || !wa || !wb || (!d_noisevarchrom && !uniform_c) || !d_madL || !(scale > 0)) return ART_HP_ERR_INVALID;
+    if (with_L && !d_noisevarlum && !uniform_l) return ART_HP_ERR_INVALID;
+    art_hp_wavelet* wab[2] = {wa, wb};
+    const float nvab[2] = {noisevar_a, noisevar_b};
+    for (int c = 0; c < 2; ++c)
+        if (wL->nlev != wab[c]->nlev || wL->W != wab[c]->W || wL->H != wab[c]->H) return ctx->fail(ART_HP_ERR_INVALID, "L and ab decompositions differ in shape");
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int maxlvlL = std::min(wL->nlev, 5);
+    if (2 * 3 * wL->nlev + 3 * maxlvlL > SH_MAXJOBS) return ctx->fail(ART_HP_ERR_INVALID, "too many wavelet levels (%d)", wL->nlev);
+    BatchScratch bs;
+    int rc = batch_scratch(ctx, 2 * 3 * wL->nlev + 3 * maxlvlL, (size_t)wL->lev[0].w2 * wL->lev[0].h2, true, bs);
+    if (rc) return rc;
+    if ((rc = art_reserve(ctx, ctx->d_small, 64 * sizeof(float)))) return rc;
+    float* madab = (float*)ctx->d_small.p;
+    MadBatch mb{};
+    mb.square = 1;
+    ShBatch b{};
+    for (int c = 0; c < 2; ++c) {
+        if (!(nvab[c] > 0.001f)) continue;                // L761
+        for (int l = 0; l < wL->nlev; ++l)
+            for (int d = 1; d < 4; ++d) {
+                const WLevel& L = wab[c]->lev[l];
+                const int idx = 3 * l + (d - 1);
+                float* mslot = madab + mb.njobs;
+                mb.band[mb.njobs] = L.band[d]; mb.n[mb.njobs] = L.w2 * L.h2; mb.w[mb.njobs] = L.w2; mb.out[mb.njobs] = mslot;
+                mb.njobs++;
+                ShJob& j = b.job[b.njobs];
+                j.c = L.band[d]; j.cL = wL->lev[l].band[d]; j.madL = d_madL + idx; j.madab = mslot;
+                j.W = L.w2; j.H = L.h2; j.rad = blur_radius(l, scale); j.lvlmul = 0.f;
+                j.nv = d_noisevarchrom; j.nv_uniform = uniform_c != nullptr; j.nv_value = uniform_c ? *uniform_c : 0.f; j.ab = 1;
+                j.noisevar_ab = nvab[c]; j.useCCurve = useNoiseCCurve;
+                b.njobs++;
+            }
+    }
+    if (with_L)
+        for (int l = 0; l < maxlvlL; ++l)
+            for (int d = 1; d < 4; ++d) {
+                const WLevel& L = wL->lev[l];
+                ShJob& j = b.job[b.njobs];
+                j.c = L.band[d]; j.cL = nullptr; j.madL = d_madL + 3 * l + (d - 1); j.madab = nullptr;
+                j.W = L.w2; j.H = L.h2; j.rad = blur_radius(l, scale); j.lvlmul = (float)(l + 1);
+                j.nv = d_noisevarlum; j.nv_uniform = uniform_l != nullptr; j.nv_value = uniform_l ? *uniform_l : 0.f; j.ab = 0;
+                b.njobs++;
+            }
+    for (int i = 0; i < b.njobs; ++i) { b.job[i].sf = bs.planes + (size_t)(2 * i) * bs.np; b.job[i].tmp = b.job[i].sf + bs.np; }
+    if ((rc = mad_batch(ctx, mb, bs.histo))) return rc;
     return shrink_batch(ctx, b);
 }

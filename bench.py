@@ -245,18 +245,21 @@ def find_fast_dim(dim):
     return dim
 
 
-def kernel_bytes(name, Wr, Hr, W, H, nlev=5):
-    """(algorithmic bytes per launch, description) or None.  Wr x Hr: raw frame; W x H: the developed (cropped) frame."""
+def kernel_bytes(name, Wr, Hr, W, H, nlev=5, launches=None):
+    """(algorithmic bytes per launch, description) or None.  Wr x Hr: raw frame; W x H: the developed (cropped) frame.  launches = how often
+    the kernel ran in a step: the shrink stage covers the 3 x 15 subbands of a frame in as many launches as the library chose (one since the
+    channels were merged), so its bytes per launch are the frame's bytes over that count."""
     px, sub = W * H, ((W + 1) // 2) * ((H + 1) // 2)
     ntiles = ((Wr + 16 + 127) // 128) * ((Hr + 16 + 127) // 128)
     pad = (find_fast_dim(W) + 1) * (find_fast_dim(H) + 1)
     nsub = 3 * nlev
+    nl = float(launches or 3)
     table = {
-        # shrink stage: one launch = all 15 subbands of one channel; sf: read c (+ L coefficient for a / b), write sf -> (8 + 12 + 12) / 3 on average
-        "k_shrink_sf": ((32.0 / 3.0) * sub * nsub, "15 subbands of a channel: coefficient (+ L coefficient for a, b) read, sf written"),
-        "k_shrink_h": (8.0 * sub * nsub, "15 subbands: sf read, row sums written"),
-        "k_shrink_v": (16.0 * sub * nsub, "15 subbands: row sums, sf, coefficient read, coefficient written"),
-        "k_mad_hist_all": (4.0 * sub * nsub, "15 subbands read once"),
+        # shrink stage, per frame (3 channels x 15 subbands): sf reads c (+ the L coefficient for a / b) and writes sf -> 8 + 12 + 12 B per coefficient
+        "k_shrink_sf": (32.0 * sub * nsub / nl, "45 subbands of a frame / launches: coefficient (+ L coefficient for a, b) read, sf written"),
+        "k_shrink_h": (3 * 8.0 * sub * nsub / nl, "45 subbands of a frame / launches: sf read, row sums written"),
+        "k_shrink_v": (3 * 16.0 * sub * nsub / nl, "45 subbands of a frame / launches: row sums, sf, coefficient read, coefficient written"),
+        "k_mad_hist_all": (3 * 4.0 * sub * nsub / nl, "45 subbands of a frame / launches, read once"),
         "k_dn_blocks": ((4 + 4 * (64.0 / 25.0) ** 2) * px, "residual read once + the windowed 64x64 blocks (stride 25) written"),
         "k_dn_gather": ((4 * (64.0 / 25.0) ** 2 + 8) * px, "blocks read, L read and written"),
         "k_dn_split": (24.0 * px, "3 planes read, 3 written"), "k_dn_merge": (24.0 * px, "3 planes read, 3 written"),
@@ -279,7 +282,7 @@ def kernel_bytes(name, Wr, Hr, W, H, nlev=5):
 def roofline_top(per_step, kern, calls, geo, peak, n=8):
     out = []
     for k in sorted(per_step, key=lambda k: -per_step[k])[:n]:
-        kb = kernel_bytes(k, *geo)
+        kb = kernel_bytes(k, *geo, launches=calls[k])
         e = {"kernel": k, "ms_per_step": round(per_step[k], 4), "launches_per_step": calls[k], "achieved_GBps": None, "frac": None}
         if kb is not None:
             ach = kb[0] / (kern[k] * 1e-3) / 1e9
@@ -780,7 +783,7 @@ def main():
         per_step = {k: kern[k] * calls[k] for k in kern}                     # ms per step per kernel
         top = max((k for k in per_step if k != "memset_slabs"), key=lambda k: per_step[k])
         share = per_step[top] / sum(per_step.values())
-        kb = kernel_bytes(top, *geo)
+        kb = kernel_bytes(top, *geo, launches=calls[top])
         achieved = kb[0] / (kern[top] * 1e-3) / 1e9 if kb else None          # per launch: bytes one launch moves / its mean duration
         pipe_e2e = e2e.get("packed", e2e.get("planes"))
         out = {
