@@ -584,7 +584,7 @@ def frame_split_arm(args, hp, dist, rank, world, local, W, H, wl, config, placem
         top = max(kern, key=lambda k: kern[k])
         config = dict(config)
         config["parallelism"] = ("row bands x%d of ONE frame: %d owned + up to %d halo rows per rank, demosaic on the frame's tile grid; collective = ncclAllReduce(int32, sum) "
-                                 "of the wavelet subbands' MAD histograms (3 x 15 x 65536 counters per frame), inside the library" % (world, own[1] - own[0], 2 * args.halo))
+                                 "of the wavelet subbands' MAD histograms (45 x 65536 counters per frame in two all-reduces: L, then a and b together), inside the library" % (world, own[1] - own[0], 2 * args.halo))
         out = {"metric": "Mpixel/s", "value": W * H / (ms_per_step * 1e-3) / 1e6, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": config,
