@@ -242,7 +242,8 @@ class _DevelopParamsC(ctypes.Structure):
                 ("sharpen", ctypes.c_void_p), ("chain", ctypes.c_void_p),
                 ("xtrans", ctypes.POINTER(ctypes.c_int)), ("rgb_cam", ctypes.POINTER(ctypes.c_float)),
                 ("full_frame", ctypes.c_int), ("guidedChromaRadius", ctypes.c_int), ("denoise_expcomp", ctypes.c_double),
-                ("tran", ctypes.c_int), ("hr_blend", ctypes.c_int), ("hlmax", ctypes.c_float * 3)]
+                ("tran", ctypes.c_int), ("hr_blend", ctypes.c_int), ("hlmax", ctypes.c_float * 3),
+                ("pp_x", ctypes.c_int), ("pp_y", ctypes.c_int), ("pp_width", ctypes.c_int), ("pp_height", ctypes.c_int), ("pp_skip", ctypes.c_int)]
 
 
 class _SharpenParamsC(ctypes.Structure):
@@ -362,16 +363,20 @@ class DevelopParams:
     """Parameters of art_hp_develop: the simpleprocess.cc stages on the hot path (demosaic, gains + matrix, denoise, Fattal, sharpening,
     the colour chain).  Like the reference the frame is cropped by the raw border after the demosaic (4 px for Bayer, 7 for X-Trans)
     unless full_frame; guided_chroma_radius / nl_strength are DenoiseParams' smoothing fields (0 unless smoothingEnabled);
-    denoise_expcomp = the exposure compensation ImProcFunctions::denoise brackets its stage with when positive."""
+    denoise_expcomp = the exposure compensation ImProcFunctions::denoise brackets its stage with when positive.  pp = (x, y, width, height,
+    skip): a PreviewProps window of the transformed, cropped full image (the preview path; mul must carry the 1 / skip^2 of getImage)."""
 
     def __init__(self, method=0, filters=0x94949494, initial_gain=1.0, border=4, mul=(1.0, 1.0, 1.0), do_clip=True, cam2work=None,
                  denoise=None, nl_strength=0, nl_detail=80, fattal=None, wprof=None, sharpen=None, chain=None, xtrans=None, rgb_cam=None,
-                 full_frame=False, guided_chroma_radius=0, denoise_expcomp=0.0, tran=0, hr_blend=False, hlmax=(65535.0, 65535.0, 65535.0)):
+                 full_frame=False, guided_chroma_radius=0, denoise_expcomp=0.0, tran=0, hr_blend=False, hlmax=(65535.0, 65535.0, 65535.0), pp=None):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
     def out_shape(self, H, W):
         """(rows, columns) of the developed planes for an (H, W) raw frame"""
+        if self.pp is not None:
+            x, y, w, h, skip = [int(v) for v in self.pp]
+            return (h + skip - 1) // skip, (w + skip - 1) // skip
         b = 0 if self.full_frame else (7 if self.method in (2, 3) else max(int(self.border), 0))
         return (W - 2 * b, H - 2 * b) if int(self.tran) & 1 else (H - 2 * b, W - 2 * b)       # TR_R90 / TR_R270 turn the frame
 
@@ -397,6 +402,8 @@ class DevelopParams:
         c.full_frame, c.guidedChromaRadius, c.denoise_expcomp = int(bool(self.full_frame)), int(self.guided_chroma_radius), float(self.denoise_expcomp)
         c.tran, c.hr_blend = int(self.tran), int(bool(self.hr_blend))
         c.hlmax = (ctypes.c_float * 3)(*[float(x) for x in self.hlmax])
+        if self.pp is not None:
+            c.pp_x, c.pp_y, c.pp_width, c.pp_height, c.pp_skip = [int(v) for v in self.pp]
         if self.fattal is not None:
             thr, amt, sat = self.fattal
             c.fattal_enabled, c.fattal_threshold, c.fattal_amount, c.fattal_satcontrol = 1, int(thr), int(amt), int(bool(sat))

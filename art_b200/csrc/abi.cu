@@ -965,12 +965,12 @@ int art_hp_denoise_compute_params(art_hp_ctx* ctx, int W, int H, float* const* r
 int art_hp_develop_size(const art_hp_develop_params* params, int W, int H, int* out_w, int* out_h, int* border)
 {
     if (!params) return ART_HP_ERR_INVALID;
-    int bd, Wo, Ho;
-    art_develop_geometry(params, W, H, &bd, &Wo, &Ho);
-    if (out_w) *out_w = Wo;
-    if (out_h) *out_h = Ho;
-    if (border) *border = bd;
-    return ART_HP_OK;
+    art_dev_geo g;
+    const int rc = art_develop_geometry2(params, W, H, &g);
+    if (out_w) *out_w = g.Wo;
+    if (out_h) *out_h = g.Ho;
+    if (border) *border = g.bd;
+    return rc;
 }
 
 int art_hp_denoise_guided_smoothing_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
@@ -1409,9 +1409,12 @@ static int check_develop(art_hp_ctx* ctx, const art_hp_develop_params* p, int W,
     }
     if (W < 32 || H < 32 || W > 32767 || H > 32767) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
     {
-        int bd, Wo, Ho;
-        art_develop_geometry(p, W, H, &bd, &Wo, &Ho);
-        if (Wo < 24 || Ho < 24) return ctx->fail(ART_HP_ERR_INVALID, "frame %dx%d is too small for a border of %d", W, H, bd);
+        if (p->tran < 0 || p->tran > 15) return ctx->fail(ART_HP_ERR_INVALID, "tran %d is not a combination of TR_R90 / R180 / R270, TR_VFLIP, TR_HFLIP", p->tran);
+        art_dev_geo g;
+        if (art_develop_geometry2(p, W, H, &g))
+            return ctx->fail(ART_HP_ERR_INVALID, "the PreviewProps window (%d, %d, %d x %d, skip %d) leaves the developed frame", p->pp_x, p->pp_y, p->pp_width, p->pp_height, p->pp_skip);
+        if (g.Wo < 24 || g.Ho < 24) return ctx->fail(ART_HP_ERR_INVALID, "frame %dx%d (developed %dx%d) is too small for a border of %d", W, H, g.Wo, g.Ho, g.bd);
+        if (g.skip > 64) return ctx->fail(ART_HP_ERR_INVALID, "pp_skip %d", g.skip);
     }
     if (p->guidedChromaRadius < 0) return ctx->fail(ART_HP_ERR_INVALID, "guidedChromaRadius %d", p->guidedChromaRadius);
     if (p->tran < 0 || p->tran > 15) return ctx->fail(ART_HP_ERR_INVALID, "tran %d is not a combination of TR_R90 / R180 / R270, TR_VFLIP, TR_HFLIP", p->tran);

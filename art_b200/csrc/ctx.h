@@ -158,7 +158,8 @@ int art_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, flo
                           const float mul[3], int doClip, const double* mat);
 int art_scale_convert_crop_dev(art_hp_ctx* ctx, int W, int H, const float* sr, const float* sg, const float* sb, size_t sp,
                                float* r, float* g, float* b, size_t pitch, const float mul[3], int doClip, const double* mat,
-                               int tran = 0, int hr_blend = 0, const float* hlmax = nullptr);
+                               int tran = 0, int hr_blend = 0, const float* hlmax = nullptr,
+                               int skip = 1, int sx1 = 0, int sy1 = 0, int maxx = 0, int maxy = 0);      // skip > 1: sr / sg / sb are the un-offset planes
 // denoise::denoiseGuidedSmoothing (smoothing.cu), planes in place
 int art_guided_smoothing_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const double* ws9, int guidedChromaRadius, double scale);
 // scaleColors (Bayer): in place; d_chmax_bits = 3 device ints receiving the float bit patterns of chmax[0..2]
@@ -228,6 +229,10 @@ int art_scanlines_dev(art_hp_ctx* ctx, int W, int H, const float* r, const float
                       void* out, size_t stride_bytes);
 // output size of art_hp_develop for a W x H raw frame
 void art_develop_geometry(const art_hp_develop_params* p, int W, int H, int* b, int* Wo, int* Ho);
+// the same with getImage's source rectangle: (sx1, sy1) = transformRect's origin in the raw frame, iw x ih = imwidth x imheight (the source-orientation
+// line geometry; Wo x Ho is the turned image), skip.  ART_HP_ERR_INVALID when the PreviewProps window leaves the frame.
+struct art_dev_geo { int bd, Wo, Ho, sx1, sy1, iw, ih, skip; bool window; };
+int art_develop_geometry2(const art_hp_develop_params* p, int W, int H, art_dev_geo* g);
 int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int W, int H, const float* raw, size_t rp,
                     float* r, float* g, float* b, size_t op);
 // one frame across GPUs: geometry of a rank's band and the band pipeline (develop.cu); the collective (comm.cu)

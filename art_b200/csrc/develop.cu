@@ -134,20 +134,54 @@ int art_denoise_stage_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t 
     return ART_HP_OK;
 }
 
-void art_develop_geometry(const art_hp_develop_params* p, int W, int H, int* b, int* Wo, int* Ho)
+int art_develop_geometry2(const art_hp_develop_params* p, int W, int H, art_dev_geo* g)
 {   // RawImageSource::border: 4 for Bayer sensors (the caller's value), 7 for X-Trans (rawimagesource.cc L1345-1352, computeFullSize L1163-1175)
     const bool xt = p->method == ART_HP_XTRANS_3PASS || p->method == ART_HP_XTRANS_1PASS;
     const int bd = p->full_frame ? 0 : (xt ? 7 : (p->border > 0 ? p->border : 0));
-    *b = bd; *Wo = W - 2 * bd; *Ho = H - 2 * bd;
-    if (p->tran & 1) std::swap(*Wo, *Ho);          // TR_R90 / TR_R270: the developed frame is turned
+    const int rot = p->tran & 3;
+    const bool turned = rot == 1 || rot == 3;
+    // the transformed, border-cropped full image (getFullSize)
+    const int fw = (turned ? H : W) - 2 * bd, fh = (turned ? W : H) - 2 * bd;
+    g->bd = bd; g->window = p->pp_skip > 0;
+    const int skip = g->window ? p->pp_skip : 1;
+    const int px = g->window ? p->pp_x : 0, py = g->window ? p->pp_y : 0;
+    const int pw = g->window ? p->pp_width : fw, ph = g->window ? p->pp_height : fh;
+    g->skip = skip;
+    if (px < 0 || py < 0 || pw < 1 || ph < 1 || px + pw > fw || py + ph > fh) { g->Wo = g->Ho = g->iw = g->ih = 0; g->sx1 = g->sy1 = 0; return ART_HP_ERR_INVALID; }
+    // RawImageSource::getSize(pp, w, h), L1199-1203: the image getImage fills
+    g->Wo = pw / skip + (pw % skip > 0);
+    g->Ho = ph / skip + (ph % skip > 0);
+    // RawImageSource::transformRect for a standard CCD, L664-751 (the window lies inside the image, so no clamp of its size fires)
+    const int sw = turned ? H : W, sh = turned ? W : H;
+    int ppx = px + bd, ppy = py + bd;
+    if (p->tran & 8) ppx = std::max(sw - (px + bd) - pw, 0);
+    if (p->tran & 4) ppy = std::max(sh - (py + bd) - ph, 0);
+    int sx1 = ppx, sy1 = ppy;
+    if (rot == 2) { sx1 = std::max(W - ppx - pw, 0); sy1 = std::max(H - ppy - ph, 0); }
+    else if (rot == 1) { sx1 = ppy; sy1 = std::max(H - ppx - pw, 0); }
+    else if (rot == 3) { sx1 = std::max(W - ppy - ph, 0); sy1 = ppx; }
+    g->sx1 = sx1; g->sy1 = sy1;
+    // imwidth / imheight: transformRect's size clamped to the image's (L855-861) = the image's, in the source orientation
+    g->iw = turned ? g->Ho : g->Wo;
+    g->ih = turned ? g->Wo : g->Ho;
+    return ART_HP_OK;
+}
+
+void art_develop_geometry(const art_hp_develop_params* p, int W, int H, int* b, int* Wo, int* Ho)
+{
+    art_dev_geo g;
+    art_develop_geometry2(p, W, H, &g);
+    *b = g.bd; *Wo = g.Wo; *Ho = g.Ho;
 }
 
 int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr, int Hr, const float* raw, size_t rp,
                     float* r, float* g, float* b, size_t op)
 {
-    int rc, bd, W, H;
-    art_develop_geometry(p, Wr, Hr, &bd, &W, &H);
-    const bool oop = bd || p->tran || p->hr_blend;        // getImage's stage runs out of place: crop, coarse transform, highlight reconstruction
+    int rc;
+    art_dev_geo geo;
+    if (art_develop_geometry2(p, Wr, Hr, &geo)) return ctx->fail(ART_HP_ERR_INVALID, "the PreviewProps window (%d, %d, %d x %d, skip %d) leaves the developed frame", p->pp_x, p->pp_y, p->pp_width, p->pp_height, p->pp_skip);
+    const int bd = geo.bd, W = geo.Wo, H = geo.Ho;
+    const bool oop = bd || p->tran || p->hr_blend || geo.window;        // getImage's stage runs out of place: crop, coarse transform, highlight reconstruction, preview window
     // then the demosaicer writes context-owned planes and getImage's stage crops / turns them into the caller's planes
     float* dm[3] = {r, g, b};
     size_t dmp = op;
@@ -171,6 +205,7 @@ int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr, int
         float est[3];
         const size_t off0 = (size_t)bd * dmp + bd;
         if (p->tran) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "the automatic chroma estimator with a coarse transform: its crops are cut from the turned frame (pass the estimate, chrominanceMethod 0)");
+        if (geo.window) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "the automatic chroma estimator on a preview window: it measures crops of the whole frame (run it once on the frame and pass the estimate, chrominanceMethod 0)");
         if ((rc = art_denoise_auto_chroma_dev(ctx, dm[0] + off0, dm[1] + off0, dm[2] + off0, dmp, W, H, p->mul, p->doClip, p->cam2work, p->wprof,
                                               dn->gamma, dn->aggressive, est, nullptr))) return rc;
         dn_resolved = *dn;
@@ -182,10 +217,11 @@ int art_develop_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr, int
         dn = &dn_resolved;
     }
     if (oop) {
-        const size_t off = (size_t)bd * dmp + bd;
-        const int sw = Wr - 2 * bd, sh = Hr - 2 * bd;       // the source lines (imwidth x imheight); W x H is the turned frame
-        rc = art_scale_convert_crop_dev(ctx, sw, sh, dm[0] + off, dm[1] + off, dm[2] + off, dmp, r, g, b, op, p->mul, p->doClip, p->cam2work,
-                                        p->tran, p->hr_blend, p->hlmax);
+        // the source lines are geo.iw x geo.ih from (sx1, sy1); W x H is the turned image.  At skip 1 the planes are passed at that origin,
+        // at skip > 1 un-offset (the box sum clamps its own origin against the frame, L945 / L949)
+        const size_t off = geo.skip > 1 ? 0 : (size_t)geo.sy1 * dmp + geo.sx1;
+        rc = art_scale_convert_crop_dev(ctx, geo.iw, geo.ih, dm[0] + off, dm[1] + off, dm[2] + off, dmp, r, g, b, op, p->mul, p->doClip, p->cam2work,
+                                        p->tran, p->hr_blend, p->hlmax, geo.skip, geo.sx1, geo.sy1, Wr, Hr);
     } else rc = art_scale_convert_dev(ctx, W, H, r, g, b, op, p->mul, p->doClip, p->cam2work);
     if (rc) return rc;
     if (dn) {
@@ -247,6 +283,7 @@ int art_develop_band_dev(art_hp_ctx* ctx, const art_hp_develop_params* p, int Wr
     art_develop_geometry(p, Wr, Hr, &bd, &W, &H);
     if (p->method != ART_HP_BAYER_AMAZE && p->method != ART_HP_BAYER_RCD) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: Bayer methods only");
     if (p->tran) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: the coarse transform is not split (rows of the turned frame are columns of the raw frame)");
+    if (p->pp_skip > 0) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: a preview window is one GPU's work");
     if (p->fattal_enabled) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: Fattal's Poisson solve is a transform of the whole frame");
     if (p->denoise && p->denoise->chrominanceMethod == 1) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: the automatic chroma estimator measures crops of the whole frame");
     if (p->nlStrength) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "row bands: NL-means is not split");

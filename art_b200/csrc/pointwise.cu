@@ -126,7 +126,7 @@ __device__ __forceinline__ void hl_blend_pixel(const HlArgs& h, float& rin, floa
 // (W - 2 border) x (H - 2 border) image (rawimagesource.cc L943-1025 with sx1 = sy1 = border, transformRect L664-700): gains / clip, the optional
 // "Blend" highlight reconstruction, the coarse rotation of rotateLine (L57-87) and the mirrors (L1079-1086) as the store's address, then the matrix.
 // W / H below are the SOURCE line geometry (imwidth / imheight); a quarter turn writes an H-wide, W-high image.
-struct ScCropArgs { const float *sr, *sg, *sb; size_t sp; ScArgs d; int tran, hr; HlArgs hl; };
+struct ScCropArgs { const float *sr, *sg, *sb; size_t sp; ScArgs d; int tran, hr; HlArgs hl; int skip, sx1, sy1, maxx, maxy; };      // skip > 1: the preview form, source planes un-offset
 __global__ void __launch_bounds__(256) k_scale_convert_crop(ScCropArgs c)
 {
     const ScArgs& a = c.d;
@@ -134,8 +134,20 @@ __global__ void __launch_bounds__(256) k_scale_convert_crop(ScCropArgs c)
     if (x >= a.W) return;
     const int rot = c.tran & 3, ow = (rot & 1) ? a.H : a.W, oh = (rot & 1) ? a.W : a.H;
     for (int y = blockIdx.y; y < a.H; y += gridDim.y) {
-        const size_t i = (size_t)y * c.sp + x;
-        float r = c.sr[i], g = c.sg[i], b = c.sb[i];
+        float r, g, b;
+        if (c.skip <= 1) {
+            const size_t i = (size_t)y * c.sp + x;
+            r = c.sr[i]; g = c.sg[i]; b = c.sb[i];
+        } else {
+            // the preview form (L943-968): skip x skip box sum from (min(sy1 + skip y, maxy - skip), min(sx1 + skip x, maxx - skip)), rows outer, from 0
+            const int i0 = min(c.sy1 + c.skip * y, c.maxy - c.skip), j0 = min(c.sx1 + c.skip * x, c.maxx - c.skip);
+            r = g = b = 0.f;
+            for (int m = 0; m < c.skip; ++m)
+                for (int n = 0; n < c.skip; ++n) {
+                    const size_t i = (size_t)(i0 + m) * c.sp + (j0 + n);
+                    r += c.sr[i]; g += c.sg[i]; b += c.sb[i];
+                }
+        }
         r *= a.mul[0]; g *= a.mul[1]; b *= a.mul[2];
         if (a.do_clip) { r = clip65535(r); g = clip65535(g); b = clip65535(b); }
         if (c.hr) hl_blend_pixel(c.hl, r, g, b);
@@ -270,10 +282,11 @@ int art_scale_convert_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, flo
 
 int art_scale_convert_crop_dev(art_hp_ctx* ctx, int W, int H, const float* sr, const float* sg, const float* sb, size_t sp,
                                float* r, float* g, float* b, size_t pitch, const float mul[3], int doClip, const double* mat,
-                               int tran, int hr_blend, const float* hlmax)
+                               int tran, int hr_blend, const float* hlmax, int skip, int sx1, int sy1, int maxx, int maxy)
 {
     ScCropArgs c;
     c.sr = sr; c.sg = sg; c.sb = sb; c.sp = sp;
+    c.skip = skip; c.sx1 = sx1; c.sy1 = sy1; c.maxx = maxx; c.maxy = maxy;
     c.tran = tran; c.hr = hr_blend && hlmax;
     if (c.hr) {       // the line constants of HLRecovery_blend (L3623-3640), maxval = 65535
         const float minpt = std::min(std::min(hlmax[0], hlmax[1]), hlmax[2]);

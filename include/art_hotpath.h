@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ART_HP_ABI_VERSION 3
+#define ART_HP_ABI_VERSION 4
 
 typedef enum art_hp_status {
     ART_HP_OK = 0,
@@ -640,8 +640,18 @@ typedef struct art_hp_develop_params {
     int hr_blend;               /* 1 = ExposureParams::HR_BLEND: hlRecovery -> HLRecovery_blend on every line after the gains (L1013-1015, L3613-3755);
                                    the reference then leaves doClip off (L882) -- the caller passes doClip as it computed it */
     float hlmax[3];             /* clmax[c] * {rm, gm, bm} (L916-918), used by hr_blend */
+    /* ---- ABI version 4: the preview path (rtengine/improccoordinator.cc L377, rtengine/dcrop.cc L204: imgsrc->getImage(wb, tr, image, pp, ...)) ---- */
+    int pp_x, pp_y, pp_width, pp_height, pp_skip;
+                                /* PreviewProps: a window of the transformed, border-cropped full image and the subsampling step.  pp_skip <= 0: the
+                                   whole frame at skip 1 (versions 1-3).  getImage renders ceil(pp_width / pp_skip) x ceil(pp_height / pp_skip) pixels
+                                   (getSize, L1199-1203): each the pp_skip x pp_skip box sum of the demosaiced frame from transformRect's origin
+                                   (L664-751, L943-968) times mul[] -- the caller folds the 1 / pp_skip^2 of L928-931 into mul[], as it folds the
+                                   other factors.  The later stages take their `scale` (= pp_skip) in their own parameter blocks, as the reference's
+                                   ImProcFunctions does.  The window must lie inside the full image.  Not with the automatic chroma estimator (it
+                                   measures the whole frame: run it once, pass the estimate) and not on a band. */
 } art_hp_develop_params;
-/* output size of art_hp_develop for a W x H raw frame: *out_w = W - 2 b, *out_h = H - 2 b, b = the border it crops (0 with full_frame) */
+/* output size of art_hp_develop for a W x H raw frame: *out_w = W - 2 b, *out_h = H - 2 b, b = the border it crops (0 with full_frame); with a
+ * PreviewProps window (pp_skip > 0) the size of that window's image; ART_HP_ERR_INVALID when the window leaves the full image */
 int art_hp_develop_size(const art_hp_develop_params* params, int W, int H, int* out_w, int* out_h, int* border);
 int art_hp_develop(art_hp_ctx* ctx, const art_hp_develop_params* params, int W, int H, float* const* rawData,
                    float* const* red, float* const* green, float* const* blue);

@@ -792,6 +792,66 @@ extern "C" int artref_getimage(int W, int H, const float* r, const float* g, con
     }
     return 0;
 }
+
+// ---- the preview form: RawImageSource::transformRect (cut from rawimagesource.cc) and getImage's line loop at any skip, its skip x skip box sum
+// cut from rawimagesource.cc (the standard-CCD branch, L949-981).  Written here: the stand-ins and the loops around the two cuts.
+namespace rtengine {
+struct PreviewPropsShim { int x, y, w, h, skip; int getX() const { return x; } int getY() const { return y; } int getWidth() const { return w; }
+    int getHeight() const { return h; } int getSkip() const { return skip; } };
+#define PreviewProps PreviewPropsShim
+struct RiGetImage { int get_FujiWidth() const { return 0; } };
+struct RawImageSourceGetImage {
+    int W, H, border; bool d1x, fuji; RiGetImage* ri;
+    void transformRect(const PreviewProps &pp, int tran, int &ssx1, int &ssy1, int &width, int &height, int &fw);
+};
+#define RawImageSource RawImageSourceGetImage
+#include "getimage_transformrect.inc"
+#undef RawImageSource
+}
+extern "C" int artref_transform_rect(int W, int H, int border, int x, int y, int w, int h, int skip, int tran, int* out4)
+{
+    rtengine::RiGetImage ri;
+    rtengine::RawImageSourceGetImage s{W, H, border, false, false, &ri};
+    rtengine::PreviewPropsShim pp{x, y, w, h, skip};
+    int fw = 0;
+    s.transformRect(pp, tran, out4[0], out4[1], out4[2], out4[3], fw);
+    return 0;
+}
+// source planes W x H (the demosaiced frame); sx1 / sy1 / imwidth / imheight from transformRect; output imwidth x imheight (turned for the quarter turns)
+extern "C" int artref_getimage_pp(int W, int H, const float* r, const float* g, const float* b, long stride, const float* mul, int doClip,
+                                  int doHr, const float* hlmax, int tran, int sx1, int sy1, int imwidth, int imheight, int skip,
+                                  float* outr, float* outg, float* outb, long ostride)
+{
+    using rtengine::CLIP;
+    const bool swap = (tran & TR_ROT) == TR_R90 || (tran & TR_ROT) == TR_R270;
+    const int ow = swap ? imheight : imwidth, oh = swap ? imwidth : imheight;
+    rtengine::PlanarPtr<float> pr{outr, ostride}, pg{outg, ostride}, pb{outb, ostride};
+    std::vector<float> line_red(imwidth), line_grn(imwidth), line_blue(imwidth);
+    std::vector<const float*> red(H), green(H), blue(H);
+    for (int i = 0; i < H; ++i) { red[i] = r + (long)i * stride; green[i] = g + (long)i * stride; blue[i] = b + (long)i * stride; }
+    const float rm = mul[0], gm = mul[1], bm = mul[2];
+    const int maxx = W, maxy = H;
+    for (int ix = 0; ix < imheight; ix++) {
+        int i = sy1 + skip * ix;
+        i = std::min(i, maxy - skip); // avoid trouble
+#include "getimage_boxsum.inc"
+        if (doHr) artref_hl_blend(line_red.data(), line_grn.data(), line_blue.data(), imwidth, 65535.0f, hlmax);
+        rotateLine(line_red.data(), pr, tran, ix, imwidth, imheight);
+        rotateLine(line_grn.data(), pg, tran, ix, imwidth, imheight);
+        rotateLine(line_blue.data(), pb, tran, ix, imwidth, imheight);
+    }
+    float* planes[3] = {outr, outg, outb};
+    for (int c = 0; c < 3; ++c) {
+        float* v = planes[c];
+        if (tran & TR_HFLIP)
+            for (int i = 0; i < oh; i++)
+                for (int j = 0; j < ow / 2; j++) std::swap(v[(long)i * ostride + j], v[(long)i * ostride + ow - 1 - j]);
+        if (tran & TR_VFLIP)
+            for (int i = 0; i < oh / 2; i++)
+                for (int j = 0; j < ow; j++) std::swap(v[(long)i * ostride + j], v[(long)(oh - 1 - i) * ostride + j]);
+    }
+    return 0;
+}
 """
 
 
@@ -2031,6 +2091,10 @@ def extract(det):
     open(os.path.join(sub, "shim_hlblend.cc"), "w").write(SHIM_HLBLEND_TU)
     open(os.path.join(sub, "getimage_rotateline.inc"), "w").write(
         cut_function(os.path.join(RT, "rawimagesource.cc"), r"^void rotateLine \(const float\* const line, rtengine::PlanarPtr<float> &channel, const int tran, const int i, const int w, const int h\)"))
+    open(os.path.join(sub, "getimage_transformrect.inc"), "w").write(
+        cut_function(os.path.join(RT, "rawimagesource.cc"), r"^void RawImageSource::transformRect \(const PreviewProps &pp, int tran, int &ssx1, int &ssy1, int &width, int &height, int &fw\)"))
+    open(os.path.join(sub, "getimage_boxsum.inc"), "w").write(
+        cut_block(os.path.join(RT, "rawimagesource.cc"), r"for \(int j = 0, jx = sx1; j < imwidth; j\+\+, jx \+= skip\) \{(?=\s*jx = std::min\(jx, maxx - skip\); // avoid trouble)"))
     open(os.path.join(sub, "shim_getimage.cc"), "w").write(SHIM_GETIMAGE_TU)
     vg = os.path.join(RT, "vng4_demosaic_RT.cc")
     open(os.path.join(sub, "vng4_rowrb.inc"), "w").write(cut_function(vg, r"^inline void vng4interpolate_row_redblue \(const RawImage \*ri[^)]*\)"))

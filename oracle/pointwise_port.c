@@ -169,3 +169,85 @@ int artoracle_getimage(int W, int H, const float* r, const float* g, const float
     free(lr);
     return 0;
 }
+
+/* RawImageSource::transformRect for a standard CCD (rawimagesource.cc L664-751; no D1X, no Fuji SuperCCD): the source rectangle of a PreviewProps
+ * window (x, y, w, h in the coordinates of the TRANSFORMED, border-cropped image; skip) under the coarse transform, and the size of the image
+ * getImage renders from it.  out4 = sx1, sy1, width, height. */
+int artoracle_transform_rect(int W, int H, int border, int x, int y, int w, int h, int skip, int tran, int* out4)
+{
+    int pp_x = x + border, pp_y = y + border, pp_width = w, pp_height = h;
+    const int rot = tran & 3;
+    int sw = W, sh = H;
+    if (rot == 1 || rot == 3) { sw = H; sh = W; }
+    if (pp_width > sw - 2 * border) pp_width = sw - 2 * border;
+    if (pp_height > sh - 2 * border) pp_height = sh - 2 * border;
+    int ppx = pp_x, ppy = pp_y;
+    if (tran & 8) { ppx = sw - pp_x - pp_width; if (ppx < 0) ppx = 0; }
+    if (tran & 4) { ppy = sh - pp_y - pp_height; if (ppy < 0) ppy = 0; }
+#define MIN_(a, b) ((a) < (b) ? (a) : (b))
+#define MAX_(a, b) ((a) > (b) ? (a) : (b))
+    int sx1 = ppx, sy1 = ppy, sx2 = MIN_(ppx + pp_width, W - 1), sy2 = MIN_(ppy + pp_height, H - 1);
+    if (rot == 2) {
+        sx1 = MAX_(W - ppx - pp_width, 0); sy1 = MAX_(H - ppy - pp_height, 0);
+        sx2 = MIN_(sx1 + pp_width, W - 1); sy2 = MIN_(sy1 + pp_height, H - 1);
+    } else if (rot == 1) {
+        sx1 = ppy; sy1 = MAX_(H - ppx - pp_width, 0);
+        sx2 = MIN_(sx1 + pp_height, W - 1); sy2 = MIN_(sy1 + pp_width, H - 1);
+    } else if (rot == 3) {
+        sx1 = MAX_(W - ppy - pp_height, 0); sy1 = ppx;
+        sx2 = MIN_(sx1 + pp_height, W - 1); sy2 = MIN_(sy1 + pp_width, H - 1);
+    }
+#undef MIN_
+#undef MAX_
+    out4[0] = sx1; out4[1] = sy1;
+    out4[2] = (sx2 + 1 - sx1) / skip + ((sx2 + 1 - sx1) % skip > 0);
+    out4[3] = (sy2 + 1 - sy1) / skip + ((sy2 + 1 - sy1) % skip > 0);
+    return 0;
+}
+
+/* RawImageSource::getImage's line loop at any skip (rawimagesource.cc L943-1025): output pixel (ix, j) is the skip x skip box sum (rows outer,
+ * columns inner, from 0) of the demosaiced planes at (min(sy1 + skip ix, H - skip), min(sx1 + skip j, W - skip)) times the gain (the caller's
+ * rm / gm / bm already hold the 1 / skip^2 of L928-931), clipped, optionally highlight-reconstructed, then turned / mirrored as at skip 1. */
+int artoracle_getimage_pp(int W, int H, const float* r, const float* g, const float* b, long stride, const float* mul, int doClip,
+                          int doHr, const float* hlmax, int tran, int sx1, int sy1, int imwidth, int imheight, int skip,
+                          float* outr, float* outg, float* outb, long ostride)
+{
+    const int rot = tran & 3, swap = rot == 1 || rot == 3;
+    const int ow = swap ? imheight : imwidth, oh = swap ? imwidth : imheight;
+    float* lr = (float*)malloc(sizeof(float) * (size_t)imwidth * 3);
+    if (!lr) return 1;
+    float *lg = lr + imwidth, *lb = lg + imwidth;
+    for (int ix = 0; ix < imheight; ++ix) {
+        int i = sy1 + skip * ix;
+        if (i > H - skip) i = H - skip;
+        for (int j = 0; j < imwidth; ++j) {
+            int jx = sx1 + skip * j;
+            if (jx > W - skip) jx = W - skip;
+            float rtot = 0.f, gtot = 0.f, btot = 0.f;
+            for (int m = 0; m < skip; m++)
+                for (int n = 0; n < skip; n++) {
+                    const size_t k = (size_t)(i + m) * stride + (jx + n);
+                    rtot += r[k]; gtot += g[k]; btot += b[k];
+                }
+            rtot *= mul[0]; gtot *= mul[1]; btot *= mul[2];
+            if (doClip) { rtot = clip65535_(rtot); gtot = clip65535_(gtot); btot = clip65535_(btot); }
+            lr[j] = rtot; lg[j] = gtot; lb[j] = btot;
+        }
+        if (doHr) artoracle_hl_blend(lr, lg, lb, imwidth, 65535.0f, hlmax);
+        for (int j = 0; j < imwidth; ++j) {
+            int row, col;
+            switch (rot) {
+            case 2: row = imheight - 1 - ix; col = imwidth - 1 - j; break;
+            case 1: row = j; col = imheight - 1 - ix; break;
+            case 3: row = imwidth - 1 - j; col = ix; break;
+            default: row = ix; col = j;
+            }
+            if (tran & 8) col = ow - 1 - col;
+            if (tran & 4) row = oh - 1 - row;
+            const size_t o = (size_t)row * ostride + col;
+            outr[o] = lr[j]; outg[o] = lg[j]; outb[o] = lb[j];
+        }
+    }
+    free(lr);
+    return 0;
+}

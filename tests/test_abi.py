@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, "declared in include/art_hotpath.h but not exported: %s" % missing
     for s in api.ABI_SYMBOLS:
         assert getattr(lib, s) is not None
-    assert lib.art_hp_abi_version() == 3
+    assert lib.art_hp_abi_version() == 4
 
 
 def test_header_is_plain_c():
