@@ -57,7 +57,11 @@ NCU_TRAFFIC = {"k_dirinterp": 0.974235e9 + 1.551996e9, "k_rbdiag": 0.854833e9 + 
                # profiles/r1_develop_ncu_full.csv (isolated replays, cold L2; a 45 MB plane written by a shrink kernel can stay in the 126 MB L2)
                "k_dn_blocks": 358.347e6 + 1137.494e6, "k_fbox_h": 44.786e6 + 3.397e6, "k_fbox_v": 44.808e6 + 6.248e6,
                "k_sf_apply": 134.296e6 + 18.761e6, "k_sf_AB": 89.535e6 + 18.726e6, "k_mad_hist": 44.784e6, "k_wav_sy_sub": 358.56e6 + 137.405e6,
-               "k_fat_dct_rows": 184.989e6 + 316.294e6, "k_fat_dct_solve": 370.647e6 + 327.235e6, "k_fat_dct_exp": 370.152e6 + 156.166e6}
+               "k_fat_dct_rows": 184.989e6 + 316.294e6, "k_fat_dct_solve": 370.647e6 + 327.235e6, "k_fat_dct_exp": 370.152e6 + 156.166e6,
+               # profiles/r2_ncu_k_shrink_*_merged.txt, r2_ncu_k_mad_hist_all_merged.txt: the merged launches (a, b and L of a frame in one grid) at 8192x5464;
+               # k_mad_hist_all has two launches per frame (15 luminance subbands: 0.67 GB, 30 chroma subbands: 1.34 GB), the mean is quoted
+               "k_shrink_v": 6.030872e9 + 1.984292e9, "k_shrink_h": 2.124376e9 + 2.047802e9, "k_shrink_sf": 2.077135e9 + 1.971890e9,
+               "k_mad_hist_all": (1.340461e9 + 7.640832e6) * 0.75}
 
 
 def parse():
@@ -84,6 +88,35 @@ def parse():
     dw, dh = {"c3": (6240, 4160), "c4": (12288, 8192)}.get(a.workload, (W45, H45))
     a.width, a.height = a.width or dw, a.height or dh
     return a
+
+
+def tensor_peak():
+    """TF32 dense peak for a kernel timed inside a long step: half the measured sustained bf16 matmul rate (MEASURED_PEAKS.json; Blackwell's dense TF32
+    rate is half its bf16 rate), else half the profiling guide's 2250 TFLOP/s nominal figure."""
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["bf16_tflops_sustained"]) / 2.0, "measured (MEASURED_PEAKS.json: bf16_tflops_sustained / 2 for kind::tf32)"
+    except Exception:
+        return 1125.0, "fallback (B200_PROFILING.md: 2250 TFLOP/s bf16 nominal / 2)"
+
+
+# kernels bounded by the tensor pipe, not HBM: TF32 flops per developed pixel.  k_dn_blocks: four 64^3 products per 64x64 block at stride 25, each
+# run as three TF32 passes (3xTF32 split): 153 GFLOP of fp32-grade work = 459 GFLOP of tcgen05 kind::tf32 at 44.65 MP (DESIGN.md 5b)
+TENSOR_KERNEL_FLOPS_PER_PX = {"k_dn_blocks": 459.0e9 / (8184.0 * 5456.0)}
+
+
+def kernel_roofline(name, kernel_ms, geo, launches, hbm_peak):
+    """roofline entry of one kernel: (bound, achieved, peak, unit, frac, algorithmic work per launch, description, peak source or None)"""
+    if name in TENSOR_KERNEL_FLOPS_PER_PX:
+        tp, how = tensor_peak()
+        flops = TENSOR_KERNEL_FLOPS_PER_PX[name] * geo[2] * geo[3] / max(1, launches)
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        return "tensor", ach, tp, "TFLOP/s", ach / tp, flops, "tcgen05 kind::tf32 flops of the block DCTs (3 passes per product)", how
+    kb = kernel_bytes(name, *geo, launches=launches)
+    if kb is None:
+        return "hbm", None, hbm_peak, "GB/s", None, None, None, None
+    ach = kb[0] / (kernel_ms * 1e-3) / 1e9
+    return "hbm", ach, hbm_peak, "GB/s", ach / hbm_peak, kb[0], kb[1], None
 
 
 def peaks():
@@ -282,11 +315,12 @@ def kernel_bytes(name, Wr, Hr, W, H, nlev=5, launches=None):
 def roofline_top(per_step, kern, calls, geo, peak, n=8):
     out = []
     for k in sorted(per_step, key=lambda k: -per_step[k])[:n]:
-        kb = kernel_bytes(k, *geo, launches=calls[k])
-        e = {"kernel": k, "ms_per_step": round(per_step[k], 4), "launches_per_step": calls[k], "achieved_GBps": None, "frac": None}
-        if kb is not None:
-            ach = kb[0] / (kern[k] * 1e-3) / 1e9
-            e.update(achieved_GBps=round(ach, 1), frac=round(ach / peak, 4), traffic=NCU_TRAFFIC.get(k))
+        bound, ach, pk, unit, frac, work, what, how = kernel_roofline(k, kern[k], geo, calls[k], peak)
+        e = {"kernel": k, "ms_per_step": round(per_step[k], 4), "launches_per_step": calls[k], "bound": bound, "achieved_GBps": None, "frac": None}
+        if ach is not None and bound == "hbm":
+            e.update(achieved_GBps=round(ach, 1), frac=round(frac, 4), traffic=NCU_TRAFFIC.get(k))
+        elif ach is not None:
+            e.update(achieved_TFLOPs=round(ach, 1), peak_TFLOPs=round(pk, 1), frac=round(frac, 4), traffic=NCU_TRAFFIC.get(k))
         out.append(e)
     return out
 
@@ -783,8 +817,8 @@ def main():
         per_step = {k: kern[k] * calls[k] for k in kern}                     # ms per step per kernel
         top = max((k for k in per_step if k != "memset_slabs"), key=lambda k: per_step[k])
         share = per_step[top] / sum(per_step.values())
-        kb = kernel_bytes(top, *geo, launches=calls[top])
-        achieved = kb[0] / (kern[top] * 1e-3) / 1e9 if kb else None          # per launch: bytes one launch moves / its mean duration
+        # per launch: bytes (or tensor flops) one launch moves / its mean duration
+        rl_bound, achieved, rl_peak, rl_unit, rl_frac, rl_work, rl_what, rl_how = kernel_roofline(top, kern[top], geo, calls[top], peak)
         pipe_e2e = e2e.get("packed", e2e.get("planes"))
         out = {
             "metric": "Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
@@ -800,11 +834,11 @@ def main():
                              "(three float planes out)")
                     if pipeline else "art_hp_demosaic_bayer (synchronous, banded copy/compute overlap inside the call)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None,
-                         "traffic": NCU_TRAFFIC.get(top), "peak_source": how,
+            "roofline": {"bound": rl_bound, "kernel": top, "achieved": achieved, "peak": rl_peak, "unit": rl_unit,
+                         "frac": rl_frac,
+                         "traffic": NCU_TRAFFIC.get(top), "peak_source": rl_how or how,
                          "kernel_ms": kern[top], "launches_per_step": calls[top], "share_of_step": share,
-                         "algorithmic_bytes_per_launch": kb[0] if kb else None, "what": kb[1] if kb else None,
+                         ("algorithmic_flops_per_launch" if rl_bound == "tensor" else "algorithmic_bytes_per_launch"): rl_work, "what": rl_what,
                          "note": "dominant kernel by device time; achieved = algorithmic bytes per launch / mean CUDA-event "
                                  "duration of that kernel (events on the launching stream, separate pass of --steps steps)"},
             "step_roofline": {"achieved": step_achieved, "frac": step_achieved / peak, "unit": "GB/s",
