@@ -225,6 +225,79 @@ __device__ __forceinline__ void rgb_tone(const ChainArgs& a, float& r, float& g,
     set_lut_val_c(a, b);
     g = b + ((r - b) * (gold - bold) / (rold - bold));
 }
+__device__ __forceinline__ float lim_f(float v, float lo, float hi) { const float m = hi < v ? hi : v; return lo < m ? m : lo; }      // rt_math.h LIM
+// WeightedStdToneCurve::Triangle / Apply, curves.h L499-562
+__device__ __forceinline__ float triangle(float a, float a1, float b, float whitept)
+{
+    if (a != b) {
+        const float a2 = a1 - a;
+        return b < a ? b + a2 * b / a : b + a2 * (whitept - b) / (whitept - a);
+    }
+    return a1;
+}
+__device__ __forceinline__ void weighted_std_tone(const ChainArgs& A, float& ir, float& ig, float& ib)
+{
+    const float w = A.Lmax;
+    const float r = lim_f(ir, 0.f, w), g = lim_f(ig, 0.f, w), b = lim_f(ib, 0.f, w);
+    float r1 = r; set_lut_val_c(A, r1);
+    const float g1 = triangle(r, r1, g, w), b1 = triangle(r, r1, b, w);
+    float g2 = g; set_lut_val_c(A, g2);
+    const float r2 = triangle(g, g2, r, w), b2 = triangle(g, g2, b, w);
+    float b3 = b; set_lut_val_c(A, b3);
+    const float r3 = triangle(b, b3, r, w), g3 = triangle(b, b3, g, w);
+    ir = lim_f(r1 * 0.50f + r2 * 0.25f + r3 * 0.25f, 0.f, w);
+    ig = lim_f(g1 * 0.25f + g2 * 0.50f + g3 * 0.25f, 0.f, w);
+    ib = lim_f(b1 * 0.25f + b2 * 0.25f + b3 * 0.50f, 0.f, w);
+}
+// SatAndValueBlendingToneCurve::Apply, curves.h L634-668, with Color::rgb2hsvtc / hsv2rgbdcp (color.h L423-506); reads the LUT directly
+__device__ __forceinline__ void sat_value_tone(const ChainArgs& A, float& ir, float& ig, float& ib)
+{
+    float r = lim_f(ir, 0.f, 65535.f), g = lim_f(ig, 0.f, 65535.f), b = lim_f(ib, 0.f, 65535.f);
+    const float lum = (r + g + b) / 3.f;
+    const float newLum = lut_s(A.tc_lut, 65536, CLIP_BELOW | CLIP_ABOVE, lum);
+    if (newLum == lum) return;
+    float h, s;
+    const float mn0 = g < r ? g : r, var_Min = b < mn0 ? b : mn0;
+    const float mx0 = r < g ? g : r, var_Max = mx0 < b ? b : mx0;
+    const float del_Max = var_Max - var_Min;
+    const float v = var_Max / 65535.f;
+    if (del_Max < 0.00001f) { h = 0.f; s = 0.f; }
+    else {
+        s = del_Max / var_Max;
+        if (r == var_Max) h = (g < b ? 6.f : 0.f) + (g - b) / del_Max;
+        else if (g == var_Max) h = 2.f + (b - r) / del_Max;
+        else h = 4.f + (r - g) / del_Max;
+    }
+    float dV;
+    if (newLum > lum) { const float coef = (newLum - lum) / (65535.f - lum); dV = (1.f - v) * coef; s *= 1.f - coef; }
+    else { const float coef = (newLum - lum) / lum; dV = v * coef; }
+    float vv = v + dV;
+    const int sector = (int)h;
+    const float f = h - sector;
+    vv *= 65535.f;
+    const float vs = vv * s, p = vv - vs, q = vv - f * vs, t = p + vv - q;
+    switch (sector) {
+    case 1: r = q; g = vv; b = p; break;
+    case 2: r = p; g = vv; b = t; break;
+    case 3: r = p; g = q; b = vv; break;
+    case 4: r = t; g = p; b = vv; break;
+    case 5: r = vv; g = p; b = q; break;
+    default: r = vv; g = t; b = p;
+    }
+    ir = r; ig = g; ib = b;
+}
+// LuminanceToneCurve::Apply, curves.h L474-496; the luminance row of the float TMatrix (apply_tc, iptonecurve.cc L73-84)
+__device__ __forceinline__ void luminance_tone(const ChainArgs& A, float& ir, float& ig, float& ib)
+{
+    const float w = A.Lmax;
+    const float r = lim_f(ir, 0.f, w), g = lim_f(ig, 0.f, w), b = lim_f(ib, 0.f, w);
+    float currLuminance = r * A.wy0 + g * A.wy1 + b * A.wy2;
+    float newLuminance = currLuminance;
+    set_lut_val_c(A, newLuminance);
+    currLuminance = currLuminance == 0.f ? 0.00001f : currLuminance;
+    const float coef = newLuminance / currLuminance;
+    ir = lim_f(r * coef, 0.f, w); ig = lim_f(g * coef, 0.f, w); ib = lim_f(b * coef, 0.f, w);
+}
 __device__ __forceinline__ float lim01(float a) { const float m = 1.f < a ? 1.f : a; return 0.f < m ? m : 0.f; }
 __device__ __forceinline__ float gauss_hue(float x, float b, float c) { return sleef::xexpf_scalar(-((x - b) * (x - b)) / (2 * (c * c))); }
 
@@ -345,6 +418,9 @@ __device__ __forceinline__ void rgb_stages(const ChainArgs& a, float& r, float& 
     } else if (a.tc_mode >= 0) {
         filmlike_clip(r, g, b, a.Lmax);
         if (a.tc_mode == 0) { set_lut_val_c(a, r); set_lut_val_c(a, g); set_lut_val_c(a, b); }
+        else if (a.tc_mode == 3) weighted_std_tone(a, r, g, b);
+        else if (a.tc_mode == 4) sat_value_tone(a, r, g, b);
+        else if (a.tc_mode == 5) luminance_tone(a, r, g, b);
         else {
             r = maxr(0.f, minr(r, a.Lmax)); g = maxr(0.f, minr(g, a.Lmax)); b = maxr(0.f, minr(b, a.Lmax));
             if (r >= g) {
@@ -488,7 +564,8 @@ int art_chain_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, s
     if ((do_sat || p->lab_enabled || jz) && !p->ws) return ctx->fail(ART_HP_ERR_INVALID, "ws is required by the saturation, NEUTRAL tone curve and Lab stages");
     if (jz && !p->iws) return ctx->fail(ART_HP_ERR_INVALID, "the NEUTRAL tone curve and the saturation curve need iws");
     if (p->lab_enabled && (!p->iws || !p->lab_lcurve || !p->lab_acurve || !p->lab_bcurve)) return ctx->fail(ART_HP_ERR_INVALID, "Lab stage needs iws and the three curves");
-    if (tc_mode > 2) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "tone curve mode %d", tc_mode);
+    if (tc_mode > 5) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "tone curve mode %d (PERCEPTUAL is not built)", tc_mode);
+    if (tc_mode == 5 && !p->ws) return ctx->fail(ART_HP_ERR_INVALID, "the LUMINANCE tone curve needs ws");
     const float whitecoeff = p->tonecurve_whitept > 0.f ? p->tonecurve_whitept : 1.f;
     const int nstages = (tc_mode >= 0 && p->tonecurve_stages) ? p->tonecurve_nstages : 0;
     if (nstages < 0 || nstages > 4) return ctx->fail(ART_HP_ERR_INVALID, "tonecurve_nstages %d (0..4)", nstages);

@@ -399,7 +399,9 @@ int art_hp_scale_convert_dev(art_hp_ctx* ctx, int W, int H,
  *                      branch: filmlike_clip then StandardToneCurve::Apply [tonecurve_mode 0] or AdobeToneCurve::Apply [1],
  *                      rtengine/curves.h L360-368, L425-472; or, tonecurve_mode 2, the reference's default single NEUTRAL curve:
  *                      NeutralToneCurve::BatchApply, rtengine/curves.cc L891-1037, base curve LINEAR, no filmlike_clip pass before
- *                      it, iptonecurve.cc L581-589; then apply_satcurve, L398-441), rgbCurves (rtengine/iprgbcurves.cc L113-146) and
+ *                      it, iptonecurve.cc L581-589; or, after filmlike_clip like STD, tonecurve_mode 3 WeightedStdToneCurve::Apply
+ *                      (curves.h L499-562), 4 SatAndValueBlendingToneCurve::Apply (L634-668), 5 LuminanceToneCurve::Apply (L474-496);
+ *                      TcMode::PERCEPTUAL returns ART_HP_ERR_UNSUPPORTED; then apply_satcurve, L398-441), rgbCurves (rtengine/iprgbcurves.cc L113-146) and
  *                      labAdjustments (rtengine/iplabadjustments.cc L252-283 between Imagefloat::setMode(LAB) and the
  *                      setMode(RGB) of the next stage, rtengine/imagefloat.cc L841-878, L949-972).
  *                      Curves stay host-built (rtengine/curves.cc) and are passed by pointer as the LUT<float> data they fill:
@@ -426,7 +428,8 @@ typedef struct art_hp_curve_stage {
 typedef struct art_hp_chain_params {
     int   exposure_enabled;  float exp_scale, black;
     int   saturation_enabled, saturation, vibrance;      /* procparams::SaturationParams, integers as in the GUI */
-    int   tonecurve_mode;    const float* tonecurve_lut;  /* 0 = STD, 1 = FILMLIKE, 2 = NEUTRAL (the reference default); NULL = no tone curve */
+    int   tonecurve_mode;    const float* tonecurve_lut;  /* 0 = STD, 1 = FILMLIKE, 2 = NEUTRAL (the reference default), 3 = WEIGHTEDSTD,
+                                                             4 = SATANDVALBLENDING, 5 = LUMINANCE (needs ws); NULL = no tone curve */
     const float *rcurve, *gcurve, *bcurve;                /* rgbCurves LUTs, each may be NULL */
     int   lab_enabled;       const float *lab_lcurve, *lab_acurve, *lab_bcurve;  float lab_chroma;
     const double* ws;        /* ICCStore::workingSpaceMatrix, 9 doubles (saturation luminance, rgb -> Lab) */

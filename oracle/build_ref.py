@@ -1533,6 +1533,9 @@ namespace curves {
 class ToneCurve { public: LUTf lutToneCurve; float whitecoeff; float whitept; const Curve* curve; ToneCurve() : whitecoeff(1.f), whitept(65535.f), curve(nullptr) {} };
 class StandardToneCurve : public ToneCurve { public: void Apply(float& r, float& g, float& b) const; };
 class AdobeToneCurve : public ToneCurve { void RGBTone(float& r, float& g, float& b) const; public: void Apply(float& r, float& g, float& b) const; };
+class SatAndValueBlendingToneCurve : public ToneCurve { public: void Apply(float& r, float& g, float& b) const; };
+class WeightedStdToneCurve : public ToneCurve { float Triangle(float refX, float refY, float X2) const; public: void Apply(float& r, float& g, float& b) const; };
+class LuminanceToneCurve : public ToneCurve { public: void Apply(float& r, float& g, float& b, const float ws[3][3]) const; };
 #include "chain_tonecurves.inc"
 
 namespace {
@@ -1596,6 +1599,34 @@ int artref_chain_tonecurve(float* R, float* G, float* B, int W, int H, int mode,
         c.whitecoeff = whitept; c.whitept = 65535.f * whitept;
         apply(c, &im, W, H, true);
     }
+    im.store(R, G, B);
+    return 0;
+}
+// apply_tc's other per-pixel classes (iptonecurve.cc L48-85): mode 3 = WEIGHTEDSTD, 4 = SATANDVALBLENDING, 5 = LUMINANCE (ws = the
+// float TMatrix of the working space), after the filmlike_clip pass ImProcFunctions::toneCurve runs first (L581-589)
+int artref_chain_tonecurve_ex(float* R, float* G, float* B, int W, int H, int mode, const float* lut, float whitept, const double* wsd)
+{
+    Imagefloat im(W, H, R, G, B, (const double[9]){1,0,0,0,1,0,0,0,1}, nullptr);
+    Imagefloat* rgb = &im;
+    filmlike_clip(&im, whitept, true);
+    if (mode == 3) {
+        WeightedStdToneCurve c; c.lutToneCurve(65536); for (int i = 0; i < 65536; ++i) c.lutToneCurve[i] = lut[i];
+        c.whitecoeff = whitept; c.whitept = 65535.f * whitept;
+        apply(c, &im, W, H, true);
+    } else if (mode == 4) {
+        SatAndValueBlendingToneCurve c; c.lutToneCurve(65536); for (int i = 0; i < 65536; ++i) c.lutToneCurve[i] = lut[i];
+        c.whitecoeff = whitept; c.whitept = 65535.f * whitept;
+        apply(c, &im, W, H, true);
+    } else if (mode == 5) {
+        LuminanceToneCurve c_; c_.lutToneCurve(65536); for (int i = 0; i < 65536; ++i) c_.lutToneCurve[i] = lut[i];
+        c_.whitecoeff = whitept; c_.whitept = 65535.f * whitept;
+        const LuminanceToneCurve& c = c_;
+        float wsm[3][3]; for (int i = 0; i < 9; ++i) (&wsm[0][0])[i] = (float)wsd[i];
+        TMatrix ws = wsm;
+        const bool multithread = true;
+#pragma omp parallel for if (multithread)
+#include "chain_lumtone_loop.inc"
+    } else return -1;
     im.store(R, G, B);
     return 0;
 }
@@ -2023,13 +2054,21 @@ def extract(det):
     open(os.path.join(sub, "chain_tonecurves.inc"), "w").write("\n".join([
         cut_function(cvh, r"^inline void StandardToneCurve::Apply \(float& r, float& g, float& b\) const"),
         cut_function(cvh, r"^inline void AdobeToneCurve::RGBTone \(float& r, float& g, float& b\) const"),
-        cut_function(cvh, r"^inline void AdobeToneCurve::Apply \(float& ir, float& ig, float& ib\) const")]))
+        cut_function(cvh, r"^inline void AdobeToneCurve::Apply \(float& ir, float& ig, float& ib\) const"),
+        cut_function(cvh, r"^inline void LuminanceToneCurve::Apply\(float &ir, float &ig, float &ib, const float ws\[3\]\[3\]\) const"),
+        cut_function(cvh, r"^inline float WeightedStdToneCurve::Triangle\(float a, float a1, float b\) const"),
+        cut_function(cvh, r"^inline void WeightedStdToneCurve::Apply \(float& ir, float& ig, float& ib\) const"),
+        cut_function(cvh, r"^inline void SatAndValueBlendingToneCurve::Apply \(float& ir, float& ig, float& ib\) const")]))
+    open(os.path.join(sub, "chain_lumtone_loop.inc"), "w").write(
+        block_after(ipt, r"for \(int y = 0; y < H; \+\+y\) \{(?=\s*for \(int x = 0; x < W; \+\+x\) \{\s*c\.Apply\(rgb->r\(y, x\), rgb->g\(y, x\), rgb->b\(y, x\), ws\);)"))
     imf = os.path.join(RT, "imagefloat.cc")
     open(os.path.join(sub, "chain_imagefloat.inc"), "w").write("\n".join([
         cut_function(imf, r"^inline void Imagefloat::rgb_to_lab\(int y, int x, float &L, float &a, float &b\)"),
         cut_function(imf, r"^void Imagefloat::rgb_to_lab\(bool multithread\)"),
         cut_function(imf, r"^void Imagefloat::lab_to_rgb\(bool multithread\)")]))
     hm = [cut_function(ch, r"static float rgbLuminance\(float r, float g, float b, const T workingspace\[3\]\[3\]\)"),
+          cut_function(ch, r"static inline void rgb2hsvtc\(float r, float g, float b, float &h, float &s, float &v\)"),
+          cut_function(ch, r"static inline void hsv2rgbdcp \(float h, float s, float v, float &r, float &g, float &b\)"),
           cut_function(ch, r"static inline float f2xyz\(float f\)"),
           cut_function(ch, r"static inline vfloat f2xyz\(vfloat f\)"),
           cut_function(ch, r"static void rgb2lab\(float R, float G, float B, float &l, float &a, float &b, const T ws\[3\]\[3\]\)"),

@@ -173,6 +173,88 @@ int artoracle_chain_tonecurve(float* R, float* G, float* B, int W, int H, int mo
     return 0;
 }
 
+/* ---- the other per-pixel tone-curve classes apply_tc dispatches to (iptonecurve.cc L48-85), after the same filmlike_clip pass:
+ * mode 3 = WeightedStdToneCurve::Apply (curves.h L499-562), 4 = SatAndValueBlendingToneCurve::Apply (L634-668, Color::rgb2hsvtc /
+ * hsv2rgbdcp, color.h L423-506), 5 = LuminanceToneCurve::Apply (L474-496; ws = the float TMatrix) ---- */
+static inline float lim_f(float v, float lo, float hi) { const float m = hi < v ? hi : v; return lo < m ? m : lo; }   /* LIM = max(low, min(val, high)) with std::min / max operand order */
+static inline float triangle(float a, float a1, float b, float whitept)
+{
+    if (a != b) {
+        const float a2 = a1 - a;
+        return b < a ? b + a2 * b / a : b + a2 * (whitept - b) / (whitept - a);
+    }
+    return a1;
+}
+static inline float min3f(float a, float b, float c) { const float m = b < a ? b : a; return c < m ? c : m; }   /* rt_math.h min(a, b, c) = min(min(a, b), min(c)) */
+static inline float max3f(float a, float b, float c) { const float m = a < b ? b : a; return m < c ? c : m; }
+int artoracle_chain_tonecurve_ex(float* R, float* G, float* B, int W, int H, int mode, const float* lut, float whitecoeff, const double* wsd)
+{
+    const float whitept = 65535.f * whitecoeff;
+    float wy[3] = {0.f, 0.f, 0.f};
+    if (mode < 3 || mode > 5) return -1;
+    if (mode == 5) { if (!wsd) return -1; for (int i = 0; i < 3; ++i) wy[i] = (float)wsd[3 + i]; }
+    for (size_t i = 0; i < (size_t)W * H; ++i) {
+        filmlike_clip(&R[i], &G[i], &B[i], whitept);
+        if (mode == 3) {
+            float r = lim_f(R[i], 0.f, whitept), g = lim_f(G[i], 0.f, whitept), b = lim_f(B[i], 0.f, whitept);
+            float r1 = r; set_lut_val(lut, &r1);
+            const float g1 = triangle(r, r1, g, whitept), b1 = triangle(r, r1, b, whitept);
+            float g2 = g; set_lut_val(lut, &g2);
+            const float r2 = triangle(g, g2, r, whitept), b2 = triangle(g, g2, b, whitept);
+            float b3 = b; set_lut_val(lut, &b3);
+            const float r3 = triangle(b, b3, r, whitept), g3 = triangle(b, b3, g, whitept);
+            R[i] = lim_f(r1 * 0.50f + r2 * 0.25f + r3 * 0.25f, 0.f, whitept);
+            G[i] = lim_f(g1 * 0.25f + g2 * 0.50f + g3 * 0.25f, 0.f, whitept);
+            B[i] = lim_f(b1 * 0.25f + b2 * 0.25f + b3 * 0.50f, 0.f, whitept);
+        } else if (mode == 4) {
+            float r = lim_f(R[i], 0.f, 65535.f), g = lim_f(G[i], 0.f, 65535.f), b = lim_f(B[i], 0.f, 65535.f);      /* CLIP */
+            const float lum = (r + g + b) / 3.f;
+            const float newLum = lut_s(lut, 65536, CLIP_BELOW | CLIP_ABOVE, lum);
+            if (newLum == lum) continue;            /* the reference returns before writing back: the pixel keeps its unclipped values */
+            float h, s, v;
+            {
+                const float var_Min = min3f(r, g, b), var_Max = max3f(r, g, b), del_Max = var_Max - var_Min;
+                v = var_Max / 65535.f;
+                if (del_Max < 0.00001f) { h = 0.f; s = 0.f; }
+                else {
+                    s = del_Max / var_Max;
+                    if (r == var_Max) h = (g < b ? 6.f : 0.f) + (g - b) / del_Max;
+                    else if (g == var_Max) h = 2.f + (b - r) / del_Max;
+                    else h = 4.f + (r - g) / del_Max;
+                }
+            }
+            float dV;
+            if (newLum > lum) { const float coef = (newLum - lum) / (65535.f - lum); dV = (1.f - v) * coef; s *= 1.f - coef; }
+            else { const float coef = (newLum - lum) / lum; dV = v * coef; }
+            {
+                float vv = v + dV;
+                const int sector = (int)h;
+                const float f = h - sector;
+                vv *= 65535.f;
+                const float vs = vv * s, p = vv - vs, q = vv - f * vs, t = p + vv - q;
+                switch (sector) {
+                case 1: r = q; g = vv; b = p; break;
+                case 2: r = p; g = vv; b = t; break;
+                case 3: r = p; g = q; b = vv; break;
+                case 4: r = t; g = p; b = vv; break;
+                case 5: r = vv; g = p; b = q; break;
+                default: r = vv; g = t; b = p;
+                }
+            }
+            R[i] = r; G[i] = g; B[i] = b;
+        } else {
+            float r = lim_f(R[i], 0.f, whitept), g = lim_f(G[i], 0.f, whitept), b = lim_f(B[i], 0.f, whitept);
+            float currLuminance = r * wy[0] + g * wy[1] + b * wy[2];
+            float newLuminance = currLuminance;
+            set_lut_val(lut, &newLuminance);
+            currLuminance = currLuminance == 0.f ? 0.00001f : currLuminance;
+            const float coef = newLuminance / currLuminance;
+            R[i] = lim_f(r * coef, 0.f, whitept); G[i] = lim_f(g * coef, 0.f, whitept); B[i] = lim_f(b * coef, 0.f, whitept);
+        }
+    }
+    return 0;
+}
+
 /* ---- rgbCurves: LUTs built with flags 0 (no clipping) ---- */
 int artoracle_chain_rgbcurves(float* R, float* G, float* B, int W, int H, const float* rc, const float* gc, const float* bc)
 {

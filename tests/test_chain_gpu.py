@@ -21,7 +21,7 @@ def lab_luts():
     return lc, curve_lut(65536, 1.1, 65535.0, 1), curve_lut(65536, 0.9, 65535.0, 2)
 
 
-def oracle_chain(planes, exposure=None, saturation=None, tonecurve=None, rgbcurves=None, lab=None):
+def oracle_chain(planes, exposure=None, saturation=None, tonecurve=None, rgbcurves=None, lab=None, whitept=1.0):
     lib = oracle.port().lib
     out = planes
     if exposure is not None:
@@ -29,8 +29,10 @@ def oracle_chain(planes, exposure=None, saturation=None, tonecurve=None, rgbcurv
         out = call(lib, "artoracle_chain_expcomp", out, F(np.float32(2.0) ** np.float32(ev)), F(np.float32(black) * np.float32(2000.0)))
     if saturation is not None and (saturation[0] or saturation[1]):
         out = call(lib, "artoracle_chain_saturation", out, saturation[0], saturation[1], PROPHOTO.ctypes.data_as(dp))
-    if tonecurve is not None:
-        out = call(lib, "artoracle_chain_tonecurve", out, tonecurve[0], tonecurve[1].ctypes.data_as(fp), F(1.0))
+    if tonecurve is not None and tonecurve[0] >= 3:     # WEIGHTEDSTD / SATANDVALBLENDING / LUMINANCE
+        out = call(lib, "artoracle_chain_tonecurve_ex", out, tonecurve[0], tonecurve[1].ctypes.data_as(fp), F(whitept), PROPHOTO.ctypes.data_as(dp))
+    elif tonecurve is not None:
+        out = call(lib, "artoracle_chain_tonecurve", out, tonecurve[0], tonecurve[1].ctypes.data_as(fp), F(whitept))
     if rgbcurves is not None:
         out = call(lib, "artoracle_chain_rgbcurves", out, *[c.ctypes.data_as(fp) if c is not None else None for c in rgbcurves])
     if lab is not None:
@@ -57,6 +59,15 @@ STAGES = {
     "lab": dict(lab=lab_luts() + (1.35,)),
     "lab_lowchroma": dict(lab=lab_luts() + (0.4,)),
 }
+STAGES["tone_weighted"] = dict(tonecurve=(3, curve_lut(gamma=0.6, seed=3)))
+STAGES["tone_satval"] = dict(tonecurve=(4, curve_lut(gamma=0.6, seed=4)))
+STAGES["tone_satval_dark"] = dict(tonecurve=(4, curve_lut(gamma=1.5, seed=4)))
+STAGES["tone_luminance"] = dict(tonecurve=(5, curve_lut(gamma=0.6, seed=5)))
+STAGES["tone_weighted_white2"] = dict(tonecurve=(3, curve_lut(gamma=0.7, seed=3)), whitept=2.0)
+STAGES["tone_luminance_white2"] = dict(tonecurve=(5, curve_lut(gamma=1.3, seed=5)), whitept=2.0)
+STAGES["all_weighted"] = dict(STAGES["exposure"], **STAGES["satvib"], **STAGES["tone_weighted"], **STAGES["rgbcurves"], **STAGES["lab"])
+STAGES["all_satval"] = dict(STAGES["exposure_neg"], **STAGES["saturation"], **STAGES["tone_satval"], **STAGES["lab_lowchroma"])
+STAGES["all_luminance"] = dict(STAGES["exposure"], **STAGES["vibrance"], **STAGES["tone_luminance"], **STAGES["rgbcurves"], **STAGES["lab"])
 STAGES["all_std"] = dict(STAGES["exposure"], **STAGES["satvib"], **STAGES["tone_std"], **STAGES["rgbcurves"], **STAGES["lab"])
 STAGES["all_film"] = dict(STAGES["exposure_neg"], **STAGES["saturation"], **STAGES["tone_film"],
                           rgbcurves=[curve_lut(gamma=0.9, seed=i) for i in range(3)], **STAGES["lab_lowchroma"])
@@ -67,6 +78,15 @@ STAGES["all_film"] = dict(STAGES["exposure_neg"], **STAGES["saturation"], **STAG
 def test_chain_matches_oracle(hot_path, W, H, name):
     planes = image(H, W, W * 17 + H)
     same(gpu_chain(hot_path, planes, **STAGES[name]), oracle_chain(planes, **STAGES[name]))
+
+
+def test_chain_rejects_perceptual_and_luminance_without_ws(hot_path):
+    import art_b200
+    planes = image(8, 8, 1)
+    with pytest.raises(art_b200.HotPathError):
+        hot_path.color_chain(planes[0], planes[1], planes[2], ChainParams(ws=PROPHOTO, iws=PROPHOTO_INV, tonecurve=(6, curve_lut())))
+    with pytest.raises(art_b200.HotPathError):
+        hot_path.color_chain(planes[0], planes[1], planes[2], ChainParams(tonecurve=(5, curve_lut())))
 
 
 def test_chain_in_range_image(hot_path):

@@ -97,6 +97,23 @@ def test_tonecurve(W, H, mode, whitept):
 
 
 @needs_ref
+@pytest.mark.parametrize("W,H", SIZES + [(301, 211)])
+@pytest.mark.parametrize("mode", [3, 4, 5])
+@pytest.mark.parametrize("whitept", [1.0, 2.0])
+@pytest.mark.parametrize("gamma", [0.6, 1.4])
+def test_tonecurve_other_modes(W, H, mode, whitept, gamma):
+    """WEIGHTEDSTD (3), SATANDVALBLENDING (4), LUMINANCE (5) against the reference's own Apply members (curves.h L474-668)"""
+    planes = image(H, W, W * 7 + H + mode)
+    planes[0][0, :2] = planes[1][0, :2] = planes[2][0, :2] = 0.0          # black: LuminanceToneCurve's 0.00001 guard, rgb2hsvtc's grey branch
+    lut = curve_lut(gamma=gamma, seed=mode)
+    if mode == 4:
+        lut[20000:20100] = np.arange(20000, 20100, dtype=np.float32)      # newLum == lum for some pixels: the early return
+        planes[0][-1, :] = planes[1][-1, :] = planes[2][-1, :] = 20050.0
+    args = (mode, lut.ctypes.data_as(fp), F(whitept), PROPHOTO.ctypes.data_as(dp))
+    same(call(oracle.port().lib, "artoracle_chain_tonecurve_ex", planes, *args), call(oracle.ref().lib, "artref_chain_tonecurve_ex", planes, *args))
+
+
+@needs_ref
 @pytest.mark.parametrize("W,H", SIZES)
 @pytest.mark.parametrize("which", [(1, 1, 1), (1, 0, 0), (0, 1, 1)])
 def test_rgbcurves(W, H, which):
