@@ -124,6 +124,8 @@ def load_library(build_if_missing=True):
         "art_hp_dual_demosaic_bayer_dev": (i, [vp, i, i, i, i, u, u, vp, sz, vp, vp, vp, sz, d, i, d, i, vp]),
         "art_hp_dual_demosaic_xtrans": (i, [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, i]),
         "art_hp_dual_demosaic_xtrans_dev": (i, [vp, i, i, i, i, vp, vp, vp, sz, vp, vp, vp, sz, d, i, vp]),
+        "art_hp_hsl_equalizer": (i, [vp, i, i, vp, vp, vp, vp]),
+        "art_hp_hsl_equalizer_dev": (i, [vp, i, i, vp, vp, vp, sz, vp]),
         "art_hp_channel_mixer": (i, [vp, i, i, vp, vp, vp, vp]),
         "art_hp_channel_mixer_dev": (i, [vp, i, i, vp, vp, vp, sz, vp]),
         "art_hp_find_hot_dead_pixels": (i, [vp, i, i, vp, vp, f, i, i, vp, sz, ctypes.POINTER(i)]),
@@ -275,6 +277,44 @@ class _CurveStageC(ctypes.Structure):      # art_hp_curve_stage
     _dp = ctypes.POINTER(ctypes.c_double)
     _fields_ = [("kind", ctypes.c_int), ("poly_x", _dp), ("poly_y", _dp), ("n", ctypes.c_int),
                 ("a", ctypes.c_double), ("b", ctypes.c_double), ("w", ctypes.c_double)]
+
+
+class _FlatCurveC(ctypes.Structure):       # art_hp_flat_curve
+    _dp = ctypes.POINTER(ctypes.c_double)
+    _fields_ = [("n", ctypes.c_int), ("poly_x", _dp), ("poly_y", _dp), ("dy_by_dx", _dp)]
+
+
+class _HslParamsC(ctypes.Structure):       # art_hp_hsl_params
+    _fields_ = [("hcurve", _FlatCurveC), ("scurve", _FlatCurveC), ("lcurve", _FlatCurveC), ("coeff", _FlatCurveC),
+                ("smoothing", ctypes.c_int), ("scale", ctypes.c_double), ("ws", ctypes.POINTER(ctypes.c_double))]
+
+
+class HslParams:
+    """art_hp_hsl_params: hcurve / scurve / lcurve / coeff = (poly_x, poly_y, dy_by_dx) of the host-built FlatCurve or None for an
+    identity curve; smoothing = params->hsl.smoothing; scale = ImProcFunctions::scale; ws = the working-space matrix."""
+
+    def __init__(self, hcurve=None, scurve=None, lcurve=None, coeff=None, smoothing=0, scale=1.0, ws=None):
+        self.__dict__.update(locals())
+        del self.__dict__["self"]
+
+    def c_struct(self):
+        c = _HslParamsC()
+        self._keep = []
+        dp = ctypes.POINTER(ctypes.c_double)
+        for name in ("hcurve", "scurve", "lcurve", "coeff"):
+            cv = getattr(self, name)
+            if cv is None or len(cv[0]) == 0:
+                continue
+            arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in cv]
+            self._keep += arrs
+            f = getattr(c, name)
+            f.n, f.poly_x, f.poly_y, f.dy_by_dx = int(arrs[0].size), arrs[0].ctypes.data_as(dp), arrs[1].ctypes.data_as(dp), arrs[2].ctypes.data_as(dp)
+        c.smoothing, c.scale = int(self.smoothing), float(self.scale)
+        if self.ws is not None:
+            w = np.ascontiguousarray(self.ws, dtype=np.float64).reshape(9)
+            self._keep.append(w)
+            c.ws = w.ctypes.data_as(dp)
+        return c
 
 
 class _ChainParamsC(ctypes.Structure):
@@ -706,6 +746,17 @@ class HotPath:
                                                          cam.ctypes.data_as(ctypes.c_void_p), row_table(raw), *[row_table(o) for o in out],
                                                          ctypes.byref(c), int(bool(auto_contrast))))
         return out, c.value
+
+    def hsl_equalizer(self, r, g, b, params):
+        """ImProcFunctions::hslEqualizer in place on three host (H, W) float32 working-space RGB planes."""
+        H, W = r.shape
+        c = params.c_struct()
+        self._check(self.lib.art_hp_hsl_equalizer(self.h, W, H, row_table(r), row_table(g), row_table(b), ctypes.byref(c)))
+        return r, g, b
+
+    def hsl_equalizer_dev(self, W, H, d_r, d_g, d_b, pitch, params):
+        c = params.c_struct()
+        self._check(self.lib.art_hp_hsl_equalizer_dev(self.h, W, H, d_r, d_g, d_b, pitch, ctypes.byref(c)))
 
     def channel_mixer(self, r, g, b, matrix):
         """ImProcFunctions::channelMixer's loop in place on three host (H, W) float32 planes; matrix = 9 floats (RGB_MATRIX: sliders / 1000.f)."""

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ART_HP_ABI_VERSION 4
+#define ART_HP_ABI_VERSION 5
 
 typedef enum art_hp_status {
     ART_HP_OK = 0,
@@ -532,6 +532,33 @@ int art_hp_interpolate_bad_pixels_bayer_dev(art_hp_ctx* ctx, int W, int H, unsig
  */
 int art_hp_channel_mixer(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b, const float matrix[9]);
 int art_hp_channel_mixer_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch, const float matrix[9]);
+
+/* ---- HSL equalizer ----------------------------------------------------------------- */
+/*
+ * art_hp_hsl_equalizer   ImProcFunctions::hslEqualizer (rtengine/iphsl.cc L29-221; STAGE_1 of ImProcFunctions::process, improcfun.cc
+ *                        L580-584) in place on working-space RGB planes in [0, 65535], including the Imagefloat::setMode(YUV) it starts with
+ *                        (rtengine/imagefloat.cc L700-725) and the setMode(RGB) the next stage applies to the YUV image it leaves (L779-803):
+ *                        hue / saturation of the chroma plane (Color::yuv2hsl, rtengine/color.cc L6691-6695), then per enabled curve -- S, L, H --
+ *                        the hue-indexed FlatCurve value smoothed by guidedFilter(Y, mask, mask, radius, eps) (radius 4 / scale * smooth for S and H,
+ *                        25 / scale * smooth for L; smooth = pow(10, LIM01(smoothing / 10)) - 1) and applied to saturation, luminance or hue.
+ *                        Curves stay host-built: each is the polyline the reference's FlatCurve constructor produces (poly_x, poly_y, dyByDx of
+ *                        rtengine/curves.h; FlatCurve(points, true, CURVES_MIN_POLY_POINTS / scale)), n = 0 for an identity curve (isIdentity(), the
+ *                        reference then skips that curve); `coeff` is the function's local FlatCurve of L119-123 built the same way (needed with a
+ *                        saturation curve).  Bit-identical to the reference.
+ */
+typedef struct art_hp_flat_curve {
+    int n;                                        /* points of the polyline; 0 = identity */
+    const double *poly_x, *poly_y, *dy_by_dx;     /* n doubles each (dy_by_dx: n - 1 used) */
+} art_hp_flat_curve;
+typedef struct art_hp_hsl_params {
+    art_hp_flat_curve hcurve, scurve, lcurve;     /* params->hsl.hCurve / sCurve / lCurve */
+    art_hp_flat_curve coeff;
+    int smoothing;                                /* params->hsl.smoothing */
+    double scale;                                 /* ImProcFunctions::scale */
+    const double* ws;                             /* ICCStore::workingSpaceMatrix, 9 doubles */
+} art_hp_hsl_params;
+int art_hp_hsl_equalizer(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b, const art_hp_hsl_params* params);
+int art_hp_hsl_equalizer_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch, const art_hp_hsl_params* params);
 
 /* ---- dual demosaic ----------------------------------------------------------------- */
 /*

@@ -35,6 +35,8 @@ SHIM_TONE_TU = r"""
 #include "sleef.h"
 #include "linalgebra.h"
 #include "iccmatrices.h"
+#include "array2D.h"
+namespace rtengine { void guidedFilter(const array2D<float> &guide, const array2D<float> &src, array2D<float> &dst, int r, float epsilon, bool multithread, int subsampling=0); }   // guidedfilter.h L27; defined in the guided translation unit
 
 enum DiagonalCurveType { DCT_Empty = -1, DCT_Linear, DCT_Spline, DCT_Parametric, DCT_NURBS, DCT_CatmullRom, DCT_Unchanged };   // rtgui/mydiagonalcurve.h L31-40
 enum FlatCurveType { FCT_Empty = -1, FCT_Linear, FCT_MinMaxCPoints, FCT_Unchanged };                                           // rtgui/myflatcurve.h L29-36
@@ -57,6 +59,7 @@ public:
     constexpr static double sRGBGammaCurve = 2.4;
     static LUTf gamma2curve, igammatab_srgb, gammatab_srgb, jzazbz_pq_, jzazbz_pq_inv_;
 #include "tone_color_h.inc"
+#include "tone_color_yuv.inc"
     static void init()
     {   // color.cc L236-256, L322-326
         if (gammatab_srgb) return;
@@ -243,6 +246,81 @@ int artref_tone_satcurve(float* R, float* G, float* B_, int W, int H, const doub
     apply_satcurve(&im, satlcurve, satccurve, "", whitept, true);
     return 0;
 }
+// the polyline FlatCurve::getVal searches (flatcurves.cc L339-365): returns the point count (0 = FCT_Empty, the identity), fills up to cap
+struct FlatPeek : public FlatCurve { using FlatCurve::poly_x; using FlatCurve::poly_y; using FlatCurve::dyByDx; };
+int artref_flat_polyline(const double* pts, int npts, int periodic, int poly_pn, double* px, double* py, double* dy, int cap)
+{
+    std::vector<double> v(pts, pts + npts);
+    const FlatCurve c(v, periodic != 0, poly_pn);
+    const FlatPeek* p = static_cast<const FlatPeek*>(&c);
+    if (c.isIdentity()) return 0;
+    const int n = (int)p->poly_x.size();
+    for (int i = 0; i < n && i < cap; ++i) { px[i] = p->poly_x[i]; py[i] = p->poly_y[i]; if (i < (int)p->dyByDx.size()) dy[i] = p->dyByDx[i]; }
+    return n;
+}
+double artref_flat_getval(const double* pts, int npts, int periodic, int poly_pn, double t)
+{
+    std::vector<double> v(pts, pts + npts);
+    const FlatCurve c(v, periodic != 0, poly_pn);
+    return c.getVal(t);
+}
+}   // extern "C"
+
+// ---- ImProcFunctions::hslEqualizer (iphsl.cc L29-221) over a stand-in Imagefloat whose setMode / normalize members are the
+// reference's own loops (imagefloat.cc rgb_to_yuv L700-725, yuv_to_rgb L779-803, multiply L396-425)
+namespace hsl {
+struct Plane { float* base; int stride; float** ptrs; float& operator()(int y, int x) { return ptrs[y][x]; } };
+class Imagefloat {
+public:
+    enum class Mode { RGB, YUV };
+    int width, height; Plane r, g, b;
+    float ws_[3][3]; vfloat vws_[3][3];
+    Imagefloat(int w, int h, const float* R, const float* G, const float* B, const double* ws) : width(w), height(h)
+    {
+        const int st = (w + 3) / 4 * 4;
+        Plane* pl[3] = {&r, &g, &b}; const float* src[3] = {R, G, B};
+        for (int c = 0; c < 3; ++c) {
+            void* p = nullptr; if (posix_memalign(&p, 64, sizeof(float) * (size_t)st * h)) abort();
+            pl[c]->base = (float*)p; pl[c]->stride = st; pl[c]->ptrs = new float*[h];
+            for (int y = 0; y < h; ++y) { pl[c]->ptrs[y] = pl[c]->base + (size_t)y * st; memcpy(pl[c]->ptrs[y], src[c] + (size_t)y * w, sizeof(float) * w); }
+        }
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { ws_[i][j] = float(ws[3 * i + j]); vws_[i][j] = F2V(float(ws[3 * i + j])); }
+    }
+    ~Imagefloat() { Plane* pl[3] = {&r, &g, &b}; for (int c = 0; c < 3; ++c) { free(pl[c]->base); delete[] pl[c]->ptrs; } }
+    void store(float* R, float* G, float* B) { Plane* pl[3] = {&r, &g, &b}; float* dst[3] = {R, G, B};
+        for (int c = 0; c < 3; ++c) for (int y = 0; y < height; ++y) memcpy(dst[c] + (size_t)y * width, pl[c]->ptrs[y], sizeof(float) * width); }
+    int getWidth() const { return width; }
+    int getHeight() const { return height; }
+    void get_ws() {}
+    void multiply(float factor, bool multithread);
+    void normalizeFloatTo1(bool multithread);
+    void normalizeFloatTo65535(bool multithread);
+    void rgb_to_yuv(bool multithread);
+    void yuv_to_rgb(bool multithread);
+    void setMode(Mode m, bool multithread) { if (m == Mode::YUV) rgb_to_yuv(multithread); else yuv_to_rgb(multithread); }    // imagefloat.cc L620-650 for these two modes
+};
+#include "hsl_imagefloat.inc"
+struct Whatever { float& v(int, int) { static float f; return f; } void fill(float) {} };
+struct HslParams { std::vector<double> hCurve, sCurve, lCurve; int smoothing; bool enabled; };
+struct Params { HslParams hsl; };
+
+extern "C" int artref_hsl_equalizer(float* R, float* G, float* B, int W_, int H_, const double* ws9, const double* hc, int nh, const double* sc, int ns,
+                                    const double* lc, int nl, int smoothing, double scale_)
+{
+    Color::init();
+    Params P; const Params* params = &P;
+    P.hsl.hCurve.assign(hc, hc + nh); P.hsl.sCurve.assign(sc, sc + ns); P.hsl.lCurve.assign(lc, lc + nl); P.hsl.smoothing = smoothing; P.hsl.enabled = true;
+    Imagefloat im(W_, H_, R, G, B, ws9); Imagefloat* img = &im;
+    const double scale = scale_;
+    const bool multiThread = true;
+    Whatever* editWhatever = nullptr;
+#include "hsl_body.inc"
+    img->setMode(Imagefloat::Mode::RGB, multiThread);       // what the next stage's setMode(RGB) does to the YUV image hslEqualizer leaves
+    im.store(R, G, B);
+    return 0;
+}
+}   // namespace hsl
+extern "C" {
 int artref_tone_tables(float* pq, float* pq_inv, float* gamma2curve)
 {
     Color::init();
@@ -303,5 +381,21 @@ def extract(sub):
         cut_function(ipt, r"^void apply_satcurve\(Imagefloat \*rgb, const FlatCurve &curve"),
         cut_function(ipt, r"^class DoubleCurve: public Curve") + ";"]))
     w("tone_assembly.inc", between(rd(ipt), r"^        const auto expand =", r"^        DiagonalCurve tcurve2\("))
+    w("tone_color_yuv.inc", "\n".join([
+        "template <class T>\n" + cut_function(ch, r"static float rgbLuminance\(float r, float g, float b, const T workingspace\[3\]\[3\]\)"),
+        "static " + cut_function(ch, r"vfloat rgbLuminance\(vfloat r, vfloat g, vfloat b, const vfloat workingspace\[3\]\[3\]\)"),
+        "template <class T>\n" + cut_function(ch, r"static void rgb2yuv\(float r, float g, float b, float &Y, float &u, float &v, const T workingspace\[3\]\[3\]\)"),
+        "template <class T>\n" + cut_function(ch, r"static void yuv2rgb\(float Y, float u, float v, float &r, float &g, float &b, const T workingspace\[3\]\[3\]\)"),
+        cut_function(ch, r"static void rgb2yuv\(vfloat r, vfloat g, vfloat b, vfloat &Y, vfloat &u, vfloat &v, const vfloat workingspace\[3\]\[3\]\)"),
+        cut_function(ch, r"static void yuv2rgb\(vfloat Y, vfloat u, vfloat v, vfloat &r, vfloat &g, vfloat &b, const vfloat workingspace\[3\]\[3\]\)")]))
+    imf = os.path.join(RT, "imagefloat.cc")
+    w("hsl_imagefloat.inc", "\n".join([
+        cut_function(imf, r"^void Imagefloat::multiply\(float factor, bool multithread\)"),
+        cut_function(imf, r"^void Imagefloat::normalizeFloatTo1\(bool multithread\)"),
+        cut_function(imf, r"^void Imagefloat::normalizeFloatTo65535\(bool multithread\)"),
+        cut_function(imf, r"^void Imagefloat::rgb_to_yuv\(bool multithread\)"),
+        cut_function(imf, r"^void Imagefloat::yuv_to_rgb\(bool multithread\)")]))
+    w("hsl_body.inc", between(rd(os.path.join(RT, "iphsl.cc")), r"^    img->setMode\(Imagefloat::Mode::YUV, multiThread\);", r"^\} // namespace rtengine")
+      .rstrip().rstrip("}"))
     w("shim_tone.cc", SHIM_TONE_TU)
     return os.path.join(sub, "shim_tone.cc")

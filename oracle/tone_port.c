@@ -357,3 +357,7 @@ int artoracle_tone_satcurve(float* R, float* G, float* B, int W, int H, const fl
     }
     return 0;
 }
+
+/* sleef's xatan2f / xsincosf for the other ports (hsl_port.c) */
+float artoracle_xatan2f(float y, float x) { return xatan2f__(y, x); }
+void artoracle_xsincosf(float d, float* sn, float* cs) { xsincosf__(d, sn, cs); }

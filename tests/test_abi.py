@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, "declared in include/art_hotpath.h but not exported: %s" % missing
     for s in api.ABI_SYMBOLS:
         assert getattr(lib, s) is not None
-    assert lib.art_hp_abi_version() == 4
+    assert lib.art_hp_abi_version() == 5
 
 
 def test_header_is_plain_c():
@@ -71,6 +71,8 @@ def test_ctypes_structs_match_the_header(tmp_path):
         "art_hp_chain_params": (api._ChainParamsC, ["exposure_enabled", "exp_scale", "black", "saturation_enabled", "vibrance", "tonecurve_mode",
                                                      "tonecurve_lut", "rcurve", "bcurve", "lab_enabled", "lab_lcurve", "lab_bcurve", "lab_chroma", "ws", "iws",
                                                      "tonecurve_whitept", "tonecurve_stages", "tonecurve_nstages", "neutral_to_out", "neutral_to_work", "satcurve_lut"]),
+        "art_hp_flat_curve": (api._FlatCurveC, ["n", "poly_x", "poly_y", "dy_by_dx"]),
+        "art_hp_hsl_params": (api._HslParamsC, ["hcurve", "scurve", "lcurve", "coeff", "smoothing", "scale", "ws"]),
         "art_hp_curve_stage": (api._CurveStageC, ["kind", "poly_x", "poly_y", "n", "a", "b", "w"]),
         "art_hp_sharpen_params": (api._SharpenParamsC, ["contrast", "radius", "amount", "threshold", "edgesonly", "halocontrol", "halocontrol_amount", "scale", "method", "deconvradius", "deconvamount", "deconvCornerBoost", "deconvCornerLatitude", "offset_x", "full_height", "edges_radius", "edges_tolerance"]),
     }
