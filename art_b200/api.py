@@ -124,6 +124,8 @@ def load_library(build_if_missing=True):
         "art_hp_dual_demosaic_bayer_dev": (i, [vp, i, i, i, i, u, u, vp, sz, vp, vp, vp, sz, d, i, d, i, vp]),
         "art_hp_dual_demosaic_xtrans": (i, [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, i]),
         "art_hp_dual_demosaic_xtrans_dev": (i, [vp, i, i, i, i, vp, vp, vp, sz, vp, vp, vp, sz, d, i, vp]),
+        "art_hp_lab_histogram": (i, [vp, i, i, vp, vp, vp, vp, vp]),
+        "art_hp_lab_histogram_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, vp]),
         "art_hp_hsl_equalizer": (i, [vp, i, i, vp, vp, vp, vp]),
         "art_hp_hsl_equalizer_dev": (i, [vp, i, i, vp, vp, vp, sz, vp]),
         "art_hp_channel_mixer": (i, [vp, i, i, vp, vp, vp, vp]),
@@ -326,7 +328,7 @@ class _ChainParamsC(ctypes.Structure):
                 ("lab_enabled", ctypes.c_int), ("lab_lcurve", _fp), ("lab_acurve", _fp), ("lab_bcurve", _fp), ("lab_chroma", ctypes.c_float),
                 ("ws", _dp), ("iws", _dp),
                 ("tonecurve_whitept", ctypes.c_float), ("tonecurve_stages", ctypes.POINTER(_CurveStageC)), ("tonecurve_nstages", ctypes.c_int),
-                ("neutral_to_out", _fp), ("neutral_to_work", _fp), ("satcurve_lut", _fp)]
+                ("neutral_to_out", _fp), ("neutral_to_work", _fp), ("satcurve_lut", _fp), ("softlight_lut", _fp)]
 
 
 class ChainParams:
@@ -335,10 +337,11 @@ class ChainParams:
     tonecurve = (mode, 65536-entry LUT) with mode 0 STD, 1 FILMLIKE, 2 NEUTRAL (ToneCurveParams::TcMode, the reference default);
     whitept = ToneCurve::whitecoeff; stages = the Curve::getVal chain above the LUT as (kind, poly_x, poly_y, a, b, w) tuples
     (art_hp_curve_stage); to_out / to_work = NeutralToneCurve::ApplyState's 3x3 float matrices or None; satcurve = apply_satcurve's
-    65536-entry table; rgbcurves = three LUTs or None each; lab = (L LUT of 32770, a LUT, b LUT, chroma)."""
+    65536-entry table; rgbcurves = three LUTs or None each; lab = (L LUT of 32770, a LUT, b LUT, chroma); softlight = softLight's
+    65536-entry table or None."""
 
     def __init__(self, exposure=None, saturation=None, tonecurve=None, rgbcurves=None, lab=None, ws=None, iws=None,
-                 whitept=1.0, stages=None, to_out=None, to_work=None, satcurve=None):
+                 whitept=1.0, stages=None, to_out=None, to_work=None, satcurve=None, softlight=None):
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
@@ -396,6 +399,7 @@ class ChainParams:
                 self._keep.append(v)
                 setattr(c, name, v.ctypes.data_as(fp))
         c.satcurve_lut = lut(self.satcurve, 65536)
+        c.softlight_lut = lut(self.softlight, 65536)
         return c
 
 
@@ -883,6 +887,14 @@ class HotPath:
         H, W = r.shape
         c = params.c_struct()
         self._check(self.lib.art_hp_color_chain(self.h, W, H, row_table(r), row_table(g), row_table(b), ctypes.byref(c)))
+
+    def lab_histogram(self, r, g, b, params):
+        """labAdjustments' hist16 (65536 uint32 counts of (int)L) of three host planes after the stages of `params` that precede the Lab stage."""
+        H, W = r.shape
+        c = params.c_struct()
+        hist = np.zeros(65536, np.uint32)
+        self._check(self.lib.art_hp_lab_histogram(self.h, W, H, row_table(r), row_table(g), row_table(b), ctypes.byref(c), hist.ctypes.data_as(ctypes.c_void_p)))
+        return hist
 
     def color_chain_dev(self, W, H, d_r, d_g, d_b, pitch, params):
         c = params.c_struct()

@@ -1033,6 +1033,46 @@ int art_hp_color_chain(art_hp_ctx* ctx, int W, int H, float* const* r, float* co
     return ART_HP_OK;
 }
 
+static int lab_hist_finish(art_hp_ctx* ctx, const unsigned* d_hist, unsigned* hist16)
+{
+    ART_CUDA(ctx, cudaMemcpyAsync(hist16, d_hist, 65536 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
+int art_hp_lab_histogram_dev(art_hp_ctx* ctx, int W, int H, const float* d_r, const float* d_g, const float* d_b, size_t pitch,
+                             const art_hp_chain_params* params, unsigned hist16[65536])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_r || !d_g || !d_b || !params || !hist16) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = art_reserve(ctx, ctx->d_small2, 65536 * sizeof(unsigned)))) return rc;
+    if ((rc = art_chain_lab_hist_dev(ctx, W, H, d_r, d_g, d_b, pitch, params, (unsigned*)ctx->d_small2.p))) return rc;
+    return lab_hist_finish(ctx, (const unsigned*)ctx->d_small2.p, hist16);
+}
+
+int art_hp_lab_histogram(art_hp_ctx* ctx, int W, int H, const float* const* r, const float* const* g, const float* const* b,
+                         const art_hp_chain_params* params, unsigned hist16[65536])
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!r || !g || !b || !params || !hist16) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    const size_t plane = pitch * (size_t)H * sizeof(float);
+    int rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], plane))) return rc;
+    if ((rc = art_reserve(ctx, ctx->d_small2, 65536 * sizeof(unsigned)))) return rc;
+    Plane io[3] = {{r, (float*)ctx->d_out[0].p}, {g, (float*)ctx->d_out[1].p},
+                   {b, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_chain_lab_hist_dev(ctx, W, H, io[0].dev, io[1].dev, io[2].dev, pitch, params, (unsigned*)ctx->d_small2.p))) return rc;
+    return lab_hist_finish(ctx, (const unsigned*)ctx->d_small2.p, hist16);
+}
+
 int art_hp_sharpen_usm_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
                            const art_hp_sharpen_params* params, const double ws[9])
 {

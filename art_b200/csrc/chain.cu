@@ -27,6 +27,8 @@ struct ChainArgs {
     int do_exp; float exp_scale, black;
     int do_sat, vib_on; float saturation, vibrance, noise, wy0, wy1, wy2;
     int tc_mode; const float* tc_lut; float Lmax, whitecoeff;
+    unsigned* hist;
+    const float* sl;
     const art_hp_curve_stage* stages; int nstages;           // device copies (poly arrays in device memory)
     const float *pq, *pq_inv, *satlut, *hues;                 // jzazbz_pq_, jzazbz_pq_inv_ (color.cc L322-326), satcurve_lut's table, ApplyState's hue constants
     float to_out[9], to_work[9];
@@ -476,6 +478,15 @@ __device__ __forceinline__ void lab_tail(const ChainArgs& A, float L, float a, f
     b = A.iws[6] * X + A.iws[7] * Y + A.iws[8] * Z;
 }
 
+// ImProcFunctions::softLight's apply lambda (ipsoftlight.cc L57-66): LUTf f(65536) clips below and above; scalar loop in the reference
+__device__ __forceinline__ float soft_light(const float* __restrict__ f, float x) { return x <= 65535.f ? lut_s(f, 65536, CLIP_BELOW | CLIP_ABOVE, x) : x; }
+
+// (int)f as x86's cvttss2si gives it: NaN and out-of-range values become INT_MIN (CUDA's conversion saturates and maps NaN to 0)
+__device__ __forceinline__ int cvtt_x86(float v) { return (v >= -2147483648.f && v < 2147483648.f) ? (int)v : (int)0x80000000; }
+
+// HIST: labAdjustments' hist16 (iplabadjustments.cc L307-334: hist16thr[(int)L]++ over the Lab L plane, LUT<T>::operator[](int) clamps the
+// index, LUT.h L308-311) of the frame as it stands after the stages before the Lab stage; nothing is stored
+template <bool HIST>
 __global__ void __launch_bounds__(256) k_chain(ChainArgs A)
 {
     const int gx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -520,8 +531,14 @@ __global__ void __launch_bounds__(256) k_chain(ChainArgs A)
                         a = 500.f * (fx - fy);
                         bb = 200.f * (fy - fz);
                     }
-                    lab_tail<true>(A, L, a, bb, r[k], g[k], b[k]);
+                    if (HIST) atomicAdd(A.hist + min(max(cvtt_x86(L), 0), 65535), 1u);
+                    else lab_tail<true>(A, L, a, bb, r[k], g[k], b[k]);
                 }
+            }
+            if (HIST) continue;
+            if (A.sl) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { r[k] = soft_light(A.sl, r[k]); g[k] = soft_light(A.sl, g[k]); b[k] = soft_light(A.sl, b[k]); }
             }
             *reinterpret_cast<float4*>(A.r + row + x0) = make_float4(r[0], r[1], r[2], r[3]);
             *reinterpret_cast<float4*>(A.g + row + x0) = make_float4(g[0], g[1], g[2], g[3]);
@@ -537,8 +554,10 @@ __global__ void __launch_bounds__(256) k_chain(ChainArgs A)
                     const float xd = Xs / D50X, zd = Zs / D50Z;
                     const float fx = xyz2lab_f(A.cachef, xd), fy = xyz2lab_f(A.cachef, Ys), fz = xyz2lab_f(A.cachef, zd);
                     const float L = xyz2lab_fy(A.cachefy, Ys);
+                    if (HIST) { atomicAdd(A.hist + min(max(cvtt_x86(L), 0), 65535), 1u); continue; }
                     lab_tail<false>(A, L, 500.0f * (fx - fy), 200.0f * (fy - fz), r, g, b);
                 }
+                if (A.sl) { r = soft_light(A.sl, r); g = soft_light(A.sl, g); b = soft_light(A.sl, b); }
                 A.r[row + x] = r; A.g[row + x] = g; A.b[row + x] = b;
             }
         }
@@ -548,12 +567,27 @@ __global__ void __launch_bounds__(256) k_chain(ChainArgs A)
 }  // namespace
 
 // LUT slots in the context's device / pinned staging: 0 tone curve, 1-3 rgb curves, 4 L curve, 5-6 a / b curves, 7-8 cachef / cachefy,
-// 9-10 jzazbz_pq_ / jzazbz_pq_inv_, 11 the saturation curve's table, 12 ApplyState's hue constants (device-computed)
+// 9-10 jzazbz_pq_ / jzazbz_pq_inv_, 11 the saturation curve's table, 12 ApplyState's hue constants (device-computed), 13 softLight's table
 constexpr size_t LUT_SLOT = 65536 + 64;
-constexpr int N_SLOTS = 13;
+constexpr int N_SLOTS = 14;
 constexpr int STAGE_SLOTS = 4;     // pinned staging only: the curve stages above the LUT when they fit (1 MB), else a pageable copy
 
+static int chain_run(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch, const art_hp_chain_params* p, unsigned* d_hist);
+
 int art_chain_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch, const art_hp_chain_params* p)
+{
+    return chain_run(ctx, W, H, r, g, b, pitch, p, nullptr);
+}
+
+// labAdjustments' hist16 of the frame as the Lab stage would see it (the stages before it applied on the fly, the planes untouched)
+int art_chain_lab_hist_dev(art_hp_ctx* ctx, int W, int H, const float* r, const float* g, const float* b, size_t pitch, const art_hp_chain_params* p, unsigned* d_hist)
+{
+    if (!p->ws) return ctx->fail(ART_HP_ERR_INVALID, "the Lab histogram needs ws");
+    ART_CUDA(ctx, cudaMemsetAsync(d_hist, 0, 65536 * sizeof(unsigned), ctx->stream));
+    return chain_run(ctx, W, H, const_cast<float*>(r), const_cast<float*>(g), const_cast<float*>(b), pitch, p, d_hist);
+}
+
+static int chain_run(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch, const art_hp_chain_params* p, unsigned* d_hist)
 {
     // every check comes before the first upload: a rejected call leaves the staging buffer and its event untouched
     if ((pitch & 3) || (reinterpret_cast<uintptr_t>(r) & 15) || (reinterpret_cast<uintptr_t>(g) & 15) || (reinterpret_cast<uintptr_t>(b) & 15))
@@ -563,7 +597,7 @@ int art_chain_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, s
     const bool jz = tc_mode == 2 || p->satcurve_lut;
     if ((do_sat || p->lab_enabled || jz) && !p->ws) return ctx->fail(ART_HP_ERR_INVALID, "ws is required by the saturation, NEUTRAL tone curve and Lab stages");
     if (jz && !p->iws) return ctx->fail(ART_HP_ERR_INVALID, "the NEUTRAL tone curve and the saturation curve need iws");
-    if (p->lab_enabled && (!p->iws || !p->lab_lcurve || !p->lab_acurve || !p->lab_bcurve)) return ctx->fail(ART_HP_ERR_INVALID, "Lab stage needs iws and the three curves");
+    if (!d_hist && p->lab_enabled && (!p->iws || !p->lab_lcurve || !p->lab_acurve || !p->lab_bcurve)) return ctx->fail(ART_HP_ERR_INVALID, "Lab stage needs iws and the three curves");
     if (tc_mode > 5) return ctx->fail(ART_HP_ERR_UNSUPPORTED, "tone curve mode %d (PERCEPTUAL is not built)", tc_mode);
     if (tc_mode == 5 && !p->ws) return ctx->fail(ART_HP_ERR_INVALID, "the LUMINANCE tone curve needs ws");
     const float whitecoeff = p->tonecurve_whitept > 0.f ? p->tonecurve_whitept : 1.f;
@@ -631,14 +665,16 @@ int art_chain_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, s
     a.whitecoeff = whitecoeff;
     a.Lmax = 65535.f * whitecoeff;
     a.rc = up(1, p->rcurve, 65536); a.gc = up(2, p->gcurve, 65536); a.bc = up(3, p->bcurve, 65536);
-    a.do_lab = p->lab_enabled;
+    a.do_lab = p->lab_enabled || d_hist;
+    a.hist = d_hist;
     if (a.do_lab) {
-        a.lc = up(4, p->lab_lcurve, 32770); a.ac = up(5, p->lab_acurve, 65536); a.bcl = up(6, p->lab_bcurve, 65536);
+        if (!d_hist) { a.lc = up(4, p->lab_lcurve, 32770); a.ac = up(5, p->lab_acurve, 65536); a.bcl = up(6, p->lab_bcurve, 65536); }
         a.chroma = p->lab_chroma;
         a.cachef = d + 7 * LUT_SLOT; a.cachefy = d + 8 * LUT_SLOT;
     }
     a.pq = d + 9 * LUT_SLOT; a.pq_inv = d + 10 * LUT_SLOT; a.hues = d + 12 * LUT_SLOT;
     a.satlut = up(11, p->satcurve_lut, 65536);
+    a.sl = d_hist ? nullptr : up(13, p->softlight_lut, 65536);
     static const float ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     for (int i = 0; i < 9; ++i) { a.to_out[i] = p->neutral_to_out ? p->neutral_to_out[i] : ident[i]; a.to_work[i] = p->neutral_to_work ? p->neutral_to_work[i] : ident[i]; }
     if (p->ws) { a.wy0 = (float)p->ws[3]; a.wy1 = (float)p->ws[4]; a.wy2 = (float)p->ws[5]; for (int i = 0; i < 9; ++i) a.ws[i] = (float)p->ws[i]; }
@@ -681,8 +717,8 @@ int art_chain_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, s
         a.nstages = nstages;
     }
     const dim3 blk(64, 1), grid(((W + 3) / 4 + 63) / 64, std::min(H, 148 * 16));
-    art_prof_begin(ctx, "k_chain");
-    k_chain<<<grid, blk, 0, st>>>(a);
+    art_prof_begin(ctx, d_hist ? "k_chain_hist" : "k_chain");
+    if (d_hist) k_chain<true><<<grid, blk, 0, st>>>(a); else k_chain<false><<<grid, blk, 0, st>>>(a);
     art_prof_end(ctx);
     ctx->launches++;
     ART_CUDA(ctx, cudaGetLastError());

@@ -212,6 +212,7 @@ int art_median_dev(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, siz
 // 2-D REDFT00 of a contiguous n0 x n1 float array (the transform of tmo_fattal02.cc L768-772 alone)
 int art_redft00_2d_dev(art_hp_ctx* ctx, const float* in, float* out, int n0, int n1);
 // ImProcFunctions::process per-pixel chain (chain.cu), planes in place
+int art_chain_lab_hist_dev(art_hp_ctx* ctx, int W, int H, const float* r, const float* g, const float* b, size_t pitch, const art_hp_chain_params* p, unsigned* d_hist);
 int art_chain_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t pitch, const art_hp_chain_params* p);
 // doSharpening, "usm" route (usm.cu), planes in place
 int art_usm_dev(art_hp_ctx* ctx, float* r, float* g, float* b, size_t ip, int W, int H, const art_hp_sharpen_params* p, const double* ws9);

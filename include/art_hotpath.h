@@ -442,11 +442,24 @@ typedef struct art_hp_chain_params {
                                                              NULL = identity (no matrix for the output profile) */
     const float* satcurve_lut;                            /* apply_satcurve's table (satcurve_lut, iptonecurve.cc L365-374), 65536 floats; NULL = identity
                                                              saturation curve.  White point 1 and identity `saturation2` only */
+    /* ---- ABI version 5 ---- */
+    const float* softlight_lut;                           /* ImProcFunctions::softLight (rtengine/ipsoftlight.cc L44-81, the stage after labAdjustments): its
+                                                             table f[i] = sl(strength / 100, i), 65536 floats, read for samples <= 65535; NULL = disabled */
 } art_hp_chain_params;
 int art_hp_color_chain(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b,
                        const art_hp_chain_params* params);
 int art_hp_color_chain_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch,
                            const art_hp_chain_params* params);
+/*
+ * art_hp_lab_histogram   the L histogram ImProcFunctions::labAdjustments takes when labCurve.contrast != 0 (rtengine/iplabadjustments.cc L307-334:
+ *                        hist16[(int)L]++ over the Lab image) and hands to the host's get_L_curve: the stages of `params` that precede the Lab
+ *                        stage run on the fly, the frame goes to Lab exactly as Imagefloat::setMode(LAB) does, the planes are NOT modified and
+ *                        the Lab curves of `params` are not read.  The caller builds lab_lcurve from it and calls art_hp_color_chain.  Exact (integer).
+ */
+int art_hp_lab_histogram(art_hp_ctx* ctx, int W, int H, const float* const* r, const float* const* g, const float* const* b,
+                         const art_hp_chain_params* params, unsigned hist16[65536]);
+int art_hp_lab_histogram_dev(art_hp_ctx* ctx, int W, int H, const float* d_r, const float* d_g, const float* d_b, size_t pitch,
+                             const art_hp_chain_params* params, unsigned hist16[65536]);
 
 /* ---- sharpening ------------------------------------------------------------------- */
 /*

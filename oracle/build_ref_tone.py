@@ -60,6 +60,7 @@ public:
     static LUTf gamma2curve, igammatab_srgb, gammatab_srgb, jzazbz_pq_, jzazbz_pq_inv_;
 #include "tone_color_h.inc"
 #include "tone_color_yuv.inc"
+#include "tone_color_gamma.inc"
     static void init()
     {   // color.cc L236-256, L322-326
         if (gammatab_srgb) return;
@@ -320,6 +321,23 @@ extern "C" int artref_hsl_equalizer(float* R, float* G, float* B, int W_, int H_
     return 0;
 }
 }   // namespace hsl
+// ---- ImProcFunctions::softLight (ipsoftlight.cc L29-81): the reference's sl() and its table + apply loop
+namespace softlight {
+namespace {
+#include "softlight_sl.inc"
+}
+struct SoftLightParams { bool enabled; int strength; };
+struct Params { SoftLightParams softlight; };
+extern "C" int artref_softlight(float* R, float* G, float* B_, int W, int H, int strength, float* lut_out)
+{
+    Color::init();
+    Params P; P.softlight.enabled = true; P.softlight.strength = strength; const Params* params = &P;
+    Imagefloat im{W, H, {R, W}, {G, W}, {B_, W}}; Imagefloat* rgb = &im;
+#include "softlight_body.inc"
+    if (lut_out) for (int i = 0; i < 65536; ++i) lut_out[i] = f[i];
+    return 0;
+}
+}   // namespace softlight
 extern "C" {
 int artref_tone_tables(float* pq, float* pq_inv, float* gamma2curve)
 {
@@ -397,5 +415,11 @@ def extract(sub):
         cut_function(imf, r"^void Imagefloat::yuv_to_rgb\(bool multithread\)")]))
     w("hsl_body.inc", between(rd(os.path.join(RT, "iphsl.cc")), r"^    img->setMode\(Imagefloat::Mode::YUV, multiThread\);", r"^\} // namespace rtengine")
       .rstrip().rstrip("}"))
+    w("tone_color_gamma.inc", "\n".join([
+        cut_function(ch, r"static inline float  gamma_srgb       \(float x\)"),
+        cut_function(ch, r"static inline float  igamma_srgb      \(float x\)")]))
+    ipsl = os.path.join(RT, "ipsoftlight.cc")
+    w("softlight_sl.inc", cut_function(ipsl, r"^inline float sl\(float blend, float x\)"))
+    w("softlight_body.inc", between(rd(ipsl), r"^    const float blend = params->softlight\.strength / 100\.f;", r"^\}\n\n\} // namespace rtengine"))
     w("shim_tone.cc", SHIM_TONE_TU)
     return os.path.join(sub, "shim_tone.cc")

@@ -271,6 +271,18 @@ int artoracle_chain_rgbcurves(float* R, float* G, float* B, int W, int H, const 
     return 0;
 }
 
+/* ---- softLight: the apply lambda of ImProcFunctions::softLight (ipsoftlight.cc L57-78) over its host-built table f (LUTf(65536): clips below and above) ---- */
+int artoracle_chain_softlight(float* R, float* G, float* B, int W, int H, const float* f)
+{
+    float* ch[3] = {R, G, B};
+    for (int c = 0; c < 3; ++c)
+        for (size_t i = 0; i < (size_t)W * H; ++i) {
+            const float x = ch[c][i];
+            ch[c][i] = x <= 65535.f ? lut_s(f, 65536, CLIP_BELOW | CLIP_ABOVE, x) : x;
+        }
+    return 0;
+}
+
 /* ---- Lab ---- */
 static float g_cachef[65536], g_cachefy[65536];
 static int g_cache_ready = 0;

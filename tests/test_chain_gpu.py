@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 from art_b200.api import ChainParams
-from test_oracle_chain import F, PROPHOTO, PROPHOTO_INV, call, curve_lut, dp, fp, image, same
+from test_oracle_chain import F, PROPHOTO, PROPHOTO_INV, call, curve_lut, dp, fp, image, same, softlight_lut
 
 pytestmark = pytest.mark.gpu
 
@@ -21,7 +21,7 @@ def lab_luts():
     return lc, curve_lut(65536, 1.1, 65535.0, 1), curve_lut(65536, 0.9, 65535.0, 2)
 
 
-def oracle_chain(planes, exposure=None, saturation=None, tonecurve=None, rgbcurves=None, lab=None, whitept=1.0):
+def oracle_chain(planes, exposure=None, saturation=None, tonecurve=None, rgbcurves=None, lab=None, whitept=1.0, softlight=None):
     lib = oracle.port().lib
     out = planes
     if exposure is not None:
@@ -38,6 +38,8 @@ def oracle_chain(planes, exposure=None, saturation=None, tonecurve=None, rgbcurv
     if lab is not None:
         out = call(lib, "artoracle_chain_lab", out, lab[0].ctypes.data_as(fp), lab[1].ctypes.data_as(fp), lab[2].ctypes.data_as(fp), F(lab[3]),
                    PROPHOTO.ctypes.data_as(dp), PROPHOTO_INV.ctypes.data_as(dp))
+    if softlight is not None:
+        out = call(lib, "artoracle_chain_softlight", out, softlight.ctypes.data_as(fp))
     return out
 
 
@@ -68,6 +70,8 @@ STAGES["tone_luminance_white2"] = dict(tonecurve=(5, curve_lut(gamma=1.3, seed=5
 STAGES["all_weighted"] = dict(STAGES["exposure"], **STAGES["satvib"], **STAGES["tone_weighted"], **STAGES["rgbcurves"], **STAGES["lab"])
 STAGES["all_satval"] = dict(STAGES["exposure_neg"], **STAGES["saturation"], **STAGES["tone_satval"], **STAGES["lab_lowchroma"])
 STAGES["all_luminance"] = dict(STAGES["exposure"], **STAGES["vibrance"], **STAGES["tone_luminance"], **STAGES["rgbcurves"], **STAGES["lab"])
+STAGES["softlight"] = dict(softlight=softlight_lut(30))
+STAGES["all_softlight"] = dict(STAGES["exposure"], **STAGES["saturation"], **STAGES["tone_film"], **STAGES["lab"], softlight=softlight_lut(100))
 STAGES["all_std"] = dict(STAGES["exposure"], **STAGES["satvib"], **STAGES["tone_std"], **STAGES["rgbcurves"], **STAGES["lab"])
 STAGES["all_film"] = dict(STAGES["exposure_neg"], **STAGES["saturation"], **STAGES["tone_film"],
                           rgbcurves=[curve_lut(gamma=0.9, seed=i) for i in range(3)], **STAGES["lab_lowchroma"])
@@ -137,3 +141,23 @@ def test_channel_mixer_matches_oracle(hot_path, W, H, mixer):
     got = hot_path.channel_mixer(*[p.copy() for p in planes], m)
     for g, w in zip(got, want):
         assert ((g == w) | (np.isnan(g) & np.isnan(w))).all()
+
+
+@pytest.mark.parametrize("W,H", SIZES + [(2001, 1333)])
+@pytest.mark.parametrize("name", ["none", "exposure", "all_before_lab"])
+def test_lab_histogram_matches_oracle(hot_path, W, H, name):
+    """art_hp_lab_histogram = labAdjustments' hist16 (iplabadjustments.cc L307-334): the oracle's stages, its rgb -> Lab (pinned to
+    Imagefloat::setMode(LAB) in test_oracle_chain.py), then hist[LIM((int)L, 0, 65535)]++ (LUT<T>::operator[](int)).  Exact; planes untouched."""
+    kw = {"none": {}, "exposure": STAGES["exposure"],
+          "all_before_lab": dict(STAGES["exposure"], **STAGES["satvib"], **STAGES["tone_weighted"], **STAGES["rgbcurves"])}[name]
+    planes = image(H, W, W * 13 + H, wild=(name != "none"))
+    pre = oracle_chain(planes, **kw)
+    lab = call(oracle.port().lib, "artoracle_chain_rgb2lab", pre, PROPHOTO.ctypes.data_as(dp), PROPHOTO_INV.ctypes.data_as(dp), 0)
+    L = lab[1]
+    idx = np.clip(np.where(np.isnan(L), -2147483648.0, L), -2147483648.0, 2147483520.0).astype(np.int64)      # cvttss2si: NaN / overflow -> INT_MIN
+    want = np.bincount(np.clip(idx, 0, 65535).ravel(), minlength=65536).astype(np.uint32)
+    keep = [p.copy() for p in planes]
+    got = hot_path.lab_histogram(planes[0], planes[1], planes[2], ChainParams(ws=PROPHOTO, iws=PROPHOTO_INV, **kw))
+    assert int(got.sum()) == W * H
+    assert np.array_equal(got, want)
+    same(planes, keep)

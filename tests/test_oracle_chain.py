@@ -145,3 +145,24 @@ def test_lab_adjustments(W, H, chroma):
     bc = curve_lut(65536, 0.9, 65535.0, 2)
     args = (lc.ctypes.data_as(fp), ac.ctypes.data_as(fp), bc.ctypes.data_as(fp), F(chroma), PROPHOTO.ctypes.data_as(dp), PROPHOTO_INV.ctypes.data_as(dp))
     same(call(oracle.port().lib, "artoracle_chain_lab", planes, *args), call(oracle.ref().lib, "artref_chain_lab", planes, *args))
+
+
+def softlight_lut(strength):
+    """ImProcFunctions::softLight's table f[i] = sl(strength / 100, i), built by the reference's own code"""
+    lut = np.zeros(65536, np.float32)
+    z = [np.zeros((1, 1), np.float32) for _ in range(3)]
+    assert oracle.ref().lib.artref_softlight(z[0].ctypes.data_as(fp), z[1].ctypes.data_as(fp), z[2].ctypes.data_as(fp), 1, 1, int(strength), lut.ctypes.data_as(fp)) == 0
+    return lut
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", SIZES)
+@pytest.mark.parametrize("strength", [1, 30, 100])
+def test_softlight(W, H, strength):
+    """the port's apply loop against ImProcFunctions::softLight's own (ipsoftlight.cc L44-81), over the reference-built table"""
+    planes = image(H, W, W * 3 + H + strength)
+    planes[0][0, 0] = np.nan
+    lut = softlight_lut(strength)
+    want = call(oracle.ref().lib, "artref_softlight", planes, int(strength), None)
+    same(call(oracle.port().lib, "artoracle_chain_softlight", planes, lut.ctypes.data_as(fp)), want)
+    assert max(float(np.nanmax(np.abs(w - p))) for w, p in zip(want, planes)) > 1.0
