@@ -126,6 +126,8 @@ def load_library(build_if_missing=True):
         "art_hp_dual_demosaic_xtrans_dev": (i, [vp, i, i, i, i, vp, vp, vp, sz, vp, vp, vp, sz, d, i, vp]),
         "art_hp_lab_histogram": (i, [vp, i, i, vp, vp, vp, vp, vp]),
         "art_hp_lab_histogram_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, vp]),
+        "art_hp_tone_equalizer": (i, [vp, i, i, vp, vp, vp, vp]),
+        "art_hp_tone_equalizer_dev": (i, [vp, i, i, vp, vp, vp, sz, vp]),
         "art_hp_hsl_equalizer": (i, [vp, i, i, vp, vp, vp, vp]),
         "art_hp_hsl_equalizer_dev": (i, [vp, i, i, vp, vp, vp, sz, vp]),
         "art_hp_channel_mixer": (i, [vp, i, i, vp, vp, vp, vp]),
@@ -316,6 +318,29 @@ class HslParams:
             w = np.ascontiguousarray(self.ws, dtype=np.float64).reshape(9)
             self._keep.append(w)
             c.ws = w.ctypes.data_as(dp)
+        return c
+
+
+class _ToneEqParamsC(ctypes.Structure):    # art_hp_toneeq_params
+    _fields_ = [("bands", ctypes.c_int * 5), ("regularization", ctypes.c_int), ("pivot", ctypes.c_double), ("scale", ctypes.c_double),
+                ("ws", ctypes.POINTER(ctypes.c_double))]
+
+
+class ToneEqParams:
+    """art_hp_toneeq_params: bands = the five sliders (blacks .. whites), regularization, pivot, scale, ws = the working-space matrix."""
+
+    def __init__(self, bands=(0, 0, 0, 0, 0), regularization=0, pivot=0.0, scale=1.0, ws=None):
+        self.__dict__.update(locals())
+        del self.__dict__["self"]
+
+    def c_struct(self):
+        c = _ToneEqParamsC()
+        for k in range(5):
+            c.bands[k] = int(self.bands[k])
+        c.regularization, c.pivot, c.scale = int(self.regularization), float(self.pivot), float(self.scale)
+        if self.ws is not None:
+            self._w = np.ascontiguousarray(self.ws, dtype=np.float64).reshape(9)
+            c.ws = self._w.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
         return c
 
 
@@ -750,6 +775,13 @@ class HotPath:
                                                          cam.ctypes.data_as(ctypes.c_void_p), row_table(raw), *[row_table(o) for o in out],
                                                          ctypes.byref(c), int(bool(auto_contrast))))
         return out, c.value
+
+    def tone_equalizer(self, r, g, b, params):
+        """ImProcFunctions::toneEqualizer in place on three host (H, W) float32 working-space RGB planes."""
+        H, W = r.shape
+        c = params.c_struct()
+        self._check(self.lib.art_hp_tone_equalizer(self.h, W, H, row_table(r), row_table(g), row_table(b), ctypes.byref(c)))
+        return r, g, b
 
     def hsl_equalizer(self, r, g, b, params):
         """ImProcFunctions::hslEqualizer in place on three host (H, W) float32 working-space RGB planes."""

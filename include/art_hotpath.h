@@ -573,6 +573,28 @@ typedef struct art_hp_hsl_params {
 int art_hp_hsl_equalizer(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b, const art_hp_hsl_params* params);
 int art_hp_hsl_equalizer_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch, const art_hp_hsl_params* params);
 
+/* ---- tone equalizer ---------------------------------------------------------------- */
+/*
+ * art_hp_tone_equalizer   ImProcFunctions::toneEqualizer (rtengine/iptoneequalizer.cc L343-371; STAGE_1 of ImProcFunctions::process, improcfun.cc
+ *                         L584) with tone_eq() (L68-338), in place on working-space RGB planes in [0, 65535]: the frame is scaled by
+ *                         1 / 65535 * 2^-pivot, the luminance LIM(Y, 1e-5, 32) is smoothed -- regularization > 0: guidedFilterLog(10, Y, 5 / scale
+ *                         + 0.5, 0.014); regularization > 1: posterised to 1/5 EV and guided by the unposterised Y with radius 350 / scale (and once
+ *                         more with (reg - 1) times that radius, reg = 5 - min(regularization, 4)) -- and every pixel is multiplied by the
+ *                         correction of its luminance: five sliders spread over twelve 2-EV gaussian bands (bands[0] blacks .. bands[4] whites,
+ *                         -100 .. 100).  The colour-map preview (show_colormap, PREVIEW pipeline, lcms2) is not reproduced.  With regularization > 1
+ *                         the frame must be larger than the guided filter's window (ART_HP_ERR_INVALID otherwise; the reference indexes out of
+ *                         bounds there).  Bit-identical to the reference, SSE2 groups and scalar row tails included.
+ */
+typedef struct art_hp_toneeq_params {
+    int    bands[5];                              /* params->toneEqualizer.bands */
+    int    regularization;                        /* params->toneEqualizer.regularization */
+    double pivot;                                 /* params->toneEqualizer.pivot */
+    double scale;                                 /* ImProcFunctions::scale */
+    const double* ws;                             /* ICCStore::workingSpaceMatrix, 9 doubles */
+} art_hp_toneeq_params;
+int art_hp_tone_equalizer(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b, const art_hp_toneeq_params* params);
+int art_hp_tone_equalizer_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch, const art_hp_toneeq_params* params);
+
 /* ---- dual demosaic ----------------------------------------------------------------- */
 /*
  * art_hp_demosaic_vng4        RawImageSource::vng4_demosaic(rawData, red, green, blue) (rtengine/vng4_demosaic_RT.cc L32-397): the four-colour

@@ -24,6 +24,7 @@ SHIM_TONE_TU = r"""
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <array>
 #include <map>
 #include <memory>
 #include <string>
@@ -36,7 +37,8 @@ SHIM_TONE_TU = r"""
 #include "linalgebra.h"
 #include "iccmatrices.h"
 #include "array2D.h"
-namespace rtengine { void guidedFilter(const array2D<float> &guide, const array2D<float> &src, array2D<float> &dst, int r, float epsilon, bool multithread, int subsampling=0); }   // guidedfilter.h L27; defined in the guided translation unit
+namespace rtengine { void guidedFilter(const array2D<float> &guide, const array2D<float> &src, array2D<float> &dst, int r, float epsilon, bool multithread, int subsampling=0);   // guidedfilter.h L27; defined in the guided translation unit
+                     void guidedFilterLog(float base, array2D<float> &chan, int r, float eps, bool multithread, int subsampling=0); }
 
 enum DiagonalCurveType { DCT_Empty = -1, DCT_Linear, DCT_Spline, DCT_Parametric, DCT_NURBS, DCT_CatmullRom, DCT_Unchanged };   // rtgui/mydiagonalcurve.h L31-40
 enum FlatCurveType { FCT_Empty = -1, FCT_Linear, FCT_MinMaxCPoints, FCT_Unchanged };                                           // rtgui/myflatcurve.h L29-36
@@ -321,6 +323,55 @@ extern "C" int artref_hsl_equalizer(float* R, float* G, float* B, int W_, int H_
     return 0;
 }
 }   // namespace hsl
+// ---- ImProcFunctions::toneEqualizer (iptoneequalizer.cc L68-371): tone_eq() verbatim over stubs for what its colour-map preview branch names (lcms2, never executed here)
+namespace toneeq {
+typedef void* cmsHPROFILE; typedef void* cmsHTRANSFORM;
+enum { TYPE_RGB_FLT = 0, INTENT_RELATIVE_COLORIMETRIC = 0, cmsFLAGS_NOOPTIMIZE = 0, cmsFLAGS_NOCACHE = 0 };
+static cmsHTRANSFORM cmsCreateTransform(cmsHPROFILE, int, cmsHPROFILE, int, int, int) { abort(); }
+static void cmsDoTransform(cmsHTRANSFORM, void*, void*, int) { abort(); }
+static void cmsDeleteTransform(cmsHTRANSFORM) {}
+struct Mutex { void lock() {} void unlock() {} };
+static Mutex lcmsMutex_, *lcmsMutex = &lcmsMutex_;
+static float g_wsm[3][3];
+struct ICCStore {
+    static ICCStore* getInstance() { static ICCStore s; return &s; }
+    TMatrix workingSpaceMatrix(const std::string&) const { return g_wsm; }
+    cmsHPROFILE getsRGBProfile() const { return nullptr; }
+    cmsHPROFILE workingSpace(const std::string&) const { return nullptr; }
+};
+struct ToneEqualizerParams { bool enabled; std::array<int, 5> bands; int regularization; bool show_colormap; double pivot; };    // procparams.h L848-853
+namespace {
+static const std::vector<std::array<float, 3>> colormap;      // iptoneequalizer.cc L53-66: the preview colour map, not used here
+#include "toneeq_body.inc"
+}
+// ImProcFunctions::toneEqualizer (L343-371) on three dense planes: multiply(gain), tone_eq, multiply(1 / gain)
+extern "C" int artref_tone_equalizer(float* R_, float* G_, float* B_, int W, int H, const double* ws9, const int* bands5, int regularization, double pivot, double scale)
+{
+    for (int i = 0; i < 9; ++i) (&g_wsm[0][0])[i] = (float)ws9[i];
+    ToneEqualizerParams pp; pp.enabled = true; for (int i = 0; i < 5; ++i) pp.bands[i] = bands5[i]; pp.regularization = regularization; pp.show_colormap = false; pp.pivot = pivot;
+    const float gain = 1.f / 65535.f * std::pow(2.f, -pp.pivot);
+    // rows 16-byte aligned like the reference's Imagefloat allocation (iimage.h L653-673): tone_eq's vector loop uses aligned loads / stores
+    const int st = (W + 3) / 4 * 4;
+    float* in[3] = {R_, G_, B_};
+    float* buf[3]; float** rows[3];
+    for (int c = 0; c < 3; ++c) {
+        void* p = nullptr; if (posix_memalign(&p, 64, sizeof(float) * (size_t)st * H)) abort();
+        buf[c] = (float*)p; rows[c] = new float*[H];
+        for (int i = 0; i < H; ++i) { rows[c][i] = buf[c] + (size_t)i * st; for (int x = 0; x < W; ++x) rows[c][i][x] = in[c][(size_t)i * W + x] * gain; }      // Imagefloat::multiply(gain)
+    }
+    {
+        array2D<float> R(W, H, rows[0], ARRAY2D_BYREFERENCE), G(W, H, rows[1], ARRAY2D_BYREFERENCE), B(W, H, rows[2], ARRAY2D_BYREFERENCE);
+        tone_eq(R, G, B, pp, "", scale, true, false, nullptr);
+    }
+    const float back = 1.f / gain;
+    for (int c = 0; c < 3; ++c) {
+        for (int i = 0; i < H; ++i) for (int x = 0; x < W; ++x) in[c][(size_t)i * W + x] = rows[c][i][x] * back;
+        free(buf[c]); delete[] rows[c];
+    }
+    return 0;
+}
+}   // namespace toneeq
+
 // ---- ImProcFunctions::softLight (ipsoftlight.cc L29-81): the reference's sl() and its table + apply loop
 namespace softlight {
 namespace {
@@ -418,6 +469,8 @@ def extract(sub):
     w("tone_color_gamma.inc", "\n".join([
         cut_function(ch, r"static inline float  gamma_srgb       \(float x\)"),
         cut_function(ch, r"static inline float  igamma_srgb      \(float x\)")]))
+    w("toneeq_body.inc", cut_function(os.path.join(RT, "iptoneequalizer.cc"), r"^void tone_eq\(array2D<float> &R, array2D<float> &G, array2D<float> &B, const ToneEqualizerParams &pp")
+      .replace("const Glib::ustring &workingProfile", "const std::string &workingProfile"))
     ipsl = os.path.join(RT, "ipsoftlight.cc")
     w("softlight_sl.inc", cut_function(ipsl, r"^inline float sl\(float blend, float x\)"))
     w("softlight_body.inc", between(rd(ipsl), r"^    const float blend = params->softlight\.strength / 100\.f;", r"^\}\n\n\} // namespace rtengine"))
