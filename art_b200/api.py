@@ -136,6 +136,8 @@ def load_library(build_if_missing=True):
         "art_hp_find_hot_dead_pixels_dev": (i, [vp, i, i, vp, vp, sz, f, i, i, vp, sz, ctypes.POINTER(i)]),
         "art_hp_interpolate_bad_pixels_bayer": (i, [vp, i, i, u, vp, vp, sz, ctypes.POINTER(i)]),
         "art_hp_interpolate_bad_pixels_bayer_dev": (i, [vp, i, i, u, vp, sz, vp, sz, ctypes.POINTER(i)]),
+        "art_hp_interpolate_bad_pixels_xtrans": (i, [vp, i, i, vp, vp, vp, sz, ctypes.POINTER(i)]),
+        "art_hp_interpolate_bad_pixels_xtrans_dev": (i, [vp, i, i, vp, vp, sz, vp, sz, ctypes.POINTER(i)]),
         "art_hp_resize_lanczos": (i, [vp, i, i, vp, vp, vp, i, i, vp, vp, vp, f]),
         "art_hp_resize_lanczos_dev": (i, [vp, i, i, vp, vp, vp, sz, i, i, vp, vp, vp, sz, f]),
         "art_hp_scanlines_dev": (i, [vp, i, i, vp, vp, vp, sz, i, i, vp, sz]),
@@ -821,6 +823,16 @@ class HotPath:
         n = ctypes.c_int(0)
         self._check(self.lib.art_hp_interpolate_bad_pixels_bayer(self.h, W, H, int(filters), row_table(raw), m.ctypes.data_as(ctypes.c_void_p), m.strides[0],
                                                                  ctypes.byref(n)))
+        return n.value
+
+    def interpolate_bad_pixels_xtrans(self, raw, xtrans, bad_map):
+        """interpolateBadPixelsXtrans (raster order) in place on a host (H, W) float32 X-Trans plane; returns the number of pixels interpolated."""
+        H, W = raw.shape
+        m = np.ascontiguousarray(bad_map, dtype=np.uint8)
+        xt = np.ascontiguousarray(xtrans, dtype=np.int32)
+        n = ctypes.c_int(0)
+        self._check(self.lib.art_hp_interpolate_bad_pixels_xtrans(self.h, W, H, xt.ctypes.data_as(ctypes.c_void_p), row_table(raw), m.ctypes.data_as(ctypes.c_void_p),
+                                                                  m.strides[0], ctypes.byref(n)))
         return n.value
 
     def resize_lanczos(self, planes, scale, size=None):

@@ -1192,6 +1192,19 @@ int art_hp_interpolate_bad_pixels_bayer_dev(art_hp_ctx* ctx, int W, int H, unsig
     return read_count(ctx, (const int*)ctx->d_small2.p, count);
 }
 
+int art_hp_interpolate_bad_pixels_xtrans_dev(art_hp_ctx* ctx, int W, int H, const int* xtrans, float* d_raw, size_t raw_pitch,
+                                             const unsigned char* d_map, size_t map_pitch, int* count)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_raw || !d_map || !xtrans) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || H > 65535 || raw_pitch < (size_t)W || map_pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = art_reserve(ctx, ctx->d_small2, 256);
+    if (rc) return rc;
+    if ((rc = art_interpolate_bad_xtrans_dev(ctx, W, H, xtrans, d_raw, raw_pitch, d_map, map_pitch, (int*)ctx->d_small2.p))) return rc;
+    return read_count(ctx, (const int*)ctx->d_small2.p, count);
+}
+
 // host forms: the raw plane and the byte map travel to the device and back (the map through d_out[0], one byte per pixel)
 static int badpix_host(art_hp_ctx* ctx, int W, int H, const int* xtrans, unsigned filters, const float* const* rawData, float thresh, int hot, int dead,
                        unsigned char* map, size_t map_stride, int* count, bool interpolate)
@@ -1209,7 +1222,8 @@ static int badpix_host(art_hp_ctx* ctx, int W, int H, const int* xtrans, unsigne
     if ((rc = transfer(ctx, ctx->stream, &io, 1, W, 0, H, pitch, true))) return rc;
     ART_CUDA(ctx, cudaMemcpy2DAsync(d_map, mp, map, map_stride, (size_t)W, (size_t)H, cudaMemcpyHostToDevice, ctx->stream));
     if (interpolate) {
-        if ((rc = art_hp_interpolate_bad_pixels_bayer_dev(ctx, W, H, filters, io.dev, pitch, d_map, mp, count))) return rc;
+        if ((rc = xtrans ? art_hp_interpolate_bad_pixels_xtrans_dev(ctx, W, H, xtrans, io.dev, pitch, d_map, mp, count)
+                         : art_hp_interpolate_bad_pixels_bayer_dev(ctx, W, H, filters, io.dev, pitch, d_map, mp, count))) return rc;
         if ((rc = transfer(ctx, ctx->stream, &io, 1, W, 0, H, pitch, false))) return rc;
     } else {
         if ((rc = art_hp_find_hot_dead_pixels_dev(ctx, W, H, xtrans, io.dev, pitch, thresh, hot, dead, d_map, mp, count))) return rc;
@@ -1229,6 +1243,13 @@ int art_hp_interpolate_bad_pixels_bayer(art_hp_ctx* ctx, int W, int H, unsigned 
                                         const unsigned char* map, size_t map_stride, int* count)
 {
     return badpix_host(ctx, W, H, nullptr, filters, rawData, 0.f, 0, 0, const_cast<unsigned char*>(map), map_stride, count, true);
+}
+
+int art_hp_interpolate_bad_pixels_xtrans(art_hp_ctx* ctx, int W, int H, const int* xtrans, float* const* rawData,
+                                         const unsigned char* map, size_t map_stride, int* count)
+{
+    if (ctx && !xtrans) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    return badpix_host(ctx, W, H, xtrans, 0u, rawData, 0.f, 0, 0, const_cast<unsigned char*>(map), map_stride, count, true);
 }
 
 int art_hp_channel_mixer_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch, const float matrix[9])

@@ -162,7 +162,170 @@ __global__ void __launch_bounds__(256) k_bp_interp_bayer(float* __restrict__ raw
     if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(count, __popc(ballot));
 }
 
+// RawImageSource::interpolateBadPixelsXtrans (badpixels.cc L288-475) in the reference's one-thread (raster) order.  Every pair the function weighs is
+// checked against the map, so those reads see samples no pass ever writes; the "virtual pixel" of a red / blue site and its distance-2 partner are
+// NOT checked (L446-459): when one of them is itself a bad pixel EARLIER in raster order, the serial loop has already rewritten it.  `upd` holds the
+// values bad pixels end up with (a copy of the frame to start with); a pass recomputes every bad pixel reading earlier bad neighbours from `upd` and
+// everything else from the untouched frame, and the host repeats it until a pass changes nothing: the dependencies follow raster order (a DAG), so
+// the fixed point is the serial result, reached after as many passes as the longest chain of bad pixels feeding each other (one or two in practice).
+__global__ void __launch_bounds__(256) k_bp_interp_xtrans(const float* __restrict__ raw, size_t rp, float* upd, size_t up, unsigned char* __restrict__ ok, const unsigned char* __restrict__ map,
+                                                          size_t mp, int W, int H, const __grid_constant__ BpCfa cfa, int* __restrict__ changed)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y + 2;
+    if (!(col >= 2 && col < W - 2 && row < H - 2 && map[(size_t)row * mp + col])) return;
+#define RAW(r, c) raw[(size_t)(r) * rp + (c)]
+#define BAD(x, y) (map[(size_t)(y) * mp + (x)] != 0)
+#define XFC(r, c) cfa.m[((r) % 6) * 6 + ((c) % 6)]
+    // an unchecked read: the rewritten value when (r, c) is a bad pixel the raster order reaches before (row, col)
+    auto cur = [&](int r, int c) -> float {
+        const bool earlier = r < row || (r == row && c < col);
+        if (earlier && r >= 2 && c >= 2 && c < W - 2 && BAD(c, r)) return *(volatile const float*)(upd + (size_t)r * up + c);
+        return RAW(r, c);
+    };
+    const float eps = 1.f;
+    float wtdsum = 0.f, norm = 0.f;
+    const int pixelColor = XFC(row, col);
+    if (pixelColor == 1) {
+        if (XFC(row, col - 1) == XFC(row, col + 1)) {
+            for (int dx = -1; dx <= 1; dx += 2) {
+                if (BAD(col + dx, row - 1) || BAD(col - dx, row + 1)) continue;
+                const float dirwt = 0.70710678f / (fabsf(RAW(row - 1, col + dx) - RAW(row + 1, col - dx)) + eps);
+                wtdsum += dirwt * (RAW(row - 1, col + dx) + RAW(row + 1, col - dx));
+                norm += dirwt;
+            }
+            for (int dx = -1; dx <= 1; dx += 2) {
+                if (BAD(col + dx, row - 2) || BAD(col - dx, row + 2)) continue;
+                const float dirwt = 0.44721359f / (fabsf(RAW(row - 2, col + dx) - RAW(row + 2, col - dx)) + eps);
+                wtdsum += dirwt * (RAW(row - 2, col + dx) + RAW(row + 2, col - dx));
+                norm += dirwt;
+            }
+            for (int dx = -2; dx <= 2; dx += 4) {
+                if (BAD(col + dx, row - 1) || BAD(col - dx, row + 1)) continue;
+                const float dirwt = 0.44721359f / (fabsf(RAW(row - 1, col + dx) - RAW(row + 1, col - dx)) + eps);
+                wtdsum += dirwt * (RAW(row - 1, col + dx) + RAW(row + 1, col - dx));
+                norm += dirwt;
+            }
+        } else {
+            const int offset1 = XFC(row - 1, col - 1) == XFC(row + 1, col + 1) ? 1 : -1;
+            if (!(BAD(col - offset1, row - 1) || BAD(col + offset1, row + 1))) {
+                const float dirwt = 0.70710678f / (fabsf(RAW(row - 1, col - offset1) - RAW(row + 1, col + offset1)) + eps);
+                wtdsum += dirwt * (RAW(row - 1, col - offset1) + RAW(row + 1, col + offset1));
+                norm += dirwt;
+            }
+            int offsety = XFC(row - 1, col) != 1 ? 1 : -1;
+            int offsetx = offset1 * offsety;
+            if (!(BAD(col + offsetx, row) || BAD(col, row + offsety))) {
+                const float dirwt = 1.f / (fabsf(RAW(row, col + offsetx) - RAW(row + offsety, col)) + eps);
+                wtdsum += dirwt * (RAW(row, col + offsetx) + RAW(row + offsety, col));
+                norm += dirwt;
+            }
+            const int offsety2 = -offsety, offsetx2 = -offsetx;
+            offsetx *= 2; offsety *= 2;
+            if (!(BAD(col + offsetx, row + offsety2) || BAD(col + offsetx2, row + offsety))) {
+                const float dirwt = 0.44721359f / (fabsf(RAW(row + offsety2, col + offsetx) - RAW(row + offsety, col + offsetx2)) + eps);
+                wtdsum += dirwt * (RAW(row + offsety2, col + offsetx) + RAW(row + offsety, col + offsetx2));
+                norm += dirwt;
+            }
+        }
+    } else {
+        for (int d1 = -2, offsety = 3; d1 <= 2; d1 += 4, offsety -= 6)
+            for (int d2 = -1, offsetx = 3; d2 < 1; d2 += 2, offsetx -= 6)        // d2 = -1 only, as the reference's loop bound has it (L414)
+                if (XFC(row + d1, col + d2) == pixelColor && !(BAD(col + d2, row + d1) || BAD(col + d2 + offsetx, row + d1 + offsety))) {
+                    const float dirwt = 0.44721359f / (fabsf(RAW(row + d1, col + d2) - RAW(row + d1 + offsety, col + d2 + offsetx)) + eps);
+                    wtdsum += dirwt * (RAW(row + d1, col + d2) + RAW(row + d1 + offsety, col + d2 + offsetx));
+                    norm += dirwt;
+                }
+        bool found = false;
+        int dx, dy;
+        for (dx = -2, dy = 0; dx <= 2; dx += 4)
+            if (XFC(row, col + dx) == pixelColor) { found = true; break; }
+        if (!found)
+            for (dx = 0, dy = -2; dy <= 2; dy += 4)
+                if (XFC(row + dy, col) == pixelColor) { found = true; break; }
+        if (found) {        // always, on an X-Trans layout (the host entry checks the 6x6 table)
+            float virtualPixel;
+            if (dy == 0) virtualPixel = 0.5f * (cur(row - 1, col - dx) + cur(row + 1, col - dx));
+            else virtualPixel = 0.5f * (cur(row - dy, col - 1) + cur(row - dy, col + 1));
+            const float partner = cur(row + dy, col + dx);
+            const float dirwt = 0.5f / (fabsf(virtualPixel - partner) + eps);
+            wtdsum += dirwt * (virtualPixel + partner);
+            norm += dirwt;
+        }
+    }
+#undef RAW
+#undef BAD
+#undef XFC
+    if (norm > 0.f) {
+        const float v = wtdsum / (2.f * norm);
+        float* o = upd + (size_t)row * up + col;
+        if (__float_as_uint(v) != __float_as_uint(*(volatile float*)o)) { *(volatile float*)o = v; *changed = 1; }
+        ok[(size_t)row * mp + col] = 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bp_commit_xtrans(float* __restrict__ raw, size_t rp, const float* __restrict__ upd, size_t up, const unsigned char* __restrict__ ok,
+                                                          const unsigned char* __restrict__ map, size_t mp, int W, int H, int* __restrict__ count)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y + 2;
+    const bool done = col >= 2 && col < W - 2 && row < H - 2 && map[(size_t)row * mp + col] && ok[(size_t)row * mp + col];
+    if (done) raw[(size_t)row * rp + col] = upd[(size_t)row * up + col];
+    const unsigned ballot = __ballot_sync(0xffffffffu, done);
+    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(count, __popc(ballot));
+}
+
 }  // namespace
+
+// d_count: two device ints (the count, the pass's "changed" flag).  Synchronises the stream once per pass.
+int art_interpolate_bad_xtrans_dev(art_hp_ctx* ctx, int W, int H, const int* xtrans36, float* raw, size_t rp, const unsigned char* map, size_t mp, int* d_count)
+{
+    cudaStream_t st = ctx->stream;
+    ART_CUDA(ctx, cudaMemsetAsync(d_count, 0, 2 * sizeof(int), st));
+    if (W < 5 || H < 5) return ART_HP_OK;
+    BpCfa cfa{};
+    for (int i = 0; i < 36; ++i) {
+        if (xtrans36[i] < 0 || xtrans36[i] > 2) return ctx->fail(ART_HP_ERR_INVALID, "xtrans[%d] = %d", i, xtrans36[i]);
+        cfa.m[i] = xtrans36[i];
+    }
+    // every red / blue site of an X-Trans layout has a same-colour sample at distance 2 in its row or its column; the reference's scan (L432-450)
+    // runs off the frame when that does not hold
+    for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) {
+            const int col = xtrans36[r * 6 + c];
+            if (col == 1) continue;
+            const bool has = xtrans36[r * 6 + (c + 4) % 6] == col || xtrans36[r * 6 + (c + 2) % 6] == col || xtrans36[((r + 4) % 6) * 6 + c] == col || xtrans36[((r + 2) % 6) * 6 + c] == col;
+            if (!has) return ctx->fail(ART_HP_ERR_INVALID, "not an X-Trans layout: no same-colour sample at distance 2 of (%d, %d)", r, c);
+        }
+    const size_t up = round_up((size_t)W, 32);
+    void* blk = nullptr;
+    int rc = art_pool_alloc(ctx, up * H * sizeof(float) + mp * (size_t)H, &blk);
+    if (rc) return rc;
+    float* upd = (float*)blk;
+    unsigned char* ok = (unsigned char*)(upd + up * H);
+    auto fail_cuda = [&](cudaError_t e, const char* what) { art_pool_free(ctx, blk); return ctx->fail(ART_HP_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e)); };
+    cudaError_t e = cudaMemcpy2DAsync(upd, up * sizeof(float), raw, rp * sizeof(float), (size_t)W * sizeof(float), (size_t)H, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ok, 0, mp * (size_t)H, st);
+    if (e != cudaSuccess) return fail_cuda(e, "staging");
+    const dim3 grid((W + 255) / 256, H - 4);
+    int* d_changed = d_count + 1;
+    for (int pass = 0;; ++pass) {
+        if (pass) { e = cudaMemsetAsync(d_changed, 0, sizeof(int), st); if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync"); }
+        art_prof_begin(ctx, "k_bp_interp_xtrans");
+        k_bp_interp_xtrans<<<grid, 256, 0, st>>>(raw, rp, upd, up, ok, map, mp, W, H, cfa, d_changed);
+        art_prof_end(ctx);
+        ctx->launches++;
+        int changed = 0;
+        e = cudaMemcpyAsync(&changed, d_changed, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail_cuda(e, "pass");
+        if (!changed) break;
+        if (pass > 65536) { art_pool_free(ctx, blk); return ctx->fail(ART_HP_ERR_CUDA, "bad pixel interpolation did not settle"); }
+    }
+    k_bp_commit_xtrans<<<grid, 256, 0, st>>>(raw, rp, upd, up, ok, map, mp, W, H, d_count);
+    ctx->launches++;
+    art_pool_free(ctx, blk);
+    ART_CUDA(ctx, cudaGetLastError());
+    return ART_HP_OK;
+}
 
 // d_count: one device int, zeroed here, receives the number of pixels marked by this call
 int art_find_hot_dead_dev(art_hp_ctx* ctx, int W, int H, const int* xtrans36, const float* raw, size_t rp, float thresh, int hot, int dead,

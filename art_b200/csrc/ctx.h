@@ -180,6 +180,7 @@ int art_scale_colors_xtrans_dev(art_hp_ctx* ctx, int W, int H, const int* xtrans
 // d_count = one device int receiving the number of pixels marked / interpolated
 int art_find_hot_dead_dev(art_hp_ctx* ctx, int W, int H, const int* xtrans36, const float* raw, size_t rp, float thresh, int hot, int dead,
                           unsigned char* map, size_t mp, int* d_count);
+int art_interpolate_bad_xtrans_dev(art_hp_ctx* ctx, int W, int H, const int* xtrans36, float* raw, size_t rp, const unsigned char* map, size_t mp, int* d_count);
 int art_interpolate_bad_bayer_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* raw, size_t rp, const unsigned char* map, size_t mp, int* d_count);
 // ipresize.cc (resize.cu): ImProcFunctions::Lanczos on three planes
 int art_lanczos_dev(art_hp_ctx* ctx, const float* s0, const float* s1, const float* s2, size_t sp, int sW, int sH,

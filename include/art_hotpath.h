@@ -534,6 +534,15 @@ int art_hp_interpolate_bad_pixels_bayer(art_hp_ctx* ctx, int W, int H, unsigned 
                                         const unsigned char* map, size_t map_stride, int* count);
 int art_hp_interpolate_bad_pixels_bayer_dev(art_hp_ctx* ctx, int W, int H, unsigned filters, float* d_raw, size_t raw_pitch,
                                             const unsigned char* d_map, size_t map_pitch, int* count);
+/* RawImageSource::interpolateBadPixelsXtrans(bitmapBads) (rtengine/badpixels.cc L288-475), in place on the CFA plane, in the reference's ONE-THREAD
+ * (raster) order: the function reads the neighbours of a red / blue site's "virtual pixel" and its distance-2 partner without checking them
+ * against the map, so its OpenMP schedule decides whether such a neighbour was already rewritten -- only the serial order is a function of the
+ * input.  Bit-identical to the reference run on one thread (the device iterates to the fixed point of that order; one stream synchronisation per
+ * pass, two or three passes unless bad pixels form long chains).  `xtrans` must be an X-Trans layout (ART_HP_ERR_INVALID otherwise). */
+int art_hp_interpolate_bad_pixels_xtrans(art_hp_ctx* ctx, int W, int H, const int* xtrans, float* const* rawData,
+                                         const unsigned char* map, size_t map_stride, int* count);
+int art_hp_interpolate_bad_pixels_xtrans_dev(art_hp_ctx* ctx, int W, int H, const int* xtrans, float* d_raw, size_t raw_pitch,
+                                             const unsigned char* d_map, size_t map_pitch, int* count);
 
 /* ---- channel mixer ----------------------------------------------------------------- */
 /*

@@ -131,3 +131,92 @@ int artoracle_interpolate_bad_bayer(float* raw, int W, int H, unsigned filters, 
 #undef BAD
     return counter;
 }
+
+/* RawImageSource::interpolateBadPixelsXtrans (badpixels.cc L288-475) in raster order -- the stock loop is an OpenMP parallel for whose "virtual
+ * pixel" (and distance-2 partner) read neighbours that are not checked against the map and may already have been rewritten in place, so only its
+ * one-thread schedule is a function of the input; that schedule is the oracle (pinned against the reference run on one thread).  Also kept: the
+ * knight-move scan's inner loop visits d2 = -1 only (`d2 < 1`, L414). */
+int artoracle_interpolate_bad_xtrans(float* raw, int W, int H, const int* xt, const unsigned char* map)
+{
+    const float eps = 1.f;
+    int counter = 0;
+#define RAW(i, j) raw[(size_t)(i) * W + (j)]
+#define BAD(x, y) (map[(size_t)(y) * W + (x)] != 0)
+#define XFC(r, c) xt[((r) % 6) * 6 + ((c) % 6)]
+    for (int row = 2; row < H - 2; ++row)
+        for (int col = 2; col < W - 2; ++col) {
+            if (!BAD(col, row)) continue;
+            float wtdsum = 0.f, norm = 0.f;
+            const int pixelColor = XFC(row, col);
+            if (pixelColor == 1) {
+                if (XFC(row, col - 1) == XFC(row, col + 1)) {       /* solitary green */
+                    for (int dx = -1; dx <= 1; dx += 2) {
+                        if (BAD(col + dx, row - 1) || BAD(col - dx, row + 1)) continue;
+                        const float dirwt = 0.70710678f / (fabsf(RAW(row - 1, col + dx) - RAW(row + 1, col - dx)) + eps);
+                        wtdsum += dirwt * (RAW(row - 1, col + dx) + RAW(row + 1, col - dx));
+                        norm += dirwt;
+                    }
+                    for (int dx = -1; dx <= 1; dx += 2) {
+                        if (BAD(col + dx, row - 2) || BAD(col - dx, row + 2)) continue;
+                        const float dirwt = 0.44721359f / (fabsf(RAW(row - 2, col + dx) - RAW(row + 2, col - dx)) + eps);
+                        wtdsum += dirwt * (RAW(row - 2, col + dx) + RAW(row + 2, col - dx));
+                        norm += dirwt;
+                    }
+                    for (int dx = -2; dx <= 2; dx += 4) {
+                        if (BAD(col + dx, row - 1) || BAD(col - dx, row + 1)) continue;
+                        const float dirwt = 0.44721359f / (fabsf(RAW(row - 1, col + dx) - RAW(row + 1, col - dx)) + eps);
+                        wtdsum += dirwt * (RAW(row - 1, col + dx) + RAW(row + 1, col - dx));
+                        norm += dirwt;
+                    }
+                } else {                                            /* member of a 2x2 green square */
+                    const int offset1 = XFC(row - 1, col - 1) == XFC(row + 1, col + 1) ? 1 : -1;
+                    if (!(BAD(col - offset1, row - 1) || BAD(col + offset1, row + 1))) {
+                        const float dirwt = 0.70710678f / (fabsf(RAW(row - 1, col - offset1) - RAW(row + 1, col + offset1)) + eps);
+                        wtdsum += dirwt * (RAW(row - 1, col - offset1) + RAW(row + 1, col + offset1));
+                        norm += dirwt;
+                    }
+                    int offsety = XFC(row - 1, col) != 1 ? 1 : -1;
+                    int offsetx = offset1 * offsety;
+                    if (!(BAD(col + offsetx, row) || BAD(col, row + offsety))) {
+                        const float dirwt = 1.f / (fabsf(RAW(row, col + offsetx) - RAW(row + offsety, col)) + eps);
+                        wtdsum += dirwt * (RAW(row, col + offsetx) + RAW(row + offsety, col));
+                        norm += dirwt;
+                    }
+                    const int offsety2 = -offsety, offsetx2 = -offsetx;
+                    offsetx *= 2; offsety *= 2;
+                    if (!(BAD(col + offsetx, row + offsety2) || BAD(col + offsetx2, row + offsety))) {
+                        const float dirwt = 0.44721359f / (fabsf(RAW(row + offsety2, col + offsetx) - RAW(row + offsety, col + offsetx2)) + eps);
+                        wtdsum += dirwt * (RAW(row + offsety2, col + offsetx) + RAW(row + offsety, col + offsetx2));
+                        norm += dirwt;
+                    }
+                }
+            } else {                                                /* red / blue */
+                for (int d1 = -2, offsety = 3; d1 <= 2; d1 += 4, offsety -= 6)
+                    for (int d2 = -1, offsetx = 3; d2 < 1; d2 += 2, offsetx -= 6)
+                        if (XFC(row + d1, col + d2) == pixelColor && !(BAD(col + d2, row + d1) || BAD(col + d2 + offsetx, row + d1 + offsety))) {
+                            const float dirwt = 0.44721359f / (fabsf(RAW(row + d1, col + d2) - RAW(row + d1 + offsety, col + d2 + offsetx)) + eps);
+                            wtdsum += dirwt * (RAW(row + d1, col + d2) + RAW(row + d1 + offsety, col + d2 + offsetx));
+                            norm += dirwt;
+                        }
+                int found = 0, dx, dy;
+                for (dx = -2, dy = 0; dx <= 2; dx += 4)
+                    if (XFC(row, col + dx) == pixelColor) { found = 1; break; }
+                if (!found)
+                    for (dx = 0, dy = -2; dy <= 2; dy += 4)
+                        if (XFC(row + dy, col) == pixelColor) { found = 1; break; }
+                /* no same-colour pixel at distance 2 (not an X-Trans layout): the reference's loops leave dx = 0, dy = 6 and read out of bounds; refuse */
+                if (!found) return -1;
+                float virtualPixel;
+                if (dy == 0) virtualPixel = 0.5f * (RAW(row - 1, col - dx) + RAW(row + 1, col - dx));
+                else virtualPixel = 0.5f * (RAW(row - dy, col - 1) + RAW(row - dy, col + 1));
+                const float dirwt = 0.5f / (fabsf(virtualPixel - RAW(row + dy, col + dx)) + eps);
+                wtdsum += dirwt * (virtualPixel + RAW(row + dy, col + dx));
+                norm += dirwt;
+            }
+            if (norm > 0.f) { RAW(row, col) = wtdsum / (2.f * norm); counter++; }
+        }
+#undef XFC
+#undef RAW
+#undef BAD
+    return counter;
+}

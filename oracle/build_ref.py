@@ -530,6 +530,7 @@ struct RawImageSource {
     int W, H; unsigned filters; RawImageBadPix* ri; array2D<float>& rawData;
     unsigned FC(int row, int col) const { return (filters >> ((((row) << 1 & 14) + ((col) & 1)) << 1) & 3); }
     int interpolateBadPixelsBayer(const PixelsMap &bitmapBads, array2D<float> &rawData);
+    int interpolateBadPixelsXtrans(const PixelsMap &bitmapBads);
     int findHotDeadPixels(PixelsMap &bpMap, const float thresh, const bool findHotPixels, const bool findDeadPixels) const;
 };
 #include "badpix_body.inc"
@@ -565,6 +566,27 @@ extern "C" int artref_interpolate_bad_bayer(float* raw, int W, int H, unsigned f
         rtengine::PixelsMap pm(W, H);
         for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) if (map[(size_t)y * W + x]) pm.set(x, y);
         n = s.interpolateBadPixelsBayer(pm, rd);
+    }
+    delete[] rows;
+    return n;
+}
+// nthreads = 1: the raster order.  The stock function builds its "virtual pixel" (and reads the distance-2 pixel) from neighbours it does not check
+// against the map and that its own parallel loop may already have rewritten: with more than one thread the result depends on the schedule.
+extern "C" int artref_interpolate_bad_xtrans(float* raw, int W, int H, const int* xtrans36, const unsigned char* map, int nthreads)
+{
+    float** rows = new float*[H];
+    for (int i = 0; i < H; ++i) rows[i] = raw + (size_t)i * W;
+    int n = 0;
+    {
+        rtengine::array2D<float> rd(W, H, rows, rtengine::ARRAY2D_BYREFERENCE);
+        rtengine::RawImageBadPix ri{(int)rtengine::ST_FUJI_XTRANS, xtrans36};
+        rtengine::RawImageSource s{W, H, 0u, &ri, rd};
+        rtengine::PixelsMap pm(W, H);
+        for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) if (map[(size_t)y * W + x]) pm.set(x, y);
+        const int old = omp_get_max_threads();
+        if (nthreads > 0) omp_set_num_threads(nthreads);
+        n = s.interpolateBadPixelsXtrans(pm);
+        omp_set_num_threads(old);
     }
     delete[] rows;
     return n;
@@ -2151,6 +2173,7 @@ def extract(det):
     open(os.path.join(sub, "badpix_body.inc"), "w").write(
         bptext[a0.start():a1.end()] + "\n\n" +
         cut_function(bp, r"^int RawImageSource::interpolateBadPixelsBayer\(const PixelsMap &bitmapBads, array2D<float> &rawData\)") + "\n\n" +
+        cut_function(bp, r"^int RawImageSource::interpolateBadPixelsXtrans\(const PixelsMap &bitmapBads\)") + "\n\n" +
         cut_function(bp, r"^int RawImageSource::findHotDeadPixels\(PixelsMap &bpMap, const float thresh, const bool findHotPixels, const bool findDeadPixels\) const"))
     open(os.path.join(sub, "shim_badpix.cc"), "w").write(SHIM_BADPIX_TU)
     rz = os.path.join(RT, "ipresize.cc")

@@ -72,3 +72,37 @@ def test_full_frame(hot_path):
     assert n1 == n2 and np.array_equal(fixed, fixed_want)
     print("\n[hot / dead pixels] 8192x5464 through the host entries (pageable memory, copies included): find %.1f ms (%d marked), interpolate %.1f ms"
           % ((t1 - t0) * 1e3, gn, (t3 - t2) * 1e3))
+
+
+@pytest.mark.parametrize("dy,dx", [(0, 0), (1, 2), (4, 5)])
+@pytest.mark.parametrize("W,H", [(64, 48), (67, 53), (301, 203), (1029, 515)])
+def test_interpolate_xtrans(hot_path, dy, dx, W, H):
+    """art_hp_interpolate_bad_pixels_xtrans = interpolateBadPixelsXtrans in raster order (the oracle is pinned to the reference on one thread),
+    incl. runs of bad pixels along a row and a column whose members read the ones rewritten before them"""
+    from test_oracle_badpixels import interpolate_xtrans, xtrans_bad_map
+    xt = synth.xtrans_matrix(dy, dx)
+    raw = spiky(synth.xtrans_frame(W, H, xt, seed=W + H + dy), W + 3, max(4, W * H // 150))
+    m = xtrans_bad_map(raw, xt, W + dx)
+    want, wn = interpolate_xtrans(oracle.port().lib, "artoracle_interpolate_bad_xtrans", raw, xt, m)
+    got = raw.copy()
+    gn = hot_path.interpolate_bad_pixels_xtrans(got, xt, m)
+    assert gn == wn and np.array_equal(got, want)
+
+
+def test_interpolate_xtrans_full_frame_and_bad_layout(hot_path):
+    """configs[3]'s 26 MP frame; a 6x6 table that is not an X-Trans layout is refused (the reference's scan runs off the frame there)"""
+    import art_b200
+    from test_oracle_badpixels import interpolate_xtrans
+    W, H = 6240, 4160
+    xt = synth.xtrans_matrix()
+    raw = spiky(synth.xtrans_frame(W, H, xt, seed=3), 5, 6000)
+    m, _ = find(oracle.port().lib, "artoracle_find_hot_dead", raw, xt, 100.0, 1, 1)
+    m[1000, 500:560] = 1
+    want, wn = interpolate_xtrans(oracle.port().lib, "artoracle_interpolate_bad_xtrans", raw, xt, m)
+    got = raw.copy()
+    gn = hot_path.interpolate_bad_pixels_xtrans(got, xt, m)
+    assert gn == wn and gn > 1000 and np.array_equal(got, want)
+    bad = np.zeros((6, 6), np.int32)
+    bad[0, 0] = 2        # a lone blue site: nothing of its colour at distance 2
+    with pytest.raises(art_b200.HotPathError):
+        hot_path.interpolate_bad_pixels_xtrans(raw[:64, :64].copy(), bad, m[:64, :64])

@@ -87,3 +87,41 @@ def test_interpolate_bayer(filters, W, H):
     want, wn = interpolate(oracle.ref().lib, "artref_interpolate_bad_bayer", raw, filters, m)
     assert gn == wn and np.array_equal(got, want)
     assert (got != raw).sum() > 0 and np.array_equal(got[m == 0], raw[m == 0])
+
+
+def interpolate_xtrans(lib, name, raw, xt, m, *extra):
+    out = raw.copy()
+    H, W = out.shape
+    x = np.ascontiguousarray(xt, np.int32)
+    n = getattr(lib, name)(out.ctypes.data_as(fp), W, H, x.ctypes.data_as(ip), np.ascontiguousarray(m).ctypes.data_as(bp), *extra)
+    return out, n
+
+
+def xtrans_bad_map(raw, xt, seed):
+    """detected spikes + clumps: adjacent bad pixels of different colours (the unchecked virtual-pixel neighbours), runs along a row and a column
+    (chains of pixels that each read the one rewritten before it), a solid block (pixels without a valid pair)"""
+    m, _ = find(oracle.port().lib, "artoracle_find_hot_dead", raw, xt, 100.0, 1, 1)
+    H, W = raw.shape
+    rng = np.random.default_rng(seed)
+    ys, xs = rng.integers(2, H - 3, 40), rng.integers(2, W - 3, 40)
+    for y, x in zip(ys, xs):
+        m[y, x] = 1
+        m[y + rng.integers(-1, 2), x + rng.integers(-1, 2)] = 1
+    m[20, 10:30] = 1
+    m[12:34, 40] = 1
+    m[30:36, 20:26] = 1
+    return m
+
+
+@needs_ref
+@pytest.mark.parametrize("dy,dx", [(0, 0), (1, 2), (4, 5), (3, 1)])
+@pytest.mark.parametrize("W,H", [(64, 48), (67, 53), (301, 203)])
+def test_interpolate_xtrans(dy, dx, W, H):
+    """interpolateBadPixelsXtrans in raster order = the reference on one thread (its parallel schedule is not a function of the input)"""
+    xt = synth.xtrans_matrix(dy, dx)
+    raw = spiky(synth.xtrans_frame(W, H, xt, seed=W + H + dy), W + 3, max(4, W * H // 150))
+    m = xtrans_bad_map(raw, xt, W + dx)
+    got, gn = interpolate_xtrans(oracle.port().lib, "artoracle_interpolate_bad_xtrans", raw, xt, m)
+    want, wn = interpolate_xtrans(oracle.ref().lib, "artref_interpolate_bad_xtrans", raw, xt, m, 1)
+    assert gn == wn and gn > 0 and np.array_equal(got, want)
+    assert np.array_equal(got[m == 0], raw[m == 0])
