@@ -174,10 +174,6 @@ int art_tone_equalizer_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, fl
     if (p->regularization > 1) {
         radius2 = (int)(350.f / p->scale);
         reg = 5 - std::min(p->regularization, 4);
-        // the reference's box blurs index out of bounds when the window exceeds the frame; refuse instead of reproducing a crash
-        const int widest = radius2 * std::max(reg - 1, 1);
-        if (radius2 < 1 || 2 * widest + 1 > std::min(W, H))
-            return ctx->fail(ART_HP_ERR_INVALID, "tone equalizer regularization %d needs a frame larger than its %d-pixel window (frame %dx%d)", p->regularization, 2 * widest + 1, W, H);
     }
     const size_t yp = round_up((size_t)W, 32), n = yp * (size_t)H;
     void* blk = nullptr;

@@ -590,9 +590,7 @@ int art_hp_hsl_equalizer_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d
  *                         + 0.5, 0.014); regularization > 1: posterised to 1/5 EV and guided by the unposterised Y with radius 350 / scale (and once
  *                         more with (reg - 1) times that radius, reg = 5 - min(regularization, 4)) -- and every pixel is multiplied by the
  *                         correction of its luminance: five sliders spread over twelve 2-EV gaussian bands (bands[0] blacks .. bands[4] whites,
- *                         -100 .. 100).  The colour-map preview (show_colormap, PREVIEW pipeline, lcms2) is not reproduced.  With regularization > 1
- *                         the frame must be larger than the guided filter's window (ART_HP_ERR_INVALID otherwise; the reference indexes out of
- *                         bounds there).  Bit-identical to the reference, SSE2 groups and scalar row tails included.
+ *                         -100 .. 100).  The colour-map preview (show_colormap, PREVIEW pipeline, lcms2) is not reproduced.  Bit-identical to the reference, SSE2 groups and scalar row tails included.
  */
 typedef struct art_hp_toneeq_params {
     int    bands[5];                              /* params->toneEqualizer.bands */

@@ -51,9 +51,9 @@ def same(a, b):
 BANDS = [(0, 0, 0, 0, 0), (40, 25, 0, -20, -35), (-100, 100, -50, 50, 100), (15, 0, 0, 0, -15)]
 
 
-# regularization > 1 runs guidedFilter with radius 350 / scale (and twice that for regularization 2): the reference's box blurs need frames
-# larger than the window (they index out of bounds otherwise), so those cases use a preview scale or a larger frame
-CASES = [(96, 64, 0, 0.0, 1.0), (131, 77, 0, 1.5, 1.0), (131, 77, 1, 0.0, 1.0), (403, 301, 1, -2.0, 1.0), (403, 301, 1, 0.0, 2.0),
+# regularization > 1 runs guidedFilter with radius 350 / scale (and twice that for regularization 2); f_mean clamps the window to the frame
+CASES = [(96, 64, 2, 0.0, 1.0), (131, 77, 4, 0.5, 1.0), (403, 301, 3, 0.0, 1.0),
+         (96, 64, 0, 0.0, 1.0), (131, 77, 0, 1.5, 1.0), (131, 77, 1, 0.0, 1.0), (403, 301, 1, -2.0, 1.0), (403, 301, 1, 0.0, 2.0),
          (403, 301, 3, 0.0, 4.0), (403, 301, 4, 1.0, 4.0), (803, 602, 2, 0.0, 4.0), (1203, 900, 3, -1.0, 1.0)]
 
 

@@ -28,4 +28,4 @@ def test_toneeq_rejects_bad_parameters(hot_path):
     with pytest.raises(art_b200.HotPathError):
         hot_path.tone_equalizer(planes[0], planes[1], planes[2], ToneEqParams((1, 2, 3, 4, 5), 0, 0.0, 1.0, None))            # no ws
     with pytest.raises(art_b200.HotPathError):
-        hot_path.tone_equalizer(planes[0], planes[1], planes[2], ToneEqParams((1, 2, 3, 4, 5), 3, 0.0, 1.0, PROPHOTO))        # window larger than the frame
+        hot_path.tone_equalizer(planes[0], planes[1], planes[2], ToneEqParams((1, 2, 3, 4, 5), 1, 0.0, 0.0, PROPHOTO))        # scale 0
