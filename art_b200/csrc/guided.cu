@@ -12,7 +12,9 @@
 
 namespace {
 
-struct BoxArgs { const float* x; size_t xp; float* y; size_t yp; int W, H, radius; };
+// x2 / y2: a second plane of the same geometry filtered by the same launch (blockIdx.y = 1): the guided filter's box blurs come in independent pairs,
+// and a launch has only one thread (or a quarter of a warp) per line
+struct BoxArgs { const float* x; size_t xp; float* y; size_t yp; int W, H, radius; const float* x2; float* y2; };
 
 // one line of n samples: x[k*xs] -> y[k*ys], x and y distinct planes
 __device__ __forceinline__ void box_line(const float* x, size_t xs, float* y, size_t ys, int n, int radius, bool use_rlen)
@@ -58,7 +60,9 @@ __device__ __forceinline__ void box_line(const float* x, size_t xs, float* y, si
 __global__ void __launch_bounds__(64) k_box_h(BoxArgs a)      // thread per row (L350-381)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < a.H) box_line(a.x + (size_t)r * a.xp, 1, a.y + (size_t)r * a.yp, 1, a.W, a.radius, false);
+    const float* X = blockIdx.y ? a.x2 : a.x;
+    float* Y = blockIdx.y ? a.y2 : a.y;
+    if (r < a.H) box_line(X + (size_t)r * a.xp, 1, Y + (size_t)r * a.yp, 1, a.W, a.radius, false);
 }
 // The horizontal pass for radius <= 111: a warp owns BH_ROWS = 4 rows and streams along them in 32-column tiles -- coalesced row segments into
 // registers (the next tile's loads in flight while this one is processed), the samples parked in a shared-memory ring of `ring` columns
@@ -79,8 +83,8 @@ __global__ void __launch_bounds__(BH_WARPS * 32) k_box_h_tiles(BoxArgs a, int ri
     const float flen = (float)(2 * rad + 1);
     for (int u = blockIdx.x * BH_WARPS + warp; u < units; u += gridDim.x * BH_WARPS) {
         const int row0 = u * BH_ROWS, nrows = min(BH_ROWS, a.H - row0);
-        const float* __restrict__ src = a.x + (size_t)row0 * a.xp;
-        float* __restrict__ dst = a.y + (size_t)row0 * a.yp;
+        const float* __restrict__ src = (blockIdx.y ? a.x2 : a.x) + (size_t)row0 * a.xp;
+        float* __restrict__ dst = (blockIdx.y ? a.y2 : a.y) + (size_t)row0 * a.yp;
         float t = 0.f, len = (float)(rad + 1);
         float nxt[BH_ROWS];
 #pragma unroll
@@ -154,10 +158,12 @@ __global__ void __launch_bounds__(BH_WARPS * 32) k_box_h_tiles(BoxArgs a, int ri
     }
 }
 
-__global__ void __launch_bounds__(128) k_box_v(BoxArgs a)     // thread per column (L383-553)
+__global__ void __launch_bounds__(64) k_box_v(BoxArgs a)     // thread per column (L383-553)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < a.W) box_line(a.x + c, a.xp, a.y + c, a.yp, a.H, a.radius, true);
+    const float* X = blockIdx.y ? a.x2 : a.x;
+    float* Y = blockIdx.y ? a.y2 : a.y;
+    if (c < a.W) box_line(X + c, a.xp, Y + c, a.yp, a.H, a.radius, true);
 }
 
 struct RsArgs { const float* s; size_t sp; int Ws, Hs; float* d; size_t dp; int Wd, Hd; };
@@ -218,30 +224,34 @@ __global__ void __launch_bounds__(256) k_guided_up(UpArgs a)   // L222-238
     }
 }
 
-int box_planes(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, size_t dp, float* tmp, size_t tp, int W, int H, int radius)
+// src2 / dst2 / tmp2: an optional second plane with the pitches of the first
+int box_planes(art_hp_ctx* ctx, const float* src, size_t sp, float* dst, size_t dp, float* tmp, size_t tp, int W, int H, int radius,
+               const float* src2 = nullptr, float* dst2 = nullptr, float* tmp2 = nullptr)
 {
     cudaStream_t st = ctx->stream;
+    const unsigned np = src2 ? 2 : 1;
     if (radius == 0) {      // boxblur.h L322-335
         if (src != dst) ART_CUDA(ctx, cudaMemcpy2DAsync(dst, dp * sizeof(float), src, sp * sizeof(float), (size_t)W * sizeof(float), H, cudaMemcpyDeviceToDevice, st));
+        if (src2 && src2 != dst2) ART_CUDA(ctx, cudaMemcpy2DAsync(dst2, dp * sizeof(float), src2, sp * sizeof(float), (size_t)W * sizeof(float), H, cudaMemcpyDeviceToDevice, st));
         return ART_HP_OK;
     }
-    BoxArgs h{src, sp, tmp, tp, W, H, radius};
+    BoxArgs h{src, sp, tmp, tp, W, H, radius, src2, tmp2};
     int ring = 64;
     while (ring < 2 * radius + 33) ring *= 2;
     if (ring <= 256 && W > 2 * radius) {
         const int units = (H + BH_ROWS - 1) / BH_ROWS;
         const size_t smem = (size_t)BH_WARPS * BH_ROWS * (ring + 4 + BH_SP) * sizeof(float);       // <= 38 KB
         art_prof_begin(ctx, "k_box_h_tiles");
-        k_box_h_tiles<<<(units + BH_WARPS - 1) / BH_WARPS, BH_WARPS * 32, smem, st>>>(h, ring);
+        k_box_h_tiles<<<dim3((units + BH_WARPS - 1) / BH_WARPS, np), BH_WARPS * 32, smem, st>>>(h, ring);
         art_prof_end(ctx);
     } else {
         art_prof_begin(ctx, "k_box_h");
-        k_box_h<<<(H + 63) / 64, 64, 0, st>>>(h);
+        k_box_h<<<dim3((H + 63) / 64, np), 64, 0, st>>>(h);
         art_prof_end(ctx);
     }
-    BoxArgs v{tmp, tp, dst, dp, W, H, radius};
+    BoxArgs v{tmp, tp, dst, dp, W, H, radius, tmp2, dst2};
     art_prof_begin(ctx, "k_box_v");
-    k_box_v<<<(W + 127) / 128, 128, 0, st>>>(v);
+    k_box_v<<<dim3((W + 63) / 64, np), 64, 0, st>>>(v);
     art_prof_end(ctx);
     ctx->launches += 2;
     ART_CUDA(ctx, cudaGetLastError());
@@ -273,10 +283,10 @@ int art_guided_dev(art_hp_ctx* ctx, const float* guide, size_t gp, const float* 
     if (subsampling <= 0) subsampling = art_guided_subsampling(W, H, r);
     const int w = W / subsampling, h = H / subsampling;
     const size_t p = round_up((size_t)w, 32), n = p * (size_t)h;
-    int rc = art_reserve(ctx, ctx->d_scratch, 5 * n * sizeof(float));
+    int rc = art_reserve(ctx, ctx->d_scratch, 6 * n * sizeof(float));
     if (rc) return rc;
     float* I1 = (float*)ctx->d_scratch.p;
-    float *p1 = I1 + n, *meanI = I1 + 2 * n, *meanp = I1 + 3 * n, *tmp = I1 + 4 * n;
+    float *p1 = I1 + n, *meanI = I1 + 2 * n, *meanp = I1 + 3 * n, *tmp = I1 + 4 * n, *tmp2 = I1 + 5 * n;
     const dim3 sgrid((w + 255) / 256, std::min(h, 148 * 4));
     art_prof_begin(ctx, "k_resample");
     k_resample<<<sgrid, 256, 0, st>>>(RsArgs{guide, gp, W, H, I1, p, w, h});
@@ -285,21 +295,18 @@ int art_guided_dev(art_hp_ctx* ctx, const float* guide, size_t gp, const float* 
     ctx->launches += 2;
     int rad = (int)((float)r / subsampling);                          // f_mean's int rad <- float r1 (L161-169)
     rad = std::max(0, std::min(rad, (std::min(w, h) - 1) / 2 - 1));
-    if ((rc = box_planes(ctx, I1, p, meanI, p, tmp, p, w, h, rad))) return rc;
-    if ((rc = box_planes(ctx, p1, p, meanp, p, tmp, p, w, h, rad))) return rc;
+    if ((rc = box_planes(ctx, I1, p, meanI, p, tmp, p, w, h, rad, p1, meanp, tmp2))) return rc;      // meanI, meanp: one launch pair
     const int ewgrid = 148 * 8;
     art_prof_begin(ctx, "k_guided_ew");
     k_guided_ew<<<ewgrid, 256, 0, st>>>(EwArgs{I1, p1, nullptr, nullptr, n, epsilon, 0});
     art_prof_end(ctx);
     ctx->launches++;
-    if ((rc = box_planes(ctx, p1, p, p1, p, tmp, p, w, h, rad))) return rc;      // mean(corrIp)
-    if ((rc = box_planes(ctx, I1, p, I1, p, tmp, p, w, h, rad))) return rc;      // mean(corrI)
+    if ((rc = box_planes(ctx, p1, p, p1, p, tmp, p, w, h, rad, I1, I1, tmp2))) return rc;      // mean(corrIp), mean(corrI)
     art_prof_begin(ctx, "k_guided_ew");
     k_guided_ew<<<ewgrid, 256, 0, st>>>(EwArgs{I1, p1, meanI, meanp, n, epsilon, 1});
     art_prof_end(ctx);
     ctx->launches++;
-    if ((rc = box_planes(ctx, I1, p, I1, p, tmp, p, w, h, rad))) return rc;      // meana
-    if ((rc = box_planes(ctx, p1, p, p1, p, tmp, p, w, h, rad))) return rc;      // meanb
+    if ((rc = box_planes(ctx, I1, p, I1, p, tmp, p, w, h, rad, p1, p1, tmp2))) return rc;      // meana, meanb
     art_prof_begin(ctx, "k_guided_up");
     k_guided_up<<<dim3((W + 255) / 256, std::min(H, 148 * 4)), 256, 0, st>>>(UpArgs{I1, p1, p, w, h, guide, gp, dst, dp, W, H});
     art_prof_end(ctx);
