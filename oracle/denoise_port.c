@@ -780,3 +780,16 @@ int artoracle_denoise_auto_params(const float* stats, int isRAW, int aggressive,
 
 /* Color::computeXYZ2LabY for other ports (color.cc L1262-1274) */
 float artoracle_xyz2laby(float f) { init_cachef(); return computeXYZ2LabY(f); }
+
+/* the block DCT stand-in alone, for cross-checks against an independent implementation (tests/test_oracle_denoise.py):
+ * kind 0 = REDFT10 x REDFT10 (FTblockDN.cc L1604), 1 = REDFT01 x REDFT01 (L1614) on one n x n block */
+int artoracle_block_dct(int n, int kind, const float* in, float* out)
+{
+    const int nn[2] = {n, n};
+    const fftw_r2r_kind k[2] = {kind ? FFTW_REDFT01 : FFTW_REDFT10, kind ? FFTW_REDFT01 : FFTW_REDFT10};
+    fftwf_plan p = fftwf_plan_many_r2r(2, nn, 1, NULL, NULL, 1, n * n, NULL, NULL, 1, n * n, k, FFTW_ESTIMATE);
+    if (!p) return 1;
+    artdct_block(p, in, out);
+    fftwf_destroy_plan(p);
+    return 0;
+}

@@ -136,3 +136,24 @@ def test_gamma_lut_matches_reference_use():
     lib.artoracle_gammaf2lut(lut.ctypes.data_as(fp), F(gam), F(th), F(slope), F(65535.0), F(65535.0))
     assert np.all(np.diff(lut) > 0)
     assert abs(lut[65535] - 65535.0) < 1.0
+
+
+def test_block_dct_standin_matches_scipy_pocketfft():
+    """A second opinion on the FFTW boundary of detail_recovery (FTblockDN.cc L1604, L1614: 64 x 64 REDFT10 / REDFT01, fftw3f absent): the fp64
+    cosine-sum stand-in against scipy's pocketfft DCT-II / DCT-III, in double (definition) and in float32 (what a float FFT library returns)."""
+    import ctypes
+    import scipy.fft
+    fp_ = ctypes.POINTER(ctypes.c_float)
+    lib = oracle.port().lib
+    rng = np.random.default_rng(12)
+    for n in (64, 8):
+        for kind, tp in ((0, 2), (1, 3)):
+            a = (rng.standard_normal((n, n)) * 300).astype(np.float32)
+            out = np.zeros_like(a)
+            assert lib.artoracle_block_dct(n, kind, a.ctypes.data_as(fp_), out.ctypes.data_as(fp_)) == 0
+            want64 = scipy.fft.dctn(a.astype(np.float64), type=tp)
+            want32 = scipy.fft.dctn(a, type=tp)
+            assert want32.dtype == np.float32
+            scale = np.abs(want64).max()
+            assert np.abs(out - want64).max() <= 1e-7 * scale          # the stand-in is the definition rounded once to float
+            assert np.abs(out - want32).max() <= 4e-6 * scale          # a float32 FFT sits a few ulp of the largest coefficient away
