@@ -126,6 +126,8 @@ def load_library(build_if_missing=True):
         "art_hp_dual_demosaic_xtrans_dev": (i, [vp, i, i, i, i, vp, vp, vp, sz, vp, vp, vp, sz, d, i, vp]),
         "art_hp_lab_histogram": (i, [vp, i, i, vp, vp, vp, vp, vp]),
         "art_hp_lab_histogram_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, vp]),
+        "art_hp_black_and_white": (i, [vp, i, i, vp, vp, vp, vp]),
+        "art_hp_black_and_white_dev": (i, [vp, i, i, vp, vp, vp, sz, vp]),
         "art_hp_tone_equalizer": (i, [vp, i, i, vp, vp, vp, vp]),
         "art_hp_tone_equalizer_dev": (i, [vp, i, i, vp, vp, vp, sz, vp]),
         "art_hp_hsl_equalizer": (i, [vp, i, i, vp, vp, vp, vp]),
@@ -320,6 +322,43 @@ class HslParams:
             w = np.ascontiguousarray(self.ws, dtype=np.float64).reshape(9)
             self._keep.append(w)
             c.ws = w.ctypes.data_as(dp)
+        return c
+
+
+class _BwParamsC(ctypes.Structure):        # art_hp_bw_params
+    _fp = ctypes.POINTER(ctypes.c_float)
+    _fields_ = [("bwr", ctypes.c_float), ("bwg", ctypes.c_float), ("bwb", ctypes.c_float), ("kcorec", ctypes.c_float),
+                ("gamma_r", _fp), ("gamma_g", _fp), ("gamma_b", _fp), ("ulut", _fp), ("vlut", _fp), ("ws", ctypes.POINTER(ctypes.c_double))]
+
+
+class BwParams:
+    """art_hp_bw_params: mixer = (bwr, bwg, bwb), kcorec, gamma = three 65536-entry tables or None, cast = (ulut, vlut) or None, ws."""
+
+    def __init__(self, mixer, kcorec=1.0, gamma=None, cast=None, ws=None):
+        self.__dict__.update(locals())
+        del self.__dict__["self"]
+
+    def c_struct(self):
+        c = _BwParamsC()
+        fp = ctypes.POINTER(ctypes.c_float)
+        self._keep = []
+
+        def tab(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            assert a.size == 65536
+            self._keep.append(a)
+            return a.ctypes.data_as(fp)
+        c.bwr, c.bwg, c.bwb, c.kcorec = float(self.mixer[0]), float(self.mixer[1]), float(self.mixer[2]), float(self.kcorec)
+        if self.gamma is not None:
+            c.gamma_r, c.gamma_g, c.gamma_b = [tab(t) for t in self.gamma]
+        if self.cast is not None:
+            c.ulut, c.vlut = [tab(t) for t in self.cast]
+        if self.ws is not None:
+            w = np.ascontiguousarray(self.ws, dtype=np.float64).reshape(9)
+            self._keep.append(w)
+            c.ws = w.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
         return c
 
 
@@ -777,6 +816,13 @@ class HotPath:
                                                          cam.ctypes.data_as(ctypes.c_void_p), row_table(raw), *[row_table(o) for o in out],
                                                          ctypes.byref(c), int(bool(auto_contrast))))
         return out, c.value
+
+    def black_and_white(self, r, g, b, params):
+        """ImProcFunctions::blackAndWhite's pixel loops in place on three host (H, W) float32 working-space RGB planes."""
+        H, W = r.shape
+        c = params.c_struct()
+        self._check(self.lib.art_hp_black_and_white(self.h, W, H, row_table(r), row_table(g), row_table(b), ctypes.byref(c)))
+        return r, g, b
 
     def tone_equalizer(self, r, g, b, params):
         """ImProcFunctions::toneEqualizer in place on three host (H, W) float32 working-space RGB planes."""

@@ -602,6 +602,24 @@ typedef struct art_hp_toneeq_params {
 int art_hp_tone_equalizer(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b, const art_hp_toneeq_params* params);
 int art_hp_tone_equalizer_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch, const art_hp_toneeq_params* params);
 
+/* ---- black and white --------------------------------------------------------------- */
+/*
+ * art_hp_black_and_white   the pixel loops of ImProcFunctions::blackAndWhite (rtengine/ipbw.cc L283-312, L343-362; the last step of STAGE_3), in place
+ *                          on working-space RGB planes: r = g = b = (bwr r' + bwg g' + bwb b') kcorec with r', g', b' read through the gamma tables when
+ *                          given, then -- with ulut / vlut -- the colour cast: Imagefloat::setMode(YUV), u += ulut[Y], v += vlut[Y], and the
+ *                          setMode(RGB) the next stage applies.  bwr / bwg / bwb / kcorec are computeBWMixerConstants' results (L50-217) and the tables
+ *                          are the LUTf(65536) data the function fills (gamma_r/g/b: L264-272, all three or none; ulut / vlut: L321-341, both or none):
+ *                          host code of the reference, passed by pointer.  Bit-identical to the reference, SSE2 groups and scalar row tails included.
+ */
+typedef struct art_hp_bw_params {
+    float bwr, bwg, bwb, kcorec;
+    const float *gamma_r, *gamma_g, *gamma_b;     /* 65536 floats each, or all NULL (hasgammabw == false) */
+    const float *ulut, *vlut;                     /* 65536 floats each, or both NULL (colorCast.getBottom() == 0) */
+    const double* ws;                             /* ICCStore::workingSpaceMatrix, 9 doubles; needed with the colour cast */
+} art_hp_bw_params;
+int art_hp_black_and_white(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b, const art_hp_bw_params* params);
+int art_hp_black_and_white_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch, const art_hp_bw_params* params);
+
 /* ---- dual demosaic ----------------------------------------------------------------- */
 /*
  * art_hp_demosaic_vng4        RawImageSource::vng4_demosaic(rawData, red, green, blue) (rtengine/vng4_demosaic_RT.cc L32-397): the four-colour

@@ -322,6 +322,34 @@ extern "C" int artref_hsl_equalizer(float* R, float* G, float* B, int W_, int H_
     im.store(R, G, B);
     return 0;
 }
+// ImProcFunctions::blackAndWhite's two pixel loops (ipbw.cc L283-312, L343-362) with the mode changes of its colour cast (setMode(YUV) before the
+// second loop, the next stage's setMode(RGB) after it); the mixer constants and the five tables are the caller's (host code of the reference)
+extern "C" int artref_bw(float* R, float* G, float* B, int W_, int H_, const double* ws9, float bwr, float bwg, float bwb, float kcorec,
+                         const float* gr, const float* gg, const float* gb, const float* ul, const float* vl)
+{
+    Imagefloat im(W_, H_, R, G, B, ws9); Imagefloat* img = &im;
+    const int W = W_, H = H_;
+    const bool multiThread = true;
+    const bool hasgammabw = gr != nullptr;
+    LUTf gamma_r, gamma_g, gamma_b;
+    if (hasgammabw) {
+        gamma_r(65536); gamma_g(65536); gamma_b(65536);
+        for (int i = 0; i < 65536; ++i) { gamma_r[i] = gr[i]; gamma_g[i] = gg[i]; gamma_b[i] = gb[i]; }
+    }
+    vfloat bwr_v = F2V(bwr), bwg_v = F2V(bwg), bwb_v = F2V(bwb), kcorec_v = F2V(kcorec);
+#pragma omp parallel for if (multiThread)
+#include "bw_loop1.inc"
+    if (ul) {
+        img->setMode(Imagefloat::Mode::YUV, multiThread);
+        LUTf ulut(65536), vlut(65536);
+        for (int i = 0; i < 65536; ++i) { ulut[i] = ul[i]; vlut[i] = vl[i]; }
+#pragma omp parallel for if (multiThread)
+#include "bw_loop2.inc"
+        img->setMode(Imagefloat::Mode::RGB, multiThread);
+    }
+    im.store(R, G, B);
+    return 0;
+}
 }   // namespace hsl
 // ---- ImProcFunctions::toneEqualizer (iptoneequalizer.cc L68-371): tone_eq() verbatim over stubs for what its colour-map preview branch names (lcms2, never executed here)
 namespace toneeq {
@@ -469,6 +497,10 @@ def extract(sub):
     w("tone_color_gamma.inc", "\n".join([
         cut_function(ch, r"static inline float  gamma_srgb       \(float x\)"),
         cut_function(ch, r"static inline float  igamma_srgb      \(float x\)")]))
+    from build_ref import cut_block
+    ipbw = os.path.join(RT, "ipbw.cc")
+    w("bw_loop1.inc", cut_block(ipbw, r"for \(int y = 0; y < H; \+\+y\) \{(?=\s*int x = 0;\s*#ifdef __SSE2__\s*for \(; x < W-3; x \+= 4\) \{\s*vfloat r = LVF\(img->r\(y, x\)\);)"))
+    w("bw_loop2.inc", cut_block(ipbw, r"for \(int y = 0; y < H; \+\+y\) \{(?=\s*int x = 0;\s*#ifdef __SSE2__\s*for \(; x < W - 3; x \+= 4\) \{\s*vfloat yv = LVF\(img->g\(y, x\)\);)"))
     w("toneeq_body.inc", cut_function(os.path.join(RT, "iptoneequalizer.cc"), r"^void tone_eq\(array2D<float> &R, array2D<float> &G, array2D<float> &B, const ToneEqualizerParams &pp")
       .replace("const Glib::ustring &workingProfile", "const std::string &workingProfile"))
     ipsl = os.path.join(RT, "ipsoftlight.cc")

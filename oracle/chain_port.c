@@ -283,6 +283,38 @@ int artoracle_chain_softlight(float* R, float* G, float* B, int W, int H, const 
     return 0;
 }
 
+/* ---- blackAndWhite: the two pixel loops of ImProcFunctions::blackAndWhite (ipbw.cc L283-312 mixer with optional gamma tables, L343-362 colour cast in
+ * YUV) with Imagefloat::setMode(YUV) before the second and the next stage's setMode(RGB) after it (imagefloat.cc L700-725, L779-803).  Tables are
+ * LUTf(65536): the SSE2 groups read them with the vector rule, the row tails with the scalar one ---- */
+int artoracle_bw(float* R, float* G, float* B, int W, int H, const double* ws9, float bwr, float bwg, float bwb, float kcorec,
+                 const float* gr, const float* gg, const float* gb, const float* ul, const float* vl)
+{
+    const float w0 = (float)ws9[3], w1 = (float)ws9[4], w2 = (float)ws9[5];
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const size_t i = (size_t)y * W + x;
+            const int vec = in_group(x, W);
+            float r = R[i], g = G[i], b = B[i];
+            if (gr) {
+                r = vec ? lut_v(gr, 65536, r) : lut_s(gr, 65536, CLIP_BELOW | CLIP_ABOVE, r);
+                g = vec ? lut_v(gg, 65536, g) : lut_s(gg, 65536, CLIP_BELOW | CLIP_ABOVE, g);
+                b = vec ? lut_v(gb, 65536, b) : lut_s(gb, 65536, CLIP_BELOW | CLIP_ABOVE, b);
+            }
+            const float bw = ((bwr * r + bwg * g + bwb * b) * kcorec);
+            r = g = b = bw;
+            if (ul) {
+                const float Y = r * w0 + g * w1 + b * w2;
+                float u = Y - b, v = r - Y;
+                u += vec ? lut_v(ul, 65536, Y) : lut_s(ul, 65536, CLIP_BELOW | CLIP_ABOVE, Y);
+                v += vec ? lut_v(vl, 65536, Y) : lut_s(vl, 65536, CLIP_BELOW | CLIP_ABOVE, Y);
+                b = Y - u; r = v + Y;
+                g = (Y - r * w0 - b * w2) / w1;
+            }
+            R[i] = r; G[i] = g; B[i] = b;
+        }
+    return 0;
+}
+
 /* ---- Lab ---- */
 static float g_cachef[65536], g_cachefy[65536];
 static int g_cache_ready = 0;

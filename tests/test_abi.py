@@ -71,6 +71,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
         "art_hp_chain_params": (api._ChainParamsC, ["exposure_enabled", "exp_scale", "black", "saturation_enabled", "vibrance", "tonecurve_mode",
                                                      "tonecurve_lut", "rcurve", "bcurve", "lab_enabled", "lab_lcurve", "lab_bcurve", "lab_chroma", "ws", "iws",
                                                      "tonecurve_whitept", "tonecurve_stages", "tonecurve_nstages", "neutral_to_out", "neutral_to_work", "satcurve_lut", "softlight_lut"]),
+        "art_hp_bw_params": (api._BwParamsC, ["bwr", "bwg", "bwb", "kcorec", "gamma_r", "gamma_g", "gamma_b", "ulut", "vlut", "ws"]),
         "art_hp_toneeq_params": (api._ToneEqParamsC, ["bands", "regularization", "pivot", "scale", "ws"]),
         "art_hp_flat_curve": (api._FlatCurveC, ["n", "poly_x", "poly_y", "dy_by_dx"]),
         "art_hp_hsl_params": (api._HslParamsC, ["hcurve", "scurve", "lcurve", "coeff", "smoothing", "scale", "ws"]),

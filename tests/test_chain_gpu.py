@@ -161,3 +161,17 @@ def test_lab_histogram_matches_oracle(hot_path, W, H, name):
     assert int(got.sum()) == W * H
     assert np.array_equal(got, want)
     same(planes, keep)
+
+
+@pytest.mark.parametrize("W,H", SIZES + [(2001, 1333)])
+@pytest.mark.parametrize("gamma,cast", [(False, False), (True, False), (False, True), (True, True)])
+def test_black_and_white_matches_oracle(hot_path, W, H, gamma, cast):
+    """art_hp_black_and_white = ImProcFunctions::blackAndWhite's pixel loops (ipbw.cc L283-312, L343-362); the oracle is pinned to them in test_oracle_chain.py"""
+    from art_b200.api import BwParams
+    from test_oracle_chain import bw_args, bw_tables
+    planes = image(H, W, W * 5 + H + gamma)
+    tabs = bw_tables(W, gamma, cast)
+    want = call(oracle.port().lib, "artoracle_bw", planes, *bw_args((0.43, 0.33, 0.30), 1.06, tabs))
+    got = [p.copy() for p in planes]
+    hot_path.black_and_white(got[0], got[1], got[2], BwParams((0.43, 0.33, 0.30), 1.06, tabs[:3] if gamma else None, tabs[3:] if cast else None, PROPHOTO))
+    same(got, want)

@@ -166,3 +166,31 @@ def test_softlight(W, H, strength):
     want = call(oracle.ref().lib, "artref_softlight", planes, int(strength), None)
     same(call(oracle.port().lib, "artoracle_chain_softlight", planes, lut.ctypes.data_as(fp)), want)
     assert max(float(np.nanmax(np.abs(w - p))) for w, p in zip(want, planes)) > 1.0
+
+
+def bw_tables(seed, gamma=True, cast=True):
+    """tables shaped like ImProcFunctions::blackAndWhite builds them (ipbw.cc L264-272, L321-341): three gamma tables, the colour cast's u / v tables"""
+    x = np.arange(65536, dtype=np.float64) / 65535.0
+    g = [(x ** e * 65535.0).astype(np.float32) for e in (0.8, 1.0, 1.25)] if gamma else [None, None, None]
+    if cast:
+        y = x ** 0.9 * 65535.0
+        c = np.exp(-((x - 0.5) / 0.25) ** 2)
+        ul, vl = (y * 0.08 * c * np.cos(0.7 + seed)).astype(np.float32), (y * 0.08 * c * np.sin(0.7 + seed)).astype(np.float32)
+    else:
+        ul = vl = None
+    return g + [ul, vl]
+
+
+def bw_args(mix, kcorec, tabs):
+    return (PROPHOTO.ctypes.data_as(dp), F(mix[0]), F(mix[1]), F(mix[2]), F(kcorec), *[t.ctypes.data_as(fp) if t is not None else None for t in tabs])
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", SIZES + [(301, 211)])
+@pytest.mark.parametrize("gamma,cast", [(False, False), (True, False), (False, True), (True, True)])
+def test_black_and_white(W, H, gamma, cast):
+    """the port against ImProcFunctions::blackAndWhite's own pixel loops (ipbw.cc L283-312, L343-362) and Imagefloat's YUV round trip"""
+    planes = image(H, W, W * 5 + H + gamma)
+    tabs = bw_tables(W, gamma, cast)
+    args = bw_args((0.43, 0.33, 0.30), 1.06, tabs)
+    same(call(oracle.port().lib, "artoracle_bw", planes, *args), call(oracle.ref().lib, "artref_bw", planes, *args))
