@@ -149,6 +149,13 @@ def test_lab_adjustments(W, H, chroma):
 
 def softlight_lut(strength):
     """ImProcFunctions::softLight's table f[i] = sl(strength / 100, i), built by the reference's own code"""
+    if not oracle.have_ref():      # no oracle/_ref on this machine: the same Pegtop blend in numpy -- any table serves the parity of the apply loop
+        x = np.arange(65536, dtype=np.float64) / 65535.0
+        v = np.where(x <= 0.0031308, 12.92 * x, 1.055 * np.maximum(x, 1e-12) ** (1 / 2.4) - 0.055)
+        v = v * v + 2 * v * v - 2 * v * v * v
+        lin = np.where(v <= 0.04045, v / 12.92, ((v + 0.055) / 1.055) ** 2.4) * 65535.0
+        b = strength / 100.0
+        return (b * lin + (1 - b) * x * 65535.0).astype(np.float32)
     lut = np.zeros(65536, np.float32)
     z = [np.zeros((1, 1), np.float32) for _ in range(3)]
     assert oracle.ref().lib.artref_softlight(z[0].ctypes.data_as(fp), z[1].ctypes.data_as(fp), z[2].ctypes.data_as(fp), 1, 1, int(strength), lut.ctypes.data_as(fp)) == 0

@@ -28,8 +28,31 @@ def flat_points(seed, npts=6, amp=0.35):
     return pts
 
 
+def curve_key(pts, periodic, poly_pn):
+    import hashlib
+    return hashlib.sha1(np.array(list(pts) + [float(periodic), float(poly_pn)], np.float64).tobytes()).hexdigest()[:16]
+
+
+_GOLDEN = None
+
+
 def polyline(pts, periodic=True, poly_pn=1000):
-    """(n, px, py, dy) of the FlatCurve the reference builds from the control points; n = 0 for an identity curve"""
+    """(n, px, py, dy) of the FlatCurve the reference builds from the control points; n = 0 for an identity curve.  Read from the committed
+    fixture tests/golden/hsl_polylines.npz (made by tests/golden/make_hsl_golden.py from the reference's constructor) when it holds the curve,
+    else built by oracle/_ref."""
+    global _GOLDEN
+    if _GOLDEN is None:
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hsl_polylines.npz")
+        _GOLDEN = dict(np.load(path)) if os.path.exists(path) else {}
+    key = curve_key(pts, periodic, poly_pn)
+    if key + "_n" in _GOLDEN:
+        n = int(_GOLDEN[key + "_n"][0])
+        return n, _GOLDEN[key + "_x"].copy(), _GOLDEN[key + "_y"].copy(), _GOLDEN[key + "_d"].copy()
+    return polyline_from_reference(pts, periodic, poly_pn)
+
+
+def polyline_from_reference(pts, periodic=True, poly_pn=1000):
     lib = oracle.ref().lib
     cap = 65536
     px, py, dy = np.zeros(cap), np.zeros(cap), np.zeros(cap)
@@ -130,3 +153,10 @@ def test_flat_getval_of_the_polyline_matches_the_reference_curve():
                 lo = k
         want = lib.artref_flat_getval(a.ctypes.data_as(dp), len(pts), 1, 1000, ctypes.c_double(t))
         assert py[lo] + (tt - px[lo]) * dy[lo] == want
+
+
+@needs_ref
+def test_golden_polylines_are_the_reference_constructor_output():
+    for pts, pn in ((COEFF, 1000), (CASES["all"][0], 1000), (CASES["all"][2], 500), (CASES["s_only"][1], 1000)):
+        a, b = polyline(pts, True, pn), polyline_from_reference(pts, True, pn)
+        assert a[0] == b[0] and all(np.array_equal(x, y) for x, y in zip(a[1:], b[1:]))
