@@ -30,11 +30,11 @@ __device__ __forceinline__ void box_line(const float* x, size_t xs, float* y, si
         ++len;
     }
     const float rlen = 1.f / len;
-    // steady state, loads software-pipelined sixteen samples ahead: a launch has one thread per line (a few thousand threads), so the memory
+    // steady state, loads software-pipelined 32 samples ahead: a launch has one thread per line (a few thousand threads), so the memory
     // latency of a step is only hidden by the loads the thread itself keeps in flight
     int c = radius + 1;
     const int cend = n - radius;
-    constexpr int PF = 16;
+    constexpr int PF = 32;
     for (; c + PF - 1 < cend; c += PF) {
         float in[PF], old[PF];
         #pragma unroll
