@@ -64,12 +64,12 @@ __global__ void __launch_bounds__(64) k_box_h(BoxArgs a)      // thread per row 
     float* Y = blockIdx.y ? a.y2 : a.y;
     if (r < a.H) box_line(X + (size_t)r * a.xp, 1, Y + (size_t)r * a.yp, 1, a.W, a.radius, false);
 }
-// The horizontal pass for radius <= 111: a warp owns BH_ROWS = 4 rows and streams along them in 32-column tiles -- coalesced row segments into
+// The horizontal pass for radius <= 111: a warp owns BH_ROWS = 2 rows and streams along them in 32-column tiles -- coalesced row segments into
 // registers (the next tile's loads in flight while this one is processed), the samples parked in a shared-memory ring of `ring` columns
-// (>= 2 radius + 33), the steady-state increments (x[c + r] - x[c - r - 1]) / len formed by all lanes, then lane k < 4 walks row k's chain (one
+// (>= 2 radius + 33), the steady-state increments (x[c + r] - x[c - r - 1]) / len formed by all lanes, then lane k < 2 walks row k's chain (one
 // dependent add per step) and the means leave through the same transposing tile.  Same operations in the same order as box_line; what changes is
 // that every global access is a contiguous 128-byte row segment instead of 32 rows' worth of 4-byte samples (k_box_h: 0.46 TB/s at 45 MP).
-constexpr int BH_ROWS = 4, BH_WARPS = 2, BH_SP = 36;
+constexpr int BH_ROWS = 2, BH_WARPS = 4, BH_SP = 36;
 __global__ void __launch_bounds__(BH_WARPS * 32) k_box_h_tiles(BoxArgs a, int ring)
 {
     extern __shared__ __align__(16) float bh_shm[];
