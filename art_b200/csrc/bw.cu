@@ -34,6 +34,7 @@ struct BwArgs {
     float bwr, bwg, bwb, kcorec;
     const float *gr, *gg, *gb, *ul, *vl;
     float w0, w1, w2;
+    int aligned;
 };
 
 template <bool VEC>
@@ -62,7 +63,12 @@ __global__ void __launch_bounds__(128) k_bw(const BwArgs a)
     if (x0 >= a.W) return;
     for (int y = blockIdx.y; y < a.H; y += gridDim.y) {
         const size_t row = (size_t)y * a.ip;
-        if (x0 + 4 <= a.W) {
+        if (x0 + 4 <= a.W && a.aligned) {        // 16-byte aligned planes: one 128-bit access per plane and group
+            float4 vr = *reinterpret_cast<const float4*>(a.r + row + x0), vg = *reinterpret_cast<const float4*>(a.g + row + x0),
+                   vb = *reinterpret_cast<const float4*>(a.b + row + x0);
+            bw_pixel<true>(a, vr.x, vg.x, vb.x); bw_pixel<true>(a, vr.y, vg.y, vb.y); bw_pixel<true>(a, vr.z, vg.z, vb.z); bw_pixel<true>(a, vr.w, vg.w, vb.w);
+            *reinterpret_cast<float4*>(a.r + row + x0) = vr; *reinterpret_cast<float4*>(a.g + row + x0) = vg; *reinterpret_cast<float4*>(a.b + row + x0) = vb;
+        } else if (x0 + 4 <= a.W) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const size_t i = row + x0 + k;
@@ -107,6 +113,7 @@ int art_bw_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size
     a.r = r; a.g = g; a.b = b; a.ip = ip; a.W = W; a.H = H;
     a.bwr = p->bwr; a.bwg = p->bwg; a.bwb = p->bwb; a.kcorec = p->kcorec;
     a.gr = dev[0]; a.gg = dev[1]; a.gb = dev[2]; a.ul = dev[3]; a.vl = dev[4];
+    a.aligned = ip % 4 == 0 && ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
     if (p->ws) { a.w0 = (float)p->ws[3]; a.w1 = (float)p->ws[4]; a.w2 = (float)p->ws[5]; }
     art_prof_begin(ctx, "k_bw");
     k_bw<<<dim3(((W + 3) / 4 + 127) / 128, std::min(H, 148 * 8)), 128, 0, st>>>(a);

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) k_teq_mid(float* __restrict__ Y, float* _
 
 // L311-337, then Imagefloat::multiply(1.f / gain)
 __global__ void __launch_bounds__(128) k_teq_apply(float* __restrict__ r, float* __restrict__ g, float* __restrict__ b, size_t ip, int W, int H,
-                                                   const float* __restrict__ Y, size_t yp, const float* __restrict__ lut, const float* __restrict__ consts, float back)
+                                                   const float* __restrict__ Y, size_t yp, const float* __restrict__ lut, const float* __restrict__ consts, float back, int aligned)
 {
     __shared__ float k[13];
     if (threadIdx.x < 13) k[threadIdx.x] = consts[threadIdx.x];
@@ -135,15 +135,30 @@ __global__ void __launch_bounds__(128) k_teq_apply(float* __restrict__ r, float*
         const float* cy = Y + (size_t)y * yp;
         const size_t row = (size_t)y * ip;
         if (x0 + 4 <= W) {
-            float c[4];
+            float c[4], corr[4];
+            if (aligned) { const float4 v = *reinterpret_cast<const float4*>(cy + x0); c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w; }
+            else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) c[j] = cy[x0 + j];
+                for (int j = 0; j < 4; ++j) c[j] = cy[x0 + j];
+            }
             const bool any = c[0] > 1.f || c[1] > 1.f || c[2] > 1.f || c[3] > 1.f;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float corr = any ? vprocess_pixel(c[j], k) : lut_v(lut, 65536, c[j] * 65535.f);
-                const size_t i = row + x0 + j;
-                r[i] = r[i] * corr * back; g[i] = g[i] * corr * back; b[i] = b[i] * corr * back;
+            for (int j = 0; j < 4; ++j) corr[j] = any ? vprocess_pixel(c[j], k) : lut_v(lut, 65536, c[j] * 65535.f);
+            if (aligned) {      // 16-byte aligned planes: one 128-bit access per plane and group
+                float* pl[3] = {r, g, b};
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    float4* p4 = reinterpret_cast<float4*>(pl[q] + row + x0);
+                    float4 v = *p4;
+                    v.x = v.x * corr[0] * back; v.y = v.y * corr[1] * back; v.z = v.z * corr[2] * back; v.w = v.w * corr[3] * back;
+                    *p4 = v;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const size_t i = row + x0 + j;
+                    r[i] = r[i] * corr[j] * back; g[i] = g[i] * corr[j] * back; b[i] = b[i] * corr[j] * back;
+                }
             }
         } else {
             for (int x = x0; x < W; ++x) {
@@ -205,8 +220,9 @@ int art_tone_equalizer_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, fl
         if (!rc && reg > 1) rc = art_guided_dev(ctx, Y2, yp, Y, yp, Y, yp, W, H, radius2 * (reg - 1), epsilon / 100, 0);
     }
     if (!rc) {
+        const int aligned = ip % 4 == 0 && ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
         art_prof_begin(ctx, "k_teq_apply");
-        k_teq_apply<<<dim3(((W + 3) / 4 + 127) / 128, std::min(H, 148 * 8)), 128, 0, st>>>(r, g, b, ip, W, H, Y, yp, lut, consts, back);
+        k_teq_apply<<<dim3(((W + 3) / 4 + 127) / 128, std::min(H, 148 * 8)), 128, 0, st>>>(r, g, b, ip, W, H, Y, yp, lut, consts, back, aligned);
         art_prof_end(ctx);
         ctx->launches++;
     }
