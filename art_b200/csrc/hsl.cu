@@ -14,7 +14,10 @@
 
 namespace {
 
-struct FlatDev { int n; const double *px, *py, *dy; };
+// start: for t in [0, 2), start[(int)(512 t)] = the interval FlatCurve::getVal's binary search returns at the bucket's lower edge; the interval of t
+// is reached from there in a step or two instead of ten dependent probes
+constexpr int HSL_BUCKETS = 1024;
+struct FlatDev { int n; const double *px, *py, *dy; const int* start; };
 struct HslArgs {
     float *r, *g, *b; size_t ip;
     float* mask; size_t mp;
@@ -28,10 +31,18 @@ struct HslArgs {
 __device__ __forceinline__ double flat_getval(const FlatDev& c, double t)
 {   // FCT_MinMaxCPoints, flatcurves.cc L344-365
     if (t < c.px[0]) t += 1.0;
-    unsigned k_lo = 0, k_hi = (unsigned)c.n - 1;
-    while (k_hi > 1 + k_lo) {
-        const unsigned k = (k_hi + k_lo) / 2;
-        if (c.px[k] > t) k_hi = k; else k_lo = k;
+    unsigned k_lo;
+    if (t >= 0.0 && t < 2.0) {
+        // the search below ends on the largest k <= n - 2 with px[k] <= t (0 when there is none): the same k, walked to from the bucket's start
+        k_lo = (unsigned)c.start[(int)(t * 512.0)];
+        while (k_lo + 2 < (unsigned)c.n && c.px[k_lo + 1] <= t) ++k_lo;
+    } else {
+        k_lo = 0;
+        unsigned k_hi = (unsigned)c.n - 1;
+        while (k_hi > 1 + k_lo) {
+            const unsigned k = (k_hi + k_lo) / 2;
+            if (c.px[k] > t) k_hi = k; else k_lo = k;
+        }
     }
     return c.py[k_lo] + (t - c.px[k_lo]) * c.dy[k_lo];
 }
@@ -111,18 +122,28 @@ int art_hsl_equalizer_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, flo
     cudaStream_t st = ctx->stream;
     const size_t mp = round_up((size_t)W, 32), n = mp * (size_t)H;
     void* blk = nullptr;
-    int rc = art_pool_alloc(ctx, round_up(n * sizeof(float), 256) + (doubles + 1) * sizeof(double), &blk);
+    const size_t curve_bytes = round_up(doubles * sizeof(double), 256);
+    int rc = art_pool_alloc(ctx, round_up(n * sizeof(float), 256) + curve_bytes + 4 * HSL_BUCKETS * sizeof(int), &blk);
     if (rc) return rc;
     float* mask = (float*)blk;
     double* dcur = (double*)((char*)blk + round_up(n * sizeof(float), 256));
+    int* dstart = (int*)((char*)dcur + curve_bytes);
     FlatDev dev[4];
     {
         std::vector<double> host(doubles);
+        std::vector<int> hstart(4 * HSL_BUCKETS, 0);
         size_t off = 0;
         for (int c = 0; c < 4; ++c) {
             const int k = cv[c]->n;
             dev[c].n = k;
             dev[c].px = dcur + off; dev[c].py = dcur + off + k; dev[c].dy = dcur + off + 2 * (size_t)k;
+            dev[c].start = dstart + c * HSL_BUCKETS;
+            for (int b = 0; k && b < HSL_BUCKETS; ++b) {      // the binary search of flatcurves.cc L351-362 at t = b / 512
+                const double t = b / 512.0;
+                unsigned lo = 0, hi = (unsigned)k - 1;
+                while (hi > 1 + lo) { const unsigned m = (hi + lo) / 2; if (cv[c]->poly_x[m] > t) hi = m; else lo = m; }
+                hstart[c * HSL_BUCKETS + b] = (int)lo;
+            }
             if (k) {
                 memcpy(&host[off], cv[c]->poly_x, k * sizeof(double));
                 memcpy(&host[off + k], cv[c]->poly_y, k * sizeof(double));
@@ -132,7 +153,8 @@ int art_hsl_equalizer_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, flo
         }
         // pageable source: cudaMemcpyAsync returns once the bytes are staged, `host` may go out of scope
         if (doubles) {
-            const cudaError_t e = cudaMemcpyAsync(dcur, host.data(), doubles * sizeof(double), cudaMemcpyHostToDevice, st);
+            cudaError_t e = cudaMemcpyAsync(dcur, host.data(), doubles * sizeof(double), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dstart, hstart.data(), hstart.size() * sizeof(int), cudaMemcpyHostToDevice, st);
             if (e != cudaSuccess) { art_pool_free(ctx, blk); return ctx->fail(ART_HP_ERR_CUDA, "curve upload failed: %s", cudaGetErrorString(e)); }
         }
     }
