@@ -126,6 +126,8 @@ def load_library(build_if_missing=True):
         "art_hp_dual_demosaic_xtrans_dev": (i, [vp, i, i, i, i, vp, vp, vp, sz, vp, vp, vp, sz, d, i, vp]),
         "art_hp_lab_histogram": (i, [vp, i, i, vp, vp, vp, vp, vp]),
         "art_hp_lab_histogram_dev": (i, [vp, i, i, vp, vp, vp, sz, vp, vp]),
+        "art_hp_prophoto_blue": (i, [vp, i, i, vp, vp, vp]),
+        "art_hp_prophoto_blue_dev": (i, [vp, i, i, vp, vp, vp, sz]),
         "art_hp_black_and_white": (i, [vp, i, i, vp, vp, vp, vp]),
         "art_hp_black_and_white_dev": (i, [vp, i, i, vp, vp, vp, sz, vp]),
         "art_hp_tone_equalizer": (i, [vp, i, i, vp, vp, vp, vp]),
@@ -816,6 +818,12 @@ class HotPath:
                                                          cam.ctypes.data_as(ctypes.c_void_p), row_table(raw), *[row_table(o) for o in out],
                                                          ctypes.byref(c), int(bool(auto_contrast))))
         return out, c.value
+
+    def prophoto_blue(self, r, g, b):
+        """proPhotoBlue (improcfun.cc L312-357) in place on three host (H, W) float32 planes."""
+        H, W = r.shape
+        self._check(self.lib.art_hp_prophoto_blue(self.h, W, H, row_table(r), row_table(g), row_table(b)))
+        return r, g, b
 
     def black_and_white(self, r, g, b, params):
         """ImProcFunctions::blackAndWhite's pixel loops in place on three host (H, W) float32 working-space RGB planes."""

@@ -1307,6 +1307,34 @@ int art_hp_hsl_equalizer(art_hp_ctx* ctx, int W, int H, float* const* r, float* 
     return ART_HP_OK;
 }
 
+// ---- proPhotoBlue (bw.cu)
+int art_hp_prophoto_blue_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!d_r || !d_g || !d_b) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1 || pitch < (size_t)W) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    return art_prophoto_blue_dev(ctx, W, H, d_r, d_g, d_b, pitch);
+}
+
+int art_hp_prophoto_blue(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b)
+{
+    if (!ctx) return ART_HP_ERR_INVALID;
+    if (!r || !g || !b) return ctx->fail(ART_HP_ERR_INVALID, "null pointer");
+    if (W < 1 || H < 1) return ctx->fail(ART_HP_ERR_INVALID, "bad geometry %dx%d", W, H);
+    ART_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t pitch = round_up((size_t)W, 32);
+    int rc;
+    for (int i = 0; i < 3; ++i)
+        if ((rc = art_reserve(ctx, ctx->d_out[i], pitch * (size_t)H * sizeof(float)))) return rc;
+    Plane io[3] = {{r, (float*)ctx->d_out[0].p}, {g, (float*)ctx->d_out[1].p}, {b, (float*)ctx->d_out[2].p}};
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, true))) return rc;
+    if ((rc = art_prophoto_blue_dev(ctx, W, H, io[0].dev, io[1].dev, io[2].dev, pitch))) return rc;
+    if ((rc = transfer(ctx, ctx->stream, io, 3, W, 0, H, pitch, false))) return rc;
+    ART_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ART_HP_OK;
+}
+
 // ---- black and white (bw.cu)
 int art_hp_black_and_white_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch, const art_hp_bw_params* params)
 {

@@ -171,6 +171,7 @@ const float* art_dual_threshold_slot(art_hp_ctx* ctx);
 int art_dual_blend_dev(art_hp_ctx* ctx, int second, int W, int H, unsigned cfa, const int* xtrans36, const float* raw, size_t rp,
                        float* R, float* G, float* B, size_t op, double contrast, int auto_contrast, float* d_threshold_out);
 // ImProcFunctions::channelMixer's loop (pointwise.cu), planes in place; m = RR RG RB / GR GG GB / BR BG BB
+int art_prophoto_blue_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t ip);
 int art_bw_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t ip, const art_hp_bw_params* p);
 int art_tone_equalizer_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t ip, const art_hp_toneeq_params* p);
 int art_hsl_equalizer_dev(art_hp_ctx* ctx, int W, int H, float* r, float* g, float* b, size_t ip, const art_hp_hsl_params* p);

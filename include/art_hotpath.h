@@ -602,6 +602,16 @@ typedef struct art_hp_toneeq_params {
 int art_hp_tone_equalizer(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b, const art_hp_toneeq_params* params);
 int art_hp_tone_equalizer_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch, const art_hp_toneeq_params* params);
 
+/* ---- proPhotoBlue ------------------------------------------------------------------ */
+/*
+ * art_hp_prophoto_blue   proPhotoBlue(img, multiThread) (rtengine/improcfun.cc L312-357), the step ImProcFunctions::process STAGE_1 ends with when
+ *                        params->icm.workingProfile == "ProPhoto" (L585-587), in place on working-space RGB planes: a pixel with r == 0 or g == 0 and no
+ *                        negative channel loses 1 % of its HSV saturation (Color::rgb2hsv / hsv2rgb, rtengine/color.cc L586-622, L654-694).
+ *                        Bit-identical to the reference.
+ */
+int art_hp_prophoto_blue(art_hp_ctx* ctx, int W, int H, float* const* r, float* const* g, float* const* b);
+int art_hp_prophoto_blue_dev(art_hp_ctx* ctx, int W, int H, float* d_r, float* d_g, float* d_b, size_t pitch);
+
 /* ---- black and white --------------------------------------------------------------- */
 /*
  * art_hp_black_and_white   the pixel loops of ImProcFunctions::blackAndWhite (rtengine/ipbw.cc L283-312, L343-362; the last step of STAGE_3), in place

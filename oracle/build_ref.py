@@ -1509,6 +1509,8 @@ public:
     static void Lab2XYZ(float L, float a, float b, float &x, float &y, float &z);
     static void Lab2XYZ(vfloat L, vfloat a, vfloat b, vfloat &x, vfloat &y, vfloat &z);
     static void filmlike_clip(float *r, float *g, float *b, float Lmax);
+    static void rgb2hsv(float r, float g, float b, float &h, float &s, float &v);
+    static void hsv2rgb (float h, float s, float v, float &r, float &g, float &b);
 };
 LUTf Color::cachef, Color::cachefy;
 #include "chain_color_cc.inc"
@@ -1563,6 +1565,7 @@ class LuminanceToneCurve : public ToneCurve { public: void Apply(float& r, float
 namespace {
 #include "chain_iptonecurve.inc"
 #include "chain_vibrance.inc"
+#include "chain_prophotoblue.inc"
 }
 
 extern "C" {
@@ -1649,6 +1652,14 @@ int artref_chain_tonecurve_ex(float* R, float* G, float* B, int W, int H, int mo
 #pragma omp parallel for if (multithread)
 #include "chain_lumtone_loop.inc"
     } else return -1;
+    im.store(R, G, B);
+    return 0;
+}
+// proPhotoBlue (improcfun.cc L312-357): STAGE_1's last step when the working profile is ProPhoto
+int artref_prophoto_blue(float* R, float* G, float* B, int W, int H)
+{
+    Imagefloat im(W, H, R, G, B, (const double[9]){1,0,0,0,1,0,0,0,1}, nullptr);
+    proPhotoBlue(&im, true);
     im.store(R, G, B);
     return 0;
 }
@@ -2108,8 +2119,11 @@ def extract(det):
            cut_function(cc, r"^void Color::Lab2XYZ\(float L, float a, float b, float &x, float &y, float &z\)"),
            cut_function(cc, r"^void Color::Lab2XYZ\(vfloat L, vfloat a, vfloat b, vfloat &x, vfloat &y, vfloat &z\)"),
            cut_function(cc, r"^inline void filmlike_clip_rgb_tone\(float \*r, float \*g, float \*b, const float L\)"),
-           cut_function(cc, r"^void Color::filmlike_clip\(float \*r, float \*g, float \*b, float Lmax\)")]
+           cut_function(cc, r"^void Color::filmlike_clip\(float \*r, float \*g, float \*b, float Lmax\)"),
+           cut_function(cc, r"^void Color::rgb2hsv\(float r, float g, float b, float &h, float &s, float &v\)"),
+           cut_function(cc, r"^void Color::hsv2rgb \(float h, float s, float v, float &r, float &g, float &b\)")]
     open(os.path.join(sub, "chain_color_cc.inc"), "w").write("\n".join(ccf))
+    open(os.path.join(sub, "chain_prophotoblue.inc"), "w").write(cut_function(os.path.join(RT, "improcfun.cc"), r"^void proPhotoBlue\(Imagefloat \*rgb, bool multiThread\)"))
     open(os.path.join(sub, "shim_chain.cc"), "w").write(SHIM_CHAIN_TU)
 
     # USM sharpening (ipsharpen.cc, rt_algo.cc)

@@ -315,6 +315,47 @@ int artoracle_bw(float* R, float* G, float* B, int W, int H, const double* ws9, 
     return 0;
 }
 
+/* ---- proPhotoBlue (improcfun.cc L312-357), the step ImProcFunctions::process runs after toneEqualizer when the working profile is ProPhoto (L585-587):
+ * a pixel with r == 0 or g == 0 and no negative channel loses 1 % of its HSV saturation; Color::rgb2hsv computes in double (color.cc L586-622),
+ * Color::hsv2rgb in float (L654-694).  The SSE2 group test only skips groups without such a pixel: the rule is per pixel ---- */
+int artoracle_prophoto_blue(float* R, float* G, float* B, int W, int H)
+{
+    for (size_t i = 0; i < (size_t)W * H; ++i) {
+        const float r = R[i], g = G[i], b = B[i];
+        const float mn0 = g < r ? g : r, mn = b < mn0 ? b : mn0;       /* rtengine::min(r, g, b) */
+        if (!((r == 0.0f || g == 0.0f) && mn >= 0.f)) continue;
+        const double var_R = r / 65535.0, var_G = g / 65535.0, var_B = b / 65535.0;
+        const double m0 = var_G < var_R ? var_G : var_R, var_Min = var_B < m0 ? var_B : m0;
+        const double x0 = var_R < var_G ? var_G : var_R, var_Max = x0 < var_B ? var_B : x0;
+        const double del_Max = var_Max - var_Min;
+        float h = 0.f, s, v = (float)var_Max;
+        if (del_Max < 0.00001 && del_Max > -0.00001) s = 0.f;
+        else {
+            s = (float)(del_Max / (var_Max == 0.0 ? 1.0 : var_Max));
+            if (var_R == var_Max) h = (float)((var_G - var_B) / del_Max);
+            else if (var_G == var_Max) h = (float)(2.0 + (var_B - var_R) / del_Max);
+            else if (var_B == var_Max) h = (float)(4.0 + (var_R - var_G) / del_Max);
+            h /= 6.f;
+            if (h < 0.f) h += 1.f;
+            if (h > 1.f) h -= 1.f;
+        }
+        s *= 0.99f;
+        const float h1 = h * 6.f;
+        const int k = (int)h1;
+        const float f = h1 - k;
+        const float p = v * (1.f - s), q = v * (1.f - s * f), t = v * (1.f - s * (1.f - f));
+        float r1, g1, b1;
+        if (k == 1) { r1 = q; g1 = v; b1 = p; }
+        else if (k == 2) { r1 = p; g1 = v; b1 = t; }
+        else if (k == 3) { r1 = p; g1 = q; b1 = v; }
+        else if (k == 4) { r1 = t; g1 = p; b1 = v; }
+        else if (k == 5) { r1 = v; g1 = p; b1 = q; }
+        else { r1 = v; g1 = t; b1 = p; }
+        R[i] = r1 * 65535.0f; G[i] = g1 * 65535.0f; B[i] = b1 * 65535.0f;
+    }
+    return 0;
+}
+
 /* ---- Lab ---- */
 static float g_cachef[65536], g_cachefy[65536];
 static int g_cache_ready = 0;

@@ -175,3 +175,14 @@ def test_black_and_white_matches_oracle(hot_path, W, H, gamma, cast):
     got = [p.copy() for p in planes]
     hot_path.black_and_white(got[0], got[1], got[2], BwParams((0.43, 0.33, 0.30), 1.06, tabs[:3] if gamma else None, tabs[3:] if cast else None, PROPHOTO))
     same(got, want)
+
+
+@pytest.mark.parametrize("W,H", SIZES + [(2001, 1333)])
+def test_prophoto_blue_matches_oracle(hot_path, W, H):
+    """art_hp_prophoto_blue = proPhotoBlue (improcfun.cc L312-357); the oracle is pinned to it in test_oracle_chain.py"""
+    from test_oracle_chain import blue_image
+    planes = blue_image(H, W, W * 3 + H)
+    want = call(oracle.port().lib, "artoracle_prophoto_blue", planes)
+    got = [p.copy() for p in planes]
+    hot_path.prophoto_blue(got[0], got[1], got[2])
+    same(got, want)

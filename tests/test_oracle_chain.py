@@ -201,3 +201,25 @@ def test_black_and_white(W, H, gamma, cast):
     tabs = bw_tables(W, gamma, cast)
     args = bw_args((0.43, 0.33, 0.30), 1.06, tabs)
     same(call(oracle.port().lib, "artoracle_bw", planes, *args), call(oracle.ref().lib, "artref_bw", planes, *args))
+
+
+def blue_image(H, W, seed):
+    """saturated blues and other pixels with r == 0 or g == 0 (what proPhotoBlue touches), negatives (left alone), ordinary pixels"""
+    planes = image(H, W, seed)
+    rng = np.random.default_rng(seed + 1)
+    m = rng.random((H, W))
+    planes[0][m < 0.25] = 0.0
+    planes[1][(m > 0.2) & (m < 0.45)] = 0.0
+    planes[2][(m > 0.4) & (m < 0.5)] = 0.0
+    planes[2][m > 0.97] = 65535.0
+    return planes
+
+
+@needs_ref
+@pytest.mark.parametrize("W,H", SIZES + [(301, 211)])
+def test_prophoto_blue(W, H):
+    """the port against the reference's proPhotoBlue (improcfun.cc L312-357) with Color::rgb2hsv / hsv2rgb"""
+    planes = blue_image(H, W, W * 3 + H)
+    want = call(oracle.ref().lib, "artref_prophoto_blue", planes)
+    same(call(oracle.port().lib, "artoracle_prophoto_blue", planes), want)
+    assert sum(int((w != p).sum()) for w, p in zip(want, planes)) > 0
