@@ -186,3 +186,23 @@ def test_prophoto_blue_matches_oracle(hot_path, W, H):
     got = [p.copy() for p in planes]
     hot_path.prophoto_blue(got[0], got[1], got[2])
     same(got, want)
+
+
+def test_black_and_white_device_form_with_unaligned_pitch(hot_path):
+    """the device entry on planes whose rows are not 16-byte aligned: the scalar-access path of k_bw"""
+    import ctypes
+    torch = pytest.importorskip("torch")
+    from art_b200.api import BwParams
+    from test_oracle_chain import bw_args, bw_tables
+    W, H, pitch = 203, 41, 205
+    planes = image(H, W, 31)
+    tabs = bw_tables(5, True, True)
+    want = call(oracle.port().lib, "artoracle_bw", planes, *bw_args((0.3, 0.5, 0.2), 0.97, tabs))
+    dev = [torch.zeros((H, pitch), dtype=torch.float32, device="cuda") for _ in range(3)]
+    for d, p in zip(dev, planes):
+        d[:, :W] = torch.from_numpy(p).cuda()
+    torch.cuda.synchronize()
+    c = BwParams((0.3, 0.5, 0.2), 0.97, tabs[:3], tabs[3:], PROPHOTO).c_struct()
+    hot_path._check(hot_path.lib.art_hp_black_and_white_dev(hot_path.h, W, H, dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), pitch, ctypes.byref(c)))
+    hot_path.sync()
+    same([d[:, :W].cpu().numpy() for d in dev], want)

@@ -29,3 +29,19 @@ def test_toneeq_rejects_bad_parameters(hot_path):
         hot_path.tone_equalizer(planes[0], planes[1], planes[2], ToneEqParams((1, 2, 3, 4, 5), 0, 0.0, 1.0, None))            # no ws
     with pytest.raises(art_b200.HotPathError):
         hot_path.tone_equalizer(planes[0], planes[1], planes[2], ToneEqParams((1, 2, 3, 4, 5), 1, 0.0, 0.0, PROPHOTO))        # scale 0
+
+
+def test_toneeq_device_form_with_unaligned_pitch(hot_path):
+    """the device entry on planes whose rows are not 16-byte aligned (pitch W + 1): the scalar-access path of k_teq_apply"""
+    import ctypes
+    torch = pytest.importorskip("torch")
+    W, H, pitch = 203, 141, 205
+    planes = image(H, W, 77)
+    dev = [torch.zeros((H, pitch), dtype=torch.float32, device="cuda") for _ in range(3)]
+    for d, p in zip(dev, planes):
+        d[:, :W] = torch.from_numpy(p).cuda()
+    torch.cuda.synchronize()
+    c = ToneEqParams((40, 25, 0, -20, -35), 1, 0.5, 1.0, PROPHOTO).c_struct()
+    hot_path._check(hot_path.lib.art_hp_tone_equalizer_dev(hot_path.h, W, H, dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), pitch, ctypes.byref(c)))
+    hot_path.sync()
+    same([d[:, :W].cpu().numpy() for d in dev], port_teq(planes, (40, 25, 0, -20, -35), 1, 0.5, 1.0))
