@@ -79,3 +79,26 @@ def test_invalid_arguments(hot_path):
         hot_path.demosaic_bayer(7, raw, synth.RGGB)                        # unknown method
     with pytest.raises(art_b200.HotPathError):
         hot_path.demosaic_bayer(art_b200.BAYER_RCD, raw[:8, :8], synth.RGGB)
+
+
+def test_rawimagesource_mirror_other_sensors_and_methods(hot_path):
+    """the dispatcher mirror through the real library: X-Trans 3-pass against the oracle, VNG4 and a dual method against the entries called directly"""
+    import ctypes
+    fp = ctypes.POINTER(ctypes.c_float)
+    ip = ctypes.POINTER(ctypes.c_int)
+    xt = synth.xtrans_matrix()
+    cam = np.array(synth.XTRANS_RGB_CAM, np.float32)
+    xraw = synth.xtrans_frame(210, 150, xt, seed=4)
+    src = art_b200.RawImageSource(xraw, hot_path=hot_path, xtrans=xt, rgb_cam=cam)
+    got = src.demosaic("3-pass (best)")
+    want = [np.empty_like(xraw) for _ in range(3)]
+    assert oracle.port().lib.artoracle_xtrans(210, 150, np.ascontiguousarray(xt, np.int32).ctypes.data_as(ip), cam.ctypes.data_as(fp), 3, 1,
+                                              xraw.ctypes.data_as(fp), *[w.ctypes.data_as(fp) for w in want]) == 0
+    _cmp(got, want, "mirror x-trans")
+    f, pre = synth.RGGB, 0xb4b4b4b4
+    raw = synth.bayer_frame(300, 260, f, seed=10)
+    b = art_b200.RawImageSource(raw, f, hot_path=hot_path, prefilters=pre)
+    _cmp([p.copy() for p in b.demosaic("vng4")], hot_path.demosaic_vng4(raw, pre), "mirror vng4")
+    direct, c = hot_path.dual_demosaic_bayer(art_b200.BAYER_AMAZE, 0, raw, f, pre, 0.0, True, 1.0, 4)
+    _cmp([p.copy() for p in b.demosaic("amazebilinear", autoContrast=True)], direct, "mirror dual")
+    assert b.contrastThreshold == c
