@@ -9,6 +9,7 @@ anywhere (so the ABI can be inspected), computing without a GPU raises.
 from .api import (HotPath, HotPathError, lib_path, load_library, ABI_SYMBOLS,  # noqa: F401
                   BAYER_AMAZE, BAYER_RCD, XTRANS_3PASS, XTRANS_1PASS)
 from .rawimagesource import RawImageSource  # noqa: F401
+from .improcfun import ImProcFunctions  # noqa: F401
 from .batchqueue import BatchQueue  # noqa: F401
 from . import synth  # noqa: F401
 

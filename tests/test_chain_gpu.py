@@ -206,3 +206,37 @@ def test_black_and_white_device_form_with_unaligned_pitch(hot_path):
     hot_path._check(hot_path.lib.art_hp_black_and_white_dev(hot_path.h, W, H, dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), pitch, ctypes.byref(c)))
     hot_path.sync()
     same([d[:, :W].cpu().numpy() for d in dev], want)
+
+
+def test_improcfunctions_process_through_the_library(hot_path):
+    """art_b200.ImProcFunctions.process (the mirror of improcfun.cc L567-641) through the real entries: STAGE_1 = channelMixer, exposure, toneEqualizer
+    and STAGE_3 = one fused chain call + blackAndWhite, against the oracle ports applied in the reference's order"""
+    import ctypes
+    from types import SimpleNamespace as NS
+    from art_b200.api import BwParams, ToneEqParams
+    from art_b200.improcfun import ImProcFunctions, OUTPUT, STAGE_1, STAGE_3
+    from test_oracle_chain import bw_args, bw_tables
+    ip = ctypes.POINTER(ctypes.c_int)
+    W, H = 203, 97
+    planes = image(H, W, 123, wild=False)
+    mix = (np.array([800, 300, -100, -50, 1100, -50, 20, -400, 1380], np.float32) / np.float32(1000.0)).astype(np.float32)
+    bands = np.array([30, 10, 0, -10, -25], np.int32)
+    tabs = bw_tables(3, True, False)
+    lut = curve_lut(gamma=0.7, seed=9)
+    P = NS(chmixer=NS(enabled=True, matrix=mix), exposure=NS(enabled=True, expcomp=0.4, black=0.0), hsl=NS(enabled=False),
+           toneEqualizer=NS(enabled=True, params=ToneEqParams(bands, 0, 0.0, 1.0, PROPHOTO)), workingProfile="Rec2020",
+           saturation=NS(enabled=True, saturation=15, vibrance=5), toneCurve=NS(enabled=True, mode=0, lut=lut), rgbCurves=NS(enabled=False),
+           labCurve=NS(enabled=False), softlight=NS(enabled=True, lut=softlight_lut(30)),
+           blackwhite=NS(enabled=True, params=BwParams((0.43, 0.33, 0.30), 1.06, tabs[:3], None, PROPHOTO)))
+    got = [p.copy() for p in planes]
+    ipf = ImProcFunctions(P, hot_path, 1.0, PROPHOTO, PROPHOTO_INV)
+    ipf.process(OUTPUT, STAGE_1, *got)
+    lib = oracle.port().lib
+    want = call(lib, "artoracle_chmixer", planes, mix.ctypes.data_as(fp))
+    want = oracle_chain(want, exposure=(0.4, 0.0))
+    want = call(lib, "artoracle_tone_equalizer", want, PROPHOTO.ctypes.data_as(dp), bands.ctypes.data_as(ip), 0, ctypes.c_double(0.0), ctypes.c_double(1.0))
+    same(got, want)
+    ipf.process(OUTPUT, STAGE_3, *got)
+    want = oracle_chain(want, saturation=(15, 5), tonecurve=(0, lut), softlight=softlight_lut(30))
+    want = call(lib, "artoracle_bw", want, *bw_args((0.43, 0.33, 0.30), 1.06, tabs))
+    same(got, want)
